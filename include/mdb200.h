@@ -1,0 +1,262 @@
+/* mdb200.h — C ABI of libmdb200.so: the B200 (sm_100a) backend for the
+ * dune-multidomain assembly-and-solve hot path.
+ *
+ * There is no FFI/plugin boundary in the reference; the boundary is the C++
+ * template concept realised by Dune::PDELab::MultiDomain::GridOperator
+ * (reference dune/pdelab/multidomain/gridoperator.hh:38-214).  This header is the
+ * plain-C layer that a C++ facade with the reference's spellings
+ * (include/mdb200/multidomain.hh) lowers to.  Each entry point cites the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative MDB_E* code on failure;
+ *    mdb_last_error(ctx) returns the message.  No exception crosses the ABI.
+ *  - one context per host thread and per GPU; calls are ordered on the context's
+ *    CUDA stream.  Not re-entrant (the reference is not either:
+ *    gridoperator.hh:209-210 mutable assembler members).
+ *  - pointer arguments documented "host or device" may be either; the library
+ *    classifies them with cudaPointerGetAttributes.  Host buffers are copied
+ *    in/out inside the call (that is the e2e path); device buffers are used in
+ *    place (that is the resident path).
+ *  - all floating point is IEEE double; indices exported for parity are int64
+ *    (std::size_t in the reference), device-internal indices are int32.
+ *  - there is NO CPU fallback: if no CUDA device is usable mdb_create fails.
+ */
+#ifndef MDB200_H
+#define MDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdb_ctx mdb_ctx;
+
+/* ---- error codes -------------------------------------------------------- */
+enum {
+  MDB_OK = 0,
+  MDB_EINVAL = -1,      /* bad argument / unsupported combination (DUNE_THROW analogue) */
+  MDB_ECUDA = -2,       /* CUDA runtime error */
+  MDB_ESTATE = -3,      /* call out of order (e.g. assemble before finalize) */
+  MDB_ENOMEM = -4,
+  MDB_ENCCL = -5,
+  MDB_ENOTCONVERGED = -6
+};
+
+/* ---- finite elements (child spaces of the MultiDomainGridFunctionSpace) -- */
+enum {
+  MDB_FE_Q1 = 1,        /* QkLocalFiniteElementMap<...,1>  test/testpoisson.cc:168 */
+  MDB_FE_Q2 = 2         /* QkLocalFiniteElementMap<...,2>  test/testpoisson.cc:169 */
+};
+
+/* ---- subdomain conditions  (subdomainset.hh:82-133) ---------------------- */
+enum {
+  MDB_COND_EQUALITY = 0,  /* SubDomainEqualityCondition: set(e) == mask        */
+  MDB_COND_SUBSET = 1     /* SubDomainSubsetCondition:   set(e) contains mask  */
+};
+
+/* ---- analytic problem data.  Arbitrary user C++ functors cannot run on the
+ * device, so the data of the reference's drivers form a closed set. -------- */
+enum {
+  MDB_FN_ZERO = 0,
+  MDB_FN_CONST = 1,          /* p[0]                                                          */
+  MDB_FN_GAUSS = 2,          /* exp(-p[0] * |x - (p[1],p[2],p[3])|^2)   G of test/testpoisson.cc:92-99 (p0=1,c=.5) */
+  MDB_FN_BOX = 3,            /* p[0] if p[1]<x_d<p[2] for all d<dim else 0   F of test/testpoisson.cc:32-37 before :38 */
+  MDB_FN_TESTPOISSON_J = 4,  /* 0 on x1<1e-6 or x1>1-1e-6; -5 on x0>1-1e-6 && x1>.5+1e-6; else 0  test/testpoisson.cc:103-116 */
+  MDB_FN_INSTAT_G = 5,       /* time dependent Dirichlet data, test/testinstationarypoisson.cc:94-100 family: p[0]*sin(p[1]*t)*exp(-|x-c|^2), c=.5 */
+  MDB_FN_POLY2 = 6           /* p[0] + sum_d p[1+d]*x_d + p[4]*|x|^2  (manufactured-solution tests)     */
+};
+typedef struct mdb_function {
+  int32_t kind;
+  int32_t reserved;
+  double p[6];
+} mdb_function;
+
+enum {
+  MDB_BC_ALL_DIRICHLET = 0,
+  MDB_BC_ALL_NEUMANN = 1,
+  MDB_BC_TESTPOISSON = 2     /* test/testpoisson.cc:42-88: none on interior faces; Neumann on x1=0, x1=1 and
+                                on x0=1 && x1>.5; Dirichlet elsewhere                                        */
+};
+typedef struct mdb_bctype {
+  int32_t kind;
+  int32_t reserved;
+  double p[4];
+} mdb_bctype;
+
+/* ---- local operators (closed set) --------------------- */
+enum {
+  /* volume / boundary operators used by SubProblems */
+  MDB_OP_POISSON = 1,        /* [UPSTREAM] Dune::PDELab::Poisson<F,B,J>(f,b,j,quadOrder)  test/testpoisson.cc:218-219;
+                                 in-tree twin test/instationarypoissonoperator.hh:30-168                            */
+  MDB_OP_L2 = 2,             /* [UPSTREAM] Dune::PDELab::L2(intorder) / test/simpletimeoperator.hh:29-101 (mass)    */
+  /* coupling operators used by Couplings */
+  MDB_OP_CVCF_COUPLING = 101,     /* ContinuousValueContinuousFlowCoupling  test/proportionalflowcoupling.hh:94-239 */
+  MDB_OP_PROPFLOW_COUPLING = 102  /* ProportionalFlowCoupling               test/proportionalflowcoupling.hh:10-91  */
+};
+
+typedef struct mdb_poisson_params {
+  mdb_function f;            /* source term            */
+  mdb_bctype bc;             /* boundary-type predicate */
+  mdb_function j;            /* Neumann flux            */
+  int32_t quad_order;        /* 4 in testpoisson.cc:219, 6 in testpoisson-assembly.cc:920 */
+  int32_t reserved;
+} mdb_poisson_params;
+
+typedef struct mdb_l2_params {
+  int32_t quad_order;        /* default 2 */
+  int32_t reserved;
+} mdb_l2_params;
+
+typedef struct mdb_cvcf_params {
+  int32_t quad_order;        /* ctor arg intorder (4 in testpoisson.cc:234) */
+  int32_t reserved;
+  double intensity;          /* ctor arg intensity = alpha (argv[2])        */
+} mdb_cvcf_params;
+
+typedef struct mdb_propflow_params {
+  double intensity;
+} mdb_propflow_params;
+
+/* Jacobian mode for coupling operators. */
+enum {
+  MDB_JAC_FD_BITMATCH = 0,   /* NumericalJacobianCoupling, eps=1e-8, couplingutilities.hh:59-141, evaluated
+                                with the reference's operation order and without FMA contraction           */
+  MDB_JAC_ANALYTIC = 1       /* exact derivative of the (linear) coupling residual                          */
+};
+
+/* ---- life cycle ---------------------------------------------------------- */
+mdb_ctx* mdb_create(int device);
+void mdb_destroy(mdb_ctx* ctx);
+const char* mdb_last_error(mdb_ctx* ctx);   /* ctx may be NULL: returns the creation error */
+const char* mdb_version(void);
+
+/* ---- mesh + subdomains  (replaces YaspGrid + MultiDomainGrid marking,
+ *      test/testpoisson.cc:134-161) ---------------------------------------- */
+/* Structured axis-aligned grid, n[d] cells per axis on [lower,upper].  Cells and vertices are numbered
+ * lexicographically, axis 0 fastest (YaspGrid leaf index order [UPSTREAM]). */
+int mdb_mesh_structured(mdb_ctx* ctx, int dim, const int64_t* n, const double* lower, const double* upper);
+/* Declare this context's mesh to be a slab of a larger global mesh (multi-GPU): `global_n` cells
+ * per axis in total, this rank's cells start at `cell_offset`; faces on a cut are processor boundaries (no
+ * boundary terms); `lower/upper` given to mdb_mesh_structured are those of the local slab.
+ * Must be called after mdb_mesh_structured and before mdb_finalize. */
+int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cell_offset,
+                       const double* global_lower, const double* global_upper);
+/* One byte per cell: bit s set <=> cell belongs to subdomain s (<= 8 subdomains;
+ * FewSubDomainsTraits<dim,4> in test/testpoisson.cc:140).  Host pointer, ncells entries. */
+int mdb_subdomains(mdb_ctx* ctx, const uint8_t* cell_subdomain_bits);
+/* Device-side marking for large meshes: cells whose centre has x[axis] > threshold go to subdomain
+ * `sd_above`, the others to `sd_below` (test/testpoisson.cc:152-158). */
+int mdb_subdomains_halfspace(mdb_ctx* ctx, int axis, double threshold, int sd_below, int sd_above);
+
+/* ---- function space  (MultiDomainGridFunctionSpace children,
+ *      multidomaingridfunctionspace.hh:152,215; lexicographic child blocks) -- */
+/* Appends a child space; returns its child index >= 0.  subdomain = -1 puts the child on the
+ * MultiDomainGrid view itself, otherwise on SubDomainGrid view `subdomain`. */
+int mdb_add_space(mdb_ctx* ctx, int fe_kind, int subdomain);
+
+/* ---- participants  (subproblem.hh:44-148, coupling.hh:30-91) -------------- */
+/* Returns the subproblem index >= 0.  `children` are indices returned by mdb_add_space. */
+int mdb_add_subproblem(mdb_ctx* ctx, int op_id, const void* params, size_t params_bytes,
+                       int cond_kind, uint32_t cond_mask, const int* children, int nchildren);
+/* Returns the coupling index >= 0.  Fires on a face iff local applies to inside and remote to outside. */
+int mdb_add_coupling(mdb_ctx* ctx, int op_id, const void* params, size_t params_bytes,
+                     int local_subproblem, int remote_subproblem, int jac_mode);
+
+/* ---- DOF map (ordering update; multidomaingridfunctionspace.hh:308-369) --- */
+int mdb_finalize(mdb_ctx* ctx, int64_t* ndof);
+/* parity exports.  cell_ptr has ncells+1 entries; cell_dofs has cell_ptr[ncells] entries: the container
+ * indices of the MultiDomainLocalFunctionSpace bound to each cell, children concatenated
+ * (multidomainlocalfunctionspace.hh:348-358).  Host pointers.  Pass cell_dofs=NULL to get sizes only. */
+int mdb_get_dofmap(mdb_ctx* ctx, int64_t* cell_ptr, int64_t* cell_dofs);
+int mdb_get_child_offsets(mdb_ctx* ctx, int64_t* offsets /* nchildren+1 */);
+
+/* ---- constraints + interpolation (constraints.hh:539-558, interpolate.hh:76-81) */
+/* constraints<R>(gfs, constrainSubProblem(sp_i, bc_i)...).assemble(cg): evaluates the Dirichlet set on the
+ * device.  Returns the number of constrained DOFs in *nconstrained. */
+int mdb_constraints_assemble(mdb_ctx* ctx, const int* subproblems, const mdb_bctype* bcs, int n,
+                             int64_t* nconstrained);
+/* Alternatively set the Dirichlet set from a host list of container indices. */
+int mdb_set_constraints(mdb_ctx* ctx, int64_t n, const int64_t* dirichlet_dofs);
+/* Export: one byte per DOF, 1 = constrained.  Host pointer. */
+int mdb_get_constraints(mdb_ctx* ctx, uint8_t* flags);
+/* interpolateOnTrialSpace(gfs, x, f_0, sp_0, f_1, sp_1, ...) at time t.  x: host or device, ndof doubles. */
+int mdb_interpolate(mdb_ctx* ctx, const int* subproblems, const mdb_function* fns, int n, double time, double* x);
+/* copy_nonconstrained_dofs(cu, xold, xnew)  (gridoperator.hh:146) */
+int mdb_copy_nonconstrained(mdb_ctx* ctx, const double* xold, double* xnew);
+
+/* ---- grid operators  (gridoperator.hh:155-175) ----------------------------- */
+/* GridOperator(gfsu,gfsv,cu,cv,mb,participants...): participant order = argument order. Returns handle >= 0. */
+int mdb_gridoperator_create(mdb_ctx* ctx, const int* subproblems, int nsubproblems,
+                            const int* couplings, int ncouplings);
+/* Jacobian container + fill_pattern (gridoperator.hh:83-87): builds the CSR pattern as the union of the
+ * patterns of `gos` (OneStepGridOperator unions dt0 and dt1).  Returns a matrix handle >= 0. */
+int mdb_matrix_create(mdb_ctx* ctx, const int* gos, int ngos, int64_t* nnz);
+/* parity export in BCRS order (ascending columns per row).  Host pointers: rowptr ndof+1, colidx nnz. */
+int mdb_matrix_get_pattern(mdb_ctx* ctx, int mat, int64_t* rowptr, int64_t* colidx);
+int mdb_matrix_get_values(mdb_ctx* ctx, int mat, double* values /* host or device, nnz */);
+int mdb_matrix_zero(mdb_ctx* ctx, int mat);         /* a = 0.0 */
+/* Device pointers of the CSR arrays (int32 rowptr[ndof+1], int32 colidx[nnz], double values[nnz]) for
+ * zero-copy consumers. */
+int mdb_matrix_device_ptrs(mdb_ctx* ctx, int mat, const int32_t** rowptr, const int32_t** colidx, double** values);
+
+/* setTime / setWeight fan-out (localassembler.hh:214-255) */
+int mdb_set_time(mdb_ctx* ctx, double t);
+
+/* GridOperator::residual(x, r) (gridoperator.hh:89-92): r += weight * R(x), then constrained entries of r
+ * are set to 0 (residualassemblerengine.hh:553-567).  x, r: host or device. */
+int mdb_residual(mdb_ctx* ctx, int go, double weight, const double* x, double* r);
+/* GridOperator::jacobian(x, a) (gridoperator.hh:94-97): a += weight * J(x), then every constrained row is
+ * replaced by the unit row (jacobianassemblerengine.hh:480-504).  overwrite != 0 treats `a` as zero on entry
+ * (fuses the caller's "a = 0" into the assembly kernel). */
+int mdb_jacobian(mdb_ctx* ctx, int go, int mat, double weight, const double* x, int overwrite);
+
+/* ---- linear solve ([UPSTREAM] ISTL solver backends) ----------- */
+enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1 };
+enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2 };
+typedef struct mdb_solve_stats {
+  int32_t iterations;
+  int32_t converged;
+  double defect0;          /* initial 2-norm of the defect */
+  double defect;           /* final   2-norm of the defect */
+  double seconds;          /* device time of the Krylov loop (CUDA events) */
+} mdb_solve_stats;
+/* Solve A z = rhs to  |defect| <= reduction * |defect0|  starting from z = 0.  rhs, z: host or device. */
+int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, int maxit,
+              const double* rhs, double* z, mdb_solve_stats* stats);
+/* Run exactly `iters` Krylov iterations without convergence test (benchmarking the loop). */
+int mdb_solve_fixed(mdb_ctx* ctx, int mat, int method, int precond, int iters,
+                    const double* rhs, double* z, mdb_solve_stats* stats);
+/* y = A x (host or device pointers). */
+int mdb_spmv(mdb_ctx* ctx, int mat, const double* x, double* y);
+
+/* ---- multi-GPU plumbing -------------------------------------- */
+/* NCCL communicator for Krylov scalars: rank 0 creates the id, all ranks init. */
+int mdb_nccl_unique_id(void* id128 /* 128 bytes */);
+int mdb_comm_init(mdb_ctx* ctx, int nranks, int rank, const void* id128);
+/* Halo buffers for x (one vertex layer per slab neighbour).  Export this rank's IPC handle (64 bytes) of its
+ * receive window, then import the neighbours' handles: pushes are P2P stores over NVLink. */
+int mdb_halo_export(mdb_ctx* ctx, void* handle64, int64_t* window_bytes);
+int mdb_halo_import(mdb_ctx* ctx, int lower_rank, const void* lower_handle64, int upper_rank, const void* upper_handle64);
+/* Number of rows this rank owns / global size (for reporting). */
+int mdb_owned_rows(mdb_ctx* ctx, int64_t* owned, int64_t* local_total);
+/* Export: one byte per local DOF, 1 = owned by this rank; and the global container index of every local DOF. */
+int mdb_get_ownership(mdb_ctx* ctx, uint8_t* owned_flags, int64_t* global_index);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Device time in ms of the last call of the named phase ("jacobian_volume", "jacobian_coupling",
+ * "residual_volume", "residual_coupling", "residual_boundary", "pattern", "dofmap", "spmv", ...), measured
+ * with CUDA events on the context's stream; negative if never run. */
+double mdb_phase_ms(mdb_ctx* ctx, const char* phase);
+/* Number of kernel launches issued by this context since creation / since the last reset. */
+int64_t mdb_launch_count(mdb_ctx* ctx, int reset);
+/* Raw CUDA stream of the context (cudaStream_t as void*). */
+void* mdb_stream(mdb_ctx* ctx);
+int mdb_synchronize(mdb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDB200_H */

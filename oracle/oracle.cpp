@@ -1,0 +1,1100 @@
+// oracle/oracle.cpp — TEST INFRASTRUCTURE ONLY.  See oracle.hh for the scope statement ("parity unpinned").
+// CPU restatement of dune-multidomain's single-traversal assembly + Krylov solve.
+#include "oracle.hh"
+#include <set>
+#include <thread>
+#include <functional>
+
+namespace orc {
+
+// =============================================================================================
+// problem data (test/testpoisson.cc:32-116)
+// =============================================================================================
+double eval_function(const mdb_function& f, int dim, const double* x, double t)
+{
+  switch (f.kind) {
+  case MDB_FN_ZERO: return 0.0;
+  case MDB_FN_CONST: return f.p[0];
+  case MDB_FN_GAUSS: {                     // testpoisson.cc:92-99: center -= x; y = exp(-center.two_norm2())
+    double n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { double c = f.p[1 + d] - x[d]; n2 += c * c; }
+    return std::exp(-(f.p[0] * n2));
+  }
+  case MDB_FN_BOX: {                       // testpoisson.cc:34-37
+    for (int d = 0; d < dim; ++d) if (!(x[d] > f.p[1] && x[d] < f.p[2])) return 0.0;
+    return f.p[0];
+  }
+  case MDB_FN_TESTPOISSON_J: {             // testpoisson.cc:103-116
+    if (x[1] < 1E-6 || x[1] > 1.0 - 1E-6) return 0.0;
+    if (x[0] > 1.0 - 1E-6 && x[1] > 0.5 + 1E-6) return -5.0;
+    return 0.0;
+  }
+  case MDB_FN_INSTAT_G: {
+    double n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { double c = 0.5 - x[d]; n2 += c * c; }
+    return f.p[0] * std::sin(f.p[1] * t) * std::exp(-n2);
+  }
+  case MDB_FN_POLY2: {
+    double v = f.p[0], n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { v += f.p[1 + d] * x[d]; n2 += x[d] * x[d]; }
+    return v + f.p[4] * n2;
+  }
+  }
+  throw std::runtime_error("unknown function kind");
+}
+
+int eval_bctype(const mdb_bctype& b, int dim, const double* xg, bool is_boundary)
+{
+  (void)dim;
+  switch (b.kind) {
+  case MDB_BC_ALL_DIRICHLET: return is_boundary ? 0 : 2;
+  case MDB_BC_ALL_NEUMANN: return is_boundary ? 1 : 2;
+  case MDB_BC_TESTPOISSON:                 // testpoisson.cc:49-71
+    if (!is_boundary) return 2;
+    if (xg[1] < 1E-6 || xg[1] > 1.0 - 1E-6) return 1;
+    if (xg[0] > 1.0 - 1E-6 && xg[1] > 0.5 + 1E-6) return 1;
+    return 0;
+  }
+  throw std::runtime_error("unknown bctype kind");
+}
+
+// =============================================================================================
+// local operators
+// =============================================================================================
+namespace {
+
+// [UPSTREAM] Dune::PDELab::Poisson<F,B,J> = Laplace stiffness + source + Neumann flux; the in-tree twin is
+// test/instationarypoissonoperator.hh:30-168 (alpha_volume :52-77, lambda_volume :103-117, lambda_boundary :142-167)
+struct PoissonOp : LocalOperator {
+  mdb_poisson_params P;
+  explicit PoissonOp(const mdb_poisson_params& p) : P(p) {
+    doPatternVolume = true; doAlphaVolume = true; doLambdaVolume = true; doLambdaBoundary = true;
+  }
+  void alpha_volume(const EG& eg, const LFS& lfsu, const double* x, const LFS& lfsv, LocalVectorView& r) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsu.k, dim);
+    auto rule = tensor_rule(dim, P.quad_order);
+    double js[MAXLOC][3], gradphi[MAXLOC][3];
+    for (const auto& q : rule) {
+      B.evaluateJacobian(q.x, js);
+      for (int i = 0; i < lfsu.n; ++i)
+        for (int d = 0; d < dim; ++d) { gradphi[i][d] = 0.0; gradphi[i][d] += eg.jacInvT(d) * js[i][d]; }
+      double gradu[3] = {0, 0, 0};
+      for (int i = 0; i < lfsu.n; ++i)
+        for (int d = 0; d < dim; ++d) gradu[d] += x[lfsu.idx[i]] * gradphi[i][d];
+      double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsu.n; ++i) {
+        double dot = 0.0;
+        for (int d = 0; d < dim; ++d) dot += gradu[d] * gradphi[i][d];
+        r.accumulate(lfsv, i, dot * factor);
+      }
+    }
+  }
+  void jacobian_volume(const EG& eg, const LFS& lfsu, const double*, const LFS& lfsv, LocalMatrixView& mat) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsu.k, dim);
+    auto rule = tensor_rule(dim, P.quad_order);
+    double js[MAXLOC][3], gradphi[MAXLOC][3];
+    for (const auto& q : rule) {
+      B.evaluateJacobian(q.x, js);
+      for (int i = 0; i < lfsu.n; ++i)
+        for (int d = 0; d < dim; ++d) { gradphi[i][d] = 0.0; gradphi[i][d] += eg.jacInvT(d) * js[i][d]; }
+      double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsu.n; ++i)
+        for (int j = 0; j < lfsu.n; ++j) {
+          double dot = 0.0;
+          for (int d = 0; d < dim; ++d) dot += gradphi[j][d] * gradphi[i][d];
+          mat.accumulate(lfsv, i, lfsu, j, dot * factor);
+        }
+    }
+  }
+  void lambda_volume(const EG& eg, const LFS& lfsv, LocalVectorView& r) const override {
+    if (P.f.kind == MDB_FN_ZERO) return;   // adds exact zeros otherwise
+    const int dim = eg.g->dim;
+    QkBasis B(lfsv.k, dim);
+    auto rule = tensor_rule(dim, P.quad_order);
+    double phi[MAXLOC], xg[3];
+    for (const auto& q : rule) {
+      B.evaluateFunction(q.x, phi);
+      eg.global(q.x, xg);
+      double y = eval_function(P.f, dim, xg, time);
+      double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsv.n; ++i) r.accumulate(lfsv, i, -y * phi[i] * factor);
+    }
+  }
+  void lambda_boundary(const IG& ig, const LFS& lfsv, LocalVectorView& r) const override {
+    const int dim = ig.dim();
+    QkBasis B(lfsv.k, dim);
+    auto rule = tensor_rule(dim - 1, P.quad_order);
+    double phi[MAXLOC], local[3], xg[3];
+    for (const auto& q : rule) {
+      ig.global(q.x, xg);
+      if (eval_bctype(P.bc, dim, xg, ig.boundary) != 1) continue;     // !isNeumann
+      ig.localInside(q.x, local);
+      B.evaluateFunction(local, phi);
+      double xe[3]; ig.inside.global(local, xe);
+      double y = eval_function(P.j, dim, xe, time);
+      double factor = q.w * ig.integrationElement();
+      for (int i = 0; i < lfsv.n; ++i) r.accumulate(lfsv, i, y * phi[i] * factor);
+    }
+  }
+};
+
+// [UPSTREAM] Dune::PDELab::L2 / test/simpletimeoperator.hh:29-101
+struct L2Op : LocalOperator {
+  mdb_l2_params P;
+  explicit L2Op(const mdb_l2_params& p) : P(p) { doPatternVolume = true; doAlphaVolume = true; }
+  void alpha_volume(const EG& eg, const LFS& lfsu, const double* x, const LFS& lfsv, LocalVectorView& r) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsu.k, dim);
+    auto rule = tensor_rule(dim, P.quad_order);
+    double phi[MAXLOC];
+    for (const auto& q : rule) {
+      B.evaluateFunction(q.x, phi);
+      double u = 0.0;
+      for (int i = 0; i < lfsu.n; ++i) u += x[lfsu.idx[i]] * phi[i];
+      double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsu.n; ++i) r.accumulate(lfsv, i, u * phi[i] * factor);
+    }
+  }
+  void jacobian_volume(const EG& eg, const LFS& lfsu, const double*, const LFS& lfsv, LocalMatrixView& mat) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsu.k, dim);
+    auto rule = tensor_rule(dim, P.quad_order);
+    double phi[MAXLOC];
+    for (const auto& q : rule) {
+      B.evaluateFunction(q.x, phi);
+      double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsu.n; ++i)
+        for (int j = 0; j < lfsu.n; ++j)
+          mat.accumulate(lfsv, i, lfsu, j, phi[j] * phi[i] * factor);
+    }
+  }
+};
+
+// test/proportionalflowcoupling.hh:10-91
+struct PropFlowOp : CouplingOperator {
+  mdb_propflow_params P;
+  PropFlowOp(const mdb_propflow_params& p, int jm) : P(p) { doAlphaCoupling = true; doPatternCoupling = true; jac_mode = jm; }
+  void alpha_coupling(const IG& ig, const LFS& lfsu_s, const double* x_s, const LFS& lfsv_s,
+                      const LFS& lfsu_n, const double* x_n, const LFS& lfsv_n,
+                      LocalVectorView& r_s, LocalVectorView& r_n) const override {
+    const int dim = ig.dim();
+    const int intorder = 4;                                            // :43
+    QkBasis B1(lfsv_s.k, dim), B2(lfsv_n.k, dim);
+    auto rule = tensor_rule(dim - 1, intorder);
+    double phi1[MAXLOC], phi2[MAXLOC], local1[3], local2[3];
+    for (const auto& q : rule) {
+      ig.localInside(q.x, local1); ig.localOutside(q.x, local2);
+      B1.evaluateFunction(local1, phi1);
+      B2.evaluateFunction(local2, phi2);
+      double u_s = 0.0; for (int i = 0; i < lfsu_s.n; ++i) u_s += x_s[lfsu_s.idx[i]] * phi1[i];
+      double u_n = 0.0; for (int i = 0; i < lfsu_n.n; ++i) u_n += x_n[lfsu_n.idx[i]] * phi2[i];
+      double u_diff = P.intensity * (u_s - u_n);
+      double factor = q.w * ig.integrationElement();
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, u_diff * phi1[i] * factor);
+      for (int i = 0; i < lfsv_n.n; ++i) r_n.accumulate(lfsv_n, i, -u_diff * phi2[i] * factor);
+    }
+  }
+};
+
+// test/proportionalflowcoupling.hh:94-239
+struct CVCFOp : CouplingOperator {
+  mdb_cvcf_params P;
+  CVCFOp(const mdb_cvcf_params& p, int jm) : P(p) { doAlphaCoupling = true; doPatternCoupling = true; jac_mode = jm; }
+  void alpha_coupling(const IG& ig, const LFS& lfsu1, const double* x1, const LFS& lfsv1,
+                      const LFS& lfsu2, const double* x2, const LFS& lfsv2,
+                      LocalVectorView& r1, LocalVectorView& r2) const override {
+    const int dim = ig.dim();
+    const double h_F = ig.cornerDistance01();                           // :135
+    QkBasis B1(lfsv1.k, dim), B2(lfsv2.k, dim);
+    auto rule = tensor_rule(dim - 1, P.quad_order);
+    double phi1[MAXLOC], phi2[MAXLOC], js1[MAXLOC][3], js2[MAXLOC][3], gradphi1[MAXLOC][3], gradphi2[MAXLOC][3];
+    double local1[3], local2[3];
+    for (const auto& q : rule) {
+      ig.localInside(q.x, local1); ig.localOutside(q.x, local2);
+      B1.evaluateFunction(local1, phi1);
+      B2.evaluateFunction(local2, phi2);
+      B1.evaluateJacobian(local1, js1);
+      B2.evaluateJacobian(local2, js2);
+      for (int i = 0; i < lfsu1.n; ++i)
+        for (int d = 0; d < dim; ++d) { gradphi1[i][d] = 0.0; gradphi1[i][d] += ig.inside.jacInvT(d) * js1[i][d]; }
+      for (int i = 0; i < lfsu2.n; ++i)
+        for (int d = 0; d < dim; ++d) { gradphi2[i][d] = 0.0; gradphi2[i][d] += ig.outside.jacInvT(d) * js2[i][d]; }
+      double gradu1[3] = {0, 0, 0}, gradu2[3] = {0, 0, 0};
+      for (int i = 0; i < lfsu1.n; ++i) for (int d = 0; d < dim; ++d) gradu1[d] += x1[lfsu1.idx[i]] * gradphi1[i][d];
+      for (int i = 0; i < lfsu2.n; ++i) for (int d = 0; d < dim; ++d) gradu2[d] += x2[lfsu2.idx[i]] * gradphi2[i][d];
+      double u1 = 0.0; for (int i = 0; i < lfsu1.n; ++i) u1 += x1[lfsu1.idx[i]] * phi1[i];
+      double u2 = 0.0; for (int i = 0; i < lfsu2.n; ++i) u2 += x2[lfsu2.idx[i]] * phi2[i];
+      double normal1[3], normal2[3];
+      ig.unitOuterNormal(normal1);
+      ig.unitOuterNormal(normal2);
+      for (int d = 0; d < dim; ++d) normal2[d] *= -1;
+      const double jump_u1 = u1 - u2;
+      const double jump_u2 = u2 - u1;
+      double mean_gradu[3];
+      for (int d = 0; d < dim; ++d) { mean_gradu[d] = gradu1[d] + gradu2[d]; mean_gradu[d] *= 0.5; }
+      const double theta = 1;
+      const double alpha = P.intensity;
+      const double factor = q.w * ig.integrationElement();
+      for (int i = 0; i < lfsv1.n; ++i) {
+        double mgn = 0.0, gpn = 0.0;
+        for (int d = 0; d < dim; ++d) mgn += mean_gradu[d] * normal1[d];
+        for (int d = 0; d < dim; ++d) gpn += gradphi1[i][d] * normal1[d];
+        double value = 0.0;
+        value -= mgn * phi1[i];
+        value -= theta * 0.5 * gpn * jump_u1;
+        value += alpha / h_F * jump_u1 * phi1[i];
+        r1.accumulate(lfsv1, i, factor * value);
+      }
+      for (int i = 0; i < lfsv2.n; ++i) {
+        double mgn = 0.0, gpn = 0.0;
+        for (int d = 0; d < dim; ++d) mgn += mean_gradu[d] * normal2[d];
+        for (int d = 0; d < dim; ++d) gpn += gradphi2[i][d] * normal2[d];
+        double value = 0.0;
+        value -= mgn * phi2[i];
+        value -= theta * 0.5 * gpn * jump_u2;
+        value += alpha / h_F * jump_u2 * phi2[i];
+        r2.accumulate(lfsv2, i, factor * value);
+      }
+    }
+  }
+};
+
+} // anonymous namespace
+
+// couplingutilities.hh:75-135 (NumericalJacobianCoupling).  MDB_JAC_ANALYTIC exploits linearity of the shipped
+// coupling operators: column j = alpha_coupling(e_j) - alpha_coupling(0) evaluated exactly (no division).
+void CouplingOperator::jacobian_coupling(const IG& ig, const LFS& lfsu_s, const double* x_s, int nx_s, const LFS& lfsv_s,
+                                         const LFS& lfsu_n, const double* x_n, int nx_n, const LFS& lfsv_n,
+                                         LocalMatrixView& mat_ss, LocalMatrixView& mat_sn,
+                                         LocalMatrixView& mat_ns, LocalMatrixView& mat_nn) const
+{
+  const int m_s = lfsv_s.n, m_n = lfsv_n.n, n_s = lfsu_s.n, n_n = lfsu_n.n;
+  std::vector<double> u_s(x_s, x_s + nx_s), u_n(x_n, x_n + nx_n);
+  std::vector<double> down_s(nx_s, 0.0), up_s(nx_s, 0.0), down_n(nx_n, 0.0), up_n(nx_n, 0.0);
+  LocalVectorView dv_s{down_s.data(), 1.0}, uv_s{up_s.data(), 1.0}, dv_n{down_n.data(), 1.0}, uv_n{up_n.data(), 1.0};
+  if (jac_mode == MDB_JAC_ANALYTIC) {
+    std::fill(u_s.begin(), u_s.end(), 0.0); std::fill(u_n.begin(), u_n.end(), 0.0);
+    for (int j = 0; j < n_s; ++j) {
+      std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_n.begin(), up_n.end(), 0.0);
+      u_s[lfsu_s.idx[j]] = 1.0;
+      alpha_coupling(ig, lfsu_s, u_s.data(), lfsv_s, lfsu_n, u_n.data(), lfsv_n, uv_s, uv_n);
+      for (int i = 0; i < m_s; ++i) mat_ss.accumulate(lfsv_s, i, lfsu_s, j, up_s[lfsv_s.idx[i]]);
+      for (int i = 0; i < m_n; ++i) mat_ns.accumulate(lfsv_n, i, lfsu_s, j, up_n[lfsv_n.idx[i]]);
+      u_s[lfsu_s.idx[j]] = 0.0;
+    }
+    for (int j = 0; j < n_n; ++j) {
+      std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_n.begin(), up_n.end(), 0.0);
+      u_n[lfsu_n.idx[j]] = 1.0;
+      alpha_coupling(ig, lfsu_s, u_s.data(), lfsv_s, lfsu_n, u_n.data(), lfsv_n, uv_s, uv_n);
+      for (int i = 0; i < m_s; ++i) mat_sn.accumulate(lfsv_s, i, lfsu_n, j, up_s[lfsv_s.idx[i]]);
+      for (int i = 0; i < m_n; ++i) mat_nn.accumulate(lfsv_n, i, lfsu_n, j, up_n[lfsv_n.idx[i]]);
+      u_n[lfsu_n.idx[j]] = 0.0;
+    }
+    return;
+  }
+  // base line
+  alpha_coupling(ig, lfsu_s, u_s.data(), lfsv_s, lfsu_n, u_n.data(), lfsv_n, dv_s, dv_n);
+  // jiggle in self
+  for (int j = 0; j < n_s; ++j) {
+    std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_n.begin(), up_n.end(), 0.0);
+    double delta = epsilon * (1.0 + std::abs(u_s[lfsu_s.idx[j]]));
+    u_s[lfsu_s.idx[j]] += delta;
+    alpha_coupling(ig, lfsu_s, u_s.data(), lfsv_s, lfsu_n, u_n.data(), lfsv_n, uv_s, uv_n);
+    for (int i = 0; i < m_s; ++i)
+      mat_ss.accumulate(lfsv_s, i, lfsu_s, j, (up_s[lfsv_s.idx[i]] - down_s[lfsv_s.idx[i]]) / delta);
+    for (int i = 0; i < m_n; ++i)
+      mat_ns.accumulate(lfsv_n, i, lfsu_s, j, (up_n[lfsv_n.idx[i]] - down_n[lfsv_n.idx[i]]) / delta);
+    u_s[lfsu_s.idx[j]] = x_s[lfsu_s.idx[j]];
+  }
+  // jiggle in neighbor
+  for (int j = 0; j < n_n; ++j) {
+    std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_n.begin(), up_n.end(), 0.0);
+    double delta = epsilon * (1.0 + std::abs(u_n[lfsu_n.idx[j]]));
+    u_n[lfsu_n.idx[j]] += delta;
+    alpha_coupling(ig, lfsu_s, u_s.data(), lfsv_s, lfsu_n, u_n.data(), lfsv_n, uv_s, uv_n);
+    for (int i = 0; i < m_s; ++i)
+      mat_sn.accumulate(lfsv_s, i, lfsu_n, j, (up_s[lfsv_s.idx[i]] - down_s[lfsv_s.idx[i]]) / delta);
+    for (int i = 0; i < m_n; ++i)
+      mat_nn.accumulate(lfsv_n, i, lfsu_n, j, (up_n[lfsv_n.idx[i]] - down_n[lfsv_n.idx[i]]) / delta);
+    u_n[lfsu_n.idx[j]] = x_n[lfsu_n.idx[j]];
+  }
+}
+
+std::unique_ptr<LocalOperator> make_local_operator(int op_id, const void* params, size_t nbytes)
+{
+  switch (op_id) {
+  case MDB_OP_POISSON:
+    if (nbytes != sizeof(mdb_poisson_params)) throw std::runtime_error("bad poisson params size");
+    return std::unique_ptr<LocalOperator>(new PoissonOp(*static_cast<const mdb_poisson_params*>(params)));
+  case MDB_OP_L2:
+    if (nbytes != sizeof(mdb_l2_params)) throw std::runtime_error("bad l2 params size");
+    return std::unique_ptr<LocalOperator>(new L2Op(*static_cast<const mdb_l2_params*>(params)));
+  }
+  throw std::runtime_error("unknown local operator id");
+}
+
+std::unique_ptr<CouplingOperator> make_coupling_operator(int op_id, const void* params, size_t nbytes, int jac_mode)
+{
+  switch (op_id) {
+  case MDB_OP_CVCF_COUPLING:
+    if (nbytes != sizeof(mdb_cvcf_params)) throw std::runtime_error("bad cvcf params size");
+    return std::unique_ptr<CouplingOperator>(new CVCFOp(*static_cast<const mdb_cvcf_params*>(params), jac_mode));
+  case MDB_OP_PROPFLOW_COUPLING:
+    if (nbytes != sizeof(mdb_propflow_params)) throw std::runtime_error("bad propflow params size");
+    return std::unique_ptr<CouplingOperator>(new PropFlowOp(*static_cast<const mdb_propflow_params*>(params), jac_mode));
+  }
+  throw std::runtime_error("unknown coupling operator id");
+}
+
+// =============================================================================================
+// DOF map  ([UPSTREAM] (ii)-(iv))
+// =============================================================================================
+void Context::finalize()
+{
+  const Grid& g = grid;
+  const int dim = g.dim;
+  if ((int64_t)cell_sd.size() != g.ncells()) throw std::runtime_error("subdomains not set");
+  int64_t off = 0;
+  for (auto& ch : children) {
+    const int k = ch.k;
+    int64_t total = 1;
+    for (int d = 0; d < 3; ++d) { ch.lat_n[d] = (d < dim) ? k * g.n[d] + 1 : 1; total *= ch.lat_n[d]; }
+    std::vector<uint8_t> present(total, 0);
+    // closure of the cells of the child's grid view
+    for (int64_t c = 0; c < g.ncells(); ++c) {
+      if (ch.subdomain >= 0 && !((cell_sd[c] >> ch.subdomain) & 1)) continue;
+      int64_t ijk[3]; g.cell_ijk(c, ijk);
+      int a[3];
+      int nl = ch.nloc(dim);
+      for (int i = 0; i < nl; ++i) {
+        int rem = i; for (int d = 0; d < 3; ++d) { a[d] = (d < dim) ? rem % (k + 1) : 0; rem /= (k + 1); }
+        int64_t p = (k * ijk[0] + a[0]) + ch.lat_n[0] * ((k * ijk[1] + a[1]) + ch.lat_n[1] * (k * ijk[2] + a[2]));
+        present[p] = 1;
+      }
+    }
+    // [UPSTREAM] (ii),(iii): number per geometry type (entity dimension ascending: vertex < line < quad < hex);
+    // within a dimension entities are grouped by the set of axes they extend along (ascending bit pattern) and
+    // lexicographic (axis 0 fastest) inside a group; subdomain entity index = rank in that host order.
+    ch.lat2dof.assign(total, -1);
+    ch.dof2lat.clear();
+    int64_t cnt = 0;
+    for (int m = 0; m <= dim; ++m)
+      for (int ext = 0; ext < (1 << dim); ++ext) {
+        if (__builtin_popcount(ext) != m) continue;
+        if (k == 1 && ext != 0) continue;
+        for (int64_t p = 0; p < total; ++p) {
+          if (!present[p]) continue;
+          int64_t rem = p; int e = 0;
+          for (int d = 0; d < dim; ++d) { int64_t pd = rem % ch.lat_n[d]; rem /= ch.lat_n[d]; if (pd % k != 0) e |= (1 << d); }
+          if (e != ext) continue;
+          ch.lat2dof[p] = cnt++; ch.dof2lat.push_back(p);
+        }
+      }
+    ch.size = cnt;
+    ch.offset = off;            // [UPSTREAM] (iv) LexicographicOrderingTag: prefix sums of child sizes
+    off += cnt;
+  }
+  ndof = off;
+  constrained.assign(ndof, 0);
+  finalized = true;
+}
+
+int Context::bind(int64_t cell, int* child_off, int64_t* dofs) const
+{
+  // multidomainlocalfunctionspace.hh:104-122: a child contributes iff the cell is in the child's subdomain
+  const int dim = grid.dim;
+  int64_t ijk[3]; grid.cell_ijk(cell, ijk);
+  int n = 0;
+  for (size_t c = 0; c < children.size(); ++c) {
+    const ChildSpace& ch = children[c];
+    child_off[c] = n;
+    if (ch.subdomain >= 0 && !((cell_sd[cell] >> ch.subdomain) & 1)) continue;
+    const int k = ch.k, nl = ch.nloc(dim);
+    for (int i = 0; i < nl; ++i) {
+      int a[3]; int rem = i; for (int d = 0; d < 3; ++d) { a[d] = (d < dim) ? rem % (k + 1) : 0; rem /= (k + 1); }
+      int64_t p = (k * ijk[0] + a[0]) + ch.lat_n[0] * ((k * ijk[1] + a[1]) + ch.lat_n[1] * (k * ijk[2] + a[2]));
+      dofs[n++] = ch.offset + ch.lat2dof[p];
+    }
+  }
+  child_off[children.size()] = n;
+  return n;
+}
+
+LFS Context::subproblem_lfs(const SubProblem& sp, const int* child_off) const
+{
+  // subproblemlocalfunctionspace.hh:462-501: single-child subproblem = proxy of that child
+  if (sp.children.size() != 1) throw std::runtime_error("oracle: only single-child subproblems are restated");
+  LFS l; int c = sp.children[0];
+  l.k = children[c].k;
+  l.n = child_off[c + 1] - child_off[c];
+  for (int i = 0; i < l.n; ++i) l.idx[i] = child_off[c] + i;
+  return l;
+}
+
+// =============================================================================================
+// the traversal (globalassembler.hh:43-298) with three engines
+// =============================================================================================
+namespace {
+
+constexpr int MAXCELL = 64;  // max size of a cell-local space (sum over children)
+
+struct FaceIter {
+  // faces of a cell in grid order -x,+x,-y,+y,-z,+z
+  static bool neighbor(const Grid& g, const int64_t ijk[3], int f, int64_t nijk[3]) {
+    int a = f / 2, s = f % 2;
+    for (int d = 0; d < 3; ++d) nijk[d] = ijk[d];
+    nijk[a] += s ? 1 : -1;
+    return nijk[a] >= 0 && nijk[a] < g.n[a];
+  }
+};
+
+EG make_eg(const Context& c, int64_t cell) {
+  EG e; e.g = &c.grid; e.index = cell; c.grid.cell_ijk(cell, e.ijk); e.sd = c.cell_sd[cell]; return e;
+}
+
+enum Mode { PATTERN, RESIDUAL, JACOBIAN };
+
+struct Flags { bool visit_faces, two_sided; };
+
+Flags engine_flags(const Context& c, const GridOperatorDesc& go, Mode mode)
+{
+  bool a_skel = false, a_bnd = false, l_skel = false, l_bnd = false, two = false, a_coup = false, p_skel = false, p_coup = false;
+  for (int s : go.sps) {
+    const LocalOperator& l = *c.sps[s].lop;
+    a_skel |= l.doAlphaSkeleton; a_bnd |= l.doAlphaBoundary; l_skel |= l.doLambdaSkeleton; l_bnd |= l.doLambdaBoundary;
+    two |= l.doSkeletonTwoSided; p_skel |= l.doPatternSkeleton;
+  }
+  for (int k : go.cps) { a_coup |= c.cps[k].op->doAlphaCoupling; p_coup |= c.cps[k].op->doPatternCoupling; }
+  Flags f;
+  if (mode == PATTERN) {           // patternassemblerengine.hh:96-139
+    f.visit_faces = p_skel || p_coup;
+    f.two_sided = p_coup || two;
+  } else if (mode == JACOBIAN) {   // jacobianassemblerengine.hh:149-192
+    f.visit_faces = a_skel || a_bnd || a_coup;
+    f.two_sided = a_bnd || two || a_coup;
+  } else {                         // residualassemblerengine.hh:117-188
+    f.visit_faces = a_skel || a_bnd || a_coup || l_skel || l_bnd;
+    f.two_sided = a_bnd || l_bnd || two || a_coup;
+  }
+  return f;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// pattern  (patternassemblerengine.hh + patternassemblerfunctors.hh; [UPSTREAM] (v) union of local links, rows ascending)
+// ---------------------------------------------------------------------------------------------
+int Context::matrix_create(const int* gos_, int ngos)
+{
+  if (!finalized) throw std::runtime_error("not finalized");
+  std::vector<std::vector<int64_t>> rows(ndof);
+  const int nch = (int)children.size();
+  std::vector<int> off_s(nch + 1), off_n(nch + 1);
+  int64_t dofs_s[MAXCELL], dofs_n[MAXCELL];
+  for (int gi = 0; gi < ngos; ++gi) {
+    const GridOperatorDesc& go = gos.at(gos_[gi]);
+    Flags fl = engine_flags(*this, go, PATTERN);
+    for (int64_t cell = 0; cell < grid.ncells(); ++cell) {
+      EG eg = make_eg(*this, cell);
+      bind(cell, off_s.data(), dofs_s);
+      // volume: FullVolumePattern [UPSTREAM]
+      for (int s : go.sps) {
+        const SubProblem& sp = sps[s];
+        if (!sp.appliesTo(eg.sd) || !sp.lop->doPatternVolume) continue;
+        LFS l = subproblem_lfs(sp, off_s.data());
+        for (int i = 0; i < l.n; ++i) for (int j = 0; j < l.n; ++j) rows[dofs_s[l.idx[i]]].push_back(dofs_s[l.idx[j]]);
+      }
+      if (!fl.visit_faces) continue;
+      for (int f = 0; f < 2 * grid.dim; ++f) {
+        int64_t nijk[3];
+        if (!FaceIter::neighbor(grid, eg.ijk, f, nijk)) continue;     // pattern has no boundary terms for our operators
+        int64_t ncell = grid.cell_index(nijk);
+        if (!fl.two_sided && cell < ncell) continue;
+        EG en = make_eg(*this, ncell);
+        bind(ncell, off_n.data(), dofs_n);
+        for (int k : go.cps) {
+          const Coupling& cp = cps[k];
+          if (!cp.op->doPatternCoupling) continue;
+          const SubProblem& lsp = sps[cp.local_sp]; const SubProblem& rsp = sps[cp.remote_sp];
+          if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;     // coupling.hh:78-83
+          LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
+          // FullCouplingPattern couplingutilities.hh:35-47
+          for (int i = 0; i < ls.n; ++i) for (int j = 0; j < ln.n; ++j) rows[dofs_s[ls.idx[i]]].push_back(dofs_n[ln.idx[j]]);
+          for (int i = 0; i < ln.n; ++i) for (int j = 0; j < ls.n; ++j) rows[dofs_n[ln.idx[i]]].push_back(dofs_s[ls.idx[j]]);
+        }
+      }
+    }
+  }
+  CSR A; A.nrows = ndof; A.rowptr.assign(ndof + 1, 0);
+  for (int64_t r = 0; r < ndof; ++r) {
+    auto& v = rows[r]; std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
+    A.rowptr[r + 1] = A.rowptr[r] + (int64_t)v.size();
+  }
+  A.colidx.resize(A.rowptr[ndof]);
+  for (int64_t r = 0; r < ndof; ++r) std::copy(rows[r].begin(), rows[r].end(), A.colidx.begin() + A.rowptr[r]);
+  A.val.assign(A.colidx.size(), 0.0);
+  mats.push_back(std::move(A));
+  return (int)mats.size() - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual  (residualassemblerengine.hh + residualassemblerfunctors.hh)
+// ---------------------------------------------------------------------------------------------
+void Context::residual(int goi, double weight, const double* x, double* r) const
+{
+  const GridOperatorDesc& go = gos.at(goi);
+  Flags fl = engine_flags(*this, go, RESIDUAL);
+  const int nch = (int)children.size();
+  std::vector<int> off_s(nch + 1), off_n(nch + 1);
+  int64_t dofs_s[MAXCELL], dofs_n[MAXCELL];
+  double x_s[MAXCELL], x_n[MAXCELL], r_s[MAXCELL], r_n[MAXCELL];
+  for (int s : go.sps) sps[s].lop->time = time;
+  for (int64_t cell = 0; cell < grid.ncells(); ++cell) {
+    EG eg = make_eg(*this, cell);
+    int ns = bind(cell, off_s.data(), dofs_s);
+    for (int i = 0; i < ns; ++i) { x_s[i] = x[dofs_s[i]]; r_s[i] = 0.0; }
+    LocalVectorView rv_s{r_s, weight};
+    for (int s : go.sps) {                              // alpha_volume functor :16-35, lambda_volume :38-55
+      const SubProblem& sp = sps[s];
+      if (!sp.appliesTo(eg.sd)) continue;
+      LFS l = subproblem_lfs(sp, off_s.data());
+      if (sp.lop->doAlphaVolume) sp.lop->alpha_volume(eg, l, x_s, l, rv_s);
+    }
+    for (int s : go.sps) {
+      const SubProblem& sp = sps[s];
+      if (!sp.appliesTo(eg.sd)) continue;
+      LFS l = subproblem_lfs(sp, off_s.data());
+      if (sp.lop->doLambdaVolume) sp.lop->lambda_volume(eg, l, rv_s);
+    }
+    if (fl.visit_faces) {
+      for (int f = 0; f < 2 * grid.dim; ++f) {
+        int64_t nijk[3];
+        IG ig; ig.inside = eg; ig.axis = f / 2; ig.side = f % 2; ig.face = f;
+        if (FaceIter::neighbor(grid, eg.ijk, f, nijk)) {
+          int64_t ncell = grid.cell_index(nijk);
+          if (!fl.two_sided && cell < ncell) continue;
+          EG en = make_eg(*this, ncell);
+          ig.outside = en; ig.boundary = false; ig.oneSidedDirection = cell > ncell;
+          int nn = bind(ncell, off_n.data(), dofs_n);
+          for (int i = 0; i < nn; ++i) { x_n[i] = x[dofs_n[i]]; r_n[i] = 0.0; }
+          LocalVectorView rv_n{r_n, weight};
+          // assembleUVSkeleton: alpha_skeleton_or_boundary on subproblems (:58-88) then alpha_coupling (:165-191)
+          for (int s : go.sps) {
+            const SubProblem& sp = sps[s];
+            if (!sp.appliesTo(eg.sd)) continue;
+            if (sp.appliesTo(en.sd)) { /* alpha_skeleton: none of the restated operators has it */ }
+            else { /* alpha_boundary on an interior face: none of the restated operators has it */ }
+          }
+          for (int k : go.cps) {
+            const Coupling& cp = cps[k];
+            if (!cp.op->doAlphaCoupling) continue;
+            const SubProblem& lsp = sps[cp.local_sp]; const SubProblem& rsp = sps[cp.remote_sp];
+            if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
+            LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
+            cp.op->alpha_coupling(ig, ls, x_s, ls, ln, x_n, ln, rv_s, rv_n);
+          }
+          // assembleVSkeleton: lambda_skeleton_or_boundary (:91-120)
+          for (int s : go.sps) {
+            const SubProblem& sp = sps[s];
+            if (!sp.appliesTo(eg.sd)) continue;
+            if (sp.appliesTo(en.sd)) { /* lambda_skeleton: none */ }
+            else if (sp.lop->doLambdaBoundary) {       // subdomain interface seen as boundary (:113-118)
+              LFS l = subproblem_lfs(sp, off_s.data());
+              sp.lop->lambda_boundary(ig, l, rv_s);
+            }
+          }
+          for (int i = 0; i < nn; ++i) r[dofs_n[i]] += r_n[i];           // onUnbindLFSVOutside
+        } else {
+          ig.outside = eg; ig.boundary = true; ig.oneSidedDirection = true;
+          for (int s : go.sps) {                                          // lambda_boundary functor :145-162
+            const SubProblem& sp = sps[s];
+            if (!sp.appliesTo(eg.sd) || !sp.lop->doLambdaBoundary) continue;
+            LFS l = subproblem_lfs(sp, off_s.data());
+            sp.lop->lambda_boundary(ig, l, rv_s);
+          }
+        }
+      }
+    }
+    for (int i = 0; i < ns; ++i) r[dofs_s[i]] += r_s[i];                  // onUnbindLFSV
+  }
+  // postAssembly: constrain_residual [UPSTREAM] (vi)
+  for (int64_t i = 0; i < ndof; ++i) if (constrained[i]) r[i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// jacobian  (jacobianassemblerengine.hh + jacobianassemblerfunctors.hh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct JacScratch {
+  std::vector<int> off_s, off_n;
+  int64_t dofs_s[MAXCELL], dofs_n[MAXCELL];
+  double x_s[MAXCELL], x_n[MAXCELL];
+  std::vector<double> a_ss, a_sn, a_ns, a_nn;
+  explicit JacScratch(int nch) : off_s(nch + 1), off_n(nch + 1), a_ss(MAXCELL * MAXCELL), a_sn(MAXCELL * MAXCELL),
+                                 a_ns(MAXCELL * MAXCELL), a_nn(MAXCELL * MAXCELL) {}
+};
+
+void scatter(CSR& A, const int64_t* rd, int nr, const int64_t* cd, int nc, const double* a, bool must_exist)
+{
+  // [UPSTREAM] (vi) scatter_jacobian = plain add of every local entry whose (row,col) is in the pattern; the local
+  // blocks are dense, entries outside the operator's own pattern are exact zeros and are skipped.
+  for (int i = 0; i < nr; ++i)
+    for (int j = 0; j < nc; ++j) {
+      double v = a[i * nc + j];
+      int64_t p = A.find(rd[i], cd[j]);
+      if (p < 0) { if (v != 0.0 && must_exist) throw std::runtime_error("jacobian entry outside pattern"); continue; }
+      A.val[p] += v;
+    }
+}
+
+void jacobian_cell(const Context& c, const GridOperatorDesc& go, const Flags& fl, CSR& A, double weight, const double* x,
+                   int64_t cell, JacScratch& S)
+{
+  const Grid& grid = c.grid;
+  EG eg = make_eg(c, cell);
+  int ns = c.bind(cell, S.off_s.data(), S.dofs_s);
+  for (int i = 0; i < ns; ++i) S.x_s[i] = x[S.dofs_s[i]];
+  std::fill(S.a_ss.begin(), S.a_ss.begin() + ns * ns, 0.0);
+  LocalMatrixView m_ss{S.a_ss.data(), ns, weight};
+  for (int s : go.sps) {                                 // invoke_jacobian_volume :16-35
+    const SubProblem& sp = c.sps[s];
+    if (!sp.appliesTo(eg.sd) || !sp.lop->doAlphaVolume) continue;
+    LFS l = c.subproblem_lfs(sp, S.off_s.data());
+    sp.lop->jacobian_volume(eg, l, S.x_s, l, m_ss);
+  }
+  if (fl.visit_faces) {
+    for (int f = 0; f < 2 * grid.dim; ++f) {
+      int64_t nijk[3];
+      if (!FaceIter::neighbor(grid, eg.ijk, f, nijk)) continue;   // boundary: no alpha_boundary among restated operators
+      int64_t ncell = grid.cell_index(nijk);
+      if (!fl.two_sided && cell < ncell) continue;
+      EG en = make_eg(c, ncell);
+      bool any = false;
+      for (int k : go.cps) {
+        const Coupling& cp = c.cps[k];
+        if (cp.op->doAlphaCoupling && c.sps[cp.local_sp].appliesTo(eg.sd) && c.sps[cp.remote_sp].appliesTo(en.sd)) any = true;
+      }
+      if (!any) continue;      // the reference binds lfs_n and scatters all-zero blocks here; no effect on values
+      IG ig; ig.inside = eg; ig.outside = en; ig.axis = f / 2; ig.side = f % 2; ig.face = f; ig.boundary = false;
+      ig.oneSidedDirection = cell > ncell;
+      int nn = c.bind(ncell, S.off_n.data(), S.dofs_n);
+      for (int i = 0; i < nn; ++i) S.x_n[i] = x[S.dofs_n[i]];
+      std::fill(S.a_sn.begin(), S.a_sn.begin() + ns * nn, 0.0);
+      std::fill(S.a_ns.begin(), S.a_ns.begin() + nn * ns, 0.0);
+      std::fill(S.a_nn.begin(), S.a_nn.begin() + nn * nn, 0.0);
+      LocalMatrixView m_sn{S.a_sn.data(), nn, weight}, m_ns{S.a_ns.data(), ns, weight}, m_nn{S.a_nn.data(), nn, weight};
+      for (int k : go.cps) {                              // invoke_jacobian_coupling :91-117
+        const Coupling& cp = c.cps[k];
+        if (!cp.op->doAlphaCoupling) continue;
+        const SubProblem& lsp = c.sps[cp.local_sp]; const SubProblem& rsp = c.sps[cp.remote_sp];
+        if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
+        LFS ls = c.subproblem_lfs(lsp, S.off_s.data()), ln = c.subproblem_lfs(rsp, S.off_n.data());
+        cp.op->jacobian_coupling(ig, ls, S.x_s, ns, ls, ln, S.x_n, nn, ln, m_ss, m_sn, m_ns, m_nn);
+      }
+      // onUnbindLFSUVOutside: nn, sn, ns (jacobianassemblerengine.hh:296-330)
+      scatter(A, S.dofs_n, nn, S.dofs_n, nn, S.a_nn.data(), true);
+      scatter(A, S.dofs_s, ns, S.dofs_n, nn, S.a_sn.data(), true);
+      scatter(A, S.dofs_n, nn, S.dofs_s, ns, S.a_ns.data(), true);
+    }
+  }
+  scatter(A, S.dofs_s, ns, S.dofs_s, ns, S.a_ss.data(), true);   // onUnbindLFSUV
+}
+
+void dirichlet_rows(const Context& c, CSR& A)
+{
+  // [UPSTREAM] (vi) handle_dirichlet_constraints / set_trivial_rows: row <- 0, diagonal <- 1
+  for (int64_t r = 0; r < c.ndof; ++r) if (c.constrained[r]) {
+    for (int64_t p = A.rowptr[r]; p < A.rowptr[r + 1]; ++p) A.val[p] = (A.colidx[p] == r) ? 1.0 : 0.0;
+  }
+}
+} // namespace
+
+void Context::jacobian(int goi, int mat, double weight, const double* x)
+{
+  const GridOperatorDesc& go = gos.at(goi);
+  CSR& A = mats.at(mat);
+  Flags fl = engine_flags(*this, go, JACOBIAN);
+  JacScratch S((int)children.size());
+  for (int64_t cell = 0; cell < grid.ncells(); ++cell) jacobian_cell(*this, go, fl, A, weight, x, cell, S);
+  dirichlet_rows(*this, A);
+}
+
+void Context::jacobian_parallel(int goi, int mat, double weight, const double* x, int nthreads)
+{
+  // CPU-baseline variant: slabs along the slowest axis, two-coloured (even slabs, then odd slabs) so that
+  // concurrently processed cells never share a matrix row.  Same arithmetic per cell as jacobian().
+  const GridOperatorDesc& go = gos.at(goi);
+  CSR& A = mats.at(mat);
+  Flags fl = engine_flags(*this, go, JACOBIAN);
+  const int ax = grid.dim - 1;
+  const int64_t nslow = grid.n[ax];
+  const int64_t per = grid.ncells() / nslow;
+  if (nthreads < 1) nthreads = 1;
+  // slab thickness >= 2 layers so that coupling faces (which touch the neighbour cell's rows) stay inside a colour gap
+  int64_t nslabs = std::min<int64_t>(nslow / 2, (int64_t)nthreads * 2);
+  if (nslabs < 2) { jacobian(goi, mat, weight, x); return; }
+  if (nslabs % 2) nslabs -= 1;
+  auto slab_begin = [&](int64_t s) { return (nslow * s) / nslabs; };
+  for (int colour = 0; colour < 2; ++colour) {
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(nslabs);
+    for (int64_t s = colour; s < nslabs; s += 2) {
+      th.emplace_back([&, s]() {
+        try {
+          JacScratch S((int)children.size());
+          for (int64_t cell = slab_begin(s) * per; cell < slab_begin(s + 1) * per; ++cell)
+            jacobian_cell(*this, go, fl, A, weight, x, cell, S);
+        } catch (std::exception& e) { errs[s] = e.what(); }
+      });
+    }
+    for (auto& t : th) t.join();
+    for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
+  }
+  dirichlet_rows(*this, A);
+}
+
+// =============================================================================================
+// constraints (constraints.hh:312-558, constraintsfunctors.hh:41-131; [UPSTREAM] ConformingDirichletConstraints:
+// predicate evaluated at the face centre, all DOFs on the face are constrained — SURVEY Appendix B)
+// =============================================================================================
+void Context::constraints_assemble(const int* sps_, const mdb_bctype* bcs, int n)
+{
+  const int dim = grid.dim;
+  const int nch = (int)children.size();
+  std::vector<int> off_s(nch + 1);
+  int64_t dofs_s[MAXCELL];
+  std::fill(constrained.begin(), constrained.end(), 0);
+  for (int64_t cell = 0; cell < grid.ncells(); ++cell) {
+    EG eg = make_eg(*this, cell);
+    bind(cell, off_s.data(), dofs_s);
+    for (int f = 0; f < 2 * dim; ++f) {
+      int64_t nijk[3];
+      bool interior = FaceIter::neighbor(grid, eg.ijk, f, nijk);
+      uint8_t nsd = interior ? cell_sd[grid.cell_index(nijk)] : 0;
+      IG ig; ig.inside = eg; ig.outside = eg; ig.axis = f / 2; ig.side = f % 2; ig.face = f; ig.boundary = !interior;
+      for (int q = 0; q < n; ++q) {
+        const SubProblem& sp = sps.at(sps_[q]);
+        if (!sp.appliesTo(eg.sd)) continue;
+        // constraintsfunctors.hh:77-103: skeleton constraints if the subproblem also lives outside (none for
+        // conforming spaces), otherwise the *boundary* visitor runs, also on subdomain interfaces
+        if (interior && sp.appliesTo(nsd)) continue;
+        double centre[2] = {0.5, 0.5}, xg[3];
+        ig.global(centre, xg);
+        if (eval_bctype(bcs[q], dim, xg, ig.boundary) != 0) continue;
+        LFS l = subproblem_lfs(sp, off_s.data());
+        const int k = l.k;
+        for (int i = 0; i < l.n; ++i) {
+          int rem = i, a[3];
+          for (int d = 0; d < 3; ++d) { a[d] = (d < dim) ? rem % (k + 1) : 0; rem /= (k + 1); }
+          if (a[ig.axis] == (ig.side ? k : 0)) constrained[dofs_s[l.idx[i]]] = 1;
+        }
+      }
+    }
+  }
+}
+
+// interpolate.hh:35-73: one grid loop; for every subproblem that applies, Lagrange interpolation of f
+void Context::interpolate(const int* sps_, const mdb_function* fns, int n, double t, double* x) const
+{
+  const int dim = grid.dim;
+  const int nch = (int)children.size();
+  std::vector<int> off_s(nch + 1);
+  int64_t dofs_s[MAXCELL];
+  for (int64_t cell = 0; cell < grid.ncells(); ++cell) {
+    EG eg = make_eg(*this, cell);
+    bind(cell, off_s.data(), dofs_s);
+    for (int q = 0; q < n; ++q) {
+      const SubProblem& sp = sps.at(sps_[q]);
+      if (!sp.appliesTo(eg.sd)) continue;
+      LFS l = subproblem_lfs(sp, off_s.data());
+      const int k = l.k;
+      for (int i = 0; i < l.n; ++i) {
+        int rem = i; double local[3], xg[3];
+        for (int d = 0; d < 3; ++d) { int a = (d < dim) ? rem % (k + 1) : 0; rem /= (k + 1); local[d] = double(a) / k; }
+        eg.global(local, xg);
+        x[dofs_s[l.idx[i]]] = eval_function(fns[q], dim, xg, t);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// linear algebra  ([UPSTREAM] dune-istl: MatrixAdapter, SeqJac, SeqSSOR, SeqILU0, CGSolver, BiCGSTABSolver)
+// =============================================================================================
+void spmv(const CSR& A, const double* x, double* y)
+{
+  for (int64_t r = 0; r < A.nrows; ++r) {
+    double s = 0.0;
+    for (int64_t p = A.rowptr[r]; p < A.rowptr[r + 1]; ++p) s += A.val[p] * x[A.colidx[p]];
+    y[r] = s;
+  }
+}
+
+namespace {
+struct Precond {
+  const CSR& A; int kind; int sweeps;
+  std::vector<double> ilu; std::vector<int64_t> diag;
+  Precond(const CSR& A_, int kind_, int sweeps_) : A(A_), kind(kind_), sweeps(sweeps_) {
+    diag.resize(A.nrows);
+    for (int64_t r = 0; r < A.nrows; ++r) { diag[r] = A.find(r, r); if (diag[r] < 0) throw std::runtime_error("missing diagonal"); }
+    if (kind == MDB_PRECOND_ILU0) {          // bilu0_decomposition, IKJ variant on the pattern of A
+      ilu = A.val;
+      for (int64_t i = 0; i < A.nrows; ++i) {
+        for (int64_t p = A.rowptr[i]; p < diag[i]; ++p) {
+          int64_t k = A.colidx[p];
+          ilu[p] /= ilu[diag[k]];
+          double lik = ilu[p];
+          int64_t q = diag[k] + 1, qe = A.rowptr[k + 1];
+          int64_t s = p + 1, se = A.rowptr[i + 1];
+          while (q < qe && s < se) {
+            if (A.colidx[q] == A.colidx[s]) { ilu[s] -= lik * ilu[q]; ++q; ++s; }
+            else if (A.colidx[q] < A.colidx[s]) ++q; else ++s;
+          }
+        }
+      }
+    }
+  }
+  // v = M^{-1} d   (v starts at zero, as the ISTL solvers do)
+  void apply(double* v, const double* d) const {
+    const int64_t n = A.nrows;
+    std::fill(v, v + n, 0.0);
+    if (kind == MDB_PRECOND_NONE) { std::copy(d, d + n, v); return; }
+    if (kind == MDB_PRECOND_JACOBI) { for (int64_t i = 0; i < n; ++i) v[i] = d[i] / A.val[diag[i]]; return; }
+    if (kind == ORC_PRECOND_SSOR) {          // SeqSSOR(A,n,1.0): n x (bsorf, bsorb), (ix)
+      for (int s = 0; s < sweeps; ++s) {
+        for (int64_t i = 0; i < n; ++i) {
+          double rhs = d[i];
+          for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) rhs -= A.val[p] * v[A.colidx[p]];
+          v[i] += rhs / A.val[diag[i]];
+        }
+        for (int64_t i = n - 1; i >= 0; --i) {
+          double rhs = d[i];
+          for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) rhs -= A.val[p] * v[A.colidx[p]];
+          v[i] += rhs / A.val[diag[i]];
+        }
+      }
+      return;
+    }
+    if (kind == MDB_PRECOND_ILU0) {          // bilu_backsolve
+      for (int64_t i = 0; i < n; ++i) {
+        double s = d[i];
+        for (int64_t p = A.rowptr[i]; p < diag[i]; ++p) s -= ilu[p] * v[A.colidx[p]];
+        v[i] = s;
+      }
+      for (int64_t i = n - 1; i >= 0; --i) {
+        double s = v[i];
+        for (int64_t p = diag[i] + 1; p < A.rowptr[i + 1]; ++p) s -= ilu[p] * v[A.colidx[p]];
+        v[i] = s / ilu[diag[i]];
+      }
+      return;
+    }
+    throw std::runtime_error("unknown preconditioner");
+  }
+};
+double dot(int64_t n, const double* a, const double* b) { double s = 0; for (int64_t i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+} // namespace
+
+SolveStats solve(const CSR& A, int method, int precond, int sweeps, double reduction, int maxit, const double* b, double* x)
+{
+  const int64_t n = A.nrows;
+  Precond M(A, precond, sweeps);
+  SolveStats st;
+  std::vector<double> r(b, b + n);
+  std::fill(x, x + n, 0.0);
+  st.defect0 = std::sqrt(dot(n, r.data(), r.data()));
+  st.defect = st.defect0;
+  if (st.defect0 == 0.0) { st.converged = true; return st; }
+  if (method == MDB_SOLVER_CG) {
+    std::vector<double> p(n, 0.0), q(n);
+    double rholast = 1.0;
+    for (int it = 1; it <= maxit; ++it) {
+      M.apply(q.data(), r.data());
+      double rho = dot(n, q.data(), r.data());
+      double beta = rho / rholast;
+      for (int64_t i = 0; i < n; ++i) p[i] = p[i] * beta + q[i];
+      rholast = rho;
+      spmv(A, p.data(), q.data());
+      double alpha = dot(n, p.data(), q.data());
+      double lambda = rho / alpha;
+      for (int64_t i = 0; i < n; ++i) { x[i] += lambda * p[i]; r[i] -= lambda * q[i]; }
+      st.defect = std::sqrt(dot(n, r.data(), r.data()));
+      st.iterations = it;
+      if (st.defect <= reduction * st.defect0) { st.converged = true; break; }
+    }
+    return st;
+  }
+  // BiCGSTAB
+  std::vector<double> rt(r), p(n, 0.0), v(n, 0.0), y(n), t(n);
+  double rho = 1, alpha = 1, omega = 1;
+  for (int it = 1; it <= maxit; ++it) {
+    double rho_new = dot(n, rt.data(), r.data());
+    if (it == 1) p = r;
+    else {
+      double beta = (rho_new / rho) * (alpha / omega);
+      for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+    }
+    M.apply(y.data(), p.data());
+    spmv(A, y.data(), v.data());
+    double hh = dot(n, rt.data(), v.data());
+    alpha = rho_new / hh;
+    for (int64_t i = 0; i < n; ++i) { x[i] += alpha * y[i]; r[i] -= alpha * v[i]; }
+    st.defect = std::sqrt(dot(n, r.data(), r.data()));
+    st.iterations = it;
+    if (st.defect <= reduction * st.defect0) { st.converged = true; break; }
+    M.apply(y.data(), r.data());
+    spmv(A, y.data(), t.data());
+    omega = dot(n, t.data(), r.data()) / dot(n, t.data(), t.data());
+    for (int64_t i = 0; i < n; ++i) { x[i] += omega * y[i]; r[i] -= omega * t[i]; }
+    rho = rho_new;
+    st.defect = std::sqrt(dot(n, r.data(), r.data()));
+    if (st.defect <= reduction * st.defect0) { st.converged = true; break; }
+  }
+  return st;
+}
+
+} // namespace orc
+
+// =============================================================================================
+// C interface for ctypes (tests / bench cpu_baseline only); mirrors the shape of include/mdb200.h
+// =============================================================================================
+using orc::Context;
+#define ORC_TRY(ctx, ...) try { __VA_ARGS__; return 0; } catch (std::exception& e) { (ctx)->err = e.what(); return -1; }
+
+extern "C" {
+
+Context* orc_create() { return new Context(); }
+void orc_destroy(Context* c) { delete c; }
+const char* orc_last_error(Context* c) { return c->err.c_str(); }
+
+int orc_mesh_structured(Context* c, int dim, const int64_t* n, const double* lower, const double* upper)
+{
+  ORC_TRY(c, {
+    if (dim < 1 || dim > 3) throw std::runtime_error("dim");
+    c->grid = orc::Grid(); c->grid.dim = dim;
+    for (int d = 0; d < dim; ++d) { c->grid.n[d] = n[d]; c->grid.lower[d] = lower[d]; c->grid.upper[d] = upper[d];
+                                    c->grid.h[d] = (upper[d] - lower[d]) / n[d]; }
+    c->cell_sd.clear(); c->finalized = false;
+  })
+}
+int orc_subdomains(Context* c, const uint8_t* bits)
+{
+  ORC_TRY(c, { c->cell_sd.assign(bits, bits + c->grid.ncells()); })
+}
+int orc_subdomains_halfspace(Context* c, int axis, double threshold, int sd_below, int sd_above)
+{
+  ORC_TRY(c, {
+    c->cell_sd.resize(c->grid.ncells());
+    for (int64_t cell = 0; cell < c->grid.ncells(); ++cell) {
+      int64_t ijk[3]; c->grid.cell_ijk(cell, ijk);
+      // it->geometry().center()[axis] > threshold  (testpoisson.cc:154); [UPSTREAM] centre = lower + 0.5*(upper-lower)
+      double lo = c->grid.coord(axis, ijk[axis]), up = c->grid.coord(axis, ijk[axis] + 1);
+      double centre = lo + 0.5 * (up - lo);
+      c->cell_sd[cell] = uint8_t(1u << (centre > threshold ? sd_above : sd_below));
+    }
+  })
+}
+int orc_add_space(Context* c, int fe_kind, int subdomain)
+{
+  try {
+    orc::ChildSpace ch; ch.fe_kind = fe_kind; ch.subdomain = subdomain;
+    ch.k = (fe_kind == MDB_FE_Q1) ? 1 : (fe_kind == MDB_FE_Q2) ? 2 : -1;
+    if (ch.k < 0) throw std::runtime_error("unknown fe kind");
+    c->children.push_back(ch);
+    return (int)c->children.size() - 1;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_add_subproblem(Context* c, int op_id, const void* params, size_t nbytes, int cond_kind, uint32_t mask,
+                       const int* children, int nchildren)
+{
+  try {
+    orc::SubProblem sp; sp.lop = orc::make_local_operator(op_id, params, nbytes);
+    sp.cond_kind = cond_kind; sp.mask = mask; sp.children.assign(children, children + nchildren);
+    c->sps.push_back(std::move(sp));
+    return (int)c->sps.size() - 1;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_add_coupling(Context* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp, int jac_mode)
+{
+  try {
+    orc::Coupling cp; cp.op = orc::make_coupling_operator(op_id, params, nbytes, jac_mode);
+    cp.local_sp = local_sp; cp.remote_sp = remote_sp;
+    c->cps.push_back(std::move(cp));
+    return (int)c->cps.size() - 1;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_finalize(Context* c, int64_t* ndof) { ORC_TRY(c, { c->finalize(); *ndof = c->ndof; }) }
+int orc_get_dofmap(Context* c, int64_t* cell_ptr, int64_t* cell_dofs)
+{
+  ORC_TRY(c, {
+    std::vector<int> off(c->children.size() + 1); int64_t dofs[64]; int64_t pos = 0;
+    for (int64_t cell = 0; cell < c->grid.ncells(); ++cell) {
+      int n = c->bind(cell, off.data(), dofs);
+      cell_ptr[cell] = pos;
+      if (cell_dofs) for (int i = 0; i < n; ++i) cell_dofs[pos + i] = dofs[i];
+      pos += n;
+    }
+    cell_ptr[c->grid.ncells()] = pos;
+  })
+}
+int orc_get_child_offsets(Context* c, int64_t* offsets)
+{
+  ORC_TRY(c, { for (size_t i = 0; i < c->children.size(); ++i) offsets[i] = c->children[i].offset; offsets[c->children.size()] = c->ndof; })
+}
+int orc_constraints_assemble(Context* c, const int* sps, const mdb_bctype* bcs, int n, int64_t* ncon)
+{
+  ORC_TRY(c, { c->constraints_assemble(sps, bcs, n); int64_t k = 0; for (auto f : c->constrained) k += f; *ncon = k; })
+}
+int orc_set_constraints(Context* c, int64_t n, const int64_t* dofs)
+{
+  ORC_TRY(c, { std::fill(c->constrained.begin(), c->constrained.end(), 0); for (int64_t i = 0; i < n; ++i) c->constrained.at(dofs[i]) = 1; })
+}
+int orc_get_constraints(Context* c, uint8_t* flags) { ORC_TRY(c, { std::copy(c->constrained.begin(), c->constrained.end(), flags); }) }
+int orc_interpolate(Context* c, const int* sps, const mdb_function* fns, int n, double t, double* x) { ORC_TRY(c, { c->interpolate(sps, fns, n, t, x); }) }
+int orc_gridoperator_create(Context* c, const int* sps, int nsp, const int* cps, int ncp)
+{
+  try { orc::GridOperatorDesc g; g.sps.assign(sps, sps + nsp); g.cps.assign(cps, cps + ncp); c->gos.push_back(g); return (int)c->gos.size() - 1; }
+  catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_matrix_create(Context* c, const int* gos, int ngos, int64_t* nnz)
+{
+  try { int m = c->matrix_create(gos, ngos); *nnz = (int64_t)c->mats[m].colidx.size(); return m; }
+  catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_matrix_get_pattern(Context* c, int mat, int64_t* rowptr, int64_t* colidx)
+{
+  ORC_TRY(c, { auto& A = c->mats.at(mat); std::copy(A.rowptr.begin(), A.rowptr.end(), rowptr); std::copy(A.colidx.begin(), A.colidx.end(), colidx); })
+}
+int orc_matrix_get_values(Context* c, int mat, double* v) { ORC_TRY(c, { auto& A = c->mats.at(mat); std::copy(A.val.begin(), A.val.end(), v); }) }
+int orc_matrix_zero(Context* c, int mat) { ORC_TRY(c, { auto& A = c->mats.at(mat); std::fill(A.val.begin(), A.val.end(), 0.0); }) }
+int orc_set_time(Context* c, double t) { c->time = t; return 0; }
+int orc_residual(Context* c, int go, double weight, const double* x, double* r) { ORC_TRY(c, { c->residual(go, weight, x, r); }) }
+int orc_jacobian(Context* c, int go, int mat, double weight, const double* x) { ORC_TRY(c, { c->jacobian(go, mat, weight, x); }) }
+int orc_jacobian_parallel(Context* c, int go, int mat, double weight, const double* x, int nthreads)
+{ ORC_TRY(c, { c->jacobian_parallel(go, mat, weight, x, nthreads); }) }
+int orc_spmv(Context* c, int mat, const double* x, double* y) { ORC_TRY(c, { orc::spmv(c->mats.at(mat), x, y); }) }
+int orc_solve(Context* c, int mat, int method, int precond, int sweeps, double reduction, int maxit, const double* b, double* x,
+              mdb_solve_stats* stats)
+{
+  ORC_TRY(c, {
+    orc::SolveStats s = orc::solve(c->mats.at(mat), method, precond, sweeps, reduction, maxit, b, x);
+    if (stats) { stats->iterations = s.iterations; stats->converged = s.converged; stats->defect0 = s.defect0; stats->defect = s.defect; stats->seconds = 0; }
+  })
+}
+// element-level probes for known-answer tests: local matrix / residual of one operator on one cell
+int orc_local_jacobian_volume(Context* c, int sp, int64_t cell, double* a /* nloc*nloc row-major */)
+{
+  ORC_TRY(c, {
+    std::vector<int> off(c->children.size() + 1); int64_t dofs[64];
+    int n = c->bind(cell, off.data(), dofs);
+    orc::EG eg; eg.g = &c->grid; eg.index = cell; c->grid.cell_ijk(cell, eg.ijk); eg.sd = c->cell_sd[cell];
+    orc::LFS l = c->subproblem_lfs(c->sps.at(sp), off.data());
+    std::vector<double> full(n * n, 0.0), x(n, 0.0);
+    orc::LocalMatrixView m{full.data(), n, 1.0};
+    c->sps[sp].lop->jacobian_volume(eg, l, x.data(), l, m);
+    for (int i = 0; i < l.n; ++i) for (int j = 0; j < l.n; ++j) a[i * l.n + j] = full[l.idx[i] * n + l.idx[j]];
+  })
+}
+
+} // extern "C"

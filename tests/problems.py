@@ -1,0 +1,69 @@
+"""Problem set-ups shared by the oracle and the CUDA backend (both export the same call shapes).
+
+Every function takes an `api` object (tests/orc.Oracle or dune-multidomain_b200.Mdb) and drives it exactly the way
+the reference's drivers build their problems.
+"""
+import importlib
+from types import SimpleNamespace
+
+capi = importlib.import_module("dune-multidomain_b200").capi
+
+
+def testpoisson(api, n, intensity=2.0, split_axis=1, fe=(capi.FE_Q1, capi.FE_Q1), quad_order=4, coupling=capi.OP_CVCF_COUPLING,
+                jac_mode=capi.JAC_FD_BITMATCH, f=None, sd_bits=None, lower=None, upper=None):
+    """test/testpoisson.cc:119-298 (2-D as shipped; dim = len(n) gives the synthetic 3-D extension).
+
+    Two subdomains split at x[split_axis] > 0.5 (:152-158), one Qk space per subdomain (:168-198), Poisson(f,b,j,4)
+    on each (:218-232), ContinuousValueContinuousFlowCoupling(4, intensity) left->right (:234-237), Dirichlet
+    constraints from DirichletBoundary (:242-246), u = interpolated G (:266).
+    """
+    dim = len(n)
+    api.mesh_structured(n, lower, upper)
+    if sd_bits is None:
+        api.subdomains_halfspace(split_axis, 0.5, 0, 1)
+    else:
+        api.subdomains(sd_bits)
+    c0 = api.add_space(fe[0], 0)
+    c1 = api.add_space(fe[1], 1)
+    pp = capi.PoissonParams()
+    pp.f = f if f is not None else capi.Function(capi.FN_ZERO)          # testpoisson.cc:38: y = 0
+    pp.bc = capi.BCType(capi.BC_TESTPOISSON)
+    pp.j = capi.Function(capi.FN_TESTPOISSON_J)
+    pp.quad_order = quad_order
+    left = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 0, [c0])
+    right = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 1, [c1])
+    if coupling == capi.OP_CVCF_COUPLING:
+        cpar = capi.CVCFParams()
+        cpar.quad_order = 4
+        cpar.intensity = intensity
+    else:
+        cpar = capi.PropFlowParams()
+        cpar.intensity = intensity
+    cp = api.add_coupling(coupling, cpar, left, right, jac_mode)
+    ndof = api.finalize()
+    ncon = api.constraints_assemble([left, right], [pp.bc, pp.bc])
+    go = api.gridoperator_create([left, right], [cp])
+    mat = api.matrix_create([go])
+    g = capi.gauss()
+    return SimpleNamespace(dim=dim, ndof=ndof, ncon=ncon, go=go, mat=mat, left=left, right=right, cp=cp, g=g, sps=[left, right],
+                           gfn=[g, g], bc=pp.bc)
+
+
+def single_domain_poisson(api, n, quad_order=2, fe=capi.FE_Q1, bc=capi.BC_ALL_DIRICHLET, f=None):
+    """One subdomain covering everything, one subproblem, no coupling (test/testpoisson-assembly.cc:883-889 marks every
+    cell into subdomain 0)."""
+    import numpy as np
+    api.mesh_structured(n)
+    api.subdomains(np.ones(int(np.prod(n)), dtype=np.uint8))
+    c0 = api.add_space(fe, 0)
+    pp = capi.PoissonParams()
+    pp.f = f if f is not None else capi.Function(capi.FN_ZERO)
+    pp.bc = capi.BCType(bc)
+    pp.j = capi.Function(capi.FN_ZERO)
+    pp.quad_order = quad_order
+    sp = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1, [c0])
+    ndof = api.finalize()
+    ncon = api.constraints_assemble([sp], [pp.bc])
+    go = api.gridoperator_create([sp], [])
+    mat = api.matrix_create([go])
+    return SimpleNamespace(ndof=ndof, ncon=ncon, go=go, mat=mat, sp=sp, sps=[sp], bc=pp.bc)
