@@ -1,0 +1,596 @@
+// capi.cu — the C ABI of libmdb200.so (include/mdb200.h): context, mesh, spaces, participants, entry points.
+#include "common.cuh"
+#include <cmath>
+
+namespace mdb {
+
+static std::string g_create_error;
+
+Rule1D gauss1d(int order)
+{
+  Rule1D r;
+  int m = (order + 2) / 2;
+  if (m < 1) m = 1;
+  MDB_REQUIRE(m <= 5, MDB_EINVAL, "quadrature order too high (max 9)");
+  r.m = m;
+  switch (m) {
+  case 1: r.x[0] = 0.5; r.w[0] = 1.0; break;
+  case 2: {
+    double a = 0.5 / std::sqrt(3.0);
+    r.x[0] = 0.5 - a; r.x[1] = 0.5 + a; r.w[0] = 0.5; r.w[1] = 0.5; break; }
+  case 3: {
+    double a = 0.5 * std::sqrt(3.0 / 5.0);
+    r.x[0] = 0.5 - a; r.x[1] = 0.5; r.x[2] = 0.5 + a;
+    r.w[0] = 5.0 / 18.0; r.w[1] = 8.0 / 18.0; r.w[2] = 5.0 / 18.0; break; }
+  case 4: {
+    double s = std::sqrt(6.0 / 5.0);
+    double a = 0.5 * std::sqrt(3.0 / 7.0 - 2.0 / 7.0 * s);
+    double b = 0.5 * std::sqrt(3.0 / 7.0 + 2.0 / 7.0 * s);
+    double wa = (18.0 + std::sqrt(30.0)) / 72.0;
+    double wb = (18.0 - std::sqrt(30.0)) / 72.0;
+    r.x[0] = 0.5 - b; r.x[1] = 0.5 - a; r.x[2] = 0.5 + a; r.x[3] = 0.5 + b;
+    r.w[0] = wb; r.w[1] = wa; r.w[2] = wa; r.w[3] = wb; break; }
+  case 5: {
+    double s = 2.0 * std::sqrt(10.0 / 7.0);
+    double a = 0.5 * (1.0 / 3.0) * std::sqrt(5.0 - s);
+    double b = 0.5 * (1.0 / 3.0) * std::sqrt(5.0 + s);
+    double wa = (322.0 + 13.0 * std::sqrt(70.0)) / 1800.0;
+    double wb = (322.0 - 13.0 * std::sqrt(70.0)) / 1800.0;
+    r.x[0] = 0.5 - b; r.x[1] = 0.5 - a; r.x[2] = 0.5; r.x[3] = 0.5 + a; r.x[4] = 0.5 + b;
+    r.w[0] = wb; r.w[1] = wa; r.w[2] = 128.0 / 450.0; r.w[3] = wa; r.w[4] = wb; break; }
+  }
+  return r;
+}
+
+void* Ctx::scratch(size_t bytes)
+{
+  if (bytes > scratch_bytes) {
+    if (d_scratch) cudaFree(d_scratch);
+    d_scratch = nullptr; scratch_bytes = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&d_scratch, want);
+    if (e != cudaSuccess) throw Error(MDB_ENOMEM, "scratch cudaMalloc failed");
+    scratch_bytes = want;
+  }
+  return d_scratch;
+}
+
+void Ctx::phase_begin() { MDB_CUDA(cudaEventRecord(ev0, stream)); }
+void Ctx::phase_end(const char* name)
+{
+  MDB_CUDA(cudaEventRecord(ev1, stream));
+  MDB_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  phase_ms[name] = ms;
+}
+
+VecIn::VecIn(Ctx* c, const double* p, int64_t n, int slot)
+{
+  if (is_device_ptr(p)) { d = p; return; }
+  if (!c->d_stage[slot]) c->d_stage[slot] = dalloc<double>(c->ndof > n ? c->ndof : n);
+  MDB_CUDA(cudaMemcpyAsync(c->d_stage[slot], p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  d = c->d_stage[slot];
+}
+VecInOut::VecInOut(Ctx* c_, double* p, int64_t n_, int slot, bool load) : c(c_), n(n_)
+{
+  if (is_device_ptr(p)) { d = p; return; }
+  host = p;
+  if (!c->d_stage[slot]) c->d_stage[slot] = dalloc<double>(c->ndof > n ? c->ndof : n);
+  d = c->d_stage[slot];
+  if (load) MDB_CUDA(cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+void VecInOut::commit()
+{
+  if (host) {
+    MDB_CUDA(cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+}
+
+static void free_matrix(Matrix& m)
+{
+  dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv);
+}
+
+static void reset_spaces(Ctx* c)
+{
+  for (auto& ch : c->children) { dfree(ch.d_lat2dof); dfree(ch.d_dof2lat); }
+  for (auto& go : c->gos) for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); }
+  for (auto& m : c->mats) free_matrix(m);
+  c->gos.clear(); c->mats.clear();
+  dfree(c->d_constrained); dfree(c->d_conlist);
+  for (int i = 0; i < 4; ++i) dfree(c->d_stage[i]);
+  dfree(c->d_work); c->work_n = 0; c->work_vecs = 0;
+  dfree(c->d_owned);
+  c->finalized = false; c->ndof = 0; c->ncon = 0;
+}
+
+__global__ void k_halfspace(MeshDesc m, int axis, double threshold, int sd_below, int sd_above, uint8_t* sd)
+{
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= m.ncells()) return;
+  int ijk[3]; int64_t r = c;
+  ijk[0] = r % m.n[0]; r /= m.n[0]; ijk[1] = r % m.n[1]; ijk[2] = r / m.n[1];
+  double lo = m.coord(axis, ijk[axis]), up = m.coord(axis, ijk[axis] + 1);
+  double centre = lo + 0.5 * (up - lo);
+  sd[c] = (uint8_t)(1u << (centre > threshold ? sd_above : sd_below));
+}
+
+} // namespace mdb
+
+using namespace mdb;
+
+#define MDB_API_BEGIN(ctx)                                                       \
+  if (!(ctx)) return MDB_EINVAL;                                                 \
+  try {                                                                          \
+    cudaSetDevice((ctx)->device);
+#define MDB_API_END(ctx)                                                         \
+    return MDB_OK;                                                               \
+  } catch (mdb::Error& e) { (ctx)->err = e.what(); return e.code; }              \
+  catch (std::exception& e) { (ctx)->err = e.what(); return MDB_EINVAL; }
+
+struct mdb_ctx : mdb::Ctx {};
+
+extern "C" {
+
+const char* mdb_version(void) { return "mdb200 0.1 (sm_100a)"; }
+
+mdb_ctx* mdb_create(int device)
+{
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libmdb200 has no CPU fallback";
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return nullptr; }
+  mdb_ctx* c = new mdb_ctx();
+  c->device = device;
+  try {
+    MDB_CUDA(cudaSetDevice(device));
+    MDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreate(&c->ev0));
+    MDB_CUDA(cudaEventCreate(&c->ev1));
+    c->d_Ae = dalloc<double>(MDB_MAX_CHILDREN * MDB_MAX_SP_PER_CHILD * MDB_MAXLOC * MDB_MAXLOC);
+    c->d_scal = dalloc<double>(64);
+    c->d_partial = dalloc<double>(8 * 4096);
+    MDB_CUDA(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
+  } catch (std::exception& ex) { g_create_error = ex.what(); delete c; return nullptr; }
+  return c;
+}
+
+void mdb_destroy(mdb_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  reset_spaces(c);
+  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_scal); dfree(c->d_partial);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->d_halo_recv) cudaFree(c->d_halo_recv);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* mdb_last_error(mdb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int mdb_mesh_structured(mdb_ctx* c, int dim, const int64_t* n, const double* lower, const double* upper)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(dim == 2 || dim == 3, MDB_EINVAL, "mdb_mesh_structured: dim must be 2 or 3");
+  reset_spaces(c);
+  c->children.clear(); c->sps.clear(); c->cps.clear();
+  MeshDesc& m = c->mesh;
+  m = MeshDesc();
+  m.dim = dim;
+  int64_t total = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (d < dim) {
+      MDB_REQUIRE(n[d] >= 1 && n[d] < (1 << 20), MDB_EINVAL, "mdb_mesh_structured: bad cell count");
+      MDB_REQUIRE(upper[d] > lower[d], MDB_EINVAL, "mdb_mesh_structured: empty box");
+      m.n[d] = (int)n[d]; m.lower[d] = lower[d]; m.h[d] = (upper[d] - lower[d]) / n[d];
+    } else { m.n[d] = 1; m.lower[d] = 0; m.h[d] = 1; }
+    m.gn[d] = m.n[d]; m.off[d] = 0; m.glower[d] = m.lower[d];
+    total *= m.n[d];
+  }
+  MDB_REQUIRE(total < (int64_t)2000000000, MDB_EINVAL, "mdb_mesh_structured: more than 2e9 cells per context");
+  m.partitioned = 0;
+  dfree(c->d_cell_sd);
+  c->d_cell_sd = dalloc<uint8_t>(total);
+  c->have_mesh = true; c->have_sd = false;
+  MDB_API_END(c)
+}
+
+int mdb_mesh_partition(mdb_ctx* c, const int64_t* global_n, const int64_t* cell_offset,
+                       const double* global_lower, const double* global_upper)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_mesh_partition: call after mdb_mesh_structured, before mdb_finalize");
+  MeshDesc& m = c->mesh;
+  for (int d = 0; d < m.dim; ++d) {
+    MDB_REQUIRE(cell_offset[d] >= 0 && cell_offset[d] + m.n[d] <= global_n[d], MDB_EINVAL, "mdb_mesh_partition: slab outside the global mesh");
+    m.gn[d] = (int)global_n[d]; m.off[d] = (int)cell_offset[d]; m.glower[d] = global_lower[d];
+    m.h[d] = (global_upper[d] - global_lower[d]) / global_n[d];
+  }
+  m.partitioned = 1;
+  MDB_API_END(c)
+}
+
+int mdb_subdomains(mdb_ctx* c, const uint8_t* bits)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_subdomains: need a mesh, before mdb_finalize");
+  MDB_CUDA(cudaMemcpyAsync(c->d_cell_sd, bits, c->mesh.ncells(), cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_sd = true;
+  MDB_API_END(c)
+}
+
+int mdb_subdomains_halfspace(mdb_ctx* c, int axis, double threshold, int sd_below, int sd_above)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_subdomains_halfspace: need a mesh, before mdb_finalize");
+  MDB_REQUIRE(axis >= 0 && axis < c->mesh.dim && sd_below >= 0 && sd_below < 8 && sd_above >= 0 && sd_above < 8, MDB_EINVAL,
+              "mdb_subdomains_halfspace: bad axis or subdomain index");
+  MDB_LAUNCH(c, k_halfspace, cdiv(c->mesh.ncells(), 256), 256, 0, c->mesh, axis, threshold, sd_below, sd_above, c->d_cell_sd);
+  c->have_sd = true;
+  MDB_API_END(c)
+}
+
+int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_space: need a mesh, before mdb_finalize");
+    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2, MDB_EINVAL, "mdb_add_space: unknown finite element");
+    MDB_REQUIRE(fe_kind == MDB_FE_Q1, MDB_EINVAL, "mdb_add_space: only Q1 spaces have device kernels in this build");
+    MDB_REQUIRE(subdomain >= -1 && subdomain < 8, MDB_EINVAL, "mdb_add_space: bad subdomain");
+    MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_space: too many child spaces");
+    Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1) ? 1 : 2; ch.subdomain = subdomain;
+    c->children.push_back(ch);
+    return (int)c->children.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
+int mdb_add_subproblem(mdb_ctx* c, int op_id, const void* params, size_t nbytes, int cond_kind, uint32_t cond_mask,
+                       const int* children, int nchildren)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    MDB_REQUIRE(!c->finalized, MDB_ESTATE, "mdb_add_subproblem: before mdb_finalize");
+    MDB_REQUIRE(cond_kind == MDB_COND_EQUALITY || cond_kind == MDB_COND_SUBSET, MDB_EINVAL, "mdb_add_subproblem: bad condition");
+    MDB_REQUIRE(nchildren == 1, MDB_EINVAL, "mdb_add_subproblem: only single-child (scalar) subproblems have device kernels in this build");
+    MDB_REQUIRE(children[0] >= 0 && children[0] < (int)c->children.size(), MDB_EINVAL, "mdb_add_subproblem: bad child index");
+    SubProblemDesc sp; sp.op_id = op_id; sp.cond_kind = cond_kind; sp.mask = cond_mask;
+    sp.children.assign(children, children + nchildren);
+    if (op_id == MDB_OP_POISSON) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_poisson_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_poisson_params size");
+      std::memcpy(&sp.poisson, params, nbytes);
+    } else if (op_id == MDB_OP_L2) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_l2_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_l2_params size");
+      std::memcpy(&sp.l2, params, nbytes);
+    } else throw Error(MDB_EINVAL, "mdb_add_subproblem: unknown local operator (closed operator set, see mdb200.h)");
+    (void)gauss1d(sp.quad_order());
+    c->sps.push_back(sp);
+    return (int)c->sps.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
+int mdb_add_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp, int jac_mode)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    MDB_REQUIRE(!c->finalized, MDB_ESTATE, "mdb_add_coupling: before mdb_finalize");
+    MDB_REQUIRE(local_sp >= 0 && local_sp < (int)c->sps.size() && remote_sp >= 0 && remote_sp < (int)c->sps.size(), MDB_EINVAL,
+                "mdb_add_coupling: bad subproblem index");
+    MDB_REQUIRE(jac_mode == MDB_JAC_FD_BITMATCH || jac_mode == MDB_JAC_ANALYTIC, MDB_EINVAL, "mdb_add_coupling: bad jac_mode");
+    CouplingDesc cp; cp.op_id = op_id; cp.local_sp = local_sp; cp.remote_sp = remote_sp; cp.jac_mode = jac_mode;
+    if (op_id == MDB_OP_CVCF_COUPLING) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_cvcf_params), MDB_EINVAL, "mdb_add_coupling: bad mdb_cvcf_params size");
+      std::memcpy(&cp.cvcf, params, nbytes);
+      (void)gauss1d(cp.cvcf.quad_order);
+    } else if (op_id == MDB_OP_PROPFLOW_COUPLING) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_propflow_params), MDB_EINVAL, "mdb_add_coupling: bad mdb_propflow_params size");
+      std::memcpy(&cp.propflow, params, nbytes);
+    } else throw Error(MDB_EINVAL, "mdb_add_coupling: unknown coupling operator");
+    c->cps.push_back(cp);
+    return (int)c->cps.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
+int mdb_finalize(mdb_ctx* c, int64_t* ndof)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->have_mesh && c->have_sd, MDB_ESTATE, "mdb_finalize: mesh and subdomains must be set");
+  MDB_REQUIRE(!c->children.empty(), MDB_ESTATE, "mdb_finalize: no child spaces");
+  c->phase_begin();
+  build_dofmap(c);
+  c->phase_end("dofmap");
+  c->finalized = true;
+  if (ndof) *ndof = c->ndof;
+  MDB_API_END(c)
+}
+
+int mdb_get_dofmap(mdb_ctx* c, int64_t* cell_ptr, int64_t* cell_dofs)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_get_dofmap: not finalized");
+  export_dofmap(c, cell_ptr, cell_dofs);
+  MDB_API_END(c)
+}
+
+int mdb_get_child_offsets(mdb_ctx* c, int64_t* offsets)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_get_child_offsets: not finalized");
+  for (size_t i = 0; i < c->children.size(); ++i) offsets[i] = c->children[i].offset;
+  offsets[c->children.size()] = c->ndof;
+  MDB_API_END(c)
+}
+
+int mdb_constraints_assemble(mdb_ctx* c, const int* subproblems, const mdb_bctype* bcs, int n, int64_t* nconstrained)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_constraints_assemble: not finalized");
+  for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
+  c->phase_begin();
+  assemble_constraints(c, subproblems, bcs, n);
+  rebuild_conlist(c);
+  c->phase_end("constraints");
+  if (nconstrained) *nconstrained = c->ncon;
+  MDB_API_END(c)
+}
+
+int mdb_set_constraints(mdb_ctx* c, int64_t n, const int64_t* dofs)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_set_constraints: not finalized");
+  std::vector<uint8_t> f(c->ndof, 0);
+  for (int64_t i = 0; i < n; ++i) { MDB_REQUIRE(dofs[i] >= 0 && dofs[i] < c->ndof, MDB_EINVAL, "constraint index out of range"); f[dofs[i]] = 1; }
+  MDB_CUDA(cudaMemcpyAsync(c->d_constrained, f.data(), c->ndof, cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  rebuild_conlist(c);
+  MDB_API_END(c)
+}
+
+int mdb_get_constraints(mdb_ctx* c, uint8_t* flags)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_get_constraints: not finalized");
+  MDB_CUDA(cudaMemcpyAsync(flags, c->d_constrained, c->ndof, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  MDB_API_END(c)
+}
+
+int mdb_interpolate(mdb_ctx* c, const int* subproblems, const mdb_function* fns, int n, double time, double* x)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_interpolate: not finalized");
+  VecInOut vx(c, x, c->ndof, 0, true);
+  interpolate(c, subproblems, fns, n, time, vx.d);
+  vx.commit();
+  MDB_API_END(c)
+}
+
+int mdb_set_time(mdb_ctx* c, double t)
+{
+  if (!c) return MDB_EINVAL;
+  c->time = t;
+  return MDB_OK;
+}
+
+int mdb_gridoperator_create(mdb_ctx* c, const int* subproblems, int nsp, const int* couplings, int ncp)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    cudaSetDevice(c->device);
+    MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_gridoperator_create: not finalized");
+    GridOp go;
+    for (int i = 0; i < nsp; ++i) { MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index"); go.sps.push_back(subproblems[i]); }
+    for (int i = 0; i < ncp; ++i) { MDB_REQUIRE(couplings[i] >= 0 && couplings[i] < (int)c->cps.size(), MDB_EINVAL, "bad coupling index"); go.cps.push_back(couplings[i]); }
+    build_facelists(c, go);
+    c->gos.push_back(go);
+    return (int)c->gos.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
+int mdb_matrix_create(mdb_ctx* c, const int* gos, int ngos, int64_t* nnz)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    cudaSetDevice(c->device);
+    MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_matrix_create: not finalized");
+    Matrix m;
+    for (int i = 0; i < ngos; ++i) { MDB_REQUIRE(gos[i] >= 0 && gos[i] < (int)c->gos.size(), MDB_EINVAL, "bad grid operator handle"); m.gos.push_back(gos[i]); }
+    c->phase_begin();
+    build_pattern(c, m);
+    c->phase_end("pattern");
+    if (nnz) *nnz = m.nnz;
+    c->mats.push_back(m);
+    return (int)c->mats.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
+#define MDB_MAT(c, mat) MDB_REQUIRE((mat) >= 0 && (mat) < (int)(c)->mats.size(), MDB_EINVAL, "bad matrix handle"); Matrix& M = (c)->mats[(mat)];
+#define MDB_GO(c, go) MDB_REQUIRE((go) >= 0 && (go) < (int)(c)->gos.size(), MDB_EINVAL, "bad grid operator handle"); GridOp& G = (c)->gos[(go)];
+
+__global__ void k_widen_i32(const int32_t* in, int64_t* out, int64_t n)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+int mdb_matrix_get_pattern(mdb_ctx* c, int mat, int64_t* rowptr, int64_t* colidx)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  MDB_CUDA(cudaMemcpyAsync(rowptr, M.d_rowptr, (c->ndof + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  // widen the int32 device columns in chunks through scratch
+  const int64_t chunk = 1 << 24;
+  int64_t* d_tmp = (int64_t*)c->scratch(chunk * sizeof(int64_t));
+  for (int64_t o = 0; o < M.nnz; o += chunk) {
+    int64_t n = (M.nnz - o < chunk) ? M.nnz - o : chunk;
+    MDB_LAUNCH(c, k_widen_i32, cdiv(n, 256), 256, 0, M.d_colidx + o, d_tmp, n);
+    MDB_CUDA(cudaMemcpyAsync(colidx + o, d_tmp, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  MDB_API_END(c)
+}
+
+int mdb_matrix_get_values(mdb_ctx* c, int mat, double* values)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  MDB_CUDA(cudaMemcpyAsync(values, M.d_val, M.nnz * sizeof(double), cudaMemcpyDefault, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  MDB_API_END(c)
+}
+
+int mdb_matrix_zero(mdb_ctx* c, int mat)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  MDB_CUDA(cudaMemsetAsync(M.d_val, 0, M.nnz * sizeof(double), c->stream));
+  M.dinv_valid = false;
+  MDB_API_END(c)
+}
+
+int mdb_matrix_device_ptrs(mdb_ctx* c, int mat, const int64_t** rowptr, const int32_t** colidx, double** values)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  if (rowptr) *rowptr = M.d_rowptr;
+  if (colidx) *colidx = M.d_colidx;
+  if (values) *values = M.d_val;
+  MDB_API_END(c)
+}
+
+int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
+{
+  MDB_API_BEGIN(c)
+  MDB_GO(c, go)
+  VecIn vx(c, x, c->ndof, 0);
+  VecInOut vr(c, r, c->ndof, 1, true);
+  c->phase_begin();
+  residual_volume(c, G, weight, vx.d, vr.d);
+  c->phase_end("residual_volume");
+  c->phase_begin();
+  residual_boundary(c, G, weight, vr.d);
+  c->phase_end("residual_boundary");
+  c->phase_begin();
+  residual_coupling(c, G, weight, vx.d, vr.d);
+  constrain_residual(c, vr.d);
+  c->phase_end("residual_coupling");
+  vr.commit();
+  MDB_API_END(c)
+}
+
+int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, int overwrite)
+{
+  MDB_API_BEGIN(c)
+  MDB_GO(c, go)
+  MDB_MAT(c, mat)
+  VecIn vx(c, x, c->ndof, 0);
+  M.dinv_valid = false;
+  c->phase_begin();
+  jacobian_volume(c, G, M, weight, overwrite != 0);
+  c->phase_end("jacobian_volume");
+  c->phase_begin();
+  jacobian_coupling(c, G, M, weight, vx.d);
+  dirichlet_rows(c, M);
+  c->phase_end("jacobian_coupling");
+  MDB_API_END(c)
+}
+
+int mdb_spmv(mdb_ctx* c, int mat, const double* x, double* y)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  VecIn vx(c, x, c->ndof, 0);
+  VecInOut vy(c, y, c->ndof, 1, false);
+  c->phase_begin();
+  spmv(c, M, vx.d, vy.d);
+  c->phase_end("spmv");
+  vy.commit();
+  MDB_API_END(c)
+}
+
+int mdb_solve(mdb_ctx* c, int mat, int method, int precond, double reduction, int maxit, const double* rhs, double* z,
+              mdb_solve_stats* stats)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    cudaSetDevice(c->device);
+    MDB_MAT(c, mat)
+    VecIn vb(c, rhs, c->ndof, 0);
+    VecInOut vz(c, z, c->ndof, 1, false);
+    int rc = solve(c, M, method, precond, reduction, maxit, -1, vb.d, vz.d, stats);
+    vz.commit();
+    return rc;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+  catch (std::exception& e) { c->err = e.what(); return MDB_EINVAL; }
+}
+
+int mdb_solve_fixed(mdb_ctx* c, int mat, int method, int precond, int iters, const double* rhs, double* z, mdb_solve_stats* stats)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    cudaSetDevice(c->device);
+    MDB_MAT(c, mat)
+    VecIn vb(c, rhs, c->ndof, 0);
+    VecInOut vz(c, z, c->ndof, 1, false);
+    int rc = solve(c, M, method, precond, 0.0, iters, iters, vb.d, vz.d, stats);
+    vz.commit();
+    return rc;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+  catch (std::exception& e) { c->err = e.what(); return MDB_EINVAL; }
+}
+
+__global__ void k_copy_nonconstrained(const double* xold, double* xnew, const uint8_t* con, int64_t n)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && !con[i]) xnew[i] = xold[i];
+}
+
+int mdb_copy_nonconstrained(mdb_ctx* c, const double* xold, double* xnew)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "not finalized");
+  VecIn vo(c, xold, c->ndof, 0);
+  VecInOut vn(c, xnew, c->ndof, 1, true);
+  MDB_LAUNCH(c, k_copy_nonconstrained, cdiv(c->ndof, 256), 256, 0, vo.d, vn.d, c->d_constrained, c->ndof);
+  vn.commit();
+  MDB_API_END(c)
+}
+
+double mdb_phase_ms(mdb_ctx* c, const char* phase)
+{
+  if (!c) return -1.0;
+  auto it = c->phase_ms.find(phase);
+  return it == c->phase_ms.end() ? -1.0 : (double)it->second;
+}
+
+int64_t mdb_launch_count(mdb_ctx* c, int reset)
+{
+  if (!c) return 0;
+  int64_t v = c->launches;
+  if (reset) c->launches = 0;
+  return v;
+}
+
+void* mdb_stream(mdb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int mdb_synchronize(mdb_ctx* c)
+{
+  MDB_API_BEGIN(c)
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  MDB_API_END(c)
+}
+
+} // extern "C"

@@ -1,0 +1,293 @@
+// common.cuh — shared host/device definitions of libmdb200 (sm_100a only).
+//
+// Data layout in HBM (all device arrays are owned by the context):
+//   cell_sd      uint8  [ncells]            subdomain bit set of every cell (MultiDomainGrid marking)
+//   lat2dof_k    int32  [nlat_k]            child k: lattice point -> index inside the child block, -1 if absent
+//   dof2lat_k    int32  [size_k]            inverse map
+//   constrained  uint8  [ndof]              Dirichlet flags; conlist int32 [ncon] the same as a compact list
+//   CSR          int64 rowptr[ndof+1], int32 colidx[nnz], double val[nnz], uint32 rowinfo[ndof]
+//   rowinfo      bits 0..26: which of the 3^d own-block stencil offsets exist in the row's pattern
+//                bits 27..31: number of columns in the row that lie below the own child block (31 = search)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+
+#include "../../include/mdb200.h"
+
+#define MDB_MAX_CHILDREN 8
+#define MDB_MAX_SP_PER_CHILD 4
+#define MDB_MAXLOC 27
+
+namespace mdb {
+
+// ------------------------------------------------------------------------------------------------
+// error handling: exceptions inside the library, converted to codes at the C ABI
+// ------------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define MDB_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      throw mdb::Error(MDB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                      std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+#define MDB_REQUIRE(cond, code, msg)                                                                     \
+  do {                                                                                                   \
+    if (!(cond)) throw mdb::Error(code, std::string(msg));                                               \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// structured mesh descriptor, passed by value to kernels
+// ------------------------------------------------------------------------------------------------
+struct MeshDesc {
+  int dim;
+  int n[3];              // local cells per axis
+  double lower[3];       // local lower corner
+  double h[3];           // (upper-lower)/n  of the local box
+  // partition (multi-GPU): the local box is cells [off, off+n) of a global box of gn cells
+  int gn[3];
+  int off[3];
+  double glower[3];      // == lower - off*h conceptually; kept separately so that analytic data see global coordinates
+  int partitioned;
+
+  __host__ __device__ int64_t ncells() const { return (int64_t)n[0] * n[1] * n[2]; }
+  // coordinate of vertex plane i (local index) along axis d.  [UPSTREAM] YaspGrid equidistant coordinates: i*h.
+  // With a partition the global plane index is used so that every rank computes bit-identical coordinates.
+  __host__ __device__ double coord(int d, int i) const { return glower[d] + (double)(i + off[d]) * h[d]; }
+  __host__ __device__ bool on_global_lower(int d, int i) const { return i + off[d] == 0; }
+  __host__ __device__ bool on_global_upper(int d, int i) const { return i + off[d] == gn[d]; }
+};
+
+// device-side copies of the analytic data descriptors -------------------------------------------------
+__host__ __device__ inline double eval_function(const mdb_function& f, int dim, const double* x, double t)
+{
+  switch (f.kind) {
+  case MDB_FN_ZERO: return 0.0;
+  case MDB_FN_CONST: return f.p[0];
+  case MDB_FN_GAUSS: {
+    double n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { double c = f.p[1 + d] - x[d]; n2 += c * c; }
+    return exp(-(f.p[0] * n2));
+  }
+  case MDB_FN_BOX: {
+    for (int d = 0; d < dim; ++d) if (!(x[d] > f.p[1] && x[d] < f.p[2])) return 0.0;
+    return f.p[0];
+  }
+  case MDB_FN_TESTPOISSON_J: {
+    if (x[1] < 1E-6 || x[1] > 1.0 - 1E-6) return 0.0;
+    if (x[0] > 1.0 - 1E-6 && x[1] > 0.5 + 1E-6) return -5.0;
+    return 0.0;
+  }
+  case MDB_FN_INSTAT_G: {
+    double n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { double c = 0.5 - x[d]; n2 += c * c; }
+    return f.p[0] * sin(f.p[1] * t) * exp(-n2);
+  }
+  case MDB_FN_POLY2: {
+    double v = f.p[0], n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { v += f.p[1 + d] * x[d]; n2 += x[d] * x[d]; }
+    return v + f.p[4] * n2;
+  }
+  }
+  return 0.0;
+}
+
+// 0 = dirichlet, 1 = neumann, 2 = none
+__host__ __device__ inline int eval_bctype(const mdb_bctype& b, int dim, const double* xg, bool is_boundary)
+{
+  (void)dim;
+  switch (b.kind) {
+  case MDB_BC_ALL_DIRICHLET: return is_boundary ? 0 : 2;
+  case MDB_BC_ALL_NEUMANN: return is_boundary ? 1 : 2;
+  case MDB_BC_TESTPOISSON:
+    if (!is_boundary) return 2;
+    if (xg[1] < 1E-6 || xg[1] > 1.0 - 1E-6) return 1;
+    if (xg[0] > 1.0 - 1E-6 && xg[1] > 0.5 + 1E-6) return 1;
+    return 0;
+  }
+  return 2;
+}
+
+__host__ __device__ inline bool cond_applies(int cond_kind, uint32_t mask, uint32_t sd)
+{
+  return cond_kind == MDB_COND_EQUALITY ? (sd == mask) : ((sd & mask) == mask);
+}
+
+// Gauss-Legendre rules on [0,1]; order p -> ceil((p+1)/2) points.  Evaluated on the host with correctly rounded
+// sqrt/div so that every consumer sees the same bits.
+struct Rule1D { int m; double x[5]; double w[5]; };
+Rule1D gauss1d(int order);
+
+// ------------------------------------------------------------------------------------------------
+// host-side model
+// ------------------------------------------------------------------------------------------------
+struct Child {
+  int fe_kind = 0, k = 1, subdomain = -1;
+  int lat_n[3] = {1, 1, 1};
+  int64_t nlat = 0;
+  int32_t* d_lat2dof = nullptr;
+  int32_t* d_dof2lat = nullptr;
+  int64_t size = 0, offset = 0;
+  int nloc(int dim) const { int r = 1; for (int d = 0; d < dim; ++d) r *= (k + 1); return r; }
+};
+
+struct SubProblemDesc {
+  int op_id = 0;
+  mdb_poisson_params poisson{};
+  mdb_l2_params l2{};
+  int cond_kind = 0; uint32_t mask = 0;
+  std::vector<int> children;
+  bool doPatternVolume() const { return true; }
+  bool doAlphaVolume() const { return true; }
+  bool doLambdaVolume() const { return op_id == MDB_OP_POISSON; }
+  bool doLambdaBoundary() const { return op_id == MDB_OP_POISSON; }
+  int quad_order() const { return op_id == MDB_OP_POISSON ? poisson.quad_order : l2.quad_order; }
+};
+
+struct CouplingDesc {
+  int op_id = 0;
+  mdb_cvcf_params cvcf{};
+  mdb_propflow_params propflow{};
+  int local_sp = -1, remote_sp = -1, jac_mode = 0;
+};
+
+struct FaceList {      // interface faces on which one coupling fires, in traversal order
+  int32_t* d_cell = nullptr;     // inside cell (local index)
+  int8_t* d_face = nullptr;      // face number 0..2*dim-1
+  int64_t n = 0;
+};
+
+struct GridOp {
+  std::vector<int> sps, cps;
+  std::vector<FaceList> faces;   // one per coupling
+};
+
+struct Matrix {
+  std::vector<int> gos;
+  int64_t nnz = 0;
+  int max_row = 0;
+  int64_t* d_rowptr = nullptr;
+  int32_t* d_colidx = nullptr;
+  double* d_val = nullptr;
+  uint32_t* d_rowinfo = nullptr;
+  int32_t* d_diag = nullptr;     // offset of the diagonal inside the row
+  // preconditioner caches
+  double* d_dinv = nullptr;
+  bool dinv_valid = false;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::map<std::string, float> phase_ms;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  MeshDesc mesh{};
+  bool have_mesh = false, have_sd = false, finalized = false;
+  uint8_t* d_cell_sd = nullptr;
+  std::vector<Child> children;
+  std::vector<SubProblemDesc> sps;
+  std::vector<CouplingDesc> cps;
+  std::vector<GridOp> gos;
+  std::vector<Matrix> mats;
+  int64_t ndof = 0;
+  uint8_t* d_constrained = nullptr;
+  int32_t* d_conlist = nullptr;
+  int64_t ncon = 0;
+  double time = 0.0;
+
+  // scratch
+  void* d_scratch = nullptr; size_t scratch_bytes = 0;
+  double* d_Ae = nullptr;            // element matrix table
+  // staging for host<->device vectors
+  double* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+  // solver workspace
+  double* d_work = nullptr; int64_t work_n = 0; int work_vecs = 0;
+  double* d_scal = nullptr;          // device scalars
+  double* d_partial = nullptr;       // block partial sums
+  double* h_pinned = nullptr;        // pinned host scalars
+
+  // multi-GPU
+  void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+  uint8_t* d_owned = nullptr;        // 1 = row owned by this rank (null: all owned)
+  int64_t owned_rows = 0;
+  double* d_halo_recv = nullptr; int64_t halo_recv_n = 0;
+  double* peer_lower = nullptr; double* peer_upper = nullptr;   // mapped windows of the neighbours
+  int lower_rank = -1, upper_rank = -1;
+
+  void* scratch(size_t bytes);
+  void phase_begin();
+  void phase_end(const char* name);
+};
+
+inline bool is_device_ptr(const void* p)
+{
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// RAII view of a caller vector on the device: device pointers pass through, host pointers are staged.
+struct VecIn {
+  const double* d = nullptr;
+  VecIn(Ctx* c, const double* p, int64_t n, int slot);
+};
+struct VecInOut {
+  Ctx* c; double* d = nullptr; double* host = nullptr; int64_t n;
+  VecInOut(Ctx* c, double* p, int64_t n, int slot, bool load);
+  void commit();     // copy back to the host buffer if staged
+};
+
+// module entry points (implemented in the .cu files)
+void build_dofmap(Ctx* c);
+void assemble_constraints(Ctx* c, const int* sps, const mdb_bctype* bcs, int n);
+void rebuild_conlist(Ctx* c);
+void interpolate(Ctx* c, const int* sps, const mdb_function* fns, int n, double t, double* d_x);
+void export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs);
+void build_facelists(Ctx* c, GridOp& go);
+void build_pattern(Ctx* c, Matrix& m);
+void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
+void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r);
+void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
+void constrain_residual(Ctx* c, double* d_r);
+void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool overwrite);
+void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x);
+void dirichlet_rows(Ctx* c, Matrix& m);
+void spmv(Ctx* c, const Matrix& m, const double* d_x, double* d_y);
+int solve(Ctx* c, Matrix& m, int method, int precond, double reduction, int maxit, int fixed_iters,
+          const double* d_rhs, double* d_z, mdb_solve_stats* stats);
+
+template <typename T> inline T* dalloc(size_t n)
+{
+  T* p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+  if (e != cudaSuccess) throw Error(MDB_ENOMEM, std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+  return p;
+}
+template <typename T> inline void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+#define MDB_LAUNCH(c, kernel, grid, block, smem, ...)                           \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);              \
+    (c)->launches++;                                                            \
+    MDB_CUDA(cudaGetLastError());                                               \
+  } while (0)
+
+} // namespace mdb

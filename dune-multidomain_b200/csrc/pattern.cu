@@ -1,0 +1,194 @@
+// pattern.cu — K2: CSR sparsity pattern by per-row (segmented) sort + unique.
+//
+// Replaces fill_pattern (gridoperator.hh:83-87 -> patternassemblerengine.hh:142-187,328-337): the pattern is the union
+// over cells of the subproblems' FullVolumePattern cliques and, over coupling faces, of FullCouplingPattern's sn / ns
+// blocks (couplingutilities.hh:35-47).  Instead of materialising one (row,col) key per local link (64 per Q1 hex) and
+// sorting billions of keys, every row is one segment: a thread enumerates the row's candidate columns from the cells
+// incident to the row's lattice point, keeps them as a sorted, duplicate-free list (binary insertion), and the row
+// pointer is an exclusive scan of the segment lengths.  Pass 1 counts, pass 2 writes; the column order inside a row is
+// ascending, i.e. the BCRS order of the reference ([UPSTREAM] (v)).
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace mdb {
+
+#define MDB_MAXROW 128
+
+struct PChild { int k, subdomain, nloc; int lat_n[3]; int64_t offset, size; const int32_t* lat2dof; const int32_t* dof2lat; };
+struct PatSpec {
+  int nchild; PChild ch[MDB_MAX_CHILDREN];
+  int nsp; int sp_child[16]; int sp_kind[16]; uint32_t sp_mask[16];
+  int ncp; int cp_lchild[8], cp_lkind[8], cp_rchild[8], cp_rkind[8]; uint32_t cp_lmask[8], cp_rmask[8];
+};
+
+__device__ __forceinline__ bool on_cell(int subdomain, uint8_t sd) { return subdomain < 0 || ((sd >> subdomain) & 1); }
+
+struct RowList {
+  int32_t v[MDB_MAXROW];
+  int n; bool overflow;
+  __device__ void insert(int32_t c)
+  {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (v[mid] < c) lo = mid + 1; else hi = mid; }
+    if (lo < n && v[lo] == c) return;
+    if (n >= MDB_MAXROW) { overflow = true; return; }
+    for (int i = n; i > lo; --i) v[i] = v[i - 1];
+    v[lo] = c; ++n;
+  }
+};
+
+__device__ void add_cell_dofs(RowList& L, const MeshDesc& m, const PChild& ch, const int ijk[3])
+{
+  const int k = ch.k;
+  int kz = (m.dim > 2) ? k : 0, ky = (m.dim > 1) ? k : 0;
+  for (int az = 0; az <= kz; ++az)
+    for (int ay = 0; ay <= ky; ++ay)
+      for (int ax = 0; ax <= k; ++ax) {
+        int64_t p = (k * ijk[0] + ax) + (int64_t)ch.lat_n[0] * ((k * ijk[1] + ay) + (int64_t)ch.lat_n[1] * (k * ijk[2] + az));
+        L.insert((int32_t)(ch.offset + ch.lat2dof[p]));
+      }
+}
+
+__device__ void enumerate_row(RowList& L, const MeshDesc& m, const uint8_t* __restrict__ sd, const PatSpec& S, int child, int64_t gi)
+{
+  const PChild& ch = S.ch[child];
+  L.n = 0; L.overflow = false;
+  int64_t r = ch.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+  const int k = ch.k;
+  int lo_c[3], hi_c[3];
+  for (int d = 0; d < 3; ++d) {
+    if (d >= m.dim) { lo_c[d] = hi_c[d] = 0; continue; }
+    int c1 = p[d] / k;
+    hi_c[d] = (c1 < m.n[d]) ? c1 : m.n[d] - 1;
+    lo_c[d] = (p[d] % k == 0 && c1 > 0) ? c1 - 1 : c1;
+    if (lo_c[d] > hi_c[d]) lo_c[d] = hi_c[d];
+  }
+  for (int cz = lo_c[2]; cz <= hi_c[2]; ++cz)
+    for (int cy = lo_c[1]; cy <= hi_c[1]; ++cy)
+      for (int cx = lo_c[0]; cx <= hi_c[0]; ++cx) {
+        int ijk[3] = {cx, cy, cz};
+        uint8_t s = sd[cx + (int64_t)m.n[0] * (cy + (int64_t)m.n[1] * cz)];
+        if (!on_cell(ch.subdomain, s)) continue;
+        for (int q = 0; q < S.nsp; ++q)
+          if (S.sp_child[q] == child && cond_applies(S.sp_kind[q], S.sp_mask[q], s)) { add_cell_dofs(L, m, ch, ijk); break; }
+        for (int q = 0; q < S.ncp; ++q) {
+          bool as_local = S.cp_lchild[q] == child && cond_applies(S.cp_lkind[q], S.cp_lmask[q], s);
+          bool as_remote = S.cp_rchild[q] == child && cond_applies(S.cp_rkind[q], S.cp_rmask[q], s);
+          if (!as_local && !as_remote) continue;
+          for (int f = 0; f < 2 * m.dim; ++f) {
+            int nijk[3] = {cx, cy, cz};
+            nijk[f / 2] += (f % 2) ? 1 : -1;
+            if (nijk[f / 2] < 0 || nijk[f / 2] >= m.n[f / 2]) continue;
+            uint8_t sn = sd[nijk[0] + (int64_t)m.n[0] * (nijk[1] + (int64_t)m.n[1] * nijk[2])];
+            if (as_local && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn) && on_cell(S.ch[S.cp_rchild[q]].subdomain, sn))
+              add_cell_dofs(L, m, S.ch[S.cp_rchild[q]], nijk);      // pattern_sn: rows of the local side, columns of the remote side
+            if (as_remote && cond_applies(S.cp_lkind[q], S.cp_lmask[q], sn) && on_cell(S.ch[S.cp_lchild[q]].subdomain, sn))
+              add_cell_dofs(L, m, S.ch[S.cp_lchild[q]], nijk);      // pattern_ns: rows of the remote side, columns of the local side
+          }
+        }
+      }
+}
+
+__global__ void __launch_bounds__(128) k_pattern_count(MeshDesc m, const uint8_t* __restrict__ sd, PatSpec S, int child, int64_t* rownnz, int* err)
+{
+  int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gi >= S.ch[child].size) return;
+  RowList L;
+  enumerate_row(L, m, sd, S, child, gi);
+  if (L.overflow) atomicExch(err, 1);
+  rownnz[S.ch[child].offset + gi] = L.n;
+}
+
+__global__ void __launch_bounds__(128) k_pattern_fill(MeshDesc m, const uint8_t* __restrict__ sd, PatSpec S, int child,
+                                                      const int64_t* __restrict__ rowptr, int32_t* colidx, uint32_t* rowinfo, int32_t* diag)
+{
+  int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const PChild& ch = S.ch[child];
+  if (gi >= ch.size) return;
+  RowList L;
+  enumerate_row(L, m, sd, S, child, gi);
+  const int64_t g = ch.offset + gi;
+  const int64_t base = rowptr[g];
+  uint32_t mask = 0; int nlow = 0; int dg = -1;
+  int64_t r = ch.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+  for (int i = 0; i < L.n; ++i) {
+    int32_t col = L.v[i];
+    colidx[base + i] = col;
+    if (col == g) dg = i;
+    if (col < ch.offset) ++nlow;
+    else if (col < ch.offset + ch.size && ch.k == 1) {
+      int64_t rr = ch.dof2lat[col - ch.offset];
+      int q0 = (int)(rr % ch.lat_n[0]); rr /= ch.lat_n[0]; int q1 = (int)(rr % ch.lat_n[1]); int q2 = (int)(rr / ch.lat_n[1]);
+      int bit = (q2 - p[2] + 1) * 9 + (q1 - p[1] + 1) * 3 + (q0 - p[0] + 1);
+      mask |= (1u << bit);
+    }
+  }
+  rowinfo[g] = mask | ((uint32_t)(nlow > 31 ? 31 : nlow) << 27);
+  diag[g] = dg;
+}
+
+void build_pattern(Ctx* c, Matrix& M)
+{
+  const MeshDesc& m = c->mesh;
+  PatSpec S; std::memset(&S, 0, sizeof(S));
+  S.nchild = (int)c->children.size();
+  for (int i = 0; i < S.nchild; ++i) {
+    const Child& ch = c->children[i];
+    PChild& p = S.ch[i];
+    p.k = ch.k; p.subdomain = ch.subdomain; p.nloc = ch.nloc(m.dim);
+    for (int d = 0; d < 3; ++d) p.lat_n[d] = ch.lat_n[d];
+    p.offset = ch.offset; p.size = ch.size; p.lat2dof = ch.d_lat2dof; p.dof2lat = ch.d_dof2lat;
+  }
+  for (int gi : M.gos) {
+    const GridOp& go = c->gos[gi];
+    for (int s : go.sps) {
+      const SubProblemDesc& sp = c->sps[s];
+      if (!sp.doPatternVolume()) continue;
+      MDB_REQUIRE(S.nsp < 16, MDB_EINVAL, "too many subproblems in one matrix");
+      S.sp_child[S.nsp] = sp.children[0]; S.sp_kind[S.nsp] = sp.cond_kind; S.sp_mask[S.nsp] = sp.mask; ++S.nsp;
+    }
+    for (int k : go.cps) {
+      const CouplingDesc& cp = c->cps[k];
+      MDB_REQUIRE(S.ncp < 8, MDB_EINVAL, "too many couplings in one matrix");
+      const SubProblemDesc& l = c->sps[cp.local_sp]; const SubProblemDesc& r = c->sps[cp.remote_sp];
+      S.cp_lchild[S.ncp] = l.children[0]; S.cp_lkind[S.ncp] = l.cond_kind; S.cp_lmask[S.ncp] = l.mask;
+      S.cp_rchild[S.ncp] = r.children[0]; S.cp_rkind[S.ncp] = r.cond_kind; S.cp_rmask[S.ncp] = r.mask; ++S.ncp;
+    }
+  }
+  const int64_t n = c->ndof;
+  int64_t* d_rownnz = dalloc<int64_t>(n + 1);
+  M.d_rowptr = dalloc<int64_t>(n + 1);
+  int* d_err = dalloc<int>(1);
+  MDB_CUDA(cudaMemsetAsync(d_rownnz, 0, (n + 1) * sizeof(int64_t), c->stream));
+  MDB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+  for (int i = 0; i < S.nchild; ++i)
+    MDB_LAUNCH(c, k_pattern_count, cdiv(S.ch[i].size, 128), 128, 0, m, c->d_cell_sd, S, i, d_rownnz, d_err);
+  size_t tmp_bytes = 0, tmp2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_rownnz, M.d_rowptr, (int)(n + 1), c->stream);
+  int64_t* d_max = dalloc<int64_t>(1);
+  cub::DeviceReduce::Max(nullptr, tmp2, d_rownnz, d_max, (int)n, c->stream);
+  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+  void* d_tmp = nullptr; MDB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+  MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_rownnz, M.d_rowptr, (int)(n + 1), c->stream)); c->launches++;
+  MDB_CUDA(cub::DeviceReduce::Max(d_tmp, tmp_bytes, d_rownnz, d_max, (int)n, c->stream)); c->launches++;
+  int64_t nnz = 0, maxrow = 0; int err = 0;
+  MDB_CUDA(cudaMemcpyAsync(&nnz, M.d_rowptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(&maxrow, d_max, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_tmp); dfree(d_rownnz); dfree(d_max); dfree(d_err);
+  MDB_REQUIRE(!err, MDB_EINVAL, "a matrix row has more than 128 entries (unsupported)");
+  M.nnz = nnz; M.max_row = (int)maxrow;
+  M.d_colidx = dalloc<int32_t>(nnz);
+  M.d_val = dalloc<double>(nnz);
+  M.d_rowinfo = dalloc<uint32_t>(n);
+  M.d_diag = dalloc<int32_t>(n);
+  MDB_CUDA(cudaMemsetAsync(M.d_val, 0, nnz * sizeof(double), c->stream));
+  for (int i = 0; i < S.nchild; ++i)
+    MDB_LAUNCH(c, k_pattern_fill, cdiv(S.ch[i].size, 128), 128, 0, m, c->d_cell_sd, S, i, M.d_rowptr, M.d_colidx, M.d_rowinfo, M.d_diag);
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+} // namespace mdb

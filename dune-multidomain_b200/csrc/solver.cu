@@ -1,0 +1,407 @@
+// solver.cu — Krylov solve of the assembled system: CSR SpMV, fused vector kernels, CG and BiCGSTAB with Jacobi.
+//
+// Replaces [UPSTREAM] dune-istl CGSolver / BiCGSTABSolver + SeqJac behind PDELab's ISTLBackend_SEQ_* as called from
+// StationaryLinearProblemSolver (test/testpoisson.cc:291-298, test/explicitlycoupledpoisson.cc:297-313).  The iteration
+// formulas and their order follow ISTL (same scalars, same update order); reductions are two-stage and deterministic
+// (block partials in a fixed order), all Krylov scalars stay on the device, and the host only polls a "done" flag every
+// few iterations, so the loop is a pure stream of kernels.
+//
+// SpMV is "CSR-stream": a block streams the contiguous val/col span of its rows fully coalesced, multiplies by the
+// gathered x (L1/L2 hits: neighbouring rows share columns) into shared memory, then one thread per row sums its segment.
+// Algorithmic bytes: 12*nnz + 20*nrows.
+#include "common.cuh"
+#include <cmath>
+
+namespace mdb {
+
+#define SPMV_ROWS 128
+#define SPMV_THREADS 128
+#define VEC_THREADS 256
+#define MAX_PARTIAL_BLOCKS 2048
+
+// scalar slots
+enum { S_RHO = 0, S_RHOLAST, S_PQ, S_RR, S_RR0, S_BETA, S_LAMBDA, S_DONE, S_ITER, S_RED2, S_ALPHA, S_OMEGA, S_H, S_TR, S_TT, S_RHONEW, S_HALF };
+
+__device__ __forceinline__ double block_sum(double v, double* sh)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+  return s;     // valid in thread 0
+}
+
+// y = A x  (+ optional fused dots: partial[0][b] = sum y_i a_i ; partial[1][b] = sum y_i y_i), owned rows only in the dots
+template <int DOTS>
+__global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, int nchunks, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                                        const double* __restrict__ a, const uint8_t* __restrict__ owned, double* partial,
+                                                        const double* __restrict__ done)
+{
+  extern __shared__ double sprod[];
+  __shared__ double sh[SPMV_THREADS / 32];
+  if (done && done[S_DONE] != 0.0) return;
+  double d0 = 0.0, d1 = 0.0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t r0 = (int64_t)chunk * SPMV_ROWS;
+    const int64_t r1 = (r0 + SPMV_ROWS < n) ? r0 + SPMV_ROWS : n;
+    const int64_t span0 = rowptr[r0];
+    const int span = (int)(rowptr[r1] - span0);
+    __syncthreads();
+#pragma unroll 4
+    for (int i = threadIdx.x; i < span; i += SPMV_THREADS) sprod[i] = val[span0 + i] * x[colidx[span0 + i]];
+    __syncthreads();
+    const int64_t r = r0 + threadIdx.x;
+    if (r < r1) {
+      const int s = (int)(rowptr[r] - span0), e = (int)(rowptr[r + 1] - span0);
+      double sum = 0.0;
+      for (int i = s; i < e; ++i) sum += sprod[i];
+      y[r] = sum;
+      if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
+    }
+  }
+  if (DOTS >= 1) {
+    double s0 = block_sum(d0, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+    if (DOTS >= 2) {
+      double s1 = block_sum(d1, sh);
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+    }
+  }
+}
+
+// fallback for very long rows: one warp per row
+__global__ void k_spmv_warp(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
+                            const double* __restrict__ x, double* __restrict__ y)
+{
+  int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int64_t p = rowptr[r] + lane; p < rowptr[r + 1]; p += 32) s += val[p] * x[colidx[p]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) y[r] = s;
+}
+
+static int spmv_grid(const Ctx* c, int nchunks, size_t smem)
+{
+  (void)c;
+  int per_sm = (int)(220 * 1024 / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int g = 148 * per_sm;
+  if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
+  return g < nchunks ? g : nchunks;
+}
+
+template <int DOTS>
+static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, const double* a, double* partial, int* nblocks, const double* done)
+{
+  const int64_t n = c->ndof;
+  const size_t smem = (size_t)SPMV_ROWS * M.max_row * sizeof(double);
+  MDB_REQUIRE(smem <= 200 * 1024, MDB_EINVAL, "rows too long for the streaming SpMV");
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > 48 * 1024 && smem > configured[DOTS]) {
+    MDB_CUDA(cudaFuncSetAttribute(k_spmv<DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[DOTS] = smem;
+  }
+  const int nchunks = cdiv(n, SPMV_ROWS);
+  const int grid = spmv_grid(c, nchunks, smem);
+  if (nblocks) *nblocks = grid;
+  MDB_LAUNCH(c, k_spmv<DOTS>, grid, SPMV_THREADS, smem, n, nchunks, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
+}
+
+void spmv(Ctx* c, const Matrix& M, const double* d_x, double* d_y)
+{
+  launch_spmv<0>(c, M, d_x, d_y, nullptr, nullptr, nullptr, nullptr);
+}
+
+// ---- scalar helpers (single block) -------------------------------------------------------------------
+// out[slot_k] = sum of partial[k][0..nblocks) for k < nvals, in a fixed order (deterministic)
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nblocks, int nvals, double* scal, int slot0, int slot1, int slot2)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  for (int k = 0; k < nvals; ++k) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += partial[k * MAX_PARTIAL_BLOCKS + i];
+    double s = block_sum(v, sh);
+    if (threadIdx.x == 0) scal[k == 0 ? slot0 : (k == 1 ? slot1 : slot2)] = s;
+    __syncthreads();
+  }
+}
+
+__global__ void k_extract_dinv(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ diag, const double* __restrict__ val,
+                               double* dinv, int jacobi)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 1.0;
+  if (jacobi && diag[i] >= 0) { double a = val[rowptr[i] + diag[i]]; d = (a != 0.0) ? 1.0 / a : 1.0; }
+  dinv[i] = d;
+}
+
+// ---- CG ([UPSTREAM] dune-istl CGSolver::apply) -------------------------------------------------------
+// init: x = 0, r = b, p = 0; partial0 = sum dinv r^2 (rho), partial1 = sum r^2
+__global__ void k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv, const uint8_t* __restrict__ owned,
+                          double* x, double* r, double* p, double* partial)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double ri = b[i];
+    x[i] = 0.0; r[i] = ri; p[i] = 0.0;
+    if (!owned || owned[i]) { a0 += dinv[i] * ri * ri; a1 += ri * ri; }
+  }
+  double s0 = block_sum(a0, sh); if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+  double s1 = block_sum(a1, sh); if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+}
+
+__global__ void k_cg_init_scalars(double* s, double reduction)
+{
+  // S_RHO and S_RR were just reduced
+  s[S_RR0] = s[S_RR]; s[S_RHOLAST] = 1.0; s[S_ITER] = 0.0; s[S_RED2] = reduction * reduction;
+  s[S_BETA] = s[S_RHO] / 1.0;
+  s[S_DONE] = (s[S_RR] == 0.0) ? 1.0 : 0.0;
+}
+
+// p = beta p + dinv r      (q = M^-1 r ; p *= beta ; p += q)
+__global__ void k_cg_update_p(int64_t n, const double* __restrict__ s, const double* __restrict__ dinv, const double* __restrict__ r, double* p)
+{
+  if (s[S_DONE] != 0.0) return;
+  const double beta = s[S_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = p[i] * beta + dinv[i] * r[i];
+}
+
+// lambda = rho / (p.q)
+__global__ void k_cg_derive_a(double* s) { if (s[S_DONE] != 0.0) return; s[S_LAMBDA] = s[S_RHO] / s[S_PQ]; }
+
+// x += lambda p ; r -= lambda q ; partial0 = sum dinv r^2 (next rho), partial1 = sum r^2
+__global__ void k_cg_update_xr(int64_t n, const double* __restrict__ s, const double* __restrict__ dinv, const double* __restrict__ p,
+                               const double* __restrict__ q, const uint8_t* __restrict__ owned, double* x, double* r, double* partial)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  if (s[S_DONE] != 0.0) return;
+  const double lambda = s[S_LAMBDA];
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += lambda * p[i];
+    double ri = r[i] - lambda * q[i];
+    r[i] = ri;
+    if (!owned || owned[i]) { a0 += dinv[i] * ri * ri; a1 += ri * ri; }
+  }
+  double s0 = block_sum(a0, sh); if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+  double s1 = block_sum(a1, sh); if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+}
+
+// rholast = rho ; rho = new ; beta = rho/rholast ; iteration count ; convergence test  def <= reduction * def0
+__global__ void k_cg_derive_b(double* s)
+{
+  if (s[S_DONE] != 0.0) return;
+  s[S_ITER] += 1.0;
+  s[S_RHOLAST] = s[S_RHO];
+  s[S_RHO] = s[S_RHONEW];
+  s[S_BETA] = s[S_RHO] / s[S_RHOLAST];
+  if (s[S_RR] <= s[S_RED2] * s[S_RR0]) s[S_DONE] = 1.0;
+}
+
+// ---- BiCGSTAB ([UPSTREAM] dune-istl BiCGSTABSolver::apply, right-preconditioned as ISTL does) --------
+__global__ void k_bi_init(int64_t n, const double* __restrict__ b, const uint8_t* __restrict__ owned, double* x, double* r, double* rt,
+                          double* p, double* v, double* partial)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  double a0 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double ri = b[i];
+    x[i] = 0.0; r[i] = ri; rt[i] = ri; p[i] = 0.0; v[i] = 0.0;
+    if (!owned || owned[i]) a0 += ri * ri;
+  }
+  double s0 = block_sum(a0, sh); if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+}
+__global__ void k_bi_init_scalars(double* s, double reduction)
+{
+  // S_RR reduced; rho_new = rt.r = r.r
+  s[S_RR0] = s[S_RR]; s[S_RHONEW] = s[S_RR]; s[S_RHO] = 1.0; s[S_ALPHA] = 1.0; s[S_OMEGA] = 1.0; s[S_ITER] = 0.0;
+  s[S_RED2] = reduction * reduction; s[S_HALF] = 0.0;
+  s[S_BETA] = 0.0;          // first iteration: p = r
+  s[S_DONE] = (s[S_RR] == 0.0) ? 1.0 : 0.0;
+}
+// p = r + beta (p - omega v) ; y = dinv p
+__global__ void k_bi_update_p(int64_t n, const double* __restrict__ s, const double* __restrict__ dinv, const double* __restrict__ r,
+                              const double* __restrict__ v, double* p, double* y)
+{
+  if (s[S_DONE] != 0.0) return;
+  const double beta = s[S_BETA], omega = s[S_OMEGA];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double pi = r[i] + beta * (p[i] - omega * v[i]);
+    p[i] = pi; y[i] = dinv[i] * pi;
+  }
+}
+__global__ void k_bi_derive_alpha(double* s) { if (s[S_DONE] != 0.0) return; s[S_ALPHA] = s[S_RHONEW] / s[S_H]; }
+// x += alpha y ; r -= alpha v ; y2 = dinv r ; partial0 = sum r^2
+__global__ void k_bi_update_s(int64_t n, const double* __restrict__ s, const double* __restrict__ dinv, const double* __restrict__ y,
+                              const double* __restrict__ v, const uint8_t* __restrict__ owned, double* x, double* r, double* y2, double* partial)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  if (s[S_DONE] != 0.0) return;
+  const double alpha = s[S_ALPHA];
+  double a0 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * y[i];
+    double ri = r[i] - alpha * v[i];
+    r[i] = ri; y2[i] = dinv[i] * ri;
+    if (!owned || owned[i]) a0 += ri * ri;
+  }
+  double s0 = block_sum(a0, sh); if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+}
+// half-iteration convergence test (ISTL tests after the first update too)
+__global__ void k_bi_derive_half(double* s)
+{
+  if (s[S_DONE] != 0.0) return;
+  if (s[S_RR] <= s[S_RED2] * s[S_RR0]) { s[S_DONE] = 1.0; s[S_ITER] += 1.0; s[S_HALF] = 1.0; }
+}
+__global__ void k_bi_derive_omega(double* s) { if (s[S_DONE] != 0.0) return; s[S_OMEGA] = s[S_TR] / s[S_TT]; }
+// x += omega y2 ; r -= omega t ; partial0 = sum r^2 ; partial1 = sum rt r
+__global__ void k_bi_update_x(int64_t n, const double* __restrict__ s, const double* __restrict__ y2, const double* __restrict__ t,
+                              const double* __restrict__ rt, const uint8_t* __restrict__ owned, double* x, double* r, double* partial)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  if (s[S_DONE] != 0.0) return;
+  const double omega = s[S_OMEGA];
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += omega * y2[i];
+    double ri = r[i] - omega * t[i];
+    r[i] = ri;
+    if (!owned || owned[i]) { a0 += ri * ri; a1 += rt[i] * ri; }
+  }
+  double s0 = block_sum(a0, sh); if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+  double s1 = block_sum(a1, sh); if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+}
+__global__ void k_bi_derive_end(double* s)
+{
+  if (s[S_DONE] != 0.0) return;
+  s[S_ITER] += 1.0;
+  // S_RHONEW currently holds rho of this iteration; S_TR slot reused: new rt.r was reduced into S_PQ
+  double rho_old = s[S_RHONEW];
+  s[S_RHO] = rho_old;
+  s[S_RHONEW] = s[S_PQ];
+  s[S_BETA] = (s[S_RHONEW] / s[S_RHO]) * (s[S_ALPHA] / s[S_OMEGA]);
+  if (s[S_RR] <= s[S_RED2] * s[S_RR0]) s[S_DONE] = 1.0;
+}
+
+// multi-GPU hooks (multigpu.cu); no-ops on one rank
+void allreduce_scalars(Ctx* c, double* d_vals, int n);
+void halo_exchange(Ctx* c, double* d_x);
+
+static void reduce(Ctx* c, int nblocks, int nvals, int s0, int s1 = 0, int s2 = 0)
+{
+  MDB_LAUNCH(c, k_reduce_partials, 1, VEC_THREADS, 0, c->d_partial, nblocks, nvals, c->d_scal, s0, s1, s2);
+}
+
+static void ensure_work(Ctx* c, int nvecs)
+{
+  if (c->work_n >= c->ndof && c->work_vecs >= nvecs) return;
+  dfree(c->d_work);
+  c->d_work = dalloc<double>((size_t)nvecs * c->ndof);
+  c->work_n = c->ndof; c->work_vecs = nvecs;
+}
+
+int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxit, int fixed_iters, const double* d_b, double* d_z,
+          mdb_solve_stats* stats)
+{
+  MDB_REQUIRE(method == MDB_SOLVER_CG || method == MDB_SOLVER_BICGSTAB, MDB_EINVAL, "unknown solver");
+  MDB_REQUIRE(precond == MDB_PRECOND_NONE || precond == MDB_PRECOND_JACOBI, MDB_EINVAL,
+              "preconditioner not available in this build (Jacobi or none)");
+  const int64_t n = c->ndof;
+  const int vgrid = (cdiv(n, VEC_THREADS) < 148 * 8) ? cdiv(n, VEC_THREADS) : 148 * 8;
+  if (!M.d_dinv) M.d_dinv = dalloc<double>(n);
+  MDB_LAUNCH(c, k_extract_dinv, cdiv(n, 256), 256, 0, n, M.d_rowptr, M.d_diag, M.d_val, M.d_dinv, precond == MDB_PRECOND_JACOBI ? 1 : 0);
+  const bool multi = c->nranks > 1;
+  double* s = c->d_scal;
+  double* x = d_z;
+  int nb = 0;
+  MDB_CUDA(cudaEventRecord(c->ev0, c->stream));
+  const int check_every = (fixed_iters >= 0) ? (1 << 30) : 16;
+  int issued = 0;
+  double* hp = c->h_pinned;
+  auto poll = [&]() {
+    MDB_CUDA(cudaMemcpyAsync(hp, s, 24 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+  };
+  if (method == MDB_SOLVER_CG) {
+    ensure_work(c, 3);
+    double *r = c->d_work, *p = c->d_work + n, *q = c->d_work + 2 * n;
+    MDB_LAUNCH(c, k_cg_init, vgrid, VEC_THREADS, 0, n, d_b, M.d_dinv, c->d_owned, x, r, p, c->d_partial);
+    reduce(c, vgrid, 2, S_RHO, S_RR);
+    if (multi) allreduce_scalars(c, s + S_RHO, 1), allreduce_scalars(c, s + S_RR, 1);
+    MDB_LAUNCH(c, k_cg_init_scalars, 1, 1, 0, s, reduction);
+    while (issued < maxit) {
+      MDB_LAUNCH(c, k_cg_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, p);
+      if (multi) halo_exchange(c, p);
+      launch_spmv<1>(c, M, p, q, p, c->d_partial, &nb, s);
+      reduce(c, nb, 1, S_PQ);
+      if (multi) allreduce_scalars(c, s + S_PQ, 1);
+      MDB_LAUNCH(c, k_cg_derive_a, 1, 1, 0, s);
+      MDB_LAUNCH(c, k_cg_update_xr, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, p, q, c->d_owned, x, r, c->d_partial);
+      reduce(c, vgrid, 2, S_RHONEW, S_RR);
+      if (multi) allreduce_scalars(c, s + S_RHONEW, 1), allreduce_scalars(c, s + S_RR, 1);
+      MDB_LAUNCH(c, k_cg_derive_b, 1, 1, 0, s);
+      ++issued;
+      if (issued % check_every == 0) { poll(); if (hp[S_DONE] != 0.0) break; }
+    }
+  } else {
+    ensure_work(c, 7);
+    double *r = c->d_work, *rt = r + n, *p = rt + n, *v = p + n, *y = v + n, *y2 = y + n, *t = y2 + n;
+    MDB_LAUNCH(c, k_bi_init, vgrid, VEC_THREADS, 0, n, d_b, c->d_owned, x, r, rt, p, v, c->d_partial);
+    reduce(c, vgrid, 1, S_RR);
+    if (multi) allreduce_scalars(c, s + S_RR, 1);
+    MDB_LAUNCH(c, k_bi_init_scalars, 1, 1, 0, s, reduction);
+    while (issued < maxit) {
+      MDB_LAUNCH(c, k_bi_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, v, p, y);
+      if (multi) halo_exchange(c, y);
+      launch_spmv<1>(c, M, y, v, rt, c->d_partial, &nb, s);
+      reduce(c, nb, 1, S_H);
+      if (multi) allreduce_scalars(c, s + S_H, 1);
+      MDB_LAUNCH(c, k_bi_derive_alpha, 1, 1, 0, s);
+      MDB_LAUNCH(c, k_bi_update_s, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, y, v, c->d_owned, x, r, y2, c->d_partial);
+      reduce(c, vgrid, 1, S_RR);
+      if (multi) allreduce_scalars(c, s + S_RR, 1);
+      MDB_LAUNCH(c, k_bi_derive_half, 1, 1, 0, s);
+      if (multi) halo_exchange(c, y2);
+      launch_spmv<2>(c, M, y2, t, r, c->d_partial, &nb, s);
+      reduce(c, nb, 2, S_TR, S_TT);
+      if (multi) allreduce_scalars(c, s + S_TR, 2);
+      MDB_LAUNCH(c, k_bi_derive_omega, 1, 1, 0, s);
+      MDB_LAUNCH(c, k_bi_update_x, vgrid, VEC_THREADS, 0, n, s, y2, t, rt, c->d_owned, x, r, c->d_partial);
+      reduce(c, vgrid, 2, S_RR, S_PQ);
+      if (multi) allreduce_scalars(c, s + S_RR, 1), allreduce_scalars(c, s + S_PQ, 1);
+      MDB_LAUNCH(c, k_bi_derive_end, 1, 1, 0, s);
+      ++issued;
+      if (issued % check_every == 0) { poll(); if (hp[S_DONE] != 0.0) break; }
+    }
+  }
+  MDB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  poll();
+  float ms = 0.f;
+  MDB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->phase_ms["solve"] = ms;
+  const bool converged = hp[S_DONE] != 0.0;
+  if (stats) {
+    stats->iterations = (int)hp[S_ITER];
+    stats->converged = converged ? 1 : 0;
+    stats->defect0 = std::sqrt(hp[S_RR0]);
+    stats->defect = std::sqrt(hp[S_RR]);
+    stats->seconds = ms * 1e-3;
+  }
+  if (fixed_iters >= 0) return MDB_OK;
+  if (!converged) { c->err = "linear solver did not converge within maxit iterations"; return MDB_ENOTCONVERGED; }
+  return MDB_OK;
+}
+
+} // namespace mdb

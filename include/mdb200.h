@@ -198,9 +198,9 @@ int mdb_matrix_create(mdb_ctx* ctx, const int* gos, int ngos, int64_t* nnz);
 int mdb_matrix_get_pattern(mdb_ctx* ctx, int mat, int64_t* rowptr, int64_t* colidx);
 int mdb_matrix_get_values(mdb_ctx* ctx, int mat, double* values /* host or device, nnz */);
 int mdb_matrix_zero(mdb_ctx* ctx, int mat);         /* a = 0.0 */
-/* Device pointers of the CSR arrays (int32 rowptr[ndof+1], int32 colidx[nnz], double values[nnz]) for
+/* Device pointers of the CSR arrays (int64 rowptr[ndof+1], int32 colidx[nnz], double values[nnz]) for
  * zero-copy consumers. */
-int mdb_matrix_device_ptrs(mdb_ctx* ctx, int mat, const int32_t** rowptr, const int32_t** colidx, double** values);
+int mdb_matrix_device_ptrs(mdb_ctx* ctx, int mat, const int64_t** rowptr, const int32_t** colidx, double** values);
 
 /* setTime / setWeight fan-out (localassembler.hh:214-255) */
 int mdb_set_time(mdb_ctx* ctx, double t);

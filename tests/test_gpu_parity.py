@@ -1,0 +1,252 @@
+"""Parity of the CUDA backend (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): DOF map, constraints and CSR pattern bit-exact; matrix and residual entries within
+1e-12 relative (relative to the largest entry of the matrix / of the vector's natural scale: individual stencil entries
+that cancel to ~0 have no meaningful relative error of their own); converged solutions within 1e-10 relative."""
+import importlib
+
+import numpy as np
+import pytest
+
+import orc
+import problems
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("dune-multidomain_b200")
+capi = pkg.capi
+
+RTOL_ENTRY = 1e-12
+RTOL_SOLUTION = 1e-10
+
+CASES = {
+    "p2d_16x16": dict(n=(16, 16)),
+    "p2d_split_x": dict(n=(12, 20), split_axis=0),
+    "p3d_8": dict(n=(8, 8, 8)),
+    "p3d_ragged": dict(n=(10, 6, 7), split_axis=0, upper=(1.0, 1.0, 1.0)),
+    "p3d_split_z": dict(n=(5, 6, 8), split_axis=2),
+    "p3d_nondyadic_box": dict(n=(6, 10, 5), lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 0.7)),
+    "p2d_propflow": dict(n=(16, 8), coupling=capi.OP_PROPFLOW_COUPLING, intensity=3.5),
+    "p3d_propflow": dict(n=(6, 8, 4), coupling=capi.OP_PROPFLOW_COUPLING, intensity=0.75),
+    "p3d_analytic": dict(n=(6, 6, 6), jac_mode=capi.JAC_ANALYTIC),
+    "p2d_order6_src": dict(n=(16, 16), quad_order=6, f=capi.Function(capi.FN_BOX, 50.0, 0.25, 0.375)),
+    "p3d_thin": dict(n=(3, 2, 1)),
+}
+
+
+def _pair(case):
+    kw = CASES[case]
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    return dev, ora, problems.testpoisson(dev, **kw), problems.testpoisson(ora, **kw)
+
+
+@pytest.fixture(params=sorted(CASES))
+def pair(request):
+    dev, ora, Pd, Po = _pair(request.param)
+    yield dev, ora, Pd, Po
+    dev.close(); ora.close()
+
+
+def _x(ora, Po, kind):
+    if kind == "g":
+        u = np.zeros(Po.ndof)
+        ora.interpolate(Po.sps, Po.gfn, u)
+        return u
+    return np.random.default_rng(0).uniform(-1, 1, Po.ndof)
+
+
+def test_dofmap_constraints_pattern_bit_exact(pair):
+    dev, ora, Pd, Po = pair
+    assert Pd.ndof == Po.ndof and Pd.ncon == Po.ncon
+    assert np.array_equal(dev.get_child_offsets(), ora.get_child_offsets())
+    pd_, dd = dev.get_dofmap(); po, do = ora.get_dofmap()
+    assert np.array_equal(pd_, po) and np.array_equal(dd, do)
+    assert np.array_equal(dev.get_constraints(), ora.get_constraints())
+    assert dev.nnz[Pd.mat] == ora.nnz[Po.mat]
+    rd, cd = dev.matrix_get_pattern(Pd.mat); ro, co = ora.matrix_get_pattern(Po.mat)
+    assert np.array_equal(rd, ro) and np.array_equal(cd, co)
+
+
+def test_interpolation(pair):
+    dev, ora, Pd, Po = pair
+    ud, uo = np.full(Pd.ndof, -7.0), np.full(Po.ndof, -7.0)
+    dev.interpolate(Pd.sps, Pd.gfn, ud); ora.interpolate(Po.sps, Po.gfn, uo)
+    assert np.abs(ud - uo).max() <= 4e-16          # exp() of the device libm vs glibc: <= 2 ulp of values <= 1
+
+
+@pytest.mark.parametrize("xkind", ["g", "random"])
+def test_jacobian_entries(pair, xkind):
+    dev, ora, Pd, Po = pair
+    x = _x(ora, Po, xkind)
+    dev.jacobian(Pd.go, Pd.mat, x, overwrite=True)
+    ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+    # additive semantics (gridoperator.hh:94-97): a second call without overwrite doubles every unconstrained row,
+    # constrained rows stay unit rows
+    dev.jacobian(Pd.go, Pd.mat, x, overwrite=False)
+    ora.jacobian(Po.go, Po.mat, x, overwrite=False)
+    vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+
+
+@pytest.mark.parametrize("xkind", ["g", "random"])
+def test_residual_entries(pair, xkind):
+    dev, ora, Pd, Po = pair
+    x = _x(ora, Po, xkind)
+    rd, ro = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.residual(Pd.go, x, rd); ora.residual(Po.go, x, ro)
+    # natural scale of a residual entry: sum_j |A_ij| |x_j| (componentwise backward error)
+    ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    A = ora.csr(Po.mat)
+    scale = abs(A) @ np.abs(x) + np.abs(ro)
+    scale = np.maximum(scale, np.abs(ro).max() * 1e-3)
+    assert np.all(np.abs(rd - ro) <= RTOL_ENTRY * scale)
+    con = ora.get_constraints().astype(bool)
+    assert np.all(rd[con] == 0.0)
+    # additive with weight (one-step schemes): r += w R(x)
+    rd2, ro2 = rd.copy(), ro.copy()
+    dev.residual(Pd.go, x, rd2, weight=0.25); ora.residual(Po.go, x, ro2, weight=0.25)
+    assert np.all(np.abs(rd2 - ro2) <= 2 * RTOL_ENTRY * scale)
+
+
+def test_stationary_solve(pair):
+    """r = R(u0); J z = r; u = u0 - z  with u0 the interpolated Dirichlet extension (testpoisson.cc:266-298)."""
+    dev, ora, Pd, Po = pair
+    u0 = _x(ora, Po, "g")
+    dev.jacobian(Pd.go, Pd.mat, u0, overwrite=True); ora.jacobian(Po.go, Po.mat, u0, overwrite=True)
+    rd, ro = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.residual(Pd.go, u0, rd); ora.residual(Po.go, u0, ro)
+    zo = np.zeros(Po.ndof)
+    so = ora.solve(Po.mat, ro, zo, reduction=1e-14, maxit=20000)          # BiCGSTAB + SSOR(3) like the reference
+    assert so.converged
+    for method in (capi.SOLVER_CG, capi.SOLVER_BICGSTAB):
+        zd = np.zeros(Pd.ndof)
+        sd = dev.solve(Pd.mat, rd, zd, method=method, precond=capi.PRECOND_JACOBI, reduction=1e-13, maxit=20000)
+        assert sd.converged, (method, sd.iterations, sd.defect / sd.defect0)
+        assert np.abs(zd - zo).max() <= RTOL_SOLUTION * np.abs(zo).max(), method
+        assert np.abs((u0 - zd) - (u0 - zo)).max() <= RTOL_SOLUTION * np.abs(u0 - zo).max()
+
+
+def test_cg_iteration_counts_match_oracle_cg():
+    """Same algorithm (ISTL CG + Jacobi) on both sides: identical iteration count on a well-conditioned case."""
+    dev, ora, Pd, Po = _pair("p3d_8")
+    u0 = _x(ora, Po, "g")
+    dev.jacobian(Pd.go, Pd.mat, u0, overwrite=True); ora.jacobian(Po.go, Po.mat, u0, overwrite=True)
+    r = np.zeros(Po.ndof); ora.residual(Po.go, u0, r)
+    zd, zo = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    sd = dev.solve(Pd.mat, r, zd, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, reduction=1e-8)
+    so = ora.solve(Po.mat, r, zo, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, reduction=1e-8)
+    assert sd.converged and so.converged and sd.iterations == so.iterations
+    assert abs(sd.defect0 - so.defect0) <= 1e-13 * so.defect0
+
+
+def test_spmv(pair):
+    dev, ora, Pd, Po = pair
+    x = _x(ora, Po, "random")
+    dev.jacobian(Pd.go, Pd.mat, x, overwrite=True); ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    yd, yo = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.spmv(Pd.mat, x, yd); ora.spmv(Po.mat, x, yo)
+    A = ora.csr(Po.mat)
+    assert np.all(np.abs(yd - yo) <= 1e-13 * (abs(A) @ np.abs(x) + 1e-300))
+
+
+def test_arbitrary_subdomain_marking():
+    """Non-box subdomains (checkerboard-ish marking, cells in no subproblem's condition): numbering by rank, pattern from
+    whichever cells the conditions accept."""
+    n = (7, 6, 5)
+    rng = np.random.default_rng(3)
+    bits = rng.choice(np.array([1, 2], dtype=np.uint8), size=int(np.prod(n)))
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    Pd, Po = problems.testpoisson(dev, n, sd_bits=bits), problems.testpoisson(ora, n, sd_bits=bits)
+    assert Pd.ndof == Po.ndof and Pd.ncon == Po.ncon
+    assert np.array_equal(dev.get_dofmap()[1], ora.get_dofmap()[1])
+    rd, cd = dev.matrix_get_pattern(Pd.mat); ro, co = ora.matrix_get_pattern(Po.mat)
+    assert np.array_equal(rd, ro) and np.array_equal(cd, co)
+    x = np.random.default_rng(1).uniform(-1, 1, Po.ndof)
+    dev.jacobian(Pd.go, Pd.mat, x, overwrite=True); ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+    rd_, ro_ = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.residual(Pd.go, x, rd_); ora.residual(Po.go, x, ro_)
+    assert np.abs(rd_ - ro_).max() <= RTOL_ENTRY * np.abs(ro_).max() * 10
+
+
+def test_mass_operator_and_onestep_matrix():
+    """dt1 operator = L2 mass (testinstationarypoisson.cc:225-226), dt0 = Poisson + coupling; OneStepGridOperator builds
+    J = a * J_dt1 + b*dt * J_dt0 into one matrix whose pattern is the union of both."""
+    n = (8, 8)
+    out = []
+    for api in (pkg.Mdb(0), orc.Oracle()):
+        api.mesh_structured(n); api.subdomains_halfspace(1, 0.5, 0, 1)
+        c0, c1 = api.add_space(capi.FE_Q1, 0), api.add_space(capi.FE_Q1, 1)
+        pp = capi.PoissonParams(); pp.f = capi.Function(capi.FN_ZERO); pp.bc = capi.BCType(capi.BC_TESTPOISSON)
+        pp.j = capi.Function(capi.FN_TESTPOISSON_J); pp.quad_order = 4
+        l = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1, [c0])
+        r = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 2, [c1])
+        lp = capi.L2Params(); lp.quad_order = 2
+        ml = api.add_subproblem(capi.OP_L2, lp, capi.COND_EQUALITY, 1, [c0])
+        mr = api.add_subproblem(capi.OP_L2, lp, capi.COND_EQUALITY, 2, [c1])
+        cv = capi.PropFlowParams(); cv.intensity = 2.0
+        cp = api.add_coupling(capi.OP_PROPFLOW_COUPLING, cv, l, r)
+        nd = api.finalize()
+        api.constraints_assemble([l, r], [pp.bc, pp.bc])
+        go0 = api.gridoperator_create([l, r], [cp]); go1 = api.gridoperator_create([ml, mr], [])
+        mat = api.matrix_create([go0, go1])
+        x = np.random.default_rng(5).uniform(-1, 1, nd)
+        api.jacobian(go1, mat, x, weight=1.0, overwrite=True)
+        api.jacobian(go0, mat, x, weight=0.04 * 0.5, overwrite=False)
+        rr = np.zeros(nd)
+        api.residual(go1, x, rr, weight=1.0); api.residual(go0, x, rr, weight=0.02)
+        out.append((api.matrix_get_pattern(mat), api.matrix_get_values(mat), rr))
+    (pd_, vd, rd), (po, vo, ro) = out
+    assert np.array_equal(pd_[0], po[0]) and np.array_equal(pd_[1], po[1])
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+    assert np.abs(rd - ro).max() <= RTOL_ENTRY * np.abs(ro).max()
+
+
+def test_device_resident_vectors_and_error_paths():
+    import torch
+    dev, ora, Pd, Po = _pair("p3d_8")
+    x = _x(ora, Po, "g")
+    xd = torch.from_numpy(x).cuda()
+    rd = torch.zeros(Pd.ndof, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    dev.residual(Pd.go, xd, rd); dev.synchronize()
+    ro = np.zeros(Po.ndof); ora.residual(Po.go, x, ro)
+    assert np.abs(rd.cpu().numpy() - ro).max() <= RTOL_ENTRY * np.abs(ro).max()
+    with pytest.raises(pkg.MdbError):
+        dev.residual(99, xd, rd)                       # bad handle -> error code + message, no crash
+    with pytest.raises(pkg.MdbError, match="Q1"):
+        d2 = pkg.Mdb(0); d2.mesh_structured((4, 4)); d2.add_space(capi.FE_Q2, 0)
+
+
+@pytest.mark.parametrize("n", [(96, 96, 96), (1024, 1024)])
+def test_size_independent_properties_at_scale(n):
+    """At sizes the oracle does not reach: J annihilates constants on free rows, Dirichlet rows are unit rows, the
+    residual is affine with slope J (R(u) - R(0) = J u), CG's answer satisfies the system."""
+    import torch
+    dev = pkg.Mdb(0)
+    P = problems.testpoisson(dev, n, jac_mode=capi.JAC_ANALYTIC)
+    u = torch.zeros(P.ndof, dtype=torch.float64, device="cuda")
+    dev.interpolate(P.sps, P.gfn, u)
+    dev.jacobian(P.go, P.mat, u, overwrite=True)
+    one = torch.ones(P.ndof, dtype=torch.float64, device="cuda")
+    y = torch.zeros_like(one)
+    torch.cuda.synchronize()
+    dev.spmv(P.mat, one, y); dev.synchronize()
+    con = torch.from_numpy(dev.get_constraints().astype(bool)).cuda()
+    vals = torch.empty(dev.nnz[P.mat], dtype=torch.float64, device="cuda")
+    dev.matrix_get_values(P.mat, vals); dev.synchronize()
+    amax = vals.abs().max().item()
+    assert y[~con].abs().max().item() <= 1e-12 * amax
+    assert torch.all(y[con] == 1.0)
+    r, r0, ju = torch.zeros_like(one), torch.zeros_like(one), torch.zeros_like(one)
+    dev.residual(P.go, u, r); dev.residual(P.go, torch.zeros_like(one), r0); dev.spmv(P.mat, u, ju); dev.synchronize()
+    diff = (r - r0 - ju)[~con].abs().max().item()
+    assert diff <= 1e-12 * amax
+    z = torch.zeros_like(one)
+    st = dev.solve(P.mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, reduction=1e-10, maxit=20000)
+    assert st.converged
+    az = torch.zeros_like(one)
+    dev.spmv(P.mat, z, az); dev.synchronize()
+    assert (az - r).norm().item() <= 2e-10 * r.norm().item()

@@ -1,0 +1,210 @@
+"""Pins for the CPU oracle (no GPU).  The reference ships no expected values ("parity unpinned"), so the
+oracle is pinned by self-derived known answers: closed-form element matrices, an independent NumPy/SciPy construction of
+the DOF numbering and sparsity pattern, algebraic identities of the assembled operators, FD-vs-exact
+coupling Jacobians and SciPy direct solves."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+import orc
+import problems
+
+capi = orc.capi
+
+
+def test_q1_stiffness_2d_closed_form():
+    o = orc.Oracle()
+    P = problems.single_domain_poisson(o, (4, 4), quad_order=2)
+    a = o.local_jacobian_volume(P.sp, 5, 4)
+    ref = np.array([[4, -1, -1, -2], [-1, 4, -2, -1], [-1, -2, 4, -1], [-2, -1, -1, 4]]) / 6.0
+    assert np.abs(a - ref).max() < 1e-15
+
+
+def test_q1_stiffness_3d_closed_form():
+    # trilinear Laplace element matrix on a cube of edge h: h * (1/3, 0, -1/12, -1/12) for (self, edge, face-diag, body-diag)
+    o = orc.Oracle()
+    n = 4
+    P = problems.single_domain_poisson(o, (n, n, n), quad_order=4)
+    a = o.local_jacobian_volume(P.sp, 21, 8)
+    h = 1.0 / n
+    for i in range(8):
+        for j in range(8):
+            dist = bin(i ^ j).count("1")
+            ref = h * {0: 1 / 3.0, 1: 0.0, 2: -1 / 12.0, 3: -1 / 12.0}[dist]
+            assert abs(a[i, j] - ref) < 1e-15
+
+
+def test_q2_stiffness_rowsum_and_symmetry():
+    o = orc.Oracle()
+    P = problems.single_domain_poisson(o, (2, 2), quad_order=4, fe=capi.FE_Q2)
+    a = o.local_jacobian_volume(P.sp, 0, 9)
+    assert np.abs(a - a.T).max() < 1e-14
+    assert np.abs(a.sum(axis=1)).max() < 1e-13          # gradients of a partition of unity sum to zero
+    assert abs(np.trace(a) - (4 * 28 / 45 + 4 * 88 / 45 + 256 / 45)) < 1e-12   # biquadratic Laplace diagonal
+
+
+def test_numbering_matches_appendix_b():
+    """child block s = Q1 on subdomain s, global(s, v) = off_s + rank of v in V_s (ascending host
+    vertex index), local dof i <-> corner with offset bits of i."""
+    n = (6, 4, 5)
+    o = orc.Oracle()
+    P = problems.testpoisson(o, n, split_axis=1)
+    ptr, dofs = o.get_dofmap()
+    nx, ny, nz = n
+    vid = lambda i, j, k: i + (nx + 1) * (j + (ny + 1) * k)
+    in_sd = [set(), set()]
+    cells = []
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                s = 1 if (j + 0.5) / ny > 0.5 else 0
+                corners = [vid(i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1)) for c in range(8)]
+                cells.append((s, corners))
+                in_sd[s].update(corners)
+    rank = [{v: r for r, v in enumerate(sorted(in_sd[s]))} for s in (0, 1)]
+    off = [0, len(in_sd[0])]
+    assert P.ndof == len(in_sd[0]) + len(in_sd[1])
+    assert list(o.get_child_offsets()) == [0, len(in_sd[0]), P.ndof]
+    for c, (s, corners) in enumerate(cells):
+        assert ptr[c + 1] - ptr[c] == 8
+        assert list(dofs[ptr[c]:ptr[c + 1]]) == [off[s] + rank[s][v] for v in corners]
+
+
+def _independent_pattern(o, P, n, split_axis):
+    ptr, dofs = o.get_dofmap()
+    rows, cols = [], []
+    dim = len(n)
+    nn = list(n) + [1] * (3 - dim)
+    nloc = 2 ** dim
+    cell = lambda i, j, k: i + nn[0] * (j + nn[1] * k)
+    for k in range(nn[2]):
+        for j in range(nn[1]):
+            for i in range(nn[0]):
+                c = cell(i, j, k)
+                d = dofs[ptr[c]:ptr[c + 1]]
+                rows += list(np.repeat(d, nloc)); cols += list(np.tile(d, nloc))
+                ijk = [i, j, k]
+                if ijk[split_axis] == nn[split_axis] // 2 - 1:       # local (left) cell at the interface
+                    m = list(ijk); m[split_axis] += 1
+                    dn = dofs[ptr[cell(*m)]:ptr[cell(*m) + 1]]
+                    rows += list(np.repeat(d, nloc)); cols += list(np.tile(dn, nloc))
+                    rows += list(np.repeat(dn, nloc)); cols += list(np.tile(d, nloc))
+    A = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(P.ndof, P.ndof)).tocsr()
+    A.sum_duplicates(); A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("n,axis", [((8, 8), 1), ((6, 4), 0), ((4, 6, 4), 1), ((4, 4, 6), 2)])
+def test_pattern_is_union_of_cliques(n, axis):
+    o = orc.Oracle()
+    P = problems.testpoisson(o, n, split_axis=axis)
+    rowptr, colidx = o.matrix_get_pattern(P.mat)
+    A = _independent_pattern(o, P, n, axis)
+    assert np.array_equal(rowptr, A.indptr) and np.array_equal(colidx, A.indices)
+    for r in range(P.ndof):
+        assert np.all(np.diff(colidx[rowptr[r]:rowptr[r + 1]]) > 0)      # BCRS: ascending, no duplicates
+
+
+def test_p2d_sizes_of_the_shipped_testpoisson():
+    """testpoisson 4 2.0: 16x16 cells, Q1 on y<=.5 (17*9 dofs) and Q2 on y>=.5 (33*17 dofs): 714 in total."""
+    o = orc.Oracle()
+    P = problems.testpoisson(o, (16, 16), fe=(capi.FE_Q1, capi.FE_Q2))
+    assert P.ndof == 714
+    assert list(o.get_child_offsets()) == [0, 153, 714]
+    assert P.ncon == 9 + 9 + 17          # x=0 on both subdomains, x=1 only where y <= .5
+
+
+def test_jacobian_annihilates_constants_and_is_symmetric_on_free_rows():
+    o = orc.Oracle()
+    P = problems.testpoisson(o, (6, 6, 4), jac_mode=capi.JAC_ANALYTIC)
+    u = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u)
+    o.jacobian(P.go, P.mat, u, overwrite=True)
+    A = o.csr(P.mat)
+    con = o.get_constraints().astype(bool)
+    y = A @ np.ones(P.ndof)
+    assert np.abs(y[~con]).max() < 1e-12 * np.abs(A.data).max()
+    assert np.allclose(y[con], 1.0)
+    F = A[~con][:, ~con]
+    assert abs(F - F.T).max() < 1e-13 * np.abs(A.data).max()
+
+
+def test_fd_coupling_jacobian_close_to_exact():
+    oa, of = orc.Oracle(), orc.Oracle()
+    Pa = problems.testpoisson(oa, (8, 8), jac_mode=capi.JAC_ANALYTIC)
+    Pf = problems.testpoisson(of, (8, 8), jac_mode=capi.JAC_FD_BITMATCH)
+    u = np.zeros(Pa.ndof); oa.interpolate(Pa.sps, Pa.gfn, u)
+    oa.jacobian(Pa.go, Pa.mat, u, overwrite=True); of.jacobian(Pf.go, Pf.mat, u, overwrite=True)
+    va, vf = oa.matrix_get_values(Pa.mat), of.matrix_get_values(Pf.mat)
+    err = np.abs(va - vf).max() / np.abs(va).max()
+    assert 0 < err < 1e-6            # FD noise is ~1e-8, and it is not identically the analytic matrix
+
+
+def test_residual_is_linear_and_matches_jacobian():
+    """All restated operators are linear: R(u) = J u + R(0) on unconstrained rows."""
+    o = orc.Oracle()
+    P = problems.testpoisson(o, (8, 6), jac_mode=capi.JAC_ANALYTIC)
+    rng = np.random.default_rng(0)
+    u = rng.uniform(-1, 1, P.ndof)
+    o.jacobian(P.go, P.mat, u, overwrite=True)
+    A = o.csr(P.mat)
+    r, r0 = np.zeros(P.ndof), np.zeros(P.ndof)
+    o.residual(P.go, u, r); o.residual(P.go, np.zeros(P.ndof), r0)
+    con = o.get_constraints().astype(bool)
+    assert np.abs((A @ u + r0 - r)[~con]).max() < 1e-12 * np.abs(r).max()
+    assert np.all(r[con] == 0.0)
+    assert np.abs(r0).max() > 0        # the Neumann flux -5 on x=1, y>.5 is present
+
+
+def test_patch_test_linear_solution():
+    """A globally linear function has zero Laplace residual on every free row away from Neumann data and interface."""
+    o = orc.Oracle()
+    P = problems.single_domain_poisson(o, (5, 4, 3), quad_order=2)
+    u = np.zeros(P.ndof)
+    o.interpolate(P.sps, [capi.Function(capi.FN_POLY2, 1.0, 2.0, -3.0, 0.5, 0.0)], u)
+    r = np.zeros(P.ndof); o.residual(P.go, u, r)
+    assert np.abs(r).max() < 1e-13
+
+
+def test_stationary_solve_against_scipy():
+    """StationaryLinearProblemSolver semantics ([UPSTREAM] (vii)): r = R(u0), J z = r, u = u0 - z; BiCGSTAB + SSOR(3) as in
+    testpoisson.cc:291-298, CG + Jacobi as the device backend does, SciPy's sparse LU as the second opinion."""
+    o = orc.Oracle()
+    P = problems.testpoisson(o, (16, 16))
+    u = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u)
+    o.jacobian(P.go, P.mat, u, overwrite=True)
+    r = np.zeros(P.ndof); o.residual(P.go, u, r)
+    z_ref = sla.spsolve(o.csr(P.mat).tocsc(), r)
+    z1, z2, z3 = np.zeros(P.ndof), np.zeros(P.ndof), np.zeros(P.ndof)
+    s1 = o.solve(P.mat, r, z1, reduction=1e-13)
+    s2 = o.solve(P.mat, r, z2, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, reduction=1e-13)
+    s3 = o.solve(P.mat, r, z3, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_ILU0, reduction=1e-13)
+    for s, z in ((s1, z1), (s2, z2), (s3, z3)):
+        assert s.converged
+        assert np.abs(z - z_ref).max() <= 1e-10 * np.abs(z_ref).max()
+    assert s1.iterations < s2.iterations
+
+
+def test_mass_matrix_integrates_one():
+    o = orc.Oracle()
+    n = (4, 3, 2)
+    o.mesh_structured(n)
+    o.subdomains(np.ones(int(np.prod(n)), dtype=np.uint8))
+    c0 = o.add_space(capi.FE_Q1, 0)
+    lp = capi.L2Params(); lp.quad_order = 2
+    s = o.add_subproblem(capi.OP_L2, lp, capi.COND_EQUALITY, 1, [c0])
+    nd = o.finalize()
+    go = o.gridoperator_create([s]); mat = o.matrix_create([go])
+    o.jacobian(go, mat, np.zeros(nd), weight=2.5, overwrite=True)
+    A = o.csr(mat)
+    assert abs(A.sum() - 2.5) < 1e-13           # sum_ij weight * int phi_i phi_j = weight * |Omega|
+
+
+def test_parallel_baseline_assembly_equals_serial():
+    o1, o2 = orc.Oracle(), orc.Oracle()
+    P1, P2 = problems.testpoisson(o1, (6, 6, 12)), problems.testpoisson(o2, (6, 6, 12))
+    u = np.zeros(P1.ndof); o1.interpolate(P1.sps, P1.gfn, u)
+    o1.jacobian(P1.go, P1.mat, u, overwrite=True)
+    o2.jacobian(P2.go, P2.mat, u, overwrite=True, nthreads=4)
+    a, b = o1.matrix_get_values(P1.mat), o2.matrix_get_values(P2.mat)
+    assert np.abs(a - b).max() <= 1e-14 * np.abs(a).max()
