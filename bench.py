@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the dune-multidomain hot path on B200.
+
+Workload (BASELINE.json configs[1]): multidomain Q1 Poisson on a synthetic 3-D structured grid, two
+subdomains split at x1 > 0.5, Poisson(order 4) on each and the interior-penalty interface coupling
+ContinuousValueContinuousFlowCoupling(4, 2.0) between them (test/testpoisson.cc:119-298 extended to dim = 3).
+N=1: 256^3 cells = 17 040 642 DOFs.  N>1 (weak scaling): every rank holds a 256x256x256 slab of a 256x256x(256 N) mesh.
+
+A step = one Jacobian assembly GridOperator::jacobian(x, a) of the whole local mesh (volume rows + FD coupling +
+Dirichlet rows), x resident in HBM.  metric = assembled DOFs per second over all ranks.  Alongside: residual assembly,
+SpMV and CG-iteration rates, each kernel's achieved HBM GB/s against MEASURED_PEAKS.json, an end-to-end number with host
+buffers, and the CPU restatement of the reference path timed on the host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 256] [--impl reference]
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "jacobian_assembly_dofs_per_s"
+UNIT = "DOF/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=256, help="cells per axis of the per-GPU cube")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--cpu-sample-layers", type=int, default=2, help="z-layers of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
+
+
+def setup_problem(api, n, rank=0, nranks=1):
+    import problems
+    if nranks == 1:
+        return problems.testpoisson(api, n)
+    return problems.testpoisson_partitioned(api, n, rank, nranks)
+
+
+def cpu_baseline(size, layers, nthreads):
+    """The reference's CPU path (oracle port, oracle/oracle.cpp) on a bounded sample of the same workload: the same
+    256x256 cross-section and mesh width, `layers` z-layers of cells."""
+    import numpy as np
+    import orc
+    import problems
+    h = 1.0 / size
+    o = orc.Oracle(fast=True)
+    n = (size, size, layers)
+    t0 = time.time()
+    P = problems.testpoisson(o, n, upper=(1.0, 1.0, layers * h))
+    t_setup = time.time() - t0
+    u = np.zeros(P.ndof)
+    o.interpolate(P.sps, P.gfn, u)
+    best = None
+    for _ in range(2):
+        t0 = time.time()
+        o.jacobian(P.go, P.mat, u, overwrite=True, nthreads=nthreads if nthreads > 1 else 0)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    r = np.zeros(P.ndof)
+    t0 = time.time(); o.residual(P.go, u, r); t_res = time.time() - t0
+    # the traversal cost is per cell; convert with the DOFs-per-cell ratio of the full workload (a thin slab has more
+    # vertices per cell than the cube)
+    ncells = size * size * layers
+    dofs_per_cell = (size + 2.0) * (size + 1.0) ** 2 / float(size) ** 3
+    return {"value": ncells / best * dofs_per_cell, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "Jacobian assembly of %dx%dx%d cells of the same mesh width (%.3g cells/s x %.4f DOFs per cell of the full "
+                      "mesh), best of 2; pattern+setup %.2fs; residual %.3g cells/s"
+                      % (size, size, layers, ncells / best, dofs_per_cell, t_setup, ncells / t_res)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path with all host threads (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    import numpy as np
+    import orc
+    import problems
+    size, layers = args.size, max(args.cpu_sample_layers, 4)
+    h = 1.0 / size
+    o = orc.Oracle(fast=True)
+    P = problems.testpoisson(o, (size, size, layers), upper=(1.0, 1.0, layers * h))
+    u = np.zeros(P.ndof)
+    o.interpolate(P.sps, P.gfn, u)
+    for _ in range(min(args.warmup, 1)):
+        o.jacobian(P.go, P.mat, u, overwrite=True, nthreads=ncores)
+    t0 = time.time()
+    for _ in range(args.steps):
+        o.jacobian(P.go, P.mat, u, overwrite=True, nthreads=ncores)
+    dt = (time.time() - t0) / args.steps
+    ncells = size * size * layers
+    dofs_per_cell = (size + 2.0) * (size + 1.0) ** 2 / float(size) ** 3
+    value = ncells / dt * dofs_per_cell
+    sample = ("Jacobian assembly of %dx%dx%d cells of the same mesh width per step (%.3g cells/s x %.4f DOFs per cell of the "
+              "full mesh)" % (size, size, layers, ncells / dt, dofs_per_cell))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "M2: 3-D Q1/Q1 two-subdomain Poisson + CVCF coupling, %d^3 cells per GPU" % size,
+                       "reference_arm": "CPU restatement of the reference path (oracle port; the reference itself needs the DUNE "
+                                        "stack and cannot be built here)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("dune-multidomain_b200")
+    capi = pkg.capi
+    dev = pkg.Mdb(local_rank)
+    S = args.size
+    n = (S, S, S)
+
+    t0 = time.time()
+    P = setup_problem(dev, n, rank, world)
+    dev.synchronize()
+    t_setup = time.time() - t0
+    nnz = dev.nnz[P.mat]
+    ncells_local = dev.ncells
+    owned = P.ndof if world == 1 else dev.owned_rows()[0]
+    ndof_total = owned
+    if world > 1:
+        t = torch.tensor([owned], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        ndof_total = int(t.item())
+
+    stream = torch.cuda.ExternalStream(dev.stream())
+    u = torch.zeros(P.ndof, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    dev.interpolate(P.sps, P.gfn, u)
+    dev.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        dev.profile_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = dev.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, dev.launch_count() - l0
+
+    # ---- headline: Jacobian assembly, x resident in HBM -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_jac, launches = timed(lambda: dev.jacobian(P.go, P.mat, u, overwrite=True), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_jac_vol = dev.phase_ms("jacobian_volume")
+    ms_jac_cpl = dev.phase_ms("jacobian_coupling")
+    value = ndof_total / (ms_jac * 1e-3)
+
+    peak, peak_src = peaks()
+    # algorithmic bytes of the dominant kernel: every stored value written once + the DOF map read
+    bytes_jac = 8.0 * nnz + 4.0 * 8 * ncells_local
+    roof = {"kernel": "k_jacobian_volume_q1<3>", "bound": "hbm", "achieved": bytes_jac / (ms_jac_vol * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": bytes_jac / (ms_jac_vol * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes": bytes_jac, "ms": ms_jac_vol, "frac_of_8TBs": bytes_jac / (ms_jac_vol * 1e-3) / 8e12}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("k_jacobian_volume_q1", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- the other kernels of the path ---------------------------------------------------------------------
+    r = torch.zeros(P.ndof, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ms_res, _ = timed(lambda: dev.residual(P.go, u, r), max(args.steps // 2, 3), 2)
+    ms_res_vol = dev.phase_ms("residual_volume")
+    y = torch.zeros_like(r)
+    torch.cuda.synchronize()
+    ms_spmv, _ = timed(lambda: dev.spmv(P.mat, u, y), max(args.steps // 2, 3), 2)
+    r.zero_()
+    torch.cuda.synchronize()
+    dev.residual(P.go, u, r)
+    z = torch.zeros_like(r)
+    torch.cuda.synchronize()
+    dev.solve(P.mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, fixed_iters=5)
+    barrier()
+    st = dev.solve(P.mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, fixed_iters=args.cg_iters)
+    cg_s = st.seconds
+    if world > 1:
+        t = torch.tensor([cg_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cg_s = float(t.item())
+    st2 = dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_JACOBI, fixed_iters=max(args.cg_iters // 2, 5))
+    n_loc = P.ndof
+    bytes_res = 16.0 * n_loc + 4.0 * 8 * ncells_local
+    bytes_spmv = 12.0 * nnz + 20.0 * n_loc
+    bytes_cg = bytes_spmv + 80.0 * n_loc
+    extra = {
+        "residual_assembly": {"dofs_per_s": ndof_total / (ms_res * 1e-3), "ms": ms_res, "kernel_ms": ms_res_vol,
+                              "achieved_GBs": bytes_res / (ms_res_vol * 1e-3) / 1e9, "frac": bytes_res / (ms_res_vol * 1e-3) / 1e9 / peak},
+        "spmv": {"ms": ms_spmv, "achieved_GBs": bytes_spmv / (ms_spmv * 1e-3) / 1e9, "frac": bytes_spmv / (ms_spmv * 1e-3) / 1e9 / peak},
+        "cg": {"iters_per_s": args.cg_iters / cg_s, "ms_per_iter": cg_s * 1e3 / args.cg_iters, "iters": args.cg_iters,
+               "achieved_GBs": bytes_cg / (cg_s / args.cg_iters) / 1e9, "frac": bytes_cg / (cg_s / args.cg_iters) / 1e9 / peak,
+               "preconditioner": "jacobi"},
+        "bicgstab": {"iters_per_s": st2.iterations / st2.seconds if st2.seconds > 0 else None},
+        "jacobian_phases_ms": {"volume": ms_jac_vol, "coupling_fd_and_dirichlet": ms_jac_cpl},
+        "setup_s": {"total": t_setup, "dofmap_ms": dev.phase_ms("dofmap"), "pattern_ms": dev.phase_ms("pattern"),
+                    "constraints_ms": dev.phase_ms("constraints")},
+    }
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    xh = torch.empty(P.ndof, dtype=torch.float64, pin_memory=True)
+    xh.copy_(u.cpu())
+    xh_np = xh.numpy()
+    chk = [0.0]
+
+    def e2e_step():
+        dev.jacobian(P.go, P.mat, xh_np, overwrite=True)      # H2D of x inside the call
+        chk[0] = dev.matrix_norm2(P.mat)                      # device reduction + D2H of the result
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    k_e2e = max(args.steps // 2, 3)
+    for _ in range(k_e2e):
+        e2e_step()
+    barrier()
+    s_e2e = (time.perf_counter() - t0) / k_e2e
+    if world > 1:
+        t = torch.tensor([s_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s_e2e = float(t.item())
+    e2e = {"value": ndof_total / s_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P.ndof, "d2h_bytes_per_step": 8,
+           "ms_per_step": s_e2e * 1e3, "what": "mdb_jacobian(x in pinned host memory) + mdb_matrix_norm2 read back", "checksum": chk[0]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_jac, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "M2: 3-D Q1/Q1 two-subdomain Poisson(order 4) + CVCF coupling(4, 2.0), %d^3 cells per GPU" % S,
+                           "cells_per_gpu": ncells_local, "dofs_total": ndof_total, "nnz_per_gpu": nnz,
+                           "l2_policy": "inputs larger than L2 (matrix values %.2f GB per GPU)" % (8.0 * nnz / 1e9),
+                           "partition": "z-slabs, one per GPU" if world > 1 else "single GPU"},
+                "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(S, args.cpu_sample_layers, 1)
+        elif world == 1:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -292,6 +292,17 @@ class Mdb(Lib):
     def phase_ms(self, phase):
         return self._fn("phase_ms", C.c_double)(C.c_void_p(self.ctx), phase.encode())
 
+    def phase_count(self, phase):
+        return self._fn("phase_count")(C.c_void_p(self.ctx), phase.encode())
+
+    def profile_reset(self):
+        self._fn("profile_reset")(C.c_void_p(self.ctx))
+
+    def matrix_norm2(self, mat):
+        out = C.c_double(0.0)
+        self._check(self._fn("matrix_norm2")(C.c_void_p(self.ctx), mat, C.byref(out)), "matrix_norm2")
+        return out.value
+
     def launch_count(self, reset=False):
         return self._fn("launch_count", C.c_int64)(C.c_void_p(self.ctx), int(reset))
 

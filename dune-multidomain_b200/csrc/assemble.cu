@@ -5,13 +5,16 @@
 // plus the scatter (jacobianassemblerengine.hh:271-364) and postAssembly (:480-504, residualassemblerengine.hh:553-567).
 //
 // Design: the reference scatters every 8x8 element matrix into the BCRS matrix (64 read-modify-writes
-// per cell, ~2.4 per stored entry).  Here every matrix ROW is owned by one thread, which sums the contributions of the
-// <= 2^d incident cells in ascending cell order (the reference's accumulation order) in registers and writes each stored
-// entry exactly once — no atomics, no zero-fill pass, no column-index reads: the position of a stencil entry inside its
-// CSR row is the rank of its bit in the row's 27-bit stencil mask (rowinfo).  On a structured mesh all cells are
-// congruent, so jacobian_volume is evaluated once per subproblem (exact.cu: k_element_matrices) and staged in shared
-// memory; the kernel is bound by the 8*nnz bytes it must write.  Row values are staged in shared memory per block so
-// that the global stores are fully coalesced.
+// per cell, ~2.4 per stored entry).  Here every matrix ROW is owned by exactly one thread/warp, which sums the
+// contributions of the <= 2^d incident cells in ascending cell order (the reference's accumulation order) and writes
+// each stored entry exactly once — no atomics, no zero-fill pass, no column-index reads: the position of a stencil entry
+// inside its CSR row is the rank of its bit in the row's 27-bit stencil mask (rowinfo).  On a structured mesh all cells
+// are congruent, so jacobian_volume is evaluated once per subproblem (exact.cu: k_element_matrices) and a row whose
+// 2^d incident cells all carry the subproblem ("uniform row", > 97 % of the rows at 256^3) has the constant stencil S.
+//   k_jacobian_fill_q1   all uniform rows: a warp owns 32 consecutive rows = one contiguous span of the value array and
+//                        streams S out with fully coalesced stores (the HBM-write-bound hot kernel)
+//   k_jacobian_rows_q1   the irregular rows (boundary / subdomain boundary; a compact list built with the pattern):
+//                        generic per-row gather over the incident cells
 #include "common.cuh"
 
 namespace mdb {
@@ -26,19 +29,18 @@ struct VolSpec {
 };
 
 struct ChildQ1 {
+  int subdomain;                       // -1: the child lives on the whole MultiDomainGrid
   int lat_n[3];
   int64_t offset, size;
   const int32_t* lat2dof;
   const int32_t* dof2lat;
 };
 
-#define ROWS_PER_BLOCK 128
-
 // Accumulate the stencil row of lattice point p: acc[o] for the 3^DIM neighbour offsets o, summing over the incident
 // cells in ascending cell index and, inside a cell, over the subproblems in participant order.
 template <int DIM>
-__device__ __forceinline__ void stencil_row(const MeshDesc& m, const uint8_t* __restrict__ sd, const VolSpec& V, const double* __restrict__ sAe,
-                                            const int p[3], double* acc, uint32_t& touched)
+__device__ __forceinline__ void stencil_row(const MeshDesc& m, const uint8_t* __restrict__ sd, int subdomain, const VolSpec& V,
+                                            const double* __restrict__ sAe, const int p[3], double* acc, uint32_t& touched)
 {
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
@@ -55,6 +57,7 @@ __device__ __forceinline__ void stencil_row(const MeshDesc& m, const uint8_t* __
         bool valid = ix >= 0 && ix < m.n[0] && iy >= 0 && iy < m.n[1] && (DIM < 3 || (iz >= 0 && iz < m.n[2]));
         if (!valid) continue;
         uint8_t s = sd[ix + (int64_t)m.n[0] * (iy + (int64_t)m.n[1] * iz)];
+        if (subdomain >= 0 && !((s >> subdomain) & 1)) continue;           // the child space does not live on this cell
         const int li = (-cx) | ((-cy) << 1) | ((DIM > 2 ? -cz : 0) << 2);   // local index of p inside this cell
         for (int v = 0; v < V.n; ++v) {
           if (!cond_applies(V.cond_kind[v], V.mask[v], s)) continue;
@@ -70,61 +73,94 @@ __device__ __forceinline__ void stencil_row(const MeshDesc& m, const uint8_t* __
       }
 }
 
+__device__ __forceinline__ int columns_below(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int64_t g, uint32_t info,
+                                             int64_t child_offset)
+{
+  int nlow = (int)(info >> 27);
+  if (nlow == 31) {      // saturated counter: count the columns below the own child block by search
+    int64_t rs = rowptr[g], lo = rs, hi = rowptr[g + 1];
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (colidx[mid] < child_offset) lo = mid + 1; else hi = mid; }
+    nlow = (int)(lo - rs);
+  }
+  return nlow;
+}
+
+// ---- all simple rows ------------------------------------------------------------------------------------------------
+// A "simple" row has the full 3^d own-block stencil and nothing else.  Consecutive simple rows form runs (segments,
+// found once with the pattern) whose values are one contiguous span of the value array holding the constant row
+// stencil S over and over: one block streams a run out with fully coalesced stores.  This is the HBM-write-bound
+// hot kernel: 8 bytes written per stored entry, nothing read but the run boundaries.
+#define JF_THREADS 128
 template <int DIM>
-__global__ void __launch_bounds__(ROWS_PER_BLOCK) k_jacobian_volume_q1(
-    MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V, const double* __restrict__ Ae,
-    const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo, const int32_t* __restrict__ colidx,
-    double* __restrict__ val, int overwrite)
+__global__ void __launch_bounds__(JF_THREADS) k_jacobian_fill_q1(ChildQ1 ch, const double* __restrict__ S, const int32_t* __restrict__ seg_start,
+                                                                const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
+                                                                double* __restrict__ val, int overwrite)
+{
+  constexpr int NS = (DIM == 3) ? 27 : 9;
+  constexpr int BITBASE = (DIM == 3) ? 0 : 9;       // 2-D rows use the dz = 0 slice of the 27-bit stencil mask
+  constexpr uint32_t FULL = ((1u << NS) - 1u) << BITBASE;
+  __shared__ double sS[32];
+  const int a = seg_start[blockIdx.x], b = seg_start[blockIdx.x + 1];
+  const int64_t g0 = ch.offset + a;
+  const int64_t base = rowptr[g0];
+  if (rowinfo[g0] != FULL || rowptr[g0 + 1] - base != NS) return;      // a run of irregular rows: k_jacobian_rows_q1
+  if (threadIdx.x < NS) sS[threadIdx.x] = S[threadIdx.x];
+  __syncthreads();
+  const int n = (b - a) * NS;
+  double* out = val + base;
+  int mm = threadIdx.x % NS;
+  if (overwrite) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += JF_THREADS) { out[i] = sS[mm]; mm += JF_THREADS % NS; if (mm >= NS) mm -= NS; }
+  } else {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += JF_THREADS) { out[i] += sS[mm]; mm += JF_THREADS % NS; if (mm >= NS) mm -= NS; }
+  }
+}
+
+// ---- irregular rows (or all rows when the uniform shortcut is not valid) ---------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) k_jacobian_rows_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
+                                                         const double* __restrict__ Ae, const int32_t* __restrict__ list, int64_t nrows,
+                                                         const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
+                                                         const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
 {
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
-  constexpr int BITBASE = (DIM == 3) ? 0 : 9;       // 2-D rows use the dz = 0 slice of the 27-bit stencil mask
-  extern __shared__ double smem[];
-  double* sAe = smem;                                // V.n * NL*NL
-  double* sval = smem + MDB_MAX_SP_PER_CHILD * NL * NL;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < V.n * NL * NL; i += ROWS_PER_BLOCK) {
+  constexpr int BITBASE = (DIM == 3) ? 0 : 9;
+  __shared__ double sAe[MDB_MAX_SP_PER_CHILD * NL * NL];
+  for (int i = threadIdx.x; i < V.n * NL * NL; i += blockDim.x) {
     int v = i / (NL * NL), e = i % (NL * NL);
     sAe[i] = Ae[V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + e];
   }
-  const int64_t gi0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
-  const int64_t gi1 = (gi0 + ROWS_PER_BLOCK < ch.size) ? gi0 + ROWS_PER_BLOCK : ch.size;
-  const int64_t span0 = rowptr[ch.offset + gi0];
-  const int span = (int)(rowptr[ch.offset + gi1] - span0);
-  for (int i = tid; i < span; i += ROWS_PER_BLOCK) sval[i] = 0.0;
   __syncthreads();
-  const int64_t gi = gi0 + tid;
-  if (gi < gi1) {
-    const int64_t g = ch.offset + gi;
-    int64_t r = ch.dof2lat[gi];
-    int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
-    double acc[NS]; uint32_t touched;
-    stencil_row<DIM>(m, sd, V, sAe, p, acc, touched);
-    const uint32_t info = rowinfo[g];
-    const uint32_t mask = info & 0x7FFFFFFu;
-    int nlow = (int)(info >> 27);
-    const int64_t rs = rowptr[g];
-    if (nlow == 31) {      // saturated counter: count the columns below the own child block by search
-      int64_t lo = rs, hi = rowptr[g + 1];
-      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (colidx[mid] < ch.offset) lo = mid + 1; else hi = mid; }
-      nlow = (int)(lo - rs);
-    }
-    double* row = sval + (rs - span0) + nlow;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  const int64_t gi = list ? (int64_t)list[t] : t;
+  const int64_t g = ch.offset + gi;
+  int64_t r = ch.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+  double acc[NS]; uint32_t touched;
+  stencil_row<DIM>(m, sd, ch.subdomain, V, sAe, p, acc, touched);
+  const uint32_t info = rowinfo[g];
+  const uint32_t mask = info & 0x7FFFFFFu;
+  const int nlow = columns_below(rowptr, colidx, g, info, ch.offset);
+  const int64_t rs = rowptr[g];
+  const int len = (int)(rowptr[g + 1] - rs);
+  const int nown = __popc(mask);
+  double* row = val + rs;
+  if (overwrite) for (int k = 0; k < len; ++k) if (k < nlow || k >= nlow + nown) row[k] = 0.0;
 #pragma unroll
-    for (int o = 0; o < NS; ++o) {
-      const uint32_t bit = 1u << (o + BITBASE);
-      if (mask & bit) row[__popc(mask & (bit - 1u))] = acc[o];
-    }
+  for (int o = 0; o < NS; ++o) {
+    const uint32_t bit = 1u << (o + BITBASE);
+    if (mask & bit) { double* q = row + nlow + __popc(mask & (bit - 1u)); if (overwrite) *q = acc[o]; else *q += acc[o]; }
   }
-  __syncthreads();
-  if (overwrite) { for (int i = tid; i < span; i += ROWS_PER_BLOCK) val[span0 + i] = sval[i]; }
-  else { for (int i = tid; i < span; i += ROWS_PER_BLOCK) val[span0 + i] += sval[i]; }
 }
 
 static ChildQ1 child_q1(const Ctx* c, int i)
 {
   const Child& ch = c->children[i];
-  ChildQ1 q; for (int d = 0; d < 3; ++d) q.lat_n[d] = ch.lat_n[d];
+  ChildQ1 q; q.subdomain = ch.subdomain; for (int d = 0; d < 3; ++d) q.lat_n[d] = ch.lat_n[d];
   q.offset = ch.offset; q.size = ch.size; q.lat2dof = ch.d_lat2dof; q.dof2lat = ch.d_dof2lat;
   return q;
 }
@@ -141,58 +177,108 @@ static VolSpec vol_spec(const Ctx* c, const GridOp& go, int child)
   return V;
 }
 
+// A full own-block stencil in the matrix pattern implies "the subproblem acts on all 2^d incident cells" iff every
+// subproblem that generated pattern entries on this child (over all grid operators of the matrix) has the same
+// condition as the single subproblem being assembled.
+static bool uniform_rows_ok(const Ctx* c, const Matrix& M, const VolSpec& V, int child)
+{
+  if (V.n != 1) return false;
+  for (int gi : M.gos)
+    for (int s : c->gos[gi].sps) {
+      const SubProblemDesc& sp = c->sps[s];
+      if (sp.children[0] != child) continue;
+      if (sp.cond_kind != V.cond_kind[0] || sp.mask != V.mask[0]) return false;
+    }
+  return true;
+}
+
 void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool overwrite)
 {
   const MeshDesc& m = c->mesh;
   launch_element_matrices(c, go.sps, weight);
   const int NL = 1 << m.dim;
-  const size_t smem = (size_t)(MDB_MAX_SP_PER_CHILD * NL * NL + ROWS_PER_BLOCK * M.max_row) * sizeof(double);
-  MDB_REQUIRE(smem <= 200 * 1024, MDB_EINVAL, "matrix rows too long for the staged volume kernel");
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[m.dim - 2]) {
-    if (m.dim == 2) MDB_CUDA(cudaFuncSetAttribute(k_jacobian_volume_q1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else MDB_CUDA(cudaFuncSetAttribute(k_jacobian_volume_q1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[m.dim - 2] = smem;
-  }
   for (int i = 0; i < (int)c->children.size(); ++i) {
     VolSpec V = vol_spec(c, go, i);
-    if (V.n == 0 && !overwrite) continue;       // nothing to add; in overwrite mode the rows must still be zeroed
     ChildQ1 ch = child_q1(c, i);
     if (ch.size == 0) continue;
-    int grid = cdiv(ch.size, ROWS_PER_BLOCK);
-    if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_volume_q1<2>, grid, ROWS_PER_BLOCK, smem, m, c->d_cell_sd, ch, V, c->d_Ae, M.d_rowptr, M.d_rowinfo,
-                               M.d_colidx, M.d_val, (int)overwrite);
-    else MDB_LAUNCH(c, k_jacobian_volume_q1<3>, grid, ROWS_PER_BLOCK, smem, m, c->d_cell_sd, ch, V, c->d_Ae, M.d_rowptr, M.d_rowinfo,
-                    M.d_colidx, M.d_val, (int)overwrite);
+    if (V.n == 0) {       // nothing to add; in overwrite mode the rows must still be zeroed
+      if (overwrite) MDB_CUDA(cudaMemsetAsync(M.d_val + M.child_begin[i], 0, (M.child_end[i] - M.child_begin[i]) * sizeof(double), c->stream));
+      continue;
+    }
+    const bool uni = uniform_rows_ok(c, M, V, i);
+    const int32_t* list = uni ? M.d_irregular[i] : nullptr;
+    const int64_t nrows = uni ? M.n_irregular[i] : ch.size;
+    if (uni) {
+      const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL;
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, (int)M.n_seg[i], JF_THREADS, 0, ch, S, M.d_seg_start[i], M.d_rowptr, M.d_rowinfo, M.d_val, (int)overwrite);
+      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, (int)M.n_seg[i], JF_THREADS, 0, ch, S, M.d_seg_start[i], M.d_rowptr, M.d_rowinfo, M.d_val, (int)overwrite);
+    }
+    if (nrows > 0) {
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
+                                 M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
+      else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
+                      M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
+    }
   }
 }
 
-// r[g] += sum_o acc[o] * x[dof(p+o)]: alpha_volume of a linear operator applied matrix-free, one thread per row.
+// ---- residual: r[g] += sum_o S_g[o] * x[dof(p+o)], alpha_volume of a linear operator applied matrix-free -----------
+// One thread per row.  Uniform rows (all 2^d incident cells carry the single subproblem) use the constant stencil S and
+// need only one lattice lookup per (dy,dz) line: lattice neighbours along axis 0 that are both present are numbered
+// consecutively.  Other rows gather over their incident cells.
 template <int DIM>
-__global__ void __launch_bounds__(128) k_residual_volume_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
+__global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
                                                             const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r)
 {
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
   __shared__ double sAe[MDB_MAX_SP_PER_CHILD * NL * NL];
+  __shared__ double sS[32];
   for (int i = threadIdx.x; i < V.n * NL * NL; i += blockDim.x) {
     int v = i / (NL * NL), e = i % (NL * NL);
     sAe[i] = Ae[V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + e];
   }
+  if (threadIdx.x < NS) sS[threadIdx.x] = Ae[V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL + threadIdx.x];
   __syncthreads();
   const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (gi >= ch.size) return;
-  int64_t rr = ch.dof2lat[gi];
-  int p[3]; p[0] = (int)(rr % ch.lat_n[0]); rr /= ch.lat_n[0]; p[1] = (int)(rr % ch.lat_n[1]); p[2] = (int)(rr / ch.lat_n[1]);
-  double acc[NS]; uint32_t touched;
-  stencil_row<DIM>(m, sd, V, sAe, p, acc, touched);
-  double s = 0.0;
+  const int32_t lp = ch.dof2lat[gi];
+  int rr = lp;
+  int p[3]; p[0] = rr % ch.lat_n[0]; rr /= ch.lat_n[0]; p[1] = rr % ch.lat_n[1]; p[2] = rr / ch.lat_n[1];
+  bool uni = V.n == 1 && p[0] >= 1 && p[0] < m.n[0] && p[1] >= 1 && p[1] < m.n[1] && (DIM < 3 || (p[2] >= 1 && p[2] < m.n[2]));
+  if (uni) {
 #pragma unroll
-  for (int o = 0; o < NS; ++o) {
-    if (!(touched & (1u << o))) continue;
-    const int dx = o % 3 - 1, dy = (o / 3) % 3 - 1, dz = (DIM > 2) ? o / 9 - 1 : 0;
-    int64_t q = (p[0] + dx) + (int64_t)ch.lat_n[0] * ((p[1] + dy) + (int64_t)ch.lat_n[1] * (p[2] + dz));
-    s += acc[o] * x[ch.offset + ch.lat2dof[q]];
+    for (int cz = (DIM > 2 ? -1 : 0); cz <= 0; ++cz)
+#pragma unroll
+      for (int cy = -1; cy <= 0; ++cy)
+#pragma unroll
+        for (int cx = -1; cx <= 0; ++cx) {
+          uint8_t s = sd[(p[0] + cx) + (int64_t)m.n[0] * ((p[1] + cy) + (int64_t)m.n[1] * (p[2] + cz))];
+          uni = uni && cond_applies(V.cond_kind[0], V.mask[0], s) && (ch.subdomain < 0 || ((s >> ch.subdomain) & 1));
+        }
+  }
+  const double* xc = x + ch.offset;
+  double s = 0.0;
+  if (uni) {
+#pragma unroll
+    for (int dz = (DIM > 2 ? -1 : 0); dz <= (DIM > 2 ? 1 : 0); ++dz)
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int o = (DIM > 2 ? (dz + 1) * 9 : 0) + (dy + 1) * 3;
+        const int32_t c0 = (dy == 0 && dz == 0) ? (int32_t)gi : ch.lat2dof[lp + dy * ch.lat_n[0] + dz * ch.lat_n[0] * ch.lat_n[1]];
+        s += sS[o] * xc[c0 - 1];
+        s += sS[o + 1] * xc[c0];
+        s += sS[o + 2] * xc[c0 + 1];
+      }
+  } else {
+    double acc[NS]; uint32_t touched;
+    stencil_row<DIM>(m, sd, ch.subdomain, V, sAe, p, acc, touched);
+#pragma unroll
+    for (int o = 0; o < NS; ++o) {
+      if (!(touched & (1u << o))) continue;
+      const int dx = o % 3 - 1, dy = (o / 3) % 3 - 1, dz = (DIM > 2) ? o / 9 - 1 : 0;
+      s += acc[o] * xc[ch.lat2dof[lp + dx + dy * ch.lat_n[0] + dz * ch.lat_n[0] * ch.lat_n[1]]];
+    }
   }
   r[ch.offset + gi] += s;
 }
@@ -206,8 +292,8 @@ void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x,
     if (V.n == 0) continue;
     ChildQ1 ch = child_q1(c, i);
     if (ch.size == 0) continue;
-    if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(ch.size, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r);
-    else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(ch.size, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r);
+    if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(ch.size, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r);
+    else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(ch.size, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r);
   }
 }
 

@@ -55,14 +55,43 @@ void* Ctx::scratch(size_t bytes)
   return d_scratch;
 }
 
-void Ctx::phase_begin() { MDB_CUDA(cudaEventRecord(ev0, stream)); }
-void Ctx::phase_end(const char* name)
+void Ctx::phase_begin(const char* name)
 {
-  MDB_CUDA(cudaEventRecord(ev1, stream));
-  MDB_CUDA(cudaEventSynchronize(ev1));
-  float ms = 0.f;
-  MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-  phase_ms[name] = ms;
+  PhaseRec& r = phases[name];
+  cur_phase = nullptr;
+  if (r.used == r.ev.size()) {
+    if (r.ev.size() >= 4096) return;            // pool full: stop recording this phase until the next reset
+    cudaEvent_t a, b;
+    MDB_CUDA(cudaEventCreate(&a)); MDB_CUDA(cudaEventCreate(&b));
+    r.ev.emplace_back(a, b);
+  }
+  MDB_CUDA(cudaEventRecord(r.ev[r.used].first, stream));
+  cur_phase = &r;
+}
+void Ctx::phase_end()
+{
+  if (!cur_phase) return;
+  MDB_CUDA(cudaEventRecord(cur_phase->ev[cur_phase->used].second, stream));
+  cur_phase->used++;
+  cur_phase = nullptr;
+}
+double Ctx::phase_mean_ms(const char* name, int* count)
+{
+  auto it = phases.find(name);
+  if (count) *count = 0;
+  if (it == phases.end()) return -1.0;
+  PhaseRec& r = it->second;
+  if (r.used == 0) return r.last_ms;
+  MDB_CUDA(cudaStreamSynchronize(stream));
+  double sum = 0.0;
+  for (size_t i = 0; i < r.used; ++i) { float ms = 0.f; MDB_CUDA(cudaEventElapsedTime(&ms, r.ev[i].first, r.ev[i].second)); sum += ms; }
+  if (count) *count = (int)r.used;
+  r.last_ms = sum / r.used;
+  return r.last_ms;
+}
+void Ctx::phase_reset()
+{
+  for (auto& kv : phases) { if (kv.second.used) phase_mean_ms(kv.first.c_str(), nullptr); kv.second.used = 0; }
 }
 
 VecIn::VecIn(Ctx* c, const double* p, int64_t n, int slot)
@@ -91,6 +120,9 @@ void VecInOut::commit()
 static void free_matrix(Matrix& m)
 {
   dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv);
+  for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(m.d_irregular[i]); dfree(m.d_seg_start[i]); }
+  for (auto& kv : m.slot_tables) cudaFree(kv.second);
+  m.slot_tables.clear();
 }
 
 static void reset_spaces(Ctx* c)
@@ -167,7 +199,7 @@ void mdb_destroy(mdb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   reset_spaces(c);
-  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_scal); dfree(c->d_partial);
+  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_scal); dfree(c->d_partial);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->d_halo_recv) cudaFree(c->d_halo_recv);
@@ -308,9 +340,9 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->have_mesh && c->have_sd, MDB_ESTATE, "mdb_finalize: mesh and subdomains must be set");
   MDB_REQUIRE(!c->children.empty(), MDB_ESTATE, "mdb_finalize: no child spaces");
-  c->phase_begin();
+  c->phase_begin("dofmap");
   build_dofmap(c);
-  c->phase_end("dofmap");
+  c->phase_end();
   c->finalized = true;
   if (ndof) *ndof = c->ndof;
   MDB_API_END(c)
@@ -338,10 +370,10 @@ int mdb_constraints_assemble(mdb_ctx* c, const int* subproblems, const mdb_bctyp
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_constraints_assemble: not finalized");
   for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
-  c->phase_begin();
+  c->phase_begin("constraints");
   assemble_constraints(c, subproblems, bcs, n);
   rebuild_conlist(c);
-  c->phase_end("constraints");
+  c->phase_end();
   if (nconstrained) *nconstrained = c->ncon;
   MDB_API_END(c)
 }
@@ -407,9 +439,9 @@ int mdb_matrix_create(mdb_ctx* c, const int* gos, int ngos, int64_t* nnz)
     MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_matrix_create: not finalized");
     Matrix m;
     for (int i = 0; i < ngos; ++i) { MDB_REQUIRE(gos[i] >= 0 && gos[i] < (int)c->gos.size(), MDB_EINVAL, "bad grid operator handle"); m.gos.push_back(gos[i]); }
-    c->phase_begin();
+    c->phase_begin("pattern");
     build_pattern(c, m);
-    c->phase_end("pattern");
+    c->phase_end();
     if (nnz) *nnz = m.nnz;
     c->mats.push_back(m);
     return (int)c->mats.size() - 1;
@@ -477,16 +509,16 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   MDB_GO(c, go)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vr(c, r, c->ndof, 1, true);
-  c->phase_begin();
+  c->phase_begin("residual_volume");
   residual_volume(c, G, weight, vx.d, vr.d);
-  c->phase_end("residual_volume");
-  c->phase_begin();
+  c->phase_end();
+  c->phase_begin("residual_boundary");
   residual_boundary(c, G, weight, vr.d);
-  c->phase_end("residual_boundary");
-  c->phase_begin();
+  c->phase_end();
+  c->phase_begin("residual_coupling");
   residual_coupling(c, G, weight, vx.d, vr.d);
   constrain_residual(c, vr.d);
-  c->phase_end("residual_coupling");
+  c->phase_end();
   vr.commit();
   MDB_API_END(c)
 }
@@ -498,13 +530,13 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   MDB_MAT(c, mat)
   VecIn vx(c, x, c->ndof, 0);
   M.dinv_valid = false;
-  c->phase_begin();
+  c->phase_begin("jacobian_volume");
   jacobian_volume(c, G, M, weight, overwrite != 0);
-  c->phase_end("jacobian_volume");
-  c->phase_begin();
+  c->phase_end();
+  c->phase_begin("jacobian_coupling");
   jacobian_coupling(c, G, M, weight, vx.d);
   dirichlet_rows(c, M);
-  c->phase_end("jacobian_coupling");
+  c->phase_end();
   MDB_API_END(c)
 }
 
@@ -514,9 +546,9 @@ int mdb_spmv(mdb_ctx* c, int mat, const double* x, double* y)
   MDB_MAT(c, mat)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vy(c, y, c->ndof, 1, false);
-  c->phase_begin();
+  c->phase_begin("spmv");
   spmv(c, M, vx.d, vy.d);
-  c->phase_end("spmv");
+  c->phase_end();
   vy.commit();
   MDB_API_END(c)
 }
@@ -572,8 +604,58 @@ int mdb_copy_nonconstrained(mdb_ctx* c, const double* xold, double* xnew)
 double mdb_phase_ms(mdb_ctx* c, const char* phase)
 {
   if (!c) return -1.0;
-  auto it = c->phase_ms.find(phase);
-  return it == c->phase_ms.end() ? -1.0 : (double)it->second;
+  try { cudaSetDevice(c->device); return c->phase_mean_ms(phase, nullptr); } catch (std::exception& e) { c->err = e.what(); return -1.0; }
+}
+
+int mdb_phase_count(mdb_ctx* c, const char* phase)
+{
+  if (!c) return 0;
+  auto it = c->phases.find(phase);
+  return it == c->phases.end() ? 0 : (int)it->second.used;
+}
+
+int mdb_profile_reset(mdb_ctx* c)
+{
+  if (!c) return MDB_EINVAL;
+  c->phase_reset();
+  return MDB_OK;
+}
+
+// sum of squares of the stored matrix entries (a cheap device-side checksum of an assembly result)
+__global__ void k_norm2_partial(const double* __restrict__ v, int64_t n, double* partial)
+{
+  __shared__ double sh[8];
+  double a = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += v[i] * v[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i]; partial[blockIdx.x] = s; }
+}
+__global__ void k_norm2_final(const double* __restrict__ partial, int n, double* out)
+{
+  __shared__ double sh[8];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += partial[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i]; out[0] = s; }
+}
+
+int mdb_matrix_norm2(mdb_ctx* c, int mat, double* out)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  const int grid = 148 * 8;
+  c->phase_begin("matrix_norm2");
+  MDB_LAUNCH(c, k_norm2_partial, grid, 256, 0, M.d_val, M.nnz, c->d_partial);
+  MDB_LAUNCH(c, k_norm2_final, 1, 256, 0, c->d_partial, grid, c->d_scal + 40);
+  c->phase_end();
+  MDB_CUDA(cudaMemcpyAsync(c->h_pinned + 40, c->d_scal + 40, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c->h_pinned[40];
+  MDB_API_END(c)
 }
 
 int64_t mdb_launch_count(mdb_ctx* c, int reset)

@@ -182,6 +182,14 @@ struct Matrix {
   double* d_val = nullptr;
   uint32_t* d_rowinfo = nullptr;
   int32_t* d_diag = nullptr;     // offset of the diagonal inside the row
+  // per child block: value-array span of its rows, and the compact list of its irregular rows (stencil mask not full)
+  int64_t child_begin[MDB_MAX_CHILDREN] = {0}, child_end[MDB_MAX_CHILDREN] = {0};
+  int32_t* d_irregular[MDB_MAX_CHILDREN] = {nullptr};
+  int64_t n_irregular[MDB_MAX_CHILDREN] = {0};
+  int32_t* d_seg_start[MDB_MAX_CHILDREN] = {nullptr};   // runs of rows with equal simple/irregular status (n_seg + 1 entries)
+  int64_t n_seg[MDB_MAX_CHILDREN] = {0};
+  // per (grid operator, coupling): uint8 offsets inside the row of every entry a coupling face touches
+  std::map<std::pair<int, int>, uint8_t*> slot_tables;
   // preconditioner caches
   double* d_dinv = nullptr;
   bool dinv_valid = false;
@@ -191,7 +199,11 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  std::map<std::string, float> phase_ms;
+  // deferred per-phase device timing: event pairs recorded on the stream without host synchronisation and resolved
+  // when mdb_phase_ms() is called
+  struct PhaseRec { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; size_t used = 0; double last_ms = -1.0; };
+  std::map<std::string, PhaseRec> phases;
+  PhaseRec* cur_phase = nullptr;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -212,6 +224,7 @@ struct Ctx {
   // scratch
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   double* d_Ae = nullptr;            // element matrix table
+  double* d_ftab = nullptr;          // face shape-function tables of the coupling kernels
   // staging for host<->device vectors
   double* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
   // solver workspace
@@ -229,8 +242,10 @@ struct Ctx {
   int lower_rank = -1, upper_rank = -1;
 
   void* scratch(size_t bytes);
-  void phase_begin();
-  void phase_end(const char* name);
+  void phase_begin(const char* name);
+  void phase_end();
+  double phase_mean_ms(const char* name, int* count);
+  void phase_reset();
 };
 
 inline bool is_device_ptr(const void* p)

@@ -71,15 +71,20 @@ struct AeSpec { int n; int op[MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN]; int k[MD
                 Rule1D rule[MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN]; };
 
 // grid: one block per slot; thread t = i*nloc + j computes entry (i,j) with the reference's summation order over the
-// quadrature points.  ext[d] = up-lo of the (congruent) cells.
-template <int DIM> __global__ void k_element_matrices(AeSpec S, double ext0, double ext1, double ext2, double weight, double* Ae)
+// quadrature points.  ext[d] = up-lo of the (congruent) cells.  The shape functions are evaluated once per (quadrature
+// point, i) — in parallel over the block, chunk by chunk — and parked in shared memory; the per-entry sums then run over
+// the points in rule order, so the result has the same bits as evaluating everything per entry.
+#define AE_QCHUNK 32
+template <int DIM> __global__ void __launch_bounds__(768) k_element_matrices(AeSpec S, double ext0, double ext1, double ext2, double weight, double* Ae)
 {
+  __shared__ double sb[AE_QCHUNK][MDB_MAXLOC][4];     // {phi, dphi/dx0, dphi/dx1, dphi/dx2} in reference coordinates
+  __shared__ double sw[AE_QCHUNK];
   const int slot = blockIdx.x;
   const int k = S.k[slot];
   const int nloc = ipow(k + 1, DIM);
   const int t = threadIdx.x;
-  if (t >= nloc * nloc) return;
-  const int i = t / nloc, j = t % nloc;
+  const bool active = t < nloc * nloc;
+  const int i = active ? t / nloc : 0, j = active ? t % nloc : 0;
   const double ext[3] = {ext0, ext1, ext2};
   double jit[3];
 #pragma unroll
@@ -90,22 +95,52 @@ template <int DIM> __global__ void k_element_matrices(AeSpec S, double ext0, dou
   const Rule1D& R = S.rule[slot];
   const int nq = ipow(R.m, DIM);
   double a = 0.0;
-  for (int q = 0; q < nq; ++q) {
-    double x[3], w; quad_point<DIM>(R, q, x, w);
-    double factor = w * detj;
-    if (S.op[slot] == MDB_OP_POISSON) {
-      double gi[3], gj[3];
-      qk_grad<DIM>(k, i, x, gi); qk_grad<DIM>(k, j, x, gj);
-      double dot = 0.0;
+  for (int q0 = 0; q0 < nq; q0 += AE_QCHUNK) {
+    const int nc = (nq - q0 < AE_QCHUNK) ? nq - q0 : AE_QCHUNK;
+    __syncthreads();
+    for (int e = t; e < nc * nloc; e += blockDim.x) {
+      const int ql = e / nloc, ii = e % nloc;
+      double x[3], w; quad_point<DIM>(R, q0 + ql, x, w);
+      double g[3] = {0.0, 0.0, 0.0};
+      qk_grad<DIM>(k, ii, x, g);
+      sb[ql][ii][0] = qk_phi<DIM>(k, ii, x); sb[ql][ii][1] = g[0]; sb[ql][ii][2] = g[1]; sb[ql][ii][3] = g[2];
+      if (ii == 0) sw[ql] = w;
+    }
+    __syncthreads();
+    if (active) {
+      for (int ql = 0; ql < nc; ++ql) {
+        const double factor = sw[ql] * detj;
+        if (S.op[slot] == MDB_OP_POISSON) {
+          double dot = 0.0;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) { double a_i = 0.0 + jit[d] * gi[d]; double a_j = 0.0 + jit[d] * gj[d]; dot += a_j * a_i; }
-      a += weight * (dot * factor);
-    } else {   // MDB_OP_L2
-      double pi = qk_phi<DIM>(k, i, x), pj = qk_phi<DIM>(k, j, x);
-      a += weight * (pj * pi * factor);
+          for (int d = 0; d < DIM; ++d) { double a_i = 0.0 + jit[d] * sb[ql][i][1 + d]; double a_j = 0.0 + jit[d] * sb[ql][j][1 + d]; dot += a_j * a_i; }
+          a += weight * (dot * factor);
+        } else {   // MDB_OP_L2
+          a += weight * (sb[ql][j][0] * sb[ql][i][0] * factor);
+        }
+      }
     }
   }
-  Ae[slot * MDB_MAXLOC * MDB_MAXLOC + i * nloc + j] = a;
+  double* A = Ae + slot * MDB_MAXLOC * MDB_MAXLOC;
+  if (active) A[i * nloc + j] = a;
+  __syncthreads();
+  // Q1 only: the row stencil of a vertex all of whose 2^DIM incident cells carry this operator, summed over the cells in
+  // ascending cell index exactly like the per-row gather of assemble.cu (stencil_row); stored behind the element matrix.
+  constexpr int NS = (DIM == 3) ? 27 : 9;
+  if (k == 1 && t < NS) {
+    double s = 0.0;
+    for (int cz = (DIM > 2 ? -1 : 0); cz <= 0; ++cz)
+      for (int cy = -1; cy <= 0; ++cy)
+        for (int cx = -1; cx <= 0; ++cx) {
+          const int li = (-cx) | ((-cy) << 1) | ((DIM > 2 ? -cz : 0) << 2);
+          for (int lj = 0; lj < nloc; ++lj) {
+            const int bx = lj & 1, by = (lj >> 1) & 1, bz = (DIM > 2) ? (lj >> 2) & 1 : 0;
+            const int o = (DIM > 2 ? (cz + bz + 1) * 9 : 0) + (cy + by + 1) * 3 + (cx + bx + 1);
+            if (o == t) s += A[li * nloc + lj];
+          }
+        }
+    A[nloc * nloc + t] = s;
+  }
 }
 
 void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight)
@@ -120,8 +155,10 @@ void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight)
   }
   double ext[3] = {1, 1, 1};
   for (int d = 0; d < m.dim; ++d) ext[d] = m.coord(d, 1) - m.coord(d, 0);
-  if (m.dim == 2) MDB_LAUNCH(c, k_element_matrices<2>, S.n, 32 * 32, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
-  else MDB_LAUNCH(c, k_element_matrices<3>, S.n, 32 * 32, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
+  int nthreads = 32;
+  for (int i = 0; i < S.n; ++i) { int nl = 1; for (int d = 0; d < m.dim; ++d) nl *= (S.k[i] + 1); int t = ((nl * nl + 31) / 32) * 32; if (t > nthreads) nthreads = t; }
+  if (m.dim == 2) MDB_LAUNCH(c, k_element_matrices<2>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
+  else MDB_LAUNCH(c, k_element_matrices<3>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
 }
 
 // ---- interface geometry ------------------------------------------------------------------------------
@@ -175,21 +212,49 @@ struct CouplingParams {
   Rule1D rule;
 };
 
+// Shape-function tables on the faces of the reference cell.  The values phi_i(local) and d phi_i/d local_d at the face
+// quadrature points depend only on (face axis, which side of the cell, quadrature point), not on the cell, so they are
+// evaluated once — with the very same qk_phi / qk_grad arithmetic, hence bit-identical to evaluating them per face as
+// the reference does — and looked up by every face.  Layout: tab[(((axis*2+sideval)*nq + q)*NL + i)*4 + {phi, d0, d1, d2}].
+#define MDB_FTAB_DOUBLES (6 * 25 * 8 * 4)
+template <int DIM> __global__ void k_face_tables(Rule1D R, double* tab)
+{
+  constexpr int NL = 1 << DIM;
+  const int nq = ipow(R.m, DIM - 1);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * DIM * nq * NL) return;
+  const int i = t % NL, q = (t / NL) % nq, c = t / (NL * nq);
+  const int axis = c / 2, sideval = c % 2;
+  double pos[3], w; quad_point<DIM - 1>(R, q, pos, w);
+  double local[3]; int tt = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) local[d] = (d == axis) ? (double)sideval : pos[tt++];
+  double js[3] = {0.0, 0.0, 0.0};
+  qk_grad<DIM>(1, i, local, js);
+  double* o = tab + (size_t)t * 4;
+  o[0] = qk_phi<DIM>(1, i, local); o[1] = js[0]; o[2] = js[1]; o[3] = js[2];
+}
+
 // alpha_coupling restated for Q1 on both sides (NL = 2^DIM shape functions per side); r_s, r_n accumulate weight*value.
 template <int DIM>
-__device__ void alpha_coupling(const CouplingParams& P, const FaceGeo<DIM>& G, const double* x1, const double* x2,
-                               double* r1, double* r2, double weight)
+__device__ void alpha_coupling(const CouplingParams& P, const FaceGeo<DIM>& G, const double* __restrict__ tab, const double* x1,
+                               const double* x2, double* r1, double* r2, double weight)
 {
   constexpr int NL = 1 << DIM;
   const int nq = ipow(P.rule.m, DIM - 1);
   const double h_F = G.cornerDistance01();
+  const double* tab1 = tab + (size_t)((G.axis * 2 + G.side) * nq) * NL * 4;          // geometryInInside: local[axis] = side
+  const double* tab2 = tab + (size_t)((G.axis * 2 + (1 - G.side)) * nq) * NL * 4;    // geometryInOutside: 1 - side
+  double jit1[DIM], jit2[DIM];     // jacobianInverseTransposed of the two cells (diagonal)
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { jit1[d] = 1.0 / (G.up_i[d] - G.lo_i[d]); jit2[d] = 1.0 / (G.up_o[d] - G.lo_o[d]); }
   for (int q = 0; q < nq; ++q) {
     double pos[3], w; quad_point<DIM - 1>(P.rule, q, pos, w);
-    double local1[3], local2[3];
-    G.localInside(pos, local1); G.localOutside(pos, local2);
+    const double* t1 = tab1 + (size_t)q * NL * 4;
+    const double* t2 = tab2 + (size_t)q * NL * 4;
     double phi1[NL], phi2[NL];
 #pragma unroll
-    for (int i = 0; i < NL; ++i) { phi1[i] = qk_phi<DIM>(1, i, local1); phi2[i] = qk_phi<DIM>(1, i, local2); }
+    for (int i = 0; i < NL; ++i) { phi1[i] = __ldg(t1 + i * 4); phi2[i] = __ldg(t2 + i * 4); }
     const double factor = w * G.integrationElement();
     if (P.op == MDB_OP_PROPFLOW_COUPLING) {
       double u_s = 0.0, u_n = 0.0;
@@ -207,13 +272,10 @@ __device__ void alpha_coupling(const CouplingParams& P, const FaceGeo<DIM>& G, c
     double gradphi1[NL][DIM], gradphi2[NL][DIM];
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
-      double js[3];
-      qk_grad<DIM>(1, i, local1, js);
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) gradphi1[i][d] = 0.0 + (1.0 / (G.up_i[d] - G.lo_i[d])) * js[d];
-      qk_grad<DIM>(1, i, local2, js);
+      for (int d = 0; d < DIM; ++d) gradphi1[i][d] = 0.0 + jit1[d] * __ldg(t1 + i * 4 + 1 + d);
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) gradphi2[i][d] = 0.0 + (1.0 / (G.up_o[d] - G.lo_o[d])) * js[d];
+      for (int d = 0; d < DIM; ++d) gradphi2[i][d] = 0.0 + jit2[d] * __ldg(t2 + i * 4 + 1 + d);
     }
     double gradu1[DIM], gradu2[DIM];
 #pragma unroll
@@ -286,7 +348,7 @@ template <int DIM> __device__ __forceinline__ void cell_dofs_q1(const SideMap& S
 template <int DIM>
 __global__ void __launch_bounds__(128) k_coupling_residual(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
                                                            const int8_t* __restrict__ fface, int64_t nfaces, double weight,
-                                                           const double* __restrict__ x, double* r)
+                                                           const double* __restrict__ tab, const double* __restrict__ x, double* r)
 {
   constexpr int NL = 1 << DIM;
   int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -297,7 +359,7 @@ __global__ void __launch_bounds__(128) k_coupling_residual(MeshDesc m, CouplingP
   double x1[NL], x2[NL], r1[NL], r2[NL];
 #pragma unroll
   for (int i = 0; i < NL; ++i) { x1[i] = x[ds[i]]; x2[i] = x[dn[i]]; r1[i] = 0.0; r2[i] = 0.0; }
-  alpha_coupling<DIM>(P, G, x1, x2, r1, r2, weight);
+  alpha_coupling<DIM>(P, G, tab, x1, x2, r1, r2, weight);
 #pragma unroll
   for (int i = 0; i < NL; ++i) { atomicAdd(&r[ds[i]], r1[i]); atomicAdd(&r[dn[i]], r2[i]); }
 }
@@ -309,52 +371,89 @@ __device__ __forceinline__ int64_t find_slot(const int64_t* __restrict__ rowptr,
   return lo;   // the pattern contains every coupling link by construction
 }
 
-// One warp per interface face.  lane 0: base line ("down"); lane 1+j, j<NL: perturb self dof j; lane 1+NL+j: perturb
-// neighbour dof j.  Each perturbation lane owns one column of mat_ss/mat_ns (self) or mat_sn/mat_nn (neighbour).
+// Slot table: for every coupling face the offset inside its CSR row of each of the (2 NL)^2 entries the face touches
+// (rows: NL self dofs then NL neighbour dofs; columns likewise).  Built once per (matrix, grid operator, coupling).
 template <int DIM>
-__global__ void __launch_bounds__(128) k_coupling_jacobian(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
-                                                           const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
-                                                           const double* __restrict__ x, const int64_t* __restrict__ rowptr,
-                                                           const int32_t* __restrict__ colidx, double* val)
+__global__ void k_coupling_slots(MeshDesc m, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface,
+                                 int64_t nfaces, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, uint8_t* slots, int* err)
 {
   constexpr int NL = 1 << DIM;
-  const int lane = threadIdx.x & 31;
-  int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (f >= nfaces) return;                      // whole warp exits together
+  constexpr int NR = 2 * NL;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nfaces * NR * NR) return;
+  const int64_t f = t / (NR * NR);
+  const int ir = (int)((t / NR) % NR), jc = (int)(t % NR);
   FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
   int32_t ds[NL], dn[NL];
   cell_dofs_q1<DIM>(Ls, G.ijk, ds); cell_dofs_q1<DIM>(Rs, G.nijk, dn);
-  double u1[NL], u2[NL], r1[NL], r2[NL];
+  int32_t row = 0, col = 0;
 #pragma unroll
-  for (int i = 0; i < NL; ++i) { u1[i] = x[ds[i]]; u2[i] = x[dn[i]]; r1[i] = 0.0; r2[i] = 0.0; }
-  const int j = lane - 1;                       // perturbation index, -1 = base line
-  const bool self = j >= 0 && j < NL, nb = j >= NL && j < 2 * NL;
+  for (int i = 0; i < NL; ++i) {
+    if (ir == i) row = ds[i];
+    if (ir == NL + i) row = dn[i];
+    if (jc == i) col = ds[i];
+    if (jc == NL + i) col = dn[i];
+  }
+  const int64_t rs = rowptr[row];
+  const int64_t pos = find_slot(rowptr, colidx, row, col);
+  if (pos >= rowptr[row + 1] || colidx[pos] != col || pos - rs > 255) { atomicExch(err, 1); slots[t] = 0; return; }
+  slots[t] = (uint8_t)(pos - rs);
+}
+
+// jacobian_coupling (couplingutilities.hh:75-135).  One thread per (face, evaluation): evaluation 0 is the base line
+// ("down"), evaluation 1+j perturbs self dof j (j < NL) or neighbour dof j-NL; the base line of each face is exchanged
+// through shared memory; every perturbation thread owns one column of mat_ss/mat_ns (self) or mat_sn/mat_nn (neighbour).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_coupling_jacobian(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
+                                                           const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
+                                                           const double* __restrict__ tab, const double* __restrict__ x,
+                                                           const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slots, double* val)
+{
+  constexpr int NL = 1 << DIM;
+  constexpr int NE = 2 * NL + 1;
+  constexpr int FPB = 256 / NE;                 // faces per block
+  __shared__ double sdown[FPB][2 * NL];
+  const int fl = threadIdx.x / NE, e = threadIdx.x % NE;
+  const int64_t f = (int64_t)blockIdx.x * FPB + fl;
+  const bool active = fl < FPB && f < nfaces;
+  const int j = e - 1;                          // perturbation index, -1 = base line
+  const bool self = j >= 0 && j < NL, nb = j >= NL;
+  int32_t ds[NL], dn[NL];
+  double r1[NL], r2[NL];
   double delta = 1.0;
-  if (P.jac_mode == MDB_JAC_ANALYTIC) {
-    // the shipped coupling residuals are linear in (u_s,u_n): column j = alpha_coupling(e_j), no division
+  if (active) {
+    FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
+    cell_dofs_q1<DIM>(Ls, G.ijk, ds); cell_dofs_q1<DIM>(Rs, G.nijk, dn);
+    double u1[NL], u2[NL];
 #pragma unroll
-    for (int i = 0; i < NL; ++i) { u1[i] = (self && i == j) ? 1.0 : 0.0; u2[i] = (nb && i == j - NL) ? 1.0 : 0.0; }
-  } else {
+    for (int i = 0; i < NL; ++i) { u1[i] = x[ds[i]]; u2[i] = x[dn[i]]; r1[i] = 0.0; r2[i] = 0.0; }
+    if (P.jac_mode == MDB_JAC_ANALYTIC) {
+      // the shipped coupling residuals are linear in (u_s,u_n): column j = alpha_coupling(e_j), no division
 #pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      if (self && i == j) { delta = epsilon * (1.0 + fabs(u1[i])); u1[i] += delta; }
-      if (nb && i == j - NL) { delta = epsilon * (1.0 + fabs(u2[i])); u2[i] += delta; }
+      for (int i = 0; i < NL; ++i) { u1[i] = (self && i == j) ? 1.0 : 0.0; u2[i] = (nb && i == j - NL) ? 1.0 : 0.0; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        if (self && i == j) { delta = epsilon * (1.0 + fabs(u1[i])); u1[i] += delta; }
+        if (nb && i == j - NL) { delta = epsilon * (1.0 + fabs(u2[i])); u2[i] += delta; }
+      }
+    }
+    if (!(P.jac_mode == MDB_JAC_ANALYTIC && e == 0)) alpha_coupling<DIM>(P, G, tab, u1, u2, r1, r2, 1.0);
+    if (e == 0) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) { sdown[fl][i] = r1[i]; sdown[fl][NL + i] = r2[i]; }
     }
   }
-  alpha_coupling<DIM>(P, G, u1, u2, r1, r2, 1.0);
-  double c1[NL], c2[NL];
+  __syncthreads();
+  if (!active || e == 0) return;
+  const uint8_t* sl = slots + f * (4 * NL * NL) + j;           // column j of the face's (2NL x 2NL) slot table
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
-    double d1 = __shfl_sync(0xffffffffu, r1[i], 0), d2 = __shfl_sync(0xffffffffu, r2[i], 0);
-    if (P.jac_mode == MDB_JAC_ANALYTIC) { c1[i] = r1[i]; c2[i] = r2[i]; }
-    else { c1[i] = (r1[i] - d1) / delta; c2[i] = (r2[i] - d2) / delta; }
-  }
-  if (!(self || nb)) return;
-  const int32_t col = self ? ds[j] : dn[j - NL];
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    atomicAdd(&val[find_slot(rowptr, colidx, ds[i], col)], weight * c1[i]);     // mat_ss / mat_sn
-    atomicAdd(&val[find_slot(rowptr, colidx, dn[i], col)], weight * c2[i]);     // mat_ns / mat_nn
+    double c1, c2;
+    if (P.jac_mode == MDB_JAC_ANALYTIC) { c1 = r1[i]; c2 = r2[i]; }
+    else { c1 = (r1[i] - sdown[fl][i]) / delta; c2 = (r2[i] - sdown[fl][NL + i]) / delta; }
+    atomicAdd(&val[rowptr[ds[i]] + sl[i * 2 * NL]], weight * c1);             // mat_ss / mat_sn
+    atomicAdd(&val[rowptr[dn[i]] + sl[(NL + i) * 2 * NL]], weight * c2);      // mat_ns / mat_nn
   }
 }
 
@@ -364,6 +463,16 @@ static SideMap side_map(const Ctx* c, int sp)
   SideMap s; for (int d = 0; d < 3; ++d) s.lat_n[d] = ch.lat_n[d];
   s.offset = ch.offset; s.lat2dof = ch.d_lat2dof;
   return s;
+}
+static const double* face_tables(Ctx* c, const CouplingParams& P)
+{
+  if (!c->d_ftab) c->d_ftab = dalloc<double>(MDB_FTAB_DOUBLES);
+  const int dim = c->mesh.dim;
+  int nq = 1; for (int d = 0; d < dim - 1; ++d) nq *= P.rule.m;
+  const int total = 2 * dim * nq * (1 << dim);
+  if (dim == 2) MDB_LAUNCH(c, k_face_tables<2>, cdiv(total, 128), 128, 0, P.rule, c->d_ftab);
+  else MDB_LAUNCH(c, k_face_tables<3>, cdiv(total, 128), 128, 0, P.rule, c->d_ftab);
+  return c->d_ftab;
 }
 static CouplingParams coupling_params(const CouplingDesc& cp)
 {
@@ -382,8 +491,9 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
     if (fl.n == 0) continue;
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
-    if (m.dim == 2) MDB_LAUNCH(c, k_coupling_residual<2>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, d_x, d_r);
-    else MDB_LAUNCH(c, k_coupling_residual<3>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, d_x, d_r);
+    const double* tab = face_tables(c, P);
+    if (m.dim == 2) MDB_LAUNCH(c, k_coupling_residual<2>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, tab, d_x, d_r);
+    else MDB_LAUNCH(c, k_coupling_residual<3>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, tab, d_x, d_r);
   }
 }
 
@@ -397,11 +507,31 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const double eps = 1e-8;                    // NumericalJacobianCoupling() default, couplingutilities.hh:63-65
-    int64_t threads = fl.n * 32;
-    if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian<2>, cdiv(threads, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, d_x,
-                               M.d_rowptr, M.d_colidx, M.d_val);
-    else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(threads, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, d_x,
-                    M.d_rowptr, M.d_colidx, M.d_val);
+    const int NL = 1 << m.dim, NR = 2 * NL;
+    // slot table of this (grid operator, coupling) in this matrix, built on first use
+    const std::pair<int, int> key((int)(&go - &c->gos[0]), (int)k);
+    uint8_t* slots = nullptr;
+    auto it = M.slot_tables.find(key);
+    if (it == M.slot_tables.end()) {
+      slots = dalloc<uint8_t>((size_t)fl.n * NR * NR);
+      int* d_err = dalloc<int>(1);
+      MDB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+      const int64_t total = fl.n * NR * NR;
+      if (m.dim == 2) MDB_LAUNCH(c, k_coupling_slots<2>, cdiv(total, 256), 256, 0, m, Ls, Rs, fl.d_cell, fl.d_face, fl.n, M.d_rowptr, M.d_colidx, slots, d_err);
+      else MDB_LAUNCH(c, k_coupling_slots<3>, cdiv(total, 256), 256, 0, m, Ls, Rs, fl.d_cell, fl.d_face, fl.n, M.d_rowptr, M.d_colidx, slots, d_err);
+      int err = 0;
+      MDB_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      dfree(d_err);
+      if (err) { cudaFree(slots); throw Error(MDB_EINVAL, "coupling entries missing from the matrix pattern (was the matrix created with this grid operator?)"); }
+      M.slot_tables[key] = slots;
+    } else slots = it->second;
+    const double* tab = face_tables(c, P);
+    const int fpb = 256 / (2 * NL + 1);
+    if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
+                               M.d_rowptr, slots, M.d_val);
+    else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
+                    M.d_rowptr, slots, M.d_val);
   }
 }
 

@@ -129,6 +129,24 @@ __global__ void __launch_bounds__(128) k_pattern_fill(MeshDesc m, const uint8_t*
   diag[g] = dg;
 }
 
+// "simple" row: full 3^d own-block stencil and nothing else in the row.  flags = 1 for every other (irregular) row;
+// heads = 1 where a run of equal simple/irregular status starts.
+__global__ void k_irregular_flags(const uint32_t* __restrict__ rowinfo, const int64_t* __restrict__ rowptr, int64_t n, uint32_t full, int ns,
+                                  int32_t* flags, int32_t* heads)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto irregular = [&](int64_t r) { return (rowinfo[r] != full || rowptr[r + 1] - rowptr[r] != ns) ? 1 : 0; };   // nlow bits must be 0 too
+  const int f = irregular(i);
+  flags[i] = f;
+  heads[i] = (i == 0 || irregular(i - 1) != f) ? 1 : 0;
+}
+__global__ void k_irregular_compact(const int32_t* __restrict__ flags, const int32_t* __restrict__ scan, int64_t n, int32_t* list)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) list[scan[i]] = (int32_t)i;
+}
+
 void build_pattern(Ctx* c, Matrix& M)
 {
   const MeshDesc& m = c->mesh;
@@ -188,6 +206,44 @@ void build_pattern(Ctx* c, Matrix& M)
   MDB_CUDA(cudaMemsetAsync(M.d_val, 0, nnz * sizeof(double), c->stream));
   for (int i = 0; i < S.nchild; ++i)
     MDB_LAUNCH(c, k_pattern_fill, cdiv(S.ch[i].size, 128), 128, 0, m, c->d_cell_sd, S, i, M.d_rowptr, M.d_colidx, M.d_rowinfo, M.d_diag);
+  // per child: span of its rows in the value array and the compact (ascending) list of irregular rows
+  const uint32_t full = (m.dim == 3) ? 0x7FFFFFFu : (0x1FFu << 9);
+  int* d_cnt = dalloc<int>(1);
+  for (int i = 0; i < S.nchild; ++i) {
+    const int64_t sz = S.ch[i].size, off = S.ch[i].offset;
+    MDB_CUDA(cudaMemcpyAsync(&M.child_begin[i], M.d_rowptr + off, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaMemcpyAsync(&M.child_end[i], M.d_rowptr + off + sz, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    M.n_irregular[i] = 0; M.d_irregular[i] = nullptr;
+    if (sz == 0) continue;
+    int32_t* d_flag = dalloc<int32_t>(sz);
+    int32_t* d_head = dalloc<int32_t>(sz);
+    int32_t* d_scan = dalloc<int32_t>(sz);
+    MDB_LAUNCH(c, k_irregular_flags, cdiv(sz, 256), 256, 0, M.d_rowinfo + off, M.d_rowptr + off, sz, full, (m.dim == 3) ? 27 : 9, d_flag, d_head);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_scan, (int)sz, c->stream);
+    void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+    MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_flag, d_scan, (int)sz, c->stream)); c->launches++;
+    int32_t ls = 0, lf = 0;
+    MDB_CUDA(cudaMemcpyAsync(&ls, d_scan + sz - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaMemcpyAsync(&lf, d_flag + sz - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    M.n_irregular[i] = (int64_t)ls + lf;
+    M.d_irregular[i] = dalloc<int32_t>(M.n_irregular[i]);
+    MDB_LAUNCH(c, k_irregular_compact, cdiv(sz, 256), 256, 0, d_flag, d_scan, sz, M.d_irregular[i]);
+    // runs of consecutive rows with the same status: seg_start[0..nseg], seg_start[nseg] = sz
+    MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_head, d_scan, (int)sz, c->stream)); c->launches++;
+    MDB_CUDA(cudaMemcpyAsync(&ls, d_scan + sz - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaMemcpyAsync(&lf, d_head + sz - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    M.n_seg[i] = (int64_t)ls + lf;
+    M.d_seg_start[i] = dalloc<int32_t>(M.n_seg[i] + 1);
+    MDB_LAUNCH(c, k_irregular_compact, cdiv(sz, 256), 256, 0, d_head, d_scan, sz, M.d_seg_start[i]);
+    const int32_t sz32 = (int32_t)sz;
+    MDB_CUDA(cudaMemcpyAsync(M.d_seg_start[i] + M.n_seg[i], &sz32, 4, cudaMemcpyHostToDevice, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_t); dfree(d_flag); dfree(d_head); dfree(d_scan);
+  }
+  dfree(d_cnt);
   MDB_CUDA(cudaStreamSynchronize(c->stream));
 }
 

@@ -14,8 +14,8 @@
 
 namespace mdb {
 
-#define SPMV_ROWS 128
-#define SPMV_THREADS 128
+#define SPMV_ROWS 64
+#define SPMV_THREADS 256
 #define VEC_THREADS 256
 #define MAX_PARTIAL_BLOCKS 2048
 
@@ -35,7 +35,27 @@ __device__ __forceinline__ double block_sum(double v, double* sh)
   return s;     // valid in thread 0
 }
 
-// y = A x  (+ optional fused dots: partial[0][b] = sum y_i a_i ; partial[1][b] = sum y_i y_i), owned rows only in the dots
+// streaming loads: val/col are touched exactly once per SpMV, keep them out of L1 so that it serves the x gathers
+__device__ __forceinline__ double ld_stream_f64(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p)
+{
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ---- variant A: CSR-stream --------------------------------------------------------------------------------
+// A block owns SPMV_ROWS consecutive rows.  Phase 1: all threads stream the contiguous val/col span of those rows
+// (perfectly coalesced, SPMV_UNROLL independent loads in flight per thread), multiply with the gathered x and park the
+// products in shared memory.  Phase 2: SPMV_LPR lanes per row sum the row's segment and combine by shuffles.
+// y = A x  (+ optional fused dots: partial[0][b] = sum y_i a_i ; partial[1][b] = sum y_i y_i over owned rows)
+#define SPMV_LPR (SPMV_THREADS / SPMV_ROWS)
+#define SPMV_UNROLL 8
 template <int DOTS>
 __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, int nchunks, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                                         const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
@@ -52,14 +72,31 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, int nchunks, c
     const int64_t span0 = rowptr[r0];
     const int span = (int)(rowptr[r1] - span0);
     __syncthreads();
-#pragma unroll 4
-    for (int i = threadIdx.x; i < span; i += SPMV_THREADS) sprod[i] = val[span0 + i] * x[colidx[span0 + i]];
+    for (int base = 0; base < span; base += SPMV_THREADS * SPMV_UNROLL) {
+      int col[SPMV_UNROLL]; double v[SPMV_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SPMV_UNROLL; ++u) {
+        const int i = base + u * SPMV_THREADS + threadIdx.x;
+        col[u] = (i < span) ? ld_stream_s32(colidx + span0 + i) : -1;
+        v[u] = (i < span) ? ld_stream_f64(val + span0 + i) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < SPMV_UNROLL; ++u) {
+        const int i = base + u * SPMV_THREADS + threadIdx.x;
+        if (col[u] >= 0) sprod[i] = v[u] * x[col[u]];
+      }
+    }
     __syncthreads();
-    const int64_t r = r0 + threadIdx.x;
+    const int64_t r = r0 + threadIdx.x / SPMV_LPR;
+    const int sub = threadIdx.x % SPMV_LPR;
+    double sum = 0.0;
     if (r < r1) {
       const int s = (int)(rowptr[r] - span0), e = (int)(rowptr[r + 1] - span0);
-      double sum = 0.0;
-      for (int i = s; i < e; ++i) sum += sprod[i];
+      for (int i = s + sub; i < e; i += SPMV_LPR) sum += sprod[i];
+    }
+#pragma unroll
+    for (int o = SPMV_LPR / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, SPMV_LPR);
+    if (r < r1 && sub == 0) {
       y[r] = sum;
       if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
     }
@@ -74,29 +111,60 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int64_t n, int nchunks, c
   }
 }
 
-// fallback for very long rows: one warp per row
-__global__ void k_spmv_warp(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
-                            const double* __restrict__ x, double* __restrict__ y)
+// ---- variant B: vector CSR, LPR lanes per row, no shared memory (all of L1 serves the x gathers) -----------
+template <int DOTS, int LPR>
+__global__ void __launch_bounds__(256) k_spmv_vec(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                  const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                                  const double* __restrict__ a, const uint8_t* __restrict__ owned, double* partial,
+                                                  const double* __restrict__ done)
 {
-  int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= n) return;
-  double s = 0.0;
-  for (int64_t p = rowptr[r] + lane; p < rowptr[r + 1]; p += 32) s += val[p] * x[colidx[p]];
+  __shared__ double sh[8];
+  if (done && done[S_DONE] != 0.0) return;
+  double d0 = 0.0, d1 = 0.0;
+  const int sub = threadIdx.x % LPR;
+  const int64_t rows_per_grid = (int64_t)gridDim.x * (256 / LPR);
+  for (int64_t rb = blockIdx.x * (int64_t)(256 / LPR); rb < n; rb += rows_per_grid) {     // block-uniform trip count
+    const int64_t r = rb + threadIdx.x / LPR;
+    double sum = 0.0;
+    if (r < n) {
+      const int64_t s = rowptr[r], e = rowptr[r + 1];
+      for (int64_t p = s + sub; p < e; p += 4 * LPR) {
+        int c0 = ld_stream_s32(colidx + p);
+        int c1 = (p + LPR < e) ? ld_stream_s32(colidx + p + LPR) : -1;
+        int c2 = (p + 2 * LPR < e) ? ld_stream_s32(colidx + p + 2 * LPR) : -1;
+        int c3 = (p + 3 * LPR < e) ? ld_stream_s32(colidx + p + 3 * LPR) : -1;
+        double v0 = ld_stream_f64(val + p);
+        double v1 = (c1 >= 0) ? ld_stream_f64(val + p + LPR) : 0.0;
+        double v2 = (c2 >= 0) ? ld_stream_f64(val + p + 2 * LPR) : 0.0;
+        double v3 = (c3 >= 0) ? ld_stream_f64(val + p + 3 * LPR) : 0.0;
+        sum += v0 * x[c0];
+        if (c1 >= 0) sum += v1 * x[c1];
+        if (c2 >= 0) sum += v2 * x[c2];
+        if (c3 >= 0) sum += v3 * x[c3];
+      }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) y[r] = s;
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, LPR);
+    if (r < n && sub == 0) {
+      y[r] = sum;
+      if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
+    }
+  }
+  if (DOTS >= 1) {
+    double s0 = block_sum(d0, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+    if (DOTS >= 2) {
+      double s1 = block_sum(d1, sh);
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+    }
+  }
 }
 
-static int spmv_grid(const Ctx* c, int nchunks, size_t smem)
+static int spmv_variant()
 {
-  (void)c;
-  int per_sm = (int)(220 * 1024 / (smem + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  int g = 148 * per_sm;
-  if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
-  return g < nchunks ? g : nchunks;
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MDB_SPMV_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
 }
 
 template <int DOTS>
@@ -104,16 +172,33 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
 {
   const int64_t n = c->ndof;
   const size_t smem = (size_t)SPMV_ROWS * M.max_row * sizeof(double);
-  MDB_REQUIRE(smem <= 200 * 1024, MDB_EINVAL, "rows too long for the streaming SpMV");
-  static size_t configured[3] = {0, 0, 0};
-  if (smem > 48 * 1024 && smem > configured[DOTS]) {
-    MDB_CUDA(cudaFuncSetAttribute(k_spmv<DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[DOTS] = smem;
+  int variant = spmv_variant();
+  if (smem > 100 * 1024 && variant == 0) variant = 1;      // very long rows: no staging
+  if (variant == 0) {
+    static size_t configured[3] = {0, 0, 0};
+    if (smem > 48 * 1024 && smem > configured[DOTS]) {
+      MDB_CUDA(cudaFuncSetAttribute(k_spmv<DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[DOTS] = smem;
+    }
+    const int nchunks = cdiv(n, SPMV_ROWS);
+    int per_sm = (int)(200 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2048 / SPMV_THREADS) per_sm = 2048 / SPMV_THREADS;
+    int grid = 148 * per_sm;
+    if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
+    if (grid > nchunks) grid = nchunks;
+    if (nblocks) *nblocks = grid;
+    MDB_LAUNCH(c, k_spmv<DOTS>, grid, SPMV_THREADS, smem, n, nchunks, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
+    return;
   }
-  const int nchunks = cdiv(n, SPMV_ROWS);
-  const int grid = spmv_grid(c, nchunks, smem);
+  const int lpr = (variant == 2) ? 4 : (variant == 3) ? 16 : 8;
+  int grid = 148 * 8;
+  const int64_t need = cdiv(n, 256 / lpr);
+  if (grid > need) grid = (int)need;
   if (nblocks) *nblocks = grid;
-  MDB_LAUNCH(c, k_spmv<DOTS>, grid, SPMV_THREADS, smem, n, nchunks, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
+  if (lpr == 4) MDB_LAUNCH(c, (k_spmv_vec<DOTS, 4>), grid, 256, 0, n, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
+  else if (lpr == 16) MDB_LAUNCH(c, (k_spmv_vec<DOTS, 16>), grid, 256, 0, n, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
+  else MDB_LAUNCH(c, (k_spmv_vec<DOTS, 8>), grid, 256, 0, n, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
 }
 
 void spmv(Ctx* c, const Matrix& M, const double* d_x, double* d_y)
@@ -390,7 +475,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
   poll();
   float ms = 0.f;
   MDB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->phase_ms["solve"] = ms;
+  c->phases["solve"].last_ms = ms;
   const bool converged = hp[S_DONE] != 0.0;
   if (stats) {
     stats->iterations = (int)hp[S_ITER];

@@ -245,11 +245,18 @@ int mdb_owned_rows(mdb_ctx* ctx, int64_t* owned, int64_t* local_total);
 /* Export: one byte per local DOF, 1 = owned by this rank; and the global container index of every local DOF. */
 int mdb_get_ownership(mdb_ctx* ctx, uint8_t* owned_flags, int64_t* global_index);
 
+/* Sum of squares of the stored entries of the matrix (device reduction; a cheap checksum of an assembly
+ * result that a host caller can read back).  `out` is a host pointer. */
+int mdb_matrix_norm2(mdb_ctx* ctx, int mat, double* out);
+
 /* ---- instrumentation ------------------------------------------------------ */
-/* Device time in ms of the last call of the named phase ("jacobian_volume", "jacobian_coupling",
- * "residual_volume", "residual_coupling", "residual_boundary", "pattern", "dofmap", "spmv", ...), measured
- * with CUDA events on the context's stream; negative if never run. */
+/* Mean device time in ms of the named phase ("jacobian_volume", "jacobian_coupling", "residual_volume",
+ * "residual_coupling", "residual_boundary", "pattern", "dofmap", "spmv", "solve", ...) over all its executions
+ * since the last mdb_profile_reset, measured with CUDA events recorded on the context's stream (no host
+ * synchronisation while recording; this call synchronises).  Negative if never run. */
 double mdb_phase_ms(mdb_ctx* ctx, const char* phase);
+int mdb_phase_count(mdb_ctx* ctx, const char* phase);
+int mdb_profile_reset(mdb_ctx* ctx);
 /* Number of kernel launches issued by this context since creation / since the last reset. */
 int64_t mdb_launch_count(mdb_ctx* ctx, int reset);
 /* Raw CUDA stream of the context (cudaStream_t as void*). */

@@ -73,7 +73,7 @@ struct PoissonOp : LocalOperator {
   void alpha_volume(const EG& eg, const LFS& lfsu, const double* x, const LFS& lfsv, LocalVectorView& r) const override {
     const int dim = eg.g->dim;
     QkBasis B(lfsu.k, dim);
-    auto rule = tensor_rule(dim, P.quad_order);
+    const auto& rule = tensor_rule(dim, P.quad_order);
     double js[MAXLOC][3], gradphi[MAXLOC][3];
     for (const auto& q : rule) {
       B.evaluateJacobian(q.x, js);
@@ -93,7 +93,7 @@ struct PoissonOp : LocalOperator {
   void jacobian_volume(const EG& eg, const LFS& lfsu, const double*, const LFS& lfsv, LocalMatrixView& mat) const override {
     const int dim = eg.g->dim;
     QkBasis B(lfsu.k, dim);
-    auto rule = tensor_rule(dim, P.quad_order);
+    const auto& rule = tensor_rule(dim, P.quad_order);
     double js[MAXLOC][3], gradphi[MAXLOC][3];
     for (const auto& q : rule) {
       B.evaluateJacobian(q.x, js);
@@ -112,7 +112,7 @@ struct PoissonOp : LocalOperator {
     if (P.f.kind == MDB_FN_ZERO) return;   // adds exact zeros otherwise
     const int dim = eg.g->dim;
     QkBasis B(lfsv.k, dim);
-    auto rule = tensor_rule(dim, P.quad_order);
+    const auto& rule = tensor_rule(dim, P.quad_order);
     double phi[MAXLOC], xg[3];
     for (const auto& q : rule) {
       B.evaluateFunction(q.x, phi);
@@ -125,7 +125,7 @@ struct PoissonOp : LocalOperator {
   void lambda_boundary(const IG& ig, const LFS& lfsv, LocalVectorView& r) const override {
     const int dim = ig.dim();
     QkBasis B(lfsv.k, dim);
-    auto rule = tensor_rule(dim - 1, P.quad_order);
+    const auto& rule = tensor_rule(dim - 1, P.quad_order);
     double phi[MAXLOC], local[3], xg[3];
     for (const auto& q : rule) {
       ig.global(q.x, xg);
@@ -147,7 +147,7 @@ struct L2Op : LocalOperator {
   void alpha_volume(const EG& eg, const LFS& lfsu, const double* x, const LFS& lfsv, LocalVectorView& r) const override {
     const int dim = eg.g->dim;
     QkBasis B(lfsu.k, dim);
-    auto rule = tensor_rule(dim, P.quad_order);
+    const auto& rule = tensor_rule(dim, P.quad_order);
     double phi[MAXLOC];
     for (const auto& q : rule) {
       B.evaluateFunction(q.x, phi);
@@ -160,7 +160,7 @@ struct L2Op : LocalOperator {
   void jacobian_volume(const EG& eg, const LFS& lfsu, const double*, const LFS& lfsv, LocalMatrixView& mat) const override {
     const int dim = eg.g->dim;
     QkBasis B(lfsu.k, dim);
-    auto rule = tensor_rule(dim, P.quad_order);
+    const auto& rule = tensor_rule(dim, P.quad_order);
     double phi[MAXLOC];
     for (const auto& q : rule) {
       B.evaluateFunction(q.x, phi);
@@ -182,7 +182,7 @@ struct PropFlowOp : CouplingOperator {
     const int dim = ig.dim();
     const int intorder = 4;                                            // :43
     QkBasis B1(lfsv_s.k, dim), B2(lfsv_n.k, dim);
-    auto rule = tensor_rule(dim - 1, intorder);
+    const auto& rule = tensor_rule(dim - 1, intorder);
     double phi1[MAXLOC], phi2[MAXLOC], local1[3], local2[3];
     for (const auto& q : rule) {
       ig.localInside(q.x, local1); ig.localOutside(q.x, local2);
@@ -208,7 +208,7 @@ struct CVCFOp : CouplingOperator {
     const int dim = ig.dim();
     const double h_F = ig.cornerDistance01();                           // :135
     QkBasis B1(lfsv1.k, dim), B2(lfsv2.k, dim);
-    auto rule = tensor_rule(dim - 1, P.quad_order);
+    const auto& rule = tensor_rule(dim - 1, P.quad_order);
     double phi1[MAXLOC], phi2[MAXLOC], js1[MAXLOC][3], js2[MAXLOC][3], gradphi1[MAXLOC][3], gradphi2[MAXLOC][3];
     double local1[3], local2[3];
     for (const auto& q : rule) {

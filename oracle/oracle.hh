@@ -92,7 +92,7 @@ inline Rule1D gauss1d(int order)
 
 struct QuadPoint { double x[3]; double w; };
 
-inline std::vector<QuadPoint> tensor_rule(int dim, int order)
+inline std::vector<QuadPoint> make_tensor_rule(int dim, int order)
 {
   Rule1D r = gauss1d(order);
   std::vector<QuadPoint> q;
@@ -109,6 +109,16 @@ inline std::vector<QuadPoint> tensor_rule(int dim, int order)
     q.push_back(p);
   }
   return q;
+}
+
+// [UPSTREAM] Dune::QuadratureRules<DF,dim>::rule(gt, order) hands out cached rules
+inline const std::vector<QuadPoint>& tensor_rule(int dim, int order)
+{
+  static thread_local std::vector<QuadPoint> cache[4][12];
+  if (order < 0 || order > 11 || dim < 0 || dim > 3) throw std::runtime_error("quadrature order/dim out of range");
+  std::vector<QuadPoint>& r = cache[dim][order];
+  if (r.empty()) r = make_tensor_rule(dim, order);
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
