@@ -203,6 +203,8 @@ def main():
     P = setup_problem(dev, n, rank, world)
     dev.synchronize()
     t_setup = time.time() - t0
+    if world > 1:
+        pkg.parallel.connect(dev, dist, rank, world)      # NCCL communicator for the Krylov scalars + peer halo windows
     nnz = dev.nnz[P.mat]
     ncells_local = dev.ncells
     owned = P.ndof if world == 1 else dev.owned_rows()[0]

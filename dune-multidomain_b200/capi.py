@@ -144,6 +144,7 @@ class Lib:
         self._check(self._fn("mesh_structured")(C.c_void_p(self.ctx), dim, _ptr(nn, C.c_int64), _ptr(lo, C.c_double),
                                                 _ptr(up, C.c_double)), "mesh_structured")
         self.dim, self.n, self.ncells = dim, tuple(int(v) for v in n), int(np.prod(nn))
+        self.nchildren = 0
 
     def mesh_partition(self, global_n, cell_offset, global_lower, global_upper):
         gn, off = _i64(global_n), _i64(cell_offset)
@@ -322,24 +323,37 @@ class Mdb(Lib):
         self._check(self._fn("comm_init")(C.c_void_p(self.ctx), nranks, rank, C.c_char_p(uid)), "comm_init")
 
     def halo_export(self):
-        buf = (C.c_char * 64)()
+        buf = (C.c_char * 80)()
         nbytes = C.c_int64(0)
         self._check(self._fn("halo_export")(C.c_void_p(self.ctx), buf, C.byref(nbytes)), "halo_export")
         return bytes(buf), nbytes.value
 
-    def halo_import(self, lower_rank, lower_handle, upper_rank, upper_handle):
-        self._check(self._fn("halo_import")(C.c_void_p(self.ctx), lower_rank, C.c_char_p(lower_handle) if lower_handle else None,
-                                            upper_rank, C.c_char_p(upper_handle) if upper_handle else None), "halo_import")
+    def halo_import(self, lower_rank, lower_blob, upper_rank, upper_blob):
+        self._check(self._fn("halo_import")(C.c_void_p(self.ctx), lower_rank, C.c_char_p(lower_blob) if lower_blob else None,
+                                            upper_rank, C.c_char_p(upper_blob) if upper_blob else None), "halo_import")
+
+    def halo_push(self, x):
+        self._check(self._fn("halo_push")(C.c_void_p(self.ctx), _vecptr(x)), "halo_push")
+
+    def halo_wait(self, x):
+        self._check(self._fn("halo_wait")(C.c_void_p(self.ctx), _vecptr(x)), "halo_wait")
 
     def owned_rows(self):
         a, b = C.c_int64(0), C.c_int64(0)
         self._check(self._fn("owned_rows")(C.c_void_p(self.ctx), C.byref(a), C.byref(b)), "owned_rows")
         return a.value, b.value
 
-    def get_ownership(self):
+    def owned_counts(self):
+        out = np.zeros(self.nchildren, dtype=np.int64)
+        self._check(self._fn("owned_counts")(C.c_void_p(self.ctx), _ptr(out, C.c_int64)), "owned_counts")
+        return out
+
+    def get_ownership(self, child_global_base=None):
         flags = np.zeros(self.ndof, dtype=np.uint8)
         gidx = np.zeros(self.ndof, dtype=np.int64)
-        self._check(self._fn("get_ownership")(C.c_void_p(self.ctx), _ptr(flags, C.c_uint8), _ptr(gidx, C.c_int64)), "get_ownership")
+        base = None if child_global_base is None else _i64(child_global_base)
+        self._check(self._fn("get_ownership")(C.c_void_p(self.ctx), _ptr(base, C.c_int64) if base is not None else None,
+                                              _ptr(flags, C.c_uint8), _ptr(gidx, C.c_int64)), "get_ownership")
         return flags, gidx
 
 

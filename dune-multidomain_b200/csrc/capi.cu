@@ -134,7 +134,10 @@ static void reset_spaces(Ctx* c)
   dfree(c->d_constrained); dfree(c->d_conlist);
   for (int i = 0; i < 4; ++i) dfree(c->d_stage[i]);
   dfree(c->d_work); c->work_n = 0; c->work_vecs = 0;
-  dfree(c->d_owned);
+  dfree(c->d_owned); c->owned_rows = 0; c->child_owned.clear(); c->part_axis = -1;
+  for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  c->ipc_opened.clear(); c->peer_lower = nullptr; c->peer_upper = nullptr;
+  if (c->d_halo_recv) { cudaFree(c->d_halo_recv); c->d_halo_recv = nullptr; }
   c->finalized = false; c->ndof = 0; c->ncon = 0;
 }
 
@@ -202,7 +205,7 @@ void mdb_destroy(mdb_ctx* c)
   dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_scal); dfree(c->d_partial);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  if (c->d_halo_recv) cudaFree(c->d_halo_recv);
+  if (c->d_halo_counter) cudaFree(c->d_halo_counter);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -343,6 +346,7 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   c->phase_begin("dofmap");
   build_dofmap(c);
   c->phase_end();
+  if (c->mesh.partitioned) setup_partition(c);
   c->finalized = true;
   if (ndof) *ndof = c->ndof;
   MDB_API_END(c)
@@ -546,6 +550,10 @@ int mdb_spmv(mdb_ctx* c, int mat, const double* x, double* y)
   MDB_MAT(c, mat)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vy(c, y, c->ndof, 1, false);
+  if (c->peer_lower || c->peer_upper) {
+    MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_spmv: x must be a device vector on a partitioned context");
+    halo_exchange(c, const_cast<double*>(vx.d));
+  }
   c->phase_begin("spmv");
   spmv(c, M, vx.d, vy.d);
   c->phase_end();

@@ -233,12 +233,18 @@ struct Ctx {
   double* d_partial = nullptr;       // block partial sums
   double* h_pinned = nullptr;        // pinned host scalars
 
-  // multi-GPU
+  // multi-GPU (multigpu.cu)
   void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+  int part_axis = -1;                // cut axis of the slab partition (-1: not partitioned)
   uint8_t* d_owned = nullptr;        // 1 = row owned by this rank (null: all owned)
   int64_t owned_rows = 0;
-  double* d_halo_recv = nullptr; int64_t halo_recv_n = 0;
+  std::vector<int64_t> child_owned;  // owned rows per child block
+  double* d_halo_recv = nullptr; int64_t halo_recv_n = 0;       // receive window [parity][side][halo_cap] + sequence numbers
+  int64_t halo_cap = 0;              // doubles per (parity, side) slot
+  unsigned long long halo_seq = 0;   // exchanges issued so far (same on every rank: SPMD)
+  unsigned int* d_halo_counter = nullptr;                       // [0] block counter of the push kernel, [2] timeout flag
   double* peer_lower = nullptr; double* peer_upper = nullptr;   // mapped windows of the neighbours
+  std::vector<void*> ipc_opened;
   int lower_rank = -1, upper_rank = -1;
 
   void* scratch(size_t bytes);
@@ -285,6 +291,10 @@ void dirichlet_rows(Ctx* c, Matrix& m);
 void spmv(Ctx* c, const Matrix& m, const double* d_x, double* d_y);
 int solve(Ctx* c, Matrix& m, int method, int precond, double reduction, int maxit, int fixed_iters,
           const double* d_rhs, double* d_z, mdb_solve_stats* stats);
+void setup_partition(Ctx* c);                       // multigpu.cu: ownership flags + halo window of a partitioned mesh
+void allreduce_scalars(Ctx* c, double* d_vals, int n);
+void halo_exchange(Ctx* c, double* d_x);
+bool halo_timed_out(Ctx* c);
 
 template <typename T> inline T* dalloc(size_t n)
 {

@@ -457,6 +457,160 @@ __global__ void __launch_bounds__(256) k_coupling_jacobian(MeshDesc m, CouplingP
   }
 }
 
+// jacobian_coupling, staged variant (the default).  The FP64 pipe bounds this kernel (17 residual evaluations per face,
+// no FMA contraction), so the arithmetic that does not depend on the perturbation is hoisted out of the 17 evaluations
+// WITHOUT changing a single rounding: per (face, quadrature point, side, i) the block first parks in shared memory
+//   phi_i, c_i = (theta*0.5)*gpn_i, px_i = x_i*phi_i, pg_i[d] = x_i*gradphi_i[d]
+// (the base-line products; a perturbation of dof j changes only the j-th product, the additions are redone in the
+// reference's order), then thread (face, evaluation) runs the perturbation-dependent part of alpha_coupling.
+// Mapping: 256 threads = FPB faces x NE evaluations; evaluation 0 is the base line, 1+j perturbs dof j.
+template <int DIM>
+__global__ void __launch_bounds__(256, 3) k_coupling_jacobian_staged(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
+                                                                  const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
+                                                                  const double* __restrict__ tab, const double* __restrict__ x,
+                                                                  const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slots, double* val)
+{
+  constexpr int NL = 1 << DIM;
+  constexpr int NR = 2 * NL;
+  constexpr int NE = NR + 1;
+  constexpr int FPB = 256 / NE;
+  struct FaceS { double x[NR]; double jit[2][DIM]; double nrm[2][DIM]; double ie, aoh; int32_t dof[NR]; int axis, side; };
+  __shared__ FaceS sf[FPB];
+  __shared__ double sbuf[2][FPB][NR][6];     // {phi, c, px, pg0, pg1, pg2}
+  __shared__ double sdown[FPB][NR];
+  const int t = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * FPB;
+  const bool analytic = P.jac_mode == MDB_JAC_ANALYTIC;
+  const bool cvcf = P.op == MDB_OP_CVCF_COUPLING;
+  // ---- prologue: one thread per face sets up the geometry and gathers the coefficients
+  if (t < FPB && f0 + t < nfaces) {
+    FaceGeo<DIM> G; G.init(m, fcell[f0 + t], fface[f0 + t]);
+    FaceS& F = sf[t];
+    int32_t ds[NL], dn[NL];
+    cell_dofs_q1<DIM>(Ls, G.ijk, ds); cell_dofs_q1<DIM>(Rs, G.nijk, dn);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      F.dof[i] = ds[i]; F.dof[NL + i] = dn[i];
+      F.x[i] = analytic ? 0.0 : x[ds[i]]; F.x[NL + i] = analytic ? 0.0 : x[dn[i]];
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      F.jit[0][d] = 1.0 / (G.up_i[d] - G.lo_i[d]); F.jit[1][d] = 1.0 / (G.up_o[d] - G.lo_o[d]);
+      F.nrm[0][d] = (d == G.axis) ? (G.side ? 1.0 : -1.0) : 0.0; F.nrm[1][d] = F.nrm[0][d] * -1;
+    }
+    F.ie = G.integrationElement();
+    F.aoh = cvcf ? P.intensity / G.cornerDistance01() : 0.0;
+    F.axis = G.axis; F.side = G.side;
+  }
+  __syncthreads();
+  const int fl = t / NE, e = t % NE;
+  const bool active = fl < FPB && f0 + fl < nfaces;
+  const int j = e - 1;                              // perturbed dof in the face's 2 NL numbering, -1 = base line
+  double xp = 0.0, delta = 1.0;                     // perturbed coefficient of dof j
+  if (active && j >= 0) {
+    if (analytic) xp = 1.0;
+    else { const double u = sf[fl].x[j]; delta = epsilon * (1.0 + fabs(u)); xp = u + delta; }
+  }
+  const int jj = j < 0 ? -1 : (j < NL ? j : j - NL);
+  const int jside = j < 0 ? -1 : (j < NL ? 0 : 1);
+  double r[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) r[i] = 0.0;
+  const int nq = ipow(P.rule.m, DIM - 1);
+  // phase-1 item of this thread: (face pf, side ps, shape function pi)
+  const int pf = t / NR, pr = t % NR, ps = pr / NL, pi = pr % NL;
+  const bool pact = pf < FPB && f0 + pf < nfaces;
+  for (int q = 0; q < nq; ++q) {
+    double (*buf)[NR][6] = sbuf[q & 1];
+    if (pact) {
+      const FaceS& F = sf[pf];
+      const int sideval = ps == 0 ? F.side : 1 - F.side;     // geometryInInside: local[axis] = side; InOutside: 1 - side
+      const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + pi) * 4;
+      const double phi = __ldg(tq);
+      double gpn = 0.0, g[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[ps][d] * __ldg(tq + 1 + d);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gpn += g[d] * F.nrm[ps][d];
+      const double theta = 1;
+      const double xi = F.x[pr];
+      double* o = buf[pf][pr];
+      o[0] = phi; o[1] = theta * 0.5 * gpn; o[2] = xi * phi;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) o[3 + d] = xi * g[d];
+    }
+    __syncthreads();
+    if (active && !(analytic && e == 0)) {
+      const FaceS& F = sf[fl];
+      const double (*b)[6] = buf[fl];
+      double pos[3], w; quad_point<DIM - 1>(P.rule, q, pos, w);
+      const double factor = w * F.ie;
+      // the perturbed products of this thread's dof
+      double mypx = 0.0, mypg[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) mypg[d] = 0.0;
+      if (j >= 0) {
+        const int sideval = jside == 0 ? F.side : 1 - F.side;
+        const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + jj) * 4;
+        mypx = xp * __ldg(tq);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) mypg[d] = xp * (0.0 + F.jit[jside][d] * __ldg(tq + 1 + d));
+      }
+      double u[2] = {0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < NR; ++i) u[i / NL] += (i == j) ? mypx : b[i][2];
+      if (!cvcf) {
+        const double u_diff = P.intensity * (u[0] - u[1]);
+#pragma unroll
+        for (int i = 0; i < NL; ++i) r[i] += u_diff * b[i][0] * factor;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) r[NL + i] += -u_diff * b[NL + i][0] * factor;
+      } else {
+        double gradu[2][DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { gradu[0][d] = 0.0; gradu[1][d] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gradu[i / NL][d] += (i == j) ? mypg[d] : b[i][3 + d];
+        const double jump[2] = {u[0] - u[1], u[1] - u[0]};
+        double mean_gradu[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { mean_gradu[d] = gradu[0][d] + gradu[1][d]; mean_gradu[d] *= 0.5; }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          double mgn = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) mgn += mean_gradu[d] * F.nrm[s][d];
+          const double aj = F.aoh * jump[s];
+#pragma unroll
+          for (int i = 0; i < NL; ++i) {
+            const double phi = b[s * NL + i][0];
+            double value = 0.0;
+            value -= mgn * phi;
+            value -= b[s * NL + i][1] * jump[s];
+            value += aj * phi;
+            r[s * NL + i] += factor * value;
+          }
+        }
+      }
+    }
+  }
+  if (active && e == 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) sdown[fl][i] = r[i];
+  }
+  __syncthreads();
+  if (!active || e == 0) return;
+  const uint8_t* sl = slots + (f0 + fl) * (NR * NR) + j;          // column j of the face's (2NL x 2NL) slot table
+  const FaceS& F = sf[fl];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const double c = analytic ? r[i] : (r[i] - sdown[fl][i]) / delta;
+    atomicAdd(&val[rowptr[F.dof[i]] + sl[i * NR]], weight * c);     // mat_ss / mat_ns (j self), mat_sn / mat_nn (j neighbour)
+  }
+}
+
 static SideMap side_map(const Ctx* c, int sp)
 {
   const Child& ch = c->children[c->sps[sp].children[0]];
@@ -528,10 +682,18 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     } else slots = it->second;
     const double* tab = face_tables(c, P);
     const int fpb = 256 / (2 * NL + 1);
-    if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
-                               M.d_rowptr, slots, M.d_val);
-    else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
-                    M.d_rowptr, slots, M.d_val);
+    static const bool legacy = getenv("MDB_COUPLING_JAC_LEGACY") != nullptr;      // A/B switch for profiling only
+    if (legacy) {
+      if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
+                                 M.d_rowptr, slots, M.d_val);
+      else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
+                      M.d_rowptr, slots, M.d_val);
+    } else {
+      if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian_staged<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+                                 d_x, M.d_rowptr, slots, M.d_val);
+      else MDB_LAUNCH(c, k_coupling_jacobian_staged<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+                      d_x, M.d_rowptr, slots, M.d_val);
+    }
   }
 }
 

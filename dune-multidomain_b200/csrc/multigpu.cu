@@ -1,18 +1,419 @@
-// multigpu.cu — multi-GPU plumbing: NCCL allreduce of Krylov scalars, halo exchange of x.
+// multigpu.cu — multi-GPU plumbing of the hot path: slab partition with one ghost cell layer,
+// halo exchange of Krylov vectors by direct peer stores over NVLink, NCCL all-reduce of the Krylov scalars.
+//
+// The reference's only parallel mode is overlapping domain decomposition on an MPI grid with overlap 1
+// (test/testoverlappinginstationarypoisson.cc:232-233; gridoperator.hh:65-71 "nonoverlapping_mode = false"): every rank
+// assembles all cells that touch its rows, so assembly needs no communication and only vectors are exchanged
+// (gridoperator.hh:150-152).  The same idea here, one process per GPU:
+//   * rank r owns the cell layers [c0, c1) along the slowest axis and the vertex planes [c0, c1) (the last rank also
+//     owns the top plane); its local mesh is the owned layers plus ONE ghost layer below (c0 - 1), so all cells around
+//     an owned vertex are local and owned rows are assembled completely without communication;
+//   * the local vector carries two ghost planes (below: owned by r-1, above: owned by r+1).  Before every SpMV the
+//     owners push their boundary planes straight into the neighbours' receive windows (st.global on cudaIpc-mapped peer
+//     memory, i.e. NVLink P2P stores), followed by a release-store of a sequence number; the receiver's unpack kernel
+//     acquires the sequence number and copies the window into its ghost entries.  No host synchronisation, no staging;
+//   * dot products are reduced over owned rows only (Ctx::d_owned) and summed with ncclAllReduce on the context stream.
+// NCCL is resolved at run time (dlopen of the libnccl.so.2 the process already carries, e.g. torch's) so that the
+// single-GPU product has no link-time dependency on it.
 #include "common.cuh"
+#include <dlfcn.h>
+#include <unistd.h>
 
 namespace mdb {
-void allreduce_scalars(Ctx* c, double* d_vals, int n) { (void)c; (void)d_vals; (void)n; throw Error(MDB_ENCCL, "multi-GPU path not initialised"); }
-void halo_exchange(Ctx* c, double* d_x) { (void)c; (void)d_x; throw Error(MDB_ENCCL, "multi-GPU path not initialised"); }
+
+// ---- NCCL through dlopen ---------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };      // ncclDouble / ncclSum of nccl.h (stable ABI values)
+
+static NcclApi& nccl()
+{
+  if (g_nccl.lib) return g_nccl;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD); if (h) break; }     // the copy torch loaded
+  for (const char* n : names) { if (h) break; h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); }
+  MDB_REQUIRE(h, MDB_ENCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : ""));
+  g_nccl.GetUniqueId = (int (*)(nccl_uid_t*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  MDB_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce, MDB_ENCCL, "libnccl lacks expected symbols");
+  g_nccl.lib = h;
+  return g_nccl;
 }
+#define MDB_NCCL(call)                                                                                                   \
+  do { int r__ = (call); if (r__ != 0) throw Error(MDB_ENCCL, std::string(#call) + ": " +                                \
+                                                   (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error")); } while (0)
+
+void allreduce_scalars(Ctx* c, double* d_vals, int n)
+{
+  MDB_REQUIRE(c->nccl_comm, MDB_ENCCL, "multi-GPU solve without a communicator: call mdb_comm_init first");
+  MDB_NCCL(nccl().AllReduce(d_vals, d_vals, (size_t)n, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)c->nccl_comm, c->stream));
+  c->launches++;
+}
+
+// ---- partition geometry --------------------------------------------------------------------------------------------
+// lattice planes (along the partition axis) of child `ch` that this rank owns: [lo, hi)
+static void owned_planes(const Ctx* c, const Child& ch, int* lo, int* hi)
+{
+  const MeshDesc& m = c->mesh;
+  const int pa = c->part_axis;
+  const bool first = m.off[pa] == 0, last = m.off[pa] + m.n[pa] == m.gn[pa];
+  *lo = first ? 0 : ch.k;                                   // planes 0..k-1 belong to the ghost layer's owner
+  *hi = last ? ch.k * m.n[pa] + 1 : ch.k * m.n[pa];         // the top plane belongs to the upper neighbour
+}
+
+__global__ void k_owned_flags(int64_t size, int64_t offset, const int32_t* __restrict__ dof2lat, int64_t plane_pts, int lo, int hi, uint8_t* owned)
+{
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= size) return;
+  const int pl = (int)(dof2lat[g] / plane_pts);
+  owned[offset + g] = (pl >= lo && pl < hi) ? 1 : 0;
+}
+
+__global__ void k_count_u8(const uint8_t* __restrict__ f, int64_t n, unsigned long long* out)
+{
+  unsigned long long a = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += f[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0 && a) atomicAdd(out, a);
+}
+
+static int64_t plane_points(const Ctx* c, const Child& ch)
+{
+  int64_t p = 1;
+  for (int d = 0; d < c->part_axis; ++d) p *= ch.lat_n[d];
+  return p;
+}
+
+// called from mdb_finalize when the mesh is partitioned
+void setup_partition(Ctx* c)
+{
+  const MeshDesc& m = c->mesh;
+  int pa = -1;
+  for (int d = 0; d < m.dim; ++d)
+    if (m.n[d] != m.gn[d]) { MDB_REQUIRE(pa < 0, MDB_EINVAL, "partition: only slabs (one cut axis) are supported"); pa = d; }
+  if (pa < 0) pa = m.dim - 1;                               // a one-rank "partition"
+  MDB_REQUIRE(pa == m.dim - 1, MDB_EINVAL, "partition: the cut axis must be the slowest axis (dim-1)");
+  c->part_axis = pa;
+  dfree(c->d_owned);
+  c->d_owned = dalloc<uint8_t>(c->ndof);
+  c->child_owned.assign(c->children.size(), 0);
+  unsigned long long* d_cnt = dalloc<unsigned long long>(1);
+  c->owned_rows = 0;
+  c->halo_cap = 0;
+  for (size_t i = 0; i < c->children.size(); ++i) {
+    const Child& ch = c->children[i];
+    c->halo_cap += plane_points(c, ch) * ch.k;
+    if (ch.size == 0) continue;
+    int lo, hi; owned_planes(c, ch, &lo, &hi);
+    MDB_LAUNCH(c, k_owned_flags, cdiv(ch.size, 256), 256, 0, ch.size, ch.offset, ch.d_dof2lat, plane_points(c, ch), lo, hi, c->d_owned);
+    MDB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
+    MDB_LAUNCH(c, k_count_u8, 148 * 4, 256, 0, c->d_owned + ch.offset, ch.size, d_cnt);
+    unsigned long long h = 0;
+    MDB_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    c->child_owned[i] = (int64_t)h;
+    c->owned_rows += (int64_t)h;
+  }
+  dfree(d_cnt);
+  // receive window: [parity 2][side 2][halo_cap] doubles, then 2 sequence numbers (one per side), 64-byte aligned
+  if (c->d_halo_recv) { cudaFree(c->d_halo_recv); c->d_halo_recv = nullptr; }
+  c->halo_recv_n = 4 * c->halo_cap + 8;
+  c->d_halo_recv = dalloc<double>(c->halo_recv_n);
+  MDB_CUDA(cudaMemsetAsync(c->d_halo_recv, 0, c->halo_recv_n * sizeof(double), c->stream));
+  if (!c->d_halo_counter) c->d_halo_counter = dalloc<unsigned int>(4);
+  MDB_CUDA(cudaMemsetAsync(c->d_halo_counter, 0, 4 * sizeof(unsigned int), c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  c->halo_seq = 0;
+}
+
+// ---- halo exchange ----------------------------------------------------------------------------------------------------
+struct HaloChild { int64_t offset, plane_pts, slot_base; const int32_t* lat2dof; int k; int send_lo_plane, send_hi_plane0, ghost_hi_plane; };
+struct HaloSpec {
+  int nchild; HaloChild ch[MDB_MAX_CHILDREN];
+  int64_t cap;
+  double* peer[2];          // windows of the lower / upper neighbour (null: no such neighbour)
+  double* mine;             // own window
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Push: direction 0 sends my first owned plane to the lower neighbour (it lands in that rank's side-1 = "from above" slot);
+// direction 1 sends my last k owned planes to the upper neighbour (side-0 = "from below" slot).  The last block to finish
+// publishes the sequence number in both neighbours' windows.
+__global__ void __launch_bounds__(256) k_halo_push(HaloSpec H, const double* __restrict__ x, unsigned int* counter)
+{
+  const int parity = (int)(H.seq & 1);
+  for (int dir = 0; dir < 2; ++dir) {
+    double* win = H.peer[dir];
+    if (!win) continue;
+    double* dst = win + ((int64_t)parity * 2 + (1 - dir)) * H.cap;
+    for (int ci = 0; ci < H.nchild; ++ci) {
+      const HaloChild& ch = H.ch[ci];
+      const int np = dir == 0 ? 1 : ch.k;
+      const int p0 = dir == 0 ? ch.send_lo_plane : ch.send_hi_plane0;
+      const int64_t total = ch.plane_pts * np;
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t g = ch.lat2dof[(int64_t)p0 * ch.plane_pts + i];
+        dst[ch.slot_base + i] = g >= 0 ? x[ch.offset + g] : 0.0;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int dir = 0; dir < 2; ++dir)
+        if (H.peer[dir]) st_release_sys(reinterpret_cast<unsigned long long*>(H.peer[dir] + 4 * H.cap) + (1 - dir), H.seq);
+    }
+  }
+}
+
+// Wait + unpack: acquire the neighbours' sequence numbers, then copy the window into the ghost entries of x.  The wait is
+// bounded (about two seconds of SM clock) so that a lost peer can never hang the device; a timeout raises *err.
+__global__ void __launch_bounds__(256) k_halo_unpack(HaloSpec H, double* __restrict__ x, int has_lower, int has_upper, int* err)
+{
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(H.mine + 4 * H.cap);
+    const long long t0 = clock64();
+    bool good = true;
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? has_lower : has_upper)) continue;
+      while (ld_acquire_sys(flags + side) < H.seq) {
+        if (clock64() - t0 > 4000000000LL) { good = false; break; }
+        __nanosleep(100);
+      }
+    }
+    ok = good ? 1 : 0;
+    if (!good) atomicExch(err, 1);
+  }
+  __syncthreads();
+  if (!ok) return;
+  const int parity = (int)(H.seq & 1);
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? has_lower : has_upper)) continue;
+    const double* src = H.mine + ((int64_t)parity * 2 + side) * H.cap;
+    for (int ci = 0; ci < H.nchild; ++ci) {
+      const HaloChild& ch = H.ch[ci];
+      const int np = side == 0 ? ch.k : 1;
+      const int p0 = side == 0 ? 0 : ch.ghost_hi_plane;
+      const int64_t total = ch.plane_pts * np;
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t g = ch.lat2dof[(int64_t)p0 * ch.plane_pts + i];
+        if (g >= 0) x[ch.offset + g] = src[ch.slot_base + i];
+      }
+    }
+  }
+}
+
+static HaloSpec halo_spec(Ctx* c)
+{
+  const MeshDesc& m = c->mesh;
+  const int pa = c->part_axis;
+  HaloSpec H; H.nchild = (int)c->children.size(); H.cap = c->halo_cap; H.mine = c->d_halo_recv;
+  H.peer[0] = c->peer_lower; H.peer[1] = c->peer_upper; H.seq = c->halo_seq;
+  int64_t base = 0;
+  for (int i = 0; i < H.nchild; ++i) {
+    const Child& ch = c->children[i];
+    HaloChild& h = H.ch[i];
+    h.offset = ch.offset; h.plane_pts = plane_points(c, ch); h.slot_base = base; h.lat2dof = ch.d_lat2dof; h.k = ch.k;
+    h.send_lo_plane = ch.k;                               // first owned plane of a rank that has a lower neighbour
+    h.send_hi_plane0 = ch.k * m.n[pa] - ch.k;             // last k owned planes of a rank that has an upper neighbour
+    h.ghost_hi_plane = ch.k * m.n[pa];
+    base += h.plane_pts * ch.k;
+  }
+  return H;
+}
+
+void halo_push(Ctx* c, const double* d_x)
+{
+  MDB_REQUIRE(c->d_halo_recv, MDB_ESTATE, "halo exchange on an unpartitioned context");
+  c->halo_seq++;
+  if (!c->peer_lower && !c->peer_upper) return;
+  HaloSpec H = halo_spec(c);
+  int64_t work = 0;
+  for (int i = 0; i < H.nchild; ++i) work += H.ch[i].plane_pts * H.ch[i].k;
+  int grid = cdiv(work, 256); if (grid > 148) grid = 148; if (grid < 1) grid = 1;
+  MDB_LAUNCH(c, k_halo_push, grid, 256, 0, H, d_x, c->d_halo_counter);
+}
+
+void halo_wait(Ctx* c, double* d_x)
+{
+  MDB_REQUIRE(c->d_halo_recv, MDB_ESTATE, "halo exchange on an unpartitioned context");
+  if (!c->peer_lower && !c->peer_upper) return;
+  HaloSpec H = halo_spec(c);
+  int64_t work = 0;
+  for (int i = 0; i < H.nchild; ++i) work += H.ch[i].plane_pts * H.ch[i].k;
+  int grid = cdiv(work, 256); if (grid > 64) grid = 64; if (grid < 1) grid = 1;     // every block spins on the flags: keep the grid co-resident
+  MDB_LAUNCH(c, k_halo_unpack, grid, 256, 0, H, d_x, c->peer_lower ? 1 : 0, c->peer_upper ? 1 : 0, (int*)(c->d_halo_counter + 2));
+}
+
+void halo_exchange(Ctx* c, double* d_x)
+{
+  halo_push(c, d_x);
+  halo_wait(c, d_x);
+}
+
+bool halo_timed_out(Ctx* c)
+{
+  if (!c->d_halo_counter) return false;
+  int e = 0;
+  MDB_CUDA(cudaMemcpyAsync(&e, c->d_halo_counter + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  return e != 0;
+}
+
+} // namespace mdb
 
 using namespace mdb;
 struct mdb_ctx : mdb::Ctx {};
+
+#define MG_BEGIN(ctx) if (!(ctx)) return MDB_EINVAL; try { cudaSetDevice((ctx)->device);
+#define MG_END(ctx) return MDB_OK; } catch (mdb::Error& e) { (ctx)->err = e.what(); return e.code; } catch (std::exception& e) { (ctx)->err = e.what(); return MDB_EINVAL; }
+
+struct HaloBlob { cudaIpcMemHandle_t ipc; uint64_t raw; int32_t pid; int32_t device; };
+static_assert(sizeof(HaloBlob) <= 80, "halo blob must fit the 80-byte ABI buffer");
+
 extern "C" {
-int mdb_nccl_unique_id(void* id128) { (void)id128; return MDB_ENCCL; }
-int mdb_comm_init(mdb_ctx* c, int nranks, int rank, const void* id128) { (void)c; (void)nranks; (void)rank; (void)id128; return MDB_ENCCL; }
-int mdb_halo_export(mdb_ctx* c, void* handle64, int64_t* window_bytes) { (void)c; (void)handle64; (void)window_bytes; return MDB_ENCCL; }
-int mdb_halo_import(mdb_ctx* c, int lower_rank, const void* lh, int upper_rank, const void* uh) { (void)c; (void)lower_rank; (void)lh; (void)upper_rank; (void)uh; return MDB_ENCCL; }
-int mdb_owned_rows(mdb_ctx* c, int64_t* owned, int64_t* local_total) { if (!c) return MDB_EINVAL; *owned = c->ndof; *local_total = c->ndof; return MDB_OK; }
-int mdb_get_ownership(mdb_ctx* c, uint8_t* owned_flags, int64_t* global_index) { (void)c; (void)owned_flags; (void)global_index; return MDB_ENCCL; }
+
+int mdb_nccl_unique_id(void* id128)
+{
+  try { nccl_uid_t id; MDB_NCCL(nccl().GetUniqueId(&id)); std::memcpy(id128, &id, 128); return MDB_OK; }
+  catch (std::exception&) { return MDB_ENCCL; }
 }
+
+int mdb_comm_init(mdb_ctx* c, int nranks, int rank, const void* id128)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, MDB_EINVAL, "mdb_comm_init: bad rank");
+  c->nranks = nranks; c->rank = rank;
+  if (nranks > 1) {
+    MDB_REQUIRE(id128, MDB_EINVAL, "mdb_comm_init: unique id required");
+    nccl_uid_t id; std::memcpy(&id, id128, 128);
+    nccl_comm_t comm = nullptr;
+    MDB_NCCL(nccl().CommInitRank(&comm, nranks, id, rank));
+    c->nccl_comm = comm;
+  }
+  MG_END(c)
+}
+
+int mdb_halo_export(mdb_ctx* c, void* blob80, int64_t* window_bytes)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(c->finalized && c->d_halo_recv, MDB_ESTATE, "mdb_halo_export: finalize a partitioned mesh first");
+  HaloBlob b; std::memset(&b, 0, sizeof(b));
+  MDB_CUDA(cudaIpcGetMemHandle(&b.ipc, c->d_halo_recv));
+  b.raw = (uint64_t)(uintptr_t)c->d_halo_recv; b.pid = (int32_t)getpid(); b.device = c->device;
+  std::memset(blob80, 0, 80);
+  std::memcpy(blob80, &b, sizeof(b));
+  if (window_bytes) *window_bytes = c->halo_recv_n * (int64_t)sizeof(double);
+  MG_END(c)
+}
+
+static double* open_peer(mdb_ctx* c, const void* blob80)
+{
+  HaloBlob b; std::memcpy(&b, blob80, sizeof(b));
+  if (b.pid == (int32_t)getpid()) {                        // a context of this very process: plain pointer (+ peer access if another device)
+    if (b.device != c->device) { cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0); if (e != cudaSuccess) cudaGetLastError(); }
+    return (double*)(uintptr_t)b.raw;
+  }
+  void* p = nullptr;
+  MDB_CUDA(cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+  c->ipc_opened.push_back(p);
+  return (double*)p;
+}
+
+int mdb_halo_import(mdb_ctx* c, int lower_rank, const void* lower_blob80, int upper_rank, const void* upper_blob80)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(c->finalized && c->d_halo_recv, MDB_ESTATE, "mdb_halo_import: finalize a partitioned mesh first");
+  const MeshDesc& m = c->mesh; const int pa = c->part_axis;
+  const bool first = m.off[pa] == 0, last = m.off[pa] + m.n[pa] == m.gn[pa];
+  MDB_REQUIRE(first == (lower_blob80 == nullptr), MDB_EINVAL, "mdb_halo_import: lower neighbour does not match the partition");
+  MDB_REQUIRE(last == (upper_blob80 == nullptr), MDB_EINVAL, "mdb_halo_import: upper neighbour does not match the partition");
+  c->lower_rank = lower_blob80 ? lower_rank : -1; c->upper_rank = upper_blob80 ? upper_rank : -1;
+  c->peer_lower = lower_blob80 ? open_peer(c, lower_blob80) : nullptr;
+  c->peer_upper = upper_blob80 ? open_peer(c, upper_blob80) : nullptr;
+  MG_END(c)
+}
+
+int mdb_halo_push(mdb_ctx* c, const double* x)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_halo_push: x must be a device vector");
+  halo_push(c, x);
+  MG_END(c)
+}
+
+int mdb_halo_wait(mdb_ctx* c, double* x)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_halo_wait: x must be a device vector");
+  halo_wait(c, x);
+  MDB_REQUIRE(!halo_timed_out(c), MDB_ENCCL, "halo exchange timed out waiting for a neighbour");
+  MG_END(c)
+}
+
+int mdb_owned_rows(mdb_ctx* c, int64_t* owned, int64_t* local_total)
+{
+  if (!c) return MDB_EINVAL;
+  if (owned) *owned = c->d_owned ? c->owned_rows : c->ndof;
+  if (local_total) *local_total = c->ndof;
+  return MDB_OK;
+}
+
+int mdb_owned_counts(mdb_ctx* c, int64_t* per_child)
+{
+  if (!c || !c->finalized) return MDB_EINVAL;
+  for (size_t i = 0; i < c->children.size(); ++i) per_child[i] = c->d_owned ? c->child_owned[i] : c->children[i].size;
+  return MDB_OK;
+}
+
+int mdb_get_ownership(mdb_ctx* c, const int64_t* child_global_base, uint8_t* owned_flags, int64_t* global_index)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_get_ownership: not finalized");
+  std::vector<uint8_t> f(c->ndof, 1);
+  if (c->d_owned) {
+    MDB_CUDA(cudaMemcpyAsync(f.data(), c->d_owned, c->ndof, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (owned_flags) std::memcpy(owned_flags, f.data(), c->ndof);
+  if (global_index) {
+    // owned dofs of a child keep their relative order in the global (lexicographic, cut axis slowest) numbering
+    for (size_t i = 0; i < c->children.size(); ++i) {
+      const Child& ch = c->children[i];
+      int64_t next = child_global_base ? child_global_base[i] : ch.offset;
+      for (int64_t g = ch.offset; g < ch.offset + ch.size; ++g) global_index[g] = f[g] ? next++ : -1;
+    }
+  }
+  MG_END(c)
+}
+
+} // extern "C"

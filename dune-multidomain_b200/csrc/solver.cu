@@ -20,7 +20,8 @@ namespace mdb {
 #define MAX_PARTIAL_BLOCKS 2048
 
 // scalar slots
-enum { S_RHO = 0, S_RHOLAST, S_PQ, S_RR, S_RR0, S_BETA, S_LAMBDA, S_DONE, S_ITER, S_RED2, S_ALPHA, S_OMEGA, S_H, S_TR, S_TT, S_RHONEW, S_HALF };
+// slots reduced together are adjacent (RHONEW,RR), (RR,PQ), (TR,TT): one ncclAllReduce serves a pair
+enum { S_RHO = 0, S_RHOLAST, S_RHONEW, S_RR, S_PQ, S_RR0, S_BETA, S_LAMBDA, S_DONE, S_ITER, S_RED2, S_ALPHA, S_OMEGA, S_H, S_TR, S_TT, S_HALF };
 
 __device__ __forceinline__ double block_sum(double v, double* sh)
 {
@@ -248,7 +249,8 @@ __global__ void k_cg_init(int64_t n, const double* __restrict__ b, const double*
 
 __global__ void k_cg_init_scalars(double* s, double reduction)
 {
-  // S_RHO and S_RR were just reduced
+  // S_RHONEW and S_RR were just reduced
+  s[S_RHO] = s[S_RHONEW];
   s[S_RR0] = s[S_RR]; s[S_RHOLAST] = 1.0; s[S_ITER] = 0.0; s[S_RED2] = reduction * reduction;
   s[S_BETA] = s[S_RHO] / 1.0;
   s[S_DONE] = (s[S_RR] == 0.0) ? 1.0 : 0.0;
@@ -380,10 +382,6 @@ __global__ void k_bi_derive_end(double* s)
   if (s[S_RR] <= s[S_RED2] * s[S_RR0]) s[S_DONE] = 1.0;
 }
 
-// multi-GPU hooks (multigpu.cu); no-ops on one rank
-void allreduce_scalars(Ctx* c, double* d_vals, int n);
-void halo_exchange(Ctx* c, double* d_x);
-
 static void reduce(Ctx* c, int nblocks, int nvals, int s0, int s1 = 0, int s2 = 0)
 {
   MDB_LAUNCH(c, k_reduce_partials, 1, VEC_THREADS, 0, c->d_partial, nblocks, nvals, c->d_scal, s0, s1, s2);
@@ -423,8 +421,8 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     ensure_work(c, 3);
     double *r = c->d_work, *p = c->d_work + n, *q = c->d_work + 2 * n;
     MDB_LAUNCH(c, k_cg_init, vgrid, VEC_THREADS, 0, n, d_b, M.d_dinv, c->d_owned, x, r, p, c->d_partial);
-    reduce(c, vgrid, 2, S_RHO, S_RR);
-    if (multi) allreduce_scalars(c, s + S_RHO, 1), allreduce_scalars(c, s + S_RR, 1);
+    reduce(c, vgrid, 2, S_RHONEW, S_RR);
+    if (multi) allreduce_scalars(c, s + S_RHONEW, 2);
     MDB_LAUNCH(c, k_cg_init_scalars, 1, 1, 0, s, reduction);
     while (issued < maxit) {
       MDB_LAUNCH(c, k_cg_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, p);
@@ -435,7 +433,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       MDB_LAUNCH(c, k_cg_derive_a, 1, 1, 0, s);
       MDB_LAUNCH(c, k_cg_update_xr, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, p, q, c->d_owned, x, r, c->d_partial);
       reduce(c, vgrid, 2, S_RHONEW, S_RR);
-      if (multi) allreduce_scalars(c, s + S_RHONEW, 1), allreduce_scalars(c, s + S_RR, 1);
+      if (multi) allreduce_scalars(c, s + S_RHONEW, 2);
       MDB_LAUNCH(c, k_cg_derive_b, 1, 1, 0, s);
       ++issued;
       if (issued % check_every == 0) { poll(); if (hp[S_DONE] != 0.0) break; }
@@ -465,7 +463,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       MDB_LAUNCH(c, k_bi_derive_omega, 1, 1, 0, s);
       MDB_LAUNCH(c, k_bi_update_x, vgrid, VEC_THREADS, 0, n, s, y2, t, rt, c->d_owned, x, r, c->d_partial);
       reduce(c, vgrid, 2, S_RR, S_PQ);
-      if (multi) allreduce_scalars(c, s + S_RR, 1), allreduce_scalars(c, s + S_PQ, 1);
+      if (multi) allreduce_scalars(c, s + S_RR, 2);
       MDB_LAUNCH(c, k_bi_derive_end, 1, 1, 0, s);
       ++issued;
       if (issued % check_every == 0) { poll(); if (hp[S_DONE] != 0.0) break; }
@@ -477,6 +475,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
   MDB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->phases["solve"].last_ms = ms;
   const bool converged = hp[S_DONE] != 0.0;
+  if (multi && halo_timed_out(c)) throw Error(MDB_ENCCL, "halo exchange timed out waiting for a neighbour");
   if (stats) {
     stats->iterations = (int)hp[S_ITER];
     stats->converged = converged ? 1 : 0;

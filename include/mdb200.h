@@ -138,10 +138,14 @@ const char* mdb_version(void);
 /* Structured axis-aligned grid, n[d] cells per axis on [lower,upper].  Cells and vertices are numbered
  * lexicographically, axis 0 fastest (YaspGrid leaf index order [UPSTREAM]). */
 int mdb_mesh_structured(mdb_ctx* ctx, int dim, const int64_t* n, const double* lower, const double* upper);
-/* Declare this context's mesh to be a slab of a larger global mesh (multi-GPU): `global_n` cells
- * per axis in total, this rank's cells start at `cell_offset`; faces on a cut are processor boundaries (no
- * boundary terms); `lower/upper` given to mdb_mesh_structured are those of the local slab.
- * Must be called after mdb_mesh_structured and before mdb_finalize. */
+/* Declare this context's mesh to be a slab of a larger global mesh (multi-GPU; the reference's analogue is
+ * the overlap-1 MPI grid of test/testoverlappinginstationarypoisson.cc:232-233).  `global_n` cells per axis in total,
+ * this rank's local cells start at `cell_offset`; only the slowest axis (dim-1) may be cut.  Convention: a rank that is
+ * not the first one includes ONE ghost cell layer below its owned layers (the top layer owned by the rank below), so
+ * that every cell around an owned vertex is local and owned rows are assembled completely without communication.  Local
+ * vertex plane 0 of such a rank and the top local plane of every rank but the last are ghost planes (owned by the
+ * neighbours).  Faces on a cut are processor boundaries (no boundary terms, globalassembler.hh:275-283).  `lower/upper`
+ * given to mdb_mesh_structured are those of the local slab.  Call after mdb_mesh_structured, before mdb_finalize. */
 int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cell_offset,
                        const double* global_lower, const double* global_upper);
 /* One byte per cell: bit s set <=> cell belongs to subdomain s (<= 8 subdomains;
@@ -229,21 +233,34 @@ int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, 
 /* Run exactly `iters` Krylov iterations without convergence test (benchmarking the loop). */
 int mdb_solve_fixed(mdb_ctx* ctx, int mat, int method, int precond, int iters,
                     const double* rhs, double* z, mdb_solve_stats* stats);
-/* y = A x (host or device pointers). */
+/* y = A x (host or device pointers).  On a partitioned context with imported neighbours x must be a device vector: its
+ * ghost entries are refreshed by a halo exchange first. */
 int mdb_spmv(mdb_ctx* ctx, int mat, const double* x, double* y);
 
-/* ---- multi-GPU plumbing -------------------------------------- */
-/* NCCL communicator for Krylov scalars: rank 0 creates the id, all ranks init. */
+/* ---- multi-GPU plumbing (one process and one context per GPU) -- */
+/* NCCL communicator for the Krylov scalars: rank 0 creates the id, every rank calls mdb_comm_init.  With a communicator
+ * of more than one rank, mdb_solve / mdb_spmv exchange halos before every SpMV and reduce dot products over owned rows. */
 int mdb_nccl_unique_id(void* id128 /* 128 bytes */);
 int mdb_comm_init(mdb_ctx* ctx, int nranks, int rank, const void* id128);
-/* Halo buffers for x (one vertex layer per slab neighbour).  Export this rank's IPC handle (64 bytes) of its
- * receive window, then import the neighbours' handles: pushes are P2P stores over NVLink. */
-int mdb_halo_export(mdb_ctx* ctx, void* handle64, int64_t* window_bytes);
-int mdb_halo_import(mdb_ctx* ctx, int lower_rank, const void* lower_handle64, int upper_rank, const void* upper_handle64);
-/* Number of rows this rank owns / global size (for reporting). */
+/* Halo receive window of this rank (device memory that the neighbours write with peer stores over NVLink).  Export an
+ * 80-byte descriptor (cudaIpc handle; a raw pointer when both contexts live in one process), exchange the descriptors
+ * out of band (e.g. torch.distributed.all_gather_object) and import the neighbours' ones.  Pass NULL for a missing
+ * neighbour (first / last rank). */
+int mdb_halo_export(mdb_ctx* ctx, void* blob80, int64_t* window_bytes);
+int mdb_halo_import(mdb_ctx* ctx, int lower_rank, const void* lower_blob80, int upper_rank, const void* upper_blob80);
+/* The two halves of one exchange of the device vector x (ndof doubles): push this rank's boundary planes into the
+ * neighbours' windows, then wait for the neighbours' planes and copy them into the ghost entries of x.  Every rank must
+ * issue the same sequence of pushes and waits. */
+int mdb_halo_push(mdb_ctx* ctx, const double* x);
+int mdb_halo_wait(mdb_ctx* ctx, double* x);
+/* Rows this rank owns / all local rows (ghost rows included). */
 int mdb_owned_rows(mdb_ctx* ctx, int64_t* owned, int64_t* local_total);
-/* Export: one byte per local DOF, 1 = owned by this rank; and the global container index of every local DOF. */
-int mdb_get_ownership(mdb_ctx* ctx, uint8_t* owned_flags, int64_t* global_index);
+/* Owned rows per child block (nchildren entries). */
+int mdb_owned_counts(mdb_ctx* ctx, int64_t* per_child);
+/* Export: one byte per local DOF, 1 = owned by this rank; and the global container index of every owned local DOF (-1
+ * for ghosts) given the global index of this rank's first owned DOF of every child block (`child_global_base`,
+ * nchildren entries: global child offset + owned rows of the lower ranks; NULL = local numbering). */
+int mdb_get_ownership(mdb_ctx* ctx, const int64_t* child_global_base, uint8_t* owned_flags, int64_t* global_index);
 
 /* Sum of squares of the stored entries of the matrix (device reduction; a cheap checksum of an assembly
  * result that a host caller can read back).  `out` is a host pointer. */

@@ -607,6 +607,7 @@ void Context::residual(int goi, double weight, const double* x, double* r) const
           }
           for (int i = 0; i < nn; ++i) r[dofs_n[i]] += r_n[i];           // onUnbindLFSVOutside
         } else {
+          if (grid.processor_face(eg.ijk, f)) continue;                   // assembleVProcessor: no shipped operator has it
           ig.outside = eg; ig.boundary = true; ig.oneSidedDirection = true;
           for (int s : go.sps) {                                          // lambda_boundary functor :145-162
             const SubProblem& sp = sps[s];
@@ -772,6 +773,7 @@ void Context::constraints_assemble(const int* sps_, const mdb_bctype* bcs, int n
     for (int f = 0; f < 2 * dim; ++f) {
       int64_t nijk[3];
       bool interior = FaceIter::neighbor(grid, eg.ijk, f, nijk);
+      if (!interior && grid.processor_face(eg.ijk, f)) continue;
       uint8_t nsd = interior ? cell_sd[grid.cell_index(nijk)] : 0;
       IG ig; ig.inside = eg; ig.outside = eg; ig.axis = f / 2; ig.side = f % 2; ig.face = f; ig.boundary = !interior;
       for (int q = 0; q < n; ++q) {
@@ -976,6 +978,17 @@ int orc_mesh_structured(Context* c, int dim, const int64_t* n, const double* low
     for (int d = 0; d < dim; ++d) { c->grid.n[d] = n[d]; c->grid.lower[d] = lower[d]; c->grid.upper[d] = upper[d];
                                     c->grid.h[d] = (upper[d] - lower[d]) / n[d]; }
     c->cell_sd.clear(); c->finalized = false;
+  })
+}
+int orc_mesh_partition(Context* c, const int64_t* global_n, const int64_t* cell_offset, const double* global_lower, const double* global_upper)
+{
+  ORC_TRY(c, {
+    orc::Grid& g = c->grid;
+    for (int d = 0; d < g.dim; ++d) {
+      g.gn[d] = global_n[d]; g.off[d] = cell_offset[d]; g.glower[d] = global_lower[d];
+      g.h[d] = (global_upper[d] - global_lower[d]) / global_n[d];
+    }
+    g.partitioned = true;
   })
 }
 int orc_subdomains(Context* c, const uint8_t* bits)

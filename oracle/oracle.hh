@@ -169,8 +169,19 @@ struct Grid {
   int dim = 0;
   int64_t n[3] = {1, 1, 1};
   double lower[3] = {0, 0, 0}, upper[3] = {1, 1, 1}, h[3] = {1, 1, 1};
+  // slab of a larger mesh (multi-rank tests; include/mdb200.h mdb_mesh_partition): global cell counts, offset of the local
+  // cells, global lower corner.  Unpartitioned: gn = n, off = 0, glower = lower.
+  int64_t gn[3] = {1, 1, 1}, off[3] = {0, 0, 0};
+  double glower[3] = {0, 0, 0};
+  bool partitioned = false;
   int64_t ncells() const { return n[0] * n[1] * n[2]; }
-  double coord(int d, int64_t i) const { return lower[d] + i * h[d]; }
+  double coord(int d, int64_t i) const { return partitioned ? glower[d] + double(i + off[d]) * h[d] : lower[d] + i * h[d]; }
+  // a face without local neighbour that is not on the global boundary: processor boundary (globalassembler.hh:275-283)
+  bool processor_face(const int64_t ijk[3], int f) const {
+    if (!partitioned) return false;
+    int a = f / 2; int64_t j = ijk[a] + (f % 2 ? 1 : -1);
+    return (j < 0 || j >= n[a]) && (j + off[a] >= 0 && j + off[a] < gn[a]);
+  }
   void cell_ijk(int64_t c, int64_t ijk[3]) const { ijk[0] = c % n[0]; c /= n[0]; ijk[1] = c % n[1]; ijk[2] = c / n[1]; }
   int64_t cell_index(const int64_t ijk[3]) const { return ijk[0] + n[0] * (ijk[1] + n[1] * ijk[2]); }
 };

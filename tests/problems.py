@@ -7,10 +7,11 @@ import importlib
 from types import SimpleNamespace
 
 capi = importlib.import_module("dune-multidomain_b200").capi
+parallel = importlib.import_module("dune-multidomain_b200").parallel
 
 
 def testpoisson(api, n, intensity=2.0, split_axis=1, fe=(capi.FE_Q1, capi.FE_Q1), quad_order=4, coupling=capi.OP_CVCF_COUPLING,
-                jac_mode=capi.JAC_FD_BITMATCH, f=None, sd_bits=None, lower=None, upper=None):
+                jac_mode=capi.JAC_FD_BITMATCH, f=None, sd_bits=None, lower=None, upper=None, slab=None):
     """test/testpoisson.cc:119-298 (2-D as shipped; dim = len(n) gives the synthetic 3-D extension).
 
     Two subdomains split at x[split_axis] > 0.5 (:152-158), one Qk space per subdomain (:168-198), Poisson(f,b,j,4)
@@ -18,7 +19,10 @@ def testpoisson(api, n, intensity=2.0, split_axis=1, fe=(capi.FE_Q1, capi.FE_Q1)
     constraints from DirichletBoundary (:242-246), u = interpolated G (:266).
     """
     dim = len(n)
-    api.mesh_structured(n, lower, upper)
+    if slab is None:
+        api.mesh_structured(n, lower, upper)
+    else:                       # multi-rank: this rank's slab (+ ghost layer) of the global mesh n
+        parallel.apply_slab(api, slab)
     if sd_bits is None:
         api.subdomains_halfspace(split_axis, 0.5, 0, 1)
     else:
@@ -67,3 +71,17 @@ def single_domain_poisson(api, n, quad_order=2, fe=capi.FE_Q1, bc=capi.BC_ALL_DI
     go = api.gridoperator_create([sp], [])
     mat = api.matrix_create([go])
     return SimpleNamespace(ndof=ndof, ncon=ncon, go=go, mat=mat, sp=sp, sps=[sp], bc=pp.bc)
+
+
+def testpoisson_partitioned(api, n_per_rank, rank, nranks, **kw):
+    """Weak-scaling variant of `testpoisson`: a global mesh of n_per_rank[-1] * nranks cell layers along the slowest axis
+    (same mesh width everywhere: the domain grows with the rank count), cut into one slab per rank."""
+    dim = len(n_per_rank)
+    gn = list(n_per_rank)
+    gn[-1] = n_per_rank[-1] * nranks
+    upper = [1.0] * dim
+    upper[-1] = float(nranks)
+    s = parallel.slab(gn, rank, nranks, upper=upper)
+    P = testpoisson(api, tuple(gn), slab=s, **kw)
+    P.slab = s
+    return P

@@ -1,0 +1,196 @@
+"""World-size-2 (and 3) tests of the multi-rank host logic on CPU (`gloo`), SURVEY §8e / DESIGN.md §7.
+
+The device data path (peer stores + NCCL) needs GPUs; what can and must be checked without them is the partition
+design itself: slab arithmetic, "one ghost cell layer below" => owned rows are assembled completely without
+communication, which planes are exchanged, and the composition of global indices from per-rank owned counts.  Every rank
+drives the CPU oracle on its slab exactly as bench.py drives the CUDA backend, the halo exchange and the dot-product
+all-reduce go through torch.distributed, and the results are compared with the single-rank oracle on the global mesh.
+"""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+pkg = importlib.import_module("dune-multidomain_b200")
+parallel = pkg.parallel
+
+
+def test_slab_arithmetic_covers_the_mesh_once():
+    for n, R in [(8, 2), (9, 2), (16, 3), (7, 7), (256, 8)]:
+        owned_cells, owned_planes = [], []
+        for r in range(R):
+            s = parallel.slab((4, 4, n), r, R)
+            c0, c1 = s.owned_layers
+            owned_cells += list(range(c0, c1))
+            assert s.cell_offset[2] == c0 - (1 if r > 0 else 0) and s.local_n[2] == c1 - s.cell_offset[2]
+            lo, hi = parallel.owned_plane_range(s)
+            owned_planes += [s.cell_offset[2] + p for p in range(lo, hi)]
+            assert abs(s.local_lower[2] - s.cell_offset[2] / n) < 1e-15 and abs(s.local_upper[2] - c1 / n) < 1e-15
+        assert owned_cells == list(range(n))
+        assert owned_planes == list(range(n + 1))
+    with pytest.raises(ValueError):
+        parallel.slab((4, 4, 2), 0, 3)
+
+
+def test_global_child_bases():
+    counts = [[10, 7], [12, 7], [11, 9]]        # [rank][child]
+    for r, expect in enumerate([[0, 33], [10, 40], [22, 47]]):
+        bases, total = parallel.global_child_bases(counts, r)
+        assert list(bases) == expect and total == 56
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dof_planes(api, P, s):
+    """For every local DOF: (child, in-plane lattice key, plane index along the cut axis).  Q1: DOFs sit on vertices."""
+    ptr, dofs = api.get_dofmap()
+    off = api.get_child_offsets()
+    n = s.local_n
+    child = np.searchsorted(off, np.arange(P.ndof), side="right") - 1
+    key = np.full(P.ndof, -1, dtype=np.int64)
+    plane = np.full(P.ndof, -1, dtype=np.int64)
+    nx, ny = n[0] + 1, n[1] + 1
+    for c in range(len(ptr) - 1):
+        i, j, k = c % n[0], (c // n[0]) % n[1], c // (n[0] * n[1])
+        loc = dofs[ptr[c]:ptr[c + 1]]
+        assert len(loc) == 8               # one Q1 child lives on every cell of this problem
+        for li, g in enumerate(loc):
+            ax, ay, az = li & 1, (li >> 1) & 1, (li >> 2) & 1
+            key[g] = (i + ax) + nx * (j + ay)
+            plane[g] = k + az
+    assert (plane >= 0).all()
+    return child, key, plane
+
+
+def _worker(rank, world, port, n, ret):
+    import torch
+    import torch.distributed as dist
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import orc
+    import problems
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        # ---- this rank's slab, set up exactly like bench.py does for the device --------------------------------------
+        s = parallel.slab(n, rank, world)
+        o = orc.Oracle()
+        P = problems.testpoisson(o, n, slab=s)
+        child, key, plane = _dof_planes(o, P, s)
+        lo, hi = parallel.owned_plane_range(s)
+        owned = (plane >= lo) & (plane < hi)
+        nchild = o.nchildren
+        counts = [None] * world
+        dist.all_gather_object(counts, [int((owned & (child == c)).sum()) for c in range(nchild)])
+        bases, nglobal = parallel.global_child_bases(counts, rank)
+        gidx = np.full(P.ndof, -1, dtype=np.int64)
+        for c in range(nchild):
+            sel = np.where(owned & (child == c))[0]           # ascending local index = ascending global index
+            gidx[sel] = bases[c] + np.arange(len(sel))
+
+        # ---- halo exchange through gloo: owners send their boundary planes, keyed by (child, in-plane position) --------
+        nloc = s.local_n[2]
+
+        def plane_dofs(p):
+            sel = np.where(plane == p)[0]
+            return sel[np.lexsort((key[sel], child[sel]))]
+
+        def exchange(v):
+            reqs, recvs = [], []
+            if rank > 0:                                     # my first owned plane -> ghost plane above of rank-1
+                t = torch.from_numpy(v[plane_dofs(1)].copy())
+                reqs.append(dist.isend(t, rank - 1))
+                buf = torch.empty(len(plane_dofs(0)), dtype=torch.float64)
+                reqs.append(dist.irecv(buf, rank - 1)); recvs.append((plane_dofs(0), buf))
+            if rank < world - 1:                             # my last owned plane -> ghost plane below of rank+1
+                t2 = torch.from_numpy(v[plane_dofs(nloc - 1)].copy())
+                reqs.append(dist.isend(t2, rank + 1))
+                buf2 = torch.empty(len(plane_dofs(nloc)), dtype=torch.float64)
+                reqs.append(dist.irecv(buf2, rank + 1)); recvs.append((plane_dofs(nloc), buf2))
+            for q in reqs:
+                q.wait()
+            for idx, b in recvs:
+                v[idx] = b.numpy()
+
+        def dot(a, b):
+            t = torch.tensor([float(np.dot(a[owned], b[owned]))], dtype=torch.float64)
+            dist.all_reduce(t)
+            return float(t.item())
+
+        g = gidx.astype(np.float64)
+        exchange(g)                                           # ghosts learn their global index from their owner
+        gfull = g.astype(np.int64)
+        assert (gfull >= 0).all(), "a ghost DOF was not covered by the halo exchange"
+
+        # ---- the global problem on one rank (reference for everything below) ------------------------------------------
+        og = orc.Oracle()
+        Pg = problems.testpoisson(og, n)
+        assert nglobal == Pg.ndof
+        ug = np.zeros(Pg.ndof); og.interpolate(Pg.sps, Pg.gfn, ug)
+        og.jacobian(Pg.go, Pg.mat, ug, overwrite=True)
+        rg = np.zeros(Pg.ndof); og.residual(Pg.go, ug, rg)
+        Ag = og.csr(Pg.mat)
+
+        # ---- local assembly: owned rows must be complete without any communication -------------------------------------
+        u = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u)
+        assert np.array_equal(u, ug[gfull]), "interpolation differs from the global one"
+        assert np.array_equal(o.get_constraints()[owned], og.get_constraints()[gfull[owned]])
+        o.jacobian(P.go, P.mat, u, overwrite=True)
+        r = np.zeros(P.ndof); o.residual(P.go, u, r)
+        A = o.csr(P.mat)
+        scale = np.abs(Ag.data).max()
+        for row in np.where(owned)[0]:
+            a, b = A.indptr[row], A.indptr[row + 1]
+            ga, gb = Ag.indptr[gfull[row]], Ag.indptr[gfull[row] + 1]
+            cols = gfull[A.indices[a:b]]
+            order = np.argsort(cols)
+            assert np.array_equal(cols[order], Ag.indices[ga:gb]), "pattern of an owned row differs from the global matrix"
+            assert np.abs(A.data[a:b][order] - Ag.data[ga:gb]).max() <= 1e-13 * scale
+        assert np.abs(r[owned] - rg[gfull[owned]]).max() <= 1e-13 * np.abs(rg).max()
+
+        # ---- distributed Jacobi-CG (the iteration of solver.cu) vs the global direct solve ------------------------------
+        dinv = 1.0 / A.diagonal()
+        x = np.zeros(P.ndof); res = r.copy(); p = np.zeros(P.ndof)
+        rho = dot(res, dinv * res); rr0 = dot(res, res); beta = 0.0
+        for it in range(500):
+            p = beta * p + dinv * res
+            exchange(p)
+            q = A @ p
+            lam = rho / dot(p, q)
+            x += lam * p
+            res -= lam * q
+            rho_new = dot(res, dinv * res)
+            beta, rho = rho_new / rho, rho_new
+            if dot(res, res) <= 1e-26 * rr0:
+                break
+        zg = spla.spsolve(sp.csc_matrix(Ag), rg)
+        err = np.abs(x[owned] - zg[gfull[owned]]).max() / np.abs(zg).max()
+        assert err < 1e-10, err
+        ret[rank] = (int(owned.sum()), it + 1, float(err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, (4, 6, 8)), (3, (4, 4, 9))])
+def test_partitioned_assembly_and_solve_match_global(world, n):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    total = sum(v[0] for v in ret.values())
+    assert total == (n[0] + 1) * (n[2] + 1) * (n[1] + 2)     # (N+2)(N+1)^2-type count: interface vertices belong to both blocks
+    assert len({v[1] for v in ret.values()}) == 1             # every rank took the same number of iterations
