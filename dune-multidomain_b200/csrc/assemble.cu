@@ -92,18 +92,13 @@ __device__ __forceinline__ int columns_below(const int64_t* __restrict__ rowptr,
 // hot kernel: 8 bytes written per stored entry, nothing read but the run boundaries.
 #define JF_THREADS 128
 template <int DIM>
-__global__ void __launch_bounds__(JF_THREADS) k_jacobian_fill_q1(ChildQ1 ch, const double* __restrict__ S, const int32_t* __restrict__ seg_start,
-                                                                const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
+__global__ void __launch_bounds__(JF_THREADS) k_jacobian_fill_q1(const double* __restrict__ S, const longlong2* __restrict__ seg_span,
                                                                 double* __restrict__ val, int overwrite)
 {
   constexpr int NS = (DIM == 3) ? 27 : 9;
-  constexpr int BITBASE = (DIM == 3) ? 0 : 9;       // 2-D rows use the dz = 0 slice of the 27-bit stencil mask
-  constexpr uint32_t FULL = ((1u << NS) - 1u) << BITBASE;
   __shared__ double sS[32];
-  const int a = seg_start[blockIdx.x], b = seg_start[blockIdx.x + 1];
-  const int64_t g0 = ch.offset + a;
-  const int64_t base = rowptr[g0];
-  if (rowinfo[g0] != FULL || rowptr[g0 + 1] - base != NS) return;      // a run of irregular rows: k_jacobian_rows_q1
+  const longlong2 span = seg_span[blockIdx.x];
+  if (span.x == span.y) return;                                        // a run of irregular rows: k_jacobian_rows_q1
   if (threadIdx.x < NS) sS[threadIdx.x] = S[threadIdx.x];
   __syncthreads();
   // The run is the span [p0, p1) of the value array.  Rows are 27 (9) doubles long, so p0 is only 8-byte aligned.  The span
@@ -112,7 +107,7 @@ __global__ void __launch_bounds__(JF_THREADS) k_jacobian_fill_q1(ChildQ1 ch, con
   // on B200 (profiles/microbench/write_bw2.cu): 7.0-7.5 TB/s for this pattern against 5.5 TB/s for unaligned
   // block-strided stores and 6.6 TB/s for 16-byte stores.
   constexpr int CHUNK = 32 * NS;                                       // a multiple of NS: the phase is the same in every chunk
-  const int64_t p0 = base, p1 = base + (int64_t)(b - a) * NS;
+  const int64_t p0 = span.x, p1 = span.y;
   const int64_t a0 = p0 & ~(int64_t)31;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mm0 = (int)((a0 - p0 + lane + 4 * NS) % NS);              // (i - p0) mod NS for i = a0 + lane (a0 - p0 > -32, 4 NS >= 36)
@@ -228,8 +223,8 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
     const int64_t nrows = uni ? M.n_irregular[i] : ch.size;
     if (uni) {
       const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL;
-      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, (int)M.n_seg[i], JF_THREADS, 0, ch, S, M.d_seg_start[i], M.d_rowptr, M.d_rowinfo, M.d_val, (int)overwrite);
-      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, (int)M.n_seg[i], JF_THREADS, 0, ch, S, M.d_seg_start[i], M.d_rowptr, M.d_rowinfo, M.d_val, (int)overwrite);
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, (int)M.n_seg[i], JF_THREADS, 0, S, M.d_seg_span[i], M.d_val, (int)overwrite);
+      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, (int)M.n_seg[i], JF_THREADS, 0, S, M.d_seg_span[i], M.d_val, (int)overwrite);
     }
     if (nrows > 0) {
       if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,

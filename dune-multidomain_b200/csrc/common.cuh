@@ -188,6 +188,7 @@ struct Matrix {
   int64_t n_irregular[MDB_MAX_CHILDREN] = {0};
   int32_t* d_seg_start[MDB_MAX_CHILDREN] = {nullptr};   // runs of rows with equal simple/irregular status (n_seg + 1 entries)
   int64_t n_seg[MDB_MAX_CHILDREN] = {0};
+  longlong2* d_seg_span[MDB_MAX_CHILDREN] = {nullptr};  // value-array span [x, y) of every run (empty for irregular runs)
   // per (grid operator, coupling): uint8 offsets inside the row of every entry a coupling face touches
   std::map<std::pair<int, int>, uint8_t*> slot_tables;
   // preconditioner caches

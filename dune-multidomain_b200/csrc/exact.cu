@@ -476,7 +476,15 @@ __global__ void __launch_bounds__(256, 3) k_coupling_jacobian_staged(MeshDesc m,
   constexpr int FPB = 256 / NE;
   struct FaceS { double x[NR]; double jit[2][DIM]; double nrm[2][DIM]; double ie, aoh; int32_t dof[NR]; int axis, side; };
   __shared__ FaceS sf[FPB];
-  __shared__ double sbuf[2][FPB][NR][6];     // {phi, c, px, pg0, pg1, pg2}
+  // Shared-memory staging, all 16-byte vectors so that every access is one LDS.128 / STS.128:
+  //   spc[buf][face][i]      = {phi_i, c_i}                       perturbation-independent
+  //   sq [buf][face][i][0:2] = {px_i, pg_i[0]}, {pg_i[1], pg_i[2]}  base-line products
+  //   sq [MINE + t][0:2]     = the same quad for the perturbed dof of thread t
+  // The sums below read term i from the base-line quad or, for i == j, from the thread's own quad: ONE 32-bit index
+  // select per term instead of a 64-bit value select per double.
+  constexpr int MINE = 2 * FPB * NR;
+  __shared__ double2 spc[2 * FPB * NR];
+  __shared__ double2 sq[(MINE + 256) * 2];
   __shared__ double sdown[FPB][NR];
   const int t = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * FPB;
@@ -521,58 +529,61 @@ __global__ void __launch_bounds__(256, 3) k_coupling_jacobian_staged(MeshDesc m,
   const int pf = t / NR, pr = t % NR, ps = pr / NL, pi = pr % NL;
   const bool pact = pf < FPB && f0 + pf < nfaces;
   for (int q = 0; q < nq; ++q) {
-    double (*buf)[NR][6] = sbuf[q & 1];
+    const int bbase = (q & 1) * FPB * NR;
     if (pact) {
       const FaceS& F = sf[pf];
       const int sideval = ps == 0 ? F.side : 1 - F.side;     // geometryInInside: local[axis] = side; InOutside: 1 - side
       const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + pi) * 4;
       const double phi = __ldg(tq);
-      double gpn = 0.0, g[DIM];
+      double gpn = 0.0, g[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[ps][d] * __ldg(tq + 1 + d);
 #pragma unroll
       for (int d = 0; d < DIM; ++d) gpn += g[d] * F.nrm[ps][d];
       const double theta = 1;
       const double xi = F.x[pr];
-      double* o = buf[pf][pr];
-      o[0] = phi; o[1] = theta * 0.5 * gpn; o[2] = xi * phi;
+      const int o = bbase + pf * NR + pr;
+      spc[o] = make_double2(phi, theta * 0.5 * gpn);
+      sq[2 * o] = make_double2(xi * phi, xi * g[0]);
+      sq[2 * o + 1] = make_double2(xi * g[1], DIM > 2 ? xi * g[2] : 0.0);
+    }
+    if (active && j >= 0) {                                  // this thread's perturbed products, in its own quad
+      const FaceS& F = sf[fl];
+      const int sideval = jside == 0 ? F.side : 1 - F.side;
+      const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + jj) * 4;
+      double g[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) o[3 + d] = xi * g[d];
+      for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[jside][d] * __ldg(tq + 1 + d);
+      sq[2 * (MINE + t)] = make_double2(xp * __ldg(tq), xp * g[0]);
+      sq[2 * (MINE + t) + 1] = make_double2(xp * g[1], DIM > 2 ? xp * g[2] : 0.0);
     }
     __syncthreads();
     if (active && !(analytic && e == 0)) {
       const FaceS& F = sf[fl];
-      const double (*b)[6] = buf[fl];
+      const int fb = bbase + fl * NR;
       double pos[3], w; quad_point<DIM - 1>(P.rule, q, pos, w);
       const double factor = w * F.ie;
-      // the perturbed products of this thread's dof
-      double mypx = 0.0, mypg[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) mypg[d] = 0.0;
-      if (j >= 0) {
-        const int sideval = jside == 0 ? F.side : 1 - F.side;
-        const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + jj) * 4;
-        mypx = xp * __ldg(tq);
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) mypg[d] = xp * (0.0 + F.jit[jside][d] * __ldg(tq + 1 + d));
-      }
       double u[2] = {0.0, 0.0};
+      double gradu[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
 #pragma unroll
-      for (int i = 0; i < NR; ++i) u[i / NL] += (i == j) ? mypx : b[i][2];
+      for (int i = 0; i < NR; ++i) {
+        const int src = (i == j) ? MINE + t : fb + i;
+        const double2 a = sq[2 * src];
+        u[i / NL] += a.x;
+        if (cvcf) {
+          const double2 b2 = sq[2 * src + 1];
+          gradu[i / NL][0] += a.y;
+          gradu[i / NL][1] += b2.x;
+          if (DIM > 2) gradu[i / NL][2] += b2.y;
+        }
+      }
       if (!cvcf) {
         const double u_diff = P.intensity * (u[0] - u[1]);
 #pragma unroll
-        for (int i = 0; i < NL; ++i) r[i] += u_diff * b[i][0] * factor;
+        for (int i = 0; i < NL; ++i) r[i] += u_diff * spc[fb + i].x * factor;
 #pragma unroll
-        for (int i = 0; i < NL; ++i) r[NL + i] += -u_diff * b[NL + i][0] * factor;
+        for (int i = 0; i < NL; ++i) r[NL + i] += -u_diff * spc[fb + NL + i].x * factor;
       } else {
-        double gradu[2][DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) { gradu[0][d] = 0.0; gradu[1][d] = 0.0; }
-#pragma unroll
-        for (int i = 0; i < NR; ++i)
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) gradu[i / NL][d] += (i == j) ? mypg[d] : b[i][3 + d];
         const double jump[2] = {u[0] - u[1], u[1] - u[0]};
         double mean_gradu[DIM];
 #pragma unroll
@@ -585,11 +596,11 @@ __global__ void __launch_bounds__(256, 3) k_coupling_jacobian_staged(MeshDesc m,
           const double aj = F.aoh * jump[s];
 #pragma unroll
           for (int i = 0; i < NL; ++i) {
-            const double phi = b[s * NL + i][0];
+            const double2 pc = spc[fb + s * NL + i];
             double value = 0.0;
-            value -= mgn * phi;
-            value -= b[s * NL + i][1] * jump[s];
-            value += aj * phi;
+            value -= mgn * pc.x;
+            value -= pc.y * jump[s];
+            value += aj * pc.x;
             r[s * NL + i] += factor * value;
           }
         }

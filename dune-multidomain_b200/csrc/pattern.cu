@@ -147,6 +147,18 @@ __global__ void k_irregular_compact(const int32_t* __restrict__ flags, const int
   if (i < n && flags[i]) list[scan[i]] = (int32_t)i;
 }
 
+// value-array span [p0, p1) of every run of simple rows (p0 == p1 for a run of irregular rows): what k_jacobian_fill_q1 streams
+__global__ void k_seg_spans(const int32_t* __restrict__ seg_start, int64_t nseg, int64_t child_offset, const int64_t* __restrict__ rowptr,
+                            const uint32_t* __restrict__ rowinfo, uint32_t full, int ns, longlong2* span)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nseg) return;
+  const int64_t g0 = child_offset + seg_start[i], g1 = child_offset + seg_start[i + 1];
+  const int64_t p0 = rowptr[g0];
+  const bool simple = rowinfo[g0] == full && rowptr[g0 + 1] - p0 == ns;
+  span[i] = make_longlong2(p0, simple ? rowptr[g1] : p0);
+}
+
 void build_pattern(Ctx* c, Matrix& M)
 {
   const MeshDesc& m = c->mesh;
@@ -240,6 +252,9 @@ void build_pattern(Ctx* c, Matrix& M)
     MDB_LAUNCH(c, k_irregular_compact, cdiv(sz, 256), 256, 0, d_head, d_scan, sz, M.d_seg_start[i]);
     const int32_t sz32 = (int32_t)sz;
     MDB_CUDA(cudaMemcpyAsync(M.d_seg_start[i] + M.n_seg[i], &sz32, 4, cudaMemcpyHostToDevice, c->stream));
+    M.d_seg_span[i] = dalloc<longlong2>(M.n_seg[i]);
+    MDB_LAUNCH(c, k_seg_spans, cdiv(M.n_seg[i], 256), 256, 0, M.d_seg_start[i], M.n_seg[i], off, M.d_rowptr, M.d_rowinfo, full, (m.dim == 3) ? 27 : 9,
+               M.d_seg_span[i]);
     MDB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_t); dfree(d_flag); dfree(d_head); dfree(d_scan);
   }

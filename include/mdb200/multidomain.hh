@@ -1,0 +1,300 @@
+// mdb200/multidomain.hh — C++ facade over the C ABI (mdb200.h) with the reference's spellings.
+//
+// The reference's boundary is a C++ template concept, Dune::PDELab::MultiDomain::GridOperator and the participants it
+// is built from (gridoperator.hh:38-214, subproblem.hh:44-148, coupling.hh:30-91, subdomainset.hh:82-133).  This
+// header keeps those names, argument orders and call sequences so that a driver written against dune-multidomain
+// (test/testpoisson.cc:119-298 is the model) reads the same, and lowers every object to a handle of libmdb200.so.
+// Arbitrary user local operators cannot run on the device: the operator classes below are the closed set the backend
+// implements; anything else fails at compile time (no matching class) or throws mdb200::Exception (DUNE_THROW analogue).
+// Header-only, C++11, no dependency besides mdb200.h; link with -lmdb200.
+#ifndef MDB200_MULTIDOMAIN_HH
+#define MDB200_MULTIDOMAIN_HH
+
+#include <cstdint>
+#include <initializer_list>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../mdb200.h"
+
+namespace mdb200 {
+
+struct Exception : std::runtime_error {
+  int code;
+  Exception(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+// One device context (one per host thread and GPU; gridoperator.hh:209-210: the reference is not re-entrant either).
+class Context {
+  mdb_ctx* c_;
+  Context(const Context&);
+  Context& operator=(const Context&);
+public:
+  explicit Context(int device = 0) : c_(mdb_create(device)) {
+    if (!c_) throw Exception(MDB_ECUDA, std::string("mdb_create: ") + mdb_last_error(0));
+  }
+  ~Context() { mdb_destroy(c_); }
+  mdb_ctx* get() const { return c_; }
+  int check(int rc, const char* what) const {
+    if (rc < 0) throw Exception(rc, std::string(what) + ": " + mdb_last_error(c_));
+    return rc;
+  }
+};
+
+// ---- grid: YaspGrid + MultiDomainGrid<..., FewSubDomainsTraits<dim,8>> (test/testpoisson.cc:134-161) ---------------
+class SubDomainGridView { public: int subdomain; explicit SubDomainGridView(int s) : subdomain(s) {} };
+
+class MultiDomainGrid {
+  Context& ctx_;
+  int dim_;
+  std::vector<int64_t> n_;
+  std::vector<uint8_t> marks_;
+  bool marking_;
+public:
+  MultiDomainGrid(Context& ctx, int dim, const int64_t* cells, const double* lower, const double* upper)
+    : ctx_(ctx), dim_(dim), n_(cells, cells + dim), marking_(false) {
+    ctx_.check(mdb_mesh_structured(ctx_.get(), dim, cells, lower, upper), "mdb_mesh_structured");
+  }
+  Context& context() const { return ctx_; }
+  int dimension() const { return dim_; }
+  int64_t size0() const { int64_t t = 1; for (int d = 0; d < dim_; ++d) t *= n_[d]; return t; }
+  const std::vector<int64_t>& cells() const { return n_; }
+  SubDomainGridView subDomain(int s) const { return SubDomainGridView(s); }
+  SubDomainGridView leafGridView() const { return SubDomainGridView(-1); }      // the MultiDomainGrid view itself
+  // grid.startSubDomainMarking(); grid.addToSubDomain(s, e); grid.preUpdate/update/postUpdateSubDomains();
+  void startSubDomainMarking() { marks_.assign((size_t)size0(), 0); marking_ = true; }
+  void addToSubDomain(int s, int64_t cell) {
+    if (!marking_ || s < 0 || s > 7 || cell < 0 || cell >= size0()) throw Exception(MDB_EINVAL, "addToSubDomain: not marking / bad argument");
+    marks_[(size_t)cell] |= (uint8_t)(1u << s);
+  }
+  void preUpdateSubDomains() {}
+  void updateSubDomains() { ctx_.check(mdb_subdomains(ctx_.get(), marks_.data()), "mdb_subdomains"); marking_ = false; }
+  void postUpdateSubDomains() {}
+  // device-side marking for large meshes: centre[axis] > threshold ? above : below (test/testpoisson.cc:152-158)
+  void markHalfspace(int axis, double threshold, int below, int above) {
+    ctx_.check(mdb_subdomains_halfspace(ctx_.get(), axis, threshold, below, above), "mdb_subdomains_halfspace");
+  }
+};
+
+// ---- function spaces (multidomaingridfunctionspace.hh:152,215) -----------------------------------------------------------
+class GridFunctionSpace {            // GridFunctionSpace<SDGV, QkLocalFiniteElementMap<...,k>, ConformingDirichletConstraints, VBE>
+public:
+  SubDomainGridView gv; int k; int child;
+  GridFunctionSpace(SubDomainGridView gv_, int order) : gv(gv_), k(order), child(-1) {}
+};
+
+class MultiDomainGridFunctionSpace { // children in argument order, LexicographicOrderingTag
+  MultiDomainGrid& grid_;
+  bool finalized_;
+  int64_t ndof_;
+public:
+  MultiDomainGridFunctionSpace(MultiDomainGrid& grid, std::initializer_list<GridFunctionSpace*> children)
+    : grid_(grid), finalized_(false), ndof_(0) {
+    for (GridFunctionSpace* g : children)
+      g->child = context().check(mdb_add_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->gv.subdomain), "mdb_add_space");
+  }
+  Context& context() const { return grid_.context(); }
+  MultiDomainGrid& grid() const { return grid_; }
+  // ordering(): computed lazily on first use (multidomaingridfunctionspace.hh:308-369); participants must exist by then
+  void update() { if (!finalized_) { context().check(mdb_finalize(context().get(), &ndof_), "mdb_finalize"); finalized_ = true; } }
+  bool finalized() const { return finalized_; }
+  int64_t size() { update(); return ndof_; }
+};
+
+// ---- conditions (subdomainset.hh:82-133) -----------------------------------------------------------------------------------
+struct SubDomainEqualityCondition {
+  uint32_t mask; SubDomainEqualityCondition(std::initializer_list<int> s) : mask(0) { for (int v : s) mask |= 1u << v; }
+  static int kind() { return MDB_COND_EQUALITY; }
+};
+struct SubDomainSubsetCondition {
+  uint32_t mask; SubDomainSubsetCondition(std::initializer_list<int> s) : mask(0) { for (int v : s) mask |= 1u << v; }
+  static int kind() { return MDB_COND_SUBSET; }
+};
+
+// ---- problem data and local operators (closed set) ----------------------------------------------------------------------------
+inline mdb_function function(int kind, double p0 = 0, double p1 = 0, double p2 = 0, double p3 = 0, double p4 = 0, double p5 = 0) {
+  mdb_function f; f.kind = kind; f.reserved = 0; f.p[0] = p0; f.p[1] = p1; f.p[2] = p2; f.p[3] = p3; f.p[4] = p4; f.p[5] = p5; return f;
+}
+inline mdb_bctype boundary(int kind) { mdb_bctype b; b.kind = kind; b.reserved = 0; for (int i = 0; i < 4; ++i) b.p[i] = 0; return b; }
+
+struct Poisson {                     // Dune::PDELab::Poisson<F,B,J>(f, b, j, quadOrder), test/testpoisson.cc:218-219
+  mdb_poisson_params p;
+  Poisson(const mdb_function& f, const mdb_bctype& b, const mdb_function& j, int quadOrder) { p.f = f; p.bc = b; p.j = j; p.quad_order = quadOrder; p.reserved = 0; }
+  static int id() { return MDB_OP_POISSON; }
+  const mdb_bctype& bctype() const { return p.bc; }
+};
+struct L2 {                          // Dune::PDELab::L2(intorder) / test/simpletimeoperator.hh
+  mdb_l2_params p;
+  explicit L2(int intorder = 2) { p.quad_order = intorder; p.reserved = 0; }
+  static int id() { return MDB_OP_L2; }
+};
+struct ContinuousValueContinuousFlowCoupling {   // test/proportionalflowcoupling.hh:94-239
+  mdb_cvcf_params p; int jac_mode;
+  ContinuousValueContinuousFlowCoupling(int intorder, double intensity, int jacobian_mode = MDB_JAC_FD_BITMATCH) : jac_mode(jacobian_mode) {
+    p.quad_order = intorder; p.reserved = 0; p.intensity = intensity; }
+  static int id() { return MDB_OP_CVCF_COUPLING; }
+};
+struct ProportionalFlowCoupling {                // test/proportionalflowcoupling.hh:10-91
+  mdb_propflow_params p; int jac_mode;
+  explicit ProportionalFlowCoupling(double intensity, int jacobian_mode = MDB_JAC_FD_BITMATCH) : jac_mode(jacobian_mode) { p.intensity = intensity; }
+  static int id() { return MDB_OP_PROPFLOW_COUPLING; }
+};
+
+// ---- participants --------------------------------------------------------------------------------------------------------------
+// TypeBasedSubProblem<MultiGFS,MultiGFS,LOP,Condition,GFS...>(lop, condition): the child space is named by object here
+template <class LOP, class Condition>
+class SubProblem {
+public:
+  MultiDomainGridFunctionSpace& gfs; LOP lop; int handle;
+  SubProblem(MultiDomainGridFunctionSpace& gfs_, const LOP& lop_, const Condition& cond, const GridFunctionSpace& child) : gfs(gfs_), lop(lop_) {
+    const int ch = child.child;
+    handle = gfs.context().check(mdb_add_subproblem(gfs.context().get(), LOP::id(), &lop.p, sizeof(lop.p), Condition::kind(), cond.mask, &ch, 1),
+                                 "mdb_add_subproblem");
+  }
+};
+// Coupling<LocalSubProblem,RemoteSubProblem,CouplingOperator>(local, remote, op)   (coupling.hh:30-91)
+template <class Local, class Remote, class Op>
+class Coupling {
+public:
+  int handle;
+  Coupling(const Local& local, const Remote& remote, const Op& op) {
+    handle = local.gfs.context().check(mdb_add_coupling(local.gfs.context().get(), Op::id(), &op.p, sizeof(op.p), local.handle, remote.handle,
+                                                        op.jac_mode), "mdb_add_coupling");
+  }
+};
+
+// ---- vectors and matrices --------------------------------------------------------------------------------------------------------
+typedef std::vector<double> Vector;   // flat ISTL BlockVector<FieldVector<double,1>>; device-resident callers pass raw pointers
+
+// constraints<R>(gfs, constrainSubProblem(sp, b)...).assemble(cg)   (constraints.hh:539-558)
+class ConstraintsContainer { public: int64_t constrained; ConstraintsContainer() : constrained(0) {} int64_t size() const { return constrained; } };
+class ConstraintsAssembler {
+  MultiDomainGridFunctionSpace& gfs_; std::vector<int> sps_; std::vector<mdb_bctype> bcs_;
+public:
+  explicit ConstraintsAssembler(MultiDomainGridFunctionSpace& gfs) : gfs_(gfs) {}
+  template <class SP> ConstraintsAssembler& constrainSubProblem(const SP& sp, const mdb_bctype& b) { sps_.push_back(sp.handle); bcs_.push_back(b); return *this; }
+  void assemble(ConstraintsContainer& cg) {
+    gfs_.update();
+    gfs_.context().check(mdb_constraints_assemble(gfs_.context().get(), sps_.data(), bcs_.data(), (int)sps_.size(), &cg.constrained),
+                         "mdb_constraints_assemble");
+  }
+};
+inline ConstraintsAssembler constraints(MultiDomainGridFunctionSpace& gfs) { return ConstraintsAssembler(gfs); }
+
+// interpolateOnTrialSpace(gfs, x, f0, sp0, f1, sp1, ...)   (interpolate.hh:76-81)
+class Interpolator {
+  MultiDomainGridFunctionSpace& gfs_; std::vector<int> sps_; std::vector<mdb_function> fns_;
+public:
+  explicit Interpolator(MultiDomainGridFunctionSpace& gfs) : gfs_(gfs) {}
+  template <class SP> Interpolator& on(const mdb_function& f, const SP& sp) { fns_.push_back(f); sps_.push_back(sp.handle); return *this; }
+  void apply(double* x, double time = 0.0) {
+    gfs_.update();
+    gfs_.context().check(mdb_interpolate(gfs_.context().get(), sps_.data(), fns_.data(), (int)sps_.size(), time, x), "mdb_interpolate");
+  }
+};
+template <class SP0>
+inline void interpolateOnTrialSpace(MultiDomainGridFunctionSpace& gfs, Vector& x, const mdb_function& f0, const SP0& sp0) {
+  x.resize((size_t)gfs.size()); Interpolator(gfs).on(f0, sp0).apply(x.data());
+}
+template <class SP0, class SP1>
+inline void interpolateOnTrialSpace(MultiDomainGridFunctionSpace& gfs, Vector& x, const mdb_function& f0, const SP0& sp0,
+                                    const mdb_function& f1, const SP1& sp1) {
+  x.resize((size_t)gfs.size()); Interpolator(gfs).on(f0, sp0).on(f1, sp1).apply(x.data());
+}
+
+// ---- GridOperator (gridoperator.hh:38-214) -----------------------------------------------------------------------------------------
+class Jacobian;
+class GridOperator {
+  MultiDomainGridFunctionSpace& gfs_;
+  int handle_;
+  double weight_;
+public:
+  // GridOperator(gfsu, gfsv, cu, cv, mb, participants...): participants in argument order, subproblems then couplings
+  GridOperator(MultiDomainGridFunctionSpace& gfsu, MultiDomainGridFunctionSpace&, const ConstraintsContainer&, const ConstraintsContainer&,
+               const std::vector<int>& subproblems, const std::vector<int>& couplings) : gfs_(gfsu), weight_(1.0) {
+    gfs_.update();
+    handle_ = gfs_.context().check(mdb_gridoperator_create(gfs_.context().get(), subproblems.data(), (int)subproblems.size(),
+                                                           couplings.data(), (int)couplings.size()), "mdb_gridoperator_create");
+  }
+  int handle() const { return handle_; }
+  MultiDomainGridFunctionSpace& trialGridFunctionSpace() const { return gfs_; }
+  Context& context() const { return gfs_.context(); }
+  void setWeight(double w) { weight_ = w; }                         // localassembler.hh:220-223
+  void setTime(double t) { context().check(mdb_set_time(context().get(), t), "mdb_set_time"); }
+  // r += weight * R(x), constrained entries zeroed   (gridoperator.hh:89-92)
+  void residual(const double* x, double* r) const { context().check(mdb_residual(context().get(), handle_, weight_, x, r), "mdb_residual"); }
+  void residual(const Vector& x, Vector& r) const { r.resize(x.size()); residual(x.data(), r.data()); }
+  // a += weight * J(x), constrained rows <- unit rows   (gridoperator.hh:94-97); the caller zeroes `a` first (a = 0.0)
+  void jacobian(const double* x, Jacobian& a) const;
+  void jacobian(const Vector& x, Jacobian& a) const { jacobian(x.data(), a); }
+};
+
+// Jacobian container: `Jacobian a(go)` runs fill_pattern (gridoperator.hh:83-87); `a = 0.0` zeroes the entries
+class Jacobian {
+  Context& ctx_; int handle_; int64_t nnz_;
+public:
+  explicit Jacobian(const GridOperator& go) : ctx_(go.context()), nnz_(0) {
+    const int h = go.handle();
+    handle_ = ctx_.check(mdb_matrix_create(ctx_.get(), &h, 1, &nnz_), "mdb_matrix_create");
+  }
+  Jacobian(const GridOperator& go0, const GridOperator& go1) : ctx_(go0.context()), nnz_(0) {     // OneStepGridOperator: dt0 + dt1 pattern
+    const int h[2] = {go0.handle(), go1.handle()};
+    handle_ = ctx_.check(mdb_matrix_create(ctx_.get(), h, 2, &nnz_), "mdb_matrix_create");
+  }
+  int handle() const { return handle_; }
+  int64_t nonzeroes() const { return nnz_; }
+  Jacobian& operator=(double v) {
+    if (v != 0.0) throw Exception(MDB_EINVAL, "Jacobian = v: only 0.0 is supported");
+    ctx_.check(mdb_matrix_zero(ctx_.get(), handle_), "mdb_matrix_zero"); return *this;
+  }
+  void pattern(std::vector<int64_t>& rowptr, std::vector<int64_t>& colidx, int64_t nrows) const {
+    rowptr.resize((size_t)nrows + 1); colidx.resize((size_t)nnz_);
+    ctx_.check(mdb_matrix_get_pattern(ctx_.get(), handle_, rowptr.data(), colidx.data()), "mdb_matrix_get_pattern");
+  }
+  void values(std::vector<double>& v) const { v.resize((size_t)nnz_); ctx_.check(mdb_matrix_get_values(ctx_.get(), handle_, v.data()), "mdb_matrix_get_values"); }
+};
+inline void GridOperator::jacobian(const double* x, Jacobian& a) const {
+  context().check(mdb_jacobian(context().get(), handle_, a.handle(), weight_, x, 0), "mdb_jacobian");
+}
+
+// ---- linear solver backends + StationaryLinearProblemSolver ([UPSTREAM] PDELab; test/testpoisson.cc:291-298) --------------------------
+struct LinearSolverResult { int iterations; bool converged; double reduction; double elapsed; };
+class ISTLBackend_SEQ_Base {
+protected:
+  int method_, precond_; unsigned maxiter_;
+public:
+  LinearSolverResult res;
+  ISTLBackend_SEQ_Base(int method, int precond, unsigned maxiter) : method_(method), precond_(precond), maxiter_(maxiter) { res.iterations = 0; res.converged = false; res.reduction = 0; res.elapsed = 0; }
+  void apply(Jacobian& a, Context& ctx, double* z, const double* r, double reduction) {
+    mdb_solve_stats st;
+    int rc = mdb_solve(ctx.get(), a.handle(), method_, precond_, reduction, (int)maxiter_, r, z, &st);
+    res.iterations = st.iterations; res.converged = st.converged != 0; res.elapsed = st.seconds;
+    res.reduction = st.defect0 > 0 ? st.defect / st.defect0 : 0.0;
+    if (rc != MDB_ENOTCONVERGED) ctx.check(rc, "mdb_solve");
+  }
+};
+// the reference's SSOR is sequential by construction; the device backends offer Jacobi (north star: Jacobi or ILU0)
+struct ISTLBackend_SEQ_CG_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_JACOBI, maxiter) {} };
+struct ISTLBackend_SEQ_BCGS_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_JACOBI, maxiter) {} };
+
+// StationaryLinearProblemSolver(go, ls, reduction).apply(x): J(x0), r = R(x0), solve J z = r, x = x0 - z   (SURVEY §8c vii)
+template <class LS>
+class StationaryLinearProblemSolver {
+  GridOperator& go_; LS& ls_; double reduction_;
+public:
+  StationaryLinearProblemSolver(GridOperator& go, LS& ls, double reduction) : go_(go), ls_(ls), reduction_(reduction) {}
+  void apply(Vector& x) {
+    Jacobian a(go_);
+    a = 0.0;
+    go_.jacobian(x, a);
+    Vector r(x.size(), 0.0), z(x.size(), 0.0);
+    go_.residual(x, r);
+    ls_.apply(a, go_.context(), z.data(), r.data(), reduction_);
+    if (!ls_.res.converged) throw Exception(MDB_ENOTCONVERGED, "StationaryLinearProblemSolver: linear solver did not converge");
+    for (size_t i = 0; i < x.size(); ++i) x[i] -= z[i];
+  }
+};
+
+} // namespace mdb200
+#endif

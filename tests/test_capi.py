@@ -80,3 +80,23 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"oracle/|liboracle|orc_[a-z]+\(|import orc", t):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def _build_example(outdir):
+    exe = os.path.join(outdir, "testpoisson")
+    libdir = os.path.dirname(pkg.library_path())
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "testpoisson.cc"), "-o", exe, "-L", libdir, "-lmdb200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cxx_facade_compiles_and_fails_loudly_without_gpu(lib):
+    """include/mdb200/multidomain.hh (the reference's spellings over the C ABI) builds as C++11 and links against
+    libmdb200.so; without a GPU the driver must stop with the "no CPU fallback" error, not compute anything."""
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d)
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present (the run is covered by the gpu tests)")
+        p = subprocess.run([exe, "3", "2.0"], capture_output=True, text=True)
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr

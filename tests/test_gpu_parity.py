@@ -250,3 +250,34 @@ def test_size_independent_properties_at_scale(n):
     az = torch.zeros_like(one)
     dev.spmv(P.mat, z, az); dev.synchronize()
     assert (az - r).norm().item() <= 2e-10 * r.norm().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level,dim", [(4, 2), (3, 3)])
+def test_cxx_driver_matches_oracle(level, dim):
+    """examples/testpoisson.cc (the reference's test/testpoisson.cc written against include/mdb200/multidomain.hh) run as a
+    program: DOF counts and the solution checksum against the oracle's StationaryLinearProblemSolver restatement."""
+    import re
+    import subprocess
+    import tempfile
+    from test_capi import _build_example
+    n = (1 << level,) * dim
+    ora = orc.Oracle()
+    Po = problems.testpoisson(ora, n)
+    u = np.zeros(Po.ndof)
+    ora.interpolate(Po.sps, Po.gfn, u)
+    ora.jacobian(Po.go, Po.mat, u, overwrite=True)
+    r = np.zeros(Po.ndof)
+    ora.residual(Po.go, u, r)
+    z = np.zeros(Po.ndof)
+    ora.solve(Po.mat, r, z, reduction=1e-13)
+    u -= z
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d)
+        out = subprocess.run([exe, str(level), "2.0", str(dim)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"(\d+) dof total, (\d+) dof constrained", out.stdout)
+    assert m and int(m.group(1)) == Po.ndof and int(m.group(2)) == Po.ncon
+    m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
+    assert abs(float(m.group(1)) - u.sum()) <= 1e-8 * abs(u.sum())
+    assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-8 * np.linalg.norm(u)
