@@ -304,6 +304,11 @@ class Mdb(Lib):
         self._check(self._fn("matrix_norm2")(C.c_void_p(self.ctx), mat, C.byref(out)), "matrix_norm2")
         return out.value
 
+    def bytes_copied(self, reset=False):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self._fn("bytes_copied")(C.c_void_p(self.ctx), C.byref(a), C.byref(b), int(reset)), "bytes_copied")
+        return a.value, b.value
+
     def launch_count(self, reset=False):
         return self._fn("launch_count", C.c_int64)(C.c_void_p(self.ctx), int(reset))
 

@@ -99,6 +99,7 @@ VecIn::VecIn(Ctx* c, const double* p, int64_t n, int slot)
   if (is_device_ptr(p)) { d = p; return; }
   if (!c->d_stage[slot]) c->d_stage[slot] = dalloc<double>(c->ndof > n ? c->ndof : n);
   MDB_CUDA(cudaMemcpyAsync(c->d_stage[slot], p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += n * (int64_t)sizeof(double);
   d = c->d_stage[slot];
 }
 VecInOut::VecInOut(Ctx* c_, double* p, int64_t n_, int slot, bool load) : c(c_), n(n_)
@@ -107,13 +108,14 @@ VecInOut::VecInOut(Ctx* c_, double* p, int64_t n_, int slot, bool load) : c(c_),
   host = p;
   if (!c->d_stage[slot]) c->d_stage[slot] = dalloc<double>(c->ndof > n ? c->ndof : n);
   d = c->d_stage[slot];
-  if (load) MDB_CUDA(cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (load) { MDB_CUDA(cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * (int64_t)sizeof(double); }
 }
 void VecInOut::commit()
 {
   if (host) {
     MDB_CUDA(cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     MDB_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += n * (int64_t)sizeof(double);
   }
 }
 
@@ -128,7 +130,7 @@ static void free_matrix(Matrix& m)
 static void reset_spaces(Ctx* c)
 {
   for (auto& ch : c->children) { dfree(ch.d_lat2dof); dfree(ch.d_dof2lat); }
-  for (auto& go : c->gos) for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); }
+  for (auto& go : c->gos) { for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); } dfree(go.d_xneed); }
   for (auto& m : c->mats) free_matrix(m);
   c->gos.clear(); c->mats.clear();
   dfree(c->d_constrained); dfree(c->d_conlist);
@@ -188,6 +190,9 @@ mdb_ctx* mdb_create(int device)
     MDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     MDB_CUDA(cudaEventCreate(&c->ev0));
     MDB_CUDA(cudaEventCreate(&c->ev1));
+    MDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming));
     c->d_Ae = dalloc<double>(MDB_MAX_CHILDREN * MDB_MAX_SP_PER_CHILD * MDB_MAXLOC * MDB_MAXLOC);
     c->d_scal = dalloc<double>(64);
     c->d_partial = dalloc<double>(8 * 4096);
@@ -206,6 +211,9 @@ void mdb_destroy(mdb_ctx* c)
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->d_halo_counter) cudaFree(c->d_halo_counter);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
+  if (c->ev_stage_free) cudaEventDestroy(c->ev_stage_free);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -527,21 +535,71 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   MDB_API_END(c)
 }
 
+// x_host[list[i]] -> stage[list[i]]: the kernel reads pinned host memory directly (zero-copy over PCIe), so only the
+// coefficients the Jacobian kernels actually read cross the bus
+__global__ void k_gather_needed(const double* __restrict__ x_host, const int32_t* __restrict__ list, int64_t n, double* stage)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t g = list[i];
+    stage[g] = x_host[g];
+  }
+}
+
 int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, int overwrite)
 {
   MDB_API_BEGIN(c)
   MDB_GO(c, go)
   MDB_MAT(c, mat)
-  VecIn vx(c, x, c->ndof, 0);
   M.dinv_valid = false;
+  // The volume operators of the closed set are linear: their Jacobian does not read x.  Only the finite-difference
+  // coupling Jacobian does, and only at the DOFs of the interface cells.  With a HOST vector the upload therefore runs on
+  // the copy stream concurrently with the volume kernels, and from pinned memory only the needed entries are fetched.
+  const double* dx = x;
+  const bool host_x = !is_device_ptr(x);
+  const bool need_x = !G.cps.empty();
+  if (host_x && need_x) {
+    if (!c->d_stage[0]) c->d_stage[0] = dalloc<double>(c->ndof);
+    cudaPointerAttributes a;
+    bool pinned = cudaPointerGetAttributes(&a, x) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer != nullptr;
+    if (!pinned) cudaGetLastError();
+    static const bool full_upload = getenv("MDB_FULL_UPLOAD") != nullptr;     // measurement switch: always copy the whole vector
+    if (full_upload) pinned = false;
+    MDB_CUDA(cudaEventRecord(c->ev_stage_free, c->stream));                   // earlier calls may still read the staging vector
+    MDB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_stage_free, 0));
+    if (pinned) {
+      if (G.n_xneed < 0) build_xneed(c, G);
+      if (G.n_xneed > 0) {
+        k_gather_needed<<<cdiv(G.n_xneed, 256) < 592 ? cdiv(G.n_xneed, 256) : 592, 256, 0, c->copy_stream>>>((const double*)a.devicePointer, G.d_xneed,
+                                                                                                       G.n_xneed, c->d_stage[0]);
+        c->launches++;
+        MDB_CUDA(cudaGetLastError());
+      }
+      c->h2d_bytes += 8 * G.n_xneed;
+    } else {
+      MDB_CUDA(cudaMemcpyAsync(c->d_stage[0], x, c->ndof * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+      c->h2d_bytes += 8 * c->ndof;
+    }
+    MDB_CUDA(cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    dx = c->d_stage[0];
+  }
   c->phase_begin("jacobian_volume");
   jacobian_volume(c, G, M, weight, overwrite != 0);
   c->phase_end();
+  if (host_x && need_x) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
   c->phase_begin("jacobian_coupling");
-  jacobian_coupling(c, G, M, weight, vx.d);
+  jacobian_coupling(c, G, M, weight, dx);
   dirichlet_rows(c, M);
   c->phase_end();
   MDB_API_END(c)
+}
+
+int mdb_bytes_copied(mdb_ctx* c, int64_t* h2d, int64_t* d2h, int reset)
+{
+  if (!c) return MDB_EINVAL;
+  if (h2d) *h2d = c->h2d_bytes;
+  if (d2h) *d2h = c->d2h_bytes;
+  if (reset) { c->h2d_bytes = 0; c->d2h_bytes = 0; }
+  return MDB_OK;
 }
 
 int mdb_spmv(mdb_ctx* c, int mat, const double* x, double* y)
@@ -663,6 +721,7 @@ int mdb_matrix_norm2(mdb_ctx* c, int mat, double* out)
   MDB_CUDA(cudaMemcpyAsync(c->h_pinned + 40, c->d_scal + 40, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   *out = c->h_pinned[40];
+  c->d2h_bytes += 8;
   MDB_API_END(c)
 }
 

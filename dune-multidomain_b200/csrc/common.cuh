@@ -171,6 +171,9 @@ struct FaceList {      // interface faces on which one coupling fires, in traver
 struct GridOp {
   std::vector<int> sps, cps;
   std::vector<FaceList> faces;   // one per coupling
+  // sorted list of the DOFs whose coefficients the Jacobian kernels of this operator read (the coupling faces' cell DOFs;
+  // the volume operators of the closed set are linear).  Built on first use by mdb_jacobian with a host vector.
+  int32_t* d_xneed = nullptr; int64_t n_xneed = -1;
 };
 
 struct Matrix {
@@ -207,6 +210,10 @@ struct Ctx {
   PhaseRec* cur_phase = nullptr;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // second stream for host->device traffic that overlaps assembly kernels; byte counters of the host<->device copies
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy_done = nullptr, ev_stage_free = nullptr;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
 
   MeshDesc mesh{};
   bool have_mesh = false, have_sd = false, finalized = false;
@@ -281,6 +288,7 @@ void rebuild_conlist(Ctx* c);
 void interpolate(Ctx* c, const int* sps, const mdb_function* fns, int n, double t, double* d_x);
 void export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs);
 void build_facelists(Ctx* c, GridOp& go);
+void build_xneed(Ctx* c, GridOp& go);
 void build_pattern(Ctx* c, Matrix& m);
 void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
 void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r);

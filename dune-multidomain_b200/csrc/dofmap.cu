@@ -376,6 +376,64 @@ __global__ void k_face_compact(int nf, int64_t total, const int32_t* __restrict_
   cell[scan[t]] = (int32_t)(t / nf); face[scan[t]] = (int8_t)(t % nf);
 }
 
+// ---- which coefficients does jacobian(x, a) read? ------------------------------------------------------------------------
+struct NeedSide { int lat_n[3]; int64_t offset; const int32_t* lat2dof; };
+__global__ void k_mark_face_dofs(MeshDesc m, NeedSide L, NeedSide R, const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces,
+                                 uint8_t* flags)
+{
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nfaces) return;
+  int ijk[3]; cell_ijk(m, fcell[f], ijk);
+  int nijk[3] = {ijk[0], ijk[1], ijk[2]};
+  const int face = fface[f];
+  nijk[face / 2] += (face % 2) ? 1 : -1;
+  const int nl = 1 << m.dim;
+  for (int i = 0; i < nl; ++i) {
+    const int ax = i & 1, ay = (i >> 1) & 1, az = (m.dim > 2) ? (i >> 2) & 1 : 0;
+    int64_t p = (ijk[0] + ax) + (int64_t)L.lat_n[0] * ((ijk[1] + ay) + (int64_t)L.lat_n[1] * (ijk[2] + az));
+    flags[L.offset + L.lat2dof[p]] = 1;
+    p = (nijk[0] + ax) + (int64_t)R.lat_n[0] * ((nijk[1] + ay) + (int64_t)R.lat_n[1] * (nijk[2] + az));
+    flags[R.offset + R.lat2dof[p]] = 1;
+  }
+}
+
+void build_xneed(Ctx* c, GridOp& go)
+{
+  const int64_t n = c->ndof;
+  uint8_t* d_flags = dalloc<uint8_t>(n);
+  MDB_CUDA(cudaMemsetAsync(d_flags, 0, n, c->stream));
+  for (size_t k = 0; k < go.cps.size(); ++k) {
+    const CouplingDesc& cp = c->cps[go.cps[k]];
+    const FaceList& fl = go.faces[k];
+    if (fl.n == 0) continue;
+    NeedSide S[2];
+    const int sp[2] = {cp.local_sp, cp.remote_sp};
+    for (int q = 0; q < 2; ++q) {
+      const Child& ch = c->children[c->sps[sp[q]].children[0]];
+      for (int d = 0; d < 3; ++d) S[q].lat_n[d] = ch.lat_n[d];
+      S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof;
+    }
+    MDB_LAUNCH(c, k_mark_face_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, S[0], S[1], fl.d_cell, fl.d_face, fl.n, d_flags);
+  }
+  int32_t* d_f = dalloc<int32_t>(n);
+  int32_t* d_s = dalloc<int32_t>(n);
+  MDB_LAUNCH(c, k_u8_to_i32, cdiv(n, 256), 256, 0, d_flags, d_f, n);
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_f, d_s, (int)n, c->stream);
+  void* d_tmp = nullptr; MDB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+  MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_f, d_s, (int)n, c->stream)); c->launches++;
+  int32_t ls = 0, lf = 0;
+  MDB_CUDA(cudaMemcpyAsync(&ls, d_s + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(&lf, d_f + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  go.n_xneed = (int64_t)ls + lf;
+  dfree(go.d_xneed);
+  go.d_xneed = dalloc<int32_t>(go.n_xneed);
+  MDB_LAUNCH(c, k_compact, cdiv(n, 256), 256, 0, d_flags, d_s, go.d_xneed, n);
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_tmp); dfree(d_f); dfree(d_s); dfree(d_flags);
+}
+
 void build_facelists(Ctx* c, GridOp& go)
 {
   const MeshDesc& m = c->mesh;

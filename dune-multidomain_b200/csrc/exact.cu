@@ -464,8 +464,8 @@ __global__ void __launch_bounds__(256) k_coupling_jacobian(MeshDesc m, CouplingP
 // (the base-line products; a perturbation of dof j changes only the j-th product, the additions are redone in the
 // reference's order), then thread (face, evaluation) runs the perturbation-dependent part of alpha_coupling.
 // Mapping: 256 threads = FPB faces x NE evaluations; evaluation 0 is the base line, 1+j perturbs dof j.
-template <int DIM>
-__global__ void __launch_bounds__(256, 3) k_coupling_jacobian_staged(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_coupling_jacobian_staged(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
                                                                   const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
                                                                   const double* __restrict__ tab, const double* __restrict__ x,
                                                                   const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slots, double* val)
@@ -858,16 +858,21 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     } else slots = it->second;
     const double* tab = face_tables(c, P);
     const int fpb = 256 / (2 * NL + 1);
-    static const int variant = getenv("MDB_COUPLING_JAC_VARIANT") ? atoi(getenv("MDB_COUPLING_JAC_VARIANT")) : 2;   // A/B switch for profiling only
+    static const int variant = getenv("MDB_COUPLING_JAC_VARIANT") ? atoi(getenv("MDB_COUPLING_JAC_VARIANT")) : 1;   // A/B switch for profiling only
     if (variant == 0) {
       if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
                                  M.d_rowptr, slots, M.d_val);
       else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
                       M.d_rowptr, slots, M.d_val);
     } else if (variant == 1) {
-      if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian_staged<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 3>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                                  d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, k_coupling_jacobian_staged<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 3>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+                      d_x, M.d_rowptr, slots, M.d_val);
+    } else if (variant == 3) {
+      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 2>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+                                 d_x, M.d_rowptr, slots, M.d_val);
+      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 2>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                       d_x, M.d_rowptr, slots, M.d_val);
     } else {
       const int fpb2 = 512 / (2 * (2 * NL + 1));

@@ -216,6 +216,10 @@ int mdb_residual(mdb_ctx* ctx, int go, double weight, const double* x, double* r
  * replaced by the unit row (jacobianassemblerengine.hh:480-504).  overwrite != 0 treats `a` as zero on entry
  * (fuses the caller's "a = 0" into the assembly kernel). */
 int mdb_jacobian(mdb_ctx* ctx, int go, int mat, double weight, const double* x, int overwrite);
+/* Note on host vectors: the volume operators of the closed set are linear, so jacobian() reads x only through the
+ * finite-difference coupling Jacobian, at the DOFs of the interface cells.  A host x is therefore uploaded on a second
+ * stream while the volume kernels run; from pinned (page-locked) memory only the entries that are read are fetched
+ * (zero-copy gather), from pageable memory the whole vector is copied. */
 
 /* ---- linear solve ([UPSTREAM] ISTL solver backends) ----------- */
 enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1 };
@@ -276,6 +280,9 @@ int mdb_phase_count(mdb_ctx* ctx, const char* phase);
 int mdb_profile_reset(mdb_ctx* ctx);
 /* Number of kernel launches issued by this context since creation / since the last reset. */
 int64_t mdb_launch_count(mdb_ctx* ctx, int reset);
+/* Bytes moved between host and device by this context's calls since the last reset (staging copies of host vectors,
+ * zero-copy gathers, result read-backs). */
+int mdb_bytes_copied(mdb_ctx* ctx, int64_t* h2d, int64_t* d2h, int reset);
 /* Raw CUDA stream of the context (cudaStream_t as void*). */
 void* mdb_stream(mdb_ctx* ctx);
 int mdb_synchronize(mdb_ctx* ctx);

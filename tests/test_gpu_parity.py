@@ -281,3 +281,29 @@ def test_cxx_driver_matches_oracle(level, dim):
     m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
     assert abs(float(m.group(1)) - u.sum()) <= 1e-8 * abs(u.sum())
     assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-8 * np.linalg.norm(u)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [(12, 10), (6, 8, 5)])
+def test_jacobian_host_vector_paths_agree(n):
+    """mdb_jacobian with x in pageable host memory (whole-vector copy on the copy stream), in pinned host memory (zero-copy
+    gather of the entries the coupling kernels read) and in device memory must give the same bits; only the pinned path
+    may move fewer bytes than the vector holds."""
+    import torch
+    dev = pkg.Mdb(0)
+    P = problems.testpoisson(dev, n)
+    x = np.random.default_rng(3).uniform(-1, 1, P.ndof)
+    xd = torch.from_numpy(x).cuda()
+    xp = torch.empty(P.ndof, dtype=torch.float64, pin_memory=True)
+    xp.copy_(torch.from_numpy(x))
+    torch.cuda.synchronize()
+    vals = []
+    moved = []
+    for arg in (xd, x, xp.numpy(), x, xp.numpy()):
+        dev.bytes_copied(reset=True)
+        dev.jacobian(P.go, P.mat, arg, overwrite=True)
+        vals.append(dev.matrix_get_values(P.mat))
+        moved.append(dev.bytes_copied()[0])
+    for v in vals[1:]:
+        assert np.array_equal(v, vals[0])
+    assert moved[0] == 0 and moved[1] == 8 * P.ndof and 0 < moved[2] < 8 * P.ndof and moved[4] == moved[2]
