@@ -139,6 +139,7 @@ struct Child {
   int32_t* d_lat2dof = nullptr;
   int32_t* d_dof2lat = nullptr;
   int64_t size = 0, offset = 0;
+  int lat_lo[3] = {0, 0, 0}, lat_hi[3] = {0, 0, 0};   // bounding box (inclusive) of the lattice points that carry a DOF
   int nloc(int dim) const { int r = 1; for (int d = 0; d < dim; ++d) r *= (k + 1); return r; }
 };
 

@@ -83,6 +83,22 @@ __global__ void k_fill_i32(int32_t* a, int64_t n, int32_t v)
   if (i < n) a[i] = v;
 }
 
+// bounding box of the present lattice points: bb = {min0,min1,min2,max0,max1,max2}
+__global__ void k_lattice_bbox(const uint8_t* __restrict__ present, int64_t nlat, int lat_n0, int lat_n1, int* bb)
+{
+  int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-1, -1, -1};
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nlat; p += (int64_t)gridDim.x * blockDim.x) {
+    if (!present[p]) continue;
+    int64_t r = p;
+    const int q[3] = {(int)(r % lat_n0), (int)((r / lat_n0) % lat_n1), (int)(r / ((int64_t)lat_n0 * lat_n1))};
+    for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], q[d]); mx[d] = max(mx[d], q[d]); }
+  }
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) { mn[d] = min(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o)); mx[d] = max(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(bb + d, mn[d]); atomicMax(bb + 3 + d, mx[d]); }
+  }
+}
+
 void build_dofmap(Ctx* c)
 {
   const MeshDesc& m = c->mesh;
@@ -100,6 +116,16 @@ void build_dofmap(Ctx* c)
     MDB_CUDA(cudaMemsetAsync(d_present, 0, ch.nlat, c->stream));
     MDB_LAUNCH(c, k_mark_present, cdiv(m.ncells(), 256), 256, 0, m, c->d_cell_sd, ch.k, ch.subdomain, ch.lat_n[0], ch.lat_n[1], d_present);
     MDB_LAUNCH(c, k_fill_i32, cdiv(ch.nlat, 256), 256, 0, ch.d_lat2dof, ch.nlat, -1);
+    {
+      int h_bb[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
+      int* d_bb = dalloc<int>(6);
+      MDB_CUDA(cudaMemcpyAsync(d_bb, h_bb, sizeof(h_bb), cudaMemcpyHostToDevice, c->stream));
+      MDB_LAUNCH(c, k_lattice_bbox, 148 * 4, 256, 0, d_present, ch.nlat, ch.lat_n[0], ch.lat_n[1], d_bb);
+      MDB_CUDA(cudaMemcpyAsync(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost, c->stream));
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      dfree(d_bb);
+      for (int d = 0; d < 3; ++d) { ch.lat_lo[d] = h_bb[3 + d] < 0 ? 0 : h_bb[d]; ch.lat_hi[d] = h_bb[3 + d] < 0 ? -1 : h_bb[3 + d]; }
+    }
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flags, d_scan, (int)ch.nlat, c->stream);
     void* d_tmp = nullptr; MDB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));

@@ -287,7 +287,7 @@ def test_cxx_driver_matches_oracle(level, dim):
 @pytest.mark.parametrize("n", [(12, 10), (6, 8, 5)])
 def test_jacobian_host_vector_paths_agree(n):
     """mdb_jacobian with x in pageable host memory (whole-vector copy on the copy stream), in pinned host memory (zero-copy
-    gather of the entries the coupling kernels read) and in device memory must give the same bits; only the pinned path
+    gather of the entries the coupling kernels read) and in device memory must give the same matrix; only the pinned path
     may move fewer bytes than the vector holds."""
     import torch
     dev = pkg.Mdb(0)
@@ -304,6 +304,6 @@ def test_jacobian_host_vector_paths_agree(n):
         dev.jacobian(P.go, P.mat, arg, overwrite=True)
         vals.append(dev.matrix_get_values(P.mat))
         moved.append(dev.bytes_copied()[0])
-    for v in vals[1:]:
-        assert np.array_equal(v, vals[0])
+    for v in vals[1:]:        # the coupling blocks are accumulated with atomics: the summation order may differ in the last bit
+        assert np.abs(v - vals[0]).max() <= 1e-14 * np.abs(vals[0]).max()
     assert moved[0] == 0 and moved[1] == 8 * P.ndof and 0 < moved[2] < 8 * P.ndof and moved[4] == moved[2]
