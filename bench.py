@@ -140,7 +140,7 @@ def cpu_baseline(size, layers, nthreads):
                       % (size, size, layers, ncells / best, dofs_per_cell, t_setup, ncells / t_res)}
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the CPU restatement of the reference path with all host threads (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -149,7 +149,8 @@ def run_reference(args):
     import numpy as np
     import orc
     import problems
-    size, layers = args.size, max(args.cpu_sample_layers, 4)
+    # the threaded oracle colours z-slabs: give every thread two layers, bounded so that a step stays within a few seconds
+    size, layers = args.size, min(max(2 * ncores, 8), 64)
     h = 1.0 / size
     o = orc.Oracle(fast=True)
     P = problems.testpoisson(o, (size, size, layers), upper=(1.0, 1.0, layers * h))
@@ -174,13 +175,25 @@ def run_reference(args):
                                         "stack and cannot be built here)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there) share file
+    # descriptor 1, so route fd 1 to stderr for the whole run and keep a private handle on the real stdout for the line.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     args = parse()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out)
         return
     import numpy as np
     import torch
@@ -352,7 +365,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(S, args.cpu_sample_layers, 1)
         elif world == 1:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -205,28 +205,31 @@ static bool uniform_rows_ok(const Ctx* c, const Matrix& M, const VolSpec& V, int
   return true;
 }
 
-void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool overwrite)
+// The volume Jacobian in two independent parts (they write disjoint rows), so that mdb_jacobian can run them on different
+// streams: `part` 0 = the streamed simple rows (HBM-write bound), 1 = the irregular rows (latency bound; the coupling
+// kernels add into these rows afterwards).  launch_element_matrices must have run before either part.
+void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool overwrite, int part)
 {
   const MeshDesc& m = c->mesh;
-  launch_element_matrices(c, go.sps, weight);
+  (void)weight;
   const int NL = 1 << m.dim;
   for (int i = 0; i < (int)c->children.size(); ++i) {
     VolSpec V = vol_spec(c, go, i);
     ChildQ1 ch = child_q1(c, i);
     if (ch.size == 0) continue;
     if (V.n == 0) {       // nothing to add; in overwrite mode the rows must still be zeroed
-      if (overwrite) MDB_CUDA(cudaMemsetAsync(M.d_val + M.child_begin[i], 0, (M.child_end[i] - M.child_begin[i]) * sizeof(double), c->stream));
+      if (overwrite && part == 1) MDB_CUDA(cudaMemsetAsync(M.d_val + M.child_begin[i], 0, (M.child_end[i] - M.child_begin[i]) * sizeof(double), c->stream));
       continue;
     }
     const bool uni = uniform_rows_ok(c, M, V, i);
     const int32_t* list = uni ? M.d_irregular[i] : nullptr;
     const int64_t nrows = uni ? M.n_irregular[i] : ch.size;
-    if (uni) {
+    if (uni && part == 0) {
       const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL;
       if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, (int)M.n_seg[i], JF_THREADS, 0, S, M.d_seg_span[i], M.d_val, (int)overwrite);
       else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, (int)M.n_seg[i], JF_THREADS, 0, S, M.d_seg_span[i], M.d_val, (int)overwrite);
     }
-    if (nrows > 0) {
+    if (nrows > 0 && part == 1) {
       if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
                                  M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
       else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,

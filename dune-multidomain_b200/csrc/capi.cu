@@ -191,6 +191,9 @@ mdb_ctx* mdb_create(int device)
     MDB_CUDA(cudaEventCreate(&c->ev0));
     MDB_CUDA(cudaEventCreate(&c->ev1));
     MDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming));
     c->d_Ae = dalloc<double>(MDB_MAX_CHILDREN * MDB_MAX_SP_PER_CHILD * MDB_MAXLOC * MDB_MAXLOC);
@@ -212,6 +215,9 @@ void mdb_destroy(mdb_ctx* c)
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->d_halo_counter) cudaFree(c->d_halo_counter);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
   if (c->ev_stage_free) cudaEventDestroy(c->ev_stage_free);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -582,12 +588,31 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
     MDB_CUDA(cudaEventRecord(c->ev_copy_done, c->copy_stream));
     dx = c->d_stage[0];
   }
-  c->phase_begin("jacobian_volume");
-  jacobian_volume(c, G, M, weight, overwrite != 0);
+  // Stream plan: main  : element matrices -> [fork] -> simple rows (HBM-write bound) ------------------> [join] -> Dirichlet rows
+  //              aux   :                      [fork] -> irregular rows -> (x ready) -> FD coupling (FP64 bound) -> [join]
+  // The two branches write disjoint rows (coupling entries live in irregular rows only) and stress different units, so
+  // they overlap almost perfectly.
+  c->phase_begin("jacobian_elem");
+  launch_element_matrices(c, G.sps, weight);
   c->phase_end();
-  if (host_x && need_x) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
-  c->phase_begin("jacobian_coupling");
-  jacobian_coupling(c, G, M, weight, dx);
+  MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  {
+    StreamScope aux(c, c->aux_stream);
+    MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+    c->phase_begin("jacobian_rows");
+    jacobian_volume(c, G, M, weight, overwrite != 0, 1);
+    c->phase_end();
+    if (host_x && need_x) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+    c->phase_begin("jacobian_coupling");
+    jacobian_coupling(c, G, M, weight, dx);
+    c->phase_end();
+    MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+  }
+  c->phase_begin("jacobian_fill");
+  jacobian_volume(c, G, M, weight, overwrite != 0, 0);
+  c->phase_end();
+  MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  c->phase_begin("jacobian_dirichlet");
   dirichlet_rows(c, M);
   c->phase_end();
   MDB_API_END(c)

@@ -214,6 +214,9 @@ struct Ctx {
   // second stream for host->device traffic that overlaps assembly kernels; byte counters of the host<->device copies
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy_done = nullptr, ev_stage_free = nullptr;
+  // auxiliary compute stream: mdb_jacobian runs the irregular rows + FD coupling there while the simple rows stream out
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
 
   MeshDesc mesh{};
@@ -263,6 +266,13 @@ struct Ctx {
   void phase_reset();
 };
 
+// run a section of host code with another stream as the context's launch stream
+struct StreamScope {
+  Ctx* c; cudaStream_t save;
+  StreamScope(Ctx* c_, cudaStream_t s) : c(c_), save(c_->stream) { c->stream = s; }
+  ~StreamScope() { c->stream = save; }
+};
+
 inline bool is_device_ptr(const void* p)
 {
   cudaPointerAttributes a;
@@ -295,7 +305,8 @@ void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x,
 void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r);
 void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
 void constrain_residual(Ctx* c, double* d_r);
-void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool overwrite);
+void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight);
+void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool overwrite, int part);
 void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x);
 void dirichlet_rows(Ctx* c, Matrix& m);
 void spmv(Ctx* c, const Matrix& m, const double* d_x, double* d_y);
