@@ -13,7 +13,7 @@ import numpy as np
 # ---- enums (mirror include/mdb200.h) -----------------------------------------------------------
 FE_Q1, FE_Q2 = 1, 2
 COND_EQUALITY, COND_SUBSET = 0, 1
-FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2 = range(7)
+FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2, FN_DN_SOURCE = range(8)
 BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON = range(3)
 OP_POISSON, OP_L2 = 1, 2
 OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
@@ -303,6 +303,11 @@ class Mdb(Lib):
         out = C.c_double(0.0)
         self._check(self._fn("matrix_norm2")(C.c_void_p(self.ctx), mat, C.byref(out)), "matrix_norm2")
         return out.value
+
+    def matrix_stats(self, mat):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self._fn("matrix_stats")(C.c_void_p(self.ctx), mat, C.byref(a), C.byref(b)), "matrix_stats")
+        return a.value, b.value
 
     def bytes_copied(self, reset=False):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -191,7 +191,13 @@ mdb_ctx* mdb_create(int device)
     MDB_CUDA(cudaEventCreate(&c->ev0));
     MDB_CUDA(cudaEventCreate(&c->ev1));
     MDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    MDB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    {
+      // the auxiliary stream runs the FP64-bound coupling kernel next to the HBM-bound fill kernel: give it priority so
+      // that its blocks are placed as soon as an SM has room instead of after the fill grid has drained
+      int lo = 0, hi = 0;
+      MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      MDB_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    }
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
@@ -615,6 +621,17 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   c->phase_begin("jacobian_dirichlet");
   dirichlet_rows(c, M);
   c->phase_end();
+  MDB_API_END(c)
+}
+
+int mdb_matrix_stats(mdb_ctx* c, int mat, int64_t* simple_rows, int64_t* irregular_rows)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  int64_t irr = 0;
+  for (size_t i = 0; i < c->children.size(); ++i) irr += M.n_irregular[i];
+  if (irregular_rows) *irregular_rows = irr;
+  if (simple_rows) *simple_rows = c->ndof - irr;
   MDB_API_END(c)
 }
 

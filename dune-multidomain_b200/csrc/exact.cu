@@ -865,9 +865,19 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
       else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
                       M.d_rowptr, slots, M.d_val);
     } else if (variant == 1) {
-      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 3>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      // Optional shared-memory padding limits the residency of this FP64-bound kernel (it runs next to the HBM-bound
+      // fill kernel on another stream, capi.cu mdb_jacobian) so that both fit on an SM at the same time.
+      static const int pad_kb = getenv("MDB_COUPLING_PAD_KB") ? atoi(getenv("MDB_COUPLING_PAD_KB")) : 0;
+      static bool configured = false;
+      if (pad_kb > 0 && !configured) {
+        MDB_CUDA(cudaFuncSetAttribute(k_coupling_jacobian_staged<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024));
+        MDB_CUDA(cudaFuncSetAttribute(k_coupling_jacobian_staged<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024));
+        configured = true;
+      }
+      const size_t pad = (size_t)pad_kb * 1024;
+      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 3>), cdiv(fl.n, fpb), 256, pad, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                                  d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 3>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 3>), cdiv(fl.n, fpb), 256, pad, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                       d_x, M.d_rowptr, slots, M.d_val);
     } else if (variant == 3) {
       if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 2>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,

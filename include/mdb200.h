@@ -66,7 +66,9 @@ enum {
   MDB_FN_BOX = 3,            /* p[0] if p[1]<x_d<p[2] for all d<dim else 0   F of test/testpoisson.cc:32-37 before :38 */
   MDB_FN_TESTPOISSON_J = 4,  /* 0 on x1<1e-6 or x1>1-1e-6; -5 on x0>1-1e-6 && x1>.5+1e-6; else 0  test/testpoisson.cc:103-116 */
   MDB_FN_INSTAT_G = 5,       /* time dependent Dirichlet data, test/testinstationarypoisson.cc:94-100 family: p[0]*sin(p[1]*t)*exp(-|x-c|^2), c=.5 */
-  MDB_FN_POLY2 = 6           /* p[0] + sum_d p[1+d]*x_d + p[4]*|x|^2  (manufactured-solution tests)     */
+  MDB_FN_POLY2 = 6,          /* p[0] + sum_d p[1+d]*x_d + p[4]*|x|^2  (manufactured-solution tests)     */
+  MDB_FN_DN_SOURCE = 7       /* F of test/testpoisson-dirichlet-neumann.cc:73-87 (= testpoisson.cc:32-37 before the
+                                overwrite): 50 on (0.25,0.375)^dim; else 60 exp(-10 |x|^2) if |0.5 - x| < 0.2; else 0 */
 };
 typedef struct mdb_function {
   int32_t kind;
@@ -266,6 +268,9 @@ int mdb_owned_counts(mdb_ctx* ctx, int64_t* per_child);
  * nchildren entries: global child offset + owned rows of the lower ranks; NULL = local numbering). */
 int mdb_get_ownership(mdb_ctx* ctx, const int64_t* child_global_base, uint8_t* owned_flags, int64_t* global_index);
 
+/* Row classes of the matrix: "simple" rows carry exactly the full 3^dim own-block stencil (their values are streamed by
+ * k_jacobian_fill_q1), all others are "irregular" (boundary, subdomain boundary, interface rows). */
+int mdb_matrix_stats(mdb_ctx* ctx, int mat, int64_t* simple_rows, int64_t* irregular_rows);
 /* Sum of squares of the stored entries of the matrix (device reduction; a cheap checksum of an assembly
  * result that a host caller can read back).  `out` is a host pointer. */
 int mdb_matrix_norm2(mdb_ctx* ctx, int mat, double* out);

@@ -39,6 +39,15 @@ double eval_function(const mdb_function& f, int dim, const double* x, double t)
     for (int d = 0; d < dim; ++d) { v += f.p[1 + d] * x[d]; n2 += x[d] * x[d]; }
     return v + f.p[4] * n2;
   }
+  case MDB_FN_DN_SOURCE: {               // testpoisson-dirichlet-neumann.cc:73-87
+    bool box = true;
+    for (int d = 0; d < dim; ++d) box = box && x[d] > 0.25 && x[d] < 0.375;
+    if (box) return 50.0;
+    double m2 = 0.0, n2 = 0.0;
+    for (int d = 0; d < dim; ++d) { double c = 0.5 - x[d]; m2 += c * c; n2 += x[d] * x[d]; }
+    if (std::sqrt(m2) < 0.2) return 60 * std::exp(-10 * n2);
+    return 0.0;
+  }
   }
   throw std::runtime_error("unknown function kind");
 }

@@ -85,3 +85,11 @@ def testpoisson_partitioned(api, n_per_rank, rank, nranks, **kw):
     P = testpoisson(api, tuple(gn), slab=s, **kw)
     P.slab = s
     return P
+
+
+def dirichlet_neumann_q1(api, n):
+    """BASELINE configs[0] in its conforming-Q1 form: test/testpoisson-dirichlet-neumann.cc with the Q1
+    alternative of :966-970 / what test/testpoisson-assembly.cc:930-934 assembles — 2-D unit square (ini: refine 9 =>
+    512^2), split x0 > 0.5 (:919-925), Poisson(order 6) with the source F of :73-87 on both sides, monolithic coupling
+    ContinuousValueContinuousFlowCoupling(4, 10) (:449, ini:10)."""
+    return testpoisson(api, n, intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE))
