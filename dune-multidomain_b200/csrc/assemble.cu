@@ -306,13 +306,11 @@ __global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const ui
 // otherwise.  Global traffic per row drops from 9 map + 27 coefficient loads to ~1.5 of each, and the dependent chain
 // is map -> coefficient -> arithmetic with one barrier in between.
 template <int DIM> struct ResTile;
-template <> struct ResTile<3> { static constexpr int TX = 32, TY = 8, TZ = 8, HZ = 10, CZ = 9; };
-template <> struct ResTile<2> { static constexpr int TX = 32, TY = 8, TZ = 1, HZ = 1, CZ = 1; };
+template <> struct ResTile<3> { static constexpr int TX = 32, TY = 4, TZ = 4, HZ = 6, CZ = 5; };
+template <> struct ResTile<2> { static constexpr int TX = 32, TY = 16, TZ = 1, HZ = 1, CZ = 1; };
 
-// One thread owns the (tx, ty) column of the tile and walks it along z with a sliding register window of three planes
-// (9 coefficients each), so that a uniform row costs 9 shared-memory loads instead of 27.
 template <int DIM>
-__global__ void __launch_bounds__(256) k_residual_volume_tile(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
+__global__ void __launch_bounds__(512) k_residual_volume_tile(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
                                                               const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r,
                                                               int lo0, int lo1, int lo2, int nt0, int nt1)
 {
@@ -321,9 +319,8 @@ __global__ void __launch_bounds__(256) k_residual_volume_tile(MeshDesc m, const 
   constexpr int NS = (DIM == 3) ? 27 : 9;
   constexpr int HX = T::TX + 2, HY = T::TY + 2, HZ = T::HZ;
   constexpr int CX = T::TX + 1, CY = T::TY + 1, CZ = T::CZ;
-  constexpr int NH = HZ * HY * HX;
-  __shared__ int32_t s_lat[NH];
-  __shared__ double s_x[NH];
+  __shared__ int32_t s_lat[HZ * HY * HX];
+  __shared__ double s_x[HZ * HY * HX];
   __shared__ uint8_t s_ok[CZ * CY * CX];              // per cell: bit v set <=> subproblem v of V acts on the cell (and the child lives there)
   __shared__ double sAe[MDB_MAX_SP_PER_CHILD * NL * NL];
   __shared__ double sS[32];
@@ -335,89 +332,69 @@ __global__ void __launch_bounds__(256) k_residual_volume_tile(MeshDesc m, const 
   if (tid < NS) sS[tid] = Ae[V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL + tid];
   const int b0 = blockIdx.x % nt0, b1 = (blockIdx.x / nt0) % nt1, b2 = blockIdx.x / (nt0 * nt1);
   const int o0 = lo0 + b0 * T::TX, o1 = lo1 + b1 * T::TY, o2 = (DIM > 2) ? lo2 + b2 * T::TZ : 0;   // lattice origin of the tile
-  // stage the map (halo included; -1 outside the lattice or where the child has no DOF): one warp per halo line
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int row = warp; row < HZ * HY; row += 8) {
-    const int hy = row % HY, hz = row / HY;
-    const int p1 = o1 - 1 + hy, p2 = (DIM > 2) ? o2 - 1 + hz : 0;
-    const bool rowok = p1 >= 0 && p1 < ch.lat_n[1] && p2 >= 0 && p2 < ch.lat_n[2];
-    const int64_t base = (int64_t)ch.lat_n[0] * (p1 + (int64_t)ch.lat_n[1] * p2);
-    for (int hx = lane; hx < HX; hx += 32) {
-      const int p0 = o0 - 1 + hx;
-      s_lat[row * HX + hx] = (rowok && p0 >= 0 && p0 < ch.lat_n[0]) ? ch.lat2dof[base + p0] : -1;
-    }
+  // stage the map (halo included; -1 outside the lattice or where the child has no DOF)
+  for (int i = tid; i < HZ * HY * HX; i += blockDim.x) {
+    const int hx = i % HX, hy = (i / HX) % HY, hz = i / (HX * HY);
+    const int p0 = o0 - 1 + hx, p1 = o1 - 1 + hy, p2 = (DIM > 2) ? o2 - 1 + hz : 0;
+    int32_t g = -1;
+    if (p0 >= 0 && p0 < ch.lat_n[0] && p1 >= 0 && p1 < ch.lat_n[1] && p2 >= 0 && p2 < ch.lat_n[2])
+      g = ch.lat2dof[p0 + ch.lat_n[0] * (p1 + ch.lat_n[1] * p2)];              // < 2^31 lattice points per child (build_dofmap)
+    s_lat[i] = g;
   }
   // cells around the tile: cell (c0,c1,c2) has its lower corner at lattice point (c0,c1,c2) (Q1: lattice = vertices)
-  for (int row = warp; row < CZ * CY; row += 8) {
-    const int cy = row % CY, cz = row / CY;
-    const int c1 = o1 - 1 + cy, c2 = (DIM > 2) ? o2 - 1 + cz : 0;
-    const bool rowok = c1 >= 0 && c1 < m.n[1] && c2 >= 0 && c2 < m.n[2];
-    const int64_t base = (int64_t)m.n[0] * (c1 + (int64_t)m.n[1] * c2);
-    for (int cx = lane; cx < CX; cx += 32) {
-      const int c0 = o0 - 1 + cx;
-      uint8_t ok = 0;
-      if (rowok && c0 >= 0 && c0 < m.n[0]) {
-        const uint8_t sdc = sd[base + c0];
-        if (ch.subdomain < 0 || ((sdc >> ch.subdomain) & 1))
-          for (int v = 0; v < V.n; ++v) if (cond_applies(V.cond_kind[v], V.mask[v], sdc)) ok |= (uint8_t)(1u << v);
-      }
-      s_ok[row * CX + cx] = ok;
+  for (int i = tid; i < CZ * CY * CX; i += blockDim.x) {
+    const int cx = i % CX, cy = (i / CX) % CY, cz = i / (CX * CY);
+    const int c0 = o0 - 1 + cx, c1 = o1 - 1 + cy, c2 = (DIM > 2) ? o2 - 1 + cz : 0;
+    uint8_t ok = 0;
+    if (c0 >= 0 && c0 < m.n[0] && c1 >= 0 && c1 < m.n[1] && c2 >= 0 && c2 < m.n[2]) {
+      const uint8_t sdc = sd[c0 + m.n[0] * (c1 + m.n[1] * c2)];                   // < 2^31 cells per context (mdb_mesh_structured)
+      if (ch.subdomain < 0 || ((sdc >> ch.subdomain) & 1))
+        for (int v = 0; v < V.n; ++v) if (cond_applies(V.cond_kind[v], V.mask[v], sdc)) ok |= (uint8_t)(1u << v);
     }
+    s_ok[i] = ok;
   }
   __syncthreads();
   const double* xc = x + ch.offset;
-  for (int i = tid; i < NH; i += 256) { const int32_t g = s_lat[i]; s_x[i] = g >= 0 ? xc[g] : 0.0; }
+  for (int i = tid; i < HZ * HY * HX; i += blockDim.x) { const int32_t g = s_lat[i]; s_x[i] = g >= 0 ? xc[g] : 0.0; }
   __syncthreads();
-  const int tx = tid % T::TX, ty = tid / T::TX;
-  // sliding window over the planes hz = tz, tz+1, tz+2 of the halo tile: win[k][3*(dy+1) + (dx+1)]
-  constexpr int ZW = (DIM > 2) ? 3 : 1;
-  double win[ZW][9];
-  auto load_plane = [&](int hz, double* w) {
+  const int tx = tid % T::TX, ty = (tid / T::TX) % T::TY, tz = tid / (T::TX * T::TY);
+  if (DIM > 2 ? tz >= T::TZ : tid >= T::TX * T::TY) return;
+  const int hc = (tx + 1) + HX * ((ty + 1) + HY * (DIM > 2 ? tz + 1 : 0));       // this point inside the halo tile
+  const int32_t g = s_lat[hc];
+  if (g < 0) return;
+  // incident cells: cell offsets (cx,cy,cz) in {-1,0}; inside s_ok the cell with lower corner = this point is (tx+1, ty+1, tz+1)
+  uint8_t okc[NL]; uint8_t all = 1;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+  for (int k = 0; k < NL; ++k) {
+    const int cx = (k & 1) - 1, cy = ((k >> 1) & 1) - 1, cz = (DIM > 2) ? ((k >> 2) & 1) - 1 : 0;
+    okc[k] = s_ok[(tx + 1 + cx) + CX * ((ty + 1 + cy) + CY * (DIM > 2 ? tz + 1 + cz : 0))];
+    all &= okc[k];
+  }
+  double s = 0.0;
+  if (V.n == 1 && (all & 1)) {
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) w[3 * dy + dx] = s_x[(tx + dx) + HX * ((ty + dy) + HY * hz)];
-  };
-  if (DIM > 2) { load_plane(0, win[0]); load_plane(1, win[1 % ZW]); } 
-#pragma unroll
-  for (int tz = 0; tz < T::TZ; ++tz) {
-    load_plane(DIM > 2 ? tz + 2 : 0, win[(tz + 2) % ZW]);
-    const int hc = (tx + 1) + HX * ((ty + 1) + HY * (DIM > 2 ? tz + 1 : 0));       // this point inside the halo tile
-    const int32_t g = s_lat[hc];
-    if (g < 0) continue;
-    // incident cells: offsets (cx,cy,cz) in {-1,0}; the cell whose lower corner is this point sits at (tx+1, ty+1, tz+1) in s_ok
-    uint8_t okc[NL]; uint8_t all = 1;
-#pragma unroll
-    for (int k = 0; k < NL; ++k) {
-      const int cx = (k & 1) - 1, cy = ((k >> 1) & 1) - 1, cz = (DIM > 2) ? ((k >> 2) & 1) - 1 : 0;
-      okc[k] = s_ok[(tx + 1 + cx) + CX * ((ty + 1 + cy) + CY * (DIM > 2 ? tz + 1 + cz : 0))];
-      all &= okc[k];
+    for (int o = 0; o < NS; ++o) {
+      const int dx = o % 3 - 1, dy = (o / 3) % 3 - 1, dz = (DIM > 2) ? o / 9 - 1 : 0;
+      s += sS[o] * s_x[hc + dx + HX * (dy + HY * dz)];
     }
-    double s = 0.0;
-    if (V.n == 1 && (all & 1)) {
+  } else {
 #pragma unroll
-      for (int dz = 0; dz < ZW; ++dz)
+    for (int k = 0; k < NL; ++k) {                   // ascending cell index, like the reference's traversal
+      if (!okc[k]) continue;
+      const int cx = (k & 1) - 1, cy = ((k >> 1) & 1) - 1, cz = (DIM > 2) ? ((k >> 2) & 1) - 1 : 0;
+      const int li = (-cx) | ((-cy) << 1) | ((DIM > 2 ? -cz : 0) << 2);
+      for (int v = 0; v < V.n; ++v) {
+        if (!((okc[k] >> v) & 1)) continue;
+        const double* A = sAe + v * NL * NL + li * NL;
 #pragma unroll
-        for (int o = 0; o < 9; ++o) s += sS[9 * dz + o] * win[(tz + dz) % ZW][o];
-    } else {
-#pragma unroll
-      for (int k = 0; k < NL; ++k) {                   // ascending cell index, like the reference's traversal
-        if (!okc[k]) continue;
-        const int cx = (k & 1) - 1, cy = ((k >> 1) & 1) - 1, cz = (DIM > 2) ? ((k >> 2) & 1) - 1 : 0;
-        const int li = (-cx) | ((-cy) << 1) | ((DIM > 2 ? -cz : 0) << 2);
-        for (int v = 0; v < V.n; ++v) {
-          if (!((okc[k] >> v) & 1)) continue;
-          const double* A = sAe + v * NL * NL + li * NL;
-#pragma unroll
-          for (int lj = 0; lj < NL; ++lj) {
-            const int bx = lj & 1, by = (lj >> 1) & 1, bz = (DIM > 2) ? (lj >> 2) & 1 : 0;
-            s += A[lj] * s_x[hc + (cx + bx) + HX * ((cy + by) + HY * (cz + bz))];
-          }
+        for (int lj = 0; lj < NL; ++lj) {
+          const int bx = lj & 1, by = (lj >> 1) & 1, bz = (DIM > 2) ? (lj >> 2) & 1 : 0;
+          s += A[lj] * s_x[hc + (cx + bx) + HX * ((cy + by) + HY * (cz + bz))];
         }
       }
     }
-    r[ch.offset + g] += s;
   }
+  r[ch.offset + g] += s;
 }
 
 void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r)
@@ -438,12 +415,12 @@ void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x,
     // tiles over the bounding box of the child's lattice points
     const Child& hc = c->children[i];
     int lo[3], nt[3];
-    const int T[3] = {32, 8, m.dim == 3 ? 8 : 1};
+    const int T[3] = {32, m.dim == 3 ? 4 : 16, m.dim == 3 ? 4 : 1};
     for (int d = 0; d < 3; ++d) { lo[d] = hc.lat_lo[d]; nt[d] = (hc.lat_hi[d] - hc.lat_lo[d] + T[d]) / T[d]; if (nt[d] < 1) nt[d] = 1; }
     const int64_t nblocks = (int64_t)nt[0] * nt[1] * nt[2];
     MDB_REQUIRE(nblocks < (int64_t)2147483647, MDB_EINVAL, "residual: too many tiles");
-    if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_tile<2>, (int)nblocks, 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, lo[0], lo[1], lo[2], nt[0], nt[1]);
-    else MDB_LAUNCH(c, k_residual_volume_tile<3>, (int)nblocks, 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, lo[0], lo[1], lo[2], nt[0], nt[1]);
+    if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_tile<2>, (int)nblocks, 512, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, lo[0], lo[1], lo[2], nt[0], nt[1]);
+    else MDB_LAUNCH(c, k_residual_volume_tile<3>, (int)nblocks, 512, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, lo[0], lo[1], lo[2], nt[0], nt[1]);
   }
 }
 

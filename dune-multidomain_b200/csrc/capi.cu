@@ -187,17 +187,17 @@ mdb_ctx* mdb_create(int device)
   c->device = device;
   try {
     MDB_CUDA(cudaSetDevice(device));
-    MDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+      // the context stream carries the bandwidth-bound kernels and gets the highest priority; the auxiliary stream (irregular
+      // rows + FP64-bound FD coupling in mdb_jacobian) fills whatever SM capacity the streaming kernels leave
+      int lo = 0, hi = 0;
+      MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      MDB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+    }
     MDB_CUDA(cudaEventCreate(&c->ev0));
     MDB_CUDA(cudaEventCreate(&c->ev1));
     MDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    {
-      // the auxiliary stream runs the FP64-bound coupling kernel next to the HBM-bound fill kernel: give it priority so
-      // that its blocks are placed as soon as an SM has room instead of after the fill grid has drained
-      int lo = 0, hi = 0;
-      MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      MDB_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
-    }
+    MDB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));

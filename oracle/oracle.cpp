@@ -1091,6 +1091,11 @@ int orc_matrix_get_pattern(Context* c, int mat, int64_t* rowptr, int64_t* colidx
 int orc_matrix_get_values(Context* c, int mat, double* v) { ORC_TRY(c, { auto& A = c->mats.at(mat); std::copy(A.val.begin(), A.val.end(), v); }) }
 int orc_matrix_zero(Context* c, int mat) { ORC_TRY(c, { auto& A = c->mats.at(mat); std::fill(A.val.begin(), A.val.end(), 0.0); }) }
 int orc_set_time(Context* c, double t) { c->time = t; return 0; }
+// copy_nonconstrained_dofs(cu, xold, xnew)  (gridoperator.hh:146)
+int orc_copy_nonconstrained(Context* c, const double* xold, double* xnew)
+{
+  ORC_TRY(c, { for (int64_t i = 0; i < c->ndof; ++i) if (!c->constrained[i]) xnew[i] = xold[i]; })
+}
 int orc_residual(Context* c, int go, double weight, const double* x, double* r) { ORC_TRY(c, { c->residual(go, weight, x, r); }) }
 int orc_jacobian(Context* c, int go, int mat, double weight, const double* x) { ORC_TRY(c, { c->jacobian(go, mat, weight, x); }) }
 int orc_jacobian_parallel(Context* c, int go, int mat, double weight, const double* x, int nthreads)

@@ -93,3 +93,54 @@ def dirichlet_neumann_q1(api, n):
     512^2), split x0 > 0.5 (:919-925), Poisson(order 6) with the source F of :73-87 on both sides, monolithic coupling
     ContinuousValueContinuousFlowCoupling(4, 10) (:449, ini:10)."""
     return testpoisson(api, n, intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE))
+
+
+def instationary(api, n, k=2.0, split_axis=0):
+    """BASELINE configs[2] in the form the reference's live code supports (SURVEY M3 / §8d reality check 3):
+    test/testinstationarypoisson.cc:225-305 — dt0 operator = Poisson (stiffness + source + Neumann) on both subdomains plus
+    ProportionalFlowCoupling(k) (test/proportionalflowcoupling.hh:10-91), dt1 operator = L2 mass, one matrix whose pattern is
+    the union of both (OneStepGridOperator), time-dependent Dirichlet data g(t) (:94-100 family)."""
+    api.mesh_structured(n)
+    api.subdomains_halfspace(split_axis, 0.5, 0, 1)
+    c0, c1 = api.add_space(capi.FE_Q1, 0), api.add_space(capi.FE_Q1, 1)
+    pp = capi.PoissonParams()
+    pp.f = capi.Function(capi.FN_DN_SOURCE)
+    pp.bc = capi.BCType(capi.BC_TESTPOISSON)
+    pp.j = capi.Function(capi.FN_TESTPOISSON_J)
+    pp.quad_order = 4
+    l = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1, [c0])
+    r = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 2, [c1])
+    lp = capi.L2Params()
+    lp.quad_order = 2
+    ml = api.add_subproblem(capi.OP_L2, lp, capi.COND_EQUALITY, 1, [c0])
+    mr = api.add_subproblem(capi.OP_L2, lp, capi.COND_EQUALITY, 2, [c1])
+    cv = capi.PropFlowParams()
+    cv.intensity = k
+    cp = api.add_coupling(capi.OP_PROPFLOW_COUPLING, cv, l, r)
+    ndof = api.finalize()
+    ncon = api.constraints_assemble([l, r], [pp.bc, pp.bc])
+    go0 = api.gridoperator_create([l, r], [cp])
+    go1 = api.gridoperator_create([ml, mr], [])
+    mat = api.matrix_create([go0, go1])
+    g = capi.Function(capi.FN_INSTAT_G, 1.0, 3.0)
+    return SimpleNamespace(ndof=ndof, ncon=ncon, go0=go0, go1=go1, mat=mat, sps=[l, r], gfn=[g, g])
+
+
+def implicit_euler_step(api, P, u_old, t_new, dt, solve):
+    """One step of the one-step-theta scheme with theta = 1 as OneStepMethod / OneStepGridOperator drive the two grid
+    operators: new Dirichlet values by interpolation + copy_nonconstrained_dofs (gridoperator.hh:139-153),
+    R(u) = r1(u) - r1(u_old) + dt r0(u), J = J1 + dt J0 (setWeight, localassembler.hh:220-223), u_new = u - J^-1 R(u)."""
+    import numpy as np
+    api.set_time(t_new)
+    u = np.zeros(P.ndof)
+    api.interpolate(P.sps, P.gfn, u, time=t_new)
+    api.copy_nonconstrained(u_old, u)
+    api.jacobian(P.go1, P.mat, u, weight=1.0, overwrite=True)
+    api.jacobian(P.go0, P.mat, u, weight=dt, overwrite=False)
+    R = np.zeros(P.ndof)
+    api.residual(P.go1, u, R, weight=1.0)
+    api.residual(P.go1, u_old, R, weight=-1.0)
+    api.residual(P.go0, u, R, weight=dt)
+    z = np.zeros(P.ndof)
+    solve(P.mat, R, z)
+    return u - z

@@ -30,6 +30,9 @@ CASES = {
     "p3d_analytic": dict(n=(6, 6, 6), jac_mode=capi.JAC_ANALYTIC),
     "p2d_order6_src": dict(n=(16, 16), quad_order=6, f=capi.Function(capi.FN_BOX, 50.0, 0.25, 0.375)),
     "p3d_thin": dict(n=(3, 2, 1)),
+    # BASELINE configs[0] in its Q1 form: source of testpoisson-dirichlet-neumann.cc:73-87, order 6, coupling(4, 10), split x0
+    "p2d_dn_q1": dict(n=(32, 32), intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE)),
+    "p3d_dn_src": dict(n=(8, 8, 8), intensity=10.0, split_axis=0, quad_order=4, f=capi.Function(capi.FN_DN_SOURCE)),
 }
 
 
@@ -307,3 +310,29 @@ def test_jacobian_host_vector_paths_agree(n):
     for v in vals[1:]:        # the coupling blocks are accumulated with atomics: the summation order may differ in the last bit
         assert np.abs(v - vals[0]).max() <= 1e-14 * np.abs(vals[0]).max()
     assert moved[0] == 0 and moved[1] == 8 * P.ndof and 0 < moved[2] < 8 * P.ndof and moved[4] == moved[2]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [(16, 12), (6, 5, 4)])
+def test_implicit_euler_steps_match_oracle(n):
+    """BASELINE configs[2] (synthetic M3): instationary two-subdomain problem with proportional-flow coupling, implicit Euler.
+    Five steps driven through the two grid operators (dt0 = Poisson + coupling, dt1 = mass) exactly as OneStepGridOperator
+    does; device vs oracle after every step."""
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    Pd, Po = problems.instationary(dev, n), problems.instationary(ora, n)
+    assert Pd.ndof == Po.ndof and Pd.ncon == Po.ncon
+    assert all(np.array_equal(a, b) for a, b in zip(dev.matrix_get_pattern(Pd.mat), ora.matrix_get_pattern(Po.mat)))
+
+    def dsolve(mat, R, z):
+        st = dev.solve(mat, R, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_JACOBI, reduction=1e-13, maxit=5000)
+        assert st.converged
+
+    ud = np.zeros(Po.ndof)
+    ora.interpolate(Po.sps, Po.gfn, ud, time=0.0)
+    uo = ud.copy()
+    dt = 0.04
+    for step in range(1, 6):
+        uo = problems.implicit_euler_step(ora, Po, uo, step * dt, dt, lambda mat, R, z: ora.solve(mat, R, z, reduction=1e-13))
+        ud = problems.implicit_euler_step(dev, Pd, ud, step * dt, dt, dsolve)
+        assert np.abs(ud - uo).max() <= 1e-9 * np.abs(uo).max(), step
+    assert np.abs(uo).max() > 0.05          # something actually evolved

@@ -208,3 +208,33 @@ def test_parallel_baseline_assembly_equals_serial():
     o2.jacobian(P2.go, P2.mat, u, overwrite=True, nthreads=4)
     a, b = o1.matrix_get_values(P1.mat), o2.matrix_get_values(P2.mat)
     assert np.abs(a - b).max() <= 1e-14 * np.abs(a).max()
+
+
+def test_implicit_euler_against_scipy():
+    """The two-operator driver of tests/problems.implicit_euler_step (OneStepGridOperator restated) against a direct SciPy
+    solve of (M + dt K) u_new = M u_old + dt b assembled from the oracle's matrices: R is affine in u."""
+    o = orc.Oracle()
+    P = problems.instationary(o, (10, 8))
+    dt, t1 = 0.05, 0.05
+    u0 = np.zeros(P.ndof)
+    o.interpolate(P.sps, P.gfn, u0, time=0.0)
+    u1 = problems.implicit_euler_step(o, P, u0, t1, dt, lambda mat, R, z: o.solve(mat, R, z, reduction=1e-13))
+    # independent: J = J1 + dt J0 (already in the matrix), R(u) evaluated at the Dirichlet-updated guess
+    J = o.csr(P.mat)
+    guess = np.zeros(P.ndof)
+    o.interpolate(P.sps, P.gfn, guess, time=t1)
+    o.copy_nonconstrained(u0, guess)
+    R = np.zeros(P.ndof)
+    o.residual(P.go1, guess, R, weight=1.0)
+    o.residual(P.go1, u0, R, weight=-1.0)
+    o.residual(P.go0, guess, R, weight=dt)
+    z = sla.spsolve(sp.csc_matrix(J), R)
+    assert np.abs((guess - z) - u1).max() <= 1e-10 * np.abs(u1).max()
+    con = o.get_constraints().astype(bool)
+    assert np.array_equal(u1[con], guess[con])            # Dirichlet values come from the interpolation at the new time
+    # the new iterate satisfies the discrete equation on free rows: R(u1) = 0
+    R1 = np.zeros(P.ndof)
+    o.residual(P.go1, u1, R1, weight=1.0)
+    o.residual(P.go1, u0, R1, weight=-1.0)
+    o.residual(P.go0, u1, R1, weight=dt)
+    assert np.abs(R1).max() <= 1e-9 * np.abs(R).max()
