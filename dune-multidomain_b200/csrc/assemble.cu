@@ -92,15 +92,18 @@ __device__ __forceinline__ int columns_below(const int64_t* __restrict__ rowptr,
 // hot kernel: 8 bytes written per stored entry, nothing read but the run boundaries.
 #define JF_THREADS 128
 template <int DIM>
-__global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const double* __restrict__ S, const longlong2* __restrict__ seg_span,
+__global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const double* __restrict__ S, const longlong2* __restrict__ seg_span, int64_t nseg,
                                                                 double* __restrict__ val, int overwrite)
 {
   constexpr int NS = (DIM == 3) ? 27 : 9;
   __shared__ double sS[32];
-  const longlong2 span = seg_span[blockIdx.x];
-  if (span.x == span.y) return;                                        // a run of irregular rows: k_jacobian_rows_q1
   if (threadIdx.x < NS) sS[threadIdx.x] = S[threadIdx.x];
   __syncthreads();
+  // grid = nseg: one run per block; a smaller (persistent) grid walks the runs with a grid stride, which bounds how much
+  // of every SM this kernel occupies when the FD coupling kernel runs next to it on the auxiliary stream
+  for (int64_t run = blockIdx.x; run < nseg; run += gridDim.x) {
+  const longlong2 span = seg_span[run];
+  if (span.x == span.y) continue;                                      // a run of irregular rows: k_jacobian_rows_q1
   // The run is the span [p0, p1) of the value array.  Rows are 27 (9) doubles long, so p0 is only 8-byte aligned.  The span
   // is cut into chunks of 32 rows' worth of doubles that start on 256-byte boundaries; a warp writes a chunk as NS
   // consecutive, fully aligned 256-byte stores (32 lanes x 8 B) and only the two edges of the run are masked.  Measured
@@ -129,44 +132,77 @@ __global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const doubl
       }
     }
   }
+  }
 }
 
 // ---- irregular rows (or all rows when the uniform shortcut is not valid) ---------------------------------------
+// One thread gathers one row (sum over the incident cells, popcount placement) into a row image in shared memory; the
+// warp then writes its 32 row images out cooperatively, consecutive lanes to consecutive entries, so that a row costs
+// ~len/4 store sectors instead of one sector per entry.
+#define JR_THREADS 64
+#define JR_MAXLEN 48           // longest row image staged in shared memory (Q1 hex interface row: 27 + 18); longer rows go direct
 template <int DIM>
-__global__ void __launch_bounds__(128) k_jacobian_rows_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
-                                                         const double* __restrict__ Ae, const int32_t* __restrict__ list, int64_t nrows,
-                                                         const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
-                                                         const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
+__global__ void __launch_bounds__(JR_THREADS) k_jacobian_rows_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
+                                                                const double* __restrict__ Ae, const int32_t* __restrict__ list, int64_t nrows,
+                                                                const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
+                                                                const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
 {
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
   constexpr int BITBASE = (DIM == 3) ? 0 : 9;
+  constexpr int STRIDE = JR_MAXLEN + 1;               // odd stride in doubles: the per-thread image writes are bank-conflict free
   __shared__ double sAe[MDB_MAX_SP_PER_CHILD * NL * NL];
+  __shared__ double img[JR_THREADS / 32][32 * STRIDE];
   for (int i = threadIdx.x; i < V.n * NL * NL; i += blockDim.x) {
     int v = i / (NL * NL), e = i % (NL * NL);
     sAe[i] = Ae[V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + e];
   }
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= nrows) return;
-  const int64_t gi = list ? (int64_t)list[t] : t;
-  const int64_t g = ch.offset + gi;
-  int64_t r = ch.dof2lat[gi];
-  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
-  double acc[NS]; uint32_t touched;
-  stencil_row<DIM>(m, sd, ch.subdomain, V, sAe, p, acc, touched);
-  const uint32_t info = rowinfo[g];
-  const uint32_t mask = info & 0x7FFFFFFu;
-  const int nlow = columns_below(rowptr, colidx, g, info, ch.offset);
-  const int64_t rs = rowptr[g];
-  const int len = (int)(rowptr[g + 1] - rs);
-  const int nown = __popc(mask);
-  double* row = val + rs;
-  if (overwrite) for (int k = 0; k < len; ++k) if (k < nlow || k >= nlow + nown) row[k] = 0.0;
+  const bool have = t < nrows;
+  int64_t rs = 0; int len = 0;
+  if (have) {
+    const int64_t gi = list ? (int64_t)list[t] : t;
+    const int64_t g = ch.offset + gi;
+    int64_t r = ch.dof2lat[gi];
+    int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+    double acc[NS]; uint32_t touched;
+    stencil_row<DIM>(m, sd, ch.subdomain, V, sAe, p, acc, touched);
+    const uint32_t info = rowinfo[g];
+    const uint32_t mask = info & 0x7FFFFFFu;
+    const int nlow = columns_below(rowptr, colidx, g, info, ch.offset);
+    rs = rowptr[g];
+    len = (int)(rowptr[g + 1] - rs);
+    if (len <= JR_MAXLEN) {
+      double* im = img[warp] + lane * STRIDE;
+      for (int k = 0; k < len; ++k) im[k] = 0.0;
 #pragma unroll
-  for (int o = 0; o < NS; ++o) {
-    const uint32_t bit = 1u << (o + BITBASE);
-    if (mask & bit) { double* q = row + nlow + __popc(mask & (bit - 1u)); if (overwrite) *q = acc[o]; else *q += acc[o]; }
+      for (int o = 0; o < NS; ++o) {
+        const uint32_t bit = 1u << (o + BITBASE);
+        if (mask & bit) im[nlow + __popc(mask & (bit - 1u))] = acc[o];
+      }
+    } else {                                           // very long row: write it directly
+      const int nown = __popc(mask);
+      double* row = val + rs;
+      if (overwrite) for (int k = 0; k < len; ++k) if (k < nlow || k >= nlow + nown) row[k] = 0.0;
+#pragma unroll
+      for (int o = 0; o < NS; ++o) {
+        const uint32_t bit = 1u << (o + BITBASE);
+        if (mask & bit) { double* q = row + nlow + __popc(mask & (bit - 1u)); if (overwrite) *q = acc[o]; else *q += acc[o]; }
+      }
+      len = 0;
+    }
+  }
+  __syncwarp();
+  for (int rr = 0; rr < 32; ++rr) {
+    const int64_t rs_r = __shfl_sync(0xffffffffu, rs, rr);
+    const int len_r = __shfl_sync(0xffffffffu, len, rr);
+    const double* im = img[warp] + rr * STRIDE;
+    for (int k = lane; k < len_r; k += 32) {
+      if (overwrite) val[rs_r + k] = im[k];
+      else if (im[k] != 0.0) val[rs_r + k] += im[k];
+    }
   }
 }
 
@@ -226,13 +262,16 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
     const int64_t nrows = uni ? M.n_irregular[i] : ch.size;
     if (uni && part == 0) {
       const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL;
-      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, (int)M.n_seg[i], JF_THREADS, 0, S, M.d_seg_span[i], M.d_val, (int)overwrite);
-      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, (int)M.n_seg[i], JF_THREADS, 0, S, M.d_seg_span[i], M.d_val, (int)overwrite);
+      static const int per_sm = getenv("MDB_FILL_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_BLOCKS_PER_SM")) : 0;   // 0: one run per block
+      int grid = (int)M.n_seg[i];
+      if (per_sm > 0 && grid > 148 * per_sm) grid = 148 * per_sm;
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
+      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
     }
     if (nrows > 0 && part == 1) {
-      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, cdiv(nrows, JR_THREADS), JR_THREADS, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
                                  M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
-      else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, cdiv(nrows, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
+      else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, cdiv(nrows, JR_THREADS), JR_THREADS, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
                       M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
     }
   }
