@@ -206,7 +206,9 @@ struct Matrix {
   std::map<std::pair<int, int>, uint8_t*> slot_tables;
   // preconditioner caches
   double* d_dinv = nullptr;
-  bool dinv_valid = false;
+  bool dinv_valid = false; int dinv_precond = -1;
+  // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
+  int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
 };
 
 struct Ctx {

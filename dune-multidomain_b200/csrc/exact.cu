@@ -7,7 +7,7 @@
 //                       L2 / test/simpletimeoperator.hh:68-101 on the (congruent) cells of a structured mesh
 //   k_coupling_residual alpha_coupling of ContinuousValueContinuousFlowCoupling (test/proportionalflowcoupling.hh:113-233)
 //                       and ProportionalFlowCoupling (:27-86), one thread per interface face
-//   k_coupling_jacobian jacobian_coupling: one warp per interface face, lane 0 = base line, lane 1+j = perturbation j
+//   k_coupling_jacobian_staged  jacobian_coupling: (face, evaluation) threads; evaluation 0 = base line, 1+j = perturbation j
 //   k_lambda_volume / k_lambda_boundary   source and Neumann terms of Poisson (test/instationarypoissonoperator.hh:103-167)
 #include "common.cuh"
 
@@ -400,72 +400,15 @@ __global__ void k_coupling_slots(MeshDesc m, SideMap Ls, SideMap Rs, const int32
   slots[t] = (uint8_t)(pos - rs);
 }
 
-// jacobian_coupling (couplingutilities.hh:75-135).  One thread per (face, evaluation): evaluation 0 is the base line
-// ("down"), evaluation 1+j perturbs self dof j (j < NL) or neighbour dof j-NL; the base line of each face is exchanged
-// through shared memory; every perturbation thread owns one column of mat_ss/mat_ns (self) or mat_sn/mat_nn (neighbour).
-template <int DIM>
-__global__ void __launch_bounds__(256) k_coupling_jacobian(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
-                                                           const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
-                                                           const double* __restrict__ tab, const double* __restrict__ x,
-                                                           const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slots, double* val)
-{
-  constexpr int NL = 1 << DIM;
-  constexpr int NE = 2 * NL + 1;
-  constexpr int FPB = 256 / NE;                 // faces per block
-  __shared__ double sdown[FPB][2 * NL];
-  const int fl = threadIdx.x / NE, e = threadIdx.x % NE;
-  const int64_t f = (int64_t)blockIdx.x * FPB + fl;
-  const bool active = fl < FPB && f < nfaces;
-  const int j = e - 1;                          // perturbation index, -1 = base line
-  const bool self = j >= 0 && j < NL, nb = j >= NL;
-  int32_t ds[NL], dn[NL];
-  double r1[NL], r2[NL];
-  double delta = 1.0;
-  if (active) {
-    FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
-    cell_dofs_q1<DIM>(Ls, G.ijk, ds); cell_dofs_q1<DIM>(Rs, G.nijk, dn);
-    double u1[NL], u2[NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) { u1[i] = x[ds[i]]; u2[i] = x[dn[i]]; r1[i] = 0.0; r2[i] = 0.0; }
-    if (P.jac_mode == MDB_JAC_ANALYTIC) {
-      // the shipped coupling residuals are linear in (u_s,u_n): column j = alpha_coupling(e_j), no division
-#pragma unroll
-      for (int i = 0; i < NL; ++i) { u1[i] = (self && i == j) ? 1.0 : 0.0; u2[i] = (nb && i == j - NL) ? 1.0 : 0.0; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        if (self && i == j) { delta = epsilon * (1.0 + fabs(u1[i])); u1[i] += delta; }
-        if (nb && i == j - NL) { delta = epsilon * (1.0 + fabs(u2[i])); u2[i] += delta; }
-      }
-    }
-    if (!(P.jac_mode == MDB_JAC_ANALYTIC && e == 0)) alpha_coupling<DIM>(P, G, tab, u1, u2, r1, r2, 1.0);
-    if (e == 0) {
-#pragma unroll
-      for (int i = 0; i < NL; ++i) { sdown[fl][i] = r1[i]; sdown[fl][NL + i] = r2[i]; }
-    }
-  }
-  __syncthreads();
-  if (!active || e == 0) return;
-  const uint8_t* sl = slots + f * (4 * NL * NL) + j;           // column j of the face's (2NL x 2NL) slot table
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    double c1, c2;
-    if (P.jac_mode == MDB_JAC_ANALYTIC) { c1 = r1[i]; c2 = r2[i]; }
-    else { c1 = (r1[i] - sdown[fl][i]) / delta; c2 = (r2[i] - sdown[fl][NL + i]) / delta; }
-    atomicAdd(&val[rowptr[ds[i]] + sl[i * 2 * NL]], weight * c1);             // mat_ss / mat_sn
-    atomicAdd(&val[rowptr[dn[i]] + sl[(NL + i) * 2 * NL]], weight * c2);      // mat_ns / mat_nn
-  }
-}
-
 // jacobian_coupling, staged variant (the default).  The FP64 pipe bounds this kernel (17 residual evaluations per face,
 // no FMA contraction), so the arithmetic that does not depend on the perturbation is hoisted out of the 17 evaluations
 // WITHOUT changing a single rounding: per (face, quadrature point, side, i) the block first parks in shared memory
 //   phi_i, c_i = (theta*0.5)*gpn_i, px_i = x_i*phi_i, pg_i[d] = x_i*gradphi_i[d]
 // (the base-line products; a perturbation of dof j changes only the j-th product, the additions are redone in the
 // reference's order), then thread (face, evaluation) runs the perturbation-dependent part of alpha_coupling.
-// Mapping: 256 threads = FPB faces x NE evaluations; evaluation 0 is the base line, 1+j perturbs dof j.
-template <int DIM, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_coupling_jacobian_staged(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
+// Mapping: NT threads = FPB faces x NE evaluations; evaluation 0 is the base line, 1+j perturbs dof j.
+template <int DIM, int NT>
+__global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
                                                                   const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
                                                                   const double* __restrict__ tab, const double* __restrict__ x,
                                                                   const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slots, double* val)
@@ -473,7 +416,7 @@ __global__ void __launch_bounds__(256, MINB) k_coupling_jacobian_staged(MeshDesc
   constexpr int NL = 1 << DIM;
   constexpr int NR = 2 * NL;
   constexpr int NE = NR + 1;
-  constexpr int FPB = 256 / NE;
+  constexpr int FPB = NT / NE;
   struct FaceS { double x[NR]; double jit[2][DIM]; double nrm[2][DIM]; double ie, aoh; int32_t dof[NR]; int axis, side; };
   __shared__ FaceS sf[FPB];
   // Shared-memory staging, all 16-byte vectors so that every access is one LDS.128 / STS.128:
@@ -484,7 +427,7 @@ __global__ void __launch_bounds__(256, MINB) k_coupling_jacobian_staged(MeshDesc
   // select per term instead of a 64-bit value select per double.
   constexpr int MINE = 2 * FPB * NR;
   __shared__ double2 spc[2 * FPB * NR];
-  __shared__ double2 sq[(MINE + 256) * 2];
+  __shared__ double2 sq[(MINE + NT) * 2];
   __shared__ double sdown[FPB][NR];
   const int t = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * FPB;
@@ -622,171 +565,6 @@ __global__ void __launch_bounds__(256, MINB) k_coupling_jacobian_staged(MeshDesc
   }
 }
 
-// jacobian_coupling, side-split variant: as the staged kernel, but every evaluation is carried by TWO adjacent lanes, one
-// per side of the face.  Lane s sums side s (u_s, grad u_s), the pair swaps the four sums by shuffle, and each lane
-// accumulates the NL residual entries of its own side.  Same roundings as the staged kernel (IEEE addition commutes, so
-// mean_gradu = gradu_1 + gradu_2 has the same bits from either lane); half the registers per thread, twice the threads.
-// Mapping: 512 threads = FPB faces x NE evaluations x 2 sides.
-template <int DIM>
-__global__ void __launch_bounds__(512, 2) k_coupling_jacobian_split(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
-                                                                    const int8_t* __restrict__ fface, int64_t nfaces, double weight, double epsilon,
-                                                                    const double* __restrict__ tab, const double* __restrict__ x,
-                                                                    const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slots, double* val)
-{
-  constexpr int NL = 1 << DIM;
-  constexpr int NR = 2 * NL;
-  constexpr int NE = NR + 1;
-  constexpr int FPB = 512 / (2 * NE);
-  struct FaceS { double x[NR]; double jit[2][DIM]; double nrm[2][DIM]; double ie, aoh; int32_t dof[NR]; int axis, side; };
-  __shared__ FaceS sf[FPB];
-  constexpr int MINE = 2 * FPB * NR;
-  __shared__ double2 spc[2 * FPB * NR];                 // {phi_i, c_i}
-  __shared__ double2 sq[(MINE + 256) * 2];              // base-line quads, then one quad per (face, evaluation) pair
-  __shared__ double sdown[FPB][NR];
-  const int t = threadIdx.x;
-  const int64_t f0 = (int64_t)blockIdx.x * FPB;
-  const bool analytic = P.jac_mode == MDB_JAC_ANALYTIC;
-  const bool cvcf = P.op == MDB_OP_CVCF_COUPLING;
-  if (t < FPB && f0 + t < nfaces) {
-    FaceGeo<DIM> G; G.init(m, fcell[f0 + t], fface[f0 + t]);
-    FaceS& F = sf[t];
-    int32_t ds[NL], dn[NL];
-    cell_dofs_q1<DIM>(Ls, G.ijk, ds); cell_dofs_q1<DIM>(Rs, G.nijk, dn);
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      F.dof[i] = ds[i]; F.dof[NL + i] = dn[i];
-      F.x[i] = analytic ? 0.0 : x[ds[i]]; F.x[NL + i] = analytic ? 0.0 : x[dn[i]];
-    }
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      F.jit[0][d] = 1.0 / (G.up_i[d] - G.lo_i[d]); F.jit[1][d] = 1.0 / (G.up_o[d] - G.lo_o[d]);
-      F.nrm[0][d] = (d == G.axis) ? (G.side ? 1.0 : -1.0) : 0.0; F.nrm[1][d] = F.nrm[0][d] * -1;
-    }
-    F.ie = G.integrationElement();
-    F.aoh = cvcf ? P.intensity / G.cornerDistance01() : 0.0;
-    F.axis = G.axis; F.side = G.side;
-  }
-  __syncthreads();
-  const int pair = t >> 1, s = t & 1;               // s: the side this lane carries
-  const int fl = pair / NE, e = pair % NE;
-  const bool active = fl < FPB && f0 + fl < nfaces;
-  const int j = e - 1;
-  double xp = 0.0, delta = 1.0;
-  if (active && j >= 0) {
-    if (analytic) xp = 1.0;
-    else { const double u = sf[fl].x[j]; delta = epsilon * (1.0 + fabs(u)); xp = u + delta; }
-  }
-  const int jj = j < 0 ? -1 : (j < NL ? j : j - NL);
-  const int jside = j < 0 ? -1 : (j < NL ? 0 : 1);
-  const int myi = (jside == s) ? jj : -1;           // index inside my side that is perturbed (or none)
-  double r[NL];
-#pragma unroll
-  for (int i = 0; i < NL; ++i) r[i] = 0.0;
-  const int nq = ipow(P.rule.m, DIM - 1);
-  const int pf = t / NR, pr = t % NR, ps = pr / NL, pi = pr % NL;
-  const bool pact = pf < FPB && f0 + pf < nfaces;
-  for (int q = 0; q < nq; ++q) {
-    const int bbase = (q & 1) * FPB * NR;
-    if (pact) {
-      const FaceS& F = sf[pf];
-      const int sideval = ps == 0 ? F.side : 1 - F.side;
-      const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + pi) * 4;
-      const double phi = __ldg(tq);
-      double gpn = 0.0, g[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[ps][d] * __ldg(tq + 1 + d);
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) gpn += g[d] * F.nrm[ps][d];
-      const double theta = 1;
-      const double xi = F.x[pr];
-      const int o = bbase + pf * NR + pr;
-      spc[o] = make_double2(phi, theta * 0.5 * gpn);
-      sq[2 * o] = make_double2(xi * phi, xi * g[0]);
-      sq[2 * o + 1] = make_double2(xi * g[1], DIM > 2 ? xi * g[2] : 0.0);
-    }
-    if (active && myi >= 0) {                          // the lane on the perturbed side parks the perturbed quad of the pair
-      const FaceS& F = sf[fl];
-      const int sideval = s == 0 ? F.side : 1 - F.side;
-      const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + myi) * 4;
-      double g[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[s][d] * __ldg(tq + 1 + d);
-      sq[2 * (MINE + pair)] = make_double2(xp * __ldg(tq), xp * g[0]);
-      sq[2 * (MINE + pair) + 1] = make_double2(xp * g[1], DIM > 2 ? xp * g[2] : 0.0);
-    }
-    __syncthreads();
-    const bool work = active && !(analytic && e == 0);
-    double us = 0.0, gs[3] = {0.0, 0.0, 0.0};
-    const int fb = bbase + fl * NR + s * NL;
-    if (work) {
-#pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        const int src = (i == myi) ? MINE + pair : fb + i;
-        const double2 a = sq[2 * src];
-        us += a.x;
-        if (cvcf) {
-          const double2 b2 = sq[2 * src + 1];
-          gs[0] += a.y; gs[1] += b2.x;
-          if (DIM > 2) gs[2] += b2.y;
-        }
-      }
-    }
-    // swap the sums with the partner lane (all lanes take part in the shuffles)
-    const double uo = __shfl_xor_sync(0xffffffffu, us, 1);
-    double go[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) go[d] = (cvcf && d < DIM) ? __shfl_xor_sync(0xffffffffu, gs[d], 1) : 0.0;
-    if (work) {
-      const FaceS& F = sf[fl];
-      double pos[3], w; quad_point<DIM - 1>(P.rule, q, pos, w);
-      const double factor = w * F.ie;
-      if (!cvcf) {
-        const double u_diff = P.intensity * (s == 0 ? us - uo : uo - us);     // intensity * (u_s - u_n) on both lanes
-        if (s == 0) {
-#pragma unroll
-          for (int i = 0; i < NL; ++i) r[i] += u_diff * spc[fb + i].x * factor;
-        } else {
-#pragma unroll
-          for (int i = 0; i < NL; ++i) r[i] += -u_diff * spc[fb + i].x * factor;
-        }
-      } else {
-        const double jump = us - uo;                       // side 0: u1 - u2, side 1: u2 - u1
-        double mgn = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          double mg = (s == 0) ? gs[d] + go[d] : go[d] + gs[d];       // gradu1 + gradu2
-          mg *= 0.5;
-          mgn += mg * F.nrm[s][d];
-        }
-        const double aj = F.aoh * jump;
-#pragma unroll
-        for (int i = 0; i < NL; ++i) {
-          const double2 pc = spc[fb + i];
-          double value = 0.0;
-          value -= mgn * pc.x;
-          value -= pc.y * jump;
-          value += aj * pc.x;
-          r[i] += factor * value;
-        }
-      }
-    }
-  }
-  if (active && e == 0) {
-#pragma unroll
-    for (int i = 0; i < NL; ++i) sdown[fl][s * NL + i] = r[i];
-  }
-  __syncthreads();
-  if (!active || e == 0) return;
-  const uint8_t* sl = slots + (f0 + fl) * (NR * NR) + j;
-  const FaceS& F = sf[fl];
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    const int row = s * NL + i;
-    const double c = analytic ? r[i] : (r[i] - sdown[fl][row]) / delta;
-    atomicAdd(&val[rowptr[F.dof[row]] + sl[row * NR]], weight * c);
-  }
-}
-
 static SideMap side_map(const Ctx* c, int sp)
 {
   const Child& ch = c->children[c->sps[sp].children[0]];
@@ -858,37 +636,17 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     } else slots = it->second;
     const double* tab = face_tables(c, P);
     const int fpb = 256 / (2 * NL + 1);
-    static const int variant = getenv("MDB_COUPLING_JAC_VARIANT") ? atoi(getenv("MDB_COUPLING_JAC_VARIANT")) : 1;   // A/B switch for profiling only
-    if (variant == 0) {
-      if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian<2>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
-                                 M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, k_coupling_jacobian<3>, cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab, d_x,
-                      M.d_rowptr, slots, M.d_val);
-    } else if (variant == 1) {
-      // Optional shared-memory padding limits the residency of this FP64-bound kernel (it runs next to the HBM-bound
-      // fill kernel on another stream, capi.cu mdb_jacobian) so that both fit on an SM at the same time.
-      static const int pad_kb = getenv("MDB_COUPLING_PAD_KB") ? atoi(getenv("MDB_COUPLING_PAD_KB")) : 0;
-      static bool configured = false;
-      if (pad_kb > 0 && !configured) {
-        MDB_CUDA(cudaFuncSetAttribute(k_coupling_jacobian_staged<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024));
-        MDB_CUDA(cudaFuncSetAttribute(k_coupling_jacobian_staged<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024));
-        configured = true;
-      }
-      const size_t pad = (size_t)pad_kb * 1024;
-      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 3>), cdiv(fl.n, fpb), 256, pad, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+    static const int nt = getenv("MDB_COUPLING_JAC_THREADS") ? atoi(getenv("MDB_COUPLING_JAC_THREADS")) : 256;   // A/B switch for profiling only
+    if (nt == 128) {
+      const int fpb128 = 128 / (2 * NL + 1);
+      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 128>), cdiv(fl.n, fpb128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                                  d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 3>), cdiv(fl.n, fpb), 256, pad, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
-                      d_x, M.d_rowptr, slots, M.d_val);
-    } else if (variant == 3) {
-      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 2>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
-                                 d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 2>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 128>), cdiv(fl.n, fpb128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                       d_x, M.d_rowptr, slots, M.d_val);
     } else {
-      const int fpb2 = 512 / (2 * (2 * NL + 1));
-      if (m.dim == 2) MDB_LAUNCH(c, k_coupling_jacobian_split<2>, cdiv(fl.n, fpb2), 512, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 256>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                                  d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, k_coupling_jacobian_split<3>, cdiv(fl.n, fpb2), 512, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 256>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
                       d_x, M.d_rowptr, slots, M.d_val);
     }
   }

@@ -212,7 +212,7 @@ void build_pattern(Ctx* c, Matrix& M)
   MDB_REQUIRE(!err, MDB_EINVAL, "a matrix row has more than 128 entries (unsupported)");
   M.nnz = nnz; M.max_row = (int)maxrow;
   M.d_colidx = dalloc<int32_t>(nnz);
-  M.d_val = dalloc<double>(nnz);
+  M.d_val = dalloc<double>(nnz + 16);     // + 16: the SpMV stages 128-byte aligned windows (solver.cu)
   M.d_rowinfo = dalloc<uint32_t>(n);
   M.d_diag = dalloc<int32_t>(n);
   MDB_CUDA(cudaMemsetAsync(M.d_val, 0, nnz * sizeof(double), c->stream));

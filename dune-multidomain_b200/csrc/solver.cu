@@ -11,6 +11,7 @@
 // Algorithmic bytes: 12*nnz + 20*nrows.
 #include "common.cuh"
 #include <cmath>
+#include <cub/cub.cuh>
 
 namespace mdb {
 
@@ -161,10 +162,266 @@ __global__ void __launch_bounds__(256) k_spmv_vec(int64_t n, const int64_t* __re
   }
 }
 
+// ---- variant C: TMA-fed, thread-per-row, stencil-aware (the default on Q1 spaces) --------------------------------------
+// A block owns ST_ROWS consecutive rows of one child block = ONE contiguous span of the value array.  One elected thread
+// fetches that span AND the 3^(d-1) segments of x the rows read into shared memory with bulk-async copies (cp.async.bulk, the
+// 1-D TMA path) on one mbarrier: no per-thread global loads on the hot path, the bytes arrive while the other resident blocks
+// compute.  Every thread then owns one row and sums it sequentially in column order (= the summation order of a
+// sequential CSR product).
+// Why the x segments are known without colidx: when the DOF-carrying lattice points of a child block fill their bounding box
+// (half-space subdomains: always), the block is numbered lexicographically over that box
+// (multidomaingridfunctionspace.hh:308-369), so a row r whose columns all lie in its own block ("affine": every row but the
+// interface rows) has the columns r + dx + dy*bx + dz*bx*by for the set bits (dx,dy,dz) of its stencil mask (rowinfo), in
+// ascending order.  The 108 bytes of colidx per row are never read, and ST_ROWS consecutive rows read 3^(d-1) contiguous
+// segments of x of ST_ROWS + 2 entries.  The other rows (~1.5 %) walk their colidx entries, 8 lanes per row.
+// Traffic per simple row: 216 B values + 12 B (rowptr, rowinfo) + 16 B vectors instead of 216 + 108 + 28.
+#define ST_ROWS 128
+#define ST_BLOCKS 5
+#define ST_VCAP (ST_ROWS * 28 + 2)           // doubles of value staging per block (simple rows: 27 per row + alignment slack)
+#define ST_XSEG (ST_ROWS + 4)                // doubles per staged x segment
+struct SpmvChild { int64_t offset, size, chunk0; int box, bx, bxy; };
+struct SpmvSpace { int nchild; int64_t nchunks; SpmvChild ch[MDB_MAX_CHILDREN]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// x segments of the chunk [r0, r1) of child ch: entries [r0 - 1 + off, r1 + 1 + off) for off = dy*bx + dz*bxy.  The chunk takes
+// the staged path only when every segment (widened by one entry for 16-byte alignment) lies inside the vector.
+__host__ __device__ inline bool spmv_chunk_staged(const SpmvChild& ch, int dim, int64_t r0, int64_t r1, int64_t n)
+{
+  const int64_t reach = (dim == 3) ? (int64_t)ch.bx + ch.bxy : ch.bx;
+  return r1 > r0 && ch.box && r0 - 1 - reach - 1 >= 0 && r1 + 1 + reach + 1 <= n;
+}
+// a row the stencil kernel sums: its chunk is staged and all its columns are own-block stencil neighbours
+__device__ __forceinline__ uint32_t spmv_affine_mask(int dim, uint32_t info, int64_t rowlen)
+{
+  const uint32_t m = (dim == 3) ? (info & 0x7FFFFFFu) : ((info >> 9) & 0x1FFu);
+  return rowlen == __popc(m) ? m : 0u;
+}
+
+// flags[r] = 1 for every row the stencil kernel does NOT sum
+__global__ void k_spmv_rest_flags(int64_t n, SpmvSpace sp, int dim, const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo, int32_t* flags)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int ci = 0;
+  while (ci + 1 < sp.nchild && r >= sp.ch[ci + 1].offset) ++ci;
+  const SpmvChild& ch = sp.ch[ci];
+  const int64_t r0 = ch.offset + (r - ch.offset) / ST_ROWS * ST_ROWS;
+  const int64_t r1 = (r0 + ST_ROWS < ch.offset + ch.size) ? r0 + ST_ROWS : ch.offset + ch.size;
+  const bool mine = spmv_chunk_staged(ch, dim, r0, r1, n) && spmv_affine_mask(dim, rowinfo[r], rowptr[r + 1] - rowptr[r]) != 0u;
+  flags[r] = mine ? 0 : 1;
+}
+__global__ void k_spmv_rest_compact(int64_t n, const int32_t* __restrict__ flags, const int32_t* __restrict__ scan, int32_t* list)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r < n && flags[r]) list[scan[r]] = (int32_t)r;
+}
+
+// y[r] = (A x)[r] for the rows of a list, 8 lanes per row (the vector-CSR kernel over a row list); partial sums of the fused
+// dots go to partial[pofs + block]
+template <int DOTS>
+__global__ void __launch_bounds__(256) k_spmv_rows(int64_t nlist, const int32_t* __restrict__ list, const int64_t* __restrict__ rowptr,
+                                                   const int32_t* __restrict__ colidx, const double* __restrict__ val, const double* __restrict__ x,
+                                                   double* __restrict__ y, const double* __restrict__ a, const uint8_t* __restrict__ owned, double* partial,
+                                                   int pofs, const double* __restrict__ done)
+{
+  constexpr int LPR = 8;
+  __shared__ double sh[8];
+  if (done && done[S_DONE] != 0.0) return;
+  double d0 = 0.0, d1 = 0.0;
+  const int sub = threadIdx.x % LPR;
+  const int64_t rows_per_grid = (int64_t)gridDim.x * (256 / LPR);
+  for (int64_t ib = blockIdx.x * (int64_t)(256 / LPR); ib < nlist; ib += rows_per_grid) {     // block-uniform trip count
+    const int64_t i = ib + threadIdx.x / LPR;
+    double sum = 0.0;
+    int64_t r = -1;
+    if (i < nlist) {
+      r = list[i];
+      const int64_t s = rowptr[r], e = rowptr[r + 1];
+      for (int64_t p = s + sub; p < e; p += 4 * LPR) {
+        int c0 = ld_stream_s32(colidx + p);
+        int c1 = (p + LPR < e) ? ld_stream_s32(colidx + p + LPR) : -1;
+        int c2 = (p + 2 * LPR < e) ? ld_stream_s32(colidx + p + 2 * LPR) : -1;
+        int c3 = (p + 3 * LPR < e) ? ld_stream_s32(colidx + p + 3 * LPR) : -1;
+        double v0 = ld_stream_f64(val + p);
+        double v1 = (c1 >= 0) ? ld_stream_f64(val + p + LPR) : 0.0;
+        double v2 = (c2 >= 0) ? ld_stream_f64(val + p + 2 * LPR) : 0.0;
+        double v3 = (c3 >= 0) ? ld_stream_f64(val + p + 3 * LPR) : 0.0;
+        sum += v0 * x[c0];
+        if (c1 >= 0) sum += v1 * x[c1];
+        if (c2 >= 0) sum += v2 * x[c2];
+        if (c3 >= 0) sum += v3 * x[c3];
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, LPR);
+    if (r >= 0 && sub == 0) {
+      y[r] = sum;
+      if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
+    }
+  }
+  if (DOTS >= 1) {
+    double s0 = block_sum(d0, sh);
+    if (threadIdx.x == 0) partial[pofs + blockIdx.x] = s0;
+    if (DOTS >= 2) {
+      double s1 = block_sum(d1, sh);
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + pofs + blockIdx.x] = s1;
+    }
+  }
+}
+
+template <int DIM, int DOTS>
+__global__ void __launch_bounds__(ST_ROWS, ST_BLOCKS) k_spmv_stencil(int64_t n, SpmvSpace sp, const int64_t* __restrict__ rowptr,
+                                                                     const uint32_t* __restrict__ rowinfo, const double* __restrict__ val,
+                                                                     const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ a,
+                                                                     const uint8_t* __restrict__ owned, double* partial, const double* __restrict__ done)
+{
+  constexpr int NS = DIM == 3 ? 27 : 9;
+  constexpr int NL = NS / 3;                                                      // x segments: one per (dy, dz)
+  __shared__ __align__(16) double sv[ST_VCAP];
+  __shared__ __align__(16) double sx[NL * ST_XSEG];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ double sh[ST_ROWS / 32];
+  if (done && done[S_DONE] != 0.0) return;
+  const int t = threadIdx.x;
+  const int xpar = (int)(((uintptr_t)x >> 3) & 1);                              // bulk copies need 16-byte aligned sources
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // chunk -> (child, row range); chunks never straddle two child blocks
+  struct Chunk { int ci; int64_t r0, r1, span0, span1; };
+  int zero;                                                                       // opaque 0: keeps the prefetched metadata in per-thread
+  asm volatile("mov.u32 %0, 0;" : "=r"(zero));                                   // registers (no early uniform-register move that would wait for the load)
+  auto locate = [&](int64_t chunk, Chunk& C) {
+    C.ci = 0; C.r0 = C.r1 = C.span0 = C.span1 = 0;
+    if (chunk >= sp.nchunks) return;
+    int ci = 0;
+    while (ci + 1 < sp.nchild && chunk >= sp.ch[ci + 1].chunk0) ++ci;
+    const SpmvChild& ch = sp.ch[ci];
+    C.ci = ci;
+    C.r0 = ch.offset + (chunk - ch.chunk0) * ST_ROWS;
+    C.r1 = (C.r0 + ST_ROWS < ch.offset + ch.size) ? C.r0 + ST_ROWS : ch.offset + ch.size;
+    C.span0 = rowptr[C.r0 + zero]; C.span1 = rowptr[C.r1 + zero];
+  };
+  // a chunk is staged (values + x segments) when its x segments lie inside the vector and its value span fits the buffer
+  auto staged_of = [&](const Chunk& C) {
+    const int64_t a0 = C.span0 & ~(int64_t)1;
+    return spmv_chunk_staged(sp.ch[C.ci], DIM, C.r0, C.r1, n) && (((C.span1 - a0) + 1) & ~(int64_t)1) <= ST_VCAP;
+  };
+  auto issue = [&](const Chunk& C) {                                              // thread 0 only
+    const bool xst = spmv_chunk_staged(sp.ch[C.ci], DIM, C.r0, C.r1, n);
+    const bool vst = staged_of(C);
+    if (!xst) return;
+    const int64_t a0 = C.span0 & ~(int64_t)1;
+    const uint32_t vbytes = vst ? (uint32_t)((((C.span1 - a0) + 1) & ~(int64_t)1) * 8) : 0u;
+    const int len = (int)(C.r1 - C.r0) + 2;
+    uint32_t total = vbytes;
+    if (xst) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+        const int64_t g0 = C.r0 - 1 + dy * sp.ch[C.ci].bx + (int64_t)dz * sp.ch[C.ci].bxy;
+        const int64_t al = g0 - ((g0 + xpar) & 1);
+        total += (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8);
+      }
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(total) : "memory");
+    if (vst)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sv)), "l"(val + a0),
+                   "r"(vbytes), "r"(smem_u32(&bar))
+                   : "memory");
+    if (xst) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+        const int64_t g0 = C.r0 - 1 + dy * sp.ch[C.ci].bx + (int64_t)dz * sp.ch[C.ci].bxy;
+        const int64_t al = g0 - ((g0 + xpar) & 1);
+        const uint32_t bytes = (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sx + l * ST_XSEG)),
+                     "l"(x + al), "r"(bytes), "r"(smem_u32(&bar))
+                     : "memory");
+      }
+    }
+  };
+  auto load_meta = [&](const Chunk& C, int64_t& s_, int64_t& e_, uint32_t& info_) {
+    s_ = 0; e_ = 0; info_ = 0;
+    if (C.r0 + t < C.r1) { s_ = rowptr[C.r0 + t]; e_ = rowptr[C.r0 + t + 1]; info_ = rowinfo[C.r0 + t]; }
+  };
+  uint32_t phase = 0;
+  double d0 = 0.0, d1 = 0.0;
+  Chunk C, Cn;
+  int64_t s, e;
+  uint32_t info;
+  locate(blockIdx.x, C);
+  load_meta(C, s, e, info);
+  if (t == 0 && (int64_t)blockIdx.x < sp.nchunks) issue(C);
+  for (int64_t chunk = blockIdx.x; chunk < sp.nchunks; chunk += gridDim.x) {     // block-uniform trip count
+    // the block's next chunk: metadata loads are in flight while this one is summed
+    int64_t s_n, e_n;
+    uint32_t info_n;
+    locate(chunk + gridDim.x, Cn);
+    load_meta(Cn, s_n, e_n, info_n);
+    const int64_t r = C.r0 + t;
+    const bool live = r < C.r1;
+    const int64_t a0 = C.span0 & ~(int64_t)1;
+    const bool xst = spmv_chunk_staged(sp.ch[C.ci], DIM, C.r0, C.r1, n), vst = staged_of(C);      // block-uniform
+    const int bx = sp.ch[C.ci].bx, bxy = sp.ch[C.ci].bxy;
+    // affine rows of a staged chunk are summed here, every other row by k_spmv_rows (same predicate: k_spmv_rest_flags)
+    const uint32_t m27 = (live && xst) ? spmv_affine_mask(DIM, info, e - s) : 0u;
+    const bool affine = m27 != 0;
+    const bool full = m27 == (1u << NS) - 1u;
+    double sum = 0.0;
+    if (xst) {
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
+      phase ^= 1;
+    }
+    if (affine) {
+      const double* v = vst ? sv + (s - a0) : val + s;
+      // segment l holds x[al_l ...], al_l = g0_l rounded down to a 16-byte boundary (g0_l = r0 - 1 + off_l): entry (t, dx) sits
+      // at (g0_l - al_l) + t + dx + 1
+      if (full) {
+#pragma unroll
+        for (int o = 0; o < NS; ++o) {
+          const int dx = o % 3 - 1, l = o / 3, dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+          const int sh_l = (int)((C.r0 - 1 + dy * bx + (int64_t)dz * bxy + xpar) & 1);
+          sum += v[o] * sx[l * ST_XSEG + sh_l + t + dx + 1];
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < NS; ++o) {
+          const int dx = o % 3 - 1, l = o / 3, dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+          const int sh_l = (int)((C.r0 - 1 + dy * bx + (int64_t)dz * bxy + xpar) & 1);
+          if ((m27 >> o) & 1u) sum += v[__popc(m27 & ((1u << o) - 1u))] * sx[l * ST_XSEG + sh_l + t + dx + 1];
+        }
+      }
+    }
+    __syncthreads();                                                             // the staging buffers are free again:
+    if (t == 0 && chunk + gridDim.x < sp.nchunks) issue(Cn);                      // next chunk's copies fly during the tail below
+    if (affine) {
+      y[r] = sum;
+      if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
+    }
+    C = Cn; s = s_n; e = e_n; info = info_n;
+  }
+  if (DOTS >= 1) {
+    double s0 = block_sum(d0, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+    if (DOTS >= 2) {
+      double s1 = block_sum(d1, sh);
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+    }
+  }
+}
+
 static int spmv_variant()
 {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MDB_SPMV_VARIANT"); v = e ? atoi(e) : 1; }
+  if (v < 0) { const char* e = getenv("MDB_SPMV_VARIANT"); v = e ? atoi(e) : 4; }     // 4 = stencil-aware (Q1 spaces only)
   return v;
 }
 
@@ -191,6 +448,53 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
     if (nblocks) *nblocks = grid;
     MDB_LAUNCH(c, k_spmv<DOTS>, grid, SPMV_THREADS, smem, n, nchunks, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
     return;
+  }
+  if (variant == 4) {
+    bool q1 = true;
+    for (const Child& ch : c->children) q1 = q1 && ch.k == 1;
+    if (q1) {
+      SpmvSpace sp; sp.nchild = (int)c->children.size(); sp.nchunks = 0;
+      const int dim = c->mesh.dim;
+      for (int i = 0; i < sp.nchild; ++i) {
+        const Child& ch = c->children[i];
+        int64_t vol = 1;
+        for (int d = 0; d < dim; ++d) vol *= ch.lat_hi[d] - ch.lat_lo[d] + 1;
+        sp.ch[i].offset = ch.offset; sp.ch[i].size = ch.size; sp.ch[i].box = (ch.size > 0 && vol == ch.size) ? 1 : 0;
+        sp.ch[i].bx = ch.lat_hi[0] - ch.lat_lo[0] + 1; sp.ch[i].bxy = sp.ch[i].bx * (ch.lat_hi[1] - ch.lat_lo[1] + 1);
+        sp.ch[i].chunk0 = sp.nchunks; sp.nchunks += (ch.size + ST_ROWS - 1) / ST_ROWS;
+      }
+      if (M.n_spmv_rest < 0) {                // first product with this matrix: the rows the stencil kernel leaves out
+        Matrix& Mm = const_cast<Matrix&>(M);
+        int32_t* d_flag = dalloc<int32_t>(n);
+        int32_t* d_scan = dalloc<int32_t>(n);
+        MDB_LAUNCH(c, k_spmv_rest_flags, cdiv(n, 256), 256, 0, n, sp, dim, M.d_rowptr, M.d_rowinfo, d_flag);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_scan, (int)n, c->stream);
+        void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+        MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_flag, d_scan, (int)n, c->stream)); c->launches++;
+        int32_t ls = 0, lf = 0;
+        MDB_CUDA(cudaMemcpyAsync(&ls, d_scan + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+        MDB_CUDA(cudaMemcpyAsync(&lf, d_flag + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+        MDB_CUDA(cudaStreamSynchronize(c->stream));
+        Mm.d_spmv_rest = dalloc<int32_t>((int64_t)ls + lf);
+        MDB_LAUNCH(c, k_spmv_rest_compact, cdiv(n, 256), 256, 0, n, d_flag, d_scan, Mm.d_spmv_rest);
+        MDB_CUDA(cudaStreamSynchronize(c->stream));
+        Mm.n_spmv_rest = (int64_t)ls + lf;
+        cudaFree(d_t); dfree(d_flag); dfree(d_scan);
+      }
+      int grid = 148 * ST_BLOCKS;
+      if (grid > sp.nchunks) grid = (int)sp.nchunks;
+      int grid2 = 148 * 8;
+      if (grid2 > cdiv(M.n_spmv_rest, 32)) grid2 = cdiv(M.n_spmv_rest, 32);
+      if (nblocks) *nblocks = grid + grid2;
+      if (dim == 3) MDB_LAUNCH(c, (k_spmv_stencil<3, DOTS>), grid, ST_ROWS, 0, n, sp, M.d_rowptr, M.d_rowinfo, M.d_val, x, y, a, c->d_owned, partial, done);
+      else MDB_LAUNCH(c, (k_spmv_stencil<2, DOTS>), grid, ST_ROWS, 0, n, sp, M.d_rowptr, M.d_rowinfo, M.d_val, x, y, a, c->d_owned, partial, done);
+      if (grid2 > 0)
+        MDB_LAUNCH(c, k_spmv_rows<DOTS>, grid2, 256, 0, M.n_spmv_rest, M.d_spmv_rest, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, grid,
+                   done);
+      return;
+    }
+    variant = 1;
   }
   const int lpr = (variant == 2) ? 4 : (variant == 3) ? 16 : 8;
   int grid = 148 * 8;
@@ -403,8 +707,11 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
               "preconditioner not available in this build (Jacobi or none)");
   const int64_t n = c->ndof;
   const int vgrid = (cdiv(n, VEC_THREADS) < 148 * 8) ? cdiv(n, VEC_THREADS) : 148 * 8;
-  if (!M.d_dinv) M.d_dinv = dalloc<double>(n);
-  MDB_LAUNCH(c, k_extract_dinv, cdiv(n, 256), 256, 0, n, M.d_rowptr, M.d_diag, M.d_val, M.d_dinv, precond == MDB_PRECOND_JACOBI ? 1 : 0);
+  if (!M.d_dinv) { M.d_dinv = dalloc<double>(n); M.dinv_valid = false; }
+  if (!M.dinv_valid || M.dinv_precond != precond) {     // the inverse diagonal survives until the matrix values change (mdb_jacobian / mdb_matrix_zero)
+    MDB_LAUNCH(c, k_extract_dinv, cdiv(n, 256), 256, 0, n, M.d_rowptr, M.d_diag, M.d_val, M.d_dinv, precond == MDB_PRECOND_JACOBI ? 1 : 0);
+    M.dinv_valid = true; M.dinv_precond = precond;
+  }
   const bool multi = c->nranks > 1;
   double* s = c->d_scal;
   double* x = d_z;
