@@ -19,8 +19,8 @@ OP_POISSON, OP_L2 = 1, 2
 OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
 JAC_FD_BITMATCH, JAC_ANALYTIC = 0, 1
 SOLVER_CG, SOLVER_BICGSTAB = 0, 1
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0 = 0, 1, 2
-PRECOND_SSOR_ORACLE = 100  # oracle only (ISTL SeqSSOR); the device backend offers Jacobi / ILU0
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR = 0, 1, 2, 3
+PRECOND_SSOR_ORACLE = 100  # the oracle's own id for ISTL SeqSSOR (tests/orc.py maps PRECOND_SSOR to it)
 
 
 class Function(C.Structure):
@@ -284,6 +284,9 @@ class Mdb(Lib):
         if rc != -6:  # MDB_ENOTCONVERGED is reported through stats
             self._check(rc, "solve")
         return st
+
+    def set_ssor_sweeps(self, sweeps):
+        self._check(self._fn("set_ssor_sweeps")(C.c_void_p(self.ctx), int(sweeps)), "set_ssor_sweeps")
 
     def matrix_device_ptrs(self, mat):
         rp, ci, va = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)

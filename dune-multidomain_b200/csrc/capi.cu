@@ -121,7 +121,7 @@ void VecInOut::commit()
 
 static void free_matrix(Matrix& m)
 {
-  dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv); dfree(m.d_spmv_rest);
+  dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv); dfree(m.d_spmv_rest); dfree(m.d_ready); dfree(m.d_sweep_counter); dfree(m.d_sweep_perm); dfree(m.d_vrec); dfree(m.d_ilu);
   for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(m.d_irregular[i]); dfree(m.d_seg_start[i]); dfree(m.d_seg_span[i]); }
   for (auto& kv : m.slot_tables) cudaFree(kv.second);
   m.slot_tables.clear();
@@ -513,7 +513,7 @@ int mdb_matrix_zero(mdb_ctx* c, int mat)
   MDB_API_BEGIN(c)
   MDB_MAT(c, mat)
   MDB_CUDA(cudaMemsetAsync(M.d_val, 0, M.nnz * sizeof(double), c->stream));
-  M.dinv_valid = false;
+  M.dinv_valid = false; M.ilu_valid = false;
   MDB_API_END(c)
 }
 
@@ -562,7 +562,7 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   MDB_API_BEGIN(c)
   MDB_GO(c, go)
   MDB_MAT(c, mat)
-  M.dinv_valid = false;
+  M.dinv_valid = false; M.ilu_valid = false;
   // The volume operators of the closed set are linear: their Jacobian does not read x.  Only the finite-difference
   // coupling Jacobian does, and only at the DOFs of the interface cells.  With a HOST vector the upload therefore runs on
   // the copy stream concurrently with the volume kernels, and from pinned memory only the needed entries are fetched.
@@ -675,6 +675,14 @@ int mdb_solve(mdb_ctx* c, int mat, int method, int precond, double reduction, in
     return rc;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
   catch (std::exception& e) { c->err = e.what(); return MDB_EINVAL; }
+}
+
+int mdb_set_ssor_sweeps(mdb_ctx* c, int sweeps)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(sweeps >= 1, MDB_EINVAL, "SSOR needs at least one sweep");
+  c->ssor_sweeps = sweeps;
+  MDB_API_END(c)
 }
 
 int mdb_solve_fixed(mdb_ctx* c, int mat, int method, int precond, int iters, const double* rhs, double* z, mdb_solve_stats* stats)

@@ -207,6 +207,9 @@ struct Matrix {
   // preconditioner caches
   double* d_dinv = nullptr;
   bool dinv_valid = false; int dinv_precond = -1;
+  // sequential preconditioners (precond.cu): ready flags / row counter of the sync-free sweeps, ILU(0) factors
+  int* d_ready = nullptr; unsigned long long* d_sweep_counter = nullptr; int sweep_epoch = 0; int32_t* d_sweep_perm = nullptr; ulonglong2* d_vrec = nullptr;
+  double* d_ilu = nullptr; bool ilu_valid = false;
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
 };
@@ -243,6 +246,7 @@ struct Ctx {
   int32_t* d_conlist = nullptr;
   int64_t ncon = 0;
   double time = 0.0;
+  int ssor_sweeps = 3;               // SeqSSOR(A, n, 1.0): ISTLBackend_SEQ_BCGS_SSOR uses n = 3 (test/testpoisson.cc:291)
 
   // scratch
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -327,6 +331,7 @@ void setup_partition(Ctx* c);                       // multigpu.cu: ownership fl
 void allreduce_scalars(Ctx* c, double* d_vals, int n);
 void halo_exchange(Ctx* c, double* d_x);
 bool halo_timed_out(Ctx* c);
+void precond_apply(Ctx* c, Matrix& m, int kind, int sweeps, const double* d_d, double* d_v);   // precond.cu: SSOR / ILU0
 
 template <typename T> inline T* dalloc(size_t n)
 {

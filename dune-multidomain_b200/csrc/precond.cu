@@ -1,0 +1,283 @@
+// precond.cu — the reference's sequential preconditioners on the device: SeqSSOR and SeqILU0 with ISTL's arithmetic.
+//
+// Replaces [UPSTREAM] dune-istl SeqSSOR (gsetc.hh bsorf/bsorb) and SeqILU0 (ilu.hh bilu0_decomposition / bilu_backsolve)
+// as PDELab's ISTLBackend_SEQ_BCGS_SSOR / ISTLBackend_SEQ_CG_SSOR / *_ILU0 drive them (test/testpoisson.cc:291-292,
+// test/explicitlycoupledpoisson.cc:297-313).  Both are Gauss-Seidel-like recurrences over the rows in index order.  They
+// are run here WITHOUT a level analysis and WITHOUT changing a single operation of the sequential algorithm:
+//   * one warp owns one row; warps take rows from a global counter in a WAVEFRONT order: rows sorted by (child block,
+//     ix + 2 iy + 4 iz) of their lattice point, a topological order of the lower-triangular dependency graph of a
+//     lexicographically numbered lattice block (every lower stencil neighbour has a strictly smaller key; other blocks come
+//     first).  The rows in flight are then (nearly) independent, so the whole wavefront works in parallel; the ARITHMETIC is
+//     untouched by the order in which independent rows are executed;
+//   * a row that needs the new value of row j spins on ready[j] == epoch (acquire) and then reads v[j] from L2;
+//   * the owner publishes v[i] and then ready[i] = epoch (release).  Every row a warp can wait for has already been taken
+//     by a running warp (the dispatch order is topological), so the scheme cannot deadlock, whatever the grid size;
+//   * the row sum is accumulated in column order, one subtraction at a time, products rounded separately (no FMA) — the
+//     bits of the sequential CPU sweep, so Krylov iteration counts match the reference's solver stack.
+// The sweeps are latency-bound (critical path = longest dependency chain, ~7N rows on an N^3 lattice); they are the
+// drop-in for the reference's default solver configuration, the fast path is Jacobi (solver.cu).
+// Assumption: the pattern is structurally symmetric (true for every pattern this backend builds: unions of cliques and
+// two-sided coupling blocks), so a row never reads an entry that a later row of the same sweep is already overwriting.
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace mdb {
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v)
+{
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+enum { SW_SSOR_FWD = 0, SW_SSOR_BWD = 1, SW_ILU_LOWER = 2, SW_ILU_UPPER = 3 };
+
+// The iterate travels between warps as self-validating 16-byte records (the layout of NCCL's LL protocol): two 64-bit words,
+// each = (tag << 32) | half of the double.  64-bit stores are single-copy atomic, so a reader that sees the sweep's tag in
+// BOTH words has the complete value — one store and one polling load per dependency, no fence, no separate flag.
+__device__ __forceinline__ ulonglong2 ld_record(const ulonglong2* p)
+{
+  ulonglong2 w;
+  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(p) : "memory");
+  return w;
+}
+__device__ __forceinline__ void st_record(ulonglong2* p, double v, unsigned tag)
+{
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long t = (unsigned long long)tag << 32;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(t | (b & 0xffffffffull)), "l"(t | (b >> 32)) : "memory");
+}
+__device__ __forceinline__ double record_value(const ulonglong2& w) { return __longlong_as_double((long long)((w.y << 32) | (w.x & 0xffffffffull))); }
+__device__ __forceinline__ bool record_tagged(const ulonglong2& w, unsigned tag) { return (unsigned)(w.x >> 32) == tag && (unsigned)(w.y >> 32) == tag; }
+
+// One sweep.  a = matrix values (SSOR) or the ILU factors; d = right-hand side; vt = the iterate as records (updated in place).
+//   SSOR fwd/bwd (gsetc.hh bsorf/bsorb, w = 1):  rhs = d_i - sum_j a_ij v_j over ALL j of the row (j < i new / j >= i old in
+//                                                the forward sweep, mirrored in the backward one); v_i += rhs / a_ii
+//   ILU lower (bilu_backsolve, first loop):      v_i = d_i - sum_{j<i} L_ij v_j
+//   ILU upper (second loop):                     v_i = Uinv_ii * (v_i - sum_{j>i} U_ij v_j), the diagonal holds the inverse
+template <int MODE>
+__global__ void __launch_bounds__(256) k_sweep(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                               const int32_t* __restrict__ diag, const double* __restrict__ a, const double* __restrict__ d,
+                                               ulonglong2* vt, const int32_t* __restrict__ perm, unsigned epoch, unsigned long long* counter)
+{
+  constexpr bool ASC = (MODE == SW_SSOR_FWD || MODE == SW_ILU_LOWER);
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long k = 0;
+    if (lane == 0) k = atomicAdd(counter, 1ull);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= (unsigned long long)n) return;
+    const int64_t i = perm[ASC ? (int64_t)k : n - 1 - (int64_t)k];
+    const int64_t s = rowptr[i], e = rowptr[i + 1];
+    const int64_t pd = s + diag[i];
+    const double aii = a[pd];                                               // issued early: needed only at the end of the chain
+    const double vi = (MODE == SW_ILU_LOWER) ? 0.0 : record_value(ld_record(vt + i));   // row i is written by this warp only
+    // the entries this mode sums, in column order
+    int64_t p0 = s, p1 = e;
+    if (MODE == SW_ILU_LOWER) p1 = pd;
+    if (MODE == SW_ILU_UPPER) p0 = pd + 1;
+    double acc = (MODE == SW_ILU_UPPER) ? vi : d[i];
+    for (int64_t pb = p0; pb < p1; pb += 32) {
+      const int64_t p = pb + lane;
+      const bool live = p < p1;
+      const int col = live ? colidx[p] : 0;
+      const double av = live ? a[p] : 0.0;
+      const bool dep = live && (ASC ? (col < i) : (col > i));
+      ulonglong2 w = make_ulonglong2(0ull, 0ull);
+      for (int tries = 0;; ++tries) {                                       // warp-wide wait: the row needs all its dependencies anyway
+        if (live) w = ld_record(vt + col);
+        if (__all_sync(0xffffffffu, !dep || record_tagged(w, epoch))) break;
+        __nanosleep(tries < 8 ? 32 : 128);
+      }
+      const double prod = live ? __dmul_rn(av, record_value(w)) : 0.0;
+      const int cnt = (p1 - pb < 32) ? (int)(p1 - pb) : 32;
+      for (int l = 0; l < cnt; ++l) acc = __dsub_rn(acc, __shfl_sync(0xffffffffu, prod, l));
+    }
+    if (lane == 0) {
+      double out;
+      if (MODE == SW_SSOR_FWD || MODE == SW_SSOR_BWD) out = __dadd_rn(vi, __ddiv_rn(acc, aii));
+      else if (MODE == SW_ILU_LOWER) out = acc;
+      else out = __dmul_rn(aii, acc);
+      st_record(vt + i, out, epoch);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void k_records_to_vector(int64_t n, const ulonglong2* __restrict__ vt, double* v)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) v[i] = record_value(vt[i]);
+}
+
+// ILU(0) on the pattern of A (ilu.hh bilu0_decomposition): for every row i, for every k < i of the row in ascending order:
+//   L_ik = a_ik * Uinv_kk ; a_ij -= L_ik * U_kj for the j > k present in both rows ; finally the diagonal is inverted.
+// A warp owns row i and keeps its entries in registers (EPL per lane); row k's upper part is streamed through the lanes.
+template <int EPL>
+__global__ void __launch_bounds__(256) k_ilu0_factor(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                     const int32_t* __restrict__ diag, double* f, const int32_t* __restrict__ perm, int* ready, int epoch,
+                                                     unsigned long long* counter)
+{
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long kk = 0;
+    if (lane == 0) kk = atomicAdd(counter, 1ull);
+    kk = __shfl_sync(0xffffffffu, kk, 0);
+    if (kk >= (unsigned long long)n) return;
+    const int64_t i = perm[kk];
+    const int64_t s = rowptr[i];
+    const int len = (int)(rowptr[i + 1] - s), dg = diag[i];
+    int col[EPL]; double val[EPL];
+#pragma unroll
+    for (int u = 0; u < EPL; ++u) {
+      const int idx = u * 32 + lane;
+      col[u] = (idx < len) ? colidx[s + idx] : -1;
+      val[u] = (idx < len) ? f[s + idx] : 0.0;        // f starts as a copy of A; row i is touched by this warp only
+    }
+    for (int pl = 0; pl < dg; ++pl) {                  // the entries left of the diagonal, ascending
+      int csel = col[0];
+#pragma unroll
+      for (int u = 1; u < EPL; ++u) if ((pl >> 5) == u) csel = col[u];       // pl >> 5 is warp-uniform
+      const int k = __shfl_sync(0xffffffffu, csel, pl & 31);
+      for (int tries = 0; ld_acquire_s32(ready + k) != epoch; ++tries) __nanosleep(tries < 8 ? 32 : 128);
+      const int64_t ks = rowptr[k];
+      const int kd = diag[k], klen = (int)(rowptr[k + 1] - ks);
+      const double uinv = __ldcg(f + ks + kd);
+      double lik = 0.0;
+#pragma unroll
+      for (int u = 0; u < EPL; ++u)
+        if (u * 32 + lane == pl) { val[u] = __dmul_rn(val[u], uinv); lik = val[u]; }
+      lik = __shfl_sync(0xffffffffu, lik, pl & 31);
+      for (int qb = kd + 1; qb < klen; qb += 32) {
+        const int q = qb + lane;
+        const int cq = (q < klen) ? colidx[ks + q] : -2;
+        const double uq = (q < klen) ? __ldcg(f + ks + q) : 0.0;
+        const int cnt = (klen - qb < 32) ? klen - qb : 32;
+        for (int t = 0; t < cnt; ++t) {
+          const int c = __shfl_sync(0xffffffffu, cq, t);
+          const double uu = __shfl_sync(0xffffffffu, uq, t);
+#pragma unroll
+          for (int u = 0; u < EPL; ++u)
+            if (col[u] == c) val[u] = __dsub_rn(val[u], __dmul_rn(lik, uu));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EPL; ++u) {
+      const int idx = u * 32 + lane;
+      if (idx == dg) val[u] = __ddiv_rn(1.0, val[u]);  // (*ij).invert()
+      if (idx < len) __stcg(f + s + idx, val[u]);
+    }
+    __threadfence();                                   // every lane's stores are visible device-wide ...
+    __syncwarp();
+    if (lane == 0) st_release_s32(ready + i, epoch);   // ... before the row is published
+  }
+}
+
+// wavefront key of every row: (child block, ix + 2 iy + 4 iz)
+struct KeyChild { int64_t offset; int n0, n1; const int32_t* dof2lat; };
+struct KeySpace { int nchild; KeyChild ch[MDB_MAX_CHILDREN]; };
+__global__ void k_sweep_keys(int64_t n, KeySpace sp, uint32_t* key, int32_t* row)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int ci = 0;
+  while (ci + 1 < sp.nchild && r >= sp.ch[ci + 1].offset) ++ci;
+  const KeyChild& ch = sp.ch[ci];
+  const int64_t p = ch.dof2lat[r - ch.offset];
+  const int ix = (int)(p % ch.n0), iy = (int)((p / ch.n0) % ch.n1), iz = (int)(p / ((int64_t)ch.n0 * ch.n1));
+  key[r] = ((uint32_t)ci << 24) | (uint32_t)(ix + 2 * iy + 4 * iz);
+  row[r] = (int32_t)r;
+}
+__global__ void k_iota(int64_t n, int32_t* row)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r < n) row[r] = (int32_t)r;
+}
+
+static void ensure_precond_state(Ctx* c, Matrix& M)
+{
+  if (M.d_ready) return;
+  const int64_t n = c->ndof;
+  M.d_ready = dalloc<int>(n);
+  MDB_CUDA(cudaMemsetAsync(M.d_ready, 0, n * sizeof(int), c->stream));
+  M.d_sweep_counter = dalloc<unsigned long long>(1);
+  M.sweep_epoch = 0;
+  // dispatch order of the rows.  The wavefront key is a topological order only for lexicographically numbered (Q1) lattice
+  // blocks whose lattice fits the key; anything else keeps the index order (always topological, little parallelism).
+  M.d_sweep_perm = dalloc<int32_t>(n);
+  bool lattice = true;
+  KeySpace sp; sp.nchild = (int)c->children.size();
+  for (int i = 0; i < sp.nchild; ++i) {
+    const Child& ch = c->children[i];
+    lattice = lattice && ch.k == 1 && (int64_t)ch.lat_n[0] + 2 * (int64_t)ch.lat_n[1] + 4 * (int64_t)ch.lat_n[2] < (1 << 24);
+    sp.ch[i].offset = ch.offset; sp.ch[i].n0 = ch.lat_n[0]; sp.ch[i].n1 = ch.lat_n[1]; sp.ch[i].dof2lat = ch.d_dof2lat;
+  }
+  if (!lattice) { MDB_LAUNCH(c, k_iota, cdiv(n, 256), 256, 0, n, M.d_sweep_perm); return; }
+  uint32_t* d_key = dalloc<uint32_t>(n); uint32_t* d_key2 = dalloc<uint32_t>(n);
+  int32_t* d_row = dalloc<int32_t>(n);
+  MDB_LAUNCH(c, k_sweep_keys, cdiv(n, 256), 256, 0, n, sp, d_key, d_row);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_row, M.d_sweep_perm, (int)n, 0, 32, c->stream);
+  void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+  MDB_CUDA(cub::DeviceRadixSort::SortPairs(d_t, tb, d_key, d_key2, d_row, M.d_sweep_perm, (int)n, 0, 32, c->stream)); c->launches++;   // stable: ties keep index order
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_t); dfree(d_key); dfree(d_key2); dfree(d_row);
+}
+
+template <int MODE>
+static void sweep(Ctx* c, Matrix& M, const double* a, const double* d)
+{
+  MDB_CUDA(cudaMemsetAsync(M.d_sweep_counter, 0, sizeof(unsigned long long), c->stream));
+  ++M.sweep_epoch;
+  int grid = 148 * 8;
+  if (grid > cdiv(c->ndof, 8)) grid = cdiv(c->ndof, 8);
+  MDB_LAUNCH(c, k_sweep<MODE>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, a, d, M.d_vrec, M.d_sweep_perm, (unsigned)M.sweep_epoch,
+             M.d_sweep_counter);
+}
+
+void ilu0_factorize(Ctx* c, Matrix& M)
+{
+  ensure_precond_state(c, M);
+  if (!M.d_ilu) M.d_ilu = dalloc<double>(M.nnz);
+  MDB_CUDA(cudaMemcpyAsync(M.d_ilu, M.d_val, M.nnz * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  MDB_CUDA(cudaMemsetAsync(M.d_sweep_counter, 0, sizeof(unsigned long long), c->stream));
+  ++M.sweep_epoch;
+  int grid = 148 * 8;
+  if (grid > cdiv(c->ndof, 8)) grid = cdiv(c->ndof, 8);
+  MDB_REQUIRE(M.max_row <= 128, MDB_EINVAL, "ILU0: rows longer than 128 entries are not supported");
+  if (M.max_row <= 32)
+    MDB_LAUNCH(c, k_ilu0_factor<1>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+  else if (M.max_row <= 64)
+    MDB_LAUNCH(c, k_ilu0_factor<2>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+  else
+    MDB_LAUNCH(c, k_ilu0_factor<4>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+  M.ilu_valid = true;
+}
+
+// v = M^-1 d  (v starts at zero, as the ISTL solvers do: pre() / apply() with v = 0)
+void precond_apply(Ctx* c, Matrix& M, int kind, int sweeps, const double* d, double* v)
+{
+  const int64_t n = c->ndof;
+  MDB_REQUIRE(c->nranks == 1, MDB_EINVAL, "SSOR / ILU0 are sequential preconditioners: single-rank contexts only (use Jacobi on a partition)");
+  ensure_precond_state(c, M);
+  if (!M.d_vrec) M.d_vrec = dalloc<ulonglong2>(n);
+  if (kind == MDB_PRECOND_SSOR) {
+    MDB_CUDA(cudaMemsetAsync(M.d_vrec, 0, n * sizeof(ulonglong2), c->stream));      // value 0.0, tag 0 (epochs start at 1)
+    for (int it = 0; it < sweeps; ++it) {
+      sweep<SW_SSOR_FWD>(c, M, M.d_val, d);
+      sweep<SW_SSOR_BWD>(c, M, M.d_val, d);
+    }
+  } else {
+    if (!M.ilu_valid) ilu0_factorize(c, M);
+    sweep<SW_ILU_LOWER>(c, M, M.d_ilu, d);
+    sweep<SW_ILU_UPPER>(c, M, M.d_ilu, d);
+  }
+  MDB_LAUNCH(c, k_records_to_vector, cdiv(n, 256), 256, 0, n, M.d_vrec, v);
+}
+
+} // namespace mdb

@@ -686,6 +686,18 @@ __global__ void k_bi_derive_end(double* s)
   if (s[S_RR] <= s[S_RED2] * s[S_RR0]) s[S_DONE] = 1.0;
 }
 
+// partial0 = sum a_i b_i over owned rows
+__global__ void k_dot(int64_t n, const double* __restrict__ s, const double* __restrict__ a, const double* __restrict__ b, const uint8_t* __restrict__ owned,
+                      double* partial)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  if (s[S_DONE] != 0.0) return;
+  double a0 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!owned || owned[i]) a0 += a[i] * b[i];
+  double s0 = block_sum(a0, sh); if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+}
+
 static void reduce(Ctx* c, int nblocks, int nvals, int s0, int s1 = 0, int s2 = 0)
 {
   MDB_LAUNCH(c, k_reduce_partials, 1, VEC_THREADS, 0, c->d_partial, nblocks, nvals, c->d_scal, s0, s1, s2);
@@ -703,8 +715,12 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
           mdb_solve_stats* stats)
 {
   MDB_REQUIRE(method == MDB_SOLVER_CG || method == MDB_SOLVER_BICGSTAB, MDB_EINVAL, "unknown solver");
-  MDB_REQUIRE(precond == MDB_PRECOND_NONE || precond == MDB_PRECOND_JACOBI, MDB_EINVAL,
-              "preconditioner not available in this build (Jacobi or none)");
+  MDB_REQUIRE(precond == MDB_PRECOND_NONE || precond == MDB_PRECOND_JACOBI || precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0, MDB_EINVAL,
+              "unknown preconditioner");
+  // Jacobi (and none) are fused into the vector kernels through the inverse diagonal; SSOR / ILU0 are explicit applications
+  // z = M^-1 r (precond.cu) between the same kernels run with a unit "inverse diagonal"
+  const bool general = precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0;
+  MDB_REQUIRE(!general || c->nranks == 1, MDB_EINVAL, "SSOR / ILU0 are sequential preconditioners: single-rank contexts only");
   const int64_t n = c->ndof;
   const int vgrid = (cdiv(n, VEC_THREADS) < 148 * 8) ? cdiv(n, VEC_THREADS) : 148 * 8;
   if (!M.d_dinv) { M.d_dinv = dalloc<double>(n); M.dinv_valid = false; }
@@ -717,7 +733,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
   double* x = d_z;
   int nb = 0;
   MDB_CUDA(cudaEventRecord(c->ev0, c->stream));
-  const int check_every = (fixed_iters >= 0) ? (1 << 30) : 16;
+  const int check_every = (fixed_iters >= 0) ? (1 << 30) : (general ? 1 : 16);     // a sweep costs far more than a poll
   int issued = 0;
   double* hp = c->h_pinned;
   auto poll = [&]() {
@@ -725,14 +741,21 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     MDB_CUDA(cudaStreamSynchronize(c->stream));
   };
   if (method == MDB_SOLVER_CG) {
-    ensure_work(c, 3);
-    double *r = c->d_work, *p = c->d_work + n, *q = c->d_work + 2 * n;
+    ensure_work(c, general ? 4 : 3);
+    double *r = c->d_work, *p = c->d_work + n, *q = c->d_work + 2 * n, *zv = general ? c->d_work + 3 * n : nullptr;
+    MDB_CUDA(cudaMemsetAsync(s + S_DONE, 0, sizeof(double), c->stream));
     MDB_LAUNCH(c, k_cg_init, vgrid, VEC_THREADS, 0, n, d_b, M.d_dinv, c->d_owned, x, r, p, c->d_partial);
     reduce(c, vgrid, 2, S_RHONEW, S_RR);
     if (multi) allreduce_scalars(c, s + S_RHONEW, 2);
+    auto precondition = [&]() {            // zv = M^-1 r ; rho_new = zv . r
+      precond_apply(c, M, precond, c->ssor_sweeps, r, zv);
+      MDB_LAUNCH(c, k_dot, vgrid, VEC_THREADS, 0, n, s, zv, r, c->d_owned, c->d_partial);
+      reduce(c, vgrid, 1, S_RHONEW);
+    };
+    if (general) precondition();
     MDB_LAUNCH(c, k_cg_init_scalars, 1, 1, 0, s, reduction);
     while (issued < maxit) {
-      MDB_LAUNCH(c, k_cg_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, p);
+      MDB_LAUNCH(c, k_cg_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, general ? zv : r, p);
       if (multi) halo_exchange(c, p);
       launch_spmv<1>(c, M, p, q, p, c->d_partial, &nb, s);
       reduce(c, nb, 1, S_PQ);
@@ -741,6 +764,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       MDB_LAUNCH(c, k_cg_update_xr, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, p, q, c->d_owned, x, r, c->d_partial);
       reduce(c, vgrid, 2, S_RHONEW, S_RR);
       if (multi) allreduce_scalars(c, s + S_RHONEW, 2);
+      if (general) precondition();
       MDB_LAUNCH(c, k_cg_derive_b, 1, 1, 0, s);
       ++issued;
       if (issued % check_every == 0) { poll(); if (hp[S_DONE] != 0.0) break; }
@@ -754,6 +778,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     MDB_LAUNCH(c, k_bi_init_scalars, 1, 1, 0, s, reduction);
     while (issued < maxit) {
       MDB_LAUNCH(c, k_bi_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, v, p, y);
+      if (general) precond_apply(c, M, precond, c->ssor_sweeps, p, y);
       if (multi) halo_exchange(c, y);
       launch_spmv<1>(c, M, y, v, rt, c->d_partial, &nb, s);
       reduce(c, nb, 1, S_H);
@@ -763,6 +788,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       reduce(c, vgrid, 1, S_RR);
       if (multi) allreduce_scalars(c, s + S_RR, 1);
       MDB_LAUNCH(c, k_bi_derive_half, 1, 1, 0, s);
+      if (general) precond_apply(c, M, precond, c->ssor_sweeps, r, y2);
       if (multi) halo_exchange(c, y2);
       launch_spmv<2>(c, M, y2, t, r, c->d_partial, &nb, s);
       reduce(c, nb, 2, S_TR, S_TT);

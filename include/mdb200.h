@@ -225,7 +225,10 @@ int mdb_jacobian(mdb_ctx* ctx, int go, int mat, double weight, const double* x, 
 
 /* ---- linear solve ([UPSTREAM] ISTL solver backends) ----------- */
 enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1 };
-enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2 };
+/* Jacobi is the fast path.  SSOR and ILU0 reproduce the reference's sequential ISTL preconditioners (SeqSSOR(A, n, 1.0),
+ * SeqILU0) operation for operation; they are single-rank only.  [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SSOR(3),
+ * ISTLBackend_SEQ_CG_SSOR = CG + SSOR(1)  (test/testpoisson.cc:291-292, test/explicitlycoupledpoisson.cc:297-313). */
+enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2, MDB_PRECOND_SSOR = 3 };
 typedef struct mdb_solve_stats {
   int32_t iterations;
   int32_t converged;
@@ -236,6 +239,8 @@ typedef struct mdb_solve_stats {
 /* Solve A z = rhs to  |defect| <= reduction * |defect0|  starting from z = 0.  rhs, z: host or device. */
 int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, int maxit,
               const double* rhs, double* z, mdb_solve_stats* stats);
+/* Number of symmetric sweeps n of MDB_PRECOND_SSOR (default 3). */
+int mdb_set_ssor_sweeps(mdb_ctx* ctx, int sweeps);
 /* Run exactly `iters` Krylov iterations without convergence test (benchmarking the loop). */
 int mdb_solve_fixed(mdb_ctx* ctx, int mat, int method, int precond, int iters,
                     const double* rhs, double* z, mdb_solve_stats* stats);

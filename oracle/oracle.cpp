@@ -850,12 +850,12 @@ struct Precond {
   Precond(const CSR& A_, int kind_, int sweeps_) : A(A_), kind(kind_), sweeps(sweeps_) {
     diag.resize(A.nrows);
     for (int64_t r = 0; r < A.nrows; ++r) { diag[r] = A.find(r, r); if (diag[r] < 0) throw std::runtime_error("missing diagonal"); }
-    if (kind == MDB_PRECOND_ILU0) {          // bilu0_decomposition, IKJ variant on the pattern of A
-      ilu = A.val;
+    if (kind == MDB_PRECOND_ILU0) {          // [UPSTREAM] ilu.hh bilu0_decomposition on the pattern of A: L_ik = a_ik * (a_kk)^-1 with
+      ilu = A.val;                           // the pivot of every finished row stored INVERTED ((*ij).rightmultiply(*jj), (*ij).invert())
       for (int64_t i = 0; i < A.nrows; ++i) {
         for (int64_t p = A.rowptr[i]; p < diag[i]; ++p) {
           int64_t k = A.colidx[p];
-          ilu[p] /= ilu[diag[k]];
+          ilu[p] = ilu[p] * ilu[diag[k]];
           double lik = ilu[p];
           int64_t q = diag[k] + 1, qe = A.rowptr[k + 1];
           int64_t s = p + 1, se = A.rowptr[i + 1];
@@ -864,6 +864,7 @@ struct Precond {
             else if (A.colidx[q] < A.colidx[s]) ++q; else ++s;
           }
         }
+        ilu[diag[i]] = 1.0 / ilu[diag[i]];
       }
     }
   }
@@ -897,7 +898,7 @@ struct Precond {
       for (int64_t i = n - 1; i >= 0; --i) {
         double s = v[i];
         for (int64_t p = diag[i] + 1; p < A.rowptr[i + 1]; ++p) s -= ilu[p] * v[A.colidx[p]];
-        v[i] = s / ilu[diag[i]];
+        v[i] = ilu[diag[i]] * s;            // the diagonal holds the inverse pivot
       }
       return;
     }

@@ -33,6 +33,8 @@ class Oracle(capi.Lib):
 
     def solve(self, mat, rhs, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR_ORACLE, sweeps=3, reduction=1e-10, maxit=5000):
         st = capi.SolveStats()
+        if precond == capi.PRECOND_SSOR:
+            precond = capi.PRECOND_SSOR_ORACLE
         self._check(self._fn("solve")(C.c_void_p(self.ctx), mat, method, precond, sweeps, C.c_double(reduction), maxit,
                                       capi._vecptr(rhs), capi._vecptr(z), C.byref(st)), "solve")
         return st
