@@ -250,6 +250,10 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
   (void)weight;
   const int NL = 1 << m.dim;
   for (int i = 0; i < (int)c->children.size(); ++i) {
+    if (c->children[i].k != 1) {          // Qk, k > 1: every row through the generic owner-computes kernel (generic.cu)
+      if (part == 1) jacobian_volume_generic(c, go, M, i, overwrite);
+      continue;
+    }
     VolSpec V = vol_spec(c, go, i);
     ChildQ1 ch = child_q1(c, i);
     if (ch.size == 0) continue;
@@ -441,6 +445,7 @@ void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x,
   const MeshDesc& m = c->mesh;
   launch_element_matrices(c, go.sps, weight);
   for (int i = 0; i < (int)c->children.size(); ++i) {
+    if (c->children[i].k != 1) { residual_volume_generic(c, go, i, d_x, d_r); continue; }
     VolSpec V = vol_spec(c, go, i);
     if (V.n == 0) continue;
     ChildQ1 ch = child_q1(c, i);

@@ -303,7 +303,6 @@ int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
   try {
     MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_space: need a mesh, before mdb_finalize");
     MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2, MDB_EINVAL, "mdb_add_space: unknown finite element");
-    MDB_REQUIRE(fe_kind == MDB_FE_Q1, MDB_EINVAL, "mdb_add_space: only Q1 spaces have device kernels in this build");
     MDB_REQUIRE(subdomain >= -1 && subdomain < 8, MDB_EINVAL, "mdb_add_space: bad subdomain");
     MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_space: too many child spaces");
     Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1) ? 1 : 2; ch.subdomain = subdomain;

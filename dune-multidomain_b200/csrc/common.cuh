@@ -252,6 +252,7 @@ struct Ctx {
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   double* d_Ae = nullptr;            // element matrix table
   double* d_ftab = nullptr;          // face shape-function tables of the coupling kernels
+  double* d_ftab_g = nullptr;        // the same for Qk x Qk couplings (generic.cu)
   // staging for host<->device vectors
   double* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
   // solver workspace
@@ -323,6 +324,8 @@ void constrain_residual(Ctx* c, double* d_r);
 void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight);
 void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool overwrite, int part);
 void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x);
+void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& m, int child, bool overwrite);      // generic.cu: Qk children, k > 1
+void residual_volume_generic(Ctx* c, const GridOp& go, int child, const double* d_x, double* d_r);
 void dirichlet_rows(Ctx* c, Matrix& m);
 void spmv(Ctx* c, const Matrix& m, const double* d_x, double* d_y);
 int solve(Ctx* c, Matrix& m, int method, int precond, double reduction, int maxit, int fixed_iters,

@@ -403,7 +403,7 @@ __global__ void k_face_compact(int nf, int64_t total, const int32_t* __restrict_
 }
 
 // ---- which coefficients does jacobian(x, a) read? ------------------------------------------------------------------------
-struct NeedSide { int lat_n[3]; int64_t offset; const int32_t* lat2dof; };
+struct NeedSide { int k; int lat_n[3]; int64_t offset; const int32_t* lat2dof; };
 __global__ void k_mark_face_dofs(MeshDesc m, NeedSide L, NeedSide R, const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces,
                                  uint8_t* flags)
 {
@@ -413,13 +413,16 @@ __global__ void k_mark_face_dofs(MeshDesc m, NeedSide L, NeedSide R, const int32
   int nijk[3] = {ijk[0], ijk[1], ijk[2]};
   const int face = fface[f];
   nijk[face / 2] += (face % 2) ? 1 : -1;
-  const int nl = 1 << m.dim;
-  for (int i = 0; i < nl; ++i) {
-    const int ax = i & 1, ay = (i >> 1) & 1, az = (m.dim > 2) ? (i >> 2) & 1 : 0;
-    int64_t p = (ijk[0] + ax) + (int64_t)L.lat_n[0] * ((ijk[1] + ay) + (int64_t)L.lat_n[1] * (ijk[2] + az));
-    flags[L.offset + L.lat2dof[p]] = 1;
-    p = (nijk[0] + ax) + (int64_t)R.lat_n[0] * ((nijk[1] + ay) + (int64_t)R.lat_n[1] * (nijk[2] + az));
-    flags[R.offset + R.lat2dof[p]] = 1;
+  for (int side = 0; side < 2; ++side) {
+    const NeedSide& S = side ? R : L;
+    const int* c = side ? nijk : ijk;
+    const int k = S.k, kz = (m.dim > 2) ? k : 0;
+    for (int az = 0; az <= kz; ++az)
+      for (int ay = 0; ay <= k; ++ay)
+        for (int ax = 0; ax <= k; ++ax) {
+          const int64_t p = (k * c[0] + ax) + (int64_t)S.lat_n[0] * ((k * c[1] + ay) + (int64_t)S.lat_n[1] * (k * c[2] + az));
+          flags[S.offset + S.lat2dof[p]] = 1;
+        }
   }
 }
 
@@ -437,7 +440,7 @@ void build_xneed(Ctx* c, GridOp& go)
     for (int q = 0; q < 2; ++q) {
       const Child& ch = c->children[c->sps[sp[q]].children[0]];
       for (int d = 0; d < 3; ++d) S[q].lat_n[d] = ch.lat_n[d];
-      S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof;
+      S[q].k = ch.k; S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof;
     }
     MDB_LAUNCH(c, k_mark_face_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, S[0], S[1], fl.d_cell, fl.d_face, fl.n, d_flags);
   }

@@ -9,62 +9,9 @@
 //                       and ProportionalFlowCoupling (:27-86), one thread per interface face
 //   k_coupling_jacobian_staged  jacobian_coupling: (face, evaluation) threads; evaluation 0 = base line, 1+j = perturbation j
 //   k_lambda_volume / k_lambda_boundary   source and Neumann terms of Poisson (test/instationarypoissonoperator.hh:103-167)
-#include "common.cuh"
+#include "exact_common.cuh"
 
 namespace mdb {
-
-// ---- Qk basis ([UPSTREAM] QkLocalBasis) ---------------------------------------------------------------
-__device__ __forceinline__ double qk_p(int k, int i, double x)
-{
-  double result = 1.0;
-  for (int j = 0; j <= k; ++j) if (j != i) result *= (k * x - j) / (i - j);
-  return result;
-}
-__device__ __forceinline__ double qk_dp(int k, int i, double x)
-{
-  double result = 0.0;
-  for (int j = 0; j <= k; ++j) if (j != i) {
-    double prod = (k * 1.0) / (i - j);
-    for (int l = 0; l <= k; ++l) if (l != i && l != j) prod *= (k * x - l) / (i - l);
-    result += prod;
-  }
-  return result;
-}
-template <int DIM> __device__ __forceinline__ void qk_alpha(int k, int i, int a[3])
-{
-  for (int d = 0; d < 3; ++d) { a[d] = (d < DIM) ? i % (k + 1) : 0; i /= (k + 1); }
-}
-template <int DIM> __device__ __forceinline__ double qk_phi(int k, int i, const double* x)
-{
-  int a[3]; qk_alpha<DIM>(k, i, a);
-  double out = 1.0;
-#pragma unroll
-  for (int j = 0; j < DIM; ++j) out *= qk_p(k, a[j], x[j]);
-  return out;
-}
-template <int DIM> __device__ __forceinline__ void qk_grad(int k, int i, const double* x, double* out)
-{
-  int a[3]; qk_alpha<DIM>(k, i, a);
-#pragma unroll
-  for (int j = 0; j < DIM; ++j) {
-    out[j] = qk_dp(k, a[j], x[j]);
-#pragma unroll
-    for (int l = 0; l < DIM; ++l) if (l != j) out[j] *= qk_p(k, a[l], x[l]);
-  }
-}
-
-template <int DIM> __device__ __forceinline__ void quad_point(const Rule1D& R, int idx, double* x, double& w)
-{
-  // tensor rule, axis 0 fastest; weight = ((w0*w1)*w2)
-#pragma unroll
-  for (int d = 0; d < DIM; ++d) {
-    int i = idx % R.m; idx /= R.m;
-    x[d] = R.x[i];
-    w = (d == 0) ? R.w[i] : w * R.w[i];
-  }
-  if (DIM == 0) w = 1.0;
-}
-__device__ __forceinline__ int ipow(int b, int e) { int r = 1; for (int i = 0; i < e; ++i) r *= b; return r; }
 
 // ---- element matrices --------------------------------------------------------------------------------
 struct AeSpec { int n; int op[MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN]; int k[MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN];
@@ -160,57 +107,6 @@ void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight)
   if (m.dim == 2) MDB_LAUNCH(c, k_element_matrices<2>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
   else MDB_LAUNCH(c, k_element_matrices<3>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
 }
-
-// ---- interface geometry ------------------------------------------------------------------------------
-template <int DIM> struct FaceGeo {
-  int ijk[3], nijk[3], axis, side;
-  double lo_i[3], up_i[3], lo_o[3], up_o[3];
-  __device__ void init(const MeshDesc& m, int64_t cell, int face)
-  {
-    int64_t c = cell;
-    ijk[0] = (int)(c % m.n[0]); c /= m.n[0]; ijk[1] = (int)(c % m.n[1]); ijk[2] = (int)(c / m.n[1]);
-    axis = face / 2; side = face % 2;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) nijk[d] = ijk[d];
-    nijk[axis] += side ? 1 : -1;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      lo_i[d] = m.coord(d, ijk[d]); up_i[d] = m.coord(d, ijk[d] + 1);
-      lo_o[d] = m.coord(d, nijk[d]); up_o[d] = m.coord(d, nijk[d] + 1);
-    }
-  }
-  __device__ double integrationElement() const
-  {
-    double v = 1.0; bool first = true;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) if (d != axis) { double e = up_i[d] - lo_i[d]; v = first ? e : v * e; first = false; }
-    return v;
-  }
-  __device__ double cornerDistance01() const
-  {
-    int t0 = (axis == 0) ? 1 : 0;
-    double d = lo_i[t0] - up_i[t0];
-    return sqrt(d * d);
-  }
-  __device__ void localInside(const double* pos, double* local) const
-  {
-    int t = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) local[d] = (d == axis) ? (double)side : pos[t++];
-  }
-  __device__ void localOutside(const double* pos, double* local) const
-  {
-    int t = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) local[d] = (d == axis) ? (double)(1 - side) : pos[t++];
-  }
-};
-
-struct CouplingParams {
-  int op; int jac_mode;
-  double intensity;
-  Rule1D rule;
-};
 
 // Shape-function tables on the faces of the reference cell.  The values phi_i(local) and d phi_i/d local_d at the face
 // quadrature points depend only on (face axis, which side of the cell, quadrature point), not on the cell, so they are
@@ -332,19 +228,6 @@ __device__ void alpha_coupling(const CouplingParams& P, const FaceGeo<DIM>& G, c
   }
 }
 
-struct SideMap { int lat_n[3]; int64_t offset; const int32_t* lat2dof; };
-
-template <int DIM> __device__ __forceinline__ void cell_dofs_q1(const SideMap& S, const int ijk[3], int32_t* dofs)
-{
-  constexpr int NL = 1 << DIM;
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    int ax = i & 1, ay = (i >> 1) & 1, az = (DIM > 2) ? (i >> 2) & 1 : 0;
-    int64_t p = (ijk[0] + ax) + (int64_t)S.lat_n[0] * ((ijk[1] + ay) + (int64_t)S.lat_n[1] * (ijk[2] + az));
-    dofs[i] = (int32_t)(S.offset + S.lat2dof[p]);
-  }
-}
-
 template <int DIM>
 __global__ void __launch_bounds__(128) k_coupling_residual(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
                                                            const int8_t* __restrict__ fface, int64_t nfaces, double weight,
@@ -362,13 +245,6 @@ __global__ void __launch_bounds__(128) k_coupling_residual(MeshDesc m, CouplingP
   alpha_coupling<DIM>(P, G, tab, x1, x2, r1, r2, weight);
 #pragma unroll
   for (int i = 0; i < NL; ++i) { atomicAdd(&r[ds[i]], r1[i]); atomicAdd(&r[dn[i]], r2[i]); }
-}
-
-__device__ __forceinline__ int64_t find_slot(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t row, int32_t col)
-{
-  int64_t lo = rowptr[row], hi = rowptr[row + 1];
-  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (colidx[mid] < col) lo = mid + 1; else hi = mid; }
-  return lo;   // the pattern contains every coupling link by construction
 }
 
 // Slot table: for every coupling face the offset inside its CSR row of each of the (2 NL)^2 entries the face touches
@@ -565,6 +441,12 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshD
   }
 }
 
+// generic.cu: Qk x Qk couplings with at least one side that is not Q1
+void residual_coupling_generic(Ctx* c, const CouplingParams& P, const SideMap& Ls, const SideMap& Rs, int k1, int k2, const FaceList& fl, double weight,
+                               const double* d_x, double* d_r);
+void jacobian_coupling_generic(Ctx* c, const CouplingParams& P, const SideMap& Ls, const SideMap& Rs, int k1, int k2, const FaceList& fl, Matrix& M,
+                               std::pair<int, int> key, double weight, double eps, const double* d_x);
+
 static SideMap side_map(const Ctx* c, int sp)
 {
   const Child& ch = c->children[c->sps[sp].children[0]];
@@ -599,6 +481,8 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
     if (fl.n == 0) continue;
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
+    const int k1 = c->children[c->sps[cp.local_sp].children[0]].k, k2 = c->children[c->sps[cp.remote_sp].children[0]].k;
+    if (k1 != 1 || k2 != 1) { residual_coupling_generic(c, P, Ls, Rs, k1, k2, fl, weight, d_x, d_r); continue; }
     const double* tab = face_tables(c, P);
     if (m.dim == 2) MDB_LAUNCH(c, k_coupling_residual<2>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, tab, d_x, d_r);
     else MDB_LAUNCH(c, k_coupling_residual<3>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, tab, d_x, d_r);
@@ -615,6 +499,11 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const double eps = 1e-8;                    // NumericalJacobianCoupling() default, couplingutilities.hh:63-65
+    const int k1 = c->children[c->sps[cp.local_sp].children[0]].k, k2 = c->children[c->sps[cp.remote_sp].children[0]].k;
+    if (k1 != 1 || k2 != 1) {
+      jacobian_coupling_generic(c, P, Ls, Rs, k1, k2, fl, M, std::pair<int, int>((int)(&go - &c->gos[0]), (int)k), weight, eps, d_x);
+      continue;
+    }
     const int NL = 1 << m.dim, NR = 2 * NL;
     // slot table of this (grid operator, coupling) in this matrix, built on first use
     const std::pair<int, int> key((int)(&go - &c->gos[0]), (int)k);
@@ -656,10 +545,10 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
 struct LambdaSpec { int cond_kind; uint32_t mask; mdb_function f; mdb_bctype bc; mdb_function j; Rule1D rule; };
 
 // lambda_volume: r_i -= f(x_q) phi_i(x_q) w_q |det J|  (instationarypoissonoperator.hh:103-117), one thread per cell
-template <int DIM>
+template <int DIM, int K>
 __global__ void k_lambda_volume(MeshDesc m, const uint8_t* __restrict__ sd, LambdaSpec S, SideMap map, double weight, double t, double* r)
 {
-  constexpr int NL = 1 << DIM;
+  constexpr int NL = cpow(K + 1, DIM);
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= m.ncells()) return;
   if (!cond_applies(S.cond_kind, S.mask, sd[c])) return;
@@ -683,21 +572,21 @@ __global__ void k_lambda_volume(MeshDesc m, const uint8_t* __restrict__ sd, Lamb
     double y = eval_function(S.f, DIM, xg, t);
     double factor = w * detj;
 #pragma unroll
-    for (int i = 0; i < NL; ++i) rl[i] += weight * (-y * qk_phi<DIM>(1, i, x) * factor);
+    for (int i = 0; i < NL; ++i) rl[i] += weight * (-y * qk_phi<DIM>(K, i, x) * factor);
   }
   int32_t dofs[NL];
-  cell_dofs_q1<DIM>(map, ijk, dofs);
+  cell_dofs_qk<DIM, K>(map, ijk, dofs);
 #pragma unroll
   for (int i = 0; i < NL; ++i) atomicAdd(&r[dofs[i]], rl[i]);
 }
 
 // lambda_boundary on the faces of one boundary plane (axis, side): r_i += j(x_q) phi_i w_q |J_f| where isNeumann
 // (instationarypoissonoperator.hh:142-167).  One thread per boundary face.
-template <int DIM>
+template <int DIM, int K>
 __global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, LambdaSpec S, SideMap map, int axis, int side, double weight,
                                   double t, double* r)
 {
-  constexpr int NL = 1 << DIM;
+  constexpr int NL = cpow(K + 1, DIM);
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int t0 = (axis == 0) ? 1 : 0, t1 = (axis == 2) ? 1 : 2;
   int64_t nplane = (int64_t)m.n[t0] * ((DIM > 2) ? m.n[t1] : 1);
@@ -733,10 +622,10 @@ __global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, La
     double y = eval_function(S.j, DIM, xe, t);
     double factor = w * fe;
 #pragma unroll
-    for (int i = 0; i < NL; ++i) rl[i] += weight * (y * qk_phi<DIM>(1, i, local) * factor);
+    for (int i = 0; i < NL; ++i) rl[i] += weight * (y * qk_phi<DIM>(K, i, local) * factor);
   }
   int32_t dofs[NL];
-  cell_dofs_q1<DIM>(map, ijk, dofs);
+  cell_dofs_qk<DIM, K>(map, ijk, dofs);
 #pragma unroll
   for (int i = 0; i < NL; ++i) if (rl[i] != 0.0) atomicAdd(&r[dofs[i]], rl[i]);
 }
@@ -750,9 +639,12 @@ void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r)
     LambdaSpec S; S.cond_kind = sp.cond_kind; S.mask = sp.mask; S.f = sp.poisson.f; S.bc = sp.poisson.bc; S.j = sp.poisson.j;
     S.rule = gauss1d(sp.poisson.quad_order);
     SideMap map = side_map(c, s);
+    const int K = c->children[sp.children[0]].k;
     if (sp.poisson.f.kind != MDB_FN_ZERO) {       // f == 0 contributes exact zeros
-      if (m.dim == 2) MDB_LAUNCH(c, k_lambda_volume<2>, cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
-      else MDB_LAUNCH(c, k_lambda_volume<3>, cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
+      if (m.dim == 2 && K == 1) MDB_LAUNCH(c, (k_lambda_volume<2, 1>), cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
+      else if (m.dim == 3 && K == 1) MDB_LAUNCH(c, (k_lambda_volume<3, 1>), cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
+      else if (m.dim == 2) MDB_LAUNCH(c, (k_lambda_volume<2, 2>), cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
+      else MDB_LAUNCH(c, (k_lambda_volume<3, 2>), cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
     }
     if (sp.poisson.bc.kind == MDB_BC_ALL_DIRICHLET) continue;   // no Neumann face anywhere
     for (int axis = 0; axis < m.dim; ++axis)
@@ -762,8 +654,10 @@ void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r)
         if (side == 1 && !m.on_global_upper(axis, m.n[axis])) continue;
         int t0 = (axis == 0) ? 1 : 0, t1 = (axis == 2) ? 1 : 2;
         int64_t nplane = (int64_t)m.n[t0] * ((m.dim > 2) ? m.n[t1] : 1);
-        if (m.dim == 2) MDB_LAUNCH(c, k_lambda_boundary<2>, cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
-        else MDB_LAUNCH(c, k_lambda_boundary<3>, cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
+        if (m.dim == 2 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<2, 1>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
+        else if (m.dim == 3 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<3, 1>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
+        else if (m.dim == 2) MDB_LAUNCH(c, (k_lambda_boundary<2, 2>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
+        else MDB_LAUNCH(c, (k_lambda_boundary<3, 2>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
       }
   }
 }

@@ -12,7 +12,7 @@
 
 namespace mdb {
 
-#define MDB_MAXROW 128
+#define MDB_MAXROW 256
 
 struct PChild { int k, subdomain, nloc; int lat_n[3]; int64_t offset, size; const int32_t* lat2dof; const int32_t* dof2lat; };
 struct PatSpec {
@@ -209,7 +209,7 @@ void build_pattern(Ctx* c, Matrix& M)
   MDB_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_tmp); dfree(d_rownnz); dfree(d_max); dfree(d_err);
-  MDB_REQUIRE(!err, MDB_EINVAL, "a matrix row has more than 128 entries (unsupported)");
+  MDB_REQUIRE(!err, MDB_EINVAL, "a matrix row has more than 256 entries (unsupported)");
   M.nnz = nnz; M.max_row = (int)maxrow;
   M.d_colidx = dalloc<int32_t>(nnz);
   M.d_val = dalloc<double>(nnz + 16);     // + 16: the SpMV stages 128-byte aligned windows (solver.cu)

@@ -249,11 +249,13 @@ void ilu0_factorize(Ctx* c, Matrix& M)
   ++M.sweep_epoch;
   int grid = 148 * 8;
   if (grid > cdiv(c->ndof, 8)) grid = cdiv(c->ndof, 8);
-  MDB_REQUIRE(M.max_row <= 128, MDB_EINVAL, "ILU0: rows longer than 128 entries are not supported");
+  MDB_REQUIRE(M.max_row <= 256, MDB_EINVAL, "ILU0: rows longer than 256 entries are not supported");
   if (M.max_row <= 32)
     MDB_LAUNCH(c, k_ilu0_factor<1>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
   else if (M.max_row <= 64)
     MDB_LAUNCH(c, k_ilu0_factor<2>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+  else if (M.max_row > 128)
+    MDB_LAUNCH(c, k_ilu0_factor<8>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
   else
     MDB_LAUNCH(c, k_ilu0_factor<4>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
   M.ilu_valid = true;

@@ -33,6 +33,13 @@ CASES = {
     # BASELINE configs[0] in its Q1 form: source of testpoisson-dirichlet-neumann.cc:73-87, order 6, coupling(4, 10), split x0
     "p2d_dn_q1": dict(n=(32, 32), intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE)),
     "p3d_dn_src": dict(n=(8, 8, 8), intensity=10.0, split_axis=0, quad_order=4, f=capi.Function(capi.FN_DN_SOURCE)),
+    # Qk spaces beyond Q1.  p2d_q1q2 is the reference's shipped testpoisson ("4 2.0": 16x16 cells, Q1 left / Q2 right, 714 DOFs)
+    "p2d_q1q2": dict(n=(16, 16), fe=(capi.FE_Q1, capi.FE_Q2)),
+    "p2d_q2q1_split_x": dict(n=(10, 6), split_axis=0, fe=(capi.FE_Q2, capi.FE_Q1), f=capi.Function(capi.FN_DN_SOURCE)),
+    "p2d_q2q2_propflow": dict(n=(8, 8), fe=(capi.FE_Q2, capi.FE_Q2), coupling=capi.OP_PROPFLOW_COUPLING, intensity=1.5),
+    "p3d_q1q2": dict(n=(4, 4, 4), fe=(capi.FE_Q1, capi.FE_Q2)),
+    "p3d_q2q2": dict(n=(3, 4, 2), fe=(capi.FE_Q2, capi.FE_Q2), split_axis=0, f=capi.Function(capi.FN_BOX, 50.0, 0.25, 0.375)),
+    "p3d_q2q1_analytic": dict(n=(3, 3, 4), fe=(capi.FE_Q2, capi.FE_Q1), split_axis=2, jac_mode=capi.JAC_ANALYTIC),
 }
 
 
@@ -263,8 +270,8 @@ def test_device_resident_vectors_and_error_paths():
     assert np.abs(rd.cpu().numpy() - ro).max() <= RTOL_ENTRY * np.abs(ro).max()
     with pytest.raises(pkg.MdbError):
         dev.residual(99, xd, rd)                       # bad handle -> error code + message, no crash
-    with pytest.raises(pkg.MdbError, match="Q1"):
-        d2 = pkg.Mdb(0); d2.mesh_structured((4, 4)); d2.add_space(capi.FE_Q2, 0)
+    with pytest.raises(pkg.MdbError, match="finite element"):
+        d2 = pkg.Mdb(0); d2.mesh_structured((4, 4)); d2.add_space(7, 0)     # closed set of spaces: Q1, Q2
 
 
 @pytest.mark.parametrize("n", [(96, 96, 96), (1024, 1024)])
