@@ -2,12 +2,13 @@
 // (include/mdb200/multidomain.hh).  Same sequence of objects and calls; dim is a run-time argument so that the same
 // program runs the shipped 2-D case ("4 2.0", test/CMakeLists.txt:31-32) and the synthetic 3-D extension.
 //
-//   testpoisson <refinement level> <coupling intensity> [dim=2]
+//   testpoisson <refinement level> <coupling intensity> [dim=2] [k left=1] [k right=2] [solver: ssor (default, as shipped) | jac]
 //
 // Prints the DOF / constrained-DOF line of the reference (testpoisson.cc:269), the solver statistics and a checksum of u.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "mdb200/multidomain.hh"
 
@@ -16,8 +17,10 @@ using namespace mdb200;
 int main(int argc, char** argv)
 {
   try {
-    if (argc < 3) { std::fprintf(stderr, "Usage: %s <refinement level> <coupling intensity> [dim]\n", argv[0]); return 1; }
+    if (argc < 3) { std::fprintf(stderr, "Usage: %s <refinement level> <coupling intensity> [dim] [k left] [k right] [ssor|jac]\n", argv[0]); return 1; }
     const int dim = argc > 3 ? std::atoi(argv[3]) : 2;
+    const int k0 = argc > 4 ? std::atoi(argv[4]) : 1, k1 = argc > 5 ? std::atoi(argv[5]) : 2;   // Q1 left, Q2 right (:168-169)
+    const bool jacobi = argc > 6 && std::string(argv[6]) == "jac";
     const int64_t cells = (int64_t)1 << std::atoi(argv[1]);          // YaspGrid 1^d cells, globalRefine(level)
     const int64_t n[3] = {cells, cells, cells};
     const double lower[3] = {0, 0, 0}, upper[3] = {1, 1, 1};
@@ -31,7 +34,7 @@ int main(int argc, char** argv)
     }
     grid.preUpdateSubDomains(); grid.updateSubDomains(); grid.postUpdateSubDomains();
 
-    GridFunctionSpace gfs0(grid.subDomain(0), 1), gfs1(grid.subDomain(1), 1);      // Q1 / Q1 (the device build has no Q2 yet)
+    GridFunctionSpace gfs0(grid.subDomain(0), k0), gfs1(grid.subDomain(1), k1);
     MultiDomainGridFunctionSpace multigfs(grid, {&gfs0, &gfs1});
 
     const mdb_bctype b = boundary(MDB_BC_TESTPOISSON);               // DirichletBoundary :42-88
@@ -56,13 +59,20 @@ int main(int argc, char** argv)
 
     GridOperator gridoperator(multigfs, multigfs, cg, cg, {left_sp.handle, right_sp.handle}, {coupling.handle});
 
-    ISTLBackend_SEQ_BCGS_Jac ls(5000);
-    StationaryLinearProblemSolver<ISTLBackend_SEQ_BCGS_Jac> pdesolver(gridoperator, ls, 1e-10);
-    pdesolver.apply(u);
+    LinearSolverResult res;
+    if (jacobi) {                                                    // the fast device path
+      ISTLBackend_SEQ_BCGS_Jac ls(5000);
+      StationaryLinearProblemSolver<ISTLBackend_SEQ_BCGS_Jac> pdesolver(gridoperator, ls, 1e-10);
+      pdesolver.apply(u); res = ls.res;
+    } else {                                                         // ISTLBackend_SEQ_BCGS_SSOR(5000, verb), :291-298
+      ISTLBackend_SEQ_BCGS_SSOR ls(5000);
+      StationaryLinearProblemSolver<ISTLBackend_SEQ_BCGS_SSOR> pdesolver(gridoperator, ls, 1e-10);
+      pdesolver.apply(u); res = ls.res;
+    }
 
     double sum = 0.0, sum2 = 0.0;
     for (size_t i = 0; i < u.size(); ++i) { sum += u[i]; sum2 += u[i] * u[i]; }
-    std::printf("solver: %d iterations, reduction %.3e, %.3f ms\n", ls.res.iterations, ls.res.reduction, ls.res.elapsed * 1e3);
+    std::printf("solver: %d iterations, reduction %.3e, %.3f ms\n", res.iterations, res.reduction, res.elapsed * 1e3);
     std::printf("checksum: sum(u) = %.12e  |u|_2 = %.12e\n", sum, std::sqrt(sum2));
     return 0;
   } catch (Exception& e) {

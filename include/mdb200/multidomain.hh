@@ -262,19 +262,26 @@ inline void GridOperator::jacobian(const double* x, Jacobian& a) const {
 struct LinearSolverResult { int iterations; bool converged; double reduction; double elapsed; };
 class ISTLBackend_SEQ_Base {
 protected:
-  int method_, precond_; unsigned maxiter_;
+  int method_, precond_; unsigned maxiter_; int sweeps_;
 public:
   LinearSolverResult res;
-  ISTLBackend_SEQ_Base(int method, int precond, unsigned maxiter) : method_(method), precond_(precond), maxiter_(maxiter) { res.iterations = 0; res.converged = false; res.reduction = 0; res.elapsed = 0; }
+  ISTLBackend_SEQ_Base(int method, int precond, unsigned maxiter, int sweeps = 0) : method_(method), precond_(precond), maxiter_(maxiter), sweeps_(sweeps) { res.iterations = 0; res.converged = false; res.reduction = 0; res.elapsed = 0; }
   void apply(Jacobian& a, Context& ctx, double* z, const double* r, double reduction) {
     mdb_solve_stats st;
+    if (sweeps_ > 0) ctx.check(mdb_set_ssor_sweeps(ctx.get(), sweeps_), "mdb_set_ssor_sweeps");
     int rc = mdb_solve(ctx.get(), a.handle(), method_, precond_, reduction, (int)maxiter_, r, z, &st);
     res.iterations = st.iterations; res.converged = st.converged != 0; res.elapsed = st.seconds;
     res.reduction = st.defect0 > 0 ? st.defect / st.defect0 : 0.0;
     if (rc != MDB_ENOTCONVERGED) ctx.check(rc, "mdb_solve");
   }
 };
-// the reference's SSOR is sequential by construction; the device backends offer Jacobi (north star: Jacobi or ILU0)
+// Jacobi is the fast device path.  The SSOR / ILU0 backends run the reference's sequential ISTL preconditioners operation
+// for operation (sync-free sweeps, csrc/precond.cu): [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SeqSSOR(A, 3, 1.0)
+// (test/testpoisson.cc:291-292), ISTLBackend_SEQ_CG_SSOR = CG + SeqSSOR(A, 1, 1.0) (test/explicitlycoupledpoisson.cc:297-313).
+struct ISTLBackend_SEQ_BCGS_SSOR : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_SSOR(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_SSOR, maxiter, 3) {} };
+struct ISTLBackend_SEQ_CG_SSOR : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_SSOR(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_SSOR, maxiter, 1) {} };
+struct ISTLBackend_SEQ_BCGS_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_ILU0(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_ILU0, maxiter) {} };
+struct ISTLBackend_SEQ_CG_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_ILU0(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_ILU0, maxiter) {} };
 struct ISTLBackend_SEQ_CG_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_JACOBI, maxiter) {} };
 struct ISTLBackend_SEQ_BCGS_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_JACOBI, maxiter) {} };
 

@@ -307,31 +307,39 @@ def test_size_independent_properties_at_scale(n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("level,dim", [(4, 2), (3, 3)])
-def test_cxx_driver_matches_oracle(level, dim):
+@pytest.mark.parametrize("level,dim,ks,solver", [(4, 2, (1, 2), "ssor"), (4, 2, (1, 1), "jac"), (5, 2, (1, 2), "jac"), (3, 3, (1, 1), "ssor"), (2, 3, (2, 1), "jac")])
+def test_cxx_driver_matches_oracle(level, dim, ks, solver):
     """examples/testpoisson.cc (the reference's test/testpoisson.cc written against include/mdb200/multidomain.hh) run as a
-    program: DOF counts and the solution checksum against the oracle's StationaryLinearProblemSolver restatement."""
+    program: DOF counts, BiCGSTAB+SSOR(3) iteration count and the solution checksum against the oracle's
+    StationaryLinearProblemSolver restatement.  (4, 2, (1, 2), "ssor") is the shipped invocation "testpoisson 4 2.0":
+    16x16 cells, Q1 left / Q2 right, ISTLBackend_SEQ_BCGS_SSOR."""
     import re
     import subprocess
     import tempfile
     from test_capi import _build_example
     n = (1 << level,) * dim
+    fe = tuple(capi.FE_Q1 if k == 1 else capi.FE_Q2 for k in ks)
     ora = orc.Oracle()
-    Po = problems.testpoisson(ora, n)
+    Po = problems.testpoisson(ora, n, fe=fe)
     u = np.zeros(Po.ndof)
     ora.interpolate(Po.sps, Po.gfn, u)
     ora.jacobian(Po.go, Po.mat, u, overwrite=True)
     r = np.zeros(Po.ndof)
     ora.residual(Po.go, u, r)
     z = np.zeros(Po.ndof)
+    so = ora.solve(Po.mat, r, z, reduction=1e-10)                      # BiCGSTAB + SSOR(3), reduction 1e-10 (:291-297)
+    its_ssor = so.iterations
     ora.solve(Po.mat, r, z, reduction=1e-13)
     u -= z
     with tempfile.TemporaryDirectory() as d:
         exe = _build_example(d)
-        out = subprocess.run([exe, str(level), "2.0", str(dim)], capture_output=True, text=True, timeout=300)
+        out = subprocess.run([exe, str(level), "2.0", str(dim), str(ks[0]), str(ks[1]), solver], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     m = re.search(r"(\d+) dof total, (\d+) dof constrained", out.stdout)
     assert m and int(m.group(1)) == Po.ndof and int(m.group(2)) == Po.ncon
+    if solver == "ssor":
+        m = re.search(r"solver: (\d+) iterations", out.stdout)
+        assert abs(int(m.group(1)) - its_ssor) <= 1, (m.group(1), its_ssor)
     m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
     assert abs(float(m.group(1)) - u.sum()) <= 1e-8 * abs(u.sum())
     assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-8 * np.linalg.norm(u)
