@@ -277,16 +277,20 @@ def _main(out):
     nchild_launch = 2
     bytes_fill = 8.0 * stencil * simple_rows / nchild_launch          # per launch
     ms_fill = phases["fill"] / nchild_launch                           # mean launch duration
-    roof = {"kernel": "k_jacobian_fill_q1<%d>" % len(n), "bound": "hbm", "achieved": bytes_fill / (ms_fill * 1e-3) / 1e9, "peak": peak,
+    fill_kernel = "k_jacobian_fill_q1" if os.environ.get("MDB_FILL_NO_TMA") else "k_jacobian_fill_tma"
+    roof = {"kernel": "%s<%d>" % (fill_kernel, len(n)), "bound": "hbm", "achieved": bytes_fill / (ms_fill * 1e-3) / 1e9, "peak": peak,
             "unit": "GB/s", "frac": bytes_fill / (ms_fill * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes": bytes_fill, "ms": ms_fill, "launches_per_step": nchild_launch,
             "frac_of_8TBs": bytes_fill / (ms_fill * 1e-3) / 8e12,
-            "note": "write-only kernel: the copy-measured peak counts read+write; the write-only ceiling measured with "
-                    "profiles/microbench/write_bw2.cu is 7.3-7.5 TB/s"}
+            "note": "write-only kernel timed INSIDE the step, where it shares the SMs with the irregular-row and FD-coupling kernels of the "
+                    "auxiliary stream (that overlap is the point of the bulk-store variant: whole step 0.93 ms against 1.10 ms with the "
+                    "per-thread store kernel, which alone reaches 0.95 of the peak: MDB_FILL_NO_TMA=1); alone the bulk-store kernel "
+                    "sustains 5.3 TB/s (profiles/fill_ab.py).  The copy-measured peak counts read+write; the write-only ceiling measured "
+                    "with profiles/microbench/write_bw2.cu is 7.3-7.5 TB/s"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get("k_jacobian_fill_q1", {}).get("dram_bytes_per_launch")
+            roof["traffic"] = json.load(open(tr)).get(fill_kernel, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
 
@@ -331,7 +335,8 @@ def _main(out):
                "preconditioner": "jacobi"},
         "bicgstab": {"iters_per_s": st2.iterations / st2.seconds if st2.seconds > 0 else None},
         "jacobian_phases_ms": phases,
-        "jacobian_streams": "main: elem -> fill -> dirichlet | aux: irregular rows -> FD coupling | copy: gather of x (host vectors)",
+        "jacobian_streams": "main: elem -> fill (bulk-async stores) -> dirichlet | aux: irregular rows -> FD coupling | copy: gather of x (host vectors)",
+        "jacobian_step_GBs": 8.0 * nnz / (ms_jac * 1e-3) / 1e9,
         "setup_s": {"total": t_setup, "dofmap_ms": dev.phase_ms("dofmap"), "pattern_ms": dev.phase_ms("pattern"),
                     "constraints_ms": dev.phase_ms("constraints")},
     }

@@ -135,18 +135,74 @@ __global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const doubl
   }
 }
 
+// ---- the same fill through the bulk-async (TMA) store path ---------------------------------------------------------------
+// The streamed values are periodic (the constant row stencil S over and over), so a block keeps ONE image of FT_ROWS rows in
+// shared memory and an elected thread copies it to run after run with cp.async.bulk.global.shared::cta: no per-thread store
+// instructions, no registers, two 32-thread blocks per SM drive the store engines — the SMs stay free for the irregular-row
+// and FD-coupling kernels that mdb_jacobian runs on the auxiliary stream at the same time.
+// Alignment: bulk copies need 16-byte aligned addresses and sizes.  A run starts at an arbitrary 8-byte aligned entry p0; an odd
+// head / tail entry is stored directly, the 16-byte aligned interior starts at stencil phase (a0 - p0) mod NS, which is reached
+// inside the image at the even offset phase or phase + NS (NS is odd).
+#define FT_ROWS 256
+#define FT_THREADS 256                 // 8 warps share one image; each warp's elected lane issues the copies of its own runs
+template <int DIM>
+__global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(const double* __restrict__ S, const longlong2* __restrict__ seg_span, int64_t nseg,
+                                                          double* __restrict__ val)
+{
+  constexpr int NS = (DIM == 3) ? 27 : 9;
+  constexpr int CH = NS * FT_ROWS;                                       // doubles per bulk copy: a multiple of NS (phase preserved) and even
+  extern __shared__ __align__(128) double img[];                         // CH + 2 NS doubles, img[i] = S[i mod NS]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = FT_THREADS / 32;
+  for (int i = threadIdx.x; i < CH + 2 * NS; i += FT_THREADS) img[i] = S[i % NS];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> visible to the bulk-copy engine
+  __syncthreads();
+  const uint32_t img_s = (uint32_t)__cvta_generic_to_shared(img);
+  for (int64_t run = (int64_t)blockIdx.x * NW + warp; run < nseg; run += (int64_t)gridDim.x * NW) {
+    const longlong2 span = seg_span[run];
+    const int64_t p0 = span.x, p1 = span.y;
+    if (p0 == p1) continue;                                              // a run of irregular rows: k_jacobian_rows_q1
+    // 16-byte aligned interior [a0, a1); an odd head / tail entry is stored directly (whole 128-byte lines were measured: no gain)
+    int64_t a0 = (p0 + 1) & ~(int64_t)1;
+    const int64_t a1 = p1 & ~(int64_t)1;
+    if (lane == 0 && (p0 & 1)) val[p0] = img[0];
+    if (lane == 1 && (p1 & 1) && p1 - 1 > p0) val[p1 - 1] = img[(p1 - 1 - p0) % NS];
+    if (lane == 0) {
+      const int phase = (int)((a0 - p0) % NS);
+      const uint32_t src = img_s + 8u * (uint32_t)((phase & 1) ? phase + NS : phase);
+      while (a0 < a1) {
+        const int64_t n = (a1 - a0 < CH) ? a1 - a0 : CH;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(val + a0), "r"(src), "r"((uint32_t)(n * 8)) : "memory");
+        a0 += n;
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the image must outlive the copies that read it
+  __syncthreads();
+}
+
 // ---- irregular rows (or all rows when the uniform shortcut is not valid) ---------------------------------------
 // One thread gathers one row (sum over the incident cells, popcount placement) into a row image in shared memory; the
 // warp then writes its 32 row images out cooperatively, consecutive lanes to consecutive entries, so that a row costs
 // ~len/4 store sectors instead of one sector per entry.
 #define JR_THREADS 64
 #define JR_MAXLEN 48           // longest row image staged in shared memory (Q1 hex interface row: 27 + 18); longer rows go direct
+// All children of a grid operator go through ONE launch (the kernel is latency bound: the children's rows overlap).
+struct RowsJob { ChildQ1 ch; VolSpec V; const int32_t* list; int64_t nrows; int block0; };
+struct RowsJobs { int n; RowsJob job[MDB_MAX_CHILDREN]; };
 template <int DIM>
-__global__ void __launch_bounds__(JR_THREADS) k_jacobian_rows_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
-                                                                const double* __restrict__ Ae, const int32_t* __restrict__ list, int64_t nrows,
+__global__ void __launch_bounds__(JR_THREADS) k_jacobian_rows_q1(MeshDesc m, const uint8_t* __restrict__ sd, RowsJobs J,
+                                                                const double* __restrict__ Ae,
                                                                 const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
                                                                 const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
 {
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.job[jb + 1].block0) ++jb;
+  const ChildQ1& ch = J.job[jb].ch;
+  const VolSpec& V = J.job[jb].V;
+  const int32_t* __restrict__ list = J.job[jb].list;
+  const int64_t nrows = J.job[jb].nrows;
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
   constexpr int BITBASE = (DIM == 3) ? 0 : 9;
@@ -159,7 +215,7 @@ __global__ void __launch_bounds__(JR_THREADS) k_jacobian_rows_q1(MeshDesc m, con
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t t = (blockIdx.x - J.job[jb].block0) * (int64_t)blockDim.x + threadIdx.x;
   const bool have = t < nrows;
   int64_t rs = 0; int len = 0;
   if (have) {
@@ -249,6 +305,8 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
   const MeshDesc& m = c->mesh;
   (void)weight;
   const int NL = 1 << m.dim;
+  RowsJobs J; J.n = 0;
+  int nblocks = 0;
   for (int i = 0; i < (int)c->children.size(); ++i) {
     if (c->children[i].k != 1) {          // Qk, k > 1: every row through the generic owner-computes kernel (generic.cu)
       if (part == 1) jacobian_volume_generic(c, go, M, i, overwrite);
@@ -269,15 +327,34 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
       static const int per_sm = getenv("MDB_FILL_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_BLOCKS_PER_SM")) : 0;   // 0: one run per block
       int grid = (int)M.n_seg[i];
       if (per_sm > 0 && grid > 148 * per_sm) grid = 148 * per_sm;
-      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
+      static const bool no_tma = getenv("MDB_FILL_NO_TMA") != nullptr;                  // A/B switch for profiling only
+      if (overwrite && !no_tma) {
+        const int ns = (m.dim == 3) ? 27 : 9;
+        const size_t smem = (size_t)(ns * FT_ROWS + 2 * ns) * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+          MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((9 * FT_ROWS + 18) * sizeof(double))));
+          MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((27 * FT_ROWS + 54) * sizeof(double))));
+          configured = true;
+        }
+        static const int tma_blocks = getenv("MDB_FILL_TMA_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_TMA_BLOCKS_PER_SM")) : 2;
+        int tgrid = 148 * tma_blocks;
+        if (tgrid > cdiv(M.n_seg[i], FT_THREADS / 32)) tgrid = cdiv(M.n_seg[i], FT_THREADS / 32);
+        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val);
+        else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val);
+      } else if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
       else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
     }
     if (nrows > 0 && part == 1) {
-      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, cdiv(nrows, JR_THREADS), JR_THREADS, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
-                                 M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
-      else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, cdiv(nrows, JR_THREADS), JR_THREADS, 0, m, c->d_cell_sd, ch, V, c->d_Ae, list, nrows, M.d_rowptr,
-                      M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
+      RowsJob& jb = J.job[J.n++];
+      jb.ch = ch; jb.V = V; jb.list = list; jb.nrows = nrows; jb.block0 = nblocks;
+      nblocks += cdiv(nrows, JR_THREADS);
     }
+  }
+  if (J.n > 0) {
+    if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, nblocks, JR_THREADS, 0, m, c->d_cell_sd, J, c->d_Ae, M.d_rowptr, M.d_rowinfo, M.d_colidx, M.d_val,
+                               (int)overwrite);
+    else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, nblocks, JR_THREADS, 0, m, c->d_cell_sd, J, c->d_Ae, M.d_rowptr, M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
   }
 }
 

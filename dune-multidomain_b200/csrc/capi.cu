@@ -192,12 +192,13 @@ mdb_ctx* mdb_create(int device)
       // rows + FP64-bound FD coupling in mdb_jacobian) fills whatever SM capacity the streaming kernels leave
       int lo = 0, hi = 0;
       MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      MDB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+      static const bool aux_hi = getenv("MDB_AUX_PRIO") != nullptr;
+      MDB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, aux_hi ? lo : hi));
+      MDB_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, aux_hi ? hi : lo));
     }
     MDB_CUDA(cudaEventCreate(&c->ev0));
     MDB_CUDA(cudaEventCreate(&c->ev1));
     MDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    MDB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));

@@ -102,7 +102,7 @@ void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight)
   }
   double ext[3] = {1, 1, 1};
   for (int d = 0; d < m.dim; ++d) ext[d] = m.coord(d, 1) - m.coord(d, 0);
-  int nthreads = 32;
+  int nthreads = 256;      // at least 256: the shape-function tables of a quadrature chunk are evaluated by the whole block
   for (int i = 0; i < S.n; ++i) { int nl = 1; for (int d = 0; d < m.dim; ++d) nl *= (S.k[i] + 1); int t = ((nl * nl + 31) / 32) * 32; if (t > nthreads) nthreads = t; }
   if (m.dim == 2) MDB_LAUNCH(c, k_element_matrices<2>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
   else MDB_LAUNCH(c, k_element_matrices<3>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);
@@ -276,12 +276,19 @@ __global__ void k_coupling_slots(MeshDesc m, SideMap Ls, SideMap Rs, const int32
   slots[t] = (uint8_t)(pos - rs);
 }
 
-// jacobian_coupling, staged variant (the default).  The FP64 pipe bounds this kernel (17 residual evaluations per face,
-// no FMA contraction), so the arithmetic that does not depend on the perturbation is hoisted out of the 17 evaluations
-// WITHOUT changing a single rounding: per (face, quadrature point, side, i) the block first parks in shared memory
-//   phi_i, c_i = (theta*0.5)*gpn_i, px_i = x_i*phi_i, pg_i[d] = x_i*gradphi_i[d]
-// (the base-line products; a perturbation of dof j changes only the j-th product, the additions are redone in the
-// reference's order), then thread (face, evaluation) runs the perturbation-dependent part of alpha_coupling.
+// jacobian_coupling, staged variant (the default).  17 residual evaluations per face, no FMA contraction; shared-memory
+// traffic and the FP64 pipe bound this kernel, so everything that does not depend on the perturbation is hoisted out of the
+// 17 evaluations WITHOUT changing a single rounding of the numbers that reach the matrix:
+//   * per (face, quadrature point, side, i) the block first parks in shared memory
+//       phi_i, c_i = (theta*0.5)*gpn_i, px_i = x_i*phi_i, pga_i = x_i*gradphi_i[axis]
+//     Only the NORMAL component of the gradients is kept: the face normal is +-e_axis, so the reference's dot products with
+//     the normal add exact zeros for the tangential components (a + (+-0) == a; the sign of a zero result is normalised by
+//     the leading "0.0 +" exactly as in the reference's accumulation from 0.0);
+//   * the base-line sums u_s, gradu_s[axis] of each side are formed once per quadrature point, in the reference's order, by
+//     a sequential shuffle chain over the 2^d lanes that hold the products of one (face, side);
+//   * a perturbation of dof j changes only the j-th product of j's side: the evaluation thread re-sums that side in the
+//     reference's order with its own j-th product and takes the other side's base-line sums as they are (same terms, same
+//     order: same bits).
 // Mapping: NT threads = FPB faces x NE evaluations; evaluation 0 is the base line, 1+j perturbs dof j.
 template <int DIM, int NT>
 __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshDesc m, CouplingParams P, SideMap Ls, SideMap Rs, const int32_t* __restrict__ fcell,
@@ -293,17 +300,17 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshD
   constexpr int NR = 2 * NL;
   constexpr int NE = NR + 1;
   constexpr int FPB = NT / NE;
-  struct FaceS { double x[NR]; double jit[2][DIM]; double nrm[2][DIM]; double ie, aoh; int32_t dof[NR]; int axis, side; };
+  struct FaceS { double x[NR]; double jit[2]; double nrm[2]; double ie, aoh; int32_t dof[NR]; int axis, side; };   // jit, nrm: the axis component
   __shared__ FaceS sf[FPB];
-  // Shared-memory staging, all 16-byte vectors so that every access is one LDS.128 / STS.128:
-  //   spc[buf][face][i]      = {phi_i, c_i}                       perturbation-independent
-  //   sq [buf][face][i][0:2] = {px_i, pg_i[0]}, {pg_i[1], pg_i[2]}  base-line products
-  //   sq [MINE + t][0:2]     = the same quad for the perturbed dof of thread t
-  // The sums below read term i from the base-line quad or, for i == j, from the thread's own quad: ONE 32-bit index
-  // select per term instead of a 64-bit value select per double.
+  // Shared-memory staging, 16-byte vectors (one LDS.128 / STS.128 per access), double-buffered over the quadrature points:
+  //   spc  [buf][face][i] = {phi_i, c_i}             perturbation-independent
+  //   sq   [buf][face][i] = {px_i, pga_i}            base-line products
+  //   sq   [MINE + t]     = the same pair for the perturbed dof of thread t
+  //   sbase[buf][face][s] = {u_s, gradu_s[axis]}     base-line sums of side s
   constexpr int MINE = 2 * FPB * NR;
   __shared__ double2 spc[2 * FPB * NR];
-  __shared__ double2 sq[(MINE + NT) * 2];
+  __shared__ double2 sq[MINE + NT];
+  __shared__ double2 sbase[2 * FPB * 2];
   __shared__ double sdown[FPB][NR];
   const int t = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * FPB;
@@ -321,10 +328,11 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshD
       F.x[i] = analytic ? 0.0 : x[ds[i]]; F.x[NL + i] = analytic ? 0.0 : x[dn[i]];
     }
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      F.jit[0][d] = 1.0 / (G.up_i[d] - G.lo_i[d]); F.jit[1][d] = 1.0 / (G.up_o[d] - G.lo_o[d]);
-      F.nrm[0][d] = (d == G.axis) ? (G.side ? 1.0 : -1.0) : 0.0; F.nrm[1][d] = F.nrm[0][d] * -1;
-    }
+    for (int d = 0; d < DIM; ++d)
+      if (d == G.axis) {
+        F.jit[0] = 1.0 / (G.up_i[d] - G.lo_i[d]); F.jit[1] = 1.0 / (G.up_o[d] - G.lo_o[d]);
+        F.nrm[0] = G.side ? 1.0 : -1.0; F.nrm[1] = F.nrm[0] * -1;
+      }
     F.ie = G.integrationElement();
     F.aoh = cvcf ? P.intensity / G.cornerDistance01() : 0.0;
     F.axis = G.axis; F.side = G.side;
@@ -344,37 +352,42 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshD
 #pragma unroll
   for (int i = 0; i < NR; ++i) r[i] = 0.0;
   const int nq = ipow(P.rule.m, DIM - 1);
-  // phase-1 item of this thread: (face pf, side ps, shape function pi)
+  // phase-1 item of this thread: (face pf, side ps, shape function pi); the NL items of one (face, side) sit in NL adjacent lanes
   const int pf = t / NR, pr = t % NR, ps = pr / NL, pi = pr % NL;
   const bool pact = pf < FPB && f0 + pf < nfaces;
+  const int lane0 = (t & 31) - pi;                  // first lane of this (face, side) group
   for (int q = 0; q < nq; ++q) {
     const int bbase = (q & 1) * FPB * NR;
+    double px = 0.0, pga = 0.0;
     if (pact) {
       const FaceS& F = sf[pf];
       const int sideval = ps == 0 ? F.side : 1 - F.side;     // geometryInInside: local[axis] = side; InOutside: 1 - side
       const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + pi) * 4;
       const double phi = __ldg(tq);
-      double gpn = 0.0, g[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[ps][d] * __ldg(tq + 1 + d);
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) gpn += g[d] * F.nrm[ps][d];
+      const double ga = 0.0 + F.jit[ps] * __ldg(tq + 1 + F.axis);
+      const double gpn = 0.0 + ga * F.nrm[ps];
       const double theta = 1;
       const double xi = F.x[pr];
       const int o = bbase + pf * NR + pr;
+      px = xi * phi; pga = xi * ga;
       spc[o] = make_double2(phi, theta * 0.5 * gpn);
-      sq[2 * o] = make_double2(xi * phi, xi * g[0]);
-      sq[2 * o + 1] = make_double2(xi * g[1], DIM > 2 ? xi * g[2] : 0.0);
+      sq[o] = make_double2(px, pga);
     }
-    if (active && j >= 0) {                                  // this thread's perturbed products, in its own quad
+    {                                                        // base-line sums of the side, in the reference's order (all lanes shuffle)
+      double us = 0.0, gs = 0.0;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        us += __shfl_sync(0xffffffffu, px, lane0 + i);
+        gs += __shfl_sync(0xffffffffu, pga, lane0 + i);
+      }
+      if (pact && pi == 0) sbase[(q & 1) * FPB * 2 + pf * 2 + ps] = make_double2(us, gs);
+    }
+    if (active && j >= 0) {                                  // this thread's perturbed products, in its own slot
       const FaceS& F = sf[fl];
       const int sideval = jside == 0 ? F.side : 1 - F.side;
       const double* tq = tab + ((size_t)((F.axis * 2 + sideval) * nq + q) * NL + jj) * 4;
-      double g[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) g[d] = 0.0 + F.jit[jside][d] * __ldg(tq + 1 + d);
-      sq[2 * (MINE + t)] = make_double2(xp * __ldg(tq), xp * g[0]);
-      sq[2 * (MINE + t) + 1] = make_double2(xp * g[1], DIM > 2 ? xp * g[2] : 0.0);
+      const double ga = 0.0 + F.jit[jside] * __ldg(tq + 1 + F.axis);
+      sq[MINE + t] = make_double2(xp * __ldg(tq), xp * ga);
     }
     __syncthreads();
     if (active && !(analytic && e == 0)) {
@@ -382,19 +395,18 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshD
       const int fb = bbase + fl * NR;
       double pos[3], w; quad_point<DIM - 1>(P.rule, q, pos, w);
       const double factor = w * F.ie;
-      double u[2] = {0.0, 0.0};
-      double gradu[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+      const double2 b0 = sbase[(q & 1) * FPB * 2 + fl * 2], b1 = sbase[(q & 1) * FPB * 2 + fl * 2 + 1];
+      double u[2] = {b0.x, b1.x};
+      double ga[2] = {b0.y, b1.y};
+      if (j >= 0) {                                          // re-sum the perturbed side with this thread's j-th product
+        double us = 0.0, gs = 0.0;
+        const int sb = fb + jside * NL;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        const int src = (i == j) ? MINE + t : fb + i;
-        const double2 a = sq[2 * src];
-        u[i / NL] += a.x;
-        if (cvcf) {
-          const double2 b2 = sq[2 * src + 1];
-          gradu[i / NL][0] += a.y;
-          gradu[i / NL][1] += b2.x;
-          if (DIM > 2) gradu[i / NL][2] += b2.y;
+        for (int i = 0; i < NL; ++i) {
+          const double2 a = sq[(i == jj) ? MINE + t : sb + i];
+          us += a.x; gs += a.y;
         }
+        if (jside == 0) { u[0] = us; ga[0] = gs; } else { u[1] = us; ga[1] = gs; }
       }
       if (!cvcf) {
         const double u_diff = P.intensity * (u[0] - u[1]);
@@ -404,14 +416,11 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_coupling_jacobian_staged(MeshD
         for (int i = 0; i < NL; ++i) r[NL + i] += -u_diff * spc[fb + NL + i].x * factor;
       } else {
         const double jump[2] = {u[0] - u[1], u[1] - u[0]};
-        double mean_gradu[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) { mean_gradu[d] = gradu[0][d] + gradu[1][d]; mean_gradu[d] *= 0.5; }
+        double mean_ga = ga[0] + ga[1];
+        mean_ga *= 0.5;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          double mgn = 0.0;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) mgn += mean_gradu[d] * F.nrm[s][d];
+          const double mgn = 0.0 + mean_ga * F.nrm[s];
           const double aj = F.aoh * jump[s];
 #pragma unroll
           for (int i = 0; i < NL; ++i) {
@@ -525,19 +534,20 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     } else slots = it->second;
     const double* tab = face_tables(c, P);
     const int fpb = 256 / (2 * NL + 1);
-    static const int nt = getenv("MDB_COUPLING_JAC_THREADS") ? atoi(getenv("MDB_COUPLING_JAC_THREADS")) : 256;   // A/B switch for profiling only
-    if (nt == 128) {
-      const int fpb128 = 128 / (2 * NL + 1);
-      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 128>), cdiv(fl.n, fpb128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
-                                 d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 128>), cdiv(fl.n, fpb128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
-                      d_x, M.d_rowptr, slots, M.d_val);
-    } else {
-      if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 256>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
-                                 d_x, M.d_rowptr, slots, M.d_val);
-      else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 256>), cdiv(fl.n, fpb), 256, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
-                      d_x, M.d_rowptr, slots, M.d_val);
+    static const int pad_kb = getenv("MDB_COUPLING_PAD_KB") ? atoi(getenv("MDB_COUPLING_PAD_KB")) : 0;   // occupancy experiment knob
+    const size_t pad = (size_t)pad_kb * 1024;
+    if (pad > 0) {
+      static bool configured = false;
+      if (!configured) {
+        MDB_CUDA(cudaFuncSetAttribute(k_coupling_jacobian_staged<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+        MDB_CUDA(cudaFuncSetAttribute(k_coupling_jacobian_staged<3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+        configured = true;
+      }
     }
+    if (m.dim == 2) MDB_LAUNCH(c, (k_coupling_jacobian_staged<2, 256>), cdiv(fl.n, fpb), 256, pad, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+                               d_x, M.d_rowptr, slots, M.d_val);
+    else MDB_LAUNCH(c, (k_coupling_jacobian_staged<3, 256>), cdiv(fl.n, fpb), 256, pad, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, eps, tab,
+                    d_x, M.d_rowptr, slots, M.d_val);
   }
 }
 
