@@ -20,6 +20,7 @@ OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
 JAC_FD_BITMATCH, JAC_ANALYTIC = 0, 1
 SOLVER_CG, SOLVER_BICGSTAB = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR = 0, 1, 2, 3
+ONESTEP_IMPLICIT_EULER, ONESTEP_THETA, ONESTEP_ALEXANDER2 = 0, 1, 2
 PRECOND_SSOR_ORACLE = 100  # the oracle's own id for ISTL SeqSSOR (tests/orc.py maps PRECOND_SSOR to it)
 
 
@@ -283,6 +284,17 @@ class Mdb(Lib):
                                          _vecptr(rhs), _vecptr(z), C.byref(st))
         if rc != -6:  # MDB_ENOTCONVERGED is reported through stats
             self._check(rc, "solve")
+        return st
+
+    def onestep_apply(self, go0, go1, mat, subproblems, fns, time, dt, u_old, u_new, scheme=0, theta=1.0, method=SOLVER_BICGSTAB,
+                      precond=PRECOND_JACOBI, reduction=1e-10, maxit=5000):
+        """One time step on the device (mdb_onestep_apply); `time` is the time at the START of the step (OneStepMethod::apply)."""
+        st = SolveStats()
+        sp = np.ascontiguousarray(subproblems, dtype=np.int32)
+        arr = (Function * len(fns))(*fns)
+        self._check(self._fn("onestep_apply")(C.c_void_p(self.ctx), go0, go1, mat, _ptr(sp, C.c_int), arr, len(fns), C.c_double(time), C.c_double(dt),
+                                              int(scheme), C.c_double(theta), method, precond, C.c_double(reduction), maxit, _vecptr(u_old), _vecptr(u_new), C.byref(st)),
+                    "onestep_apply")
         return st
 
     def set_ssor_sweeps(self, sweeps):

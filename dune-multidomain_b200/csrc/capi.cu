@@ -136,6 +136,7 @@ static void reset_spaces(Ctx* c)
   dfree(c->d_constrained); dfree(c->d_conlist);
   for (int i = 0; i < 4; ++i) dfree(c->d_stage[i]);
   dfree(c->d_work); c->work_n = 0; c->work_vecs = 0;
+  dfree(c->d_onestep); c->onestep_n = 0;
   dfree(c->d_owned); c->owned_rows = 0; c->child_owned.clear(); c->part_axis = -1;
   for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear(); c->peer_lower = nullptr; c->peer_upper = nullptr;
@@ -713,6 +714,71 @@ int mdb_copy_nonconstrained(mdb_ctx* c, const double* xold, double* xnew)
   VecIn vo(c, xold, c->ndof, 0);
   VecInOut vn(c, xnew, c->ndof, 1, true);
   MDB_LAUNCH(c, k_copy_nonconstrained, cdiv(c->ndof, 256), 256, 0, vo.d, vn.d, c->d_constrained, c->ndof);
+  vn.commit();
+  MDB_API_END(c)
+}
+
+__global__ void k_sub(const double* __restrict__ a, const double* __restrict__ b, double* out, int64_t n)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
+}
+
+// One time step the way [UPSTREAM] PDELab::OneStepMethod drives OneStepGridOperator(go0, go1)
+// (test/testinstationarypoisson.cc:320-403) for the diagonally implicit schemes of [UPSTREAM]
+// TimeSteppingParameterInterface: stage r = 1..s solves
+//   sum_{i<r} [a_ri r1(x_i) + b_ri dt r0(x_i)]  +  a_rr r1(x) + b_rr dt r0(x) = 0,   r0 at time t + d_i dt,
+// with one Newton step (the operators are linear; StationaryLinearProblemSolver): start value = new Dirichlet values by
+// interpolation at the stage time + copy_nonconstrained_dofs from the previous stage (gridoperator.hh:139-153),
+// J = a_rr J1 + b_rr dt J0 (setWeight, localassembler.hh:214-255), x_r = x - J^-1 R(x).  Everything stays on the device.
+int mdb_onestep_apply(mdb_ctx* c, int go0, int go1, int mat, const int* subproblems, const mdb_function* g, int n, double time, double dt, int scheme,
+                      double theta, int method, int precond, double reduction, int maxit, const double* u_old, double* u_new, mdb_solve_stats* stats)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_onestep_apply: not finalized");
+  MDB_REQUIRE(go0 >= 0 && go0 < (int)c->gos.size() && go1 >= 0 && go1 < (int)c->gos.size(), MDB_EINVAL, "bad grid operator handle");
+  // Butcher-like tables ([UPSTREAM] ImplicitEulerParameter, OneStepThetaParameter, Alexander2Parameter)
+  int s = 1;
+  double A[2][3] = {{-1.0, 1.0, 0.0}, {0.0, 0.0, 0.0}}, B[2][3] = {{0.0, 1.0, 0.0}, {0.0, 0.0, 0.0}}, D[3] = {0.0, 1.0, 0.0};
+  if (scheme == MDB_ONESTEP_THETA) { B[0][0] = 1.0 - theta; B[0][1] = theta; }
+  else if (scheme == MDB_ONESTEP_ALEXANDER2) {
+    const double al = 1.0 - 0.5 * sqrt(2.0);
+    s = 2;
+    A[0][0] = -1.0; A[0][1] = 1.0; A[0][2] = 0.0; A[1][0] = -1.0; A[1][1] = 0.0; A[1][2] = 1.0;
+    B[0][0] = 0.0; B[0][1] = al; B[0][2] = 0.0; B[1][0] = 0.0; B[1][1] = 1.0 - al; B[1][2] = al;
+    D[0] = 0.0; D[1] = al; D[2] = 1.0;
+  } else MDB_REQUIRE(scheme == MDB_ONESTEP_IMPLICIT_EULER, MDB_EINVAL, "unknown one-step scheme");
+  const int64_t nd = c->ndof;
+  if (c->onestep_n < nd) { dfree(c->d_onestep); c->d_onestep = dalloc<double>(4 * nd); c->onestep_n = nd; }
+  double *xs[3] = {nullptr, c->d_onestep, c->d_onestep + nd}, *R = c->d_onestep + 2 * nd, *z = c->d_onestep + 3 * nd;
+  VecIn vo(c, u_old, nd, 2);
+  VecInOut vn(c, u_new, nd, 3, false);
+  xs[0] = const_cast<double*>(vo.d);
+  int rc;
+  mdb_solve_stats st_total; std::memset(&st_total, 0, sizeof(st_total)); st_total.converged = 1;
+  for (int r = 1; r <= s; ++r) {
+    double* x = xs[r];
+    const double tr = time + D[r] * dt;
+    c->time = tr;
+    MDB_CUDA(cudaMemsetAsync(x, 0, nd * sizeof(double), c->stream));
+    interpolate(c, subproblems, g, n, tr, x);
+    MDB_LAUNCH(c, k_copy_nonconstrained, cdiv(nd, 256), 256, 0, xs[r - 1], x, c->d_constrained, nd);
+    if ((rc = mdb_jacobian(c, go1, mat, A[r - 1][r], x, 1)) != MDB_OK) return rc;
+    if ((rc = mdb_jacobian(c, go0, mat, B[r - 1][r] * dt, x, 0)) != MDB_OK) return rc;
+    MDB_CUDA(cudaMemsetAsync(R, 0, nd * sizeof(double), c->stream));
+    for (int i = 0; i <= r; ++i) {
+      const double* xi = (i == r) ? x : xs[i];
+      c->time = time + D[i] * dt;
+      if (A[r - 1][i] != 0.0 && (rc = mdb_residual(c, go1, A[r - 1][i], xi, R)) != MDB_OK) return rc;
+      if (B[r - 1][i] != 0.0 && (rc = mdb_residual(c, go0, B[r - 1][i] * dt, xi, R)) != MDB_OK) return rc;
+    }
+    c->time = tr;
+    mdb_solve_stats st;
+    if ((rc = mdb_solve(c, mat, method, precond, reduction, maxit, R, z, &st)) != MDB_OK) return rc;
+    st_total.iterations += st.iterations; st_total.converged &= st.converged; st_total.seconds += st.seconds;
+    st_total.defect0 = st.defect0; st_total.defect = st.defect;
+    MDB_LAUNCH(c, k_sub, 148 * 8, 256, 0, x, z, (r == s) ? vn.d : x, nd);
+  }
+  if (stats) *stats = st_total;
   vn.commit();
   MDB_API_END(c)
 }

@@ -257,6 +257,7 @@ struct Ctx {
   double* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
   // solver workspace
   double* d_work = nullptr; int64_t work_n = 0; int work_vecs = 0;
+  double* d_onestep = nullptr; int64_t onestep_n = 0;      // u, R, z of mdb_onestep_apply
   double* d_scal = nullptr;          // device scalars
   double* d_partial = nullptr;       // block partial sums
   double* h_pinned = nullptr;        // pinned host scalars

@@ -244,6 +244,16 @@ int mdb_set_ssor_sweeps(mdb_ctx* ctx, int sweeps);
 /* Run exactly `iters` Krylov iterations without convergence test (benchmarking the loop). */
 int mdb_solve_fixed(mdb_ctx* ctx, int mat, int method, int precond, int iters,
                     const double* rhs, double* z, mdb_solve_stats* stats);
+/* One time step of the instationary problem (go0 = spatial operator, go1 = temporal/mass operator, mat created from both):
+ * [UPSTREAM] OneStepMethod + OneStepGridOperator as in test/testinstationarypoisson.cc:320-403 with the diagonally implicit
+ * schemes ImplicitEulerParameter, OneStepThetaParameter(theta), Alexander2Parameter (the reference driver's choice, :320).
+ * Per stage: Dirichlet DOFs = interpolation of g[0..n) on the listed subproblems at the stage time, the other DOFs from the
+ * previous stage (gridoperator.hh:139-153); J = a_rr J1 + b_rr dt J0; one Newton step with the linear solver given.
+ * stats: iterations / seconds summed over the stages.  u_old, u_new: host or device, may not alias. */
+enum { MDB_ONESTEP_IMPLICIT_EULER = 0, MDB_ONESTEP_THETA = 1, MDB_ONESTEP_ALEXANDER2 = 2 };
+int mdb_onestep_apply(mdb_ctx* ctx, int go0, int go1, int mat, const int* subproblems, const mdb_function* g, int n,
+                      double time, double dt, int scheme, double theta, int method, int precond, double reduction, int maxit,
+                      const double* u_old, double* u_new, mdb_solve_stats* stats);
 /* y = A x (host or device pointers).  On a partitioned context with imported neighbours x must be a device vector: its
  * ghost entries are refreshed by a halo exchange first. */
 int mdb_spmv(mdb_ctx* ctx, int mat, const double* x, double* y);

@@ -274,6 +274,10 @@ public:
     res.reduction = st.defect0 > 0 ? st.defect / st.defect0 : 0.0;
     if (rc != MDB_ENOTCONVERGED) ctx.check(rc, "mdb_solve");
   }
+  int method() const { return method_; }
+  int precond() const { return precond_; }
+  unsigned maxiter() const { return maxiter_; }
+  void configure(Context& ctx) const { if (sweeps_ > 0) ctx.check(mdb_set_ssor_sweeps(ctx.get(), sweeps_), "mdb_set_ssor_sweeps"); }
 };
 // Jacobi is the fast device path.  The SSOR / ILU0 backends run the reference's sequential ISTL preconditioners operation
 // for operation (sync-free sweeps, csrc/precond.cu): [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SeqSSOR(A, 3, 1.0)
@@ -300,6 +304,51 @@ public:
     ls_.apply(a, go_.context(), z.data(), r.data(), reduction_);
     if (!ls_.res.converged) throw Exception(MDB_ENOTCONVERGED, "StationaryLinearProblemSolver: linear solver did not converge");
     for (size_t i = 0; i < x.size(); ++i) x[i] -= z[i];
+  }
+};
+
+// ---- instationary problems ([UPSTREAM] PDELab OneStepGridOperator / OneStepMethod; test/testinstationarypoisson.cc:285-403) ------------
+// interpolateOnSubProblems(g, sp0, g, sp1): the boundary-value functor handed to OneStepMethod::apply (:373)
+struct SubProblemFunctions { std::vector<int> sps; std::vector<mdb_function> fns; };
+template <class SP0, class SP1>
+inline SubProblemFunctions interpolateOnSubProblems(const mdb_function& f0, const SP0& sp0, const mdb_function& f1, const SP1& sp1) {
+  SubProblemFunctions f; f.sps.push_back(sp0.handle); f.fns.push_back(f0); f.sps.push_back(sp1.handle); f.fns.push_back(f1); return f;
+}
+// time-stepping parameter sets (the diagonally implicit ones)
+struct ImplicitEulerParameter { static int scheme() { return MDB_ONESTEP_IMPLICIT_EULER; } double theta() const { return 1.0; } };
+struct OneStepThetaParameter { double th; explicit OneStepThetaParameter(double t) : th(t) {} static int scheme() { return MDB_ONESTEP_THETA; } double theta() const { return th; } };
+struct Alexander2Parameter { static int scheme() { return MDB_ONESTEP_ALEXANDER2; } double theta() const { return 0.0; } };
+// OneStepGridOperator(go_dt0, go_dt1): one matrix whose pattern is the union of both operators' patterns
+class OneStepGridOperator {
+  GridOperator& go0_; GridOperator& go1_; Jacobian a_;
+public:
+  OneStepGridOperator(GridOperator& go0, GridOperator& go1) : go0_(go0), go1_(go1), a_(go0, go1) {}
+  GridOperator& spatial() { return go0_; }
+  GridOperator& temporal() { return go1_; }
+  Jacobian& matrix() { return a_; }
+  Context& context() const { return go0_.context(); }
+};
+// OneStepMethod(method, gridoperator, linear solver backend, reduction).apply(time, dt, xold, f, xnew): one mdb_onestep_apply per step;
+// xold / xnew may be host vectors or device pointers (DeviceVector keeps the state in HBM between steps)
+template <class Parameter, class LS>
+class OneStepMethod {
+  Parameter method_; OneStepGridOperator& go_; LS& ls_; double reduction_;
+public:
+  LinearSolverResult res;
+  OneStepMethod(const Parameter& method, OneStepGridOperator& go, LS& ls, double reduction) : method_(method), go_(go), ls_(ls), reduction_(reduction) {}
+  void apply(double time, double dt, const double* xold, const SubProblemFunctions& f, double* xnew) {
+    Context& ctx = go_.context();
+    mdb_solve_stats st;
+    ls_.configure(ctx);
+    int rc = mdb_onestep_apply(ctx.get(), go_.spatial().handle(), go_.temporal().handle(), go_.matrix().handle(), f.sps.data(), f.fns.data(),
+                               (int)f.sps.size(), time, dt, Parameter::scheme(), method_.theta(), ls_.method(), ls_.precond(), reduction_,
+                               (int)ls_.maxiter(), xold, xnew, &st);
+    res.iterations = st.iterations; res.converged = st.converged != 0; res.elapsed = st.seconds;
+    res.reduction = st.defect0 > 0 ? st.defect / st.defect0 : 0.0;
+    ctx.check(rc, "mdb_onestep_apply");
+  }
+  void apply(double time, double dt, const Vector& xold, const SubProblemFunctions& f, Vector& xnew) {
+    xnew.resize(xold.size()); apply(time, dt, xold.data(), f, xnew.data());
   }
 };
 

@@ -144,3 +144,41 @@ def implicit_euler_step(api, P, u_old, t_new, dt, solve):
     z = np.zeros(P.ndof)
     solve(P.mat, R, z)
     return u - z
+
+
+def one_step_method(api, P, u_old, t, dt, solve, scheme="implicit_euler", theta=1.0):
+    """[UPSTREAM] PDELab::OneStepMethod::apply(time, dt, xold, f, xnew) for the diagonally implicit parameter sets
+    ImplicitEulerParameter / OneStepThetaParameter / Alexander2Parameter (test/testinstationarypoisson.cc:320-322, :373),
+    driven through the two grid operators with weights exactly as OneStepGridOperator does.  Stage r solves
+    sum_{i<r} [a_ri r1(x_i) + b_ri dt r0(x_i)] + a_rr r1(x) + b_rr dt r0(x) = 0 with one Newton step."""
+    import math
+    import numpy as np
+    if scheme == "implicit_euler":
+        a, b, d = [[-1.0, 1.0]], [[0.0, 1.0]], [0.0, 1.0]
+    elif scheme == "theta":
+        a, b, d = [[-1.0, 1.0]], [[1.0 - theta, theta]], [0.0, 1.0]
+    else:
+        al = 1.0 - 0.5 * math.sqrt(2.0)
+        a, b, d = [[-1.0, 1.0, 0.0], [-1.0, 0.0, 1.0]], [[0.0, al, 0.0], [0.0, 1.0 - al, al]], [0.0, al, 1.0]
+    xs = [np.ascontiguousarray(u_old)]
+    for r in range(1, len(a) + 1):
+        tr = t + d[r] * dt
+        api.set_time(tr)
+        x = np.zeros(P.ndof)
+        api.interpolate(P.sps, P.gfn, x, time=tr)
+        api.copy_nonconstrained(xs[r - 1], x)
+        api.jacobian(P.go1, P.mat, x, weight=a[r - 1][r], overwrite=True)
+        api.jacobian(P.go0, P.mat, x, weight=b[r - 1][r] * dt, overwrite=False)
+        R = np.zeros(P.ndof)
+        for i in range(r + 1):
+            xi = x if i == r else xs[i]
+            api.set_time(t + d[i] * dt)
+            if a[r - 1][i] != 0.0:
+                api.residual(P.go1, xi, R, weight=a[r - 1][i])
+            if b[r - 1][i] != 0.0:
+                api.residual(P.go0, xi, R, weight=b[r - 1][i] * dt)
+        api.set_time(tr)
+        z = np.zeros(P.ndof)
+        solve(P.mat, R, z)
+        xs.append(x - z)
+    return xs[-1]

@@ -82,11 +82,11 @@ def test_product_does_not_reference_the_oracle():
     assert not bad, bad
 
 
-def _build_example(outdir):
-    exe = os.path.join(outdir, "testpoisson")
+def _build_example(outdir, name="testpoisson"):
+    exe = os.path.join(outdir, name)
     libdir = os.path.dirname(pkg.library_path())
     subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "testpoisson.cc"), "-o", exe, "-L", libdir, "-lmdb200", "-Wl,-rpath," + libdir])
+                           os.path.join(ROOT, "examples", name + ".cc"), "-o", exe, "-L", libdir, "-lmdb200", "-Wl,-rpath," + libdir])
     return exe
 
 
@@ -96,6 +96,7 @@ def test_cxx_facade_compiles_and_fails_loudly_without_gpu(lib):
     import torch
     with tempfile.TemporaryDirectory() as d:
         exe = _build_example(d)
+        _build_example(d, "testinstationarypoisson")          # the instationary driver must at least compile and link
         if torch.cuda.is_available():
             pytest.skip("a GPU is present (the run is covered by the gpu tests)")
         p = subprocess.run([exe, "3", "2.0"], capture_output=True, text=True)

@@ -395,3 +395,62 @@ def test_implicit_euler_steps_match_oracle(n):
         ud = problems.implicit_euler_step(dev, Pd, ud, step * dt, dt, dsolve)
         assert np.abs(ud - uo).max() <= 1e-9 * np.abs(uo).max(), step
     assert np.abs(uo).max() > 0.05          # something actually evolved
+    dev.close(); ora.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme,theta", [("implicit_euler", 1.0), ("theta", 0.5), ("alexander2", 0.0)])
+def test_onestep_driver_matches_oracle(scheme, theta):
+    """mdb_onestep_apply (one C-ABI call per time step, all vectors resident in HBM) against OneStepMethod restated over the
+    oracle (tests/problems.py::one_step_method): implicit Euler, Crank-Nicolson (theta = 1/2) and Alexander2, the scheme the
+    reference's instationary driver uses (test/testinstationarypoisson.cc:320)."""
+    import torch
+    n = (12, 10)
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    Pd, Po = problems.instationary(dev, n), problems.instationary(ora, n)
+    code = {"implicit_euler": capi.ONESTEP_IMPLICIT_EULER, "theta": capi.ONESTEP_THETA, "alexander2": capi.ONESTEP_ALEXANDER2}[scheme]
+    uo = np.zeros(Po.ndof)
+    ora.interpolate(Po.sps, Po.gfn, uo, time=0.0)
+    a = torch.from_numpy(uo.copy()).cuda(); b = torch.zeros_like(a)
+    torch.cuda.synchronize()
+    dt = 0.04
+    for step in range(4):
+        uo = problems.one_step_method(ora, Po, uo, step * dt, dt, lambda mat, R, z: ora.solve(mat, R, z, reduction=1e-13), scheme, theta)
+        st = dev.onestep_apply(Pd.go0, Pd.go1, Pd.mat, Pd.sps, Pd.gfn, step * dt, dt, a, b, scheme=code, theta=theta, reduction=1e-13)
+        assert st.converged
+        a, b = b, a
+        dev.synchronize()
+        assert np.abs(a.cpu().numpy() - uo).max() <= 1e-9 * np.abs(uo).max(), step
+    assert np.abs(uo).max() > 0.05
+    dev.close(); ora.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["alexander2", "euler"])
+def test_cxx_instationary_driver_matches_oracle(scheme):
+    """examples/testinstationarypoisson.cc (test/testinstationarypoisson.cc against the facade: OneStepGridOperator +
+    OneStepMethod, Alexander2 as shipped) run as a program against OneStepMethod restated over the oracle."""
+    import re
+    import subprocess
+    import tempfile
+    from test_capi import _build_example
+    level, k, dt, tend = 3, 2.0, 0.05, 0.2
+    n = (1 << level,) * 2
+    ora = orc.Oracle()
+    Po = problems.instationary(ora, n, k=k)
+    u = np.zeros(Po.ndof)
+    ora.interpolate(Po.sps, Po.gfn, u, time=0.0)
+    t = 0.0
+    while t < tend - 1e-8:
+        u = problems.one_step_method(ora, Po, u, t, dt, lambda mat, R, z: ora.solve(mat, R, z, reduction=1e-13),
+                                     "alexander2" if scheme == "alexander2" else "implicit_euler")
+        t += dt
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d, "testinstationarypoisson")
+        out = subprocess.run([exe, str(level), str(k), str(dt), str(tend), "2", scheme], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"(\d+) dof total, (\d+) dof constrained", out.stdout)
+    assert m and int(m.group(1)) == Po.ndof and int(m.group(2)) == Po.ncon
+    m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
+    assert abs(float(m.group(1)) - u.sum()) <= 1e-7 * abs(u.sum())
+    assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-7 * np.linalg.norm(u)
