@@ -16,8 +16,16 @@
 //   k_jacobian_rows_q1   the irregular rows (boundary / subdomain boundary; a compact list built with the pattern):
 //                        generic per-row gather over the incident cells
 #include "common.cuh"
+#include <cub/cub.cuh>
 
 namespace mdb {
+
+__global__ void k_list_compact(const int32_t* __restrict__ flags, const int32_t* __restrict__ scan, int64_t n, int32_t* list)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) list[scan[i]] = (int32_t)i;
+}
+
 
 void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight);   // exact.cu
 
@@ -364,7 +372,8 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
 // consecutively.  Other rows gather over their incident cells.
 template <int DIM>
 __global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
-                                                            const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r)
+                                                            const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r,
+                                                            const int32_t* __restrict__ list, int64_t nlist)
 {
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
@@ -376,8 +385,9 @@ __global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const ui
   }
   if (threadIdx.x < NS) sS[threadIdx.x] = Ae[V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL + threadIdx.x];
   __syncthreads();
-  const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gi >= ch.size) return;
+  const int64_t ti = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (ti >= (list ? nlist : ch.size)) return;
+  const int64_t gi = list ? (int64_t)list[ti] : ti;
   const int32_t lp = ch.dof2lat[gi];
   int rr = lp;
   int p[3]; p[0] = rr % ch.lat_n[0]; rr /= ch.lat_n[0]; p[1] = rr % ch.lat_n[1]; p[2] = rr / ch.lat_n[1];
@@ -517,6 +527,176 @@ __global__ void __launch_bounds__(512) k_residual_volume_tile(MeshDesc m, const 
   r[ch.offset + g] += s;
 }
 
+// ---- residual, bulk-copy stencil variant (the default on box children with one subproblem) --------------------------------
+// On a uniform row (all 2^d incident cells carry the subproblem) of a child block whose lattice points fill their bounding
+// box, alpha_volume of the linear operator is the constant row stencil S applied to x at r + dx + dy*bx + dz*bx*by (the same
+// index arithmetic as k_spmv_stencil in solver.cu).  A block owns RS_ROWS consecutive rows; an elected thread fetches the
+// 3^(d-1) segments of x they read with bulk-async copies (cp.async.bulk, 1-D TMA) on one mbarrier; every thread then sums
+// its row from shared memory.  Which rows qualify is decided once per (grid operator, child) — k_residual_plan — and kept
+// as a byte per row; the other rows (boundary, subdomain boundary, chunks at the ends of the vector) go through the
+// per-row gather kernel over a compact list.  Bytes per row: 8 (x, via L2) + 16 (r read-modify-write) + 1.
+#define RS_ROWS 128
+#define RS_XSEG (RS_ROWS + 4)
+#define RS_BLOCKS 10
+struct ResChild { int64_t offset, size; int bx, bxy; };
+
+__host__ __device__ inline bool res_chunk_staged(const ResChild& ch, int dim, int64_t r0, int64_t r1, int64_t n)
+{
+  const int64_t reach = (dim == 3) ? (int64_t)ch.bx + ch.bxy : ch.bx;
+  return r1 > r0 && r0 - 1 - reach - 1 >= 0 && r1 + 1 + reach + 1 <= n;
+}
+
+template <int DIM>
+__global__ void k_residual_plan(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V, ResChild rc, int64_t n, uint8_t* fast, int32_t* flags)
+{
+  const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gi >= ch.size) return;
+  int rr = ch.dof2lat[gi];
+  int p[3]; p[0] = rr % ch.lat_n[0]; rr /= ch.lat_n[0]; p[1] = rr % ch.lat_n[1]; p[2] = rr / ch.lat_n[1];
+  bool uni = p[0] >= 1 && p[0] < m.n[0] && p[1] >= 1 && p[1] < m.n[1] && (DIM < 3 || (p[2] >= 1 && p[2] < m.n[2]));
+  if (uni) {
+    for (int cz = (DIM > 2 ? -1 : 0); cz <= 0; ++cz)
+      for (int cy = -1; cy <= 0; ++cy)
+        for (int cx = -1; cx <= 0; ++cx) {
+          const uint8_t s = sd[(p[0] + cx) + (int64_t)m.n[0] * ((p[1] + cy) + (int64_t)m.n[1] * (p[2] + cz))];
+          uni = uni && cond_applies(V.cond_kind[0], V.mask[0], s) && (ch.subdomain < 0 || ((s >> ch.subdomain) & 1));
+        }
+  }
+  const int64_t r = rc.offset + gi;
+  const int64_t r0 = rc.offset + gi / RS_ROWS * RS_ROWS;
+  const int64_t r1 = (r0 + RS_ROWS < rc.offset + rc.size) ? r0 + RS_ROWS : rc.offset + rc.size;
+  (void)r;
+  const bool f = uni && res_chunk_staged(rc, DIM, r0, r1, n);
+  fast[gi] = f ? 1 : 0;
+  flags[gi] = f ? 0 : 1;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t n, ResChild ch, const double* __restrict__ S, const uint8_t* __restrict__ fast,
+                                                                  const double* __restrict__ x, double* __restrict__ res)
+{
+  constexpr int NS = DIM == 3 ? 27 : 9;
+  constexpr int NL = NS / 3;
+  __shared__ __align__(16) double sx[2][NL * RS_XSEG];                           // double-buffered: chunk i+1 lands while chunk i is summed
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ double sS[32];                                                      // (registers were measured: lower occupancy costs more)
+  const int t = threadIdx.x;
+  const int xpar = (int)(((uintptr_t)x >> 3) & 1);                              // bulk copies need 16-byte aligned sources
+  if (t < NS) sS[t] = S[t];
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nchunks = (ch.size + RS_ROWS - 1) / RS_ROWS;
+  auto issue = [&](int64_t chunk, int buf) {                                      // thread 0 only
+    const int64_t r0 = ch.offset + chunk * RS_ROWS;
+    const int64_t r1 = (r0 + RS_ROWS < ch.offset + ch.size) ? r0 + RS_ROWS : ch.offset + ch.size;
+    if (!res_chunk_staged(ch, DIM, r0, r1, n)) return;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar[buf]), sx_s = (uint32_t)__cvta_generic_to_shared(sx[buf]);
+    const int len = (int)(r1 - r0) + 2;
+    uint32_t total = 0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+      const int64_t g0 = r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy;
+      const int64_t al = g0 - ((g0 + xpar) & 1);
+      total += (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8);
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+      const int64_t g0 = r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy;
+      const int64_t al = g0 - ((g0 + xpar) & 1);
+      const uint32_t bytes = (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sx_s + (uint32_t)(l * RS_XSEG * 8)),
+                   "l"(x + al), "r"(bytes), "r"(bar_s)
+                   : "memory");
+    }
+  };
+  if (t == 0 && (int64_t)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+  uint32_t phasebits = 0;
+  int it = 0;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {  // block-uniform trip count
+    const int buf = it & 1;
+    // the other buffer was released by the barrier that ended the previous iteration
+    if (t == 0 && chunk + gridDim.x < nchunks) issue(chunk + gridDim.x, buf ^ 1);
+    const int64_t r0 = ch.offset + chunk * RS_ROWS;
+    const int64_t r1 = (r0 + RS_ROWS < ch.offset + ch.size) ? r0 + RS_ROWS : ch.offset + ch.size;
+    const bool staged = res_chunk_staged(ch, DIM, r0, r1, n);                    // block-uniform
+    const int64_t r = r0 + t;
+    const bool mine = staged && r < r1 && fast[r - ch.offset] != 0;
+    const double rold = mine ? res[r] : 0.0;                                      // in flight while the copies land
+    if (staged) {
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(&bar[buf])), "r"((phasebits >> buf) & 1u) : "memory");
+      phasebits ^= 1u << buf;
+    }
+    if (mine) {
+      const double* sxb = sx[buf];
+      double sum = 0.0;
+#pragma unroll
+      for (int o = 0; o < NS; ++o) {
+        const int dx = o % 3 - 1, l = o / 3, dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+        const int sh_l = (int)((r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy + xpar) & 1);
+        sum += sS[o] * sxb[l * RS_XSEG + sh_l + t + dx + 1];
+      }
+      res[r] = rold + sum;
+    }
+    __syncthreads();                                                             // this buffer is free again
+  }
+}
+
+// returns false when the child does not qualify (the caller falls back to the tile kernel)
+static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, const VolSpec& V, const double* d_x, double* d_r)
+{
+  static const bool off = getenv("MDB_RESIDUAL_TILE") != nullptr;                 // A/B switch for profiling only
+  const MeshDesc& m = c->mesh;
+  const Child& hc = c->children[child];
+  if (off || V.n != 1 || hc.k != 1 || hc.size == 0) return false;
+  int64_t vol = 1;
+  for (int d = 0; d < m.dim; ++d) vol *= hc.lat_hi[d] - hc.lat_lo[d] + 1;
+  if (vol != hc.size) return false;                                               // not a box: the stencil offsets are not constant
+  ResChild rc; rc.offset = hc.offset; rc.size = hc.size;
+  rc.bx = hc.lat_hi[0] - hc.lat_lo[0] + 1; rc.bxy = rc.bx * (hc.lat_hi[1] - hc.lat_lo[1] + 1);
+  const int64_t n = c->ndof;
+  if (go.n_res_rest[child] < 0) {                                                 // first residual with this operator: plan the child
+    go.d_res_fast[child] = dalloc<uint8_t>(hc.size);
+    int32_t* d_flag = dalloc<int32_t>(hc.size);
+    int32_t* d_scan = dalloc<int32_t>(hc.size);
+    if (m.dim == 2) MDB_LAUNCH(c, k_residual_plan<2>, cdiv(hc.size, 256), 256, 0, m, c->d_cell_sd, ch, V, rc, n, go.d_res_fast[child], d_flag);
+    else MDB_LAUNCH(c, k_residual_plan<3>, cdiv(hc.size, 256), 256, 0, m, c->d_cell_sd, ch, V, rc, n, go.d_res_fast[child], d_flag);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_scan, (int)hc.size, c->stream);
+    void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+    MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_flag, d_scan, (int)hc.size, c->stream)); c->launches++;
+    int32_t ls = 0, lf = 0;
+    MDB_CUDA(cudaMemcpyAsync(&ls, d_scan + hc.size - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaMemcpyAsync(&lf, d_flag + hc.size - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    go.d_res_rest[child] = dalloc<int32_t>((int64_t)ls + lf);
+    MDB_LAUNCH(c, k_list_compact, cdiv(hc.size, 256), 256, 0, d_flag, d_scan, hc.size, go.d_res_rest[child]);
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    go.n_res_rest[child] = (int64_t)ls + lf;
+    cudaFree(d_t); dfree(d_flag); dfree(d_scan);
+  }
+  const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + (1 << m.dim) * (1 << m.dim);
+  int grid = 148 * RS_BLOCKS;
+  if (grid > cdiv(hc.size, RS_ROWS)) grid = cdiv(hc.size, RS_ROWS);
+  if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, S, go.d_res_fast[child], d_x, d_r);
+  else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, S, go.d_res_fast[child], d_x, d_r);
+  const int64_t nrest = go.n_res_rest[child];
+  if (nrest > 0) {
+    if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
+    else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
+  }
+  return true;
+}
+
 void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r)
 {
   const MeshDesc& m = c->mesh;
@@ -529,10 +709,11 @@ void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x,
     if (ch.size == 0) continue;
     static const bool legacy = getenv("MDB_RESIDUAL_LEGACY") != nullptr;          // A/B switch for profiling only
     if (legacy) {
-      if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(ch.size, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r);
-      else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(ch.size, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r);
+      if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(ch.size, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, nullptr, 0);
+      else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(ch.size, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, nullptr, 0);
       continue;
     }
+    if (residual_stencil(c, const_cast<GridOp&>(go), i, ch, V, d_x, d_r)) continue;
     // tiles over the bounding box of the child's lattice points
     const Child& hc = c->children[i];
     int lo[3], nt[3];

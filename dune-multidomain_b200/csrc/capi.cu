@@ -130,7 +130,7 @@ static void free_matrix(Matrix& m)
 static void reset_spaces(Ctx* c)
 {
   for (auto& ch : c->children) { dfree(ch.d_lat2dof); dfree(ch.d_dof2lat); }
-  for (auto& go : c->gos) { for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); } dfree(go.d_xneed); }
+  for (auto& go : c->gos) { for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); } dfree(go.d_xneed); for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(go.d_res_fast[i]); dfree(go.d_res_rest[i]); go.n_res_rest[i] = -1; } }
   for (auto& m : c->mats) free_matrix(m);
   c->gos.clear(); c->mats.clear();
   dfree(c->d_constrained); dfree(c->d_conlist);

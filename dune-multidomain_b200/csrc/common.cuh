@@ -184,6 +184,9 @@ struct GridOp {
   // sorted list of the DOFs whose coefficients the Jacobian kernels of this operator read (the coupling faces' cell DOFs;
   // the volume operators of the closed set are linear).  Built on first use by mdb_jacobian with a host vector.
   int32_t* d_xneed = nullptr; int64_t n_xneed = -1;
+  // residual_volume plan per child (assemble.cu): 1 = row taken by the bulk-copy stencil kernel; the other rows as a list
+  uint8_t* d_res_fast[MDB_MAX_CHILDREN] = {nullptr}; int32_t* d_res_rest[MDB_MAX_CHILDREN] = {nullptr};
+  int64_t n_res_rest[MDB_MAX_CHILDREN] = {-1, -1, -1, -1, -1, -1, -1, -1};
 };
 
 struct Matrix {

@@ -592,12 +592,17 @@ __global__ void k_lambda_volume(MeshDesc m, const uint8_t* __restrict__ sd, Lamb
 
 // lambda_boundary on the faces of one boundary plane (axis, side): r_i += j(x_q) phi_i w_q |J_f| where isNeumann
 // (instationarypoissonoperator.hh:142-167).  One thread per boundary face.
+// All boundary planes of a subproblem go through ONE launch (the kernel is latency bound): job = (axis, side), blocks [block0, ...)
+struct PlaneJobs { int n; int axis[6], side[6], block0[7]; };
 template <int DIM, int K>
-__global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, LambdaSpec S, SideMap map, int axis, int side, double weight,
+__global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, LambdaSpec S, SideMap map, PlaneJobs J, double weight,
                                   double t, double* r)
 {
   constexpr int NL = cpow(K + 1, DIM);
-  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.block0[jb + 1]) ++jb;
+  const int axis = J.axis[jb], side = J.side[jb];
+  int64_t idx = (blockIdx.x - J.block0[jb]) * (int64_t)blockDim.x + threadIdx.x;
   int t0 = (axis == 0) ? 1 : 0, t1 = (axis == 2) ? 1 : 2;
   int64_t nplane = (int64_t)m.n[t0] * ((DIM > 2) ? m.n[t1] : 1);
   if (idx >= nplane) return;
@@ -657,6 +662,7 @@ void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r)
       else MDB_LAUNCH(c, (k_lambda_volume<3, 2>), cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
     }
     if (sp.poisson.bc.kind == MDB_BC_ALL_DIRICHLET) continue;   // no Neumann face anywhere
+    PlaneJobs J; J.n = 0; J.block0[0] = 0;
     for (int axis = 0; axis < m.dim; ++axis)
       for (int side = 0; side < 2; ++side) {
         // only physical boundary planes: a partition cut is a processor boundary (no boundary terms, globalassembler.hh:275-283)
@@ -664,11 +670,14 @@ void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r)
         if (side == 1 && !m.on_global_upper(axis, m.n[axis])) continue;
         int t0 = (axis == 0) ? 1 : 0, t1 = (axis == 2) ? 1 : 2;
         int64_t nplane = (int64_t)m.n[t0] * ((m.dim > 2) ? m.n[t1] : 1);
-        if (m.dim == 2 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<2, 1>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
-        else if (m.dim == 3 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<3, 1>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
-        else if (m.dim == 2) MDB_LAUNCH(c, (k_lambda_boundary<2, 2>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
-        else MDB_LAUNCH(c, (k_lambda_boundary<3, 2>), cdiv(nplane, 128), 128, 0, m, c->d_cell_sd, S, map, axis, side, weight, c->time, d_r);
+        J.axis[J.n] = axis; J.side[J.n] = side; J.block0[J.n + 1] = J.block0[J.n] + cdiv(nplane, 128); ++J.n;
       }
+    if (J.n == 0) continue;
+    const int nb = J.block0[J.n];
+    if (m.dim == 2 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<2, 1>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
+    else if (m.dim == 3 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<3, 1>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
+    else if (m.dim == 2) MDB_LAUNCH(c, (k_lambda_boundary<2, 2>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
+    else MDB_LAUNCH(c, (k_lambda_boundary<3, 2>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
   }
 }
 
