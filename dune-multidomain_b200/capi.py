@@ -17,6 +17,7 @@ FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2, FN
 BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON = range(3)
 OP_POISSON, OP_L2 = 1, 2
 OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
+OP_MORTAR_POISSON_COUPLING = 201
 JAC_FD_BITMATCH, JAC_ANALYTIC = 0, 1
 SOLVER_CG, SOLVER_BICGSTAB = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR = 0, 1, 2, 3
@@ -58,6 +59,10 @@ class CVCFParams(C.Structure):
 
 class PropFlowParams(C.Structure):
     _fields_ = [("intensity", C.c_double)]
+
+
+class MortarParams(C.Structure):
+    _fields_ = [("gamma_0", C.c_double)]
 
 
 class SolveStats(C.Structure):
@@ -176,6 +181,17 @@ class Lib:
     def add_coupling(self, op_id, params, local_sp, remote_sp, jac_mode=JAC_FD_BITMATCH):
         return self._check(self._fn("add_coupling")(C.c_void_p(self.ctx), op_id, C.byref(params), C.c_size_t(C.sizeof(params)),
                                                     local_sp, remote_sp, jac_mode), "add_coupling")
+
+    def add_coupling_space(self, fe_kind, left_cond, right_cond):
+        """left_cond / right_cond = (cond_kind, mask) of the SubProblemSubProblemInterface predicate."""
+        r = self._check(self._fn("add_coupling_space")(C.c_void_p(self.ctx), fe_kind, left_cond[0], C.c_uint32(left_cond[1]),
+                                                       right_cond[0], C.c_uint32(right_cond[1])), "add_coupling_space")
+        self.nchildren += 1
+        return r
+
+    def add_enriched_coupling(self, op_id, params, local_sp, remote_sp, coupling_child, jac_mode=JAC_FD_BITMATCH):
+        return self._check(self._fn("add_enriched_coupling")(C.c_void_p(self.ctx), op_id, C.byref(params), C.c_size_t(C.sizeof(params)),
+                                                             local_sp, remote_sp, coupling_child, jac_mode), "add_enriched_coupling")
 
     def finalize(self):
         nd = C.c_int64(0)

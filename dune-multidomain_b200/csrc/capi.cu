@@ -313,6 +313,24 @@ int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
 }
 
+int mdb_add_coupling_space(mdb_ctx* c, int fe_kind, int left_cond_kind, uint32_t left_cond_mask, int right_cond_kind, uint32_t right_cond_mask)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_coupling_space: need a mesh, before mdb_finalize");
+    MDB_REQUIRE(fe_kind == MDB_FE_Q1, MDB_EINVAL, "mdb_add_coupling_space: only Q1 coupling spaces (vertex-attached mortar DOFs) have device kernels");
+    MDB_REQUIRE(c->mesh.dim >= 2, MDB_EINVAL, "mdb_add_coupling_space: needs dim >= 2");
+    MDB_REQUIRE(!c->mesh.partitioned, MDB_EINVAL, "mdb_add_coupling_space: coupling spaces are not supported on a partitioned mesh");
+    auto ok = [](int k) { return k == MDB_COND_EQUALITY || k == MDB_COND_SUBSET; };
+    MDB_REQUIRE(ok(left_cond_kind) && ok(right_cond_kind), MDB_EINVAL, "mdb_add_coupling_space: bad condition");
+    MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_coupling_space: too many child spaces");
+    Child ch; ch.fe_kind = fe_kind; ch.k = 1; ch.subdomain = MDB_SUBDOMAIN_IFACE; ch.iface = true;
+    ch.lkind = left_cond_kind; ch.lmask = left_cond_mask; ch.rkind = right_cond_kind; ch.rmask = right_cond_mask;
+    c->children.push_back(ch);
+    return (int)c->children.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
 int mdb_add_subproblem(mdb_ctx* c, int op_id, const void* params, size_t nbytes, int cond_kind, uint32_t cond_mask,
                        const int* children, int nchildren)
 {
@@ -322,6 +340,7 @@ int mdb_add_subproblem(mdb_ctx* c, int op_id, const void* params, size_t nbytes,
     MDB_REQUIRE(cond_kind == MDB_COND_EQUALITY || cond_kind == MDB_COND_SUBSET, MDB_EINVAL, "mdb_add_subproblem: bad condition");
     MDB_REQUIRE(nchildren == 1, MDB_EINVAL, "mdb_add_subproblem: only single-child (scalar) subproblems have device kernels in this build");
     MDB_REQUIRE(children[0] >= 0 && children[0] < (int)c->children.size(), MDB_EINVAL, "mdb_add_subproblem: bad child index");
+    MDB_REQUIRE(!c->children[children[0]].iface, MDB_EINVAL, "mdb_add_subproblem: a coupling space cannot carry a subproblem");
     SubProblemDesc sp; sp.op_id = op_id; sp.cond_kind = cond_kind; sp.mask = cond_mask;
     sp.children.assign(children, children + nchildren);
     if (op_id == MDB_OP_POISSON) {
@@ -354,6 +373,25 @@ int mdb_add_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, i
       MDB_REQUIRE(nbytes == sizeof(mdb_propflow_params), MDB_EINVAL, "mdb_add_coupling: bad mdb_propflow_params size");
       std::memcpy(&cp.propflow, params, nbytes);
     } else throw Error(MDB_EINVAL, "mdb_add_coupling: unknown coupling operator");
+    c->cps.push_back(cp);
+    return (int)c->cps.size() - 1;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+}
+
+int mdb_add_enriched_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp, int coupling_child, int jac_mode)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    MDB_REQUIRE(!c->finalized, MDB_ESTATE, "mdb_add_enriched_coupling: before mdb_finalize");
+    MDB_REQUIRE(local_sp >= 0 && local_sp < (int)c->sps.size() && remote_sp >= 0 && remote_sp < (int)c->sps.size(), MDB_EINVAL,
+                "mdb_add_enriched_coupling: bad subproblem index");
+    MDB_REQUIRE(coupling_child >= 0 && coupling_child < (int)c->children.size() && c->children[coupling_child].iface, MDB_EINVAL,
+                "mdb_add_enriched_coupling: coupling_child must come from mdb_add_coupling_space");
+    MDB_REQUIRE(jac_mode == MDB_JAC_FD_BITMATCH || jac_mode == MDB_JAC_ANALYTIC, MDB_EINVAL, "mdb_add_enriched_coupling: bad jac_mode");
+    MDB_REQUIRE(op_id == MDB_OP_MORTAR_POISSON_COUPLING, MDB_EINVAL, "mdb_add_enriched_coupling: unknown enriched coupling operator");
+    MDB_REQUIRE(nbytes == sizeof(mdb_mortar_params), MDB_EINVAL, "mdb_add_enriched_coupling: bad mdb_mortar_params size");
+    CouplingDesc cp; cp.op_id = op_id; cp.local_sp = local_sp; cp.remote_sp = remote_sp; cp.jac_mode = jac_mode; cp.coupling_child = coupling_child;
+    std::memcpy(&cp.mortar, params, nbytes);
     c->cps.push_back(cp);
     return (int)c->cps.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }

@@ -141,8 +141,15 @@ Rule1D gauss1d(int order);
 // ------------------------------------------------------------------------------------------------
 // host-side model
 // ------------------------------------------------------------------------------------------------
+// `subdomain` of a coupling (mortar) space: no cell carries its DOFs — it is bound per intersection (globalassembler.hh:212-231);
+// bit 30 of a cell's subdomain byte is never set, so every "child lives on this cell" test of the volume kernels fails
+#define MDB_SUBDOMAIN_IFACE 30
+
 struct Child {
   int fe_kind = 0, k = 1, subdomain = -1;
+  // CouplingGridFunctionSpace (couplinggridfunctionspace.hh:45-249): lives on the intersections whose inside cell satisfies
+  // the left condition and whose outside cell satisfies the right one (SubProblemSubProblemInterface :14-44)
+  bool iface = false; int lkind = 0, rkind = 0; uint32_t lmask = 0, rmask = 0;
   int lat_n[3] = {1, 1, 1};
   int64_t nlat = 0;
   int32_t* d_lat2dof = nullptr;
@@ -169,7 +176,10 @@ struct CouplingDesc {
   int op_id = 0;
   mdb_cvcf_params cvcf{};
   mdb_propflow_params propflow{};
+  mdb_mortar_params mortar{};
   int local_sp = -1, remote_sp = -1, jac_mode = 0;
+  int coupling_child = -1;       // >= 0: EnrichedCoupling (coupling.hh:123-192) with this coupling space
+  bool enriched() const { return coupling_child >= 0; }
 };
 
 struct FaceList {      // interface faces on which one coupling fires, in traversal order
@@ -328,6 +338,10 @@ void constrain_residual(Ctx* c, double* d_r);
 void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight);
 void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool overwrite, int part);
 void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x);
+// mortar.cu: EnrichedCoupling with MortarPoissonCoupling (test/testmortarpoisson.cc:117-250)
+void residual_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r);
+void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight, const double* d_x);
+void mark_iface_present(Ctx* c, const Child& ch, uint8_t* d_present);
 void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& m, int child, bool overwrite);      // generic.cu: Qk children, k > 1
 void residual_volume_generic(Ctx* c, const GridOp& go, int child, const double* d_x, double* d_r);
 void dirichlet_rows(Ctx* c, Matrix& m);

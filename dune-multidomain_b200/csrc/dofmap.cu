@@ -99,6 +99,36 @@ __global__ void k_lattice_bbox(const uint8_t* __restrict__ present, int64_t nlat
   }
 }
 
+// ---- K1a': coupling space — the vertices of the intersections its predicate accepts (couplinggfsordering.hh:113-201).
+// The ordering numbers the used vertices by ascending MultiDomainGrid vertex index (entity_dof_offsets is indexed by it and
+// partial-summed, :185-200), which is what the class-0 scan below does with these marks.
+__global__ void k_mark_present_iface(MeshDesc m, const uint8_t* __restrict__ sd, int lk, uint32_t lmask, int rk, uint32_t rmask, int lat_n0, int lat_n1,
+                                     uint8_t* present)
+{
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int nf = 2 * m.dim;
+  if (t >= m.ncells() * nf) return;
+  int64_t c = t / nf; int f = (int)(t % nf);
+  int ijk[3]; cell_ijk(m, c, ijk);
+  const int axis = f / 2, side = f % 2;
+  int nijk[3] = {ijk[0], ijk[1], ijk[2]};
+  nijk[axis] += side ? 1 : -1;
+  if (nijk[axis] < 0 || nijk[axis] >= m.n[axis]) return;                          // !is.neighbor()
+  if (!(cond_applies(lk, lmask, sd[c]) && cond_applies(rk, rmask, sd[cell_index(m, nijk)]))) return;
+  for (int i = 0; i < (1 << (m.dim - 1)); ++i) {
+    int v[3] = {ijk[0], ijk[1], ijk[2]}; int tt = 0;
+    for (int d = 0; d < m.dim; ++d) { if (d == axis) v[d] += side; else { v[d] += (i >> tt) & 1; ++tt; } }
+    present[v[0] + (int64_t)lat_n0 * (v[1] + (int64_t)lat_n1 * v[2])] = 1;
+  }
+}
+
+void mark_iface_present(Ctx* c, const Child& ch, uint8_t* d_present)
+{
+  const MeshDesc& m = c->mesh;
+  MDB_LAUNCH(c, k_mark_present_iface, cdiv(m.ncells() * 2 * m.dim, 256), 256, 0, m, c->d_cell_sd, ch.lkind, ch.lmask, ch.rkind, ch.rmask, ch.lat_n[0],
+             ch.lat_n[1], d_present);
+}
+
 void build_dofmap(Ctx* c)
 {
   const MeshDesc& m = c->mesh;
@@ -114,7 +144,8 @@ void build_dofmap(Ctx* c)
     ch.d_lat2dof = dalloc<int32_t>(ch.nlat);
     int32_t* d_dof2lat_tmp = dalloc<int32_t>(ch.nlat);
     MDB_CUDA(cudaMemsetAsync(d_present, 0, ch.nlat, c->stream));
-    MDB_LAUNCH(c, k_mark_present, cdiv(m.ncells(), 256), 256, 0, m, c->d_cell_sd, ch.k, ch.subdomain, ch.lat_n[0], ch.lat_n[1], d_present);
+    if (ch.iface) mark_iface_present(c, ch, d_present);
+    else MDB_LAUNCH(c, k_mark_present, cdiv(m.ncells(), 256), 256, 0, m, c->d_cell_sd, ch.k, ch.subdomain, ch.lat_n[0], ch.lat_n[1], d_present);
     MDB_LAUNCH(c, k_fill_i32, cdiv(ch.nlat, 256), 256, 0, ch.d_lat2dof, ch.nlat, -1);
     {
       int h_bb[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
@@ -426,6 +457,22 @@ __global__ void k_mark_face_dofs(MeshDesc m, NeedSide L, NeedSide R, const int32
   }
 }
 
+// the mortar DOFs of the coupling faces (coefficients x_c the enriched FD Jacobian reads)
+__global__ void k_mark_face_mortar_dofs(MeshDesc m, NeedSide C, const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces,
+                                        uint8_t* flags)
+{
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nfaces) return;
+  int ijk[3]; cell_ijk(m, fcell[f], ijk);
+  const int axis = fface[f] / 2, side = fface[f] % 2;
+  for (int i = 0; i < (1 << (m.dim - 1)); ++i) {
+    int v[3] = {ijk[0], ijk[1], ijk[2]}; int t = 0;
+    for (int d = 0; d < m.dim; ++d) { if (d == axis) v[d] += side; else { v[d] += (i >> t) & 1; ++t; } }
+    const int32_t g = C.lat2dof[v[0] + (int64_t)C.lat_n[0] * (v[1] + (int64_t)C.lat_n[1] * v[2])];
+    if (g >= 0) flags[C.offset + g] = 1;
+  }
+}
+
 void build_xneed(Ctx* c, GridOp& go)
 {
   const int64_t n = c->ndof;
@@ -443,6 +490,12 @@ void build_xneed(Ctx* c, GridOp& go)
       S[q].k = ch.k; S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof;
     }
     MDB_LAUNCH(c, k_mark_face_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, S[0], S[1], fl.d_cell, fl.d_face, fl.n, d_flags);
+    if (cp.enriched()) {
+      const Child& ch = c->children[cp.coupling_child];
+      NeedSide C; for (int d = 0; d < 3; ++d) C.lat_n[d] = ch.lat_n[d];
+      C.k = ch.k; C.offset = ch.offset; C.lat2dof = ch.d_lat2dof;
+      MDB_LAUNCH(c, k_mark_face_mortar_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, C, fl.d_cell, fl.d_face, fl.n, d_flags);
+    }
   }
   int32_t* d_f = dalloc<int32_t>(n);
   int32_t* d_s = dalloc<int32_t>(n);

@@ -488,6 +488,7 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
     const CouplingDesc& cp = c->cps[go.cps[k]];
     const FaceList& fl = go.faces[k];
     if (fl.n == 0) continue;
+    if (cp.enriched()) { residual_enriched(c, cp, fl, weight, d_x, d_r); continue; }      // mortar.cu
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const int k1 = c->children[c->sps[cp.local_sp].children[0]].k, k2 = c->children[c->sps[cp.remote_sp].children[0]].k;
@@ -505,6 +506,7 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     const CouplingDesc& cp = c->cps[go.cps[k]];
     const FaceList& fl = go.faces[k];
     if (fl.n == 0) continue;
+    if (cp.enriched()) { jacobian_enriched(c, cp, fl, M, weight, d_x); continue; }        // mortar.cu
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const double eps = 1e-8;                    // NumericalJacobianCoupling() default, couplingutilities.hh:63-65

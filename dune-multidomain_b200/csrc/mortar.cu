@@ -1,0 +1,238 @@
+// mortar.cu — EnrichedCoupling with a coupling (mortar) space: MortarPoissonCoupling of test/testmortarpoisson.cc:117-250.
+// COMPILED WITH --fmad=false like exact.cu / generic.cu: the finite-difference Jacobians
+// (NumericalJacobianEnrichedCouplingTo{First,Second}SubProblem, couplingutilities.hh:292-484) must reproduce the CPU evaluation.
+//
+// Per intersection on which the coupling fires (coupling.hh:178-183: local subproblem on the inside cell, remote one on the
+// outside cell) the reference calls alpha_enriched_coupling_first(inside, mortar) and _second(outside, mortar)
+// (residualassemblerfunctors.hh:219-257); both are alpha_generic<sign> (:156-244):
+//   r_i   += w [ -(n.grad u) v_i - (u - lambda) (n.grad v_i) + 2 gamma (u - lambda) v_i ]
+//   r_c,i += w [ (n.grad u) - 2 gamma (u - lambda) ] mu_i,        gamma = gamma_0 / |face|,  n = outer normal of the INSIDE cell
+// with the element basis evaluated through geometryInInside (sign > 0) or geometryInOutside (sign < 0).
+//
+//   k_mortar_residual   one thread per intersection: both sides, r_s / r_n / r_c added atomically
+//   k_mortar_jacobian   one thread per (intersection, side, perturbed coefficient): base line + perturbed evaluation, column j of
+//                       mat_ss|mat_cs (j in the element) or mat_sc|mat_cc (j in the mortar space), couplingutilities.hh:338-386
+// This is a correctness configuration ("small"), interface-sized work: plain kernels, columns by binary search.
+#include "exact_common.cuh"
+
+namespace mdb {
+
+struct MortarSpec {
+  double gamma_0; int jac_mode;
+  Rule1D rule1, rule2;                 // qorder = 2 max(order(lfsu), order(lfsu_c)) per side, testmortarpoisson.cc:193-195
+  int lkind, rkind; uint32_t lmask, rmask;    // the coupling space's own predicate (gfs.contains(is))
+};
+
+// corner i of face (axis, side) of cell ijk: bit t of i = coordinate along the t-th axis other than `axis` ([UPSTREAM] Yasp)
+template <int DIM> __device__ __forceinline__ void face_dofs(const SideMap& C, const int ijk[3], int axis, int side, int32_t* dofs)
+{
+  constexpr int NC = 1 << (DIM - 1);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    int v[3] = {ijk[0], ijk[1], ijk[2]}; int t = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { if (d == axis) v[d] += side; else { v[d] += (i >> t) & 1; ++t; } }
+    dofs[i] = (int32_t)(C.offset + C.lat2dof[v[0] + (int64_t)C.lat_n[0] * (v[1] + (int64_t)C.lat_n[1] * v[2])]);
+  }
+}
+
+// alpha_generic<sign> (testmortarpoisson.cc:156-244); same statements, same order as the CPU restatement.
+// __noinline__ on purpose: inlined into mortar_column (two calls around a dynamically indexed store into u / uc) nvcc 12.9
+// produced NaN coefficients for the second call whenever NL > 4 (observed on B200, both Jacobian modes; the host build of
+// the same source under ASan/UBSan is clean).  As a real call the function is correct for every instantiation.
+template <int DIM, int K>
+__device__ __noinline__ void mortar_alpha(int sign, double gamma_0, const Rule1D& R, const FaceGeo<DIM>& G, const double* x, const double* x_c, int nc, double* r,
+                             double* r_c, double weight)
+{
+  constexpr int NL = cpow(K + 1, DIM);
+  const int nq = ipow(R.m, DIM - 1);
+  const double gamma = gamma_0 / G.integrationElement();
+  double jit[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) jit[d] = sign > 0 ? 1.0 / (G.up_i[d] - G.lo_i[d]) : 1.0 / (G.up_o[d] - G.lo_o[d]);
+  for (int q = 0; q < nq; ++q) {
+    double pos[3] = {0.0, 0.0, 0.0}, w; quad_point<DIM - 1>(R, q, pos, w);
+    double element_pos[3];
+    if (sign > 0) G.localInside(pos, element_pos); else G.localOutside(pos, element_pos);
+    double normal[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) normal[d] = (d == G.axis) ? (G.side ? 1.0 : -1.0) : 0.0;
+    double v[NL], gradv[NL][DIM], mu[1 << (DIM - 1)];
+    for (int i = 0; i < NL; ++i) {
+      v[i] = qk_phi<DIM>(K, i, element_pos);
+      double js[3]; qk_grad<DIM>(K, i, element_pos, js);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gradv[i][d] = 0.0 + jit[d] * js[d];
+    }
+    for (int i = 0; i < nc; ++i) mu[i] = qk_phi<DIM - 1>(1, i, pos);
+    double u = 0.0, gradu[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gradu[d] = 0.0;
+    for (int i = 0; i < NL; ++i) {
+      u += x[i] * v[i];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gradu[d] += x[i] * gradv[i][d];
+    }
+    double lambda = 0.0;
+    for (int i = 0; i < nc; ++i) lambda += x_c[i] * mu[i];
+    const double factor = w * G.integrationElement();
+    double ngu = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) ngu += normal[d] * gradu[d];
+    for (int i = 0; i < NL; ++i) {
+      double ngv = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) ngv += normal[d] * gradv[i][d];
+      r[i] += weight * ((-ngu * v[i] - (u - lambda) * ngv + 2 * gamma * (u - lambda) * v[i]) * factor);
+    }
+    for (int i = 0; i < nc; ++i) r_c[i] += weight * ((ngu - 2 * gamma * (u - lambda)) * mu[i] * factor);
+  }
+}
+
+template <int DIM, int K1, int K2>
+__global__ void __launch_bounds__(64) k_mortar_residual(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, SideMap Cs,
+                                                        const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces, double weight,
+                                                        const double* __restrict__ x, double* r)
+{
+  constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NC = 1 << (DIM - 1);
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nfaces) return;
+  FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
+  int32_t ds[NL1], dn[NL2], dc[NC];
+  cell_dofs_qk<DIM, K1>(Ls, G.ijk, ds); cell_dofs_qk<DIM, K2>(Rs, G.nijk, dn);
+  const uint8_t s_in = sd[fcell[f]], s_out = sd[G.nijk[0] + (int64_t)m.n[0] * (G.nijk[1] + (int64_t)m.n[1] * G.nijk[2])];
+  const int nc = (cond_applies(P.lkind, P.lmask, s_in) && cond_applies(P.rkind, P.rmask, s_out)) ? NC : 0;   // lfs_c.bind(is): empty if !contains(is)
+  if (nc) face_dofs<DIM>(Cs, G.ijk, G.axis, G.side, dc);
+  double x1[NL1], x2[NL2], xc[NC], r1[NL1], r2[NL2], rc[NC];
+  for (int i = 0; i < NL1; ++i) { x1[i] = x[ds[i]]; r1[i] = 0.0; }
+  for (int i = 0; i < NL2; ++i) { x2[i] = x[dn[i]]; r2[i] = 0.0; }
+  for (int i = 0; i < nc; ++i) { xc[i] = x[dc[i]]; rc[i] = 0.0; }
+  mortar_alpha<DIM, K1>(+1, P.gamma_0, P.rule1, G, x1, xc, nc, r1, rc, weight);
+  mortar_alpha<DIM, K2>(-1, P.gamma_0, P.rule2, G, x2, xc, nc, r2, rc, weight);
+  for (int i = 0; i < NL1; ++i) atomicAdd(&r[ds[i]], r1[i]);
+  for (int i = 0; i < NL2; ++i) atomicAdd(&r[dn[i]], r2[i]);
+  for (int i = 0; i < nc; ++i) atomicAdd(&r[dc[i]], rc[i]);
+}
+
+// one column of jacobian_enriched_coupling_{first,second} (couplingutilities.hh:305-388 / :404-484)
+template <int DIM, int K>
+__device__ void mortar_column(int sign, const MortarSpec& P, const Rule1D& R, const FaceGeo<DIM>& G, const int32_t* de, const int32_t* dc, int nc, int j,
+                              double weight, double epsilon, const double* __restrict__ x, const int64_t* __restrict__ rowptr,
+                              const int32_t* __restrict__ colidx, double* val)
+{
+  constexpr int NL = cpow(K + 1, DIM), NC = 1 << (DIM - 1);
+  const bool analytic = P.jac_mode == MDB_JAC_ANALYTIC;
+  double u[NL], uc[NC], down[NL], down_c[NC], up[NL], up_c[NC];
+  for (int i = 0; i < NL; ++i) { u[i] = analytic ? 0.0 : x[de[i]]; down[i] = 0.0; up[i] = 0.0; }
+  for (int i = 0; i < NC; ++i) { uc[i] = (analytic || i >= nc) ? 0.0 : x[dc[i]]; down_c[i] = 0.0; up_c[i] = 0.0; }
+  double delta = 1.0;
+  if (!analytic) mortar_alpha<DIM, K>(sign, P.gamma_0, R, G, u, uc, nc, down, down_c, 1.0);          // base line
+  if (j < NL) {                                                                                        // jiggle in self
+    if (!analytic) delta = epsilon * (1.0 + fabs(u[j]));
+    u[j] += delta;
+  } else {                                                                                             // jiggle in coupling
+    if (!analytic) delta = epsilon * (1.0 + fabs(uc[j - NL]));
+    uc[j - NL] += delta;
+  }
+  mortar_alpha<DIM, K>(sign, P.gamma_0, R, G, u, uc, nc, up, up_c, 1.0);
+  const int32_t col = (j < NL) ? de[j] : dc[j - NL];
+  for (int i = 0; i < NL; ++i) {                                                                      // mat_ss / mat_sc
+    const double cval = (up[i] - down[i]) / delta;
+    atomicAdd(&val[find_slot(rowptr, colidx, de[i], col)], weight * cval);
+  }
+  for (int i = 0; i < nc; ++i) {                                                                      // mat_cs / mat_cc
+    const double cval = (up_c[i] - down_c[i]) / delta;
+    atomicAdd(&val[find_slot(rowptr, colidx, dc[i], col)], weight * cval);
+  }
+}
+
+template <int DIM, int K1, int K2>
+__global__ void __launch_bounds__(64) k_mortar_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, SideMap Cs,
+                                                        const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces, double weight,
+                                                        double epsilon, const double* __restrict__ x, const int64_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ colidx, double* val)
+{
+  constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NC = 1 << (DIM - 1);
+  constexpr int NP = NL1 + NC + NL2 + NC;              // perturbations per intersection: first (element, mortar), second (element, mortar)
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nfaces * NP) return;
+  const int64_t f = t / NP; const int e = (int)(t % NP);
+  FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
+  const uint8_t s_in = sd[fcell[f]], s_out = sd[G.nijk[0] + (int64_t)m.n[0] * (G.nijk[1] + (int64_t)m.n[1] * G.nijk[2])];
+  const int nc = (cond_applies(P.lkind, P.lmask, s_in) && cond_applies(P.rkind, P.rmask, s_out)) ? NC : 0;
+  int32_t dc[NC];
+  if (nc) face_dofs<DIM>(Cs, G.ijk, G.axis, G.side, dc);
+  if (e < NL1 + NC) {
+    if (e >= NL1 && nc == 0) return;
+    int32_t ds[NL1]; cell_dofs_qk<DIM, K1>(Ls, G.ijk, ds);
+    mortar_column<DIM, K1>(+1, P, P.rule1, G, ds, dc, nc, e, weight, epsilon, x, rowptr, colidx, val);
+  } else {
+    const int j = e - (NL1 + NC);
+    if (j >= NL2 && nc == 0) return;
+    int32_t dn[NL2]; cell_dofs_qk<DIM, K2>(Rs, G.nijk, dn);
+    mortar_column<DIM, K2>(-1, P, P.rule2, G, dn, dc, nc, j, weight, epsilon, x, rowptr, colidx, val);
+  }
+}
+
+static SideMap side_map_child(const Ctx* c, int child)
+{
+  const Child& ch = c->children[child];
+  SideMap s; for (int d = 0; d < 3; ++d) s.lat_n[d] = ch.lat_n[d];
+  s.offset = ch.offset; s.lat2dof = ch.d_lat2dof;
+  return s;
+}
+
+static MortarSpec mortar_spec(const Ctx* c, const CouplingDesc& cp, int k1, int k2)
+{
+  MortarSpec P; P.gamma_0 = cp.mortar.gamma_0; P.jac_mode = cp.jac_mode;
+  const Child& cc = c->children[cp.coupling_child];
+  P.rule1 = gauss1d(2 * (k1 > cc.k ? k1 : cc.k)); P.rule2 = gauss1d(2 * (k2 > cc.k ? k2 : cc.k));
+  P.lkind = cc.lkind; P.lmask = cc.lmask; P.rkind = cc.rkind; P.rmask = cc.rmask;
+  return P;
+}
+
+#define MDB_DISPATCH_MORTAR(DIMV, K1V, K2V, CALL)                             \
+  do {                                                                        \
+    if (DIMV == 2 && K1V == 1 && K2V == 2) { CALL(2, 1, 2); }                 \
+    else if (DIMV == 2 && K1V == 2 && K2V == 1) { CALL(2, 2, 1); }            \
+    else if (DIMV == 2 && K1V == 2 && K2V == 2) { CALL(2, 2, 2); }            \
+    else if (DIMV == 2) { CALL(2, 1, 1); }                                    \
+    else if (K1V == 1 && K2V == 2) { CALL(3, 1, 2); }                         \
+    else if (K1V == 2 && K2V == 1) { CALL(3, 2, 1); }                         \
+    else if (K1V == 2 && K2V == 2) { CALL(3, 2, 2); }                         \
+    else { CALL(3, 1, 1); }                                                   \
+  } while (0)
+
+void residual_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r)
+{
+  const MeshDesc& m = c->mesh;
+  MDB_REQUIRE(m.dim >= 2, MDB_EINVAL, "enriched couplings need dim >= 2");
+  const int cl = c->sps[cp.local_sp].children[0], cr = c->sps[cp.remote_sp].children[0];
+  const int k1 = c->children[cl].k, k2 = c->children[cr].k;
+  MDB_REQUIRE(k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2, MDB_EINVAL, "enriched coupling kernels exist for Q1 and Q2 spaces");
+  const MortarSpec P = mortar_spec(c, cp, k1, k2);
+  const SideMap Ls = side_map_child(c, cl), Rs = side_map_child(c, cr), Cs = side_map_child(c, cp.coupling_child);
+#define CALL(D, A, B) MDB_LAUNCH(c, (k_mortar_residual<D, A, B>), cdiv(fl.n, 64), 64, 0, m, c->d_cell_sd, P, Ls, Rs, Cs, fl.d_cell, fl.d_face, fl.n, weight, d_x, d_r)
+  MDB_DISPATCH_MORTAR(m.dim, k1, k2, CALL);
+#undef CALL
+}
+
+void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& M, double weight, const double* d_x)
+{
+  const MeshDesc& m = c->mesh;
+  MDB_REQUIRE(m.dim >= 2, MDB_EINVAL, "enriched couplings need dim >= 2");
+  const int cl = c->sps[cp.local_sp].children[0], cr = c->sps[cp.remote_sp].children[0];
+  const int k1 = c->children[cl].k, k2 = c->children[cr].k;
+  MDB_REQUIRE(k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2, MDB_EINVAL, "enriched coupling kernels exist for Q1 and Q2 spaces");
+  const MortarSpec P = mortar_spec(c, cp, k1, k2);
+  const SideMap Ls = side_map_child(c, cl), Rs = side_map_child(c, cr), Cs = side_map_child(c, cp.coupling_child);
+  int nl1 = 1, nl2 = 1;
+  for (int d = 0; d < m.dim; ++d) { nl1 *= k1 + 1; nl2 *= k2 + 1; }
+  const int64_t total = fl.n * (nl1 + nl2 + 2 * (1 << (m.dim - 1)));
+  const double eps = 1e-8;                      // NumericalJacobianEnrichedCouplingTo*SubProblem() default, couplingutilities.hh:296-298
+#define CALL(D, A, B) MDB_LAUNCH(c, (k_mortar_jacobian<D, A, B>), cdiv(total, 64), 64, 0, m, c->d_cell_sd, P, Ls, Rs, Cs, fl.d_cell, fl.d_face, fl.n, weight, eps, d_x, M.d_rowptr, M.d_colidx, M.d_val)
+  MDB_DISPATCH_MORTAR(m.dim, k1, k2, CALL);
+#undef CALL
+}
+
+} // namespace mdb

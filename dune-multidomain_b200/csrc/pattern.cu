@@ -14,11 +14,13 @@ namespace mdb {
 
 #define MDB_MAXROW 256
 
-struct PChild { int k, subdomain, nloc; int lat_n[3]; int64_t offset, size; const int32_t* lat2dof; const int32_t* dof2lat; };
+struct PChild { int k, subdomain, nloc; int lat_n[3]; int64_t offset, size; const int32_t* lat2dof; const int32_t* dof2lat;
+                int iface, lkind, rkind; uint32_t lmask, rmask; };
 struct PatSpec {
   int nchild; PChild ch[MDB_MAX_CHILDREN];
   int nsp; int sp_child[16]; int sp_kind[16]; uint32_t sp_mask[16];
   int ncp; int cp_lchild[8], cp_lkind[8], cp_rchild[8], cp_rkind[8]; uint32_t cp_lmask[8], cp_rmask[8];
+  int cp_cchild[8];      // >= 0: EnrichedCoupling with this coupling space (sc/cs/nc/cn/cc links instead of sn/ns)
 };
 
 __device__ __forceinline__ bool on_cell(int subdomain, uint8_t sd) { return subdomain < 0 || ((sd >> subdomain) & 1); }
@@ -49,9 +51,62 @@ __device__ void add_cell_dofs(RowList& L, const MeshDesc& m, const PChild& ch, c
       }
 }
 
+// the mortar DOFs of face f of cell ijk (CouplingLocalFunctionSpace::bind, couplinglocalfunctionspace.hh:208-287)
+__device__ void add_face_dofs(RowList& L, const MeshDesc& m, const PChild& C, const int ijk[3], int f)
+{
+  const int axis = f / 2, side = f % 2;
+  for (int i = 0; i < (1 << (m.dim - 1)); ++i) {
+    int v[3] = {ijk[0], ijk[1], ijk[2]}; int t = 0;
+    for (int d = 0; d < m.dim; ++d) { if (d == axis) v[d] += side; else { v[d] += (i >> t) & 1; ++t; } }
+    L.insert((int32_t)(C.offset + C.lat2dof[v[0] + (int64_t)C.lat_n[0] * (v[1] + (int64_t)C.lat_n[1] * v[2])]));
+  }
+}
+__device__ __forceinline__ bool iface_contains(const PChild& C, uint8_t sd_in, uint8_t sd_out)
+{
+  return cond_applies(C.lkind, C.lmask, sd_in) && cond_applies(C.rkind, C.rmask, sd_out);     // couplinggridfunctionspace.hh:29-35
+}
+
+// row of a coupling space: FullEnrichedCoupling{First,Second}SubProblemPattern's cs / cn links and FullEnrichedCouplingPattern's
+// cc links (couplingutilities.hh:219-286) over every intersection that contains the row's vertex and on which the coupling fires
+__device__ void enumerate_iface_row(RowList& L, const MeshDesc& m, const uint8_t* __restrict__ sd, const PatSpec& S, int child, int64_t gi)
+{
+  const PChild& C = S.ch[child];
+  L.n = 0; L.overflow = false;
+  int64_t r = C.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % C.lat_n[0]); r /= C.lat_n[0]; p[1] = (int)(r % C.lat_n[1]); p[2] = (int)(r / C.lat_n[1]);
+  int lo_c[3], hi_c[3];
+  for (int d = 0; d < 3; ++d) {
+    if (d >= m.dim) { lo_c[d] = hi_c[d] = 0; continue; }
+    hi_c[d] = (p[d] < m.n[d]) ? p[d] : m.n[d] - 1;
+    lo_c[d] = (p[d] > 0) ? p[d] - 1 : 0;
+  }
+  for (int cz = lo_c[2]; cz <= hi_c[2]; ++cz)
+    for (int cy = lo_c[1]; cy <= hi_c[1]; ++cy)
+      for (int cx = lo_c[0]; cx <= hi_c[0]; ++cx) {
+        const int ijk[3] = {cx, cy, cz};
+        const uint8_t s = sd[cx + (int64_t)m.n[0] * (cy + (int64_t)m.n[1] * cz)];
+        for (int a = 0; a < m.dim; ++a) {
+          const int f = 2 * a + (p[a] - ijk[a]);                      // the face of this cell along axis a that holds the vertex
+          int nijk[3] = {cx, cy, cz};
+          nijk[a] += (f % 2) ? 1 : -1;
+          if (nijk[a] < 0 || nijk[a] >= m.n[a]) continue;
+          const uint8_t sn = sd[nijk[0] + (int64_t)m.n[0] * (nijk[1] + (int64_t)m.n[1] * nijk[2])];
+          if (!iface_contains(C, s, sn)) continue;
+          for (int q = 0; q < S.ncp; ++q) {
+            if (S.cp_cchild[q] != child) continue;
+            if (!(cond_applies(S.cp_lkind[q], S.cp_lmask[q], s) && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn))) continue;
+            if (on_cell(S.ch[S.cp_lchild[q]].subdomain, s)) add_cell_dofs(L, m, S.ch[S.cp_lchild[q]], ijk);      // pattern_cs
+            if (on_cell(S.ch[S.cp_rchild[q]].subdomain, sn)) add_cell_dofs(L, m, S.ch[S.cp_rchild[q]], nijk);    // pattern_cn
+            add_face_dofs(L, m, C, ijk, f);                                                                     // pattern_cc
+          }
+        }
+      }
+}
+
 __device__ void enumerate_row(RowList& L, const MeshDesc& m, const uint8_t* __restrict__ sd, const PatSpec& S, int child, int64_t gi)
 {
   const PChild& ch = S.ch[child];
+  if (ch.iface) { enumerate_iface_row(L, m, sd, S, child, gi); return; }
   L.n = 0; L.overflow = false;
   int64_t r = ch.dof2lat[gi];
   int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
@@ -81,6 +136,12 @@ __device__ void enumerate_row(RowList& L, const MeshDesc& m, const uint8_t* __re
             nijk[f / 2] += (f % 2) ? 1 : -1;
             if (nijk[f / 2] < 0 || nijk[f / 2] >= m.n[f / 2]) continue;
             uint8_t sn = sd[nijk[0] + (int64_t)m.n[0] * (nijk[1] + (int64_t)m.n[1] * nijk[2])];
+            if (S.cp_cchild[q] >= 0) {       // enriched coupling: pattern_sc (fired from this cell) / pattern_nc (fired from the neighbour)
+              const PChild& C = S.ch[S.cp_cchild[q]];
+              if (as_local && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn) && iface_contains(C, s, sn)) add_face_dofs(L, m, C, ijk, f);
+              if (as_remote && cond_applies(S.cp_lkind[q], S.cp_lmask[q], sn) && iface_contains(C, sn, s)) add_face_dofs(L, m, C, nijk, f ^ 1);
+              continue;
+            }
             if (as_local && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn) && on_cell(S.ch[S.cp_rchild[q]].subdomain, sn))
               add_cell_dofs(L, m, S.ch[S.cp_rchild[q]], nijk);      // pattern_sn: rows of the local side, columns of the remote side
             if (as_remote && cond_applies(S.cp_lkind[q], S.cp_lmask[q], sn) && on_cell(S.ch[S.cp_lchild[q]].subdomain, sn))
@@ -170,6 +231,7 @@ void build_pattern(Ctx* c, Matrix& M)
     p.k = ch.k; p.subdomain = ch.subdomain; p.nloc = ch.nloc(m.dim);
     for (int d = 0; d < 3; ++d) p.lat_n[d] = ch.lat_n[d];
     p.offset = ch.offset; p.size = ch.size; p.lat2dof = ch.d_lat2dof; p.dof2lat = ch.d_dof2lat;
+    p.iface = ch.iface ? 1 : 0; p.lkind = ch.lkind; p.lmask = ch.lmask; p.rkind = ch.rkind; p.rmask = ch.rmask;
   }
   for (int gi : M.gos) {
     const GridOp& go = c->gos[gi];
@@ -184,7 +246,8 @@ void build_pattern(Ctx* c, Matrix& M)
       MDB_REQUIRE(S.ncp < 8, MDB_EINVAL, "too many couplings in one matrix");
       const SubProblemDesc& l = c->sps[cp.local_sp]; const SubProblemDesc& r = c->sps[cp.remote_sp];
       S.cp_lchild[S.ncp] = l.children[0]; S.cp_lkind[S.ncp] = l.cond_kind; S.cp_lmask[S.ncp] = l.mask;
-      S.cp_rchild[S.ncp] = r.children[0]; S.cp_rkind[S.ncp] = r.cond_kind; S.cp_rmask[S.ncp] = r.mask; ++S.ncp;
+      S.cp_rchild[S.ncp] = r.children[0]; S.cp_rkind[S.ncp] = r.cond_kind; S.cp_rmask[S.ncp] = r.mask;
+      S.cp_cchild[S.ncp] = cp.coupling_child; ++S.ncp;
     }
   }
   const int64_t n = c->ndof;

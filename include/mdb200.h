@@ -96,7 +96,9 @@ enum {
   MDB_OP_L2 = 2,             /* [UPSTREAM] Dune::PDELab::L2(intorder) / test/simpletimeoperator.hh:29-101 (mass)    */
   /* coupling operators used by Couplings */
   MDB_OP_CVCF_COUPLING = 101,     /* ContinuousValueContinuousFlowCoupling  test/proportionalflowcoupling.hh:94-239 */
-  MDB_OP_PROPFLOW_COUPLING = 102  /* ProportionalFlowCoupling               test/proportionalflowcoupling.hh:10-91  */
+  MDB_OP_PROPFLOW_COUPLING = 102, /* ProportionalFlowCoupling               test/proportionalflowcoupling.hh:10-91  */
+  /* enriched (mortar) coupling operators used by EnrichedCouplings */
+  MDB_OP_MORTAR_POISSON_COUPLING = 201   /* MortarPoissonCoupling(gamma_0)  test/testmortarpoisson.cc:117-250        */
 };
 
 typedef struct mdb_poisson_params {
@@ -121,6 +123,10 @@ typedef struct mdb_cvcf_params {
 typedef struct mdb_propflow_params {
   double intensity;
 } mdb_propflow_params;
+
+typedef struct mdb_mortar_params {
+  double gamma_0;            /* ctor arg ("scaling factor for coupling", test/testmortarpoisson.cc:402): gamma = gamma_0 / |face| */
+} mdb_mortar_params;
 
 /* Jacobian mode for coupling operators. */
 enum {
@@ -162,6 +168,13 @@ int mdb_subdomains_halfspace(mdb_ctx* ctx, int axis, double threshold, int sd_be
 /* Appends a child space; returns its child index >= 0.  subdomain = -1 puts the child on the
  * MultiDomainGrid view itself, otherwise on SubDomainGrid view `subdomain`. */
 int mdb_add_space(mdb_ctx* ctx, int fe_kind, int subdomain);
+/* CouplingGridFunctionSpace<MDGV, QkLocalFiniteElementMap<(dim-1)-cube, 1>, SubProblemSubProblemInterface(left, right)>
+ * (couplinggridfunctionspace.hh:14-249): a Q1 space on the interface faces whose inside cell satisfies the left condition and
+ * whose outside cell satisfies the right one — the mortar space of test/testmortarpoisson.cc:343-375.  Its DOFs are the
+ * vertices of those faces, numbered by ascending vertex index (couplinggfsordering.hh:150-200); like every child it
+ * becomes one block of the lexicographic MultiDomainGridFunctionSpace ordering.  Returns the child index. */
+int mdb_add_coupling_space(mdb_ctx* ctx, int fe_kind, int left_cond_kind, uint32_t left_cond_mask,
+                           int right_cond_kind, uint32_t right_cond_mask);
 
 /* ---- participants  (subproblem.hh:44-148, coupling.hh:30-91) -------------- */
 /* Returns the subproblem index >= 0.  `children` are indices returned by mdb_add_space. */
@@ -170,6 +183,14 @@ int mdb_add_subproblem(mdb_ctx* ctx, int op_id, const void* params, size_t param
 /* Returns the coupling index >= 0.  Fires on a face iff local applies to inside and remote to outside. */
 int mdb_add_coupling(mdb_ctx* ctx, int op_id, const void* params, size_t params_bytes,
                      int local_subproblem, int remote_subproblem, int jac_mode);
+/* EnrichedCoupling<Local, Remote, Op, couplingLFSIndex> (coupling.hh:123-192): as mdb_add_coupling, with the coupling
+ * (mortar) space `coupling_child` returned by mdb_add_coupling_space.  Per face the operator's
+ * alpha_enriched_coupling_first(inside, mortar) and _second(outside, mortar) run (residualassemblerfunctors.hh:219-257);
+ * Jacobians by NumericalJacobianEnrichedCouplingTo{First,Second}SubProblem (couplingutilities.hh:292-484); pattern =
+ * FullEnrichedCoupling{First,Second}SubProblemPattern + FullEnrichedCouplingPattern (:203-286).  Returns a coupling index
+ * (same index space as mdb_add_coupling). */
+int mdb_add_enriched_coupling(mdb_ctx* ctx, int op_id, const void* params, size_t params_bytes,
+                              int local_subproblem, int remote_subproblem, int coupling_child, int jac_mode);
 
 /* ---- DOF map (ordering update; multidomaingridfunctionspace.hh:308-369) --- */
 int mdb_finalize(mdb_ctx* ctx, int64_t* ndof);

@@ -331,6 +331,82 @@ void CouplingOperator::jacobian_coupling(const IG& ig, const LFS& lfsu_s, const 
   }
 }
 
+// test/testmortarpoisson.cc:156-244 (MortarPoissonCoupling::alpha_generic<sign>): sign = +1 works on the inside element
+// (alpha_enriched_coupling_first :131-139), sign = -1 on the outside element (_second :143-151).  Both use the unit outer
+// normal of the INSIDE element (:198) and the mortar basis at the face-local quadrature point (:204).
+void EnrichedOperator::alpha_generic(int sign, const IG& ig, const LFS& lfsu, const double* x, const LFS& lfsv, const LFS& lfsu_c,
+                                     const double* x_c, const LFS& lfsv_c, LocalVectorView& r, LocalVectorView& r_c) const
+{
+  const int dim = ig.dim();
+  const double gamma = gamma_0 / ig.integrationElement();                 // :191, [UPSTREAM] volume() of an axis-aligned face
+  const int qorder = 2 * std::max(lfsu.k, lfsu_c.k);                      // :193-195, [UPSTREAM] QkLocalBasis::order() = k
+  QkBasis B(lfsu.k, dim), Bc(lfsu_c.k, dim - 1);
+  const auto& rule = tensor_rule(dim - 1, qorder);
+  const EG& elem = sign > 0 ? ig.inside : ig.outside;
+  double v[MAXLOC], mu[MAXLOC], js[MAXLOC][3], gradv[MAXLOC][3], element_pos[3], normal[3];
+  for (const auto& q : rule) {
+    if (sign > 0) ig.localInside(q.x, element_pos); else ig.localOutside(q.x, element_pos);
+    ig.unitOuterNormal(normal);
+    B.evaluateFunction(element_pos, v);
+    Bc.evaluateFunction(q.x, mu);
+    B.evaluateJacobian(element_pos, js);
+    for (int i = 0; i < lfsu.n; ++i)
+      for (int d = 0; d < dim; ++d) { gradv[i][d] = 0.0; gradv[i][d] += elem.jacInvT(d) * js[i][d]; }
+    double u = 0.0, gradu[3] = {0, 0, 0};
+    for (int i = 0; i < lfsu.n; ++i) {
+      u += x[lfsu.idx[i]] * v[i];
+      for (int d = 0; d < dim; ++d) gradu[d] += x[lfsu.idx[i]] * gradv[i][d];
+    }
+    double lambda = 0.0;
+    for (int i = 0; i < lfsu_c.n; ++i) lambda += x_c[lfsu_c.idx[i]] * mu[i];
+    const double factor = q.w * ig.integrationElement();
+    double ngu = 0.0; for (int d = 0; d < dim; ++d) ngu += normal[d] * gradu[d];
+    for (int i = 0; i < lfsu.n; ++i) {
+      double ngv = 0.0; for (int d = 0; d < dim; ++d) ngv += normal[d] * gradv[i][d];
+      r.accumulate(lfsv, i, (-ngu * v[i] - (u - lambda) * ngv + 2 * gamma * (u - lambda) * v[i]) * factor);
+    }
+    for (int i = 0; i < lfsu_c.n; ++i)
+      r_c.accumulate(lfsv_c, i, (ngu - 2 * gamma * (u - lambda)) * mu[i] * factor);
+  }
+}
+
+// couplingutilities.hh:305-388 / :404-484 (NumericalJacobianEnrichedCouplingTo{First,Second}SubProblem; the two differ only
+// in which alpha_enriched_coupling_* they call).  MDB_JAC_ANALYTIC: the operator is linear in (u, lambda), column j = alpha(e_j).
+void EnrichedOperator::jacobian_generic(int sign, const IG& ig, const LFS& lfsu, const double* x, int nx, const LFS& lfsv,
+                                        const LFS& lfsu_c, const double* x_c, int nxc, const LFS& lfsv_c, LocalMatrixView& mat_ss,
+                                        LocalMatrixView& mat_sc, LocalMatrixView& mat_cs, LocalMatrixView& mat_cc) const
+{
+  const int m_s = lfsv.n, m_c = lfsv_c.n, n_s = lfsu.n, n_c = lfsu_c.n;
+  std::vector<double> u_s(x, x + nx), u_c(x_c, x_c + nxc);
+  std::vector<double> down_s(nx, 0.0), up_s(nx, 0.0), down_c(std::max(nxc, 1), 0.0), up_c(std::max(nxc, 1), 0.0);
+  LocalVectorView dv_s{down_s.data(), 1.0}, uv_s{up_s.data(), 1.0}, dv_c{down_c.data(), 1.0}, uv_c{up_c.data(), 1.0};
+  const bool analytic = jac_mode == MDB_JAC_ANALYTIC;
+  if (analytic) { std::fill(u_s.begin(), u_s.end(), 0.0); std::fill(u_c.begin(), u_c.end(), 0.0); }
+  else alpha_generic(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, dv_s, dv_c);     // base line
+  for (int j = 0; j < n_s; ++j) {                                                                      // jiggle in self
+    std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_c.begin(), up_c.end(), 0.0);
+    double& uj = u_s[lfsu.idx[j]];
+    const double keep = uj;
+    const double delta = analytic ? 1.0 : epsilon * (1.0 + std::abs(uj));
+    uj += delta;
+    alpha_generic(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, uv_s, uv_c);
+    for (int i = 0; i < m_s; ++i) mat_ss.accumulate(lfsv, i, lfsu, j, (up_s[lfsv.idx[i]] - down_s[lfsv.idx[i]]) / delta);
+    for (int i = 0; i < m_c; ++i) mat_cs.accumulate(lfsv_c, i, lfsu, j, (up_c[lfsv_c.idx[i]] - down_c[lfsv_c.idx[i]]) / delta);
+    uj = keep;
+  }
+  for (int j = 0; j < n_c; ++j) {                                                                      // jiggle in coupling
+    std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_c.begin(), up_c.end(), 0.0);
+    double& uj = u_c[lfsu_c.idx[j]];
+    const double keep = uj;
+    const double delta = analytic ? 1.0 : epsilon * (1.0 + std::abs(uj));
+    uj += delta;
+    alpha_generic(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, uv_s, uv_c);
+    for (int i = 0; i < m_s; ++i) mat_sc.accumulate(lfsv, i, lfsu_c, j, (up_s[lfsv.idx[i]] - down_s[lfsv.idx[i]]) / delta);
+    for (int i = 0; i < m_c; ++i) mat_cc.accumulate(lfsv_c, i, lfsu_c, j, (up_c[lfsv_c.idx[i]] - down_c[lfsv_c.idx[i]]) / delta);
+    uj = keep;
+  }
+}
+
 std::unique_ptr<LocalOperator> make_local_operator(int op_id, const void* params, size_t nbytes)
 {
   switch (op_id) {
@@ -371,8 +447,28 @@ void Context::finalize()
     int64_t total = 1;
     for (int d = 0; d < 3; ++d) { ch.lat_n[d] = (d < dim) ? k * g.n[d] + 1 : 1; total *= ch.lat_n[d]; }
     std::vector<uint8_t> present(total, 0);
+    // coupling space (couplinggfsordering.hh:113-201): the used entities are the vertices of the intersections the
+    // predicate accepts; entity_dof_offsets is indexed by the MultiDomainGrid vertex index, so after the partial sum the
+    // DOFs are numbered by ascending vertex index — the same rule as the k = 1 branch below.
+    if (ch.iface) {
+      if (k != 1) throw std::runtime_error("oracle: coupling spaces are restated for Q1 only");
+      for (int64_t c = 0; c < g.ncells(); ++c) {
+        int64_t ijk[3]; g.cell_ijk(c, ijk);
+        for (int f = 0; f < 2 * dim; ++f) {
+          int a = f / 2, sgn = f % 2; int64_t nijk[3] = {ijk[0], ijk[1], ijk[2]};
+          nijk[a] += sgn ? 1 : -1;
+          if (nijk[a] < 0 || nijk[a] >= g.n[a]) continue;                          // !is.neighbor()
+          if (!iface_applies(ch, cell_sd[c], cell_sd[g.cell_index(nijk)])) continue;
+          for (int i = 0; i < (1 << (dim - 1)); ++i) {
+            int64_t v[3] = {ijk[0], ijk[1], ijk[2]}; int t = 0;
+            for (int d = 0; d < dim; ++d) { if (d == a) v[d] += sgn; else { v[d] += (i >> t) & 1; ++t; } }
+            present[v[0] + ch.lat_n[0] * (v[1] + ch.lat_n[1] * v[2])] = 1;
+          }
+        }
+      }
+    }
     // closure of the cells of the child's grid view
-    for (int64_t c = 0; c < g.ncells(); ++c) {
+    for (int64_t c = 0; c < g.ncells() && !ch.iface; ++c) {
       if (ch.subdomain >= 0 && !((cell_sd[c] >> ch.subdomain) & 1)) continue;
       int64_t ijk[3]; g.cell_ijk(c, ijk);
       int a[3];
@@ -419,6 +515,7 @@ int Context::bind(int64_t cell, int* child_off, int64_t* dofs) const
   for (size_t c = 0; c < children.size(); ++c) {
     const ChildSpace& ch = children[c];
     child_off[c] = n;
+    if (ch.iface) continue;      // bound per intersection (globalassembler.hh:212-231), not per cell
     if (ch.subdomain >= 0 && !((cell_sd[cell] >> ch.subdomain) & 1)) continue;
     const int k = ch.k, nl = ch.nloc(dim);
     for (int i = 0; i < nl; ++i) {
@@ -429,6 +526,37 @@ int Context::bind(int64_t cell, int* child_off, int64_t* dofs) const
   }
   child_off[children.size()] = n;
   return n;
+}
+
+bool Context::iface_applies(const ChildSpace& ch, uint8_t sd_in, uint8_t sd_out) const
+{
+  // SubProblemSubProblemInterface::operator() couplinggridfunctionspace.hh:29-35
+  auto cond = [](int kind, uint32_t mask, uint8_t sd) {
+    return kind == MDB_COND_EQUALITY ? uint32_t(sd) == mask : (uint32_t(sd) & mask) == mask;
+  };
+  return cond(ch.lkind, ch.lmask, sd_in) && cond(ch.rkind, ch.rmask, sd_out);
+}
+
+int Context::bind_coupling(int child, int64_t cell, int f, int64_t* dofs) const
+{
+  // couplinglocalfunctionspace.hh:208-287: local DOF i <-> corner i of the intersection (Q1 on the face), mapped to the
+  // inside element's vertex by DOFMapper::mapSubIndex (dofmapper.hh:37-50).  [UPSTREAM] Yasp: corner i of face (axis, side)
+  // has bit t of i = coordinate along the t-th axis other than `axis`.
+  const ChildSpace& ch = children[child];
+  const int dim = grid.dim;
+  int64_t ijk[3]; grid.cell_ijk(cell, ijk);
+  const int a = f / 2, sgn = f % 2;
+  int64_t nijk[3] = {ijk[0], ijk[1], ijk[2]};
+  nijk[a] += sgn ? 1 : -1;
+  if (nijk[a] < 0 || nijk[a] >= grid.n[a]) return 0;
+  if (!iface_applies(ch, cell_sd[cell], cell_sd[grid.cell_index(nijk)])) return 0;     // !gfs.contains(is)
+  const int nl = 1 << (dim - 1);
+  for (int i = 0; i < nl; ++i) {
+    int64_t v[3] = {ijk[0], ijk[1], ijk[2]}; int t = 0;
+    for (int d = 0; d < dim; ++d) { if (d == a) v[d] += sgn; else { v[d] += (i >> t) & 1; ++t; } }
+    dofs[i] = ch.offset + ch.lat2dof[v[0] + ch.lat_n[0] * (v[1] + ch.lat_n[1] * v[2])];
+  }
+  return nl;
 }
 
 LFS Context::subproblem_lfs(const SubProblem& sp, const int* child_off) const
@@ -475,17 +603,21 @@ Flags engine_flags(const Context& c, const GridOperatorDesc& go, Mode mode)
     a_skel |= l.doAlphaSkeleton; a_bnd |= l.doAlphaBoundary; l_skel |= l.doLambdaSkeleton; l_bnd |= l.doLambdaBoundary;
     two |= l.doSkeletonTwoSided; p_skel |= l.doPatternSkeleton;
   }
-  for (int k : go.cps) { a_coup |= c.cps[k].op->doAlphaCoupling; p_coup |= c.cps[k].op->doPatternCoupling; }
+  bool enr = false;                // do{Alpha,Pattern}EnrichedCouplingToSubProblems: all true for the restated mortar operator
+  for (int k : go.cps) {
+    if (c.cps[k].eop) { enr = true; continue; }
+    a_coup |= c.cps[k].op->doAlphaCoupling; p_coup |= c.cps[k].op->doPatternCoupling;
+  }
   Flags f;
   if (mode == PATTERN) {           // patternassemblerengine.hh:96-139
-    f.visit_faces = p_skel || p_coup;
-    f.two_sided = p_coup || two;
+    f.visit_faces = p_skel || p_coup || enr;
+    f.two_sided = p_coup || two || enr;
   } else if (mode == JACOBIAN) {   // jacobianassemblerengine.hh:149-192
-    f.visit_faces = a_skel || a_bnd || a_coup;
-    f.two_sided = a_bnd || two || a_coup;
+    f.visit_faces = a_skel || a_bnd || a_coup || enr;
+    f.two_sided = a_bnd || two || a_coup || enr;
   } else {                         // residualassemblerengine.hh:117-188
-    f.visit_faces = a_skel || a_bnd || a_coup || l_skel || l_bnd;
-    f.two_sided = a_bnd || l_bnd || two || a_coup;
+    f.visit_faces = a_skel || a_bnd || a_coup || l_skel || l_bnd || enr;
+    f.two_sided = a_bnd || l_bnd || two || a_coup || enr;
   }
   return f;
 }
@@ -525,6 +657,20 @@ int Context::matrix_create(const int* gos_, int ngos)
         bind(ncell, off_n.data(), dofs_n);
         for (int k : go.cps) {
           const Coupling& cp = cps[k];
+          if (cp.eop) {                                                        // invoke_pattern_enriched_coupling :116-150
+            const SubProblem& lsp = sps[cp.local_sp]; const SubProblem& rsp = sps[cp.remote_sp];
+            if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
+            LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
+            int64_t dofs_c[MAXLOC];
+            const int nc = bind_coupling(cp.coupling_child, cell, f, dofs_c);
+            // FullEnrichedCoupling{First,Second}SubProblemPattern + FullEnrichedCouplingPattern couplingutilities.hh:219-286
+            for (int i = 0; i < ls.n; ++i) for (int j = 0; j < nc; ++j) rows[dofs_s[ls.idx[i]]].push_back(dofs_c[j]);
+            for (int i = 0; i < nc; ++i) for (int j = 0; j < ls.n; ++j) rows[dofs_c[i]].push_back(dofs_s[ls.idx[j]]);
+            for (int i = 0; i < ln.n; ++i) for (int j = 0; j < nc; ++j) rows[dofs_n[ln.idx[i]]].push_back(dofs_c[j]);
+            for (int i = 0; i < nc; ++i) for (int j = 0; j < ln.n; ++j) rows[dofs_c[i]].push_back(dofs_n[ln.idx[j]]);
+            for (int i = 0; i < nc; ++i) for (int j = 0; j < nc; ++j) rows[dofs_c[i]].push_back(dofs_c[j]);
+            continue;
+          }
           if (!cp.op->doPatternCoupling) continue;
           const SubProblem& lsp = sps[cp.local_sp]; const SubProblem& rsp = sps[cp.remote_sp];
           if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;     // coupling.hh:78-83
@@ -598,7 +744,7 @@ void Context::residual(int goi, double weight, const double* x, double* r) const
           }
           for (int k : go.cps) {
             const Coupling& cp = cps[k];
-            if (!cp.op->doAlphaCoupling) continue;
+            if (cp.eop || !cp.op->doAlphaCoupling) continue;
             const SubProblem& lsp = sps[cp.local_sp]; const SubProblem& rsp = sps[cp.remote_sp];
             if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
             LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
@@ -613,6 +759,23 @@ void Context::residual(int goi, double weight, const double* x, double* r) const
               LFS l = subproblem_lfs(sp, off_s.data());
               sp.lop->lambda_boundary(ig, l, rv_s);
             }
+          }
+          // assembleUVEnrichedCoupling (globalassembler.hh:210-238; alpha_enriched_coupling functor :219-257): the mortar
+          // space is bound to the intersection, first works on (inside, mortar), second on (outside, mortar)
+          for (int k : go.cps) {
+            const Coupling& cp = cps[k];
+            if (!cp.eop) continue;
+            const SubProblem& lsp = sps[cp.local_sp]; const SubProblem& rsp = sps[cp.remote_sp];
+            if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
+            LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
+            int64_t dofs_c[MAXLOC]; double x_c[MAXLOC], r_c[MAXLOC];
+            LFS lc; lc.k = children[cp.coupling_child].k;
+            lc.n = bind_coupling(cp.coupling_child, cell, f, dofs_c);
+            for (int i = 0; i < lc.n; ++i) { lc.idx[i] = i; x_c[i] = x[dofs_c[i]]; r_c[i] = 0.0; }
+            LocalVectorView rv_c{r_c, weight};
+            cp.eop->alpha_generic(+1, ig, ls, x_s, ls, lc, x_c, lc, rv_s, rv_c);
+            cp.eop->alpha_generic(-1, ig, ln, x_n, ln, lc, x_c, lc, rv_n, rv_c);
+            for (int i = 0; i < lc.n; ++i) r[dofs_c[i]] += r_c[i];           // onUnbindLFSVCoupling
           }
           for (int i = 0; i < nn; ++i) r[dofs_n[i]] += r_n[i];           // onUnbindLFSVOutside
         } else {
@@ -684,7 +847,7 @@ void jacobian_cell(const Context& c, const GridOperatorDesc& go, const Flags& fl
       bool any = false;
       for (int k : go.cps) {
         const Coupling& cp = c.cps[k];
-        if (cp.op->doAlphaCoupling && c.sps[cp.local_sp].appliesTo(eg.sd) && c.sps[cp.remote_sp].appliesTo(en.sd)) any = true;
+        if ((cp.eop || cp.op->doAlphaCoupling) && c.sps[cp.local_sp].appliesTo(eg.sd) && c.sps[cp.remote_sp].appliesTo(en.sd)) any = true;
       }
       if (!any) continue;      // the reference binds lfs_n and scatters all-zero blocks here; no effect on values
       IG ig; ig.inside = eg; ig.outside = en; ig.axis = f / 2; ig.side = f % 2; ig.face = f; ig.boundary = false;
@@ -697,11 +860,34 @@ void jacobian_cell(const Context& c, const GridOperatorDesc& go, const Flags& fl
       LocalMatrixView m_sn{S.a_sn.data(), nn, weight}, m_ns{S.a_ns.data(), ns, weight}, m_nn{S.a_nn.data(), nn, weight};
       for (int k : go.cps) {                              // invoke_jacobian_coupling :91-117
         const Coupling& cp = c.cps[k];
-        if (!cp.op->doAlphaCoupling) continue;
+        if (cp.eop || !cp.op->doAlphaCoupling) continue;
         const SubProblem& lsp = c.sps[cp.local_sp]; const SubProblem& rsp = c.sps[cp.remote_sp];
         if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
         LFS ls = c.subproblem_lfs(lsp, S.off_s.data()), ln = c.subproblem_lfs(rsp, S.off_n.data());
         cp.op->jacobian_coupling(ig, ls, S.x_s, ns, ls, ln, S.x_n, nn, ln, m_ss, m_sn, m_ns, m_nn);
+      }
+      for (int k : go.cps) {                              // invoke_jacobian_enriched_coupling :121-158
+        const Coupling& cp = c.cps[k];
+        if (!cp.eop) continue;
+        const SubProblem& lsp = c.sps[cp.local_sp]; const SubProblem& rsp = c.sps[cp.remote_sp];
+        if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
+        LFS ls = c.subproblem_lfs(lsp, S.off_s.data()), ln = c.subproblem_lfs(rsp, S.off_n.data());
+        int64_t dofs_c[MAXLOC]; double x_c[MAXLOC];
+        LFS lc; lc.k = c.children[cp.coupling_child].k;
+        lc.n = c.bind_coupling(cp.coupling_child, cell, f, dofs_c);
+        const int ncl = lc.n;
+        for (int i = 0; i < ncl; ++i) { lc.idx[i] = i; x_c[i] = x[dofs_c[i]]; }
+        std::vector<double> a_cc(ncl * ncl, 0.0), a_sc(ns * ncl, 0.0), a_cs(ncl * ns, 0.0), a_nc(nn * ncl, 0.0), a_cn(ncl * nn, 0.0);
+        LocalMatrixView m_cc{a_cc.data(), ncl, weight}, m_sc{a_sc.data(), ncl, weight}, m_cs{a_cs.data(), ns, weight},
+                        m_nc{a_nc.data(), ncl, weight}, m_cn{a_cn.data(), nn, weight};
+        cp.eop->jacobian_generic(+1, ig, ls, S.x_s, ns, ls, lc, x_c, ncl, lc, m_ss, m_sc, m_cs, m_cc);
+        cp.eop->jacobian_generic(-1, ig, ln, S.x_n, nn, ln, lc, x_c, ncl, lc, m_nn, m_nc, m_cn, m_cc);
+        // onUnbindLFSUVCoupling: cc, sc, cs, nc, cn (jacobianassemblerengine.hh:332-377)
+        scatter(A, dofs_c, ncl, dofs_c, ncl, a_cc.data(), true);
+        scatter(A, S.dofs_s, ns, dofs_c, ncl, a_sc.data(), true);
+        scatter(A, dofs_c, ncl, S.dofs_s, ns, a_cs.data(), true);
+        scatter(A, S.dofs_n, nn, dofs_c, ncl, a_nc.data(), true);
+        scatter(A, dofs_c, ncl, S.dofs_n, nn, a_cn.data(), true);
       }
       // onUnbindLFSUVOutside: nn, sn, ns (jacobianassemblerengine.hh:296-330)
       scatter(A, S.dofs_n, nn, S.dofs_n, nn, S.a_nn.data(), true);
@@ -1043,6 +1229,30 @@ int orc_add_coupling(Context* c, int op_id, const void* params, size_t nbytes, i
   try {
     orc::Coupling cp; cp.op = orc::make_coupling_operator(op_id, params, nbytes, jac_mode);
     cp.local_sp = local_sp; cp.remote_sp = remote_sp;
+    c->cps.push_back(std::move(cp));
+    return (int)c->cps.size() - 1;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_add_coupling_space(Context* c, int fe_kind, int lkind, uint32_t lmask, int rkind, uint32_t rmask)
+{
+  try {
+    if (fe_kind != MDB_FE_Q1) throw std::runtime_error("coupling spaces: Q1 only");
+    orc::ChildSpace ch; ch.fe_kind = fe_kind; ch.subdomain = -1; ch.k = 1;
+    ch.iface = true; ch.lkind = lkind; ch.lmask = lmask; ch.rkind = rkind; ch.rmask = rmask;
+    c->children.push_back(ch);
+    return (int)c->children.size() - 1;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_add_enriched_coupling(Context* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp,
+                              int coupling_child, int jac_mode)
+{
+  try {
+    if (op_id != MDB_OP_MORTAR_POISSON_COUPLING || nbytes != sizeof(mdb_mortar_params)) throw std::runtime_error("unknown enriched coupling operator");
+    if (coupling_child < 0 || coupling_child >= (int)c->children.size() || !c->children[coupling_child].iface)
+      throw std::runtime_error("coupling_child is not a coupling space");
+    orc::Coupling cp; cp.eop.reset(new orc::EnrichedOperator());
+    cp.eop->gamma_0 = static_cast<const mdb_mortar_params*>(params)->gamma_0; cp.eop->jac_mode = jac_mode;
+    cp.local_sp = local_sp; cp.remote_sp = remote_sp; cp.coupling_child = coupling_child;
     c->cps.push_back(std::move(cp));
     return (int)c->cps.size() - 1;
   } catch (std::exception& e) { c->err = e.what(); return -1; }

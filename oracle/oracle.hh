@@ -281,6 +281,20 @@ struct CouplingOperator {
                          LocalMatrixView& mat_ns, LocalMatrixView& mat_nn) const;
 };
 
+// enriched (mortar) coupling operator: test/testmortarpoisson.cc:117-250 + couplingutilities.hh:288-484
+struct EnrichedOperator {
+  double gamma_0 = 1.0;
+  double epsilon = 1e-8;       // NumericalJacobianEnrichedCouplingTo{First,Second}SubProblem default
+  int jac_mode = MDB_JAC_FD_BITMATCH;
+  // alpha_generic<sign>: sign = +1 first (inside element), -1 second (outside element)
+  void alpha_generic(int sign, const IG& ig, const LFS& lfsu, const double* x, const LFS& lfsv, const LFS& lfsu_c, const double* x_c,
+                     const LFS& lfsv_c, LocalVectorView& r, LocalVectorView& r_c) const;
+  // jacobian_enriched_coupling_first / _second (identical algorithm, couplingutilities.hh:305-388 / :404-484)
+  void jacobian_generic(int sign, const IG& ig, const LFS& lfsu, const double* x, int nx, const LFS& lfsv, const LFS& lfsu_c,
+                        const double* x_c, int nxc, const LFS& lfsv_c, LocalMatrixView& mat_ss, LocalMatrixView& mat_sc,
+                        LocalMatrixView& mat_cs, LocalMatrixView& mat_cc) const;
+};
+
 std::unique_ptr<LocalOperator> make_local_operator(int op_id, const void* params, size_t nbytes);
 std::unique_ptr<CouplingOperator> make_coupling_operator(int op_id, const void* params, size_t nbytes, int jac_mode);
 
@@ -289,6 +303,8 @@ std::unique_ptr<CouplingOperator> make_coupling_operator(int op_id, const void* 
 // ---------------------------------------------------------------------------------------------
 struct ChildSpace {
   int fe_kind; int k; int subdomain;           // subdomain -1: MultiDomainGrid view
+  // coupling (mortar) space on the interface faces inside in L / outside in R (couplinggridfunctionspace.hh:14-44)
+  bool iface = false; int lkind = 0, rkind = 0; uint32_t lmask = 0, rmask = 0;
   int64_t lat_n[3];                             // lattice points per axis = k*n+1
   std::vector<int64_t> lat2dof;                 // lattice point -> index within the child block, -1 absent
   std::vector<int64_t> dof2lat;
@@ -309,6 +325,8 @@ struct SubProblem {
 struct Coupling {
   std::unique_ptr<CouplingOperator> op;
   int local_sp, remote_sp;
+  std::unique_ptr<EnrichedOperator> eop;       // EnrichedCoupling (coupling.hh:123-192): op is null
+  int coupling_child = -1;
 };
 
 struct GridOperatorDesc { std::vector<int> sps, cps; };
@@ -346,6 +364,9 @@ struct Context {
   // MultiDomainLocalFunctionSpace::bind(e): children offsets in the cell-local vector + container indices
   int bind(int64_t cell, int* child_off /*nchildren+1*/, int64_t* dofs) const;
   LFS subproblem_lfs(const SubProblem& sp, const int* child_off) const;
+  // CouplingLocalFunctionSpace::bind(intersection): the mortar DOFs of face f of `cell` in face-local order; returns their number
+  int bind_coupling(int child, int64_t cell, int f, int64_t* dofs) const;
+  bool iface_applies(const ChildSpace& ch, uint8_t sd_in, uint8_t sd_out) const;
 
   void constraints_assemble(const int* sps_, const mdb_bctype* bcs, int n);
   void interpolate(const int* sps_, const mdb_function* fns, int n, double t, double* x) const;

@@ -33,6 +33,9 @@ CASES = {
     # the reference's shipped driver as it stands: Q1 on the left subdomain, Q2 on the right (test/testpoisson.cc:168-198), "4 2.0"
     "p2d_16x16_q1q2": ((16, 16), dict(intensity=2.0, fe=(capi.FE_Q1, capi.FE_Q2))),
     "p3d_3x4x3_q2q1": ((3, 4, 3), dict(intensity=2.0, fe=(capi.FE_Q2, capi.FE_Q1))),
+    # test/testmortarpoisson.cc as shipped ("5 1.0": 32x32 cells, Q1 | Q1 | Q1 mortar space, 1155 DOFs) and a 3-D Q1|Q2 variant
+    "p2d_32x32_mortar": ((32, 32), dict(problem="mortar", gamma_0=1.0)),
+    "p3d_4x3x3_mortar_q1q2": ((4, 3, 3), dict(problem="mortar", gamma_0=2.5, fe=(capi.FE_Q1, capi.FE_Q2))),
 }
 
 
@@ -74,7 +77,9 @@ def main():
         if os.path.exists(os.path.join(HERE, name + ".npz")) and "--all" not in sys.argv:
             continue                                    # frozen fixtures are not regenerated unless asked for
         o = orc.Oracle()
-        P = problems.testpoisson(o, n, **kw)
+        kw = dict(kw)
+        problem = kw.pop("problem", "poisson")
+        P = problems.testmortarpoisson(o, n, **kw) if problem == "mortar" else problems.testpoisson(o, n, **kw)
         ptr, dofs = o.get_dofmap()
         rp, ci = o.matrix_get_pattern(P.mat)
         u = np.zeros(P.ndof)
@@ -92,9 +97,9 @@ def main():
         z = np.zeros(P.ndof)
         o.solve(P.mat, r, z, reduction=1e-13)
         # independent check of the volume rows: rows that are neither constrained nor touched by the coupling
-        split = kw.get("split_axis", 1)
+        split = kw.get("split_axis", 0 if problem == "mortar" else 1)
         fe = kw.get("fe", (capi.FE_Q1, capi.FE_Q1))
-        if n[split] % 2 == 0 and fe == (capi.FE_Q1, capi.FE_Q1):
+        if n[split] % 2 == 0 and fe == (capi.FE_Q1, capi.FE_Q1) and problem == "poisson":
             K = kron_volume(n, split)
             A = sp.csr_matrix((vals, ci, rp), shape=(P.ndof, P.ndof))
             con = o.get_constraints().astype(bool)
@@ -109,7 +114,8 @@ def main():
             assert err < 1e-13, (name, err)
             print("%s: Kronecker volume check on %d rows, max diff %.2e" % (name, int(free.sum()), err))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), n=np.array(n), split_axis=split, intensity=kw.get("intensity", 2.0),
-                            coupling=kw.get("coupling", capi.OP_CVCF_COUPLING), fe=np.array(fe), ndof=P.ndof, ncon=P.ncon,
+                            coupling=kw.get("coupling", capi.OP_MORTAR_POISSON_COUPLING if problem == "mortar" else capi.OP_CVCF_COUPLING),
+                            gamma_0=kw.get("gamma_0", 0.0), child_offsets=o.get_child_offsets(), fe=np.array(fe), ndof=P.ndof, ncon=P.ncon,
                             cell_ptr=ptr, cell_dofs=dofs, constrained=o.get_constraints(), rowptr=rp, colidx=ci, u=u,
                             jac_at_u=vals, res_at_u=r, x_rand=xr, jac_at_rand=vals_rand, res_at_rand=rr, solution_z=z)
         print("%s: ndof %d ncon %d nnz %d" % (name, P.ndof, P.ncon, len(ci)))

@@ -95,6 +95,39 @@ def dirichlet_neumann_q1(api, n):
     return testpoisson(api, n, intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE))
 
 
+def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE_Q1), jac_mode=capi.JAC_FD_BITMATCH, sd_bits=None):
+    """test/testmortarpoisson.cc:281-432 (BASELINE configs[3]; 2-D refine 5 as shipped, dim = len(n) for the synthetic 3-D
+    form): subdomains x0 < 0.5 -> 0, x0 > 0.5 -> 1 (:325-330), a Q1 space on each (:359-362), a Q1 mortar space
+    on the interface faces inside in {0} / outside in {1} as the LAST child (:365-384), Poisson(f,b,j,4) on both sides
+    (:400-401; f = 0, :38), EnrichedCoupling<SubProblem0,SubProblem1,MortarPoissonCoupling,2>(gamma_0) (:411-412)."""
+    dim = len(n)
+    api.mesh_structured(n)
+    if sd_bits is None:
+        api.subdomains_halfspace(split_axis, 0.5, 0, 1)
+    else:
+        api.subdomains(sd_bits)
+    c0 = api.add_space(fe[0], 0)
+    c1 = api.add_space(fe[1], 1)
+    cc = api.add_coupling_space(capi.FE_Q1, (capi.COND_EQUALITY, 1 << 0), (capi.COND_EQUALITY, 1 << 1))
+    pp = capi.PoissonParams()
+    pp.f = capi.Function(capi.FN_ZERO)
+    pp.bc = capi.BCType(capi.BC_TESTPOISSON)
+    pp.j = capi.Function(capi.FN_TESTPOISSON_J)
+    pp.quad_order = 4
+    left = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 0, [c0])
+    right = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 1, [c1])
+    mp = capi.MortarParams()
+    mp.gamma_0 = gamma_0
+    cp = api.add_enriched_coupling(capi.OP_MORTAR_POISSON_COUPLING, mp, left, right, cc, jac_mode)
+    ndof = api.finalize()
+    ncon = api.constraints_assemble([left, right], [pp.bc, pp.bc])
+    go = api.gridoperator_create([left, right], [cp])
+    mat = api.matrix_create([go])
+    g = capi.gauss()
+    return SimpleNamespace(dim=dim, ndof=ndof, ncon=ncon, go=go, mat=mat, left=left, right=right, cp=cp, g=g, sps=[left, right],
+                           gfn=[g, g], bc=pp.bc, children=(c0, c1, cc))
+
+
 def instationary(api, n, k=2.0, split_axis=0):
     """BASELINE configs[2] in the form the reference's live code supports (SURVEY M3 / §8d reality check 3):
     test/testinstationarypoisson.cc:225-305 — dt0 operator = Poisson (stiffness + source + Neumann) on both subdomains plus

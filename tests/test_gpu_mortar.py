@@ -1,0 +1,146 @@
+"""Parity of the CUDA enriched-coupling (mortar) path against the CPU oracle — SURVEY §8 a11, BASELINE configs[3]
+(test/testmortarpoisson.cc: Q1 | Q1 | Q1 mortar space on the interface, MortarPoissonCoupling, FD Jacobians).
+Bars as everywhere: DOF map / constraints / pattern bit-exact, entries 1e-12, solutions 1e-10."""
+import importlib
+
+import numpy as np
+import pytest
+
+import orc
+import problems
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("dune-multidomain_b200")
+capi = pkg.capi
+
+RTOL_ENTRY = 1e-12
+RTOL_SOLUTION = 1e-10
+
+
+def _stairs(n):
+    """A non-planar interface: subdomain 1 = cells right of a staircase in the (x0, x1) plane."""
+    idx = np.indices(n[::-1])[::-1]            # idx[d] = cell coordinate along axis d, array in (.., x1, x0) order
+    right = idx[0] >= n[0] // 2 + (idx[1] % 3) - 1
+    return np.where(right, 2, 1).astype(np.uint8).ravel()
+
+
+CASES = {
+    "m2d_shipped_32": dict(n=(32, 32)),                                    # testmortarpoisson "5 1.0"
+    "m2d_ragged": dict(n=(10, 7), gamma_0=3.0),
+    "m2d_split_y": dict(n=(6, 12), split_axis=1),
+    "m2d_q1q2": dict(n=(8, 8), fe=(capi.FE_Q1, capi.FE_Q2)),
+    "m2d_q2q2": dict(n=(6, 4), fe=(capi.FE_Q2, capi.FE_Q2), gamma_0=0.5),
+    "m2d_analytic": dict(n=(12, 8), jac_mode=capi.JAC_ANALYTIC),
+    "m3d_8": dict(n=(8, 8, 8)),
+    "m3d_ragged_split_z": dict(n=(5, 6, 4), split_axis=2, gamma_0=2.0),
+    "m3d_q2q1": dict(n=(4, 3, 3), fe=(capi.FE_Q2, capi.FE_Q1)),
+    "m2d_stairs": dict(n=(12, 9), sd_bits="stairs"),
+    "m3d_stairs": dict(n=(8, 6, 3), sd_bits="stairs"),
+}
+
+
+def _pair(case):
+    kw = dict(CASES[case])
+    if kw.get("sd_bits") == "stairs":
+        kw["sd_bits"] = _stairs(kw["n"])
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    return dev, ora, problems.testmortarpoisson(dev, **kw), problems.testmortarpoisson(ora, **kw)
+
+
+@pytest.fixture(params=sorted(CASES))
+def pair(request):
+    dev, ora, Pd, Po = _pair(request.param)
+    yield dev, ora, Pd, Po
+    dev.close(); ora.close()
+
+
+def _x(ora, Po, kind):
+    if kind == "g":
+        u = np.zeros(Po.ndof)
+        ora.interpolate(Po.sps, Po.gfn, u)
+        return u
+    return np.random.default_rng(0).uniform(-1, 1, Po.ndof)
+
+
+def test_dofmap_constraints_pattern_bit_exact(pair):
+    dev, ora, Pd, Po = pair
+    assert Pd.ndof == Po.ndof and Pd.ncon == Po.ncon
+    assert np.array_equal(dev.get_child_offsets(), ora.get_child_offsets())
+    pd_, dd = dev.get_dofmap(); po, do = ora.get_dofmap()
+    assert np.array_equal(pd_, po) and np.array_equal(dd, do)
+    assert np.array_equal(dev.get_constraints(), ora.get_constraints())
+    assert dev.nnz[Pd.mat] == ora.nnz[Po.mat]
+    rd, cd = dev.matrix_get_pattern(Pd.mat); ro, co = ora.matrix_get_pattern(Po.mat)
+    assert np.array_equal(rd, ro) and np.array_equal(cd, co)
+
+
+@pytest.mark.parametrize("xkind", ["g", "random"])
+def test_jacobian_entries(pair, xkind):
+    dev, ora, Pd, Po = pair
+    x = _x(ora, Po, xkind)
+    dev.jacobian(Pd.go, Pd.mat, x, overwrite=True)
+    ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+    dev.jacobian(Pd.go, Pd.mat, x, weight=0.5, overwrite=False)           # additive, weighted (gridoperator.hh:94-97)
+    ora.jacobian(Po.go, Po.mat, x, weight=0.5, overwrite=False)
+    vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+
+
+@pytest.mark.parametrize("xkind", ["g", "random"])
+def test_residual_entries(pair, xkind):
+    dev, ora, Pd, Po = pair
+    x = _x(ora, Po, xkind)
+    rd, ro = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.residual(Pd.go, x, rd); ora.residual(Po.go, x, ro)
+    ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    A = ora.csr(Po.mat)
+    scale = abs(A) @ np.abs(x) + np.abs(ro)
+    scale = np.maximum(scale, np.abs(ro).max() * 1e-3)
+    assert np.all(np.abs(rd - ro) <= RTOL_ENTRY * scale)
+    rd2, ro2 = rd.copy(), ro.copy()
+    dev.residual(Pd.go, x, rd2, weight=0.25); ora.residual(Po.go, x, ro2, weight=0.25)
+    assert np.all(np.abs(rd2 - ro2) <= 2 * RTOL_ENTRY * scale)
+
+
+def test_spmv(pair):
+    dev, ora, Pd, Po = pair
+    x = _x(ora, Po, "random")
+    dev.jacobian(Pd.go, Pd.mat, x, overwrite=True); ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    yd, yo = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.spmv(Pd.mat, x, yd); ora.spmv(Po.mat, x, yo)
+    A = ora.csr(Po.mat)
+    assert np.all(np.abs(yd - yo) <= 1e-13 * (abs(A) @ np.abs(x) + 1e-300))
+
+
+def test_stationary_solve_bcgs_ssor(pair):
+    """pdesolver.apply(u) of testmortarpoisson.cc:456-463: ISTLBackend_SEQ_BCGS_SSOR (BiCGSTAB + SeqSSOR(3)) on the system with
+    the mortar block; same algorithm on both sides — iteration counts agree (+-1), solutions to 1e-10."""
+    dev, ora, Pd, Po = pair
+    u0 = _x(ora, Po, "g")
+    dev.jacobian(Pd.go, Pd.mat, u0, overwrite=True); ora.jacobian(Po.go, Po.mat, u0, overwrite=True)
+    rd, ro = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.residual(Pd.go, u0, rd); ora.residual(Po.go, u0, ro)
+    zd, zo = np.zeros(Pd.ndof), np.zeros(Po.ndof)
+    dev.set_ssor_sweeps(3)
+    sd = dev.solve(Pd.mat, rd, zd, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, reduction=1e-13, maxit=5000)
+    so = ora.solve(Po.mat, ro, zo, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, sweeps=3, reduction=1e-13, maxit=5000)
+    assert sd.converged and so.converged
+    # BiCGSTAB on this indefinite system is sensitive to the reduction order of its dot products once the defect nears
+    # 1e-13: the counts agree to a few iterations, not exactly
+    assert abs(sd.iterations - so.iterations) <= max(2, so.iterations // 6), (sd.iterations, so.iterations)
+    assert np.abs(zd - zo).max() <= RTOL_SOLUTION * np.abs(zo).max()
+
+
+def test_host_vector_upload_covers_the_mortar_coefficients():
+    """mdb_jacobian with x in pinned host memory fetches only the coefficients the FD kernels read: these now include x_c."""
+    torch = pytest.importorskip("torch")
+    dev, ora, Pd, Po = _pair("m3d_8")
+    x = np.random.default_rng(2).uniform(-1, 1, Po.ndof)
+    xp = torch.from_numpy(x.copy()).pin_memory()
+    dev.jacobian(Pd.go, Pd.mat, xp.numpy(), overwrite=True)
+    ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
+    assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
+    dev.close(); ora.close()
