@@ -81,7 +81,19 @@ public:
 class GridFunctionSpace {            // GridFunctionSpace<SDGV, QkLocalFiniteElementMap<...,k>, ConformingDirichletConstraints, VBE>
 public:
   SubDomainGridView gv; int k; int child;
-  GridFunctionSpace(SubDomainGridView gv_, int order) : gv(gv_), k(order), child(-1) {}
+  bool coupling; int lkind, rkind; uint32_t lmask, rmask;      // set by CouplingGridFunctionSpace only
+  GridFunctionSpace(SubDomainGridView gv_, int order) : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0) {}
+};
+
+// CouplingGridFunctionSpace<MDGV, QkLocalFiniteElementMap<(dim-1)-cube,1>, SubProblemSubProblemInterface<MDGV,Left,Right>, NoConstraints, VBE>
+// (couplinggridfunctionspace.hh:14-249; test/testmortarpoisson.cc:365-375): a Q1 space on the intersections whose inside cell
+// satisfies `left` and whose outside cell satisfies `right`.  Pass it to MultiDomainGridFunctionSpace like any other child.
+class CouplingGridFunctionSpace : public GridFunctionSpace {
+public:
+  template <class Left, class Right>
+  CouplingGridFunctionSpace(int order, const Left& left, const Right& right) : GridFunctionSpace(SubDomainGridView(-1), order) {
+    coupling = true; lkind = Left::kind(); lmask = left.mask; rkind = Right::kind(); rmask = right.mask;
+  }
 };
 
 class MultiDomainGridFunctionSpace { // children in argument order, LexicographicOrderingTag
@@ -92,7 +104,9 @@ public:
   MultiDomainGridFunctionSpace(MultiDomainGrid& grid, std::initializer_list<GridFunctionSpace*> children)
     : grid_(grid), finalized_(false), ndof_(0) {
     for (GridFunctionSpace* g : children)
-      g->child = context().check(mdb_add_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->gv.subdomain), "mdb_add_space");
+      g->child = g->coupling
+        ? context().check(mdb_add_coupling_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->lkind, g->lmask, g->rkind, g->rmask), "mdb_add_coupling_space")
+        : context().check(mdb_add_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->gv.subdomain), "mdb_add_space");
   }
   Context& context() const { return grid_.context(); }
   MultiDomainGrid& grid() const { return grid_; }
@@ -141,6 +155,12 @@ struct ProportionalFlowCoupling {                // test/proportionalflowcouplin
   static int id() { return MDB_OP_PROPFLOW_COUPLING; }
 };
 
+struct MortarPoissonCoupling {                   // test/testmortarpoisson.cc:117-250, ctor arg = "scaling factor for coupling" (:402)
+  mdb_mortar_params p; int jac_mode;
+  explicit MortarPoissonCoupling(double gamma_0, int jacobian_mode = MDB_JAC_FD_BITMATCH) : jac_mode(jacobian_mode) { p.gamma_0 = gamma_0; }
+  static int id() { return MDB_OP_MORTAR_POISSON_COUPLING; }
+};
+
 // ---- participants --------------------------------------------------------------------------------------------------------------
 // TypeBasedSubProblem<MultiGFS,MultiGFS,LOP,Condition,GFS...>(lop, condition): the child space is named by object here
 template <class LOP, class Condition>
@@ -161,6 +181,18 @@ public:
   Coupling(const Local& local, const Remote& remote, const Op& op) {
     handle = local.gfs.context().check(mdb_add_coupling(local.gfs.context().get(), Op::id(), &op.p, sizeof(op.p), local.handle, remote.handle,
                                                         op.jac_mode), "mdb_add_coupling");
+  }
+};
+
+// EnrichedCoupling<LocalSubProblem,RemoteSubProblem,CouplingOperator,couplingLFSIndex>(local, remote, op)   (coupling.hh:123-192); the
+// coupling space is named by object instead of by its child index
+template <class Local, class Remote, class Op>
+class EnrichedCoupling {
+public:
+  int handle;
+  EnrichedCoupling(const Local& local, const Remote& remote, const Op& op, const CouplingGridFunctionSpace& couplinggfs) {
+    handle = local.gfs.context().check(mdb_add_enriched_coupling(local.gfs.context().get(), Op::id(), &op.p, sizeof(op.p), local.handle, remote.handle,
+                                                                 couplinggfs.child, op.jac_mode), "mdb_add_enriched_coupling");
   }
 };
 

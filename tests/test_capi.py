@@ -97,6 +97,7 @@ def test_cxx_facade_compiles_and_fails_loudly_without_gpu(lib):
     with tempfile.TemporaryDirectory() as d:
         exe = _build_example(d)
         _build_example(d, "testinstationarypoisson")          # the instationary driver must at least compile and link
+        _build_example(d, "testmortarpoisson")                # ... and so must the mortar (enriched coupling) driver
         if torch.cuda.is_available():
             pytest.skip("a GPU is present (the run is covered by the gpu tests)")
         p = subprocess.run([exe, "3", "2.0"], capture_output=True, text=True)

@@ -144,3 +144,39 @@ def test_host_vector_upload_covers_the_mortar_coefficients():
     vd, vo = dev.matrix_get_values(Pd.mat), ora.matrix_get_values(Po.mat)
     assert np.abs(vd - vo).max() <= RTOL_ENTRY * np.abs(vo).max()
     dev.close(); ora.close()
+
+
+@pytest.mark.parametrize("refinement,scaling,dim", [(5, 1.0, 2), (4, 2.5, 2), (3, 1.0, 3)])
+def test_cxx_mortar_driver_matches_oracle(refinement, scaling, dim):
+    """examples/testmortarpoisson.cc (test/testmortarpoisson.cc against include/mdb200/multidomain.hh) run as a program; (5, 1.0, 2)
+    is the reference's default invocation: ordering size 1155, BiCGSTAB + SSOR(3) to 1e-10."""
+    import re
+    import subprocess
+    import tempfile
+    from test_capi import _build_example
+    n = (1 << refinement,) * dim
+    ora = orc.Oracle()
+    Po = problems.testmortarpoisson(ora, n, gamma_0=scaling)
+    u = np.zeros(Po.ndof)
+    ora.interpolate(Po.sps, Po.gfn, u)
+    ora.jacobian(Po.go, Po.mat, u, overwrite=True)
+    r = np.zeros(Po.ndof)
+    ora.residual(Po.go, u, r)
+    z = np.zeros(Po.ndof)
+    so = ora.solve(Po.mat, r, z, reduction=1e-10)
+    ora.solve(Po.mat, r, z, reduction=1e-13)
+    un = u - z
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d, "testmortarpoisson")
+        out = subprocess.run([exe, str(refinement), str(scaling), str(dim)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert int(out.stdout.split()[0]) == Po.ndof
+    m = re.search(r"(\d+) dof total, (\d+) dof constrained, (\d+) nonzeroes", out.stdout)
+    assert m and int(m.group(1)) == Po.ndof and int(m.group(2)) == Po.ncon and int(m.group(3)) == ora.nnz[Po.mat]
+    m = re.search(r"\|r\|_2 = (\S+)", out.stdout)
+    assert abs(float(m.group(1)) - np.linalg.norm(r)) <= 1e-11 * np.linalg.norm(r)
+    m = re.search(r"solver: (\d+) iterations", out.stdout)
+    assert abs(int(m.group(1)) - so.iterations) <= max(2, so.iterations // 6), (m.group(1), so.iterations)
+    m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
+    assert abs(float(m.group(1)) - un.sum()) <= 1e-7 * abs(un.sum())
+    assert abs(float(m.group(2)) - np.linalg.norm(un)) <= 1e-7 * np.linalg.norm(un)
