@@ -18,6 +18,10 @@ BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON = range(3)
 OP_POISSON, OP_L2 = 1, 2
 OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
 OP_MORTAR_POISSON_COUPLING = 201
+OP_ND_COUPLING = 103
+ND_MODE_NEUMANN, ND_MODE_DIRICHLET, ND_MODE_BOTH = 0, 1, 2
+DG_METHOD_NIPG, DG_METHOD_SIPG = 0, 1
+DG_WEIGHTS_OFF, DG_WEIGHTS_ON = 0, 1
 JAC_FD_BITMATCH, JAC_ANALYTIC = 0, 1
 SOLVER_CG, SOLVER_BICGSTAB = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR = 0, 1, 2, 3
@@ -59,6 +63,10 @@ class CVCFParams(C.Structure):
 
 class PropFlowParams(C.Structure):
     _fields_ = [("intensity", C.c_double)]
+
+
+class NDCouplingParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("method", C.c_int32), ("weights", C.c_int32), ("intorderadd", C.c_int32), ("alpha", C.c_double)]
 
 
 class MortarParams(C.Structure):
@@ -300,6 +308,16 @@ class Mdb(Lib):
                                          _vecptr(rhs), _vecptr(z), C.byref(st))
         if rc != -6:  # MDB_ENOTCONVERGED is reported through stats
             self._check(rc, "solve")
+        return st
+
+    def solve_block(self, mat, child, rhs, z, method=SOLVER_BICGSTAB, precond=PRECOND_SSOR, sweeps=3, reduction=1e-10, maxit=5000):
+        """mdb_solve_block: the diagonal block of child space `child` only (ISTL_SEQ_Subblock_Backend)."""
+        st = SolveStats()
+        if precond == PRECOND_SSOR:
+            self.set_ssor_sweeps(sweeps)
+        rc = self._fn("solve_block")(C.c_void_p(self.ctx), mat, child, method, precond, C.c_double(reduction), maxit, _vecptr(rhs), _vecptr(z), C.byref(st))
+        if rc != -6:
+            self._check(rc, "solve_block")
         return st
 
     def onestep_apply(self, go0, go1, mat, subproblems, fns, time, dt, u_old, u_new, scheme=0, theta=1.0, method=SOLVER_BICGSTAB,

@@ -372,6 +372,11 @@ int mdb_add_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, i
     } else if (op_id == MDB_OP_PROPFLOW_COUPLING) {
       MDB_REQUIRE(nbytes == sizeof(mdb_propflow_params), MDB_EINVAL, "mdb_add_coupling: bad mdb_propflow_params size");
       std::memcpy(&cp.propflow, params, nbytes);
+    } else if (op_id == MDB_OP_ND_COUPLING) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_ndcoupling_params), MDB_EINVAL, "mdb_add_coupling: bad mdb_ndcoupling_params size");
+      std::memcpy(&cp.nd, params, nbytes);
+      MDB_REQUIRE(cp.nd.mode >= MDB_ND_MODE_NEUMANN && cp.nd.mode <= MDB_ND_MODE_BOTH, MDB_EINVAL, "mdb_add_coupling: bad Neumann-Dirichlet coupling mode");
+      MDB_REQUIRE(!c->mesh.partitioned, MDB_EINVAL, "mdb_add_coupling: the Neumann-Dirichlet coupling is not supported on a partitioned mesh");
     } else throw Error(MDB_EINVAL, "mdb_add_coupling: unknown coupling operator");
     c->cps.push_back(cp);
     return (int)c->cps.size() - 1;
@@ -649,7 +654,7 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
     c->phase_end();
     if (host_x && need_x) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
     c->phase_begin("jacobian_coupling");
-    jacobian_coupling(c, G, M, weight, dx);
+    jacobian_coupling(c, G, M, weight, dx, false);
     c->phase_end();
     MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
   }
@@ -657,6 +662,7 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   jacobian_volume(c, G, M, weight, overwrite != 0, 0);
   c->phase_end();
   MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  jacobian_coupling(c, G, M, weight, dx, true);            // couplings without a pattern of their own: after every volume row is written
   c->phase_begin("jacobian_dirichlet");
   dirichlet_rows(c, M);
   c->phase_end();
@@ -714,6 +720,58 @@ int mdb_solve(mdb_ctx* c, int mat, int method, int precond, double reduction, in
     return rc;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
   catch (std::exception& e) { c->err = e.what(); return MDB_EINVAL; }
+}
+
+// flag[0] = 1 if the matrix has an entry whose row and column lie on different sides of the block boundary
+__global__ void k_block_decoupled(int64_t n, int64_t lo, int64_t hi, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int* flag)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const bool rin = r >= lo && r < hi;
+  for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p) {
+    const int32_t cidx = colidx[p];
+    if ((cidx >= lo && cidx < hi) != rin) { *flag = 1; return; }
+  }
+}
+__global__ void k_copy_block(const double* __restrict__ src, double* dst, int64_t n, int64_t lo, int64_t hi, int zero_outside)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i >= lo && i < hi) dst[i] = src[i];
+  else if (zero_outside) dst[i] = 0.0;
+}
+
+int mdb_solve_block(mdb_ctx* c, int mat, int child, int method, int precond, double reduction, int maxit, const double* rhs, double* z,
+                    mdb_solve_stats* stats)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  MDB_REQUIRE(child >= 0 && child < (int)c->children.size(), MDB_EINVAL, "mdb_solve_block: bad child index");
+  MDB_REQUIRE(c->nranks == 1, MDB_EINVAL, "mdb_solve_block: single-rank contexts only");
+  const int64_t n = c->ndof, lo = c->children[child].offset, hi = lo + c->children[child].size;
+  // The Krylov loop runs on the whole vector with the right-hand side zeroed outside the block.  That IS the solve of the
+  // diagonal block provided the matrix does not couple the block with the rest (then every iterate stays exactly zero outside
+  // the block and every scalar of the iteration is the block's own); rows without entries act as identity rows.
+  int* d_flag = dalloc<int>(1);
+  MDB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+  MDB_LAUNCH(c, k_block_decoupled, cdiv(n, 256), 256, 0, n, lo, hi, M.d_rowptr, M.d_colidx, d_flag);
+  int coupled = 0;
+  MDB_CUDA(cudaMemcpyAsync(&coupled, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  dfree(d_flag);
+  MDB_REQUIRE(!coupled, MDB_EINVAL, "mdb_solve_block: the matrix couples the block with other blocks (assemble the block's own operator into its own matrix)");
+  VecIn vr(c, rhs, n, 0);
+  VecInOut vz(c, z, n, 1, true);
+  if (!c->d_stage[2]) c->d_stage[2] = dalloc<double>(n);
+  if (!c->d_stage[3]) c->d_stage[3] = dalloc<double>(n);
+  double* br = c->d_stage[2]; double* bz = c->d_stage[3];
+  MDB_LAUNCH(c, k_copy_block, cdiv(n, 256), 256, 0, vr.d, br, n, lo, hi, 1);
+  MDB_CUDA(cudaMemsetAsync(bz, 0, n * sizeof(double), c->stream));
+  int rc = solve(c, M, method, precond, reduction, maxit, -1, br, bz, stats);
+  MDB_LAUNCH(c, k_copy_block, cdiv(n, 256), 256, 0, bz, vz.d, n, lo, hi, 0);
+  vz.commit();
+  if (rc != MDB_OK) return rc;
+  MDB_API_END(c)
 }
 
 int mdb_set_ssor_sweeps(mdb_ctx* c, int sweeps)

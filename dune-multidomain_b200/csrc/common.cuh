@@ -177,6 +177,7 @@ struct CouplingDesc {
   mdb_cvcf_params cvcf{};
   mdb_propflow_params propflow{};
   mdb_mortar_params mortar{};
+  mdb_ndcoupling_params nd{};
   int local_sp = -1, remote_sp = -1, jac_mode = 0;
   int coupling_child = -1;       // >= 0: EnrichedCoupling (coupling.hh:123-192) with this coupling space
   bool enriched() const { return coupling_child >= 0; }
@@ -337,10 +338,13 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
 void constrain_residual(Ctx* c, double* d_r);
 void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight);
 void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool overwrite, int part);
-void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x);
+void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x, bool late);
 // mortar.cu: EnrichedCoupling with MortarPoissonCoupling (test/testmortarpoisson.cc:117-250)
 void residual_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r);
 void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight, const double* d_x);
+// nd.cu: ConvectionDiffusionDGNeumannDirichletCoupling (test/neumanndirichletcoupling.hh)
+void residual_nd(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r);
+void jacobian_nd(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight);
 void mark_iface_present(Ctx* c, const Child& ch, uint8_t* d_present);
 void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& m, int child, bool overwrite);      // generic.cu: Qk children, k > 1
 void residual_volume_generic(Ctx* c, const GridOp& go, int child, const double* d_x, double* d_r);

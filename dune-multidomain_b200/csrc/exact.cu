@@ -489,6 +489,7 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
     const FaceList& fl = go.faces[k];
     if (fl.n == 0) continue;
     if (cp.enriched()) { residual_enriched(c, cp, fl, weight, d_x, d_r); continue; }      // mortar.cu
+    if (cp.op_id == MDB_OP_ND_COUPLING) { residual_nd(c, cp, fl, weight, d_x, d_r); continue; }   // nd.cu
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const int k1 = c->children[c->sps[cp.local_sp].children[0]].k, k2 = c->children[c->sps[cp.remote_sp].children[0]].k;
@@ -499,14 +500,20 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
   }
 }
 
-void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const double* d_x)
+// `late` selects the couplings of one pass of mdb_jacobian: false = those whose entries all lie in irregular rows (they declare a
+// coupling pattern on every DOF of the cells they touch) and may therefore run beside the streamed simple rows; true = the
+// Neumann-Dirichlet coupling, which declares no pattern (its mat_ss also hits full-stencil rows one vertex layer off the
+// interface) and must run after the volume fill.
+void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const double* d_x, bool late)
 {
   const MeshDesc& m = c->mesh;
   for (size_t k = 0; k < go.cps.size(); ++k) {
     const CouplingDesc& cp = c->cps[go.cps[k]];
     const FaceList& fl = go.faces[k];
     if (fl.n == 0) continue;
+    if ((cp.op_id == MDB_OP_ND_COUPLING) != late) continue;
     if (cp.enriched()) { jacobian_enriched(c, cp, fl, M, weight, d_x); continue; }        // mortar.cu
+    if (cp.op_id == MDB_OP_ND_COUPLING) { jacobian_nd(c, cp, fl, M, weight); continue; }          // nd.cu
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const double eps = 1e-8;                    // NumericalJacobianCoupling() default, couplingutilities.hh:63-65

@@ -243,6 +243,7 @@ void build_pattern(Ctx* c, Matrix& M)
     }
     for (int k : go.cps) {
       const CouplingDesc& cp = c->cps[k];
+      if (cp.op_id == MDB_OP_ND_COUPLING) continue;      // no pattern of its own (test/neumanndirichletcoupling.hh:51-52)
       MDB_REQUIRE(S.ncp < 8, MDB_EINVAL, "too many couplings in one matrix");
       const SubProblemDesc& l = c->sps[cp.local_sp]; const SubProblemDesc& r = c->sps[cp.remote_sp];
       S.cp_lchild[S.ncp] = l.children[0]; S.cp_lkind[S.ncp] = l.cond_kind; S.cp_lmask[S.ncp] = l.mask;

@@ -73,13 +73,14 @@ __global__ void __launch_bounds__(256) k_sweep(int64_t n, const int64_t* __restr
     if (k >= (unsigned long long)n) return;
     const int64_t i = perm[ASC ? (int64_t)k : n - 1 - (int64_t)k];
     const int64_t s = rowptr[i], e = rowptr[i + 1];
-    const int64_t pd = s + diag[i];
-    const double aii = a[pd];                                               // issued early: needed only at the end of the chain
+    const bool norow = diag[i] < 0;          // a row without entries (a block no participant of the matrix's operators lives on): identity row
+    const int64_t pd = norow ? s : s + diag[i];
+    const double aii = norow ? 1.0 : a[pd];                                 // issued early: needed only at the end of the chain
     const double vi = (MODE == SW_ILU_LOWER) ? 0.0 : record_value(ld_record(vt + i));   // row i is written by this warp only
     // the entries this mode sums, in column order
     int64_t p0 = s, p1 = e;
     if (MODE == SW_ILU_LOWER) p1 = pd;
-    if (MODE == SW_ILU_UPPER) p0 = pd + 1;
+    if (MODE == SW_ILU_UPPER) p0 = norow ? e : pd + 1;
     double acc = (MODE == SW_ILU_UPPER) ? vi : d[i];
     for (int64_t pb = p0; pb < p1; pb += 32) {
       const int64_t p = pb + lane;
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(256) k_sweep(int64_t n, const int64_t* __restr
     }
     if (lane == 0) {
       double out;
-      if (MODE == SW_SSOR_FWD || MODE == SW_SSOR_BWD) out = __dadd_rn(vi, __ddiv_rn(acc, aii));
+      if (norow) out = acc;
+      else if (MODE == SW_SSOR_FWD || MODE == SW_SSOR_BWD) out = __dadd_rn(vi, __ddiv_rn(acc, aii));
       else if (MODE == SW_ILU_LOWER) out = acc;
       else out = __dmul_rn(aii, acc);
       st_record(vt + i, out, epoch);

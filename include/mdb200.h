@@ -97,6 +97,8 @@ enum {
   /* coupling operators used by Couplings */
   MDB_OP_CVCF_COUPLING = 101,     /* ContinuousValueContinuousFlowCoupling  test/proportionalflowcoupling.hh:94-239 */
   MDB_OP_PROPFLOW_COUPLING = 102, /* ProportionalFlowCoupling               test/proportionalflowcoupling.hh:10-91  */
+  MDB_OP_ND_COUPLING = 103,       /* ConvectionDiffusionDGNeumannDirichletCoupling<CouplingParameters>  test/neumanndirichletcoupling.hh:41-441,
+                                     parameter class test/testpoisson-dirichlet-neumann.cc:36-69 (A = I, b = 0, c = 0)                  */
   /* enriched (mortar) coupling operators used by EnrichedCouplings */
   MDB_OP_MORTAR_POISSON_COUPLING = 201   /* MortarPoissonCoupling(gamma_0)  test/testmortarpoisson.cc:117-250        */
 };
@@ -123,6 +125,20 @@ typedef struct mdb_cvcf_params {
 typedef struct mdb_propflow_params {
   double intensity;
 } mdb_propflow_params;
+
+/* ConvectionDiffusionDGNeumannDirichletCoupling(coupling_mode, param, method, weights, alpha, intorderadd)
+ * (test/neumanndirichletcoupling.hh:56-74).  One-directional: alpha_coupling writes r_s only, jacobian_coupling mat_ss only
+ * (:85-283, :291-432); analytic Jacobian (jac_mode is ignored); no pattern of its own (:51-52). */
+enum { MDB_ND_MODE_NEUMANN = 0, MDB_ND_MODE_DIRICHLET = 1, MDB_ND_MODE_BOTH = 2 };       /* CouplingMode :19-24 */
+enum { MDB_DG_METHOD_NIPG = 0, MDB_DG_METHOD_SIPG = 1 };                                 /* ConvectionDiffusionDGMethod [UPSTREAM] */
+enum { MDB_DG_WEIGHTS_OFF = 0, MDB_DG_WEIGHTS_ON = 1 };                                  /* ConvectionDiffusionDGWeights [UPSTREAM] */
+typedef struct mdb_ndcoupling_params {
+  int32_t mode;              /* MDB_ND_MODE_*                                                          */
+  int32_t method;            /* MDB_DG_METHOD_*: theta = 1 (NIPG) or -1 (SIPG), :72-73                 */
+  int32_t weights;           /* MDB_DG_WEIGHTS_*                                                        */
+  int32_t intorderadd;       /* quadrature order = intorderadd + 2 * max basis order, :107              */
+  double alpha;              /* interior penalty parameter                                              */
+} mdb_ndcoupling_params;
 
 typedef struct mdb_mortar_params {
   double gamma_0;            /* ctor arg ("scaling factor for coupling", test/testmortarpoisson.cc:402): gamma = gamma_0 / |face| */
@@ -258,6 +274,13 @@ typedef struct mdb_solve_stats {
   double seconds;          /* device time of the Krylov loop (CUDA events) */
 } mdb_solve_stats;
 /* Solve A z = rhs to  |defect| <= reduction * |defect0|  starting from z = 0.  rhs, z: host or device. */
+/* ISTL_SEQ_Subblock_Backend<Preconditioner, Solver>::apply (test/testpoisson-dirichlet-neumann.cc:264-370), the linear solver of the
+ * Dirichlet-Neumann iteration: solves raw(A)[child][child] z_child = rhs_child with the diagonal block of child space `child`
+ * and leaves every other entry of z untouched.  The matrix must not couple the block with the others (assemble the block's own
+ * grid operator — e.g. {left subproblem, its coupling} — into its own matrix, as the reference's LeftOperator / RightOperator
+ * do); MDB_EINVAL otherwise.  Same stats / return codes as mdb_solve. */
+int mdb_solve_block(mdb_ctx* ctx, int mat, int child, int method, int precond, double reduction, int maxit, const double* rhs, double* z,
+                    mdb_solve_stats* stats);
 int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, int maxit,
               const double* rhs, double* z, mdb_solve_stats* stats);
 /* Number of symmetric sweeps n of MDB_PRECOND_SSOR (default 3). */

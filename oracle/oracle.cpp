@@ -270,6 +270,126 @@ struct CVCFOp : CouplingOperator {
   }
 };
 
+// test/neumanndirichletcoupling.hh:41-441 with the parameter class CouplingParameters of
+// test/testpoisson-dirichlet-neumann.cc:36-69 (A = identity, b = 0, c = 0).  One-directional: only r_s / mat_ss are written
+// (r_r, mat_sr, mat_rs, mat_rr are const references there); the Jacobian is the operator's own analytic jacobian_coupling
+// (:291-432), which deliberately has no derivative with respect to the remote coefficients (explicit coupling).
+struct NDCouplingOp : CouplingOperator {
+  mdb_ndcoupling_params P;
+  double theta;
+  explicit NDCouplingOp(const mdb_ndcoupling_params& p) : P(p) {
+    doAlphaCoupling = true; doPatternCoupling = false;                  // :51-55 "no additional pattern relative to the subproblems"
+    own_jacobian = true;
+    theta = 1.0; if (P.method == MDB_DG_METHOD_SIPG) theta = -1.0;      // :72-73
+  }
+  struct Setup { double An_F_s[3], n_F[3], penalty_factor; int intorder; };
+  Setup setup(const IG& ig, const LFS& lfsu_s, const LFS& lfsu_r) const {
+    Setup S; const int dim = ig.dim();
+    const int order = std::max(lfsu_s.k, lfsu_r.k);                     // :100-106 (lfsv = lfsu)
+    S.intorder = P.intorderadd + 2 * order;                             // quadrature_factor(2) :69, :107
+    // A_s = A_n = I (param.A), h_F = min(vol_s, vol_n) / vol_face (:128, the element_size value is overwritten)
+    const double h_F = std::min(ig.inside.integrationElement(), ig.outside.integrationElement()) / ig.integrationElement();
+    ig.unitOuterNormal(S.n_F);
+    double An_F_n[3];
+    for (int i = 0; i < dim; ++i) {                                     // A.mv(n_F, An_F): y_i = sum_j A_ij x_j
+      S.An_F_s[i] = 0.0; An_F_n[i] = 0.0;
+      for (int j = 0; j < dim; ++j) { S.An_F_s[i] += ((i == j) ? 1.0 : 0.0) * S.n_F[j]; An_F_n[i] += ((i == j) ? 1.0 : 0.0) * S.n_F[j]; }
+    }
+    double harmonic_average = 0.0;
+    if (P.weights == MDB_DG_WEIGHTS_ON) {                               // :149-155
+      double delta_s = 0.0, delta_n = 0.0;
+      for (int d = 0; d < dim; ++d) { delta_s += S.An_F_s[d] * S.n_F[d]; delta_n += An_F_n[d] * S.n_F[d]; }
+      harmonic_average = 2.0 * delta_s * delta_n / (delta_s + delta_n + 1e-20);
+    } else harmonic_average = 1.0;
+    const int degree = std::max(lfsu_s.k, lfsu_r.k);                    // :163-165
+    S.penalty_factor = (P.alpha / h_F) * harmonic_average * degree * (degree + dim - 1);     // :168
+    return S;
+  }
+  void alpha_coupling(const IG& ig, const LFS& lfsu_s, const double* x_s, const LFS& lfsv_s,
+                      const LFS& lfsu_r, const double* x_r, const LFS&, LocalVectorView& r_s, LocalVectorView&) const override {
+    const int dim = ig.dim();
+    const Setup S = setup(ig, lfsu_s, lfsu_r);
+    QkBasis Bs(lfsu_s.k, dim), Br(lfsu_r.k, dim);
+    const auto& rule = tensor_rule(dim - 1, S.intorder);
+    double psi_s[MAXLOC], phi_r[MAXLOC], js[MAXLOC][3], tgrad_r[MAXLOC][3], tgrad_s[MAXLOC][3], iplocal_s[3], iplocal_n[3];
+    for (const auto& q : rule) {
+      const double* n_F_local = S.n_F;                                  // ig.unitOuterNormal(pos): constant on an axis-aligned face
+      ig.localInside(q.x, iplocal_s); ig.localOutside(q.x, iplocal_n);
+      Bs.evaluateFunction(iplocal_s, psi_s);
+      const double factor = q.w * ig.integrationElement();
+      double normalflux = 0.0;                                          // b = 0 (param.b)
+      for (int d = 0; d < dim; ++d) normalflux += 0.0 * n_F_local[d];
+      Br.evaluateFunction(iplocal_n, phi_r);
+      double u_r = 0.0;
+      for (int i = 0; i < lfsu_r.n; ++i) u_r += x_r[lfsu_r.idx[i]] * phi_r[i];
+      if (P.mode == MDB_ND_MODE_NEUMANN || P.mode == MDB_ND_MODE_BOTH) {      // :194-217: flux of the neighbour
+        Br.evaluateJacobian(iplocal_n, js);
+        for (int i = 0; i < lfsu_r.n; ++i)
+          for (int d = 0; d < dim; ++d) { tgrad_r[i][d] = 0.0; tgrad_r[i][d] += ig.outside.jacInvT(d) * js[i][d]; }
+        double gradu_r[3] = {0, 0, 0};
+        for (int i = 0; i < lfsu_r.n; ++i) for (int d = 0; d < dim; ++d) gradu_r[d] += x_r[lfsu_r.idx[i]] * tgrad_r[i][d];
+        double gn = 0.0; for (int d = 0; d < dim; ++d) gn += gradu_r[d] * n_F_local[d];
+        const double j = normalflux * u_r - gn;
+        for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, j * psi_s[i] * factor);
+        if (P.mode == MDB_ND_MODE_NEUMANN) continue;
+      }
+      const double* phi_s = psi_s;                                      // lfsu_s = lfsv_s: the same basis at the same point
+      double u_s = 0.0;
+      for (int i = 0; i < lfsu_s.n; ++i) u_s += x_s[lfsu_s.idx[i]] * phi_s[i];
+      Bs.evaluateJacobian(iplocal_s, js);
+      for (int i = 0; i < lfsu_s.n; ++i)
+        for (int d = 0; d < dim; ++d) { tgrad_s[i][d] = 0.0; tgrad_s[i][d] += ig.inside.jacInvT(d) * js[i][d]; }
+      double gradu_s[3] = {0, 0, 0};
+      for (int i = 0; i < lfsu_s.n; ++i) for (int d = 0; d < dim; ++d) gradu_s[d] += x_s[lfsu_s.idx[i]] * tgrad_s[i][d];
+      const double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0, omegaup_r = normalflux >= 0.0 ? 0.0 : 1.0;
+      const double term1 = (omegaup_s * u_s + omegaup_r * u_r) * normalflux * factor;               // convection
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsu_s, i, term1 * psi_s[i]);
+      double Agu = 0.0; for (int d = 0; d < dim; ++d) Agu += S.An_F_s[d] * gradu_s[d];
+      const double term2 = -factor * Agu;                                                            // diffusion
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term2 * psi_s[i]);
+      const double term3 = (u_s - u_r) * factor;                                                     // (non-)symmetric IP term
+      for (int i = 0; i < lfsv_s.n; ++i) {
+        double Agp = 0.0; for (int d = 0; d < dim; ++d) Agp += S.An_F_s[d] * tgrad_s[i][d];
+        r_s.accumulate(lfsv_s, i, term3 * theta * Agp);
+      }
+      const double term4 = S.penalty_factor * (u_s - u_r) * factor;                                  // standard IP term
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term4 * psi_s[i]);
+    }
+  }
+  void jacobian_own(const IG& ig, const LFS& lfsu_s, const LFS& lfsu_r, LocalMatrixView& mat_ss) const override {
+    if (P.mode == MDB_ND_MODE_NEUMANN) return;                          // :299-300
+    const int dim = ig.dim();
+    const Setup S = setup(ig, lfsu_s, lfsu_r);
+    QkBasis Bs(lfsu_s.k, dim);
+    const auto& rule = tensor_rule(dim - 1, S.intorder);
+    double phi_s[MAXLOC], js[MAXLOC][3], tgrad_s[MAXLOC][3], iplocal_s[3];
+    for (const auto& q : rule) {
+      const double* n_F_local = S.n_F;
+      ig.localInside(q.x, iplocal_s);
+      Bs.evaluateFunction(iplocal_s, phi_s);
+      Bs.evaluateJacobian(iplocal_s, js);
+      for (int i = 0; i < lfsu_s.n; ++i)
+        for (int d = 0; d < dim; ++d) { tgrad_s[i][d] = 0.0; tgrad_s[i][d] += ig.inside.jacInvT(d) * js[i][d]; }
+      double normalflux = 0.0;
+      for (int d = 0; d < dim; ++d) normalflux += 0.0 * n_F_local[d];
+      const double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0;
+      const double factor = q.w * ig.integrationElement();
+      const double ipfactor = S.penalty_factor * factor;
+      for (int j = 0; j < lfsu_s.n; ++j) {                              // :421-429: I convection, II diffusion, III consistency, IV ip
+        double Agj = 0.0; for (int d = 0; d < dim; ++d) Agj += S.An_F_s[d] * tgrad_s[j][d];
+        const double temp1 = -Agj * factor;
+        for (int i = 0; i < lfsu_s.n; ++i) {
+          double Agi = 0.0; for (int d = 0; d < dim; ++d) Agi += S.An_F_s[d] * tgrad_s[i][d];
+          mat_ss.accumulate(lfsu_s, i, lfsu_s, j, omegaup_s * phi_s[j] * normalflux * factor * phi_s[i]);
+          mat_ss.accumulate(lfsu_s, i, lfsu_s, j, temp1 * phi_s[i]);
+          mat_ss.accumulate(lfsu_s, i, lfsu_s, j, phi_s[j] * factor * theta * Agi);
+          mat_ss.accumulate(lfsu_s, i, lfsu_s, j, phi_s[j] * ipfactor * phi_s[i]);
+        }
+      }
+    }
+  }
+};
+
 } // anonymous namespace
 
 // couplingutilities.hh:75-135 (NumericalJacobianCoupling).  MDB_JAC_ANALYTIC exploits linearity of the shipped
@@ -279,6 +399,7 @@ void CouplingOperator::jacobian_coupling(const IG& ig, const LFS& lfsu_s, const 
                                          LocalMatrixView& mat_ss, LocalMatrixView& mat_sn,
                                          LocalMatrixView& mat_ns, LocalMatrixView& mat_nn) const
 {
+  if (own_jacobian) { jacobian_own(ig, lfsu_s, lfsu_n, mat_ss); return; }      // the operator implements jacobian_coupling itself
   const int m_s = lfsv_s.n, m_n = lfsv_n.n, n_s = lfsu_s.n, n_n = lfsu_n.n;
   std::vector<double> u_s(x_s, x_s + nx_s), u_n(x_n, x_n + nx_n);
   std::vector<double> down_s(nx_s, 0.0), up_s(nx_s, 0.0), down_n(nx_n, 0.0), up_n(nx_n, 0.0);
@@ -429,6 +550,9 @@ std::unique_ptr<CouplingOperator> make_coupling_operator(int op_id, const void* 
   case MDB_OP_PROPFLOW_COUPLING:
     if (nbytes != sizeof(mdb_propflow_params)) throw std::runtime_error("bad propflow params size");
     return std::unique_ptr<CouplingOperator>(new PropFlowOp(*static_cast<const mdb_propflow_params*>(params), jac_mode));
+  case MDB_OP_ND_COUPLING:
+    if (nbytes != sizeof(mdb_ndcoupling_params)) throw std::runtime_error("bad ndcoupling params size");
+    return std::unique_ptr<CouplingOperator>(new NDCouplingOp(*static_cast<const mdb_ndcoupling_params*>(params)));
   }
   throw std::runtime_error("unknown coupling operator id");
 }
@@ -1312,6 +1436,26 @@ int orc_jacobian(Context* c, int go, int mat, double weight, const double* x) { 
 int orc_jacobian_parallel(Context* c, int go, int mat, double weight, const double* x, int nthreads)
 { ORC_TRY(c, { c->jacobian_parallel(go, mat, weight, x, nthreads); }) }
 int orc_spmv(Context* c, int mat, const double* x, double* y) { ORC_TRY(c, { orc::spmv(c->mats.at(mat), x, y); }) }
+// ISTL_SEQ_Subblock_Backend<Preconditioner, Solver>::apply (test/testpoisson-dirichlet-neumann.cc:264-370): the solver runs on
+// the diagonal block raw(A)[block][block] and the matching blocks of z and r only; every other entry of z is left untouched.
+// The blocks of the flat vectors are the child blocks of the MultiDomainGridFunctionSpace.
+int orc_solve_block(Context* c, int mat, int child, int method, int precond, int sweeps, double reduction, int maxit, const double* b, double* x,
+                    mdb_solve_stats* stats)
+{
+  ORC_TRY(c, {
+    const orc::CSR& A = c->mats.at(mat);
+    const orc::ChildSpace& ch = c->children.at(child);
+    const int64_t lo = ch.offset, n = ch.size;
+    orc::CSR B; B.nrows = n; B.rowptr.assign(n + 1, 0);
+    for (int64_t r = 0; r < n; ++r) {
+      for (int64_t p = A.rowptr[lo + r]; p < A.rowptr[lo + r + 1]; ++p)
+        if (A.colidx[p] >= lo && A.colidx[p] < lo + n) { B.colidx.push_back(A.colidx[p] - lo); B.val.push_back(A.val[p]); }
+      B.rowptr[r + 1] = (int64_t)B.colidx.size();
+    }
+    orc::SolveStats s = orc::solve(B, method, precond, sweeps, reduction, maxit, b + lo, x + lo);
+    if (stats) { stats->iterations = s.iterations; stats->converged = s.converged; stats->defect0 = s.defect0; stats->defect = s.defect; stats->seconds = 0; }
+  })
+}
 int orc_solve(Context* c, int mat, int method, int precond, int sweeps, double reduction, int maxit, const double* b, double* x,
               mdb_solve_stats* stats)
 {

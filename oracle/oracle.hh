@@ -270,6 +270,8 @@ struct CouplingOperator {
   bool doAlphaCoupling = false, doPatternCoupling = false;
   double epsilon = 1e-8;       // NumericalJacobianCoupling default, couplingutilities.hh:63-65
   int jac_mode = MDB_JAC_FD_BITMATCH;
+  bool own_jacobian = false;   // the operator has its own jacobian_coupling (test/neumanndirichletcoupling.hh:291-432) writing mat_ss only
+  virtual void jacobian_own(const IG&, const LFS& /*lfsu_s*/, const LFS& /*lfsu_r*/, LocalMatrixView& /*mat_ss*/) const {}
   virtual ~CouplingOperator() {}
   virtual void alpha_coupling(const IG&, const LFS& lfsu_s, const double* x_s, const LFS& lfsv_s,
                               const LFS& lfsu_n, const double* x_n, const LFS& lfsv_n,

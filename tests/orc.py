@@ -39,6 +39,14 @@ class Oracle(capi.Lib):
                                       capi._vecptr(rhs), capi._vecptr(z), C.byref(st)), "solve")
         return st
 
+    def solve_block(self, mat, child, rhs, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR_ORACLE, sweeps=3, reduction=1e-10, maxit=5000):
+        st = capi.SolveStats()
+        if precond == capi.PRECOND_SSOR:
+            precond = capi.PRECOND_SSOR_ORACLE
+        self._check(self._fn("solve_block")(C.c_void_p(self.ctx), mat, child, method, precond, sweeps, C.c_double(reduction), maxit,
+                                            capi._vecptr(rhs), capi._vecptr(z), C.byref(st)), "solve_block")
+        return st
+
     def local_jacobian_volume(self, sp, cell, nloc):
         a = np.zeros((nloc, nloc))
         self._check(self._fn("local_jacobian_volume")(C.c_void_p(self.ctx), sp, C.c_int64(cell), capi._vecptr(a)), "local_jacobian_volume")

@@ -128,6 +128,92 @@ def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE
                            gfn=[g, g], bc=pp.bc, children=(c0, c1, cc))
 
 
+def dirichlet_neumann(api, n, alpha=2.0, left_mode=capi.ND_MODE_DIRICHLET, right_mode=capi.ND_MODE_NEUMANN, fe=(capi.FE_Q1, capi.FE_Q1), quad_order=6,
+                      scaling=10.0):
+    """BASELINE configs[0]: test/testpoisson-dirichlet-neumann.cc `solve()` (:371-862) instantiated with conforming Qk spaces and
+    Poisson (what test/testpoisson-assembly.cc:919-934 assembles; the shipped main() passes DG-Q2 + ConvectionDiffusionDG, an
+    upstream operator — DESIGN.md §9).  2-D unit square (ini: refine 9), split x0 > 0.5 (:919-925), Poisson with the source F of
+    :73-87 on both sides, and three sets of participants on the same spaces:
+      monolithic   left_sp, right_sp, Coupling(left, right, ContinuousValueContinuousFlowCoupling(4, scaling))      (:449-456, :619-624)
+      left op      left_sp, Coupling(left, right, NDCoupling(mode = ini dn.coupling.right, SIPG, weightsOn, alpha))  (:517-528, :566-578)
+      right op     right_sp, Coupling(right, left, NDCoupling(mode = ini dn.coupling.left, ...))                     (:505-515, :530-540, :580-592)
+      full op      left_sp, dirichlet_coupling, right_sp, neumann_coupling                                           (:542-564)
+    NOTE the reference's naming: `nd_coupling_dirichlet` (used by the LEFT operator) is built from ini key dn.coupling.RIGHT
+    (= Neumann as shipped) and `nd_coupling_neumann` (RIGHT operator) from dn.coupling.LEFT (= Dirichlet); `left_mode` /
+    `right_mode` here are the ini keys dn.coupling.left / dn.coupling.right."""
+    api.mesh_structured(n)
+    api.subdomains_halfspace(0, 0.5, 0, 1)
+    c0, c1 = api.add_space(fe[0], 0), api.add_space(fe[1], 1)
+    pp = capi.PoissonParams()
+    pp.f = capi.Function(capi.FN_DN_SOURCE)
+    pp.bc = capi.BCType(capi.BC_TESTPOISSON)
+    pp.j = capi.Function(capi.FN_TESTPOISSON_J)
+    pp.quad_order = quad_order
+    left = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 0, [c0])
+    right = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 1, [c1])
+    cv = capi.CVCFParams()
+    cv.quad_order = 4
+    cv.intensity = scaling
+    mono = api.add_coupling(capi.OP_CVCF_COUPLING, cv, left, right)
+
+    def nd(mode):
+        p = capi.NDCouplingParams()
+        p.mode, p.method, p.weights, p.intorderadd, p.alpha = mode, capi.DG_METHOD_SIPG, capi.DG_WEIGHTS_ON, 0, alpha
+        return p
+    dirichlet_coupling = api.add_coupling(capi.OP_ND_COUPLING, nd(right_mode), left, right)      # local = left
+    neumann_coupling = api.add_coupling(capi.OP_ND_COUPLING, nd(left_mode), right, left)         # local = right
+    ndof = api.finalize()
+    ncon = api.constraints_assemble([left, right], [pp.bc, pp.bc])
+    go = api.gridoperator_create([left, right], [mono])
+    full = api.gridoperator_create([left, right], [dirichlet_coupling, neumann_coupling])
+    lop = api.gridoperator_create([left], [dirichlet_coupling])
+    rop = api.gridoperator_create([right], [neumann_coupling])
+    mat = api.matrix_create([go])
+    lmat = api.matrix_create([lop])
+    rmat = api.matrix_create([rop])
+    g = capi.gauss()
+    return SimpleNamespace(ndof=ndof, ncon=ncon, go=go, full=full, lop=lop, rop=rop, mat=mat, lmat=lmat, rmat=rmat, left=left, right=right,
+                           children=(c0, c1), sps=[left, right], gfn=[g, g], bc=pp.bc)
+
+
+def dn_iteration(api, P, u, iterations=200, damping=0.75, reduction=1e-8, maxerror=1e-99, left_reduction=(1e-4, 1e-4, 0.2),
+                 right_reduction=(1e-4, 1e-4, 0.2), solve_block=None, history=None):
+    """The Dirichlet-Neumann loop of test/testpoisson-dirichlet-neumann.cc:721-822 with the ini's parameters
+    (poisson-dirichlet-neumann.ini [dn.*]): per sweep a StationaryLinearProblemSolver step with the left operator (BiCGSTAB +
+    SSOR(3) on diagonal block 0, ISTL_SEQ_Subblock_Backend :264-370), damping, the same with the right operator on block 1,
+    damping, then the residual of the full operator.  reassemble = false: the Jacobians are assembled in the first sweep only
+    (apply(u, keep_matrix = i > 0), :806, :813).  *_reduction = (solver.reduction, solver.minreduction, solver.reductiondecay)."""
+    import numpy as np
+    if solve_block is None:
+        solve_block = api.solve_block
+    res = np.zeros(P.ndof)
+    api.residual(P.full, u, res)
+    r = start_r = float(np.linalg.norm(res))
+    l_off = 1.0 / (1.0 - left_reduction[0] / left_reduction[1]) if left_reduction[0] != left_reduction[1] else float("inf")
+    r_off = 1.0 / (1.0 - right_reduction[0] / right_reduction[1]) if right_reduction[0] != right_reduction[1] else float("inf")
+    i = 0
+    while r / start_r > reduction and r > maxerror and i < iterations:
+        for (op, mat, child, red, off) in ((P.lop, P.lmat, P.children[0], left_reduction, l_off), (P.rop, P.rmat, P.children[1], right_reduction, r_off)):
+            u_old = u.copy()
+            red_i = red[1] * (1.0 - 1.0 / (off + red[2] * i))
+            # StationaryLinearProblemSolver::apply(x, keep_matrix) [UPSTREAM] (vii): r = R(x); solve J z = r; x -= z
+            if i == 0:
+                api.jacobian(op, mat, u, overwrite=True)
+            rr = np.zeros(P.ndof)
+            api.residual(op, u, rr)
+            z = np.zeros(P.ndof)
+            solve_block(mat, child, rr, z, reduction=red_i)
+            u = u - z
+            u = damping * u + (1.0 - damping) * u_old                       # u *= alpha; u.axpy(1 - alpha, u_old)
+        res[:] = 0.0
+        api.residual(P.full, u, res)
+        r = float(np.linalg.norm(res))
+        i += 1
+        if history is not None:
+            history.append(r)
+    return u, i, r
+
+
 def instationary(api, n, k=2.0, split_axis=0):
     """BASELINE configs[2] in the form the reference's live code supports (SURVEY M3 / §8d reality check 3):
     test/testinstationarypoisson.cc:225-305 — dt0 operator = Poisson (stiffness + source + Neumann) on both subdomains plus

@@ -39,8 +39,9 @@ def test_struct_layouts_match_c():
 #include <stdio.h>
 #include "mdb200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mdb_function), sizeof(mdb_bctype), sizeof(mdb_poisson_params),
-         sizeof(mdb_l2_params), sizeof(mdb_cvcf_params), sizeof(mdb_propflow_params), sizeof(mdb_solve_stats));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mdb_function), sizeof(mdb_bctype), sizeof(mdb_poisson_params),
+         sizeof(mdb_l2_params), sizeof(mdb_cvcf_params), sizeof(mdb_propflow_params), sizeof(mdb_solve_stats),
+         sizeof(mdb_mortar_params), sizeof(mdb_ndcoupling_params));
   return 0; }
 """
     with tempfile.TemporaryDirectory() as d:
@@ -49,7 +50,7 @@ int main(void) {
         out = subprocess.check_output([os.path.join(d, "t")]).split()
     sizes = [int(x) for x in out]
     mine = [C.sizeof(t) for t in (capi.Function, capi.BCType, capi.PoissonParams, capi.L2Params, capi.CVCFParams,
-                                  capi.PropFlowParams, capi.SolveStats)]
+                                  capi.PropFlowParams, capi.SolveStats, capi.MortarParams, capi.NDCouplingParams)]
     assert sizes == mine
 
 
