@@ -155,6 +155,21 @@ struct ProportionalFlowCoupling {                // test/proportionalflowcouplin
   static int id() { return MDB_OP_PROPFLOW_COUPLING; }
 };
 
+// Dune::PDELab::ConvectionDiffusionDGNeumannDirichletCoupling<CouplingParameters>(coupling_mode, param, method, weights, alpha, intorderadd)
+// (test/neumanndirichletcoupling.hh:56-74) with the parameter class of test/testpoisson-dirichlet-neumann.cc:36-69 (A = I, b = 0, c = 0)
+namespace CouplingMode { enum Type { Neumann = MDB_ND_MODE_NEUMANN, Dirichlet = MDB_ND_MODE_DIRICHLET, Both = MDB_ND_MODE_BOTH }; }
+namespace ConvectionDiffusionDGMethod { enum Type { NIPG = MDB_DG_METHOD_NIPG, SIPG = MDB_DG_METHOD_SIPG }; }
+namespace ConvectionDiffusionDGWeights { enum Type { weightsOff = MDB_DG_WEIGHTS_OFF, weightsOn = MDB_DG_WEIGHTS_ON }; }
+struct ConvectionDiffusionDGNeumannDirichletCoupling {
+  mdb_ndcoupling_params p; int jac_mode;
+  ConvectionDiffusionDGNeumannDirichletCoupling(CouplingMode::Type mode, ConvectionDiffusionDGMethod::Type method = ConvectionDiffusionDGMethod::NIPG,
+                                                ConvectionDiffusionDGWeights::Type weights = ConvectionDiffusionDGWeights::weightsOff, double alpha = 0.0,
+                                                int intorderadd = 0) : jac_mode(MDB_JAC_ANALYTIC) {
+    p.mode = mode; p.method = method; p.weights = weights; p.intorderadd = intorderadd; p.alpha = alpha;
+  }
+  static int id() { return MDB_OP_ND_COUPLING; }
+};
+
 struct MortarPoissonCoupling {                   // test/testmortarpoisson.cc:117-250, ctor arg = "scaling factor for coupling" (:402)
   mdb_mortar_params p; int jac_mode;
   explicit MortarPoissonCoupling(double gamma_0, int jacobian_mode = MDB_JAC_FD_BITMATCH) : jac_mode(jacobian_mode) { p.gamma_0 = gamma_0; }
@@ -321,19 +336,42 @@ struct ISTLBackend_SEQ_CG_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ
 struct ISTLBackend_SEQ_CG_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_JACOBI, maxiter) {} };
 struct ISTLBackend_SEQ_BCGS_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_JACOBI, maxiter) {} };
 
-// StationaryLinearProblemSolver(go, ls, reduction).apply(x): J(x0), r = R(x0), solve J z = r, x = x0 - z   (SURVEY §8c vii)
+// ISTL_SEQ_Subblock_Backend<Dune::SeqSSOR, Dune::BiCGSTABSolver>(block, maxiter) (test/testpoisson-dirichlet-neumann.cc:264-370):
+// BiCGSTAB + SeqSSOR(3) on the diagonal block of one child space; z outside the block is left untouched
+class ISTL_SEQ_Subblock_Backend {
+  int child_; unsigned maxiter_;
+public:
+  LinearSolverResult res;
+  explicit ISTL_SEQ_Subblock_Backend(const GridFunctionSpace& block, unsigned maxiter = 5000) : child_(block.child), maxiter_(maxiter) {
+    res.iterations = 0; res.converged = false; res.reduction = 0; res.elapsed = 0; }
+  void apply(Jacobian& a, Context& ctx, double* z, const double* r, double reduction) {
+    mdb_solve_stats st;
+    ctx.check(mdb_set_ssor_sweeps(ctx.get(), 3), "mdb_set_ssor_sweeps");
+    int rc = mdb_solve_block(ctx.get(), a.handle(), child_, MDB_SOLVER_BICGSTAB, MDB_PRECOND_SSOR, reduction, (int)maxiter_, r, z, &st);
+    res.iterations = st.iterations; res.converged = st.converged != 0; res.elapsed = st.seconds;
+    res.reduction = st.defect0 > 0 ? st.defect / st.defect0 : 0.0;
+    if (rc != MDB_ENOTCONVERGED) ctx.check(rc, "mdb_solve_block");
+  }
+};
+
+// StationaryLinearProblemSolver(go, ls, reduction).apply(x [, keep_matrix]): J(x0), r = R(x0), solve J z = r, x = x0 - z
+// (SURVEY §8c vii); keep_matrix = true reuses the Jacobian of the previous call (test/testpoisson-dirichlet-neumann.cc:806, :813)
 template <class LS>
 class StationaryLinearProblemSolver {
-  GridOperator& go_; LS& ls_; double reduction_;
+  GridOperator& go_; LS& ls_; double reduction_; Jacobian* a_;
+  StationaryLinearProblemSolver(const StationaryLinearProblemSolver&);
+  StationaryLinearProblemSolver& operator=(const StationaryLinearProblemSolver&);
 public:
-  StationaryLinearProblemSolver(GridOperator& go, LS& ls, double reduction) : go_(go), ls_(ls), reduction_(reduction) {}
-  void apply(Vector& x) {
-    Jacobian a(go_);
-    a = 0.0;
-    go_.jacobian(x, a);
+  StationaryLinearProblemSolver(GridOperator& go, LS& ls, double reduction) : go_(go), ls_(ls), reduction_(reduction), a_(0) {}
+  ~StationaryLinearProblemSolver() { delete a_; }
+  void setReduction(double reduction) { reduction_ = reduction; }
+  double reduction() const { return reduction_; }
+  void apply(Vector& x, bool keep_matrix = false) {
+    if (!a_) { a_ = new Jacobian(go_); keep_matrix = false; }
+    if (!keep_matrix) { *a_ = 0.0; go_.jacobian(x, *a_); }
     Vector r(x.size(), 0.0), z(x.size(), 0.0);
     go_.residual(x, r);
-    ls_.apply(a, go_.context(), z.data(), r.data(), reduction_);
+    ls_.apply(*a_, go_.context(), z.data(), r.data(), reduction_);
     if (!ls_.res.converged) throw Exception(MDB_ENOTCONVERGED, "StationaryLinearProblemSolver: linear solver did not converge");
     for (size_t i = 0; i < x.size(); ++i) x[i] -= z[i];
   }

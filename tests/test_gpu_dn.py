@@ -130,3 +130,40 @@ def test_dn_iteration_matches_oracle():
     assert abs(itd - ito) <= 1 and hd[-1] / hd[0] <= 1e-8 * 40 and ho[-1] / ho[0] <= 1e-8 * 40
     assert np.abs(ud - uo).max() <= 1e-5 * np.abs(uo).max()
     dev.close(); ora.close()
+
+
+@pytest.mark.parametrize("refine,ks", [(5, (1, 1)), (4, (2, 2)), (4, (1, 2))])
+def test_cxx_dn_driver_matches_oracle(refine, ks):
+    """examples/testpoisson-dirichlet-neumann.cc with examples/poisson-dirichlet-neumann.ini (the reference's keys): DOF counts, the
+    monolithic BiCGSTAB + SSOR(3) solve, the start residual of the full operator and the Dirichlet-Neumann sweep count / solution."""
+    import os
+    import re
+    import subprocess
+    import tempfile
+    from test_capi import _build_example, ROOT
+    n = (1 << refine,) * 2
+    fe = tuple(capi.FE_Q1 if k == 1 else capi.FE_Q2 for k in ks)
+    ora = orc.Oracle()
+    Po = problems.dirichlet_neumann(ora, n, fe=fe)
+    u0 = np.zeros(Po.ndof); ora.interpolate(Po.sps, Po.gfn, u0)
+    ora.jacobian(Po.go, Po.mat, u0, overwrite=True)
+    r = np.zeros(Po.ndof); ora.residual(Po.go, u0, r)
+    z = np.zeros(Po.ndof); ora.solve(Po.mat, r, z, reduction=1e-13)
+    umono = u0 - z
+    rf = np.zeros(Po.ndof); ora.residual(Po.full, u0, rf)
+    udn, its, _ = problems.dn_iteration(ora, Po, u0.copy())
+    ini = open(os.path.join(ROOT, "examples", "poisson-dirichlet-neumann.ini")).read().replace("refine = 6", "refine = %d" % refine)
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d, "testpoisson-dirichlet-neumann")
+        open(os.path.join(d, "t.ini"), "w").write(ini)
+        out = subprocess.run([exe, os.path.join(d, "t.ini"), str(ks[0]), str(ks[1])], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"(\d+) dof total, (\d+) dof constrained", out.stdout)
+    assert m and int(m.group(1)) == Po.ndof and int(m.group(2)) == Po.ncon
+    m = re.search(r"Monolithic solver: .* sum\(u\) = (\S+) \|u\|_2 = (\S+)", out.stdout)
+    assert abs(float(m.group(2)) - np.linalg.norm(umono)) <= 1e-6 * np.linalg.norm(umono)       # monolithic reduction 1e-8
+    m = re.search(r"Start residual: (\S+)", out.stdout)
+    assert abs(float(m.group(1)) - np.linalg.norm(rf)) <= 1e-11 * np.linalg.norm(rf)
+    m = re.search(r"Dirichlet-Neumann solver: (\d+) sweeps, (\d+) inner iterations, sum\(u\) = (\S+) \|u\|_2 = (\S+)", out.stdout)
+    assert m and abs(int(m.group(1)) - its) <= 1
+    assert abs(float(m.group(4)) - np.linalg.norm(udn)) <= 1e-5 * np.linalg.norm(udn)
