@@ -538,6 +538,11 @@ __global__ void __launch_bounds__(512) k_residual_volume_tile(MeshDesc m, const 
 #define RS_ROWS 128
 #define RS_XSEG (RS_ROWS + 4)
 #define RS_BLOCKS 10
+// The row stencils of the grid operator's subproblems (k_element_matrices writes them behind each element matrix), copied
+// device-to-device into constant memory on the stream before the stencil kernels run: the multiplications then take the
+// coefficient as a constant-bank operand.  From shared memory the 27 coefficient loads were half of the kernel's
+// shared-memory traffic, which is what bounds it (54 LDS.64 per row -> 27).
+__constant__ double c_resS[MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN][32];
 struct ResChild { int64_t offset, size; int bx, bxy; };
 
 __host__ __device__ inline bool res_chunk_staged(const ResChild& ch, int dim, int64_t r0, int64_t r1, int64_t n)
@@ -572,17 +577,16 @@ __global__ void k_residual_plan(MeshDesc m, const uint8_t* __restrict__ sd, Chil
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t n, ResChild ch, const double* __restrict__ S, const uint8_t* __restrict__ fast,
+__global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t n, ResChild ch, int slot, const uint8_t* __restrict__ fast,
                                                                   const double* __restrict__ x, double* __restrict__ res)
 {
   constexpr int NS = DIM == 3 ? 27 : 9;
   constexpr int NL = NS / 3;
   __shared__ __align__(16) double sx[2][NL * RS_XSEG];                           // double-buffered: chunk i+1 lands while chunk i is summed
   __shared__ __align__(8) unsigned long long bar[2];
-  __shared__ double sS[32];                                                      // (registers were measured: lower occupancy costs more)
   const int t = threadIdx.x;
   const int xpar = (int)(((uintptr_t)x >> 3) & 1);                              // bulk copies need 16-byte aligned sources
-  if (t < NS) sS[t] = S[t];
+  const double* __restrict__ cS = c_resS[slot];                                  // block-uniform: constant-bank operands
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[1])));
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
       for (int o = 0; o < NS; ++o) {
         const int dx = o % 3 - 1, l = o / 3, dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
         const int sh_l = (int)((r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy + xpar) & 1);
-        sum += sS[o] * sxb[l * RS_XSEG + sh_l + t + dx + 1];
+        sum += cS[o] * sxb[l * RS_XSEG + sh_l + t + dx + 1];
       }
       res[r] = rold + sum;
     }
@@ -685,10 +689,12 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
     cudaFree(d_t); dfree(d_flag); dfree(d_scan);
   }
   const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + (1 << m.dim) * (1 << m.dim);
+  MDB_CUDA(cudaMemcpyToSymbolAsync(c_resS, S, ((m.dim == 3) ? 27 : 9) * sizeof(double), (size_t)V.slot[0] * 32 * sizeof(double), cudaMemcpyDeviceToDevice,
+                                   c->stream));
   int grid = 148 * RS_BLOCKS;
   if (grid > cdiv(hc.size, RS_ROWS)) grid = cdiv(hc.size, RS_ROWS);
-  if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, S, go.d_res_fast[child], d_x, d_r);
-  else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, S, go.d_res_fast[child], d_x, d_r);
+  if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
+  else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
   const int64_t nrest = go.n_res_rest[child];
   if (nrest > 0) {
     if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
