@@ -155,10 +155,10 @@ __global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const doubl
 #define FT_THREADS 256                 // 8 warps share one image; each warp's elected lane issues the copies of its own runs
 template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(const double* __restrict__ S, const longlong2* __restrict__ seg_span, int64_t nseg,
-                                                          double* __restrict__ val)
+                                                          double* __restrict__ val, int ft_rows)
 {
   constexpr int NS = (DIM == 3) ? 27 : 9;
-  constexpr int CH = NS * FT_ROWS;                                       // doubles per bulk copy: a multiple of NS (phase preserved) and even
+  const int CH = NS * ft_rows;                                           // doubles per bulk copy: a multiple of NS (phase preserved) and even (ft_rows is)
   extern __shared__ __align__(128) double img[];                         // CH + 2 NS doubles, img[i] = S[i mod NS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = FT_THREADS / 32;
@@ -338,7 +338,11 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
       static const bool no_tma = getenv("MDB_FILL_NO_TMA") != nullptr;                  // A/B switch for profiling only
       if (overwrite && !no_tma) {
         const int ns = (m.dim == 3) ? 27 : 9;
-        const size_t smem = (size_t)(ns * FT_ROWS + 2 * ns) * sizeof(double);
+        // rows per shared-memory image = rows per bulk copy.  Small images leave the SM's shared memory to the irregular-row
+        // and FD-coupling kernels running beside the fill (their occupancy is shared-memory bound).
+        static const int ft_rows_env = getenv("MDB_FILL_TMA_ROWS") ? atoi(getenv("MDB_FILL_TMA_ROWS")) : FT_ROWS;
+        const int ft_rows = (ft_rows_env >= 2 && ft_rows_env <= FT_ROWS) ? (ft_rows_env & ~1) : FT_ROWS;
+        const size_t smem = (size_t)(ns * ft_rows + 2 * ns) * sizeof(double);
         static bool configured = false;
         if (!configured) {
           MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((9 * FT_ROWS + 18) * sizeof(double))));
@@ -348,8 +352,8 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
         static const int tma_blocks = getenv("MDB_FILL_TMA_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_TMA_BLOCKS_PER_SM")) : 2;
         int tgrid = 148 * tma_blocks;
         if (tgrid > cdiv(M.n_seg[i], FT_THREADS / 32)) tgrid = cdiv(M.n_seg[i], FT_THREADS / 32);
-        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val);
-        else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val);
+        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows);
+        else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows);
       } else if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
       else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
     }
@@ -594,39 +598,38 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
   }
   __syncthreads();
   const int64_t nchunks = (ch.size + RS_ROWS - 1) / RS_ROWS;
-  auto issue = [&](int64_t chunk, int buf) {                                      // thread 0 only
+  // lanes 0 .. NL-1 of warp 0, one x segment each: the nine 64-bit address computations run side by side instead of one
+  // after the other in a single thread — that thread's ~280 instructions per chunk were the block's critical path (every
+  // other warp waits for it at the barrier that ends the iteration)
+  constexpr unsigned ISSUE_MASK = 0xFFFFu;                                       // the first 16 lanes call issue(); lanes >= NL carry 0 bytes
+  auto issue = [&](int64_t chunk, int buf) {
     const int64_t r0 = ch.offset + chunk * RS_ROWS;
     const int64_t r1 = (r0 + RS_ROWS < ch.offset + ch.size) ? r0 + RS_ROWS : ch.offset + ch.size;
-    if (!res_chunk_staged(ch, DIM, r0, r1, n)) return;
+    if (!res_chunk_staged(ch, DIM, r0, r1, n)) return;                            // uniform over the issuing lanes
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar[buf]), sx_s = (uint32_t)__cvta_generic_to_shared(sx[buf]);
     const int len = (int)(r1 - r0) + 2;
-    uint32_t total = 0;
+    const int l = t;
+    const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
+    const int64_t g0 = r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy;
+    const int64_t al = g0 - ((g0 + xpar) & 1);
+    const uint32_t bytes = (l < NL) ? (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8) : 0u;
+    uint32_t total = bytes;
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
-      const int64_t g0 = r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy;
-      const int64_t al = g0 - ((g0 + xpar) & 1);
-      total += (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8);
-    }
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
-      const int64_t g0 = r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy;
-      const int64_t al = g0 - ((g0 + xpar) & 1);
-      const uint32_t bytes = (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8);
+    for (int o = 1; o < 16; o <<= 1) total += __shfl_xor_sync(ISSUE_MASK, total, o);
+    if (l == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+    __syncwarp(ISSUE_MASK);
+    if (l < NL)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sx_s + (uint32_t)(l * RS_XSEG * 8)),
                    "l"(x + al), "r"(bytes), "r"(bar_s)
                    : "memory");
-    }
   };
-  if (t == 0 && (int64_t)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+  if (t < 16 && (int64_t)blockIdx.x < nchunks) issue(blockIdx.x, 0);
   uint32_t phasebits = 0;
   int it = 0;
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {  // block-uniform trip count
     const int buf = it & 1;
     // the other buffer was released by the barrier that ended the previous iteration
-    if (t == 0 && chunk + gridDim.x < nchunks) issue(chunk + gridDim.x, buf ^ 1);
+    if (t < 16 && chunk + gridDim.x < nchunks) issue(chunk + gridDim.x, buf ^ 1);
     const int64_t r0 = ch.offset + chunk * RS_ROWS;
     const int64_t r1 = (r0 + RS_ROWS < ch.offset + ch.size) ? r0 + RS_ROWS : ch.offset + ch.size;
     const bool staged = res_chunk_staged(ch, DIM, r0, r1, n);                    // block-uniform
@@ -641,13 +644,17 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
       phasebits ^= 1u << buf;
     }
     if (mine) {
-      const double* sxb = sx[buf];
+      // where element g0 of line l landed: its 16-byte aligned copy starts at g0 - ((g0 + xpar) & 1) (see issue()), and
+      // parity(g0) = parity(r0 - 1 + xpar) ^ (dy odd & bx odd) ^ (dz odd & bxy odd) — three bits per chunk instead of nine
+      // 64-bit index computations in every warp (the kernel is issue bound: 243 -> ~90 instructions per 32 rows)
+      const int p0 = (int)((r0 - 1 + xpar) & 1), pb = ch.bx & 1, pbxy = ch.bxy & 1;
+      const double* sxb = sx[buf] + t + 1;
       double sum = 0.0;
 #pragma unroll
       for (int o = 0; o < NS; ++o) {
         const int dx = o % 3 - 1, l = o / 3, dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
-        const int sh_l = (int)((r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy + xpar) & 1);
-        sum += cS[o] * sxb[l * RS_XSEG + sh_l + t + dx + 1];
+        const int sh_l = p0 ^ ((dy != 0) ? pb : 0) ^ ((dz != 0) ? pbxy : 0);
+        sum += cS[o] * sxb[l * RS_XSEG + sh_l + dx];
       }
       res[r] = rold + sum;
     }
