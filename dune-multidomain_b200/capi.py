@@ -171,6 +171,11 @@ class Lib:
         assert b.size == self.ncells
         self._check(self._fn("subdomains")(C.c_void_p(self.ctx), _ptr(b, C.c_uint8)), "subdomains")
 
+    def get_subdomains(self):
+        b = np.zeros(self.ncells, dtype=np.uint8)
+        self._check(self._fn("get_subdomains")(C.c_void_p(self.ctx), _ptr(b, C.c_uint8)), "get_subdomains")
+        return b
+
     def subdomains_halfspace(self, axis, threshold, sd_below, sd_above):
         self._check(self._fn("subdomains_halfspace")(C.c_void_p(self.ctx), axis, C.c_double(threshold), sd_below, sd_above),
                     "subdomains_halfspace")

@@ -288,6 +288,16 @@ int mdb_subdomains(mdb_ctx* c, const uint8_t* bits)
   MDB_API_END(c)
 }
 
+int mdb_get_subdomains(mdb_ctx* c, uint8_t* bits)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->have_sd && bits, MDB_ESTATE, "mdb_get_subdomains: subdomains not set");
+  MDB_CUDA(cudaMemcpyAsync(bits, c->d_cell_sd, c->mesh.ncells(), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += c->mesh.ncells();
+  MDB_API_END(c)
+}
+
 int mdb_subdomains_halfspace(mdb_ctx* c, int axis, double threshold, int sd_below, int sd_above)
 {
   MDB_API_BEGIN(c)

@@ -3,12 +3,16 @@
 // (CouplingGridFunctionSpace, last child), Poisson on both sides, EnrichedCoupling with MortarPoissonCoupling(scaling),
 // residual + Jacobian, BiCGSTAB + SSOR(3) to 1e-10.
 //
-//   testmortarpoisson <refinement> <scaling factor for coupling> [dim=2]        (defaults of the reference: 5 1.0, :285-286)
+//   testmortarpoisson <refinement> <scaling factor for coupling> [dim=2] [output prefix]   (reference defaults: 5 1.0, :285-286)
+//
+// With an output prefix the program also writes what the reference writes: <prefix>jacobian.mat (Dune::writeMatrixToMatlab, :453)
+// and the solution per subdomain as <prefix>testmortarpoisson-left.vtu / -right.vtu (:465-486).
 //
 // Prints multigfs.ordering().size() like the reference (:386), the solver statistics and a checksum of u.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "mdb200/multidomain.hh"
 
@@ -20,6 +24,7 @@ int main(int argc, char** argv)
     const int refinement = argc >= 3 ? std::atoi(argv[1]) : 5;
     const double scaling = argc >= 3 ? std::atof(argv[2]) : 1.0;
     const int dim = argc > 3 ? std::atoi(argv[3]) : 2;
+    const std::string out = argc > 4 ? argv[4] : "";
     const int64_t cells = (int64_t)1 << refinement;                  // YaspGrid 1^d cells, globalRefine(refinement) (:291-296)
     const int64_t n[3] = {cells, cells, cells};
     const double lower[3] = {0, 0, 0}, upper[3] = {1, 1, 1};
@@ -61,11 +66,19 @@ int main(int argc, char** argv)
     gridoperator.residual(u, r);                                     // :442-444
     Jacobian J(gridoperator);
     gridoperator.jacobian(u, J);                                     // :446-448
+    if (!out.empty()) writeMatrixToMatlab(J, (int64_t)u.size(), out + "jacobian.mat");        // :453
     std::printf("%lld dof total, %lld dof constrained, %lld nonzeroes\n", (long long)u.size(), (long long)cg.size(), (long long)J.nonzeroes());
 
     ISTLBackend_SEQ_BCGS_SSOR ls(5000);                              // :456-457
     StationaryLinearProblemSolver<ISTLBackend_SEQ_BCGS_SSOR> pdesolver(gridoperator, ls, 1e-10);
     pdesolver.apply(u);
+
+    if (!out.empty()) {
+      VTKWriter left(grid, grid.subDomain(0)), right(grid, grid.subDomain(1));
+      left.addSolution(multigfs, u, {&gfs0, &gfs1, &couplinggfs});   // addSolutionToVTKWriter(..., subdomain_predicate(sdgv0.grid().domain()))
+      right.addSolution(multigfs, u, {&gfs0, &gfs1, &couplinggfs});
+      left.write(out + "testmortarpoisson-left"); right.write(out + "testmortarpoisson-right");
+    }
 
     double sum = 0.0, sum2 = 0.0, rsum2 = 0.0;
     for (size_t i = 0; i < u.size(); ++i) { sum += u[i]; sum2 += u[i] * u[i]; rsum2 += r[i] * r[i]; }

@@ -177,6 +177,8 @@ int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cel
 int mdb_subdomains(mdb_ctx* ctx, const uint8_t* cell_subdomain_bits);
 /* Device-side marking for large meshes: cells whose centre has x[axis] > threshold go to subdomain
  * `sd_above`, the others to `sd_below` (test/testpoisson.cc:152-158). */
+/* Parity / output export of the marking: one subdomain bit set per cell (what gv.indexSet().subDomains(e) returns). */
+int mdb_get_subdomains(mdb_ctx* ctx, uint8_t* cell_subdomain_bits);
 int mdb_subdomains_halfspace(mdb_ctx* ctx, int axis, double threshold, int sd_below, int sd_above);
 
 /* ---- function space  (MultiDomainGridFunctionSpace children,

@@ -11,6 +11,7 @@
 #define MDB200_MULTIDOMAIN_HH
 
 #include <cstdint>
+#include <cstdio>
 #include <initializer_list>
 #include <stdexcept>
 #include <string>
@@ -49,11 +50,14 @@ class MultiDomainGrid {
   Context& ctx_;
   int dim_;
   std::vector<int64_t> n_;
+  std::vector<double> lower_, upper_;
   std::vector<uint8_t> marks_;
   bool marking_;
 public:
+  const std::vector<double>& lower() const { return lower_; }
+  const std::vector<double>& upper() const { return upper_; }
   MultiDomainGrid(Context& ctx, int dim, const int64_t* cells, const double* lower, const double* upper)
-    : ctx_(ctx), dim_(dim), n_(cells, cells + dim), marking_(false) {
+    : ctx_(ctx), dim_(dim), n_(cells, cells + dim), lower_(lower, lower + dim), upper_(upper, upper + dim), marking_(false) {
     ctx_.check(mdb_mesh_structured(ctx_.get(), dim, cells, lower, upper), "mdb_mesh_structured");
   }
   Context& context() const { return ctx_; }
@@ -421,6 +425,127 @@ public:
     xnew.resize(xold.size()); apply(time, dt, xold.data(), f, xnew.data());
   }
 };
+
+// ---- output ([UPSTREAM] Dune::VTKWriter + multidomain/vtk.hh:83-98 addSolutionToVTKWriter; dune-istl writeMatrixToMatlab) -----------
+// VTKWriter<SDGV> vtkwriter(sdgv, VTK::conforming); addSolutionToVTKWriter(vtkwriter, multigfs, u, subdomain_predicate(sd));
+// vtkwriter.write(name, VTK::ascii)  — as every reference driver ends (e.g. test/testpoisson.cc:301-323).  One unstructured-grid
+// piece per subdomain: its cells (VTK_QUAD / VTK_HEXAHEDRON), their vertices, and per child space living on that subdomain one
+// point-data array with the solution at the vertices (conforming output: for Q2 the corner values, like VTK::conforming).
+class VTKWriter {
+  MultiDomainGrid& grid_; int subdomain_;
+  struct Field { std::string name; std::vector<double> point_values; };
+  std::vector<Field> fields_;
+  std::vector<int64_t> cells_;                 // MultiDomainGrid indices of the subdomain's cells, host order
+  std::vector<int64_t> vertex_of_point_;       // MultiDomainGrid vertex index of every output point (ascending = subdomain vertex order)
+  std::vector<int64_t> point_of_vertex_;
+  void collect() {
+    if (!cells_.empty()) return;
+    std::vector<uint8_t> sd((size_t)grid_.size0());
+    grid_.context().check(mdb_get_subdomains(grid_.context().get(), sd.data()), "mdb_get_subdomains");
+    const int dim = grid_.dimension(); const std::vector<int64_t>& n = grid_.cells();
+    int64_t nv = 1; for (int d = 0; d < dim; ++d) nv *= n[d] + 1;
+    std::vector<char> used((size_t)nv, 0);
+    for (int64_t e = 0; e < grid_.size0(); ++e) {
+      if (subdomain_ >= 0 && !((sd[(size_t)e] >> subdomain_) & 1)) continue;
+      cells_.push_back(e);
+      for (int c = 0; c < (1 << dim); ++c) used[(size_t)vertex(e, c)] = 1;
+    }
+    point_of_vertex_.assign((size_t)nv, -1);
+    for (int64_t v = 0; v < nv; ++v) if (used[(size_t)v]) { point_of_vertex_[(size_t)v] = (int64_t)vertex_of_point_.size(); vertex_of_point_.push_back(v); }
+  }
+  int64_t vertex(int64_t e, int corner) const {          // [UPSTREAM] Yasp: corner bit d = offset along axis d; vertices lexicographic
+    const int dim = grid_.dimension(); const std::vector<int64_t>& n = grid_.cells();
+    int64_t idx = 0, stride = 1, rem = e;
+    for (int d = 0; d < dim; ++d) { const int64_t i = rem % n[d] + ((corner >> d) & 1); rem /= n[d]; idx += i * stride; stride *= n[d] + 1; }
+    return idx;
+  }
+public:
+  VTKWriter(MultiDomainGrid& grid, const SubDomainGridView& gv) : grid_(grid), subdomain_(gv.subdomain) {}
+  // addSolutionToVTKWriter(vtkwriter, multigfs, x, subdomain_predicate): every child space whose grid view is this writer's subdomain
+  void addSolution(MultiDomainGridFunctionSpace& gfs, const Vector& x, std::initializer_list<const GridFunctionSpace*> children, const std::string& name = "u") {
+    collect();
+    gfs.update();
+    Context& ctx = gfs.context();
+    const int dim = grid_.dimension();
+    std::vector<int64_t> ptr((size_t)grid_.size0() + 1);
+    ctx.check(mdb_get_dofmap(ctx.get(), ptr.data(), 0), "mdb_get_dofmap");
+    std::vector<int64_t> dofs((size_t)ptr.back());
+    ctx.check(mdb_get_dofmap(ctx.get(), ptr.data(), dofs.data()), "mdb_get_dofmap");
+    std::vector<uint8_t> sd((size_t)grid_.size0());
+    ctx.check(mdb_get_subdomains(ctx.get(), sd.data()), "mdb_get_subdomains");
+    int nout = 0;
+    for (const GridFunctionSpace* g : children) {
+      if (g->coupling || g->gv.subdomain != subdomain_) continue;              // the predicate
+      Field f; f.name = (nout++ == 0) ? name : name + "_" + std::to_string(nout - 1);
+      f.point_values.assign(vertex_of_point_.size(), 0.0);
+      for (size_t ci = 0; ci < cells_.size(); ++ci) {
+        const int64_t e = cells_[ci];
+        // position of this child's block inside the cell's local space: children in order, each present iff its subdomain holds the cell
+        int64_t off = ptr[(size_t)e];
+        for (const GridFunctionSpace* h : children) {
+          if (h == g) break;
+          if (h->coupling) continue;
+          if (h->gv.subdomain < 0 || ((sd[(size_t)e] >> h->gv.subdomain) & 1)) { int nl = 1; for (int d = 0; d < dim; ++d) nl *= h->k + 1; off += nl; }
+        }
+        for (int c = 0; c < (1 << dim); ++c) {
+          int li = 0, stride = 1;                                               // Qk local index of the corner: a_d = k * bit_d
+          for (int d = 0; d < dim; ++d) { li += g->k * ((c >> d) & 1) * stride; stride *= g->k + 1; }
+          f.point_values[(size_t)point_of_vertex_[(size_t)vertex(e, c)]] = x[(size_t)dofs[(size_t)(off + li)]];
+        }
+      }
+      fields_.push_back(f);
+    }
+  }
+  // write(name, VTK::ascii): name.vtu
+  void write(const std::string& name) {
+    collect();
+    const int dim = grid_.dimension(); const std::vector<int64_t>& n = grid_.cells();
+    std::FILE* fp = std::fopen((name + ".vtu").c_str(), "w");
+    if (!fp) throw Exception(MDB_EINVAL, "VTKWriter: cannot open " + name + ".vtu");
+    std::fprintf(fp, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n");
+    std::fprintf(fp, "<Piece NumberOfPoints=\"%lld\" NumberOfCells=\"%lld\">\n", (long long)vertex_of_point_.size(), (long long)cells_.size());
+    std::fprintf(fp, "<PointData%s>\n", fields_.empty() ? "" : (" Scalars=\"" + fields_[0].name + "\"").c_str());
+    for (size_t f = 0; f < fields_.size(); ++f) {
+      std::fprintf(fp, "<DataArray type=\"Float64\" Name=\"%s\" NumberOfComponents=\"1\" format=\"ascii\">\n", fields_[f].name.c_str());
+      for (size_t i = 0; i < fields_[f].point_values.size(); ++i) std::fprintf(fp, "%.17g\n", fields_[f].point_values[i]);
+      std::fprintf(fp, "</DataArray>\n");
+    }
+    std::fprintf(fp, "</PointData>\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+    for (size_t p = 0; p < vertex_of_point_.size(); ++p) {
+      int64_t rem = vertex_of_point_[p]; double xyz[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d) { xyz[d] = grid_.lower()[d] + (double)(rem % (n[d] + 1)) * ((grid_.upper()[d] - grid_.lower()[d]) / (double)n[d]); rem /= n[d] + 1; }
+      std::fprintf(fp, "%.17g %.17g %.17g\n", xyz[0], xyz[1], xyz[2]);
+    }
+    std::fprintf(fp, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n");
+    static const int vtk_quad[4] = {0, 1, 3, 2}, vtk_hex[8] = {0, 1, 3, 2, 4, 5, 7, 6};      // DUNE corner order -> VTK order
+    for (size_t ci = 0; ci < cells_.size(); ++ci) {
+      for (int c = 0; c < (1 << dim); ++c) {
+        const int dc = dim == 3 ? vtk_hex[c] : dim == 2 ? vtk_quad[c] : c;
+        std::fprintf(fp, "%lld ", (long long)point_of_vertex_[(size_t)vertex(cells_[ci], dc)]);
+      }
+      std::fprintf(fp, "\n");
+    }
+    std::fprintf(fp, "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n");
+    for (size_t ci = 0; ci < cells_.size(); ++ci) std::fprintf(fp, "%lld\n", (long long)((ci + 1) << dim));
+    std::fprintf(fp, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+    for (size_t ci = 0; ci < cells_.size(); ++ci) std::fprintf(fp, "%d\n", dim == 3 ? 12 : dim == 2 ? 9 : 3);
+    std::fprintf(fp, "</DataArray>\n</Cells>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+    std::fclose(fp);
+  }
+};
+
+// Dune::writeMatrixToMatlab(J.base(), "jacobian.mat") (test/testmortarpoisson.cc:453; [UPSTREAM] dune-istl io.hh): one line
+// "row col value" per stored entry, 1-based indices, rows ascending, entries in BCRS (ascending column) order, 18 digits
+inline void writeMatrixToMatlab(const Jacobian& a, int64_t nrows, const std::string& filename, int outputPrecision = 18) {
+  std::vector<int64_t> rowptr, colidx; std::vector<double> v;
+  a.pattern(rowptr, colidx, nrows); a.values(v);
+  std::FILE* fp = std::fopen(filename.c_str(), "w");
+  if (!fp) throw Exception(MDB_EINVAL, "writeMatrixToMatlab: cannot open " + filename);
+  for (int64_t r = 0; r < nrows; ++r)
+    for (int64_t p = rowptr[(size_t)r]; p < rowptr[(size_t)r + 1]; ++p)
+      std::fprintf(fp, "%lld %lld %.*g\n", (long long)(r + 1), (long long)(colidx[(size_t)p] + 1), outputPrecision, v[(size_t)p]);
+  std::fclose(fp);
+}
 
 } // namespace mdb200
 #endif

@@ -1315,6 +1315,7 @@ int orc_subdomains(Context* c, const uint8_t* bits)
 {
   ORC_TRY(c, { c->cell_sd.assign(bits, bits + c->grid.ncells()); })
 }
+int orc_get_subdomains(Context* c, uint8_t* bits) { ORC_TRY(c, { std::copy(c->cell_sd.begin(), c->cell_sd.end(), bits); }) }
 int orc_subdomains_halfspace(Context* c, int axis, double threshold, int sd_below, int sd_above)
 {
   ORC_TRY(c, {

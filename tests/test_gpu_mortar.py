@@ -180,3 +180,41 @@ def test_cxx_mortar_driver_matches_oracle(refinement, scaling, dim):
     m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
     assert abs(float(m.group(1)) - un.sum()) <= 1e-7 * abs(un.sum())
     assert abs(float(m.group(2)) - np.linalg.norm(un)) <= 1e-7 * np.linalg.norm(un)
+
+
+def test_driver_output_files_match_oracle(tmp_path):
+    """What the reference drivers write (test/testmortarpoisson.cc:453, :465-486): jacobian.mat by writeMatrixToMatlab ("row col value",
+    1-based, BCRS order) and the solution per subdomain as VTK point data — parsed back and compared with the oracle."""
+    import re
+    import subprocess
+    import tempfile
+    from test_capi import _build_example
+    n = (8, 8)
+    ora = orc.Oracle()
+    Po = problems.testmortarpoisson(ora, n)
+    u = np.zeros(Po.ndof); ora.interpolate(Po.sps, Po.gfn, u)
+    ora.jacobian(Po.go, Po.mat, u, overwrite=True)
+    r = np.zeros(Po.ndof); ora.residual(Po.go, u, r)
+    z = np.zeros(Po.ndof); ora.solve(Po.mat, r, z, reduction=1e-13)
+    un = u - z
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d, "testmortarpoisson")
+        prefix = str(tmp_path) + "/"
+        out = subprocess.run([exe, "3", "1.0", "2", prefix], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    trip = np.loadtxt(prefix + "jacobian.mat")
+    rp, ci = ora.matrix_get_pattern(Po.mat)
+    rows = np.repeat(np.arange(Po.ndof), np.diff(rp))
+    assert np.array_equal(trip[:, 0].astype(int) - 1, rows) and np.array_equal(trip[:, 1].astype(int) - 1, ci)
+    vo = ora.matrix_get_values(Po.mat)
+    assert np.abs(trip[:, 2] - vo).max() <= 1e-12 * np.abs(vo).max()
+    off = ora.get_child_offsets()
+    for k, side in enumerate(("left", "right")):
+        txt = open(prefix + "testmortarpoisson-%s.vtu" % side).read()
+        m = re.search(r'NumberOfPoints="(\d+)" NumberOfCells="(\d+)"', txt)
+        assert int(m.group(1)) == off[k + 1] - off[k] and int(m.group(2)) == n[0] * n[1] // 2
+        vals = np.array(re.search(r'Name="u"[^>]*>\n(.*?)</DataArray>', txt, re.S).group(1).split(), dtype=float)
+        # Q1: the points are the subdomain's vertices in ascending index = the child block's DOF order
+        assert np.abs(vals - un[off[k]:off[k + 1]]).max() <= 1e-7 * np.abs(un).max()
+        pts = np.array(re.search(r'<Points>\n<DataArray[^>]*>\n(.*?)</DataArray>', txt, re.S).group(1).split(), dtype=float).reshape(-1, 3)
+        assert (pts[:, 0].min(), pts[:, 0].max()) == ((0.0, 0.5) if k == 0 else (0.5, 1.0))
