@@ -62,7 +62,8 @@ __device__ __forceinline__ bool record_tagged(const ulonglong2& w, unsigned tag)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_sweep(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                                const int32_t* __restrict__ diag, const double* __restrict__ a, const double* __restrict__ d,
-                                               ulonglong2* vt, const int32_t* __restrict__ perm, unsigned epoch, unsigned long long* counter)
+                                               ulonglong2* vt, const int32_t* __restrict__ perm, unsigned epoch, unsigned long long* counter,
+                                               const uint8_t* __restrict__ owned)
 {
   constexpr bool ASC = (MODE == SW_SSOR_FWD || MODE == SW_ILU_LOWER);
   const int lane = threadIdx.x & 31;
@@ -72,6 +73,9 @@ __global__ void __launch_bounds__(256) k_sweep(int64_t n, const int64_t* __restr
     k = __shfl_sync(0xffffffffu, k, 0);
     if (k >= (unsigned long long)n) return;
     const int64_t i = perm[ASC ? (int64_t)k : n - 1 - (int64_t)k];
+    // partitioned context: block-Jacobi over the ranks — the sweep runs on the owned x owned block of the local matrix; ghost
+    // rows carry 0 and ghost columns are left out
+    if (owned && !owned[i]) { if (lane == 0) st_record(vt + i, 0.0, epoch); __syncwarp(); continue; }
     const int64_t s = rowptr[i], e = rowptr[i + 1];
     const bool norow = diag[i] < 0;          // a row without entries (a block no participant of the matrix's operators lives on): identity row
     const int64_t pd = norow ? s : s + diag[i];
@@ -84,8 +88,9 @@ __global__ void __launch_bounds__(256) k_sweep(int64_t n, const int64_t* __restr
     double acc = (MODE == SW_ILU_UPPER) ? vi : d[i];
     for (int64_t pb = p0; pb < p1; pb += 32) {
       const int64_t p = pb + lane;
-      const bool live = p < p1;
+      bool live = p < p1;
       const int col = live ? colidx[p] : 0;
+      if (live && owned && !owned[col]) live = false;
       const double av = live ? a[p] : 0.0;
       const bool dep = live && (ASC ? (col < i) : (col > i));
       ulonglong2 w = make_ulonglong2(0ull, 0ull);
@@ -122,7 +127,7 @@ __global__ void k_records_to_vector(int64_t n, const ulonglong2* __restrict__ vt
 template <int EPL>
 __global__ void __launch_bounds__(256) k_ilu0_factor(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                                      const int32_t* __restrict__ diag, double* f, const int32_t* __restrict__ perm, int* ready, int epoch,
-                                                     unsigned long long* counter)
+                                                     unsigned long long* counter, const uint8_t* __restrict__ owned)
 {
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int64_t n, const int64_t* _
     kk = __shfl_sync(0xffffffffu, kk, 0);
     if (kk >= (unsigned long long)n) return;
     const int64_t i = perm[kk];
+    if (owned && !owned[i]) { if (lane == 0) st_release_s32(ready + i, epoch); __syncwarp(); continue; }     // ghost row: not part of the block
     const int64_t s = rowptr[i];
     const int len = (int)(rowptr[i + 1] - s), dg = diag[i];
     int col[EPL]; double val[EPL];
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int64_t n, const int64_t* _
 #pragma unroll
       for (int u = 1; u < EPL; ++u) if ((pl >> 5) == u) csel = col[u];       // pl >> 5 is warp-uniform
       const int k = __shfl_sync(0xffffffffu, csel, pl & 31);
+      if (owned && !owned[k]) continue;                                      // a ghost column: outside the owned x owned block (warp-uniform)
       for (int tries = 0; ld_acquire_s32(ready + k) != epoch; ++tries) __nanosleep(tries < 8 ? 32 : 128);
       const int64_t ks = rowptr[k];
       const int kd = diag[k], klen = (int)(rowptr[k + 1] - ks);
@@ -239,7 +246,7 @@ static void sweep(Ctx* c, Matrix& M, const double* a, const double* d)
   int grid = 148 * 8;
   if (grid > cdiv(c->ndof, 8)) grid = cdiv(c->ndof, 8);
   MDB_LAUNCH(c, k_sweep<MODE>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, a, d, M.d_vrec, M.d_sweep_perm, (unsigned)M.sweep_epoch,
-             M.d_sweep_counter);
+             M.d_sweep_counter, c->d_owned);
 }
 
 void ilu0_factorize(Ctx* c, Matrix& M)
@@ -253,13 +260,13 @@ void ilu0_factorize(Ctx* c, Matrix& M)
   if (grid > cdiv(c->ndof, 8)) grid = cdiv(c->ndof, 8);
   MDB_REQUIRE(M.max_row <= 256, MDB_EINVAL, "ILU0: rows longer than 256 entries are not supported");
   if (M.max_row <= 32)
-    MDB_LAUNCH(c, k_ilu0_factor<1>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+    MDB_LAUNCH(c, k_ilu0_factor<1>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter, c->d_owned);
   else if (M.max_row <= 64)
-    MDB_LAUNCH(c, k_ilu0_factor<2>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+    MDB_LAUNCH(c, k_ilu0_factor<2>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter, c->d_owned);
   else if (M.max_row > 128)
-    MDB_LAUNCH(c, k_ilu0_factor<8>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+    MDB_LAUNCH(c, k_ilu0_factor<8>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter, c->d_owned);
   else
-    MDB_LAUNCH(c, k_ilu0_factor<4>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter);
+    MDB_LAUNCH(c, k_ilu0_factor<4>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, M.d_ilu, M.d_sweep_perm, M.d_ready, M.sweep_epoch, M.d_sweep_counter, c->d_owned);
   M.ilu_valid = true;
 }
 
@@ -267,7 +274,7 @@ void ilu0_factorize(Ctx* c, Matrix& M)
 void precond_apply(Ctx* c, Matrix& M, int kind, int sweeps, const double* d, double* v)
 {
   const int64_t n = c->ndof;
-  MDB_REQUIRE(c->nranks == 1, MDB_EINVAL, "SSOR / ILU0 are sequential preconditioners: single-rank contexts only (use Jacobi on a partition)");
+  // on a partition: block-Jacobi — every rank applies the sequential preconditioner of its owned x owned block (k_sweep's `owned`)
   ensure_precond_state(c, M);
   if (!M.d_vrec) M.d_vrec = dalloc<ulonglong2>(n);
   if (kind == MDB_PRECOND_SSOR) {

@@ -720,7 +720,8 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
   // Jacobi (and none) are fused into the vector kernels through the inverse diagonal; SSOR / ILU0 are explicit applications
   // z = M^-1 r (precond.cu) between the same kernels run with a unit "inverse diagonal"
   const bool general = precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0;
-  MDB_REQUIRE(!general || c->nranks == 1, MDB_EINVAL, "SSOR / ILU0 are sequential preconditioners: single-rank contexts only");
+  // on a partition SSOR / ILU0 become block-Jacobi over the ranks: each rank applies the sequential preconditioner of its owned
+  // block (precond.cu); iteration counts then depend on the number of ranks
   const int64_t n = c->ndof;
   const int vgrid = (cdiv(n, VEC_THREADS) < 148 * 8) ? cdiv(n, VEC_THREADS) : 148 * 8;
   if (!M.d_dinv) { M.d_dinv = dalloc<double>(n); M.dinv_valid = false; }
@@ -751,6 +752,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       precond_apply(c, M, precond, c->ssor_sweeps, r, zv);
       MDB_LAUNCH(c, k_dot, vgrid, VEC_THREADS, 0, n, s, zv, r, c->d_owned, c->d_partial);
       reduce(c, vgrid, 1, S_RHONEW);
+      if (multi) allreduce_scalars(c, s + S_RHONEW, 1);
     };
     if (general) precondition();
     MDB_LAUNCH(c, k_cg_init_scalars, 1, 1, 0, s, reduction);
