@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const doubl
 #define FT_THREADS 256                 // 8 warps share one image; each warp's elected lane issues the copies of its own runs
 template <int DIM>
 __global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(const double* __restrict__ S, const longlong2* __restrict__ seg_span, int64_t nseg,
-                                                          double* __restrict__ val, int ft_rows)
+                                                          double* __restrict__ val, int ft_rows, int evict_first)
 {
   constexpr int NS = (DIM == 3) ? 27 : 9;
   const int CH = NS * ft_rows;                                           // doubles per bulk copy: a multiple of NS (phase preserved) and even (ft_rows is)
@@ -178,9 +178,18 @@ __global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(const double* 
     if (lane == 0) {
       const int phase = (int)((a0 - p0) % NS);
       const uint32_t src = img_s + 8u * (uint32_t)((phase & 1) ? phase + NS : phase);
+      // the 3.4 GB of streamed values are not read again inside the step: written with an evict-first L2 policy they do not
+      // push the working set of the irregular-row and FD-coupling kernels (row images, slot tables, atomics) out of the L2
+      unsigned long long pol = 0;
+      if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       while (a0 < a1) {
         const int64_t n = (a1 - a0 < CH) ? a1 - a0 : CH;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(val + a0), "r"(src), "r"((uint32_t)(n * 8)) : "memory");
+        if (evict_first)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(val + a0), "r"(src), "r"((uint32_t)(n * 8)),
+                       "l"(pol)
+                       : "memory");
+        else
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(val + a0), "r"(src), "r"((uint32_t)(n * 8)) : "memory");
         a0 += n;
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -352,8 +361,9 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
         static const int tma_blocks = getenv("MDB_FILL_TMA_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_TMA_BLOCKS_PER_SM")) : 2;
         int tgrid = 148 * tma_blocks;
         if (tgrid > cdiv(M.n_seg[i], FT_THREADS / 32)) tgrid = cdiv(M.n_seg[i], FT_THREADS / 32);
-        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows);
-        else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows);
+        static const int evict_first = getenv("MDB_FILL_EVICT_FIRST") ? atoi(getenv("MDB_FILL_EVICT_FIRST")) : 0;
+        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows, evict_first);
+        else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows, evict_first);
       } else if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
       else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
     }
@@ -635,7 +645,6 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
     const bool staged = res_chunk_staged(ch, DIM, r0, r1, n);                    // block-uniform
     const int64_t r = r0 + t;
     const bool mine = staged && r < r1 && fast[r - ch.offset] != 0;
-    const double rold = mine ? res[r] : 0.0;                                      // in flight while the copies land
     if (staged) {
       uint32_t ok = 0;
       while (!ok)
@@ -656,22 +665,32 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
         const int sh_l = p0 ^ ((dy != 0) ? pb : 0) ^ ((dz != 0) ? pbxy : 0);
         sum += cS[o] * sxb[l * RS_XSEG + sh_l + dx];
       }
-      res[r] = rold + sum;
+      // residual() is additive (gridoperator.hh:89-92) and the coupling terms of the interface cells add to some of these rows
+      // from the auxiliary stream at the same time (mdb_residual): one reduction at the L2, no load, no lost update
+      atomicAdd(res + r, sum);
     }
     __syncthreads();                                                             // this buffer is free again
   }
 }
 
 // returns false when the child does not qualify (the caller falls back to the tile kernel)
-static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, const VolSpec& V, const double* d_x, double* d_r)
+static bool residual_stencil_applies(const Ctx* c, int child, const VolSpec& V)
 {
-  static const bool off = getenv("MDB_RESIDUAL_TILE") != nullptr;                 // A/B switch for profiling only
+  static const bool off = getenv("MDB_RESIDUAL_TILE") != nullptr || getenv("MDB_RESIDUAL_LEGACY") != nullptr;     // A/B switches for profiling only
   const MeshDesc& m = c->mesh;
   const Child& hc = c->children[child];
   if (off || V.n != 1 || hc.k != 1 || hc.size == 0) return false;
   int64_t vol = 1;
   for (int d = 0; d < m.dim; ++d) vol *= hc.lat_hi[d] - hc.lat_lo[d] + 1;
-  if (vol != hc.size) return false;                                               // not a box: the stencil offsets are not constant
+  return vol == hc.size;                                                          // not a box: the stencil offsets are not constant
+}
+
+// part: -1 = both kernels, 0 = the streamed uniform rows, 1 = the other rows of the child (row-list gather)
+static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, const VolSpec& V, const double* d_x, double* d_r, int part = -1)
+{
+  const MeshDesc& m = c->mesh;
+  const Child& hc = c->children[child];
+  if (!residual_stencil_applies(c, child, V)) return false;
   ResChild rc; rc.offset = hc.offset; rc.size = hc.size;
   rc.bx = hc.lat_hi[0] - hc.lat_lo[0] + 1; rc.bxy = rc.bx * (hc.lat_hi[1] - hc.lat_lo[1] + 1);
   const int64_t n = c->ndof;
@@ -695,19 +714,58 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
     go.n_res_rest[child] = (int64_t)ls + lf;
     cudaFree(d_t); dfree(d_flag); dfree(d_scan);
   }
-  const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + (1 << m.dim) * (1 << m.dim);
-  MDB_CUDA(cudaMemcpyToSymbolAsync(c_resS, S, ((m.dim == 3) ? 27 : 9) * sizeof(double), (size_t)V.slot[0] * 32 * sizeof(double), cudaMemcpyDeviceToDevice,
-                                   c->stream));
-  int grid = 148 * RS_BLOCKS;
-  if (grid > cdiv(hc.size, RS_ROWS)) grid = cdiv(hc.size, RS_ROWS);
-  if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
-  else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
+  if (part != 1 && part != 2) {
+    const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + (1 << m.dim) * (1 << m.dim);
+    MDB_CUDA(cudaMemcpyToSymbolAsync(c_resS, S, ((m.dim == 3) ? 27 : 9) * sizeof(double), (size_t)V.slot[0] * 32 * sizeof(double), cudaMemcpyDeviceToDevice,
+                                     c->stream));
+    int grid = 148 * RS_BLOCKS;
+    if (grid > cdiv(hc.size, RS_ROWS)) grid = cdiv(hc.size, RS_ROWS);
+    if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
+    else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
+  }
   const int64_t nrest = go.n_res_rest[child];
-  if (nrest > 0) {
+  if (nrest > 0 && part != 0 && part != 2) {
     if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
     else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
   }
   return true;
+}
+
+// True when every child the operator acts on goes through the streamed stencil kernel + row list pair.  Then the residual can
+// be split (mdb_residual): part 0 = the streamed uniform rows, which nothing else touches, on the context stream; part 1 = the
+// row lists, followed by the boundary and coupling terms, on the auxiliary stream beside them.  (A child on one of the
+// all-rows fallback kernels also owns the boundary / interface rows the face terms add to: no split then.)
+bool residual_can_split(Ctx* c, const GridOp& go)
+{
+  bool any = false;
+  for (int i = 0; i < (int)c->children.size(); ++i) {
+    VolSpec V = vol_spec(c, go, i);
+    if (V.n == 0 || c->children[i].size == 0) continue;
+    if (!residual_stencil_applies(c, i, V)) return false;
+    any = true;
+  }
+  return any;
+}
+
+// part as in residual_stencil; launch_element_matrices must have run (the caller forks the two parts behind it)
+void residual_volume_part(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r, int part)
+{
+  (void)weight;
+  for (int i = 0; i < (int)c->children.size(); ++i) {
+    VolSpec V = vol_spec(c, go, i);
+    if (V.n == 0 || c->children[i].size == 0) continue;
+    residual_stencil(c, const_cast<GridOp&>(go), i, child_q1(c, i), V, d_x, d_r, part);
+  }
+}
+
+// plans (fast flags + row lists) of every child, built on the context stream before a split residual forks
+void residual_prepare(Ctx* c, const GridOp& go)
+{
+  for (int i = 0; i < (int)c->children.size(); ++i) {
+    VolSpec V = vol_spec(c, go, i);
+    if (V.n == 0 || c->children[i].size == 0) continue;
+    if (go.n_res_rest[i] < 0) residual_stencil(c, const_cast<GridOp&>(go), i, child_q1(c, i), V, nullptr, nullptr, 2);   // plan only
+  }
 }
 
 void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r)

@@ -587,16 +587,43 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   MDB_GO(c, go)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vr(c, r, c->ndof, 1, true);
-  c->phase_begin("residual_volume");
-  residual_volume(c, G, weight, vx.d, vr.d);
-  c->phase_end();
-  c->phase_begin("residual_boundary");
-  residual_boundary(c, G, weight, vr.d);
-  c->phase_end();
-  c->phase_begin("residual_coupling");
-  residual_coupling(c, G, weight, vx.d, vr.d);
-  constrain_residual(c, vr.d);
-  c->phase_end();
+  static const bool serial = getenv("MDB_RESIDUAL_SERIAL") != nullptr;          // A/B switch for profiling only
+  if (!serial && residual_can_split(c, G)) {
+    // main: element matrices -> [fork] -> streamed uniform rows of every child (issue / shared-memory bound) --------> [join] -> constrain
+    // aux :                     [fork] -> row lists -> boundary terms -> coupling terms (latency bound, atomics) ------> [join]
+    // The streamed rows are interior rows all of whose cells carry the subproblem: no row list and no boundary term touches them;
+    // the coupling terms of the interface cells do (their vertices one layer off the interface), which is why the stencil kernel
+    // adds with a reduction instead of load + store.
+    residual_prepare(c, G);
+    c->phase_begin("residual_volume");
+    launch_element_matrices(c, G.sps, weight);
+    MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    {
+      StreamScope aux(c, c->aux_stream);
+      MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+      residual_volume_part(c, G, weight, vx.d, vr.d, 1);
+      residual_boundary(c, G, weight, vr.d);
+      residual_coupling(c, G, weight, vx.d, vr.d);
+      MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+    }
+    residual_volume_part(c, G, weight, vx.d, vr.d, 0);
+    c->phase_end();
+    MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->phase_begin("residual_coupling");
+    constrain_residual(c, vr.d);
+    c->phase_end();
+  } else {
+    c->phase_begin("residual_volume");
+    residual_volume(c, G, weight, vx.d, vr.d);
+    c->phase_end();
+    c->phase_begin("residual_boundary");
+    residual_boundary(c, G, weight, vr.d);
+    c->phase_end();
+    c->phase_begin("residual_coupling");
+    residual_coupling(c, G, weight, vx.d, vr.d);
+    constrain_residual(c, vr.d);
+    c->phase_end();
+  }
   vr.commit();
   MDB_API_END(c)
 }
@@ -655,13 +682,21 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   c->phase_begin("jacobian_elem");
   launch_element_matrices(c, G.sps, weight);
   c->phase_end();
+  static const bool rows_first = getenv("MDB_JAC_ROWS_FIRST") != nullptr;   // A/B: irregular rows alone before the fork
+  if (rows_first) {
+    c->phase_begin("jacobian_rows");
+    jacobian_volume(c, G, M, weight, overwrite != 0, 1);
+    c->phase_end();
+  }
   MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
   {
     StreamScope aux(c, c->aux_stream);
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
-    c->phase_begin("jacobian_rows");
-    jacobian_volume(c, G, M, weight, overwrite != 0, 1);
-    c->phase_end();
+    if (!rows_first) {
+      c->phase_begin("jacobian_rows");
+      jacobian_volume(c, G, M, weight, overwrite != 0, 1);
+      c->phase_end();
+    }
     if (host_x && need_x) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
     c->phase_begin("jacobian_coupling");
     jacobian_coupling(c, G, M, weight, dx, false);

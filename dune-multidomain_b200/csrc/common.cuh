@@ -333,6 +333,9 @@ void build_facelists(Ctx* c, GridOp& go);
 void build_xneed(Ctx* c, GridOp& go);
 void build_pattern(Ctx* c, Matrix& m);
 void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
+bool residual_can_split(Ctx* c, const GridOp& go);
+void residual_prepare(Ctx* c, const GridOp& go);
+void residual_volume_part(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r, int part);
 void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r);
 void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
 void constrain_residual(Ctx* c, double* d_r);
