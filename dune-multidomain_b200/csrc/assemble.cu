@@ -440,7 +440,8 @@ __global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const ui
       s += acc[o] * xc[ch.lat2dof[lp + dx + dy * ch.lat_n[0] + dz * ch.lat_n[0] * ch.lat_n[1]]];
     }
   }
-  r[ch.offset + gi] += s;
+  if (list) atomicAdd(r + ch.offset + gi, s);        // row-list mode runs beside the boundary / coupling terms (mdb_residual): reduction, not load + store
+  else r[ch.offset + gi] += s;
 }
 
 // ---- residual, tiled variant (the default) ---------------------------------------------------------------------------------

@@ -590,7 +590,8 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   static const bool serial = getenv("MDB_RESIDUAL_SERIAL") != nullptr;          // A/B switch for profiling only
   if (!serial && residual_can_split(c, G)) {
     // main: element matrices -> [fork] -> streamed uniform rows of every child (issue / shared-memory bound) --------> [join] -> constrain
-    // aux :                     [fork] -> row lists -> boundary terms -> coupling terms (latency bound, atomics) ------> [join]
+    // aux :                     [fork] -> row lists (latency bound) -------------------------------------------------> [join]
+    // third:                    [fork] -> boundary terms -> coupling terms (latency bound) ---------------------------> [join]
     // The streamed rows are interior rows all of whose cells carry the subproblem: no row list and no boundary term touches them;
     // the coupling terms of the interface cells do (their vertices one layer off the interface), which is why the stencil kernel
     // adds with a reduction instead of load + store.
@@ -602,13 +603,19 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
       StreamScope aux(c, c->aux_stream);
       MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
       residual_volume_part(c, G, weight, vx.d, vr.d, 1);
+      MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+    }
+    {
+      StreamScope third(c, c->copy_stream);                                     // every update of r on the three branches is a reduction
+      MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
       residual_boundary(c, G, weight, vr.d);
       residual_coupling(c, G, weight, vx.d, vr.d);
-      MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+      MDB_CUDA(cudaEventRecord(c->ev_copy_done, c->stream));
     }
     residual_volume_part(c, G, weight, vx.d, vr.d, 0);
     c->phase_end();
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
     c->phase_begin("residual_coupling");
     constrain_residual(c, vr.d);
     c->phase_end();
