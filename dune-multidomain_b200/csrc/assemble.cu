@@ -550,20 +550,49 @@ __global__ void __launch_bounds__(512) k_residual_volume_tile(MeshDesc m, const 
 // its row from shared memory.  Which rows qualify is decided once per (grid operator, child) — k_residual_plan — and kept
 // as a byte per row; the other rows (boundary, subdomain boundary, chunks at the ends of the vector) go through the
 // per-row gather kernel over a compact list.  Bytes per row: 8 (x, via L2) + 16 (r read-modify-write) + 1.
-#define RS_ROWS 128
+#define RS_ROWS 128                    // x extent of a tile = threads per block
+#ifndef RS_RY
+#define RS_RY 4                        // y-lines per tile = rows per thread
+#endif
 #define RS_XSEG (RS_ROWS + 4)
-#define RS_BLOCKS 10
+#ifndef RS_NBUF
+#define RS_NBUF 1                      // 1: one buffer, 8 resident blocks per SM hide the copy latency (measured best: 65 us per child at
+                                       // 256^3); 2: tile i+1 lands while tile i is summed, but only 5 blocks fit (85 us)
+#endif
+#ifndef RS_BLOCKS
+#define RS_BLOCKS 8
+#endif
 // The row stencils of the grid operator's subproblems (k_element_matrices writes them behind each element matrix), copied
 // device-to-device into constant memory on the stream before the stencil kernels run: the multiplications then take the
 // coefficient as a constant-bank operand.  From shared memory the 27 coefficient loads were half of the kernel's
-// shared-memory traffic, which is what bounds it (54 LDS.64 per row -> 27).
+// shared-memory traffic (54 LDS.64 per row -> 27).
 __constant__ double c_resS[MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN][32];
-struct ResChild { int64_t offset, size; int bx, bxy; };
+struct ResChild { int64_t offset, size; int bx, bxy; int nl, nxc; };          // nl = lines of the child (size / bx), nxc = tiles per line
 
-__host__ __device__ inline bool res_chunk_staged(const ResChild& ch, int dim, int64_t r0, int64_t r1, int64_t n)
+// Tiles.  A box child is numbered r = offset + s + bx * L with s the position on an x-line and L = iy + by * iz the line.  A tile
+// is 128 consecutive positions of RS_RY consecutive lines: thread t owns position t of each of its lines, so a value of x read from
+// shared memory serves up to three of the thread's rows (dy = -1, 0, 1) — 3 (RS_RY + 2) / RS_RY = 4.5 segment reads per row-line
+// group instead of 9, which is what the kernel is bound by (issue slots and the shared-memory pipe, not HBM).
+struct ResTileId { int64_t r0; int npos, nlines; };
+__host__ __device__ inline ResTileId res_tile(const ResChild& ch, int64_t tile)
 {
-  const int64_t reach = (dim == 3) ? (int64_t)ch.bx + ch.bxy : ch.bx;
-  return r1 > r0 && r0 - 1 - reach - 1 >= 0 && r1 + 1 + reach + 1 <= n;
+  const int sb = (int)tile / ch.nxc, xc = (int)tile - sb * ch.nxc;             // fewer than 2^31 tiles (ndof < 2^31): 32-bit division
+  ResTileId T;
+  T.r0 = ch.offset + (int64_t)sb * (RS_RY * ch.bx) + xc * RS_ROWS;
+  T.npos = (ch.bx - xc * RS_ROWS < RS_ROWS) ? ch.bx - xc * RS_ROWS : RS_ROWS;
+  T.nlines = (ch.nl - sb * RS_RY < RS_RY) ? ch.nl - sb * RS_RY : RS_RY;
+  return T;
+}
+__host__ __device__ inline int64_t res_ntiles(const ResChild& ch)
+{
+  return (int64_t)((ch.nl + RS_RY - 1) / RS_RY) * ch.nxc;
+}
+// every segment of the tile (lines -1 .. RS_RY of the three z-planes, widened by one entry for the 16-byte alignment) inside the vector
+__host__ __device__ inline bool res_tile_staged(const ResChild& ch, int dim, const ResTileId& T, int64_t n)
+{
+  const int64_t reach_lo = (dim == 3) ? (int64_t)ch.bx + ch.bxy : ch.bx;
+  const int64_t reach_hi = (dim == 3) ? (int64_t)RS_RY * ch.bx + ch.bxy : (int64_t)RS_RY * ch.bx;
+  return T.r0 - 1 - reach_lo - 1 >= 0 && T.r0 + T.npos + 1 + reach_hi + 1 <= n;
 }
 
 template <int DIM>
@@ -582,11 +611,9 @@ __global__ void k_residual_plan(MeshDesc m, const uint8_t* __restrict__ sd, Chil
           uni = uni && cond_applies(V.cond_kind[0], V.mask[0], s) && (ch.subdomain < 0 || ((s >> ch.subdomain) & 1));
         }
   }
-  const int64_t r = rc.offset + gi;
-  const int64_t r0 = rc.offset + gi / RS_ROWS * RS_ROWS;
-  const int64_t r1 = (r0 + RS_ROWS < rc.offset + rc.size) ? r0 + RS_ROWS : rc.offset + rc.size;
-  (void)r;
-  const bool f = uni && res_chunk_staged(rc, DIM, r0, r1, n);
+  const int line = (int)(gi / rc.bx), spos = (int)(gi - (int64_t)line * rc.bx);
+  const ResTileId T = res_tile(rc, (int64_t)(line / RS_RY) * rc.nxc + spos / RS_ROWS);
+  const bool f = uni && res_tile_staged(rc, DIM, T, n);
   fast[gi] = f ? 1 : 0;
   flags[gi] = f ? 0 : 1;
 }
@@ -595,9 +622,9 @@ template <int DIM>
 __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t n, ResChild ch, int slot, const uint8_t* __restrict__ fast,
                                                                   const double* __restrict__ x, double* __restrict__ res)
 {
-  constexpr int NS = DIM == 3 ? 27 : 9;
-  constexpr int NL = NS / 3;
-  __shared__ __align__(16) double sx[2][NL * RS_XSEG];                           // double-buffered: chunk i+1 lands while chunk i is summed
+  constexpr int NZ = DIM == 3 ? 3 : 1;                                           // z-planes of the stencil
+  constexpr int NSEG = NZ * (RS_RY + 2);                                         // x segments per tile
+  __shared__ __align__(16) double sx[RS_NBUF][NSEG * RS_XSEG];
   __shared__ __align__(8) unsigned long long bar[2];
   const int t = threadIdx.x;
   const int xpar = (int)(((uintptr_t)x >> 3) & 1);                              // bulk copies need 16-byte aligned sources
@@ -608,67 +635,79 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int64_t nchunks = (ch.size + RS_ROWS - 1) / RS_ROWS;
-  // lanes 0 .. NL-1 of warp 0, one x segment each: the nine 64-bit address computations run side by side instead of one
-  // after the other in a single thread — that thread's ~280 instructions per chunk were the block's critical path (every
-  // other warp waits for it at the barrier that ends the iteration)
-  constexpr unsigned ISSUE_MASK = 0xFFFFu;                                       // the first 16 lanes call issue(); lanes >= NL carry 0 bytes
-  auto issue = [&](int64_t chunk, int buf) {
-    const int64_t r0 = ch.offset + chunk * RS_ROWS;
-    const int64_t r1 = (r0 + RS_ROWS < ch.offset + ch.size) ? r0 + RS_ROWS : ch.offset + ch.size;
-    if (!res_chunk_staged(ch, DIM, r0, r1, n)) return;                            // uniform over the issuing lanes
+  const int64_t ntiles = res_ntiles(ch);
+  // segment g = (zz, yy): line offset (yy - 1) of z-plane (zz - 1); the lanes of warp 0 issue one bulk copy each, side by side
+  auto issue = [&](int64_t tile, int buf) {
+    const ResTileId T = res_tile(ch, tile);
+    if (!res_tile_staged(ch, DIM, T, n)) return;                                  // uniform over the warp
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar[buf]), sx_s = (uint32_t)__cvta_generic_to_shared(sx[buf]);
-    const int len = (int)(r1 - r0) + 2;
-    const int l = t;
-    const int dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
-    const int64_t g0 = r0 - 1 + dy * ch.bx + (int64_t)dz * ch.bxy;
+    const int len = T.npos + 2;
+    const int g = t;
+    const int yy = g % (RS_RY + 2), zz = g / (RS_RY + 2);
+    const int64_t g0 = T.r0 - 1 + (int64_t)(yy - 1) * ch.bx + (int64_t)(DIM == 3 ? zz - 1 : 0) * ch.bxy;
     const int64_t al = g0 - ((g0 + xpar) & 1);
-    const uint32_t bytes = (l < NL) ? (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8) : 0u;
+    const uint32_t bytes = (g < NSEG) ? (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8) : 0u;
     uint32_t total = bytes;
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) total += __shfl_xor_sync(ISSUE_MASK, total, o);
-    if (l == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
-    __syncwarp(ISSUE_MASK);
-    if (l < NL)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sx_s + (uint32_t)(l * RS_XSEG * 8)),
+    for (int o = 1; o < 32; o <<= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (g == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+    __syncwarp();
+    if (g < NSEG)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sx_s + (uint32_t)(g * RS_XSEG * 8)),
                    "l"(x + al), "r"(bytes), "r"(bar_s)
                    : "memory");
   };
-  if (t < 16 && (int64_t)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+  if (RS_NBUF == 2 && t < 32 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   uint32_t phasebits = 0;
   int it = 0;
-  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {  // block-uniform trip count
-    const int buf = it & 1;
-    // the other buffer was released by the barrier that ended the previous iteration
-    if (t < 16 && chunk + gridDim.x < nchunks) issue(chunk + gridDim.x, buf ^ 1);
-    const int64_t r0 = ch.offset + chunk * RS_ROWS;
-    const int64_t r1 = (r0 + RS_ROWS < ch.offset + ch.size) ? r0 + RS_ROWS : ch.offset + ch.size;
-    const bool staged = res_chunk_staged(ch, DIM, r0, r1, n);                    // block-uniform
-    const int64_t r = r0 + t;
-    const bool mine = staged && r < r1 && fast[r - ch.offset] != 0;
+  const int pb = ch.bx & 1, pbxy = ch.bxy & 1;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {      // block-uniform trip count
+    const int buf = (RS_NBUF == 2) ? (it & 1) : 0;
+    // the other buffer (or, single-buffered, this one) was released by the barrier that ended the previous iteration
+    if (RS_NBUF == 2) { if (t < 32 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, buf ^ 1); }
+    else if (t < 32) issue(tile, 0);
+    const ResTileId T = res_tile(ch, tile);
+    const bool staged = res_tile_staged(ch, DIM, T, n);                          // block-uniform
+    // which of this thread's rows are streamed rows (a byte per row, fetched while the copies land)
+    bool mine[RS_RY];
+#pragma unroll
+    for (int j = 0; j < RS_RY; ++j) {
+      const int64_t r = T.r0 + (int64_t)j * ch.bx + t;
+      mine[j] = staged && t < T.npos && j < T.nlines && fast[r - ch.offset] != 0;
+    }
     if (staged) {
       uint32_t ok = 0;
       while (!ok)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(&bar[buf])), "r"((phasebits >> buf) & 1u) : "memory");
       phasebits ^= 1u << buf;
-    }
-    if (mine) {
-      // where element g0 of line l landed: its 16-byte aligned copy starts at g0 - ((g0 + xpar) & 1) (see issue()), and
-      // parity(g0) = parity(r0 - 1 + xpar) ^ (dy odd & bx odd) ^ (dz odd & bxy odd) — three bits per chunk instead of nine
-      // 64-bit index computations in every warp (the kernel is issue bound: 243 -> ~90 instructions per 32 rows)
-      const int p0 = (int)((r0 - 1 + xpar) & 1), pb = ch.bx & 1, pbxy = ch.bxy & 1;
+      // where element g0 of a segment landed: its 16-byte aligned copy starts at g0 - ((g0 + xpar) & 1) (see issue()), and
+      // parity(g0) = parity(r0 - 1 + xpar) ^ ((yy - 1) odd & bx odd) ^ ((zz - 1) odd & bxy odd)
+      const int p0 = (int)((T.r0 - 1 + xpar) & 1);
       const double* sxb = sx[buf] + t + 1;
-      double sum = 0.0;
+      double sum[RS_RY];
 #pragma unroll
-      for (int o = 0; o < NS; ++o) {
-        const int dx = o % 3 - 1, l = o / 3, dy = l % 3 - 1, dz = (DIM == 3) ? l / 3 - 1 : 0;
-        const int sh_l = p0 ^ ((dy != 0) ? pb : 0) ^ ((dz != 0) ? pbxy : 0);
-        sum += cS[o] * sxb[l * RS_XSEG + sh_l + dx];
-      }
+      for (int j = 0; j < RS_RY; ++j) sum[j] = 0.0;
+#pragma unroll
+      for (int zz = 0; zz < NZ; ++zz)
+#pragma unroll
+        for (int yy = 0; yy < RS_RY + 2; ++yy) {
+          const int sh = p0 ^ (((yy - 1) & 1) ? pb : 0) ^ ((DIM == 3 && ((zz - 1) & 1)) ? pbxy : 0);
+          const double* seg = sxb + (zz * (RS_RY + 2) + yy) * RS_XSEG + sh;
+          const double xm = seg[-1], x0 = seg[0], xp = seg[1];
+#pragma unroll
+          for (int j = 0; j < RS_RY; ++j) {
+            const int dy = yy - 1 - j;                                           // this segment is line j + dy of the tile
+            if (dy < -1 || dy > 1) continue;
+            const int o = (zz * 3 + (dy + 1)) * 3;                               // stencil index of (dx = -1, dy, dz): the sum runs in stencil order per row
+            sum[j] += cS[o] * xm; sum[j] += cS[o + 1] * x0; sum[j] += cS[o + 2] * xp;
+          }
+        }
       // residual() is additive (gridoperator.hh:89-92) and the coupling terms of the interface cells add to some of these rows
-      // from the auxiliary stream at the same time (mdb_residual): one reduction at the L2, no load, no lost update
-      atomicAdd(res + r, sum);
+      // from another stream at the same time (mdb_residual): one reduction at the L2 per row, no load, no lost update
+#pragma unroll
+      for (int j = 0; j < RS_RY; ++j)
+        if (mine[j]) atomicAdd(res + T.r0 + (int64_t)j * ch.bx + t, sum[j]);
     }
     __syncthreads();                                                             // this buffer is free again
   }
@@ -694,6 +733,7 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
   if (!residual_stencil_applies(c, child, V)) return false;
   ResChild rc; rc.offset = hc.offset; rc.size = hc.size;
   rc.bx = hc.lat_hi[0] - hc.lat_lo[0] + 1; rc.bxy = rc.bx * (hc.lat_hi[1] - hc.lat_lo[1] + 1);
+  rc.nl = (int)(hc.size / rc.bx); rc.nxc = (rc.bx + RS_ROWS - 1) / RS_ROWS;
   const int64_t n = c->ndof;
   if (go.n_res_rest[child] < 0) {                                                 // first residual with this operator: plan the child
     go.d_res_fast[child] = dalloc<uint8_t>(hc.size);
@@ -720,7 +760,7 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
     MDB_CUDA(cudaMemcpyToSymbolAsync(c_resS, S, ((m.dim == 3) ? 27 : 9) * sizeof(double), (size_t)V.slot[0] * 32 * sizeof(double), cudaMemcpyDeviceToDevice,
                                      c->stream));
     int grid = 148 * RS_BLOCKS;
-    if (grid > cdiv(hc.size, RS_ROWS)) grid = cdiv(hc.size, RS_ROWS);
+    if (grid > res_ntiles(rc)) grid = (int)res_ntiles(rc);
     if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
     else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
   }
