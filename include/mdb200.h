@@ -210,6 +210,19 @@ int mdb_add_coupling(mdb_ctx* ctx, int op_id, const void* params, size_t params_
 int mdb_add_enriched_coupling(mdb_ctx* ctx, int op_id, const void* params, size_t params_bytes,
                               int local_subproblem, int remote_subproblem, int coupling_child, int jac_mode);
 
+/* PowerCouplingGridFunctionSpace<CouplingGFS, ncomp, VBE> (test/testpowermortarpoisson.cc:384-386): `ncomp` copies of the coupling
+ * space of mdb_add_coupling_space, ordered lexicographically — i.e. ncomp consecutive child blocks.  Returns the index of the
+ * first block; the others follow.  (The reference counts the power space as ONE child of the MultiDomainGridFunctionSpace; here
+ * every component block is a child of its own, the global numbering is the same.) */
+int mdb_add_power_coupling_space(mdb_ctx* ctx, int fe_kind, int left_cond_kind, uint32_t left_cond_mask,
+                                 int right_cond_kind, uint32_t right_cond_mask, int ncomp);
+/* EnrichedCoupling over a power coupling space: the operator of test/testpowermortarpoisson.cc:117-262 loops over the component
+ * blocks (`for c_block < PowerLFSU_C::CHILDREN`, :186-189) and applies MortarPoissonCoupling::alpha_generic with each block's
+ * multiplier; the finite-difference Jacobians differentiate that sum as a whole (couplingutilities.hh:292-484).
+ * `first_coupling_child` comes from mdb_add_power_coupling_space; ncomp = 1 is mdb_add_enriched_coupling. */
+int mdb_add_power_enriched_coupling(mdb_ctx* ctx, int op_id, const void* params, size_t params_bytes, int local_subproblem,
+                                    int remote_subproblem, int first_coupling_child, int ncomp, int jac_mode);
+
 /* ---- DOF map (ordering update; multidomaingridfunctionspace.hh:308-369) --- */
 int mdb_finalize(mdb_ctx* ctx, int64_t* ndof);
 /* parity exports.  cell_ptr has ncells+1 entries; cell_dofs has cell_ptr[ncells] entries: the container

@@ -491,6 +491,20 @@ void EnrichedOperator::alpha_generic(int sign, const IG& ig, const LFS& lfsu, co
   }
 }
 
+// test/testpowermortarpoisson.cc:186-262: `for (c_block < PowerLFSU_C::CHILDREN)` around the body of alpha_generic, each block
+// with its own multiplier coefficients and its own rows of r_c; the element residual r collects every block's terms
+void EnrichedOperator::alpha_power(int sign, const IG& ig, const LFS& lfsu, const double* x, const LFS& lfsv, const LFS& lfsu_c,
+                                   const double* x_c, const LFS& lfsv_c, LocalVectorView& r, LocalVectorView& r_c) const
+{
+  if (ncomp == 1) { alpha_generic(sign, ig, lfsu, x, lfsv, lfsu_c, x_c, lfsv_c, r, r_c); return; }
+  const int nb = lfsu_c.n / ncomp;
+  for (int c_block = 0; c_block < ncomp; ++c_block) {
+    LFS child; child.k = lfsu_c.k; child.n = nb;
+    for (int i = 0; i < nb; ++i) child.idx[i] = lfsu_c.idx[c_block * nb + i];
+    alpha_generic(sign, ig, lfsu, x, lfsv, child, x_c, child, r, r_c);
+  }
+}
+
 // couplingutilities.hh:305-388 / :404-484 (NumericalJacobianEnrichedCouplingTo{First,Second}SubProblem; the two differ only
 // in which alpha_enriched_coupling_* they call).  MDB_JAC_ANALYTIC: the operator is linear in (u, lambda), column j = alpha(e_j).
 void EnrichedOperator::jacobian_generic(int sign, const IG& ig, const LFS& lfsu, const double* x, int nx, const LFS& lfsv,
@@ -503,14 +517,14 @@ void EnrichedOperator::jacobian_generic(int sign, const IG& ig, const LFS& lfsu,
   LocalVectorView dv_s{down_s.data(), 1.0}, uv_s{up_s.data(), 1.0}, dv_c{down_c.data(), 1.0}, uv_c{up_c.data(), 1.0};
   const bool analytic = jac_mode == MDB_JAC_ANALYTIC;
   if (analytic) { std::fill(u_s.begin(), u_s.end(), 0.0); std::fill(u_c.begin(), u_c.end(), 0.0); }
-  else alpha_generic(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, dv_s, dv_c);     // base line
+  else alpha_power(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, dv_s, dv_c);     // base line
   for (int j = 0; j < n_s; ++j) {                                                                      // jiggle in self
     std::fill(up_s.begin(), up_s.end(), 0.0); std::fill(up_c.begin(), up_c.end(), 0.0);
     double& uj = u_s[lfsu.idx[j]];
     const double keep = uj;
     const double delta = analytic ? 1.0 : epsilon * (1.0 + std::abs(uj));
     uj += delta;
-    alpha_generic(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, uv_s, uv_c);
+    alpha_power(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, uv_s, uv_c);
     for (int i = 0; i < m_s; ++i) mat_ss.accumulate(lfsv, i, lfsu, j, (up_s[lfsv.idx[i]] - down_s[lfsv.idx[i]]) / delta);
     for (int i = 0; i < m_c; ++i) mat_cs.accumulate(lfsv_c, i, lfsu, j, (up_c[lfsv_c.idx[i]] - down_c[lfsv_c.idx[i]]) / delta);
     uj = keep;
@@ -521,7 +535,7 @@ void EnrichedOperator::jacobian_generic(int sign, const IG& ig, const LFS& lfsu,
     const double keep = uj;
     const double delta = analytic ? 1.0 : epsilon * (1.0 + std::abs(uj));
     uj += delta;
-    alpha_generic(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, uv_s, uv_c);
+    alpha_power(sign, ig, lfsu, u_s.data(), lfsv, lfsu_c, u_c.data(), lfsv_c, uv_s, uv_c);
     for (int i = 0; i < m_s; ++i) mat_sc.accumulate(lfsv, i, lfsu_c, j, (up_s[lfsv.idx[i]] - down_s[lfsv.idx[i]]) / delta);
     for (int i = 0; i < m_c; ++i) mat_cc.accumulate(lfsv_c, i, lfsu_c, j, (up_c[lfsv_c.idx[i]] - down_c[lfsv_c.idx[i]]) / delta);
     uj = keep;
@@ -683,6 +697,13 @@ int Context::bind_coupling(int child, int64_t cell, int f, int64_t* dofs) const
   return nl;
 }
 
+int Context::bind_coupling_power(const Coupling& cp, int64_t cell, int f, int64_t* dofs) const
+{
+  int n = 0;
+  for (int c = 0; c < cp.ncomp; ++c) n += bind_coupling(cp.coupling_child + c, cell, f, dofs + n);
+  return n;
+}
+
 LFS Context::subproblem_lfs(const SubProblem& sp, const int* child_off) const
 {
   // subproblemlocalfunctionspace.hh:462-501: single-child subproblem = proxy of that child
@@ -786,7 +807,7 @@ int Context::matrix_create(const int* gos_, int ngos)
             if (!(lsp.appliesTo(eg.sd) && rsp.appliesTo(en.sd))) continue;
             LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
             int64_t dofs_c[MAXLOC];
-            const int nc = bind_coupling(cp.coupling_child, cell, f, dofs_c);
+            const int nc = bind_coupling_power(cp, cell, f, dofs_c);
             // FullEnrichedCoupling{First,Second}SubProblemPattern + FullEnrichedCouplingPattern couplingutilities.hh:219-286
             for (int i = 0; i < ls.n; ++i) for (int j = 0; j < nc; ++j) rows[dofs_s[ls.idx[i]]].push_back(dofs_c[j]);
             for (int i = 0; i < nc; ++i) for (int j = 0; j < ls.n; ++j) rows[dofs_c[i]].push_back(dofs_s[ls.idx[j]]);
@@ -894,11 +915,11 @@ void Context::residual(int goi, double weight, const double* x, double* r) const
             LFS ls = subproblem_lfs(lsp, off_s.data()), ln = subproblem_lfs(rsp, off_n.data());
             int64_t dofs_c[MAXLOC]; double x_c[MAXLOC], r_c[MAXLOC];
             LFS lc; lc.k = children[cp.coupling_child].k;
-            lc.n = bind_coupling(cp.coupling_child, cell, f, dofs_c);
+            lc.n = bind_coupling_power(cp, cell, f, dofs_c);
             for (int i = 0; i < lc.n; ++i) { lc.idx[i] = i; x_c[i] = x[dofs_c[i]]; r_c[i] = 0.0; }
             LocalVectorView rv_c{r_c, weight};
-            cp.eop->alpha_generic(+1, ig, ls, x_s, ls, lc, x_c, lc, rv_s, rv_c);
-            cp.eop->alpha_generic(-1, ig, ln, x_n, ln, lc, x_c, lc, rv_n, rv_c);
+            cp.eop->alpha_power(+1, ig, ls, x_s, ls, lc, x_c, lc, rv_s, rv_c);
+            cp.eop->alpha_power(-1, ig, ln, x_n, ln, lc, x_c, lc, rv_n, rv_c);
             for (int i = 0; i < lc.n; ++i) r[dofs_c[i]] += r_c[i];           // onUnbindLFSVCoupling
           }
           for (int i = 0; i < nn; ++i) r[dofs_n[i]] += r_n[i];           // onUnbindLFSVOutside
@@ -998,7 +1019,7 @@ void jacobian_cell(const Context& c, const GridOperatorDesc& go, const Flags& fl
         LFS ls = c.subproblem_lfs(lsp, S.off_s.data()), ln = c.subproblem_lfs(rsp, S.off_n.data());
         int64_t dofs_c[MAXLOC]; double x_c[MAXLOC];
         LFS lc; lc.k = c.children[cp.coupling_child].k;
-        lc.n = c.bind_coupling(cp.coupling_child, cell, f, dofs_c);
+        lc.n = c.bind_coupling_power(cp, cell, f, dofs_c);
         const int ncl = lc.n;
         for (int i = 0; i < ncl; ++i) { lc.idx[i] = i; x_c[i] = x[dofs_c[i]]; }
         std::vector<double> a_cc(ncl * ncl, 0.0), a_sc(ns * ncl, 0.0), a_cs(ncl * ns, 0.0), a_nc(nn * ncl, 0.0), a_cn(ncl * nn, 0.0);
@@ -1381,6 +1402,25 @@ int orc_add_enriched_coupling(Context* c, int op_id, const void* params, size_t 
     c->cps.push_back(std::move(cp));
     return (int)c->cps.size() - 1;
   } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
+int orc_add_coupling_space(Context* c, int fe_kind, int lkind, uint32_t lmask, int rkind, uint32_t rmask);
+int orc_add_power_coupling_space(Context* c, int fe_kind, int lkind, uint32_t lmask, int rkind, uint32_t rmask, int ncomp)
+{
+  if (ncomp < 1 || ncomp > 2) { c->err = "power coupling spaces: 1 or 2 components"; return -1; }
+  int first = -1;
+  for (int k = 0; k < ncomp; ++k) { int ch = orc_add_coupling_space(c, fe_kind, lkind, lmask, rkind, rmask); if (ch < 0) return ch; if (k == 0) first = ch; }
+  return first;
+}
+int orc_add_enriched_coupling(Context* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp, int coupling_child, int jac_mode);
+int orc_add_power_enriched_coupling(Context* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp, int first_child,
+                                    int ncomp, int jac_mode)
+{
+  if (ncomp < 1 || ncomp > 2 || first_child < 0 || first_child + ncomp > (int)c->children.size()) { c->err = "bad power coupling space"; return -1; }
+  for (int k = 0; k < ncomp; ++k) if (!c->children[first_child + k].iface) { c->err = "bad power coupling space"; return -1; }
+  int h = orc_add_enriched_coupling(c, op_id, params, nbytes, local_sp, remote_sp, first_child, jac_mode);
+  if (h < 0) return h;
+  c->cps[h].ncomp = ncomp; c->cps[h].eop->ncomp = ncomp;
+  return h;
 }
 int orc_finalize(Context* c, int64_t* ndof) { ORC_TRY(c, { c->finalize(); *ndof = c->ndof; }) }
 int orc_get_dofmap(Context* c, int64_t* cell_ptr, int64_t* cell_dofs)

@@ -288,6 +288,10 @@ struct EnrichedOperator {
   double gamma_0 = 1.0;
   double epsilon = 1e-8;       // NumericalJacobianEnrichedCouplingTo{First,Second}SubProblem default
   int jac_mode = MDB_JAC_FD_BITMATCH;
+  int ncomp = 1;               // component blocks of a PowerCouplingGridFunctionSpace (test/testpowermortarpoisson.cc:186-189)
+  // the operator on the whole (power) coupling space: loop over the component blocks, lfsu_c / x_c / r_c hold ncomp blocks of equal size
+  void alpha_power(int sign, const IG& ig, const LFS& lfsu, const double* x, const LFS& lfsv, const LFS& lfsu_c, const double* x_c,
+                   const LFS& lfsv_c, LocalVectorView& r, LocalVectorView& r_c) const;
   // alpha_generic<sign>: sign = +1 first (inside element), -1 second (outside element)
   void alpha_generic(int sign, const IG& ig, const LFS& lfsu, const double* x, const LFS& lfsv, const LFS& lfsu_c, const double* x_c,
                      const LFS& lfsv_c, LocalVectorView& r, LocalVectorView& r_c) const;
@@ -328,7 +332,7 @@ struct Coupling {
   std::unique_ptr<CouplingOperator> op;
   int local_sp, remote_sp;
   std::unique_ptr<EnrichedOperator> eop;       // EnrichedCoupling (coupling.hh:123-192): op is null
-  int coupling_child = -1;
+  int coupling_child = -1, ncomp = 1;          // ncomp consecutive child blocks from coupling_child on (power coupling space)
 };
 
 struct GridOperatorDesc { std::vector<int> sps, cps; };
@@ -368,6 +372,7 @@ struct Context {
   LFS subproblem_lfs(const SubProblem& sp, const int* child_off) const;
   // CouplingLocalFunctionSpace::bind(intersection): the mortar DOFs of face f of `cell` in face-local order; returns their number
   int bind_coupling(int child, int64_t cell, int f, int64_t* dofs) const;
+  int bind_coupling_power(const Coupling& cp, int64_t cell, int f, int64_t* dofs) const;     // all component blocks, block after block
   bool iface_applies(const ChildSpace& ch, uint8_t sd_in, uint8_t sd_out) const;
 
   void constraints_assemble(const int* sps_, const mdb_bctype* bcs, int n);
