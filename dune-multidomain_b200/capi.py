@@ -202,6 +202,16 @@ class Lib:
         self.nchildren += 1
         return r
 
+    def add_power_coupling_space(self, fe_kind, left_cond, right_cond, ncomp):
+        r = self._check(self._fn("add_power_coupling_space")(C.c_void_p(self.ctx), fe_kind, left_cond[0], C.c_uint32(left_cond[1]),
+                                                             right_cond[0], C.c_uint32(right_cond[1]), ncomp), "add_power_coupling_space")
+        self.nchildren += ncomp
+        return r
+
+    def add_power_enriched_coupling(self, op_id, params, local_sp, remote_sp, first_child, ncomp, jac_mode=JAC_FD_BITMATCH):
+        return self._check(self._fn("add_power_enriched_coupling")(C.c_void_p(self.ctx), op_id, C.byref(params), C.c_size_t(C.sizeof(params)),
+                                                                   local_sp, remote_sp, first_child, ncomp, jac_mode), "add_power_enriched_coupling")
+
     def add_enriched_coupling(self, op_id, params, local_sp, remote_sp, coupling_child, jac_mode=JAC_FD_BITMATCH):
         return self._check(self._fn("add_enriched_coupling")(C.c_void_p(self.ctx), op_id, C.byref(params), C.c_size_t(C.sizeof(params)),
                                                              local_sp, remote_sp, coupling_child, jac_mode), "add_enriched_coupling")

@@ -412,6 +412,34 @@ int mdb_add_enriched_coupling(mdb_ctx* c, int op_id, const void* params, size_t 
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
 }
 
+int mdb_add_power_coupling_space(mdb_ctx* c, int fe_kind, int left_cond_kind, uint32_t left_cond_mask, int right_cond_kind, uint32_t right_cond_mask,
+                                 int ncomp)
+{
+  if (!c) return MDB_EINVAL;
+  if (ncomp < 1 || ncomp > 2) { c->err = "mdb_add_power_coupling_space: 1 or 2 component blocks"; return MDB_EINVAL; }
+  int first = -1;
+  for (int k = 0; k < ncomp; ++k) {
+    const int ch = mdb_add_coupling_space(c, fe_kind, left_cond_kind, left_cond_mask, right_cond_kind, right_cond_mask);
+    if (ch < 0) return ch;
+    if (k == 0) first = ch;
+  }
+  return first;
+}
+
+int mdb_add_power_enriched_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, int local_sp, int remote_sp, int first_coupling_child,
+                                    int ncomp, int jac_mode)
+{
+  if (!c) return MDB_EINVAL;
+  if (ncomp < 1 || ncomp > 2 || first_coupling_child < 0 || first_coupling_child + ncomp > (int)c->children.size()) {
+    c->err = "mdb_add_power_enriched_coupling: bad power coupling space"; return MDB_EINVAL;
+  }
+  for (int k = 0; k < ncomp; ++k)
+    if (!c->children[first_coupling_child + k].iface) { c->err = "mdb_add_power_enriched_coupling: bad power coupling space"; return MDB_EINVAL; }
+  const int h = mdb_add_enriched_coupling(c, op_id, params, nbytes, local_sp, remote_sp, first_coupling_child, jac_mode);
+  if (h >= 0) c->cps[h].ncomp = ncomp;
+  return h;
+}
+
 int mdb_finalize(mdb_ctx* c, int64_t* ndof)
 {
   MDB_API_BEGIN(c)

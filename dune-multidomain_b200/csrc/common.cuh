@@ -180,6 +180,7 @@ struct CouplingDesc {
   mdb_ndcoupling_params nd{};
   int local_sp = -1, remote_sp = -1, jac_mode = 0;
   int coupling_child = -1;       // >= 0: EnrichedCoupling (coupling.hh:123-192) with this coupling space
+  int ncomp = 1;                 // component blocks of a power coupling space: children coupling_child .. coupling_child + ncomp - 1
   bool enriched() const { return coupling_child >= 0; }
 };
 

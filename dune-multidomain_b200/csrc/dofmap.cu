@@ -490,8 +490,8 @@ void build_xneed(Ctx* c, GridOp& go)
       S[q].k = ch.k; S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof;
     }
     MDB_LAUNCH(c, k_mark_face_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, S[0], S[1], fl.d_cell, fl.d_face, fl.n, d_flags);
-    if (cp.enriched()) {
-      const Child& ch = c->children[cp.coupling_child];
+    for (int kc = 0; cp.enriched() && kc < cp.ncomp; ++kc) {
+      const Child& ch = c->children[cp.coupling_child + kc];
       NeedSide C; for (int d = 0; d < 3; ++d) C.lat_n[d] = ch.lat_n[d];
       C.k = ch.k; C.offset = ch.offset; C.lat2dof = ch.d_lat2dof;
       MDB_LAUNCH(c, k_mark_face_mortar_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, C, fl.d_cell, fl.d_face, fl.n, d_flags);

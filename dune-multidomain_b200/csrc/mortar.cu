@@ -17,8 +17,10 @@
 
 namespace mdb {
 
+#define MORTAR_MAXCOMP 2
 struct MortarSpec {
   double gamma_0; int jac_mode;
+  int ncomp;                           // component blocks of a power coupling space (test/testpowermortarpoisson.cc:186-189), <= MORTAR_MAXCOMP
   Rule1D rule1, rule2;                 // qorder = 2 max(order(lfsu), order(lfsu_c)) per side, testmortarpoisson.cc:193-195
   int lkind, rkind; uint32_t lmask, rmask;    // the coupling space's own predicate (gfs.contains(is))
 };
@@ -89,29 +91,41 @@ __device__ __noinline__ void mortar_alpha(int sign, double gamma_0, const Rule1D
   }
 }
 
+// the operator on a power coupling space: the body of alpha_generic once per component block, each with its own multiplier
+// coefficients x_c[b * NC ..] and its own rows r_c[b * NC ..]; the element residual collects every block's terms
+template <int DIM, int K>
+__device__ __forceinline__ void mortar_alpha_power(int sign, const MortarSpec& P, const Rule1D& R, const FaceGeo<DIM>& G, const double* x, const double* x_c,
+                                                   int nc, double* r, double* r_c, double weight)
+{
+  constexpr int NC = 1 << (DIM - 1);
+  for (int b = 0; b < P.ncomp; ++b) mortar_alpha<DIM, K>(sign, P.gamma_0, R, G, x, x_c + b * NC, nc, r, r_c + b * NC, weight);
+}
+
+struct MortarMaps { SideMap c[MORTAR_MAXCOMP]; };
+
 template <int DIM, int K1, int K2>
-__global__ void __launch_bounds__(64) k_mortar_residual(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, SideMap Cs,
+__global__ void __launch_bounds__(64) k_mortar_residual(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, MortarMaps Cs,
                                                         const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces, double weight,
                                                         const double* __restrict__ x, double* r)
 {
-  constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NC = 1 << (DIM - 1);
+  constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NC = 1 << (DIM - 1), NCT = MORTAR_MAXCOMP * NC;
   const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (f >= nfaces) return;
   FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
-  int32_t ds[NL1], dn[NL2], dc[NC];
+  int32_t ds[NL1], dn[NL2], dc[NCT];
   cell_dofs_qk<DIM, K1>(Ls, G.ijk, ds); cell_dofs_qk<DIM, K2>(Rs, G.nijk, dn);
   const uint8_t s_in = sd[fcell[f]], s_out = sd[G.nijk[0] + (int64_t)m.n[0] * (G.nijk[1] + (int64_t)m.n[1] * G.nijk[2])];
   const int nc = (cond_applies(P.lkind, P.lmask, s_in) && cond_applies(P.rkind, P.rmask, s_out)) ? NC : 0;   // lfs_c.bind(is): empty if !contains(is)
-  if (nc) face_dofs<DIM>(Cs, G.ijk, G.axis, G.side, dc);
-  double x1[NL1], x2[NL2], xc[NC], r1[NL1], r2[NL2], rc[NC];
+  if (nc) for (int b = 0; b < P.ncomp; ++b) face_dofs<DIM>(Cs.c[b], G.ijk, G.axis, G.side, dc + b * NC);
+  double x1[NL1], x2[NL2], xc[NCT], r1[NL1], r2[NL2], rc[NCT];
   for (int i = 0; i < NL1; ++i) { x1[i] = x[ds[i]]; r1[i] = 0.0; }
   for (int i = 0; i < NL2; ++i) { x2[i] = x[dn[i]]; r2[i] = 0.0; }
-  for (int i = 0; i < nc; ++i) { xc[i] = x[dc[i]]; rc[i] = 0.0; }
-  mortar_alpha<DIM, K1>(+1, P.gamma_0, P.rule1, G, x1, xc, nc, r1, rc, weight);
-  mortar_alpha<DIM, K2>(-1, P.gamma_0, P.rule2, G, x2, xc, nc, r2, rc, weight);
+  for (int i = 0; i < NCT; ++i) { xc[i] = (nc && i < P.ncomp * NC) ? x[dc[i]] : 0.0; rc[i] = 0.0; }
+  mortar_alpha_power<DIM, K1>(+1, P, P.rule1, G, x1, xc, nc, r1, rc, weight);
+  mortar_alpha_power<DIM, K2>(-1, P, P.rule2, G, x2, xc, nc, r2, rc, weight);
   for (int i = 0; i < NL1; ++i) atomicAdd(&r[ds[i]], r1[i]);
   for (int i = 0; i < NL2; ++i) atomicAdd(&r[dn[i]], r2[i]);
-  for (int i = 0; i < nc; ++i) atomicAdd(&r[dc[i]], rc[i]);
+  if (nc) for (int i = 0; i < P.ncomp * NC; ++i) atomicAdd(&r[dc[i]], rc[i]);
 }
 
 // one column of jacobian_enriched_coupling_{first,second} (couplingutilities.hh:305-388 / :404-484)
@@ -120,13 +134,14 @@ __device__ void mortar_column(int sign, const MortarSpec& P, const Rule1D& R, co
                               double weight, double epsilon, const double* __restrict__ x, const int64_t* __restrict__ rowptr,
                               const int32_t* __restrict__ colidx, double* val)
 {
-  constexpr int NL = cpow(K + 1, DIM), NC = 1 << (DIM - 1);
+  constexpr int NL = cpow(K + 1, DIM), NC = MORTAR_MAXCOMP * (1 << (DIM - 1));
+  const int nct = nc * P.ncomp;                                                                        // coefficients of the (power) coupling space on this face
   const bool analytic = P.jac_mode == MDB_JAC_ANALYTIC;
   double u[NL], uc[NC], down[NL], down_c[NC], up[NL], up_c[NC];
   for (int i = 0; i < NL; ++i) { u[i] = analytic ? 0.0 : x[de[i]]; down[i] = 0.0; up[i] = 0.0; }
-  for (int i = 0; i < NC; ++i) { uc[i] = (analytic || i >= nc) ? 0.0 : x[dc[i]]; down_c[i] = 0.0; up_c[i] = 0.0; }
+  for (int i = 0; i < NC; ++i) { uc[i] = (analytic || i >= nct) ? 0.0 : x[dc[i]]; down_c[i] = 0.0; up_c[i] = 0.0; }
   double delta = 1.0;
-  if (!analytic) mortar_alpha<DIM, K>(sign, P.gamma_0, R, G, u, uc, nc, down, down_c, 1.0);          // base line
+  if (!analytic) mortar_alpha_power<DIM, K>(sign, P, R, G, u, uc, nc, down, down_c, 1.0);            // base line
   if (j < NL) {                                                                                        // jiggle in self
     if (!analytic) delta = epsilon * (1.0 + fabs(u[j]));
     u[j] += delta;
@@ -134,34 +149,35 @@ __device__ void mortar_column(int sign, const MortarSpec& P, const Rule1D& R, co
     if (!analytic) delta = epsilon * (1.0 + fabs(uc[j - NL]));
     uc[j - NL] += delta;
   }
-  mortar_alpha<DIM, K>(sign, P.gamma_0, R, G, u, uc, nc, up, up_c, 1.0);
+  mortar_alpha_power<DIM, K>(sign, P, R, G, u, uc, nc, up, up_c, 1.0);
   const int32_t col = (j < NL) ? de[j] : dc[j - NL];
   for (int i = 0; i < NL; ++i) {                                                                      // mat_ss / mat_sc
     const double cval = (up[i] - down[i]) / delta;
     atomicAdd(&val[find_slot(rowptr, colidx, de[i], col)], weight * cval);
   }
-  for (int i = 0; i < nc; ++i) {                                                                      // mat_cs / mat_cc
+  for (int i = 0; i < nct; ++i) {                                                                     // mat_cs / mat_cc
     const double cval = (up_c[i] - down_c[i]) / delta;
     atomicAdd(&val[find_slot(rowptr, colidx, dc[i], col)], weight * cval);
   }
 }
 
 template <int DIM, int K1, int K2>
-__global__ void __launch_bounds__(64) k_mortar_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, SideMap Cs,
+__global__ void __launch_bounds__(64) k_mortar_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, MortarMaps Cs,
                                                         const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces, double weight,
                                                         double epsilon, const double* __restrict__ x, const int64_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx, double* val)
 {
-  constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NC = 1 << (DIM - 1);
-  constexpr int NP = NL1 + NC + NL2 + NC;              // perturbations per intersection: first (element, mortar), second (element, mortar)
+  constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NCB = 1 << (DIM - 1);
+  const int NC = P.ncomp * NCB;                        // coefficients of the (power) coupling space per face
+  const int NP = NL1 + NC + NL2 + NC;                  // perturbations per intersection: first (element, mortar), second (element, mortar)
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= nfaces * NP) return;
   const int64_t f = t / NP; const int e = (int)(t % NP);
   FaceGeo<DIM> G; G.init(m, fcell[f], fface[f]);
   const uint8_t s_in = sd[fcell[f]], s_out = sd[G.nijk[0] + (int64_t)m.n[0] * (G.nijk[1] + (int64_t)m.n[1] * G.nijk[2])];
-  const int nc = (cond_applies(P.lkind, P.lmask, s_in) && cond_applies(P.rkind, P.rmask, s_out)) ? NC : 0;
-  int32_t dc[NC];
-  if (nc) face_dofs<DIM>(Cs, G.ijk, G.axis, G.side, dc);
+  const int nc = (cond_applies(P.lkind, P.lmask, s_in) && cond_applies(P.rkind, P.rmask, s_out)) ? NCB : 0;
+  int32_t dc[MORTAR_MAXCOMP * NCB];
+  if (nc) for (int b = 0; b < P.ncomp; ++b) face_dofs<DIM>(Cs.c[b], G.ijk, G.axis, G.side, dc + b * NCB);
   if (e < NL1 + NC) {
     if (e >= NL1 && nc == 0) return;
     int32_t ds[NL1]; cell_dofs_qk<DIM, K1>(Ls, G.ijk, ds);
@@ -188,7 +204,16 @@ static MortarSpec mortar_spec(const Ctx* c, const CouplingDesc& cp, int k1, int 
   const Child& cc = c->children[cp.coupling_child];
   P.rule1 = gauss1d(2 * (k1 > cc.k ? k1 : cc.k)); P.rule2 = gauss1d(2 * (k2 > cc.k ? k2 : cc.k));
   P.lkind = cc.lkind; P.lmask = cc.lmask; P.rkind = cc.rkind; P.rmask = cc.rmask;
+  P.ncomp = cp.ncomp;
   return P;
+}
+
+static MortarMaps mortar_maps(const Ctx* c, const CouplingDesc& cp)
+{
+  MDB_REQUIRE(cp.ncomp >= 1 && cp.ncomp <= MORTAR_MAXCOMP, MDB_EINVAL, "power coupling spaces: at most 2 component blocks");
+  MortarMaps M;
+  for (int b = 0; b < MORTAR_MAXCOMP; ++b) M.c[b] = side_map_child(c, cp.coupling_child + (b < cp.ncomp ? b : 0));
+  return M;
 }
 
 #define MDB_DISPATCH_MORTAR(DIMV, K1V, K2V, CALL)                             \
@@ -211,7 +236,8 @@ void residual_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, doubl
   const int k1 = c->children[cl].k, k2 = c->children[cr].k;
   MDB_REQUIRE(k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2, MDB_EINVAL, "enriched coupling kernels exist for Q1 and Q2 spaces");
   const MortarSpec P = mortar_spec(c, cp, k1, k2);
-  const SideMap Ls = side_map_child(c, cl), Rs = side_map_child(c, cr), Cs = side_map_child(c, cp.coupling_child);
+  const SideMap Ls = side_map_child(c, cl), Rs = side_map_child(c, cr);
+  const MortarMaps Cs = mortar_maps(c, cp);
 #define CALL(D, A, B) MDB_LAUNCH(c, (k_mortar_residual<D, A, B>), cdiv(fl.n, 64), 64, 0, m, c->d_cell_sd, P, Ls, Rs, Cs, fl.d_cell, fl.d_face, fl.n, weight, d_x, d_r)
   MDB_DISPATCH_MORTAR(m.dim, k1, k2, CALL);
 #undef CALL
@@ -225,10 +251,11 @@ void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matri
   const int k1 = c->children[cl].k, k2 = c->children[cr].k;
   MDB_REQUIRE(k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2, MDB_EINVAL, "enriched coupling kernels exist for Q1 and Q2 spaces");
   const MortarSpec P = mortar_spec(c, cp, k1, k2);
-  const SideMap Ls = side_map_child(c, cl), Rs = side_map_child(c, cr), Cs = side_map_child(c, cp.coupling_child);
+  const SideMap Ls = side_map_child(c, cl), Rs = side_map_child(c, cr);
+  const MortarMaps Cs = mortar_maps(c, cp);
   int nl1 = 1, nl2 = 1;
   for (int d = 0; d < m.dim; ++d) { nl1 *= k1 + 1; nl2 *= k2 + 1; }
-  const int64_t total = fl.n * (nl1 + nl2 + 2 * (1 << (m.dim - 1)));
+  const int64_t total = fl.n * (nl1 + nl2 + 2 * cp.ncomp * (1 << (m.dim - 1)));
   const double eps = 1e-8;                      // NumericalJacobianEnrichedCouplingTo*SubProblem() default, couplingutilities.hh:296-298
 #define CALL(D, A, B) MDB_LAUNCH(c, (k_mortar_jacobian<D, A, B>), cdiv(total, 64), 64, 0, m, c->d_cell_sd, P, Ls, Rs, Cs, fl.d_cell, fl.d_face, fl.n, weight, eps, d_x, M.d_rowptr, M.d_colidx, M.d_val)
   MDB_DISPATCH_MORTAR(m.dim, k1, k2, CALL);

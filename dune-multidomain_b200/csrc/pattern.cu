@@ -21,6 +21,7 @@ struct PatSpec {
   int nsp; int sp_child[16]; int sp_kind[16]; uint32_t sp_mask[16];
   int ncp; int cp_lchild[8], cp_lkind[8], cp_rchild[8], cp_rkind[8]; uint32_t cp_lmask[8], cp_rmask[8];
   int cp_cchild[8];      // >= 0: EnrichedCoupling with this coupling space (sc/cs/nc/cn/cc links instead of sn/ns)
+  int cp_ncomp[8];       // component blocks of a power coupling space (children cp_cchild .. cp_cchild + ncomp - 1)
 };
 
 __device__ __forceinline__ bool on_cell(int subdomain, uint8_t sd) { return subdomain < 0 || ((sd >> subdomain) & 1); }
@@ -93,11 +94,11 @@ __device__ void enumerate_iface_row(RowList& L, const MeshDesc& m, const uint8_t
           const uint8_t sn = sd[nijk[0] + (int64_t)m.n[0] * (nijk[1] + (int64_t)m.n[1] * nijk[2])];
           if (!iface_contains(C, s, sn)) continue;
           for (int q = 0; q < S.ncp; ++q) {
-            if (S.cp_cchild[q] != child) continue;
+            if (S.cp_cchild[q] < 0 || child < S.cp_cchild[q] || child >= S.cp_cchild[q] + S.cp_ncomp[q]) continue;
             if (!(cond_applies(S.cp_lkind[q], S.cp_lmask[q], s) && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn))) continue;
             if (on_cell(S.ch[S.cp_lchild[q]].subdomain, s)) add_cell_dofs(L, m, S.ch[S.cp_lchild[q]], ijk);      // pattern_cs
             if (on_cell(S.ch[S.cp_rchild[q]].subdomain, sn)) add_cell_dofs(L, m, S.ch[S.cp_rchild[q]], nijk);    // pattern_cn
-            add_face_dofs(L, m, C, ijk, f);                                                                     // pattern_cc
+            for (int k = 0; k < S.cp_ncomp[q]; ++k) add_face_dofs(L, m, S.ch[S.cp_cchild[q] + k], ijk, f);      // pattern_cc: full over the power space
           }
         }
       }
@@ -137,9 +138,11 @@ __device__ void enumerate_row(RowList& L, const MeshDesc& m, const uint8_t* __re
             if (nijk[f / 2] < 0 || nijk[f / 2] >= m.n[f / 2]) continue;
             uint8_t sn = sd[nijk[0] + (int64_t)m.n[0] * (nijk[1] + (int64_t)m.n[1] * nijk[2])];
             if (S.cp_cchild[q] >= 0) {       // enriched coupling: pattern_sc (fired from this cell) / pattern_nc (fired from the neighbour)
-              const PChild& C = S.ch[S.cp_cchild[q]];
-              if (as_local && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn) && iface_contains(C, s, sn)) add_face_dofs(L, m, C, ijk, f);
-              if (as_remote && cond_applies(S.cp_lkind[q], S.cp_lmask[q], sn) && iface_contains(C, sn, s)) add_face_dofs(L, m, C, nijk, f ^ 1);
+              for (int k = 0; k < S.cp_ncomp[q]; ++k) {
+                const PChild& C = S.ch[S.cp_cchild[q] + k];
+                if (as_local && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn) && iface_contains(C, s, sn)) add_face_dofs(L, m, C, ijk, f);
+                if (as_remote && cond_applies(S.cp_lkind[q], S.cp_lmask[q], sn) && iface_contains(C, sn, s)) add_face_dofs(L, m, C, nijk, f ^ 1);
+              }
               continue;
             }
             if (as_local && cond_applies(S.cp_rkind[q], S.cp_rmask[q], sn) && on_cell(S.ch[S.cp_rchild[q]].subdomain, sn))
@@ -248,7 +251,7 @@ void build_pattern(Ctx* c, Matrix& M)
       const SubProblemDesc& l = c->sps[cp.local_sp]; const SubProblemDesc& r = c->sps[cp.remote_sp];
       S.cp_lchild[S.ncp] = l.children[0]; S.cp_lkind[S.ncp] = l.cond_kind; S.cp_lmask[S.ncp] = l.mask;
       S.cp_rchild[S.ncp] = r.children[0]; S.cp_rkind[S.ncp] = r.cond_kind; S.cp_rmask[S.ncp] = r.mask;
-      S.cp_cchild[S.ncp] = cp.coupling_child; ++S.ncp;
+      S.cp_cchild[S.ncp] = cp.coupling_child; S.cp_ncomp[S.ncp] = cp.ncomp; ++S.ncp;
     }
   }
   const int64_t n = c->ndof;

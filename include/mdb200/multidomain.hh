@@ -86,7 +86,8 @@ class GridFunctionSpace {            // GridFunctionSpace<SDGV, QkLocalFiniteEle
 public:
   SubDomainGridView gv; int k; int child;
   bool coupling; int lkind, rkind; uint32_t lmask, rmask;      // set by CouplingGridFunctionSpace only
-  GridFunctionSpace(SubDomainGridView gv_, int order) : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0) {}
+  int ncomp;                                                   // > 1: PowerCouplingGridFunctionSpace
+  GridFunctionSpace(SubDomainGridView gv_, int order) : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1) {}
 };
 
 // CouplingGridFunctionSpace<MDGV, QkLocalFiniteElementMap<(dim-1)-cube,1>, SubProblemSubProblemInterface<MDGV,Left,Right>, NoConstraints, VBE>
@@ -100,6 +101,14 @@ public:
   }
 };
 
+// PowerCouplingGridFunctionSpace<CouplingGFS, k, VBE>(couplinggfs)   (powercouplinggridfunctionspace.hh:13-75;
+// test/testpowermortarpoisson.cc:384-386): k copies of a coupling space, block after block.  Pass IT (not the CouplingGFS it was
+// built from) to MultiDomainGridFunctionSpace; `child` is then the first component block.
+class PowerCouplingGridFunctionSpace : public GridFunctionSpace {
+public:
+  PowerCouplingGridFunctionSpace(const CouplingGridFunctionSpace& c, int k_) : GridFunctionSpace(c) { ncomp = k_; child = -1; }
+};
+
 class MultiDomainGridFunctionSpace { // children in argument order, LexicographicOrderingTag
   MultiDomainGrid& grid_;
   bool finalized_;
@@ -108,7 +117,9 @@ public:
   MultiDomainGridFunctionSpace(MultiDomainGrid& grid, std::initializer_list<GridFunctionSpace*> children)
     : grid_(grid), finalized_(false), ndof_(0) {
     for (GridFunctionSpace* g : children)
-      g->child = g->coupling
+      g->child = g->coupling && g->ncomp > 1
+        ? context().check(mdb_add_power_coupling_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->lkind, g->lmask, g->rkind, g->rmask, g->ncomp), "mdb_add_power_coupling_space")
+        : g->coupling
         ? context().check(mdb_add_coupling_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->lkind, g->lmask, g->rkind, g->rmask), "mdb_add_coupling_space")
         : context().check(mdb_add_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->gv.subdomain), "mdb_add_space");
   }
@@ -212,6 +223,11 @@ public:
   EnrichedCoupling(const Local& local, const Remote& remote, const Op& op, const CouplingGridFunctionSpace& couplinggfs) {
     handle = local.gfs.context().check(mdb_add_enriched_coupling(local.gfs.context().get(), Op::id(), &op.p, sizeof(op.p), local.handle, remote.handle,
                                                                  couplinggfs.child, op.jac_mode), "mdb_add_enriched_coupling");
+  }
+  // the operator of test/testpowermortarpoisson.cc:117-262 on a power coupling space (one pass of alpha_generic per component block)
+  EnrichedCoupling(const Local& local, const Remote& remote, const Op& op, const PowerCouplingGridFunctionSpace& couplinggfs) {
+    handle = local.gfs.context().check(mdb_add_power_enriched_coupling(local.gfs.context().get(), Op::id(), &op.p, sizeof(op.p), local.handle, remote.handle,
+                                                                       couplinggfs.child, couplinggfs.ncomp, op.jac_mode), "mdb_add_power_enriched_coupling");
   }
 };
 

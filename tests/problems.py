@@ -95,7 +95,7 @@ def dirichlet_neumann_q1(api, n):
     return testpoisson(api, n, intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE))
 
 
-def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE_Q1), jac_mode=capi.JAC_FD_BITMATCH, sd_bits=None):
+def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE_Q1), jac_mode=capi.JAC_FD_BITMATCH, sd_bits=None, ncomp=1):
     """test/testmortarpoisson.cc:281-432 (BASELINE configs[3]; 2-D refine 5 as shipped, dim = len(n) for the synthetic 3-D
     form): subdomains x0 < 0.5 -> 0, x0 > 0.5 -> 1 (:325-330), a Q1 space on each (:359-362), a Q1 mortar space
     on the interface faces inside in {0} / outside in {1} as the LAST child (:365-384), Poisson(f,b,j,4) on both sides
@@ -108,7 +108,12 @@ def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE
         api.subdomains(sd_bits)
     c0 = api.add_space(fe[0], 0)
     c1 = api.add_space(fe[1], 1)
-    cc = api.add_coupling_space(capi.FE_Q1, (capi.COND_EQUALITY, 1 << 0), (capi.COND_EQUALITY, 1 << 1))
+    # ncomp = 2: test/testpowermortarpoisson.cc — PowerCouplingGridFunctionSpace<CouplingGFS,2,VBE> (:384-386), the operator loops
+    # over the component blocks (:186-189)
+    if ncomp == 1:
+        cc = api.add_coupling_space(capi.FE_Q1, (capi.COND_EQUALITY, 1 << 0), (capi.COND_EQUALITY, 1 << 1))
+    else:
+        cc = api.add_power_coupling_space(capi.FE_Q1, (capi.COND_EQUALITY, 1 << 0), (capi.COND_EQUALITY, 1 << 1), ncomp)
     pp = capi.PoissonParams()
     pp.f = capi.Function(capi.FN_ZERO)
     pp.bc = capi.BCType(capi.BC_TESTPOISSON)
@@ -118,14 +123,17 @@ def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE
     right = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 1, [c1])
     mp = capi.MortarParams()
     mp.gamma_0 = gamma_0
-    cp = api.add_enriched_coupling(capi.OP_MORTAR_POISSON_COUPLING, mp, left, right, cc, jac_mode)
+    if ncomp == 1:
+        cp = api.add_enriched_coupling(capi.OP_MORTAR_POISSON_COUPLING, mp, left, right, cc, jac_mode)
+    else:
+        cp = api.add_power_enriched_coupling(capi.OP_MORTAR_POISSON_COUPLING, mp, left, right, cc, ncomp, jac_mode)
     ndof = api.finalize()
     ncon = api.constraints_assemble([left, right], [pp.bc, pp.bc])
     go = api.gridoperator_create([left, right], [cp])
     mat = api.matrix_create([go])
     g = capi.gauss()
     return SimpleNamespace(dim=dim, ndof=ndof, ncon=ncon, go=go, mat=mat, left=left, right=right, cp=cp, g=g, sps=[left, right],
-                           gfn=[g, g], bc=pp.bc, children=(c0, c1, cc))
+                           gfn=[g, g], bc=pp.bc, children=(c0, c1, cc), ncomp=ncomp)
 
 
 def dirichlet_neumann(api, n, alpha=2.0, left_mode=capi.ND_MODE_DIRICHLET, right_mode=capi.ND_MODE_NEUMANN, fe=(capi.FE_Q1, capi.FE_Q1), quad_order=6,

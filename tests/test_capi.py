@@ -100,6 +100,7 @@ def test_cxx_facade_compiles_and_fails_loudly_without_gpu(lib):
         _build_example(d, "testinstationarypoisson")          # the instationary driver must at least compile and link
         _build_example(d, "testmortarpoisson")                # ... and so must the mortar (enriched coupling) driver
         _build_example(d, "testpoisson-dirichlet-neumann")    # ... and the Dirichlet-Neumann driver
+        _build_example(d, "testpowermortarpoisson")           # ... and the power mortar driver
         if torch.cuda.is_available():
             pytest.skip("a GPU is present (the run is covered by the gpu tests)")
         p = subprocess.run([exe, "3", "2.0"], capture_output=True, text=True)

@@ -36,6 +36,13 @@ CASES = {
     "m3d_q2q1": dict(n=(4, 3, 3), fe=(capi.FE_Q2, capi.FE_Q1)),
     "m2d_stairs": dict(n=(12, 9), sd_bits="stairs"),
     "m3d_stairs": dict(n=(8, 6, 3), sd_bits="stairs"),
+    # test/testpowermortarpoisson.cc: PowerCouplingGridFunctionSpace<CouplingGFS,2,VBE>, the operator loops over the blocks
+    "p2d_shipped_32": dict(n=(32, 32), ncomp=2),                           # testpowermortarpoisson "5 1.0"
+    "p2d_ragged_q1q2": dict(n=(6, 5), ncomp=2, fe=(capi.FE_Q1, capi.FE_Q2), gamma_0=3.0),
+    "p2d_analytic_split_y": dict(n=(6, 8), ncomp=2, split_axis=1, jac_mode=capi.JAC_ANALYTIC),
+    "p3d_6": dict(n=(6, 5, 4), ncomp=2),
+    "p3d_q2q1": dict(n=(4, 3, 3), ncomp=2, fe=(capi.FE_Q2, capi.FE_Q1)),
+    "p2d_stairs": dict(n=(12, 9), ncomp=2, sd_bits="stairs"),
 }
 
 
@@ -126,11 +133,27 @@ def test_stationary_solve_bcgs_ssor(pair):
     dev.set_ssor_sweeps(3)
     sd = dev.solve(Pd.mat, rd, zd, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, reduction=1e-13, maxit=5000)
     so = ora.solve(Po.mat, ro, zo, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, sweeps=3, reduction=1e-13, maxit=5000)
-    assert sd.converged and so.converged
+    if not so.converged:
+        # p3d_q2q1: the reference's solver configuration itself stagnates on this synthetic power-space system (defect 3e-2 after
+        # 5000 iterations in the oracle) — the device must not claim otherwise; the entries are compared by the other tests
+        assert not sd.converged
+        return
+    assert sd.converged
     # BiCGSTAB on this indefinite system is sensitive to the reduction order of its dot products once the defect nears
     # 1e-13: the counts agree to a few iterations, not exactly
     assert abs(sd.iterations - so.iterations) <= max(2, so.iterations // 6), (sd.iterations, so.iterations)
-    assert np.abs(zd - zo).max() <= RTOL_SOLUTION * np.abs(zo).max()
+    diff = zd - zo
+    if Po.ncomp > 1:
+        # The power operator as shipped (every block adds the element-element terms again) can be singular up to the FD noise:
+        # on the 2-D default invocation the exact Jacobian has a null vector (u_left on the interface = 2 lambda_0 = 2 lambda_1 =
+        # const; sigma_min = 2.5e-10 with FD entries, 6e-15 analytic).  The solution is then defined up to that vector only, so
+        # its component is taken out of the comparison (nothing is removed when the matrix is regular, e.g. in 3-D).
+        U, S, Vt = np.linalg.svd(ora.csr(Po.mat).toarray())
+        for k in np.nonzero(S < 1e-7 * S[0])[0]:
+            diff = diff - Vt[k] * (Vt[k] @ diff)
+        A = ora.csr(Po.mat)
+        assert np.abs(A @ zd - ro).max() <= 1e-11 * np.abs(ro).max()
+    assert np.abs(diff).max() <= RTOL_SOLUTION * np.abs(zo).max()
 
 
 def test_host_vector_upload_covers_the_mortar_coefficients():
@@ -146,17 +169,18 @@ def test_host_vector_upload_covers_the_mortar_coefficients():
     dev.close(); ora.close()
 
 
-@pytest.mark.parametrize("refinement,scaling,dim", [(5, 1.0, 2), (4, 2.5, 2), (3, 1.0, 3)])
-def test_cxx_mortar_driver_matches_oracle(refinement, scaling, dim):
-    """examples/testmortarpoisson.cc (test/testmortarpoisson.cc against include/mdb200/multidomain.hh) run as a program; (5, 1.0, 2)
-    is the reference's default invocation: ordering size 1155, BiCGSTAB + SSOR(3) to 1e-10."""
+@pytest.mark.parametrize("refinement,scaling,dim,ncomp", [(5, 1.0, 2, 1), (4, 2.5, 2, 1), (3, 1.0, 3, 1), (5, 1.0, 2, 2), (3, 2.0, 3, 2)])
+def test_cxx_mortar_driver_matches_oracle(refinement, scaling, dim, ncomp):
+    """examples/testmortarpoisson.cc / testpowermortarpoisson.cc (test/test[power]mortarpoisson.cc against include/mdb200/multidomain.hh)
+    run as programs; (5, 1.0, 2) is the reference's default invocation: ordering size 1155 (1188 with the power space), BiCGSTAB +
+    SSOR(3) to 1e-10."""
     import re
     import subprocess
     import tempfile
     from test_capi import _build_example
     n = (1 << refinement,) * dim
     ora = orc.Oracle()
-    Po = problems.testmortarpoisson(ora, n, gamma_0=scaling)
+    Po = problems.testmortarpoisson(ora, n, gamma_0=scaling, ncomp=ncomp)
     u = np.zeros(Po.ndof)
     ora.interpolate(Po.sps, Po.gfn, u)
     ora.jacobian(Po.go, Po.mat, u, overwrite=True)
@@ -167,7 +191,7 @@ def test_cxx_mortar_driver_matches_oracle(refinement, scaling, dim):
     ora.solve(Po.mat, r, z, reduction=1e-13)
     un = u - z
     with tempfile.TemporaryDirectory() as d:
-        exe = _build_example(d, "testmortarpoisson")
+        exe = _build_example(d, "testmortarpoisson" if ncomp == 1 else "testpowermortarpoisson")
         out = subprocess.run([exe, str(refinement), str(scaling), str(dim)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert int(out.stdout.split()[0]) == Po.ndof
@@ -178,6 +202,11 @@ def test_cxx_mortar_driver_matches_oracle(refinement, scaling, dim):
     m = re.search(r"solver: (\d+) iterations", out.stdout)
     assert abs(int(m.group(1)) - so.iterations) <= max(2, so.iterations // 6), (m.group(1), so.iterations)
     m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
+    if ncomp > 1 and dim == 2:
+        # power space in 2-D: the shipped system is singular up to FD noise (see test_stationary_solve_bcgs_ssor); the 1e-10 solve
+        # carries an O(1) multiple of the null vector (FD noise of the right-hand side / sigma_min) that depends on where the
+        # Krylov iteration stops — the checksum is not a property of the problem
+        return
     assert abs(float(m.group(1)) - un.sum()) <= 1e-7 * abs(un.sum())
     assert abs(float(m.group(2)) - np.linalg.norm(un)) <= 1e-7 * np.linalg.norm(un)
 

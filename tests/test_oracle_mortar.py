@@ -134,3 +134,88 @@ def test_mortar_stationary_solve_against_scipy():
     off = o.get_child_offsets()
     ul = un[off[0]:off[1]].reshape(n[1] + 1, n[0] // 2 + 1)[:, -1]
     assert np.abs(ul - un[off[2]:]).max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PowerCouplingGridFunctionSpace<CouplingGFS, 2, VBE> (test/testpowermortarpoisson.cc:384-386): two copies of the mortar
+# space, block after block (LexicographicOrderingTag), the operator loops over the blocks (:186-189)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_sizes_of_the_shipped_testpowermortarpoisson():
+    """refinement 5 (testpowermortarpoisson.cc:296): two 17x33 Q1 blocks and two mortar blocks of 33 DOFs each."""
+    o, P = _setup((32, 32), ncomp=2)
+    assert list(o.get_child_offsets()) == [0, 561, 1122, 1155, 1188]
+    assert P.ndof == 1188
+
+
+@pytest.mark.parametrize("n,fe", [((6, 4), (capi.FE_Q1, capi.FE_Q1)), ((4, 4), (capi.FE_Q2, capi.FE_Q1)), ((4, 3, 2), (capi.FE_Q1, capi.FE_Q1))])
+def test_power_pattern_from_the_single_mortar_pattern(n, fe):
+    """The local coupling space of an intersection is the concatenation of the component blocks' spaces, and every enriched pattern
+    is full over it (couplingutilities.hh:219-286): with S the single-mortar pattern in blocks [ee ec; ce cc], the power pattern is
+    [ee ec ec; ce cc cc; ce cc cc] — including the cross links between the two multiplier blocks, which the operator never fills."""
+    o1, P1 = _setup(n, fe=fe)
+    o2, P2 = _setup(n, fe=fe, ncomp=2)
+    off = o1.get_child_offsets()
+    ne, nm = off[2], off[3] - off[2]
+    assert list(o2.get_child_offsets()) == [off[0], off[1], off[2], ne + nm, ne + 2 * nm]
+    rp, ci = o1.matrix_get_pattern(P1.mat)
+    S = sp.csr_matrix((np.ones(len(ci)), ci, rp), shape=(ne + nm, ne + nm))
+    ee, ec, ce, cc = S[:ne, :ne], S[:ne, ne:], S[ne:, :ne], S[ne:, ne:]
+    ref = sp.bmat([[ee, ec, ec], [ce, cc, cc], [ce, cc, cc]], format="csr")
+    ref.sort_indices()
+    rp2, ci2 = o2.matrix_get_pattern(P2.mat)
+    assert np.array_equal(rp2, ref.indptr) and np.array_equal(ci2, ref.indices)
+
+
+@pytest.mark.parametrize("n,fe", [((8, 6), (capi.FE_Q1, capi.FE_Q1)), ((4, 4), (capi.FE_Q1, capi.FE_Q2)), ((4, 3, 3), (capi.FE_Q1, capi.FE_Q1))])
+def test_power_jacobian_from_the_single_mortar_jacobian(n, fe):
+    """Each component block runs the whole body of alpha_generic, so (exact derivative, free rows): the element-element coupling
+    terms are added once per block (ee_power = vol + 2 (ee_single - vol)), every block has the single space's ec / ce / cc blocks,
+    and the stored cross links cc_01, cc_10 stay zero."""
+    o1, P1 = _setup(n, fe=fe, jac_mode=capi.JAC_ANALYTIC)
+    o2, P2 = _setup(n, fe=fe, jac_mode=capi.JAC_ANALYTIC, ncomp=2)
+    gov = o1.gridoperator_create(P1.sps, [])             # the two Poisson subproblems without the coupling
+    matv = o1.matrix_create([gov])
+    z1, z2 = np.zeros(P1.ndof), np.zeros(P2.ndof)
+    o1.jacobian(P1.go, P1.mat, z1, overwrite=True); o1.jacobian(gov, matv, z1, overwrite=True); o2.jacobian(P2.go, P2.mat, z2, overwrite=True)
+    A1, V, A2 = o1.csr(P1.mat), o1.csr(matv), o2.csr(P2.mat)
+    off = o1.get_child_offsets()
+    ne, nm = off[2], off[3] - off[2]
+    free = ~o1.get_constraints().astype(bool)[:ne]
+    scale = abs(A1).max()
+    ee = (V[:ne, :ne] + 2 * (A1[:ne, :ne] - V[:ne, :ne]))
+    assert abs((A2[:ne, :ne] - ee)[free]).max() < 1e-13 * scale
+    for b in range(2):
+        lo, hi = ne + b * nm, ne + (b + 1) * nm
+        assert abs((A2[:ne, lo:hi] - A1[:ne, ne:])[free]).max() < 1e-13 * scale
+        assert abs(A2[lo:hi, :ne] - A1[ne:, :ne]).max() < 1e-13 * scale
+        assert abs(A2[lo:hi, lo:hi] - A1[ne:, ne:]).max() < 1e-13 * scale
+    assert abs(A2[ne:ne + nm, ne + nm:]).max() == 0.0 and abs(A2[ne + nm:, ne:ne + nm]).max() == 0.0
+    assert A2[ne:ne + nm, ne + nm:].nnz > 0              # ... but they are stored (full pattern over the power space)
+
+
+@pytest.mark.parametrize("n", [(8, 8), (4, 4, 3)])
+def test_power_fd_jacobian_and_affine_residual(n):
+    """FD Jacobian of the power operator within FD noise of the exact one; R(x) = J x + R(0) on the free rows; and with equal
+    multiplier blocks the residual's element rows equal vol + 2 (single - vol)."""
+    o, P = _setup(n, ncomp=2)
+    oa, Pa = _setup(n, ncomp=2, jac_mode=capi.JAC_ANALYTIC)
+    x = np.random.default_rng(1).uniform(-1, 1, P.ndof)
+    o.jacobian(P.go, P.mat, x, overwrite=True); oa.jacobian(Pa.go, Pa.mat, x, overwrite=True)
+    A, B = o.csr(P.mat), oa.csr(Pa.mat)
+    assert abs(A - B).max() < 2e-6 * abs(B).max()
+    free = ~o.get_constraints().astype(bool)
+    r0, rx = np.zeros(P.ndof), np.zeros(P.ndof)
+    o.residual(P.go, np.zeros(P.ndof), r0); o.residual(P.go, x, rx)
+    assert np.abs((B @ x + r0 - rx)[free]).max() < 1e-12 * np.abs(rx).max()
+    o1, P1 = _setup(n)
+    gov = o1.gridoperator_create(P1.sps, [])
+    off = o1.get_child_offsets()
+    ne, nm = off[2], off[3] - off[2]
+    x1 = x[:ne + nm]
+    x2 = np.concatenate([x1, x1[ne:]])
+    r1, rv, r2 = np.zeros(P1.ndof), np.zeros(P1.ndof), np.zeros(P.ndof)
+    o1.residual(P1.go, x1, r1); o1.residual(gov, x1, rv); o.residual(P.go, x2, r2)
+    f1 = free[:ne]
+    assert np.abs((r2[:ne] - (rv[:ne] + 2 * (r1[:ne] - rv[:ne])))[f1]).max() < 1e-13 * np.abs(r1).max()
+    assert np.abs(r2[ne:ne + nm] - r1[ne:]).max() < 1e-13 * np.abs(r1).max() and np.array_equal(r2[ne:ne + nm], r2[ne + nm:])
