@@ -12,10 +12,11 @@ import numpy as np
 
 # ---- enums (mirror include/mdb200.h) -----------------------------------------------------------
 FE_Q1, FE_Q2 = 1, 2
+FE_DGQ1, FE_DGQ2 = 11, 12
 COND_EQUALITY, COND_SUBSET = 0, 1
 FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2, FN_DN_SOURCE = range(8)
 BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON = range(3)
-OP_POISSON, OP_L2 = 1, 2
+OP_POISSON, OP_L2, OP_CONVDIFF_DG = 1, 2, 3
 OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
 OP_MORTAR_POISSON_COUPLING = 201
 OP_ND_COUPLING = 103
@@ -67,6 +68,11 @@ class PropFlowParams(C.Structure):
 
 class NDCouplingParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("method", C.c_int32), ("weights", C.c_int32), ("intorderadd", C.c_int32), ("alpha", C.c_double)]
+
+
+class ConvDiffDGParams(C.Structure):
+    _fields_ = [("f", Function), ("bc", BCType), ("g", Function), ("j", Function), ("method", C.c_int32), ("weights", C.c_int32),
+                ("intorderadd", C.c_int32), ("reserved", C.c_int32), ("alpha", C.c_double)]
 
 
 class MortarParams(C.Structure):

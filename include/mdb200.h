@@ -48,7 +48,12 @@ enum {
 /* ---- finite elements (child spaces of the MultiDomainGridFunctionSpace) -- */
 enum {
   MDB_FE_Q1 = 1,        /* QkLocalFiniteElementMap<...,1>  test/testpoisson.cc:168 */
-  MDB_FE_Q2 = 2         /* QkLocalFiniteElementMap<...,2>  test/testpoisson.cc:169 */
+  MDB_FE_Q2 = 2,        /* QkLocalFiniteElementMap<...,2>  test/testpoisson.cc:169 */
+  /* QkDGLocalFiniteElementMap<DF,double,k,dim> (test/testpoisson-dirichlet-neumann.cc:925-926): the Qk Lagrange basis with all
+   * (k+1)^dim coefficients attached to the cell — DOF = (index of the cell in its subdomain) * (k+1)^dim + i [UPSTREAM (iii)];
+   * no DOF is shared, ConformingDirichletConstraints constrains nothing (Dirichlet data enter weakly through the operator). */
+  MDB_FE_DGQ1 = 11,
+  MDB_FE_DGQ2 = 12      /* the shipped spaces of BASELINE configs[0] (test/testpoisson-dirichlet-neumann.cc:968-971) */
 };
 
 /* ---- subdomain conditions  (subdomainset.hh:82-133) ---------------------- */
@@ -94,6 +99,9 @@ enum {
   MDB_OP_POISSON = 1,        /* [UPSTREAM] Dune::PDELab::Poisson<F,B,J>(f,b,j,quadOrder)  test/testpoisson.cc:218-219;
                                  in-tree twin test/instationarypoissonoperator.hh:30-168                            */
   MDB_OP_L2 = 2,             /* [UPSTREAM] Dune::PDELab::L2(intorder) / test/simpletimeoperator.hh:29-101 (mass)    */
+  MDB_OP_CONVDIFF_DG = 3,    /* [UPSTREAM] Dune::PDELab::ConvectionDiffusionDG<ConvectionDiffusionModelProblem,FEM>(param, method,
+                                 weights, alpha)  test/testpoisson-dirichlet-neumann.cc:864-881 (dglop), parameter class :169-285
+                                 (A = I, b = 0, c = 0): volume + interior-penalty skeleton + weak boundary terms             */
   /* coupling operators used by Couplings */
   MDB_OP_CVCF_COUPLING = 101,     /* ContinuousValueContinuousFlowCoupling  test/proportionalflowcoupling.hh:94-239 */
   MDB_OP_PROPFLOW_COUPLING = 102, /* ProportionalFlowCoupling               test/proportionalflowcoupling.hh:10-91  */
@@ -139,6 +147,28 @@ typedef struct mdb_ndcoupling_params {
   int32_t intorderadd;       /* quadrature order = intorderadd + 2 * max basis order, :107              */
   double alpha;              /* interior penalty parameter                                              */
 } mdb_ndcoupling_params;
+
+/* ConvectionDiffusionDG(param, method, weights, alpha, intorderadd = 0) [UPSTREAM dune-pdelab convectiondiffusiondg.hh; its face
+ * terms are the ones test/neumanndirichletcoupling.hh:85-283 was derived from].  The parameter class is the reference's
+ * ConvectionDiffusionModelProblem (test/testpoisson-dirichlet-neumann.cc:169-285): A = identity, b = 0, c = 0, and
+ *   f        source, evaluated at the quadrature points of the cell (:203-218 = MDB_FN_DN_SOURCE)
+ *   bc       boundary type at the FACE CENTRE: Dirichlet / Neumann / None — None on every interior face (:226-229), which is what
+ *            makes alpha_boundary a no-op when the assembler calls it on a subdomain interface (residualassemblerfunctors.hh:80-86)
+ *   g        Dirichlet value (:244-252 = MDB_FN_GAUSS), imposed weakly (Nitsche terms)
+ *   j        Neumann flux (:254-268 = MDB_FN_TESTPOISSON_J)
+ * doAlphaVolume, doAlphaSkeleton, doAlphaBoundary, doLambdaVolume, doPatternVolume, doPatternSkeleton; doSkeletonTwoSided = false.
+ * Quadrature order = intorderadd + 2 * basis order for every term. */
+typedef struct mdb_convdiffdg_params {
+  mdb_function f;
+  mdb_bctype bc;
+  mdb_function g;
+  mdb_function j;
+  int32_t method;            /* MDB_DG_METHOD_*: SIPG in dglop() (:876)      */
+  int32_t weights;           /* MDB_DG_WEIGHTS_*: weightsOn in dglop() (:877) */
+  int32_t intorderadd;       /* 0                                             */
+  int32_t reserved;
+  double alpha;              /* interior penalty parameter: 2.0 in dglop() (:878) */
+} mdb_convdiffdg_params;
 
 typedef struct mdb_mortar_params {
   double gamma_0;            /* ctor arg ("scaling factor for coupling", test/testmortarpoisson.cc:402): gamma = gamma_0 / |face| */

@@ -181,6 +181,268 @@ struct L2Op : LocalOperator {
   }
 };
 
+// [UPSTREAM] Dune::PDELab::ConvectionDiffusionDG<T,FEM> (dune-pdelab convectiondiffusiondg.hh, the 2.0/2.4-dev version with the
+// "Houston" face diameter — the same text test/neumanndirichletcoupling.hh:85-432 was derived from and can be read against),
+// instantiated by dglop() (test/testpoisson-dirichlet-neumann.cc:864-881) with the parameter class ConvectionDiffusionModelProblem
+// (:169-285): A = I, b = 0, c = 0.  Restated from the published algorithm; the velocity terms are kept (with b = 0) so that the
+// operation count per entry is the upstream one.
+struct ConvDiffDGOp : LocalOperator {
+  mdb_convdiffdg_params P;
+  double theta;
+  explicit ConvDiffDGOp(const mdb_convdiffdg_params& p) : P(p) {
+    doPatternVolume = true; doPatternSkeleton = true;
+    doAlphaVolume = true; doAlphaSkeleton = true; doAlphaBoundary = true; doLambdaVolume = true;
+    doSkeletonTwoSided = false;
+    theta = 1.0; if (P.method == MDB_DG_METHOD_SIPG) theta = -1.0;
+  }
+  static void tgrad(const QkBasis& B, const EG& e, const double* local, int n, double (*js)[3], double (*out)[3]) {
+    B.evaluateJacobian(local, js);
+    for (int i = 0; i < n; ++i)
+      for (int d = 0; d < B.dim; ++d) { out[i][d] = 0.0; out[i][d] += e.jacInvT(d) * js[i][d]; }     // jac.mv(js[i][0], gradphi[i])
+  }
+  // ---- volume ------------------------------------------------------------------------------------------------------
+  void alpha_volume(const EG& eg, const LFS& lfsu, const double* x, const LFS& lfsv, LocalVectorView& r) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsu.k, dim);
+    const auto& rule = tensor_rule(dim, P.intorderadd + 2 * lfsu.k);
+    double phi[MAXLOC], js[MAXLOC][3], gradphi[MAXLOC][3];
+    for (const auto& q : rule) {
+      B.evaluateFunction(q.x, phi);
+      double u = 0.0;
+      for (int i = 0; i < lfsu.n; ++i) u += x[lfsu.idx[i]] * phi[i];
+      tgrad(B, eg, q.x, lfsu.n, js, gradphi);
+      double gradu[3] = {0, 0, 0};
+      for (int i = 0; i < lfsu.n; ++i) for (int d = 0; d < dim; ++d) gradu[d] += x[lfsu.idx[i]] * gradphi[i][d];
+      double Agradu[3];
+      for (int i = 0; i < dim; ++i) { Agradu[i] = 0.0; for (int j = 0; j < dim; ++j) Agradu[i] += ((i == j) ? 1.0 : 0.0) * gradu[j]; }
+      const double c = 0.0;
+      const double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsv.n; ++i) {
+        double Agg = 0.0, bg = 0.0;
+        for (int d = 0; d < dim; ++d) { Agg += Agradu[d] * gradphi[i][d]; bg += 0.0 * gradphi[i][d]; }
+        r.accumulate(lfsv, i, (Agg - u * bg + c * u * phi[i]) * factor);
+      }
+    }
+  }
+  void jacobian_volume(const EG& eg, const LFS& lfsu, const double*, const LFS& lfsv, LocalMatrixView& mat) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsu.k, dim);
+    const auto& rule = tensor_rule(dim, P.intorderadd + 2 * lfsu.k);
+    double phi[MAXLOC], js[MAXLOC][3], gradphi[MAXLOC][3];
+    for (const auto& q : rule) {
+      B.evaluateFunction(q.x, phi);
+      tgrad(B, eg, q.x, lfsu.n, js, gradphi);
+      const double c = 0.0;
+      const double factor = q.w * eg.integrationElement();
+      for (int j = 0; j < lfsu.n; ++j)
+        for (int i = 0; i < lfsu.n; ++i) {
+          double Agg = 0.0, bg = 0.0;
+          for (int d = 0; d < dim; ++d) { Agg += gradphi[j][d] * gradphi[i][d]; bg += 0.0 * gradphi[i][d]; }     // Agradphi[j] = gradphi[j]
+          mat.accumulate(lfsv, i, lfsu, j, (Agg - phi[j] * bg + c * phi[j] * phi[i]) * factor);
+        }
+    }
+  }
+  void lambda_volume(const EG& eg, const LFS& lfsv, LocalVectorView& r) const override {
+    const int dim = eg.g->dim;
+    QkBasis B(lfsv.k, dim);
+    const auto& rule = tensor_rule(dim, P.intorderadd + 2 * lfsv.k);
+    double phi[MAXLOC], xg[3];
+    for (const auto& q : rule) {
+      B.evaluateFunction(q.x, phi);
+      eg.global(q.x, xg);
+      const double f = eval_function(P.f, dim, xg, time);
+      const double factor = q.w * eg.integrationElement();
+      for (int i = 0; i < lfsv.n; ++i) r.accumulate(lfsv, i, -f * phi[i] * factor);
+    }
+  }
+  // ---- interior faces ----------------------------------------------------------------------------------------------
+  struct Face { double n_F[3], omega_s, omega_n, penalty_factor; int intorder; };
+  Face face(const IG& ig, int k_s, int k_n, bool boundary) const {
+    Face F; const int dim = ig.dim();
+    const int order = std::max(k_s, k_n);
+    F.intorder = P.intorderadd + 2 * order;
+    const double h_F = (boundary ? ig.inside.integrationElement()
+                                 : std::min(ig.inside.integrationElement(), ig.outside.integrationElement())) / ig.integrationElement();
+    ig.unitOuterNormal(F.n_F);                                           // An_F_s = An_F_n = n_F (A = I)
+    double harmonic_average;
+    if (P.weights == MDB_DG_WEIGHTS_ON) {
+      double delta_s = 0.0, delta_n = 0.0;
+      for (int d = 0; d < dim; ++d) { delta_s += F.n_F[d] * F.n_F[d]; delta_n += F.n_F[d] * F.n_F[d]; }
+      if (boundary) { F.omega_s = 1.0; F.omega_n = 0.0; harmonic_average = delta_s; }
+      else {
+        F.omega_s = delta_n / (delta_s + delta_n + 1e-20); F.omega_n = delta_s / (delta_s + delta_n + 1e-20);
+        harmonic_average = 2.0 * delta_s * delta_n / (delta_s + delta_n + 1e-20);
+      }
+    } else { F.omega_s = F.omega_n = 0.5; harmonic_average = 1.0; if (boundary) { F.omega_s = 1.0; F.omega_n = 0.0; } }
+    const int degree = order;
+    F.penalty_factor = (P.alpha / h_F) * harmonic_average * degree * (degree + dim - 1);
+    return F;
+  }
+  void alpha_skeleton(const IG& ig, const LFS& lfsu_s, const double* x_s, const LFS& lfsv_s, const LFS& lfsu_n, const double* x_n,
+                      const LFS& lfsv_n, LocalVectorView& r_s, LocalVectorView& r_n) const override {
+    const int dim = ig.dim();
+    const Face F = face(ig, lfsu_s.k, lfsu_n.k, false);
+    QkBasis Bs(lfsu_s.k, dim), Bn(lfsu_n.k, dim);
+    const auto& rule = tensor_rule(dim - 1, F.intorder);
+    double phi_s[MAXLOC], phi_n[MAXLOC], js[MAXLOC][3], tg_s[MAXLOC][3], tg_n[MAXLOC][3], ip_s[3], ip_n[3];
+    for (const auto& q : rule) {
+      ig.localInside(q.x, ip_s); ig.localOutside(q.x, ip_n);
+      Bs.evaluateFunction(ip_s, phi_s); Bn.evaluateFunction(ip_n, phi_n);
+      double u_s = 0.0, u_n = 0.0;
+      for (int i = 0; i < lfsu_s.n; ++i) u_s += x_s[lfsu_s.idx[i]] * phi_s[i];
+      for (int i = 0; i < lfsu_n.n; ++i) u_n += x_n[lfsu_n.idx[i]] * phi_n[i];
+      tgrad(Bs, ig.inside, ip_s, lfsu_s.n, js, tg_s); tgrad(Bn, ig.outside, ip_n, lfsu_n.n, js, tg_n);
+      double gradu_s[3] = {0, 0, 0}, gradu_n[3] = {0, 0, 0};
+      for (int i = 0; i < lfsu_s.n; ++i) for (int d = 0; d < dim; ++d) gradu_s[d] += x_s[lfsu_s.idx[i]] * tg_s[i][d];
+      for (int i = 0; i < lfsu_n.n; ++i) for (int d = 0; d < dim; ++d) gradu_n[d] += x_n[lfsu_n.idx[i]] * tg_n[i][d];
+      double normalflux = 0.0; for (int d = 0; d < dim; ++d) normalflux += 0.0 * F.n_F[d];             // b = 0
+      const double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0, omegaup_n = normalflux >= 0.0 ? 0.0 : 1.0;
+      const double factor = q.w * ig.integrationElement();
+      const double term1 = (omegaup_s * u_s + omegaup_n * u_n) * normalflux * factor;                   // convection
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term1 * phi_s[i]);
+      for (int i = 0; i < lfsv_n.n; ++i) r_n.accumulate(lfsv_n, i, -term1 * phi_n[i]);
+      double Ags = 0.0, Agn = 0.0; for (int d = 0; d < dim; ++d) { Ags += F.n_F[d] * gradu_s[d]; Agn += F.n_F[d] * gradu_n[d]; }
+      const double term2 = -(F.omega_s * Ags + F.omega_n * Agn) * factor;                               // diffusion
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term2 * phi_s[i]);
+      for (int i = 0; i < lfsv_n.n; ++i) r_n.accumulate(lfsv_n, i, -term2 * phi_n[i]);
+      const double term3 = (u_s - u_n) * factor;                                                        // (non-)symmetric IP term
+      for (int i = 0; i < lfsv_s.n; ++i) { double a = 0.0; for (int d = 0; d < dim; ++d) a += F.n_F[d] * tg_s[i][d]; r_s.accumulate(lfsv_s, i, term3 * theta * F.omega_s * a); }
+      for (int i = 0; i < lfsv_n.n; ++i) { double a = 0.0; for (int d = 0; d < dim; ++d) a += F.n_F[d] * tg_n[i][d]; r_n.accumulate(lfsv_n, i, term3 * theta * F.omega_n * a); }
+      const double term4 = F.penalty_factor * (u_s - u_n) * factor;                                     // standard IP term
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term4 * phi_s[i]);
+      for (int i = 0; i < lfsv_n.n; ++i) r_n.accumulate(lfsv_n, i, -term4 * phi_n[i]);
+    }
+  }
+  void jacobian_skeleton(const IG& ig, const LFS& lfsu_s, const double*, const LFS& lfsv_s, const LFS& lfsu_n, const double*, const LFS& lfsv_n,
+                         LocalMatrixView& mat_ss, LocalMatrixView& mat_sn, LocalMatrixView& mat_ns, LocalMatrixView& mat_nn) const override {
+    const int dim = ig.dim();
+    const Face F = face(ig, lfsu_s.k, lfsu_n.k, false);
+    QkBasis Bs(lfsu_s.k, dim), Bn(lfsu_n.k, dim);
+    const auto& rule = tensor_rule(dim - 1, F.intorder);
+    double phi_s[MAXLOC], phi_n[MAXLOC], js[MAXLOC][3], tg_s[MAXLOC][3], tg_n[MAXLOC][3], ip_s[3], ip_n[3], an_s[MAXLOC], an_n[MAXLOC];
+    for (const auto& q : rule) {
+      ig.localInside(q.x, ip_s); ig.localOutside(q.x, ip_n);
+      Bs.evaluateFunction(ip_s, phi_s); Bn.evaluateFunction(ip_n, phi_n);
+      tgrad(Bs, ig.inside, ip_s, lfsu_s.n, js, tg_s); tgrad(Bn, ig.outside, ip_n, lfsu_n.n, js, tg_n);
+      for (int i = 0; i < lfsu_s.n; ++i) { an_s[i] = 0.0; for (int d = 0; d < dim; ++d) an_s[i] += F.n_F[d] * tg_s[i][d]; }       // An_F_s * tgradphi_s[i]
+      for (int i = 0; i < lfsu_n.n; ++i) { an_n[i] = 0.0; for (int d = 0; d < dim; ++d) an_n[i] += F.n_F[d] * tg_n[i][d]; }
+      double normalflux = 0.0; for (int d = 0; d < dim; ++d) normalflux += 0.0 * F.n_F[d];
+      const double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0, omegaup_n = normalflux >= 0.0 ? 0.0 : 1.0;
+      const double factor = q.w * ig.integrationElement();
+      const double ipfactor = F.penalty_factor * factor;
+      // all terms in the order: I convection, II diffusion, III consistency, IV ip
+      for (int j = 0; j < lfsu_s.n; ++j) {
+        const double temp1 = -an_s[j] * F.omega_s * factor;
+        for (int i = 0; i < lfsv_s.n; ++i) {
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, omegaup_s * phi_s[j] * normalflux * factor * phi_s[i]);
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, temp1 * phi_s[i]);
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, phi_s[j] * factor * theta * F.omega_s * an_s[i]);
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, phi_s[j] * ipfactor * phi_s[i]);
+        }
+      }
+      for (int j = 0; j < lfsu_n.n; ++j) {
+        const double temp1 = -an_n[j] * F.omega_n * factor;
+        for (int i = 0; i < lfsv_s.n; ++i) {
+          mat_sn.accumulate(lfsv_s, i, lfsu_n, j, omegaup_n * phi_n[j] * normalflux * factor * phi_s[i]);
+          mat_sn.accumulate(lfsv_s, i, lfsu_n, j, temp1 * phi_s[i]);
+          mat_sn.accumulate(lfsv_s, i, lfsu_n, j, -phi_n[j] * factor * theta * F.omega_s * an_s[i]);
+          mat_sn.accumulate(lfsv_s, i, lfsu_n, j, -phi_n[j] * ipfactor * phi_s[i]);
+        }
+      }
+      for (int j = 0; j < lfsu_s.n; ++j) {
+        const double temp1 = -an_s[j] * F.omega_s * factor;
+        for (int i = 0; i < lfsv_n.n; ++i) {
+          mat_ns.accumulate(lfsv_n, i, lfsu_s, j, -omegaup_s * phi_s[j] * normalflux * factor * phi_n[i]);
+          mat_ns.accumulate(lfsv_n, i, lfsu_s, j, -temp1 * phi_n[i]);
+          mat_ns.accumulate(lfsv_n, i, lfsu_s, j, phi_s[j] * factor * theta * F.omega_n * an_n[i]);
+          mat_ns.accumulate(lfsv_n, i, lfsu_s, j, -phi_s[j] * ipfactor * phi_n[i]);
+        }
+      }
+      for (int j = 0; j < lfsu_n.n; ++j) {
+        const double temp1 = -an_n[j] * F.omega_n * factor;
+        for (int i = 0; i < lfsv_n.n; ++i) {
+          mat_nn.accumulate(lfsv_n, i, lfsu_n, j, -omegaup_n * phi_n[j] * normalflux * factor * phi_n[i]);
+          mat_nn.accumulate(lfsv_n, i, lfsu_n, j, -temp1 * phi_n[i]);
+          mat_nn.accumulate(lfsv_n, i, lfsu_n, j, -phi_n[j] * factor * theta * F.omega_n * an_n[i]);
+          mat_nn.accumulate(lfsv_n, i, lfsu_n, j, phi_n[j] * ipfactor * phi_n[i]);
+        }
+      }
+    }
+  }
+  // ---- boundary faces (and subdomain interfaces, where the parameter class answers None) -----------------------------------
+  int bctype(const IG& ig) const {          // evaluated at the face centre
+    double centre[2] = {0.5, 0.5}, xg[3];
+    ig.global(centre, xg);
+    return eval_bctype(P.bc, ig.dim(), xg, ig.boundary);
+  }
+  void alpha_boundary(const IG& ig, const LFS& lfsu_s, const double* x_s, const LFS& lfsv_s, LocalVectorView& r_s) const override {
+    const int bc = bctype(ig);
+    if (bc == 2) return;                                                // ConvectionDiffusionBoundaryConditions::None
+    const int dim = ig.dim();
+    const Face F = face(ig, lfsu_s.k, lfsu_s.k, true);
+    QkBasis Bs(lfsu_s.k, dim);
+    const auto& rule = tensor_rule(dim - 1, F.intorder);
+    double phi_s[MAXLOC], js[MAXLOC][3], tg_s[MAXLOC][3], ip_s[3], xg[3];
+    for (const auto& q : rule) {
+      ig.localInside(q.x, ip_s);
+      Bs.evaluateFunction(ip_s, phi_s);
+      const double factor = q.w * ig.integrationElement();
+      if (bc == 1) {                                                    // Neumann: j at the face point
+        ig.global(q.x, xg);
+        const double j = eval_function(P.j, dim, xg, time);
+        for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, j * phi_s[i] * factor);
+        continue;
+      }
+      double u_s = 0.0;
+      for (int i = 0; i < lfsu_s.n; ++i) u_s += x_s[lfsu_s.idx[i]] * phi_s[i];
+      double normalflux = 0.0; for (int d = 0; d < dim; ++d) normalflux += 0.0 * F.n_F[d];
+      tgrad(Bs, ig.inside, ip_s, lfsu_s.n, js, tg_s);
+      double gradu_s[3] = {0, 0, 0};
+      for (int i = 0; i < lfsu_s.n; ++i) for (int d = 0; d < dim; ++d) gradu_s[d] += x_s[lfsu_s.idx[i]] * tg_s[i][d];
+      ig.inside.global(ip_s, xg);
+      const double g = eval_function(P.g, dim, xg, time);               // param.g(inside, iplocal_s)
+      const double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0, omegaup_n = normalflux >= 0.0 ? 0.0 : 1.0;
+      const double term1 = (omegaup_s * u_s + omegaup_n * g) * normalflux * factor;
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term1 * phi_s[i]);
+      double Ag = 0.0; for (int d = 0; d < dim; ++d) Ag += F.n_F[d] * gradu_s[d];
+      const double term2 = Ag * factor;
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, -term2 * phi_s[i]);
+      const double term3 = (u_s - g) * factor;
+      for (int i = 0; i < lfsv_s.n; ++i) { double a = 0.0; for (int d = 0; d < dim; ++d) a += F.n_F[d] * tg_s[i][d]; r_s.accumulate(lfsv_s, i, term3 * theta * a); }
+      const double term4 = F.penalty_factor * (u_s - g) * factor;
+      for (int i = 0; i < lfsv_s.n; ++i) r_s.accumulate(lfsv_s, i, term4 * phi_s[i]);
+    }
+  }
+  void jacobian_boundary(const IG& ig, const LFS& lfsu_s, const double*, const LFS& lfsv_s, LocalMatrixView& mat_ss) const override {
+    const int bc = bctype(ig);
+    if (bc == 2 || bc == 1) return;                                     // None / Neumann: no dependence on u
+    const int dim = ig.dim();
+    const Face F = face(ig, lfsu_s.k, lfsu_s.k, true);
+    QkBasis Bs(lfsu_s.k, dim);
+    const auto& rule = tensor_rule(dim - 1, F.intorder);
+    double phi_s[MAXLOC], js[MAXLOC][3], tg_s[MAXLOC][3], ip_s[3], an_s[MAXLOC];
+    for (const auto& q : rule) {
+      ig.localInside(q.x, ip_s);
+      Bs.evaluateFunction(ip_s, phi_s);
+      tgrad(Bs, ig.inside, ip_s, lfsu_s.n, js, tg_s);
+      for (int i = 0; i < lfsu_s.n; ++i) { an_s[i] = 0.0; for (int d = 0; d < dim; ++d) an_s[i] += F.n_F[d] * tg_s[i][d]; }
+      double normalflux = 0.0; for (int d = 0; d < dim; ++d) normalflux += 0.0 * F.n_F[d];
+      const double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0;
+      const double factor = q.w * ig.integrationElement();
+      const double ipfactor = F.penalty_factor * factor;
+      for (int j = 0; j < lfsu_s.n; ++j) {
+        const double temp1 = -an_s[j] * factor;
+        for (int i = 0; i < lfsv_s.n; ++i) {
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, omegaup_s * phi_s[j] * normalflux * factor * phi_s[i]);
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, temp1 * phi_s[i]);
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, phi_s[j] * factor * theta * an_s[i]);
+          mat_ss.accumulate(lfsv_s, i, lfsu_s, j, phi_s[j] * ipfactor * phi_s[i]);
+        }
+      }
+    }
+  }
+};
+
 // test/proportionalflowcoupling.hh:10-91
 struct PropFlowOp : CouplingOperator {
   mdb_propflow_params P;
@@ -551,6 +813,9 @@ std::unique_ptr<LocalOperator> make_local_operator(int op_id, const void* params
   case MDB_OP_L2:
     if (nbytes != sizeof(mdb_l2_params)) throw std::runtime_error("bad l2 params size");
     return std::unique_ptr<LocalOperator>(new L2Op(*static_cast<const mdb_l2_params*>(params)));
+  case MDB_OP_CONVDIFF_DG:
+    if (nbytes != sizeof(mdb_convdiffdg_params)) throw std::runtime_error("bad convdiffdg params size");
+    return std::unique_ptr<LocalOperator>(new ConvDiffDGOp(*static_cast<const mdb_convdiffdg_params*>(params)));
   }
   throw std::runtime_error("unknown local operator id");
 }
@@ -584,6 +849,17 @@ void Context::finalize()
     const int k = ch.k;
     int64_t total = 1;
     for (int d = 0; d < 3; ++d) { ch.lat_n[d] = (d < dim) ? k * g.n[d] + 1 : 1; total *= ch.lat_n[d]; }
+    if (ch.dg) {
+      // [UPSTREAM] (ii),(iii): all (k+1)^dim coefficients sit on the cell (codim 0): container index = subdomain cell index * nloc + i,
+      // subdomain cell index = rank among the subdomain's cells in host order
+      ch.cellblk.assign(g.ncells(), -1);
+      int64_t cnt = 0;
+      for (int64_t c = 0; c < g.ncells(); ++c)
+        if (ch.subdomain < 0 || ((cell_sd[c] >> ch.subdomain) & 1)) ch.cellblk[c] = cnt++;
+      ch.size = cnt * ch.nloc(dim); ch.offset = off; off += ch.size;
+      ch.lat2dof.clear(); ch.dof2lat.clear();
+      continue;
+    }
     std::vector<uint8_t> present(total, 0);
     // coupling space (couplinggfsordering.hh:113-201): the used entities are the vertices of the intersections the
     // predicate accepts; entity_dof_offsets is indexed by the MultiDomainGrid vertex index, so after the partial sum the
@@ -656,6 +932,7 @@ int Context::bind(int64_t cell, int* child_off, int64_t* dofs) const
     if (ch.iface) continue;      // bound per intersection (globalassembler.hh:212-231), not per cell
     if (ch.subdomain >= 0 && !((cell_sd[cell] >> ch.subdomain) & 1)) continue;
     const int k = ch.k, nl = ch.nloc(dim);
+    if (ch.dg) { for (int i = 0; i < nl; ++i) dofs[n++] = ch.offset + ch.cellblk[cell] * nl + i; continue; }
     for (int i = 0; i < nl; ++i) {
       int a[3]; int rem = i; for (int d = 0; d < 3; ++d) { a[d] = (d < dim) ? rem % (k + 1) : 0; rem /= (k + 1); }
       int64_t p = (k * ijk[0] + a[0]) + ch.lat_n[0] * ((k * ijk[1] + a[1]) + ch.lat_n[1] * (k * ijk[2] + a[2]));
@@ -709,7 +986,7 @@ LFS Context::subproblem_lfs(const SubProblem& sp, const int* child_off) const
   // subproblemlocalfunctionspace.hh:462-501: single-child subproblem = proxy of that child
   if (sp.children.size() != 1) throw std::runtime_error("oracle: only single-child subproblems are restated");
   LFS l; int c = sp.children[0];
-  l.k = children[c].k;
+  l.k = children[c].k; l.dg = children[c].dg;
   l.n = child_off[c + 1] - child_off[c];
   for (int i = 0; i < l.n; ++i) l.idx[i] = child_off[c] + i;
   return l;
@@ -800,6 +1077,15 @@ int Context::matrix_create(const int* gos_, int ngos)
         if (!fl.two_sided && cell < ncell) continue;
         EG en = make_eg(*this, ncell);
         bind(ncell, off_n.data(), dofs_n);
+        for (int s : go.sps) {                                                 // invoke_pattern_skeleton_or_boundary :36-66
+          const SubProblem& sp = sps[s];
+          if (!sp.appliesTo(eg.sd) || !sp.appliesTo(en.sd)) continue;          // (pattern_boundary: none of the restated operators)
+          if (!sp.lop->doPatternSkeleton || !(sp.lop->doSkeletonTwoSided || cell > ncell)) continue;
+          LFS ls = subproblem_lfs(sp, off_s.data()), ln = subproblem_lfs(sp, off_n.data());
+          // [UPSTREAM] FullSkeletonPattern: sn and ns
+          for (int i = 0; i < ls.n; ++i) for (int j = 0; j < ln.n; ++j) rows[dofs_s[ls.idx[i]]].push_back(dofs_n[ln.idx[j]]);
+          for (int i = 0; i < ln.n; ++i) for (int j = 0; j < ls.n; ++j) rows[dofs_n[ln.idx[i]]].push_back(dofs_s[ls.idx[j]]);
+        }
         for (int k : go.cps) {
           const Coupling& cp = cps[k];
           if (cp.eop) {                                                        // invoke_pattern_enriched_coupling :116-150
@@ -884,8 +1170,12 @@ void Context::residual(int goi, double weight, const double* x, double* r) const
           for (int s : go.sps) {
             const SubProblem& sp = sps[s];
             if (!sp.appliesTo(eg.sd)) continue;
-            if (sp.appliesTo(en.sd)) { /* alpha_skeleton: none of the restated operators has it */ }
-            else { /* alpha_boundary on an interior face: none of the restated operators has it */ }
+            LFS l = subproblem_lfs(sp, off_s.data());
+            if (sp.appliesTo(en.sd)) {
+              if (!sp.lop->doAlphaSkeleton || !(sp.lop->doSkeletonTwoSided || ig.oneSidedDirection)) continue;
+              LFS ln = subproblem_lfs(sp, off_n.data());
+              sp.lop->alpha_skeleton(ig, l, x_s, l, ln, x_n, ln, rv_s, rv_n);
+            } else if (sp.lop->doAlphaBoundary) sp.lop->alpha_boundary(ig, l, x_s, l, rv_s);     // the interface seen as boundary (:80-86)
           }
           for (int k : go.cps) {
             const Coupling& cp = cps[k];
@@ -926,6 +1216,12 @@ void Context::residual(int goi, double weight, const double* x, double* r) const
         } else {
           if (grid.processor_face(eg.ijk, f)) continue;                   // assembleVProcessor: no shipped operator has it
           ig.outside = eg; ig.boundary = true; ig.oneSidedDirection = true;
+          for (int s : go.sps) {                                          // alpha_boundary functor :123-143
+            const SubProblem& sp = sps[s];
+            if (!sp.appliesTo(eg.sd) || !sp.lop->doAlphaBoundary) continue;
+            LFS l = subproblem_lfs(sp, off_s.data());
+            sp.lop->alpha_boundary(ig, l, x_s, l, rv_s);
+          }
           for (int s : go.sps) {                                          // lambda_boundary functor :145-162
             const SubProblem& sp = sps[s];
             if (!sp.appliesTo(eg.sd) || !sp.lop->doLambdaBoundary) continue;
@@ -985,11 +1281,25 @@ void jacobian_cell(const Context& c, const GridOperatorDesc& go, const Flags& fl
   if (fl.visit_faces) {
     for (int f = 0; f < 2 * grid.dim; ++f) {
       int64_t nijk[3];
-      if (!FaceIter::neighbor(grid, eg.ijk, f, nijk)) continue;   // boundary: no alpha_boundary among restated operators
+      if (!FaceIter::neighbor(grid, eg.ijk, f, nijk)) {
+        if (grid.processor_face(eg.ijk, f)) continue;
+        IG ig; ig.inside = eg; ig.outside = eg; ig.axis = f / 2; ig.side = f % 2; ig.face = f; ig.boundary = true; ig.oneSidedDirection = true;
+        for (int s : go.sps) {                              // invoke_jacobian_boundary :76-94
+          const SubProblem& sp = c.sps[s];
+          if (!sp.appliesTo(eg.sd) || !sp.lop->doAlphaBoundary) continue;
+          LFS l = c.subproblem_lfs(sp, S.off_s.data());
+          sp.lop->jacobian_boundary(ig, l, S.x_s, l, m_ss);
+        }
+        continue;
+      }
       int64_t ncell = grid.cell_index(nijk);
       if (!fl.two_sided && cell < ncell) continue;
       EG en = make_eg(c, ncell);
       bool any = false;
+      for (int s : go.sps) {
+        const SubProblem& sp = c.sps[s];
+        if (sp.appliesTo(eg.sd) && (sp.lop->doAlphaSkeleton || sp.lop->doAlphaBoundary)) any = true;
+      }
       for (int k : go.cps) {
         const Coupling& cp = c.cps[k];
         if ((cp.eop || cp.op->doAlphaCoupling) && c.sps[cp.local_sp].appliesTo(eg.sd) && c.sps[cp.remote_sp].appliesTo(en.sd)) any = true;
@@ -1003,6 +1313,16 @@ void jacobian_cell(const Context& c, const GridOperatorDesc& go, const Flags& fl
       std::fill(S.a_ns.begin(), S.a_ns.begin() + nn * ns, 0.0);
       std::fill(S.a_nn.begin(), S.a_nn.begin() + nn * nn, 0.0);
       LocalMatrixView m_sn{S.a_sn.data(), nn, weight}, m_ns{S.a_ns.data(), ns, weight}, m_nn{S.a_nn.data(), nn, weight};
+      for (int s : go.sps) {                              // invoke_jacobian_skeleton_or_boundary :36-72
+        const SubProblem& sp = c.sps[s];
+        if (!sp.appliesTo(eg.sd)) continue;
+        LFS l = c.subproblem_lfs(sp, S.off_s.data());
+        if (sp.appliesTo(en.sd)) {
+          if (!sp.lop->doAlphaSkeleton || !(sp.lop->doSkeletonTwoSided || ig.oneSidedDirection)) continue;
+          LFS ln = c.subproblem_lfs(sp, S.off_n.data());
+          sp.lop->jacobian_skeleton(ig, l, S.x_s, l, ln, S.x_n, ln, m_ss, m_sn, m_ns, m_nn);
+        } else if (sp.lop->doAlphaBoundary) sp.lop->jacobian_boundary(ig, l, S.x_s, l, m_ss);
+      }
       for (int k : go.cps) {                              // invoke_jacobian_coupling :91-117
         const Coupling& cp = c.cps[k];
         if (cp.eop || !cp.op->doAlphaCoupling) continue;
@@ -1126,6 +1446,7 @@ void Context::constraints_assemble(const int* sps_, const mdb_bctype* bcs, int n
         ig.global(centre, xg);
         if (eval_bctype(bcs[q], dim, xg, ig.boundary) != 0) continue;
         LFS l = subproblem_lfs(sp, off_s.data());
+        if (l.dg) continue;          // [UPSTREAM] ConformingDirichletConstraints skips coefficients with localKey().codim() == 0
         const int k = l.k;
         for (int i = 0; i < l.n; ++i) {
           int rem = i, a[3];
@@ -1354,7 +1675,8 @@ int orc_add_space(Context* c, int fe_kind, int subdomain)
 {
   try {
     orc::ChildSpace ch; ch.fe_kind = fe_kind; ch.subdomain = subdomain;
-    ch.k = (fe_kind == MDB_FE_Q1) ? 1 : (fe_kind == MDB_FE_Q2) ? 2 : -1;
+    ch.k = (fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_DGQ1) ? 1 : (fe_kind == MDB_FE_Q2 || fe_kind == MDB_FE_DGQ2) ? 2 : -1;
+    ch.dg = fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2;
     if (ch.k < 0) throw std::runtime_error("unknown fe kind");
     c->children.push_back(ch);
     return (int)c->children.size() - 1;

@@ -243,6 +243,7 @@ struct LFS {
   int n = 0;          // size()
   int idx[MAXLOC];    // localIndex(i): position in the cell-local coefficient vector
   int k = 1;          // Qk order
+  bool dg = false;    // QkDG space: every coefficient belongs to the cell (local key codim 0)
 };
 
 struct LocalVectorView {   // [UPSTREAM] LocalVector::WeightedAccumulationView
@@ -264,6 +265,12 @@ struct LocalOperator {
   virtual void jacobian_volume(const EG&, const LFS&, const double*, const LFS&, LocalMatrixView&) const {}
   virtual void lambda_volume(const EG&, const LFS&, LocalVectorView&) const {}
   virtual void lambda_boundary(const IG&, const LFS&, LocalVectorView&) const {}
+  virtual void alpha_skeleton(const IG&, const LFS& /*lfsu_s*/, const double* /*x_s*/, const LFS& /*lfsv_s*/, const LFS& /*lfsu_n*/,
+                              const double* /*x_n*/, const LFS& /*lfsv_n*/, LocalVectorView& /*r_s*/, LocalVectorView& /*r_n*/) const {}
+  virtual void jacobian_skeleton(const IG&, const LFS&, const double*, const LFS&, const LFS&, const double*, const LFS&,
+                                 LocalMatrixView& /*ss*/, LocalMatrixView& /*sn*/, LocalMatrixView& /*ns*/, LocalMatrixView& /*nn*/) const {}
+  virtual void alpha_boundary(const IG&, const LFS&, const double*, const LFS&, LocalVectorView&) const {}
+  virtual void jacobian_boundary(const IG&, const LFS&, const double*, const LFS&, LocalMatrixView&) const {}
 };
 
 struct CouplingOperator {
@@ -311,6 +318,8 @@ struct ChildSpace {
   int fe_kind; int k; int subdomain;           // subdomain -1: MultiDomainGrid view
   // coupling (mortar) space on the interface faces inside in L / outside in R (couplinggridfunctionspace.hh:14-44)
   bool iface = false; int lkind = 0, rkind = 0; uint32_t lmask = 0, rmask = 0;
+  bool dg = false;                              // QkDG: DOF = cellblk[cell] * nloc + i
+  std::vector<int64_t> cellblk;                 // dg: index of the cell in the child's grid view (-1 outside)
   int64_t lat_n[3];                             // lattice points per axis = k*n+1
   std::vector<int64_t> lat2dof;                 // lattice point -> index within the child block, -1 absent
   std::vector<int64_t> dof2lat;

@@ -136,6 +136,43 @@ def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE
                            gfn=[g, g], bc=pp.bc, children=(c0, c1, cc), ncomp=ncomp)
 
 
+def dirichlet_neumann_dg(api, n, k=2, scaling=10.0, alpha=2.0, method=capi.DG_METHOD_SIPG, weights=capi.DG_WEIGHTS_ON, sd_bits=None, f=None,
+                         g=None, bc=None, coupled=True):
+    """BASELINE configs[0] AS SHIPPED: test/testpoisson-dirichlet-neumann.cc main() (:883-977) calls solve() with DGFEM2 =
+    QkDGLocalFiniteElementMap<DF,double,2,dim> on both subdomains and dglop() = ConvectionDiffusionDG(params, SIPG, weightsOn, 2.0)
+    (:864-881) over ConvectionDiffusionModelProblem (:169-285); the monolithic system (:449-456, :619-624) couples the two
+    subproblems with ContinuousValueContinuousFlowCoupling(4, monolithic.coupling.scaling = 10) (ini:10).  Split x0 > 0.5 (:919-925);
+    ini mesh.refine = 9 -> 512^2 cells, 2 * 512 * 256 * 9 = 2 359 296 DOFs.  ConformingDirichletConstraints on a DG space
+    constrains nothing: the Dirichlet data enter through alpha_boundary."""
+    dim = len(n)
+    api.mesh_structured(n)
+    if sd_bits is None:
+        api.subdomains_halfspace(0, 0.5, 0, 1)
+    else:
+        api.subdomains(sd_bits)
+    fe = capi.FE_DGQ1 if k == 1 else capi.FE_DGQ2
+    c0, c1 = api.add_space(fe, 0), api.add_space(fe, 1)
+    pp = capi.ConvDiffDGParams()
+    pp.f = f if f is not None else capi.Function(capi.FN_DN_SOURCE)
+    pp.bc = bc if bc is not None else capi.BCType(capi.BC_TESTPOISSON)
+    pp.g = g if g is not None else capi.gauss()
+    pp.j = capi.Function(capi.FN_TESTPOISSON_J)
+    pp.method, pp.weights, pp.intorderadd, pp.alpha = method, weights, 0, alpha
+    left = api.add_subproblem(capi.OP_CONVDIFF_DG, pp, capi.COND_EQUALITY, 1 << 0, [c0])
+    right = api.add_subproblem(capi.OP_CONVDIFF_DG, pp, capi.COND_EQUALITY, 1 << 1, [c1])
+    cps = []
+    if coupled:
+        cv = capi.CVCFParams()
+        cv.quad_order, cv.intensity = 4, scaling
+        cps = [api.add_coupling(capi.OP_CVCF_COUPLING, cv, left, right)]
+    ndof = api.finalize()
+    ncon = api.constraints_assemble([left, right], [pp.bc, pp.bc])
+    go = api.gridoperator_create([left, right], cps)
+    mat = api.matrix_create([go])
+    return SimpleNamespace(dim=dim, ndof=ndof, ncon=ncon, go=go, mat=mat, left=left, right=right, g=pp.g, sps=[left, right],
+                           gfn=[pp.g, pp.g], bc=pp.bc, children=(c0, c1), k=k)
+
+
 def dirichlet_neumann(api, n, alpha=2.0, left_mode=capi.ND_MODE_DIRICHLET, right_mode=capi.ND_MODE_NEUMANN, fe=(capi.FE_Q1, capi.FE_Q1), quad_order=6,
                       scaling=10.0):
     """BASELINE configs[0]: test/testpoisson-dirichlet-neumann.cc `solve()` (:371-862) instantiated with conforming Qk spaces and
