@@ -325,6 +325,10 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
   RowsJobs J; J.n = 0;
   int nblocks = 0;
   for (int i = 0; i < (int)c->children.size(); ++i) {
+    if (c->children[i].dg) {              // QkDG: volume + skeleton + boundary blocks, one thread per row (dg.cu)
+      if (part == 1) jacobian_dg(c, go, M, i, weight, overwrite);
+      continue;
+    }
     if (c->children[i].k != 1) {          // Qk, k > 1: every row through the generic owner-computes kernel (generic.cu)
       if (part == 1) jacobian_volume_generic(c, go, M, i, overwrite);
       continue;
@@ -719,7 +723,7 @@ static bool residual_stencil_applies(const Ctx* c, int child, const VolSpec& V)
   static const bool off = getenv("MDB_RESIDUAL_TILE") != nullptr || getenv("MDB_RESIDUAL_LEGACY") != nullptr;     // A/B switches for profiling only
   const MeshDesc& m = c->mesh;
   const Child& hc = c->children[child];
-  if (off || V.n != 1 || hc.k != 1 || hc.size == 0) return false;
+  if (off || V.n != 1 || hc.k != 1 || hc.dg || hc.size == 0) return false;
   int64_t vol = 1;
   for (int d = 0; d < m.dim; ++d) vol *= hc.lat_hi[d] - hc.lat_lo[d] + 1;
   return vol == hc.size;                                                          // not a box: the stencil offsets are not constant
@@ -814,6 +818,7 @@ void residual_volume(Ctx* c, const GridOp& go, double weight, const double* d_x,
   const MeshDesc& m = c->mesh;
   launch_element_matrices(c, go.sps, weight);
   for (int i = 0; i < (int)c->children.size(); ++i) {
+    if (c->children[i].dg) { residual_dg(c, go, i, weight, d_x, d_r); continue; }
     if (c->children[i].k != 1) { residual_volume_generic(c, go, i, d_x, d_r); continue; }
     VolSpec V = vol_spec(c, go, i);
     if (V.n == 0) continue;

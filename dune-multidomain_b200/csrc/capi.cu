@@ -218,7 +218,7 @@ void mdb_destroy(mdb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   reset_spaces(c);
-  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_scal); dfree(c->d_partial);
+  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_ftab_g); dfree(c->d_dgtab); dfree(c->d_scal); dfree(c->d_partial);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->d_halo_counter) cudaFree(c->d_halo_counter);
@@ -314,10 +314,12 @@ int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
   if (!c) return MDB_EINVAL;
   try {
     MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_space: need a mesh, before mdb_finalize");
-    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2, MDB_EINVAL, "mdb_add_space: unknown finite element");
+    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2 || fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2, MDB_EINVAL, "mdb_add_space: unknown finite element");
     MDB_REQUIRE(subdomain >= -1 && subdomain < 8, MDB_EINVAL, "mdb_add_space: bad subdomain");
     MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_space: too many child spaces");
-    Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1) ? 1 : 2; ch.subdomain = subdomain;
+    Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_DGQ1) ? 1 : 2; ch.subdomain = subdomain;
+    ch.dg = fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2;
+    MDB_REQUIRE(!(ch.dg && c->mesh.partitioned), MDB_EINVAL, "mdb_add_space: QkDG spaces are not supported on a partitioned mesh");
     c->children.push_back(ch);
     return (int)c->children.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
@@ -359,7 +361,15 @@ int mdb_add_subproblem(mdb_ctx* c, int op_id, const void* params, size_t nbytes,
     } else if (op_id == MDB_OP_L2) {
       MDB_REQUIRE(nbytes == sizeof(mdb_l2_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_l2_params size");
       std::memcpy(&sp.l2, params, nbytes);
+    } else if (op_id == MDB_OP_CONVDIFF_DG) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_convdiffdg_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_convdiffdg_params size");
+      std::memcpy(&sp.cddg, params, nbytes);
+      MDB_REQUIRE(c->children[children[0]].dg, MDB_EINVAL, "mdb_add_subproblem: ConvectionDiffusionDG has device kernels on QkDG spaces only");
+      MDB_REQUIRE(sp.cddg.method == MDB_DG_METHOD_SIPG || sp.cddg.method == MDB_DG_METHOD_NIPG, MDB_EINVAL, "mdb_add_subproblem: bad DG method");
+      sp.dg_k = c->children[children[0]].k;
     } else throw Error(MDB_EINVAL, "mdb_add_subproblem: unknown local operator (closed operator set, see mdb200.h)");
+    MDB_REQUIRE(c->children[children[0]].dg == (op_id == MDB_OP_CONVDIFF_DG), MDB_EINVAL,
+                "mdb_add_subproblem: QkDG spaces carry ConvectionDiffusionDG, conforming spaces Poisson / L2 (closed operator set)");
     (void)gauss1d(sp.quad_order());
     c->sps.push_back(sp);
     return (int)c->sps.size() - 1;

@@ -147,6 +147,11 @@ Rule1D gauss1d(int order);
 
 struct Child {
   int fe_kind = 0, k = 1, subdomain = -1;
+  // QkDG (MDB_FE_DGQk): every coefficient belongs to its cell.  The child keeps the lattice bookkeeping of the conforming spaces
+  // with lattice stride k + 1 instead of k (cell c, local index a <-> lattice point (k+1) c + a: no point is shared), numbered
+  // cell block after cell block: DOF = (index of the cell in the subdomain) * (k+1)^dim + local index
+  bool dg = false;
+  int stride() const { return dg ? k + 1 : k; }
   // CouplingGridFunctionSpace (couplinggridfunctionspace.hh:45-249): lives on the intersections whose inside cell satisfies
   // the left condition and whose outside cell satisfies the right one (SubProblemSubProblemInterface :14-44)
   bool iface = false; int lkind = 0, rkind = 0; uint32_t lmask = 0, rmask = 0;
@@ -163,13 +168,16 @@ struct SubProblemDesc {
   int op_id = 0;
   mdb_poisson_params poisson{};
   mdb_l2_params l2{};
+  mdb_convdiffdg_params cddg{};
+  int dg_k = 1;                // MDB_OP_CONVDIFF_DG: degree of the child space (quadrature order = intorderadd + 2 k)
   int cond_kind = 0; uint32_t mask = 0;
   std::vector<int> children;
   bool doPatternVolume() const { return true; }
+  bool doPatternSkeleton() const { return op_id == MDB_OP_CONVDIFF_DG; }
   bool doAlphaVolume() const { return true; }
   bool doLambdaVolume() const { return op_id == MDB_OP_POISSON; }
   bool doLambdaBoundary() const { return op_id == MDB_OP_POISSON; }
-  int quad_order() const { return op_id == MDB_OP_POISSON ? poisson.quad_order : l2.quad_order; }
+  int quad_order() const { return op_id == MDB_OP_POISSON ? poisson.quad_order : op_id == MDB_OP_CONVDIFF_DG ? cddg.intorderadd + 2 * dg_k : l2.quad_order; }
 };
 
 struct CouplingDesc {
@@ -268,6 +276,7 @@ struct Ctx {
   double* d_Ae = nullptr;            // element matrix table
   double* d_ftab = nullptr;          // face shape-function tables of the coupling kernels
   double* d_ftab_g = nullptr;        // the same for Qk x Qk couplings (generic.cu)
+  double* d_dgtab = nullptr;         // skeleton / boundary block tables of the QkDG kernels (dg.cu)
   // staging for host<->device vectors
   double* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};
   // solver workspace
@@ -350,6 +359,9 @@ void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matri
 void residual_nd(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r);
 void jacobian_nd(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight);
 void mark_iface_present(Ctx* c, const Child& ch, uint8_t* d_present);
+// dg.cu: QkDG children with ConvectionDiffusionDG (volume + skeleton + boundary terms, owner-computes)
+void jacobian_dg(Ctx* c, const GridOp& go, Matrix& m, int child, double weight, bool overwrite);
+void residual_dg(Ctx* c, const GridOp& go, int child, double weight, const double* d_x, double* d_r);
 void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& m, int child, bool overwrite);      // generic.cu: Qk children, k > 1
 void residual_volume_generic(Ctx* c, const GridOp& go, int child, const double* d_x, double* d_r);
 void dirichlet_rows(Ctx* c, Matrix& m);

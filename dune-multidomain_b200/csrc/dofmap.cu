@@ -10,6 +10,7 @@ namespace mdb {
 
 struct ChildDev {
   int k, subdomain, nloc;
+  int st, dg;              // lattice stride (k, or k + 1 for a QkDG child)
   int lat_n[3];
   int64_t offset;
   const int32_t* lat2dof;
@@ -19,7 +20,7 @@ struct ChildDev {
 static ChildDev child_dev(const Ctx* c, int i)
 {
   const Child& ch = c->children[i];
-  ChildDev d; d.k = ch.k; d.subdomain = ch.subdomain; d.nloc = ch.nloc(c->mesh.dim);
+  ChildDev d; d.k = ch.k; d.subdomain = ch.subdomain; d.nloc = ch.nloc(c->mesh.dim); d.st = ch.stride(); d.dg = ch.dg ? 1 : 0;
   for (int a = 0; a < 3; ++a) d.lat_n[a] = ch.lat_n[a];
   d.offset = ch.offset; d.lat2dof = ch.d_lat2dof; d.dof2lat = ch.d_dof2lat;
   return d;
@@ -36,7 +37,7 @@ __device__ __forceinline__ int64_t cell_index(const MeshDesc& m, const int ijk[3
 __device__ __forceinline__ bool child_on_cell(int subdomain, uint8_t sd) { return subdomain < 0 || ((sd >> subdomain) & 1); }
 
 // ---- K1a: mark the lattice points in the closure of the child's grid view --------------------------
-__global__ void k_mark_present(MeshDesc m, const uint8_t* __restrict__ sd, int k, int subdomain, int lat_n0, int lat_n1, uint8_t* present)
+__global__ void k_mark_present(MeshDesc m, const uint8_t* __restrict__ sd, int k, int st, int subdomain, int lat_n0, int lat_n1, uint8_t* present)
 {
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= m.ncells()) return;
@@ -46,7 +47,7 @@ __global__ void k_mark_present(MeshDesc m, const uint8_t* __restrict__ sd, int k
   for (int az = 0; az <= kz; ++az)
     for (int ay = 0; ay <= ky; ++ay)
       for (int ax = 0; ax <= k; ++ax) {
-        int64_t p = (k * ijk[0] + ax) + (int64_t)lat_n0 * ((k * ijk[1] + ay) + (int64_t)lat_n1 * (k * ijk[2] + az));
+        int64_t p = (st * ijk[0] + ax) + (int64_t)lat_n0 * ((st * ijk[1] + ay) + (int64_t)lat_n1 * (st * ijk[2] + az));
         present[p] = 1;
       }
 }
@@ -129,6 +130,31 @@ void mark_iface_present(Ctx* c, const Child& ch, uint8_t* d_present)
              ch.lat_n[1], d_present);
 }
 
+// QkDG numbering ([UPSTREAM] (ii),(iii): all coefficients on the cell): flags of the cells in the child's subdomain, scanned in host
+// order, give the subdomain cell index b; DOF = b * nloc + local index
+__global__ void k_dg_cell_flags(MeshDesc m, const uint8_t* __restrict__ sd, int subdomain, int32_t* flags)
+{
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c < m.ncells()) flags[c] = child_on_cell(subdomain, sd[c]) ? 1 : 0;
+}
+__global__ void k_dg_assign(MeshDesc m, const int32_t* __restrict__ flags, const int32_t* __restrict__ scan, int k, int lat_n0, int lat_n1,
+                            int32_t* lat2dof, int32_t* dof2lat)
+{
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= m.ncells() || !flags[c]) return;
+  int ijk[3]; cell_ijk(m, c, ijk);
+  const int st = k + 1;
+  int nl = 1; for (int d = 0; d < m.dim; ++d) nl *= st;
+  int kz = (m.dim > 2) ? k : 0, ky = (m.dim > 1) ? k : 0, i = 0;
+  for (int az = 0; az <= kz; ++az)
+    for (int ay = 0; ay <= ky; ++ay)
+      for (int ax = 0; ax <= k; ++ax, ++i) {
+        int64_t p = (st * ijk[0] + ax) + (int64_t)lat_n0 * ((st * ijk[1] + ay) + (int64_t)lat_n1 * (st * ijk[2] + az));
+        const int32_t g = scan[c] * nl + i;
+        lat2dof[p] = g; dof2lat[g] = (int32_t)p;
+      }
+}
+
 void build_dofmap(Ctx* c)
 {
   const MeshDesc& m = c->mesh;
@@ -136,7 +162,7 @@ void build_dofmap(Ctx* c)
   for (auto& ch : c->children) {
     dfree(ch.d_lat2dof); dfree(ch.d_dof2lat);
     ch.nlat = 1;
-    for (int d = 0; d < 3; ++d) { ch.lat_n[d] = (d < m.dim) ? ch.k * m.n[d] + 1 : 1; ch.nlat *= ch.lat_n[d]; }
+    for (int d = 0; d < 3; ++d) { ch.lat_n[d] = (d < m.dim) ? (ch.dg ? (ch.k + 1) * m.n[d] : ch.k * m.n[d] + 1) : 1; ch.nlat *= ch.lat_n[d]; }
     MDB_REQUIRE(ch.nlat < (int64_t)2147000000, MDB_EINVAL, "child space too large for int32 device indices");
     uint8_t* d_present = dalloc<uint8_t>(ch.nlat);
     int32_t* d_flags = dalloc<int32_t>(ch.nlat);
@@ -145,7 +171,7 @@ void build_dofmap(Ctx* c)
     int32_t* d_dof2lat_tmp = dalloc<int32_t>(ch.nlat);
     MDB_CUDA(cudaMemsetAsync(d_present, 0, ch.nlat, c->stream));
     if (ch.iface) mark_iface_present(c, ch, d_present);
-    else MDB_LAUNCH(c, k_mark_present, cdiv(m.ncells(), 256), 256, 0, m, c->d_cell_sd, ch.k, ch.subdomain, ch.lat_n[0], ch.lat_n[1], d_present);
+    else MDB_LAUNCH(c, k_mark_present, cdiv(m.ncells(), 256), 256, 0, m, c->d_cell_sd, ch.k, ch.stride(), ch.subdomain, ch.lat_n[0], ch.lat_n[1], d_present);
     MDB_LAUNCH(c, k_fill_i32, cdiv(ch.nlat, 256), 256, 0, ch.d_lat2dof, ch.nlat, -1);
     {
       int h_bb[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
@@ -161,12 +187,25 @@ void build_dofmap(Ctx* c)
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flags, d_scan, (int)ch.nlat, c->stream);
     void* d_tmp = nullptr; MDB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
     int32_t base = 0;
+    if (ch.dg) {
+      const int64_t nc = m.ncells();
+      MDB_REQUIRE(nc <= ch.nlat, MDB_EINVAL, "internal: DG scratch");
+      MDB_LAUNCH(c, k_dg_cell_flags, cdiv(nc, 256), 256, 0, m, c->d_cell_sd, ch.subdomain, d_flags);
+      MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flags, d_scan, (int)nc, c->stream)); c->launches++;
+      MDB_LAUNCH(c, k_dg_assign, cdiv(nc, 256), 256, 0, m, d_flags, d_scan, ch.k, ch.lat_n[0], ch.lat_n[1], ch.d_lat2dof, d_dof2lat_tmp);
+      int32_t last_scan = 0, last_flag = 0;
+      MDB_CUDA(cudaMemcpyAsync(&last_scan, d_scan + nc - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+      MDB_CUDA(cudaMemcpyAsync(&last_flag, d_flags + nc - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      base = (last_scan + last_flag) * ch.nloc(m.dim);
+    }
     // [UPSTREAM] ordering: entity dimension ascending (vertex < line < quad < hex); inside one dimension grouped by the
     // set of extension axes (ascending bit pattern); lexicographic inside a group.  For Q1 only class 0 exists.
     for (int mdim = 0; mdim <= m.dim; ++mdim)
       for (int ext = 0; ext < (1 << m.dim); ++ext) {
         if (__builtin_popcount(ext) != mdim) continue;
         if (ch.k == 1 && ext != 0) continue;
+        if (ch.dg) continue;
         MDB_LAUNCH(c, k_class_flags, cdiv(ch.nlat, 256), 256, 0, m.dim, ch.k, ch.lat_n[0], ch.lat_n[1], ch.nlat, ext, d_present, d_flags);
         MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flags, d_scan, (int)ch.nlat, c->stream)); c->launches++;
         MDB_LAUNCH(c, k_assign, cdiv(ch.nlat, 256), 256, 0, ch.nlat, d_flags, d_scan, base, ch.d_lat2dof, d_dof2lat_tmp);
@@ -214,12 +253,12 @@ __global__ void k_cell_dofs(MeshDesc m, const uint8_t* __restrict__ sd, ChildSet
   for (int i = 0; i < cs.n; ++i) {
     const ChildDev& ch = cs.ch[i];
     if (!child_on_cell(ch.subdomain, sd[c])) continue;
-    int k = ch.k;
+    int k = ch.k; const int st = ch.st;
     int kz = (m.dim > 2) ? k : 0, ky = (m.dim > 1) ? k : 0;
     for (int az = 0; az <= kz; ++az)
       for (int ay = 0; ay <= ky; ++ay)
         for (int ax = 0; ax <= k; ++ax) {
-          int64_t p = (k * ijk[0] + ax) + (int64_t)ch.lat_n[0] * ((k * ijk[1] + ay) + (int64_t)ch.lat_n[1] * (k * ijk[2] + az));
+          int64_t p = (st * ijk[0] + ax) + (int64_t)ch.lat_n[0] * ((st * ijk[1] + ay) + (int64_t)ch.lat_n[1] * (st * ijk[2] + az));
           dofs[o++] = ch.offset + ch.lat2dof[p];
         }
   }
@@ -291,6 +330,7 @@ __global__ void k_constraints(MeshDesc m, const uint8_t* __restrict__ sd, ChildS
     if (eval_bctype(spec.bc[q], m.dim, xg, !global_nb) != 0) continue;
     const ChildDev& ch = cs.ch[spec.child[q]];
     if (!child_on_cell(ch.subdomain, sde)) continue;
+    if (ch.dg) continue;           // [UPSTREAM] ConformingDirichletConstraints skips coefficients attached to the cell (codim 0)
     int k = ch.k;
     int kz = (m.dim > 2) ? k : 0, ky = (m.dim > 1) ? k : 0;
     for (int az = 0; az <= kz; ++az)
@@ -363,14 +403,14 @@ __global__ void k_interpolate(MeshDesc m, const uint8_t* __restrict__ sd, ChildD
   if (g >= child_size) return;
   int64_t r = ch.dof2lat[g];
   int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
-  const int k = ch.k;
-  // candidate cells along each axis: c = floor(p/k) and, if p is on a cell boundary, c-1
+  const int k = ch.k, st = ch.st;
+  // candidate cells along each axis: c = floor(p/k) and, if p is on a cell boundary, c-1 (QkDG: the one cell that owns the point)
   int lo_c[3], hi_c[3];
   for (int d = 0; d < 3; ++d) {
     if (d >= m.dim) { lo_c[d] = hi_c[d] = 0; continue; }
-    int c1 = p[d] / k;
+    int c1 = p[d] / st;
     hi_c[d] = (c1 < m.n[d]) ? c1 : m.n[d] - 1;
-    lo_c[d] = (p[d] % k == 0 && c1 > 0) ? c1 - 1 : c1;
+    lo_c[d] = (!ch.dg && p[d] % k == 0 && c1 > 0) ? c1 - 1 : c1;
     if (lo_c[d] > hi_c[d]) lo_c[d] = hi_c[d];
   }
   for (int cz = hi_c[2]; cz >= lo_c[2]; --cz)
@@ -385,7 +425,7 @@ __global__ void k_interpolate(MeshDesc m, const uint8_t* __restrict__ sd, ChildD
           double xg[3];
           for (int d = 0; d < m.dim; ++d) {
             double lo = m.coord(d, ijk[d]), up = m.coord(d, ijk[d] + 1);
-            double local = (double)(p[d] - k * ijk[d]) / k;
+            double local = (double)(p[d] - st * ijk[d]) / k;
             xg[d] = lo + local * (up - lo);
           }
           x[ch.offset + g] = eval_function(spec.fn[q], m.dim, xg, t);
@@ -434,7 +474,7 @@ __global__ void k_face_compact(int nf, int64_t total, const int32_t* __restrict_
 }
 
 // ---- which coefficients does jacobian(x, a) read? ------------------------------------------------------------------------
-struct NeedSide { int k; int lat_n[3]; int64_t offset; const int32_t* lat2dof; };
+struct NeedSide { int k; int lat_n[3]; int64_t offset; const int32_t* lat2dof; int st; };
 __global__ void k_mark_face_dofs(MeshDesc m, NeedSide L, NeedSide R, const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces,
                                  uint8_t* flags)
 {
@@ -451,7 +491,7 @@ __global__ void k_mark_face_dofs(MeshDesc m, NeedSide L, NeedSide R, const int32
     for (int az = 0; az <= kz; ++az)
       for (int ay = 0; ay <= k; ++ay)
         for (int ax = 0; ax <= k; ++ax) {
-          const int64_t p = (k * c[0] + ax) + (int64_t)S.lat_n[0] * ((k * c[1] + ay) + (int64_t)S.lat_n[1] * (k * c[2] + az));
+          const int64_t p = (S.st * c[0] + ax) + (int64_t)S.lat_n[0] * ((S.st * c[1] + ay) + (int64_t)S.lat_n[1] * (S.st * c[2] + az));
           flags[S.offset + S.lat2dof[p]] = 1;
         }
   }
@@ -487,13 +527,13 @@ void build_xneed(Ctx* c, GridOp& go)
     for (int q = 0; q < 2; ++q) {
       const Child& ch = c->children[c->sps[sp[q]].children[0]];
       for (int d = 0; d < 3; ++d) S[q].lat_n[d] = ch.lat_n[d];
-      S[q].k = ch.k; S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof;
+      S[q].k = ch.k; S[q].offset = ch.offset; S[q].lat2dof = ch.d_lat2dof; S[q].st = ch.stride();
     }
     MDB_LAUNCH(c, k_mark_face_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, S[0], S[1], fl.d_cell, fl.d_face, fl.n, d_flags);
     for (int kc = 0; cp.enriched() && kc < cp.ncomp; ++kc) {
       const Child& ch = c->children[cp.coupling_child + kc];
       NeedSide C; for (int d = 0; d < 3; ++d) C.lat_n[d] = ch.lat_n[d];
-      C.k = ch.k; C.offset = ch.offset; C.lat2dof = ch.d_lat2dof;
+      C.k = ch.k; C.offset = ch.offset; C.lat2dof = ch.d_lat2dof; C.st = ch.stride();
       MDB_LAUNCH(c, k_mark_face_mortar_dofs, cdiv(fl.n, 256), 256, 0, c->mesh, C, fl.d_cell, fl.d_face, fl.n, d_flags);
     }
   }

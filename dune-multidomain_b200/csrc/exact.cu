@@ -98,7 +98,8 @@ void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight)
   if (S.n == 0) return;
   for (int i = 0; i < S.n; ++i) {
     const SubProblemDesc& sp = c->sps[sps[i]];
-    S.op[i] = sp.op_id; S.k[i] = c->children[sp.children[0]].k; S.rule[i] = gauss1d(sp.quad_order());
+    // ConvectionDiffusionDG with A = I, b = 0, c = 0: its volume matrix is the stiffness matrix under the rule of order intorderadd + 2 k
+    S.op[i] = sp.op_id == MDB_OP_CONVDIFF_DG ? MDB_OP_POISSON : sp.op_id; S.k[i] = c->children[sp.children[0]].k; S.rule[i] = gauss1d(sp.quad_order());
   }
   double ext[3] = {1, 1, 1};
   for (int d = 0; d < m.dim; ++d) ext[d] = m.coord(d, 1) - m.coord(d, 0);
@@ -460,7 +461,7 @@ static SideMap side_map(const Ctx* c, int sp)
 {
   const Child& ch = c->children[c->sps[sp].children[0]];
   SideMap s; for (int d = 0; d < 3; ++d) s.lat_n[d] = ch.lat_n[d];
-  s.offset = ch.offset; s.lat2dof = ch.d_lat2dof;
+  s.offset = ch.offset; s.lat2dof = ch.d_lat2dof; s.dg = ch.dg ? 1 : 0;
   return s;
 }
 static const double* face_tables(Ctx* c, const CouplingParams& P)
@@ -493,7 +494,7 @@ void residual_coupling(Ctx* c, const GridOp& go, double weight, const double* d_
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const int k1 = c->children[c->sps[cp.local_sp].children[0]].k, k2 = c->children[c->sps[cp.remote_sp].children[0]].k;
-    if (k1 != 1 || k2 != 1) { residual_coupling_generic(c, P, Ls, Rs, k1, k2, fl, weight, d_x, d_r); continue; }
+    if (k1 != 1 || k2 != 1 || Ls.dg || Rs.dg) { residual_coupling_generic(c, P, Ls, Rs, k1, k2, fl, weight, d_x, d_r); continue; }
     const double* tab = face_tables(c, P);
     if (m.dim == 2) MDB_LAUNCH(c, k_coupling_residual<2>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, tab, d_x, d_r);
     else MDB_LAUNCH(c, k_coupling_residual<3>, cdiv(fl.n, 128), 128, 0, m, P, Ls, Rs, fl.d_cell, fl.d_face, fl.n, weight, tab, d_x, d_r);
@@ -518,7 +519,7 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);
     const double eps = 1e-8;                    // NumericalJacobianCoupling() default, couplingutilities.hh:63-65
     const int k1 = c->children[c->sps[cp.local_sp].children[0]].k, k2 = c->children[c->sps[cp.remote_sp].children[0]].k;
-    if (k1 != 1 || k2 != 1) {
+    if (k1 != 1 || k2 != 1 || Ls.dg || Rs.dg) {
       jacobian_coupling_generic(c, P, Ls, Rs, k1, k2, fl, M, std::pair<int, int>((int)(&go - &c->gos[0]), (int)k), weight, eps, d_x);
       continue;
     }

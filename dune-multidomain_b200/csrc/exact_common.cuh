@@ -111,7 +111,7 @@ struct CouplingParams {
   Rule1D rule;
 };
 
-struct SideMap { int lat_n[3]; int64_t offset; const int32_t* lat2dof; };
+struct SideMap { int lat_n[3]; int64_t offset; const int32_t* lat2dof; int dg; };     // dg: lattice stride K + 1 (QkDG child)
 
 template <int DIM> __device__ __forceinline__ void cell_dofs_q1(const SideMap& S, const int ijk[3], int32_t* dofs)
 {
@@ -131,7 +131,8 @@ template <int DIM, int K> __device__ __forceinline__ void cell_dofs_qk(const Sid
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     const int ax = i % (K + 1), ay = (i / (K + 1)) % (K + 1), az = (DIM > 2) ? i / ((K + 1) * (K + 1)) : 0;
-    int64_t p = (K * ijk[0] + ax) + (int64_t)S.lat_n[0] * ((K * ijk[1] + ay) + (int64_t)S.lat_n[1] * (K * ijk[2] + az));
+    const int st = K + S.dg;
+    int64_t p = (st * ijk[0] + ax) + (int64_t)S.lat_n[0] * ((st * ijk[1] + ay) + (int64_t)S.lat_n[1] * (st * ijk[2] + az));
     dofs[i] = (int32_t)(S.offset + S.lat2dof[p]);
   }
 }

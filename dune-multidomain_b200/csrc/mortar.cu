@@ -194,7 +194,7 @@ static SideMap side_map_child(const Ctx* c, int child)
 {
   const Child& ch = c->children[child];
   SideMap s; for (int d = 0; d < 3; ++d) s.lat_n[d] = ch.lat_n[d];
-  s.offset = ch.offset; s.lat2dof = ch.d_lat2dof;
+  s.offset = ch.offset; s.lat2dof = ch.d_lat2dof; s.dg = ch.dg ? 1 : 0;
   return s;
 }
 

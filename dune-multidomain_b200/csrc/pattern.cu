@@ -14,11 +14,12 @@ namespace mdb {
 
 #define MDB_MAXROW 256
 
-struct PChild { int k, subdomain, nloc; int lat_n[3]; int64_t offset, size; const int32_t* lat2dof; const int32_t* dof2lat;
+struct PChild { int k, subdomain, nloc; int st, dg; int lat_n[3]; int64_t offset, size; const int32_t* lat2dof; const int32_t* dof2lat;
                 int iface, lkind, rkind; uint32_t lmask, rmask; };
 struct PatSpec {
   int nchild; PChild ch[MDB_MAX_CHILDREN];
   int nsp; int sp_child[16]; int sp_kind[16]; uint32_t sp_mask[16];
+  int sp_skel[16];       // doPatternSkeleton: FullSkeletonPattern links to the face neighbours on which the subproblem also applies
   int ncp; int cp_lchild[8], cp_lkind[8], cp_rchild[8], cp_rkind[8]; uint32_t cp_lmask[8], cp_rmask[8];
   int cp_cchild[8];      // >= 0: EnrichedCoupling with this coupling space (sc/cs/nc/cn/cc links instead of sn/ns)
   int cp_ncomp[8];       // component blocks of a power coupling space (children cp_cchild .. cp_cchild + ncomp - 1)
@@ -42,12 +43,12 @@ struct RowList {
 
 __device__ void add_cell_dofs(RowList& L, const MeshDesc& m, const PChild& ch, const int ijk[3])
 {
-  const int k = ch.k;
+  const int k = ch.k, st = ch.st;
   int kz = (m.dim > 2) ? k : 0, ky = (m.dim > 1) ? k : 0;
   for (int az = 0; az <= kz; ++az)
     for (int ay = 0; ay <= ky; ++ay)
       for (int ax = 0; ax <= k; ++ax) {
-        int64_t p = (k * ijk[0] + ax) + (int64_t)ch.lat_n[0] * ((k * ijk[1] + ay) + (int64_t)ch.lat_n[1] * (k * ijk[2] + az));
+        int64_t p = (st * ijk[0] + ax) + (int64_t)ch.lat_n[0] * ((st * ijk[1] + ay) + (int64_t)ch.lat_n[1] * (st * ijk[2] + az));
         L.insert((int32_t)(ch.offset + ch.lat2dof[p]));
       }
 }
@@ -111,13 +112,13 @@ __device__ void enumerate_row(RowList& L, const MeshDesc& m, const uint8_t* __re
   L.n = 0; L.overflow = false;
   int64_t r = ch.dof2lat[gi];
   int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
-  const int k = ch.k;
+  const int k = ch.k, st = ch.st;
   int lo_c[3], hi_c[3];
   for (int d = 0; d < 3; ++d) {
     if (d >= m.dim) { lo_c[d] = hi_c[d] = 0; continue; }
-    int c1 = p[d] / k;
+    int c1 = p[d] / st;
     hi_c[d] = (c1 < m.n[d]) ? c1 : m.n[d] - 1;
-    lo_c[d] = (p[d] % k == 0 && c1 > 0) ? c1 - 1 : c1;
+    lo_c[d] = (!ch.dg && p[d] % k == 0 && c1 > 0) ? c1 - 1 : c1;      // a QkDG point belongs to exactly one cell
     if (lo_c[d] > hi_c[d]) lo_c[d] = hi_c[d];
   }
   for (int cz = lo_c[2]; cz <= hi_c[2]; ++cz)
@@ -128,6 +129,18 @@ __device__ void enumerate_row(RowList& L, const MeshDesc& m, const uint8_t* __re
         if (!on_cell(ch.subdomain, s)) continue;
         for (int q = 0; q < S.nsp; ++q)
           if (S.sp_child[q] == child && cond_applies(S.sp_kind[q], S.sp_mask[q], s)) { add_cell_dofs(L, m, ch, ijk); break; }
+        // invoke_pattern_skeleton_or_boundary (patternassemblerfunctors.hh:36-66) with [UPSTREAM] FullSkeletonPattern: the face is
+        // visited from its higher-index cell, pattern_sn / pattern_ns link both cells' rows with both cells' columns
+        for (int q = 0; q < S.nsp; ++q) {
+          if (S.sp_child[q] != child || !S.sp_skel[q] || !cond_applies(S.sp_kind[q], S.sp_mask[q], s)) continue;
+          for (int f = 0; f < 2 * m.dim; ++f) {
+            int nijk[3] = {cx, cy, cz};
+            nijk[f / 2] += (f % 2) ? 1 : -1;
+            if (nijk[f / 2] < 0 || nijk[f / 2] >= m.n[f / 2]) continue;
+            const uint8_t sn = sd[nijk[0] + (int64_t)m.n[0] * (nijk[1] + (int64_t)m.n[1] * nijk[2])];
+            if (cond_applies(S.sp_kind[q], S.sp_mask[q], sn) && on_cell(ch.subdomain, sn)) add_cell_dofs(L, m, ch, nijk);
+          }
+        }
         for (int q = 0; q < S.ncp; ++q) {
           bool as_local = S.cp_lchild[q] == child && cond_applies(S.cp_lkind[q], S.cp_lmask[q], s);
           bool as_remote = S.cp_rchild[q] == child && cond_applies(S.cp_rkind[q], S.cp_rmask[q], s);
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(128) k_pattern_fill(MeshDesc m, const uint8_t*
     colidx[base + i] = col;
     if (col == g) dg = i;
     if (col < ch.offset) ++nlow;
-    else if (col < ch.offset + ch.size && ch.k == 1) {
+    else if (col < ch.offset + ch.size && ch.k == 1 && !ch.dg) {
       int64_t rr = ch.dof2lat[col - ch.offset];
       int q0 = (int)(rr % ch.lat_n[0]); rr /= ch.lat_n[0]; int q1 = (int)(rr % ch.lat_n[1]); int q2 = (int)(rr / ch.lat_n[1]);
       int bit = (q2 - p[2] + 1) * 9 + (q1 - p[1] + 1) * 3 + (q0 - p[0] + 1);
@@ -231,7 +244,7 @@ void build_pattern(Ctx* c, Matrix& M)
   for (int i = 0; i < S.nchild; ++i) {
     const Child& ch = c->children[i];
     PChild& p = S.ch[i];
-    p.k = ch.k; p.subdomain = ch.subdomain; p.nloc = ch.nloc(m.dim);
+    p.k = ch.k; p.subdomain = ch.subdomain; p.nloc = ch.nloc(m.dim); p.st = ch.stride(); p.dg = ch.dg ? 1 : 0;
     for (int d = 0; d < 3; ++d) p.lat_n[d] = ch.lat_n[d];
     p.offset = ch.offset; p.size = ch.size; p.lat2dof = ch.d_lat2dof; p.dof2lat = ch.d_dof2lat;
     p.iface = ch.iface ? 1 : 0; p.lkind = ch.lkind; p.lmask = ch.lmask; p.rkind = ch.rkind; p.rmask = ch.rmask;
@@ -242,7 +255,7 @@ void build_pattern(Ctx* c, Matrix& M)
       const SubProblemDesc& sp = c->sps[s];
       if (!sp.doPatternVolume()) continue;
       MDB_REQUIRE(S.nsp < 16, MDB_EINVAL, "too many subproblems in one matrix");
-      S.sp_child[S.nsp] = sp.children[0]; S.sp_kind[S.nsp] = sp.cond_kind; S.sp_mask[S.nsp] = sp.mask; ++S.nsp;
+      S.sp_child[S.nsp] = sp.children[0]; S.sp_kind[S.nsp] = sp.cond_kind; S.sp_mask[S.nsp] = sp.mask; S.sp_skel[S.nsp] = sp.doPatternSkeleton() ? 1 : 0; ++S.nsp;
     }
     for (int k : go.cps) {
       const CouplingDesc& cp = c->cps[k];

@@ -223,7 +223,7 @@ static void ensure_precond_state(Ctx* c, Matrix& M)
   KeySpace sp; sp.nchild = (int)c->children.size();
   for (int i = 0; i < sp.nchild; ++i) {
     const Child& ch = c->children[i];
-    lattice = lattice && ch.k == 1 && (int64_t)ch.lat_n[0] + 2 * (int64_t)ch.lat_n[1] + 4 * (int64_t)ch.lat_n[2] < (1 << 24);
+    lattice = lattice && ch.k == 1 && !ch.dg && (int64_t)ch.lat_n[0] + 2 * (int64_t)ch.lat_n[1] + 4 * (int64_t)ch.lat_n[2] < (1 << 24);
     sp.ch[i].offset = ch.offset; sp.ch[i].n0 = ch.lat_n[0]; sp.ch[i].n1 = ch.lat_n[1]; sp.ch[i].dof2lat = ch.d_dof2lat;
   }
   if (!lattice) { MDB_LAUNCH(c, k_iota, cdiv(n, 256), 256, 0, n, M.d_sweep_perm); return; }

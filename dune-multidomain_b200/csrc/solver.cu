@@ -451,7 +451,7 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
   }
   if (variant == 4) {
     bool q1 = true;
-    for (const Child& ch : c->children) q1 = q1 && ch.k == 1;
+    for (const Child& ch : c->children) q1 = q1 && ch.k == 1 && !ch.dg;
     if (q1) {
       SpmvSpace sp; sp.nchild = (int)c->children.size(); sp.nchunks = 0;
       const int dim = c->mesh.dim;
