@@ -174,7 +174,7 @@ def dirichlet_neumann_dg(api, n, k=2, scaling=10.0, alpha=2.0, method=capi.DG_ME
 
 
 def dirichlet_neumann(api, n, alpha=2.0, left_mode=capi.ND_MODE_DIRICHLET, right_mode=capi.ND_MODE_NEUMANN, fe=(capi.FE_Q1, capi.FE_Q1), quad_order=6,
-                      scaling=10.0):
+                      scaling=10.0, dg=False):
     """BASELINE configs[0]: test/testpoisson-dirichlet-neumann.cc `solve()` (:371-862) instantiated with conforming Qk spaces and
     Poisson (what test/testpoisson-assembly.cc:919-934 assembles; the shipped main() passes DG-Q2 + ConvectionDiffusionDG, an
     upstream operator — DESIGN.md §9).  2-D unit square (ini: refine 9), split x0 > 0.5 (:919-925), Poisson with the source F of
@@ -185,17 +185,26 @@ def dirichlet_neumann(api, n, alpha=2.0, left_mode=capi.ND_MODE_DIRICHLET, right
       full op      left_sp, dirichlet_coupling, right_sp, neumann_coupling                                           (:542-564)
     NOTE the reference's naming: `nd_coupling_dirichlet` (used by the LEFT operator) is built from ini key dn.coupling.RIGHT
     (= Neumann as shipped) and `nd_coupling_neumann` (RIGHT operator) from dn.coupling.LEFT (= Dirichlet); `left_mode` /
-    `right_mode` here are the ini keys dn.coupling.left / dn.coupling.right."""
+    `right_mode` here are the ini keys dn.coupling.left / dn.coupling.right.
+    dg = True: the shipped instantiation — fe = QkDG spaces, both subproblems ConvectionDiffusionDG(params, SIPG, weightsOn, 2.0)
+    (:864-881, :968-971)."""
     api.mesh_structured(n)
     api.subdomains_halfspace(0, 0.5, 0, 1)
     c0, c1 = api.add_space(fe[0], 0), api.add_space(fe[1], 1)
-    pp = capi.PoissonParams()
-    pp.f = capi.Function(capi.FN_DN_SOURCE)
-    pp.bc = capi.BCType(capi.BC_TESTPOISSON)
-    pp.j = capi.Function(capi.FN_TESTPOISSON_J)
-    pp.quad_order = quad_order
-    left = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 0, [c0])
-    right = api.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1 << 1, [c1])
+    if dg:
+        pp = capi.ConvDiffDGParams()
+        pp.f, pp.bc, pp.g, pp.j = capi.Function(capi.FN_DN_SOURCE), capi.BCType(capi.BC_TESTPOISSON), capi.gauss(), capi.Function(capi.FN_TESTPOISSON_J)
+        pp.method, pp.weights, pp.intorderadd, pp.alpha = capi.DG_METHOD_SIPG, capi.DG_WEIGHTS_ON, 0, 2.0
+        op = capi.OP_CONVDIFF_DG
+    else:
+        pp = capi.PoissonParams()
+        pp.f = capi.Function(capi.FN_DN_SOURCE)
+        pp.bc = capi.BCType(capi.BC_TESTPOISSON)
+        pp.j = capi.Function(capi.FN_TESTPOISSON_J)
+        pp.quad_order = quad_order
+        op = capi.OP_POISSON
+    left = api.add_subproblem(op, pp, capi.COND_EQUALITY, 1 << 0, [c0])
+    right = api.add_subproblem(op, pp, capi.COND_EQUALITY, 1 << 1, [c1])
     cv = capi.CVCFParams()
     cv.quad_order = 4
     cv.intensity = scaling

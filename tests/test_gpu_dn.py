@@ -21,6 +21,10 @@ CASES = {
     "dn2d_both": dict(n=(10, 8), left_mode=capi.ND_MODE_BOTH, right_mode=capi.ND_MODE_BOTH),
     "dn2d_q2q1": dict(n=(8, 6), fe=(capi.FE_Q2, capi.FE_Q1), right_mode=capi.ND_MODE_BOTH),
     "dn2d_q1q2": dict(n=(6, 8), fe=(capi.FE_Q1, capi.FE_Q2), left_mode=capi.ND_MODE_BOTH, right_mode=capi.ND_MODE_DIRICHLET),
+    # the shipped instantiation of solve(): DG-Q2 spaces with ConvectionDiffusionDG on both sides (:968-971)
+    "dn2d_dgq2_shipped": dict(n=(16, 16), fe=(capi.FE_DGQ2, capi.FE_DGQ2), dg=True),
+    "dn2d_dgq1_both": dict(n=(10, 6), fe=(capi.FE_DGQ1, capi.FE_DGQ1), dg=True, left_mode=capi.ND_MODE_BOTH, right_mode=capi.ND_MODE_BOTH, alpha=3.0),
+    "dn2d_dgq2_dgq1": dict(n=(6, 8), fe=(capi.FE_DGQ2, capi.FE_DGQ1), dg=True, left_mode=capi.ND_MODE_NEUMANN, right_mode=capi.ND_MODE_DIRICHLET),
 }
 
 
@@ -113,10 +117,11 @@ def test_solve_block_rejects_a_coupled_matrix():
     dev.close(); ora.close()
 
 
-def test_dn_iteration_matches_oracle():
+@pytest.mark.parametrize("case", ["dn2d_shipped_modes", "dn2d_dgq2_shipped"])
+def test_dn_iteration_matches_oracle(case):
     """The Dirichlet-Neumann loop (:721-822).  With tight inner solves the iterates agree to 1e-9; with the ini's loose inner
     reductions (1e-4) the outer iteration counts agree (+-1) and both reach the 1e-8 reduction of the full-operator residual."""
-    dev, ora, Pd, Po = _pair("dn2d_shipped_modes")
+    dev, ora, Pd, Po = _pair(case)
     u0 = np.zeros(Po.ndof); ora.interpolate(Po.sps, Po.gfn, u0)
     tight = (1e-13, 1e-13, 0.2)
     hd, ho = [], []

@@ -151,3 +151,22 @@ def test_solve_against_scipy_and_convergence_order():
             errs[k, m] = np.abs((x0 - zs) - ex).max()
     assert errs[2, 4] < 1e-10 and errs[2, 8] < 1e-10                        # exact in Q2
     assert errs[1, 8] < 0.4 * errs[1, 4]                                    # second order in Q1 (nodal error)
+
+
+def test_dirichlet_neumann_iteration_on_the_shipped_dg_spaces():
+    """solve() as main() instantiates it (DG-Q2 + ConvectionDiffusionDG, :968-971) with the Neumann-Dirichlet couplings: the loop
+    of :721-822 reaches the 1e-8 reduction of the full-operator residual, and its limit and the monolithic solution (a different,
+    symmetric coupling operator) are two discretisations of the same problem: they approach each other under refinement."""
+    diffs = []
+    for m in (8, 16):
+        o = orc.Oracle()
+        P = problems.dirichlet_neumann(o, (m, m), fe=(capi.FE_DGQ2, capi.FE_DGQ2), dg=True)
+        u0 = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u0)
+        h = []
+        u, its, _ = problems.dn_iteration(o, P, u0.copy(), history=h)
+        assert its < 40 and h[-1] <= 1e-8 * 40 * h[0]
+        o.jacobian(P.go, P.mat, u0, overwrite=True)
+        r = np.zeros(P.ndof); o.residual(P.go, u0, r)
+        z = sla.spsolve(o.csr(P.mat).tocsc(), r)
+        diffs.append(np.abs((u0 - z) - u).max())
+    assert diffs[1] < 0.7 * diffs[0]
