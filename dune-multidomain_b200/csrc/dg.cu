@@ -15,9 +15,11 @@
 //   K                        volume (the stiffness matrix: launch_element_matrices, exact.cu)
 //   SS_f, SN_f, NS_f, NN_f   jacobian_skeleton of face f of the inside cell
 //   BD_f                     jacobian_boundary, Dirichlet branch
-// evaluated once per call by k_dg_face_matrices (inside the timed region, like the element matrices).  One thread per row then
-// writes its row (Jacobian) or applies it to x (residual: the operator is affine, R(x) = J x + b, with b — source, Dirichlet
-// and Neumann data — integrated per row by quadrature).  Entries agree with the sequential scatter to rounding (1e-12 bar).
+// evaluated once per call by k_dg_face_matrices (inside the timed region, like the element matrices).  The Jacobian kernel gives a
+// warp to every cell: the rows of a cell are consecutive and share their column set, so the cell's values are one contiguous
+// dense image that the lanes write with coalesced stores.  The residual kernel gives a thread to every row and applies it to x
+// (the operator is affine, R(x) = J x + b, with b — source, Dirichlet and Neumann data — integrated per row by quadrature).
+// Entries agree with the sequential scatter to rounding (1e-12 bar).
 #include "exact_common.cuh"
 
 namespace mdb {
@@ -160,28 +162,49 @@ template <int DIM> struct DgRow {
   }
 };
 
+// One warp per cell.  The (k+1)^d rows of a cell are consecutive DOFs with the same column set, so their values are one contiguous
+// nl x (nblk nl) row-major image in the value array: the lanes write it with coalesced stores, element e = (row i, block bb, column j).
+// A block is the cell's own one (K + the face terms seen from this cell), a skeleton neighbour's (SN_f / NS_f^1), or a block that
+// only a coupling operator fills (zero here; the coupling kernels add to it afterwards on the same stream).
 template <int DIM>
-__global__ void __launch_bounds__(128) k_dg_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, DgSpec S, const double* __restrict__ K,
+__global__ void __launch_bounds__(256) k_dg_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, DgSpec S, const double* __restrict__ K,
                                                      const double* __restrict__ T, const int64_t* __restrict__ rowptr,
                                                      const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
 {
-  const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gi >= S.size) return;
-  const int64_t g = S.offset + gi;
-  const int64_t rs = rowptr[g], re = rowptr[g + 1];
-  if (overwrite) for (int64_t q = rs; q < re; ++q) val[q] = 0.0;          // the caller's a = 0, fused (this thread owns the row)
-  DgRow<DIM> R; R.init(m, sd, S, gi);
-  if (!R.active) return;
-  auto locate = [&](int32_t col) { int64_t lo = rs, hi = re; while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (colidx[mid] < col) lo = mid + 1; else hi = mid; } return lo; };
-  double acc[DG_MAXNL];
-  R.own_row(S, K, T, acc);
-  int64_t pos = locate(R.first_own);
-  for (int jj = 0; jj < S.nl; ++jj) val[pos + jj] += acc[jj];
-  for (int f = 0; f < 2 * DIM; ++f) {
-    const double* M = R.nb_row(S, T, f);
-    if (!M) continue;
-    pos = locate(R.first_nb[f]);
-    for (int jj = 0; jj < S.nl; ++jj) val[pos + jj] += M[jj];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nl = S.nl, nl2 = nl * nl;
+  const int64_t ncell = S.size / nl;
+  for (int64_t b = warp; b < ncell; b += nwarps) {
+    const int64_t gi = b * nl, g = S.offset + gi;
+    const int64_t rs = rowptr[g];
+    const int len = (int)(rowptr[g + 1] - rs), total = len * nl;
+    DgRow<DIM> R; R.init(m, sd, S, gi);                       // li = 0: the cell's first row
+    if (!R.active) { if (overwrite) for (int e = lane; e < total; e += 32) val[rs + e] = 0.0; continue; }
+    for (int e = lane; e < total; e += 32) {
+      const int i = e / len, rem = e - i * len, bb = rem / nl, j = rem - bb * nl;
+      const int32_t first = colidx[rs + bb * nl];
+      const int ij = i * nl + j;
+      double v = 0.0;
+      if (first == R.first_own) {
+        v = K[ij];
+#pragma unroll
+        for (int f = 0; f < 2 * DIM; ++f) {
+          if (R.kind[f] == 1) v += T[((size_t)f * DG_MATS + 0) * DG_MAXNL * DG_MAXNL + ij];
+          else if (R.kind[f] == 2) v += T[((size_t)(f ^ 1) * DG_MATS + 3) * DG_MAXNL * DG_MAXNL + ij];
+          else if (R.kind[f] == 3) v += T[((size_t)f * DG_MATS + 4) * DG_MAXNL * DG_MAXNL + ij];
+        }
+      } else {
+#pragma unroll
+        for (int f = 0; f < 2 * DIM; ++f) {
+          if (first != R.first_nb[f]) continue;
+          if (R.kind[f] == 1) v = T[((size_t)f * DG_MATS + 1) * DG_MAXNL * DG_MAXNL + ij];
+          else if (R.kind[f] == 2) v = T[((size_t)(f ^ 1) * DG_MATS + 2) * DG_MAXNL * DG_MAXNL + ij];
+        }
+      }
+      (void)nl2;
+      if (overwrite) val[rs + e] = v; else if (v != 0.0) val[rs + e] += v;
+    }
   }
 }
 
@@ -290,8 +313,11 @@ void jacobian_dg(Ctx* c, const GridOp& go, Matrix& M, int child, double weight, 
   }
   const double* T = dg_tables(c, S, slot, weight);
   const double* K = c->d_Ae + (size_t)slot * MDB_MAXLOC * MDB_MAXLOC;
-  if (m.dim == 2) MDB_LAUNCH(c, k_dg_jacobian<2>, cdiv(S.size, 128), 128, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
-  else MDB_LAUNCH(c, k_dg_jacobian<3>, cdiv(S.size, 128), 128, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  const int64_t ncell = S.size / S.nl;
+  int grid = cdiv(ncell, 8);                                  // 8 warps per block, one cell per warp and pass
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (m.dim == 2) MDB_LAUNCH(c, k_dg_jacobian<2>, grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  else MDB_LAUNCH(c, k_dg_jacobian<3>, grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
 }
 
 void residual_dg(Ctx* c, const GridOp& go, int child, double weight, const double* d_x, double* d_r)

@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int64_t n, const int64_t* _
   }
 }
 
-// wavefront key of every row: (child block, ix + 2 iy + 4 iz)
-struct KeyChild { int64_t offset; int n0, n1; const int32_t* dof2lat; };
+// wavefront key of every row: (child block, ix + 2 iy + 4 iz); QkDG blocks: the coordinates of the row's CELL (st = lattice stride)
+struct KeyChild { int64_t offset; int n0, n1; const int32_t* dof2lat; int st; };
 struct KeySpace { int nchild; KeyChild ch[MDB_MAX_CHILDREN]; };
 __global__ void k_sweep_keys(int64_t n, KeySpace sp, uint32_t* key, int32_t* row)
 {
@@ -198,7 +198,7 @@ __global__ void k_sweep_keys(int64_t n, KeySpace sp, uint32_t* key, int32_t* row
   while (ci + 1 < sp.nchild && r >= sp.ch[ci + 1].offset) ++ci;
   const KeyChild& ch = sp.ch[ci];
   const int64_t p = ch.dof2lat[r - ch.offset];
-  const int ix = (int)(p % ch.n0), iy = (int)((p / ch.n0) % ch.n1), iz = (int)(p / ((int64_t)ch.n0 * ch.n1));
+  const int ix = (int)(p % ch.n0) / ch.st, iy = (int)((p / ch.n0) % ch.n1) / ch.st, iz = (int)(p / ((int64_t)ch.n0 * ch.n1)) / ch.st;
   key[r] = ((uint32_t)ci << 24) | (uint32_t)(ix + 2 * iy + 4 * iz);
   row[r] = (int32_t)r;
 }
@@ -218,13 +218,16 @@ static void ensure_precond_state(Ctx* c, Matrix& M)
   M.sweep_epoch = 0;
   // dispatch order of the rows.  The wavefront key is a topological order only for lexicographically numbered (Q1) lattice
   // blocks whose lattice fits the key; anything else keeps the index order (always topological, little parallelism).
+  // QkDG blocks are numbered cell block after cell block, cells in host order: a row depends on the earlier rows of its own cell
+  // (same key; the stable sort keeps them in index order) and on the cells at -x, -y, -z (smaller key) — the same key on cell
+  // coordinates is topological.
   M.d_sweep_perm = dalloc<int32_t>(n);
   bool lattice = true;
   KeySpace sp; sp.nchild = (int)c->children.size();
   for (int i = 0; i < sp.nchild; ++i) {
     const Child& ch = c->children[i];
-    lattice = lattice && ch.k == 1 && !ch.dg && (int64_t)ch.lat_n[0] + 2 * (int64_t)ch.lat_n[1] + 4 * (int64_t)ch.lat_n[2] < (1 << 24);
-    sp.ch[i].offset = ch.offset; sp.ch[i].n0 = ch.lat_n[0]; sp.ch[i].n1 = ch.lat_n[1]; sp.ch[i].dof2lat = ch.d_dof2lat;
+    lattice = lattice && (ch.k == 1 || ch.dg) && (int64_t)ch.lat_n[0] + 2 * (int64_t)ch.lat_n[1] + 4 * (int64_t)ch.lat_n[2] < (1 << 24);
+    sp.ch[i].offset = ch.offset; sp.ch[i].n0 = ch.lat_n[0]; sp.ch[i].n1 = ch.lat_n[1]; sp.ch[i].dof2lat = ch.d_dof2lat; sp.ch[i].st = ch.dg ? ch.stride() : 1;
   }
   if (!lattice) { MDB_LAUNCH(c, k_iota, cdiv(n, 256), 256, 0, n, M.d_sweep_perm); return; }
   uint32_t* d_key = dalloc<uint32_t>(n); uint32_t* d_key2 = dalloc<uint32_t>(n);

@@ -1,8 +1,11 @@
 // examples/testpoisson-dirichlet-neumann.cc — the reference driver test/testpoisson-dirichlet-neumann.cc (`solve()` :371-862, main
-// :881-975) written against the B200 facade, with the conforming alternative the reference keeps next to the shipped DG call
-// (:955-962: FEMk + Poisson(f,b,j,6) instead of QkDG + ConvectionDiffusionDG, an upstream operator outside this backend).
+// :883-977) written against the B200 facade.  main() picks the instantiation of solve() like the reference's (commented)
+// alternatives :964-975:
 //
-//   testpoisson-dirichlet-neumann <ini file> [k left = 1] [k right = 1]
+//   testpoisson-dirichlet-neumann <ini file> [fem left = dg2] [fem right = dg2]
+//       dg1 / dg2   QkDGLocalFiniteElementMap<DF,double,k,dim> + dglop() = ConvectionDiffusionDG(params, SIPG, weightsOn, 2.0)  — dg2 dg2 is
+//                   what the reference ships (:968-971)
+//       1 / 2       QkLocalFiniteElementMap<SDGV,DF,double,k> + cglop = Poisson(f,b,j,6) (:955-956, the commented alternative)
 //
 // Monolithic solve: left_sp, right_sp, Coupling(ContinuousValueContinuousFlowCoupling(4, scaling)), BiCGSTAB + SSOR(3) (:619-665).
 // Dirichlet-Neumann solve (:683-822): LeftOperator {left_sp, Coupling(left,right,ND)} and RightOperator {right_sp,
@@ -56,12 +59,9 @@ static CouplingMode::Type parse_coupling_type(const std::string& name) {      //
 
 static double norm2(const Vector& v) { double s = 0.0; for (size_t i = 0; i < v.size(); ++i) s += v[i] * v[i]; return std::sqrt(s); }
 
-int main(int argc, char** argv)
+template <class LOP>
+static int solve(const ParameterTree& parameters, int k0, int k1, bool dg, const LOP& lop)
 {
-  try {
-    if (argc < 2) { std::fprintf(stderr, "Usage: %s <ini file> [k left] [k right]\n", argv[0]); return 1; }
-    ParameterTree parameters(argv[1]);
-    const int k0 = argc > 2 ? std::atoi(argv[2]) : 1, k1 = argc > 3 ? std::atoi(argv[3]) : 1;
     const int dim = 2;
     const int64_t cells = (int64_t)1 << (int)parameters.get("mesh.refine");
     const int64_t n[3] = {cells, cells, 1};
@@ -74,18 +74,15 @@ int main(int argc, char** argv)
       grid.addToSubDomain(((e % cells) + 0.5) / cells > 0.5 ? 1 : 0, e);
     grid.preUpdateSubDomains(); grid.updateSubDomains(); grid.postUpdateSubDomains();
 
-    GridFunctionSpace gfs0(grid.subDomain(0), k0), gfs1(grid.subDomain(1), k1);
+    GridFunctionSpace gfs0(grid.subDomain(0), k0, dg), gfs1(grid.subDomain(1), k1, dg);
     MultiDomainGridFunctionSpace multigfs(grid, {&gfs0, &gfs1});
 
     const mdb_bctype b = boundary(MDB_BC_TESTPOISSON);                // DirichletBoundary :89-135
-    const mdb_function f = function(MDB_FN_DN_SOURCE);                // F :73-87
     const mdb_function g = function(MDB_FN_GAUSS, 1.0, 0.5, 0.5, 0.5);
-    const mdb_function j = function(MDB_FN_TESTPOISSON_J);
-    Poisson cglop(f, b, j, 6);                                        // CGLOP cglop(f,b,j,6) :946-947
 
     SubDomainEqualityCondition c0({0}), c1({1});
-    typedef SubProblem<Poisson, SubDomainEqualityCondition> SP;
-    SP left_sp(multigfs, cglop, c0, gfs0), right_sp(multigfs, cglop, c1, gfs1);
+    typedef SubProblem<LOP, SubDomainEqualityCondition> SP;
+    SP left_sp(multigfs, lop, c0, gfs0), right_sp(multigfs, lop, c1, gfs1);
 
     ContinuousValueContinuousFlowCoupling proportionalFlowCoupling(4, parameters.get("monolithic.coupling.scaling"));
     Coupling<SP, SP, ContinuousValueContinuousFlowCoupling> coupling(left_sp, right_sp, proportionalFlowCoupling);
@@ -161,6 +158,27 @@ int main(int argc, char** argv)
       std::printf("Dirichlet-Neumann solver: %zu sweeps, %d inner iterations, sum(u) = %.12e |u|_2 = %.12e\n", i, inner, sum, norm2(u));
     }
     return 0;
+}
+
+int main(int argc, char** argv)
+{
+  try {
+    if (argc < 2) { std::fprintf(stderr, "Usage: %s <ini file> [fem left = dg2] [fem right = dg2]   (fem: dg1, dg2, 1, 2)\n", argv[0]); return 1; }
+    ParameterTree parameters(argv[1]);
+    const std::string fem0 = argc > 2 ? argv[2] : "dg2", fem1 = argc > 3 ? argv[3] : "dg2";
+    const bool dg = fem0.compare(0, 2, "dg") == 0;
+    if (dg != (fem1.compare(0, 2, "dg") == 0)) throw Exception(MDB_EINVAL, "both sides conforming (1, 2) or both sides DG (dg1, dg2)");
+    const int k0 = std::atoi(fem0.c_str() + (dg ? 2 : 0)), k1 = std::atoi(fem1.c_str() + (dg ? 2 : 0));
+    const mdb_bctype b = boundary(MDB_BC_TESTPOISSON);                // DirichletBoundary :89-135 / bctype :220-242
+    const mdb_function f = function(MDB_FN_DN_SOURCE);                // F :73-87 / f :203-218
+    const mdb_function g = function(MDB_FN_GAUSS, 1.0, 0.5, 0.5, 0.5);
+    const mdb_function j = function(MDB_FN_TESTPOISSON_J);
+    if (dg) {
+      ConvectionDiffusionModelProblem params(f, b, g, j);             // :958-962
+      return solve(parameters, k0, k1, true, ConvectionDiffusionDG(params, ConvectionDiffusionDGMethod::SIPG,
+                                                                   ConvectionDiffusionDGWeights::weightsOn, 2.0));   // dglop() :864-881
+    }
+    return solve(parameters, k0, k1, false, Poisson(f, b, j, 6));      // CGLOP cglop(f,b,j,6) :955-956
   } catch (Exception& e) {
     std::fprintf(stderr, "mdb200 error %d: %s\n", e.code, e.what());
     return 1;

@@ -87,7 +87,15 @@ public:
   SubDomainGridView gv; int k; int child;
   bool coupling; int lkind, rkind; uint32_t lmask, rmask;      // set by CouplingGridFunctionSpace only
   int ncomp;                                                   // > 1: PowerCouplingGridFunctionSpace
-  GridFunctionSpace(SubDomainGridView gv_, int order) : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1) {}
+  bool dg;                                                     // QkDGLocalFiniteElementMap<DF,RF,k,dim> instead of QkLocalFiniteElementMap
+  GridFunctionSpace(SubDomainGridView gv_, int order, bool dg_ = false)
+    : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1), dg(dg_) {}
+  int fe() const { return dg ? (k == 1 ? MDB_FE_DGQ1 : MDB_FE_DGQ2) : (k == 1 ? MDB_FE_Q1 : MDB_FE_Q2); }
+};
+// GridFunctionSpace<SDGV, QkDGLocalFiniteElementMap<DF,double,k,dim>, CON, VBE> (test/testpoisson-dirichlet-neumann.cc:925-926, :968-971)
+class QkDGGridFunctionSpace : public GridFunctionSpace {
+public:
+  QkDGGridFunctionSpace(SubDomainGridView gv_, int order) : GridFunctionSpace(gv_, order, true) {}
 };
 
 // CouplingGridFunctionSpace<MDGV, QkLocalFiniteElementMap<(dim-1)-cube,1>, SubProblemSubProblemInterface<MDGV,Left,Right>, NoConstraints, VBE>
@@ -121,7 +129,7 @@ public:
         ? context().check(mdb_add_power_coupling_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->lkind, g->lmask, g->rkind, g->rmask, g->ncomp), "mdb_add_power_coupling_space")
         : g->coupling
         ? context().check(mdb_add_coupling_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->lkind, g->lmask, g->rkind, g->rmask), "mdb_add_coupling_space")
-        : context().check(mdb_add_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->gv.subdomain), "mdb_add_space");
+        : context().check(mdb_add_space(context().get(), g->fe(), g->gv.subdomain), "mdb_add_space");
   }
   Context& context() const { return grid_.context(); }
   MultiDomainGrid& grid() const { return grid_; }
@@ -158,6 +166,24 @@ struct L2 {                          // Dune::PDELab::L2(intorder) / test/simple
   explicit L2(int intorder = 2) { p.quad_order = intorder; p.reserved = 0; }
   static int id() { return MDB_OP_L2; }
 };
+// [UPSTREAM] Dune::PDELab::ConvectionDiffusionDG<Params,FEM>(params, method, weights, alpha) as built by dglop()
+// (test/testpoisson-dirichlet-neumann.cc:864-881) over the parameter class ConvectionDiffusionModelProblem (:169-285): A = I, b = 0,
+// c = 0, source f, boundary type b (None on interior faces), Dirichlet value g, Neumann flux j.  QkDG spaces only.
+namespace ConvectionDiffusionDGMethod { enum Type { NIPG = MDB_DG_METHOD_NIPG, SIPG = MDB_DG_METHOD_SIPG }; }
+namespace ConvectionDiffusionDGWeights { enum Type { weightsOff = MDB_DG_WEIGHTS_OFF, weightsOn = MDB_DG_WEIGHTS_ON }; }
+struct ConvectionDiffusionModelProblem {
+  mdb_function f, g, j; mdb_bctype b;
+  ConvectionDiffusionModelProblem(const mdb_function& f_, const mdb_bctype& b_, const mdb_function& g_, const mdb_function& j_) : f(f_), g(g_), j(j_), b(b_) {}
+};
+struct ConvectionDiffusionDG {
+  mdb_convdiffdg_params p;
+  ConvectionDiffusionDG(const ConvectionDiffusionModelProblem& param, ConvectionDiffusionDGMethod::Type method = ConvectionDiffusionDGMethod::NIPG,
+                        ConvectionDiffusionDGWeights::Type weights = ConvectionDiffusionDGWeights::weightsOff, double alpha = 0.0, int intorderadd = 0) {
+    p.f = param.f; p.bc = param.b; p.g = param.g; p.j = param.j; p.method = method; p.weights = weights; p.intorderadd = intorderadd; p.reserved = 0; p.alpha = alpha;
+  }
+  static int id() { return MDB_OP_CONVDIFF_DG; }
+  const mdb_bctype& bctype() const { return p.bc; }
+};
 struct ContinuousValueContinuousFlowCoupling {   // test/proportionalflowcoupling.hh:94-239
   mdb_cvcf_params p; int jac_mode;
   ContinuousValueContinuousFlowCoupling(int intorder, double intensity, int jacobian_mode = MDB_JAC_FD_BITMATCH) : jac_mode(jacobian_mode) {
@@ -173,8 +199,6 @@ struct ProportionalFlowCoupling {                // test/proportionalflowcouplin
 // Dune::PDELab::ConvectionDiffusionDGNeumannDirichletCoupling<CouplingParameters>(coupling_mode, param, method, weights, alpha, intorderadd)
 // (test/neumanndirichletcoupling.hh:56-74) with the parameter class of test/testpoisson-dirichlet-neumann.cc:36-69 (A = I, b = 0, c = 0)
 namespace CouplingMode { enum Type { Neumann = MDB_ND_MODE_NEUMANN, Dirichlet = MDB_ND_MODE_DIRICHLET, Both = MDB_ND_MODE_BOTH }; }
-namespace ConvectionDiffusionDGMethod { enum Type { NIPG = MDB_DG_METHOD_NIPG, SIPG = MDB_DG_METHOD_SIPG }; }
-namespace ConvectionDiffusionDGWeights { enum Type { weightsOff = MDB_DG_WEIGHTS_OFF, weightsOn = MDB_DG_WEIGHTS_ON }; }
 struct ConvectionDiffusionDGNeumannDirichletCoupling {
   mdb_ndcoupling_params p; int jac_mode;
   ConvectionDiffusionDGNeumannDirichletCoupling(CouplingMode::Type mode, ConvectionDiffusionDGMethod::Type method = ConvectionDiffusionDGMethod::NIPG,

@@ -137,7 +137,7 @@ def test_dn_iteration_matches_oracle(case):
     dev.close(); ora.close()
 
 
-@pytest.mark.parametrize("refine,ks", [(5, (1, 1)), (4, (2, 2)), (4, (1, 2))])
+@pytest.mark.parametrize("refine,ks", [(5, (1, 1)), (4, (2, 2)), (4, (1, 2)), (4, ("dg2", "dg2")), (4, ("dg1", "dg1"))])
 def test_cxx_dn_driver_matches_oracle(refine, ks):
     """examples/testpoisson-dirichlet-neumann.cc with examples/poisson-dirichlet-neumann.ini (the reference's keys): DOF counts, the
     monolithic BiCGSTAB + SSOR(3) solve, the start residual of the full operator and the Dirichlet-Neumann sweep count / solution."""
@@ -147,9 +147,9 @@ def test_cxx_dn_driver_matches_oracle(refine, ks):
     import tempfile
     from test_capi import _build_example, ROOT
     n = (1 << refine,) * 2
-    fe = tuple(capi.FE_Q1 if k == 1 else capi.FE_Q2 for k in ks)
+    fe = tuple({1: capi.FE_Q1, 2: capi.FE_Q2, "dg1": capi.FE_DGQ1, "dg2": capi.FE_DGQ2}[k] for k in ks)      # ("dg2", "dg2") = as shipped
     ora = orc.Oracle()
-    Po = problems.dirichlet_neumann(ora, n, fe=fe)
+    Po = problems.dirichlet_neumann(ora, n, fe=fe, dg=isinstance(ks[0], str))
     u0 = np.zeros(Po.ndof); ora.interpolate(Po.sps, Po.gfn, u0)
     ora.jacobian(Po.go, Po.mat, u0, overwrite=True)
     r = np.zeros(Po.ndof); ora.residual(Po.go, u0, r)
