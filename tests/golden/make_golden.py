@@ -36,6 +36,12 @@ CASES = {
     # test/testmortarpoisson.cc as shipped ("5 1.0": 32x32 cells, Q1 | Q1 | Q1 mortar space, 1155 DOFs) and a 3-D Q1|Q2 variant
     "p2d_32x32_mortar": ((32, 32), dict(problem="mortar", gamma_0=1.0)),
     "p3d_4x3x3_mortar_q1q2": ((4, 3, 3), dict(problem="mortar", gamma_0=2.5, fe=(capi.FE_Q1, capi.FE_Q2))),
+    # test/testpowermortarpoisson.cc (PowerCouplingGridFunctionSpace<CouplingGFS,2,VBE>) in 3-D, where its matrix is regular
+    "p3d_6x5x4_powermortar": ((6, 5, 4), dict(problem="mortar", gamma_0=1.0, ncomp=2)),
+    # test/testpoisson-dirichlet-neumann.cc as shipped (DG-Q2 | DG-Q2, ConvectionDiffusionDG(SIPG, weightsOn, 2), CVCF(4, 10)) at
+    # mesh.refine = 3, and a 3-D DG-Q1 variant
+    "dg2d_8x8_q2_shipped": ((8, 8), dict(problem="dg", k=2, scaling=10.0)),
+    "dg3d_4x3x2_q1": ((4, 3, 2), dict(problem="dg", k=1, scaling=3.0)),
 }
 
 
@@ -79,7 +85,8 @@ def main():
         o = orc.Oracle()
         kw = dict(kw)
         problem = kw.pop("problem", "poisson")
-        P = problems.testmortarpoisson(o, n, **kw) if problem == "mortar" else problems.testpoisson(o, n, **kw)
+        if problem == "dg": P = problems.dirichlet_neumann_dg(o, n, **kw)
+        else: P = problems.testmortarpoisson(o, n, **kw) if problem == "mortar" else problems.testpoisson(o, n, **kw)
         ptr, dofs = o.get_dofmap()
         rp, ci = o.matrix_get_pattern(P.mat)
         u = np.zeros(P.ndof)
@@ -97,7 +104,7 @@ def main():
         z = np.zeros(P.ndof)
         o.solve(P.mat, r, z, reduction=1e-13)
         # independent check of the volume rows: rows that are neither constrained nor touched by the coupling
-        split = kw.get("split_axis", 0 if problem == "mortar" else 1)
+        split = kw.get("split_axis", 0 if problem in ("mortar", "dg") else 1)
         fe = kw.get("fe", (capi.FE_Q1, capi.FE_Q1))
         if n[split] % 2 == 0 and fe == (capi.FE_Q1, capi.FE_Q1) and problem == "poisson":
             K = kron_volume(n, split)
@@ -113,7 +120,8 @@ def main():
             err = abs(diff[free]).max()
             assert err < 1e-13, (name, err)
             print("%s: Kronecker volume check on %d rows, max diff %.2e" % (name, int(free.sum()), err))
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), n=np.array(n), split_axis=split, intensity=kw.get("intensity", 2.0),
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), problem=problem, ncomp=kw.get("ncomp", 1), k=kw.get("k", 0), scaling=kw.get("scaling", 0.0),
+                            n=np.array(n), split_axis=split, intensity=kw.get("intensity", 2.0),
                             coupling=kw.get("coupling", capi.OP_MORTAR_POISSON_COUPLING if problem == "mortar" else capi.OP_CVCF_COUPLING),
                             gamma_0=kw.get("gamma_0", 0.0), child_offsets=o.get_child_offsets(), fe=np.array(fe), ndof=P.ndof, ncon=P.ncon,
                             cell_ptr=ptr, cell_dofs=dofs, constrained=o.get_constraints(), rowptr=rp, colidx=ci, u=u,
