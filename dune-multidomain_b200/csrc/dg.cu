@@ -166,43 +166,56 @@ template <int DIM> struct DgRow {
 // nl x (nblk nl) row-major image in the value array: the lanes write it with coalesced stores, element e = (row i, block bb, column j).
 // A block is the cell's own one (K + the face terms seen from this cell), a skeleton neighbour's (SN_f / NS_f^1), or a block that
 // only a coupling operator fills (zero here; the coupling kernels add to it afterwards on the same stream).
-template <int DIM>
+template <int DIM, int KDEG>
 __global__ void __launch_bounds__(256) k_dg_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, DgSpec S, const double* __restrict__ K,
                                                      const double* __restrict__ T, const int64_t* __restrict__ rowptr,
                                                      const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
 {
+  constexpr int NL = cpow(KDEG + 1, DIM), MM = DG_MAXNL * DG_MAXNL;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int nl = S.nl, nl2 = nl * nl;
-  const int64_t ncell = S.size / nl;
+  const int64_t ncell = S.size / NL;
   for (int64_t b = warp; b < ncell; b += nwarps) {
-    const int64_t gi = b * nl, g = S.offset + gi;
+    const int64_t gi = b * NL, g = S.offset + gi;
     const int64_t rs = rowptr[g];
-    const int len = (int)(rowptr[g + 1] - rs), total = len * nl;
+    const int len = (int)(rowptr[g + 1] - rs), total = len * NL, nblk = len / NL;
     DgRow<DIM> R; R.init(m, sd, S, gi);                       // li = 0: the cell's first row
     if (!R.active) { if (overwrite) for (int e = lane; e < total; e += 32) val[rs + e] = 0.0; continue; }
-    for (int e = lane; e < total; e += 32) {
-      const int i = e / len, rem = e - i * len, bb = rem / nl, j = rem - bb * nl;
-      const int32_t first = colidx[rs + bb * nl];
-      const int ij = i * nl + j;
-      double v = 0.0;
-      if (first == R.first_own) {
-        v = K[ij];
-#pragma unroll
-        for (int f = 0; f < 2 * DIM; ++f) {
-          if (R.kind[f] == 1) v += T[((size_t)f * DG_MATS + 0) * DG_MAXNL * DG_MAXNL + ij];
-          else if (R.kind[f] == 2) v += T[((size_t)(f ^ 1) * DG_MATS + 3) * DG_MAXNL * DG_MAXNL + ij];
-          else if (R.kind[f] == 3) v += T[((size_t)f * DG_MATS + 4) * DG_MAXNL * DG_MAXNL + ij];
-        }
-      } else {
+    // classification of the row's blocks, one block per lane: table offset of the block's matrix (-1: a block only a coupling
+    // operator fills, -2: the cell's own block), handed to every lane by shuffles — no column-index read in the element loop
+    int code = -1;
+    if (lane < nblk) {
+      const int32_t first = colidx[rs + lane * NL];
+      if (first == R.first_own) code = -2;
+      else {
 #pragma unroll
         for (int f = 0; f < 2 * DIM; ++f) {
           if (first != R.first_nb[f]) continue;
-          if (R.kind[f] == 1) v = T[((size_t)f * DG_MATS + 1) * DG_MAXNL * DG_MAXNL + ij];
-          else if (R.kind[f] == 2) v = T[((size_t)(f ^ 1) * DG_MATS + 2) * DG_MAXNL * DG_MAXNL + ij];
+          if (R.kind[f] == 1) code = (f * DG_MATS + 1) * MM;              // SN_f
+          else if (R.kind[f] == 2) code = ((f ^ 1) * DG_MATS + 2) * MM;   // NS of the neighbour's face
         }
       }
-      (void)nl2;
+    }
+    int own_off[2 * DIM];                                     // the face terms of the own block
+#pragma unroll
+    for (int f = 0; f < 2 * DIM; ++f)
+      own_off[f] = R.kind[f] == 1 ? (f * DG_MATS + 0) * MM : R.kind[f] == 2 ? ((f ^ 1) * DG_MATS + 3) * MM : R.kind[f] == 3 ? (f * DG_MATS + 4) * MM : -1;
+    const float inv_len = 1.0f / (float)len;
+#pragma unroll 4
+    for (int e0 = 0; e0 < total; e0 += 32) {                  // uniform trip count: every lane takes part in the shuffle
+      const int e = e0 + lane;
+      const bool live = e < total;
+      const int i = (int)(((float)e + 0.5f) * inv_len);      // e / len: the quotient's fractional part is >= 0.5 / len, far from float rounding
+      const int rem = e - i * len, bb = live ? rem / NL : 0, j = rem - bb * NL;
+      const int ij = i * NL + j;
+      const int cb = __shfl_sync(0xffffffffu, code, bb);
+      if (!live) continue;
+      double v = 0.0;
+      if (cb == -2) {
+        v = K[ij];
+#pragma unroll
+        for (int f = 0; f < 2 * DIM; ++f) if (own_off[f] >= 0) v += T[own_off[f] + ij];
+      } else if (cb >= 0) v = T[cb + ij];
       if (overwrite) val[rs + e] = v; else if (v != 0.0) val[rs + e] += v;
     }
   }
@@ -316,8 +329,10 @@ void jacobian_dg(Ctx* c, const GridOp& go, Matrix& M, int child, double weight, 
   const int64_t ncell = S.size / S.nl;
   int grid = cdiv(ncell, 8);                                  // 8 warps per block, one cell per warp and pass
   if (grid > 148 * 16) grid = 148 * 16;
-  if (m.dim == 2) MDB_LAUNCH(c, k_dg_jacobian<2>, grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
-  else MDB_LAUNCH(c, k_dg_jacobian<3>, grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  if (m.dim == 2 && S.k == 1) MDB_LAUNCH(c, (k_dg_jacobian<2, 1>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  else if (m.dim == 2) MDB_LAUNCH(c, (k_dg_jacobian<2, 2>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  else if (S.k == 1) MDB_LAUNCH(c, (k_dg_jacobian<3, 1>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  else MDB_LAUNCH(c, (k_dg_jacobian<3, 2>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
 }
 
 void residual_dg(Ctx* c, const GridOp& go, int child, double weight, const double* d_x, double* d_r)

@@ -14,7 +14,7 @@ for refine in refines:
     dev.synchronize(); t_setup = time.perf_counter() - t0
     u = torch.zeros(P.ndof, dtype=torch.float64, device="cuda"); r = torch.zeros_like(u); z = torch.zeros_like(u)
     nnz = dev.nnz[P.mat]
-    def timed(fn, reps=20):
+    def timed(fn, reps=int(os.environ.get("DG_TIME_REPS", "20"))):
         for _ in range(3): fn()
         dev.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); t = time.perf_counter()
@@ -28,6 +28,8 @@ for refine in refines:
     print("refine=%d ndof=%d nnz=%d setup(dofmap+pattern) %.1f ms | jacobian %.3f ms = %.2f GDOF/s, %.0f GB/s of values | residual %.3f ms | spmv %.3f ms = %.0f GB/s"
           % (refine, P.ndof, nnz, t_setup * 1e3, t_jac, P.ndof / t_jac / 1e6, 8 * nnz / t_jac / 1e6, t_res, t_spmv, (12 * nnz + 20 * P.ndof) / t_spmv / 1e6), flush=True)
     r.zero_(); dev.residual(P.go, u, r)
+    if os.environ.get("DG_TIME_NO_SOLVE"):
+        dev.close(); continue
     for name, method, precond, sweeps, maxit in (("BiCGSTAB+Jacobi", capi.SOLVER_BICGSTAB, capi.PRECOND_JACOBI, 1, 20000),
                                                  ("BiCGSTAB+SSOR(3)", capi.SOLVER_BICGSTAB, capi.PRECOND_SSOR, 3, 12 if refine > 7 else 5000)):
         dev.set_ssor_sweeps(sweeps)
