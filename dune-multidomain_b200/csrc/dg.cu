@@ -68,26 +68,33 @@ template <int DIM> __global__ void __launch_bounds__(768) k_dg_face_matrices(int
   const int f = blockIdx.x, axis = f / 2, side = f % 2;
   const int nl = ipow(k + 1, DIM);
   const int t = threadIdx.x;
-  if (t >= nl * nl) return;
-  const int i = t / nl, j = t % nl;
   const double ext[3] = {ext0, ext1, ext2};
   const double jit = 1.0 / ext[axis], nrm = side ? 1.0 : -1.0;
   const double area = dg_area<DIM>(ext, axis), penalty = dg_penalty<DIM>(alpha, k, ext, axis);
   const double omega = 0.5;
   const int nq = ipow(R.m, DIM - 1);
-  double ss = 0.0, sn = 0.0, ns = 0.0, nn = 0.0, bd = 0.0;
-  for (int q = 0; q < nq; ++q) {
+  // shape functions of both cells at the face points, evaluated once per (point, function) by the first nq * nl threads
+  __shared__ double s_ps[9][DG_MAXNL], s_pn[9][DG_MAXNL], s_as[9][DG_MAXNL], s_an[9][DG_MAXNL], s_w[9];
+  for (int u = t; u < nq * nl; u += blockDim.x) {
+    const int q = u / nl, ii = u % nl;
     double pos[3], w; quad_point<DIM - 1>(R, q, pos, w);
     double ls[3], ln[3]; int tt = 0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) { if (d == axis) { ls[d] = (double)side; ln[d] = (double)(1 - side); } else { ls[d] = pos[tt]; ln[d] = pos[tt]; ++tt; } }
     double gr[3];
-    const double ps_i = qk_phi<DIM>(k, i, ls), ps_j = qk_phi<DIM>(k, j, ls), pn_i = qk_phi<DIM>(k, i, ln), pn_j = qk_phi<DIM>(k, j, ln);
-    qk_grad<DIM>(k, i, ls, gr); const double as_i = nrm * (jit * gr[axis]);      // An_F_s * tgradphi_s[i] = n . grad phi_i (inside cell)
-    qk_grad<DIM>(k, j, ls, gr); const double as_j = nrm * (jit * gr[axis]);
-    qk_grad<DIM>(k, i, ln, gr); const double an_i = nrm * (jit * gr[axis]);      // ... of the outside cell, with the INSIDE normal
-    qk_grad<DIM>(k, j, ln, gr); const double an_j = nrm * (jit * gr[axis]);
-    const double factor = w * area, ipf = penalty * factor;
+    s_ps[q][ii] = qk_phi<DIM>(k, ii, ls); s_pn[q][ii] = qk_phi<DIM>(k, ii, ln);
+    qk_grad<DIM>(k, ii, ls, gr); s_as[q][ii] = nrm * (jit * gr[axis]);      // An_F_s * tgradphi_s[i] = n . grad phi_i (inside cell)
+    qk_grad<DIM>(k, ii, ln, gr); s_an[q][ii] = nrm * (jit * gr[axis]);      // ... of the outside cell, with the INSIDE normal
+    if (ii == 0) s_w[q] = w;
+  }
+  __syncthreads();
+  if (t >= nl * nl) return;
+  const int i = t / nl, j = t % nl;
+  double ss = 0.0, sn = 0.0, ns = 0.0, nn = 0.0, bd = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    const double ps_i = s_ps[q][i], ps_j = s_ps[q][j], pn_i = s_pn[q][i], pn_j = s_pn[q][j];
+    const double as_i = s_as[q][i], as_j = s_as[q][j], an_i = s_an[q][i], an_j = s_an[q][j];
+    const double factor = s_w[q] * area, ipf = penalty * factor;
     ss += -as_j * omega * factor * ps_i + ps_j * factor * theta * omega * as_i + ps_j * ipf * ps_i;
     sn += -an_j * omega * factor * ps_i - pn_j * factor * theta * omega * as_i - pn_j * ipf * ps_i;
     ns += as_j * omega * factor * pn_i + ps_j * factor * theta * omega * an_i - ps_j * ipf * pn_i;
@@ -107,11 +114,16 @@ template <int DIM> struct DgRow {
   int kind[2 * DIM]; int32_t first_nb[2 * DIM];
   __device__ void init(const MeshDesc& m, const uint8_t* __restrict__ sd, const DgSpec& S, int64_t gi)
   {
-    int64_t r = S.dof2lat[gi];
-    int p[3]; p[0] = (int)(r % S.lat_n[0]); r /= S.lat_n[0]; p[1] = (int)(r % S.lat_n[1]); p[2] = (int)(r / S.lat_n[1]);
+    // 32-bit arithmetic throughout (a child has < 2^31 lattice points): 64-bit divisions cost ~100 instructions each and every
+    // lane of a warp-per-cell kernel runs this
+    const unsigned r = (unsigned)S.dof2lat[gi], n0 = (unsigned)S.lat_n[0], n1 = (unsigned)S.lat_n[1], st = (unsigned)S.st;
+    const unsigned r1 = r / n0;
+    unsigned p[3]; p[0] = r - r1 * n0; p[2] = (DIM > 2) ? r1 / n1 : 0u; p[1] = r1 - p[2] * n1;
     int a[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) { ijk[d] = (d < DIM) ? p[d] / S.st : 0; a[d] = (d < DIM) ? p[d] % S.st : 0; }
+    for (int d = 0; d < 3; ++d) {
+      if (d < DIM) { const unsigned c = p[d] / st; ijk[d] = (int)c; a[d] = (int)(p[d] - c * st); } else { ijk[d] = 0; a[d] = 0; }
+    }
     li = a[0] + (S.k + 1) * (a[1] + (S.k + 1) * a[2]);
     cell = ijk[0] + (int64_t)m.n[0] * (ijk[1] + (int64_t)m.n[1] * ijk[2]);
     active = cond_applies(S.cond_kind, S.mask, sd[cell]);
@@ -162,61 +174,87 @@ template <int DIM> struct DgRow {
   }
 };
 
-// One warp per cell.  The (k+1)^d rows of a cell are consecutive DOFs with the same column set, so their values are one contiguous
-// nl x (nblk nl) row-major image in the value array: the lanes write it with coalesced stores, element e = (row i, block bb, column j).
-// A block is the cell's own one (K + the face terms seen from this cell), a skeleton neighbour's (SN_f / NS_f^1), or a block that
-// only a coupling operator fills (zero here; the coupling kernels add to it afterwards on the same stream).
+// The (k+1)^d rows of a cell are consecutive DOFs with the same column set, so a cell's values are one contiguous
+// nl x (nblk nl) row-major image in the value array.  A block of the image is the cell's own one (K + the face terms seen from this
+// cell), a skeleton neighbour's (SN_f / NS_f^1), or a block that only a coupling operator fills (zero here; the coupling kernels add
+// to it afterwards on the same stream).  Which is which is a 42-bit SIGNATURE of the cell (face kinds, block roles, block count), and
+// on a structured mesh long runs of consecutive cells share it.  A warp takes 32 consecutive cells: each LANE works out the
+// signature of one cell (the index arithmetic and the dependent loads are spent once per cell, not once per lane and cell), then
+// the warp walks through the 32 cells, rebuilds its image in shared memory only when the signature changes, and copies it out
+// with coalesced stores — a few instructions per 256 bytes written.
 template <int DIM, int KDEG>
 __global__ void __launch_bounds__(256) k_dg_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, DgSpec S, const double* __restrict__ K,
                                                      const double* __restrict__ T, const int64_t* __restrict__ rowptr,
-                                                     const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite)
+                                                     const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite, int cpw)
 {
-  constexpr int NL = cpow(KDEG + 1, DIM), MM = DG_MAXNL * DG_MAXNL;
+  constexpr int NL = cpow(KDEG + 1, DIM), NF = 2 * DIM, MM = DG_MAXNL * DG_MAXNL, IMG = NL * (NF + 1) * NL;
+  extern __shared__ double s_img[];
+  double* img = s_img + (size_t)(threadIdx.x >> 5) * IMG;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t ncell = S.size / NL;
-  for (int64_t b = warp; b < ncell; b += nwarps) {
-    const int64_t gi = b * NL, g = S.offset + gi;
-    const int64_t rs = rowptr[g];
-    const int len = (int)(rowptr[g + 1] - rs), total = len * NL, nblk = len / NL;
-    DgRow<DIM> R; R.init(m, sd, S, gi);                       // li = 0: the cell's first row
-    if (!R.active) { if (overwrite) for (int e = lane; e < total; e += 32) val[rs + e] = 0.0; continue; }
-    // classification of the row's blocks, one block per lane: table offset of the block's matrix (-1: a block only a coupling
-    // operator fills, -2: the cell's own block), handed to every lane by shuffles — no column-index read in the element loop
-    int code = -1;
-    if (lane < nblk) {
-      const int32_t first = colidx[rs + lane * NL];
-      if (first == R.first_own) code = -2;
-      else {
+  unsigned long long cur = ~0ull;                             // signature of the image in shared memory
+  for (int64_t b0 = warp * cpw; b0 < ncell; b0 += nwarps * cpw) {       // cpw <= 32 cells per warp and pass (fewer on small meshes)
+    // ---- one cell per lane: signature and position
+    const int64_t b = b0 + lane;
+    unsigned long long sig = ~0ull; long long rs = 0; int len = 0, act = 0;
+    if (lane < cpw && b < ncell) {
+      const int64_t gi = b * NL, g = S.offset + gi;
+      rs = rowptr[g]; len = (int)(rowptr[g + 1] - rs);
+      DgRow<DIM> R; R.init(m, sd, S, gi);                     // li = 0: the cell's first row
+      act = R.active ? 1 : 0;
+      if (act) {
+        const int nblk = len / NL;
+        sig = (unsigned long long)nblk << 39;
 #pragma unroll
-        for (int f = 0; f < 2 * DIM; ++f) {
-          if (first != R.first_nb[f]) continue;
-          if (R.kind[f] == 1) code = (f * DG_MATS + 1) * MM;              // SN_f
-          else if (R.kind[f] == 2) code = ((f ^ 1) * DG_MATS + 2) * MM;   // NS of the neighbour's face
+        for (int f = 0; f < NF; ++f) sig |= (unsigned long long)R.kind[f] << (3 * f);
+        for (int bb = 0; bb < nblk; ++bb) {                   // role of block bb: face f (0..5), 6 = own, 7 = filled by a coupling only
+          const int32_t first = colidx[rs + bb * NL];
+          int role = 7;
+          if (first == R.first_own) role = 6;
+          else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) if (first == R.first_nb[f] && (R.kind[f] == 1 || R.kind[f] == 2)) role = f;
+          }
+          sig |= (unsigned long long)role << (18 + 3 * bb);
         }
       }
     }
-    int own_off[2 * DIM];                                     // the face terms of the own block
+    // ---- the warp walks through its cells
+    const int ncl = (ncell - b0 < cpw) ? (int)(ncell - b0) : cpw;
+    for (int l = 0; l < ncl; ++l) {
+      const unsigned long long sg = __shfl_sync(0xffffffffu, sig, l);
+      const long long rsl = __shfl_sync(0xffffffffu, rs, l);
+      const int lenl = __shfl_sync(0xffffffffu, len, l), actl = __shfl_sync(0xffffffffu, act, l);
+      const int total = lenl * NL;
+      double* dst = val + rsl;
+      if (!actl) { if (overwrite) for (int e = lane; e < total; e += 32) dst[e] = 0.0; continue; }
+      if (sg != cur) {                                        // (re)build the image: rare
+        __syncwarp();
+        for (int e = lane; e < total; e += 32) {
+          const int i = e / lenl, rem = e - i * lenl, bb = rem / NL, j = rem - bb * NL, ij = i * NL + j;
+          const int role = (int)((sg >> (18 + 3 * bb)) & 7);
+          double v = 0.0;
+          if (role == 6) {
+            v = K[ij];
 #pragma unroll
-    for (int f = 0; f < 2 * DIM; ++f)
-      own_off[f] = R.kind[f] == 1 ? (f * DG_MATS + 0) * MM : R.kind[f] == 2 ? ((f ^ 1) * DG_MATS + 3) * MM : R.kind[f] == 3 ? (f * DG_MATS + 4) * MM : -1;
-    const float inv_len = 1.0f / (float)len;
-#pragma unroll 4
-    for (int e0 = 0; e0 < total; e0 += 32) {                  // uniform trip count: every lane takes part in the shuffle
-      const int e = e0 + lane;
-      const bool live = e < total;
-      const int i = (int)(((float)e + 0.5f) * inv_len);      // e / len: the quotient's fractional part is >= 0.5 / len, far from float rounding
-      const int rem = e - i * len, bb = live ? rem / NL : 0, j = rem - bb * NL;
-      const int ij = i * NL + j;
-      const int cb = __shfl_sync(0xffffffffu, code, bb);
-      if (!live) continue;
-      double v = 0.0;
-      if (cb == -2) {
-        v = K[ij];
-#pragma unroll
-        for (int f = 0; f < 2 * DIM; ++f) if (own_off[f] >= 0) v += T[own_off[f] + ij];
-      } else if (cb >= 0) v = T[cb + ij];
-      if (overwrite) val[rs + e] = v; else if (v != 0.0) val[rs + e] += v;
+            for (int f = 0; f < NF; ++f) {
+              const int kd = (int)((sg >> (3 * f)) & 7);
+              if (kd == 1) v += T[(f * DG_MATS + 0) * MM + ij];               // SS_f
+              else if (kd == 2) v += T[((f ^ 1) * DG_MATS + 3) * MM + ij];    // NN of the neighbour's face f^1
+              else if (kd == 3) v += T[(f * DG_MATS + 4) * MM + ij];          // BD_f
+            }
+          } else if (role < 6) {
+            const int kd = (int)((sg >> (3 * role)) & 7);
+            v = kd == 1 ? T[(role * DG_MATS + 1) * MM + ij] : T[((role ^ 1) * DG_MATS + 2) * MM + ij];     // SN_f / NS of the neighbour's face
+          }
+          img[e] = v;
+        }
+        cur = sg;
+        __syncwarp();
+      }
+      if (overwrite) { for (int e = lane; e < total; e += 32) dst[e] = img[e]; }
+      else { for (int e = lane; e < total; e += 32) { const double v = img[e]; if (v != 0.0) dst[e] += v; } }
     }
   }
 }
@@ -303,6 +341,7 @@ static DgSpec dg_spec(Ctx* c, const GridOp& go, int child, int* slot)
 
 static double* dg_tables(Ctx* c, const DgSpec& S, int slot, double weight)
 {
+  MDB_REQUIRE(S.rule.m <= 3, MDB_EINVAL, "ConvectionDiffusionDG: face rule larger than the block-table kernel's staging (intorderadd too large)");
   if (!c->d_dgtab) c->d_dgtab = dalloc<double>((size_t)MDB_MAX_SP_PER_CHILD * MDB_MAX_CHILDREN * DG_SLOT_DOUBLES);
   double* T = c->d_dgtab + (size_t)slot * DG_SLOT_DOUBLES;
   const MeshDesc& m = c->mesh;
@@ -327,12 +366,23 @@ void jacobian_dg(Ctx* c, const GridOp& go, Matrix& M, int child, double weight, 
   const double* T = dg_tables(c, S, slot, weight);
   const double* K = c->d_Ae + (size_t)slot * MDB_MAXLOC * MDB_MAXLOC;
   const int64_t ncell = S.size / S.nl;
-  int grid = cdiv(ncell, 8);                                  // 8 warps per block, one cell per warp and pass
-  if (grid > 148 * 16) grid = 148 * 16;
-  if (m.dim == 2 && S.k == 1) MDB_LAUNCH(c, (k_dg_jacobian<2, 1>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
-  else if (m.dim == 2) MDB_LAUNCH(c, (k_dg_jacobian<2, 2>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
-  else if (S.k == 1) MDB_LAUNCH(c, (k_dg_jacobian<3, 1>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
-  else MDB_LAUNCH(c, (k_dg_jacobian<3, 2>), grid, 256, 0, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);
+  const int nf = 2 * m.dim;
+  const size_t img_bytes = (size_t)S.nl * (nf + 1) * S.nl * sizeof(double);     // one image per warp
+  int wpb = (int)(48 * 1024 / img_bytes);                                       // warps per block
+  if (wpb > 8) wpb = 8;
+  MDB_REQUIRE(wpb >= 1, MDB_EINVAL, "internal: DG cell image larger than shared memory");
+  // cells per warp and pass.  Measured at 131 072 cells per child (512^2 DG-Q2): 32 cells (4096 warps) 108 us, 16 cells (8192 warps)
+  // 136-148 us — fewer image rebuilds beat more warps; smaller batches only when the mesh cannot give every SM a few warps
+  int cpw = 32;
+  while (cpw > 4 && ncell / cpw < 148 * 16) cpw /= 2;
+  int grid = cdiv(ncell, cpw * wpb);
+  const int cap = 148 * (64 / wpb);
+  if (grid > cap) grid = cap;
+  const size_t smem = img_bytes * wpb;
+  if (m.dim == 2 && S.k == 1) MDB_LAUNCH(c, (k_dg_jacobian<2, 1>), grid, 32 * wpb, smem, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, cpw);
+  else if (m.dim == 2) MDB_LAUNCH(c, (k_dg_jacobian<2, 2>), grid, 32 * wpb, smem, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, cpw);
+  else if (S.k == 1) MDB_LAUNCH(c, (k_dg_jacobian<3, 1>), grid, 32 * wpb, smem, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, cpw);
+  else MDB_LAUNCH(c, (k_dg_jacobian<3, 2>), grid, 32 * wpb, smem, m, c->d_cell_sd, S, K, T, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, cpw);
 }
 
 void residual_dg(Ctx* c, const GridOp& go, int child, double weight, const double* d_x, double* d_r)
