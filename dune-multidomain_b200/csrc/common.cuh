@@ -233,6 +233,7 @@ struct Matrix {
   // sequential preconditioners (precond.cu): ready flags / row counter of the sync-free sweeps, ILU(0) factors
   int* d_ready = nullptr; unsigned long long* d_sweep_counter = nullptr; int sweep_epoch = 0; int32_t* d_sweep_perm = nullptr; ulonglong2* d_vrec = nullptr;
   double* d_ilu = nullptr; bool ilu_valid = false;
+  int32_t* d_cell_perm = nullptr; int64_t sweep_cells = 0; int sweep_cell_img = 0;   // all-DG matrices: cells in wavefront order (first row of each), image doubles per warp
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
 };

@@ -202,6 +202,115 @@ __global__ void k_sweep_keys(int64_t n, KeySpace sp, uint32_t* key, int32_t* row
   key[r] = ((uint32_t)ci << 24) | (uint32_t)(ix + 2 * iy + 4 * iz);
   row[r] = (int32_t)r;
 }
+// ---- QkDG matrices: the sweeps cell by cell -----------------------------------------------------------------------------------------
+// The rows of a DG cell form a dense diagonal block, so inside a cell every row depends on the row before it: with one warp per ROW
+// the critical path of a sweep is (rows per cell) x (cells on the longest wavefront) round trips through L2 (~1.8 us each).  Here a
+// warp owns a CELL: it stages the cell's value image (contiguous: the rows share their column set) and the iterate at the cell's
+// columns in shared memory, lane i carries row i, and the in-cell recurrence runs through shared memory — only whole cells talk to
+// each other through the record array.  Arithmetic and its order are those of the row kernel (= the sequential sweep): the row sum
+// in column order, one separately rounded product and one subtraction at a time, v_i += rhs / a_ii.
+//   forward :  row i = [lower blocks, new] [own columns < i, new] [own columns >= i, old] [upper blocks, old]
+//   backward:  row i = [lower blocks, old] [own columns <= i, old] [own columns > i, new] [upper blocks, new]
+// Cells are dispatched in wavefront order of their coordinates (cx + cy + cz inside a child block, child blocks in order), a
+// topological order of the cell dependency graph (face neighbours and earlier child blocks) — the deadlock argument of k_sweep.
+struct CellSpace { int nchild; int64_t offset[MDB_MAX_CHILDREN]; int nl[MDB_MAX_CHILDREN]; };
+
+template <bool FWD>
+__global__ void __launch_bounds__(256) k_sweep_cells(int64_t ncells, const int32_t* __restrict__ cell_perm, CellSpace sp, int img_doubles, int maxrow,
+                                                     const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                     const double* __restrict__ a, const double* __restrict__ d, ulonglong2* vt, unsigned epoch,
+                                                     unsigned long long* counter)
+{
+  extern __shared__ double s_cells[];
+  const int lane = threadIdx.x & 31;
+  double* aimg = s_cells + (size_t)(threadIdx.x >> 5) * (img_doubles + maxrow);
+  double* vv = aimg + img_doubles;
+  for (;;) {
+    unsigned long long k = 0;
+    if (lane == 0) k = atomicAdd(counter, 1ull);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= (unsigned long long)ncells) return;
+    const int64_t row0 = cell_perm[FWD ? (int64_t)k : ncells - 1 - (int64_t)k];
+    int ci = 0;
+    while (ci + 1 < sp.nchild && row0 >= sp.offset[ci + 1]) ++ci;
+    const int nl = sp.nl[ci];
+    const int64_t rs = rowptr[row0];
+    const int len = (int)(rowptr[row0 + 1] - rs);
+    if (len == 0) {                                       // rows without entries (a block no participant of the matrix's operators lives on): identity rows
+      if (lane < nl) st_record(vt + row0 + lane, d[row0 + lane], epoch);
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();
+    for (int e = lane; e < nl * len; e += 32) aimg[e] = a[rs + e];
+    // the iterate at the cell's columns (at most 64: two per lane).  All records are requested at once, so the old values the cell
+    // needs anyway arrive while it waits (warp-wide, as in k_sweep) for the columns of the cells it depends on
+    const int c1 = lane + 32;
+    const bool live0 = lane < len, live1 = c1 < len;
+    const int col0 = live0 ? colidx[rs + lane] : 0, col1 = live1 ? colidx[rs + c1] : 0;
+    const bool dep0 = live0 && (FWD ? (col0 < row0) : (col0 >= row0 + nl)), dep1 = live1 && (FWD ? (col1 < row0) : (col1 >= row0 + nl));
+    ulonglong2 w0 = make_ulonglong2(0ull, 0ull), w1 = w0;
+    if (live0) w0 = ld_record(vt + col0);
+    if (live1) w1 = ld_record(vt + col1);
+    for (int tries = 0;; ++tries) {
+      const bool ok0 = !dep0 || record_tagged(w0, epoch), ok1 = !dep1 || record_tagged(w1, epoch);
+      if (__all_sync(0xffffffffu, ok0 && ok1)) break;
+      __nanosleep(tries < 8 ? 32 : 128);
+      if (!ok0) w0 = ld_record(vt + col0);
+      if (!ok1) w1 = ld_record(vt + col1);
+    }
+    if (live0) vv[lane] = record_value(w0);
+    if (live1) vv[c1] = record_value(w1);
+    int own_start = 0;
+    {
+      const unsigned hit0 = __ballot_sync(0xffffffffu, live0 && col0 == (int)row0), hit1 = __ballot_sync(0xffffffffu, live1 && col1 == (int)row0);
+      own_start = hit0 ? __ffs(hit0) - 1 : 32 + __ffs(hit1) - 1;
+    }
+    __syncwarp();
+    const bool mine = lane < nl;
+    const double* ar = aimg + (size_t)(mine ? lane : 0) * len;
+    double acc = mine ? d[row0 + lane] : 0.0;
+    if (FWD) {
+      if (mine) for (int c = 0; c < own_start; ++c) acc = __dsub_rn(acc, __dmul_rn(ar[c], vv[c]));
+      for (int j = 0; j < nl; ++j) {
+        if (lane == j) {
+          for (int c = own_start + j; c < len; ++c) acc = __dsub_rn(acc, __dmul_rn(ar[c], vv[c]));
+          vv[own_start + j] = __dadd_rn(vv[own_start + j], __ddiv_rn(acc, ar[own_start + j]));
+        }
+        __syncwarp();
+        if (mine && lane > j) acc = __dsub_rn(acc, __dmul_rn(ar[own_start + j], vv[own_start + j]));
+      }
+    } else {
+      if (mine) for (int c = 0; c <= own_start + lane; ++c) acc = __dsub_rn(acc, __dmul_rn(ar[c], vv[c]));
+      for (int j = nl - 1; j >= 0; --j) {
+        if (lane == j) {
+          for (int c = own_start + j + 1; c < len; ++c) acc = __dsub_rn(acc, __dmul_rn(ar[c], vv[c]));
+          // the diagonal term a_jj v_j (old) was subtracted in the prefix; v_j += rhs / a_jj
+          vv[own_start + j] = __dadd_rn(vv[own_start + j], __ddiv_rn(acc, ar[own_start + j]));
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    if (mine) st_record(vt + row0 + lane, vv[own_start + lane], epoch);
+    __syncwarp();
+  }
+}
+
+__global__ void k_cell_keys(int64_t ncells, CellSpace sp, KeySpace ks, uint32_t* key, int32_t* row)
+{
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= ncells) return;
+  int ci = 0; int64_t first = 0;                       // cells are enumerated child block after child block
+  while (ci + 1 < sp.nchild) { const int64_t nc = (sp.offset[ci + 1] - sp.offset[ci]) / sp.nl[ci]; if (t < first + nc) break; first += nc; ++ci; }
+  const int64_t row0 = sp.offset[ci] + (t - first) * sp.nl[ci];
+  const KeyChild& ch = ks.ch[ci];
+  const int64_t p = ch.dof2lat[row0 - ch.offset];
+  const int cx = (int)(p % ch.n0) / ch.st, cy = (int)((p / ch.n0) % ch.n1) / ch.st, cz = (int)(p / ((int64_t)ch.n0 * ch.n1)) / ch.st;
+  key[t] = ((uint32_t)ci << 24) | (uint32_t)(cx + cy + cz);
+  row[t] = (int32_t)row0;
+}
+
 __global__ void k_iota(int64_t n, int32_t* row)
 {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -229,6 +338,33 @@ static void ensure_precond_state(Ctx* c, Matrix& M)
     lattice = lattice && (ch.k == 1 || ch.dg) && (int64_t)ch.lat_n[0] + 2 * (int64_t)ch.lat_n[1] + 4 * (int64_t)ch.lat_n[2] < (1 << 24);
     sp.ch[i].offset = ch.offset; sp.ch[i].n0 = ch.lat_n[0]; sp.ch[i].n1 = ch.lat_n[1]; sp.ch[i].dof2lat = ch.d_dof2lat; sp.ch[i].st = ch.dg ? ch.stride() : 1;
   }
+  // all-DG systems whose cell image fits a warp's share of shared memory: the cell-by-cell sweeps (k_sweep_cells)
+  {
+    bool all_dg = !c->children.empty() && !c->mesh.partitioned;
+    CellSpace cs; cs.nchild = (int)c->children.size();
+    int nlmax = 1; int64_t ncells = 0;
+    for (int i = 0; i < cs.nchild; ++i) {
+      const Child& ch = c->children[i];
+      all_dg = all_dg && ch.dg;
+      cs.offset[i] = ch.offset; cs.nl[i] = ch.nloc(c->mesh.dim);
+      if (cs.nl[i] > nlmax) nlmax = cs.nl[i];
+      ncells += ch.size / cs.nl[i];
+    }
+    static const bool off = getenv("MDB_SWEEP_ROWS") != nullptr;          // A/B switch: the row kernel on DG matrices
+    if (all_dg && !off && lattice && ncells > 0 && M.max_row <= 64 && (size_t)(nlmax * M.max_row + M.max_row) * sizeof(double) <= 6 * 1024) {
+      M.sweep_cells = ncells; M.sweep_cell_img = nlmax * M.max_row;
+      M.d_cell_perm = dalloc<int32_t>(ncells);
+      uint32_t* d_key = dalloc<uint32_t>(ncells); uint32_t* d_key2 = dalloc<uint32_t>(ncells);
+      int32_t* d_row = dalloc<int32_t>(ncells);
+      MDB_LAUNCH(c, k_cell_keys, cdiv(ncells, 256), 256, 0, ncells, cs, sp, d_key, d_row);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_row, M.d_cell_perm, (int)ncells, 0, 32, c->stream);
+      void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+      MDB_CUDA(cub::DeviceRadixSort::SortPairs(d_t, tb, d_key, d_key2, d_row, M.d_cell_perm, (int)ncells, 0, 32, c->stream)); c->launches++;
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(d_t); dfree(d_key); dfree(d_key2); dfree(d_row);
+    }
+  }
   if (!lattice) { MDB_LAUNCH(c, k_iota, cdiv(n, 256), 256, 0, n, M.d_sweep_perm); return; }
   uint32_t* d_key = dalloc<uint32_t>(n); uint32_t* d_key2 = dalloc<uint32_t>(n);
   int32_t* d_row = dalloc<int32_t>(n);
@@ -246,6 +382,16 @@ static void sweep(Ctx* c, Matrix& M, const double* a, const double* d)
 {
   MDB_CUDA(cudaMemsetAsync(M.d_sweep_counter, 0, sizeof(unsigned long long), c->stream));
   ++M.sweep_epoch;
+  if (M.sweep_cells > 0 && (MODE == SW_SSOR_FWD || MODE == SW_SSOR_BWD)) {
+    CellSpace cs; cs.nchild = (int)c->children.size();
+    for (int i = 0; i < cs.nchild; ++i) { cs.offset[i] = c->children[i].offset; cs.nl[i] = c->children[i].nloc(c->mesh.dim); }
+    int grid = 148 * 6;
+    if (grid > cdiv(M.sweep_cells, 8)) grid = cdiv(M.sweep_cells, 8);
+    const size_t smem = (size_t)8 * (M.sweep_cell_img + M.max_row) * sizeof(double);
+    MDB_LAUNCH(c, (k_sweep_cells<MODE == SW_SSOR_FWD>), grid, 256, smem, M.sweep_cells, M.d_cell_perm, cs, M.sweep_cell_img, M.max_row, M.d_rowptr, M.d_colidx,
+               a, d, M.d_vrec, (unsigned)M.sweep_epoch, M.d_sweep_counter);
+    return;
+  }
   int grid = 148 * 8;
   if (grid > cdiv(c->ndof, 8)) grid = cdiv(c->ndof, 8);
   MDB_LAUNCH(c, k_sweep<MODE>, grid, 256, 0, c->ndof, M.d_rowptr, M.d_colidx, M.d_diag, a, d, M.d_vrec, M.d_sweep_perm, (unsigned)M.sweep_epoch,
