@@ -26,7 +26,8 @@ namespace mdb {
 
 #define DG_MAXNL 27
 #define DG_MATS 5                                  // SS, SN, NS, NN, BD
-#define DG_SLOT_DOUBLES (6 * DG_MATS * DG_MAXNL * DG_MAXNL)
+#define DG_PHI_OFFSET (6 * DG_MATS * DG_MAXNL * DG_MAXNL)      // phi_i at the volume quadrature points, behind the block matrices
+#define DG_SLOT_DOUBLES (DG_PHI_OFFSET + DG_MAXNL * DG_MAXNL)
 
 struct DgSpec {
   int k, nl, st, subdomain;
@@ -86,6 +87,13 @@ template <int DIM> __global__ void __launch_bounds__(768) k_dg_face_matrices(int
     qk_grad<DIM>(k, ii, ls, gr); s_as[q][ii] = nrm * (jit * gr[axis]);      // An_F_s * tgradphi_s[i] = n . grad phi_i (inside cell)
     qk_grad<DIM>(k, ii, ln, gr); s_an[q][ii] = nrm * (jit * gr[axis]);      // ... of the outside cell, with the INSIDE normal
     if (ii == 0) s_w[q] = w;
+  }
+  if (f == 0 && ipow(R.m, DIM) <= DG_MAXNL) {                 // PHI[q * nl + i] for the residual's source term (rule of order 2k: nl points)
+    const int nqv = ipow(R.m, DIM);
+    for (int u = t; u < nqv * nl; u += blockDim.x) {
+      double xl[3], w; quad_point<DIM>(R, u / nl, xl, w);
+      T[DG_PHI_OFFSET + u] = qk_phi<DIM>(k, u % nl, xl);
+    }
   }
   __syncthreads();
   if (t >= nl * nl) return;
@@ -260,41 +268,83 @@ __global__ void __launch_bounds__(256) k_dg_jacobian(MeshDesc m, const uint8_t* 
 }
 
 // R(x)_row = (J x)_row + b_row:  b = lambda_volume (- int f phi_i) + on Dirichlet faces the g terms of alpha_boundary
-// (- theta g (n . grad phi_i) - penalty g phi_i) + on Neumann faces int j phi_i
+// (- theta g (n . grad phi_i) - penalty g phi_i) + on Neumann faces int j phi_i.
+// One thread per row; the block size is a multiple of the rows per cell, so the threads of a cell sit in one block: the volume rule
+// of order 2k has as many points as the cell has rows, thread li evaluates the source at point li (once per cell, not once per row)
+// and the cell's threads read each other's values from shared memory; phi_i at the volume points comes from a table (PHI, written
+// by k_dg_face_matrices) instead of nine Lagrange evaluations with their divisions per row.
 template <int DIM>
 __global__ void __launch_bounds__(128) k_dg_residual(MeshDesc m, const uint8_t* __restrict__ sd, DgSpec S, const double* __restrict__ K,
                                                      const double* __restrict__ T, double weight, double time, const double* __restrict__ x,
                                                      double* __restrict__ res)
 {
+  __shared__ double s_f[128];
   const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gi >= S.size) return;
-  DgRow<DIM> R; R.init(m, sd, S, gi);
-  if (!R.active) return;
-  double acc[DG_MAXNL];
-  R.own_row(S, K, T, acc);
-  double sum = 0.0;
-  for (int jj = 0; jj < S.nl; ++jj) sum += acc[jj] * x[R.first_own + jj];
-  for (int f = 0; f < 2 * DIM; ++f) {
-    const double* M = R.nb_row(S, T, f);
-    if (!M) continue;
-    double s2 = 0.0;
-    for (int jj = 0; jj < S.nl; ++jj) s2 += M[jj] * x[R.first_nb[f] + jj];
-    sum += s2;
-  }
+  const bool in = gi < S.size;
+  DgRow<DIM> R; R.init(m, sd, S, in ? gi : 0);
+  const bool act = in && R.active;
+  const int nl = S.nl, li = R.li;
   double lo[3], ext[3];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { lo[d] = m.coord(d, R.ijk[d]); ext[d] = m.coord(d, R.ijk[d] + 1) - lo[d]; }
+  const int nqv = ipow(S.rule.m, DIM);
+  const bool shared_f = S.f.kind != MDB_FN_ZERO && nqv == nl;      // uniform over the grid
+  if (shared_f) {
+    double fq = 0.0;
+    if (act) {
+      double detj = ext[0];
+#pragma unroll
+      for (int d = 1; d < DIM; ++d) detj *= ext[d];
+      double xl[3], w, xg[3]; quad_point<DIM>(S.rule, li, xl, w);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) xg[d] = lo[d] + xl[d] * ext[d];
+      fq = eval_function(S.f, DIM, xg, time) * (w * detj);
+    }
+    s_f[threadIdx.x] = fq;
+    __syncthreads();
+  }
+  if (!act) return;
+  double sum = 0.0;
+  {
+    const double* Kr = K + li * nl;
+    const double* Mr[2 * DIM];
+#pragma unroll
+    for (int f = 0; f < 2 * DIM; ++f) {
+      Mr[f] = nullptr;
+      if (R.kind[f] == 1) Mr[f] = T + ((size_t)f * DG_MATS + 0) * DG_MAXNL * DG_MAXNL + li * nl;              // SS_f
+      else if (R.kind[f] == 2) Mr[f] = T + ((size_t)(f ^ 1) * DG_MATS + 3) * DG_MAXNL * DG_MAXNL + li * nl;   // NN of the neighbour's face
+      else if (R.kind[f] == 3) Mr[f] = T + ((size_t)f * DG_MATS + 4) * DG_MAXNL * DG_MAXNL + li * nl;         // BD_f
+    }
+    const double* xo = x + R.first_own;
+    for (int jj = 0; jj < nl; ++jj) {
+      double v = Kr[jj];
+#pragma unroll
+      for (int f = 0; f < 2 * DIM; ++f) if (Mr[f]) v += Mr[f][jj];
+      sum += v * xo[jj];
+    }
+  }
+  for (int f = 0; f < 2 * DIM; ++f) {
+    const double* M = R.nb_row(S, T, f);
+    if (!M) continue;
+    const double* xn = x + R.first_nb[f];
+    double s2 = 0.0;
+    for (int jj = 0; jj < nl; ++jj) s2 += M[jj] * xn[jj];
+    sum += s2;
+  }
   double b = 0.0;
-  if (S.f.kind != MDB_FN_ZERO) {
+  if (shared_f) {
+    const double* PHI = T + DG_PHI_OFFSET;                          // PHI[q * nl + i] = phi_i at volume point q
+    const double* fc = s_f + (threadIdx.x - li);
+    for (int q = 0; q < nl; ++q) b -= fc[q] * PHI[q * nl + li];
+  } else if (S.f.kind != MDB_FN_ZERO) {
     double detj = ext[0];
 #pragma unroll
     for (int d = 1; d < DIM; ++d) detj *= ext[d];
-    const int nq = ipow(S.rule.m, DIM);
-    for (int q = 0; q < nq; ++q) {
+    for (int q = 0; q < nqv; ++q) {
       double xl[3], w, xg[3]; quad_point<DIM>(S.rule, q, xl, w);
 #pragma unroll
       for (int d = 0; d < DIM; ++d) xg[d] = lo[d] + xl[d] * ext[d];
-      b += -eval_function(S.f, DIM, xg, time) * qk_phi<DIM>(S.k, R.li, xl) * (w * detj);
+      b += -eval_function(S.f, DIM, xg, time) * qk_phi<DIM>(S.k, li, xl) * (w * detj);
     }
   }
   for (int f = 0; f < 2 * DIM; ++f) {
@@ -308,9 +358,9 @@ __global__ void __launch_bounds__(128) k_dg_residual(MeshDesc m, const uint8_t* 
       double ls[3], xg[3]; int tt = 0;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) { ls[d] = (d == axis) ? (double)side : pos[tt++]; xg[d] = lo[d] + ls[d] * ext[d]; }
-      const double phi = qk_phi<DIM>(S.k, R.li, ls), factor = w * area;
+      const double phi = qk_phi<DIM>(S.k, li, ls), factor = w * area;
       if (R.kind[f] == 4) { b += eval_function(S.j, DIM, xg, time) * phi * factor; continue; }
-      double gr[3]; qk_grad<DIM>(S.k, R.li, ls, gr);
+      double gr[3]; qk_grad<DIM>(S.k, li, ls, gr);
       const double gv = eval_function(S.g, DIM, xg, time);
       b += -gv * factor * S.theta * (nrm * (jit * gr[axis])) - penalty * gv * factor * phi;
     }
@@ -375,6 +425,8 @@ void jacobian_dg(Ctx* c, const GridOp& go, Matrix& M, int child, double weight, 
   // 136-148 us — fewer image rebuilds beat more warps; smaller batches only when the mesh cannot give every SM a few warps
   int cpw = 32;
   while (cpw > 4 && ncell / cpw < 148 * 16) cpw /= 2;
+  static const int wpb_env = getenv("MDB_DG_WPB") ? atoi(getenv("MDB_DG_WPB")) : 0;   // A/B switch for profiling only
+  if (wpb_env > 0 && wpb_env < wpb) wpb = wpb_env;
   int grid = cdiv(ncell, cpw * wpb);
   const int cap = 148 * (64 / wpb);
   if (grid > cap) grid = cap;
@@ -392,8 +444,9 @@ void residual_dg(Ctx* c, const GridOp& go, int child, double weight, const doubl
   if (S.size == 0 || slot < 0) return;
   const double* T = dg_tables(c, S, slot, weight);
   const double* K = c->d_Ae + (size_t)slot * MDB_MAXLOC * MDB_MAXLOC;
-  if (m.dim == 2) MDB_LAUNCH(c, k_dg_residual<2>, cdiv(S.size, 128), 128, 0, m, c->d_cell_sd, S, K, T, weight, c->time, d_x, d_r);
-  else MDB_LAUNCH(c, k_dg_residual<3>, cdiv(S.size, 128), 128, 0, m, c->d_cell_sd, S, K, T, weight, c->time, d_x, d_r);
+  const int bs = S.nl * (128 / S.nl);                          // a multiple of the rows per cell: the threads of a cell share a block
+  if (m.dim == 2) MDB_LAUNCH(c, k_dg_residual<2>, cdiv(S.size, bs), bs, 0, m, c->d_cell_sd, S, K, T, weight, c->time, d_x, d_r);
+  else MDB_LAUNCH(c, k_dg_residual<3>, cdiv(S.size, bs), bs, 0, m, c->d_cell_sd, S, K, T, weight, c->time, d_x, d_r);
 }
 
 } // namespace mdb
