@@ -13,6 +13,8 @@ import numpy as np
 # ---- enums (mirror include/mdb200.h) -----------------------------------------------------------
 FE_Q1, FE_Q2 = 1, 2
 FE_DGQ1, FE_DGQ2 = 11, 12
+FE_P1 = 21
+ETYPE_TRIANGLE = 2
 COND_EQUALITY, COND_SUBSET = 0, 1
 FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2, FN_DN_SOURCE = range(8)
 BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON = range(3)
@@ -164,6 +166,16 @@ class Lib:
         self._check(self._fn("mesh_structured")(C.c_void_p(self.ctx), dim, _ptr(nn, C.c_int64), _ptr(lo, C.c_double),
                                                 _ptr(up, C.c_double)), "mesh_structured")
         self.dim, self.n, self.ncells = dim, tuple(int(v) for v in n), int(np.prod(nn))
+        self.nchildren = 0
+
+    def mesh_unstructured(self, xy, conn):
+        """2-D triangle mesh: xy (nv, 2) float64, conn (ne, 3) vertex indices (mdb_mesh_unstructured)."""
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        cn = np.ascontiguousarray(conn, dtype=np.int64)
+        assert xy.ndim == 2 and xy.shape[1] == 2 and cn.ndim == 2 and cn.shape[1] == 3
+        self._check(self._fn("mesh_unstructured")(C.c_void_p(self.ctx), 2, C.c_int64(xy.shape[0]), _ptr(xy, C.c_double),
+                                                  C.c_int64(cn.shape[0]), ETYPE_TRIANGLE, _ptr(cn, C.c_int64)), "mesh_unstructured")
+        self.dim, self.n, self.ncells = 2, (int(cn.shape[0]),), int(cn.shape[0])
         self.nchildren = 0
 
     def mesh_partition(self, global_n, cell_offset, global_lower, global_upper):

@@ -218,6 +218,7 @@ void mdb_destroy(mdb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   reset_spaces(c);
+  um_free(c);
   dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_ftab_g); dfree(c->d_dgtab); dfree(c->d_scal); dfree(c->d_partial);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -241,6 +242,7 @@ int mdb_mesh_structured(mdb_ctx* c, int dim, const int64_t* n, const double* low
   MDB_API_BEGIN(c)
   MDB_REQUIRE(dim == 2 || dim == 3, MDB_EINVAL, "mdb_mesh_structured: dim must be 2 or 3");
   reset_spaces(c);
+  um_free(c);
   c->children.clear(); c->sps.clear(); c->cps.clear();
   MeshDesc& m = c->mesh;
   m = MeshDesc();
@@ -278,6 +280,26 @@ int mdb_mesh_partition(mdb_ctx* c, const int64_t* global_n, const int64_t* cell_
   MDB_API_END(c)
 }
 
+int mdb_mesh_unstructured(mdb_ctx* c, int dim, int64_t nv, const double* xyz, int64_t ne, int etype, const int64_t* conn)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(dim == 2 && etype == MDB_ETYPE_TRIANGLE, MDB_EINVAL, "mdb_mesh_unstructured: this build has device kernels for 2-D triangle meshes only");
+  MDB_REQUIRE(xyz && conn, MDB_EINVAL, "mdb_mesh_unstructured: null pointer");
+  reset_spaces(c);
+  c->children.clear(); c->sps.clear(); c->cps.clear();
+  um_ingest(c, nv, xyz, ne, conn);
+  MeshDesc& m = c->mesh;
+  m = MeshDesc();
+  m.dim = 2;
+  m.n[0] = (int)ne; m.n[1] = 1; m.n[2] = 1;          // ncells() = ne: the per-cell subdomain calls are shared with the structured path
+  for (int d = 0; d < 3; ++d) { m.gn[d] = m.n[d]; m.off[d] = 0; m.lower[d] = 0; m.glower[d] = 0; m.h[d] = 1; }
+  m.partitioned = 0;
+  dfree(c->d_cell_sd);
+  c->d_cell_sd = dalloc<uint8_t>(ne);
+  c->have_mesh = true; c->have_sd = false;
+  MDB_API_END(c)
+}
+
 int mdb_subdomains(mdb_ctx* c, const uint8_t* bits)
 {
   MDB_API_BEGIN(c)
@@ -304,6 +326,7 @@ int mdb_subdomains_halfspace(mdb_ctx* c, int axis, double threshold, int sd_belo
   MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_subdomains_halfspace: need a mesh, before mdb_finalize");
   MDB_REQUIRE(axis >= 0 && axis < c->mesh.dim && sd_below >= 0 && sd_below < 8 && sd_above >= 0 && sd_above < 8, MDB_EINVAL,
               "mdb_subdomains_halfspace: bad axis or subdomain index");
+  MDB_REQUIRE(!c->um, MDB_EINVAL, "mdb_subdomains_halfspace: structured meshes only (use mdb_subdomains)");
   MDB_LAUNCH(c, k_halfspace, cdiv(c->mesh.ncells(), 256), 256, 0, c->mesh, axis, threshold, sd_below, sd_above, c->d_cell_sd);
   c->have_sd = true;
   MDB_API_END(c)
@@ -314,7 +337,8 @@ int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
   if (!c) return MDB_EINVAL;
   try {
     MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_space: need a mesh, before mdb_finalize");
-    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2 || fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2, MDB_EINVAL, "mdb_add_space: unknown finite element");
+    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2 || fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2 || fe_kind == MDB_FE_P1, MDB_EINVAL, "mdb_add_space: unknown finite element");
+    MDB_REQUIRE((fe_kind == MDB_FE_P1) == (c->um != nullptr), MDB_EINVAL, "mdb_add_space: simplex meshes carry MDB_FE_P1 spaces, structured cube meshes the Qk / QkDG spaces");
     MDB_REQUIRE(subdomain >= -1 && subdomain < 8, MDB_EINVAL, "mdb_add_space: bad subdomain");
     MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_space: too many child spaces");
     Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_DGQ1) ? 1 : 2; ch.subdomain = subdomain;
@@ -329,6 +353,7 @@ int mdb_add_coupling_space(mdb_ctx* c, int fe_kind, int left_cond_kind, uint32_t
 {
   if (!c) return MDB_EINVAL;
   try {
+    MDB_REQUIRE(!c->um, MDB_EINVAL, "mdb_add_coupling_space: not supported on unstructured meshes in this build");
     MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_coupling_space: need a mesh, before mdb_finalize");
     MDB_REQUIRE(fe_kind == MDB_FE_Q1, MDB_EINVAL, "mdb_add_coupling_space: only Q1 coupling spaces (vertex-attached mortar DOFs) have device kernels");
     MDB_REQUIRE(c->mesh.dim >= 2, MDB_EINVAL, "mdb_add_coupling_space: needs dim >= 2");
@@ -371,6 +396,10 @@ int mdb_add_subproblem(mdb_ctx* c, int op_id, const void* params, size_t nbytes,
     MDB_REQUIRE(c->children[children[0]].dg == (op_id == MDB_OP_CONVDIFF_DG), MDB_EINVAL,
                 "mdb_add_subproblem: QkDG spaces carry ConvectionDiffusionDG, conforming spaces Poisson / L2 (closed operator set)");
     (void)gauss1d(sp.quad_order());
+    if (c->um) {
+      MDB_REQUIRE(op_id == MDB_OP_POISSON || op_id == MDB_OP_L2, MDB_EINVAL, "mdb_add_subproblem: unstructured meshes carry Poisson / L2 in this build");
+      MDB_REQUIRE(sp.quad_order() >= 0 && sp.quad_order() <= 4, MDB_EINVAL, "mdb_add_subproblem: simplex quadrature rules up to order 4");
+    }
     c->sps.push_back(sp);
     return (int)c->sps.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
@@ -398,6 +427,7 @@ int mdb_add_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, i
       MDB_REQUIRE(cp.nd.mode >= MDB_ND_MODE_NEUMANN && cp.nd.mode <= MDB_ND_MODE_BOTH, MDB_EINVAL, "mdb_add_coupling: bad Neumann-Dirichlet coupling mode");
       MDB_REQUIRE(!c->mesh.partitioned, MDB_EINVAL, "mdb_add_coupling: the Neumann-Dirichlet coupling is not supported on a partitioned mesh");
     } else throw Error(MDB_EINVAL, "mdb_add_coupling: unknown coupling operator");
+    MDB_REQUIRE(!c->um || op_id == MDB_OP_PROPFLOW_COUPLING, MDB_EINVAL, "mdb_add_coupling: unstructured meshes carry ProportionalFlowCoupling in this build");
     c->cps.push_back(cp);
     return (int)c->cps.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
@@ -456,7 +486,7 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   MDB_REQUIRE(c->have_mesh && c->have_sd, MDB_ESTATE, "mdb_finalize: mesh and subdomains must be set");
   MDB_REQUIRE(!c->children.empty(), MDB_ESTATE, "mdb_finalize: no child spaces");
   c->phase_begin("dofmap");
-  build_dofmap(c);
+  if (c->um) um_build_dofmap(c); else build_dofmap(c);
   c->phase_end();
   if (c->mesh.partitioned) setup_partition(c);
   c->finalized = true;
@@ -468,7 +498,7 @@ int mdb_get_dofmap(mdb_ctx* c, int64_t* cell_ptr, int64_t* cell_dofs)
 {
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_get_dofmap: not finalized");
-  export_dofmap(c, cell_ptr, cell_dofs);
+  if (c->um) um_export_dofmap(c, cell_ptr, cell_dofs); else export_dofmap(c, cell_ptr, cell_dofs);
   MDB_API_END(c)
 }
 
@@ -487,7 +517,7 @@ int mdb_constraints_assemble(mdb_ctx* c, const int* subproblems, const mdb_bctyp
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_constraints_assemble: not finalized");
   for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
   c->phase_begin("constraints");
-  assemble_constraints(c, subproblems, bcs, n);
+  if (c->um) um_assemble_constraints(c, subproblems, bcs, n); else assemble_constraints(c, subproblems, bcs, n);
   rebuild_conlist(c);
   c->phase_end();
   if (nconstrained) *nconstrained = c->ncon;
@@ -520,7 +550,8 @@ int mdb_interpolate(mdb_ctx* c, const int* subproblems, const mdb_function* fns,
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_interpolate: not finalized");
   VecInOut vx(c, x, c->ndof, 0, true);
-  interpolate(c, subproblems, fns, n, time, vx.d);
+  for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
+  if (c->um) um_interpolate(c, subproblems, fns, n, time, vx.d); else interpolate(c, subproblems, fns, n, time, vx.d);
   vx.commit();
   MDB_API_END(c)
 }
@@ -541,7 +572,7 @@ int mdb_gridoperator_create(mdb_ctx* c, const int* subproblems, int nsp, const i
     GridOp go;
     for (int i = 0; i < nsp; ++i) { MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index"); go.sps.push_back(subproblems[i]); }
     for (int i = 0; i < ncp; ++i) { MDB_REQUIRE(couplings[i] >= 0 && couplings[i] < (int)c->cps.size(), MDB_EINVAL, "bad coupling index"); go.cps.push_back(couplings[i]); }
-    build_facelists(c, go);
+    if (c->um) um_build_facelists(c, go); else build_facelists(c, go);
     c->gos.push_back(go);
     return (int)c->gos.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
@@ -556,7 +587,7 @@ int mdb_matrix_create(mdb_ctx* c, const int* gos, int ngos, int64_t* nnz)
     Matrix m;
     for (int i = 0; i < ngos; ++i) { MDB_REQUIRE(gos[i] >= 0 && gos[i] < (int)c->gos.size(), MDB_EINVAL, "bad grid operator handle"); m.gos.push_back(gos[i]); }
     c->phase_begin("pattern");
-    build_pattern(c, m);
+    if (c->um) um_build_pattern(c, m); else build_pattern(c, m);
     c->phase_end();
     if (nnz) *nnz = m.nnz;
     c->mats.push_back(m);
@@ -625,6 +656,7 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   MDB_GO(c, go)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vr(c, r, c->ndof, 1, true);
+  if (c->um) { um_residual(c, G, weight, vx.d, vr.d); vr.commit(); return MDB_OK; }
   static const bool serial = getenv("MDB_RESIDUAL_SERIAL") != nullptr;          // A/B switch for profiling only
   if (!serial && residual_can_split(c, G)) {
     // main: element matrices -> [fork] -> streamed uniform rows of every child (issue / shared-memory bound) --------> [join] -> constrain
@@ -689,6 +721,7 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   MDB_GO(c, go)
   MDB_MAT(c, mat)
   M.dinv_valid = false; M.ilu_valid = false;
+  if (c->um) { VecIn vx(c, x, c->ndof, 0); um_jacobian(c, G, M, weight, vx.d, overwrite != 0); return MDB_OK; }
   // The volume operators of the closed set are linear: their Jacobian does not read x.  Only the finite-difference
   // coupling Jacobian does, and only at the DOFs of the interface cells.  With a HOST vector the upload therefore runs on
   // the copy stream concurrently with the volume kernels, and from pinned memory only the needed entries are fetched.
@@ -946,7 +979,7 @@ int mdb_onestep_apply(mdb_ctx* c, int go0, int go1, int mat, const int* subprobl
     const double tr = time + D[r] * dt;
     c->time = tr;
     MDB_CUDA(cudaMemsetAsync(x, 0, nd * sizeof(double), c->stream));
-    interpolate(c, subproblems, g, n, tr, x);
+    if (c->um) um_interpolate(c, subproblems, g, n, tr, x); else interpolate(c, subproblems, g, n, tr, x);
     MDB_LAUNCH(c, k_copy_nonconstrained, cdiv(nd, 256), 256, 0, xs[r - 1], x, c->d_constrained, nd);
     if ((rc = mdb_jacobian(c, go1, mat, A[r - 1][r], x, 1)) != MDB_OK) return rc;
     if ((rc = mdb_jacobian(c, go0, mat, B[r - 1][r] * dt, x, 0)) != MDB_OK) return rc;

@@ -198,6 +198,17 @@ struct FaceList {      // interface faces on which one coupling fires, in traver
   int64_t n = 0;
 };
 
+// Unstructured simplex mesh (2-D triangles; unstructured.cu): the mesh a grid manager such as UGGrid hands to the reference's
+// drivers after GmshReader (test/stokesdarcy2.cc:575-604).  Cell and vertex indices are the caller's ([UPSTREAM] leaf index order).
+struct UMesh {
+  int64_t nv = 0, ne = 0;
+  double* d_xy = nullptr;        // [nv][2] vertex coordinates
+  int32_t* d_conn = nullptr;     // [ne][3] vertex indices, local vertex i <-> P1 shape function i
+  int32_t* d_nbr = nullptr;      // [ne][3] neighbour over face f (DUNE simplex numbering: face 0 = {0,1}, 1 = {0,2}, 2 = {1,2}); -1 = boundary
+  int32_t* d_v2c_ptr = nullptr;  // [nv+1] vertex -> incident cells
+  int32_t* d_v2c = nullptr;      // [3 ne] 4 * cell + local vertex index, cells ascending per vertex
+};
+
 struct GridOp {
   std::vector<int> sps, cps;
   std::vector<FaceList> faces;   // one per coupling
@@ -258,6 +269,7 @@ struct Ctx {
   int64_t h2d_bytes = 0, d2h_bytes = 0;
 
   MeshDesc mesh{};
+  UMesh* um = nullptr;               // non-null: unstructured mesh (mesh.dim = 2, mesh.n = {ne, 1, 1} so that ncells() holds)
   bool have_mesh = false, have_sd = false, finalized = false;
   uint8_t* d_cell_sd = nullptr;
   std::vector<Child> children;
@@ -373,6 +385,17 @@ void setup_partition(Ctx* c);                       // multigpu.cu: ownership fl
 void allreduce_scalars(Ctx* c, double* d_vals, int n);
 void halo_exchange(Ctx* c, double* d_x);
 bool halo_timed_out(Ctx* c);
+// unstructured.cu: the same steps on an unstructured triangle mesh with P1 spaces
+void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn);
+void um_free(Ctx* c);
+void um_build_dofmap(Ctx* c);
+void um_export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs);
+void um_assemble_constraints(Ctx* c, const int* sps, const mdb_bctype* bcs, int n);
+void um_interpolate(Ctx* c, const int* sps, const mdb_function* fns, int n, double t, double* d_x);
+void um_build_facelists(Ctx* c, GridOp& go);
+void um_build_pattern(Ctx* c, Matrix& m);
+void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
+void um_jacobian(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x, bool overwrite);
 void precond_apply(Ctx* c, Matrix& m, int kind, int sweeps, const double* d_d, double* d_v);   // precond.cu: SSOR / ILU0
 
 template <typename T> inline T* dalloc(size_t n)

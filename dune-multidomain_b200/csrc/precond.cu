@@ -331,7 +331,7 @@ static void ensure_precond_state(Ctx* c, Matrix& M)
   // (same key; the stable sort keeps them in index order) and on the cells at -x, -y, -z (smaller key) — the same key on cell
   // coordinates is topological.
   M.d_sweep_perm = dalloc<int32_t>(n);
-  bool lattice = true;
+  bool lattice = c->um == nullptr;            // unstructured meshes: index order
   KeySpace sp; sp.nchild = (int)c->children.size();
   for (int i = 0; i < sp.nchild; ++i) {
     const Child& ch = c->children[i];

@@ -450,7 +450,7 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
     return;
   }
   if (variant == 4) {
-    bool q1 = true;
+    bool q1 = c->um == nullptr;               // the stencil kernel needs lattice blocks
     for (const Child& ch : c->children) q1 = q1 && ch.k == 1 && !ch.dg;
     if (q1) {
       SpmvSpace sp; sp.nchild = (int)c->children.size(); sp.nchunks = 0;

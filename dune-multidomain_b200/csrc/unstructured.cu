@@ -1,0 +1,775 @@
+// unstructured.cu — the assembly path on an unstructured conforming triangle mesh with P1 spaces: the mesh class the reference's
+// Stokes-Darcy drivers read with GmshReader<UGGrid<2>> (test/stokesdarcy2.cc:575-604) and the north star's "refined gmsh meshes".
+//
+// Same design as the structured path, without the lattice:
+//   DOF map      vertex flags -> scan -> assign per child (ascending vertex index of the child's subdomain,
+//                multidomaingridfunctionspace.hh:308-369 with [UPSTREAM] (ii),(iii))
+//   pattern      one thread per row: union of the links of the incident cells (FullVolumePattern) and of the coupling faces
+//                of those cells (couplingutilities.hh:35-47), sorted-unique insertion, count + fill
+//   Jacobian     owner-computes rows: the thread of a row sums its incident cells in ascending cell order (the reference's
+//                accumulation order) and writes every stored entry once; coupling faces add by atomics afterwards
+//   residual     owner-computes rows for the volume terms; boundary and coupling faces add by atomics
+// Geometry is per element (affine): gradients of the P1 shape functions and the integration element are recomputed from the
+// vertex coordinates where they are used (3 coordinates pairs per cell = 48 B against 72 B of matrix row written).
+// Compiled with --fmad=false: the finite-difference coupling Jacobian must see the reference's operation order.
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+
+namespace mdb {
+
+namespace {
+
+constexpr int UM_MAXROW = 128;     // column capacity of the per-thread sorted set while a row's pattern is enumerated
+
+struct UMDev {
+  int64_t nv, ne;
+  const double* xy; const int32_t* conn; const int32_t* nbr; const int32_t* v2c_ptr; const int32_t* v2c; const uint8_t* sd;
+};
+struct UMSpace { int nchild; int64_t offset[MDB_MAX_CHILDREN]; const int32_t* v2d[MDB_MAX_CHILDREN]; const int32_t* d2v[MDB_MAX_CHILDREN]; int64_t size[MDB_MAX_CHILDREN]; };
+struct UMSp { int op_id, child, cond_kind; uint32_t mask; int quad_order; mdb_poisson_params P; };
+struct UMCp { int op_id, childL, childR, kindL, kindR; uint32_t maskL, maskR; int jac_mode; double intensity; };
+struct UMOps { int nsp, ncp; UMSp sp[8]; UMCp cp[4]; };
+
+UMDev um_dev(const Ctx* c)
+{
+  const UMesh* u = c->um;
+  UMDev m; m.nv = u->nv; m.ne = u->ne; m.xy = u->d_xy; m.conn = u->d_conn; m.nbr = u->d_nbr; m.v2c_ptr = u->d_v2c_ptr; m.v2c = u->d_v2c; m.sd = c->d_cell_sd;
+  return m;
+}
+UMSpace um_space(const Ctx* c)
+{
+  UMSpace S; S.nchild = (int)c->children.size();
+  for (int i = 0; i < S.nchild; ++i) { S.offset[i] = c->children[i].offset; S.v2d[i] = c->children[i].d_lat2dof; S.d2v[i] = c->children[i].d_dof2lat; S.size[i] = c->children[i].size; }
+  return S;
+}
+UMOps um_ops(const Ctx* c, const std::vector<int>& sps, const std::vector<int>& cps)
+{
+  UMOps O; O.nsp = 0; O.ncp = 0;
+  MDB_REQUIRE(sps.size() <= 8 && cps.size() <= 4, MDB_EINVAL, "unstructured mesh: at most 8 subproblems and 4 couplings per grid operator");
+  for (int s : sps) {
+    const SubProblemDesc& d = c->sps[s];
+    UMSp& o = O.sp[O.nsp++];
+    o.op_id = d.op_id; o.child = d.children[0]; o.cond_kind = d.cond_kind; o.mask = d.mask; o.quad_order = d.quad_order(); o.P = d.poisson;
+  }
+  for (int q : cps) {
+    const CouplingDesc& d = c->cps[q];
+    const SubProblemDesc& L = c->sps[d.local_sp]; const SubProblemDesc& R = c->sps[d.remote_sp];
+    UMCp& o = O.cp[O.ncp++];
+    o.op_id = d.op_id; o.childL = L.children[0]; o.childR = R.children[0]; o.kindL = L.cond_kind; o.kindR = R.cond_kind; o.maskL = L.mask; o.maskR = R.mask;
+    o.jac_mode = d.jac_mode; o.intensity = d.propflow.intensity;
+  }
+  return O;
+}
+
+// ---- triangle geometry and rules ---------------------------------------------------------------------------------------
+// Reference triangle (0,0),(1,0),(0,1) [UPSTREAM dune-geometry]; x = p0 + J xi, J = [p1 - p0 | p2 - p0].
+struct Tri {
+  double p[3][2];
+  double t[2][2];      // J^{-T}
+  double ie;           // integration element |det J|
+};
+__device__ inline Tri tri_geometry(const UMDev& m, int cell)
+{
+  Tri g;
+  for (int i = 0; i < 3; ++i) { const int v = m.conn[3 * cell + i]; g.p[i][0] = m.xy[2 * v]; g.p[i][1] = m.xy[2 * v + 1]; }
+  const double ax = g.p[1][0] - g.p[0][0], ay = g.p[1][1] - g.p[0][1];
+  const double bx = g.p[2][0] - g.p[0][0], by = g.p[2][1] - g.p[0][1];
+  const double det = ax * by - ay * bx;
+  g.t[0][0] = by / det; g.t[0][1] = -ay / det;
+  g.t[1][0] = -bx / det; g.t[1][1] = ax / det;
+  g.ie = fabs(det);
+  return g;
+}
+// gradients of the P1 shape functions: J^{-T} applied to (-1,-1), (1,0), (0,1)
+__device__ inline void tri_gradients(const Tri& g, double gp[3][2])
+{
+  const double js[3][2] = {{-1.0, -1.0}, {1.0, 0.0}, {0.0, 1.0}};
+  for (int i = 0; i < 3; ++i)
+    for (int d = 0; d < 2; ++d) { double s = 0.0; s += g.t[d][0] * js[i][0]; s += g.t[d][1] * js[i][1]; gp[i][d] = s; }
+}
+__device__ inline void p1_basis(double x, double y, double phi[3]) { phi[0] = 1.0 - x - y; phi[1] = x; phi[2] = y; }
+
+// [UPSTREAM] Dune::QuadratureRules<DF,2>::rule(simplex, order): published symmetric rules on the reference triangle (weights sum
+// to 1/2): order <= 1 centroid; order 2 the 3-point interior rule; orders 3, 4 the 6-point degree-4 rule (Dunavant).
+__device__ inline int tri_rule(int order, double pts[6][2], double w[6])
+{
+  if (order <= 1) { pts[0][0] = 1.0 / 3.0; pts[0][1] = 1.0 / 3.0; w[0] = 0.5; return 1; }
+  if (order == 2) {
+    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+    pts[0][0] = a; pts[0][1] = a; pts[1][0] = b; pts[1][1] = a; pts[2][0] = a; pts[2][1] = b;
+    w[0] = w[1] = w[2] = 1.0 / 6.0; return 3;
+  }
+  const double a = 0.445948490915965, wa = 0.5 * 0.223381589678011;
+  const double b = 0.091576213509771, wb = 0.5 * 0.109951743655322;
+  const double a2 = 1.0 - 2.0 * a, b2 = 1.0 - 2.0 * b;
+  pts[0][0] = a; pts[0][1] = a; pts[1][0] = a2; pts[1][1] = a; pts[2][0] = a; pts[2][1] = a2;
+  pts[3][0] = b; pts[3][1] = b; pts[4][0] = b2; pts[4][1] = b; pts[5][0] = b; pts[5][1] = b2;
+  w[0] = w[1] = w[2] = wa; w[3] = w[4] = w[5] = wb; return 6;
+}
+// Gauss-Legendre on [0,1], order p -> ceil((p+1)/2) points (<= 3 here)
+__device__ inline int line_rule(int order, double x[3], double w[3])
+{
+  const int m = (order + 2) / 2;
+  if (m <= 1) { x[0] = 0.5; w[0] = 1.0; return 1; }
+  if (m == 2) { const double a = 0.5 / sqrt(3.0); x[0] = 0.5 - a; x[1] = 0.5 + a; w[0] = 0.5; w[1] = 0.5; return 2; }
+  const double a = 0.5 * sqrt(3.0 / 5.0);
+  x[0] = 0.5 - a; x[1] = 0.5; x[2] = 0.5 + a; w[0] = 5.0 / 18.0; w[1] = 8.0 / 18.0; w[2] = 5.0 / 18.0; return 3;
+}
+// local vertices of face f and the reference corners
+__device__ __constant__ int c_face_v[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+__device__ __constant__ double c_ref[3][2] = {{0.0, 0.0}, {1.0, 0.0}, {0.0, 1.0}};
+
+__device__ inline bool um_applies(const UMSp& s, uint32_t sd) { return cond_applies(s.cond_kind, s.mask, sd); }
+
+__device__ inline int um_find(const int32_t* cols, int len, int32_t col)
+{
+  int lo = 0, hi = len - 1;
+  while (lo <= hi) { const int mid = (lo + hi) >> 1; const int32_t v = cols[mid]; if (v == col) return mid; if (v < col) lo = mid + 1; else hi = mid - 1; }
+  return -1;
+}
+
+// ---- DOF map --------------------------------------------------------------------------------------------------------------
+__global__ void k_um_mark(UMDev m, int subdomain, int32_t* flag)
+{
+  const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= m.nv) return;
+  int f = 0;
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const int cell = m.v2c[e] >> 2;
+    if (subdomain < 0 || ((m.sd[cell] >> subdomain) & 1)) { f = 1; break; }
+  }
+  flag[v] = f;
+}
+__global__ void k_um_assign(int64_t nv, const int32_t* flag, const int32_t* scan, int32_t* v2d, int32_t* d2v)
+{
+  const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  if (flag[v]) { v2d[v] = scan[v]; d2v[scan[v]] = (int32_t)v; } else v2d[v] = -1;
+}
+
+// ---- constraints + interpolation ------------------------------------------------------------------------------------------
+struct UMBcs { int n; UMSp sp[8]; mdb_bctype bc[8]; mdb_function fn[8]; };
+
+// constraintsfunctors.hh:75-103: on a face whose outside cell is not in the subproblem (physical boundary or subdomain interface)
+// the boundary constraints run; [UPSTREAM] ConformingDirichletConstraints asks the predicate at the face centre and constrains the
+// coefficients attached to the face's sub-entities (P1: its two vertices).
+__global__ void k_um_constraints(UMDev m, UMSpace S, UMBcs B, uint8_t* constrained)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= 3 * m.ne) return;
+  const int cell = (int)(i / 3), f = (int)(i % 3);
+  const uint32_t sd = m.sd[cell];
+  const int nb = m.nbr[3 * cell + f];
+  const bool interior = nb >= 0;
+  const int va = m.conn[3 * cell + c_face_v[f][0]], vb = m.conn[3 * cell + c_face_v[f][1]];
+  double xg[2];
+  for (int d = 0; d < 2; ++d) { const double pa = m.xy[2 * va + d], pb = m.xy[2 * vb + d]; xg[d] = pa + 0.5 * (pb - pa); }
+  for (int q = 0; q < B.n; ++q) {
+    const UMSp& s = B.sp[q];
+    if (!um_applies(s, sd)) continue;
+    if (interior && um_applies(s, m.sd[nb])) continue;
+    if (eval_bctype(B.bc[q], 2, xg, !interior) != 0) continue;
+    const int32_t da = S.v2d[s.child][va], db = S.v2d[s.child][vb];
+    if (da >= 0) constrained[S.offset[s.child] + da] = 1;
+    if (db >= 0) constrained[S.offset[s.child] + db] = 1;
+  }
+}
+
+// interpolate.hh:35-73: cells in order, every subproblem that applies writes f at the cell's vertices; per DOF the last writer wins
+__global__ void k_um_interpolate(UMDev m, UMSpace S, UMBcs B, int child, double t, double* x)
+{
+  const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= S.size[child]) return;
+  const int v = S.d2v[child][d];
+  const double xv[2] = {m.xy[2 * v], m.xy[2 * v + 1]};
+  bool have = false; double val = 0.0;
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const uint32_t sd = m.sd[m.v2c[e] >> 2];
+    for (int q = 0; q < B.n; ++q)
+      if (B.sp[q].child == child && um_applies(B.sp[q], sd)) { val = eval_function(B.fn[q], 2, xv, t); have = true; }
+  }
+  if (have) x[S.offset[child] + d] = val;
+}
+
+// ---- coupling faces ---------------------------------------------------------------------------------------------------------
+__global__ void k_um_face_flags(UMDev m, UMCp cp, int32_t* flag)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= 3 * m.ne) return;
+  const int nb = m.nbr[i];
+  flag[i] = (nb >= 0 && cond_applies(cp.kindL, cp.maskL, m.sd[i / 3]) && cond_applies(cp.kindR, cp.maskR, m.sd[nb])) ? 1 : 0;
+}
+__global__ void k_um_face_compact(int64_t n, const int32_t* flag, const int32_t* scan, int32_t* cell, int8_t* face)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  cell[scan[i]] = (int32_t)(i / 3); face[scan[i]] = (int8_t)(i % 3);
+}
+
+// ---- pattern ----------------------------------------------------------------------------------------------------------------
+__device__ inline void um_insert(int32_t* cols, int& n, int32_t col, int* overflow)
+{
+  int pos = n;
+  while (pos > 0 && cols[pos - 1] > col) --pos;
+  if (pos > 0 && cols[pos - 1] == col) return;
+  if (n >= UM_MAXROW) { *overflow = 1; return; }
+  for (int k = n; k > pos; --k) cols[k] = cols[k - 1];
+  cols[pos] = col; ++n;
+}
+__device__ inline void um_insert_cell(const UMDev& m, const UMSpace& S, int child, int cell, int32_t* cols, int& n, int* overflow)
+{
+  for (int j = 0; j < 3; ++j) {
+    const int32_t d = S.v2d[child][m.conn[3 * cell + j]];
+    if (d >= 0) um_insert(cols, n, (int32_t)(S.offset[child] + d), overflow);
+  }
+}
+// columns of the row of vertex v in child block `child`
+__device__ int um_row_columns(const UMDev& m, const UMSpace& S, const UMOps& O, int child, int v, int32_t* cols, int* overflow)
+{
+  int n = 0;
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const int cell = m.v2c[e] >> 2;
+    const uint32_t sd = m.sd[cell];
+    for (int s = 0; s < O.nsp; ++s)
+      if (O.sp[s].child == child && um_applies(O.sp[s], sd)) um_insert_cell(m, S, child, cell, cols, n, overflow);
+    for (int q = 0; q < O.ncp; ++q) {
+      const UMCp& cp = O.cp[q];
+      // pattern_coupling links lfsv_s x lfsu_n and lfsv_n x lfsu_s of every face the coupling fires on (couplingutilities.hh:35-47)
+      if (cp.childL == child && cond_applies(cp.kindL, cp.maskL, sd))
+        for (int f = 0; f < 3; ++f) { const int nb = m.nbr[3 * cell + f]; if (nb >= 0 && cond_applies(cp.kindR, cp.maskR, m.sd[nb])) um_insert_cell(m, S, cp.childR, nb, cols, n, overflow); }
+      if (cp.childR == child && cond_applies(cp.kindR, cp.maskR, sd))
+        for (int f = 0; f < 3; ++f) { const int nb = m.nbr[3 * cell + f]; if (nb >= 0 && cond_applies(cp.kindL, cp.maskL, m.sd[nb])) um_insert_cell(m, S, cp.childL, nb, cols, n, overflow); }
+    }
+  }
+  return n;
+}
+__global__ void k_um_pattern_count(UMDev m, UMSpace S, UMOps O, int child, int32_t* count, int* overflow)
+{
+  const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= S.size[child]) return;
+  int32_t cols[UM_MAXROW];
+  count[S.offset[child] + d] = um_row_columns(m, S, O, child, S.d2v[child][d], cols, overflow);
+}
+__global__ void k_um_pattern_fill(UMDev m, UMSpace S, UMOps O, int child, const int64_t* rowptr, int32_t* colidx, int32_t* diag)
+{
+  const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= S.size[child]) return;
+  int32_t cols[UM_MAXROW]; int ov = 0;
+  const int64_t row = S.offset[child] + d;
+  const int n = um_row_columns(m, S, O, child, S.d2v[child][d], cols, &ov);
+  const int64_t p0 = rowptr[row];
+  int dg = -1;
+  for (int k = 0; k < n; ++k) { colidx[p0 + k] = cols[k]; if (cols[k] == (int32_t)row) dg = k; }
+  diag[row] = dg;
+}
+__global__ void k_um_widen(int64_t n, const int32_t* count, const int64_t* scan, int64_t* rowptr)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) rowptr[i] = scan[i];
+  if (i == n - 1) rowptr[n] = scan[i] + count[i];
+}
+__global__ void k_um_to64(int64_t n, const int32_t* in, int64_t* out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// ---- volume terms ---------------------------------------------------------------------------------------------------------------
+// Row i of the element matrix of subproblem s on a cell: Poisson ([UPSTREAM] PDELab::Poisson / test/instationarypoissonoperator.hh:52-77)
+// or L2 ([UPSTREAM] PDELab::L2 / test/simpletimeoperator.hh:29-101), accumulated point by point with the weight as the reference's
+// weighted local views do (localassembler.hh:214-255).
+__device__ inline void um_matrix_row(const UMSp& s, const Tri& g, const double gp[3][2], int i, double weight, double a[3])
+{
+  double pts[6][2], w[6];
+  const int nq = tri_rule(s.quad_order, pts, w);
+  a[0] = a[1] = a[2] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    const double factor = w[q] * g.ie;
+    if (s.op_id == MDB_OP_POISSON) {
+      for (int j = 0; j < 3; ++j) { double dot = 0.0; dot += gp[j][0] * gp[i][0]; dot += gp[j][1] * gp[i][1]; a[j] += weight * (dot * factor); }
+    } else {
+      double phi[3]; p1_basis(pts[q][0], pts[q][1], phi);
+      for (int j = 0; j < 3; ++j) a[j] += weight * (phi[j] * phi[i] * factor);
+    }
+  }
+}
+
+__global__ void k_um_jacobian_rows(UMDev m, UMSpace S, UMOps O, int child, double weight, int overwrite, const int64_t* rowptr, const int32_t* colidx, double* val)
+{
+  const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= S.size[child]) return;
+  const int v = S.d2v[child][d];
+  const int64_t row = S.offset[child] + d;
+  const int64_t p0 = rowptr[row]; const int len = (int)(rowptr[row + 1] - p0);
+  if (overwrite) for (int k = 0; k < len; ++k) val[p0 + k] = 0.0;
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const int cell = m.v2c[e] >> 2, li = m.v2c[e] & 3;
+    const uint32_t sd = m.sd[cell];
+    bool any = false;
+    for (int s = 0; s < O.nsp; ++s) any = any || (O.sp[s].child == child && um_applies(O.sp[s], sd));
+    if (!any) continue;
+    const Tri g = tri_geometry(m, cell);
+    double gp[3][2]; tri_gradients(g, gp);
+    int pos[3];
+    for (int j = 0; j < 3; ++j) pos[j] = um_find(colidx + p0, len, (int32_t)(S.offset[child] + S.v2d[child][m.conn[3 * cell + j]]));
+    for (int s = 0; s < O.nsp; ++s) {
+      if (O.sp[s].child != child || !um_applies(O.sp[s], sd)) continue;
+      double a[3]; um_matrix_row(O.sp[s], g, gp, li, weight, a);
+      for (int j = 0; j < 3; ++j) if (pos[j] >= 0) val[p0 + pos[j]] += a[j];
+    }
+  }
+}
+
+// r[row] += sum over the incident cells of (alpha_volume + lambda_volume)_i
+__global__ void k_um_residual_rows(UMDev m, UMSpace S, UMOps O, int child, double weight, double t, const double* __restrict__ x, double* r)
+{
+  const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= S.size[child]) return;
+  const int v = S.d2v[child][d];
+  const int64_t row = S.offset[child] + d;
+  double acc = 0.0;
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const int cell = m.v2c[e] >> 2, li = m.v2c[e] & 3;
+    const uint32_t sd = m.sd[cell];
+    bool any = false;
+    for (int s = 0; s < O.nsp; ++s) any = any || (O.sp[s].child == child && um_applies(O.sp[s], sd));
+    if (!any) continue;
+    const Tri g = tri_geometry(m, cell);
+    double gp[3][2]; tri_gradients(g, gp);
+    double xl[3];
+    for (int j = 0; j < 3; ++j) xl[j] = x[S.offset[child] + S.v2d[child][m.conn[3 * cell + j]]];
+    double rl = 0.0;
+    for (int s = 0; s < O.nsp; ++s) {
+      const UMSp& sp = O.sp[s];
+      if (sp.child != child || !um_applies(sp, sd)) continue;
+      double pts[6][2], w[6];
+      const int nq = tri_rule(sp.quad_order, pts, w);
+      for (int q = 0; q < nq; ++q) {
+        const double factor = w[q] * g.ie;
+        double phi[3]; p1_basis(pts[q][0], pts[q][1], phi);
+        if (sp.op_id == MDB_OP_POISSON) {
+          double gradu[2] = {0.0, 0.0};
+          for (int j = 0; j < 3; ++j) for (int dd = 0; dd < 2; ++dd) gradu[dd] += xl[j] * gp[j][dd];
+          double dot = 0.0; dot += gradu[0] * gp[li][0]; dot += gradu[1] * gp[li][1];
+          rl += weight * (dot * factor);
+        } else {
+          double u = 0.0; for (int j = 0; j < 3; ++j) u += xl[j] * phi[j];
+          rl += weight * (u * phi[li] * factor);
+        }
+      }
+      if (sp.op_id == MDB_OP_POISSON && sp.P.f.kind != MDB_FN_ZERO)
+        for (int q = 0; q < nq; ++q) {
+          const double factor = w[q] * g.ie;
+          double phi[3]; p1_basis(pts[q][0], pts[q][1], phi);
+          double xg[2];
+          for (int dd = 0; dd < 2; ++dd) xg[dd] = g.p[0][dd] + (g.p[1][dd] - g.p[0][dd]) * pts[q][0] + (g.p[2][dd] - g.p[0][dd]) * pts[q][1];
+          const double y = eval_function(sp.P.f, 2, xg, t);
+          rl += weight * (-y * phi[li] * factor);
+        }
+    }
+    acc += rl;
+  }
+  r[row] += acc;
+}
+
+// lambda_boundary of Poisson on the physical boundary faces (residualassemblerfunctors.hh:123-162).  On a subdomain interface the
+// assembler calls the same method with an interior intersection; the predicate answers "no boundary condition" there
+// (test/testpoisson.cc:54-57), so only faces without a neighbour do work.
+__global__ void k_um_boundary(UMDev m, UMSpace S, UMOps O, double weight, double t, double* r)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= 3 * m.ne) return;
+  if (m.nbr[i] >= 0) return;
+  const int cell = (int)(i / 3), f = (int)(i % 3);
+  const uint32_t sd = m.sd[cell];
+  const int la = c_face_v[f][0], lb = c_face_v[f][1];
+  double pa[2], pb[2];
+  for (int d = 0; d < 2; ++d) { pa[d] = m.xy[2 * m.conn[3 * cell + la] + d]; pb[d] = m.xy[2 * m.conn[3 * cell + lb] + d]; }
+  const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
+  const double ie = sqrt(dx * dx + dy * dy);
+  for (int s = 0; s < O.nsp; ++s) {
+    const UMSp& sp = O.sp[s];
+    if (sp.op_id != MDB_OP_POISSON || !um_applies(sp, sd)) continue;
+    double qx[3], qw[3];
+    const int nq = line_rule(sp.quad_order, qx, qw);
+    double rl[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < nq; ++q) {
+      double xg[2] = {pa[0] + qx[q] * dx, pa[1] + qx[q] * dy};
+      if (eval_bctype(sp.P.bc, 2, xg, true) != 1) continue;
+      const double lx = c_ref[la][0] + qx[q] * (c_ref[lb][0] - c_ref[la][0]), ly = c_ref[la][1] + qx[q] * (c_ref[lb][1] - c_ref[la][1]);
+      double phi[3]; p1_basis(lx, ly, phi);
+      const double y = eval_function(sp.P.j, 2, xg, t);
+      const double factor = qw[q] * ie;
+      for (int k = 0; k < 3; ++k) rl[k] += weight * (y * phi[k] * factor);
+    }
+    for (int k = 0; k < 3; ++k) {
+      const int32_t dd = S.v2d[sp.child][m.conn[3 * cell + k]];
+      if (rl[k] != 0.0 && dd >= 0) atomicAdd(&r[S.offset[sp.child] + dd], rl[k]);
+    }
+  }
+}
+
+// ---- coupling terms ---------------------------------------------------------------------------------------------------------------
+struct UMFace {
+  double phi1[3][3], phi2[3][3];   // [point][shape function]
+  double factor[3];
+  int nq;
+};
+// face-local quadrature points seen from the inside and the outside cell (geometryInInside / geometryInOutside)
+__device__ inline void um_face_setup(const UMDev& m, int cell, int f, int nb, UMFace& F)
+{
+  const int la = c_face_v[f][0], lb = c_face_v[f][1];
+  const int va = m.conn[3 * cell + la], vb = m.conn[3 * cell + lb];
+  int ia = 0, ib = 0;
+  for (int k = 0; k < 3; ++k) { const int v = m.conn[3 * nb + k]; if (v == va) ia = k; if (v == vb) ib = k; }
+  const double dx = m.xy[2 * vb] - m.xy[2 * va], dy = m.xy[2 * vb + 1] - m.xy[2 * va + 1];
+  const double ie = sqrt(dx * dx + dy * dy);
+  double qx[3], qw[3];
+  F.nq = line_rule(4, qx, qw);                       // ProportionalFlowCoupling: intorder fixed to 4 (test/proportionalflowcoupling.hh:43)
+  for (int q = 0; q < F.nq; ++q) {
+    const double x1 = c_ref[la][0] + qx[q] * (c_ref[lb][0] - c_ref[la][0]), y1 = c_ref[la][1] + qx[q] * (c_ref[lb][1] - c_ref[la][1]);
+    const double x2 = c_ref[ia][0] + qx[q] * (c_ref[ib][0] - c_ref[ia][0]), y2 = c_ref[ia][1] + qx[q] * (c_ref[ib][1] - c_ref[ia][1]);
+    p1_basis(x1, y1, F.phi1[q]); p1_basis(x2, y2, F.phi2[q]);
+    F.factor[q] = qw[q] * ie;
+  }
+}
+// ProportionalFlowCoupling::alpha_coupling (test/proportionalflowcoupling.hh:27-86) into weighted local views
+__device__ inline void um_propflow(const UMFace& F, double k, const double xs[3], const double xn[3], double weight, double rs[3], double rn[3])
+{
+  for (int q = 0; q < F.nq; ++q) {
+    double u_s = 0.0; for (int i = 0; i < 3; ++i) u_s += xs[i] * F.phi1[q][i];
+    double u_n = 0.0; for (int i = 0; i < 3; ++i) u_n += xn[i] * F.phi2[q][i];
+    const double u_diff = k * (u_s - u_n);
+    for (int i = 0; i < 3; ++i) rs[i] += weight * (u_diff * F.phi1[q][i] * F.factor[q]);
+    for (int i = 0; i < 3; ++i) rn[i] += weight * (-u_diff * F.phi2[q][i] * F.factor[q]);
+  }
+}
+
+__global__ void k_um_coupling_residual(UMDev m, UMSpace S, UMCp cp, const int32_t* fcell, const int8_t* fface, int64_t nf, double weight,
+                                       const double* __restrict__ x, double* r)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  const int cell = fcell[i], f = fface[i], nb = m.nbr[3 * cell + f];
+  UMFace F; um_face_setup(m, cell, f, nb, F);
+  int64_t gs[3], gn[3]; double xs[3], xn[3];
+  for (int k = 0; k < 3; ++k) {
+    gs[k] = S.offset[cp.childL] + S.v2d[cp.childL][m.conn[3 * cell + k]]; gn[k] = S.offset[cp.childR] + S.v2d[cp.childR][m.conn[3 * nb + k]];
+    xs[k] = x[gs[k]]; xn[k] = x[gn[k]];
+  }
+  double rs[3] = {0.0, 0.0, 0.0}, rn[3] = {0.0, 0.0, 0.0};
+  um_propflow(F, cp.intensity, xs, xn, weight, rs, rn);
+  for (int k = 0; k < 3; ++k) { atomicAdd(&r[gs[k]], rs[k]); atomicAdd(&r[gn[k]], rn[k]); }
+}
+
+// NumericalJacobianCoupling (couplingutilities.hh:75-135): base line, then one evaluation per coefficient of the inside and of the
+// outside cell, entries (up - down) / delta with delta = eps (1 + |u_j|), eps = 1e-8; MDB_JAC_ANALYTIC: columns alpha(e_j) exactly.
+__global__ void k_um_coupling_jacobian(UMDev m, UMSpace S, UMCp cp, const int32_t* fcell, const int8_t* fface, int64_t nf, double weight,
+                                       const double* __restrict__ x, const int64_t* rowptr, const int32_t* colidx, double* val)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  const int cell = fcell[i], f = fface[i], nb = m.nbr[3 * cell + f];
+  UMFace F; um_face_setup(m, cell, f, nb, F);
+  int32_t g[6]; double u[6];
+  for (int k = 0; k < 3; ++k) {
+    g[k] = (int32_t)(S.offset[cp.childL] + S.v2d[cp.childL][m.conn[3 * cell + k]]); g[3 + k] = (int32_t)(S.offset[cp.childR] + S.v2d[cp.childR][m.conn[3 * nb + k]]);
+  }
+  const bool analytic = cp.jac_mode == MDB_JAC_ANALYTIC;
+  for (int k = 0; k < 6; ++k) u[k] = analytic ? 0.0 : x[g[k]];
+  double down[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (!analytic) um_propflow(F, cp.intensity, u, u + 3, 1.0, down, down + 3);
+  for (int j = 0; j < 6; ++j) {
+    const double keep = u[j];
+    const double delta = analytic ? 1.0 : 1e-8 * (1.0 + fabs(u[j]));
+    u[j] = analytic ? 1.0 : u[j] + delta;
+    double up[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    um_propflow(F, cp.intensity, u, u + 3, 1.0, up, up + 3);
+    u[j] = keep;
+    for (int r = 0; r < 6; ++r) {
+      const double entry = analytic ? up[r] : (up[r] - down[r]) / delta;
+      const int64_t p0 = rowptr[g[r]];
+      const int pos = um_find(colidx + p0, (int)(rowptr[g[r] + 1] - p0), g[j]);
+      if (pos >= 0) atomicAdd(&val[p0 + pos], weight * entry);
+    }
+  }
+}
+
+__global__ void k_um_dirichlet_rows(const int32_t* conlist, int64_t ncon, const int64_t* rowptr, const int32_t* diag, double* val)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= ncon) return;
+  const int64_t row = conlist[i];
+  const int64_t p0 = rowptr[row], p1 = rowptr[row + 1];
+  for (int64_t p = p0; p < p1; ++p) val[p] = 0.0;
+  if (diag[row] >= 0) val[p0 + diag[row]] = 1.0;
+}
+
+int64_t um_scan(Ctx* c, const int32_t* d_in, int32_t* d_out, int64_t n)
+{
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, d_in, d_out, (int)n, c->stream);
+  void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+  MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_in, d_out, (int)n, c->stream)); c->launches++;
+  int32_t last_s = 0, last_f = 0;
+  MDB_CUDA(cudaMemcpyAsync(&last_s, d_out + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(&last_f, d_in + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_t);
+  return (int64_t)last_s + last_f;
+}
+
+template <typename T> void um_dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+} // anonymous namespace
+
+// ---- host entry points ----------------------------------------------------------------------------------------------------------------
+void um_free(Ctx* c)
+{
+  if (!c->um) return;
+  UMesh* u = c->um;
+  um_dfree(u->d_xy); um_dfree(u->d_conn); um_dfree(u->d_nbr); um_dfree(u->d_v2c_ptr); um_dfree(u->d_v2c);
+  delete u; c->um = nullptr;
+}
+
+// Mesh ingest: validation and the connectivity a grid manager provides (face neighbours, vertex -> cell), built once on the host.
+void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn)
+{
+  MDB_REQUIRE(nv >= 3 && ne >= 1 && nv < (int64_t)1 << 30 && ne < (int64_t)1 << 29, MDB_EINVAL, "mdb_mesh_unstructured: bad vertex / cell count");
+  std::vector<int32_t> hconn(3 * ne), nbr(3 * ne, -1), vptr(nv + 1, 0), v2c(3 * ne);
+  for (int64_t i = 0; i < 3 * ne; ++i) {
+    MDB_REQUIRE(conn[i] >= 0 && conn[i] < nv, MDB_EINVAL, "mdb_mesh_unstructured: vertex index out of range");
+    hconn[i] = (int32_t)conn[i];
+  }
+  for (int64_t e = 0; e < ne; ++e) {
+    const int32_t* v = &hconn[3 * e];
+    const double ax = xy[2 * v[1]] - xy[2 * v[0]], ay = xy[2 * v[1] + 1] - xy[2 * v[0] + 1];
+    const double bx = xy[2 * v[2]] - xy[2 * v[0]], by = xy[2 * v[2] + 1] - xy[2 * v[0] + 1];
+    MDB_REQUIRE(v[0] != v[1] && v[0] != v[2] && v[1] != v[2] && ax * by - ay * bx != 0.0, MDB_EINVAL, "mdb_mesh_unstructured: degenerate cell");
+  }
+  static const int fv[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  std::vector<std::pair<uint64_t, int32_t>> edges(3 * ne);
+  for (int64_t e = 0; e < ne; ++e)
+    for (int f = 0; f < 3; ++f) {
+      uint64_t a = hconn[3 * e + fv[f][0]], b = hconn[3 * e + fv[f][1]];
+      if (a > b) std::swap(a, b);
+      edges[3 * e + f] = {(a << 32) | b, (int32_t)(3 * e + f)};
+    }
+  std::sort(edges.begin(), edges.end());
+  for (size_t i = 0; i < edges.size();) {
+    size_t j = i + 1;
+    while (j < edges.size() && edges[j].first == edges[i].first) ++j;
+    MDB_REQUIRE(j - i <= 2, MDB_EINVAL, "mdb_mesh_unstructured: more than two cells share a face (non-manifold mesh)");
+    if (j - i == 2) { nbr[edges[i].second] = edges[i + 1].second / 3; nbr[edges[i + 1].second] = edges[i].second / 3; }
+    i = j;
+  }
+  for (int64_t i = 0; i < 3 * ne; ++i) vptr[hconn[i] + 1]++;
+  for (int64_t v = 0; v < nv; ++v) vptr[v + 1] += vptr[v];
+  {
+    std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
+    for (int64_t e = 0; e < ne; ++e) for (int k = 0; k < 3; ++k) v2c[fill[hconn[3 * e + k]]++] = (int32_t)(4 * e + k);    // cells ascending per vertex
+  }
+  um_free(c);
+  UMesh* u = new UMesh(); c->um = u;
+  u->nv = nv; u->ne = ne;
+  u->d_xy = dalloc<double>(2 * nv); u->d_conn = dalloc<int32_t>(3 * ne); u->d_nbr = dalloc<int32_t>(3 * ne);
+  u->d_v2c_ptr = dalloc<int32_t>(nv + 1); u->d_v2c = dalloc<int32_t>(3 * ne);
+  MDB_CUDA(cudaMemcpyAsync(u->d_xy, xy, 2 * nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(u->d_conn, hconn.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(u->d_nbr, nbr.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(u->d_v2c_ptr, vptr.data(), (nv + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(u->d_v2c, v2c.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  c->h2d_bytes += 2 * nv * 8 + 3 * ne * 12 + (nv + 1) * 4;
+}
+
+void um_build_dofmap(Ctx* c)
+{
+  const UMDev m = um_dev(c);
+  int32_t* d_flag = dalloc<int32_t>(m.nv); int32_t* d_scan = dalloc<int32_t>(m.nv);
+  int64_t offset = 0;
+  for (Child& ch : c->children) {
+    MDB_REQUIRE(ch.fe_kind == MDB_FE_P1, MDB_EINVAL, "unstructured mesh: only MDB_FE_P1 child spaces");
+    ch.nlat = m.nv; ch.lat_n[0] = (int)m.nv; ch.lat_n[1] = ch.lat_n[2] = 1;
+    um_dfree(ch.d_lat2dof); um_dfree(ch.d_dof2lat);
+    ch.d_lat2dof = dalloc<int32_t>(m.nv);
+    MDB_LAUNCH(c, k_um_mark, cdiv(m.nv, 256), 256, 0, m, ch.subdomain, d_flag);
+    ch.size = um_scan(c, d_flag, d_scan, m.nv);
+    ch.d_dof2lat = dalloc<int32_t>(ch.size);
+    MDB_LAUNCH(c, k_um_assign, cdiv(m.nv, 256), 256, 0, m.nv, d_flag, d_scan, ch.d_lat2dof, ch.d_dof2lat);
+    ch.offset = offset; offset += ch.size;
+  }
+  MDB_REQUIRE(offset < (int64_t)2000000000, MDB_EINVAL, "unstructured mesh: more than 2e9 DOFs per context");
+  c->ndof = offset;
+  um_dfree(c->d_constrained);
+  c->d_constrained = dalloc<uint8_t>(c->ndof);
+  MDB_CUDA(cudaMemsetAsync(c->d_constrained, 0, c->ndof, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_flag); cudaFree(d_scan);
+}
+
+// parity export: the MultiDomainLocalFunctionSpace of every cell, children concatenated (multidomainlocalfunctionspace.hh:348-358)
+void um_export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs)
+{
+  const UMesh* u = c->um;
+  std::vector<int32_t> conn(3 * u->ne); std::vector<uint8_t> sd(u->ne);
+  MDB_CUDA(cudaMemcpy(conn.data(), u->d_conn, 3 * u->ne * 4, cudaMemcpyDeviceToHost));
+  MDB_CUDA(cudaMemcpy(sd.data(), c->d_cell_sd, u->ne, cudaMemcpyDeviceToHost));
+  std::vector<std::vector<int32_t>> v2d(c->children.size());
+  for (size_t k = 0; k < c->children.size(); ++k) {
+    v2d[k].resize(u->nv);
+    MDB_CUDA(cudaMemcpy(v2d[k].data(), c->children[k].d_lat2dof, u->nv * 4, cudaMemcpyDeviceToHost));
+  }
+  int64_t p = 0;
+  for (int64_t e = 0; e < u->ne; ++e) {
+    cell_ptr[e] = p;
+    for (size_t k = 0; k < c->children.size(); ++k) {
+      const Child& ch = c->children[k];
+      if (!(ch.subdomain < 0 || ((sd[e] >> ch.subdomain) & 1))) continue;
+      for (int i = 0; i < 3; ++i) { if (cell_dofs) cell_dofs[p] = ch.offset + v2d[k][conn[3 * e + i]]; ++p; }
+    }
+  }
+  cell_ptr[u->ne] = p;
+}
+
+static UMBcs um_bcs(Ctx* c, const int* sps, const mdb_bctype* bcs, const mdb_function* fns, int n)
+{
+  MDB_REQUIRE(n <= 8, MDB_EINVAL, "unstructured mesh: at most 8 subproblems per call");
+  UMBcs B; B.n = n;
+  for (int i = 0; i < n; ++i) {
+    const SubProblemDesc& d = c->sps[sps[i]];
+    B.sp[i].op_id = d.op_id; B.sp[i].child = d.children[0]; B.sp[i].cond_kind = d.cond_kind; B.sp[i].mask = d.mask; B.sp[i].quad_order = 0; B.sp[i].P = d.poisson;
+    if (bcs) B.bc[i] = bcs[i]; else B.bc[i] = mdb_bctype{};
+    if (fns) B.fn[i] = fns[i]; else B.fn[i] = mdb_function{};
+  }
+  return B;
+}
+
+void um_assemble_constraints(Ctx* c, const int* sps, const mdb_bctype* bcs, int n)
+{
+  const UMDev m = um_dev(c);
+  MDB_CUDA(cudaMemsetAsync(c->d_constrained, 0, c->ndof, c->stream));
+  MDB_LAUNCH(c, k_um_constraints, cdiv(3 * m.ne, 256), 256, 0, m, um_space(c), um_bcs(c, sps, bcs, nullptr, n), c->d_constrained);
+}
+
+void um_interpolate(Ctx* c, const int* sps, const mdb_function* fns, int n, double t, double* d_x)
+{
+  const UMDev m = um_dev(c);
+  const UMSpace S = um_space(c);
+  const UMBcs B = um_bcs(c, sps, nullptr, fns, n);
+  for (int k = 0; k < S.nchild; ++k)
+    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_interpolate, cdiv(S.size[k], 256), 256, 0, m, S, B, k, t, d_x);
+}
+
+void um_build_facelists(Ctx* c, GridOp& go)
+{
+  const UMDev m = um_dev(c);
+  const UMOps O = um_ops(c, go.sps, go.cps);
+  const int64_t n = 3 * m.ne;
+  int32_t* d_flag = dalloc<int32_t>(n); int32_t* d_scan = dalloc<int32_t>(n);
+  go.faces.clear();
+  for (int q = 0; q < O.ncp; ++q) {
+    MDB_LAUNCH(c, k_um_face_flags, cdiv(n, 256), 256, 0, m, O.cp[q], d_flag);
+    FaceList fl; fl.n = um_scan(c, d_flag, d_scan, n);
+    fl.d_cell = dalloc<int32_t>(fl.n); fl.d_face = dalloc<int8_t>(fl.n);
+    MDB_LAUNCH(c, k_um_face_compact, cdiv(n, 256), 256, 0, n, d_flag, d_scan, fl.d_cell, fl.d_face);
+    go.faces.push_back(fl);
+  }
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_flag); cudaFree(d_scan);
+}
+
+void um_build_pattern(Ctx* c, Matrix& M)
+{
+  const UMDev m = um_dev(c);
+  const UMSpace S = um_space(c);
+  std::vector<int> sps, cps;
+  for (int g : M.gos) { for (int s : c->gos[g].sps) if (std::find(sps.begin(), sps.end(), s) == sps.end()) sps.push_back(s);
+                        for (int q : c->gos[g].cps) if (std::find(cps.begin(), cps.end(), q) == cps.end()) cps.push_back(q); }
+  const UMOps O = um_ops(c, sps, cps);
+  const int64_t n = c->ndof;
+  int32_t* d_count = dalloc<int32_t>(n); int* d_over = dalloc<int>(1);
+  MDB_CUDA(cudaMemsetAsync(d_count, 0, n * 4, c->stream));
+  MDB_CUDA(cudaMemsetAsync(d_over, 0, 4, c->stream));
+  for (int k = 0; k < S.nchild; ++k)
+    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_pattern_count, cdiv(S.size[k], 128), 128, 0, m, S, O, k, d_count, d_over);
+  int over = 0;
+  MDB_CUDA(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_over);
+  if (over) { cudaFree(d_count); throw Error(MDB_EINVAL, "unstructured mesh: a matrix row has more than 128 entries (vertex valence too high)"); }
+  // row pointers: 64-bit scan of the counts
+  int64_t* d_c64 = dalloc<int64_t>(n); int64_t* d_s64 = dalloc<int64_t>(n);
+  MDB_LAUNCH(c, k_um_to64, cdiv(n, 256), 256, 0, n, d_count, d_c64);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, d_c64, d_s64, (int)n, c->stream);
+  void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+  MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_c64, d_s64, (int)n, c->stream)); c->launches++;
+  M.d_rowptr = dalloc<int64_t>(n + 1);
+  MDB_LAUNCH(c, k_um_widen, cdiv(n, 256), 256, 0, n, d_count, d_s64, M.d_rowptr);
+  int64_t nnz = 0;
+  MDB_CUDA(cudaMemcpyAsync(&nnz, M.d_rowptr + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  int32_t maxrow = 0;
+  {
+    size_t tb2 = 0; int32_t* d_max = dalloc<int32_t>(1);
+    cub::DeviceReduce::Max(nullptr, tb2, d_count, d_max, (int)n, c->stream);
+    void* d_t2 = nullptr; MDB_CUDA(cudaMalloc(&d_t2, tb2 ? tb2 : 1));
+    MDB_CUDA(cub::DeviceReduce::Max(d_t2, tb2, d_count, d_max, (int)n, c->stream)); c->launches++;
+    MDB_CUDA(cudaMemcpyAsync(&maxrow, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_t2); cudaFree(d_max);
+  }
+  cudaFree(d_t); cudaFree(d_c64); cudaFree(d_s64); cudaFree(d_count);
+  M.nnz = nnz; M.max_row = maxrow;
+  M.d_colidx = dalloc<int32_t>(nnz); M.d_val = dalloc<double>(nnz); M.d_diag = dalloc<int32_t>(n);
+  MDB_CUDA(cudaMemsetAsync(M.d_val, 0, nnz * sizeof(double), c->stream));
+  for (int k = 0; k < S.nchild; ++k) {
+    M.child_begin[k] = S.offset[k]; M.child_end[k] = S.offset[k] + S.size[k];
+    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_pattern_fill, cdiv(S.size[k], 128), 128, 0, m, S, O, k, M.d_rowptr, M.d_colidx, M.d_diag);
+  }
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r)
+{
+  const UMDev m = um_dev(c);
+  const UMSpace S = um_space(c);
+  const UMOps O = um_ops(c, go.sps, go.cps);
+  c->phase_begin("residual_volume");
+  for (int k = 0; k < S.nchild; ++k)
+    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_residual_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, c->time, d_x, d_r);
+  c->phase_end();
+  c->phase_begin("residual_boundary");
+  MDB_LAUNCH(c, k_um_boundary, cdiv(3 * m.ne, 128), 128, 0, m, S, O, weight, c->time, d_r);
+  c->phase_end();
+  c->phase_begin("residual_coupling");
+  for (int q = 0; q < O.ncp; ++q)
+    if (go.faces[q].n > 0)
+      MDB_LAUNCH(c, k_um_coupling_residual, cdiv(go.faces[q].n, 128), 128, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x, d_r);
+  constrain_residual(c, d_r);
+  c->phase_end();
+}
+
+void um_jacobian(Ctx* c, const GridOp& go, Matrix& M, double weight, const double* d_x, bool overwrite)
+{
+  const UMDev m = um_dev(c);
+  const UMSpace S = um_space(c);
+  const UMOps O = um_ops(c, go.sps, go.cps);
+  c->phase_begin("jacobian_rows");
+  for (int k = 0; k < S.nchild; ++k)
+    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_jacobian_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, overwrite ? 1 : 0, M.d_rowptr, M.d_colidx, M.d_val);
+  c->phase_end();
+  c->phase_begin("jacobian_coupling");
+  for (int q = 0; q < O.ncp; ++q)
+    if (go.faces[q].n > 0)
+      MDB_LAUNCH(c, k_um_coupling_jacobian, cdiv(go.faces[q].n, 64), 64, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x,
+                 M.d_rowptr, M.d_colidx, M.d_val);
+  c->phase_end();
+  c->phase_begin("jacobian_dirichlet");
+  if (c->ncon > 0) MDB_LAUNCH(c, k_um_dirichlet_rows, cdiv(c->ncon, 128), 128, 0, c->d_conlist, c->ncon, M.d_rowptr, M.d_diag, M.d_val);
+  c->phase_end();
+}
+
+} // namespace mdb

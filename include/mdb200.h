@@ -53,7 +53,11 @@ enum {
    * (k+1)^dim coefficients attached to the cell — DOF = (index of the cell in its subdomain) * (k+1)^dim + i [UPSTREAM (iii)];
    * no DOF is shared, ConformingDirichletConstraints constrains nothing (Dirichlet data enter weakly through the operator). */
   MDB_FE_DGQ1 = 11,
-  MDB_FE_DGQ2 = 12      /* the shipped spaces of BASELINE configs[0] (test/testpoisson-dirichlet-neumann.cc:968-971) */
+  MDB_FE_DGQ2 = 12,     /* the shipped spaces of BASELINE configs[0] (test/testpoisson-dirichlet-neumann.cc:968-971) */
+  /* PkLocalFiniteElementMap<GV,DF,RF,1> on simplices (the P1 space of test/stokesdarcy2.cc:614, test/testcouplinggfs.cc:263):
+   * one DOF per vertex, shape functions 1-x-y, x, y at the cell's vertices 0, 1, 2; numbered by ascending vertex index of the
+   * child's (sub)domain [UPSTREAM (ii),(iii)].  Unstructured meshes only (mdb_mesh_unstructured). */
+  MDB_FE_P1 = 21
 };
 
 /* ---- subdomain conditions  (subdomainset.hh:82-133) ---------------------- */
@@ -192,6 +196,17 @@ const char* mdb_version(void);
 /* Structured axis-aligned grid, n[d] cells per axis on [lower,upper].  Cells and vertices are numbered
  * lexicographically, axis 0 fastest (YaspGrid leaf index order [UPSTREAM]). */
 int mdb_mesh_structured(mdb_ctx* ctx, int dim, const int64_t* n, const double* lower, const double* upper);
+/* Unstructured conforming simplex mesh: what Dune::GmshReader<UGGrid<2>>::read hands to the reference's drivers
+ * (test/stokesdarcy2.cc:575-583; fixtures test/stokesdarcy*.msh).  dim = 2, etype = MDB_ETYPE_TRIANGLE; `xyz` holds nv points of `dim`
+ * doubles, `conn` ne cells of 3 vertex indices (0-based).  Cell and vertex indices are the caller's order ([UPSTREAM]: the leaf
+ * index order of the host grid); local vertex i of a cell carries the P1 shape function i; face f of a cell is opposite to
+ * local vertex 2 - f (DUNE simplex numbering: face 0 = {0,1}, 1 = {0,2}, 2 = {1,2}).  The call validates the mesh (indices in
+ * range, no degenerate cell, at most two cells per face) and builds the face neighbours and the vertex -> cell adjacency (the
+ * grid manager's job in the reference).  Spaces: MDB_FE_P1; operators: MDB_OP_POISSON, MDB_OP_L2, MDB_OP_PROPFLOW_COUPLING
+ * (MDB_EINVAL for the others in this build); linear solvers as on structured meshes.  Subdomains: mdb_subdomains with
+ * one byte per cell (physical group -> subdomain as in test/stokesdarcy2.cc:596-601). */
+enum { MDB_ETYPE_TRIANGLE = 2 };   /* gmsh element type 2 */
+int mdb_mesh_unstructured(mdb_ctx* ctx, int dim, int64_t nv, const double* xyz, int64_t ne, int etype, const int64_t* conn);
 /* Declare this context's mesh to be a slab of a larger global mesh (multi-GPU; the reference's analogue is
  * the overlap-1 MPI grid of test/testoverlappinginstationarypoisson.cc:232-233).  `global_n` cells per axis in total,
  * this rank's local cells start at `cell_offset`; only the slowest axis (dim-1) may be cut.  Convention: a rank that is

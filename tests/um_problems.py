@@ -1,0 +1,104 @@
+"""Unstructured-mesh test problems, driven identically through the product binding (capi.Mdb) and the Python oracle
+(oracle/um_oracle.UMOracle): two-subdomain Poisson on a triangle mesh with P1 spaces and ProportionalFlowCoupling — the
+operators of test/testpoisson.cc / test/proportionalflowcoupling.hh on the grid class of test/stokesdarcy2.cc:575-604."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+capi = importlib.import_module("dune-multidomain_b200").capi
+
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import um_oracle  # noqa: E402  (test infrastructure)
+
+
+def oracle():
+    return um_oracle.UMOracle()
+
+
+def square_mesh(nx, ny, seed=0, jitter=0.15, shuffle=True, lower=(0.0, 0.0), upper=(1.0, 1.0)):
+    """nx x ny squares cut into two triangles each (alternating diagonals), interior vertices moved by `jitter` mesh widths,
+    boundary vertices only along the boundary; vertex order, cell order and the local vertex order of every cell are shuffled
+    (seeded) so that no numbering coincides with a lattice."""
+    rng = np.random.default_rng(seed)
+    hx, hy = (upper[0] - lower[0]) / nx, (upper[1] - lower[1]) / ny
+    X, Y = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    xy = np.stack([lower[0] + X.ravel() * hx, lower[1] + Y.ravel() * hy], axis=1)
+    if jitter > 0:
+        inner_x = (X.ravel() > 0) & (X.ravel() < nx)
+        inner_y = (Y.ravel() > 0) & (Y.ravel() < ny)
+        # keep the vertical mid line straight when nx is even: it is the subdomain interface of the tests
+        straight = (nx % 2 == 0) & (X.ravel() == nx // 2)
+        xy[:, 0] += np.where(inner_x & ~straight, rng.uniform(-jitter, jitter, xy.shape[0]) * hx, 0.0)
+        xy[:, 1] += np.where(inner_y, rng.uniform(-jitter, jitter, xy.shape[0]) * hy, 0.0)
+    conn = []
+    vid = lambda i, j: j * (nx + 1) + i
+    for j in range(ny):
+        for i in range(nx):
+            a, b, c, d = vid(i, j), vid(i + 1, j), vid(i, j + 1), vid(i + 1, j + 1)
+            if (i + j) % 2 == 0:
+                conn += [[a, b, d], [a, d, c]]
+            else:
+                conn += [[a, b, c], [b, d, c]]
+    conn = np.array(conn, dtype=np.int64)
+    if shuffle:
+        pv = rng.permutation(xy.shape[0])                # new index of old vertex v = pv[v]
+        xy2 = np.empty_like(xy); xy2[pv] = xy
+        conn = pv[conn]
+        conn = conn[rng.permutation(conn.shape[0])]
+        for e in range(conn.shape[0]):
+            conn[e] = np.roll(conn[e], rng.integers(0, 3))
+            if rng.integers(0, 2):
+                conn[e] = conn[e][::-1]                  # orientation is free (|det J|)
+        xy = xy2
+    return np.ascontiguousarray(xy), np.ascontiguousarray(conn)
+
+
+def halves(xy, conn, axis=0, threshold=0.5):
+    """subdomain 1 where the cell centroid has x[axis] > threshold, else 0 (test/testpoisson.cc:152-158)."""
+    c = xy[conn].mean(axis=1)
+    return np.where(c[:, axis] > threshold, 2, 1).astype(np.uint8)
+
+
+def setup(lib, xy, conn, sd, *, shared_space=False, jac_mode=capi.JAC_FD_BITMATCH, k=2.5, orders=(4, 2), f=None, with_mass=False,
+          bc=None, coupling=True):
+    """Spaces, subproblems, coupling, constraints, linearisation point.  Returns a dict of handles."""
+    lib.mesh_unstructured(xy, conn)
+    lib.subdomains(sd)
+    if shared_space:
+        c0 = c1 = lib.add_space(capi.FE_P1, -1)
+    else:
+        c0, c1 = lib.add_space(capi.FE_P1, 0), lib.add_space(capi.FE_P1, 1)
+    bc = capi.BCType(capi.BC_TESTPOISSON) if bc is None else bc
+    f = capi.Function(capi.FN_POLY2, 1.0, 2.0, -3.0, 0.0, 4.0) if f is None else f
+    P = []
+    for o in orders:
+        p = capi.PoissonParams()
+        p.f, p.bc, p.j, p.quad_order = f, bc, capi.Function(capi.FN_TESTPOISSON_J), o
+        P.append(p)
+    sp0 = lib.add_subproblem(capi.OP_POISSON, P[0], capi.COND_EQUALITY, 1, [c0])
+    sp1 = lib.add_subproblem(capi.OP_POISSON, P[1], capi.COND_EQUALITY, 2, [c1])
+    H = dict(sp=(sp0, sp1), P=P)
+    if with_mass:
+        l2 = capi.L2Params(); l2.quad_order = 2
+        H["mass_sp"] = (lib.add_subproblem(capi.OP_L2, l2, capi.COND_EQUALITY, 1, [c0]),
+                        lib.add_subproblem(capi.OP_L2, l2, capi.COND_EQUALITY, 2, [c1]))
+    cps = []
+    if coupling:
+        pf = capi.PropFlowParams(); pf.intensity = k
+        cps = [lib.add_coupling(capi.OP_PROPFLOW_COUPLING, pf, sp0, sp1, jac_mode)]
+    H["ndof"] = lib.finalize()
+    H["ncon"] = lib.constraints_assemble([sp0, sp1], [bc, bc])
+    H["go"] = lib.gridoperator_create([sp0, sp1], cps)
+    gos = [H["go"]]
+    if with_mass:
+        H["go1"] = lib.gridoperator_create(list(H["mass_sp"]), [])
+        gos.append(H["go1"])
+    H["mat"] = lib.matrix_create(gos)
+    x = np.zeros(H["ndof"])
+    lib.interpolate([sp0, sp1], [capi.gauss(), capi.gauss()], x)
+    H["x0"] = x
+    return H
