@@ -12,9 +12,12 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <fstream>
 #include <initializer_list>
+#include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../mdb200.h"
@@ -43,6 +46,119 @@ public:
   }
 };
 
+// ---- unstructured grids: Dune::GmshReader<UGGrid<2>> (test/stokesdarcy2.cc:575-583) ------------------------------------------
+// The mesh a GmshReader hands over: vertices, triangles, and the two index -> physical-group maps the reference's drivers use to
+// mark subdomains (`elementIndexToPhysicalGroup[index(e)] > 0 ? 1 : 0`, test/stokesdarcy2.cc:596-601).
+struct GmshMesh {
+  int dim;
+  std::vector<double> vertices;                    // dim doubles per vertex
+  std::vector<int64_t> elements;                   // 3 vertex indices per triangle
+  std::vector<int> elementIndexToPhysicalGroup;
+  std::vector<int64_t> boundarySegments;           // 2 vertex indices per boundary line
+  std::vector<int> boundaryIndexToPhysicalGroup;
+  GmshMesh() : dim(2) {}
+  int64_t numVertices() const { return (int64_t)vertices.size() / dim; }
+  int64_t numElements() const { return (int64_t)elements.size() / 3; }
+  // baseGrid.globalRefine(levels): regular ("red") refinement, every triangle into four; children inherit the physical group.
+  // New vertices (edge midpoints) are appended in order of creation, children replace their father in place:
+  // (v0,m01,m02), (m01,v1,m12), (m02,m12,v2), (m01,m12,m02).  [UPSTREAM] UG's own leaf index order after refinement is an
+  // implementation detail of UG; this order is ours.
+  void globalRefine(int levels) {
+    for (int l = 0; l < levels; ++l) {
+      std::map<std::pair<int64_t, int64_t>, int64_t> mid;
+      auto midpoint = [&](int64_t a, int64_t b) -> int64_t {
+        const std::pair<int64_t, int64_t> key(a < b ? a : b, a < b ? b : a);
+        std::map<std::pair<int64_t, int64_t>, int64_t>::const_iterator it = mid.find(key);
+        if (it != mid.end()) return it->second;
+        const int64_t v = numVertices();
+        for (int d = 0; d < dim; ++d) vertices.push_back(0.5 * (vertices[(size_t)(a * dim + d)] + vertices[(size_t)(b * dim + d)]));
+        mid[key] = v; return v;
+      };
+      std::vector<int64_t> ne; std::vector<int> ng;
+      for (int64_t e = 0; e < numElements(); ++e) {
+        const int64_t v0 = elements[(size_t)(3 * e)], v1 = elements[(size_t)(3 * e + 1)], v2 = elements[(size_t)(3 * e + 2)];
+        const int64_t m01 = midpoint(v0, v1), m02 = midpoint(v0, v2), m12 = midpoint(v1, v2);
+        const int64_t c[12] = {v0, m01, m02, m01, v1, m12, m02, m12, v2, m01, m12, m02};
+        ne.insert(ne.end(), c, c + 12);
+        for (int k = 0; k < 4; ++k) ng.push_back(elementIndexToPhysicalGroup[(size_t)e]);
+      }
+      std::vector<int64_t> nb; std::vector<int> nbg;
+      for (size_t b = 0; b < boundarySegments.size() / 2; ++b) {
+        const int64_t a0 = boundarySegments[2 * b], a1 = boundarySegments[2 * b + 1], m = midpoint(a0, a1);
+        const int64_t c[4] = {a0, m, m, a1};
+        nb.insert(nb.end(), c, c + 4);
+        nbg.push_back(boundaryIndexToPhysicalGroup[b]); nbg.push_back(boundaryIndexToPhysicalGroup[b]);
+      }
+      elements.swap(ne); elementIndexToPhysicalGroup.swap(ng); boundarySegments.swap(nb); boundaryIndexToPhysicalGroup.swap(nbg);
+    }
+  }
+};
+
+// Dune::GmshReader<Grid>::read(filename, boundaryIndexToPhysicalGroup, elementIndexToPhysicalGroup, verbose, insertBoundarySegments)
+// for the Gmsh 2.x ASCII format of the reference's fixtures (test/stokesdarcy*.msh: "$MeshFormat 2.1 0 8", $Nodes, $Elements with
+// 2-node lines = boundary segments and 3-node triangles = elements; the first tag is the physical group).  [UPSTREAM dune-grid
+// gmshreader.hh] only nodes used by a line or a triangle become vertices, numbered in order of first appearance in $Elements;
+// elements and boundary segments keep the file order.  Other element types (points, type 15) are skipped; quadrilaterals and
+// second-order elements are rejected.
+class GmshReader {
+public:
+  static GmshMesh read(const std::string& filename, bool verbose = false, bool insertBoundarySegments = true) {
+    std::ifstream in(filename.c_str());
+    if (!in) throw Exception(MDB_EINVAL, "GmshReader: cannot open " + filename);
+    GmshMesh m;
+    std::string tok;
+    std::map<int64_t, int64_t> node_line;             // gmsh node id -> position in `xyz`
+    std::vector<double> xyz;
+    std::map<int64_t, int64_t> renumber;
+    bool have_format = false;
+    while (in >> tok) {
+      if (tok == "$MeshFormat") {
+        double version; int type, size;
+        if (!(in >> version >> type >> size)) throw Exception(MDB_EINVAL, "GmshReader: bad $MeshFormat");
+        if (version < 2.0 || version >= 3.0 || type != 0) throw Exception(MDB_EINVAL, "GmshReader: only the ASCII 2.x format is supported");
+        have_format = true;
+      } else if (tok == "$Nodes") {
+        int64_t n; in >> n;
+        xyz.resize((size_t)(3 * n));
+        for (int64_t i = 0; i < n; ++i) {
+          int64_t id; in >> id >> xyz[(size_t)(3 * i)] >> xyz[(size_t)(3 * i + 1)] >> xyz[(size_t)(3 * i + 2)];
+          node_line[id] = i;
+        }
+        if (!in) throw Exception(MDB_EINVAL, "GmshReader: truncated $Nodes section");
+      } else if (tok == "$Elements") {
+        int64_t n; in >> n;
+        for (int64_t i = 0; i < n; ++i) {
+          int64_t id; int type, ntags;
+          if (!(in >> id >> type >> ntags)) throw Exception(MDB_EINVAL, "GmshReader: truncated $Elements section");
+          int physical = 0;
+          for (int t = 0; t < ntags; ++t) { int tag; in >> tag; if (t == 0) physical = tag; }
+          const int nn = type == 1 ? 2 : type == 2 ? 3 : type == 15 ? 1 : -1;
+          if (nn < 0) throw Exception(MDB_EINVAL, "GmshReader: element type " + std::to_string(type) + " is not supported (lines, triangles and points only)");
+          int64_t v[3];
+          for (int k = 0; k < nn; ++k) {
+            in >> v[k];
+            if (node_line.find(v[k]) == node_line.end()) throw Exception(MDB_EINVAL, "GmshReader: element refers to an unknown node");
+          }
+          if (type == 15) continue;
+          for (int k = 0; k < nn; ++k)
+            if (renumber.find(v[k]) == renumber.end()) {
+              const int64_t nv = (int64_t)renumber.size();
+              renumber[v[k]] = nv;
+              const int64_t line = node_line[v[k]];
+              m.vertices.push_back(xyz[(size_t)(3 * line)]); m.vertices.push_back(xyz[(size_t)(3 * line + 1)]);
+            }
+          if (type == 2) { for (int k = 0; k < 3; ++k) m.elements.push_back(renumber[v[k]]); m.elementIndexToPhysicalGroup.push_back(physical); }
+          else if (insertBoundarySegments) { for (int k = 0; k < 2; ++k) m.boundarySegments.push_back(renumber[v[k]]); m.boundaryIndexToPhysicalGroup.push_back(physical); }
+        }
+      }
+    }
+    if (!have_format || m.elements.empty()) throw Exception(MDB_EINVAL, "GmshReader: " + filename + " holds no 2.x triangle mesh");
+    if (verbose) std::printf("Reading 2d Gmsh grid...\nnumber of real vertices = %lld\nnumber of boundary elements = %lld\nnumber of elements = %lld\n",
+                             (long long)m.numVertices(), (long long)m.boundaryIndexToPhysicalGroup.size(), (long long)m.numElements());
+    return m;
+  }
+};
+
 // ---- grid: YaspGrid + MultiDomainGrid<..., FewSubDomainsTraits<dim,8>> (test/testpoisson.cc:134-161) ---------------
 class SubDomainGridView { public: int subdomain; explicit SubDomainGridView(int s) : subdomain(s) {} };
 
@@ -53,6 +169,7 @@ class MultiDomainGrid {
   std::vector<double> lower_, upper_;
   std::vector<uint8_t> marks_;
   bool marking_;
+  bool unstructured_ = false;
 public:
   const std::vector<double>& lower() const { return lower_; }
   const std::vector<double>& upper() const { return upper_; }
@@ -60,9 +177,16 @@ public:
     : ctx_(ctx), dim_(dim), n_(cells, cells + dim), lower_(lower, lower + dim), upper_(upper, upper + dim), marking_(false) {
     ctx_.check(mdb_mesh_structured(ctx_.get(), dim, cells, lower, upper), "mdb_mesh_structured");
   }
+  // MultiDomainGrid<UGGrid<2>, ...> grid(baseGrid, false) over a mesh read by GmshReader (test/stokesdarcy2.cc:585-586)
+  MultiDomainGrid(Context& ctx, const GmshMesh& mesh)
+    : ctx_(ctx), dim_(mesh.dim), n_(1, mesh.numElements()), lower_(mesh.dim, 0.0), upper_(mesh.dim, 1.0), marking_(false), unstructured_(true) {
+    ctx_.check(mdb_mesh_unstructured(ctx_.get(), mesh.dim, mesh.numVertices(), mesh.vertices.data(), mesh.numElements(), MDB_ETYPE_TRIANGLE,
+                                     mesh.elements.data()), "mdb_mesh_unstructured");
+  }
+  bool unstructured() const { return unstructured_; }
   Context& context() const { return ctx_; }
   int dimension() const { return dim_; }
-  int64_t size0() const { int64_t t = 1; for (int d = 0; d < dim_; ++d) t *= n_[d]; return t; }
+  int64_t size0() const { if (unstructured_) return n_[0]; int64_t t = 1; for (int d = 0; d < dim_; ++d) t *= n_[d]; return t; }
   const std::vector<int64_t>& cells() const { return n_; }
   SubDomainGridView subDomain(int s) const { return SubDomainGridView(s); }
   SubDomainGridView leafGridView() const { return SubDomainGridView(-1); }      // the MultiDomainGrid view itself
@@ -88,9 +212,18 @@ public:
   bool coupling; int lkind, rkind; uint32_t lmask, rmask;      // set by CouplingGridFunctionSpace only
   int ncomp;                                                   // > 1: PowerCouplingGridFunctionSpace
   bool dg;                                                     // QkDGLocalFiniteElementMap<DF,RF,k,dim> instead of QkLocalFiniteElementMap
+  bool simplex;                                                // PkLocalFiniteElementMap (simplex meshes)
   GridFunctionSpace(SubDomainGridView gv_, int order, bool dg_ = false)
-    : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1), dg(dg_) {}
-  int fe() const { return dg ? (k == 1 ? MDB_FE_DGQ1 : MDB_FE_DGQ2) : (k == 1 ? MDB_FE_Q1 : MDB_FE_Q2); }
+    : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1), dg(dg_), simplex(false) {}
+  int fe() const {
+    if (simplex) { if (k != 1) throw Exception(MDB_EINVAL, "PkGridFunctionSpace: only k = 1 has device kernels in this build"); return MDB_FE_P1; }
+    return dg ? (k == 1 ? MDB_FE_DGQ1 : MDB_FE_DGQ2) : (k == 1 ? MDB_FE_Q1 : MDB_FE_Q2);
+  }
+};
+// GridFunctionSpace<SDGV, PkLocalFiniteElementMap<SDGV,DF,RF,k>, CON, VBE> on a simplex mesh (test/stokesdarcy2.cc:613-614, :646-655)
+class PkGridFunctionSpace : public GridFunctionSpace {
+public:
+  PkGridFunctionSpace(SubDomainGridView gv_, int order) : GridFunctionSpace(gv_, order) { simplex = true; }
 };
 // GridFunctionSpace<SDGV, QkDGLocalFiniteElementMap<DF,double,k,dim>, CON, VBE> (test/testpoisson-dirichlet-neumann.cc:925-926, :968-971)
 class QkDGGridFunctionSpace : public GridFunctionSpace {
@@ -479,6 +612,7 @@ class VTKWriter {
   std::vector<int64_t> vertex_of_point_;       // MultiDomainGrid vertex index of every output point (ascending = subdomain vertex order)
   std::vector<int64_t> point_of_vertex_;
   void collect() {
+    if (grid_.unstructured()) throw Exception(MDB_EINVAL, "VTKWriter: simplex meshes are not written in this build");
     if (!cells_.empty()) return;
     std::vector<uint8_t> sd((size_t)grid_.size0());
     grid_.context().check(mdb_get_subdomains(grid_.context().get(), sd.data()), "mdb_get_subdomains");

@@ -1,0 +1,86 @@
+"""the Gmsh 2.x reader, uniform refinement and physical-group -> subdomain marking of the C++ facade
+(include/mdb200/multidomain.hh: GmshReader, GmshMesh::globalRefine; reference test/stokesdarcy2.cc:575-604), through the example
+driver examples/testgmshpoisson.cc.  CPU part: the reader's output sizes against an independent Python reading of the same file
+(the driver stops at the context: no CPU fallback).  GPU part: the driver's DOF counts and solution checksums against the oracle."""
+import importlib
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spla
+
+import um_problems as ump
+
+pkg = importlib.import_module("dune-multidomain_b200")
+capi = pkg.capi
+ROOT = ump.ROOT
+
+
+def _build(outdir):
+    exe = os.path.join(outdir, "testgmshpoisson")
+    libdir = os.path.dirname(pkg.library_path())
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "testgmshpoisson.cc"), "-o", exe, "-L", libdir, "-lmdb200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def _fixture(path, nx=7, ny=5, seed=2, **kw):
+    xy, conn = ump.square_mesh(nx, ny, seed=seed)
+    groups = np.where(xy[conn].mean(axis=1)[:, 0] > 0.5, 3, 0)          # physical group 3 -> subdomain 1, group 0 -> subdomain 0
+    ump.write_gmsh(path, xy, conn, groups, **kw)
+    return xy, conn, groups
+
+
+def test_reader_and_refinement_sizes_on_cpu():
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build(d)
+        msh = os.path.join(d, "square.msh")
+        _fixture(msh, node_id_offset=5, extra_nodes=3)
+        xy, conn, groups = ump.read_gmsh(msh)
+        assert xy.shape[0] == 8 * 6 and conn.shape[0] == 70               # the unused nodes and the point element are dropped
+        for r in (0, 2):
+            p = subprocess.run([exe, msh, str(r)], capture_output=True, text=True)
+            rx, rc, rg = xy, conn, groups
+            for _ in range(r):
+                rx, rc, rg = ump.refine(rx, rc, rg)
+            assert "number of real vertices = %d" % xy.shape[0] in p.stdout and "number of elements = 70" in p.stdout
+            assert "%d vertices, %d elements after %d refinements" % (rx.shape[0], rc.shape[0], r) in p.stdout
+            if not torch.cuda.is_available():
+                assert p.returncode != 0 and "mdb_create" in p.stderr        # no CPU fallback
+        bad = os.path.join(d, "bad.msh")
+        open(bad, "w").write(open(msh).read().replace(" 2 3 ", " 3 3 ", 1))  # a quadrilateral record
+        p = subprocess.run([exe, bad], capture_output=True, text=True)
+        assert p.returncode != 0 and "not supported" in p.stderr
+        p = subprocess.run([exe, os.path.join(d, "missing.msh")], capture_output=True, text=True)
+        assert p.returncode != 0 and "cannot open" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("refinements,solver", [(0, "ssor"), (1, "ssor"), (2, "jac")])
+def test_driver_against_oracle(refinements, solver):
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build(d)
+        msh = os.path.join(d, "square.msh")
+        _fixture(msh)
+        out = subprocess.run([exe, msh, str(refinements), "2.0", solver], capture_output=True, text=True, check=True).stdout
+        xy, conn, groups = ump.read_gmsh(msh)
+        for _ in range(refinements):
+            xy, conn, groups = ump.refine(xy, conn, groups)
+        o = ump.oracle()
+        sd = np.where(groups > 0, 2, 1).astype(np.uint8)
+        H = ump.setup(o, xy, conn, sd, k=2.0, orders=(2, 2), f=capi.Function(capi.FN_CONST, 1.0), bc=capi.BCType(capi.BC_ALL_DIRICHLET))
+        x0 = np.zeros(H["ndof"])
+        o.jacobian(H["go"], H["mat"], x0, overwrite=True)
+        r = o.residual(H["go"], x0, np.zeros(H["ndof"]))
+        rp, ci = o.matrix_get_pattern(H["mat"])
+        u = x0 - spla.spsolve(sps.csr_matrix((o.matrix_get_values(H["mat"]), ci, rp), shape=(H["ndof"],) * 2).tocsc(), r)
+        m = re.search(r"(\d+) dof total, (\d+) dof constrained", out)
+        assert (int(m.group(1)), int(m.group(2))) == (H["ndof"], H["ncon"])
+        m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out)
+        assert abs(float(m.group(1)) - u.sum()) <= 1e-9 * abs(u.sum())
+        assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-9 * np.linalg.norm(u)

@@ -102,3 +102,76 @@ def setup(lib, xy, conn, sd, *, shared_space=False, jac_mode=capi.JAC_FD_BITMATC
     lib.interpolate([sp0, sp1], [capi.gauss(), capi.gauss()], x)
     H["x0"] = x
     return H
+
+
+# ---- Gmsh 2.x ASCII: a writer for fixtures and an independent Python reading of the reader's rules ---------------------------
+def write_gmsh(path, xy, conn, groups, with_boundary=True, node_id_offset=1, extra_nodes=0):
+    """Triangles (type 2) with their physical group as first tag, optionally the boundary edges as lines (type 1, group 7) in
+    front of them and a point element (type 15), node ids starting at `node_id_offset`, `extra_nodes` unused nodes in front."""
+    edges = {}
+    for e in range(conn.shape[0]):
+        for a, b in ((0, 1), (0, 2), (1, 2)):
+            edges.setdefault((min(conn[e, a], conn[e, b]), max(conn[e, a], conn[e, b])), []).append(e)
+    lines = [k for k, v in sorted(edges.items()) if len(v) == 1] if with_boundary else []
+    nid = lambda v: int(v) + node_id_offset + extra_nodes
+    with open(path, "w") as fp:
+        fp.write("$MeshFormat\n2.1 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % (xy.shape[0] + extra_nodes))
+        for i in range(extra_nodes):
+            fp.write("%d %r %r 0\n" % (node_id_offset + i, -1.0 - i, -1.0))
+        for v in range(xy.shape[0]):
+            fp.write("%d %r %r 0\n" % (nid(v), float(xy[v, 0]), float(xy[v, 1])))
+        fp.write("$EndNodes\n$Elements\n%d\n" % (1 + len(lines) + conn.shape[0]))
+        k = 1
+        fp.write("%d 15 3 0 1 0 %d\n" % (k, nid(0))); k += 1
+        for a, b in lines:
+            fp.write("%d 1 3 7 1 0 %d %d\n" % (k, nid(a), nid(b))); k += 1
+        for e in range(conn.shape[0]):
+            fp.write("%d 2 3 %d %d 0 %d %d %d\n" % (k, groups[e], 10 + groups[e], nid(conn[e, 0]), nid(conn[e, 1]), nid(conn[e, 2]))); k += 1
+        fp.write("$EndElements\n")
+
+
+def read_gmsh(path):
+    """[UPSTREAM dune-grid GmshReader]: nodes used by lines / triangles become vertices in order of first appearance."""
+    tok = open(path).read().split()
+    i = tok.index("$Nodes") + 1
+    n = int(tok[i]); i += 1
+    nodes = {}
+    for _ in range(n):
+        nodes[int(tok[i])] = (float(tok[i + 1]), float(tok[i + 2])); i += 4
+    i = tok.index("$Elements") + 1
+    m = int(tok[i]); i += 1
+    ren, xy, conn, groups = {}, [], [], []
+    for _ in range(m):
+        typ, ntags = int(tok[i + 1]), int(tok[i + 2])
+        phys = int(tok[i + 3]) if ntags > 0 else 0
+        nn = {1: 2, 2: 3, 15: 1}[typ]
+        vs = [int(t) for t in tok[i + 3 + ntags:i + 3 + ntags + nn]]
+        i += 3 + ntags + nn
+        if typ == 15:
+            continue
+        for v in vs:
+            if v not in ren:
+                ren[v] = len(ren); xy.append(nodes[v])
+        if typ == 2:
+            conn.append([ren[v] for v in vs]); groups.append(phys)
+    return np.array(xy, dtype=np.float64), np.array(conn, dtype=np.int64), np.array(groups)
+
+
+def refine(xy, conn, groups):
+    """GmshMesh::globalRefine(1) of the facade: red refinement, midpoints appended in order of creation (triangles first)."""
+    xy = [tuple(p) for p in xy]
+    mid = {}
+
+    def midpoint(a, b):
+        key = (min(a, b), max(a, b))
+        if key not in mid:
+            mid[key] = len(xy)
+            xy.append((0.5 * (xy[a][0] + xy[b][0]), 0.5 * (xy[a][1] + xy[b][1])))
+        return mid[key]
+    out, g = [], []
+    for e in range(conn.shape[0]):
+        v0, v1, v2 = (int(v) for v in conn[e])
+        m01, m02, m12 = midpoint(v0, v1), midpoint(v0, v2), midpoint(v1, v2)
+        out += [[v0, m01, m02], [m01, v1, m12], [m02, m12, v2], [m01, m12, m02]]
+        g += [groups[e]] * 4
+    return np.array(xy, dtype=np.float64), np.array(out, dtype=np.int64), np.array(g)
