@@ -207,6 +207,8 @@ struct UMesh {
   int32_t* d_nbr = nullptr;      // [ne][3] neighbour over face f (DUNE simplex numbering: face 0 = {0,1}, 1 = {0,2}, 2 = {1,2}); -1 = boundary
   int32_t* d_v2c_ptr = nullptr;  // [nv+1] vertex -> incident cells
   int32_t* d_v2c = nullptr;      // [3 ne] 4 * cell + local vertex index, cells ascending per vertex
+  int32_t* d_bface = nullptr;    // [nbface] 3 * cell + face of the faces without a neighbour (the physical boundary), ascending
+  int64_t nbface = 0;
 };
 
 struct GridOp {

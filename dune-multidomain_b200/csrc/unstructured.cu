@@ -28,9 +28,11 @@ struct UMDev {
   const double* xy; const int32_t* conn; const int32_t* nbr; const int32_t* v2c_ptr; const int32_t* v2c; const uint8_t* sd;
 };
 struct UMSpace { int nchild; int64_t offset[MDB_MAX_CHILDREN]; const int32_t* v2d[MDB_MAX_CHILDREN]; const int32_t* d2v[MDB_MAX_CHILDREN]; int64_t size[MDB_MAX_CHILDREN]; };
-struct UMSp { int op_id, child, cond_kind; uint32_t mask; int quad_order; mdb_poisson_params P; };
+struct UMSp { int op_id, child, cond_kind; uint32_t mask; int quad_order; double wsum; mdb_poisson_params P; };   // wsum: sum of the triangle rule's weights, in rule order
 struct UMCp { int op_id, childL, childR, kindL, kindR; uint32_t maskL, maskR; int jac_mode; double intensity; };
 struct UMOps { int nsp, ncp; UMSp sp[8]; UMCp cp[4]; };
+
+double tri_weight_sum(int order);
 
 UMDev um_dev(const Ctx* c)
 {
@@ -52,6 +54,7 @@ UMOps um_ops(const Ctx* c, const std::vector<int>& sps, const std::vector<int>& 
     const SubProblemDesc& d = c->sps[s];
     UMSp& o = O.sp[O.nsp++];
     o.op_id = d.op_id; o.child = d.children[0]; o.cond_kind = d.cond_kind; o.mask = d.mask; o.quad_order = d.quad_order(); o.P = d.poisson;
+    o.wsum = tri_weight_sum(o.quad_order);
   }
   for (int q : cps) {
     const CouplingDesc& d = c->cps[q];
@@ -77,36 +80,47 @@ __device__ inline Tri tri_geometry(const UMDev& m, int cell)
   const double ax = g.p[1][0] - g.p[0][0], ay = g.p[1][1] - g.p[0][1];
   const double bx = g.p[2][0] - g.p[0][0], by = g.p[2][1] - g.p[0][1];
   const double det = ax * by - ay * bx;
-  g.t[0][0] = by / det; g.t[0][1] = -ay / det;
-  g.t[1][0] = -bx / det; g.t[1][1] = ax / det;
+  const double inv = 1.0 / det;                  // one division per cell (the reference divides four times: 1 ulp apart)
+  g.t[0][0] = by * inv; g.t[0][1] = -(ay * inv);
+  g.t[1][0] = -(bx * inv); g.t[1][1] = ax * inv;
   g.ie = fabs(det);
   return g;
 }
 // gradients of the P1 shape functions: J^{-T} applied to (-1,-1), (1,0), (0,1)
 __device__ inline void tri_gradients(const Tri& g, double gp[3][2])
 {
-  const double js[3][2] = {{-1.0, -1.0}, {1.0, 0.0}, {0.0, 1.0}};
-  for (int i = 0; i < 3; ++i)
-    for (int d = 0; d < 2; ++d) { double s = 0.0; s += g.t[d][0] * js[i][0]; s += g.t[d][1] * js[i][1]; gp[i][d] = s; }
+  for (int d = 0; d < 2; ++d) { gp[1][d] = g.t[d][0]; gp[2][d] = g.t[d][1]; gp[0][d] = -g.t[d][0] - g.t[d][1]; }
 }
 __device__ inline void p1_basis(double x, double y, double phi[3]) { phi[0] = 1.0 - x - y; phi[1] = x; phi[2] = y; }
+// v[i] for a run-time i without putting v into local memory
+__device__ inline double pick3(const double v0, const double v1, const double v2, int i) { return i == 0 ? v0 : (i == 1 ? v1 : v2); }
 
 // [UPSTREAM] Dune::QuadratureRules<DF,2>::rule(simplex, order): published symmetric rules on the reference triangle (weights sum
 // to 1/2): order <= 1 centroid; order 2 the 3-point interior rule; orders 3, 4 the 6-point degree-4 rule (Dunavant).
-__device__ inline int tri_rule(int order, double pts[6][2], double w[6])
+#define UM_TA 0.445948490915965
+#define UM_TB 0.091576213509771
+#define UM_WA (0.5 * 0.223381589678011)
+#define UM_WB (0.5 * 0.109951743655322)
+// rows 0 | 1-3 | 4-9: the 1-, 3- and 6-point rules (x, y, weight)
+#define UM_TRI_TABLE {{1.0 / 3.0, 1.0 / 3.0, 0.5},                                                                                  \
+                      {1.0 / 6.0, 1.0 / 6.0, 1.0 / 6.0}, {2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0}, {1.0 / 6.0, 2.0 / 3.0, 1.0 / 6.0},         \
+                      {UM_TA, UM_TA, UM_WA}, {1.0 - 2.0 * UM_TA, UM_TA, UM_WA}, {UM_TA, 1.0 - 2.0 * UM_TA, UM_WA},                    \
+                      {UM_TB, UM_TB, UM_WB}, {1.0 - 2.0 * UM_TB, UM_TB, UM_WB}, {UM_TB, 1.0 - 2.0 * UM_TB, UM_WB}}
+__device__ __constant__ double c_tri[10][3] = UM_TRI_TABLE;
+static const double h_tri[10][3] = UM_TRI_TABLE;
+// number of points; *first = first row of the rule in the table
+__host__ __device__ inline int tri_rule(int order, int* first)
 {
-  if (order <= 1) { pts[0][0] = 1.0 / 3.0; pts[0][1] = 1.0 / 3.0; w[0] = 0.5; return 1; }
-  if (order == 2) {
-    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
-    pts[0][0] = a; pts[0][1] = a; pts[1][0] = b; pts[1][1] = a; pts[2][0] = a; pts[2][1] = b;
-    w[0] = w[1] = w[2] = 1.0 / 6.0; return 3;
-  }
-  const double a = 0.445948490915965, wa = 0.5 * 0.223381589678011;
-  const double b = 0.091576213509771, wb = 0.5 * 0.109951743655322;
-  const double a2 = 1.0 - 2.0 * a, b2 = 1.0 - 2.0 * b;
-  pts[0][0] = a; pts[0][1] = a; pts[1][0] = a2; pts[1][1] = a; pts[2][0] = a; pts[2][1] = a2;
-  pts[3][0] = b; pts[3][1] = b; pts[4][0] = b2; pts[4][1] = b; pts[5][0] = b; pts[5][1] = b2;
-  w[0] = w[1] = w[2] = wa; w[3] = w[4] = w[5] = wb; return 6;
+  if (order <= 1) { *first = 0; return 1; }
+  if (order == 2) { *first = 1; return 3; }
+  *first = 4; return 6;
+}
+double tri_weight_sum(int order)
+{
+  int q0; const int nq = tri_rule(order, &q0);
+  double s = 0.0;
+  for (int q = 0; q < nq; ++q) s += h_tri[q0 + q][2];
+  return s;
 }
 // Gauss-Legendre on [0,1], order p -> ceil((p+1)/2) points (<= 3 here)
 __device__ inline int line_rule(int order, double x[3], double w[3])
@@ -252,7 +266,10 @@ __global__ void k_um_pattern_count(UMDev m, UMSpace S, UMOps O, int child, int32
   int32_t cols[UM_MAXROW];
   count[S.offset[child] + d] = um_row_columns(m, S, O, child, S.d2v[child][d], cols, overflow);
 }
-__global__ void k_um_pattern_fill(UMDev m, UMSpace S, UMOps O, int child, const int64_t* rowptr, int32_t* colidx, int32_t* diag)
+// Also fills the slot table of the child block: for every (vertex, incident cell) entry e of v2c and every local vertex j of that
+// cell, slot[3 e + j] = position inside the row of (child, vertex) of the column of (child, vertex j of the cell); 255 = not stored.
+// The Jacobian kernel places the element-matrix rows with it: no column search and no DOF-map gather per assembly.
+__global__ void k_um_pattern_fill(UMDev m, UMSpace S, UMOps O, int child, const int64_t* rowptr, int32_t* colidx, int32_t* diag, uint8_t* slot)
 {
   const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (d >= S.size[child]) return;
@@ -263,6 +280,15 @@ __global__ void k_um_pattern_fill(UMDev m, UMSpace S, UMOps O, int child, const 
   int dg = -1;
   for (int k = 0; k < n; ++k) { colidx[p0 + k] = cols[k]; if (cols[k] == (int32_t)row) dg = k; }
   diag[row] = dg;
+  const int v = S.d2v[child][d];
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const int cell = m.v2c[e] >> 2;
+    for (int j = 0; j < 3; ++j) {
+      const int32_t dj = S.v2d[child][m.conn[3 * cell + j]];
+      const int pos = dj >= 0 ? um_find(cols, n, (int32_t)(S.offset[child] + dj)) : -1;
+      slot[3 * (int64_t)e + j] = (pos >= 0 && pos < 255) ? (uint8_t)pos : (uint8_t)255;
+    }
+  }
 }
 __global__ void k_um_widen(int64_t n, const int32_t* count, const int64_t* scan, int64_t* rowptr)
 {
@@ -282,17 +308,22 @@ __global__ void k_um_to64(int64_t n, const int32_t* in, int64_t* out)
 // weighted local views do (localassembler.hh:214-255).
 __device__ inline void um_matrix_row(const UMSp& s, const Tri& g, const double gp[3][2], int i, double weight, double a[3])
 {
-  double pts[6][2], w[6];
-  const int nq = tri_rule(s.quad_order, pts, w);
+  if (s.op_id == MDB_OP_POISSON) {
+    // the integrand is constant on the cell: sum_q weight (dot w_q |det J|) = weight (dot (sum_q w_q) |det J|) up to rounding
+    const double vol = s.wsum * g.ie;
+    const double gix = pick3(gp[0][0], gp[1][0], gp[2][0], i), giy = pick3(gp[0][1], gp[1][1], gp[2][1], i);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { double dot = 0.0; dot += gp[j][0] * gix; dot += gp[j][1] * giy; a[j] = weight * (dot * vol); }
+    return;
+  }
+  int q0; const int nq = tri_rule(s.quad_order, &q0);
   a[0] = a[1] = a[2] = 0.0;
   for (int q = 0; q < nq; ++q) {
-    const double factor = w[q] * g.ie;
-    if (s.op_id == MDB_OP_POISSON) {
-      for (int j = 0; j < 3; ++j) { double dot = 0.0; dot += gp[j][0] * gp[i][0]; dot += gp[j][1] * gp[i][1]; a[j] += weight * (dot * factor); }
-    } else {
-      double phi[3]; p1_basis(pts[q][0], pts[q][1], phi);
-      for (int j = 0; j < 3; ++j) a[j] += weight * (phi[j] * phi[i] * factor);
-    }
+    const double factor = c_tri[q0 + q][2] * g.ie;
+    double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
+    const double phii = pick3(phi[0], phi[1], phi[2], i);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[j] += weight * (phi[j] * phii * factor);
   }
 }
 
@@ -322,6 +353,57 @@ __global__ void k_um_jacobian_rows(UMDev m, UMSpace S, UMOps O, int child, doubl
   }
 }
 
+// The same rows, staged: the values of the 128 consecutive rows of a block are one contiguous span of the value array.  The block
+// keeps that span in shared memory, every thread adds its row's element-matrix rows at the precomputed slots, and the span goes
+// out (and, when accumulating, comes in) with coalesced accesses.  Spans longer than the image fall back to global updates.
+constexpr int UM_JROWS = 128;
+constexpr int UM_IMG = UM_JROWS * 20;
+__global__ void __launch_bounds__(UM_JROWS) k_um_jacobian_staged(UMDev m, UMSpace S, UMOps O, int child, double weight, int overwrite,
+                                                                 const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ slot, double* val)
+{
+  __shared__ double img[UM_IMG];
+  const int64_t d0 = blockIdx.x * (int64_t)UM_JROWS;
+  const int nrows = (int)((S.size[child] - d0) < UM_JROWS ? (S.size[child] - d0) : UM_JROWS);
+  const int64_t row0 = S.offset[child] + d0;
+  const int64_t base = rowptr[row0];
+  const int total = (int)(rowptr[row0 + nrows] - base);
+  const bool staged = total <= UM_IMG;
+  const int tid = threadIdx.x;
+  if (staged) {
+    if (overwrite) for (int k = tid; k < total; k += UM_JROWS) img[k] = 0.0;
+    else for (int k = tid; k < total; k += UM_JROWS) img[k] = val[base + k];
+    __syncthreads();
+  }
+  if (tid < nrows) {
+    const int64_t row = row0 + tid;
+    const int64_t p0 = rowptr[row];
+    double* dst = staged ? img + (p0 - base) : val + p0;
+    if (!staged && overwrite) { const int len = (int)(rowptr[row + 1] - p0); for (int k = 0; k < len; ++k) dst[k] = 0.0; }
+    const int v = S.d2v[child][d0 + tid];
+    for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+      const int cell = m.v2c[e] >> 2, li = m.v2c[e] & 3;
+      const uint32_t sd = m.sd[cell];
+      bool any = false;
+      for (int s = 0; s < O.nsp; ++s) any = any || (O.sp[s].child == child && um_applies(O.sp[s], sd));
+      if (!any) continue;
+      const Tri g = tri_geometry(m, cell);
+      double gp[3][2]; tri_gradients(g, gp);
+      const uint8_t s0 = slot[3 * (int64_t)e], s1 = slot[3 * (int64_t)e + 1], s2 = slot[3 * (int64_t)e + 2];
+      for (int s = 0; s < O.nsp; ++s) {
+        if (O.sp[s].child != child || !um_applies(O.sp[s], sd)) continue;
+        double a[3]; um_matrix_row(O.sp[s], g, gp, li, weight, a);
+        if (s0 != 255) dst[s0] += a[0];
+        if (s1 != 255) dst[s1] += a[1];
+        if (s2 != 255) dst[s2] += a[2];
+      }
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    for (int k = tid; k < total; k += UM_JROWS) val[base + k] = img[k];
+  }
+}
+
 // r[row] += sum over the incident cells of (alpha_volume + lambda_volume)_i
 __global__ void k_um_residual_rows(UMDev m, UMSpace S, UMOps O, int child, double weight, double t, const double* __restrict__ x, double* r)
 {
@@ -344,29 +426,28 @@ __global__ void k_um_residual_rows(UMDev m, UMSpace S, UMOps O, int child, doubl
     for (int s = 0; s < O.nsp; ++s) {
       const UMSp& sp = O.sp[s];
       if (sp.child != child || !um_applies(sp, sd)) continue;
-      double pts[6][2], w[6];
-      const int nq = tri_rule(sp.quad_order, pts, w);
-      for (int q = 0; q < nq; ++q) {
-        const double factor = w[q] * g.ie;
-        double phi[3]; p1_basis(pts[q][0], pts[q][1], phi);
-        if (sp.op_id == MDB_OP_POISSON) {
-          double gradu[2] = {0.0, 0.0};
-          for (int j = 0; j < 3; ++j) for (int dd = 0; dd < 2; ++dd) gradu[dd] += xl[j] * gp[j][dd];
-          double dot = 0.0; dot += gradu[0] * gp[li][0]; dot += gradu[1] * gp[li][1];
-          rl += weight * (dot * factor);
-        } else {
+      int q0; const int nq = tri_rule(sp.quad_order, &q0);
+      if (sp.op_id == MDB_OP_POISSON) {               // constant integrand: one term instead of one per quadrature point (see um_matrix_row)
+        double gradu[2] = {0.0, 0.0};
+        for (int j = 0; j < 3; ++j) for (int dd = 0; dd < 2; ++dd) gradu[dd] += xl[j] * gp[j][dd];
+        double dot = 0.0; dot += gradu[0] * pick3(gp[0][0], gp[1][0], gp[2][0], li); dot += gradu[1] * pick3(gp[0][1], gp[1][1], gp[2][1], li);
+        rl += weight * (dot * (sp.wsum * g.ie));
+      } else {
+        for (int q = 0; q < nq; ++q) {
+          const double factor = c_tri[q0 + q][2] * g.ie;
+          double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
           double u = 0.0; for (int j = 0; j < 3; ++j) u += xl[j] * phi[j];
-          rl += weight * (u * phi[li] * factor);
+          rl += weight * (u * pick3(phi[0], phi[1], phi[2], li) * factor);
         }
       }
       if (sp.op_id == MDB_OP_POISSON && sp.P.f.kind != MDB_FN_ZERO)
         for (int q = 0; q < nq; ++q) {
-          const double factor = w[q] * g.ie;
-          double phi[3]; p1_basis(pts[q][0], pts[q][1], phi);
+          const double factor = c_tri[q0 + q][2] * g.ie;
+          double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
           double xg[2];
-          for (int dd = 0; dd < 2; ++dd) xg[dd] = g.p[0][dd] + (g.p[1][dd] - g.p[0][dd]) * pts[q][0] + (g.p[2][dd] - g.p[0][dd]) * pts[q][1];
+          for (int dd = 0; dd < 2; ++dd) xg[dd] = g.p[0][dd] + (g.p[1][dd] - g.p[0][dd]) * c_tri[q0 + q][0] + (g.p[2][dd] - g.p[0][dd]) * c_tri[q0 + q][1];
           const double y = eval_function(sp.P.f, 2, xg, t);
-          rl += weight * (-y * phi[li] * factor);
+          rl += weight * (-y * pick3(phi[0], phi[1], phi[2], li) * factor);
         }
     }
     acc += rl;
@@ -377,12 +458,12 @@ __global__ void k_um_residual_rows(UMDev m, UMSpace S, UMOps O, int child, doubl
 // lambda_boundary of Poisson on the physical boundary faces (residualassemblerfunctors.hh:123-162).  On a subdomain interface the
 // assembler calls the same method with an interior intersection; the predicate answers "no boundary condition" there
 // (test/testpoisson.cc:54-57), so only faces without a neighbour do work.
-__global__ void k_um_boundary(UMDev m, UMSpace S, UMOps O, double weight, double t, double* r)
+__global__ void k_um_boundary(UMDev m, UMSpace S, UMOps O, const int32_t* __restrict__ bface, int64_t nbface, double weight, double t, double* r)
 {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= 3 * m.ne) return;
-  if (m.nbr[i] >= 0) return;
-  const int cell = (int)(i / 3), f = (int)(i % 3);
+  const int64_t ib = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (ib >= nbface) return;
+  const int i = bface[ib];
+  const int cell = i / 3, f = i % 3;
   const uint32_t sd = m.sd[cell];
   const int la = c_face_v[f][0], lb = c_face_v[f][1];
   double pa[2], pb[2];
@@ -530,7 +611,7 @@ void um_free(Ctx* c)
 {
   if (!c->um) return;
   UMesh* u = c->um;
-  um_dfree(u->d_xy); um_dfree(u->d_conn); um_dfree(u->d_nbr); um_dfree(u->d_v2c_ptr); um_dfree(u->d_v2c);
+  um_dfree(u->d_xy); um_dfree(u->d_conn); um_dfree(u->d_nbr); um_dfree(u->d_v2c_ptr); um_dfree(u->d_v2c); um_dfree(u->d_bface);
   delete u; c->um = nullptr;
 }
 
@@ -581,6 +662,11 @@ void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* 
   MDB_CUDA(cudaMemcpyAsync(u->d_nbr, nbr.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaMemcpyAsync(u->d_v2c_ptr, vptr.data(), (nv + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaMemcpyAsync(u->d_v2c, v2c.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
+  std::vector<int32_t> bface;
+  for (int64_t i = 0; i < 3 * ne; ++i) if (nbr[i] < 0) bface.push_back((int32_t)i);
+  u->nbface = (int64_t)bface.size();
+  u->d_bface = dalloc<int32_t>(bface.size());
+  if (!bface.empty()) MDB_CUDA(cudaMemcpyAsync(u->d_bface, bface.data(), bface.size() * 4, cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   c->h2d_bytes += 2 * nv * 8 + 3 * ne * 12 + (nv + 1) * 4;
 }
@@ -640,7 +726,7 @@ static UMBcs um_bcs(Ctx* c, const int* sps, const mdb_bctype* bcs, const mdb_fun
   UMBcs B; B.n = n;
   for (int i = 0; i < n; ++i) {
     const SubProblemDesc& d = c->sps[sps[i]];
-    B.sp[i].op_id = d.op_id; B.sp[i].child = d.children[0]; B.sp[i].cond_kind = d.cond_kind; B.sp[i].mask = d.mask; B.sp[i].quad_order = 0; B.sp[i].P = d.poisson;
+    B.sp[i].op_id = d.op_id; B.sp[i].child = d.children[0]; B.sp[i].cond_kind = d.cond_kind; B.sp[i].mask = d.mask; B.sp[i].quad_order = 0; B.sp[i].wsum = 0.5; B.sp[i].P = d.poisson;
     if (bcs) B.bc[i] = bcs[i]; else B.bc[i] = mdb_bctype{};
     if (fns) B.fn[i] = fns[i]; else B.fn[i] = mdb_function{};
   }
@@ -727,7 +813,11 @@ void um_build_pattern(Ctx* c, Matrix& M)
   MDB_CUDA(cudaMemsetAsync(M.d_val, 0, nnz * sizeof(double), c->stream));
   for (int k = 0; k < S.nchild; ++k) {
     M.child_begin[k] = S.offset[k]; M.child_end[k] = S.offset[k] + S.size[k];
-    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_pattern_fill, cdiv(S.size[k], 128), 128, 0, m, S, O, k, M.d_rowptr, M.d_colidx, M.d_diag);
+    if (S.size[k] == 0) continue;
+    uint8_t* d_slot = dalloc<uint8_t>(9 * m.ne);
+    MDB_CUDA(cudaMemsetAsync(d_slot, 255, 9 * m.ne, c->stream));
+    M.slot_tables[std::make_pair(k, -1)] = d_slot;            // freed with the matrix
+    MDB_LAUNCH(c, k_um_pattern_fill, cdiv(S.size[k], 128), 128, 0, m, S, O, k, M.d_rowptr, M.d_colidx, M.d_diag, d_slot);
   }
   MDB_CUDA(cudaStreamSynchronize(c->stream));
 }
@@ -742,7 +832,7 @@ void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, dou
     if (S.size[k] > 0) MDB_LAUNCH(c, k_um_residual_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, c->time, d_x, d_r);
   c->phase_end();
   c->phase_begin("residual_boundary");
-  MDB_LAUNCH(c, k_um_boundary, cdiv(3 * m.ne, 128), 128, 0, m, S, O, weight, c->time, d_r);
+  if (c->um->nbface > 0) MDB_LAUNCH(c, k_um_boundary, cdiv(c->um->nbface, 128), 128, 0, m, S, O, c->um->d_bface, c->um->nbface, weight, c->time, d_r);
   c->phase_end();
   c->phase_begin("residual_coupling");
   for (int q = 0; q < O.ncp; ++q)
@@ -758,8 +848,15 @@ void um_jacobian(Ctx* c, const GridOp& go, Matrix& M, double weight, const doubl
   const UMSpace S = um_space(c);
   const UMOps O = um_ops(c, go.sps, go.cps);
   c->phase_begin("jacobian_rows");
-  for (int k = 0; k < S.nchild; ++k)
-    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_jacobian_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, overwrite ? 1 : 0, M.d_rowptr, M.d_colidx, M.d_val);
+  static const bool simple = getenv("MDB_UM_JAC_SIMPLE") != nullptr;      // A/B switch: the unstaged row kernel
+  for (int k = 0; k < S.nchild; ++k) {
+    if (S.size[k] == 0) continue;
+    auto it = M.slot_tables.find(std::make_pair(k, -1));
+    if (simple || it == M.slot_tables.end())
+      MDB_LAUNCH(c, k_um_jacobian_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, overwrite ? 1 : 0, M.d_rowptr, M.d_colidx, M.d_val);
+    else
+      MDB_LAUNCH(c, k_um_jacobian_staged, cdiv(S.size[k], UM_JROWS), UM_JROWS, 0, m, S, O, k, weight, overwrite ? 1 : 0, M.d_rowptr, it->second, M.d_val);
+  }
   c->phase_end();
   c->phase_begin("jacobian_coupling");
   for (int q = 0; q < O.ncp; ++q)
