@@ -455,6 +455,58 @@ __global__ void k_um_residual_rows(UMDev m, UMSpace S, UMOps O, int child, doubl
   r[row] += acc;
 }
 
+// The same terms cell by cell: one thread per cell evaluates alpha_volume + lambda_volume once (the row kernel evaluates every
+// cell once per vertex) and adds its three entries with L2 reductions (RED.ADD.F64) — residual() is additive and the boundary and
+// coupling kernels add to the same rows anyway.  A third of the gathers of the row kernel; the summation order inside a row is no
+// longer fixed (differences at rounding level, far inside the 1e-12 bar).
+__global__ void k_um_residual_cells(UMDev m, UMSpace S, UMOps O, double weight, double t, const double* __restrict__ x, double* r)
+{
+  const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (cell >= m.ne) return;
+  const uint32_t sd = m.sd[cell];
+  bool any = false;
+  for (int s = 0; s < O.nsp; ++s) any = any || um_applies(O.sp[s], sd);
+  if (!any) return;
+  const Tri g = tri_geometry(m, (int)cell);
+  double gp[3][2]; tri_gradients(g, gp);
+  int vtx[3];
+  for (int j = 0; j < 3; ++j) vtx[j] = m.conn[3 * cell + j];
+  for (int s = 0; s < O.nsp; ++s) {
+    const UMSp& sp = O.sp[s];
+    if (!um_applies(sp, sd)) continue;
+    int64_t dof[3]; double xl[3];
+    bool present = true;
+    for (int j = 0; j < 3; ++j) { const int32_t dj = S.v2d[sp.child][vtx[j]]; present = present && dj >= 0; dof[j] = S.offset[sp.child] + dj; }
+    if (!present) continue;
+    for (int j = 0; j < 3; ++j) xl[j] = x[dof[j]];
+    double rl[3] = {0.0, 0.0, 0.0};
+    int q0; const int nq = tri_rule(sp.quad_order, &q0);
+    if (sp.op_id == MDB_OP_POISSON) {
+      double gradu[2] = {0.0, 0.0};
+      for (int j = 0; j < 3; ++j) for (int dd = 0; dd < 2; ++dd) gradu[dd] += xl[j] * gp[j][dd];
+      const double vol = sp.wsum * g.ie;
+      for (int i = 0; i < 3; ++i) { double dot = 0.0; dot += gradu[0] * gp[i][0]; dot += gradu[1] * gp[i][1]; rl[i] += weight * (dot * vol); }
+      if (sp.P.f.kind != MDB_FN_ZERO)
+        for (int q = 0; q < nq; ++q) {
+          const double factor = c_tri[q0 + q][2] * g.ie;
+          double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
+          double xg[2];
+          for (int dd = 0; dd < 2; ++dd) xg[dd] = g.p[0][dd] + (g.p[1][dd] - g.p[0][dd]) * c_tri[q0 + q][0] + (g.p[2][dd] - g.p[0][dd]) * c_tri[q0 + q][1];
+          const double y = eval_function(sp.P.f, 2, xg, t);
+          for (int i = 0; i < 3; ++i) rl[i] += weight * (-y * phi[i] * factor);
+        }
+    } else {
+      for (int q = 0; q < nq; ++q) {
+        const double factor = c_tri[q0 + q][2] * g.ie;
+        double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
+        double u = 0.0; for (int j = 0; j < 3; ++j) u += xl[j] * phi[j];
+        for (int i = 0; i < 3; ++i) rl[i] += weight * (u * phi[i] * factor);
+      }
+    }
+    for (int i = 0; i < 3; ++i) atomicAdd(&r[dof[i]], rl[i]);
+  }
+}
+
 // lambda_boundary of Poisson on the physical boundary faces (residualassemblerfunctors.hh:123-162).  On a subdomain interface the
 // assembler calls the same method with an interior intersection; the predicate answers "no boundary condition" there
 // (test/testpoisson.cc:54-57), so only faces without a neighbour do work.
@@ -828,8 +880,11 @@ void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, dou
   const UMSpace S = um_space(c);
   const UMOps O = um_ops(c, go.sps, go.cps);
   c->phase_begin("residual_volume");
-  for (int k = 0; k < S.nchild; ++k)
-    if (S.size[k] > 0) MDB_LAUNCH(c, k_um_residual_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, c->time, d_x, d_r);
+  static const bool by_rows = getenv("MDB_UM_RES_ROWS") != nullptr;       // A/B switch: the owner-computes row kernel (fixed summation order)
+  if (by_rows) {
+    for (int k = 0; k < S.nchild; ++k)
+      if (S.size[k] > 0) MDB_LAUNCH(c, k_um_residual_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, c->time, d_x, d_r);
+  } else if (O.nsp > 0) MDB_LAUNCH(c, k_um_residual_cells, cdiv(m.ne, 128), 128, 0, m, S, O, weight, c->time, d_x, d_r);
   c->phase_end();
   c->phase_begin("residual_boundary");
   if (c->um->nbface > 0) MDB_LAUNCH(c, k_um_boundary, cdiv(c->um->nbface, 128), 128, 0, m, S, O, c->um->d_bface, c->um->nbface, weight, c->time, d_r);
