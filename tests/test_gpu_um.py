@@ -160,3 +160,16 @@ def test_size_independent_properties_at_scale():
     r2 = dev.residual(H["go"], x - z, np.zeros(n))
     assert np.abs(r2).max() <= 1e-9 * np.abs(r1).max()
     dev.close()
+
+
+@pytest.mark.parametrize("path", ump.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_device_reproduces_golden(path):
+    """The committed fixtures of tests/golden/um (frozen oracle output incl. the SciPy solution) through the C ABI."""
+    def solve(dev, H, r):
+        z = np.zeros(H["ndof"])
+        st = dev.solve(H["mat"], r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, reduction=1e-12, maxit=2000)
+        assert st.converged
+        return z
+    dev = pkg.Mdb(0)
+    ump.check_golden(dev, path, solve)
+    dev.close()

@@ -179,3 +179,12 @@ def test_shared_space_variant_runs(case):
     assert H["ndof"] == xy.shape[0]
     o.jacobian(H["go"], H["mat"], H["x0"], overwrite=True)
     assert np.isfinite(o.matrix_get_values(H["mat"])).all()
+
+
+@pytest.mark.parametrize("path", ump.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_reproduces_golden(path):
+    ump.check_golden(ump.oracle(), path)
+
+
+def test_golden_fixtures_exist():
+    assert len(ump.golden_cases()) >= 3

@@ -175,3 +175,37 @@ def refine(xy, conn, groups):
         out += [[v0, m01, m02], [m01, v1, m12], [m02, m12, v2], [m01, m12, m02]]
         g += [groups[e]] * 4
     return np.array(xy, dtype=np.float64), np.array(out, dtype=np.int64), np.array(g)
+
+
+# ---- golden fixtures (tests/golden/um, generated by tests/golden/make_golden_um.py) ---------------------------------------------
+def golden_cases():
+    import glob
+    return sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "um", "*.npz")))
+
+
+def check_golden(lib, path, solve=None):
+    """Drive `lib` (oracle or device binding) through the fixture's problem and compare: integers bit-exact, entries 1e-12 of the
+    largest entry, solution 1e-10."""
+    g = np.load(path)
+    kw = {str(k): float(v) for k, v in zip(g["kw_keys"], g["kw_vals"])}
+    for key in ("with_mass", "shared_space"):
+        if key in kw:
+            kw[key] = bool(kw[key])
+    H = setup(lib, g["xy"], g["conn"], g["sd"], **kw)
+    assert H["ndof"] == int(g["ndof"]) and H["ncon"] == int(g["ncon"])
+    assert np.array_equal(lib.get_child_offsets(), g["offsets"])
+    ptr, dofs = lib.get_dofmap()
+    assert np.array_equal(ptr, g["cell_ptr"]) and np.array_equal(dofs, g["cell_dofs"])
+    assert np.array_equal(lib.get_constraints(), g["constrained"])
+    rp, ci = lib.matrix_get_pattern(H["mat"])
+    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(ci, g["colidx"])
+    x0 = g["x0"].copy()
+    assert np.abs(H["x0"] - x0).max() <= 1e-15
+    lib.jacobian(H["go"], H["mat"], x0, overwrite=True)
+    val = lib.matrix_get_values(H["mat"])
+    assert np.abs(val - g["values"]).max() <= 1e-12 * np.abs(g["values"]).max()
+    r = lib.residual(H["go"], x0, np.zeros(H["ndof"]))
+    assert np.abs(r - g["residual"]).max() <= 1e-12 * np.abs(g["residual"]).max()
+    if solve is not None:
+        u = x0 - solve(lib, H, r)
+        assert np.abs(u - g["solution"]).max() <= 1e-10 * np.abs(g["solution"]).max()
