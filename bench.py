@@ -178,6 +178,65 @@ def run_reference(args, out):
     print(json.dumps(line), file=out)
 
 
+def unstructured_extra(pkg, capi, peak, n=1024, reps=10):
+    """Side line of the benchmark (extra.unstructured): the same path on an unstructured triangle mesh (csrc/unstructured.cu) —
+    n x n squares cut into two triangles each, jittered, P1 | P1, Poisson + ProportionalFlowCoupling with the FD Jacobian."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(0)
+    i, j = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="xy")
+    xy = np.stack([i.ravel() / n, j.ravel() / n], axis=1)
+    inner = (i.ravel() > 0) & (i.ravel() < n) & (j.ravel() > 0) & (j.ravel() < n) & (i.ravel() != n // 2)
+    xy[inner] += rng.uniform(-0.15, 0.15, (int(inner.sum()), 2)) / n
+    ci, cj = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    a = (cj * (n + 1) + ci).ravel(); b = a + 1; c = a + n + 1; d = c + 1
+    even = ((ci + cj) % 2 == 0).ravel()
+    conn = np.empty((2 * n * n, 3), dtype=np.int64)
+    conn[0::2] = np.where(even[:, None], np.stack([a, b, d], 1), np.stack([a, b, c], 1))
+    conn[1::2] = np.where(even[:, None], np.stack([a, d, c], 1), np.stack([b, d, c], 1))
+    sd = np.where(xy[conn].mean(axis=1)[:, 0] > 0.5, 2, 1).astype(np.uint8)
+    dev = pkg.Mdb(0)
+    try:
+        t0 = time.perf_counter()
+        dev.mesh_unstructured(xy, conn); dev.subdomains(sd)
+        t_ingest = time.perf_counter() - t0
+        c0, c1 = dev.add_space(capi.FE_P1, 0), dev.add_space(capi.FE_P1, 1)
+        p = capi.PoissonParams(); p.f = capi.Function(capi.FN_ZERO); p.bc = capi.BCType(capi.BC_TESTPOISSON)
+        p.j = capi.Function(capi.FN_TESTPOISSON_J); p.quad_order = 4
+        s0 = dev.add_subproblem(capi.OP_POISSON, p, capi.COND_EQUALITY, 1, [c0])
+        s1 = dev.add_subproblem(capi.OP_POISSON, p, capi.COND_EQUALITY, 2, [c1])
+        pf = capi.PropFlowParams(); pf.intensity = 2.0
+        cp = dev.add_coupling(capi.OP_PROPFLOW_COUPLING, pf, s0, s1)
+        t0 = time.perf_counter()
+        ndof = dev.finalize(); dev.constraints_assemble([s0, s1], [p.bc, p.bc])
+        go = dev.gridoperator_create([s0, s1], [cp]); mat = dev.matrix_create([go])
+        dev.synchronize(); t_setup = time.perf_counter() - t0
+        nnz = dev.nnz[mat]
+        u = torch.zeros(ndof, dtype=torch.float64, device="cuda"); r = torch.zeros_like(u)
+        dev.interpolate([s0, s1], [capi.gauss(), capi.gauss()], u)
+
+        def timed_ms(fn):
+            for _ in range(3):
+                fn()
+            dev.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            s = torch.cuda.ExternalStream(dev.stream())
+            e0.record(s)
+            for _ in range(reps):
+                fn()
+            e1.record(s); e1.synchronize()
+            return e0.elapsed_time(e1) / reps
+        ms_jac = timed_ms(lambda: dev.jacobian(go, mat, u, overwrite=True))
+        ms_res = timed_ms(lambda: dev.residual(go, u, r))
+        ne = conn.shape[0]
+        b_jac = 8.0 * nnz + 24.0 * ne + 16.0 * xy.shape[0]          # values + DOF map + geometry (SURVEY 8d, unstructured)
+        return {"workload": "2-D triangles (%d x %d squares, jittered), P1 | P1, Poisson + ProportionalFlowCoupling (FD Jacobian)" % (n, n),
+                "cells": int(ne), "dofs": int(ndof), "nnz": int(nnz), "ingest_host_s": t_ingest, "dofmap_constraints_pattern_s": t_setup,
+                "jacobian_ms": ms_jac, "jacobian_dofs_per_s": ndof / (ms_jac * 1e-3), "jacobian_achieved_GBs": b_jac / (ms_jac * 1e-3) / 1e9,
+                "jacobian_frac": b_jac / (ms_jac * 1e-3) / 1e9 / peak, "residual_ms": ms_res, "residual_dofs_per_s": ndof / (ms_res * 1e-3)}
+    finally:
+        dev.close()
+
+
 def main():
     # The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there) share file
     # descriptor 1, so route fd 1 to stderr for the whole run and keep a private handle on the real stdout for the line.
@@ -382,6 +441,11 @@ def _main(out):
                            "l2_policy": "inputs larger than L2 (matrix values %.2f GB per GPU)" % (8.0 * nnz / 1e9),
                            "partition": "z-slabs, one per GPU" if world > 1 else "single GPU"},
                 "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
+        if world == 1 and not os.environ.get("MDB_BENCH_NO_UNSTRUCTURED"):
+            try:
+                extra["unstructured"] = unstructured_extra(pkg, capi, peak)
+            except Exception as e:          # a side line must never take the benchmark line down
+                extra["unstructured"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(S, args.cpu_sample_layers, 1)
         elif world == 1:

@@ -427,7 +427,10 @@ int mdb_add_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, i
       MDB_REQUIRE(cp.nd.mode >= MDB_ND_MODE_NEUMANN && cp.nd.mode <= MDB_ND_MODE_BOTH, MDB_EINVAL, "mdb_add_coupling: bad Neumann-Dirichlet coupling mode");
       MDB_REQUIRE(!c->mesh.partitioned, MDB_EINVAL, "mdb_add_coupling: the Neumann-Dirichlet coupling is not supported on a partitioned mesh");
     } else throw Error(MDB_EINVAL, "mdb_add_coupling: unknown coupling operator");
-    MDB_REQUIRE(!c->um || op_id == MDB_OP_PROPFLOW_COUPLING, MDB_EINVAL, "mdb_add_coupling: unstructured meshes carry ProportionalFlowCoupling in this build");
+    MDB_REQUIRE(!c->um || op_id == MDB_OP_PROPFLOW_COUPLING || op_id == MDB_OP_CVCF_COUPLING, MDB_EINVAL,
+                "mdb_add_coupling: unstructured meshes carry the two proportional-flow couplings in this build");
+    MDB_REQUIRE(!c->um || op_id != MDB_OP_CVCF_COUPLING || (cp.cvcf.quad_order >= 0 && cp.cvcf.quad_order <= 5), MDB_EINVAL,
+                "mdb_add_coupling: face rules up to order 5 on simplex meshes");
     c->cps.push_back(cp);
     return (int)c->cps.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }

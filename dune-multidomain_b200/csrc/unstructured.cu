@@ -29,7 +29,7 @@ struct UMDev {
 };
 struct UMSpace { int nchild; int64_t offset[MDB_MAX_CHILDREN]; const int32_t* v2d[MDB_MAX_CHILDREN]; const int32_t* d2v[MDB_MAX_CHILDREN]; int64_t size[MDB_MAX_CHILDREN]; };
 struct UMSp { int op_id, child, cond_kind; uint32_t mask; int quad_order; double wsum; mdb_poisson_params P; };   // wsum: sum of the triangle rule's weights, in rule order
-struct UMCp { int op_id, childL, childR, kindL, kindR; uint32_t maskL, maskR; int jac_mode; double intensity; };
+struct UMCp { int op_id, childL, childR, kindL, kindR; uint32_t maskL, maskR; int jac_mode, quad_order; double intensity; };
 struct UMOps { int nsp, ncp; UMSp sp[8]; UMCp cp[4]; };
 
 double tri_weight_sum(int order);
@@ -61,7 +61,9 @@ UMOps um_ops(const Ctx* c, const std::vector<int>& sps, const std::vector<int>& 
     const SubProblemDesc& L = c->sps[d.local_sp]; const SubProblemDesc& R = c->sps[d.remote_sp];
     UMCp& o = O.cp[O.ncp++];
     o.op_id = d.op_id; o.childL = L.children[0]; o.childR = R.children[0]; o.kindL = L.cond_kind; o.kindR = R.cond_kind; o.maskL = L.mask; o.maskR = R.mask;
-    o.jac_mode = d.jac_mode; o.intensity = d.propflow.intensity;
+    o.jac_mode = d.jac_mode;
+    o.intensity = d.op_id == MDB_OP_CVCF_COUPLING ? d.cvcf.intensity : d.propflow.intensity;
+    o.quad_order = d.op_id == MDB_OP_CVCF_COUPLING ? d.cvcf.quad_order : 4;     // ProportionalFlowCoupling: intorder fixed to 4 (test/proportionalflowcoupling.hh:43)
   }
   return O;
 }
@@ -548,10 +550,13 @@ __global__ void k_um_boundary(UMDev m, UMSpace S, UMOps O, const int32_t* __rest
 struct UMFace {
   double phi1[3][3], phi2[3][3];   // [point][shape function]
   double factor[3];
+  double gp1[3][2], gp2[3][2];     // gradients of the shape functions of the inside / outside cell (constant on the cell)
+  double normal[2];                // unit outer normal of the inside cell
+  double h_F;                      // |corner 0 - corner 1| of the intersection (test/proportionalflowcoupling.hh:135)
   int nq;
 };
 // face-local quadrature points seen from the inside and the outside cell (geometryInInside / geometryInOutside)
-__device__ inline void um_face_setup(const UMDev& m, int cell, int f, int nb, UMFace& F)
+__device__ inline void um_face_setup(const UMDev& m, int cell, int f, int nb, int quad_order, bool gradients, UMFace& F)
 {
   const int la = c_face_v[f][0], lb = c_face_v[f][1];
   const int va = m.conn[3 * cell + la], vb = m.conn[3 * cell + lb];
@@ -560,7 +565,18 @@ __device__ inline void um_face_setup(const UMDev& m, int cell, int f, int nb, UM
   const double dx = m.xy[2 * vb] - m.xy[2 * va], dy = m.xy[2 * vb + 1] - m.xy[2 * va + 1];
   const double ie = sqrt(dx * dx + dy * dy);
   double qx[3], qw[3];
-  F.nq = line_rule(4, qx, qw);                       // ProportionalFlowCoupling: intorder fixed to 4 (test/proportionalflowcoupling.hh:43)
+  F.nq = line_rule(quad_order, qx, qw);
+  F.h_F = ie;
+  if (gradients) {
+    const Tri g1 = tri_geometry(m, cell), g2 = tri_geometry(m, nb);
+    tri_gradients(g1, F.gp1); tri_gradients(g2, F.gp2);
+    // the normal points away from the inside cell's vertex opposite to the face (local vertex 2 - f)
+    const int vo = m.conn[3 * cell + (2 - f)];
+    double nx = dy / ie, ny = -dx / ie;
+    const double side = nx * (m.xy[2 * vo] - m.xy[2 * va]) + ny * (m.xy[2 * vo + 1] - m.xy[2 * va + 1]);
+    if (side > 0.0) { nx = -nx; ny = -ny; }
+    F.normal[0] = nx; F.normal[1] = ny;
+  }
   for (int q = 0; q < F.nq; ++q) {
     const double x1 = c_ref[la][0] + qx[q] * (c_ref[lb][0] - c_ref[la][0]), y1 = c_ref[la][1] + qx[q] * (c_ref[lb][1] - c_ref[la][1]);
     const double x2 = c_ref[ia][0] + qx[q] * (c_ref[ib][0] - c_ref[ia][0]), y2 = c_ref[ia][1] + qx[q] * (c_ref[ib][1] - c_ref[ia][1]);
@@ -580,20 +596,63 @@ __device__ inline void um_propflow(const UMFace& F, double k, const double xs[3]
   }
 }
 
+// ContinuousValueContinuousFlowCoupling::alpha_coupling (test/proportionalflowcoupling.hh:113-233), theta = 1, in the reference's
+// operation order (the finite-difference Jacobian differentiates exactly this arithmetic)
+__device__ inline void um_cvcf(const UMFace& F, double alpha, const double x1[3], const double x2[3], double weight, double r1[3], double r2[3])
+{
+  for (int q = 0; q < F.nq; ++q) {
+    double gradu1[2] = {0.0, 0.0}, gradu2[2] = {0.0, 0.0};
+    for (int i = 0; i < 3; ++i) for (int d = 0; d < 2; ++d) gradu1[d] += x1[i] * F.gp1[i][d];
+    for (int i = 0; i < 3; ++i) for (int d = 0; d < 2; ++d) gradu2[d] += x2[i] * F.gp2[i][d];
+    double u1 = 0.0; for (int i = 0; i < 3; ++i) u1 += x1[i] * F.phi1[q][i];
+    double u2 = 0.0; for (int i = 0; i < 3; ++i) u2 += x2[i] * F.phi2[q][i];
+    const double n1[2] = {F.normal[0], F.normal[1]}, n2[2] = {-F.normal[0], -F.normal[1]};
+    const double jump_u1 = u1 - u2, jump_u2 = u2 - u1;
+    double mean_gradu[2];
+    for (int d = 0; d < 2; ++d) { mean_gradu[d] = gradu1[d] + gradu2[d]; mean_gradu[d] *= 0.5; }
+    const double factor = F.factor[q];
+    for (int i = 0; i < 3; ++i) {
+      double mgn = 0.0, gpn = 0.0;
+      for (int d = 0; d < 2; ++d) mgn += mean_gradu[d] * n1[d];
+      for (int d = 0; d < 2; ++d) gpn += F.gp1[i][d] * n1[d];
+      double value = 0.0;
+      value -= mgn * F.phi1[q][i];
+      value -= 0.5 * gpn * jump_u1;
+      value += alpha / F.h_F * jump_u1 * F.phi1[q][i];
+      r1[i] += weight * (factor * value);
+    }
+    for (int i = 0; i < 3; ++i) {
+      double mgn = 0.0, gpn = 0.0;
+      for (int d = 0; d < 2; ++d) mgn += mean_gradu[d] * n2[d];
+      for (int d = 0; d < 2; ++d) gpn += F.gp2[i][d] * n2[d];
+      double value = 0.0;
+      value -= mgn * F.phi2[q][i];
+      value -= 0.5 * gpn * jump_u2;
+      value += alpha / F.h_F * jump_u2 * F.phi2[q][i];
+      r2[i] += weight * (factor * value);
+    }
+  }
+}
+__device__ inline void um_alpha_coupling(const UMCp& cp, const UMFace& F, const double xs[3], const double xn[3], double weight, double rs[3], double rn[3])
+{
+  if (cp.op_id == MDB_OP_CVCF_COUPLING) um_cvcf(F, cp.intensity, xs, xn, weight, rs, rn);
+  else um_propflow(F, cp.intensity, xs, xn, weight, rs, rn);
+}
+
 __global__ void k_um_coupling_residual(UMDev m, UMSpace S, UMCp cp, const int32_t* fcell, const int8_t* fface, int64_t nf, double weight,
                                        const double* __restrict__ x, double* r)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nf) return;
   const int cell = fcell[i], f = fface[i], nb = m.nbr[3 * cell + f];
-  UMFace F; um_face_setup(m, cell, f, nb, F);
+  UMFace F; um_face_setup(m, cell, f, nb, cp.quad_order, cp.op_id == MDB_OP_CVCF_COUPLING, F);
   int64_t gs[3], gn[3]; double xs[3], xn[3];
   for (int k = 0; k < 3; ++k) {
     gs[k] = S.offset[cp.childL] + S.v2d[cp.childL][m.conn[3 * cell + k]]; gn[k] = S.offset[cp.childR] + S.v2d[cp.childR][m.conn[3 * nb + k]];
     xs[k] = x[gs[k]]; xn[k] = x[gn[k]];
   }
   double rs[3] = {0.0, 0.0, 0.0}, rn[3] = {0.0, 0.0, 0.0};
-  um_propflow(F, cp.intensity, xs, xn, weight, rs, rn);
+  um_alpha_coupling(cp, F, xs, xn, weight, rs, rn);
   for (int k = 0; k < 3; ++k) { atomicAdd(&r[gs[k]], rs[k]); atomicAdd(&r[gn[k]], rn[k]); }
 }
 
@@ -605,7 +664,7 @@ __global__ void k_um_coupling_jacobian(UMDev m, UMSpace S, UMCp cp, const int32_
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nf) return;
   const int cell = fcell[i], f = fface[i], nb = m.nbr[3 * cell + f];
-  UMFace F; um_face_setup(m, cell, f, nb, F);
+  UMFace F; um_face_setup(m, cell, f, nb, cp.quad_order, cp.op_id == MDB_OP_CVCF_COUPLING, F);
   int32_t g[6]; double u[6];
   for (int k = 0; k < 3; ++k) {
     g[k] = (int32_t)(S.offset[cp.childL] + S.v2d[cp.childL][m.conn[3 * cell + k]]); g[3 + k] = (int32_t)(S.offset[cp.childR] + S.v2d[cp.childR][m.conn[3 * nb + k]]);
@@ -613,13 +672,13 @@ __global__ void k_um_coupling_jacobian(UMDev m, UMSpace S, UMCp cp, const int32_
   const bool analytic = cp.jac_mode == MDB_JAC_ANALYTIC;
   for (int k = 0; k < 6; ++k) u[k] = analytic ? 0.0 : x[g[k]];
   double down[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (!analytic) um_propflow(F, cp.intensity, u, u + 3, 1.0, down, down + 3);
+  if (!analytic) um_alpha_coupling(cp, F, u, u + 3, 1.0, down, down + 3);
   for (int j = 0; j < 6; ++j) {
     const double keep = u[j];
     const double delta = analytic ? 1.0 : 1e-8 * (1.0 + fabs(u[j]));
     u[j] = analytic ? 1.0 : u[j] + delta;
     double up[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    um_propflow(F, cp.intensity, u, u + 3, 1.0, up, up + 3);
+    um_alpha_coupling(cp, F, u, u + 3, 1.0, up, up + 3);
     u[j] = keep;
     for (int r = 0; r < 6; ++r) {
       const double entry = analytic ? up[r] : (up[r] - down[r]) / delta;

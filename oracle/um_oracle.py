@@ -15,7 +15,7 @@ GlobalAssembler::assemble (globalassembler.hh:43-298):
                 not in the subproblem -> the operator's boundary methods, which answer "no condition" there)
   Jacobian      jacobianassemblerengine.hh:195-504; coupling Jacobian by NumericalJacobianCoupling couplingutilities.hh:75-135
   operators     [UPSTREAM] PDELab::Poisson = test/instationarypoissonoperator.hh:30-168, PDELab::L2 = test/simpletimeoperator.hh:29-101,
-                ProportionalFlowCoupling test/proportionalflowcoupling.hh:27-86
+                ProportionalFlowCoupling test/proportionalflowcoupling.hh:27-86, ContinuousValueContinuousFlowCoupling :113-233
   constraints   constraints.hh:312-558, constraintsfunctors.hh:75-103 ([UPSTREAM] ConformingDirichletConstraints: predicate at the
                 face centre, the face's vertices are constrained)
   interpolation interpolate.hh:35-73
@@ -33,7 +33,7 @@ import numpy as np
 
 FACE_V = ((0, 1), (0, 2), (1, 2))
 REF = ((0.0, 0.0), (1.0, 0.0), (0.0, 1.0))
-OP_POISSON, OP_L2, OP_PROPFLOW = 1, 2, 102
+OP_POISSON, OP_L2, OP_CVCF, OP_PROPFLOW = 1, 2, 101, 102
 JAC_FD, JAC_ANALYTIC = 0, 1
 
 
@@ -167,8 +167,9 @@ class UMOracle:
         return len(self.sps) - 1
 
     def add_coupling(self, op_id, params, local_sp, remote_sp, jac_mode=JAC_FD):
-        assert op_id == OP_PROPFLOW
-        self.cps.append(dict(k=params.intensity, local=local_sp, remote=remote_sp, jac_mode=jac_mode))
+        assert op_id in (OP_PROPFLOW, OP_CVCF)
+        order = params.quad_order if op_id == OP_CVCF else 4          # ProportionalFlowCoupling: intorder fixed to 4 (:43)
+        self.cps.append(dict(op=op_id, k=params.intensity, order=order, local=local_sp, remote=remote_sp, jac_mode=jac_mode))
         return len(self.cps) - 1
 
     def _present(self, k, e):
@@ -216,7 +217,8 @@ class UMOracle:
         ax, ay = p[1][0] - p[0][0], p[1][1] - p[0][1]
         bx, by = p[2][0] - p[0][0], p[2][1] - p[0][1]
         det = ax * by - ay * bx
-        t = ((by / det, -ay / det), (-bx / det, ax / det))
+        inv = 1.0 / det            # [UPSTREAM] dune-common FMatrixHelp::invertMatrix (2x2) multiplies by the reciprocal determinant
+        t = ((by * inv, -(ay * inv)), (-(bx * inv), ax * inv))
         js = ((-1.0, -1.0), (1.0, 0.0), (0.0, 1.0))
         gp = []
         for i in range(3):
@@ -338,13 +340,64 @@ class UMOracle:
             for i in range(3):
                 rn[i] += weight * (-u_diff * phi2[i] * factor)
 
-    def _face_points(self, e, f):
+    # ContinuousValueContinuousFlowCoupling::alpha_coupling (test/proportionalflowcoupling.hh:113-233), theta = 1
+    def _cvcf(self, F, G, alpha, x1, x2, weight, r1, r2):
+        gp1, gp2, n1, h_F = G
+        n2 = (-n1[0], -n1[1])
+        for phi1, phi2, factor in F:
+            gradu1, gradu2 = [0.0, 0.0], [0.0, 0.0]
+            for i in range(3):
+                for d in range(2):
+                    gradu1[d] += x1[i] * gp1[i][d]
+            for i in range(3):
+                for d in range(2):
+                    gradu2[d] += x2[i] * gp2[i][d]
+            u1 = 0.0
+            for i in range(3):
+                u1 += x1[i] * phi1[i]
+            u2 = 0.0
+            for i in range(3):
+                u2 += x2[i] * phi2[i]
+            jump_u1, jump_u2 = u1 - u2, u2 - u1
+            mean_gradu = [(gradu1[d] + gradu2[d]) * 0.5 for d in range(2)]
+            for gp, n, phi, jump, r in ((gp1, n1, phi1, jump_u1, r1), (gp2, n2, phi2, jump_u2, r2)):
+                for i in range(3):
+                    mgn = 0.0
+                    for d in range(2):
+                        mgn += mean_gradu[d] * n[d]
+                    gpn = 0.0
+                    for d in range(2):
+                        gpn += gp[i][d] * n[d]
+                    value = 0.0
+                    value -= mgn * phi[i]
+                    value -= 0.5 * gpn * jump
+                    value += alpha / h_F * jump * phi[i]
+                    r[i] += weight * (factor * value)
+
+    def _alpha_coupling(self, cp, e, f, xs, xn, weight, rs, rn):
+        F = self._face_points(e, f, cp["order"])
+        if cp["op"] == OP_CVCF:
+            self._cvcf(F, self._face_gradients(e, f), cp["k"], xs, xn, weight, rs, rn)
+        else:
+            self._propflow(F, cp["k"], xs, xn, weight, rs, rn)
+
+    def _face_gradients(self, e, f):
+        nb = int(self.nbr[e, f])
+        la, lb, va, vb, pa, dx, dy, ie = self._face(e, f)
+        po = self.xy[self.conn[e, 2 - f]]                 # the inside cell's vertex opposite to the face
+        nx, ny = dy / ie, -dx / ie
+        side = nx * (po[0] - pa[0]) + ny * (po[1] - pa[1])
+        if side > 0.0:
+            nx, ny = -nx, -ny
+        return self._tri(e)[1], self._tri(nb)[1], (nx, ny), ie
+
+    def _face_points(self, e, f, order=4):
         nb = int(self.nbr[e, f])
         la, lb, va, vb, pa, dx, dy, ie = self._face(e, f)
         cn = list(self.conn[nb])
         ia, ib = cn.index(va), cn.index(vb)
         F = []
-        for qx, qw in line_rule(4):                       # intorder fixed to 4 (:43)
+        for qx, qw in line_rule(order):
             x1 = REF[la][0] + qx * (REF[lb][0] - REF[la][0])
             y1 = REF[la][1] + qx * (REF[lb][1] - REF[la][1])
             x2 = REF[ia][0] + qx * (REF[ib][0] - REF[ia][0])
@@ -419,7 +472,7 @@ class UMOracle:
                     ds = self._dofs(self.sps[cp["local"]].child, e)
                     dn = self._dofs(self.sps[cp["remote"]].child, nb)
                     rs, rn = [0.0] * 3, [0.0] * 3
-                    self._propflow(self._face_points(e, f), cp["k"], [x[d] for d in ds], [x[d] for d in dn], weight, rs, rn)
+                    self._alpha_coupling(cp, e, f, [x[d] for d in ds], [x[d] for d in dn], weight, rs, rn)
                     for i in range(3):
                         r[ds[i]] += rs[i]
                         r[dn[i]] += rn[i]
@@ -469,20 +522,19 @@ class UMOracle:
                     cp = self.cps[q]
                     nb = int(self.nbr[e, f])
                     g = self._dofs(self.sps[cp["local"]].child, e) + self._dofs(self.sps[cp["remote"]].child, nb)
-                    F = self._face_points(e, f)
                     analytic = cp["jac_mode"] == JAC_ANALYTIC
                     u = [0.0 if analytic else float(x[d]) for d in g]
                     down = [0.0] * 6
                     if not analytic:                                      # base line (couplingutilities.hh:94-97)
                         rs, rn = [0.0] * 3, [0.0] * 3
-                        self._propflow(F, cp["k"], u[:3], u[3:], 1.0, rs, rn)
+                        self._alpha_coupling(cp, e, f, u[:3], u[3:], 1.0, rs, rn)
                         down = rs + rn
                     for j in range(6):                                    # jiggle in self, then in the neighbour (:99-133)
                         keep = u[j]
                         delta = 1.0 if analytic else 1e-8 * (1.0 + abs(u[j]))
                         u[j] = 1.0 if analytic else u[j] + delta
                         rs, rn = [0.0] * 3, [0.0] * 3
-                        self._propflow(F, cp["k"], u[:3], u[3:], 1.0, rs, rn)
+                        self._alpha_coupling(cp, e, f, u[:3], u[3:], 1.0, rs, rn)
                         up = rs + rn
                         u[j] = keep
                         for i in range(6):

@@ -22,6 +22,7 @@ CASES = {
     "um2d_6x5_propflow_fd": (6, 5, 3, 0, dict()),
     "um2d_9x7_split_y_mass": (9, 7, 8, 1, dict(with_mass=True, k=4.0)),
     "um2d_5x5_shared_space": (5, 5, 1, 0, dict(shared_space=True)),
+    "um2d_8x6_cvcf": (8, 6, 4, 0, dict(cvcf=True, k=2.0)),
 }
 
 

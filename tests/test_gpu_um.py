@@ -26,6 +26,10 @@ CASES = {
     "um_no_coupling_dirichlet": dict(mesh=(5, 9, 6), coupling=False, bc=capi.BCType(capi.BC_ALL_DIRICHLET)),
     "um_2x1": dict(mesh=(2, 1, 0)),                            # four triangles, two free DOFs per subdomain at most
     "um_40x30": dict(mesh=(40, 30, 7)),
+    # ContinuousValueContinuousFlowCoupling (the coupling of test/testpoisson.cc) with the FD Jacobian / exact derivative
+    "um_cvcf": dict(mesh=(8, 6, 9), cvcf=True, k=2.0),
+    "um_cvcf_split_y_analytic": dict(mesh=(7, 9, 10), axis=1, cvcf=True, k=10.0, jac_mode=capi.JAC_ANALYTIC),
+    "um_cvcf_shared_space": dict(mesh=(6, 6, 12), cvcf=True, k=3.0, shared_space=True),
 }
 
 

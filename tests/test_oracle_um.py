@@ -124,6 +124,32 @@ def test_patch_test_and_coupling_vanishes_on_continuous_functions(case):
     assert np.abs(r).max() > 1e-2                           # the one-sided flux on the interface rows is there
 
 
+def test_cvcf_coupling_is_consistent_and_symmetric(case):
+    """With ContinuousValueContinuousFlowCoupling (theta = 1: symmetric interior penalty) the two-subdomain problem is consistent:
+    a globally linear function has zero residual on EVERY unconstrained row, interface rows included (the coupling's flux term
+    cancels the one-sided boundary flux of the volume terms, its jump terms vanish) — which is not so without the coupling.  The
+    exact-derivative Jacobian of the coupled problem is symmetric on the unconstrained block."""
+    xy, conn, sd = case
+    lin = capi.Function(capi.FN_POLY2, 1.0, 2.0, -3.0, 0.0, 0.0)
+    o = ump.oracle()
+    H = ump.setup(o, xy, conn, sd, cvcf=True, k=2.0, f=capi.Function(capi.FN_ZERO), bc=capi.BCType(capi.BC_ALL_DIRICHLET),
+                  jac_mode=capi.JAC_ANALYTIC)
+    x = o.interpolate(list(H["sp"]), [lin, lin], np.zeros(H["ndof"]))
+    r = o.residual(H["go"], x, np.zeros(H["ndof"]))
+    assert np.abs(r).max() < 1e-13
+    o.jacobian(H["go"], H["mat"], x, overwrite=True)
+    free = o.get_constraints() == 0
+    A = _csr(o, H["mat"]).toarray()[np.ix_(free, free)]
+    assert np.abs(A - A.T).max() < 1e-12 * np.abs(A).max()
+    assert np.linalg.eigvalsh(0.5 * (A + A.T)).min() > 0           # penalty 2 / h_F is enough on this mesh
+    o2 = ump.oracle()
+    H2 = ump.setup(o2, xy, conn, sd, cvcf=True, k=2.0, f=capi.Function(capi.FN_ZERO), bc=capi.BCType(capi.BC_ALL_DIRICHLET))
+    o2.jacobian(H2["go"], H2["mat"], x, overwrite=True)
+    fd = _csr(o2, H2["mat"]).toarray()
+    an = _csr(o, H["mat"]).toarray()
+    assert 0 < np.abs(fd - an).max() < 1e-5 * np.abs(an).max()     # FD noise, and nothing more
+
+
 def test_fd_coupling_jacobian_against_closed_form(case):
     xy, conn, sd = case
     k = 2.5

@@ -64,7 +64,7 @@ def halves(xy, conn, axis=0, threshold=0.5):
 
 
 def setup(lib, xy, conn, sd, *, shared_space=False, jac_mode=capi.JAC_FD_BITMATCH, k=2.5, orders=(4, 2), f=None, with_mass=False,
-          bc=None, coupling=True):
+          bc=None, coupling=True, cvcf=False):
     """Spaces, subproblems, coupling, constraints, linearisation point.  Returns a dict of handles."""
     lib.mesh_unstructured(xy, conn)
     lib.subdomains(sd)
@@ -87,7 +87,10 @@ def setup(lib, xy, conn, sd, *, shared_space=False, jac_mode=capi.JAC_FD_BITMATC
         H["mass_sp"] = (lib.add_subproblem(capi.OP_L2, l2, capi.COND_EQUALITY, 1, [c0]),
                         lib.add_subproblem(capi.OP_L2, l2, capi.COND_EQUALITY, 2, [c1]))
     cps = []
-    if coupling:
+    if coupling and cvcf:                                    # the coupling of test/testpoisson.cc:234 (intorder 4)
+        cv = capi.CVCFParams(); cv.quad_order, cv.intensity = 4, k
+        cps = [lib.add_coupling(capi.OP_CVCF_COUPLING, cv, sp0, sp1, jac_mode)]
+    elif coupling:
         pf = capi.PropFlowParams(); pf.intensity = k
         cps = [lib.add_coupling(capi.OP_PROPFLOW_COUPLING, pf, sp0, sp1, jac_mode)]
     H["ndof"] = lib.finalize()
@@ -188,7 +191,7 @@ def check_golden(lib, path, solve=None):
     largest entry, solution 1e-10."""
     g = np.load(path)
     kw = {str(k): float(v) for k, v in zip(g["kw_keys"], g["kw_vals"])}
-    for key in ("with_mass", "shared_space"):
+    for key in ("with_mass", "shared_space", "cvcf"):
         if key in kw:
             kw[key] = bool(kw[key])
     H = setup(lib, g["xy"], g["conn"], g["sd"], **kw)
