@@ -202,8 +202,8 @@ int mdb_mesh_structured(mdb_ctx* ctx, int dim, const int64_t* n, const double* l
  * index order of the host grid); local vertex i of a cell carries the P1 shape function i; face f of a cell is opposite to
  * local vertex 2 - f (DUNE simplex numbering: face 0 = {0,1}, 1 = {0,2}, 2 = {1,2}).  The call validates the mesh (indices in
  * range, no degenerate cell, at most two cells per face) and builds the face neighbours and the vertex -> cell adjacency (the
- * grid manager's job in the reference).  Spaces: MDB_FE_P1; operators: MDB_OP_POISSON, MDB_OP_L2, MDB_OP_PROPFLOW_COUPLING
- * (MDB_EINVAL for the others in this build); linear solvers as on structured meshes.  Subdomains: mdb_subdomains with
+ * grid manager's job in the reference).  Spaces: MDB_FE_P1; operators: MDB_OP_POISSON, MDB_OP_L2, MDB_OP_CVCF_COUPLING,
+ * MDB_OP_PROPFLOW_COUPLING (MDB_EINVAL for the others in this build); linear solvers as on structured meshes.  Subdomains: mdb_subdomains with
  * one byte per cell (physical group -> subdomain as in test/stokesdarcy2.cc:596-601). */
 enum { MDB_ETYPE_TRIANGLE = 2 };   /* gmsh element type 2 */
 int mdb_mesh_unstructured(mdb_ctx* ctx, int dim, int64_t nv, const double* xyz, int64_t ne, int etype, const int64_t* conn);
