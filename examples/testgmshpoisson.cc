@@ -3,7 +3,7 @@
 // physical group > 0 -> subdomain 1), the problem part is test/testpoisson.cc:163-298 with P1 spaces on both subdomains and the
 // reference's ProportionalFlowCoupling (test/proportionalflowcoupling.hh:10-91) across the interface.
 //
-//   testgmshpoisson <mesh.msh> [refinements=0] [coupling intensity=2.0] [solver: ssor (default) | jac]
+//   testgmshpoisson <mesh.msh> [refinements=0] [coupling intensity=2.0] [solver: ssor (default) | jac] [vtk output prefix]
 //
 // Prints the grid sizes, the DOF / constrained-DOF line, the solver statistics and a checksum of u.
 #include <cmath>
@@ -22,6 +22,7 @@ int main(int argc, char** argv)
     const int refine = argc > 2 ? std::atoi(argv[2]) : 0;
     const double intensity = argc > 3 ? std::atof(argv[3]) : 2.0;
     const bool jacobi = argc > 4 && std::string(argv[4]) == "jac";
+    const std::string out = argc > 5 ? argv[5] : "";
 
     GmshMesh mesh = GmshReader::read(argv[1], true, false);          // gmshreader.read(filename, b2p, e2p, true, false)  (:578)
     mesh.globalRefine(refine);
@@ -68,6 +69,13 @@ int main(int argc, char** argv)
       ISTLBackend_SEQ_BCGS_SSOR ls(5000);
       StationaryLinearProblemSolver<ISTLBackend_SEQ_BCGS_SSOR> pdesolver(gridoperator, ls, 1e-10);
       pdesolver.apply(u); res = ls.res;
+    }
+
+    if (!out.empty()) {                                              // one piece per subdomain, as every reference driver ends (vtk.hh:83-98)
+      VTKWriter left(grid, grid.subDomain(0)), right(grid, grid.subDomain(1));
+      left.addSolution(multigfs, u, {&gfs0, &gfs1});
+      right.addSolution(multigfs, u, {&gfs0, &gfs1});
+      left.write(out + "testgmshpoisson-left"); right.write(out + "testgmshpoisson-right");
     }
 
     double sum = 0.0, sum2 = 0.0;

@@ -170,6 +170,7 @@ class MultiDomainGrid {
   std::vector<uint8_t> marks_;
   bool marking_;
   bool unstructured_ = false;
+  std::vector<double> uvertices_; std::vector<int64_t> uelements_;
 public:
   const std::vector<double>& lower() const { return lower_; }
   const std::vector<double>& upper() const { return upper_; }
@@ -179,11 +180,14 @@ public:
   }
   // MultiDomainGrid<UGGrid<2>, ...> grid(baseGrid, false) over a mesh read by GmshReader (test/stokesdarcy2.cc:585-586)
   MultiDomainGrid(Context& ctx, const GmshMesh& mesh)
-    : ctx_(ctx), dim_(mesh.dim), n_(1, mesh.numElements()), lower_(mesh.dim, 0.0), upper_(mesh.dim, 1.0), marking_(false), unstructured_(true) {
+    : ctx_(ctx), dim_(mesh.dim), n_(1, mesh.numElements()), lower_(mesh.dim, 0.0), upper_(mesh.dim, 1.0), marking_(false), unstructured_(true),
+      uvertices_(mesh.vertices), uelements_(mesh.elements) {
     ctx_.check(mdb_mesh_unstructured(ctx_.get(), mesh.dim, mesh.numVertices(), mesh.vertices.data(), mesh.numElements(), MDB_ETYPE_TRIANGLE,
                                      mesh.elements.data()), "mdb_mesh_unstructured");
   }
   bool unstructured() const { return unstructured_; }
+  const std::vector<double>& vertices() const { return uvertices_; }        // simplex meshes: dim doubles per vertex
+  const std::vector<int64_t>& elements() const { return uelements_; }       // simplex meshes: dim + 1 vertex indices per cell
   Context& context() const { return ctx_; }
   int dimension() const { return dim_; }
   int64_t size0() const { if (unstructured_) return n_[0]; int64_t t = 1; for (int d = 0; d < dim_; ++d) t *= n_[d]; return t; }
@@ -602,7 +606,7 @@ public:
 // ---- output ([UPSTREAM] Dune::VTKWriter + multidomain/vtk.hh:83-98 addSolutionToVTKWriter; dune-istl writeMatrixToMatlab) -----------
 // VTKWriter<SDGV> vtkwriter(sdgv, VTK::conforming); addSolutionToVTKWriter(vtkwriter, multigfs, u, subdomain_predicate(sd));
 // vtkwriter.write(name, VTK::ascii)  — as every reference driver ends (e.g. test/testpoisson.cc:301-323).  One unstructured-grid
-// piece per subdomain: its cells (VTK_QUAD / VTK_HEXAHEDRON), their vertices, and per child space living on that subdomain one
+// piece per subdomain: its cells (VTK_QUAD / VTK_HEXAHEDRON, VTK_TRIANGLE on simplex meshes), their vertices, and per child space living on that subdomain one
 // point-data array with the solution at the vertices (conforming output: for Q2 the corner values, like VTK::conforming).
 class VTKWriter {
   MultiDomainGrid& grid_; int subdomain_;
@@ -611,24 +615,26 @@ class VTKWriter {
   std::vector<int64_t> cells_;                 // MultiDomainGrid indices of the subdomain's cells, host order
   std::vector<int64_t> vertex_of_point_;       // MultiDomainGrid vertex index of every output point (ascending = subdomain vertex order)
   std::vector<int64_t> point_of_vertex_;
+  int corners() const { return grid_.unstructured() ? grid_.dimension() + 1 : (1 << grid_.dimension()); }
   void collect() {
-    if (grid_.unstructured()) throw Exception(MDB_EINVAL, "VTKWriter: simplex meshes are not written in this build");
     if (!cells_.empty()) return;
     std::vector<uint8_t> sd((size_t)grid_.size0());
     grid_.context().check(mdb_get_subdomains(grid_.context().get(), sd.data()), "mdb_get_subdomains");
     const int dim = grid_.dimension(); const std::vector<int64_t>& n = grid_.cells();
     int64_t nv = 1; for (int d = 0; d < dim; ++d) nv *= n[d] + 1;
+    if (grid_.unstructured()) nv = (int64_t)grid_.vertices().size() / dim;
     std::vector<char> used((size_t)nv, 0);
     for (int64_t e = 0; e < grid_.size0(); ++e) {
       if (subdomain_ >= 0 && !((sd[(size_t)e] >> subdomain_) & 1)) continue;
       cells_.push_back(e);
-      for (int c = 0; c < (1 << dim); ++c) used[(size_t)vertex(e, c)] = 1;
+      for (int c = 0; c < corners(); ++c) used[(size_t)vertex(e, c)] = 1;
     }
     point_of_vertex_.assign((size_t)nv, -1);
     for (int64_t v = 0; v < nv; ++v) if (used[(size_t)v]) { point_of_vertex_[(size_t)v] = (int64_t)vertex_of_point_.size(); vertex_of_point_.push_back(v); }
   }
   int64_t vertex(int64_t e, int corner) const {          // [UPSTREAM] Yasp: corner bit d = offset along axis d; vertices lexicographic
     const int dim = grid_.dimension(); const std::vector<int64_t>& n = grid_.cells();
+    if (grid_.unstructured()) return grid_.elements()[(size_t)(e * (dim + 1) + corner)];
     int64_t idx = 0, stride = 1, rem = e;
     for (int d = 0; d < dim; ++d) { const int64_t i = rem % n[d] + ((corner >> d) & 1); rem /= n[d]; idx += i * stride; stride *= n[d] + 1; }
     return idx;
@@ -659,11 +665,12 @@ public:
         for (const GridFunctionSpace* h : children) {
           if (h == g) break;
           if (h->coupling) continue;
-          if (h->gv.subdomain < 0 || ((sd[(size_t)e] >> h->gv.subdomain) & 1)) { int nl = 1; for (int d = 0; d < dim; ++d) nl *= h->k + 1; off += nl; }
+          if (h->gv.subdomain < 0 || ((sd[(size_t)e] >> h->gv.subdomain) & 1)) { int nl = 1; for (int d = 0; d < dim; ++d) nl *= h->k + 1; if (h->simplex) nl = dim + 1; off += nl; }
         }
-        for (int c = 0; c < (1 << dim); ++c) {
+        for (int c = 0; c < corners(); ++c) {
           int li = 0, stride = 1;                                               // Qk local index of the corner: a_d = k * bit_d
           for (int d = 0; d < dim; ++d) { li += g->k * ((c >> d) & 1) * stride; stride *= g->k + 1; }
+          if (g->simplex) li = c;                                               // P1: shape function c sits at corner c
           f.point_values[(size_t)point_of_vertex_[(size_t)vertex(e, c)]] = x[(size_t)dofs[(size_t)(off + li)]];
         }
       }
@@ -687,22 +694,23 @@ public:
     std::fprintf(fp, "</PointData>\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n");
     for (size_t p = 0; p < vertex_of_point_.size(); ++p) {
       int64_t rem = vertex_of_point_[p]; double xyz[3] = {0, 0, 0};
-      for (int d = 0; d < dim; ++d) { xyz[d] = grid_.lower()[d] + (double)(rem % (n[d] + 1)) * ((grid_.upper()[d] - grid_.lower()[d]) / (double)n[d]); rem /= n[d] + 1; }
+      if (grid_.unstructured()) for (int d = 0; d < dim; ++d) xyz[d] = grid_.vertices()[(size_t)(rem * dim + d)];
+      else for (int d = 0; d < dim; ++d) { xyz[d] = grid_.lower()[d] + (double)(rem % (n[d] + 1)) * ((grid_.upper()[d] - grid_.lower()[d]) / (double)n[d]); rem /= n[d] + 1; }
       std::fprintf(fp, "%.17g %.17g %.17g\n", xyz[0], xyz[1], xyz[2]);
     }
     std::fprintf(fp, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n");
     static const int vtk_quad[4] = {0, 1, 3, 2}, vtk_hex[8] = {0, 1, 3, 2, 4, 5, 7, 6};      // DUNE corner order -> VTK order
     for (size_t ci = 0; ci < cells_.size(); ++ci) {
-      for (int c = 0; c < (1 << dim); ++c) {
-        const int dc = dim == 3 ? vtk_hex[c] : dim == 2 ? vtk_quad[c] : c;
+      for (int c = 0; c < corners(); ++c) {
+        const int dc = grid_.unstructured() ? c : dim == 3 ? vtk_hex[c] : dim == 2 ? vtk_quad[c] : c;
         std::fprintf(fp, "%lld ", (long long)point_of_vertex_[(size_t)vertex(cells_[ci], dc)]);
       }
       std::fprintf(fp, "\n");
     }
     std::fprintf(fp, "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n");
-    for (size_t ci = 0; ci < cells_.size(); ++ci) std::fprintf(fp, "%lld\n", (long long)((ci + 1) << dim));
+    for (size_t ci = 0; ci < cells_.size(); ++ci) std::fprintf(fp, "%lld\n", (long long)((ci + 1) * (size_t)corners()));
     std::fprintf(fp, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
-    for (size_t ci = 0; ci < cells_.size(); ++ci) std::fprintf(fp, "%d\n", dim == 3 ? 12 : dim == 2 ? 9 : 3);
+    for (size_t ci = 0; ci < cells_.size(); ++ci) std::fprintf(fp, "%d\n", grid_.unstructured() ? (dim == 3 ? 10 : 5) : dim == 3 ? 12 : dim == 2 ? 9 : 3);
     std::fprintf(fp, "</DataArray>\n</Cells>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
     std::fclose(fp);
   }

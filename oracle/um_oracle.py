@@ -61,6 +61,12 @@ def eval_function(f, x, t=0.0):
         if x[0] > 1.0 - 1e-6 and x[1] > 0.5 + 1e-6:
             return -5.0
         return 0.0
+    if k == 5:                                            # test/testinstationarypoisson.cc:94-100 family (time dependent Dirichlet data)
+        n2 = 0.0
+        for d in range(2):
+            c = 0.5 - x[d]
+            n2 += c * c
+        return p[0] * math.sin(p[1] * t) * math.exp(-n2)
     if k == 6:
         v, n2 = p[0], 0.0
         for d in range(2):

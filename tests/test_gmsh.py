@@ -67,7 +67,7 @@ def test_driver_against_oracle(refinements, solver):
         exe = _build(d)
         msh = os.path.join(d, "square.msh")
         _fixture(msh)
-        out = subprocess.run([exe, msh, str(refinements), "2.0", solver], capture_output=True, text=True, check=True).stdout
+        out = subprocess.run([exe, msh, str(refinements), "2.0", solver, d + "/"], capture_output=True, text=True, check=True).stdout
         xy, conn, groups = ump.read_gmsh(msh)
         for _ in range(refinements):
             xy, conn, groups = ump.refine(xy, conn, groups)
@@ -84,3 +84,20 @@ def test_driver_against_oracle(refinements, solver):
         m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out)
         assert abs(float(m.group(1)) - u.sum()) <= 1e-9 * abs(u.sum())
         assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-9 * np.linalg.norm(u)
+        # VTK output per subdomain (vtk.hh:83-98): triangles of the subdomain, its vertices, the solution as point data
+        off = o.get_child_offsets()
+        for side, sdi in (("left", 0), ("right", 1)):
+            txt = open(os.path.join(d, "testgmshpoisson-%s.vtu" % side)).read()
+            cells = np.nonzero((sd >> sdi) & 1)[0]
+            verts = np.unique(conn[cells])
+            assert 'NumberOfPoints="%d" NumberOfCells="%d"' % (verts.size, cells.size) in txt
+
+            def block(name_attr):
+                body = txt.split(name_attr, 1)[1].split(">", 1)[1].split("</DataArray>", 1)[0]
+                return np.array(body.split(), dtype=np.float64)
+            vals = block('Name="u"')
+            pts = block('NumberOfComponents="3"').reshape(-1, 3)
+            con = block('Name="connectivity"').astype(np.int64).reshape(-1, 3)
+            assert np.array_equal(block('Name="types"'), np.full(cells.size, 5.0))
+            assert np.abs(pts[:, :2] - xy[verts]).max() == 0.0 and np.array_equal(verts[con], conn[cells])
+            assert np.abs(vals - u[off[sdi]:off[sdi + 1]]).max() <= 1e-9 * np.abs(u).max()     # DOF order = subdomain vertex order

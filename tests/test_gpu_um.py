@@ -177,3 +177,47 @@ def test_device_reproduces_golden(path):
     dev = pkg.Mdb(0)
     ump.check_golden(dev, path, solve)
     dev.close()
+
+
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_one_step_theta_on_a_triangle_mesh(theta):
+    """mdb_onestep_apply (the instationary glue of test/testinstationarypoisson.cc:320-403: OneStepGridOperator over a spatial and
+    a temporal grid operator, time dependent Dirichlet data) on the unstructured path, two steps of the one-step-theta scheme
+    against the same stage equations formed from the oracle's residuals and Jacobians and solved by SciPy.  Every step starts both
+    sides from the SAME vector: the finite-difference coupling Jacobian turns a 1e-14 difference of the linearisation point into
+    1e-8 relative noise of its entries, so two free-running trajectories agree only to ~1e-9 after the first step
+    (profiles/scripts/dbg_onestep.py) — a property of the reference's algorithm, not of either implementation."""
+    xy, conn = ump.square_mesh(9, 8, seed=21)
+    sd = ump.halves(xy, conn)
+    dev, ora = pkg.Mdb(0), ump.oracle()
+    Hd = ump.setup(dev, xy, conn, sd, with_mass=True, cvcf=True, k=2.0)
+    Ho = ump.setup(ora, xy, conn, sd, with_mass=True, cvcf=True, k=2.0)
+    g = capi.Function(capi.FN_INSTAT_G, 1.5, 3.0)
+    n, dt, t = Ho["ndof"], 0.05, 0.1
+    ud = np.random.default_rng(3).uniform(-1.0, 1.0, n)
+    free = ora.get_constraints() == 0
+    rp, ci = ora.matrix_get_pattern(Ho["mat"])
+    for step in range(2):
+        new = np.zeros(n)
+        st = dev.onestep_apply(Hd["go"], Hd["go1"], Hd["mat"], list(Hd["sp"]), [g, g], t, dt, ud, new, scheme=capi.ONESTEP_THETA, theta=theta,
+                               method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, reduction=1e-13, maxit=2000)
+        assert st.converged
+        uo, ud = ud, new                                         # uo: the vector this step started from
+        # the oracle's stage: x = g(t + dt) on the Dirichlet DOFs, the old values elsewhere; J = J1 + theta dt J0;
+        # R = R1(x) - R1(u_old) + dt ((1 - theta) R0(u_old, t) + theta R0(x, t + dt)); u_new = x - J^-1 R
+        x = ora.interpolate(list(Ho["sp"]), [g, g], np.zeros(n), time=t + dt)
+        x[free] = uo[free]
+        ora.jacobian(Ho["go1"], Ho["mat"], x, weight=1.0, overwrite=True)
+        ora.jacobian(Ho["go"], Ho["mat"], x, weight=theta * dt)
+        R = np.zeros(n)
+        ora.set_time(t)
+        ora.residual(Ho["go1"], uo, R, weight=-1.0)
+        if theta != 1.0:
+            ora.residual(Ho["go"], uo, R, weight=(1.0 - theta) * dt)
+        ora.set_time(t + dt)
+        ora.residual(Ho["go1"], x, R, weight=1.0)
+        ora.residual(Ho["go"], x, R, weight=theta * dt)
+        A = sps.csr_matrix((ora.matrix_get_values(Ho["mat"]), ci, rp), shape=(n, n))
+        assert _close(ud, x - spla.spsolve(A.tocsc(), R), RTOL_SOLUTION)
+        t += dt
+    dev.close()
