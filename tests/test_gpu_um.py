@@ -30,6 +30,10 @@ CASES = {
     "um_cvcf": dict(mesh=(8, 6, 9), cvcf=True, k=2.0),
     "um_cvcf_split_y_analytic": dict(mesh=(7, 9, 10), axis=1, cvcf=True, k=10.0, jac_mode=capi.JAC_ANALYTIC),
     "um_cvcf_shared_space": dict(mesh=(6, 6, 12), cvcf=True, k=3.0, shared_space=True),
+    # ragged markings: an empty subdomain (its child block has no DOF, the coupling no face) and cells that belong to no subdomain
+    # (no DOFs there; the faces towards them are interior faces without a condition, residualassemblerfunctors.hh:80-86)
+    "um_empty_right_subdomain": dict(mesh=(6, 5, 13), marks="all_left"),
+    "um_holes": dict(mesh=(9, 8, 14), marks="holes", cvcf=True),
 }
 
 
@@ -39,6 +43,13 @@ def _make(case):
     axis = kw.pop("axis", 0)
     xy, conn = ump.square_mesh(nx, ny, seed=seed)
     sd = ump.halves(xy, conn, axis=axis)
+    marks = kw.pop("marks", None)
+    if marks == "all_left":
+        sd[:] = 1
+    elif marks == "holes":
+        c = xy[conn].mean(axis=1)
+        sd[(np.abs(c[:, 0] - 0.27) < 0.12) & (np.abs(c[:, 1] - 0.6) < 0.15)] = 0       # a hole inside the left subdomain
+        sd[(np.abs(c[:, 0] - 0.5) < 0.1) & (np.abs(c[:, 1] - 0.3) < 0.1)] = 0          # and one across the interface
     dev, ora = pkg.Mdb(0), ump.oracle()
     return dev, ora, ump.setup(dev, xy, conn, sd, **kw), ump.setup(ora, xy, conn, sd, **kw)
 
