@@ -170,7 +170,7 @@ def run_reference(args, out):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "M2: 3-D Q1/Q1 two-subdomain Poisson + CVCF coupling, %d^3 cells per GPU" % size,
+            "config": {"workload": "M2: 3-D Q1/Q1 two-subdomain Poisson(order 4) + CVCF coupling(4, 2.0), %d^3 cells per GPU" % size,
                        "reference_arm": "CPU restatement of the reference path (oracle port; the reference itself needs the DUNE "
                                         "stack and cannot be built here)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
