@@ -60,6 +60,35 @@ def test_reader_and_refinement_sizes_on_cpu():
         assert p.returncode != 0 and "cannot open" in p.stderr
 
 
+def test_reader_and_refinement_entry_by_entry_on_cpu():
+    """GmshReader + GmshMesh::globalRefine against the independent Python reading (um_problems.read_gmsh / refine): vertex numbering by
+    first appearance in $Elements (boundary lines come first in this fixture, so the numbering differs from the node order), element
+    order, physical groups, boundary segments, and the refinement's vertex / child order — all bit-exact."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "gmsh_dump")
+        libdir = os.path.dirname(pkg.library_path())
+        subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "gmsh_dump.cc"),
+                               "-o", exe, "-L", libdir, "-lmdb200", "-Wl,-rpath," + libdir])
+        msh = os.path.join(d, "square.msh")
+        _fixture(msh, nx=5, ny=4, seed=9, node_id_offset=3, extra_nodes=2)
+        xy, conn, groups = ump.read_gmsh(msh)
+        assert not np.array_equal(xy, ump.square_mesh(5, 4, seed=9)[0])            # the reader renumbers
+        for r in (0, 1, 2):
+            tok = subprocess.run([exe, msh, str(r)], capture_output=True, text=True, check=True).stdout.split()
+            nv, ne, nb = int(tok[0]), int(tok[1]), int(tok[2])
+            rx, rc, rg = xy, conn, groups
+            for _ in range(r):
+                rx, rc, rg = ump.refine(rx, rc, rg)
+            assert (nv, ne, nb) == (rx.shape[0], rc.shape[0], 2 * (5 + 4) * 2 ** r)
+            v = np.array(tok[3:3 + 2 * nv], dtype=np.float64).reshape(nv, 2)
+            e = np.array(tok[3 + 2 * nv:3 + 2 * nv + 4 * ne], dtype=np.int64).reshape(ne, 4)
+            b = np.array(tok[3 + 2 * nv + 4 * ne:], dtype=np.int64).reshape(nb, 3)
+            assert np.array_equal(v, rx) and np.array_equal(e[:, :3], rc) and np.array_equal(e[:, 3], rg)
+            assert np.all(b[:, 2] == 7)
+            on_boundary = lambda p: (np.minimum(np.abs(p[:, 0]), np.abs(p[:, 0] - 1)) == 0) | (np.minimum(np.abs(p[:, 1]), np.abs(p[:, 1] - 1)) == 0)
+            assert on_boundary(v[b[:, 0]]).all() and on_boundary(v[b[:, 1]]).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("refinements,solver", [(0, "ssor"), (1, "ssor"), (2, "jac")])
 def test_driver_against_oracle(refinements, solver):
