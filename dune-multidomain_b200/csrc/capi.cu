@@ -270,6 +270,7 @@ int mdb_mesh_partition(mdb_ctx* c, const int64_t* global_n, const int64_t* cell_
 {
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_mesh_partition: call after mdb_mesh_structured, before mdb_finalize");
+  MDB_REQUIRE(!c->um, MDB_EINVAL, "mdb_mesh_partition: slab partitions exist for structured meshes only (unstructured meshes: single GPU in this build)");
   MeshDesc& m = c->mesh;
   for (int d = 0; d < m.dim; ++d) {
     MDB_REQUIRE(cell_offset[d] >= 0 && cell_offset[d] + m.n[d] <= global_n[d], MDB_EINVAL, "mdb_mesh_partition: slab outside the global mesh");

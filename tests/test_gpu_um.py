@@ -132,6 +132,9 @@ def test_rejects_what_this_build_has_no_kernels_for():
     bad = conn.copy(); bad[0, 0] = xy.shape[0]
     with pytest.raises(capi.MdbError):
         dev.mesh_unstructured(xy, bad)                           # index out of range
+    dev.mesh_unstructured(xy, conn)
+    with pytest.raises(capi.MdbError):
+        dev.mesh_partition((3, 6), (0, 0), (0.0, 0.0), (1.0, 1.0))   # slab partitions are a structured-mesh feature
     dev.mesh_structured((4, 4))
     with pytest.raises(capi.MdbError):
         dev.add_space(capi.FE_P1, 0)
