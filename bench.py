@@ -178,6 +178,34 @@ def run_reference(args, out):
     print(json.dumps(line), file=out)
 
 
+def unstructured_cpu_port(xy, conn, sd):
+    """CPU figure beside extra.unstructured: the volume part of the same Jacobian (P1 Poisson element matrices of every cell,
+    summed into one CSR matrix per subdomain block) as a vectorised NumPy / SciPy port on the host — not the reference's cell loop
+    (that is oracle/um_oracle.py, far too slow to time at this size), so it flatters the CPU.  Returns (seconds, dofs)."""
+    import numpy as np
+    import scipy.sparse as sps
+    t0 = time.perf_counter()
+    ndof = 0
+    for s in (0, 1):
+        cells = np.nonzero((sd >> s) & 1)[0]
+        c = conn[cells]
+        verts, local = np.unique(c, return_inverse=True)
+        local = local.reshape(c.shape)
+        p = xy[c]
+        a, b = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]
+        det = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+        inv = 1.0 / det
+        g1 = np.stack([b[:, 1] * inv, -b[:, 0] * inv], axis=1)
+        g2 = np.stack([-a[:, 1] * inv, a[:, 0] * inv], axis=1)
+        g = np.stack([-g1 - g2, g1, g2], axis=1)                                   # (cells, 3, 2)
+        ke = np.einsum("cid,cjd->cij", g, g) * (0.5 * np.abs(det))[:, None, None]
+        rows = np.repeat(local, 3, axis=1).ravel()
+        cols = np.tile(local, (1, 3)).ravel()
+        A = sps.coo_matrix((ke.ravel(), (rows, cols)), shape=(verts.size, verts.size)).tocsr()
+        ndof += A.shape[0]
+    return time.perf_counter() - t0, ndof
+
+
 def unstructured_extra(pkg, capi, peak, n=1024, reps=10):
     """Side line of the benchmark (extra.unstructured): the same path on an unstructured triangle mesh (csrc/unstructured.cu) —
     n x n squares cut into two triangles each, jittered, P1 | P1, Poisson + ProportionalFlowCoupling with the FD Jacobian."""
@@ -229,7 +257,15 @@ def unstructured_extra(pkg, capi, peak, n=1024, reps=10):
         ms_res = timed_ms(lambda: dev.residual(go, u, r))
         ne = conn.shape[0]
         b_jac = 8.0 * nnz + 24.0 * ne + 16.0 * xy.shape[0]          # values + DOF map + geometry (unstructured)
-        return {"workload": "2-D triangles (%d x %d squares, jittered), P1 | P1, Poisson + ProportionalFlowCoupling (FD Jacobian)" % (n, n),
+        cpu = None
+        try:
+            cpu_s, cpu_dofs = unstructured_cpu_port(xy, conn, sd)
+            cpu = {"jacobian_dofs_per_s": cpu_dofs / cpu_s, "seconds": cpu_s, "cores": 1,
+                   "kind": "port (vectorised NumPy/SciPy assembly of the volume terms; not the reference's cell loop)"}
+        except Exception as e:
+            cpu = {"error": repr(e)}
+        return {"cpu_port": cpu,
+                "workload": "2-D triangles (%d x %d squares, jittered), P1 | P1, Poisson + ProportionalFlowCoupling (FD Jacobian)" % (n, n),
                 "cells": int(ne), "dofs": int(ndof), "nnz": int(nnz), "ingest_host_s": t_ingest, "dofmap_constraints_pattern_s": t_setup,
                 "jacobian_ms": ms_jac, "jacobian_dofs_per_s": ndof / (ms_jac * 1e-3), "jacobian_achieved_GBs": b_jac / (ms_jac * 1e-3) / 1e9,
                 "jacobian_frac": b_jac / (ms_jac * 1e-3) / 1e9 / peak, "residual_ms": ms_res, "residual_dofs_per_s": ndof / (ms_res * 1e-3)}
