@@ -4,7 +4,8 @@ Restates, for one interface edge of a triangle mesh, the reference's Stokes-Darc
 StokesDarcyCouplingOperator::alpha_coupling (test/stokesdarcycouplingoperator.hh:104-245) and the local bases it is evaluated
 with: Taylor-Hood velocity P2 per component on the Stokes (inside) cell, DG-P3 hydraulic head on the Darcy (outside) cell
 (test/stokesdarcy2.cc:613-616, :646-700).  PARITY UNPINNED at the upstream boundary like every oracle in this directory; pinned by
-tests/test_oracle_stokesdarcy.py (basis identities, closed-form row sums, hydrostatic equilibrium).
+tests/test_oracle_stokesdarcy.py (basis identities, closed-form row sums, hydrostatic equilibrium).  The second half restates the
+Darcy subproblem's operator, [UPSTREAM] ConvectionDiffusionDG(SIPG, weightsOn) on DG-Pk triangles with a tensor (class DGTriangles).
 
 [UPSTREAM] dune-localfunctions Pk2DLocalBasis<D,R,k>: Lagrange basis on the lattice (i/k, j/k), i + j <= k, numbered with i fastest:
     phi_n(x, y) = prod_{a<i} (x - a/k)/(i/k - a/k) * prod_{b<j} (y - b/k)/(j/k - b/k) * prod_{c=i+j+1..k} (c/k - x - y)/(c/k - i/k - j/k)
@@ -149,3 +150,139 @@ def pk_interpolate(k, tri, f):
             x = p[0] + (p[1] - p[0]) * (i / float(k)) + (p[2] - p[0]) * (j / float(k))
             out.append(f(x[0], x[1]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# [UPSTREAM] Dune::PDELab::ConvectionDiffusionDG<DarcyParams, DarcyFEM>(SIPG, weightsOn, alpha) (test/stokesdarcy2.cc:733-739) on a
+# triangle mesh with DG-Pk spaces (b = 0, c = 0, a piecewise constant tensor A per cell): the published algorithm of dune-pdelab's
+# convectiondiffusiondg.hh in the form oracle/oracle.cpp restates for cubes (volume term, interior-penalty skeleton term with harmonic
+# weights delta = n.A n and the "Houston" face diameter min(|T_s|, |T_n|) / |F|, weak Dirichlet / Neumann boundary term), now with the
+# tensor.  The integrands are polynomials, so any exact rule gives the reference's integrals up to rounding: a conical Gauss product rule
+# is used.  Pinned by consistency (a degree-k polynomial solves the scheme exactly), SIPG symmetry and coercivity.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def tri_rule_exact(order):
+    m = order // 2 + 2
+    x, w = np.polynomial.legendre.leggauss(m)
+    x, w = 0.5 * (x + 1.0), 0.5 * w
+    return [((s, t * (1.0 - s)), ws * wt * (1.0 - s)) for s, ws in zip(x, w) for t, wt in zip(x, w)]
+
+
+class DGTriangles:
+    """residual(x) of ConvectionDiffusionDG on the triangles `conn` of `xy`; DOF = cell * nk + i (cell-blocked, [UPSTREAM] (iii))."""
+
+    def __init__(self, xy, conn, k, A, f, bctype, g, j, alpha=2.0, theta=-1.0, weights=True, intorderadd=0):
+        self.xy, self.conn, self.k, self.nk = np.asarray(xy, float), np.asarray(conn), k, pk_size(k)
+        self.A = [np.asarray(a, float) for a in A]                  # one 2x2 tensor per cell
+        self.f, self.bctype, self.g, self.j = f, bctype, g, j       # f(x,y), bctype(x,y) -> 'D' | 'N' | None at the face centre, g, j
+        self.alpha, self.theta, self.weights, self.intorder = alpha, theta, weights, intorderadd + 2 * k
+        self.ne = self.conn.shape[0]
+        self.ndof = self.ne * self.nk
+        edge = {}
+        self.nbr = -np.ones((self.ne, 3), dtype=int)
+        for e in range(self.ne):
+            for fc in range(3):
+                a, b = self.conn[e, FACE_V[fc][0]], self.conn[e, FACE_V[fc][1]]
+                key = (min(a, b), max(a, b))
+                if key in edge:
+                    e2, f2 = edge[key]
+                    self.nbr[e, fc], self.nbr[e2, f2] = e2, e
+                else:
+                    edge[key] = (e, fc)
+
+    def _geo(self, e):
+        p = self.xy[self.conn[e]]
+        J = np.array([p[1] - p[0], p[2] - p[0]]).T
+        return p, np.linalg.inv(J).T, abs(np.linalg.det(J))
+
+    def _eval(self, e, lx, ly):
+        p, JinvT, ie = self._geo(e)
+        phi = np.array(pk_basis(self.k, lx, ly))
+        grad = np.array([JinvT @ np.array(gr) for gr in pk_gradients(self.k, lx, ly)])
+        return phi, grad, p[0] + (p[1] - p[0]) * lx + (p[2] - p[0]) * ly
+
+    def residual(self, x):
+        r = np.zeros(self.ndof)
+        nk = self.nk
+        for e in range(self.ne):
+            xs = x[e * nk:(e + 1) * nk]
+            p, JinvT, ie = self._geo(e)
+            A_s = self.A[e]
+            for (lx, ly), w in tri_rule_exact(self.intorder):                                 # alpha_volume + lambda_volume
+                phi, grad, xg = self._eval(e, lx, ly)
+                Agradu = A_s @ (xs @ grad)
+                factor = w * ie
+                r[e * nk:(e + 1) * nk] += (grad @ Agradu - self.f(xg[0], xg[1]) * phi) * factor
+            for fc in range(3):
+                nb = int(self.nbr[e, fc])
+                la, lb = FACE_V[fc]
+                pa, pb = p[la], p[lb]
+                edge = pb - pa
+                fie = math.hypot(edge[0], edge[1])
+                n_F = np.array([edge[1], -edge[0]]) / fie
+                if np.dot(n_F, p[2 - fc] - pa) > 0:
+                    n_F = -n_F
+                if nb >= 0 and nb < e:
+                    continue                                                                   # interior faces once, from the lower-index cell
+                boundary = nb < 0
+                An_s = A_s @ n_F
+                delta_s = float(An_s @ n_F)
+                if boundary:
+                    centre = pa + 0.5 * edge
+                    bc = self.bctype(centre[0], centre[1])
+                    if bc is None:
+                        continue
+                    omega_s, omega_n, harmonic, vol = 1.0, 0.0, delta_s, 0.5 * ie
+                else:
+                    pn, JinvTn, ien = self._geo(nb)
+                    An_n = self.A[nb] @ n_F
+                    delta_n = float(An_n @ n_F)
+                    if self.weights:
+                        omega_s, omega_n = delta_n / (delta_s + delta_n + 1e-20), delta_s / (delta_s + delta_n + 1e-20)
+                        harmonic = 2.0 * delta_s * delta_n / (delta_s + delta_n + 1e-20)
+                    else:
+                        omega_s = omega_n = 0.5
+                        harmonic = 1.0
+                    vol = min(0.5 * ie, 0.5 * ien)
+                    cn = list(self.conn[nb])
+                    ia, ib = cn.index(self.conn[e, la]), cn.index(self.conn[e, lb])
+                    xn = x[nb * nk:(nb + 1) * nk]
+                if not self.weights and boundary:
+                    harmonic = 1.0
+                h_F = vol / fie
+                penalty = (self.alpha / h_F) * harmonic * self.k * (self.k + 2 - 1)
+                for t, w in gauss_line(self.intorder):
+                    factor = w * fie
+                    lx, ly = REF[la][0] + t * (REF[lb][0] - REF[la][0]), REF[la][1] + t * (REF[lb][1] - REF[la][1])
+                    phi_s, grad_s, xg = self._eval(e, lx, ly)
+                    u_s, gradu_s = float(xs @ phi_s), xs @ grad_s
+                    if boundary and bc == 'N':
+                        r[e * nk:(e + 1) * nk] += self.j(xg[0], xg[1]) * phi_s * factor
+                        continue
+                    if boundary:                                                               # weak Dirichlet (Nitsche)
+                        gval = self.g(xg[0], xg[1])
+                        rs = -float(An_s @ gradu_s) * factor * phi_s
+                        rs += (u_s - gval) * factor * self.theta * (grad_s @ An_s)
+                        rs += penalty * (u_s - gval) * factor * phi_s
+                        r[e * nk:(e + 1) * nk] += rs
+                        continue
+                    mx, my = REF[ia][0] + t * (REF[ib][0] - REF[ia][0]), REF[ia][1] + t * (REF[ib][1] - REF[ia][1])
+                    phi_n, grad_n, _ = self._eval(nb, mx, my)
+                    u_n, gradu_n = float(xn @ phi_n), xn @ grad_n
+                    term2 = -(omega_s * float(An_s @ gradu_s) + omega_n * float(An_n @ gradu_n)) * factor
+                    term3 = (u_s - u_n) * factor
+                    term4 = penalty * (u_s - u_n) * factor
+                    r[e * nk:(e + 1) * nk] += term2 * phi_s + term3 * self.theta * omega_s * (grad_s @ An_s) + term4 * phi_s
+                    r[nb * nk:(nb + 1) * nk] += -term2 * phi_n + term3 * self.theta * omega_n * (grad_n @ An_n) - term4 * phi_n
+        return r
+
+    def jacobian(self):
+        """The residual is affine: column j = R(e_j) - R(0) (small meshes only)."""
+        r0 = self.residual(np.zeros(self.ndof))
+        J = np.zeros((self.ndof, self.ndof))
+        for jcol in range(self.ndof):
+            ej = np.zeros(self.ndof); ej[jcol] = 1.0
+            J[:, jcol] = self.residual(ej) - r0
+        return J, r0
+
+    def interpolate(self, u):
+        return np.concatenate([pk_interpolate(self.k, self.xy[self.conn[e]], u) for e in range(self.ne)])

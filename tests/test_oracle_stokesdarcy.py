@@ -87,3 +87,56 @@ def test_hydrostatic_state_and_the_loop_bound_quirk():
     a = sd.alpha_coupling(P, STOKES, 0, darcy, zero_v, head6, quirk=True)
     b = sd.alpha_coupling(P, STOKES, 0, darcy, zero_v, head6, quirk=False)
     assert np.allclose(a[0], b[0], rtol=0, atol=1e-12 * np.abs(b[0]).max())
+
+
+def _dg_mesh():
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import um_problems as ump
+    return ump.square_mesh(3, 2, seed=5)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_dg_on_triangles_is_consistent_symmetric_and_coercive(k):
+    """ConvectionDiffusionDG on triangles with a piecewise constant tensor (the Darcy subproblem of stokesdarcy2): a polynomial of
+    degree k with continuous normal flux solves the scheme exactly (zero residual with f = -div(A grad u), weak Dirichlet data g = u
+    and Neumann data j = -A grad u . n on one side); the SIPG matrix is symmetric and positive definite; NIPG is not symmetric."""
+    xy, conn = _dg_mesh()
+    A0 = np.array([[2.0, 0.3], [0.3, 1.0]])
+    A = [A0 for _ in range(conn.shape[0])]
+    c = {1: (0, 0, 0, 0), 2: (0.7, -0.4, 0, 0), 3: (0.7, -0.4, 0.5, -0.3)}[k]
+    u = lambda x, y: 1.0 + 2.0 * x - y + c[0] * x * x + c[1] * x * y + c[2] * x ** 3 + c[3] * x * y * y
+    gu = lambda x, y: np.array([2.0 + 2 * c[0] * x + c[1] * y + 3 * c[2] * x * x + c[3] * y * y, -1.0 + c[1] * x + 2 * c[3] * x * y])
+    hess = lambda x, y: np.array([[2 * c[0] + 6 * c[2] * x, c[1] + 2 * c[3] * y], [c[1] + 2 * c[3] * y, 2 * c[3] * x]])
+    f = lambda x, y: -float(np.sum(A0 * hess(x, y)))
+    bctype = lambda x, y: 'N' if x > 1.0 - 1e-9 else 'D'                           # Neumann on the right side, outer normal (1, 0)
+    j = lambda x, y: -float((A0 @ gu(x, y))[0])
+    dg = sd.DGTriangles(xy, conn, k, A, f, bctype, u, j, alpha=4.0)
+    x = dg.interpolate(u)
+    assert np.abs(dg.residual(x)).max() < 1e-10
+    J, r0 = dg.jacobian()
+    assert np.abs(J - J.T).max() < 1e-11 * np.abs(J).max()
+    assert np.linalg.eigvalsh(0.5 * (J + J.T)).min() > 0
+    assert np.abs(np.linalg.solve(J, -r0) - x).max() < 1e-9                       # the discrete solution is the polynomial
+    nipg = sd.DGTriangles(xy, conn, k, A, f, bctype, u, j, alpha=4.0, theta=1.0)
+    assert np.abs(nipg.residual(x)).max() < 1e-10
+    Jn, _ = nipg.jacobian()
+    assert np.abs(Jn - Jn.T).max() > 1e-3
+
+
+def test_dg_harmonic_weights_with_a_jumping_tensor():
+    """Two tensors across x = 0.5 (here the mesh line closest to it): a piecewise linear u with continuous normal flux
+    A_l u_l' = A_r u_r' is reproduced (consistency with weightsOn), and the SIPG matrix stays symmetric."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import um_problems as ump
+    xy, conn = ump.square_mesh(4, 2, seed=2, jitter=0.0)
+    kl, kr = 1.0, 5.0
+    left = xy[conn].mean(axis=1)[:, 0] < 0.5
+    A = [np.eye(2) * (kl if l else kr) for l in left]
+    u = lambda x, y: x / kl if x <= 0.5 else 0.5 / kl + (x - 0.5) / kr              # flux 1 everywhere
+    bctype = lambda x, y: 'D' if (x < 1e-9 or x > 1 - 1e-9) else 'N'
+    dg = sd.DGTriangles(xy, conn, 1, A, lambda x, y: 0.0, bctype, u, lambda x, y: 0.0, alpha=3.0)
+    # interpolate per cell with the cell's own branch (u is only piecewise smooth)
+    x = np.concatenate([[(p[0] / kl if l else 0.5 / kl + (p[0] - 0.5) / kr) for p in xy[conn[e]]] for e, l in enumerate(left)])
+    assert np.abs(dg.residual(x)).max() < 1e-12
+    J, _ = dg.jacobian()
+    assert np.abs(J - J.T).max() < 1e-12 * np.abs(J).max()
