@@ -286,3 +286,94 @@ class DGTriangles:
 
     def interpolate(self, u):
         return np.concatenate([pk_interpolate(self.k, self.xy[self.conn[e]], u) for e in range(self.ne)])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# [UPSTREAM] Dune::PDELab::TaylorHoodNavierStokes<NavierStokesParams>(params, stokes_q) (test/stokesdarcy2.cc:719-720) on a triangle mesh:
+# velocity P2 per component, pressure P1 (test/stokesdarcy2.cc:613-614), composite ordering [v_0 | v_1 | p] (:633-656).  Published
+# algorithm of dune-pdelab's taylorhoodnavierstokes.hh (Stokes case, no convection): for every velocity component d and test function i
+#     r_v(d, i) += ( mu grad(u_d) . grad(v_i) - p d_d v_i - f_d v_i ) w |det J|        (full-gradient viscous form)
+# and for every pressure test function     r_p(i) += -( div u ) q_i w |det J|,
+# which makes the operator symmetric.  The SIGN of the continuity rows and the viscous form are assumptions about upstream (flagged);
+# the pins are internal: a quadratic divergence-free velocity with a linear pressure solves the scheme exactly, the matrix is symmetric,
+# and constants are in the kernel of the pressure gradient block on interior rows.
+# Numbering assumption [UPSTREAM (iii)]: per P2 block vertices first (ascending vertex index), then edges; edge indices here are the
+# order of first appearance in (cell, local face) order — UG's own edge numbering is an implementation detail of UG.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+class StokesTaylorHood:
+    def __init__(self, xy, conn, mu=1.0, f=lambda x, y: (0.0, 0.0), qorder=4):
+        self.xy, self.conn, self.mu, self.f, self.qorder = np.asarray(xy, float), np.asarray(conn), mu, f, qorder
+        self.nv, self.ne = self.xy.shape[0], self.conn.shape[0]
+        self.edge_index, self.cell_edges = {}, []
+        for e in range(self.ne):
+            ce = []
+            for fc in range(3):
+                a, b = self.conn[e, FACE_V[fc][0]], self.conn[e, FACE_V[fc][1]]
+                ce.append(self.edge_index.setdefault((min(a, b), max(a, b)), len(self.edge_index)))
+            self.cell_edges.append(ce)
+        self.n2 = self.nv + len(self.edge_index)                   # size of one P2 block
+        self.ndof = 2 * self.n2 + self.nv
+
+    def p2_dofs(self, e):
+        """Block-local indices of the six Pk2D (k = 2) functions of cell e: lattice order (0,0),(1/2,0),(1,0),(0,1/2),(1/2,1/2),(0,1):
+        vertex 0, edge {0,1} = face 0, vertex 1, edge {0,2} = face 1, edge {1,2} = face 2, vertex 2."""
+        c, ed = self.conn[e], self.cell_edges[e]
+        return [c[0], self.nv + ed[0], c[1], self.nv + ed[1], self.nv + ed[2], c[2]]
+
+    def dofs(self, e):
+        v = self.p2_dofs(e)
+        return [v, [self.n2 + i for i in v], [2 * self.n2 + int(i) for i in self.conn[e]]]
+
+    def residual(self, x):
+        r = np.zeros(self.ndof)
+        for e in range(self.ne):
+            p = self.xy[self.conn[e]]
+            J = np.array([p[1] - p[0], p[2] - p[0]]).T
+            JinvT, ie = np.linalg.inv(J).T, abs(np.linalg.det(J))
+            d0, d1, dp = self.dofs(e)
+            xv = [x[d0], x[d1]]
+            xp = x[dp]
+            for (lx, ly), w in tri_rule_exact(self.qorder):
+                phi = np.array(pk_basis(2, lx, ly))
+                grad = np.array([JinvT @ np.array(g) for g in pk_gradients(2, lx, ly)])
+                psi = np.array(pk_basis(1, lx, ly))
+                xg = p[0] + (p[1] - p[0]) * lx + (p[2] - p[0]) * ly
+                fx = self.f(xg[0], xg[1])
+                jacu = [xv[0] @ grad, xv[1] @ grad]                 # grad u_d
+                pres = float(xp @ psi)
+                divu = jacu[0][0] + jacu[1][1]
+                factor = w * ie
+                for d, dofs in ((0, d0), (1, d1)):
+                    r[dofs] += (self.mu * (grad @ jacu[d]) - pres * grad[:, d] - fx[d] * phi) * factor
+                r[dp] += -divu * psi * factor
+        return r
+
+    def jacobian(self):
+        r0 = self.residual(np.zeros(self.ndof))
+        Jm = np.zeros((self.ndof, self.ndof))
+        for j in range(self.ndof):
+            ej = np.zeros(self.ndof); ej[j] = 1.0
+            Jm[:, j] = self.residual(ej) - r0
+        return Jm, r0
+
+    def interpolate(self, u, pfun):
+        x = np.zeros(self.ndof)
+        for e in range(self.ne):
+            d0, d1, dp = self.dofs(e)
+            tri = self.xy[self.conn[e]]
+            x[d0] = pk_interpolate(2, tri, lambda a, b: u(a, b)[0])
+            x[d1] = pk_interpolate(2, tri, lambda a, b: u(a, b)[1])
+            x[dp] = pk_interpolate(1, tri, pfun)
+        return x
+
+    def boundary_velocity_dofs(self):
+        """Velocity DOFs on the physical boundary (vertices and edges of faces without a neighbour), both components."""
+        count = {}
+        for e in range(self.ne):
+            for fc in range(3):
+                count[self.cell_edges[e][fc]] = count.get(self.cell_edges[e][fc], 0) + 1
+        out = set()
+        for (a, b), idx in self.edge_index.items():
+            if count[idx] == 1:
+                out.update([a, b, self.nv + idx])
+        return sorted(out) + [self.n2 + i for i in sorted(out)]

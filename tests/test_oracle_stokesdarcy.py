@@ -140,3 +140,31 @@ def test_dg_harmonic_weights_with_a_jumping_tensor():
     assert np.abs(dg.residual(x)).max() < 1e-12
     J, _ = dg.jacobian()
     assert np.abs(J - J.T).max() < 1e-12 * np.abs(J).max()
+
+
+def test_taylor_hood_stokes_manufactured_solution_and_symmetry():
+    """u = (y^2, x^2) (divergence free, in P2), p = 1 + x - 2 y (in P1), f = -mu Laplace(u) + grad(p): every pressure row and every
+    velocity row of a DOF off the boundary vanishes at the interpolant; the operator is symmetric; with the boundary velocity fixed and
+    the pressure pinned at one vertex the discrete solution IS the interpolant."""
+    xy, conn = _dg_mesh()
+    mu = 0.7
+    u = lambda x, y: (y * y, x * x)
+    p = lambda x, y: 1.0 + x - 2.0 * y
+    f = lambda x, y: (-mu * 2.0 + 1.0, -mu * 2.0 - 2.0)
+    th = sd.StokesTaylorHood(xy, conn, mu=mu, f=f)
+    x = th.interpolate(u, p)
+    r = th.residual(x)
+    bnd = th.boundary_velocity_dofs()
+    free = np.ones(th.ndof, dtype=bool); free[bnd] = False
+    assert np.abs(r[free]).max() < 1e-12 and np.abs(r[~free]).max() > 1e-2
+    J, r0 = th.jacobian()
+    assert np.abs(J - J.T).max() < 1e-12 * np.abs(J).max()
+    # saddle point: velocity block positive definite on the free velocity DOFs, pressure block zero
+    nv2 = 2 * th.n2
+    vfree = free.copy(); vfree[nv2:] = False
+    assert np.linalg.eigvalsh(J[np.ix_(vfree, vfree)]).min() > 0 and np.abs(J[nv2:, nv2:]).max() == 0.0
+    # solve with Dirichlet velocity on the boundary and the pressure fixed at vertex 0
+    fixed = ~free; fixed[nv2] = True
+    A = J.copy(); b = -r0.copy()
+    A[fixed] = 0.0; A[fixed, fixed] = 1.0; b[fixed] = x[fixed]
+    assert np.abs(np.linalg.solve(A, b) - x).max() < 1e-9
