@@ -89,6 +89,37 @@ def test_reader_and_refinement_entry_by_entry_on_cpu():
             assert on_boundary(v[b[:, 0]]).all() and on_boundary(v[b[:, 1]]).all()
 
 
+REF_MSH = "/root/reference/test"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MSH), reason="the reference's mesh fixtures exist in the build container only")
+def test_reader_on_the_reference_fixtures():
+    """The C++ reader on the reference's own test/*.msh files (Gmsh 2.1 ASCII, the input of stokesdarcy2): sizes, cells per physical
+    group and checksums of coordinates / connectivity in the reader's numbering against tests/golden/gmsh_fixture_sizes.json (written
+    by tests/golden/make_golden_gmsh.py with the independent Python reader).  Runs where /root/reference exists; never on the GPU box."""
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "gmsh_fixture_sizes.json")))
+    assert gold["stokesdarcy2-fine.msh"]["triangles"] == 4805                       # SURVEY §8d-5
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "gmsh_dump")
+        libdir = os.path.dirname(pkg.library_path())
+        subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "gmsh_dump.cc"),
+                               "-o", exe, "-L", libdir, "-lmdb200", "-Wl,-rpath," + libdir])
+        for name, g in sorted(gold.items()):
+            tok = subprocess.run([exe, os.path.join(REF_MSH, name), "0"], capture_output=True, text=True, check=True).stdout.split()
+            nv, ne, nb = int(tok[0]), int(tok[1]), int(tok[2])
+            assert (nv, ne) == (g["vertices"], g["triangles"]), name
+            v = np.array(tok[3:3 + 2 * nv], dtype=np.float64).reshape(nv, 2)
+            e = np.array(tok[3 + 2 * nv:3 + 2 * nv + 4 * ne], dtype=np.int64).reshape(ne, 4)
+            grp, cnt = np.unique(e[:, 3], return_counts=True)
+            assert {str(int(a)): int(b) for a, b in zip(grp, cnt)} == g["groups"], name
+            assert v[:, 0].sum() == g["sum_x"] and v[:, 1].sum() == g["sum_y"], name
+            assert int(e[:, :3].sum()) == g["sum_conn"] and int((e[:, :3] * np.array([1, 3, 7])).sum()) == g["weighted_conn"], name
+            p = v[e[:, :3]]
+            det = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0])
+            assert np.all(det != 0.0), name                                         # no degenerate cell: mdb_mesh_unstructured would take it
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("refinements,solver", [(0, "ssor"), (1, "ssor"), (2, "jac")])
 def test_driver_against_oracle(refinements, solver):
