@@ -82,3 +82,50 @@ def connect(dev, dist, rank, nranks):
     dist.all_gather_object(counts, [int(v) for v in dev.owned_counts()])
     bases, total = global_child_bases(counts, rank)
     return SimpleNamespace(child_global_base=bases, global_ndof=total, counts=counts)
+
+
+# ---- unstructured meshes ("gmsh meshes -> recursive coordinate bisection of cell centroids, rows owned by the lowest
+# rank touching the DOF").  Host-side partition design only; the device path of unstructured meshes is single-GPU in this build.
+# The design mirrors the slab partition: every rank also holds the ghost cells it needs so that the rows it owns are assembled
+# completely without matrix communication (tests/test_multirank_gloo.py checks exactly that with the CPU oracle over gloo). ----------
+def um_partition(xy, conn, nranks):
+    """Recursive coordinate bisection of the cell centroids into `nranks` parts (sizes differ by at most one cell per cut).
+    Returns (cell_rank [ne], vertex_owner [nv]): a vertex (hence every DOF attached to it) is owned by the lowest rank among its cells."""
+    cent = xy[conn].mean(axis=1)
+    cell_rank = np.zeros(conn.shape[0], dtype=np.int64)
+
+    def cut(cells, r0, r1):
+        if r1 - r0 <= 1:
+            cell_rank[cells] = r0
+            return
+        axis = int(np.argmax(cent[cells].max(axis=0) - cent[cells].min(axis=0)))
+        order = cells[np.lexsort((cells, cent[cells, axis]))]                 # ties broken by cell index: deterministic
+        rm = (r0 + r1) // 2
+        k = len(order) * (rm - r0) // (r1 - r0)
+        cut(order[:k], r0, rm)
+        cut(order[k:], rm, r1)
+
+    cut(np.arange(conn.shape[0]), 0, nranks)
+    vertex_owner = np.full(xy.shape[0], nranks, dtype=np.int64)
+    np.minimum.at(vertex_owner, conn.ravel(), np.repeat(cell_rank, conn.shape[1]))
+    return cell_rank, vertex_owner
+
+
+def um_local_mesh(conn, vertex_owner, rank):
+    """The local mesh of `rank`: every cell around an owned vertex, plus the face neighbours of those cells (a coupling face adds
+    links between ALL DOFs of its two cells, so the row of an owned vertex needs the cell across each face of its own cells).  Cells
+    and vertices keep their global order, so local numberings are monotone in the global ones.
+    Returns (cells [global cell ids, ascending], verts [global vertex ids, ascending], local_conn)."""
+    ne = conn.shape[0]
+    touch = (vertex_owner[conn] == rank).any(axis=1)
+    edges = {}
+    for e in range(ne):
+        for a, b in ((0, 1), (0, 2), (1, 2)):
+            edges.setdefault((min(conn[e, a], conn[e, b]), max(conn[e, a], conn[e, b])), []).append(e)
+    keep = touch.copy()
+    for cells in edges.values():
+        if len(cells) == 2 and (touch[cells[0]] or touch[cells[1]]):
+            keep[cells[0]] = keep[cells[1]] = True
+    cells = np.nonzero(keep)[0]
+    verts = np.unique(conn[cells])
+    return cells, verts, np.searchsorted(verts, conn[cells])

@@ -224,3 +224,87 @@ def test_partitioned_assembly_and_solve_match_global(world, n):
     total = sum(v[0] for v in ret.values())
     assert total == (n[0] + 1) * (n[2] + 1) * (n[1] + 2)     # (N+2)(N+1)^2-type count: interface vertices belong to both blocks
     assert len({v[1] for v in ret.values()}) == 1             # every rank took the same number of iterations
+
+
+# ---- unstructured meshes: recursive coordinate bisection, rows owned by the lowest rank touching the vertex ----------
+def test_um_partition_invariants():
+    import um_problems as ump
+    xy, conn = ump.square_mesh(9, 7, seed=4)
+    for R in (1, 2, 3, 5):
+        cell_rank, owner = parallel.um_partition(xy, conn, R)
+        counts = np.bincount(cell_rank, minlength=R)
+        assert counts.sum() == conn.shape[0] and counts.max() - counts.min() <= R      # balanced up to the rounding of each cut
+        assert owner.min() >= 0 and owner.max() < R
+        for v in range(xy.shape[0]):
+            assert owner[v] == cell_rank[(conn == v).any(axis=1)].min()                 # lowest rank among the vertex's cells
+        covered = np.zeros(xy.shape[0], dtype=int)
+        for r in range(R):
+            cells, verts, lconn = parallel.um_local_mesh(conn, owner, r)
+            assert np.array_equal(verts[lconn], conn[cells]) and np.all(np.diff(cells) > 0) and np.all(np.diff(verts) > 0)
+            mine = np.nonzero(owner == r)[0]
+            covered[mine] += 1
+            for v in mine:                                                              # the full cell ring of every owned vertex is local
+                assert np.isin(np.nonzero((conn == v).any(axis=1))[0], cells).all()
+        assert np.all(covered == 1)
+
+
+def _um_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    import torch
+    import um_problems as ump
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        capi = ump.capi
+        xy, conn = ump.square_mesh(8, 6, seed=17)
+        sd = ump.halves(xy, conn)
+        kw = dict(cvcf=True, k=2.0)
+        # the global problem (every rank computes it: the reference for its own rows)
+        og = ump.oracle(); Hg = ump.setup(og, xy, conn, sd, **kw)
+        og.jacobian(Hg["go"], Hg["mat"], Hg["x0"], overwrite=True)
+        rg = og.residual(Hg["go"], Hg["x0"], np.zeros(Hg["ndof"]))
+        rpg, cig = og.matrix_get_pattern(Hg["mat"]); vg = og.matrix_get_values(Hg["mat"])
+        offg = og.get_child_offsets()
+        # the local problem on the rank's part + ghost cells
+        cell_rank, owner = parallel.um_partition(xy, conn, world)
+        cells, verts, lconn = parallel.um_local_mesh(conn, owner, rank)
+        ol = ump.oracle(); Hl = ump.setup(ol, xy[verts], lconn, sd[cells], **kw)
+        offl = ol.get_child_offsets()
+        # local DOF -> global DOF through (child, vertex); owned = the vertex is owned by this rank
+        l2g = -np.ones(Hl["ndof"], dtype=np.int64); owned = np.zeros(Hl["ndof"], dtype=bool)
+        for k in range(2):
+            vl = ol.children[k]["v2d"]; vgl = og.children[k]["v2d"]
+            for lv in np.nonzero(vl >= 0)[0]:
+                l2g[offl[k] + vl[lv]] = offg[k] + vgl[verts[lv]]
+                owned[offl[k] + vl[lv]] = owner[verts[lv]] == rank
+        assert (l2g >= 0).all()
+        # the linearisation point: the global one restricted (ghost values come from their owners in a real run)
+        xl = Hg["x0"][l2g]
+        ol.jacobian(Hl["go"], Hl["mat"], xl, overwrite=True)
+        rl = ol.residual(Hl["go"], xl, np.zeros(Hl["ndof"]))
+        rpl, cil = ol.matrix_get_pattern(Hl["mat"]); vl_ = ol.matrix_get_values(Hl["mat"])
+        scale = np.abs(vg).max()
+        conl, cong = ol.get_constraints(), og.get_constraints()
+        for i in np.nonzero(owned)[0]:
+            g = l2g[i]
+            cols = l2g[cil[rpl[i]:rpl[i + 1]]]
+            assert np.array_equal(cols, cig[rpg[g]:rpg[g + 1]]), "pattern of an owned row differs from the global one"   # monotone maps keep the order
+            assert np.abs(vl_[rpl[i]:rpl[i + 1]] - vg[rpg[g]:rpg[g + 1]]).max() <= 1e-13 * scale
+            assert abs(rl[i] - rg[g]) <= 1e-13 * np.abs(rg).max() and conl[i] == cong[g]
+        # every global row is owned exactly once
+        t = torch.zeros(Hg["ndof"], dtype=torch.float64); t[l2g[owned]] = 1.0
+        dist.all_reduce(t)
+        assert bool((t == 1.0).all())
+        ret[rank] = int(owned.sum())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_um_partitioned_assembly_owned_rows_match_global(world):
+    """Unstructured partition design on CPU ranks: each rank assembles its part plus ghost cells with the oracle; the rows it owns —
+    pattern, FD-coupling Jacobian entries, residual, constraint flags — equal the global ones without any communication."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_um_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world and sum(ret.values()) > 0
