@@ -295,6 +295,40 @@ def _um_worker(rank, world, port, ret):
         dist.all_reduce(t)
         assert bool((t == 1.0).all())
         ret[rank] = int(owned.sum())
+        # ---- distributed Jacobi-CG on the owned rows: ghost entries come from their owners, dots are all-reduced -------------------
+        import scipy.sparse as sps
+        import scipy.sparse.linalg as spla
+        Al = sps.csr_matrix((vl_, cil, rpl), shape=(Hl["ndof"],) * 2)
+        Ag = sps.csr_matrix((vg, cig, rpg), shape=(Hg["ndof"],) * 2)
+        zg = spla.spsolve(Ag.tocsc(), rg)
+
+        def exchange(v):                                        # test plumbing: owners publish, everybody reads its ghosts
+            t = torch.zeros(Hg["ndof"], dtype=torch.float64)
+            t[l2g[owned]] = torch.from_numpy(v[owned].copy())
+            dist.all_reduce(t)
+            return t.numpy()[l2g]
+
+        def dot(a, b):
+            t = torch.tensor([float(np.dot(a[owned], b[owned]))], dtype=torch.float64)
+            dist.all_reduce(t)
+            return float(t.item())
+
+        dinv = np.where(owned, 1.0 / np.where(Al.diagonal() != 0.0, Al.diagonal(), 1.0), 0.0)
+        b = np.where(owned, rl, 0.0)
+        z = np.zeros(Hl["ndof"]); r = b.copy(); p = np.zeros_like(z)
+        rho_old, it, d0 = 1.0, 0, np.sqrt(dot(b, b))
+        while it < 2000:
+            y = dinv * r
+            rho = dot(r, y)
+            p = y + (rho / rho_old) * p if it > 0 else y.copy()
+            q = np.where(owned, Al @ exchange(p), 0.0)
+            alpha = rho / dot(p, q)
+            z += alpha * p; r -= alpha * q
+            rho_old = rho; it += 1
+            if np.sqrt(dot(r, r)) <= 1e-13 * d0:
+                break
+        assert it < 2000, "distributed CG did not converge"
+        assert np.abs(z[owned] - zg[l2g[owned]]).max() <= 1e-9 * np.abs(zg).max()
     finally:
         dist.destroy_process_group()
 
