@@ -369,7 +369,7 @@ def _main(out):
     # CUDA events sit on the launching stream.  The other streams' kernels (irregular rows + FD coupling) run concurrently.
     simple_rows, irregular_rows = dev.matrix_stats(P.mat)
     stencil = 27 if len(n) == 3 else 9
-    nchild_launch = 2
+    nchild_launch = 1          # one launch covers both child blocks
     bytes_fill = 8.0 * stencil * simple_rows / nchild_launch          # per launch
     ms_fill = phases["fill"] / nchild_launch                           # mean launch duration
     fill_kernel = "k_jacobian_fill_q1" if os.environ.get("MDB_FILL_NO_TMA") else "k_jacobian_fill_tma"

@@ -99,17 +99,24 @@ __device__ __forceinline__ int columns_below(const int64_t* __restrict__ rowptr,
 // stencil S over and over: one block streams a run out with fully coalesced stores.  This is the HBM-write-bound
 // hot kernel: 8 bytes written per stored entry, nothing read but the run boundaries.
 #define JF_THREADS 128
+// All children of a grid operator go through ONE launch (no tail / launch gap between the children's fills): job = child, blocks [block0, ...)
+struct FillJob { const double* S; const longlong2* seg_span; int64_t nseg; int block0; };
+struct FillJobs { int n; FillJob job[MDB_MAX_CHILDREN]; int nblocks; };
 template <int DIM>
-__global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const double* __restrict__ S, const longlong2* __restrict__ seg_span, int64_t nseg,
-                                                                double* __restrict__ val, int overwrite)
+__global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(FillJobs J, double* __restrict__ val, int overwrite)
 {
   constexpr int NS = (DIM == 3) ? 27 : 9;
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.job[jb + 1].block0) ++jb;
+  const double* __restrict__ S = J.job[jb].S;
+  const longlong2* __restrict__ seg_span = J.job[jb].seg_span;
+  const int64_t nseg = J.job[jb].nseg;
+  const int nb = ((jb + 1 < J.n) ? J.job[jb + 1].block0 : J.nblocks) - J.job[jb].block0;
   __shared__ double sS[32];
   if (threadIdx.x < NS) sS[threadIdx.x] = S[threadIdx.x];
   __syncthreads();
-  // grid = nseg: one run per block; a smaller (persistent) grid walks the runs with a grid stride, which bounds how much
-  // of every SM this kernel occupies when the FD coupling kernel runs next to it on the auxiliary stream
-  for (int64_t run = blockIdx.x; run < nseg; run += gridDim.x) {
+  // one run per block; a smaller (persistent) share of the grid walks the runs with a stride
+  for (int64_t run = blockIdx.x - J.job[jb].block0; run < nseg; run += nb) {
   const longlong2 span = seg_span[run];
   if (span.x == span.y) continue;                                      // a run of irregular rows: k_jacobian_rows_q1
   // The run is the span [p0, p1) of the value array.  Rows are 27 (9) doubles long, so p0 is only 8-byte aligned.  The span
@@ -154,10 +161,16 @@ __global__ void __launch_bounds__(JF_THREADS, 12) k_jacobian_fill_q1(const doubl
 #define FT_ROWS 256
 #define FT_THREADS 256                 // 8 warps share one image; each warp's elected lane issues the copies of its own runs
 template <int DIM>
-__global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(const double* __restrict__ S, const longlong2* __restrict__ seg_span, int64_t nseg,
-                                                          double* __restrict__ val, int ft_rows, int evict_first)
+__global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(FillJobs J, double* __restrict__ val, int ft_rows, int evict_first)
 {
   constexpr int NS = (DIM == 3) ? 27 : 9;
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.job[jb + 1].block0) ++jb;
+  const double* __restrict__ S = J.job[jb].S;
+  const longlong2* __restrict__ seg_span = J.job[jb].seg_span;
+  const int64_t nseg = J.job[jb].nseg;
+  const int nb = ((jb + 1 < J.n) ? J.job[jb + 1].block0 : J.nblocks) - J.job[jb].block0;
+  const int bid = blockIdx.x - J.job[jb].block0;
   const int CH = NS * ft_rows;                                           // doubles per bulk copy: a multiple of NS (phase preserved) and even (ft_rows is)
   extern __shared__ __align__(128) double img[];                         // CH + 2 NS doubles, img[i] = S[i mod NS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(const double* 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> visible to the bulk-copy engine
   __syncthreads();
   const uint32_t img_s = (uint32_t)__cvta_generic_to_shared(img);
-  for (int64_t run = (int64_t)blockIdx.x * NW + warp; run < nseg; run += (int64_t)gridDim.x * NW) {
+  for (int64_t run = (int64_t)bid * NW + warp; run < nseg; run += (int64_t)nb * NW) {
     const longlong2 span = seg_span[run];
     const int64_t p0 = span.x, p1 = span.y;
     if (p0 == p1) continue;                                              // a run of irregular rows: k_jacobian_rows_q1
@@ -279,6 +292,140 @@ __global__ void __launch_bounds__(JR_THREADS) k_jacobian_rows_q1(MeshDesc m, con
   }
 }
 
+
+// ---- irregular rows from static records (the default when a child's uniform rows are streamed) -------------------------------
+// What a row needs besides the element matrices never changes after the pattern is built: where its values start, how long it is,
+// which stencil offsets it stores, how many columns lie below the own block, and the subdomain bytes of its 2^d incident cells.
+// k_rowrec_build gathers that once per (matrix, child) — the dependent chain list -> dof2lat -> cell bytes / rowptr / rowinfo / colidx
+// that k_jacobian_rows_q1 walks on every call — into four coalesced arrays; k_jacobian_rows_rec then reads 24 bytes per row, forms
+// the row image with the arithmetic of stencil_row (same cells, same order: same bits) and writes the images of a warp out as
+// contiguous runs: the 32 images sit back to back in shared memory (warp scan of the lengths), and rows that follow each other
+// in the value array (boundary planes, interface lines) leave as one flat, fully coalesced copy.
+#define RR_THREADS 64
+#define RR_MAXLEN 48           // longest row image staged in shared memory; a child with a longer irregular row stays with k_jacobian_rows_q1
+template <int DIM>
+__global__ void k_rowrec_build(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, const int32_t* __restrict__ list, int64_t nrows,
+                               const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo, const int32_t* __restrict__ colidx,
+                               int64_t* rr_rs, uint32_t* rr_mask, uint32_t* rr_meta, unsigned long long* rr_sd, int* bad)
+{
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  const int64_t gi = list[t], g = ch.offset + gi;
+  int64_t r = ch.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+  unsigned long long sdb = 0; uint32_t valid = 0; int k = 0;
+  for (int cz = (DIM > 2 ? -1 : 0); cz <= 0; ++cz)
+    for (int cy = -1; cy <= 0; ++cy)
+      for (int cx = -1; cx <= 0; ++cx, ++k) {
+        const int ix = p[0] + cx, iy = p[1] + cy, iz = p[2] + cz;
+        if (!(ix >= 0 && ix < m.n[0] && iy >= 0 && iy < m.n[1] && (DIM < 3 || (iz >= 0 && iz < m.n[2])))) continue;
+        const uint8_t s = sd[ix + (int64_t)m.n[0] * (iy + (int64_t)m.n[1] * iz)];
+        if (ch.subdomain >= 0 && !((s >> ch.subdomain) & 1)) continue;         // the child space does not live on this cell
+        valid |= 1u << k; sdb |= (unsigned long long)s << (8 * k);
+      }
+  const uint32_t info = rowinfo[g];
+  const int nlow = columns_below(rowptr, colidx, g, info, ch.offset);
+  const int64_t rs = rowptr[g];
+  const int64_t len = rowptr[g + 1] - rs;
+  rr_rs[t] = rs; rr_mask[t] = info & 0x7FFFFFFu; rr_sd[t] = sdb;
+  if (len > RR_MAXLEN || nlow > 0xFF) { atomicExch(bad, 1); return; }           // not representable / not stageable: the gather kernel keeps this child
+  rr_meta[t] = (uint32_t)len | ((uint32_t)nlow << 16) | (valid << 24);
+}
+
+struct RecJob { VolSpec V; const int64_t* rs; const uint32_t* mask; const uint32_t* meta; const unsigned long long* sd; int64_t nrows; int block0; };
+struct RecJobs { int n; RecJob job[MDB_MAX_CHILDREN]; };
+template <int DIM>
+__global__ void __launch_bounds__(RR_THREADS) k_jacobian_rows_rec(RecJobs J, const double* __restrict__ Ae, double* __restrict__ val, int overwrite)
+{
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.job[jb + 1].block0) ++jb;
+  const RecJob& R = J.job[jb];
+  const VolSpec& V = R.V;
+  constexpr int NL = 1 << DIM;
+  constexpr int NS = (DIM == 3) ? 27 : 9;
+  constexpr int BITBASE = (DIM == 3) ? 0 : 9;
+  __shared__ double sAe[MDB_MAX_SP_PER_CHILD * NL * NL];
+  __shared__ double img[RR_THREADS / 32][32 * RR_MAXLEN];
+  for (int i = threadIdx.x; i < V.n * NL * NL; i += blockDim.x) {
+    int v = i / (NL * NL), e = i % (NL * NL);
+    sAe[i] = Ae[V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + e];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = (blockIdx.x - R.block0) * (int64_t)blockDim.x + threadIdx.x;
+  const bool have = t < R.nrows;
+  int64_t rs = 0; int len = 0, nlow = 0; uint32_t mask = 0, valid = 0; unsigned long long sdb = 0;
+  if (have) {
+    rs = R.rs[t]; mask = R.mask[t]; sdb = R.sd[t];
+    const uint32_t meta = R.meta[t];
+    len = (int)(meta & 0xFFFFu); nlow = (int)((meta >> 16) & 0xFFu); valid = meta >> 24;
+  }
+  double acc[NS]; uint32_t touched = 0;
+#pragma unroll
+  for (int o = 0; o < NS; ++o) acc[o] = 0.0;
+  {
+    int k = 0;
+#pragma unroll
+    for (int cz = (DIM > 2 ? -1 : 0); cz <= 0; ++cz)
+#pragma unroll
+      for (int cy = -1; cy <= 0; ++cy)
+#pragma unroll
+        for (int cx = -1; cx <= 0; ++cx, ++k) {
+          if (!((valid >> k) & 1)) continue;
+          const uint32_t s = (uint32_t)(sdb >> (8 * k)) & 0xFFu;
+          const int li = (-cx) | ((-cy) << 1) | ((DIM > 2 ? -cz : 0) << 2);
+          for (int v = 0; v < V.n; ++v) {
+            if (!cond_applies(V.cond_kind[v], V.mask[v], s)) continue;
+            const double* A = sAe + v * NL * NL + li * NL;
+#pragma unroll
+            for (int lj = 0; lj < NL; ++lj) {
+              const int bx = lj & 1, by = (lj >> 1) & 1, bz = (DIM > 2) ? (lj >> 2) & 1 : 0;
+              const int o = (DIM > 2 ? (cz + bz + 1) * 9 : 0) + (cy + by + 1) * 3 + (cx + bx + 1);
+              acc[o] += A[lj];
+              touched |= (1u << o);
+            }
+          }
+        }
+  }
+  (void)touched;
+  const int slen = have ? len : 0;
+  // back-to-back placement of the warp's images
+  int off = slen;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += v; }
+  off -= slen;
+  double* im = img[warp] + off;
+  for (int k = 0; k < slen; ++k) im[k] = 0.0;
+  if (slen > 0) {
+#pragma unroll
+    for (int o = 0; o < NS; ++o) {
+      const uint32_t bit = 1u << (o + BITBASE);
+      if (mask & bit) im[nlow + __popc(mask & (bit - 1u))] = acc[o];
+    }
+  }
+  // runs of rows that follow each other in the value array leave as one flat copy
+  const int64_t prev_end = __shfl_up_sync(0xffffffffu, rs + slen, 1);
+  const int prev_len = __shfl_up_sync(0xffffffffu, slen, 1);           // every lane takes part in the shuffle (no short-circuit around it)
+  const bool head = slen > 0 && (lane == 0 || prev_end != rs || prev_len == 0);
+  uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const uint32_t live = __ballot_sync(0xffffffffu, slen > 0);
+  __syncwarp();
+  while (heads) {
+    const int h = __ffs(heads) - 1;
+    heads &= heads - 1;
+    // the run: lanes h .. e-1, e = next head or the first dead lane after h
+    const uint32_t after = (heads | ~live) & ~((2u << h) - 1u);
+    const int e = after ? __ffs(after) - 1 : 32;
+    const int64_t g0 = __shfl_sync(0xffffffffu, rs, h);
+    const int o0 = __shfl_sync(0xffffffffu, off, h);
+    const int o1 = (e < 32) ? __shfl_sync(0xffffffffu, off, e & 31) : __shfl_sync(0xffffffffu, off + slen, 31);
+    const double* src = img[warp] + o0;
+    const int n = o1 - o0;
+    if (overwrite) for (int k = lane; k < n; k += 32) val[g0 + k] = src[k];
+    else for (int k = lane; k < n; k += 32) { const double a = src[k]; if (a != 0.0) val[g0 + k] += a; }
+  }
+}
+
 static ChildQ1 child_q1(const Ctx* c, int i)
 {
   const Child& ch = c->children[i];
@@ -324,6 +471,10 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
   const int NL = 1 << m.dim;
   RowsJobs J; J.n = 0;
   int nblocks = 0;
+  RecJobs JR; JR.n = 0;
+  int nblocks_rec = 0;
+  FillJobs FJ; FJ.n = 0; FJ.nblocks = 0;
+  static const bool no_rec = getenv("MDB_ROWS_GATHER") != nullptr;          // A/B switch: always the gather kernel
   for (int i = 0; i < (int)c->children.size(); ++i) {
     if (c->children[i].dg) {              // QkDG: volume + skeleton + boundary blocks, one thread per row (dg.cu)
       if (part == 1) jacobian_dg(c, go, M, i, weight, overwrite);
@@ -343,44 +494,87 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
     const bool uni = uniform_rows_ok(c, M, V, i);
     const int32_t* list = uni ? M.d_irregular[i] : nullptr;
     const int64_t nrows = uni ? M.n_irregular[i] : ch.size;
-    if (uni && part == 0) {
-      const double* S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL;
-      static const int per_sm = getenv("MDB_FILL_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_BLOCKS_PER_SM")) : 0;   // 0: one run per block
-      int grid = (int)M.n_seg[i];
-      if (per_sm > 0 && grid > 148 * per_sm) grid = 148 * per_sm;
-      static const bool no_tma = getenv("MDB_FILL_NO_TMA") != nullptr;                  // A/B switch for profiling only
-      if (overwrite && !no_tma) {
-        const int ns = (m.dim == 3) ? 27 : 9;
-        // rows per shared-memory image = rows per bulk copy.  Small images leave the SM's shared memory to the irregular-row
-        // and FD-coupling kernels running beside the fill (their occupancy is shared-memory bound).
-        static const int ft_rows_env = getenv("MDB_FILL_TMA_ROWS") ? atoi(getenv("MDB_FILL_TMA_ROWS")) : FT_ROWS;
-        const int ft_rows = (ft_rows_env >= 2 && ft_rows_env <= FT_ROWS) ? (ft_rows_env & ~1) : FT_ROWS;
-        const size_t smem = (size_t)(ns * ft_rows + 2 * ns) * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-          MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((9 * FT_ROWS + 18) * sizeof(double))));
-          MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((27 * FT_ROWS + 54) * sizeof(double))));
-          configured = true;
-        }
-        static const int tma_blocks = getenv("MDB_FILL_TMA_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_TMA_BLOCKS_PER_SM")) : 2;
-        int tgrid = 148 * tma_blocks;
-        if (tgrid > cdiv(M.n_seg[i], FT_THREADS / 32)) tgrid = cdiv(M.n_seg[i], FT_THREADS / 32);
-        static const int evict_first = getenv("MDB_FILL_EVICT_FIRST") ? atoi(getenv("MDB_FILL_EVICT_FIRST")) : 0;
-        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows, evict_first);
-        else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, tgrid, FT_THREADS, smem, S, M.d_seg_span[i], M.n_seg[i], M.d_val, ft_rows, evict_first);
-      } else if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
-      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, grid, JF_THREADS, 0, S, M.d_seg_span[i], M.n_seg[i], M.d_val, (int)overwrite);
+    if (uni && part == 0 && M.n_seg[i] > 0) {
+      FillJob& fj = FJ.job[FJ.n++];
+      fj.S = c->d_Ae + V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL; fj.seg_span = M.d_seg_span[i]; fj.nseg = M.n_seg[i]; fj.block0 = 0;
     }
-    if (nrows > 0 && part == 1) {
+    if (nrows > 0 && part == 1 && uni && !no_rec && M.rr_state[i] == 0) {       // records of the irregular rows, once per (matrix, child)
+      M.d_rr_rs[i] = dalloc<int64_t>(nrows); M.d_rr_mask[i] = dalloc<uint32_t>(nrows); M.d_rr_meta[i] = dalloc<uint32_t>(nrows);
+      M.d_rr_sd[i] = dalloc<unsigned long long>(nrows);
+      int* d_bad = dalloc<int>(1);
+      MDB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+      if (m.dim == 2) MDB_LAUNCH(c, k_rowrec_build<2>, cdiv(nrows, 256), 256, 0, m, c->d_cell_sd, ch, list, nrows, M.d_rowptr, M.d_rowinfo, M.d_colidx,
+                                 M.d_rr_rs[i], M.d_rr_mask[i], M.d_rr_meta[i], M.d_rr_sd[i], d_bad);
+      else MDB_LAUNCH(c, k_rowrec_build<3>, cdiv(nrows, 256), 256, 0, m, c->d_cell_sd, ch, list, nrows, M.d_rowptr, M.d_rowinfo, M.d_colidx,
+                      M.d_rr_rs[i], M.d_rr_mask[i], M.d_rr_meta[i], M.d_rr_sd[i], d_bad);
+      int bad = 0;
+      MDB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      dfree(d_bad);
+      M.rr_state[i] = bad ? -1 : 1;
+    }
+    if (nrows > 0 && part == 1 && uni && !no_rec && M.rr_state[i] == 1) {
+      RecJob& jb = JR.job[JR.n++];
+      jb.V = V; jb.rs = M.d_rr_rs[i]; jb.mask = M.d_rr_mask[i]; jb.meta = M.d_rr_meta[i]; jb.sd = M.d_rr_sd[i]; jb.nrows = nrows; jb.block0 = nblocks_rec;
+      nblocks_rec += cdiv(nrows, RR_THREADS);
+    } else if (nrows > 0 && part == 1) {
       RowsJob& jb = J.job[J.n++];
       jb.ch = ch; jb.V = V; jb.list = list; jb.nrows = nrows; jb.block0 = nblocks;
       nblocks += cdiv(nrows, JR_THREADS);
+    }
+  }
+  if (FJ.n > 0) {
+    static const bool no_tma = getenv("MDB_FILL_NO_TMA") != nullptr;                  // A/B switch for profiling only
+    int64_t total_seg = 0;
+    for (int j = 0; j < FJ.n; ++j) total_seg += FJ.job[j].nseg;
+    if (overwrite && !no_tma) {
+      const int ns = (m.dim == 3) ? 27 : 9;
+      // rows per shared-memory image = rows per bulk copy.  Small images leave the SM's shared memory to the irregular-row
+      // and FD-coupling kernels running beside the fill (their occupancy is shared-memory bound).
+      static const int ft_rows_env = getenv("MDB_FILL_TMA_ROWS") ? atoi(getenv("MDB_FILL_TMA_ROWS")) : FT_ROWS;
+      const int ft_rows = (ft_rows_env >= 2 && ft_rows_env <= FT_ROWS) ? (ft_rows_env & ~1) : FT_ROWS;
+      const size_t smem = (size_t)(ns * ft_rows + 2 * ns) * sizeof(double);
+      static bool configured = false;
+      if (!configured) {
+        MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((9 * FT_ROWS + 18) * sizeof(double))));
+        MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((27 * FT_ROWS + 54) * sizeof(double))));
+        configured = true;
+      }
+      static const int tma_blocks = getenv("MDB_FILL_TMA_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_TMA_BLOCKS_PER_SM")) : 2;
+      // the blocks of the launch are shared out among the children in proportion to their runs (a block keeps ONE child's image)
+      const int tgrid = 148 * tma_blocks;
+      int b0 = 0;
+      for (int j = 0; j < FJ.n; ++j) {
+        int nb = (int)((FJ.job[j].nseg * tgrid + total_seg - 1) / total_seg);
+        if (nb < 1) nb = 1;
+        if (nb > cdiv(FJ.job[j].nseg, FT_THREADS / 32)) nb = cdiv(FJ.job[j].nseg, FT_THREADS / 32);
+        FJ.job[j].block0 = b0; b0 += nb;
+      }
+      FJ.nblocks = b0;
+      static const int evict_first = getenv("MDB_FILL_EVICT_FIRST") ? atoi(getenv("MDB_FILL_EVICT_FIRST")) : 0;
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, FJ.nblocks, FT_THREADS, smem, FJ, M.d_val, ft_rows, evict_first);
+      else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, FJ.nblocks, FT_THREADS, smem, FJ, M.d_val, ft_rows, evict_first);
+    } else {
+      static const int per_sm = getenv("MDB_FILL_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_BLOCKS_PER_SM")) : 0;   // 0: one run per block
+      int b0 = 0;
+      for (int j = 0; j < FJ.n; ++j) {
+        int64_t nb = FJ.job[j].nseg;
+        if (per_sm > 0) { const int64_t cap = (FJ.job[j].nseg * 148 * per_sm + total_seg - 1) / total_seg; if (nb > cap) nb = cap < 1 ? 1 : cap; }
+        FJ.job[j].block0 = b0; b0 += (int)nb;
+      }
+      FJ.nblocks = b0;
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_q1<2>, FJ.nblocks, JF_THREADS, 0, FJ, M.d_val, (int)overwrite);
+      else MDB_LAUNCH(c, k_jacobian_fill_q1<3>, FJ.nblocks, JF_THREADS, 0, FJ, M.d_val, (int)overwrite);
     }
   }
   if (J.n > 0) {
     if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_q1<2>, nblocks, JR_THREADS, 0, m, c->d_cell_sd, J, c->d_Ae, M.d_rowptr, M.d_rowinfo, M.d_colidx, M.d_val,
                                (int)overwrite);
     else MDB_LAUNCH(c, k_jacobian_rows_q1<3>, nblocks, JR_THREADS, 0, m, c->d_cell_sd, J, c->d_Ae, M.d_rowptr, M.d_rowinfo, M.d_colidx, M.d_val, (int)overwrite);
+  }
+  if (JR.n > 0) {
+    if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_rec<2>, nblocks_rec, RR_THREADS, 0, JR, c->d_Ae, M.d_val, (int)overwrite);
+    else MDB_LAUNCH(c, k_jacobian_rows_rec<3>, nblocks_rec, RR_THREADS, 0, JR, c->d_Ae, M.d_val, (int)overwrite);
   }
 }
 

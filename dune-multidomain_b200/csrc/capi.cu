@@ -122,9 +122,11 @@ void VecInOut::commit()
 static void free_matrix(Matrix& m)
 {
   dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv); dfree(m.d_spmv_rest); dfree(m.d_ready); dfree(m.d_sweep_counter); dfree(m.d_sweep_perm); dfree(m.d_cell_perm); dfree(m.d_vrec); dfree(m.d_ilu);
-  for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(m.d_irregular[i]); dfree(m.d_seg_start[i]); dfree(m.d_seg_span[i]); }
+  for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(m.d_irregular[i]); dfree(m.d_seg_start[i]); dfree(m.d_seg_span[i]); dfree(m.d_rr_rs[i]); dfree(m.d_rr_mask[i]); dfree(m.d_rr_meta[i]); dfree(m.d_rr_sd[i]); }
   for (auto& kv : m.slot_tables) cudaFree(kv.second);
   m.slot_tables.clear();
+  for (auto& kv : m.fd_plans) fd_plan_free(kv.second);
+  m.fd_plans.clear();
 }
 
 static void reset_spaces(Ctx* c)
@@ -770,9 +772,10 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
     jacobian_volume(c, G, M, weight, overwrite != 0, 1);
     c->phase_end();
   }
+  static const bool serial = getenv("MDB_JAC_SERIAL") != nullptr;           // A/B: the auxiliary branch on the main stream (stand-alone kernel times)
   MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
   {
-    StreamScope aux(c, c->aux_stream);
+    StreamScope aux(c, serial ? c->stream : c->aux_stream);
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
     if (!rows_first) {
       c->phase_begin("jacobian_rows");

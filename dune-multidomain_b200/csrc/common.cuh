@@ -222,6 +222,9 @@ struct GridOp {
   int64_t n_res_rest[MDB_MAX_CHILDREN] = {-1, -1, -1, -1, -1, -1, -1, -1};
 };
 
+struct FdPlan;                      // fdcoupling.cu: tables of the register-variant FD coupling kernel on a planar interface
+void fd_plan_free(FdPlan* p);
+
 struct Matrix {
   std::vector<int> gos;
   int64_t nnz = 0;
@@ -235,11 +238,17 @@ struct Matrix {
   int64_t child_begin[MDB_MAX_CHILDREN] = {0}, child_end[MDB_MAX_CHILDREN] = {0};
   int32_t* d_irregular[MDB_MAX_CHILDREN] = {nullptr};
   int64_t n_irregular[MDB_MAX_CHILDREN] = {0};
+  // static records of the irregular rows (assemble.cu: k_rowrec_build / k_jacobian_rows_rec), built on first use:
+  // value-array start, stencil mask | columns below the block, length | validity of the 2^d incident cells, their subdomain bytes
+  int64_t* d_rr_rs[MDB_MAX_CHILDREN] = {nullptr}; uint32_t* d_rr_mask[MDB_MAX_CHILDREN] = {nullptr}; uint32_t* d_rr_meta[MDB_MAX_CHILDREN] = {nullptr};
+  unsigned long long* d_rr_sd[MDB_MAX_CHILDREN] = {nullptr};
+  int rr_state[MDB_MAX_CHILDREN] = {0};          // 0 not built, 1 usable, -1 a row cannot be staged: gather kernel
   int32_t* d_seg_start[MDB_MAX_CHILDREN] = {nullptr};   // runs of rows with equal simple/irregular status (n_seg + 1 entries)
   int64_t n_seg[MDB_MAX_CHILDREN] = {0};
   longlong2* d_seg_span[MDB_MAX_CHILDREN] = {nullptr};  // value-array span [x, y) of every run (empty for irregular runs)
   // per (grid operator, coupling): uint8 offsets inside the row of every entry a coupling face touches
   std::map<std::pair<int, int>, uint8_t*> slot_tables;
+  std::map<std::pair<int, int>, FdPlan*> fd_plans;
   // preconditioner caches
   double* d_dinv = nullptr;
   bool dinv_valid = false; int dinv_precond = -1;

@@ -542,6 +542,7 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
       if (err) { cudaFree(slots); throw Error(MDB_EINVAL, "coupling entries missing from the matrix pattern (was the matrix created with this grid operator?)"); }
       M.slot_tables[key] = slots;
     } else slots = it->second;
+    if (jacobian_coupling_fd_fast(c, P, Ls, Rs, fl, M, key, slots, weight, eps, d_x)) continue;      // planar interface: fdcoupling.cu
     const double* tab = face_tables(c, P);
     const int fpb = 256 / (2 * NL + 1);
     static const int pad_kb = getenv("MDB_COUPLING_PAD_KB") ? atoi(getenv("MDB_COUPLING_PAD_KB")) : 0;   // occupancy experiment knob

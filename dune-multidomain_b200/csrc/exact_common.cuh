@@ -113,6 +113,10 @@ struct CouplingParams {
 
 struct SideMap { int lat_n[3]; int64_t offset; const int32_t* lat2dof; int dg; };     // dg: lattice stride K + 1 (QkDG child)
 
+// fdcoupling.cu; false = not applicable (the caller runs k_coupling_jacobian_staged)
+bool jacobian_coupling_fd_fast(Ctx* c, const CouplingParams& P, const SideMap& Ls, const SideMap& Rs, const FaceList& fl, Matrix& M, std::pair<int, int> key,
+                               const uint8_t* slots, double weight, double eps, const double* d_x);
+
 template <int DIM> __device__ __forceinline__ void cell_dofs_q1(const SideMap& S, const int ijk[3], int32_t* dofs)
 {
   constexpr int NL = 1 << DIM;
