@@ -364,6 +364,16 @@ class Mdb(Lib):
                     "onestep_apply")
         return st
 
+    def stationary_solve(self, go, mat, x, method=SOLVER_CG, precond=PRECOND_JACOBI, reduction=1e-10, maxit=5000, keep_matrix=False):
+        st = SolveStats()
+        rc = self._fn("stationary_solve")(C.c_void_p(self.ctx), go, mat, method, precond, C.c_double(reduction), maxit, _vecptr(x), int(keep_matrix),
+                                          C.byref(st))
+        self._check(rc, "stationary_solve")
+        return st
+
+    def set_halo_timeout(self, seconds):
+        self._check(self._fn("set_halo_timeout")(C.c_void_p(self.ctx), C.c_double(seconds)), "set_halo_timeout")
+
     def set_ssor_sweeps(self, sweeps):
         self._check(self._fn("set_ssor_sweeps")(C.c_void_p(self.ctx), int(sweeps)), "set_ssor_sweeps")
 

@@ -94,6 +94,13 @@ void Ctx::phase_reset()
   for (auto& kv : phases) { if (kv.second.used) phase_mean_ms(kv.first.c_str(), nullptr); kv.second.used = 0; }
 }
 
+static bool is_pinned_host(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 VecIn::VecIn(Ctx* c, const double* p, int64_t n, int slot)
 {
   if (is_device_ptr(p)) { d = p; return; }
@@ -101,6 +108,9 @@ VecIn::VecIn(Ctx* c, const double* p, int64_t n, int slot)
   MDB_CUDA(cudaMemcpyAsync(c->d_stage[slot], p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->h2d_bytes += n * (int64_t)sizeof(double);
   d = c->d_stage[slot];
+  // Host vectors are plain inputs: the caller may reuse the buffer as soon as the call returns.  A copy from pageable memory
+  // is staged before cudaMemcpyAsync returns; a copy from page-locked memory is a real DMA, so wait for it here.
+  if (is_pinned_host(p)) MDB_CUDA(cudaStreamSynchronize(c->stream));
 }
 VecInOut::VecInOut(Ctx* c_, double* p, int64_t n_, int slot, bool load) : c(c_), n(n_)
 {
@@ -108,7 +118,10 @@ VecInOut::VecInOut(Ctx* c_, double* p, int64_t n_, int slot, bool load) : c(c_),
   host = p;
   if (!c->d_stage[slot]) c->d_stage[slot] = dalloc<double>(c->ndof > n ? c->ndof : n);
   d = c->d_stage[slot];
-  if (load) { MDB_CUDA(cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * (int64_t)sizeof(double); }
+  if (load) {
+    MDB_CUDA(cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * (int64_t)sizeof(double);
+    if (is_pinned_host(p)) MDB_CUDA(cudaStreamSynchronize(c->stream));      // see VecIn
+  }
 }
 void VecInOut::commit()
 {
@@ -219,6 +232,7 @@ void mdb_destroy(mdb_ctx* c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  nccl_comm_release(c);
   reset_spaces(c);
   um_free(c);
   dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_ftab_g); dfree(c->d_dgtab); dfree(c->d_scal); dfree(c->d_partial);
@@ -494,7 +508,15 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   c->phase_begin("dofmap");
   if (c->um) um_build_dofmap(c); else build_dofmap(c);
   c->phase_end();
-  if (c->mesh.partitioned) setup_partition(c);
+  if (c->mesh.partitioned) {
+    // the add_* calls refuse these on a partitioned mesh; mdb_mesh_partition may also come AFTER them, so check again here
+    for (const Child& ch : c->children)
+      MDB_REQUIRE(!ch.dg && !ch.iface && ch.k == 1, MDB_EINVAL, "mdb_finalize: a partitioned mesh carries Q1 spaces only (no Q2 / QkDG / coupling spaces)");
+    for (const CouplingDesc& cp : c->cps)
+      MDB_REQUIRE(cp.op_id != MDB_OP_ND_COUPLING && !cp.enriched(), MDB_EINVAL,
+                  "mdb_finalize: Neumann-Dirichlet and enriched couplings are not supported on a partitioned mesh");
+    setup_partition(c);
+  }
   c->finalized = true;
   if (ndof) *ndof = c->ndof;
   MDB_API_END(c)
@@ -796,6 +818,9 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   c->phase_begin("jacobian_dirichlet");
   dirichlet_rows(c, M);
   c->phase_end();
+  // a host x is only read during the call (mdb200.h): the gather / upload from page-locked memory is asynchronous, so wait for it
+  // (the copy stream's work is a few microseconds and long finished; the assembly kernels keep running)
+  if (host_x && need_x) MDB_CUDA(cudaEventSynchronize(c->ev_copy_done));
   MDB_API_END(c)
 }
 
@@ -825,12 +850,11 @@ int mdb_spmv(mdb_ctx* c, int mat, const double* x, double* y)
   MDB_MAT(c, mat)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vy(c, y, c->ndof, 1, false);
+  c->phase_begin("spmv");
   if (c->peer_lower || c->peer_upper) {
     MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_spmv: x must be a device vector on a partitioned context");
-    halo_exchange(c, const_cast<double*>(vx.d));
-  }
-  c->phase_begin("spmv");
-  spmv(c, M, vx.d, vy.d);
+    spmv_partitioned(c, M, const_cast<double*>(vx.d), vy.d);      // push -> interior rows -> wait -> boundary rows
+  } else spmv(c, M, vx.d, vy.d);
   c->phase_end();
   vy.commit();
   MDB_API_END(c)
@@ -1030,6 +1054,46 @@ int mdb_profile_reset(mdb_ctx* c)
 }
 
 // sum of squares of the stored matrix entries (a cheap device-side checksum of an assembly result)
+// [UPSTREAM] PDELab StationaryLinearProblemSolver::apply as the reference's drivers call it (test/testpoisson.cc:295-298,
+// SURVEY 8c (vii)): assemble J(x0) and r = R(x0) at the incoming x0, solve J z = r to the relative defect reduction, x <- x0 - z.
+// One call, everything on the device; x may be a host vector (uploaded once, the solution is copied back) or a device vector
+// (updated in place).  keep_matrix != 0 reuses the values already in `mat` (the reference's keep_matrix of the Dirichlet-Neumann loop).
+int mdb_stationary_solve(mdb_ctx* c, int go, int mat, int method, int precond, double reduction, int maxit, double* x, int keep_matrix,
+                         mdb_solve_stats* stats)
+{
+  if (!c) return MDB_EINVAL;
+  try {
+    cudaSetDevice(c->device);
+    MDB_MAT(c, mat)
+    MDB_REQUIRE(go >= 0 && go < (int)c->gos.size(), MDB_EINVAL, "bad grid operator handle");
+    MDB_REQUIRE(x, MDB_EINVAL, "mdb_stationary_solve: null vector");
+    const int64_t nd = c->ndof;
+    if (c->onestep_n < nd) { dfree(c->d_onestep); c->d_onestep = dalloc<double>(4 * nd); c->onestep_n = nd; }
+    const bool host = !is_device_ptr(x);
+    double* u = host ? c->d_onestep : x;
+    double* r = c->d_onestep + 2 * nd;
+    double* z = c->d_onestep + 3 * nd;
+    c->phase_begin("stationary_upload");
+    if (host) { MDB_CUDA(cudaMemcpyAsync(u, x, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += nd * (int64_t)sizeof(double); }
+    c->phase_end();
+    int rc = MDB_OK;
+    if (!keep_matrix) { rc = mdb_jacobian(c, go, mat, 1.0, u, 1); if (rc != MDB_OK) return rc; }
+    MDB_CUDA(cudaMemsetAsync(r, 0, nd * sizeof(double), c->stream));
+    rc = mdb_residual(c, go, 1.0, u, r);
+    if (rc != MDB_OK) return rc;
+    rc = solve(c, M, method, precond, reduction, maxit, -1, r, z, stats);
+    if (rc != MDB_OK) return rc;
+    MDB_LAUNCH(c, k_sub, 148 * 8, 256, 0, u, z, u, nd);
+    if (host) {
+      MDB_CUDA(cudaMemcpyAsync(x, u, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      c->d2h_bytes += nd * (int64_t)sizeof(double);
+    }
+    return MDB_OK;
+  } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
+  catch (std::exception& e) { c->err = e.what(); return MDB_EINVAL; }
+}
+
 __global__ void k_norm2_partial(const double* __restrict__ v, int64_t n, double* partial)
 {
   __shared__ double sh[8];

@@ -323,6 +323,7 @@ struct Ctx {
   double* peer_lower = nullptr; double* peer_upper = nullptr;   // mapped windows of the neighbours
   std::vector<void*> ipc_opened;
   int lower_rank = -1, upper_rank = -1;
+  double halo_timeout_s = 0.0;       // bound of the halo wait (mdb_set_halo_timeout; 0: MDB_HALO_TIMEOUT_S or 30 s)
 
   void* scratch(size_t bytes);
   void phase_begin(const char* name);
@@ -390,11 +391,15 @@ void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& m, int child, boo
 void residual_volume_generic(Ctx* c, const GridOp& go, int child, const double* d_x, double* d_r);
 void dirichlet_rows(Ctx* c, Matrix& m);
 void spmv(Ctx* c, const Matrix& m, const double* d_x, double* d_y);
+void spmv_partitioned(Ctx* c, const Matrix& m, double* d_x, double* d_y);   // halo exchange overlapped with the interior rows
 int solve(Ctx* c, Matrix& m, int method, int precond, double reduction, int maxit, int fixed_iters,
           const double* d_rhs, double* d_z, mdb_solve_stats* stats);
 void setup_partition(Ctx* c);                       // multigpu.cu: ownership flags + halo window of a partitioned mesh
 void allreduce_scalars(Ctx* c, double* d_vals, int n);
-void halo_exchange(Ctx* c, double* d_x);
+void halo_exchange(Ctx* c, double* d_x, double* d_done = nullptr);   // d_done: the solver's S_DONE slot, set when the wait times out
+void halo_push(Ctx* c, const double* d_x);
+void halo_wait(Ctx* c, double* d_x, double* d_done = nullptr);
+void nccl_comm_release(Ctx* c);
 bool halo_timed_out(Ctx* c);
 // unstructured.cu: the same steps on an unstructured triangle mesh with P1 spaces
 void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn);

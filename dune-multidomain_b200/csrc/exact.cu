@@ -102,7 +102,9 @@ void launch_element_matrices(Ctx* c, const std::vector<int>& sps, double weight)
     S.op[i] = sp.op_id == MDB_OP_CONVDIFF_DG ? MDB_OP_POISSON : sp.op_id; S.k[i] = c->children[sp.children[0]].k; S.rule[i] = gauss1d(sp.quad_order());
   }
   double ext[3] = {1, 1, 1};
-  for (int d = 0; d < m.dim; ++d) ext[d] = m.coord(d, 1) - m.coord(d, 0);
+  // the extent of the (congruent) cells: coord(1) - coord(0) evaluated at global offset 0, so that every rank of a partition gets
+  // the bits of the single-rank matrix (with off > 0 the difference of two large products differs in the last place)
+  for (int d = 0; d < m.dim; ++d) ext[d] = (m.glower[d] + 1.0 * m.h[d]) - (m.glower[d] + 0.0 * m.h[d]);
   int nthreads = 256;      // at least 256: the shape-function tables of a quadrature chunk are evaluated by the whole block
   for (int i = 0; i < S.n; ++i) { int nl = 1; for (int d = 0; d < m.dim; ++d) nl *= (S.k[i] + 1); int t = ((nl * nl + 31) / 32) * 32; if (t > nthreads) nthreads = t; }
   if (m.dim == 2) MDB_LAUNCH(c, k_element_matrices<2>, S.n, nthreads, 0, S, ext[0], ext[1], ext[2], weight, c->d_Ae);

@@ -63,6 +63,12 @@ void allreduce_scalars(Ctx* c, double* d_vals, int n)
   c->launches++;
 }
 
+void nccl_comm_release(Ctx* c)
+{
+  if (c->nccl_comm && g_nccl.lib && g_nccl.CommDestroy) g_nccl.CommDestroy((nccl_comm_t)c->nccl_comm);
+  c->nccl_comm = nullptr;
+}
+
 // ---- partition geometry --------------------------------------------------------------------------------------------
 // lattice planes (along the partition axis) of child `ch` that this rank owns: [lo, hi)
 static void owned_planes(const Ctx* c, const Child& ch, int* lo, int* hi)
@@ -196,7 +202,8 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloSpec H, const double* __r
 
 // Wait + unpack: acquire the neighbours' sequence numbers, then copy the window into the ghost entries of x.  The wait is
 // bounded (about two seconds of SM clock) so that a lost peer can never hang the device; a timeout raises *err.
-__global__ void __launch_bounds__(256) k_halo_unpack(HaloSpec H, double* __restrict__ x, int has_lower, int has_upper, int* err)
+__global__ void __launch_bounds__(256) k_halo_unpack(HaloSpec H, double* __restrict__ x, int has_lower, int has_upper, int* err, long long timeout_clocks,
+                                                     double* done)
 {
   __shared__ int ok;
   if (threadIdx.x == 0) {
@@ -206,12 +213,12 @@ __global__ void __launch_bounds__(256) k_halo_unpack(HaloSpec H, double* __restr
     for (int side = 0; side < 2; ++side) {
       if (!(side == 0 ? has_lower : has_upper)) continue;
       while (ld_acquire_sys(flags + side) < H.seq) {
-        if (clock64() - t0 > 4000000000LL) { good = false; break; }
+        if (clock64() - t0 > timeout_clocks) { good = false; break; }
         __nanosleep(100);
       }
     }
     ok = good ? 1 : 0;
-    if (!good) atomicExch(err, 1);
+    if (!good) { atomicExch(err, 1); if (done) *done = 1.0; }        // a Krylov loop on this stream stops instead of iterating on stale ghosts
   }
   __syncthreads();
   if (!ok) return;
@@ -263,7 +270,15 @@ void halo_push(Ctx* c, const double* d_x)
   MDB_LAUNCH(c, k_halo_push, grid, 256, 0, H, d_x, c->d_halo_counter);
 }
 
-void halo_wait(Ctx* c, double* d_x)
+static long long halo_timeout_clocks(const Ctx* c)
+{
+  double s = c->halo_timeout_s;
+  if (s <= 0.0) { const char* e = getenv("MDB_HALO_TIMEOUT_S"); s = e ? atof(e) : 30.0; }
+  if (s < 1e-3) s = 1e-3;
+  return (long long)(s * 1.9e9);                         // SM clocks at ~1.9 GHz
+}
+
+void halo_wait(Ctx* c, double* d_x, double* d_done)
 {
   MDB_REQUIRE(c->d_halo_recv, MDB_ESTATE, "halo exchange on an unpartitioned context");
   if (!c->peer_lower && !c->peer_upper) return;
@@ -271,13 +286,14 @@ void halo_wait(Ctx* c, double* d_x)
   int64_t work = 0;
   for (int i = 0; i < H.nchild; ++i) work += H.ch[i].plane_pts * H.ch[i].k;
   int grid = cdiv(work, 256); if (grid > 64) grid = 64; if (grid < 1) grid = 1;     // every block spins on the flags: keep the grid co-resident
-  MDB_LAUNCH(c, k_halo_unpack, grid, 256, 0, H, d_x, c->peer_lower ? 1 : 0, c->peer_upper ? 1 : 0, (int*)(c->d_halo_counter + 2));
+  MDB_LAUNCH(c, k_halo_unpack, grid, 256, 0, H, d_x, c->peer_lower ? 1 : 0, c->peer_upper ? 1 : 0, (int*)(c->d_halo_counter + 2),
+             halo_timeout_clocks(c), d_done);
 }
 
-void halo_exchange(Ctx* c, double* d_x)
+void halo_exchange(Ctx* c, double* d_x, double* d_done)
 {
   halo_push(c, d_x);
-  halo_wait(c, d_x);
+  halo_wait(c, d_x, d_done);
 }
 
 bool halo_timed_out(Ctx* c)
@@ -286,6 +302,8 @@ bool halo_timed_out(Ctx* c)
   int e = 0;
   MDB_CUDA(cudaMemcpyAsync(&e, c->d_halo_counter + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
+  // report once: a transient stall of a neighbour (a profiler replay, a descheduled rank) must not fail every later exchange
+  if (e != 0) { MDB_CUDA(cudaMemsetAsync(c->d_halo_counter + 2, 0, sizeof(int), c->stream)); MDB_CUDA(cudaStreamSynchronize(c->stream)); }
   return e != 0;
 }
 
@@ -297,7 +315,18 @@ struct mdb_ctx : mdb::Ctx {};
 #define MG_BEGIN(ctx) if (!(ctx)) return MDB_EINVAL; try { cudaSetDevice((ctx)->device);
 #define MG_END(ctx) return MDB_OK; } catch (mdb::Error& e) { (ctx)->err = e.what(); return e.code; } catch (std::exception& e) { (ctx)->err = e.what(); return MDB_EINVAL; }
 
-struct HaloBlob { cudaIpcMemHandle_t ipc; uint64_t raw; int32_t pid; int32_t device; };
+struct HaloBlob { cudaIpcMemHandle_t ipc; uint64_t raw; uint32_t token; int32_t device; };
+// "same process" is decided by a random per-process token, not by the pid alone (pids repeat across pid namespaces)
+static uint32_t process_token()
+{
+  static uint32_t t = 0;
+  if (!t) {
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (f) { if (fread(&t, sizeof(t), 1, f) != 1) t = 0; fclose(f); }
+    if (!t) t = (uint32_t)getpid() * 2654435761u ^ (uint32_t)((uintptr_t)&t & 0xFFFFFFFFu) ^ 0x9E3779B9u;
+  }
+  return t;
+}
 static_assert(sizeof(HaloBlob) <= 80, "halo blob must fit the 80-byte ABI buffer");
 
 extern "C" {
@@ -317,10 +346,18 @@ int mdb_comm_init(mdb_ctx* c, int nranks, int rank, const void* id128)
     MDB_REQUIRE(id128, MDB_EINVAL, "mdb_comm_init: unique id required");
     nccl_uid_t id; std::memcpy(&id, id128, 128);
     nccl_comm_t comm = nullptr;
+    if (c->nccl_comm) { nccl().CommDestroy((nccl_comm_t)c->nccl_comm); c->nccl_comm = nullptr; }      // re-initialisation
     MDB_NCCL(nccl().CommInitRank(&comm, nranks, id, rank));
     c->nccl_comm = comm;
   }
   MG_END(c)
+}
+
+int mdb_set_halo_timeout(mdb_ctx* c, double seconds)
+{
+  if (!c) return MDB_EINVAL;
+  c->halo_timeout_s = seconds;
+  return MDB_OK;
 }
 
 int mdb_halo_export(mdb_ctx* c, void* blob80, int64_t* window_bytes)
@@ -329,7 +366,7 @@ int mdb_halo_export(mdb_ctx* c, void* blob80, int64_t* window_bytes)
   MDB_REQUIRE(c->finalized && c->d_halo_recv, MDB_ESTATE, "mdb_halo_export: finalize a partitioned mesh first");
   HaloBlob b; std::memset(&b, 0, sizeof(b));
   MDB_CUDA(cudaIpcGetMemHandle(&b.ipc, c->d_halo_recv));
-  b.raw = (uint64_t)(uintptr_t)c->d_halo_recv; b.pid = (int32_t)getpid(); b.device = c->device;
+  b.raw = (uint64_t)(uintptr_t)c->d_halo_recv; b.device = c->device; b.token = process_token();
   std::memset(blob80, 0, 80);
   std::memcpy(blob80, &b, sizeof(b));
   if (window_bytes) *window_bytes = c->halo_recv_n * (int64_t)sizeof(double);
@@ -339,7 +376,7 @@ int mdb_halo_export(mdb_ctx* c, void* blob80, int64_t* window_bytes)
 static double* open_peer(mdb_ctx* c, const void* blob80)
 {
   HaloBlob b; std::memcpy(&b, blob80, sizeof(b));
-  if (b.pid == (int32_t)getpid()) {                        // a context of this very process: plain pointer (+ peer access if another device)
+  if (b.token == process_token()) {                        // a context of this very process: plain pointer (+ peer access if another device)
     if (b.device != c->device) { cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0); if (e != cudaSuccess) cudaGetLastError(); }
     return (double*)(uintptr_t)b.raw;
   }
@@ -375,7 +412,7 @@ int mdb_halo_wait(mdb_ctx* c, double* x)
 {
   MG_BEGIN(c)
   MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_halo_wait: x must be a device vector");
-  halo_wait(c, x);
+  halo_wait(c, x, nullptr);
   MDB_REQUIRE(!halo_timed_out(c), MDB_ENCCL, "halo exchange timed out waiting for a neighbour");
   MG_END(c)
 }

@@ -179,7 +179,11 @@ __global__ void __launch_bounds__(256) k_spmv_vec(int64_t n, const int64_t* __re
 #define ST_BLOCKS 5
 #define ST_VCAP (ST_ROWS * 28 + 2)           // doubles of value staging per block (simple rows: 27 per row + alignment slack)
 #define ST_XSEG (ST_ROWS + 4)                // doubles per staged x segment
-struct SpmvChild { int64_t offset, size, chunk0; int box, bx, bxy; };
+// chunk0: first VIRTUAL chunk of the child in this launch.  A launch covers all chunks of the child (skip_len = 0), only its interior
+// chunks [a, b) (skip_lo = 0, skip_len = a, b - a virtual chunks) or all but those (skip_lo = a, skip_len = b - a): virtual chunk v of
+// the child is its chunk v < skip_lo ? v : v + skip_len.  On a partition the interior chunks read no ghost entry of x, so they run
+// while the halo planes are in flight (solver: push -> interior -> wait -> the rest).
+struct SpmvChild { int64_t offset, size, chunk0, skip_lo, skip_len; int box, bx, bxy; };
 struct SpmvSpace { int nchild; int64_t nchunks; SpmvChild ch[MDB_MAX_CHILDREN]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -274,7 +278,8 @@ template <int DIM, int DOTS>
 __global__ void __launch_bounds__(ST_ROWS, ST_BLOCKS) k_spmv_stencil(int64_t n, SpmvSpace sp, const int64_t* __restrict__ rowptr,
                                                                      const uint32_t* __restrict__ rowinfo, const double* __restrict__ val,
                                                                      const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ a,
-                                                                     const uint8_t* __restrict__ owned, double* partial, const double* __restrict__ done)
+                                                                     const uint8_t* __restrict__ owned, double* partial, int pofs,
+                                                                     const double* __restrict__ done)
 {
   constexpr int NS = DIM == 3 ? 27 : 9;
   constexpr int NL = NS / 3;                                                      // x segments: one per (dy, dz)
@@ -301,7 +306,8 @@ __global__ void __launch_bounds__(ST_ROWS, ST_BLOCKS) k_spmv_stencil(int64_t n, 
     while (ci + 1 < sp.nchild && chunk >= sp.ch[ci + 1].chunk0) ++ci;
     const SpmvChild& ch = sp.ch[ci];
     C.ci = ci;
-    C.r0 = ch.offset + (chunk - ch.chunk0) * ST_ROWS;
+    const int64_t v = chunk - ch.chunk0;
+    C.r0 = ch.offset + (v < ch.skip_lo ? v : v + ch.skip_len) * ST_ROWS;
     C.r1 = (C.r0 + ST_ROWS < ch.offset + ch.size) ? C.r0 + ST_ROWS : ch.offset + ch.size;
     C.span0 = rowptr[C.r0 + zero]; C.span1 = rowptr[C.r1 + zero];
   };
@@ -410,10 +416,10 @@ __global__ void __launch_bounds__(ST_ROWS, ST_BLOCKS) k_spmv_stencil(int64_t n, 
   }
   if (DOTS >= 1) {
     double s0 = block_sum(d0, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = s0;
+    if (threadIdx.x == 0) partial[pofs + blockIdx.x] = s0;
     if (DOTS >= 2) {
       double s1 = block_sum(d1, sh);
-      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + blockIdx.x] = s1;
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + pofs + blockIdx.x] = s1;
     }
   }
 }
@@ -425,8 +431,17 @@ static int spmv_variant()
   return v;
 }
 
+// part: 0 = the whole product; on a partition 1 = the rows that read no ghost entry (issued while the halo is in flight), 2 = the
+// rest (after the halo wait).  *nblocks is the number of partial sums written so far: part 2 appends to part 1's.
+static bool spmv_can_split(const Ctx* c)
+{
+  if (spmv_variant() != 4 || c->um || c->part_axis < 0) return false;
+  for (const Child& ch : c->children) if (ch.k != 1 || ch.dg) return false;
+  return true;
+}
+
 template <int DOTS>
-static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, const double* a, double* partial, int* nblocks, const double* done)
+static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, const double* a, double* partial, int* nblocks, const double* done, int part = 0)
 {
   const int64_t n = c->ndof;
   const size_t smem = (size_t)SPMV_ROWS * M.max_row * sizeof(double);
@@ -461,7 +476,18 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
         for (int d = 0; d < dim; ++d) vol *= ch.lat_hi[d] - ch.lat_lo[d] + 1;
         sp.ch[i].offset = ch.offset; sp.ch[i].size = ch.size; sp.ch[i].box = (ch.size > 0 && vol == ch.size) ? 1 : 0;
         sp.ch[i].bx = ch.lat_hi[0] - ch.lat_lo[0] + 1; sp.ch[i].bxy = sp.ch[i].bx * (ch.lat_hi[1] - ch.lat_lo[1] + 1);
-        sp.ch[i].chunk0 = sp.nchunks; sp.nchunks += (ch.size + ST_ROWS - 1) / ST_ROWS;
+        const int64_t all = (ch.size + ST_ROWS - 1) / ST_ROWS;
+        // interior chunks: rows of the lattice planes [zlo, zhi) along the cut axis, whose stencils stay clear of the ghost planes
+        int64_t ia = 0, ib = 0;
+        if (part != 0 && sp.ch[i].box && c->part_axis == dim - 1) {
+          const int64_t nz = ch.lat_hi[dim - 1] - ch.lat_lo[dim - 1] + 1, plane = (dim == 3) ? sp.ch[i].bxy : sp.ch[i].bx;
+          const int64_t zlo = c->peer_lower ? 2 : 0, zhi = c->peer_upper ? nz - 2 : nz;
+          if (zhi > zlo) { ia = (zlo * plane + ST_ROWS - 1) / ST_ROWS; ib = (zhi * plane) / ST_ROWS; if (ib < ia) ib = ia; if (ib > all) ib = all; }
+        }
+        sp.ch[i].chunk0 = sp.nchunks;
+        if (part == 1) { sp.ch[i].skip_lo = 0; sp.ch[i].skip_len = ia; sp.nchunks += ib - ia; }
+        else if (part == 2) { sp.ch[i].skip_lo = ia; sp.ch[i].skip_len = ib - ia; sp.nchunks += all - (ib - ia); }
+        else { sp.ch[i].skip_lo = 0; sp.ch[i].skip_len = 0; sp.nchunks += all; }
       }
       if (M.n_spmv_rest < 0) {                // first product with this matrix: the rows the stencil kernel leaves out
         Matrix& Mm = const_cast<Matrix&>(M);
@@ -482,16 +508,22 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
         Mm.n_spmv_rest = (int64_t)ls + lf;
         cudaFree(d_t); dfree(d_flag); dfree(d_scan);
       }
+      const int pofs = (part == 2 && nblocks) ? *nblocks : 0;
       int grid = 148 * ST_BLOCKS;
+      if (part == 2) grid = 148 * 2;                                   // the boundary planes are a few hundred chunks
       if (grid > sp.nchunks) grid = (int)sp.nchunks;
-      int grid2 = 148 * 8;
+      int grid2 = (part == 1) ? 0 : 148 * 8;                           // the row list (interface rows, vector ends) may read ghosts: with the rest
       if (grid2 > cdiv(M.n_spmv_rest, 32)) grid2 = cdiv(M.n_spmv_rest, 32);
-      if (nblocks) *nblocks = grid + grid2;
-      if (dim == 3) MDB_LAUNCH(c, (k_spmv_stencil<3, DOTS>), grid, ST_ROWS, 0, n, sp, M.d_rowptr, M.d_rowinfo, M.d_val, x, y, a, c->d_owned, partial, done);
-      else MDB_LAUNCH(c, (k_spmv_stencil<2, DOTS>), grid, ST_ROWS, 0, n, sp, M.d_rowptr, M.d_rowinfo, M.d_val, x, y, a, c->d_owned, partial, done);
+      if (grid2 > MAX_PARTIAL_BLOCKS - pofs - grid) grid2 = MAX_PARTIAL_BLOCKS - pofs - grid;      // one partial sum per block (grid-stride kernels)
+      if (nblocks) *nblocks = pofs + grid + grid2;
+      MDB_REQUIRE(pofs + grid + grid2 <= MAX_PARTIAL_BLOCKS, MDB_EINVAL, "spmv: too many partial sums");
+      if (grid > 0) {
+        if (dim == 3) MDB_LAUNCH(c, (k_spmv_stencil<3, DOTS>), grid, ST_ROWS, 0, n, sp, M.d_rowptr, M.d_rowinfo, M.d_val, x, y, a, c->d_owned, partial, pofs, done);
+        else MDB_LAUNCH(c, (k_spmv_stencil<2, DOTS>), grid, ST_ROWS, 0, n, sp, M.d_rowptr, M.d_rowinfo, M.d_val, x, y, a, c->d_owned, partial, pofs, done);
+      }
       if (grid2 > 0)
-        MDB_LAUNCH(c, k_spmv_rows<DOTS>, grid2, 256, 0, M.n_spmv_rest, M.d_spmv_rest, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, grid,
-                   done);
+        MDB_LAUNCH(c, k_spmv_rows<DOTS>, grid2, 256, 0, M.n_spmv_rest, M.d_spmv_rest, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial,
+                   pofs + grid, done);
       return;
     }
     variant = 1;
@@ -506,9 +538,33 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
   else MDB_LAUNCH(c, (k_spmv_vec<DOTS, 8>), grid, 256, 0, n, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, done);
 }
 
+// y = A x on a partition: the owners' boundary planes travel while the interior rows are summed
+template <int DOTS>
+static void spmv_halo(Ctx* c, const Matrix& M, double* x, double* y, const double* a, double* partial, int* nblocks, double* s)
+{
+  // Measured on 2 x B200 (profiles/r02/README.md): every rank pushes right after an all-reduce, so the planes arrive within microseconds
+  // and there is no waiting time to hide; splitting the product costs a second, poorly filled launch (0.694 against 0.682 ms per
+  // product, CG 984 against 994 iterations/s).  The split is therefore opt-in (MDB_HALO_OVERLAP=1: for fabrics with slower neighbours).
+  static const bool overlap = getenv("MDB_HALO_OVERLAP") != nullptr;
+  if (!overlap || !spmv_can_split(c)) {
+    halo_exchange(c, x, s ? s + S_DONE : nullptr);
+    launch_spmv<DOTS>(c, M, x, y, a, partial, nblocks, s);
+    return;
+  }
+  halo_push(c, x);
+  launch_spmv<DOTS>(c, M, x, y, a, partial, nblocks, s, 1);
+  halo_wait(c, x, s ? s + S_DONE : nullptr);
+  launch_spmv<DOTS>(c, M, x, y, a, partial, nblocks, s, 2);
+}
+
 void spmv(Ctx* c, const Matrix& M, const double* d_x, double* d_y)
 {
   launch_spmv<0>(c, M, d_x, d_y, nullptr, nullptr, nullptr, nullptr);
+}
+void spmv_partitioned(Ctx* c, const Matrix& M, double* d_x, double* d_y)
+{
+  int nb = 0;
+  spmv_halo<0>(c, M, d_x, d_y, nullptr, nullptr, &nb, nullptr);
 }
 
 // ---- scalar helpers (single block) -------------------------------------------------------------------
@@ -758,8 +814,8 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     MDB_LAUNCH(c, k_cg_init_scalars, 1, 1, 0, s, reduction);
     while (issued < maxit) {
       MDB_LAUNCH(c, k_cg_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, general ? zv : r, p);
-      if (multi) halo_exchange(c, p);
-      launch_spmv<1>(c, M, p, q, p, c->d_partial, &nb, s);
+      if (multi) spmv_halo<1>(c, M, p, q, p, c->d_partial, &nb, s);
+      else launch_spmv<1>(c, M, p, q, p, c->d_partial, &nb, s);
       reduce(c, nb, 1, S_PQ);
       if (multi) allreduce_scalars(c, s + S_PQ, 1);
       MDB_LAUNCH(c, k_cg_derive_a, 1, 1, 0, s);
@@ -781,8 +837,8 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     while (issued < maxit) {
       MDB_LAUNCH(c, k_bi_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, v, p, y);
       if (general) precond_apply(c, M, precond, c->ssor_sweeps, p, y);
-      if (multi) halo_exchange(c, y);
-      launch_spmv<1>(c, M, y, v, rt, c->d_partial, &nb, s);
+      if (multi) spmv_halo<1>(c, M, y, v, rt, c->d_partial, &nb, s);
+      else launch_spmv<1>(c, M, y, v, rt, c->d_partial, &nb, s);
       reduce(c, nb, 1, S_H);
       if (multi) allreduce_scalars(c, s + S_H, 1);
       MDB_LAUNCH(c, k_bi_derive_alpha, 1, 1, 0, s);
@@ -791,8 +847,8 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       if (multi) allreduce_scalars(c, s + S_RR, 1);
       MDB_LAUNCH(c, k_bi_derive_half, 1, 1, 0, s);
       if (general) precond_apply(c, M, precond, c->ssor_sweeps, r, y2);
-      if (multi) halo_exchange(c, y2);
-      launch_spmv<2>(c, M, y2, t, r, c->d_partial, &nb, s);
+      if (multi) spmv_halo<2>(c, M, y2, t, r, c->d_partial, &nb, s);
+      else launch_spmv<2>(c, M, y2, t, r, c->d_partial, &nb, s);
       reduce(c, nb, 2, S_TR, S_TT);
       if (multi) allreduce_scalars(c, s + S_TR, 2);
       MDB_LAUNCH(c, k_bi_derive_omega, 1, 1, 0, s);

@@ -318,12 +318,15 @@ int mdb_jacobian(mdb_ctx* ctx, int go, int mat, double weight, const double* x, 
 /* Note on host vectors: the volume operators of the closed set are linear, so jacobian() reads x only through the
  * finite-difference coupling Jacobian, at the DOFs of the interface cells.  A host x is therefore uploaded on a second
  * stream while the volume kernels run; from pinned (page-locked) memory only the entries that are read are fetched
- * (zero-copy gather), from pageable memory the whole vector is copied. */
+ * (zero-copy gather), from pageable memory the whole vector is copied.  Lifetime: a host vector is only read DURING the
+ * call — every entry point waits for its host-to-device copy (or gather) before it returns, so the caller may overwrite
+ * or free the buffer immediately afterwards; the kernels that consume the device copy keep running asynchronously. */
 
 /* ---- linear solve ([UPSTREAM] ISTL solver backends) ----------- */
 enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1 };
 /* Jacobi is the fast path.  SSOR and ILU0 reproduce the reference's sequential ISTL preconditioners (SeqSSOR(A, n, 1.0),
- * SeqILU0) operation for operation; they are single-rank only.  [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SSOR(3),
+ * SeqILU0) operation for operation on one rank; on a partition they act as block-Jacobi over the ranks (each rank applies
+ * the sequential preconditioner of its owned x owned block, so iteration counts depend on the rank count).  [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SSOR(3),
  * ISTLBackend_SEQ_CG_SSOR = CG + SSOR(1)  (test/testpoisson.cc:291-292, test/explicitlycoupledpoisson.cc:297-313). */
 enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2, MDB_PRECOND_SSOR = 3 };
 typedef struct mdb_solve_stats {
@@ -345,6 +348,13 @@ int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, 
               const double* rhs, double* z, mdb_solve_stats* stats);
 /* Number of symmetric sweeps n of MDB_PRECOND_SSOR (default 3). */
 int mdb_set_ssor_sweeps(mdb_ctx* ctx, int sweeps);
+/* [UPSTREAM] PDELab StationaryLinearProblemSolver::apply(x) as the reference's drivers use it (test/testpoisson.cc:295-298,
+ * test/testpoisson-dirichlet-neumann.cc:721-822): assemble J(x0) into `mat` and r = R(x0) at the incoming x0, solve J z = r to the
+ * relative defect reduction, x <- x0 - z — in one call, on the device.  x (ndof doubles) is a host vector (uploaded once, solution
+ * copied back before the call returns) or a device vector (updated in place).  keep_matrix != 0 reuses the values in `mat`.
+ * Returns MDB_ENOTCONVERGED like mdb_solve; x is then left unchanged on the host. */
+int mdb_stationary_solve(mdb_ctx* ctx, int go, int mat, int method, int precond, double reduction, int maxit, double* x, int keep_matrix,
+                         mdb_solve_stats* stats);
 /* Run exactly `iters` Krylov iterations without convergence test (benchmarking the loop). */
 int mdb_solve_fixed(mdb_ctx* ctx, int mat, int method, int precond, int iters,
                     const double* rhs, double* z, mdb_solve_stats* stats);
@@ -378,6 +388,9 @@ int mdb_halo_import(mdb_ctx* ctx, int lower_rank, const void* lower_blob80, int 
  * issue the same sequence of pushes and waits. */
 int mdb_halo_push(mdb_ctx* ctx, const double* x);
 int mdb_halo_wait(mdb_ctx* ctx, double* x);
+/* Bound of the device-side wait for a neighbour's planes (default: environment MDB_HALO_TIMEOUT_S, else 30 s).  A timeout is
+ * reported once by the call that hit it (MDB_ENCCL) — a running Krylov loop stops at once — and then cleared. */
+int mdb_set_halo_timeout(mdb_ctx* ctx, double seconds);
 /* Rows this rank owns / all local rows (ghost rows included). */
 int mdb_owned_rows(mdb_ctx* ctx, int64_t* owned, int64_t* local_total);
 /* Owned rows per child block (nchildren entries). */

@@ -506,6 +506,16 @@ public:
   int precond() const { return precond_; }
   unsigned maxiter() const { return maxiter_; }
   void configure(Context& ctx) const { if (sweeps_ > 0) ctx.check(mdb_set_ssor_sweeps(ctx.get(), sweeps_), "mdb_set_ssor_sweeps"); }
+  // StationaryLinearProblemSolver::apply in one device call (mdb_stationary_solve): x <- x - J(x)^-1 R(x)
+  bool applyStationary(Context& ctx, int go, int mat, double* x, double reduction, bool keep_matrix) {
+    mdb_solve_stats st;
+    configure(ctx);
+    int rc = mdb_stationary_solve(ctx.get(), go, mat, method_, precond_, reduction, (int)maxiter_, x, keep_matrix ? 1 : 0, &st);
+    res.iterations = st.iterations; res.converged = st.converged != 0; res.elapsed = st.seconds;
+    res.reduction = st.defect0 > 0 ? st.defect / st.defect0 : 0.0;
+    if (rc != MDB_ENOTCONVERGED) ctx.check(rc, "mdb_stationary_solve");
+    return true;
+  }
 };
 // Jacobi is the fast device path.  The SSOR / ILU0 backends run the reference's sequential ISTL preconditioners operation
 // for operation (sync-free sweeps, csrc/precond.cu): [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SeqSSOR(A, 3, 1.0)
@@ -525,6 +535,7 @@ public:
   LinearSolverResult res;
   explicit ISTL_SEQ_Subblock_Backend(const GridFunctionSpace& block, unsigned maxiter = 5000) : child_(block.child), maxiter_(maxiter) {
     res.iterations = 0; res.converged = false; res.reduction = 0; res.elapsed = 0; }
+  bool applyStationary(Context&, int, int, double*, double, bool) { return false; }      // block solves keep the three-call path
   void apply(Jacobian& a, Context& ctx, double* z, const double* r, double reduction) {
     mdb_solve_stats st;
     ctx.check(mdb_set_ssor_sweeps(ctx.get(), 3), "mdb_set_ssor_sweeps");
@@ -549,6 +560,10 @@ public:
   double reduction() const { return reduction_; }
   void apply(Vector& x, bool keep_matrix = false) {
     if (!a_) { a_ = new Jacobian(go_); keep_matrix = false; }
+    if (ls_.applyStationary(go_.context(), go_.handle(), a_->handle(), x.data(), reduction_, keep_matrix)) {
+      if (!ls_.res.converged) throw Exception(MDB_ENOTCONVERGED, "StationaryLinearProblemSolver: linear solver did not converge");
+      return;
+    }
     if (!keep_matrix) { *a_ = 0.0; go_.jacobian(x, *a_); }
     Vector r(x.size(), 0.0), z(x.size(), 0.0);
     go_.residual(x, r);

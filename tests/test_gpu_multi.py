@@ -1,7 +1,7 @@
 """GPU tests of the multi-GPU path (multigpu.cu) through the C ABI.
 
 * one GPU: two contexts of one process act as two ranks.  Their windows are exchanged as raw pointers (the 80-byte
-  descriptor carries the pid), pushes and waits are issued in an order in which no kernel ever waits for a kernel that
+  descriptor carries a per-process token), pushes and waits are issued in an order in which no kernel ever waits for a kernel that
   has not been launched yet, so this is safe on a single device.  Checks: partitioned assembly vs the oracle's global
   matrix through the exported global indices, halo push / wait, distributed SpMV.
 * two or more GPUs (skipped otherwise): one process per GPU, NCCL + cudaIpc windows, full Krylov solves against the
