@@ -14,19 +14,22 @@ import numpy as np
 FE_Q1, FE_Q2 = 1, 2
 FE_DGQ1, FE_DGQ2 = 11, 12
 FE_P1 = 21
+FE_P2 = 22
+FE_OPB1, FE_OPB2, FE_OPB3 = 31, 32, 33
 ETYPE_TRIANGLE = 2
 COND_EQUALITY, COND_SUBSET = 0, 1
-FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2, FN_DN_SOURCE = range(8)
-BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON = range(3)
-OP_POISSON, OP_L2, OP_CONVDIFF_DG = 1, 2, 3
+FN_ZERO, FN_CONST, FN_GAUSS, FN_BOX, FN_TESTPOISSON_J, FN_INSTAT_G, FN_POLY2, FN_DN_SOURCE, FN_DARCY_G, FN_DARCY_J, FN_PRESSURE_DROP = range(11)
+BC_ALL_DIRICHLET, BC_ALL_NEUMANN, BC_TESTPOISSON, BC_DARCY_RIGHT = range(4)
+OP_POISSON, OP_L2, OP_CONVDIFF_DG, OP_TAYLORHOOD_STOKES, OP_DARCY_DG = 1, 2, 3, 4, 5
 OP_CVCF_COUPLING, OP_PROPFLOW_COUPLING = 101, 102
+OP_STOKESDARCY_COUPLING = 104
 OP_MORTAR_POISSON_COUPLING = 201
 OP_ND_COUPLING = 103
 ND_MODE_NEUMANN, ND_MODE_DIRICHLET, ND_MODE_BOTH = 0, 1, 2
 DG_METHOD_NIPG, DG_METHOD_SIPG = 0, 1
 DG_WEIGHTS_OFF, DG_WEIGHTS_ON = 0, 1
 JAC_FD_BITMATCH, JAC_ANALYTIC = 0, 1
-SOLVER_CG, SOLVER_BICGSTAB = 0, 1
+SOLVER_CG, SOLVER_BICGSTAB, SOLVER_DIRECT = 0, 1, 2
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR = 0, 1, 2, 3
 ONESTEP_IMPLICIT_EULER, ONESTEP_THETA, ONESTEP_ALEXANDER2 = 0, 1, 2
 PRECOND_SSOR_ORACLE = 100  # the oracle's own id for ISTL SeqSSOR (tests/orc.py maps PRECOND_SSOR to it)
@@ -75,6 +78,24 @@ class NDCouplingParams(C.Structure):
 class ConvDiffDGParams(C.Structure):
     _fields_ = [("f", Function), ("bc", BCType), ("g", Function), ("j", Function), ("method", C.c_int32), ("weights", C.c_int32),
                 ("intorderadd", C.c_int32), ("reserved", C.c_int32), ("alpha", C.c_double)]
+
+
+class TaylorHoodParams(C.Structure):
+    """mdb_taylorhood_params: [UPSTREAM] TaylorHoodNavierStokes<NavierStokesParameters>(params, stokes_q), test/stokesdarcy2.cc:226-251, :719-720."""
+    _fields_ = [("mu", C.c_double), ("rho", C.c_double), ("f", C.c_double * 2), ("bc", BCType), ("j", Function), ("quad_order", C.c_int32),
+                ("full_tensor", C.c_int32)]
+
+
+class DarcyParams(C.Structure):
+    """mdb_darcy_params: [UPSTREAM] ConvectionDiffusionDG<DarcyParameters, OPB>(SIPG, weightsOn, alpha), test/stokesdarcy2.cc:254-407, :733-739."""
+    _fields_ = [("kabs", C.c_double), ("kabs_low", C.c_double), ("bc", BCType), ("g", Function), ("j", Function), ("high_group", C.c_int32),
+                ("method", C.c_int32), ("weights", C.c_int32), ("intorderadd", C.c_int32), ("alpha", C.c_double)]
+
+
+class StokesDarcyParams(C.Structure):
+    """mdb_stokesdarcy_params: CouplingParameters of test/stokesdarcycouplingoperator.hh:11-77 (+ the vsize/dsize loop quirk switch)."""
+    _fields_ = [("gravity", C.c_double), ("alpha", C.c_double), ("viscosity", C.c_double), ("porosity", C.c_double), ("gamma", C.c_double),
+                ("density", C.c_double), ("kabs", C.c_double), ("epsilon", C.c_double), ("quirk", C.c_int32), ("reserved", C.c_int32)]
 
 
 class MortarParams(C.Structure):
@@ -188,6 +209,12 @@ class Lib:
         b = np.ascontiguousarray(bits, dtype=np.uint8)
         assert b.size == self.ncells
         self._check(self._fn("subdomains")(C.c_void_p(self.ctx), _ptr(b, C.c_uint8)), "subdomains")
+
+    def cell_groups(self, groups):
+        """elementIndexToPhysicalGroup of the Gmsh reader (test/stokesdarcy2.cc:577-578): one int32 per cell."""
+        g = np.ascontiguousarray(groups, dtype=np.int32)
+        assert g.size == self.ncells
+        self._check(self._fn("cell_groups")(C.c_void_p(self.ctx), _ptr(g, C.c_int32)), "cell_groups")
 
     def get_subdomains(self):
         b = np.zeros(self.ncells, dtype=np.uint8)
