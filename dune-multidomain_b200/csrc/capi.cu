@@ -140,11 +140,13 @@ static void free_matrix(Matrix& m)
   m.slot_tables.clear();
   for (auto& kv : m.fd_plans) fd_plan_free(kv.second);
   m.fd_plans.clear();
+  direct_free(m);
 }
 
 static void reset_spaces(Ctx* c)
 {
-  for (auto& ch : c->children) { dfree(ch.d_lat2dof); dfree(ch.d_dof2lat); }
+  for (auto& ch : c->children) { dfree(ch.d_lat2dof); dfree(ch.d_dof2lat); dfree(ch.d_edge2dof); dfree(ch.d_cell2dof); }
+  for (auto& sp : c->sps) dfree(sp.d_lmap);
   for (auto& go : c->gos) { for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); } dfree(go.d_xneed); for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(go.d_res_fast[i]); dfree(go.d_res_rest[i]); go.n_res_rest[i] = -1; } }
   for (auto& m : c->mats) free_matrix(m);
   c->gos.clear(); c->mats.clear();
@@ -259,7 +261,7 @@ int mdb_mesh_structured(mdb_ctx* c, int dim, const int64_t* n, const double* low
   MDB_REQUIRE(dim == 2 || dim == 3, MDB_EINVAL, "mdb_mesh_structured: dim must be 2 or 3");
   reset_spaces(c);
   um_free(c);
-  c->children.clear(); c->sps.clear(); c->cps.clear();
+  c->children.clear(); c->sps.clear(); c->cps.clear(); c->ufe = false;
   MeshDesc& m = c->mesh;
   m = MeshDesc();
   m.dim = dim;
@@ -303,7 +305,7 @@ int mdb_mesh_unstructured(mdb_ctx* c, int dim, int64_t nv, const double* xyz, in
   MDB_REQUIRE(dim == 2 && etype == MDB_ETYPE_TRIANGLE, MDB_EINVAL, "mdb_mesh_unstructured: this build has device kernels for 2-D triangle meshes only");
   MDB_REQUIRE(xyz && conn, MDB_EINVAL, "mdb_mesh_unstructured: null pointer");
   reset_spaces(c);
-  c->children.clear(); c->sps.clear(); c->cps.clear();
+  c->children.clear(); c->sps.clear(); c->cps.clear(); c->ufe = false;
   um_ingest(c, nv, xyz, ne, conn);
   MeshDesc& m = c->mesh;
   m = MeshDesc();
@@ -324,6 +326,15 @@ int mdb_subdomains(mdb_ctx* c, const uint8_t* bits)
   MDB_CUDA(cudaMemcpyAsync(c->d_cell_sd, bits, c->mesh.ncells(), cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   c->have_sd = true;
+  MDB_API_END(c)
+}
+
+int mdb_cell_groups(mdb_ctx* c, const int32_t* groups)
+{
+  MDB_API_BEGIN(c)
+  MDB_REQUIRE(c->have_mesh && c->um && groups, MDB_ESTATE, "mdb_cell_groups: needs an unstructured mesh");
+  MDB_CUDA(cudaMemcpyAsync(c->um->d_group, groups, c->um->ne * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
   MDB_API_END(c)
 }
 
@@ -354,8 +365,10 @@ int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
   if (!c) return MDB_EINVAL;
   try {
     MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_space: need a mesh, before mdb_finalize");
-    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2 || fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2 || fe_kind == MDB_FE_P1, MDB_EINVAL, "mdb_add_space: unknown finite element");
-    MDB_REQUIRE((fe_kind == MDB_FE_P1) == (c->um != nullptr), MDB_EINVAL, "mdb_add_space: simplex meshes carry MDB_FE_P1 spaces, structured cube meshes the Qk / QkDG spaces");
+    const bool simplex_fe = fe_kind == MDB_FE_P1 || fe_kind == MDB_FE_P2 || (fe_kind >= MDB_FE_OPB1 && fe_kind <= MDB_FE_OPB3);
+    MDB_REQUIRE(fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_Q2 || fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2 || simplex_fe, MDB_EINVAL, "mdb_add_space: unknown finite element");
+    MDB_REQUIRE(simplex_fe == (c->um != nullptr), MDB_EINVAL, "mdb_add_space: simplex meshes carry the Pk / OPB spaces, structured cube meshes the Qk / QkDG spaces");
+    if (simplex_fe && fe_kind != MDB_FE_P1) c->ufe = true;
     MDB_REQUIRE(subdomain >= -1 && subdomain < 8, MDB_EINVAL, "mdb_add_space: bad subdomain");
     MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_space: too many child spaces");
     Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_DGQ1) ? 1 : 2; ch.subdomain = subdomain;
@@ -392,11 +405,35 @@ int mdb_add_subproblem(mdb_ctx* c, int op_id, const void* params, size_t nbytes,
   try {
     MDB_REQUIRE(!c->finalized, MDB_ESTATE, "mdb_add_subproblem: before mdb_finalize");
     MDB_REQUIRE(cond_kind == MDB_COND_EQUALITY || cond_kind == MDB_COND_SUBSET, MDB_EINVAL, "mdb_add_subproblem: bad condition");
-    MDB_REQUIRE(nchildren == 1, MDB_EINVAL, "mdb_add_subproblem: only single-child (scalar) subproblems have device kernels in this build");
-    MDB_REQUIRE(children[0] >= 0 && children[0] < (int)c->children.size(), MDB_EINVAL, "mdb_add_subproblem: bad child index");
-    MDB_REQUIRE(!c->children[children[0]].iface, MDB_EINVAL, "mdb_add_subproblem: a coupling space cannot carry a subproblem");
+    MDB_REQUIRE(nchildren >= 1 && nchildren <= 4, MDB_EINVAL, "mdb_add_subproblem: 1 to 4 child spaces");
+    for (int k = 0; k < nchildren; ++k) {
+      MDB_REQUIRE(children[k] >= 0 && children[k] < (int)c->children.size(), MDB_EINVAL, "mdb_add_subproblem: bad child index");
+      MDB_REQUIRE(!c->children[children[k]].iface, MDB_EINVAL, "mdb_add_subproblem: a coupling space cannot carry a subproblem");
+    }
     SubProblemDesc sp; sp.op_id = op_id; sp.cond_kind = cond_kind; sp.mask = cond_mask;
     sp.children.assign(children, children + nchildren);
+    if (op_id == MDB_OP_TAYLORHOOD_STOKES || op_id == MDB_OP_DARCY_DG) {
+      // the Stokes-Darcy subproblems of test/stokesdarcy2.cc (generic element path, ufe.cu); multi-child: subproblemlocalfunctionspace.hh:144-261
+      MDB_REQUIRE(c->um, MDB_EINVAL, "mdb_add_subproblem: Taylor-Hood Stokes / Darcy DG need an unstructured triangle mesh");
+      if (op_id == MDB_OP_TAYLORHOOD_STOKES) {
+        MDB_REQUIRE(nbytes == sizeof(mdb_taylorhood_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_taylorhood_params size");
+        std::memcpy(&sp.th, params, nbytes);
+        MDB_REQUIRE(nchildren == 3 && c->children[children[0]].fe_kind == MDB_FE_P2 && c->children[children[1]].fe_kind == MDB_FE_P2 &&
+                    c->children[children[2]].fe_kind == MDB_FE_P1, MDB_EINVAL, "mdb_add_subproblem: Taylor-Hood needs the children {P2, P2, P1}");
+        MDB_REQUIRE(sp.th.quad_order >= 2 && sp.th.quad_order <= 6, MDB_EINVAL, "mdb_add_subproblem: Taylor-Hood quadrature order 2..6");
+      } else {
+        MDB_REQUIRE(nbytes == sizeof(mdb_darcy_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_darcy_params size");
+        std::memcpy(&sp.darcy, params, nbytes);
+        const int fe = c->children[children[0]].fe_kind;
+        MDB_REQUIRE(nchildren == 1 && fe >= MDB_FE_OPB1 && fe <= MDB_FE_OPB3, MDB_EINVAL, "mdb_add_subproblem: the Darcy DG operator needs one MDB_FE_OPBk child");
+        MDB_REQUIRE(sp.darcy.intorderadd >= 0 && sp.darcy.intorderadd + 2 * (fe - 30) <= 6, MDB_EINVAL, "mdb_add_subproblem: DG quadrature order up to 6");
+        MDB_REQUIRE(sp.darcy.method == MDB_DG_METHOD_SIPG || sp.darcy.method == MDB_DG_METHOD_NIPG, MDB_EINVAL, "mdb_add_subproblem: bad DG method");
+      }
+      c->ufe = true;
+      c->sps.push_back(sp);
+      return (int)c->sps.size() - 1;
+    }
+    MDB_REQUIRE(nchildren == 1, MDB_EINVAL, "mdb_add_subproblem: this local operator takes one child space");
     if (op_id == MDB_OP_POISSON) {
       MDB_REQUIRE(nbytes == sizeof(mdb_poisson_params), MDB_EINVAL, "mdb_add_subproblem: bad mdb_poisson_params size");
       std::memcpy(&sp.poisson, params, nbytes);
@@ -443,6 +480,14 @@ int mdb_add_coupling(mdb_ctx* c, int op_id, const void* params, size_t nbytes, i
       std::memcpy(&cp.nd, params, nbytes);
       MDB_REQUIRE(cp.nd.mode >= MDB_ND_MODE_NEUMANN && cp.nd.mode <= MDB_ND_MODE_BOTH, MDB_EINVAL, "mdb_add_coupling: bad Neumann-Dirichlet coupling mode");
       MDB_REQUIRE(!c->mesh.partitioned, MDB_EINVAL, "mdb_add_coupling: the Neumann-Dirichlet coupling is not supported on a partitioned mesh");
+    } else if (op_id == MDB_OP_STOKESDARCY_COUPLING) {
+      MDB_REQUIRE(nbytes == sizeof(mdb_stokesdarcy_params), MDB_EINVAL, "mdb_add_coupling: bad mdb_stokesdarcy_params size");
+      std::memcpy(&cp.sd, params, nbytes);
+      MDB_REQUIRE(c->sps[local_sp].op_id == MDB_OP_TAYLORHOOD_STOKES && c->sps[remote_sp].op_id == MDB_OP_DARCY_DG, MDB_EINVAL,
+                  "mdb_add_coupling: the Stokes-Darcy coupling links a Taylor-Hood subproblem (local) with a Darcy DG subproblem (remote)");
+      MDB_REQUIRE(cp.sd.epsilon > 0.0 && cp.sd.porosity != 0.0 && cp.sd.kabs > 0.0, MDB_EINVAL, "mdb_add_coupling: bad Stokes-Darcy parameters");
+      c->cps.push_back(cp);
+      return (int)c->cps.size() - 1;
     } else throw Error(MDB_EINVAL, "mdb_add_coupling: unknown coupling operator");
     MDB_REQUIRE(!c->um || op_id == MDB_OP_PROPFLOW_COUPLING || op_id == MDB_OP_CVCF_COUPLING, MDB_EINVAL,
                 "mdb_add_coupling: unstructured meshes carry the two proportional-flow couplings in this build");
@@ -506,7 +551,13 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   MDB_REQUIRE(c->have_mesh && c->have_sd, MDB_ESTATE, "mdb_finalize: mesh and subdomains must be set");
   MDB_REQUIRE(!c->children.empty(), MDB_ESTATE, "mdb_finalize: no child spaces");
   c->phase_begin("dofmap");
-  if (c->um) um_build_dofmap(c); else build_dofmap(c);
+  if (c->um && c->ufe) {
+    for (const SubProblemDesc& sp : c->sps)
+      MDB_REQUIRE(sp.op_id == MDB_OP_TAYLORHOOD_STOKES || sp.op_id == MDB_OP_DARCY_DG, MDB_EINVAL,
+                  "mdb_finalize: P2 / OPB spaces carry the Taylor-Hood and Darcy DG subproblems (closed operator set)");
+    for (const CouplingDesc& cp : c->cps) MDB_REQUIRE(cp.op_id == MDB_OP_STOKESDARCY_COUPLING, MDB_EINVAL, "mdb_finalize: P2 / OPB spaces couple through MDB_OP_STOKESDARCY_COUPLING");
+    ufe_build_dofmap(c);
+  } else if (c->um) um_build_dofmap(c); else build_dofmap(c);
   c->phase_end();
   if (c->mesh.partitioned) {
     // the add_* calls refuse these on a partitioned mesh; mdb_mesh_partition may also come AFTER them, so check again here
@@ -526,7 +577,7 @@ int mdb_get_dofmap(mdb_ctx* c, int64_t* cell_ptr, int64_t* cell_dofs)
 {
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_get_dofmap: not finalized");
-  if (c->um) um_export_dofmap(c, cell_ptr, cell_dofs); else export_dofmap(c, cell_ptr, cell_dofs);
+  if (c->um && c->ufe) ufe_export_dofmap(c, cell_ptr, cell_dofs); else if (c->um) um_export_dofmap(c, cell_ptr, cell_dofs); else export_dofmap(c, cell_ptr, cell_dofs);
   MDB_API_END(c)
 }
 
@@ -545,7 +596,7 @@ int mdb_constraints_assemble(mdb_ctx* c, const int* subproblems, const mdb_bctyp
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_constraints_assemble: not finalized");
   for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
   c->phase_begin("constraints");
-  if (c->um) um_assemble_constraints(c, subproblems, bcs, n); else assemble_constraints(c, subproblems, bcs, n);
+  if (c->um && c->ufe) ufe_assemble_constraints(c, subproblems, bcs, n); else if (c->um) um_assemble_constraints(c, subproblems, bcs, n); else assemble_constraints(c, subproblems, bcs, n);
   rebuild_conlist(c);
   c->phase_end();
   if (nconstrained) *nconstrained = c->ncon;
@@ -577,6 +628,7 @@ int mdb_interpolate(mdb_ctx* c, const int* subproblems, const mdb_function* fns,
 {
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_interpolate: not finalized");
+  MDB_REQUIRE(!c->ufe, MDB_EINVAL, "mdb_interpolate: no device interpolation for P2 / OPB spaces in this build (test/stokesdarcy2.cc starts from u = 0)");
   VecInOut vx(c, x, c->ndof, 0, true);
   for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
   if (c->um) um_interpolate(c, subproblems, fns, n, time, vx.d); else interpolate(c, subproblems, fns, n, time, vx.d);
@@ -600,7 +652,7 @@ int mdb_gridoperator_create(mdb_ctx* c, const int* subproblems, int nsp, const i
     GridOp go;
     for (int i = 0; i < nsp; ++i) { MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index"); go.sps.push_back(subproblems[i]); }
     for (int i = 0; i < ncp; ++i) { MDB_REQUIRE(couplings[i] >= 0 && couplings[i] < (int)c->cps.size(), MDB_EINVAL, "bad coupling index"); go.cps.push_back(couplings[i]); }
-    if (c->um) um_build_facelists(c, go); else build_facelists(c, go);
+    if (c->um && c->ufe) ufe_build_facelists(c, go); else if (c->um) um_build_facelists(c, go); else build_facelists(c, go);
     c->gos.push_back(go);
     return (int)c->gos.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
@@ -615,7 +667,7 @@ int mdb_matrix_create(mdb_ctx* c, const int* gos, int ngos, int64_t* nnz)
     Matrix m;
     for (int i = 0; i < ngos; ++i) { MDB_REQUIRE(gos[i] >= 0 && gos[i] < (int)c->gos.size(), MDB_EINVAL, "bad grid operator handle"); m.gos.push_back(gos[i]); }
     c->phase_begin("pattern");
-    if (c->um) um_build_pattern(c, m); else build_pattern(c, m);
+    if (c->um && c->ufe) ufe_build_pattern(c, m); else if (c->um) um_build_pattern(c, m); else build_pattern(c, m);
     c->phase_end();
     if (nnz) *nnz = m.nnz;
     c->mats.push_back(m);
@@ -664,7 +716,7 @@ int mdb_matrix_zero(mdb_ctx* c, int mat)
   MDB_API_BEGIN(c)
   MDB_MAT(c, mat)
   MDB_CUDA(cudaMemsetAsync(M.d_val, 0, M.nnz * sizeof(double), c->stream));
-  M.dinv_valid = false; M.ilu_valid = false;
+  M.dinv_valid = false; M.ilu_valid = false; direct_invalidate(M);
   MDB_API_END(c)
 }
 
@@ -684,7 +736,7 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   MDB_GO(c, go)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vr(c, r, c->ndof, 1, true);
-  if (c->um) { um_residual(c, G, weight, vx.d, vr.d); vr.commit(); return MDB_OK; }
+  if (c->um) { if (c->ufe) ufe_residual(c, G, weight, vx.d, vr.d); else um_residual(c, G, weight, vx.d, vr.d); vr.commit(); return MDB_OK; }
   static const bool serial = getenv("MDB_RESIDUAL_SERIAL") != nullptr;          // A/B switch for profiling only
   if (!serial && residual_can_split(c, G)) {
     // main: element matrices -> [fork] -> streamed uniform rows of every child (issue / shared-memory bound) --------> [join] -> constrain
@@ -748,8 +800,8 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   MDB_API_BEGIN(c)
   MDB_GO(c, go)
   MDB_MAT(c, mat)
-  M.dinv_valid = false; M.ilu_valid = false;
-  if (c->um) { VecIn vx(c, x, c->ndof, 0); um_jacobian(c, G, M, weight, vx.d, overwrite != 0); return MDB_OK; }
+  M.dinv_valid = false; M.ilu_valid = false; direct_invalidate(M);
+  if (c->um) { VecIn vx(c, x, c->ndof, 0); if (c->ufe) ufe_jacobian(c, G, M, weight, vx.d, overwrite != 0); else um_jacobian(c, G, M, weight, vx.d, overwrite != 0); return MDB_OK; }
   // The volume operators of the closed set are linear: their Jacobian does not read x.  Only the finite-difference
   // coupling Jacobian does, and only at the DOFs of the interface cells.  With a HOST vector the upload therefore runs on
   // the copy stream concurrently with the volume kernels, and from pinned memory only the needed entries are fetched.

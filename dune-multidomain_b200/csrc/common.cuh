@@ -108,6 +108,19 @@ __host__ __device__ inline double eval_function(const mdb_function& f, int dim, 
     if (sqrt(m2) < 0.2) return 60 * exp(-10 * n2);
     return 0.0;
   }
+  case MDB_FN_DARCY_G: {                  // test/stokesdarcy2.cc:355-361
+    const double scale = x[1] / f.p[2];
+    return scale * f.p[0] + (1.0 - scale) * f.p[1];
+  }
+  case MDB_FN_DARCY_J:                    // :364-371
+    return x[1] < 1E-6 ? f.p[0] * x[0] * (f.p[1] - x[0]) : 0.0;
+  case MDB_FN_PRESSURE_DROP: {            // :191-203
+    double y;
+    if (x[0] < 1E-6) y = x[1] > f.p[3] ? f.p[0] : -f.p[1];
+    else if (x[0] > f.p[2] - 1E-6) y = x[1] > f.p[3] ? -f.p[1] : f.p[0];
+    else y = 0.0;
+    return y * (f.p[4] - x[1]);
+  }
   }
   return 0.0;
 }
@@ -124,6 +137,11 @@ __host__ __device__ inline int eval_bctype(const mdb_bctype& b, int dim, const d
     if (xg[1] < 1E-6 || xg[1] > 1.0 - 1E-6) return 1;
     if (xg[0] > 1.0 - 1E-6 && xg[1] > 0.5 + 1E-6) return 1;
     return 0;
+  case MDB_BC_DARCY_RIGHT:                // test/stokesdarcy2.cc:338-353; Outflow (b = 0) acts like Neumann with o = j
+    if (!is_boundary) return 2;
+    if (xg[1] < 1E-6 && xg[0] < b.p[0]) return 1;
+    if (xg[0] > b.p[0] - 1E-6 && xg[1] < b.p[1]) return 0;
+    return 1;
   }
   return 2;
 }
@@ -162,6 +180,9 @@ struct Child {
   int64_t size = 0, offset = 0;
   int lat_lo[3] = {0, 0, 0}, lat_hi[3] = {0, 0, 0};   // bounding box (inclusive) of the lattice points that carry a DOF
   int nloc(int dim) const { int r = 1; for (int d = 0; d < dim; ++d) r *= (k + 1); return r; }
+  // generic spaces on a triangle mesh (ufe.cu): P2 keeps vertex DOFs (d_lat2dof, nvs of them) followed by edge DOFs (d_edge2dof);
+  // an OPB space numbers the subdomain's cells (d_cell2dof), um_nloc coefficients per cell
+  int32_t* d_edge2dof = nullptr; int32_t* d_cell2dof = nullptr; int64_t nvs = 0; int um_nloc = 3;
 };
 
 struct SubProblemDesc {
@@ -169,6 +190,9 @@ struct SubProblemDesc {
   mdb_poisson_params poisson{};
   mdb_l2_params l2{};
   mdb_convdiffdg_params cddg{};
+  mdb_taylorhood_params th{};
+  mdb_darcy_params darcy{};
+  int32_t* d_lmap = nullptr; int nloc = 0;     // ufe.cu: [ncells][nloc] container indices of the subproblem's local space (-1: not on the cell)
   int dg_k = 1;                // MDB_OP_CONVDIFF_DG: degree of the child space (quadrature order = intorderadd + 2 k)
   int cond_kind = 0; uint32_t mask = 0;
   std::vector<int> children;
@@ -186,6 +210,7 @@ struct CouplingDesc {
   mdb_propflow_params propflow{};
   mdb_mortar_params mortar{};
   mdb_ndcoupling_params nd{};
+  mdb_stokesdarcy_params sd{};
   int local_sp = -1, remote_sp = -1, jac_mode = 0;
   int coupling_child = -1;       // >= 0: EnrichedCoupling (coupling.hh:123-192) with this coupling space
   int ncomp = 1;                 // component blocks of a power coupling space: children coupling_child .. coupling_child + ncomp - 1
@@ -209,6 +234,10 @@ struct UMesh {
   int32_t* d_v2c = nullptr;      // [3 ne] 4 * cell + local vertex index, cells ascending per vertex
   int32_t* d_bface = nullptr;    // [nbface] 3 * cell + face of the faces without a neighbour (the physical boundary), ascending
   int64_t nbface = 0;
+  int64_t nedges = 0;
+  int32_t* d_cell_edge = nullptr; // [ne][3] edge index of face f: order of first appearance in (cell, local face) order
+  int32_t* d_group = nullptr;    // [ne] physical group (mdb_cell_groups), zero by default
+  void* ufe_tables = nullptr;    // ufe.cu: device tables of the generic finite elements
 };
 
 struct GridOp {
@@ -256,6 +285,7 @@ struct Matrix {
   int* d_ready = nullptr; unsigned long long* d_sweep_counter = nullptr; int sweep_epoch = 0; int32_t* d_sweep_perm = nullptr; ulonglong2* d_vrec = nullptr;
   double* d_ilu = nullptr; bool ilu_valid = false;
   int32_t* d_cell_perm = nullptr; int64_t sweep_cells = 0; int sweep_cell_img = 0;   // all-DG matrices: cells in wavefront order (first row of each), image doubles per warp
+  void* direct = nullptr;            // direct.cu: band factorisation cache
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
 };
@@ -281,6 +311,7 @@ struct Ctx {
 
   MeshDesc mesh{};
   UMesh* um = nullptr;               // non-null: unstructured mesh (mesh.dim = 2, mesh.n = {ne, 1, 1} so that ncells() holds)
+  bool ufe = false;                  // unstructured mesh with spaces / operators beyond P1 Poisson: the generic element path (ufe.cu)
   bool have_mesh = false, have_sd = false, finalized = false;
   uint8_t* d_cell_sd = nullptr;
   std::vector<Child> children;
@@ -413,6 +444,19 @@ void um_build_pattern(Ctx* c, Matrix& m);
 void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
 void um_jacobian(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x, bool overwrite);
 void precond_apply(Ctx* c, Matrix& m, int kind, int sweeps, const double* d_d, double* d_v);   // precond.cu: SSOR / ILU0
+// ufe.cu: generic finite elements on a triangle mesh (P1 / P2 / orthonormal Pk, multi-child subproblems): the Stokes-Darcy path
+void ufe_free(Ctx* c);
+void ufe_build_dofmap(Ctx* c);
+void ufe_export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs);
+void ufe_assemble_constraints(Ctx* c, const int* sps, const mdb_bctype* bcs, int n);
+void ufe_build_facelists(Ctx* c, GridOp& go);
+void ufe_build_pattern(Ctx* c, Matrix& m);
+void ufe_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r);
+void ufe_jacobian(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x, bool overwrite);
+// direct.cu: banded LU with partial pivoting (MDB_SOLVER_DIRECT)
+int direct_solve(Ctx* c, Matrix& m, const double* d_b, double* d_z, mdb_solve_stats* stats);
+void direct_free(Matrix& m);
+void direct_invalidate(Matrix& m);
 
 template <typename T> inline T* dalloc(size_t n)
 {

@@ -770,6 +770,7 @@ static void ensure_work(Ctx* c, int nvecs)
 int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxit, int fixed_iters, const double* d_b, double* d_z,
           mdb_solve_stats* stats)
 {
+  if (method == MDB_SOLVER_DIRECT) { MDB_REQUIRE(fixed_iters < 0, MDB_EINVAL, "mdb_solve_fixed: not with MDB_SOLVER_DIRECT"); return direct_solve(c, M, d_b, d_z, stats); }
   MDB_REQUIRE(method == MDB_SOLVER_CG || method == MDB_SOLVER_BICGSTAB, MDB_EINVAL, "unknown solver");
   MDB_REQUIRE(precond == MDB_PRECOND_NONE || precond == MDB_PRECOND_JACOBI || precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0, MDB_EINVAL,
               "unknown preconditioner");

@@ -722,7 +722,9 @@ void um_free(Ctx* c)
 {
   if (!c->um) return;
   UMesh* u = c->um;
+  ufe_free(c);
   um_dfree(u->d_xy); um_dfree(u->d_conn); um_dfree(u->d_nbr); um_dfree(u->d_v2c_ptr); um_dfree(u->d_v2c); um_dfree(u->d_bface);
+  um_dfree(u->d_cell_edge); um_dfree(u->d_group);
   delete u; c->um = nullptr;
 }
 
@@ -750,13 +752,21 @@ void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* 
       edges[3 * e + f] = {(a << 32) | b, (int32_t)(3 * e + f)};
     }
   std::sort(edges.begin(), edges.end());
+  // edge indices (P2 spaces, ufe.cu): the order of first appearance in (cell, local face) order.  Equal keys are sorted by their
+  // (cell, face) position, so the first member of a group is the first appearance.
+  std::vector<int32_t> first_of(3 * ne, -1), cell_edge(3 * ne, 0);
   for (size_t i = 0; i < edges.size();) {
     size_t j = i + 1;
     while (j < edges.size() && edges[j].first == edges[i].first) ++j;
     MDB_REQUIRE(j - i <= 2, MDB_EINVAL, "mdb_mesh_unstructured: more than two cells share a face (non-manifold mesh)");
     if (j - i == 2) { nbr[edges[i].second] = edges[i + 1].second / 3; nbr[edges[i + 1].second] = edges[i].second / 3; }
+    first_of[edges[i].second] = 0;
+    for (size_t k = i; k < j; ++k) cell_edge[edges[k].second] = edges[i].second;      // for now: position of the first appearance
     i = j;
   }
+  int64_t nedges = 0;
+  for (int64_t i = 0; i < 3 * ne; ++i) if (first_of[i] == 0) first_of[i] = (int32_t)nedges++;
+  for (int64_t i = 0; i < 3 * ne; ++i) cell_edge[i] = first_of[cell_edge[i]];
   for (int64_t i = 0; i < 3 * ne; ++i) vptr[hconn[i] + 1]++;
   for (int64_t v = 0; v < nv; ++v) vptr[v + 1] += vptr[v];
   {
@@ -768,6 +778,9 @@ void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* 
   u->nv = nv; u->ne = ne;
   u->d_xy = dalloc<double>(2 * nv); u->d_conn = dalloc<int32_t>(3 * ne); u->d_nbr = dalloc<int32_t>(3 * ne);
   u->d_v2c_ptr = dalloc<int32_t>(nv + 1); u->d_v2c = dalloc<int32_t>(3 * ne);
+  u->nedges = nedges; u->d_cell_edge = dalloc<int32_t>(3 * ne); u->d_group = dalloc<int32_t>(ne);
+  MDB_CUDA(cudaMemcpyAsync(u->d_cell_edge, cell_edge.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
+  MDB_CUDA(cudaMemsetAsync(u->d_group, 0, ne * 4, c->stream));
   MDB_CUDA(cudaMemcpyAsync(u->d_xy, xy, 2 * nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaMemcpyAsync(u->d_conn, hconn.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaMemcpyAsync(u->d_nbr, nbr.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));

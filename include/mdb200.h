@@ -57,7 +57,16 @@ enum {
   /* PkLocalFiniteElementMap<GV,DF,RF,1> on simplices (the P1 space of test/stokesdarcy2.cc:614, test/testcouplinggfs.cc:263):
    * one DOF per vertex, shape functions 1-x-y, x, y at the cell's vertices 0, 1, 2; numbered by ascending vertex index of the
    * child's (sub)domain [UPSTREAM (ii),(iii)].  Unstructured meshes only (mdb_mesh_unstructured). */
-  MDB_FE_P1 = 21
+  MDB_FE_P1 = 21,
+  /* PkLocalFiniteElementMap<SDGV,DF,RF,2> (the Taylor-Hood velocity space V_FEM of test/stokesdarcy2.cc:613): one DOF per vertex and
+   * per edge; Pk2D lattice order on a cell: vertex 0, edge {0,1}, vertex 1, edge {0,2}, edge {1,2}, vertex 2.  Block numbering
+   * [UPSTREAM (iii)]: the subdomain's vertices (ascending vertex index), then its edges (ascending edge index; the edge index of the
+   * host grid is the order of first appearance in (cell, local face) order). */
+  MDB_FE_P2 = 22,
+  /* OPBLocalFiniteElementMap<DF,RF,k,2,simplex,GMPField<512>> (DarcyFEM of test/stokesdarcy2.cc:615): the orthonormal polynomial basis
+   * of degree k on the reference triangle (csrc/opb_tables.h), all (k+1)(k+2)/2 coefficients attached to the cell:
+   * DOF = (index of the cell in its subdomain) * size + i. */
+  MDB_FE_OPB1 = 31, MDB_FE_OPB2 = 32, MDB_FE_OPB3 = 33
 };
 
 /* ---- subdomain conditions  (subdomainset.hh:82-133) ---------------------- */
@@ -76,8 +85,12 @@ enum {
   MDB_FN_TESTPOISSON_J = 4,  /* 0 on x1<1e-6 or x1>1-1e-6; -5 on x0>1-1e-6 && x1>.5+1e-6; else 0  test/testpoisson.cc:103-116 */
   MDB_FN_INSTAT_G = 5,       /* time dependent Dirichlet data, test/testinstationarypoisson.cc:94-100 family: p[0]*sin(p[1]*t)*exp(-|x-c|^2), c=.5 */
   MDB_FN_POLY2 = 6,          /* p[0] + sum_d p[1+d]*x_d + p[4]*|x|^2  (manufactured-solution tests)     */
-  MDB_FN_DN_SOURCE = 7       /* F of test/testpoisson-dirichlet-neumann.cc:73-87 (= testpoisson.cc:32-37 before the
+  MDB_FN_DN_SOURCE = 7,      /* F of test/testpoisson-dirichlet-neumann.cc:73-87 (= testpoisson.cc:32-37 before the
                                 overwrite): 50 on (0.25,0.375)^dim; else 60 exp(-10 |x|^2) if |0.5 - x| < 0.2; else 0 */
+  MDB_FN_DARCY_G = 8,        /* DarcyParameters::g  test/stokesdarcy2.cc:355-361: s = x1 / p[2]; s p[0] + (1 - s) p[1]            */
+  MDB_FN_DARCY_J = 9,        /* DarcyParameters::j  :364-371: p[0] x0 (p[1] - x0) on x1 < 1e-6, else 0                           */
+  MDB_FN_PRESSURE_DROP = 10  /* PressureDropFlux::evaluateGlobal  :191-203: (x0 < 1e-6 ? (x1 > p[3] ? p[0] : -p[1])
+                                : x0 > p[2] - 1e-6 ? (x1 > p[3] ? -p[1] : p[0]) : 0) * (p[4] - x1)                                */
 };
 typedef struct mdb_function {
   int32_t kind;
@@ -88,8 +101,11 @@ typedef struct mdb_function {
 enum {
   MDB_BC_ALL_DIRICHLET = 0,
   MDB_BC_ALL_NEUMANN = 1,
-  MDB_BC_TESTPOISSON = 2     /* test/testpoisson.cc:42-88: none on interior faces; Neumann on x1=0, x1=1 and
+  MDB_BC_TESTPOISSON = 2,    /* test/testpoisson.cc:42-88: none on interior faces; Neumann on x1=0, x1=1 and
                                 on x0=1 && x1>.5; Dirichlet elsewhere                                        */
+  MDB_BC_DARCY_RIGHT = 3     /* DarcyParameters::bctype test/stokesdarcy2.cc:338-353: none on interior faces; Outflow on x1 < 1e-6 &&
+                                x0 < p[0] (with b = 0 it acts like Neumann with o = j); Dirichlet on x0 > p[0] - 1e-6 && x1 < p[1];
+                                Neumann elsewhere                                                                */
 };
 typedef struct mdb_bctype {
   int32_t kind;
@@ -106,7 +122,15 @@ enum {
   MDB_OP_CONVDIFF_DG = 3,    /* [UPSTREAM] Dune::PDELab::ConvectionDiffusionDG<ConvectionDiffusionModelProblem,FEM>(param, method,
                                  weights, alpha)  test/testpoisson-dirichlet-neumann.cc:864-881 (dglop), parameter class :169-285
                                  (A = I, b = 0, c = 0): volume + interior-penalty skeleton + weak boundary terms             */
+  /* [UPSTREAM] Dune::PDELab::TaylorHoodNavierStokes<NavierStokesParameters>(params, stokes_q) with navier = false, full_tensor = true
+   * (test/stokesdarcy2.cc:226-251, :719-720) on THREE children {v_0, v_1 : MDB_FE_P2, p : MDB_FE_P1}: the multi-child subproblem of
+   * subproblemlocalfunctionspace.hh:144-261 */
+  MDB_OP_TAYLORHOOD_STOKES = 4,
+  /* [UPSTREAM] ConvectionDiffusionDG<DarcyParameters, OPB>(SIPG, weightsOn, alpha) (test/stokesdarcy2.cc:254-407, :733-739) on an
+   * MDB_FE_OPBk child of a triangle mesh, tensor by physical group (mdb_cell_groups) */
+  MDB_OP_DARCY_DG = 5,
   /* coupling operators used by Couplings */
+  MDB_OP_STOKESDARCY_COUPLING = 104, /* StokesDarcyCouplingOperator<CouplingParameters>  test/stokesdarcycouplingoperator.hh:79-252 */
   MDB_OP_CVCF_COUPLING = 101,     /* ContinuousValueContinuousFlowCoupling  test/proportionalflowcoupling.hh:94-239 */
   MDB_OP_PROPFLOW_COUPLING = 102, /* ProportionalFlowCoupling               test/proportionalflowcoupling.hh:10-91  */
   MDB_OP_ND_COUPLING = 103,       /* ConvectionDiffusionDGNeumannDirichletCoupling<CouplingParameters>  test/neumanndirichletcoupling.hh:41-441,
@@ -174,6 +198,45 @@ typedef struct mdb_convdiffdg_params {
   double alpha;              /* interior penalty parameter: 2.0 in dglop() (:878) */
 } mdb_convdiffdg_params;
 
+/* NavierStokesParameters of test/stokesdarcy2.cc:226-251 over [UPSTREAM] NavierStokesDefaultParameters<GV,RF,F,B,V,J,false,true>:
+ * Stokes (no convective term), full (symmetric-gradient) viscous tensor.  Residual rows, for velocity component d and test function v_i,
+ * pressure test function q_i:   int mu (grad u_d . grad v_i + sum_dd d_d u_dd d_dd v_i) - p d_d v_i - f_d v_i ;   - int (div u) q_i ;
+ * on faces of the physical boundary whose type is StressNeumann:  + int j (n_d v_i)  (the scalar flux times the outer normal). */
+typedef struct mdb_taylorhood_params {
+  double mu, rho;            /* parameters.fluid.mu, fluid.rho (rho only multiplies the disabled convective term)          */
+  double f[2];               /* NavierStokesParameters::f = (0, -gravity)  :239-249                                        */
+  mdb_bctype bc;             /* StokesBoundaryType :117-142: MDB_BC_ALL_NEUMANN = StressNeumann on the whole boundary (as shipped),
+                                MDB_BC_ALL_DIRICHLET = VelocityDirichlet; interior faces: DoNothing                        */
+  mdb_function j;            /* PressureDropFlux :171-205 = MDB_FN_PRESSURE_DROP                                           */
+  int32_t quad_order;        /* stokes_q = 2 * stokes_k = 4  :610                                                          */
+  int32_t full_tensor;       /* 1 as shipped                                                                               */
+} mdb_taylorhood_params;
+
+/* DarcyParameters of test/stokesdarcy2.cc:254-407: A = (group == high_group ? kabs : kabs_low) * identity per cell (:285-290),
+ * b = 0, c = 0, f = 0; ConvectionDiffusionDG(params, method, weights, alpha) :733-739. */
+typedef struct mdb_darcy_params {
+  double kabs, kabs_low;     /* parameters.soil.permeability, soil.permeability.low                                        */
+  mdb_bctype bc;             /* MDB_BC_DARCY_RIGHT (p[0] = domain length 100, p[1] = 13)                                   */
+  mdb_function g;            /* MDB_FN_DARCY_G(rightpotential.top, rightpotential.bottom, 15)                              */
+  mdb_function j;            /* MDB_FN_DARCY_J(bottomflux, 100); also the outflow flux o  :374-378                         */
+  int32_t high_group;        /* 1                                                                                          */
+  int32_t method;            /* MDB_DG_METHOD_SIPG                                                                         */
+  int32_t weights;           /* MDB_DG_WEIGHTS_ON                                                                          */
+  int32_t intorderadd;       /* 0: quadrature order 2 k                                                                    */
+  double alpha;              /* parameters.darcy.alpha                                                                     */
+} mdb_darcy_params;
+
+/* CouplingParameters of test/stokesdarcycouplingoperator.hh:11-77.  The operator's Jacobian is NumericalJacobianCoupling(epsilon)
+ * (:97-101; epsilon = 1e-2 in test/topbottomfiltration.ini:10).  quirk = 1 keeps the operator as written: the loop that transforms
+ * the Darcy gradients runs over the number of VELOCITY functions (:194-195), so the gradients of the last head functions stay zero. */
+typedef struct mdb_stokesdarcy_params {
+  double gravity, alpha, viscosity, porosity, gamma, density;
+  double kabs;               /* soil.permeability (isotropic tensor)                                                       */
+  double epsilon;
+  int32_t quirk;
+  int32_t reserved;
+} mdb_stokesdarcy_params;
+
 typedef struct mdb_mortar_params {
   double gamma_0;            /* ctor arg ("scaling factor for coupling", test/testmortarpoisson.cc:402): gamma = gamma_0 / |face| */
 } mdb_mortar_params;
@@ -222,6 +285,9 @@ int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cel
 int mdb_subdomains(mdb_ctx* ctx, const uint8_t* cell_subdomain_bits);
 /* Device-side marking for large meshes: cells whose centre has x[axis] > threshold go to subdomain
  * `sd_above`, the others to `sd_below` (test/testpoisson.cc:152-158). */
+/* elementIndexToPhysicalGroup of the Gmsh reader (test/stokesdarcy2.cc:577-578, used by DarcyParameters::A :285-290): one int32 per
+ * cell, host pointer.  Default: all zero. */
+int mdb_cell_groups(mdb_ctx* ctx, const int32_t* groups);
 /* Parity / output export of the marking: one subdomain bit set per cell (what gv.indexSet().subDomains(e) returns). */
 int mdb_get_subdomains(mdb_ctx* ctx, uint8_t* cell_subdomain_bits);
 int mdb_subdomains_halfspace(mdb_ctx* ctx, int axis, double threshold, int sd_below, int sd_above);
@@ -323,7 +389,10 @@ int mdb_jacobian(mdb_ctx* ctx, int go, int mat, double weight, const double* x, 
  * or free the buffer immediately afterwards; the kernels that consume the device copy keep running asynchronously. */
 
 /* ---- linear solve ([UPSTREAM] ISTL solver backends) ----------- */
-enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1 };
+/* MDB_SOLVER_DIRECT: [UPSTREAM] ISTLBackend_SEQ_SuperLU (test/stokesdarcy2.cc:784-785) — a sparse direct solve.  Here: reverse
+ * Cuthill-McKee reordering, banded LU with partial pivoting on the device (csrc/direct.cu), one step of iterative refinement;
+ * `precond`, `reduction` and `maxit` are ignored, stats report the defects before / after.  Single-rank contexts. */
+enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1, MDB_SOLVER_DIRECT = 2 };
 /* Jacobi is the fast path.  SSOR and ILU0 reproduce the reference's sequential ISTL preconditioners (SeqSSOR(A, n, 1.0),
  * SeqILU0) operation for operation on one rank; on a partition they act as block-Jacobi over the ranks (each rank applies
  * the sequential preconditioner of its owned x owned block, so iteration counts depend on the rank count).  [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SSOR(3),

@@ -32,10 +32,13 @@ any exact rule gives dune-geometry's integrals up to rounding.
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.  Method names follow the ctypes binding of the
 product (dune-multidomain_b200/capi.py) so that one problem-setup function drives both."""
 import math
+import os
+import sys
 
 import numpy as np
 
-import gen_opb_tables
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import gen_opb_tables  # noqa: E402  (the offline table generator: the oracle evaluates the same rounded coefficients as the device)
 from um_oracle import cond_applies
 
 FACE_V = ((0, 1), (0, 2), (1, 2))
@@ -95,8 +98,32 @@ def eval_bctype(b, x, is_boundary):
 
 # ---- rules ---------------------------------------------------------------------------------------------------------------------------
 def gauss01(m):
-    x, w = np.polynomial.legendre.leggauss(m)
-    return [(0.5 * (xi + 1.0), 0.5 * wi) for xi, wi in zip(x, w)]
+    """Gauss-Legendre on [0, 1] in closed form (correctly rounded sqrt / division): the finite-difference coupling Jacobian with a small
+    epsilon amplifies a 1-ulp difference in a node to 1e-8 relative in the entry, so the rule constants are spelled out, not iterated."""
+    sq = math.sqrt
+    if m == 1:
+        return [(0.5, 1.0)]
+    if m == 2:
+        a = 0.5 / sq(3.0)
+        return [(0.5 - a, 0.5), (0.5 + a, 0.5)]
+    if m == 3:
+        a = 0.5 * sq(3.0 / 5.0)
+        return [(0.5 - a, 5.0 / 18.0), (0.5, 8.0 / 18.0), (0.5 + a, 5.0 / 18.0)]
+    if m == 4:
+        s = sq(6.0 / 5.0)
+        a = 0.5 * sq(3.0 / 7.0 - 2.0 / 7.0 * s)
+        b = 0.5 * sq(3.0 / 7.0 + 2.0 / 7.0 * s)
+        wa = (18.0 + sq(30.0)) / 72.0
+        wb = (18.0 - sq(30.0)) / 72.0
+        return [(0.5 - b, wb), (0.5 - a, wa), (0.5 + a, wa), (0.5 + b, wb)]
+    if m == 5:
+        s = 2.0 * sq(10.0 / 7.0)
+        a = 0.5 * (1.0 / 3.0) * sq(5.0 - s)
+        b = 0.5 * (1.0 / 3.0) * sq(5.0 + s)
+        wa = (322.0 + 13.0 * sq(70.0)) / 1800.0
+        wb = (322.0 - 13.0 * sq(70.0)) / 1800.0
+        return [(0.5 - b, wb), (0.5 - a, wa), (0.5, 128.0 / 450.0), (0.5 + a, wa), (0.5 + b, wb)]
+    raise ValueError("Gauss rules up to 5 points")
 
 
 def line_rule(order):
@@ -572,8 +599,9 @@ class SDOracle:
             psi, js = fe_eval(fe_d, *self._ref_point(ia, ib, tq))
             gradpsi = np.zeros((dsize, 2))                                                 # value-initialised FieldVectors
             for i in range(vsize if P.quirk else dsize):                                   # :194-195 loops i < vsize
-                if i < dsize:
-                    gradpsi[i] = tn @ js[i]
+                if i < dsize:                                                              # jac.mv(js[i][0], gradpsi[i]), scalar order
+                    gradpsi[i, 0] = tn[0][0] * js[i][0] + tn[0][1] * js[i][1]
+                    gradpsi[i, 1] = tn[1][0] * js[i][0] + tn[1][1] * js[i][1]
             phi, gradphi = 0.0, np.zeros(2)
             for i in range(dsize):
                 phi += xn[i] * psi[i]

@@ -16,6 +16,7 @@ import sd_problems as sdp
 capi = sdp.capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_opb_tables  # noqa: E402
 import um_sd_oracle as sdo  # noqa: E402
 
