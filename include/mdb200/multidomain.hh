@@ -185,6 +185,12 @@ public:
     ctx_.check(mdb_mesh_unstructured(ctx_.get(), mesh.dim, mesh.numVertices(), mesh.vertices.data(), mesh.numElements(), MDB_ETYPE_TRIANGLE,
                                      mesh.elements.data()), "mdb_mesh_unstructured");
   }
+  // elementIndexToPhysicalGroup of the reader, for parameter classes that look a cell's group up (DarcyParameters::A, test/stokesdarcy2.cc:285-290)
+  void setPhysicalGroups(const std::vector<int>& groups) {
+    std::vector<int32_t> g(groups.begin(), groups.end());
+    if ((int64_t)g.size() != size0()) throw Exception(MDB_EINVAL, "setPhysicalGroups: one group per cell");
+    ctx_.check(mdb_cell_groups(ctx_.get(), g.data()), "mdb_cell_groups");
+  }
   bool unstructured() const { return unstructured_; }
   const std::vector<double>& vertices() const { return uvertices_; }        // simplex meshes: dim doubles per vertex
   const std::vector<int64_t>& elements() const { return uelements_; }       // simplex meshes: dim + 1 vertex indices per cell
@@ -217,10 +223,17 @@ public:
   int ncomp;                                                   // > 1: PowerCouplingGridFunctionSpace
   bool dg;                                                     // QkDGLocalFiniteElementMap<DF,RF,k,dim> instead of QkLocalFiniteElementMap
   bool simplex;                                                // PkLocalFiniteElementMap (simplex meshes)
+  bool opb;                                                    // OPBLocalFiniteElementMap (orthonormal basis, simplex meshes)
+  std::vector<GridFunctionSpace*> leaves;                      // non-empty: a composite / vector space (its leaf children, in order)
   GridFunctionSpace(SubDomainGridView gv_, int order, bool dg_ = false)
-    : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1), dg(dg_), simplex(false) {}
+    : gv(gv_), k(order), child(-1), coupling(false), lkind(0), rkind(0), lmask(0), rmask(0), ncomp(1), dg(dg_), simplex(false), opb(false) {}
+  virtual ~GridFunctionSpace() {}
+  // the leaf spaces in lexicographic order (LexicographicOrderingTag of the composite spaces, test/stokesdarcy2.cc:657-664)
+  void collect(std::vector<GridFunctionSpace*>& out) { if (leaves.empty()) out.push_back(this); else for (GridFunctionSpace* g : leaves) g->collect(out); }
+  void collect_children(std::vector<int>& out) const { if (leaves.empty()) out.push_back(child); else for (const GridFunctionSpace* g : leaves) g->collect_children(out); }
   int fe() const {
-    if (simplex) { if (k != 1) throw Exception(MDB_EINVAL, "PkGridFunctionSpace: only k = 1 has device kernels in this build"); return MDB_FE_P1; }
+    if (opb) { if (k < 1 || k > 3) throw Exception(MDB_EINVAL, "OPBGridFunctionSpace: k = 1, 2, 3"); return MDB_FE_OPB1 + k - 1; }
+    if (simplex) { if (k != 1 && k != 2) throw Exception(MDB_EINVAL, "PkGridFunctionSpace: k = 1, 2 have device kernels in this build"); return k == 1 ? MDB_FE_P1 : MDB_FE_P2; }
     return dg ? (k == 1 ? MDB_FE_DGQ1 : MDB_FE_DGQ2) : (k == 1 ? MDB_FE_Q1 : MDB_FE_Q2);
   }
 };
@@ -228,6 +241,27 @@ public:
 class PkGridFunctionSpace : public GridFunctionSpace {
 public:
   PkGridFunctionSpace(SubDomainGridView gv_, int order) : GridFunctionSpace(gv_, order) { simplex = true; }
+};
+// GridFunctionSpace<SDGV, OPBLocalFiniteElementMap<DF,RF,k,dim,simplex,GMPField<512>>, NoConstraints, VBE> (test/stokesdarcy2.cc:615, :666-668)
+class OPBGridFunctionSpace : public GridFunctionSpace {
+public:
+  OPBGridFunctionSpace(SubDomainGridView gv_, int order) : GridFunctionSpace(gv_, order) { simplex = true; opb = true; }
+};
+// VectorGridFunctionSpace<SDGV, PkLocalFiniteElementMap<..,k>, dim, VBE, VBE, CON> (test/stokesdarcy2.cc:646-655): dim copies of the
+// scalar space, component block after component block
+class VectorGridFunctionSpace : public GridFunctionSpace {
+  std::vector<PkGridFunctionSpace> comps_;
+public:
+  VectorGridFunctionSpace(SubDomainGridView gv_, int order, int dim) : GridFunctionSpace(gv_, order), comps_((size_t)dim, PkGridFunctionSpace(gv_, order)) {
+    simplex = true;
+    for (PkGridFunctionSpace& c : comps_) leaves.push_back(&c);
+  }
+  VectorGridFunctionSpace(const VectorGridFunctionSpace&) = delete;
+};
+// CompositeGridFunctionSpace<VBE, LexicographicOrderingTag, Children...> (test/stokesdarcy2.cc:657-664)
+class CompositeGridFunctionSpace : public GridFunctionSpace {
+public:
+  CompositeGridFunctionSpace(std::initializer_list<GridFunctionSpace*> children) : GridFunctionSpace(SubDomainGridView(-1), 0) { leaves.assign(children.begin(), children.end()); }
 };
 // GridFunctionSpace<SDGV, QkDGLocalFiniteElementMap<DF,double,k,dim>, CON, VBE> (test/testpoisson-dirichlet-neumann.cc:925-926, :968-971)
 class QkDGGridFunctionSpace : public GridFunctionSpace {
@@ -261,7 +295,9 @@ class MultiDomainGridFunctionSpace { // children in argument order, Lexicographi
 public:
   MultiDomainGridFunctionSpace(MultiDomainGrid& grid, std::initializer_list<GridFunctionSpace*> children)
     : grid_(grid), finalized_(false), ndof_(0) {
-    for (GridFunctionSpace* g : children)
+    std::vector<GridFunctionSpace*> flat;
+    for (GridFunctionSpace* g : children) g->collect(flat);
+    for (GridFunctionSpace* g : flat)
       g->child = g->coupling && g->ncomp > 1
         ? context().check(mdb_add_power_coupling_space(context().get(), g->k == 1 ? MDB_FE_Q1 : MDB_FE_Q2, g->lkind, g->lmask, g->rkind, g->rmask, g->ncomp), "mdb_add_power_coupling_space")
         : g->coupling
@@ -321,6 +357,48 @@ struct ConvectionDiffusionDG {
   static int id() { return MDB_OP_CONVDIFF_DG; }
   const mdb_bctype& bctype() const { return p.bc; }
 };
+// ---- the Stokes-Darcy operators of test/stokesdarcy2.cc ------------------------------------------------------------------------------
+// [UPSTREAM] TaylorHoodNavierStokes<NavierStokesParameters>(params, stokes_q) (test/stokesdarcy2.cc:226-251, :719-720): Stokes, full tensor
+struct NavierStokesParameters {
+  mdb_taylorhood_params p;
+  // params.sub("parameters"): fluid.mu, fluid.rho, gravity; b = StokesBoundaryType (MDB_BC_ALL_NEUMANN = StressNeumann as shipped); j = PressureDropFlux
+  NavierStokesParameters(double mu, double rho, double gravity, const mdb_bctype& b, const mdb_function& j) {
+    p.mu = mu; p.rho = rho; p.f[0] = 0.0; p.f[1] = -gravity; p.bc = b; p.j = j; p.quad_order = 4; p.full_tensor = 1;
+  }
+};
+struct TaylorHoodNavierStokes {
+  mdb_taylorhood_params p;
+  TaylorHoodNavierStokes(const NavierStokesParameters& params, int superintegration_order) : p(params.p) { p.quad_order = superintegration_order; }
+  static int id() { return MDB_OP_TAYLORHOOD_STOKES; }
+  const mdb_bctype& bctype() const { return p.bc; }
+};
+// DarcyParameters (test/stokesdarcy2.cc:254-407) + [UPSTREAM] ConvectionDiffusionDG<DarcyParameters, OPB>(params, method, weights, alpha) (:733-739)
+struct DarcyParameters {
+  mdb_darcy_params p;
+  DarcyParameters(double kabs, double kabs_low, const mdb_bctype& b, const mdb_function& g, const mdb_function& j) {
+    p.kabs = kabs; p.kabs_low = kabs_low; p.bc = b; p.g = g; p.j = j; p.high_group = 1; p.method = MDB_DG_METHOD_SIPG; p.weights = MDB_DG_WEIGHTS_ON; p.intorderadd = 0; p.alpha = 1.0;
+  }
+};
+struct DarcyConvectionDiffusionDG {
+  mdb_darcy_params p;
+  DarcyConvectionDiffusionDG(const DarcyParameters& params, ConvectionDiffusionDGMethod::Type method, ConvectionDiffusionDGWeights::Type weights, double alpha)
+    : p(params.p) { p.method = method; p.weights = weights; p.alpha = alpha; }
+  static int id() { return MDB_OP_DARCY_DG; }
+};
+// CouplingParameters + StokesDarcyCouplingOperator (test/stokesdarcycouplingoperator.hh:11-252); Jacobian = NumericalJacobianCoupling(epsilon)
+struct CouplingParameters {
+  mdb_stokesdarcy_params p;
+  CouplingParameters(double alpha, double gamma, double porosity, double gravity, double density, double viscosity, double epsilon, double kabs) {
+    p.alpha = alpha; p.gamma = gamma; p.porosity = porosity; p.gravity = gravity; p.density = density; p.viscosity = viscosity; p.epsilon = epsilon; p.kabs = kabs;
+    p.quirk = 1; p.reserved = 0;
+  }
+};
+struct StokesDarcyCouplingOperator {
+  mdb_stokesdarcy_params p; int jac_mode;
+  explicit StokesDarcyCouplingOperator(const CouplingParameters& params, int jac = MDB_JAC_FD_BITMATCH) : p(params.p), jac_mode(jac) {}
+  static int id() { return MDB_OP_STOKESDARCY_COUPLING; }
+};
+
 struct ContinuousValueContinuousFlowCoupling {   // test/proportionalflowcoupling.hh:94-239
   mdb_cvcf_params p; int jac_mode;
   ContinuousValueContinuousFlowCoupling(int intorder, double intensity, int jacobian_mode = MDB_JAC_FD_BITMATCH) : jac_mode(jacobian_mode) {
@@ -358,9 +436,10 @@ template <class LOP, class Condition>
 class SubProblem {
 public:
   MultiDomainGridFunctionSpace& gfs; LOP lop; int handle;
+  // `child` may be a composite space: the subproblem then spans all its leaves (subproblemlocalfunctionspace.hh:144-261)
   SubProblem(MultiDomainGridFunctionSpace& gfs_, const LOP& lop_, const Condition& cond, const GridFunctionSpace& child) : gfs(gfs_), lop(lop_) {
-    const int ch = child.child;
-    handle = gfs.context().check(mdb_add_subproblem(gfs.context().get(), LOP::id(), &lop.p, sizeof(lop.p), Condition::kind(), cond.mask, &ch, 1),
+    std::vector<int> ch; child.collect_children(ch);
+    handle = gfs.context().check(mdb_add_subproblem(gfs.context().get(), LOP::id(), &lop.p, sizeof(lop.p), Condition::kind(), cond.mask, ch.data(), (int)ch.size()),
                                  "mdb_add_subproblem");
   }
 };
@@ -526,6 +605,8 @@ struct ISTLBackend_SEQ_BCGS_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_S
 struct ISTLBackend_SEQ_CG_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_ILU0(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_ILU0, maxiter) {} };
 struct ISTLBackend_SEQ_CG_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_JACOBI, maxiter) {} };
 struct ISTLBackend_SEQ_BCGS_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_JACOBI, maxiter) {} };
+// [UPSTREAM] ISTLBackend_SEQ_SuperLU(verbose) (test/stokesdarcy2.cc:784-785): a direct solve — banded LU with partial pivoting on the device
+struct ISTLBackend_SEQ_SuperLU : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_SuperLU(bool = true) : ISTLBackend_SEQ_Base(MDB_SOLVER_DIRECT, MDB_PRECOND_NONE, 1) {} };
 
 // ISTL_SEQ_Subblock_Backend<Dune::SeqSSOR, Dune::BiCGSTABSolver>(block, maxiter) (test/testpoisson-dirichlet-neumann.cc:264-370):
 // BiCGSTAB + SeqSSOR(3) on the diagonal block of one child space; z outside the block is left untouched

@@ -97,3 +97,38 @@ def setup(lib, xy, conn, groups, *, jac_mode=capi.JAC_FD_BITMATCH, params=None, 
     rng = np.random.default_rng(1234)
     H["x0"] = rng.uniform(-1.0, 1.0, H["ndof"])
     return H
+
+
+# ---- committed golden vectors (tests/golden/sd, written by tests/golden/make_golden_sd.py) -----------------------------------
+def golden_cases():
+    import glob
+    return sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "sd", "*.npz")))
+
+
+def check_golden(lib, path, solve=None):
+    """DOF map, constraints, pattern bit-exact; entries 1e-12 of the largest; the Newton step (direct solve) 1e-10 per block."""
+    g = np.load(path)
+    pk = {str(k): float(v) for k, v in zip(g["pk_keys"], g["pk_vals"])}
+    if "quirk" in pk:
+        pk["quirk"] = int(pk["quirk"])
+    H = setup(lib, g["xy"], g["conn"], g["groups"], params=ini_params(**pk))
+    assert H["ndof"] == int(g["ndof"]) and H["ncon"] == int(g["ncon"])
+    assert np.array_equal(lib.get_child_offsets(), g["offsets"])
+    ptr, dofs = lib.get_dofmap()
+    assert np.array_equal(ptr, g["cell_ptr"]) and np.array_equal(dofs, g["cell_dofs"])
+    assert np.array_equal(lib.get_constraints(), g["constrained"])
+    rp, ci = lib.matrix_get_pattern(H["mat"])
+    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(ci, g["colidx"])
+    x0 = np.ascontiguousarray(g["x0"])
+    assert np.array_equal(x0, H["x0"])
+    lib.jacobian(H["go"], H["mat"], x0, overwrite=True)
+    v = lib.matrix_get_values(H["mat"])
+    assert np.abs(v - g["values"]).max() <= 1e-12 * np.abs(g["values"]).max()
+    r = lib.residual(H["go"], x0, np.zeros(H["ndof"]))
+    assert np.abs(r - g["residual"]).max() <= 1e-12 * np.abs(g["residual"]).max()
+    if solve is not None:
+        z = solve(H, np.ascontiguousarray(g["residual"]))
+        off = g["offsets"]
+        for a in range(len(off) - 1):
+            blk = slice(int(off[a]), int(off[a + 1]))
+            assert np.abs(z[blk] - g["solution_z"][blk]).max() <= 1e-10 * np.abs(g["solution_z"][blk]).max(), a

@@ -198,3 +198,18 @@ def test_stationary_direct_solve_of_the_coupled_problem(case):
     rs = dev.residual(Hd["go"], u, np.zeros(Hd["ndof"]))
     assert np.linalg.norm(rs) <= 1e-9 * np.linalg.norm(r)
     dev.close()
+
+
+@pytest.mark.parametrize("path", sdp.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_device_reproduces_golden(path):
+    """The committed fixtures of tests/golden/sd (frozen oracle output incl. SciPy's SuperLU solution of the Newton step) through the C ABI."""
+    dev = pkg.Mdb(0)
+
+    def solve(H, r):
+        z = np.zeros(H["ndof"])
+        st = dev.solve(H["mat"], r, z, method=capi.SOLVER_DIRECT, precond=capi.PRECOND_NONE)
+        assert st.converged == 1
+        return z
+
+    sdp.check_golden(dev, path, solve)
+    dev.close()

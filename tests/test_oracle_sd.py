@@ -214,3 +214,12 @@ def test_coupling_closed_forms_and_fd_equals_exact(small):
     r0 = o.residual(H["go"], np.zeros(H["ndof"]), np.zeros(H["ndof"]))
     r1 = o.residual(H["go"], x, np.zeros(H["ndof"]))
     assert np.abs(A_ex @ x + r0 - r1).max() < 1e-10 * np.abs(r1).max()                         # the whole coupled residual is affine
+
+
+@pytest.mark.parametrize("path", sdp.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_reproduces_golden(path):
+    sdp.check_golden(sdp.oracle(), path)
+
+
+def test_golden_fixtures_exist():
+    assert len(sdp.golden_cases()) >= 3
