@@ -1,5 +1,6 @@
 // capi.cu — the C ABI of libmdb200.so (include/mdb200.h): context, mesh, spaces, participants, entry points.
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 
 namespace mdb {
@@ -58,6 +59,8 @@ void* Ctx::scratch(size_t bytes)
 void Ctx::phase_begin(const char* name)
 {
   PhaseRec& r = phases[name];
+  if (nvtx_open) nvtxRangePop();
+  nvtxRangePushA(name); nvtx_open = true;
   cur_phase = nullptr;
   if (r.used == r.ev.size()) {
     if (r.ev.size() >= 4096) return;            // pool full: stop recording this phase until the next reset
@@ -70,6 +73,7 @@ void Ctx::phase_begin(const char* name)
 }
 void Ctx::phase_end()
 {
+  if (nvtx_open) { nvtxRangePop(); nvtx_open = false; }
   if (!cur_phase) return;
   MDB_CUDA(cudaEventRecord(cur_phase->ev[cur_phase->used].second, stream));
   cur_phase->used++;
@@ -141,12 +145,14 @@ static void free_matrix(Matrix& m)
   for (auto& kv : m.fd_plans) fd_plan_free(kv.second);
   m.fd_plans.clear();
   direct_free(m);
+  for (auto& kv : m.um_pair_plans) um_pair_plan_free(kv.second);
+  m.um_pair_plans.clear();
 }
 
 static void reset_spaces(Ctx* c)
 {
   for (auto& ch : c->children) { dfree(ch.d_lat2dof); dfree(ch.d_dof2lat); dfree(ch.d_edge2dof); dfree(ch.d_cell2dof); }
-  for (auto& sp : c->sps) dfree(sp.d_lmap);
+  for (auto& sp : c->sps) { dfree(sp.d_lmap); dfree(sp.d_um_vtx); dfree(sp.d_um_dof); sp.um_ncells = 0; }
   for (auto& go : c->gos) { for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); } dfree(go.d_xneed); for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(go.d_res_fast[i]); dfree(go.d_res_rest[i]); go.n_res_rest[i] = -1; } }
   for (auto& m : c->mats) free_matrix(m);
   c->gos.clear(); c->mats.clear();
@@ -176,9 +182,13 @@ __global__ void k_halfspace(MeshDesc m, int axis, double threshold, int sd_below
 
 using namespace mdb;
 
+// every entry point is an NVTX range (named after the C function), every phase a nested range: timelines of nsys / ncu show the
+// reference's call structure (jacobian -> volume | coupling | dirichlet rows, solve -> ...)
+struct NvtxScope { explicit NvtxScope(const char* name) { nvtxRangePushA(name); } ~NvtxScope() { nvtxRangePop(); } };
 #define MDB_API_BEGIN(ctx)                                                       \
   if (!(ctx)) return MDB_EINVAL;                                                 \
   try {                                                                          \
+    NvtxScope nvtx_scope__(__func__);                                            \
     cudaSetDevice((ctx)->device);
 #define MDB_API_END(ctx)                                                         \
     return MDB_OK;                                                               \

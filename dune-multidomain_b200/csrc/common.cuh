@@ -192,6 +192,7 @@ struct SubProblemDesc {
   mdb_convdiffdg_params cddg{};
   mdb_taylorhood_params th{};
   mdb_darcy_params darcy{};
+  int32_t* d_um_vtx = nullptr; int32_t* d_um_dof = nullptr; int64_t um_ncells = 0;   // unstructured.cu: [3][um_ncells] vertex ids / container indices of the cells the subproblem applies to (Morton order)
   int32_t* d_lmap = nullptr; int nloc = 0;     // ufe.cu: [ncells][nloc] container indices of the subproblem's local space (-1: not on the cell)
   int dg_k = 1;                // MDB_OP_CONVDIFF_DG: degree of the child space (quadrature order = intorderadd + 2 k)
   int cond_kind = 0; uint32_t mask = 0;
@@ -237,6 +238,7 @@ struct UMesh {
   int64_t nedges = 0;
   int32_t* d_cell_edge = nullptr; // [ne][3] edge index of face f: order of first appearance in (cell, local face) order
   int32_t* d_group = nullptr;    // [ne] physical group (mdb_cell_groups), zero by default
+  int32_t* d_cell_order = nullptr; // [ne] cells in Morton order of their centroids: the processing order of the cell-wise kernels
   void* ufe_tables = nullptr;    // ufe.cu: device tables of the generic finite elements
 };
 
@@ -286,6 +288,7 @@ struct Matrix {
   double* d_ilu = nullptr; bool ilu_valid = false;
   int32_t* d_cell_perm = nullptr; int64_t sweep_cells = 0; int sweep_cell_img = 0;   // all-DG matrices: cells in wavefront order (first row of each), image doubles per warp
   void* direct = nullptr;            // direct.cu: band factorisation cache
+  std::map<std::vector<int>, void*> um_pair_plans;   // unstructured.cu: pair records of the owner-computes Jacobian kernel per subproblem list
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
 };
@@ -298,7 +301,7 @@ struct Ctx {
   // when mdb_phase_ms() is called
   struct PhaseRec { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; size_t used = 0; double last_ms = -1.0; };
   std::map<std::string, PhaseRec> phases;
-  PhaseRec* cur_phase = nullptr;
+  PhaseRec* cur_phase = nullptr; bool nvtx_open = false;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // second stream for host->device traffic that overlaps assembly kernels; byte counters of the host<->device copies
@@ -435,6 +438,7 @@ bool halo_timed_out(Ctx* c);
 // unstructured.cu: the same steps on an unstructured triangle mesh with P1 spaces
 void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn);
 void um_free(Ctx* c);
+void um_pair_plan_free(void* plan);
 void um_build_dofmap(Ctx* c);
 void um_export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs);
 void um_assemble_constraints(Ctx* c, const int* sps, const mdb_bctype* bcs, int n);

@@ -546,6 +546,263 @@ __global__ void k_um_boundary(UMDev m, UMSpace S, UMOps O, const int32_t* __rest
   }
 }
 
+
+// ---- cell-wise assembly on per-subproblem cell lists ----------------------------------------------------------------------------
+// One thread per (subproblem, cell it applies to).  The lists are built once (um_build_dofmap: vertex ids and container indices of
+// the cell's three functions, structure of arrays, cells in Morton order of their centroids so that neighbouring threads touch
+// neighbouring rows whatever the order of the file) and, per matrix, the CSR positions of the cell's 9 entries (um_build_pattern:
+// "precomputed CSR slots").  A thread reads 12 B of vertex ids + 36 B of slots (coalesced), gathers three coordinate pairs through
+// L2, evaluates jacobian_volume once and adds the 9 entries with reductions (RED.ADD.F64 resolves in L2): no adjacency walk, no
+// DOF-map gather, no column search.  Summation order inside an entry is not fixed (rounding level, far inside the 1e-12 bar).
+struct UMLists { int nlist; int64_t start[9]; UMSp sp[8]; const int32_t* vtx[8]; const int32_t* dof[8]; const int32_t* slot[8]; };
+
+__device__ inline Tri tri_geometry_v(const UMDev& m, int v0, int v1, int v2)
+{
+  Tri g;
+  const double2* xy2 = reinterpret_cast<const double2*>(m.xy);
+  const double2 p0 = __ldg(xy2 + v0), p1 = __ldg(xy2 + v1), p2 = __ldg(xy2 + v2);
+  g.p[0][0] = p0.x; g.p[0][1] = p0.y; g.p[1][0] = p1.x; g.p[1][1] = p1.y; g.p[2][0] = p2.x; g.p[2][1] = p2.y;
+  const double ax = p1.x - p0.x, ay = p1.y - p0.y, bx = p2.x - p0.x, by = p2.y - p0.y;
+  const double det = ax * by - ay * bx;
+  const double inv = 1.0 / det;
+  g.t[0][0] = by * inv; g.t[0][1] = -(ay * inv);
+  g.t[1][0] = -(bx * inv); g.t[1][1] = ax * inv;
+  g.ie = fabs(det);
+  return g;
+}
+__global__ void __launch_bounds__(256) k_um_jacobian_cells(UMDev m, UMLists L, double weight, double* val)
+{
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= L.start[L.nlist]) return;
+  int l = 0;
+  while (t >= L.start[l + 1]) ++l;
+  const int64_t i = t - L.start[l], n = L.start[l + 1] - L.start[l];
+  const UMSp& sp = L.sp[l];
+  const int32_t* vtx = L.vtx[l]; const int32_t* slot = L.slot[l];
+  const Tri g = tri_geometry_v(m, vtx[i], vtx[n + i], vtx[2 * n + i]);
+  double gp[3][2]; tri_gradients(g, gp);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    double row[3]; um_matrix_row(sp, g, gp, a, weight, row);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { const int32_t p = slot[(3 * a + b) * n + i]; if (p >= 0) atomicAdd(val + p, row[b]); }
+  }
+}
+// alpha_volume + lambda_volume, cell by cell on the same lists
+__global__ void __launch_bounds__(256) k_um_residual_lists(UMDev m, UMLists L, double weight, double tm, const double* __restrict__ x, double* r)
+{
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= L.start[L.nlist]) return;
+  int l = 0;
+  while (t >= L.start[l + 1]) ++l;
+  const int64_t i = t - L.start[l], n = L.start[l + 1] - L.start[l];
+  const UMSp& sp = L.sp[l];
+  const int32_t* vtx = L.vtx[l]; const int32_t* dofs = L.dof[l];
+  const Tri g = tri_geometry_v(m, vtx[i], vtx[n + i], vtx[2 * n + i]);
+  double gp[3][2]; tri_gradients(g, gp);
+  int32_t dof[3]; double xl[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { dof[j] = dofs[j * n + i]; xl[j] = __ldg(x + dof[j]); }
+  double rl[3] = {0.0, 0.0, 0.0};
+  int q0; const int nq = tri_rule(sp.quad_order, &q0);
+  if (sp.op_id == MDB_OP_POISSON) {
+    double gradu[2] = {0.0, 0.0};
+    for (int j = 0; j < 3; ++j) for (int dd = 0; dd < 2; ++dd) gradu[dd] += xl[j] * gp[j][dd];
+    const double vol = sp.wsum * g.ie;
+    for (int a = 0; a < 3; ++a) { double dot = 0.0; dot += gradu[0] * gp[a][0]; dot += gradu[1] * gp[a][1]; rl[a] += weight * (dot * vol); }
+    if (sp.P.f.kind != MDB_FN_ZERO)
+      for (int q = 0; q < nq; ++q) {
+        const double factor = c_tri[q0 + q][2] * g.ie;
+        double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
+        double xg[2];
+        for (int dd = 0; dd < 2; ++dd) xg[dd] = g.p[0][dd] + (g.p[1][dd] - g.p[0][dd]) * c_tri[q0 + q][0] + (g.p[2][dd] - g.p[0][dd]) * c_tri[q0 + q][1];
+        const double y = eval_function(sp.P.f, 2, xg, tm);
+        for (int a = 0; a < 3; ++a) rl[a] += weight * (-y * phi[a] * factor);
+      }
+  } else {
+    for (int q = 0; q < nq; ++q) {
+      const double factor = c_tri[q0 + q][2] * g.ie;
+      double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
+      double u = 0.0; for (int j = 0; j < 3; ++j) u += xl[j] * phi[j];
+      for (int a = 0; a < 3; ++a) rl[a] += weight * (u * phi[a] * factor);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) atomicAdd(r + dof[a], rl[a]);
+}
+// cell lists: flags -> compaction in Morton order -> vertex ids / container indices (structure of arrays)
+__global__ void k_um_list_flags(UMDev m, UMSp sp, const int32_t* __restrict__ order, int32_t* flag)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m.ne) return;
+  flag[i] = um_applies(sp, m.sd[order[i]]) ? 1 : 0;
+}
+__global__ void k_um_list_fill(UMDev m, UMSpace S, UMSp sp, const int32_t* __restrict__ order, const int32_t* __restrict__ flag, const int32_t* __restrict__ scan,
+                               int64_t n, int32_t* vtx, int32_t* dof)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m.ne || !flag[i]) return;
+  const int cell = order[i]; const int64_t pos = scan[i];
+  for (int j = 0; j < 3; ++j) {
+    const int v = m.conn[3 * cell + j];
+    vtx[j * n + pos] = v;
+    dof[j * n + pos] = (int32_t)(S.offset[sp.child] + S.v2d[sp.child][v]);
+  }
+}
+__global__ void k_um_list_slots(int64_t n, const int32_t* __restrict__ dof, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t* slot)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t d[3] = {dof[i], dof[n + i], dof[2 * n + i]};
+  for (int a = 0; a < 3; ++a) {
+    const int64_t p0 = rowptr[d[a]]; const int len = (int)(rowptr[d[a] + 1] - p0);
+    for (int b = 0; b < 3; ++b) { const int pos = um_find(colidx + p0, len, d[b]); slot[(3 * a + b) * n + i] = pos >= 0 ? (int32_t)(p0 + pos) : -1; }
+  }
+}
+// Morton code of the cell centroids (16 bits per axis inside the bounding box)
+__global__ void k_um_morton(UMDev m, double x0, double y0, double sx, double sy, uint32_t* code, int32_t* cell)
+{
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= m.ne) return;
+  double cx = 0.0, cy = 0.0;
+  for (int i = 0; i < 3; ++i) { const int v = m.conn[3 * e + i]; cx += m.xy[2 * v]; cy += m.xy[2 * v + 1]; }
+  uint32_t ix = (uint32_t)fmin(65535.0, fmax(0.0, (cx / 3.0 - x0) * sx)), iy = (uint32_t)fmin(65535.0, fmax(0.0, (cy / 3.0 - y0) * sy));
+  auto spread = [](uint32_t v) { v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u; return v; };
+  code[e] = spread(ix) | (spread(iy) << 1);
+  cell[e] = (int32_t)e;
+}
+
+
+// ---- owner-computes rows from per-row pair records -------------------------------------------------------------------------------
+// The staged row kernel above walks vertex -> cell -> connectivity -> coordinates per (row, cell) pair: three dependent gathers.
+// Here every pair is a 16-byte record built once per (matrix, grid operator): the cell's three vertex ids and a word with the three
+// slots inside the row, the row's local index in the cell and the subproblem.  Records are stored warp-transposed (record k of the
+// 32 rows of a warp side by side: one coalesced 512-byte load per step, as many steps as the longest row of the warp needs).  A
+// thread keeps its row in the block's shared-memory image of the 128 rows' values and the image goes out with coalesced stores: no
+// atomics (the reduction unit issues 1.29 cycles per lane, which bounds the cell-wise kernel), no adjacency walk, no zero-fill pass.
+struct UMPairPlan { int4* rec = nullptr; int64_t* wptr = nullptr; int64_t nrows = 0, nwarps = 0; };
+
+__global__ void k_um_pair_count(UMDev m, UMSpace S, UMOps O, int64_t ndof, const int32_t* __restrict__ row_child, int32_t* count)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= ndof) return;
+  const int child = row_child[r];
+  const int v = S.d2v[child][r - S.offset[child]];
+  int n = 0;
+  for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+    const uint32_t sd = m.sd[m.v2c[e] >> 2];
+    for (int s = 0; s < O.nsp; ++s) n += (O.sp[s].child == child && um_applies(O.sp[s], sd)) ? 1 : 0;
+  }
+  count[r] = n;
+}
+__global__ void k_um_pair_warpmax(int64_t ndof, const int32_t* __restrict__ count, int32_t* wmax)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int n = r < ndof ? count[r] : 0;
+  for (int o = 16; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+  if ((threadIdx.x & 31) == 0 && (r >> 5) < (ndof + 31) / 32) wmax[r >> 5] = n;
+}
+__global__ void k_um_pair_fill(UMDev m, UMSpace S, UMOps O, int64_t ndof, const int32_t* __restrict__ row_child, const uint8_t* const* __restrict__ slot_of_child,
+                               const int64_t* __restrict__ wptr, int4* rec)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = r >> 5;
+  if (w >= (ndof + 31) / 32) return;
+  const int64_t base = wptr[w]; const int steps = (int)((wptr[w + 1] - base) >> 5);
+  int k = 0;
+  if (r < ndof) {
+    const int child = row_child[r];
+    const int v = S.d2v[child][r - S.offset[child]];
+    const uint8_t* slot = slot_of_child[child];
+    for (int e = m.v2c_ptr[v]; e < m.v2c_ptr[v + 1]; ++e) {
+      const int cell = m.v2c[e] >> 2, li = m.v2c[e] & 3;
+      const uint32_t sd = m.sd[cell];
+      for (int s = 0; s < O.nsp; ++s) {
+        if (O.sp[s].child != child || !um_applies(O.sp[s], sd)) continue;
+        const uint32_t word = (uint32_t)slot[3 * (int64_t)e] | ((uint32_t)slot[3 * (int64_t)e + 1] << 8) | ((uint32_t)slot[3 * (int64_t)e + 2] << 16) | ((uint32_t)li << 24) | ((uint32_t)s << 26);
+        rec[base + (int64_t)k * 32 + lane] = make_int4(m.conn[3 * cell], m.conn[3 * cell + 1], m.conn[3 * cell + 2], (int)word);
+        ++k;
+      }
+    }
+  }
+  for (; k < steps; ++k) rec[base + (int64_t)k * 32 + lane] = make_int4(-1, -1, -1, 0);
+}
+constexpr int UM_PROWS = 128;
+constexpr int UM_PIMG = UM_PROWS * 24;
+__global__ void __launch_bounds__(UM_PROWS) k_um_jacobian_pairs(UMDev m, UMOps O, int64_t ndof, const int4* __restrict__ rec, const int64_t* __restrict__ wptr,
+                                                                double weight, int overwrite, const int64_t* __restrict__ rowptr, double* val)
+{
+  __shared__ double img[UM_PIMG];
+  const int64_t row0 = blockIdx.x * (int64_t)UM_PROWS;
+  const int nrows = (int)((ndof - row0) < UM_PROWS ? (ndof - row0) : UM_PROWS);
+  const int64_t vbase = rowptr[row0];
+  const int total = (int)(rowptr[row0 + nrows] - vbase);
+  const bool staged = total <= UM_PIMG;
+  const int tid = threadIdx.x;
+  if (staged) {
+    if (overwrite) for (int k = tid; k < total; k += UM_PROWS) img[k] = 0.0;
+    else for (int k = tid; k < total; k += UM_PROWS) img[k] = val[vbase + k];
+    __syncthreads();
+  }
+  const int64_t w = (row0 + tid) >> 5;
+  if (row0 + (tid & ~31) < ndof) {
+    const int64_t base = wptr[w]; const int steps = (int)((wptr[w + 1] - base) >> 5);
+    const int64_t row = row0 + tid;
+    double* dst = nullptr;
+    if (tid < nrows) {
+      const int64_t p0 = rowptr[row];
+      dst = staged ? img + (p0 - vbase) : val + p0;
+      if (!staged && overwrite) { const int len = (int)(rowptr[row + 1] - p0); for (int k = 0; k < len; ++k) dst[k] = 0.0; }
+    }
+    // software pipeline: record k + 2 and the coordinates of pair k + 1 are in flight while pair k is evaluated
+    const int lane = tid & 31;
+    const double2* xy2 = reinterpret_cast<const double2*>(m.xy);
+    const int4 none = make_int4(-1, -1, -1, 0);
+    int4 cur = steps > 0 ? __ldg(rec + base + lane) : none;
+    int4 nxt = steps > 1 ? __ldg(rec + base + 32 + lane) : none;
+    double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0;
+    if (cur.x >= 0) { q0 = __ldg(xy2 + cur.x); q1 = __ldg(xy2 + cur.y); q2 = __ldg(xy2 + cur.z); }
+    for (int k = 0; k < steps; ++k) {
+      const int4 c4 = cur; const double2 p0 = q0, p1 = q1, p2 = q2;
+      cur = nxt;
+      nxt = k + 2 < steps ? __ldg(rec + base + (int64_t)(k + 2) * 32 + lane) : none;
+      if (cur.x >= 0) { q0 = __ldg(xy2 + cur.x); q1 = __ldg(xy2 + cur.y); q2 = __ldg(xy2 + cur.z); }
+      if (c4.x < 0) continue;
+      const uint32_t word = (uint32_t)c4.w;
+      Tri g;
+      g.p[0][0] = p0.x; g.p[0][1] = p0.y; g.p[1][0] = p1.x; g.p[1][1] = p1.y; g.p[2][0] = p2.x; g.p[2][1] = p2.y;
+      {
+        const double ax = p1.x - p0.x, ay = p1.y - p0.y, bx = p2.x - p0.x, by = p2.y - p0.y;
+        const double det = ax * by - ay * bx;
+        const double inv = 1.0 / det;
+        g.t[0][0] = by * inv; g.t[0][1] = -(ay * inv);
+        g.t[1][0] = -(bx * inv); g.t[1][1] = ax * inv;
+        g.ie = fabs(det);
+      }
+      double gp[3][2]; tri_gradients(g, gp);
+      double a[3]; um_matrix_row(O.sp[word >> 26], g, gp, (int)((word >> 24) & 3u), weight, a);
+      const uint32_t s0 = word & 255u, s1 = (word >> 8) & 255u, s2 = (word >> 16) & 255u;
+      if (s0 != 255u) dst[s0] += a[0];
+      if (s1 != 255u) dst[s1] += a[1];
+      if (s2 != 255u) dst[s2] += a[2];
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    for (int k = tid; k < total; k += UM_PROWS) val[vbase + k] = img[k];
+  }
+}
+__global__ void k_um_row_child(UMSpace S, int64_t ndof, int32_t* row_child)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= ndof) return;
+  int k = 0;
+  while (k + 1 < S.nchild && r >= S.offset[k + 1]) ++k;
+  while (S.size[k] == 0 && k + 1 < S.nchild) ++k;
+  row_child[r] = k;
+}
+
 // ---- coupling terms ---------------------------------------------------------------------------------------------------------------
 struct UMFace {
   double phi1[3][3], phi2[3][3];   // [point][shape function]
@@ -661,8 +918,10 @@ __global__ void k_um_coupling_residual(UMDev m, UMSpace S, UMCp cp, const int32_
 __global__ void k_um_coupling_jacobian(UMDev m, UMSpace S, UMCp cp, const int32_t* fcell, const int8_t* fface, int64_t nf, double weight,
                                        const double* __restrict__ x, const int64_t* rowptr, const int32_t* colidx, double* val)
 {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= nf) return;
+  // thread (face, j): the base line and the evaluation with coefficient j perturbed -> column j of the 6 x 6 face block
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= 6 * nf) return;
+  const int64_t i = idx / 6; const int j = (int)(idx % 6);
   const int cell = fcell[i], f = fface[i], nb = m.nbr[3 * cell + f];
   UMFace F; um_face_setup(m, cell, f, nb, cp.quad_order, cp.op_id == MDB_OP_CVCF_COUPLING, F);
   int32_t g[6]; double u[6];
@@ -673,19 +932,22 @@ __global__ void k_um_coupling_jacobian(UMDev m, UMSpace S, UMCp cp, const int32_
   for (int k = 0; k < 6; ++k) u[k] = analytic ? 0.0 : x[g[k]];
   double down[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (!analytic) um_alpha_coupling(cp, F, u, u + 3, 1.0, down, down + 3);
-  for (int j = 0; j < 6; ++j) {
-    const double keep = u[j];
-    const double delta = analytic ? 1.0 : 1e-8 * (1.0 + fabs(u[j]));
-    u[j] = analytic ? 1.0 : u[j] + delta;
-    double up[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    um_alpha_coupling(cp, F, u, u + 3, 1.0, up, up + 3);
-    u[j] = keep;
-    for (int r = 0; r < 6; ++r) {
-      const double entry = analytic ? up[r] : (up[r] - down[r]) / delta;
-      const int64_t p0 = rowptr[g[r]];
-      const int pos = um_find(colidx + p0, (int)(rowptr[g[r] + 1] - p0), g[j]);
-      if (pos >= 0) atomicAdd(&val[p0 + pos], weight * entry);
-    }
+  double uj = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) if (k == j) uj = u[k];
+  const double delta = analytic ? 1.0 : 1e-8 * (1.0 + fabs(uj));
+#pragma unroll
+  for (int k = 0; k < 6; ++k) if (k == j) u[k] = analytic ? 1.0 : uj + delta;
+  double up[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  um_alpha_coupling(cp, F, u, u + 3, 1.0, up, up + 3);
+  int32_t gj = g[0];
+#pragma unroll
+  for (int k = 1; k < 6; ++k) if (k == j) gj = g[k];
+  for (int r = 0; r < 6; ++r) {
+    const double entry = analytic ? up[r] : (up[r] - down[r]) / delta;
+    const int64_t p0 = rowptr[g[r]];
+    const int pos = um_find(colidx + p0, (int)(rowptr[g[r] + 1] - p0), gj);
+    if (pos >= 0) atomicAdd(&val[p0 + pos], weight * entry);
   }
 }
 
@@ -724,7 +986,7 @@ void um_free(Ctx* c)
   UMesh* u = c->um;
   ufe_free(c);
   um_dfree(u->d_xy); um_dfree(u->d_conn); um_dfree(u->d_nbr); um_dfree(u->d_v2c_ptr); um_dfree(u->d_v2c); um_dfree(u->d_bface);
-  um_dfree(u->d_cell_edge); um_dfree(u->d_group);
+  um_dfree(u->d_cell_edge); um_dfree(u->d_group); um_dfree(u->d_cell_order);
   delete u; c->um = nullptr;
 }
 
@@ -793,6 +1055,21 @@ void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* 
   if (!bface.empty()) MDB_CUDA(cudaMemcpyAsync(u->d_bface, bface.data(), bface.size() * 4, cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   c->h2d_bytes += 2 * nv * 8 + 3 * ne * 12 + (nv + 1) * 4;
+  // processing order of the cell-wise kernels: Morton order of the centroids (the numbering itself is the caller's and stays)
+  {
+    double lo[2] = {xy[0], xy[1]}, hi[2] = {xy[0], xy[1]};
+    for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 2; ++d) { lo[d] = std::min(lo[d], xy[2 * v + d]); hi[d] = std::max(hi[d], xy[2 * v + d]); }
+    uint32_t* d_code = dalloc<uint32_t>(ne); uint32_t* d_code2 = dalloc<uint32_t>(ne); int32_t* d_cell = dalloc<int32_t>(ne);
+    u->d_cell_order = dalloc<int32_t>(ne);
+    UMDev m = um_dev(c);
+    MDB_LAUNCH(c, k_um_morton, cdiv(ne, 256), 256, 0, m, lo[0], lo[1], 65535.0 / std::max(hi[0] - lo[0], 1e-300), 65535.0 / std::max(hi[1] - lo[1], 1e-300), d_code, d_cell);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, d_code, d_code2, d_cell, u->d_cell_order, (int)ne, 0, 32, c->stream);
+    void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+    MDB_CUDA(cub::DeviceRadixSort::SortPairs(d_t, tb, d_code, d_code2, d_cell, u->d_cell_order, (int)ne, 0, 32, c->stream)); c->launches++;
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_t); cudaFree(d_code); cudaFree(d_code2); cudaFree(d_cell);
+  }
 }
 
 void um_build_dofmap(Ctx* c)
@@ -818,6 +1095,22 @@ void um_build_dofmap(Ctx* c)
   MDB_CUDA(cudaMemsetAsync(c->d_constrained, 0, c->ndof, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_flag); cudaFree(d_scan);
+  // cell lists of the subproblems (cell-wise kernels)
+  {
+    const UMSpace S = um_space(c);
+    int32_t* d_f = dalloc<int32_t>(m.ne); int32_t* d_s = dalloc<int32_t>(m.ne);
+    for (size_t si = 0; si < c->sps.size(); ++si) {
+      SubProblemDesc& d = c->sps[si];
+      const UMOps O = um_ops(c, std::vector<int>(1, (int)si), std::vector<int>());
+      um_dfree(d.d_um_vtx); um_dfree(d.d_um_dof);
+      MDB_LAUNCH(c, k_um_list_flags, cdiv(m.ne, 256), 256, 0, m, O.sp[0], c->um->d_cell_order, d_f);
+      d.um_ncells = um_scan(c, d_f, d_s, m.ne);
+      d.d_um_vtx = dalloc<int32_t>(3 * d.um_ncells); d.d_um_dof = dalloc<int32_t>(3 * d.um_ncells);
+      if (d.um_ncells > 0) MDB_LAUNCH(c, k_um_list_fill, cdiv(m.ne, 256), 256, 0, m, S, O.sp[0], c->um->d_cell_order, d_f, d_s, d.um_ncells, d.d_um_vtx, d.d_um_dof);
+    }
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_f); cudaFree(d_s);
+  }
 }
 
 // parity export: the MultiDomainLocalFunctionSpace of every cell, children concatenated (multidomainlocalfunctionspace.hh:348-358)
@@ -943,7 +1236,91 @@ void um_build_pattern(Ctx* c, Matrix& M)
     M.slot_tables[std::make_pair(k, -1)] = d_slot;            // freed with the matrix
     MDB_LAUNCH(c, k_um_pattern_fill, cdiv(S.size[k], 128), 128, 0, m, S, O, k, M.d_rowptr, M.d_colidx, M.d_diag, d_slot);
   }
+  // precomputed CSR slots of the cell-wise Jacobian kernel: 9 absolute positions per (subproblem, cell)
+  if (nnz < ((int64_t)1 << 31))
+    for (int s_id : sps) {
+      const SubProblemDesc& d = c->sps[s_id];
+      int32_t* d_slots = dalloc<int32_t>(9 * d.um_ncells);
+      M.slot_tables[std::make_pair(s_id, -2)] = reinterpret_cast<uint8_t*>(d_slots);
+      if (d.um_ncells > 0) MDB_LAUNCH(c, k_um_list_slots, cdiv(d.um_ncells, 128), 128, 0, d.um_ncells, d.d_um_dof, M.d_rowptr, M.d_colidx, d_slots);
+    }
   MDB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void um_pair_plan_free(void* p)
+{
+  UMPairPlan* P = (UMPairPlan*)p;
+  if (!P) return;
+  if (P->rec) cudaFree(P->rec);
+  if (P->wptr) cudaFree(P->wptr);
+  delete P;
+}
+__global__ void k_um_times32(int64_t n, const int32_t* in, int64_t* out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 32 * (int64_t)in[i];
+}
+__global__ void k_um_close_scan(int64_t n, const int64_t* sizes, int64_t* scan)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) scan[n] = scan[n - 1] + sizes[n - 1];
+}
+static UMPairPlan* um_pair_plan(Ctx* c, const GridOp& go, Matrix& M)
+{
+  std::vector<int> key(go.sps);
+  auto it = M.um_pair_plans.find(key);
+  if (it != M.um_pair_plans.end()) return (UMPairPlan*)it->second;
+  const UMDev m = um_dev(c);
+  const UMSpace S = um_space(c);
+  const UMOps O = um_ops(c, go.sps, std::vector<int>());
+  if (O.nsp > 7 || M.max_row > 255) { M.um_pair_plans[key] = nullptr; return nullptr; }
+  // every child of the operator needs its slot table (written by k_um_pattern_fill)
+  std::vector<const uint8_t*> h_slot(MDB_MAX_CHILDREN, nullptr);
+  for (int k = 0; k < S.nchild; ++k) { auto st = M.slot_tables.find(std::make_pair(k, -1)); if (st != M.slot_tables.end()) h_slot[k] = st->second; }
+  for (int s = 0; s < O.nsp; ++s) if (!h_slot[O.sp[s].child]) { M.um_pair_plans[key] = nullptr; return nullptr; }
+  const int64_t n = c->ndof, nw = (n + 31) / 32;
+  UMPairPlan* P = new UMPairPlan(); P->nrows = n; P->nwarps = nw;
+  int32_t* d_child = dalloc<int32_t>(n); int32_t* d_count = dalloc<int32_t>(n); int32_t* d_wmax = dalloc<int32_t>(nw);
+  int64_t* d_size = dalloc<int64_t>(nw);
+  const uint8_t** d_slot = nullptr; MDB_CUDA(cudaMalloc(&d_slot, MDB_MAX_CHILDREN * sizeof(uint8_t*)));
+  MDB_CUDA(cudaMemcpyAsync(d_slot, h_slot.data(), MDB_MAX_CHILDREN * sizeof(uint8_t*), cudaMemcpyHostToDevice, c->stream));
+  MDB_LAUNCH(c, k_um_row_child, cdiv(n, 256), 256, 0, S, n, d_child);
+  MDB_LAUNCH(c, k_um_pair_count, cdiv(n, 256), 256, 0, m, S, O, n, d_child, d_count);
+  MDB_LAUNCH(c, k_um_pair_warpmax, cdiv(nw * 32, 256), 256, 0, n, d_count, d_wmax);
+  MDB_LAUNCH(c, k_um_times32, cdiv(nw, 256), 256, 0, nw, d_wmax, d_size);
+  P->wptr = dalloc<int64_t>(nw + 1);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, d_size, P->wptr, (int)nw, c->stream);
+  void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+  MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_size, P->wptr, (int)nw, c->stream)); c->launches++;
+  MDB_LAUNCH(c, k_um_close_scan, 1, 32, 0, nw, d_size, P->wptr);
+  int64_t nrec = 0;
+  MDB_CUDA(cudaMemcpyAsync(&nrec, P->wptr + nw, 8, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  P->rec = dalloc<int4>(nrec);
+  MDB_LAUNCH(c, k_um_pair_fill, cdiv(nw * 32, 256), 256, 0, m, S, O, n, d_child, d_slot, P->wptr, P->rec);
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_t); cudaFree(d_child); cudaFree(d_count); cudaFree(d_wmax); cudaFree(d_size); cudaFree(d_slot);
+  M.um_pair_plans[key] = P;
+  return P;
+}
+
+static bool um_lists(Ctx* c, const GridOp& go, const Matrix* M, UMLists& L)
+{
+  if (go.sps.empty() || go.sps.size() > 8) return false;
+  const UMOps O = um_ops(c, go.sps, std::vector<int>());
+  L.nlist = (int)go.sps.size(); L.start[0] = 0;
+  for (int i = 0; i < L.nlist; ++i) {
+    const SubProblemDesc& d = c->sps[go.sps[i]];
+    if (!d.d_um_vtx) return false;
+    L.sp[i] = O.sp[i]; L.vtx[i] = d.d_um_vtx; L.dof[i] = d.d_um_dof; L.slot[i] = nullptr;
+    L.start[i + 1] = L.start[i] + d.um_ncells;
+    if (M) {
+      auto it = M->slot_tables.find(std::make_pair(go.sps[i], -2));
+      if (it == M->slot_tables.end()) return false;
+      L.slot[i] = reinterpret_cast<const int32_t*>(it->second);
+    }
+  }
+  return true;
 }
 
 void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r)
@@ -951,20 +1328,39 @@ void um_residual(Ctx* c, const GridOp& go, double weight, const double* d_x, dou
   const UMDev m = um_dev(c);
   const UMSpace S = um_space(c);
   const UMOps O = um_ops(c, go.sps, go.cps);
-  c->phase_begin("residual_volume");
   static const bool by_rows = getenv("MDB_UM_RES_ROWS") != nullptr;       // A/B switch: the owner-computes row kernel (fixed summation order)
-  if (by_rows) {
+  static const bool by_cells = getenv("MDB_UM_RES_CELLS") != nullptr;     // A/B switch: the cell kernel that walks the mesh arrays (no lists)
+  static const bool serial = getenv("MDB_UM_RES_SERIAL") != nullptr;      // A/B switch: boundary and coupling faces after the cells
+  auto faces = [&]() {
+    c->phase_begin("residual_boundary");
+    if (c->um->nbface > 0) MDB_LAUNCH(c, k_um_boundary, cdiv(c->um->nbface, 128), 128, 0, m, S, O, c->um->d_bface, c->um->nbface, weight, c->time, d_r);
+    c->phase_end();
+    c->phase_begin("residual_coupling");
+    for (int q = 0; q < O.ncp; ++q)
+      if (go.faces[q].n > 0)
+        MDB_LAUNCH(c, k_um_coupling_residual, cdiv(go.faces[q].n, 128), 128, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x, d_r);
+    c->phase_end();
+  };
+  // every update of r is a reduction: the boundary and coupling faces run beside the cells on the auxiliary stream
+  const bool fork = !serial && !by_rows;
+  if (fork) {
+    MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    StreamScope aux(c, c->aux_stream);
+    MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+    faces();
+    MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+  }
+  c->phase_begin("residual_volume");
+  UMLists L;
+  if (!by_rows && !by_cells && um_lists(c, go, nullptr, L)) {
+    if (L.start[L.nlist] > 0) MDB_LAUNCH(c, k_um_residual_lists, cdiv(L.start[L.nlist], 256), 256, 0, m, L, weight, c->time, d_x, d_r);
+  } else if (by_rows) {
     for (int k = 0; k < S.nchild; ++k)
       if (S.size[k] > 0) MDB_LAUNCH(c, k_um_residual_rows, cdiv(S.size[k], 128), 128, 0, m, S, O, k, weight, c->time, d_x, d_r);
   } else if (O.nsp > 0) MDB_LAUNCH(c, k_um_residual_cells, cdiv(m.ne, 128), 128, 0, m, S, O, weight, c->time, d_x, d_r);
   c->phase_end();
-  c->phase_begin("residual_boundary");
-  if (c->um->nbface > 0) MDB_LAUNCH(c, k_um_boundary, cdiv(c->um->nbface, 128), 128, 0, m, S, O, c->um->d_bface, c->um->nbface, weight, c->time, d_r);
-  c->phase_end();
-  c->phase_begin("residual_coupling");
-  for (int q = 0; q < O.ncp; ++q)
-    if (go.faces[q].n > 0)
-      MDB_LAUNCH(c, k_um_coupling_residual, cdiv(go.faces[q].n, 128), 128, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x, d_r);
+  if (fork) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); else faces();
+  c->phase_begin("residual_constrain");
   constrain_residual(c, d_r);
   c->phase_end();
 }
@@ -976,7 +1372,34 @@ void um_jacobian(Ctx* c, const GridOp& go, Matrix& M, double weight, const doubl
   const UMOps O = um_ops(c, go.sps, go.cps);
   c->phase_begin("jacobian_rows");
   static const bool simple = getenv("MDB_UM_JAC_SIMPLE") != nullptr;      // A/B switch: the unstaged row kernel
-  for (int k = 0; k < S.nchild; ++k) {
+  static const bool staged = getenv("MDB_UM_JAC_STAGED") != nullptr;      // A/B switch: the owner-computes staged row kernel (fixed summation order)
+  static const bool cells = getenv("MDB_UM_JAC_CELLS") != nullptr;        // A/B switch: cell-wise kernel with reductions into precomputed slots
+  UMLists L;
+  UMPairPlan* plan = (!simple && !staged && !cells && O.nsp > 0) ? um_pair_plan(c, go, M) : nullptr;
+  const bool cellwise = !plan && !simple && !staged && um_lists(c, go, &M, L);
+  if (plan) {
+    const UMOps Ov = um_ops(c, go.sps, std::vector<int>());
+    MDB_LAUNCH(c, k_um_jacobian_pairs, cdiv(c->ndof, UM_PROWS), UM_PROWS, 0, m, Ov, c->ndof, plan->rec, plan->wptr, weight, overwrite ? 1 : 0, M.d_rowptr, M.d_val);
+  }
+  static const bool serial = getenv("MDB_UM_JAC_SERIAL") != nullptr;      // A/B switch: coupling kernel after the volume kernel
+  bool forked = false;
+  if (cellwise) {
+    if (overwrite) MDB_CUDA(cudaMemsetAsync(M.d_val, 0, M.nnz * sizeof(double), c->stream));
+    if (!serial && O.ncp > 0) {
+      // every update of the values is a reduction: the coupling faces run beside the cells on the auxiliary stream
+      MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      StreamScope aux(c, c->aux_stream);
+      MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+      for (int q = 0; q < O.ncp; ++q)
+        if (go.faces[q].n > 0)
+          MDB_LAUNCH(c, k_um_coupling_jacobian, cdiv(6 * go.faces[q].n, 64), 64, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x,
+                     M.d_rowptr, M.d_colidx, M.d_val);
+      MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+      forked = true;
+    }
+    if (L.start[L.nlist] > 0) MDB_LAUNCH(c, k_um_jacobian_cells, cdiv(L.start[L.nlist], 256), 256, 0, m, L, weight, M.d_val);
+  }
+  for (int k = 0; k < S.nchild && !cellwise && !plan; ++k) {
     if (S.size[k] == 0) continue;
     auto it = M.slot_tables.find(std::make_pair(k, -1));
     if (simple || it == M.slot_tables.end())
@@ -985,10 +1408,11 @@ void um_jacobian(Ctx* c, const GridOp& go, Matrix& M, double weight, const doubl
       MDB_LAUNCH(c, k_um_jacobian_staged, cdiv(S.size[k], UM_JROWS), UM_JROWS, 0, m, S, O, k, weight, overwrite ? 1 : 0, M.d_rowptr, it->second, M.d_val);
   }
   c->phase_end();
+  if (forked) MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   c->phase_begin("jacobian_coupling");
-  for (int q = 0; q < O.ncp; ++q)
+  for (int q = 0; q < O.ncp && !forked; ++q)
     if (go.faces[q].n > 0)
-      MDB_LAUNCH(c, k_um_coupling_jacobian, cdiv(go.faces[q].n, 64), 64, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x,
+      MDB_LAUNCH(c, k_um_coupling_jacobian, cdiv(6 * go.faces[q].n, 64), 64, 0, m, S, O.cp[q], go.faces[q].d_cell, go.faces[q].d_face, go.faces[q].n, weight, d_x,
                  M.d_rowptr, M.d_colidx, M.d_val);
   c->phase_end();
   c->phase_begin("jacobian_dirichlet");
