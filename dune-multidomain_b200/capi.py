@@ -461,6 +461,23 @@ class Mdb(Lib):
         self._check(self._fn("halo_import")(C.c_void_p(self.ctx), lower_rank, C.c_char_p(lower_blob) if lower_blob else None,
                                             upper_rank, C.c_char_p(upper_blob) if upper_blob else None), "halo_import")
 
+    def partition_lists(self, owned, neigh, send_ptr, send_idx, recv_ptr, recv_idx):
+        """mdb_partition_lists: ownership flags and per-neighbour send / receive index lists of an unstructured partition."""
+        o = np.ascontiguousarray(owned, dtype=np.uint8)
+        nb = np.ascontiguousarray(neigh, dtype=np.int32)
+        sp, rp = _i64(send_ptr), _i64(recv_ptr)
+        si, ri = np.ascontiguousarray(send_idx, dtype=np.int32), np.ascontiguousarray(recv_idx, dtype=np.int32)
+        assert o.size == self.ndof and sp.size == nb.size + 1 and rp.size == nb.size + 1
+        self._check(self._fn("partition_lists")(C.c_void_p(self.ctx), _ptr(o, C.c_uint8), int(nb.size), _ptr(nb, C.c_int), _ptr(sp, C.c_int64),
+                                                _ptr(si, C.c_int32), _ptr(rp, C.c_int64), _ptr(ri, C.c_int32)), "partition_lists")
+
+    def halo_import_lists(self, blobs, caps, offsets, slots):
+        buf = (C.c_char * (80 * max(len(blobs), 1)))()
+        for i, b in enumerate(blobs):
+            buf[80 * i:80 * (i + 1)] = bytes(b)
+        cp, of, sl = _i64(caps), _i64(offsets), np.ascontiguousarray(slots, dtype=np.int32)
+        self._check(self._fn("halo_import_lists")(C.c_void_p(self.ctx), buf, _ptr(cp, C.c_int64), _ptr(of, C.c_int64), _ptr(sl, C.c_int)), "halo_import_lists")
+
     def halo_push(self, x):
         self._check(self._fn("halo_push")(C.c_void_p(self.ctx), _vecptr(x)), "halo_push")
 

@@ -164,6 +164,7 @@ static void reset_spaces(Ctx* c)
   for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear(); c->peer_lower = nullptr; c->peer_upper = nullptr;
   if (c->d_halo_recv) { cudaFree(c->d_halo_recv); c->d_halo_recv = nullptr; }
+  halo_lists_free(c);
   c->finalized = false; c->ndof = 0; c->ncon = 0;
 }
 
@@ -913,7 +914,11 @@ int mdb_spmv(mdb_ctx* c, int mat, const double* x, double* y)
   VecIn vx(c, x, c->ndof, 0);
   VecInOut vy(c, y, c->ndof, 1, false);
   c->phase_begin("spmv");
-  if (c->peer_lower || c->peer_upper) {
+  if (c->halo_lists && c->nranks > 1) {
+    MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_spmv: x must be a device vector on a partitioned context");
+    halo_exchange(c, const_cast<double*>(vx.d));
+    spmv(c, M, vx.d, vy.d);
+  } else if (c->peer_lower || c->peer_upper) {
     MDB_REQUIRE(is_device_ptr(x), MDB_EINVAL, "mdb_spmv: x must be a device vector on a partitioned context");
     spmv_partitioned(c, M, const_cast<double*>(vx.d), vy.d);      // push -> interior rows -> wait -> boundary rows
   } else spmv(c, M, vx.d, vy.d);

@@ -357,6 +357,7 @@ struct Ctx {
   double* peer_lower = nullptr; double* peer_upper = nullptr;   // mapped windows of the neighbours
   std::vector<void*> ipc_opened;
   int lower_rank = -1, upper_rank = -1;
+  void* halo_lists = nullptr;        // multigpu.cu: index-list halo of an unstructured partition (mdb_partition_lists)
   double halo_timeout_s = 0.0;       // bound of the halo wait (mdb_set_halo_timeout; 0: MDB_HALO_TIMEOUT_S or 30 s)
 
   void* scratch(size_t bytes);
@@ -434,6 +435,7 @@ void halo_exchange(Ctx* c, double* d_x, double* d_done = nullptr);   // d_done: 
 void halo_push(Ctx* c, const double* d_x);
 void halo_wait(Ctx* c, double* d_x, double* d_done = nullptr);
 void nccl_comm_release(Ctx* c);
+void halo_lists_free(Ctx* c);
 bool halo_timed_out(Ctx* c);
 // unstructured.cu: the same steps on an unstructured triangle mesh with P1 spaces
 void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn);

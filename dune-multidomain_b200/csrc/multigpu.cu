@@ -239,6 +239,88 @@ __global__ void __launch_bounds__(256) k_halo_unpack(HaloSpec H, double* __restr
   }
 }
 
+
+// ---- halo exchange over index lists (unstructured partitions) ------------------------------------------------------------------------
+// A recursive-bisection partition of a gmsh mesh has no planes: every rank owns an arbitrary subset of its local DOFs and
+// has up to MDB_MAX_NEIGH neighbours.  mdb_partition_lists declares, per neighbour, which owned entries are sent and which ghost entries
+// are received (same order on both sides); the window of a rank is the concatenation of its receive blocks, double-buffered by the
+// parity of the exchange number, followed by one sequence number per neighbour.  Same protocol as the plane exchange above: peer
+// stores, one release-store of the sequence number per neighbour by the last block, acquire-spin + unpack on the receiver.
+#define MDB_MAX_NEIGH 16
+struct HaloListsHost {
+  int nn = 0;
+  int ranks[MDB_MAX_NEIGH];
+  int64_t send_ptr[MDB_MAX_NEIGH + 1], recv_ptr[MDB_MAX_NEIGH + 1];
+  int32_t* d_send_idx = nullptr; int32_t* d_recv_idx = nullptr;
+  double* peer[MDB_MAX_NEIGH]; int64_t peer_cap[MDB_MAX_NEIGH], peer_off[MDB_MAX_NEIGH]; int peer_slot[MDB_MAX_NEIGH];
+  bool imported = false;
+};
+struct HaloL {
+  int nn; int64_t send_ptr[MDB_MAX_NEIGH + 1], recv_ptr[MDB_MAX_NEIGH + 1];
+  double* peer[MDB_MAX_NEIGH]; int64_t peer_cap[MDB_MAX_NEIGH], peer_off[MDB_MAX_NEIGH]; int peer_slot[MDB_MAX_NEIGH];
+  const int32_t* send_idx; const int32_t* recv_idx; double* mine; int64_t cap; unsigned long long seq;
+};
+__global__ void __launch_bounds__(256) k_halo_push_lists(HaloL H, const double* __restrict__ x, unsigned int* counter)
+{
+  const int parity = (int)(H.seq & 1);
+  const int64_t total = H.send_ptr[H.nn];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int nb = 0;
+    while (i >= H.send_ptr[nb + 1]) ++nb;
+    H.peer[nb][(int64_t)parity * H.peer_cap[nb] + H.peer_off[nb] + (i - H.send_ptr[nb])] = x[H.send_idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int nb = 0; nb < H.nn; ++nb) st_release_sys(reinterpret_cast<unsigned long long*>(H.peer[nb] + 2 * H.peer_cap[nb]) + H.peer_slot[nb], H.seq);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_halo_unpack_lists(HaloL H, double* __restrict__ x, int* err, long long timeout_clocks, double* done)
+{
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(H.mine + 2 * H.cap);
+    const long long t0 = clock64();
+    bool good = true;
+    for (int nb = 0; nb < H.nn && good; ++nb)
+      while (ld_acquire_sys(flags + nb) < H.seq) {
+        if (clock64() - t0 > timeout_clocks) { good = false; break; }
+        __nanosleep(100);
+      }
+    ok = good ? 1 : 0;
+    if (!good) { atomicExch(err, 1); if (done) *done = 1.0; }
+  }
+  __syncthreads();
+  if (!ok) return;
+  const double* src = H.mine + (int64_t)(H.seq & 1) * H.cap;
+  const int64_t total = H.recv_ptr[H.nn];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) x[H.recv_idx[i]] = src[i];
+}
+static HaloL halo_lists_spec(Ctx* c)
+{
+  const HaloListsHost* L = (const HaloListsHost*)c->halo_lists;
+  HaloL H; H.nn = L->nn;
+  for (int i = 0; i <= L->nn; ++i) { H.send_ptr[i] = L->send_ptr[i]; H.recv_ptr[i] = L->recv_ptr[i]; }
+  for (int i = 0; i < L->nn; ++i) { H.peer[i] = L->peer[i]; H.peer_cap[i] = L->peer_cap[i]; H.peer_off[i] = L->peer_off[i]; H.peer_slot[i] = L->peer_slot[i]; }
+  H.send_idx = L->d_send_idx; H.recv_idx = L->d_recv_idx; H.mine = c->d_halo_recv; H.cap = c->halo_cap; H.seq = c->halo_seq;
+  return H;
+}
+void halo_lists_free(Ctx* c)
+{
+  HaloListsHost* L = (HaloListsHost*)c->halo_lists;
+  if (!L) return;
+  if (L->d_send_idx) cudaFree(L->d_send_idx);
+  if (L->d_recv_idx) cudaFree(L->d_recv_idx);
+  delete L; c->halo_lists = nullptr;
+}
+
+static long long halo_timeout_clocks(const Ctx* c);
+
 static HaloSpec halo_spec(Ctx* c)
 {
   const MeshDesc& m = c->mesh;
@@ -262,6 +344,15 @@ void halo_push(Ctx* c, const double* d_x)
 {
   MDB_REQUIRE(c->d_halo_recv, MDB_ESTATE, "halo exchange on an unpartitioned context");
   c->halo_seq++;
+  if (c->halo_lists) {
+    const HaloListsHost* L = (const HaloListsHost*)c->halo_lists;
+    if (L->nn == 0) return;
+    MDB_REQUIRE(L->imported, MDB_ESTATE, "halo exchange before mdb_halo_import_lists");
+    const HaloL H = halo_lists_spec(c);
+    int grid = cdiv(H.send_ptr[H.nn], 256); if (grid > 148) grid = 148; if (grid < 1) grid = 1;
+    MDB_LAUNCH(c, k_halo_push_lists, grid, 256, 0, H, d_x, c->d_halo_counter);
+    return;
+  }
   if (!c->peer_lower && !c->peer_upper) return;
   HaloSpec H = halo_spec(c);
   int64_t work = 0;
@@ -281,6 +372,14 @@ static long long halo_timeout_clocks(const Ctx* c)
 void halo_wait(Ctx* c, double* d_x, double* d_done)
 {
   MDB_REQUIRE(c->d_halo_recv, MDB_ESTATE, "halo exchange on an unpartitioned context");
+  if (c->halo_lists) {
+    const HaloListsHost* L = (const HaloListsHost*)c->halo_lists;
+    if (L->nn == 0) return;
+    const HaloL Hl = halo_lists_spec(c);
+    int gridl = cdiv(Hl.recv_ptr[Hl.nn], 256); if (gridl > 64) gridl = 64; if (gridl < 1) gridl = 1;
+    MDB_LAUNCH(c, k_halo_unpack_lists, gridl, 256, 0, Hl, d_x, (int*)(c->d_halo_counter + 2), halo_timeout_clocks(c), d_done);
+    return;
+  }
   if (!c->peer_lower && !c->peer_upper) return;
   HaloSpec H = halo_spec(c);
   int64_t work = 0;
@@ -397,6 +496,66 @@ int mdb_halo_import(mdb_ctx* c, int lower_rank, const void* lower_blob80, int up
   c->lower_rank = lower_blob80 ? lower_rank : -1; c->upper_rank = upper_blob80 ? upper_rank : -1;
   c->peer_lower = lower_blob80 ? open_peer(c, lower_blob80) : nullptr;
   c->peer_upper = upper_blob80 ? open_peer(c, upper_blob80) : nullptr;
+  MG_END(c)
+}
+
+
+int mdb_partition_lists(mdb_ctx* c, const uint8_t* owned_flags, int nneigh, const int* neigh_ranks, const int64_t* send_ptr, const int32_t* send_idx,
+                        const int64_t* recv_ptr, const int32_t* recv_idx)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(c->finalized && !c->mesh.partitioned, MDB_ESTATE, "mdb_partition_lists: after mdb_finalize, on a mesh without a slab partition");
+  MDB_REQUIRE(owned_flags && nneigh >= 0 && nneigh <= MDB_MAX_NEIGH, MDB_EINVAL, "mdb_partition_lists: 0..16 neighbours");
+  MDB_REQUIRE(nneigh == 0 || (neigh_ranks && send_ptr && recv_ptr), MDB_EINVAL, "mdb_partition_lists: null list");
+  halo_lists_free(c);
+  HaloListsHost* L = new HaloListsHost(); c->halo_lists = L;
+  L->nn = nneigh; L->send_ptr[0] = L->recv_ptr[0] = 0;
+  for (int i = 0; i < nneigh; ++i) {
+    L->ranks[i] = neigh_ranks[i]; L->send_ptr[i + 1] = send_ptr[i + 1]; L->recv_ptr[i + 1] = recv_ptr[i + 1];
+    MDB_REQUIRE(send_ptr[i + 1] >= send_ptr[i] && recv_ptr[i + 1] >= recv_ptr[i] && send_ptr[0] == 0 && recv_ptr[0] == 0, MDB_EINVAL, "mdb_partition_lists: bad list pointers");
+    L->peer[i] = nullptr; L->peer_cap[i] = 0; L->peer_off[i] = 0; L->peer_slot[i] = 0;
+  }
+  const int64_t ns = L->send_ptr[nneigh], nr = L->recv_ptr[nneigh];
+  for (int64_t i = 0; i < ns; ++i) MDB_REQUIRE(send_idx[i] >= 0 && send_idx[i] < c->ndof && owned_flags[send_idx[i]], MDB_EINVAL, "mdb_partition_lists: a sent entry is not an owned DOF");
+  for (int64_t i = 0; i < nr; ++i) MDB_REQUIRE(recv_idx[i] >= 0 && recv_idx[i] < c->ndof && !owned_flags[recv_idx[i]], MDB_EINVAL, "mdb_partition_lists: a received entry is not a ghost DOF");
+  L->d_send_idx = dalloc<int32_t>(ns); L->d_recv_idx = dalloc<int32_t>(nr);
+  if (ns) MDB_CUDA(cudaMemcpyAsync(L->d_send_idx, send_idx, ns * 4, cudaMemcpyHostToDevice, c->stream));
+  if (nr) MDB_CUDA(cudaMemcpyAsync(L->d_recv_idx, recv_idx, nr * 4, cudaMemcpyHostToDevice, c->stream));
+  dfree(c->d_owned);
+  c->d_owned = dalloc<uint8_t>(c->ndof);
+  MDB_CUDA(cudaMemcpyAsync(c->d_owned, owned_flags, c->ndof, cudaMemcpyHostToDevice, c->stream));
+  c->child_owned.assign(c->children.size(), 0); c->owned_rows = 0;
+  for (size_t k = 0; k < c->children.size(); ++k) {
+    int64_t n = 0;
+    for (int64_t g = c->children[k].offset; g < c->children[k].offset + c->children[k].size; ++g) n += owned_flags[g] ? 1 : 0;
+    c->child_owned[k] = n; c->owned_rows += n;
+  }
+  // receive window: [parity 2][cap] doubles, then MDB_MAX_NEIGH sequence numbers
+  c->halo_cap = nr > 0 ? nr : 1;
+  if (c->d_halo_recv) { cudaFree(c->d_halo_recv); c->d_halo_recv = nullptr; }
+  c->halo_recv_n = 2 * c->halo_cap + MDB_MAX_NEIGH;
+  c->d_halo_recv = dalloc<double>(c->halo_recv_n);
+  MDB_CUDA(cudaMemsetAsync(c->d_halo_recv, 0, c->halo_recv_n * sizeof(double), c->stream));
+  if (!c->d_halo_counter) c->d_halo_counter = dalloc<unsigned int>(4);
+  MDB_CUDA(cudaMemsetAsync(c->d_halo_counter, 0, 4 * sizeof(unsigned int), c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  c->halo_seq = 0;
+  for (Matrix& M : c->mats) { M.dinv_valid = false; M.ilu_valid = false; }
+  MG_END(c)
+}
+
+int mdb_halo_import_lists(mdb_ctx* c, const void* blobs80, const int64_t* peer_cap, const int64_t* peer_offset, const int* peer_slot)
+{
+  MG_BEGIN(c)
+  HaloListsHost* L = (HaloListsHost*)c->halo_lists;
+  MDB_REQUIRE(L, MDB_ESTATE, "mdb_halo_import_lists: call mdb_partition_lists first");
+  for (int i = 0; i < L->nn; ++i) {
+    MDB_REQUIRE(peer_cap[i] >= 1 && peer_offset[i] >= 0 && peer_offset[i] + (L->send_ptr[i + 1] - L->send_ptr[i]) <= peer_cap[i] && peer_slot[i] >= 0 && peer_slot[i] < MDB_MAX_NEIGH,
+                MDB_EINVAL, "mdb_halo_import_lists: my block does not fit the neighbour's window");
+    L->peer[i] = open_peer(c, (const char*)blobs80 + 80 * (size_t)i);
+    L->peer_cap[i] = peer_cap[i]; L->peer_off[i] = peer_offset[i]; L->peer_slot[i] = peer_slot[i];
+  }
+  L->imported = true;
   MG_END(c)
 }
 

@@ -85,7 +85,7 @@ def connect(dev, dist, rank, nranks):
 
 
 # ---- unstructured meshes ("gmsh meshes -> recursive coordinate bisection of cell centroids, rows owned by the lowest
-# rank touching the DOF").  Host-side partition design only; the device path of unstructured meshes is single-GPU in this build.
+# rank touching the DOF").  The partition itself is host-side (every rank evaluates it identically); the data path is mdb_partition_lists.
 # The design mirrors the slab partition: every rank also holds the ghost cells it needs so that the rows it owns are assembled
 # completely without matrix communication (tests/test_multirank_gloo.py checks exactly that with the CPU oracle over gloo). ----------
 def um_partition(xy, conn, nranks):
@@ -118,14 +118,93 @@ def um_local_mesh(conn, vertex_owner, rank):
     Returns (cells [global cell ids, ascending], verts [global vertex ids, ascending], local_conn)."""
     ne = conn.shape[0]
     touch = (vertex_owner[conn] == rank).any(axis=1)
-    edges = {}
-    for e in range(ne):
-        for a, b in ((0, 1), (0, 2), (1, 2)):
-            edges.setdefault((min(conn[e, a], conn[e, b]), max(conn[e, a], conn[e, b])), []).append(e)
+    # face neighbours through sorted edge keys (vectorised: the bench partitions meshes of millions of cells)
+    a = np.concatenate([conn[:, 0], conn[:, 0], conn[:, 1]]).astype(np.int64)
+    b = np.concatenate([conn[:, 1], conn[:, 2], conn[:, 2]]).astype(np.int64)
+    key = np.minimum(a, b) * (int(conn.max()) + 1) + np.maximum(a, b)
+    cell = np.tile(np.arange(ne, dtype=np.int64), 3)
+    order = np.argsort(key, kind="stable")
+    ks, cs = key[order], cell[order]
+    same = ks[1:] == ks[:-1]                                   # interior faces: two consecutive equal keys
+    c0, c1 = cs[:-1][same], cs[1:][same]
     keep = touch.copy()
-    for cells in edges.values():
-        if len(cells) == 2 and (touch[cells[0]] or touch[cells[1]]):
-            keep[cells[0]] = keep[cells[1]] = True
+    hit = touch[c0] | touch[c1]
+    keep[c0[hit]] = True
+    keep[c1[hit]] = True
     cells = np.nonzero(keep)[0]
     verts = np.unique(conn[cells])
     return cells, verts, np.searchsorted(verts, conn[cells])
+
+
+def um_p1_numbering(nv, conn, sd, child_subdomains):
+    """Container indices of P1 child spaces on a triangle mesh ([UPSTREAM (ii),(iii)]: rank of the vertex among the vertices of the
+    child's subdomain, child blocks concatenated).  Returns (v2d [nchildren][nv] with -1 for absent, offsets [nchildren + 1])."""
+    v2d, offsets = [], [0]
+    for s in child_subdomains:
+        flag = np.zeros(nv, dtype=bool)
+        cells = np.ones(conn.shape[0], dtype=bool) if s < 0 else ((sd >> s) & 1).astype(bool)
+        flag[conn[cells].ravel()] = True
+        m = -np.ones(nv, dtype=np.int64)
+        m[flag] = np.arange(int(flag.sum()))
+        v2d.append(m)
+        offsets.append(offsets[-1] + int(flag.sum()))
+    return v2d, np.array(offsets, dtype=np.int64)
+
+
+def um_rank_problem(xy, conn, sd, nranks, rank, child_subdomains):
+    """Everything rank `rank` needs of a P1 problem on the global triangle mesh (xy, conn, sd): its local mesh and, per local DOF, the
+    global container index, the ownership flag and the owner rank."""
+    cell_rank, vertex_owner = um_partition(xy, conn, nranks)
+    cells, verts, lconn = um_local_mesh(conn, vertex_owner, rank)
+    lsd = sd[cells]
+    gv2d, goff = um_p1_numbering(xy.shape[0], conn, sd, child_subdomains)
+    lv2d, loff = um_p1_numbering(verts.size, lconn, lsd, child_subdomains)
+    ndof = int(loff[-1])
+    gid = np.zeros(ndof, dtype=np.int64)
+    owner = np.zeros(ndof, dtype=np.int64)
+    for k in range(len(child_subdomains)):
+        lv = np.nonzero(lv2d[k] >= 0)[0]
+        gid[loff[k] + lv2d[k][lv]] = goff[k] + gv2d[k][verts[lv]]
+        owner[loff[k] + lv2d[k][lv]] = vertex_owner[verts[lv]]
+    return SimpleNamespace(cells=cells, verts=verts, conn=lconn, xy=np.ascontiguousarray(xy[verts]), sd=np.ascontiguousarray(lsd), ndof=ndof,
+                           global_dof=gid, owner=owner, owned=(owner == rank), global_ndof=int(goff[-1]), cell_rank=cell_rank)
+
+
+def um_connect(dev, dist, rank, nranks, global_dof, owner):
+    """Ownership + halo lists + NCCL communicator + halo windows of an unstructured partition (mdb_partition_lists,
+    mdb_halo_import_lists).  `global_dof` / `owner` per local DOF (um_rank_problem).  Call after dev.finalize()."""
+    owned = owner == rank
+    ghosts = np.nonzero(~owned)[0]
+    need = {}
+    for q in np.unique(owner[ghosts]):
+        idx = ghosts[owner[ghosts] == q]
+        need[int(q)] = idx[np.argsort(global_dof[idx], kind="stable")]              # receive order = ascending global index
+    wants = [None] * nranks
+    dist.all_gather_object(wants, {q: [int(g) for g in global_dof[idx]] for q, idx in need.items()})
+    sends = {q: wants[q][rank] for q in range(nranks) if q != rank and rank in wants[q]}
+    neigh = sorted(set(need) | set(sends))
+    order = np.argsort(global_dof, kind="stable")
+    gsorted = global_dof[order]
+    send_ptr, recv_ptr, send_idx, recv_idx = [0], [0], [], []
+    for q in neigh:
+        g = np.asarray(sends.get(q, []), dtype=np.int64)
+        loc = order[np.searchsorted(gsorted, g)] if g.size else np.zeros(0, dtype=np.int64)
+        assert np.array_equal(global_dof[loc], g) and owned[loc].all()
+        send_idx.append(loc); send_ptr.append(send_ptr[-1] + loc.size)
+        r = need.get(q, np.zeros(0, dtype=np.int64))
+        recv_idx.append(r); recv_ptr.append(recv_ptr[-1] + r.size)
+    send_idx = np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.int64)
+    recv_idx = np.concatenate(recv_idx) if recv_idx else np.zeros(0, dtype=np.int64)
+    dev.partition_lists(owned, neigh, send_ptr, send_idx, recv_ptr, recv_idx)
+    uid = [dev.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    dev.comm_init(nranks, rank, uid[0])
+    blob, _ = dev.halo_export()
+    info = [None] * nranks
+    dist.all_gather_object(info, dict(blob=blob, neigh=neigh, recv_ptr=[int(v) for v in recv_ptr]))
+    blobs, caps, offs, slots = [], [], [], []
+    for q in neigh:
+        slot = info[q]["neigh"].index(rank)
+        blobs.append(info[q]["blob"]); caps.append(max(info[q]["recv_ptr"][-1], 1)); offs.append(info[q]["recv_ptr"][slot]); slots.append(slot)
+    dev.halo_import_lists(blobs, caps, offs, slots)
+    return SimpleNamespace(neighbours=neigh, send_count=int(send_ptr[-1]), recv_count=int(recv_ptr[-1]), owned_rows=int(owned.sum()))

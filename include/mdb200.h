@@ -460,6 +460,18 @@ int mdb_halo_wait(mdb_ctx* ctx, double* x);
 /* Bound of the device-side wait for a neighbour's planes (default: environment MDB_HALO_TIMEOUT_S, else 30 s).  A timeout is
  * reported once by the call that hit it (MDB_ENCCL) — a running Krylov loop stops at once — and then cleared. */
 int mdb_set_halo_timeout(mdb_ctx* ctx, double seconds);
+/* Partition of an UNSTRUCTURED mesh (recursive coordinate bisection of the cell centroids, a DOF belongs to the lowest rank
+ * among the cells of its entity; the reference's analogue is the overlap-1 MPI grid of test/testoverlappinginstationarypoisson.cc:232-233).
+ * The context holds the local mesh of one rank: every cell around an owned vertex plus their face neighbours, in global order, so the
+ * owned rows are assembled completely without communication.  This call declares the ownership of the local DOFs and, per neighbour
+ * rank, the owned entries sent to it and the ghost entries received from it (both sides list them in the same order).  Call after
+ * mdb_finalize; then mdb_halo_export / exchange / mdb_halo_import_lists as for slabs.  Up to 16 neighbours. */
+int mdb_partition_lists(mdb_ctx* ctx, const uint8_t* owned_flags, int nneigh, const int* neigh_ranks, const int64_t* send_ptr, const int32_t* send_idx,
+                        const int64_t* recv_ptr, const int32_t* recv_idx);
+/* blobs80: the neighbours' 80-byte window descriptors in neighbour order; peer_cap[i] = doubles per parity of neighbour i's window (its
+ * total receive count, at least 1), peer_offset[i] = where this rank's block starts inside it (neighbour i's recv_ptr of this rank),
+ * peer_slot[i] = this rank's position in neighbour i's neighbour list. */
+int mdb_halo_import_lists(mdb_ctx* ctx, const void* blobs80, const int64_t* peer_cap, const int64_t* peer_offset, const int* peer_slot);
 /* Rows this rank owns / all local rows (ghost rows included). */
 int mdb_owned_rows(mdb_ctx* ctx, int64_t* owned, int64_t* local_total);
 /* Owned rows per child block (nchildren entries). */

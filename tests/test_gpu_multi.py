@@ -252,3 +252,100 @@ def test_multi_gpu_solve_matches_global_oracle(n):
         err = float(np.abs(dev_all / np.abs(dev_all).max() - ref_all / np.abs(ref_all).max()).max())
         ratios = [float(np.abs(a).max() / np.abs(b).max()) for a, b in zip(dev_dir, ref_dir)]
         assert err <= 1e-13, "%s: err %.3e, per-rank max ratios %s" % (name, err, ratios)
+
+
+# ---- unstructured partition (recursive coordinate bisection, index-list halos: mdb_partition_lists) ------------------------------
+def _um_global(nx, ny, seed, cvcf):
+    import um_problems as ump
+    xy, conn = ump.square_mesh(nx, ny, seed=seed)
+    sd = ump.halves(xy, conn)
+    og = ump.oracle()
+    Hg = ump.setup(og, xy, conn, sd, cvcf=cvcf, jac_mode=capi.JAC_ANALYTIC)
+    og.jacobian(Hg["go"], Hg["mat"], Hg["x0"], overwrite=True)
+    rg = og.residual(Hg["go"], Hg["x0"], np.zeros(Hg["ndof"]))
+    return xy, conn, sd, og, Hg, rg
+
+
+def _um_rank_main(rank, world, port, mesh, ret):
+    import torch
+    import torch.distributed as dist
+    import um_problems as ump
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny, seed, cvcf = mesh
+        xy, conn, sd, og, Hg, rg = _um_global(nx, ny, seed, cvcf)
+        R = parallel.um_rank_problem(xy, conn, sd, world, rank, [0, 1])
+        dev = pkg.Mdb(rank)
+        H = ump.setup(dev, R.xy, R.conn, R.sd, cvcf=cvcf, jac_mode=capi.JAC_ANALYTIC)
+        assert H["ndof"] == R.ndof
+        link = parallel.um_connect(dev, dist, rank, world, R.global_dof, R.owner)
+        owned = R.owned
+        # the same linearisation point as the global problem: owned entries from the global vector, ghosts by a halo exchange
+        u = torch.from_numpy(np.where(owned, Hg["x0"][R.global_dof], 1e300)).cuda()
+        torch.cuda.synchronize()
+        dev.halo_push(u); dev.halo_wait(u); dev.synchronize()
+        halo_ok = bool(np.array_equal(u.cpu().numpy(), Hg["x0"][R.global_dof]))
+        r = torch.zeros_like(u); z = torch.zeros_like(u)
+        dev.jacobian(H["go"], H["mat"], u, overwrite=True)
+        dev.residual(H["go"], u, r)
+        rp, ci = dev.matrix_get_pattern(H["mat"])
+        va = dev.matrix_get_values(H["mat"])
+        out = {}
+        for name, method, precond in (("cg", capi.SOLVER_CG, capi.PRECOND_JACOBI), ("bicgstab", capi.SOLVER_BICGSTAB, capi.PRECOND_JACOBI),
+                                      ("bcgs_ssor", capi.SOLVER_BICGSTAB, capi.PRECOND_SSOR)):
+            st = dev.solve(H["mat"], r, z, method=method, precond=precond, reduction=1e-12, maxit=4000)
+            assert st.converged, name
+            out[name] = (st.iterations, z.cpu().numpy()[owned].copy())
+        xg = np.random.default_rng(0).uniform(-1, 1, R.global_ndof)
+        x = torch.from_numpy(np.where(owned, xg[R.global_dof], 1e300)).cuda()
+        y = torch.zeros_like(x)
+        torch.cuda.synchronize()
+        dev.spmv(H["mat"], x, y)
+        dev.synchronize()
+        ret[rank] = dict(gid=R.global_dof, owned=owned, rowptr=rp, colidx=ci, values=va, res=r.cpu().numpy(), sol=out, y=y.cpu().numpy()[owned], halo_ok=halo_ok,
+                         neighbours=link.neighbours, owned_rows=dev.owned_rows()[0])
+        dist.barrier()
+        dev.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mesh", [(14, 11, 5, False), (12, 12, 8, True)])
+def test_multi_gpu_unstructured_partition_matches_global_oracle(mesh):
+    """Recursive coordinate bisection over the GPUs of the box: the owned rows of every rank (pattern, values, residual) equal the
+    global oracle's without matrix communication; halo exchange, SpMV and the Krylov solves (Jacobi, block-Jacobi SSOR) reproduce
+    the global results."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_um_rank_main, args=(world, _free_port(), mesh, ret), nprocs=world, join=True)
+    xy, conn, sd, og, Hg, rg = _um_global(*mesh)
+    rpg, cig = og.matrix_get_pattern(Hg["mat"])
+    Ag = sp.csr_matrix((og.matrix_get_values(Hg["mat"]), cig, rpg), shape=(Hg["ndof"],) * 2)
+    zg = spla.spsolve(Ag.tocsc(), rg)
+    yg = Ag @ np.random.default_rng(0).uniform(-1, 1, Hg["ndof"])
+    seen = np.zeros(Hg["ndof"], dtype=int)
+    scale = np.abs(Ag.data).max()
+    for rank in range(world):
+        o = ret[rank]
+        assert o["halo_ok"] and o["owned_rows"] == int(o["owned"].sum())
+        gid, owned = o["gid"], o["owned"]
+        seen[gid[owned]] += 1
+        for row in np.nonzero(owned)[0]:
+            a, b = o["rowptr"][row], o["rowptr"][row + 1]
+            ga, gb = Ag.indptr[gid[row]], Ag.indptr[gid[row] + 1]
+            cols = gid[o["colidx"][a:b]]
+            assert np.array_equal(cols, Ag.indices[ga:gb])                           # monotone local numbering: same order, bit-exact pattern
+            assert np.abs(o["values"][a:b] - Ag.data[ga:gb]).max() <= 1e-12 * scale
+        assert np.abs(o["res"][owned] - rg[gid[owned]]).max() <= 1e-12 * np.abs(rg).max()
+        for name in ("cg", "bicgstab", "bcgs_ssor"):
+            assert np.abs(o["sol"][name][1] - zg[gid[owned]]).max() <= 1e-10 * np.abs(zg).max(), name
+        assert np.abs(o["y"] - yg[gid[owned]]).max() <= 1e-12 * np.abs(yg).max()
+    assert (seen == 1).all()
+    assert len({ret[r]["sol"]["cg"][0] for r in range(world)}) == 1

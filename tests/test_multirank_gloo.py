@@ -342,3 +342,73 @@ def test_um_partitioned_assembly_owned_rows_match_global(world):
     ret = mp.Manager().dict()
     mp.spawn(_um_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world and sum(ret.values()) > 0
+
+
+# ---- mdb_partition_lists plumbing (parallel.um_rank_problem / um_connect) without a GPU ------------------------------------------
+class _RecordingDev:
+    """Stands in for capi.Mdb in um_connect: records the lists instead of uploading them."""
+
+    def __init__(self, rank):
+        self.rank = rank
+
+    def partition_lists(self, owned, neigh, send_ptr, send_idx, recv_ptr, recv_idx):
+        self.owned, self.neigh = np.asarray(owned), list(neigh)
+        self.send_ptr, self.send_idx, self.recv_ptr, self.recv_idx = list(send_ptr), np.asarray(send_idx), list(recv_ptr), np.asarray(recv_idx)
+
+    def nccl_unique_id(self):
+        return b"id"
+
+    def comm_init(self, nranks, rank, uid):
+        assert uid == b"id"
+
+    def halo_export(self):
+        return b"window-of-%d" % self.rank, 0
+
+    def halo_import_lists(self, blobs, caps, offsets, slots):
+        self.blobs, self.caps, self.offsets, self.slots = list(blobs), list(caps), list(offsets), list(slots)
+
+
+def _um_lists_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    import um_problems as ump
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        xy, conn = ump.square_mesh(14, 11, seed=5)
+        sd = ump.halves(xy, conn)
+        R = parallel.um_rank_problem(xy, conn, sd, world, rank, [0, 1])
+        dev = _RecordingDev(rank)
+        info = parallel.um_connect(dev, dist, rank, world, R.global_dof, R.owner)
+        # emulate one exchange of the vector x[g] = f(global index): what the neighbours write into my window, at the offsets they were told
+        f = lambda g: np.sin(0.37 * g) + 1e-3 * g
+        x = np.where(R.owned, f(R.global_dof), np.nan)
+        packets = [None] * world
+        dist.all_gather_object(packets, {q: (dev.offsets[i], [float(v) for v in x[dev.send_idx[dev.send_ptr[i]:dev.send_ptr[i + 1]]]]) for i, q in enumerate(dev.neigh)})
+        window = np.full(max(dev.recv_ptr[-1], 1), np.nan)
+        for q in range(world):
+            if q != rank and rank in packets[q]:
+                off, vals = packets[q][rank]
+                window[off:off + len(vals)] = vals
+        x[dev.recv_idx] = window[:dev.recv_ptr[-1]]
+        ok = bool(np.allclose(x, f(R.global_dof), rtol=0, atol=0))
+        # every global DOF is owned exactly once
+        owned_ids = [None] * world
+        dist.all_gather_object(owned_ids, [int(g) for g in R.global_dof[R.owned]])
+        allg = np.sort(np.concatenate([np.asarray(o, dtype=np.int64) for o in owned_ids]))
+        once = bool(np.array_equal(allg, np.arange(R.global_ndof)))
+        sym = all(dev.blobs[i] == b"window-of-%d" % q for i, q in enumerate(dev.neigh))
+        ret[rank] = (ok, once, sym, info.send_count, info.recv_count)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_um_halo_lists_exchange_every_ghost_from_its_owner(world):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_um_lists_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        ok, once, sym, ns, nr = ret[r]
+        assert ok and once and sym and ns > 0 and nr > 0
+    assert sum(ret[r][3] for r in range(world)) == sum(ret[r][4] for r in range(world))      # everything sent is received
