@@ -301,6 +301,104 @@ def unstructured_extra(pkg, capi, peak, n=1024, reps=10):
         dev.close()
 
 
+def unstructured_partition_extra(pkg, capi, dist, rank, world, local_rank, peak, levels=None):
+    """extra.unstructured_partition, at every N: the north star's "refined gmsh meshes at 1/2/4/8 GPUs".  The committed Gmsh file
+    examples/filtration.msh (layout of the reference's test/stokesdarcy4.msh) is refined `levels` times, physical group > 0 -> subdomain 1
+    (test/stokesdarcy2.cc:596-601), P1 | P1 Poisson + ProportionalFlowCoupling; the cells are cut by recursive coordinate bisection over
+    the ranks (STRONG scaling: the global mesh is fixed), every rank assembles its owned rows with no matrix communication and the
+    Krylov vectors travel through index-list halos over NVLink (mdb_partition_lists).  Times are CUDA-event means, max over ranks."""
+    import numpy as np
+    import torch
+    levels = int(os.environ.get("MDB_BENCH_UM_LEVELS", "5")) if levels is None else levels
+    t0 = time.perf_counter()
+    xy0, conn0, g0 = pkg.gmsh.read(os.path.join(ROOT, "examples", "filtration.msh"))
+    xy, conn, groups = pkg.gmsh.refine(xy0, conn0, g0, levels)
+    sd = np.where(groups > 0, 2, 1).astype(np.uint8)
+    R = pkg.parallel.um_rank_problem(xy, conn, sd, world, rank, [0, 1])
+    t_host = time.perf_counter() - t0
+    dev = pkg.Mdb(local_rank)
+    try:
+        def build(d, lxy, lconn, lsd):
+            d.mesh_unstructured(lxy, lconn); d.subdomains(lsd)
+            c0, c1 = d.add_space(capi.FE_P1, 0), d.add_space(capi.FE_P1, 1)
+            p = capi.PoissonParams(); p.f = capi.Function(capi.FN_CONST, 1.0); p.bc = capi.BCType(capi.BC_ALL_DIRICHLET)
+            p.j = capi.Function(capi.FN_ZERO); p.quad_order = 2
+            s0 = d.add_subproblem(capi.OP_POISSON, p, capi.COND_EQUALITY, 1, [c0])
+            s1 = d.add_subproblem(capi.OP_POISSON, p, capi.COND_EQUALITY, 2, [c1])
+            pf = capi.PropFlowParams(); pf.intensity = 2.0
+            cp = d.add_coupling(capi.OP_PROPFLOW_COUPLING, pf, s0, s1, capi.JAC_ANALYTIC)
+            nd = d.finalize(); d.constraints_assemble([s0, s1], [p.bc, p.bc])
+            go = d.gridoperator_create([s0, s1], [cp]); mat = d.matrix_create([go])
+            return nd, go, mat
+        t0 = time.perf_counter()
+        ndof, go, mat = build(dev, R.xy, R.conn, R.sd)
+        assert ndof == R.ndof
+        link = pkg.parallel.um_connect(dev, dist, rank, world, R.global_dof, R.owner) if world > 1 else None
+        dev.synchronize()
+        t_setup = time.perf_counter() - t0
+        own = R.owned
+        u = torch.zeros(ndof, dtype=torch.float64, device="cuda"); r = torch.zeros_like(u); z = torch.zeros_like(u); y = torch.zeros_like(u)
+        stream = torch.cuda.ExternalStream(dev.stream())
+
+        def sync_all():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed_ms(fn, reps=10):
+            for _ in range(3):
+                fn()
+            sync_all()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream); e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+            return ms
+        ms_jac = timed_ms(lambda: dev.jacobian(go, mat, u, overwrite=True))
+        ms_res = timed_ms(lambda: dev.residual(go, u, r))
+        ms_spmv = timed_ms(lambda: dev.spmv(mat, u, y))
+        r.zero_(); dev.residual(go, u, r)
+        st = dev.solve(mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, fixed_iters=50)
+        st = dev.solve(mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, fixed_iters=200)
+        cg_s = st.seconds
+        if world > 1:
+            t = torch.tensor([cg_s], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); cg_s = float(t.item())
+        st = dev.solve(mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, reduction=1e-10, maxit=20000)
+        dev.spmv(mat, z, y)                                              # halo exchange of z inside; y = A z on owned rows
+        dev.synchronize()
+        ow = torch.from_numpy(own).cuda()
+        num = torch.stack([((y - r)[ow] ** 2).sum(), (r[ow] ** 2).sum(), z[ow].sum(), torch.tensor(float(own.sum()), device="cuda", dtype=torch.float64)])
+        if world > 1:
+            dist.all_reduce(num)
+        num = [float(v) for v in num.tolist()]
+        sizes = [int(R.conn.shape[0]), int(own.sum()), len(link.neighbours) if link else 0, int(link.send_count) if link else 0]
+        allsizes = [sizes]
+        if world > 1:
+            allsizes = [None] * world
+            dist.all_gather_object(allsizes, sizes)
+        ne_g, nnz_local = int(conn.shape[0]), int(dev.nnz[mat])
+        b_jac = 8.0 * nnz_local + 24.0 * R.conn.shape[0] + 16.0 * R.xy.shape[0]          # this rank's algorithmic bytes (SURVEY 8d, unstructured)
+        out = {"workload": "examples/filtration.msh refined %d x (%d triangles, %d DOFs), P1 | P1, Poisson + ProportionalFlowCoupling; recursive coordinate bisection over %d rank(s)"
+                           % (levels, ne_g, R.global_ndof, world),
+               "scaling": "strong", "cells_global": ne_g, "dofs_global": int(R.global_ndof), "levels": levels,
+               "cells_per_rank_with_ghosts": [a[0] for a in allsizes], "owned_rows_per_rank": [a[1] for a in allsizes],
+               "neighbours_per_rank": [a[2] for a in allsizes], "halo_entries_sent_per_rank": [a[3] for a in allsizes],
+               "host_partition_s": t_host, "device_setup_s": t_setup,
+               "jacobian_ms": ms_jac, "jacobian_dofs_per_s": R.global_ndof / (ms_jac * 1e-3), "jacobian_rank0_GBs": b_jac / (ms_jac * 1e-3) / 1e9,
+               "jacobian_rank0_frac": b_jac / (ms_jac * 1e-3) / 1e9 / peak,
+               "residual_ms": ms_res, "residual_dofs_per_s": R.global_ndof / (ms_res * 1e-3), "spmv_ms": ms_spmv, "cg_iters_per_s": 200.0 / cg_s,
+               "solve_check": {"converged": bool(st.converged), "iterations": int(st.iterations), "rel_residual": (num[0] / max(num[1], 1e-300)) ** 0.5,
+                               "checksum_sum_z": num[2], "every_dof_owned_once": int(round(num[3])) == int(R.global_ndof)}}
+        return out
+    finally:
+        dev.close()
+
+
 def main():
     # The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there) share file
     # descriptor 1, so route fd 1 to stderr for the whole run and keep a private handle on the real stdout for the line.
@@ -555,7 +653,15 @@ def _main(out):
         except Exception as e:
             extra["e2e_solve"] = {"error": repr(e)}
 
+    um_part = None
+    if not args.quick and not os.environ.get("MDB_BENCH_NO_UNSTRUCTURED"):
+        try:
+            um_part = unstructured_partition_extra(pkg, capi, dist, rank, world, local_rank, peak)
+        except Exception as e:              # a side line must never take the benchmark line down
+            um_part = {"error": repr(e)}
     if rank == 0:
+        if um_part is not None:
+            extra["unstructured_partition"] = um_part
         if world == 1 and not args.quick:
             tr, tr_src = measured_traffic(S)
             roof["traffic"] = tr.get(fill_kernel) if tr else None

@@ -5,5 +5,5 @@ reference's spellings lives in ``include/mdb200/multidomain.hh``.  This Python p
 by the tests and ``bench.py`` (ctypes binding, torch.distributed launch glue).  The directory name contains a
 hyphen, so import it with ``importlib.import_module("dune-multidomain_b200")``.
 """
-from . import capi, parallel  # noqa: F401
+from . import capi, gmsh, parallel  # noqa: F401
 from .capi import Mdb, MdbError, load_library, library_path  # noqa: F401
