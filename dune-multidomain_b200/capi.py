@@ -30,7 +30,7 @@ DG_METHOD_NIPG, DG_METHOD_SIPG = 0, 1
 DG_WEIGHTS_OFF, DG_WEIGHTS_ON = 0, 1
 JAC_FD_BITMATCH, JAC_ANALYTIC = 0, 1
 SOLVER_CG, SOLVER_BICGSTAB, SOLVER_DIRECT = 0, 1, 2
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR = 0, 1, 2, 3
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_ILU0, PRECOND_SSOR, PRECOND_MG = 0, 1, 2, 3, 4
 ONESTEP_IMPLICIT_EULER, ONESTEP_THETA, ONESTEP_ALEXANDER2 = 0, 1, 2
 PRECOND_SSOR_ORACLE = 100  # the oracle's own id for ISTL SeqSSOR (tests/orc.py maps PRECOND_SSOR to it)
 
@@ -400,6 +400,9 @@ class Mdb(Lib):
 
     def set_halo_timeout(self, seconds):
         self._check(self._fn("set_halo_timeout")(C.c_void_p(self.ctx), C.c_double(seconds)), "set_halo_timeout")
+
+    def matrix_mg_levels(self, mat):
+        return self._check(self._fn("matrix_mg_levels")(C.c_void_p(self.ctx), mat), "matrix_mg_levels")
 
     def set_ssor_sweeps(self, sweeps):
         self._check(self._fn("set_ssor_sweeps")(C.c_void_p(self.ctx), int(sweeps)), "set_ssor_sweeps")

@@ -145,6 +145,7 @@ static void free_matrix(Matrix& m)
   for (auto& kv : m.fd_plans) fd_plan_free(kv.second);
   m.fd_plans.clear();
   direct_free(m);
+  mg_free(m);
   for (auto& kv : m.um_pair_plans) um_pair_plan_free(kv.second);
   m.um_pair_plans.clear();
 }
@@ -606,6 +607,7 @@ int mdb_constraints_assemble(mdb_ctx* c, const int* subproblems, const mdb_bctyp
   MDB_API_BEGIN(c)
   MDB_REQUIRE(c->finalized, MDB_ESTATE, "mdb_constraints_assemble: not finalized");
   for (int i = 0; i < n; ++i) MDB_REQUIRE(subproblems[i] >= 0 && subproblems[i] < (int)c->sps.size(), MDB_EINVAL, "bad subproblem index");
+  c->con_sps.assign(subproblems, subproblems + n); c->con_bcs.assign(bcs, bcs + n); c->con_recorded = true;
   c->phase_begin("constraints");
   if (c->um && c->ufe) ufe_assemble_constraints(c, subproblems, bcs, n); else if (c->um) um_assemble_constraints(c, subproblems, bcs, n); else assemble_constraints(c, subproblems, bcs, n);
   rebuild_conlist(c);
@@ -622,6 +624,7 @@ int mdb_set_constraints(mdb_ctx* c, int64_t n, const int64_t* dofs)
   for (int64_t i = 0; i < n; ++i) { MDB_REQUIRE(dofs[i] >= 0 && dofs[i] < c->ndof, MDB_EINVAL, "constraint index out of range"); f[dofs[i]] = 1; }
   MDB_CUDA(cudaMemcpyAsync(c->d_constrained, f.data(), c->ndof, cudaMemcpyHostToDevice, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
+  c->con_recorded = n == 0; c->con_sps.clear(); c->con_bcs.clear();
   rebuild_conlist(c);
   MDB_API_END(c)
 }
@@ -727,8 +730,14 @@ int mdb_matrix_zero(mdb_ctx* c, int mat)
   MDB_API_BEGIN(c)
   MDB_MAT(c, mat)
   MDB_CUDA(cudaMemsetAsync(M.d_val, 0, M.nnz * sizeof(double), c->stream));
-  M.dinv_valid = false; M.ilu_valid = false; direct_invalidate(M);
+  M.dinv_valid = false; M.ilu_valid = false; direct_invalidate(M); M.asm_log.clear();
   MDB_API_END(c)
+}
+
+int mdb_matrix_mg_levels(mdb_ctx* c, int mat)
+{
+  if (!c || mat < 0 || mat >= (int)c->mats.size()) return MDB_EINVAL;
+  return mg_levels(c->mats[mat]);
 }
 
 int mdb_matrix_device_ptrs(mdb_ctx* c, int mat, const int64_t** rowptr, const int32_t** colidx, double** values)
@@ -812,6 +821,8 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   MDB_GO(c, go)
   MDB_MAT(c, mat)
   M.dinv_valid = false; M.ilu_valid = false; direct_invalidate(M);
+  if (overwrite) M.asm_log.clear();
+  M.asm_log.push_back(std::make_pair(go, weight));
   if (c->um) { VecIn vx(c, x, c->ndof, 0); if (c->ufe) ufe_jacobian(c, G, M, weight, vx.d, overwrite != 0); else um_jacobian(c, G, M, weight, vx.d, overwrite != 0); return MDB_OK; }
   // The volume operators of the closed set are linear: their Jacobian does not read x.  Only the finite-difference
   // coupling Jacobian does, and only at the DOFs of the interface cells.  With a HOST vector the upload therefore runs on

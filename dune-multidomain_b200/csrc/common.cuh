@@ -288,6 +288,8 @@ struct Matrix {
   double* d_ilu = nullptr; bool ilu_valid = false;
   int32_t* d_cell_perm = nullptr; int64_t sweep_cells = 0; int sweep_cell_img = 0;   // all-DG matrices: cells in wavefront order (first row of each), image doubles per warp
   void* direct = nullptr;            // direct.cu: band factorisation cache
+  void* mg = nullptr;                // mg.cu: multigrid hierarchy (MDB_PRECOND_MG)
+  std::vector<std::pair<int, double>> asm_log;   // (grid operator, weight) of the mdb_jacobian calls since the values were last zeroed
   std::map<std::vector<int>, void*> um_pair_plans;   // unstructured.cu: pair records of the owner-computes Jacobian kernel per subproblem list
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
@@ -327,6 +329,7 @@ struct Ctx {
   int32_t* d_conlist = nullptr;
   int64_t ncon = 0;
   double time = 0.0;
+  std::vector<int> con_sps; std::vector<mdb_bctype> con_bcs; bool con_recorded = true;   // the last mdb_constraints_assemble call (mg.cu replays it on the coarse levels)
   int ssor_sweeps = 3;               // SeqSSOR(A, n, 1.0): ISTLBackend_SEQ_BCGS_SSOR uses n = 3 (test/testpoisson.cc:291)
 
   // scratch
@@ -463,6 +466,10 @@ void ufe_jacobian(Ctx* c, const GridOp& go, Matrix& m, double weight, const doub
 int direct_solve(Ctx* c, Matrix& m, const double* d_b, double* d_z, mdb_solve_stats* stats);
 void direct_free(Matrix& m);
 void direct_invalidate(Matrix& m);
+// mg.cu: geometric multigrid V-cycle (MDB_PRECOND_MG)
+void mg_apply(Ctx* c, Matrix& m, const double* d_d, double* d_v);
+void mg_free(Matrix& m);
+int mg_levels(const Matrix& m);
 
 template <typename T> inline T* dalloc(size_t n)
 {

@@ -1,0 +1,357 @@
+// mg.cu — MDB_PRECOND_MG: a geometric multigrid V-cycle as preconditioner of the Krylov solvers of solver.cu, for the structured
+// Q1 multidomain systems (the north star's "CG/BiCGSTAB solver ... using SpMV and fused dot/axpy kernels").
+//
+// The reference's solver backends precondition with sequential ISTL sweeps (SeqSSOR / SeqILU0, precond.cu reproduces them operation
+// for operation); their iteration counts grow like 1/h and a sweep is a dependency chain, so on a GPU Jacobi-CG wins in time although
+// it needs ~1000 iterations at 256^3.  The bandwidth-bound alternative that removes the 1/h is multigrid, and on this path every
+// ingredient already exists as a streamed kernel:
+//   coarse operators   re-discretisation: the SAME assembly path on the mesh with half the cells per axis (a coarse context is built by
+//                      replaying the recorded setup: spaces, subproblems, couplings, constraints, grid operators, and the log of
+//                      (grid operator, weight) Jacobian calls that produced the fine matrix — so one-step matrices M + dt K coarsen too)
+//   transfers          per child space, trilinear interpolation between the child's lattices of two levels (the two subdomains keep
+//                      their own coefficients on the interface, exactly as in the DOF map); restriction = its transpose; constrained
+//                      coefficients are neither corrected nor restricted to
+//   smoother           Chebyshev polynomial in D^-1 A on [lambda_max / 4, 1.1 lambda_max] (lambda_max by a power iteration at set-up):
+//                      symmetric, no dependency chain, one SpMV per degree — the V-cycle is an SPD operator, valid inside CG
+//   coarsest level     the same smoother with a wider interval and more steps (a few dozen coefficients)
+// Single-rank contexts, Q1 children, meshes whose cell counts and subdomain marking coarsen (even counts, uniform 2^d blocks).
+#include "common.cuh"
+#include <cmath>
+
+struct mdb_ctx : mdb::Ctx {};
+
+namespace mdb {
+
+namespace {
+
+struct MgLevel {
+  mdb_ctx* ctx = nullptr; bool owned = false; int mat = -1;
+  int64_t n = 0;
+  double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *t = nullptr, *dinv = nullptr;
+  double lmax = 0.0;
+};
+struct MgHier {
+  std::vector<MgLevel> L;
+  std::vector<std::pair<int, double>> log;      // the assembly log the coarse matrices were built from
+  int degree = 2, coarse_degree = 16;
+  double* d_red = nullptr;
+};
+
+__global__ void k_mg_coarsen_sd(MeshDesc mf, MeshDesc mc, const uint8_t* __restrict__ sdf, uint8_t* sdc, int* bad)
+{
+  const int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (cidx >= mc.ncells()) return;
+  int I[3]; int64_t r = cidx;
+  I[0] = (int)(r % mc.n[0]); r /= mc.n[0]; I[1] = (int)(r % mc.n[1]); I[2] = (int)(r / mc.n[1]);
+  uint8_t v = 0; bool first = true;
+  for (int dz = 0; dz < (mf.dim > 2 ? 2 : 1); ++dz)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const int64_t f = (2 * I[0] + dx) + (int64_t)mf.n[0] * ((2 * I[1] + dy) + (int64_t)mf.n[1] * (mf.dim > 2 ? 2 * I[2] + dz : 0));
+        const uint8_t s = sdf[f];
+        if (first) { v = s; first = false; } else if (s != v) *bad = 1;
+      }
+  sdc[cidx] = v;
+}
+__global__ void k_mg_dinv(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ diag, const double* __restrict__ val, double* dinv)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 1.0;
+  if (diag[i] >= 0) { const double a = val[rowptr[i] + diag[i]]; d = a != 0.0 ? 1.0 / a : 1.0; }
+  dinv[i] = d;
+}
+struct MgChild { int64_t off_f, off_c, size_f, size_c; const int32_t *d2l_f, *l2d_f, *d2l_c, *l2d_c; int nf[3], nc[3]; };
+
+// x_f += P x_c on the coefficients of one child (not on constrained ones)
+__global__ void k_mg_prolong(MgChild C, int dim, const uint8_t* __restrict__ con_f, const double* __restrict__ xc, double* xf)
+{
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= C.size_f) return;
+  if (con_f[C.off_f + g]) return;
+  int64_t p = C.d2l_f[g];
+  int i[3] = {0, 0, 0};
+  i[0] = (int)(p % C.nf[0]); p /= C.nf[0]; i[1] = (int)(p % C.nf[1]); i[2] = (int)(p / C.nf[1]);
+  int lo[3], cnt[3]; double w[3];
+  for (int d = 0; d < 3; ++d) {
+    if (d >= dim) { lo[d] = 0; cnt[d] = 1; w[d] = 1.0; continue; }
+    if ((i[d] & 1) == 0) { lo[d] = i[d] >> 1; cnt[d] = 1; w[d] = 1.0; } else { lo[d] = (i[d] - 1) >> 1; cnt[d] = 2; w[d] = 0.5; }
+  }
+  double acc = 0.0;
+  for (int c = 0; c < cnt[2]; ++c)
+    for (int b = 0; b < cnt[1]; ++b)
+      for (int a = 0; a < cnt[0]; ++a) {
+        const int64_t pc = (lo[0] + a) + (int64_t)C.nc[0] * ((lo[1] + b) + (int64_t)C.nc[1] * (lo[2] + c));
+        const int32_t dc = C.l2d_c[pc];
+        if (dc >= 0) acc += w[0] * w[1] * w[2] * xc[C.off_c + dc];
+      }
+  xf[C.off_f + g] += acc;
+}
+// r_c = P^T r_f on the coefficients of one child; constrained coarse coefficients get 0
+__global__ void k_mg_restrict(MgChild C, int dim, const uint8_t* __restrict__ con_f, const uint8_t* __restrict__ con_c, const double* __restrict__ rf, double* rc)
+{
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= C.size_c) return;
+  if (con_c[C.off_c + g]) { rc[C.off_c + g] = 0.0; return; }
+  int64_t p = C.d2l_c[g];
+  int I[3] = {0, 0, 0};
+  I[0] = (int)(p % C.nc[0]); p /= C.nc[0]; I[1] = (int)(p % C.nc[1]); I[2] = (int)(p / C.nc[1]);
+  double acc = 0.0;
+  for (int c = (dim > 2 ? -1 : 0); c <= (dim > 2 ? 1 : 0); ++c)
+    for (int b = -1; b <= 1; ++b)
+      for (int a = -1; a <= 1; ++a) {
+        const int fi = 2 * I[0] + a, fj = 2 * I[1] + b, fk = 2 * I[2] + c;
+        if (fi < 0 || fi >= C.nf[0] || fj < 0 || fj >= C.nf[1] || fk < 0 || fk >= C.nf[2]) continue;
+        const int32_t df = C.l2d_f[fi + (int64_t)C.nf[0] * (fj + (int64_t)C.nf[1] * fk)];
+        if (df < 0 || con_f[C.off_f + df]) continue;
+        const double w = (a ? 0.5 : 1.0) * (b ? 0.5 : 1.0) * (c ? 0.5 : 1.0);
+        acc += w * rf[C.off_f + df];
+      }
+  rc[C.off_c + g] = acc;
+}
+// Chebyshev smoothing steps (see mg_smooth)
+__global__ void k_mg_cheb_start(int64_t n, const double* __restrict__ b, const double* __restrict__ ax, const double* __restrict__ dinv, double inv_theta,
+                                double* r, double* d, double* x, int zero_guess)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = zero_guess ? b[i] : b[i] - ax[i];
+    const double di = inv_theta * dinv[i] * ri;
+    r[i] = ri; d[i] = di;
+    x[i] = zero_guess ? di : x[i] + di;
+  }
+}
+__global__ void k_mg_cheb_step(int64_t n, const double* __restrict__ ad, const double* __restrict__ dinv, double c1, double c2, double* r, double* d, double* x)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i] - ad[i];
+    const double di = c1 * d[i] + c2 * dinv[i] * ri;
+    r[i] = ri; d[i] = di; x[i] += di;
+  }
+}
+__global__ void k_mg_sub(int64_t n, const double* __restrict__ b, const double* __restrict__ ax, double* r)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) r[i] = b[i] - ax[i];
+}
+__global__ void k_mg_scale_dinv(int64_t n, const double* __restrict__ dinv, const double* __restrict__ av, double* w)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = dinv[i] * av[i];
+}
+__global__ void k_mg_init_vec(int64_t n, double* v)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = 1.0 + 0.5 * sin(0.7 * (double)i);
+}
+__global__ void k_mg_scale(int64_t n, double a, double* v)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] *= a;
+}
+__global__ void k_mg_norm2(int64_t n, const double* __restrict__ v, double* out)
+{
+  __shared__ double sh[8];
+  double a = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += v[i] * v[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i]; atomicAdd(out, s); }
+}
+
+int vgrid(int64_t n) { const int g = cdiv(n, 256); return g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8; }
+
+double norm2(Ctx* c, MgHier* H, int64_t n, const double* v)
+{
+  MDB_CUDA(cudaMemsetAsync(H->d_red, 0, sizeof(double), c->stream));
+  MDB_LAUNCH(c, k_mg_norm2, vgrid(n), 256, 0, n, v, H->d_red);
+  double h = 0.0;
+  MDB_CUDA(cudaMemcpyAsync(&h, H->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  return std::sqrt(h);
+}
+
+#define MG_CALL(ctx, expr, what)                                                                                        \
+  do { const int rc__ = (expr); if (rc__ < 0) throw Error(rc__, std::string("multigrid set-up: ") + what + ": " + mdb_last_error(ctx)); } while (0)
+
+// build the context of the next coarser level by replaying the set-up of `f`; returns nullptr when the level does not coarsen
+mdb_ctx* coarsen(Ctx* f)
+{
+  const MeshDesc& m = f->mesh;
+  int64_t nc[3] = {1, 1, 1}; double lower[3], upper[3];
+  for (int d = 0; d < m.dim; ++d) {
+    if (m.n[d] % 2 != 0 || m.n[d] < 4) return nullptr;
+    nc[d] = m.n[d] / 2; lower[d] = m.lower[d]; upper[d] = m.lower[d] + m.h[d] * m.n[d];
+  }
+  mdb_ctx* c = mdb_create(f->device);
+  MDB_REQUIRE(c, MDB_ECUDA, "multigrid set-up: cannot create a coarse context");
+  try {
+    MG_CALL(c, mdb_mesh_structured(c, m.dim, nc, lower, upper), "mesh");
+    int* d_bad = dalloc<int>(1);
+    MDB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), f->stream));
+    MDB_LAUNCH(f, k_mg_coarsen_sd, cdiv(c->mesh.ncells(), 256), 256, 0, m, c->mesh, f->d_cell_sd, c->d_cell_sd, d_bad);
+    int bad = 0;
+    MDB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    MDB_CUDA(cudaStreamSynchronize(f->stream));
+    cudaFree(d_bad);
+    if (bad) { mdb_destroy(c); return nullptr; }       // the subdomain marking is not a union of 2^d blocks: this level is the coarsest
+    c->have_sd = true;
+    for (const Child& ch : f->children) MG_CALL(c, mdb_add_space(c, ch.fe_kind, ch.subdomain), "space");
+    for (const SubProblemDesc& sp : f->sps) {
+      const void* p = sp.op_id == MDB_OP_POISSON ? (const void*)&sp.poisson : (const void*)&sp.l2;
+      const size_t nb = sp.op_id == MDB_OP_POISSON ? sizeof(sp.poisson) : sizeof(sp.l2);
+      MG_CALL(c, mdb_add_subproblem(c, sp.op_id, p, nb, sp.cond_kind, sp.mask, sp.children.data(), (int)sp.children.size()), "subproblem");
+    }
+    for (const CouplingDesc& cp : f->cps) {
+      const void* p = cp.op_id == MDB_OP_CVCF_COUPLING ? (const void*)&cp.cvcf : (const void*)&cp.propflow;
+      const size_t nb = cp.op_id == MDB_OP_CVCF_COUPLING ? sizeof(cp.cvcf) : sizeof(cp.propflow);
+      MG_CALL(c, mdb_add_coupling(c, cp.op_id, p, nb, cp.local_sp, cp.remote_sp, MDB_JAC_ANALYTIC), "coupling");     // linear couplings: the exact derivative
+    }
+    int64_t nd = 0;
+    MG_CALL(c, mdb_finalize(c, &nd), "finalize");
+    if (!f->con_sps.empty()) { int64_t ncon = 0; MG_CALL(c, mdb_constraints_assemble(c, f->con_sps.data(), f->con_bcs.data(), (int)f->con_sps.size(), &ncon), "constraints"); }
+    mdb_set_time(c, f->time);
+    for (const GridOp& g : f->gos) MG_CALL(c, mdb_gridoperator_create(c, g.sps.data(), (int)g.sps.size(), g.cps.data(), (int)g.cps.size()), "grid operator");
+  } catch (...) { mdb_destroy(c); throw; }
+  return c;
+}
+
+void level_alloc(MgLevel& l, bool top)
+{
+  l.r = dalloc<double>(l.n); l.d = dalloc<double>(l.n); l.t = dalloc<double>(l.n); l.dinv = dalloc<double>(l.n);
+  if (!top) { l.x = dalloc<double>(l.n); l.b = dalloc<double>(l.n); }
+}
+void level_free(MgLevel& l, bool top)
+{
+  if (l.r) cudaFree(l.r); if (l.d) cudaFree(l.d); if (l.t) cudaFree(l.t); if (l.dinv) cudaFree(l.dinv);
+  if (!top) { if (l.x) cudaFree(l.x); if (l.b) cudaFree(l.b); }
+  if (l.owned && l.ctx) mdb_destroy(l.ctx);
+}
+
+// assemble the level's matrix from the log, extract D^-1, estimate lambda_max(D^-1 A)
+void level_numeric(Ctx* c, MgHier* H, size_t li)
+{
+  MgLevel& l = H->L[li];
+  Ctx* lc = l.ctx;
+  StreamScope scope(lc, c->stream);
+  Matrix& M = lc->mats[l.mat];
+  if (li > 0) {
+    MDB_CUDA(cudaMemsetAsync(l.x, 0, l.n * sizeof(double), c->stream));
+    bool first = true;
+    for (const auto& e : H->log) { MG_CALL(l.ctx, mdb_jacobian(l.ctx, e.first, l.mat, e.second, l.x, first ? 1 : 0), "coarse Jacobian"); first = false; }
+  }
+  MDB_LAUNCH(c, k_mg_dinv, cdiv(l.n, 256), 256, 0, l.n, M.d_rowptr, M.d_diag, M.d_val, l.dinv);
+  // power iteration for lambda_max(D^-1 A)
+  MDB_LAUNCH(c, k_mg_init_vec, vgrid(l.n), 256, 0, l.n, l.d);
+  double nv = norm2(c, H, l.n, l.d), lam = 1.0;
+  for (int it = 0; it < 12; ++it) {
+    MDB_LAUNCH(c, k_mg_scale, vgrid(l.n), 256, 0, l.n, 1.0 / nv, l.d);
+    spmv(lc, M, l.d, l.t);
+    MDB_LAUNCH(c, k_mg_scale_dinv, vgrid(l.n), 256, 0, l.n, l.dinv, l.t, l.d);
+    nv = norm2(c, H, l.n, l.d);
+    lam = nv;
+  }
+  l.lmax = lam;
+}
+
+// `degree` Chebyshev steps for A x = b in the D^-1-scaled operator on [lo, hi]
+void mg_smooth(Ctx* c, MgLevel& l, const double* b, double* x, bool zero_guess, int degree, double lo, double hi)
+{
+  Ctx* lc = l.ctx;
+  Matrix& M = lc->mats[l.mat];
+  const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+  double rho_old = 1.0 / sigma;
+  if (!zero_guess) spmv(lc, M, x, l.t);
+  MDB_LAUNCH(c, k_mg_cheb_start, vgrid(l.n), 256, 0, l.n, b, l.t, l.dinv, 1.0 / theta, l.r, l.d, x, zero_guess ? 1 : 0);
+  for (int k = 1; k < degree; ++k) {
+    const double rho = 1.0 / (2.0 * sigma - rho_old);
+    spmv(lc, M, l.d, l.t);
+    MDB_LAUNCH(c, k_mg_cheb_step, vgrid(l.n), 256, 0, l.n, l.t, l.dinv, rho * rho_old, 2.0 * rho / delta, l.r, l.d, x);
+    rho_old = rho;
+  }
+}
+
+MgChild child_pair(const Ctx* f, const Ctx* cc, size_t k)
+{
+  const Child& a = f->children[k]; const Child& b = cc->children[k];
+  MgChild C; C.off_f = a.offset; C.off_c = b.offset; C.size_f = a.size; C.size_c = b.size;
+  C.d2l_f = a.d_dof2lat; C.l2d_f = a.d_lat2dof; C.d2l_c = b.d_dof2lat; C.l2d_c = b.d_lat2dof;
+  for (int d = 0; d < 3; ++d) { C.nf[d] = a.lat_n[d]; C.nc[d] = b.lat_n[d]; }
+  return C;
+}
+
+void vcycle(Ctx* c, MgHier* H, size_t li)
+{
+  MgLevel& l = H->L[li];
+  StreamScope scope(l.ctx, c->stream);
+  const double hi = 1.1 * l.lmax;
+  if (li + 1 == H->L.size()) { mg_smooth(c, l, l.b, l.x, true, H->coarse_degree, hi / 30.0, hi); return; }
+  MgLevel& n = H->L[li + 1];
+  mg_smooth(c, l, l.b, l.x, true, H->degree, hi / 4.0, hi);
+  spmv(l.ctx, l.ctx->mats[l.mat], l.x, l.t);
+  MDB_LAUNCH(c, k_mg_sub, vgrid(l.n), 256, 0, l.n, l.b, l.t, l.r);
+  const int dim = l.ctx->mesh.dim;
+  for (size_t k = 0; k < l.ctx->children.size(); ++k) {
+    const MgChild C = child_pair(l.ctx, n.ctx, k);
+    if (C.size_c > 0) MDB_LAUNCH(c, k_mg_restrict, cdiv(C.size_c, 128), 128, 0, C, dim, l.ctx->d_constrained, n.ctx->d_constrained, l.r, n.b);
+  }
+  vcycle(c, H, li + 1);
+  for (size_t k = 0; k < l.ctx->children.size(); ++k) {
+    const MgChild C = child_pair(l.ctx, n.ctx, k);
+    if (C.size_f > 0) MDB_LAUNCH(c, k_mg_prolong, cdiv(C.size_f, 256), 256, 0, C, dim, l.ctx->d_constrained, n.x, l.x);
+  }
+  mg_smooth(c, l, l.b, l.x, false, H->degree, hi / 4.0, hi);
+}
+
+} // anonymous namespace
+
+void mg_free(Matrix& M)
+{
+  MgHier* H = (MgHier*)M.mg;
+  if (!H) return;
+  for (size_t i = 0; i < H->L.size(); ++i) level_free(H->L[i], i == 0);
+  if (H->d_red) cudaFree(H->d_red);
+  delete H; M.mg = nullptr;
+}
+
+// z = V-cycle(d): one cycle from a zero initial guess
+void mg_apply(Ctx* c, Matrix& M, const double* d_d, double* d_v)
+{
+  MDB_REQUIRE(c->nranks == 1 && !c->um && !c->mesh.partitioned, MDB_EINVAL, "MDB_PRECOND_MG: single-rank structured meshes only");
+  for (const Child& ch : c->children) MDB_REQUIRE(ch.fe_kind == MDB_FE_Q1, MDB_EINVAL, "MDB_PRECOND_MG: Q1 child spaces only");
+  for (const SubProblemDesc& sp : c->sps) MDB_REQUIRE(sp.op_id == MDB_OP_POISSON || sp.op_id == MDB_OP_L2, MDB_EINVAL, "MDB_PRECOND_MG: Poisson / L2 subproblems only");
+  for (const CouplingDesc& cp : c->cps) MDB_REQUIRE(cp.op_id == MDB_OP_CVCF_COUPLING || cp.op_id == MDB_OP_PROPFLOW_COUPLING, MDB_EINVAL, "MDB_PRECOND_MG: flow couplings only");
+  MDB_REQUIRE(c->con_recorded, MDB_EINVAL, "MDB_PRECOND_MG: needs constraints assembled by mdb_constraints_assemble (the coarse levels replay them)");
+  MDB_REQUIRE(!M.asm_log.empty(), MDB_ESTATE, "MDB_PRECOND_MG: assemble the matrix with mdb_jacobian first");
+  MgHier* H = (MgHier*)M.mg;
+  const int mat_index = (int)(&M - c->mats.data());
+  if (!H) {
+    c->phase_begin("mg_setup");
+    H = new MgHier(); M.mg = H;
+    H->d_red = dalloc<double>(1);
+    if (const char* e = getenv("MDB_MG_DEGREE")) H->degree = std::max(1, atoi(e));
+    MgLevel top; top.ctx = static_cast<mdb_ctx*>(c); top.owned = false; top.mat = mat_index; top.n = c->ndof;
+    level_alloc(top, true);
+    H->L.push_back(top);
+    for (int lev = 1; lev < 12; ++lev) {
+      Ctx* f = H->L.back().ctx;
+      mdb_ctx* cc = coarsen(f);
+      if (!cc) break;
+      MgLevel l; l.ctx = cc; l.owned = true; l.n = cc->ndof;
+      int64_t nnz = 0;
+      l.mat = mdb_matrix_create(cc, M.gos.data(), (int)M.gos.size(), &nnz);
+      if (l.mat < 0) { const std::string msg = mdb_last_error(cc); mdb_destroy(cc); throw Error(l.mat, "multigrid set-up: coarse matrix: " + msg); }
+      level_alloc(l, false);
+      H->L.push_back(l);
+    }
+    c->phase_end();
+  }
+  if (H->log != M.asm_log) {
+    c->phase_begin("mg_setup");
+    H->log = M.asm_log;
+    for (size_t i = 0; i < H->L.size(); ++i) level_numeric(c, H, i);
+    c->phase_end();
+  }
+  H->L[0].b = const_cast<double*>(d_d); H->L[0].x = d_v;
+  vcycle(c, H, 0);
+}
+
+int mg_levels(const Matrix& M) { return M.mg ? (int)((MgHier*)M.mg)->L.size() : 0; }
+
+} // namespace mdb

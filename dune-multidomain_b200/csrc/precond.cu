@@ -422,6 +422,7 @@ void ilu0_factorize(Ctx* c, Matrix& M)
 // v = M^-1 d  (v starts at zero, as the ISTL solvers do: pre() / apply() with v = 0)
 void precond_apply(Ctx* c, Matrix& M, int kind, int sweeps, const double* d, double* v)
 {
+  if (kind == MDB_PRECOND_MG) { mg_apply(c, M, d, v); return; }      // mg.cu: one V-cycle
   const int64_t n = c->ndof;
   // on a partition: block-Jacobi — every rank applies the sequential preconditioner of its owned x owned block (k_sweep's `owned`)
   ensure_precond_state(c, M);

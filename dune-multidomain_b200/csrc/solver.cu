@@ -772,11 +772,11 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
 {
   if (method == MDB_SOLVER_DIRECT) { MDB_REQUIRE(fixed_iters < 0, MDB_EINVAL, "mdb_solve_fixed: not with MDB_SOLVER_DIRECT"); return direct_solve(c, M, d_b, d_z, stats); }
   MDB_REQUIRE(method == MDB_SOLVER_CG || method == MDB_SOLVER_BICGSTAB, MDB_EINVAL, "unknown solver");
-  MDB_REQUIRE(precond == MDB_PRECOND_NONE || precond == MDB_PRECOND_JACOBI || precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0, MDB_EINVAL,
-              "unknown preconditioner");
+  MDB_REQUIRE(precond == MDB_PRECOND_NONE || precond == MDB_PRECOND_JACOBI || precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0 || precond == MDB_PRECOND_MG,
+              MDB_EINVAL, "unknown preconditioner");
   // Jacobi (and none) are fused into the vector kernels through the inverse diagonal; SSOR / ILU0 are explicit applications
   // z = M^-1 r (precond.cu) between the same kernels run with a unit "inverse diagonal"
-  const bool general = precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0;
+  const bool general = precond == MDB_PRECOND_SSOR || precond == MDB_PRECOND_ILU0 || precond == MDB_PRECOND_MG;
   // on a partition SSOR / ILU0 become block-Jacobi over the ranks: each rank applies the sequential preconditioner of its owned
   // block (precond.cu); iteration counts then depend on the number of ranks
   const int64_t n = c->ndof;

@@ -397,7 +397,12 @@ enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1, MDB_SOLVER_DIRECT = 2 };
  * SeqILU0) operation for operation on one rank; on a partition they act as block-Jacobi over the ranks (each rank applies
  * the sequential preconditioner of its owned x owned block, so iteration counts depend on the rank count).  [UPSTREAM] ISTLBackend_SEQ_BCGS_SSOR = BiCGSTAB + SSOR(3),
  * ISTLBackend_SEQ_CG_SSOR = CG + SSOR(1)  (test/testpoisson.cc:291-292, test/explicitlycoupledpoisson.cc:297-313). */
-enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2, MDB_PRECOND_SSOR = 3 };
+/* MDB_PRECOND_MG: one geometric multigrid V-cycle per application (csrc/mg.cu; not in the reference, whose preconditioners are
+ * the sequential ISTL sweeps above): coarse operators by re-discretisation on meshes with half the cells per axis (the coarse
+ * contexts replay the set-up and the (grid operator, weight) log of the mdb_jacobian calls that built the matrix), per-child trilinear
+ * transfers, Chebyshev-Jacobi smoothing.  Structured meshes, Q1 spaces, Poisson / L2 + flow couplings, constraints from
+ * mdb_constraints_assemble, single rank.  The V-cycle is symmetric positive definite: valid inside CG. */
+enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2, MDB_PRECOND_SSOR = 3, MDB_PRECOND_MG = 4 };
 typedef struct mdb_solve_stats {
   int32_t iterations;
   int32_t converged;
@@ -415,6 +420,8 @@ int mdb_solve_block(mdb_ctx* ctx, int mat, int child, int method, int precond, d
                     mdb_solve_stats* stats);
 int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, int maxit,
               const double* rhs, double* z, mdb_solve_stats* stats);
+/* Levels of the multigrid hierarchy built for this matrix (0 before the first MDB_PRECOND_MG solve). */
+int mdb_matrix_mg_levels(mdb_ctx* ctx, int mat);
 /* Number of symmetric sweeps n of MDB_PRECOND_SSOR (default 3). */
 int mdb_set_ssor_sweeps(mdb_ctx* ctx, int sweeps);
 /* [UPSTREAM] PDELab StationaryLinearProblemSolver::apply(x) as the reference's drivers use it (test/testpoisson.cc:295-298,
