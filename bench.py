@@ -301,6 +301,48 @@ def unstructured_extra(pkg, capi, peak, n=1024, reps=10):
         dev.close()
 
 
+def stokes_darcy_extra(pkg, capi, levels=1):
+    """extra.stokes_darcy (N = 1): BASELINE configs[4] — the Stokes-Darcy problem of test/stokesdarcy2.cc + topbottomfiltration.ini on the
+    committed Gmsh file refined `levels` times: Taylor-Hood P2/P1 + orthonormal P3 head, StokesDarcyCouplingOperator with the epsilon FD
+    Jacobian, assembly times and StationaryLinearProblemSolver with the direct solve (banded LU on the device in place of SuperLU)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sd_problems as sdp
+    xy0, conn0, g0 = pkg.gmsh.read(os.path.join(ROOT, "examples", "filtration.msh"))
+    xy, conn, groups = pkg.gmsh.refine(xy0, conn0, g0, levels)
+    dev = pkg.Mdb(0)
+    try:
+        t0 = time.perf_counter()
+        H = sdp.setup(dev, xy, conn, groups.astype(np.int32))
+        dev.synchronize()
+        t_setup = time.perf_counter() - t0
+        x = torch.zeros(H["ndof"], dtype=torch.float64, device="cuda"); r = torch.zeros_like(x)
+        for _ in range(3):
+            dev.jacobian(H["go"], H["mat"], x, overwrite=True); dev.residual(H["go"], x, r)
+        dev.profile_reset()
+        for _ in range(10):
+            dev.jacobian(H["go"], H["mat"], x, overwrite=True); dev.residual(H["go"], x, r)
+        dev.synchronize()
+        ms_jac = dev.phase_ms("jacobian_rows") + dev.phase_ms("jacobian_coupling")
+        ms_res = dev.phase_ms("residual_volume") + dev.phase_ms("residual_coupling")
+        u = np.zeros(H["ndof"])
+        dev.profile_reset()
+        t0 = time.perf_counter()
+        st = dev.stationary_solve(H["go"], H["mat"], u, method=capi.SOLVER_DIRECT, precond=capi.PRECOND_NONE)
+        t_solve = time.perf_counter() - t0
+        rs = dev.residual(H["go"], u, np.zeros(H["ndof"]))
+        r0 = dev.residual(H["go"], np.zeros(H["ndof"]), np.zeros(H["ndof"]))
+        return {"workload": "examples/filtration.msh refined %d x: %d triangles, Taylor-Hood P2/P1 + OPB-P3 head, %d DOFs, %d stored entries" % (levels, conn.shape[0], H["ndof"], dev.nnz[H["mat"]]),
+                "cells": int(conn.shape[0]), "dofs": int(H["ndof"]), "nnz": int(dev.nnz[H["mat"]]), "setup_s": t_setup,
+                "jacobian_ms": ms_jac, "jacobian_dofs_per_s": H["ndof"] / (ms_jac * 1e-3), "residual_ms": ms_res,
+                "direct_solve": {"wall_s": t_solve, "order_ms": dev.phase_ms("direct_order"), "factor_ms": dev.phase_ms("direct_factor"), "solve_ms": dev.phase_ms("direct_solve"),
+                                 "defect_reduction": float(st.defect / st.defect0) if st.defect0 > 0 else 0.0, "converged": bool(st.converged),
+                                 "residual_at_solution_over_initial": float(np.linalg.norm(rs) / np.linalg.norm(r0))}}
+    finally:
+        dev.close()
+
+
 def unstructured_partition_extra(pkg, capi, dist, rank, world, local_rank, peak, levels=None):
     """extra.unstructured_partition, at every N: the north star's "refined gmsh meshes at 1/2/4/8 GPUs".  The committed Gmsh file
     examples/filtration.msh (layout of the reference's test/stokesdarcy4.msh) is refined `levels` times, physical group > 0 -> subdomain 1
@@ -536,6 +578,8 @@ def _main(out):
     barrier()
     st = dev.solve(P.mat, r, z, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, fixed_iters=args.cg_iters)
     cg_s = allmax(st.seconds)
+    dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_JACOBI, fixed_iters=3)      # warm-up: allocates the seven work vectors
+    barrier()
     st2 = dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_JACOBI, fixed_iters=max(args.cg_iters // 2, 5))
     bi_s = allmax(st2.seconds)
     n_loc = P.ndof
@@ -572,6 +616,27 @@ def _main(out):
                    "checksum_sum_z": sums[2], "checksum_norm2_z": sums[3] ** 0.5,
                    "time_to_solution_s": allmax(stc.seconds)}
 
+    # ---- time to solution (N = 1): the same system with the multigrid V-cycle as preconditioner (MDB_PRECOND_MG, csrc/mg.cu) ------------
+    time_to_solution = None
+    if world == 1 and not args.quick:
+        try:
+            zm = torch.zeros_like(r)
+            t0 = time.perf_counter()
+            stm0 = dev.solve(P.mat, r, zm, method=capi.SOLVER_CG, precond=capi.PRECOND_MG, reduction=1e-10, maxit=500)     # builds the hierarchy
+            dev.synchronize()
+            t_first = time.perf_counter() - t0
+            stm = dev.solve(P.mat, r, zm, method=capi.SOLVER_CG, precond=capi.PRECOND_MG, reduction=1e-10, maxit=500)
+            dev.spmv(P.mat, zm, az); dev.synchronize()
+            time_to_solution = {
+                "what": "M2 system, CG to a defect reduction of 1e-10: Jacobi against one multigrid V-cycle per iteration (re-discretised coarse levels, Chebyshev-Jacobi smoothing)",
+                "cg_jacobi": {"iterations": int(stc.iterations), "seconds": float(stc.seconds)},
+                "cg_multigrid": {"iterations": int(stm.iterations), "seconds": float(stm.seconds), "converged": bool(stm.converged), "levels": int(dev.matrix_mg_levels(P.mat)),
+                                 "first_call_incl_setup_s": t_first, "rel_residual": float(((az - r).norm() / r.norm()).item()),
+                                 "max_rel_diff_to_jacobi_solution": float(((zm - z).abs().max() / z.abs().max()).item())},
+                "speedup": float(stc.seconds / stm.seconds) if stm.seconds > 0 else None}
+        except Exception as e:
+            time_to_solution = {"error": repr(e)}
+
     # ---- partition check (N > 1): a small GLOBAL mesh solved on the N ranks and, on rank 0, once more unpartitioned ------------------
     partition_check = None
     if world > 1:
@@ -590,6 +655,7 @@ def _main(out):
                "preconditioner": "jacobi"},
         "bicgstab": {"iters_per_s": st2.iterations / bi_s if bi_s > 0 else None},
         "solve_check": solve_check,
+        "time_to_solution": time_to_solution,
         "partition_check": partition_check,
         "jacobian_phases_ms": phases,
         "jacobian_streams": "main: elem -> fill (bulk-async stores) -> dirichlet | aux: irregular rows -> FD coupling | copy: gather of x (host vectors)",
@@ -682,6 +748,10 @@ def _main(out):
                 extra["unstructured"] = unstructured_extra(pkg, capi, peak)
             except Exception as e:          # a side line must never take the benchmark line down
                 extra["unstructured"] = {"error": repr(e)}
+            try:
+                extra["stokes_darcy"] = stokes_darcy_extra(pkg, capi)
+            except Exception as e:
+                extra["stokes_darcy"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1 and not args.quick:
             line["cpu_baseline"] = cpu_baseline(S, args.cpu_sample_layers, 1)
         elif world == 1:

@@ -2,7 +2,7 @@
 // B200 facade: two subdomains, dt0 operator = Poisson on both sides + ProportionalFlowCoupling, dt1 operator = L2 mass,
 // OneStepGridOperator, Alexander2 time stepping (:320), time-dependent Dirichlet data; dim is a run-time argument.
 //
-//   testinstationarypoisson <refinement level> <coupling intensity> <dt> <tend> [dim=2] [scheme: alexander2 | euler | cn]
+//   testinstationarypoisson <refinement level> <coupling intensity> <dt> <tend> [dim=2] [scheme: alexander2 | euler | cn] [solver: jac | mg]
 //
 // Prints the DOF line, per-step solver statistics and a checksum of the final state.
 #include <cmath>
@@ -14,11 +14,11 @@
 
 using namespace mdb200;
 
-template <class Param>
+template <class LS, class Param>
 static void timeloop(const Param& method, OneStepGridOperator& go, const SubProblemFunctions& f, Vector& uold, double dt, double tend)
 {
-  ISTLBackend_SEQ_BCGS_Jac ls(5000);                                 // the reference uses BCGS_SSOR (:311); Jacobi is the fast device path
-  OneStepMethod<Param, ISTLBackend_SEQ_BCGS_Jac> osm(method, go, ls, 1e-10);
+  LS ls(5000);                                                       // the reference uses BCGS_SSOR (:311); Jacobi / multigrid are the device paths
+  OneStepMethod<Param, LS> osm(method, go, ls, 1e-10);
   Vector unew(uold);
   double time = 0;
   int steps = 0, its = 0;
@@ -34,7 +34,7 @@ static void timeloop(const Param& method, OneStepGridOperator& go, const SubProb
 int main(int argc, char** argv)
 {
   try {
-    if (argc < 5) { std::fprintf(stderr, "Usage: %s <refinement level> <coupling intensity> <dt> <tend> [dim] [alexander2|euler|cn]\n", argv[0]); return 1; }
+    if (argc < 5) { std::fprintf(stderr, "Usage: %s <refinement level> <coupling intensity> <dt> <tend> [dim] [alexander2|euler|cn] [jac|mg]\n", argv[0]); return 1; }
     const int dim = argc > 5 ? std::atoi(argv[5]) : 2;
     const std::string scheme = argc > 6 ? argv[6] : "alexander2";
     const int64_t cells = (int64_t)1 << std::atoi(argv[1]);
@@ -82,9 +82,16 @@ int main(int argc, char** argv)
 
     const SubProblemFunctions f_ = interpolateOnSubProblems(g, left_sp_dt0, g, right_sp_dt0);
     const double dt = std::atof(argv[3]), tend = std::atof(argv[4]);
-    if (scheme == "euler") timeloop(ImplicitEulerParameter(), gridoperator, f_, uold, dt, tend);
-    else if (scheme == "cn") timeloop(OneStepThetaParameter(0.5), gridoperator, f_, uold, dt, tend);
-    else timeloop(Alexander2Parameter(), gridoperator, f_, uold, dt, tend);
+    const bool mg = argc > 7 && std::string(argv[7]) == "mg";      // BiCGSTAB + one multigrid V-cycle instead of BiCGSTAB + Jacobi
+    if (mg) {
+      if (scheme == "euler") timeloop<ISTLBackend_SEQ_BCGS_AMG_SSOR>(ImplicitEulerParameter(), gridoperator, f_, uold, dt, tend);
+      else if (scheme == "cn") timeloop<ISTLBackend_SEQ_BCGS_AMG_SSOR>(OneStepThetaParameter(0.5), gridoperator, f_, uold, dt, tend);
+      else timeloop<ISTLBackend_SEQ_BCGS_AMG_SSOR>(Alexander2Parameter(), gridoperator, f_, uold, dt, tend);
+    } else {
+      if (scheme == "euler") timeloop<ISTLBackend_SEQ_BCGS_Jac>(ImplicitEulerParameter(), gridoperator, f_, uold, dt, tend);
+      else if (scheme == "cn") timeloop<ISTLBackend_SEQ_BCGS_Jac>(OneStepThetaParameter(0.5), gridoperator, f_, uold, dt, tend);
+      else timeloop<ISTLBackend_SEQ_BCGS_Jac>(Alexander2Parameter(), gridoperator, f_, uold, dt, tend);
+    }
 
     double sum = 0.0, sum2 = 0.0;
     for (size_t i = 0; i < uold.size(); ++i) { sum += uold[i]; sum2 += uold[i] * uold[i]; }

@@ -605,6 +605,11 @@ struct ISTLBackend_SEQ_BCGS_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_S
 struct ISTLBackend_SEQ_CG_ILU0 : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_ILU0(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_ILU0, maxiter) {} };
 struct ISTLBackend_SEQ_CG_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_JACOBI, maxiter) {} };
 struct ISTLBackend_SEQ_BCGS_Jac : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_Jac(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_JACOBI, maxiter) {} };
+// [UPSTREAM] PDELab's multigrid-preconditioned backends ISTLBackend_SEQ_CG_AMG_SSOR / ISTLBackend_SEQ_BCGS_AMG_SSOR: here the Krylov method
+// with one GEOMETRIC multigrid V-cycle per application (MDB_PRECOND_MG, csrc/mg.cu) — structured meshes, Q1 spaces; not used by the
+// reference's drivers, offered because it turns ~1000 Jacobi-CG iterations at 256^3 into ~11
+struct ISTLBackend_SEQ_CG_AMG_SSOR : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_CG_AMG_SSOR(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_CG, MDB_PRECOND_MG, maxiter) {} };
+struct ISTLBackend_SEQ_BCGS_AMG_SSOR : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_BCGS_AMG_SSOR(unsigned maxiter = 5000) : ISTLBackend_SEQ_Base(MDB_SOLVER_BICGSTAB, MDB_PRECOND_MG, maxiter) {} };
 // [UPSTREAM] ISTLBackend_SEQ_SuperLU(verbose) (test/stokesdarcy2.cc:784-785): a direct solve — banded LU with partial pivoting on the device
 struct ISTLBackend_SEQ_SuperLU : ISTLBackend_SEQ_Base { explicit ISTLBackend_SEQ_SuperLU(bool = true) : ISTLBackend_SEQ_Base(MDB_SOLVER_DIRECT, MDB_PRECOND_NONE, 1) {} };
 
