@@ -401,6 +401,24 @@ class Mdb(Lib):
     def set_halo_timeout(self, seconds):
         self._check(self._fn("set_halo_timeout")(C.c_void_p(self.ctx), C.c_double(seconds)), "set_halo_timeout")
 
+    def mg_setup(self, mat):
+        """mdb_mg_setup: builds the multigrid hierarchy of `mat` (collective on a partition); returns the number of levels."""
+        n = C.c_int(0)
+        self._check(self._fn("mg_setup")(C.c_void_p(self.ctx), mat, C.byref(n)), "mg_setup")
+        return n.value
+
+    def mg_level(self, mat, level):
+        """The context of a coarse multigrid level as a borrowed binding (never destroyed from here): for halo_export / halo_import."""
+        f = self._fn("mg_level", C.c_void_p)
+        ptr = f(C.c_void_p(self.ctx), mat, level)
+        if not ptr:
+            raise MdbError("mdb_mg_level: no such level")
+        b = object.__new__(Mdb)
+        b.cdll, b.prefix, b.ctx, b._last_error = self.cdll, self.prefix, ptr, self._last_error
+        b.dim, b.ncells, b.ndof, b.nchildren = self.dim, 0, 0, self.nchildren
+        b.close = lambda: None                                  # borrowed: the fine context owns it
+        return b
+
     def matrix_mg_levels(self, mat):
         return self._check(self._fn("matrix_mg_levels")(C.c_void_p(self.ctx), mat), "matrix_mg_levels")
 

@@ -1063,6 +1063,39 @@ __global__ void k_dirichlet_rows(const int32_t* __restrict__ conlist, int64_t nc
   for (int64_t p = rs + l; p < re; p += 8) val[p] = (p - rs == d) ? 1.0 : 0.0;
 }
 
+// flag <- 1 if a constrained row carries the full own-block stencil and nothing else, i.e. is one of the rows the bulk-store fill streams
+__global__ void k_con_simple(const int32_t* __restrict__ conlist, int64_t ncon, const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ rowinfo,
+                             uint32_t fullmask, int ns, int* flag)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= ncon) return;
+  const int32_t g = conlist[i];
+  if ((rowinfo[g] & fullmask) == fullmask && rowptr[g + 1] - rowptr[g] == ns) *flag = 1;
+}
+// The Dirichlet pass has to follow every kernel that writes a constrained row.  The streamed fill writes simple rows only; when no
+// constrained row is simple (the rule for constraints assembled from boundary predicates: a boundary vertex lacks part of its
+// stencil) the pass can run on the auxiliary stream right after the irregular rows and the coupling faces, beside the fill.
+// Checked once per (matrix, constraint set).
+bool dirichlet_rows_off_the_fill(Ctx* c, Matrix& M)
+{
+  if (c->um || !M.d_rowinfo) return false;
+  if (M.dir_early_version == c->con_version) return M.dir_early_ok;
+  bool ok = true;
+  if (c->ncon > 0) {
+    const int dim = c->mesh.dim;
+    int* d_flag = dalloc<int>(1);
+    MDB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+    MDB_LAUNCH(c, k_con_simple, cdiv(c->ncon, 256), 256, 0, c->d_conlist, c->ncon, M.d_rowptr, M.d_rowinfo, dim == 3 ? 0x7FFFFFFu : (0x1FFu << 9), dim == 3 ? 27 : 9, d_flag);
+    int h = 0;
+    MDB_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    dfree(d_flag);
+    ok = h == 0;
+  }
+  M.dir_early_version = c->con_version; M.dir_early_ok = ok;
+  return ok;
+}
+
 void dirichlet_rows(Ctx* c, Matrix& M)
 {
   if (c->ncon == 0) return;

@@ -734,6 +734,21 @@ int mdb_matrix_zero(mdb_ctx* c, int mat)
   MDB_API_END(c)
 }
 
+int mdb_mg_setup(mdb_ctx* c, int mat, int* nlevels)
+{
+  MDB_API_BEGIN(c)
+  MDB_MAT(c, mat)
+  const int n = mg_setup(c, M);
+  if (nlevels) *nlevels = n;
+  MDB_API_END(c)
+}
+
+mdb_ctx* mdb_mg_level(mdb_ctx* c, int mat, int level)
+{
+  if (!c || mat < 0 || mat >= (int)c->mats.size()) return nullptr;
+  return mg_level_ctx(c->mats[mat], level);
+}
+
 int mdb_matrix_mg_levels(mdb_ctx* c, int mat)
 {
   if (!c || mat < 0 || mat >= (int)c->mats.size()) return MDB_EINVAL;
@@ -869,6 +884,13 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
     c->phase_end();
   }
   static const bool serial = getenv("MDB_JAC_SERIAL") != nullptr;           // A/B: the auxiliary branch on the main stream (stand-alone kernel times)
+  // Dirichlet rows beside the fill (auxiliary stream) when every writer of a constrained row is on that stream: no late coupling
+  // (Neumann-Dirichlet) and no constrained row among the streamed ones
+  static const bool dir_late = getenv("MDB_JAC_DIRICHLET_LATE") != nullptr;  // A/B: the pass after the join, as in round 1
+  bool dir_early = !dir_late && !serial && !rows_first;
+  for (int q : G.cps) dir_early = dir_early && c->cps[q].op_id != MDB_OP_ND_COUPLING;
+  for (const Child& ch : c->children) dir_early = dir_early && ch.fe_kind == MDB_FE_Q1;
+  dir_early = dir_early && dirichlet_rows_off_the_fill(c, M);
   MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
   {
     StreamScope aux(c, serial ? c->stream : c->aux_stream);
@@ -882,6 +904,11 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
     c->phase_begin("jacobian_coupling");
     jacobian_coupling(c, G, M, weight, dx, false);
     c->phase_end();
+    if (dir_early) {
+      c->phase_begin("jacobian_dirichlet");
+      dirichlet_rows(c, M);
+      c->phase_end();
+    }
     MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
   }
   c->phase_begin("jacobian_fill");
@@ -889,9 +916,11 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
   c->phase_end();
   MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   jacobian_coupling(c, G, M, weight, dx, true);            // couplings without a pattern of their own: after every volume row is written
-  c->phase_begin("jacobian_dirichlet");
-  dirichlet_rows(c, M);
-  c->phase_end();
+  if (!dir_early) {
+    c->phase_begin("jacobian_dirichlet");
+    dirichlet_rows(c, M);
+    c->phase_end();
+  }
   // a host x is only read during the call (mdb200.h): the gather / upload from page-locked memory is asynchronous, so wait for it
   // (the copy stream's work is a few microseconds and long finished; the assembly kernels keep running)
   if (host_x && need_x) MDB_CUDA(cudaEventSynchronize(c->ev_copy_done));

@@ -289,6 +289,7 @@ struct Matrix {
   int32_t* d_cell_perm = nullptr; int64_t sweep_cells = 0; int sweep_cell_img = 0;   // all-DG matrices: cells in wavefront order (first row of each), image doubles per warp
   void* direct = nullptr;            // direct.cu: band factorisation cache
   void* mg = nullptr;                // mg.cu: multigrid hierarchy (MDB_PRECOND_MG)
+  int dir_early_version = -1; bool dir_early_ok = false;   // assemble.cu: no constrained row is a streamed (simple) row for constraint version dir_early_version
   std::vector<std::pair<int, double>> asm_log;   // (grid operator, weight) of the mdb_jacobian calls since the values were last zeroed
   std::map<std::vector<int>, void*> um_pair_plans;   // unstructured.cu: pair records of the owner-computes Jacobian kernel per subproblem list
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
@@ -328,6 +329,7 @@ struct Ctx {
   uint8_t* d_constrained = nullptr;
   int32_t* d_conlist = nullptr;
   int64_t ncon = 0;
+  int con_version = 0;               // bumped whenever the constraint set changes (rebuild_conlist)
   double time = 0.0;
   std::vector<int> con_sps; std::vector<mdb_bctype> con_bcs; bool con_recorded = true;   // the last mdb_constraints_assemble call (mg.cu replays it on the coarse levels)
   int ssor_sweeps = 3;               // SeqSSOR(A, n, 1.0): ISTLBackend_SEQ_BCGS_SSOR uses n = 3 (test/testpoisson.cc:291)
@@ -348,7 +350,7 @@ struct Ctx {
   double* h_pinned = nullptr;        // pinned host scalars
 
   // multi-GPU (multigpu.cu)
-  void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+  void* nccl_comm = nullptr; int nranks = 1, rank = 0; bool comm_borrowed = false;   // borrowed: a coarse multigrid level shares the fine context's communicator
   int part_axis = -1;                // cut axis of the slab partition (-1: not partitioned)
   uint8_t* d_owned = nullptr;        // 1 = row owned by this rank (null: all owned)
   int64_t owned_rows = 0;
@@ -428,6 +430,7 @@ void residual_dg(Ctx* c, const GridOp& go, int child, double weight, const doubl
 void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& m, int child, bool overwrite);      // generic.cu: Qk children, k > 1
 void residual_volume_generic(Ctx* c, const GridOp& go, int child, const double* d_x, double* d_r);
 void dirichlet_rows(Ctx* c, Matrix& m);
+bool dirichlet_rows_off_the_fill(Ctx* c, Matrix& m);      // true: no constrained row is written by the streamed fill (the pass may run beside it)
 void spmv(Ctx* c, const Matrix& m, const double* d_x, double* d_y);
 void spmv_partitioned(Ctx* c, const Matrix& m, double* d_x, double* d_y);   // halo exchange overlapped with the interior rows
 int solve(Ctx* c, Matrix& m, int method, int precond, double reduction, int maxit, int fixed_iters,
@@ -470,6 +473,8 @@ void direct_invalidate(Matrix& m);
 void mg_apply(Ctx* c, Matrix& m, const double* d_d, double* d_v);
 void mg_free(Matrix& m);
 int mg_levels(const Matrix& m);
+int mg_setup(Ctx* c, Matrix& m);
+::mdb_ctx* mg_level_ctx(Matrix& m, int level);
 
 template <typename T> inline T* dalloc(size_t n)
 {

@@ -383,6 +383,7 @@ void rebuild_conlist(Ctx* c)
   MDB_CUDA(cudaMemcpyAsync(&lf, d_f + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
   MDB_CUDA(cudaStreamSynchronize(c->stream));
   c->ncon = (int64_t)ls + lf;
+  c->con_version++;
   dfree(c->d_conlist);
   c->d_conlist = dalloc<int32_t>(c->ncon);
   MDB_LAUNCH(c, k_compact, cdiv(n, 256), 256, 0, c->d_constrained, d_s, c->d_conlist, n);

@@ -25,6 +25,7 @@
 // of term i is chosen once per thread), evaluates the 2 NL rows for its column, and the base line of ROW j — so that the 17th
 // evaluation of the reference's loop costs 1/NR of an evaluation per thread.
 #include "exact_common.cuh"
+#include <algorithm>
 #include <type_traits>
 
 namespace mdb {
@@ -349,12 +350,17 @@ static void fd_launch(Ctx* c, const FdPlan& plan, const CouplingParams& P, const
     }
     T.w[q] = plan.h_tab[(size_t)(q * NR) * 4 + 3];
   }
+  // MDB_FD_BLOCKS_PER_SM = k bounds the kernel's footprint to k resident blocks per SM by padding its dynamic shared memory: beside
+  // the per-thread-store fill (MDB_FILL_NO_TMA) the FP64-bound faces then leave the SM's warp slots to the stores
+  static const int per_sm = getenv("MDB_FD_BLOCKS_PER_SM") ? atoi(getenv("MDB_FD_BLOCKS_PER_SM")) : 0;
+  size_t smem_bytes = sizeof(Smem);
+  if (per_sm >= 1 && per_sm <= 8) smem_bytes = std::max(smem_bytes, (size_t)(224 * 1024 / per_sm - 1024));
   static bool configured = false;
   if (!configured) {
-    MDB_CUDA(cudaFuncSetAttribute(k_fd_coupling<DIM, AXIS, SIDE, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    MDB_CUDA(cudaFuncSetAttribute(k_fd_coupling<DIM, AXIS, SIDE, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     configured = true;
   }
-  MDB_LAUNCH(c, (k_fd_coupling<DIM, AXIS, SIDE, M>), cdiv(fl.n, Smem::FPB), FD_NT, sizeof(Smem), T, c->mesh, fl.d_cell, fl.n, P.intensity,
+  MDB_LAUNCH(c, (k_fd_coupling<DIM, AXIS, SIDE, M>), cdiv(fl.n, Smem::FPB), FD_NT, smem_bytes, T, c->mesh, fl.d_cell, fl.n, P.intensity,
              (int)(P.jac_mode == MDB_JAC_ANALYTIC), weight, eps, plan.d_tab, d_x, plan.d_dofs, plan.d_rowstart, plan.d_slotsT, Mx.d_val);
 }
 

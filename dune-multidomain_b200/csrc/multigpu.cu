@@ -65,7 +65,7 @@ void allreduce_scalars(Ctx* c, double* d_vals, int n)
 
 void nccl_comm_release(Ctx* c)
 {
-  if (c->nccl_comm && g_nccl.lib && g_nccl.CommDestroy) g_nccl.CommDestroy((nccl_comm_t)c->nccl_comm);
+  if (c->nccl_comm && !c->comm_borrowed && g_nccl.lib && g_nccl.CommDestroy) g_nccl.CommDestroy((nccl_comm_t)c->nccl_comm);
   c->nccl_comm = nullptr;
 }
 

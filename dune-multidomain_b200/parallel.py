@@ -84,6 +84,19 @@ def connect(dev, dist, rank, nranks):
     return SimpleNamespace(child_global_base=bases, global_ndof=total, counts=counts)
 
 
+def connect_mg(dev, mat, dist, rank, nranks):
+    """Multigrid on a slab partition (MDB_PRECOND_MG): build the hierarchy (collective) and connect the halo windows of every coarse
+    level with its neighbours', exactly as `connect` does for the fine level.  Returns the number of levels."""
+    nlev = dev.mg_setup(mat)
+    for l in range(1, nlev):
+        lev = dev.mg_level(mat, l)
+        blob, _ = lev.halo_export()
+        blobs = [None] * nranks
+        dist.all_gather_object(blobs, blob)
+        lev.halo_import(rank - 1, blobs[rank - 1] if rank > 0 else None, rank + 1, blobs[rank + 1] if rank < nranks - 1 else None)
+    return nlev
+
+
 # ---- unstructured meshes (SURVEY §8e: "gmsh meshes -> recursive coordinate bisection of cell centroids, rows owned by the lowest
 # rank touching the DOF").  The partition itself is host-side (every rank evaluates it identically); the data path is mdb_partition_lists.
 # The design mirrors the slab partition: every rank also holds the ghost cells it needs so that the rows it owns are assembled

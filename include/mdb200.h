@@ -420,6 +420,12 @@ int mdb_solve_block(mdb_ctx* ctx, int mat, int child, int method, int precond, d
                     mdb_solve_stats* stats);
 int mdb_solve(mdb_ctx* ctx, int mat, int method, int precond, double reduction, int maxit,
               const double* rhs, double* z, mdb_solve_stats* stats);
+/* Build the multigrid hierarchy of a matrix ahead of the first MDB_PRECOND_MG solve (single rank: optional).  On a slab partition this
+ * is REQUIRED and collective: every rank coarsens its slab (owned layers [c0, c1) -> [c0/2, c1/2), one coarse ghost layer below), then
+ * the halo windows of every coarse level are connected like the fine level's: mdb_mg_level returns the (borrowed) context of level
+ * l >= 1, on which mdb_halo_export / mdb_halo_import are called; the coarse levels share the fine context's communicator. */
+int mdb_mg_setup(mdb_ctx* ctx, int mat, int* nlevels);
+mdb_ctx* mdb_mg_level(mdb_ctx* ctx, int mat, int level);
 /* Levels of the multigrid hierarchy built for this matrix (0 before the first MDB_PRECOND_MG solve). */
 int mdb_matrix_mg_levels(mdb_ctx* ctx, int mat);
 /* Number of symmetric sweeps n of MDB_PRECOND_SSOR (default 3). */
