@@ -14,7 +14,8 @@
 //   smoother           Chebyshev polynomial in D^-1 A on [lambda_max / 4, 1.1 lambda_max] (lambda_max by a power iteration at set-up):
 //                      symmetric, no dependency chain, one SpMV per degree — the V-cycle is an SPD operator, valid inside CG
 //   coarsest level     the same smoother with a wider interval and more steps (a few dozen coefficients)
-// Single-rank contexts, Q1 children, meshes whose cell counts and subdomain marking coarsen (even counts, uniform 2^d blocks).
+// Q1 children (also on a slab partition) or QkDG children (nested spaces: transfers by evaluation of the coarse cell's basis), meshes
+// whose cell counts and subdomain marking coarsen (even counts, uniform 2^d blocks).
 #include "common.cuh"
 #include <cmath>
 
@@ -67,7 +68,7 @@ __global__ void k_mg_dinv(int64_t n, const int64_t* __restrict__ rowptr, const i
   if (diag[i] >= 0) { const double a = val[rowptr[i] + diag[i]]; d = a != 0.0 ? 1.0 / a : 1.0; }
   dinv[i] = d;
 }
-struct MgChild { int64_t off_f, off_c, size_f, size_c; const int32_t *d2l_f, *l2d_f, *d2l_c, *l2d_c; int nf[3], nc[3]; int gf[3], gc[3]; };   // gf / gc: global lattice index of local plane 0 (partition)
+struct MgChild { int64_t off_f, off_c, size_f, size_c; const int32_t *d2l_f, *l2d_f, *d2l_c, *l2d_c; int nf[3], nc[3]; int gf[3], gc[3]; int k, dg; };   // gf / gc: global lattice index of local plane 0 (partition)
 
 // x_f += P x_c on the coefficients of one child (not on constrained ones)
 __global__ void k_mg_prolong(MgChild C, int dim, const uint8_t* __restrict__ con_f, const double* __restrict__ xc, double* xf)
@@ -115,6 +116,68 @@ __global__ void k_mg_restrict(MgChild C, int dim, const uint8_t* __restrict__ co
         const double w = (a ? 0.5 : 1.0) * (b ? 0.5 : 1.0) * (c ? 0.5 : 1.0);
         acc += w * rf[C.off_f + df];
       }
+  rc[C.off_c + g] = acc;
+}
+
+// QkDG children: the spaces of two levels are nested (a coarse cell's polynomial restricted to its 2^d children), so the
+// prolongation is the evaluation of the coarse cell's Lagrange basis at the fine cell's nodes and the restriction its transpose.
+// Lattice of a QkDG child: cell c, node a  <->  lattice point (k + 1) c + a per axis; nodes equidistant.
+__device__ inline double mg_lagrange(int k, int a, double xi)
+{
+  double v = 1.0;
+  for (int m = 0; m <= k; ++m) if (m != a) v *= (xi * k - m) / (double)(a - m);
+  return v;
+}
+__global__ void k_mg_prolong_dg(MgChild C, int dim, const double* __restrict__ xc, double* xf)
+{
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= C.size_f) return;
+  const int k = C.k, k1 = C.k + 1;
+  int64_t p = C.d2l_f[g];
+  int pf[3] = {0, 0, 0};
+  pf[0] = (int)(p % C.nf[0]); p /= C.nf[0]; pf[1] = (int)(p % C.nf[1]); pf[2] = (int)(p / C.nf[1]);
+  int I[3] = {0, 0, 0}; double w[3][3] = {{1, 0, 0}, {1, 0, 0}, {1, 0, 0}};
+  for (int d = 0; d < dim; ++d) {
+    const int i = pf[d] / k1, a = pf[d] % k1;
+    I[d] = i >> 1;
+    const double xi = 0.5 * ((i & 1) + (double)a / k);
+    for (int b = 0; b <= k; ++b) w[d][b] = mg_lagrange(k, b, xi);
+  }
+  double acc = 0.0;
+  for (int c = 0; c <= (dim > 2 ? k : 0); ++c)
+    for (int b = 0; b <= k; ++b)
+      for (int a = 0; a <= k; ++a) {
+        const int64_t pc = (k1 * I[0] + a) + (int64_t)C.nc[0] * ((k1 * I[1] + b) + (int64_t)C.nc[1] * (dim > 2 ? k1 * I[2] + c : 0));
+        const int32_t dc = C.l2d_c[pc];
+        if (dc >= 0) acc += w[0][a] * w[1][b] * (dim > 2 ? w[2][c] : 1.0) * xc[C.off_c + dc];
+      }
+  xf[C.off_f + g] += acc;
+}
+__global__ void k_mg_restrict_dg(MgChild C, int dim, const double* __restrict__ rf, double* rc)
+{
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= C.size_c) return;
+  const int k = C.k, k1 = C.k + 1;
+  int64_t p = C.d2l_c[g];
+  int pc[3] = {0, 0, 0};
+  pc[0] = (int)(p % C.nc[0]); p /= C.nc[0]; pc[1] = (int)(p % C.nc[1]); pc[2] = (int)(p / C.nc[1]);
+  int I[3], A[3];
+  for (int d = 0; d < 3; ++d) { I[d] = pc[d] / k1; A[d] = pc[d] % k1; }
+  double acc = 0.0;
+  const int nz = dim > 2 ? 2 * k1 : 1;
+  for (int fz = 0; fz < nz; ++fz) {
+    const double wz = dim > 2 ? mg_lagrange(k, A[2], 0.5 * ((fz / k1) + (double)(fz % k1) / k)) : 1.0;
+    for (int fy = 0; fy < 2 * k1; ++fy) {
+      const double wy = mg_lagrange(k, A[1], 0.5 * ((fy / k1) + (double)(fy % k1) / k));
+      for (int fx = 0; fx < 2 * k1; ++fx) {
+        const double wx = mg_lagrange(k, A[0], 0.5 * ((fx / k1) + (double)(fx % k1) / k));
+        // fine lattice point: cell 2 I + (f / k1), node f % k1  ->  k1 (2 I) + f
+        const int64_t lf = (2 * k1 * I[0] + fx) + (int64_t)C.nf[0] * ((2 * k1 * I[1] + fy) + (int64_t)C.nf[1] * (dim > 2 ? 2 * k1 * I[2] + fz : 0));
+        const int32_t df = C.l2d_f[lf];
+        if (df >= 0) acc += wx * wy * wz * rf[C.off_f + df];
+      }
+    }
+  }
   rc[C.off_c + g] = acc;
 }
 // Chebyshev smoothing steps (see mg_smooth)
@@ -242,8 +305,8 @@ mdb_ctx* coarsen(Ctx* f)
     c->have_sd = true;
     for (const Child& ch : f->children) MG_CALL(c, mdb_add_space(c, ch.fe_kind, ch.subdomain), "space");
     for (const SubProblemDesc& sp : f->sps) {
-      const void* p = sp.op_id == MDB_OP_POISSON ? (const void*)&sp.poisson : (const void*)&sp.l2;
-      const size_t nb = sp.op_id == MDB_OP_POISSON ? sizeof(sp.poisson) : sizeof(sp.l2);
+      const void* p = sp.op_id == MDB_OP_POISSON ? (const void*)&sp.poisson : sp.op_id == MDB_OP_CONVDIFF_DG ? (const void*)&sp.cddg : (const void*)&sp.l2;
+      const size_t nb = sp.op_id == MDB_OP_POISSON ? sizeof(sp.poisson) : sp.op_id == MDB_OP_CONVDIFF_DG ? sizeof(sp.cddg) : sizeof(sp.l2);
       MG_CALL(c, mdb_add_subproblem(c, sp.op_id, p, nb, sp.cond_kind, sp.mask, sp.children.data(), (int)sp.children.size()), "subproblem");
     }
     for (const CouplingDesc& cp : f->cps) {
@@ -321,6 +384,7 @@ MgChild child_pair(const Ctx* f, const Ctx* cc, size_t k)
   MgChild C; C.off_f = a.offset; C.off_c = b.offset; C.size_f = a.size; C.size_c = b.size;
   C.d2l_f = a.d_dof2lat; C.l2d_f = a.d_lat2dof; C.d2l_c = b.d_dof2lat; C.l2d_c = b.d_lat2dof;
   for (int d = 0; d < 3; ++d) { C.nf[d] = a.lat_n[d]; C.nc[d] = b.lat_n[d]; C.gf[d] = d < f->mesh.dim ? f->mesh.off[d] : 0; C.gc[d] = d < cc->mesh.dim ? cc->mesh.off[d] : 0; }
+  C.k = a.k; C.dg = a.dg ? 1 : 0;
   return C;
 }
 
@@ -339,13 +403,15 @@ void vcycle(Ctx* c, MgHier* H, size_t li)
   if (part) halo_exchange(l.ctx, l.r);                   // the restriction to a rank's lowest owned coarse plane reads the fine ghost plane below
   for (size_t k = 0; k < l.ctx->children.size(); ++k) {
     const MgChild C = child_pair(l.ctx, n.ctx, k);
-    if (C.size_c > 0) MDB_LAUNCH(c, k_mg_restrict, cdiv(C.size_c, 128), 128, 0, C, dim, l.ctx->d_constrained, n.ctx->d_constrained, l.r, n.b);
+    if (C.size_c > 0 && C.dg) MDB_LAUNCH(c, k_mg_restrict_dg, cdiv(C.size_c, 128), 128, 0, C, dim, l.r, n.b);
+    else if (C.size_c > 0) MDB_LAUNCH(c, k_mg_restrict, cdiv(C.size_c, 128), 128, 0, C, dim, l.ctx->d_constrained, n.ctx->d_constrained, l.r, n.b);
   }
   vcycle(c, H, li + 1);
   if (part) { StreamScope cs(n.ctx, c->stream); halo_exchange(n.ctx, n.x); }     // the prolongation reads the coarse ghost planes
   for (size_t k = 0; k < l.ctx->children.size(); ++k) {
     const MgChild C = child_pair(l.ctx, n.ctx, k);
-    if (C.size_f > 0) MDB_LAUNCH(c, k_mg_prolong, cdiv(C.size_f, 256), 256, 0, C, dim, l.ctx->d_constrained, n.x, l.x);
+    if (C.size_f > 0 && C.dg) MDB_LAUNCH(c, k_mg_prolong_dg, cdiv(C.size_f, 256), 256, 0, C, dim, n.x, l.x);
+    else if (C.size_f > 0) MDB_LAUNCH(c, k_mg_prolong, cdiv(C.size_f, 256), 256, 0, C, dim, l.ctx->d_constrained, n.x, l.x);
   }
   mg_smooth(c, l, l.b, l.x, false, H->degree, hi / 4.0, hi);
 }
@@ -364,8 +430,10 @@ void mg_free(Matrix& M)
 static void mg_check(Ctx* c, Matrix& M)
 {
   MDB_REQUIRE(!c->um, MDB_EINVAL, "MDB_PRECOND_MG: structured meshes only");
-  for (const Child& ch : c->children) MDB_REQUIRE(ch.fe_kind == MDB_FE_Q1, MDB_EINVAL, "MDB_PRECOND_MG: Q1 child spaces only");
-  for (const SubProblemDesc& sp : c->sps) MDB_REQUIRE(sp.op_id == MDB_OP_POISSON || sp.op_id == MDB_OP_L2, MDB_EINVAL, "MDB_PRECOND_MG: Poisson / L2 subproblems only");
+  for (const Child& ch : c->children)
+    MDB_REQUIRE((ch.fe_kind == MDB_FE_Q1 && !ch.iface) || (ch.dg && !c->mesh.partitioned), MDB_EINVAL, "MDB_PRECOND_MG: Q1 child spaces only (QkDG on one rank)");
+  for (const SubProblemDesc& sp : c->sps)
+    MDB_REQUIRE(sp.op_id == MDB_OP_POISSON || sp.op_id == MDB_OP_L2 || sp.op_id == MDB_OP_CONVDIFF_DG, MDB_EINVAL, "MDB_PRECOND_MG: Poisson / L2 / ConvectionDiffusionDG subproblems only");
   for (const CouplingDesc& cp : c->cps) MDB_REQUIRE(cp.op_id == MDB_OP_CVCF_COUPLING || cp.op_id == MDB_OP_PROPFLOW_COUPLING, MDB_EINVAL, "MDB_PRECOND_MG: flow couplings only");
   MDB_REQUIRE(c->con_recorded, MDB_EINVAL, "MDB_PRECOND_MG: needs constraints assembled by mdb_constraints_assemble (the coarse levels replay them)");
   (void)M;

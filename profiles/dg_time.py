@@ -31,7 +31,9 @@ for refine in refines:
     if os.environ.get("DG_TIME_NO_SOLVE"):
         dev.close(); continue
     for name, method, precond, sweeps, maxit in (("BiCGSTAB+Jacobi", capi.SOLVER_BICGSTAB, capi.PRECOND_JACOBI, 1, 20000),
-                                                 ("BiCGSTAB+SSOR(3)", capi.SOLVER_BICGSTAB, capi.PRECOND_SSOR, 3, 12 if refine > 7 else 5000)):
+                                                 ("BiCGSTAB+SSOR(3)", capi.SOLVER_BICGSTAB, capi.PRECOND_SSOR, 3, 12 if refine > 7 else 5000),
+                                                 ("BiCGSTAB+MG", capi.SOLVER_BICGSTAB, capi.PRECOND_MG, 1, 500), ("BiCGSTAB+MG again", capi.SOLVER_BICGSTAB, capi.PRECOND_MG, 1, 500)):
+        if os.environ.get("DG_TIME_ONLY") and os.environ["DG_TIME_ONLY"] not in name: continue
         dev.set_ssor_sweeps(sweeps)
         st = dev.solve(P.mat, r, z, method=method, precond=precond, reduction=1e-8, maxit=maxit)
         dev.synchronize()

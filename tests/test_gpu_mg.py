@@ -96,3 +96,26 @@ def test_refuses_what_it_cannot_coarsen():
     with pytest.raises(pkg.MdbError, match="Q1 child spaces only"):
         dev.solve(P.mat, r, np.zeros(P.ndof), method=capi.SOLVER_CG, precond=capi.PRECOND_MG)
     dev.close()
+
+
+@pytest.mark.parametrize("n,k", [((32, 32), 2), ((32, 32), 1), ((8, 8, 8), 1)])
+def test_multigrid_on_qkdg_spaces(n, k):
+    """BASELINE configs[0] as shipped (DG-Qk, SIPG, CVCF coupling): nested spaces, the transfers evaluate the coarse cell's Lagrange
+    basis at the fine nodes.  The system is that of the oracle; the V-cycle only changes the iteration count."""
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    Pd, Po = problems.dirichlet_neumann_dg(dev, n, k=k), problems.dirichlet_neumann_dg(ora, n, k=k)
+    uo = np.zeros(Po.ndof)
+    ora.jacobian(Po.go, Po.mat, uo, overwrite=True)
+    dev.jacobian(Pd.go, Pd.mat, uo, overwrite=True)
+    ro, rd = np.zeros(Po.ndof), np.zeros(Po.ndof)
+    ora.residual(Po.go, uo, ro)
+    dev.residual(Pd.go, uo, rd)
+    zo = spla.spsolve(sp.csc_matrix(ora.csr(Po.mat)), ro)
+    z = np.zeros(Pd.ndof)
+    st = dev.solve(Pd.mat, rd, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_MG, reduction=1e-13, maxit=300)
+    assert st.converged and dev.matrix_mg_levels(Pd.mat) >= 3
+    assert np.abs(z - zo).max() <= 1e-9 * np.abs(zo).max()
+    zj = np.zeros(Pd.ndof)
+    stj = dev.solve(Pd.mat, rd, zj, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_JACOBI, reduction=1e-13, maxit=20000)
+    assert stj.converged and st.iterations * 3 < stj.iterations, (st.iterations, stj.iterations)
+    dev.close(); ora.close()
