@@ -478,6 +478,21 @@ class Mdb(Lib):
         self._check(self._fn("halo_export")(C.c_void_p(self.ctx), buf, C.byref(nbytes)), "halo_export")
         return bytes(buf), nbytes.value
 
+    def scalars_export(self):
+        """mdb_scalars_export: descriptor of this rank's scalar window (peer-memory all-reduce of the Krylov scalars)."""
+        buf = (C.c_char * 80)()
+        self._check(self._fn("scalars_export")(C.c_void_p(self.ctx), buf), "scalars_export")
+        return bytes(buf)
+
+    def scalars_exchanges(self):
+        return int(self._fn("scalars_exchanges", C.c_int64)(C.c_void_p(self.ctx)))
+
+    def scalars_import(self, blobs):
+        buf = (C.c_char * (80 * len(blobs)))()
+        for i, b in enumerate(blobs):
+            buf[80 * i:80 * (i + 1)] = b
+        self._check(self._fn("scalars_import")(C.c_void_p(self.ctx), len(blobs), buf), "scalars_import")
+
     def halo_import(self, lower_rank, lower_blob, upper_rank, upper_blob):
         self._check(self._fn("halo_import")(C.c_void_p(self.ctx), lower_rank, C.c_char_p(lower_blob) if lower_blob else None,
                                             upper_rank, C.c_char_p(upper_blob) if upper_blob else None), "halo_import")

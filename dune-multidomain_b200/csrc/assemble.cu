@@ -212,6 +212,74 @@ __global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_tma(FillJobs J, do
   __syncthreads();
 }
 
+// ---- hybrid fill: bulk-async stores AND per-thread stores side by side ---------------------------------------------------------
+// The bulk-store path alone tops out at ~5.3-5.6 TB/s (the copy engines), per-thread stores need every SM full of warps to reach
+// their 7.3 TB/s.  Here the warps of a block take runs from a counter: `n_tma` of them issue bulk copies from the shared-memory image
+// (no registers, no issue slots), the others write their runs with aligned 256-byte warp stores from the same image — the two paths
+// share the memory system, and the runs divide themselves between them by how fast each path retires them.
+template <int DIM>
+__global__ void __launch_bounds__(FT_THREADS) k_jacobian_fill_hybrid(FillJobs J, double* __restrict__ val, int ft_rows, int n_tma, unsigned int* __restrict__ counters)
+{
+  constexpr int NS = (DIM == 3) ? 27 : 9;
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.job[jb + 1].block0) ++jb;
+  const double* __restrict__ S = J.job[jb].S;
+  const longlong2* __restrict__ seg_span = J.job[jb].seg_span;
+  const int64_t nseg = J.job[jb].nseg;
+  const int CH = NS * ft_rows;
+  extern __shared__ __align__(128) double img[];                         // CH + 2 NS doubles, img[i] = S[i mod NS]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < CH + 2 * NS; i += FT_THREADS) img[i] = S[i % NS];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t img_s = (uint32_t)__cvta_generic_to_shared(img);
+  const bool tma = warp < n_tma;
+  for (;;) {
+    unsigned int run = 0;
+    if (lane == 0) run = atomicAdd(counters + jb, 1u);
+    run = __shfl_sync(0xffffffffu, run, 0);
+    if ((int64_t)run >= nseg) break;
+    const longlong2 span = seg_span[run];
+    const int64_t p0 = span.x, p1 = span.y;
+    if (p0 == p1) continue;
+    if (tma) {
+      int64_t a0 = (p0 + 1) & ~(int64_t)1;
+      const int64_t a1 = p1 & ~(int64_t)1;
+      if (lane == 0 && (p0 & 1)) val[p0] = img[0];
+      if (lane == 1 && (p1 & 1) && p1 - 1 > p0) val[p1 - 1] = img[(p1 - 1 - p0) % NS];
+      if (lane == 0) {
+        const int phase = (int)((a0 - p0) % NS);
+        const uint32_t src = img_s + 8u * (uint32_t)((phase & 1) ? phase + NS : phase);
+        while (a0 < a1) {
+          const int64_t n = (a1 - a0 < CH) ? a1 - a0 : CH;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(val + a0), "r"(src), "r"((uint32_t)(n * 8)) : "memory");
+          a0 += n;
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      constexpr int CHUNK = 32 * NS;
+      const int64_t a0 = p0 & ~(int64_t)31;
+      const int mm0 = (int)((a0 - p0 + lane + 4 * NS) % NS);
+      for (int64_t cb = a0; cb < p1; cb += CHUNK) {
+        int mm = mm0;
+        if (cb >= p0 && cb + CHUNK <= p1) {
+#pragma unroll
+          for (int it = 0; it < NS; ++it) { val[cb + it * 32 + lane] = img[mm]; mm += 32 % NS; if (mm >= NS) mm -= NS; }
+        } else {
+          for (int it = 0; it < NS; ++it) {
+            const int64_t i = cb + it * 32 + lane;
+            if (i >= p0 && i < p1) val[i] = img[mm];
+            mm += 32 % NS; if (mm >= NS) mm -= NS;
+          }
+        }
+      }
+    }
+  }
+  if (tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncthreads();
+}
+
 // ---- irregular rows (or all rows when the uniform shortcut is not valid) ---------------------------------------
 // One thread gathers one row (sum over the incident cells, popcount placement) into a row image in shared memory; the
 // warp then writes its 32 row images out cooperatively, consecutive lanes to consecutive entries, so that a row costs
@@ -551,9 +619,23 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
         FJ.job[j].block0 = b0; b0 += nb;
       }
       FJ.nblocks = b0;
+      static const int hybrid_tma = getenv("MDB_FILL_HYBRID") ? atoi(getenv("MDB_FILL_HYBRID")) : -1;    // warps per block on the bulk-store path; -1: all (k_jacobian_fill_tma)
+      if (hybrid_tma >= 0 && hybrid_tma <= FT_THREADS / 32) {
+        static bool configured_h = false;
+        if (!configured_h) {
+          MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_hybrid<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((9 * FT_ROWS + 18) * sizeof(double))));
+          MDB_CUDA(cudaFuncSetAttribute(k_jacobian_fill_hybrid<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((27 * FT_ROWS + 54) * sizeof(double))));
+          configured_h = true;
+        }
+        if (!c->d_fill_ctr) c->d_fill_ctr = dalloc<unsigned int>(MDB_MAX_CHILDREN);
+        MDB_CUDA(cudaMemsetAsync(c->d_fill_ctr, 0, MDB_MAX_CHILDREN * sizeof(unsigned int), c->stream));
+        if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_hybrid<2>, FJ.nblocks, FT_THREADS, smem, FJ, M.d_val, ft_rows, hybrid_tma, c->d_fill_ctr);
+        else MDB_LAUNCH(c, k_jacobian_fill_hybrid<3>, FJ.nblocks, FT_THREADS, smem, FJ, M.d_val, ft_rows, hybrid_tma, c->d_fill_ctr);
+      } else {
       static const int evict_first = getenv("MDB_FILL_EVICT_FIRST") ? atoi(getenv("MDB_FILL_EVICT_FIRST")) : 0;
       if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_fill_tma<2>, FJ.nblocks, FT_THREADS, smem, FJ, M.d_val, ft_rows, evict_first);
       else MDB_LAUNCH(c, k_jacobian_fill_tma<3>, FJ.nblocks, FT_THREADS, smem, FJ, M.d_val, ft_rows, evict_first);
+      }
     } else {
       static const int per_sm = getenv("MDB_FILL_BLOCKS_PER_SM") ? atoi(getenv("MDB_FILL_BLOCKS_PER_SM")) : 0;   // 0: one run per block
       int b0 = 0;
@@ -911,6 +993,196 @@ __global__ void __launch_bounds__(RS_ROWS, RS_BLOCKS) k_residual_stencil(int64_t
   }
 }
 
+// ---- residual, z-marching variant (3-D box children; the default) ---------------------------------------------------------------
+// The tile kernel above re-reads every value of x 4.5 times from the L2 and 13.5 times from shared memory, and spends ~110 of its
+// ~150 warp instructions per 32 rows on tile bookkeeping.  Here a block owns RM_T consecutive positions of RM_RY consecutive x-lines
+// and MARCHES over up to `zt` z-planes: each plane's RM_RY + 2 x-segments arrive by bulk-async copies into a ring of RM_NB plane
+// buffers (one mbarrier per buffer), a thread reads its 3 (RM_RY + 2) values of the plane ONCE into registers and scatters them into
+// the partial sums of the three output planes that see this plane as dz = +1, 0, -1.  A row still receives its 27 terms in stencil
+// order (dz-major, then dy, then dx), so the result is the one of the tile kernel bit for bit.  Per row: 4.5 LDS.64, 27 DFMA with
+// constant-bank coefficients, one byte of the plan, one L2 reduction; x crosses the L2 -> SM path (RM_RY + 2) / RM_RY * (zt + 2) / zt
+// = 1.7 times.  Tiles start at box position (1, 1, 1): the first and last lattice positions of a box child are never uniform rows.
+#define RM_T 128
+#define RM_RY 4
+#define RM_NB 3
+#define RM_XSEG (RM_T + 4)
+struct MarchChild { int64_t offset; int bx, by, bz, bxy; int nxc, nyc, nzc, zt; int slot; const uint8_t* fast; int tile0; };
+struct MarchJobs { int n; MarchChild job[MDB_MAX_CHILDREN]; int ntiles; };
+struct MarchTile { int64_t r00; int npos, nlines, nplanes; };
+__host__ __device__ inline MarchTile march_tile(const MarchChild& ch, int tile)
+{
+  const int xc = tile % ch.nxc, yz = tile / ch.nxc, yc = yz % ch.nyc, zc = yz / ch.nyc;
+  const int s0 = 1 + xc * RM_T, y0 = 1 + yc * RM_RY, z0 = 1 + zc * ch.zt;
+  MarchTile T;
+  T.r00 = ch.offset + s0 + (int64_t)ch.bx * y0 + (int64_t)ch.bxy * z0;
+  T.npos = (ch.bx - 1 - s0 < RM_T) ? ch.bx - 1 - s0 : RM_T;
+  T.nlines = (ch.by - 1 - y0 < RM_RY) ? ch.by - 1 - y0 : RM_RY;
+  T.nplanes = (ch.bz - 1 - z0 < ch.zt) ? ch.bz - 1 - z0 : ch.zt;
+  return T;
+}
+// every segment the tile stages (lines -1 .. RM_RY of planes -1 .. nplanes, widened by one entry for the 16-byte alignment) inside the vector
+__host__ __device__ inline bool march_tile_staged(const MarchChild& ch, const MarchTile& T, int64_t n)
+{
+  return T.r00 - 1 - ch.bx - ch.bxy - 1 >= 0 && T.r00 + T.npos + 1 + (int64_t)RM_RY * ch.bx + (int64_t)T.nplanes * ch.bxy + 1 <= n;
+}
+static MarchChild march_child(const Child& hc, int zt)
+{
+  MarchChild mc;
+  mc.offset = hc.offset;
+  mc.bx = hc.lat_hi[0] - hc.lat_lo[0] + 1; mc.by = hc.lat_hi[1] - hc.lat_lo[1] + 1; mc.bz = hc.lat_hi[2] - hc.lat_lo[2] + 1; mc.bxy = mc.bx * mc.by;
+  mc.zt = zt;
+  mc.nxc = (mc.bx - 2 + RM_T - 1) / RM_T; mc.nyc = (mc.by - 2 + RM_RY - 1) / RM_RY; mc.nzc = (mc.bz - 2 + zt - 1) / zt;
+  if (mc.bx < 3 || mc.by < 3 || mc.bz < 3) mc.nxc = mc.nyc = mc.nzc = 0;
+  mc.slot = 0; mc.fast = nullptr; mc.tile0 = 0;
+  return mc;
+}
+static int march_zt()
+{
+  static const int zt = getenv("MDB_RESIDUAL_ZT") ? std::max(1, atoi(getenv("MDB_RESIDUAL_ZT"))) : 16;
+  return zt;
+}
+__global__ void k_residual_march(int64_t n, MarchJobs J, const double* __restrict__ x, double* __restrict__ res);
+// Resident blocks per SM of the marching kernel, capped through a dynamic shared-memory pad: the kernel runs on the low-priority
+// stream beside the latency-bound row-list / boundary / coupling kernels of mdb_residual, which need block slots and registers.
+static size_t march_smem_pad()
+{
+  static const int blocks = getenv("MDB_RESIDUAL_MARCH_BLOCKS") ? atoi(getenv("MDB_RESIDUAL_MARCH_BLOCKS")) : 8;
+  static size_t pad = 0; static bool done = false;
+  if (!done) {
+    const size_t fixed = sizeof(double) * RM_NB * (RM_RY + 2) * RM_XSEG + 8 * RM_NB + 1024;
+    if (blocks >= 1 && blocks < 8) { const size_t per = (size_t)233472 / blocks; pad = per > fixed + 256 ? ((per - fixed - 256) & ~(size_t)127) : 0; }
+    MDB_CUDA(cudaFuncSetAttribute(k_residual_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+    done = true;
+  }
+  return pad;
+}
+static bool march_enabled(int dim)
+{
+  static const bool off = getenv("MDB_RESIDUAL_NO_MARCH") != nullptr;            // A/B switch: the tile kernel in 3-D as well
+  return dim == 3 && !off;
+}
+
+__global__ void k_residual_plan_march(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V, MarchChild mc, int64_t n, uint8_t* fast, int32_t* flags)
+{
+  const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gi >= ch.size) return;
+  int rr = ch.dof2lat[gi];
+  int p[3]; p[0] = rr % ch.lat_n[0]; rr /= ch.lat_n[0]; p[1] = rr % ch.lat_n[1]; p[2] = rr / ch.lat_n[1];
+  bool uni = p[0] >= 1 && p[0] < m.n[0] && p[1] >= 1 && p[1] < m.n[1] && p[2] >= 1 && p[2] < m.n[2];
+  if (uni) {
+    for (int cz = -1; cz <= 0; ++cz)
+      for (int cy = -1; cy <= 0; ++cy)
+        for (int cx = -1; cx <= 0; ++cx) {
+          const uint8_t s = sd[(p[0] + cx) + (int64_t)m.n[0] * ((p[1] + cy) + (int64_t)m.n[1] * (p[2] + cz))];
+          uni = uni && cond_applies(V.cond_kind[0], V.mask[0], s) && (ch.subdomain < 0 || ((s >> ch.subdomain) & 1));
+        }
+  }
+  // position inside the box (the child's rows are numbered along x, then y, then z of its bounding box)
+  const int line = (int)(gi / mc.bx), bs = (int)(gi - (int64_t)line * mc.bx), biy = line % mc.by, biz = line / mc.by;
+  bool f = uni && bs >= 1 && bs <= mc.bx - 2 && biy >= 1 && biy <= mc.by - 2 && biz >= 1 && biz <= mc.bz - 2 && mc.nxc > 0;
+  if (f) {
+    const int tile = (bs - 1) / RM_T + mc.nxc * ((biy - 1) / RM_RY + mc.nyc * ((biz - 1) / mc.zt));
+    f = march_tile_staged(mc, march_tile(mc, tile), n);
+  }
+  fast[gi] = f ? 1 : 0;
+  flags[gi] = f ? 0 : 1;
+}
+
+// one plane of the march: `comp` completes (this plane is its dz = +1), `mid` takes dz = 0, `fresh` starts with dz = -1
+#define RM_PLANE(q, comp, mid, fresh)                                                                                                  \
+  do {                                                                                                                                 \
+    const int buf = (q) % RM_NB;                                                                                                       \
+    /* plan bytes of the output plane this step completes (q - 1), fetched while the copies land */                                    \
+    uint32_t fb = 0;                                                                                                                   \
+    if ((q) >= 2 && t < T.npos) {                                                                                                      \
+      _Pragma("unroll") for (int j = 0; j < RM_RY; ++j)                                                                                \
+        if (j < T.nlines) fb |= (uint32_t)(fastc[(int64_t)j * ch.bx + (int64_t)((q) - 2) * ch.bxy] != 0) << j;                         \
+    }                                                                                                                                  \
+    {                                                                                                                                  \
+      uint32_t ok = 0;                                                                                                                 \
+      const uint32_t par = (uint32_t)(((q) / RM_NB) & 1);                                                                              \
+      while (!ok)                                                                                                                      \
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"       \
+                     : "=r"(ok) : "r"(bar_s + 8u * buf), "r"(par) : "memory");                                                         \
+    }                                                                                                                                  \
+    {                                                                                                                                  \
+      const int pz = (((q) - 1) & 1) ? pbxy : 0;                                                                                       \
+      _Pragma("unroll") for (int yy = 0; yy < RM_RY + 2; ++yy) {                                                                       \
+        const int sh = p0 ^ (((yy - 1) & 1) ? pb : 0) ^ pz;                                                                            \
+        const double* seg = sx[buf] + yy * RM_XSEG + t + 1 + sh;                                                                       \
+        const double xm = seg[-1], x0 = seg[0], xp = seg[1];                                                                           \
+        _Pragma("unroll") for (int j = 0; j < RM_RY; ++j) {                                                                            \
+          const int dy = yy - j;                                           /* segment yy is line j + dy - 1 of the tile */            \
+          if (dy < 0 || dy > 2) continue;                                                                                              \
+          if (dy == 0) fresh[j] = 0.0;                                                                                                 \
+          fresh[j] += cS[dy * 3] * xm; fresh[j] += cS[dy * 3 + 1] * x0; fresh[j] += cS[dy * 3 + 2] * xp;                               \
+          mid[j] += cS[9 + dy * 3] * xm; mid[j] += cS[9 + dy * 3 + 1] * x0; mid[j] += cS[9 + dy * 3 + 2] * xp;                         \
+          comp[j] += cS[18 + dy * 3] * xm; comp[j] += cS[18 + dy * 3 + 1] * x0; comp[j] += cS[18 + dy * 3 + 2] * xp;                   \
+        }                                                                                                                              \
+      }                                                                                                                                \
+    }                                                                                                                                  \
+    __syncthreads();                                                       /* every thread has read the plane: the buffer is free */ \
+    if (t < 32 && (q) + RM_NB <= last) issue((q) + RM_NB, buf);                                                                        \
+    if (fb) {                                                                                                                          \
+      _Pragma("unroll") for (int j = 0; j < RM_RY; ++j)                                                                                \
+        if ((fb >> j) & 1u) atomicAdd(resc + (int64_t)j * ch.bx + (int64_t)((q) - 2) * ch.bxy, comp[j]);                               \
+    }                                                                                                                                  \
+  } while (0)
+
+__global__ void __launch_bounds__(RM_T, 8) k_residual_march(int64_t n, MarchJobs J, const double* __restrict__ x, double* __restrict__ res)
+{
+  __shared__ __align__(16) double sx[RM_NB][(RM_RY + 2) * RM_XSEG];
+  __shared__ __align__(8) unsigned long long bar[RM_NB];
+  const int t = threadIdx.x;
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.job[jb + 1].tile0) ++jb;
+  const MarchChild& ch = J.job[jb];
+  const MarchTile T = march_tile(ch, (int)blockIdx.x - ch.tile0);
+  if (!march_tile_staged(ch, T, n)) return;                                      // block-uniform: its rows are on the row list
+  const int xpar = (int)(((uintptr_t)x >> 3) & 1);                              // bulk copies need 16-byte aligned sources
+  const double* __restrict__ cS = c_resS[ch.slot];                               // block-uniform: constant-bank operands
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar[0]);
+  if (t == 0) {
+#pragma unroll
+    for (int b = 0; b < RM_NB; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8u * b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int last = T.nplanes + 1;                                                // staged planes q = 0 .. last  <->  tile planes -1 .. nplanes
+  // segment yy of plane q: line yy - 1 of tile plane q - 1; lanes 0 .. RM_RY + 1 of warp 0 issue one bulk copy each on the buffer's barrier
+  auto issue = [&](int q, int buf) {
+    const uint32_t sx_s = (uint32_t)__cvta_generic_to_shared(sx[buf]);
+    const int len = T.npos + 2;
+    const int64_t g0 = T.r00 - 1 + (int64_t)(t - 1) * ch.bx + (int64_t)(q - 1) * ch.bxy;
+    const int64_t al = g0 - ((g0 + xpar) & 1);
+    const uint32_t bytes = (t < RM_RY + 2) ? (uint32_t)((((g0 + len) - al + 1) & ~(int64_t)1) * 8) : 0u;
+    uint32_t total = bytes;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (t == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + 8u * buf), "r"(total) : "memory");
+    __syncwarp();
+    if (t < RM_RY + 2)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sx_s + (uint32_t)(t * RM_XSEG * 8)),
+                   "l"(x + al), "r"(bytes), "r"(bar_s + 8u * buf)
+                   : "memory");
+  };
+  if (t < 32)
+    for (int q = 0; q < RM_NB && q <= last; ++q) issue(q, q);
+  // where element g0 of a segment landed: its 16-byte aligned copy starts at g0 - ((g0 + xpar) & 1), and
+  // parity(g0) = parity(r00 - 1 + xpar) ^ ((yy - 1) odd & bx odd) ^ ((q - 1) odd & bxy odd)
+  const int p0 = (int)((T.r00 - 1 + xpar) & 1), pb = ch.bx & 1, pbxy = ch.bxy & 1;
+  const uint8_t* __restrict__ fastc = ch.fast + (T.r00 - ch.offset) + t;
+  double* __restrict__ resc = res + T.r00 + t;
+  double s0[RM_RY], s1[RM_RY], s2[RM_RY];
+#pragma unroll
+  for (int j = 0; j < RM_RY; ++j) { s0[j] = 0.0; s1[j] = 0.0; s2[j] = 0.0; }
+  for (int q = 0; q <= last; ++q) {                                              // block-uniform trip count
+    RM_PLANE(q, s0, s1, s2);
+#pragma unroll
+    for (int j = 0; j < RM_RY; ++j) { s0[j] = s1[j]; s1[j] = s2[j]; }
+  }
+}
+
 // returns false when the child does not qualify (the caller falls back to the tile kernel)
 static bool residual_stencil_applies(const Ctx* c, int child, const VolSpec& V)
 {
@@ -924,7 +1196,8 @@ static bool residual_stencil_applies(const Ctx* c, int child, const VolSpec& V)
 }
 
 // part: -1 = both kernels, 0 = the streamed uniform rows, 1 = the other rows of the child (row-list gather)
-static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, const VolSpec& V, const double* d_x, double* d_r, int part = -1)
+static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, const VolSpec& V, const double* d_x, double* d_r, int part = -1,
+                             MarchJobs* march = nullptr)
 {
   const MeshDesc& m = c->mesh;
   const Child& hc = c->children[child];
@@ -938,6 +1211,7 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
     int32_t* d_flag = dalloc<int32_t>(hc.size);
     int32_t* d_scan = dalloc<int32_t>(hc.size);
     if (m.dim == 2) MDB_LAUNCH(c, k_residual_plan<2>, cdiv(hc.size, 256), 256, 0, m, c->d_cell_sd, ch, V, rc, n, go.d_res_fast[child], d_flag);
+    else if (march_enabled(m.dim)) MDB_LAUNCH(c, k_residual_plan_march, cdiv(hc.size, 256), 256, 0, m, c->d_cell_sd, ch, V, march_child(hc, march_zt()), n, go.d_res_fast[child], d_flag);
     else MDB_LAUNCH(c, k_residual_plan<3>, cdiv(hc.size, 256), 256, 0, m, c->d_cell_sd, ch, V, rc, n, go.d_res_fast[child], d_flag);
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_scan, (int)hc.size, c->stream);
@@ -960,6 +1234,14 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
     int grid = 148 * RS_BLOCKS;
     if (grid > res_ntiles(rc)) grid = (int)res_ntiles(rc);
     if (m.dim == 2) MDB_LAUNCH(c, k_residual_stencil<2>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
+    else if (march_enabled(m.dim)) {
+      MarchJobs one; one.n = 0; one.ntiles = 0;
+      MarchJobs* J = march ? march : &one;
+      MarchChild mc = march_child(hc, march_zt());
+      mc.slot = V.slot[0]; mc.fast = go.d_res_fast[child]; mc.tile0 = J->ntiles;
+      if (mc.nxc > 0) { J->job[J->n++] = mc; J->ntiles += mc.nxc * mc.nyc * mc.nzc; }
+      if (!march && one.n > 0) MDB_LAUNCH(c, k_residual_march, one.ntiles, RM_T, march_smem_pad(), n, one, d_x, d_r);
+    }
     else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
   }
   const int64_t nrest = go.n_res_rest[child];
@@ -990,11 +1272,13 @@ bool residual_can_split(Ctx* c, const GridOp& go)
 void residual_volume_part(Ctx* c, const GridOp& go, double weight, const double* d_x, double* d_r, int part)
 {
   (void)weight;
+  MarchJobs J; J.n = 0; J.ntiles = 0;                                             // the marching tiles of all children go through ONE launch
   for (int i = 0; i < (int)c->children.size(); ++i) {
     VolSpec V = vol_spec(c, go, i);
     if (V.n == 0 || c->children[i].size == 0) continue;
-    residual_stencil(c, const_cast<GridOp&>(go), i, child_q1(c, i), V, d_x, d_r, part);
+    residual_stencil(c, const_cast<GridOp&>(go), i, child_q1(c, i), V, d_x, d_r, part, &J);
   }
+  if (J.n > 0) MDB_LAUNCH(c, k_residual_march, J.ntiles, RM_T, march_smem_pad(), c->ndof, J, d_x, d_r);
 }
 
 // plans (fast flags + row lists) of every child, built on the context stream before a split residual forks

@@ -228,7 +228,7 @@ mdb_ctx* mdb_create(int device)
     }
     MDB_CUDA(cudaEventCreate(&c->ev0));
     MDB_CUDA(cudaEventCreate(&c->ev1));
-    MDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi)); MDB_CUDA(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi)); }
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     MDB_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
@@ -246,10 +246,11 @@ void mdb_destroy(mdb_ctx* c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  sring_release(c);
   nccl_comm_release(c);
   reset_spaces(c);
   um_free(c);
-  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_ftab_g); dfree(c->d_dgtab); dfree(c->d_scal); dfree(c->d_partial);
+  dfree(c->d_cell_sd); dfree(c->d_Ae); dfree(c->d_ftab); dfree(c->d_ftab_g); dfree(c->d_dgtab); dfree(c->d_scal); dfree(c->d_fill_ctr); dfree(c->d_partial);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->d_halo_counter) cudaFree(c->d_halo_counter);
@@ -774,22 +775,18 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
   if (c->um) { if (c->ufe) ufe_residual(c, G, weight, vx.d, vr.d); else um_residual(c, G, weight, vx.d, vr.d); vr.commit(); return MDB_OK; }
   static const bool serial = getenv("MDB_RESIDUAL_SERIAL") != nullptr;          // A/B switch for profiling only
   if (!serial && residual_can_split(c, G)) {
-    // main: element matrices -> [fork] -> streamed uniform rows of every child (issue / shared-memory bound) --------> [join] -> constrain
-    // aux :                     [fork] -> row lists (latency bound) -------------------------------------------------> [join]
-    // third:                    [fork] -> boundary terms -> coupling terms (latency bound) ---------------------------> [join]
+    // main (high priority): element matrices -> [fork] -> row lists (latency bound) ---------------------------------> [join] -> constrain
+    // aux  (low priority) :                     [fork] -> streamed uniform rows of every child (HBM / issue bound) ---> [join]
+    // third (high)        :                     [fork] -> boundary terms -> coupling terms (latency bound) -----------> [join]
     // The streamed rows are interior rows all of whose cells carry the subproblem: no row list and no boundary term touches them;
     // the coupling terms of the interface cells do (their vertices one layer off the interface), which is why the stencil kernel
-    // adds with a reduction instead of load + store.
+    // adds with a reduction instead of load + store.  The streaming kernel fills every SM; on the LOW-priority stream it yields
+    // block slots to the short latency-bound kernels of the other two branches as its blocks retire (on the high-priority stream
+    // it ran first and the branches serialised behind it: 0.265 ms per call against 0.2 ms).
     residual_prepare(c, G);
     c->phase_begin("residual_volume");
     launch_element_matrices(c, G.sps, weight);
     MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-    {
-      StreamScope aux(c, c->aux_stream);
-      MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
-      residual_volume_part(c, G, weight, vx.d, vr.d, 1);
-      MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
-    }
     {
       StreamScope third(c, c->copy_stream);                                     // every update of r on the three branches is a reduction
       MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
@@ -797,7 +794,17 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
       residual_coupling(c, G, weight, vx.d, vr.d);
       MDB_CUDA(cudaEventRecord(c->ev_copy_done, c->stream));
     }
-    residual_volume_part(c, G, weight, vx.d, vr.d, 0);
+    {
+      StreamScope aux(c, c->aux_stream);
+      MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+      c->phase_end();
+      c->phase_begin("residual_streamed");                                      // events on the auxiliary stream: the streaming kernel's own time inside the call
+      residual_volume_part(c, G, weight, vx.d, vr.d, 0);
+      c->phase_end();
+      MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
+    }
+    c->phase_begin("residual_rows");
+    residual_volume_part(c, G, weight, vx.d, vr.d, 1);
     c->phase_end();
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));

@@ -346,10 +346,12 @@ struct Ctx {
   double* d_work = nullptr; int64_t work_n = 0; int work_vecs = 0;
   double* d_onestep = nullptr; int64_t onestep_n = 0;      // u, R, z of mdb_onestep_apply
   double* d_scal = nullptr;          // device scalars
+  unsigned int* d_fill_ctr = nullptr; // run counters of the hybrid fill kernel (one per child job)
   double* d_partial = nullptr;       // block partial sums
   double* h_pinned = nullptr;        // pinned host scalars
 
   // multi-GPU (multigpu.cu)
+  void* sring = nullptr; bool sring_borrowed = false;          // scalar windows of all ranks (multigpu.cu: peer-memory all-reduce of the Krylov scalars); coarse multigrid levels share the fine context's
   void* nccl_comm = nullptr; int nranks = 1, rank = 0; bool comm_borrowed = false;   // borrowed: a coarse multigrid level shares the fine context's communicator
   int part_axis = -1;                // cut axis of the slab partition (-1: not partitioned)
   uint8_t* d_owned = nullptr;        // 1 = row owned by this rank (null: all owned)
@@ -371,6 +373,50 @@ struct Ctx {
   double phase_mean_ms(const char* name, int* count);
   void phase_reset();
 };
+
+#define SR_MAXR 16
+#define SR_MAXV 4
+struct SrSpec { int nranks, rank; unsigned long long seq; double* win[SR_MAXR]; int* err; long long timeout_clocks; double* done; };
+#ifdef __CUDACC__
+// Window of a rank: double val[2][SR_MAXR][SR_MAXV] followed by unsigned long long flag[2][SR_MAXR].  Exchange number seq (the same on
+// every rank) uses parity seq & 1: thread t < nranks stores this rank's values into rank t's window and publishes seq with a
+// release store at system scope, then waits for rank t's flag in its own window; thread 0 adds the contributions in rank order, so
+// every rank obtains the same bits.  Two parities suffice: a rank publishes seq + 1 only after it has read seq, and nobody starts
+// seq + 2 before every flag of seq + 1 has arrived.  Call with all threads of ONE block; loc[] in shared memory holds the local
+// values on entry and the sums on exit.
+__device__ __forceinline__ void sr_exchange(const SrSpec& R, double* loc, int n)
+{
+  const int t = threadIdx.x, par = (int)(R.seq & 1);
+  __shared__ int sr_ok;
+  if (t == 0) sr_ok = 1;
+  __syncthreads();
+  if (t < R.nranks) {
+    double* w = R.win[t];
+    for (int k = 0; k < n; ++k) w[(par * SR_MAXR + R.rank) * SR_MAXV + k] = loc[k];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(w + 2 * SR_MAXR * SR_MAXV) + par * SR_MAXR + R.rank), "l"(R.seq) : "memory");
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(R.win[R.rank] + 2 * SR_MAXR * SR_MAXV) + par * SR_MAXR + t;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= R.seq) break;
+      if (clock64() - t0 > R.timeout_clocks) { sr_ok = 0; break; }
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    if (!sr_ok) { atomicExch(R.err, 1); if (R.done) *R.done = 1.0; }
+    const double* mine = R.win[R.rank];
+    for (int k = 0; k < n; ++k) {
+      double a = 0.0;
+      for (int r = 0; r < R.nranks; ++r) a += __ldcv(mine + (par * SR_MAXR + r) * SR_MAXV + k);
+      loc[k] = a;
+    }
+  }
+  __syncthreads();
+}
+#endif
 
 // run a section of host code with another stream as the context's launch stream
 struct StreamScope {
@@ -437,6 +483,10 @@ int solve(Ctx* c, Matrix& m, int method, int precond, double reduction, int maxi
           const double* d_rhs, double* d_z, mdb_solve_stats* stats);
 void setup_partition(Ctx* c);                       // multigpu.cu: ownership flags + halo window of a partitioned mesh
 void allreduce_scalars(Ctx* c, double* d_vals, int n);
+// Peer-memory all-reduce of up to SR_MAXV scalars (multigpu.cu).  SrSpec is passed by value to the kernel that ends in the exchange.
+bool sring_connected(const Ctx* c);
+SrSpec sring_next(Ctx* c, double* d_done);          // the descriptor of the next exchange (advances the sequence number)
+void sring_release(Ctx* c);
 void halo_exchange(Ctx* c, double* d_x, double* d_done = nullptr);   // d_done: the solver's S_DONE slot, set when the wait times out
 void halo_push(Ctx* c, const double* d_x);
 void halo_wait(Ctx* c, double* d_x, double* d_done = nullptr);

@@ -302,6 +302,7 @@ mdb_ctx* coarsen(Ctx* f)
     if (!all_ranks(f, bad == 0)) { mdb_destroy(c); return nullptr; }       // the subdomain marking is not a union of 2^d blocks: this level is the coarsest
     // the coarse level reduces over the same ranks: it borrows the communicator
     c->nccl_comm = f->nccl_comm; c->comm_borrowed = true; c->nranks = f->nranks; c->rank = f->rank;
+    c->sring = f->sring; c->sring_borrowed = f->sring != nullptr;
     c->have_sd = true;
     for (const Child& ch : f->children) MG_CALL(c, mdb_add_space(c, ch.fe_kind, ch.subdomain), "space");
     for (const SubProblemDesc& sp : f->sps) {

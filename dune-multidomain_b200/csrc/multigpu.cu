@@ -56,8 +56,50 @@ static NcclApi& nccl()
   do { int r__ = (call); if (r__ != 0) throw Error(MDB_ENCCL, std::string(#call) + ": " +                                \
                                                    (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error")); } while (0)
 
+// ---- peer-memory all-reduce of the Krylov scalars --------------------------------------------------------------------------------
+// NCCL's all-reduce of one or two doubles costs ~14 us per call on NVSwitch (launch + protocol), two or three times per Krylov
+// iteration.  Every rank instead owns a 1.3 KB window that all ranks map (cudaIpc): a block of the reducing kernel stores its values
+// straight into every peer's window over NVLink and spins on its own window (sr_exchange in common.cuh) — no library call, no extra
+// launch when the exchange is the tail of the kernel that produced the values (k_reduce_partials in solver.cu).
+struct ScalarRing { double* mine = nullptr; double* win[SR_MAXR]; int nranks = 0, rank = 0; unsigned long long seq = 0; bool connected = false; int* d_err = nullptr; };
+static const size_t SR_WINDOW_BYTES = (2 * SR_MAXR * SR_MAXV) * sizeof(double) + (2 * SR_MAXR) * sizeof(unsigned long long);
+
+static long long halo_timeout_clocks(const Ctx* c);
+bool sring_connected(const Ctx* c)
+{
+  static const bool off = getenv("MDB_SCALARS_NCCL") != nullptr;                 // A/B switch: always NCCL
+  const ScalarRing* R = (const ScalarRing*)c->sring;
+  return !off && R && R->connected && R->nranks == c->nranks;
+}
+SrSpec sring_next(Ctx* c, double* d_done)
+{
+  ScalarRing* R = (ScalarRing*)c->sring;
+  SrSpec S; S.nranks = R->nranks; S.rank = R->rank; S.seq = ++R->seq;
+  for (int i = 0; i < SR_MAXR; ++i) S.win[i] = i < R->nranks ? R->win[i] : nullptr;
+  S.err = R->d_err; S.timeout_clocks = halo_timeout_clocks(c); S.done = d_done;
+  return S;
+}
+void sring_release(Ctx* c)
+{
+  ScalarRing* R = (ScalarRing*)c->sring;
+  if (R && !c->sring_borrowed) { if (R->mine) cudaFree(R->mine); if (R->d_err) cudaFree(R->d_err); delete R; }
+  c->sring = nullptr; c->sring_borrowed = false;
+}
+__global__ void k_sr_allreduce(SrSpec R, double* vals, int n)
+{
+  __shared__ double loc[SR_MAXV];
+  if ((int)threadIdx.x < n) loc[threadIdx.x] = vals[threadIdx.x];
+  __syncthreads();
+  sr_exchange(R, loc, n);
+  if ((int)threadIdx.x < n) vals[threadIdx.x] = loc[threadIdx.x];
+}
+
 void allreduce_scalars(Ctx* c, double* d_vals, int n)
 {
+  if (sring_connected(c) && n <= SR_MAXV) {
+    MDB_LAUNCH(c, k_sr_allreduce, 1, 32, 0, sring_next(c, nullptr), d_vals, n);
+    return;
+  }
   MDB_REQUIRE(c->nccl_comm, MDB_ENCCL, "multi-GPU solve without a communicator: call mdb_comm_init first");
   MDB_NCCL(nccl().AllReduce(d_vals, d_vals, (size_t)n, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)c->nccl_comm, c->stream));
   c->launches++;
@@ -397,6 +439,13 @@ void halo_exchange(Ctx* c, double* d_x, double* d_done)
 
 bool halo_timed_out(Ctx* c)
 {
+  if (c->sring && ((ScalarRing*)c->sring)->d_err) {
+    ScalarRing* R = (ScalarRing*)c->sring;
+    int e = 0;
+    MDB_CUDA(cudaMemcpyAsync(&e, R->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    if (e != 0) { MDB_CUDA(cudaMemsetAsync(R->d_err, 0, sizeof(int), c->stream)); MDB_CUDA(cudaStreamSynchronize(c->stream)); return true; }
+  }
   if (!c->d_halo_counter) return false;
   int e = 0;
   MDB_CUDA(cudaMemcpyAsync(&e, c->d_halo_counter + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -470,6 +519,43 @@ int mdb_halo_export(mdb_ctx* c, void* blob80, int64_t* window_bytes)
   std::memcpy(blob80, &b, sizeof(b));
   if (window_bytes) *window_bytes = c->halo_recv_n * (int64_t)sizeof(double);
   MG_END(c)
+}
+
+static double* open_peer(mdb_ctx* c, const void* blob80);
+int mdb_scalars_export(mdb_ctx* c, void* blob80)
+{
+  MG_BEGIN(c)
+  MDB_REQUIRE(c->nranks > 1, MDB_ESTATE, "mdb_scalars_export: call mdb_comm_init with more than one rank first");
+  MDB_REQUIRE(c->nranks <= SR_MAXR, MDB_EINVAL, "mdb_scalars_export: at most 16 ranks");
+  sring_release(c);
+  ScalarRing* R = new ScalarRing(); c->sring = R;
+  R->nranks = c->nranks; R->rank = c->rank;
+  void* p = nullptr; MDB_CUDA(cudaMalloc(&p, SR_WINDOW_BYTES)); R->mine = (double*)p;
+  MDB_CUDA(cudaMemset(R->mine, 0, SR_WINDOW_BYTES));
+  R->d_err = dalloc<int>(1); MDB_CUDA(cudaMemset(R->d_err, 0, sizeof(int)));
+  HaloBlob b; std::memset(&b, 0, sizeof(b));
+  MDB_CUDA(cudaIpcGetMemHandle(&b.ipc, R->mine));
+  b.raw = (uint64_t)(uintptr_t)R->mine; b.device = c->device; b.token = process_token();
+  std::memset(blob80, 0, 80);
+  std::memcpy(blob80, &b, sizeof(b));
+  MG_END(c)
+}
+
+int mdb_scalars_import(mdb_ctx* c, int nranks, const void* blobs80)
+{
+  MG_BEGIN(c)
+  ScalarRing* R = (ScalarRing*)c->sring;
+  MDB_REQUIRE(R && R->mine && !c->sring_borrowed, MDB_ESTATE, "mdb_scalars_import: call mdb_scalars_export first");
+  MDB_REQUIRE(nranks == c->nranks && blobs80, MDB_EINVAL, "mdb_scalars_import: one descriptor per rank of the communicator");
+  for (int r = 0; r < nranks; ++r) R->win[r] = r == c->rank ? R->mine : open_peer(c, (const char*)blobs80 + 80 * (size_t)r);
+  R->connected = true;
+  MG_END(c)
+}
+
+int64_t mdb_scalars_exchanges(mdb_ctx* c)
+{
+  if (!c || !sring_connected(c)) return 0;
+  return (int64_t)((ScalarRing*)c->sring)->seq;
 }
 
 static double* open_peer(mdb_ctx* c, const void* blob80)

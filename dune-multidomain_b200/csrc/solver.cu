@@ -580,6 +580,23 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int nblock
     __syncthreads();
   }
 }
+// the same reduction ending in the peer-memory all-reduce over the ranks (sr_exchange, common.cuh): one launch instead of a reduction
+// kernel + an NCCL all-reduce
+__global__ void k_reduce_partials_ranks(const double* __restrict__ partial, int nblocks, int nvals, double* scal, int slot0, int slot1, int slot2, SrSpec R)
+{
+  __shared__ double sh[VEC_THREADS / 32];
+  __shared__ double loc[SR_MAXV];
+  for (int k = 0; k < nvals; ++k) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += partial[k * MAX_PARTIAL_BLOCKS + i];
+    double s = block_sum(v, sh);
+    if (threadIdx.x == 0) loc[k] = s;
+    __syncthreads();
+  }
+  sr_exchange(R, loc, nvals);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < nvals; ++k) scal[k == 0 ? slot0 : (k == 1 ? slot1 : slot2)] = loc[k];
+}
 
 __global__ void k_extract_dinv(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ diag, const double* __restrict__ val,
                                double* dinv, int jacobi)
@@ -758,6 +775,20 @@ static void reduce(Ctx* c, int nblocks, int nvals, int s0, int s1 = 0, int s2 = 
 {
   MDB_LAUNCH(c, k_reduce_partials, 1, VEC_THREADS, 0, c->d_partial, nblocks, nvals, c->d_scal, s0, s1, s2);
 }
+// block partials -> scalars s0 (, s1, s2), summed over the ranks of the communicator
+static void reduce_ranks(Ctx* c, bool multi, int nblocks, int nvals, int s0, int s1 = 0, int s2 = 0)
+{
+  if (multi && sring_connected(c)) {
+    MDB_LAUNCH(c, k_reduce_partials_ranks, 1, VEC_THREADS, 0, c->d_partial, nblocks, nvals, c->d_scal, s0, s1, s2, sring_next(c, c->d_scal + S_DONE));
+    return;
+  }
+  reduce(c, nblocks, nvals, s0, s1, s2);
+  if (multi) {
+    // NCCL reduces a contiguous range
+    MDB_REQUIRE(nvals == 1 || (s1 == s0 + 1 && (nvals == 2 || s2 == s0 + 2)), MDB_EINVAL, "reduce_ranks: scalar slots must be adjacent");
+    allreduce_scalars(c, c->d_scal + s0, nvals);
+  }
+}
 
 static void ensure_work(Ctx* c, int nvecs)
 {
@@ -803,13 +834,11 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     double *r = c->d_work, *p = c->d_work + n, *q = c->d_work + 2 * n, *zv = general ? c->d_work + 3 * n : nullptr;
     MDB_CUDA(cudaMemsetAsync(s + S_DONE, 0, sizeof(double), c->stream));
     MDB_LAUNCH(c, k_cg_init, vgrid, VEC_THREADS, 0, n, d_b, M.d_dinv, c->d_owned, x, r, p, c->d_partial);
-    reduce(c, vgrid, 2, S_RHONEW, S_RR);
-    if (multi) allreduce_scalars(c, s + S_RHONEW, 2);
+    reduce_ranks(c, multi, vgrid, 2, S_RHONEW, S_RR);
     auto precondition = [&]() {            // zv = M^-1 r ; rho_new = zv . r
       precond_apply(c, M, precond, c->ssor_sweeps, r, zv);
       MDB_LAUNCH(c, k_dot, vgrid, VEC_THREADS, 0, n, s, zv, r, c->d_owned, c->d_partial);
-      reduce(c, vgrid, 1, S_RHONEW);
-      if (multi) allreduce_scalars(c, s + S_RHONEW, 1);
+      reduce_ranks(c, multi, vgrid, 1, S_RHONEW);
     };
     if (general) precondition();
     MDB_LAUNCH(c, k_cg_init_scalars, 1, 1, 0, s, reduction);
@@ -817,12 +846,10 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
       MDB_LAUNCH(c, k_cg_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, general ? zv : r, p);
       if (multi) spmv_halo<1>(c, M, p, q, p, c->d_partial, &nb, s);
       else launch_spmv<1>(c, M, p, q, p, c->d_partial, &nb, s);
-      reduce(c, nb, 1, S_PQ);
-      if (multi) allreduce_scalars(c, s + S_PQ, 1);
+      reduce_ranks(c, multi, nb, 1, S_PQ);
       MDB_LAUNCH(c, k_cg_derive_a, 1, 1, 0, s);
       MDB_LAUNCH(c, k_cg_update_xr, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, p, q, c->d_owned, x, r, c->d_partial);
-      reduce(c, vgrid, 2, S_RHONEW, S_RR);
-      if (multi) allreduce_scalars(c, s + S_RHONEW, 2);
+      reduce_ranks(c, multi, vgrid, 2, S_RHONEW, S_RR);
       if (general) precondition();
       MDB_LAUNCH(c, k_cg_derive_b, 1, 1, 0, s);
       ++issued;
@@ -832,30 +859,25 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
     ensure_work(c, 7);
     double *r = c->d_work, *rt = r + n, *p = rt + n, *v = p + n, *y = v + n, *y2 = y + n, *t = y2 + n;
     MDB_LAUNCH(c, k_bi_init, vgrid, VEC_THREADS, 0, n, d_b, c->d_owned, x, r, rt, p, v, c->d_partial);
-    reduce(c, vgrid, 1, S_RR);
-    if (multi) allreduce_scalars(c, s + S_RR, 1);
+    reduce_ranks(c, multi, vgrid, 1, S_RR);
     MDB_LAUNCH(c, k_bi_init_scalars, 1, 1, 0, s, reduction);
     while (issued < maxit) {
       MDB_LAUNCH(c, k_bi_update_p, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, r, v, p, y);
       if (general) precond_apply(c, M, precond, c->ssor_sweeps, p, y);
       if (multi) spmv_halo<1>(c, M, y, v, rt, c->d_partial, &nb, s);
       else launch_spmv<1>(c, M, y, v, rt, c->d_partial, &nb, s);
-      reduce(c, nb, 1, S_H);
-      if (multi) allreduce_scalars(c, s + S_H, 1);
+      reduce_ranks(c, multi, nb, 1, S_H);
       MDB_LAUNCH(c, k_bi_derive_alpha, 1, 1, 0, s);
       MDB_LAUNCH(c, k_bi_update_s, vgrid, VEC_THREADS, 0, n, s, M.d_dinv, y, v, c->d_owned, x, r, y2, c->d_partial);
-      reduce(c, vgrid, 1, S_RR);
-      if (multi) allreduce_scalars(c, s + S_RR, 1);
+      reduce_ranks(c, multi, vgrid, 1, S_RR);
       MDB_LAUNCH(c, k_bi_derive_half, 1, 1, 0, s);
       if (general) precond_apply(c, M, precond, c->ssor_sweeps, r, y2);
       if (multi) spmv_halo<2>(c, M, y2, t, r, c->d_partial, &nb, s);
       else launch_spmv<2>(c, M, y2, t, r, c->d_partial, &nb, s);
-      reduce(c, nb, 2, S_TR, S_TT);
-      if (multi) allreduce_scalars(c, s + S_TR, 2);
+      reduce_ranks(c, multi, nb, 2, S_TR, S_TT);
       MDB_LAUNCH(c, k_bi_derive_omega, 1, 1, 0, s);
       MDB_LAUNCH(c, k_bi_update_x, vgrid, VEC_THREADS, 0, n, s, y2, t, rt, c->d_owned, x, r, c->d_partial);
-      reduce(c, vgrid, 2, S_RR, S_PQ);
-      if (multi) allreduce_scalars(c, s + S_RR, 2);
+      reduce_ranks(c, multi, vgrid, 2, S_RR, S_PQ);
       MDB_LAUNCH(c, k_bi_derive_end, 1, 1, 0, s);
       ++issued;
       if (issued % check_every == 0) { poll(); if (hp[S_DONE] != 0.0) break; }

@@ -68,6 +68,18 @@ def global_child_bases(per_rank_child_counts, rank):
     return child_offset + below, int(child_total.sum())
 
 
+def connect_scalars(dev, dist, rank, nranks):
+    """Map every rank's scalar window (mdb_scalars_export / mdb_scalars_import): the Krylov dot products are then all-reduced by peer
+    stores over NVLink inside the reducing kernel instead of one ncclAllReduce each.  MDB_SCALARS_NCCL=1 skips it (A/B)."""
+    import os
+    if nranks < 2 or nranks > 16 or os.environ.get("MDB_SCALARS_NCCL"):
+        return False
+    blobs = [None] * nranks
+    dist.all_gather_object(blobs, dev.scalars_export())
+    dev.scalars_import(blobs)
+    return True
+
+
 def connect(dev, dist, rank, nranks):
     """Create the NCCL communicator of `dev` and map the neighbours' halo windows.  `dist` is an initialised
     torch.distributed; call after dev.finalize()."""
@@ -78,6 +90,7 @@ def connect(dev, dist, rank, nranks):
     blobs = [None] * nranks
     dist.all_gather_object(blobs, blob)
     dev.halo_import(rank - 1, blobs[rank - 1] if rank > 0 else None, rank + 1, blobs[rank + 1] if rank < nranks - 1 else None)
+    connect_scalars(dev, dist, rank, nranks)
     counts = [None] * nranks
     dist.all_gather_object(counts, [int(v) for v in dev.owned_counts()])
     bases, total = global_child_bases(counts, rank)
@@ -220,4 +233,5 @@ def um_connect(dev, dist, rank, nranks, global_dof, owner):
         slot = info[q]["neigh"].index(rank)
         blobs.append(info[q]["blob"]); caps.append(max(info[q]["recv_ptr"][-1], 1)); offs.append(info[q]["recv_ptr"][slot]); slots.append(slot)
     dev.halo_import_lists(blobs, caps, offs, slots)
+    connect_scalars(dev, dist, rank, nranks)
     return SimpleNamespace(neighbours=neigh, send_count=int(send_ptr[-1]), recv_count=int(recv_ptr[-1]), owned_rows=int(owned.sum()))

@@ -465,6 +465,16 @@ int mdb_comm_init(mdb_ctx* ctx, int nranks, int rank, const void* id128);
  * neighbour (first / last rank). */
 int mdb_halo_export(mdb_ctx* ctx, void* blob80, int64_t* window_bytes);
 int mdb_halo_import(mdb_ctx* ctx, int lower_rank, const void* lower_blob80, int upper_rank, const void* upper_blob80);
+/* Peer-memory all-reduce of the Krylov scalars (optional; without it the scalars go through ncclAllReduce).  Every rank exports the
+ * 80-byte descriptor of a small window (after mdb_comm_init), the descriptors of ALL ranks are exchanged out of band and imported in
+ * rank order (the own entry is ignored).  From then on the dot products of mdb_solve end in a single kernel that stores this rank's
+ * partial sums into every peer's window over NVLink and adds the contributions in rank order: the same bits on every rank, no
+ * library call per reduction.  Connect before mdb_mg_setup (the coarse levels share the windows).  At most 16 ranks.  The reference's
+ * analogue is the MPI_Allreduce inside ISTL's OverlappingSchwarzScalarProduct (test/testoverlappinginstationarypoisson.cc:431-432). */
+int mdb_scalars_export(mdb_ctx* ctx, void* blob80);
+int mdb_scalars_import(mdb_ctx* ctx, int nranks, const void* blobs80);
+/* number of peer-memory all-reduces issued so far on this context's windows (0: not connected, the scalars go through NCCL) */
+int64_t mdb_scalars_exchanges(mdb_ctx* ctx);
 /* The two halves of one exchange of the device vector x (ndof doubles): push this rank's boundary planes into the
  * neighbours' windows, then wait for the neighbours' planes and copy them into the ghost entries of x.  Every rank must
  * issue the same sequence of pushes and waits. */

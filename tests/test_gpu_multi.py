@@ -176,6 +176,8 @@ def _rank_main(rank, world, port, n, ret):
         torch.cuda.synchronize()
         dev.spmv(P.mat, x, y)
         dev.synchronize()
+        import os
+        assert (dev.scalars_exchanges() > 0) == (not os.environ.get("MDB_SCALARS_NCCL")), "the Krylov scalars did not go through the peer windows"
         ret[rank] = {"gidx": gidx[owned], "sol": out, "y": y.cpu().numpy()[owned], "ndof": link.global_ndof, "pre": pre}
         dist.barrier()
         dev.close()

@@ -274,6 +274,29 @@ def test_device_resident_vectors_and_error_paths():
         d2 = pkg.Mdb(0); d2.mesh_structured((4, 4)); d2.add_space(7, 0)     # closed set of spaces: Q1, Q2
 
 
+@pytest.mark.parametrize("n,split_axis", [((140, 10, 20), 1), ((139, 7, 21), 2), ((133, 12, 5), 0), ((262, 6, 38), 1)])
+@pytest.mark.parametrize("shift", [0, 1])
+def test_residual_marching_tiles_against_oracle(n, split_axis, shift):
+    """k_residual_march (csrc/assemble.cu): several 128-position chunks along x, ragged line and plane chunks, odd and even box
+    extents (the parity of bx and bx*by moves the staged segments by one entry), and x / r vectors that are only 8-byte aligned."""
+    import torch
+    dev, ora = pkg.Mdb(0), orc.Oracle()
+    Pd, Po = problems.testpoisson(dev, n, split_axis=split_axis), problems.testpoisson(ora, n, split_axis=split_axis)
+    x = np.random.default_rng(3).uniform(-1, 1, Po.ndof)
+    ro = np.zeros(Po.ndof); ora.residual(Po.go, x, ro)
+    buf_x = torch.zeros(Pd.ndof + 2, dtype=torch.float64, device="cuda")
+    buf_r = torch.zeros(Pd.ndof + 2, dtype=torch.float64, device="cuda")
+    xd, rd = buf_x[shift:shift + Pd.ndof], buf_r[shift:shift + Pd.ndof]
+    xd.copy_(torch.from_numpy(x)); torch.cuda.synchronize()
+    dev.residual(Pd.go, xd, rd); dev.synchronize()
+    ora.jacobian(Po.go, Po.mat, x, overwrite=True)
+    scale = abs(ora.csr(Po.mat)) @ np.abs(x) + np.abs(ro)
+    scale = np.maximum(scale, np.abs(ro).max() * 1e-3)
+    assert np.all(np.abs(rd.cpu().numpy() - ro) <= RTOL_ENTRY * scale)
+    assert buf_r[:shift].abs().sum().item() == 0.0 and buf_r[shift + Pd.ndof:].abs().sum().item() == 0.0     # nothing written outside r
+    dev.close(); ora.close()
+
+
 @pytest.mark.parametrize("n", [(96, 96, 96), (1024, 1024), (256, 256, 256), (500, 500, 500)])
 def test_size_independent_properties_at_scale(n):
     """At sizes the oracle does not reach: J annihilates constants on free rows, Dirichlet rows are unit rows, the
