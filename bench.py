@@ -177,8 +177,16 @@ def run_reference(args, out):
     import numpy as np
     import orc
     import problems
-    # the threaded oracle colours z-slabs: give every thread two layers, bounded so that a step stays within a few seconds
-    size, layers = args.size, min(max(2 * ncores, 8), 64)
+    # the threaded oracle colours blocks of two z-layers with two colours: 4 layers per thread keep every thread busy in both colours
+    # (2 per thread left half of them idle: the slab figure was half the full-mesh one); bounded by the mesh and by the host memory
+    size = args.size
+    layers = min(max(4 * ncores, 8), size)
+    try:
+        import psutil
+        while layers > 8 and 2.0 * 32e9 * (size / 256.0) ** 2 * (layers / 256.0) > psutil.virtual_memory().available:
+            layers //= 2
+    except ImportError:
+        layers = min(layers, 64)
     h = 1.0 / size
     o = orc.Oracle(fast=True)
     P = problems.testpoisson(o, (size, size, layers), upper=(1.0, 1.0, layers * h))
@@ -200,9 +208,40 @@ def run_reference(args, out):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(size)},
             "reference_arm": "CPU restatement of the reference path (oracle port, all host threads; the reference itself needs the DUNE stack "
-                             "and cannot be built here); every step assembles a bounded slab of the workload's mesh, scaled per cell",
+                             "and cannot be built here); every step assembles a slab of the workload's mesh (the whole mesh when 4 z-layers per thread cover it), scaled per cell",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # one step at the workload's FULL size (same mesh, same DOF count as the GPU arm), so that the per-cell scaling of the timed slab
+    # steps can be checked against a same-config number; skipped when the host is short of memory (the oracle's pattern build keeps
+    # every local link before the sort: ~30 GB at 256^3) or with --quick
+    full = {"same_config": False, "skipped": "--quick"}
+    if layers == size:
+        full = {"same_config": True, "what": "every timed step assembled the whole %d^3 mesh" % size}
+    elif not args.quick and not os.environ.get("MDB_BENCH_NO_FULL_REFERENCE"):
+        try:
+            import psutil
+            need = 32e9 * (size / 256.0) ** 3
+            avail = psutil.virtual_memory().available
+            if avail < 2.0 * need:
+                full = {"same_config": False, "skipped": "host memory: %.0f GB available, %.0f GB wanted" % (avail / 1e9, 2.0 * need / 1e9)}
+            else:
+                o.close(); del P
+                o2 = orc.Oracle(fast=True)
+                t0 = time.time()
+                Pf = problems.testpoisson(o2, (size, size, size))
+                t_setup = time.time() - t0
+                uf = np.zeros(Pf.ndof)
+                o2.interpolate(Pf.sps, Pf.gfn, uf)
+                t0 = time.time()
+                o2.jacobian(Pf.go, Pf.mat, uf, overwrite=True, nthreads=ncores)
+                dtf = time.time() - t0
+                full = {"same_config": True, "dofs": int(Pf.ndof), "seconds": dtf, "value": Pf.ndof / dtf, "unit": UNIT, "cores": ncores,
+                        "dofmap_pattern_setup_s": t_setup, "slab_estimate_over_full": value / (Pf.ndof / dtf),
+                        "what": "ONE Jacobian assembly of the whole %d^3 mesh (the GPU arm's config) by the same port and threads" % size}
+                o2.close()
+        except Exception as e:                                  # the timed line stands on its own
+            full = {"same_config": False, "skipped": "failed: %r" % (e,)}
+    line["full_size_step"] = full
     print(json.dumps(line), file=out)
 
 
