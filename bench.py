@@ -766,6 +766,20 @@ def _main(out):
                                   "residual_at_solution_over_initial": float(rr.norm() / r.norm()),
                                   "residual_note": "a Newton step of an affine problem with the reference's FINITE-DIFFERENCE coupling Jacobian (eps = 1e-8): the "
                                                    "linear solve reaches 1e-10, the nonlinear residual stops at the FD truncation error"}
+            # the same call with the multigrid V-cycle as the preconditioner (the hierarchy exists from the time-to-solution leg: the call
+            # re-assembles the coarse operators because the Jacobian was re-assembled)
+            try:
+                xs.copy_(u.cpu())
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                stm = dev.stationary_solve(P.go, P.mat, xs.numpy(), method=capi.SOLVER_CG, precond=capi.PRECOND_MG, reduction=1e-10, maxit=500)
+                t_mg = time.perf_counter() - t0
+                extra["e2e_solve"]["multigrid"] = {"seconds": t_mg, "iterations": int(stm.iterations), "converged": bool(stm.converged),
+                                                   "dofs_per_s": P.ndof / t_mg, "krylov_seconds": stm.seconds,
+                                                   "max_rel_diff_to_jacobi_solution": float((xs.cuda() - xsol).abs().max() / xsol.abs().max()),
+                                                   "what": "the same call with MDB_PRECOND_MG (coarse operators re-assembled inside the call)"}
+            except Exception as e:
+                extra["e2e_solve"]["multigrid"] = {"error": repr(e)}
             if not args.no_cpu_baseline:
                 extra["e2e_solve"]["cpu_port"] = cpu_solve_sample()
         except Exception as e:

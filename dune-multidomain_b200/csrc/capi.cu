@@ -146,6 +146,7 @@ static void free_matrix(Matrix& m)
   m.fd_plans.clear();
   direct_free(m);
   mg_free(m);
+  for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { qk_plan_free(m.qk_plans[i]); m.qk_plans[i] = nullptr; }
   for (auto& kv : m.um_pair_plans) um_pair_plan_free(kv.second);
   m.um_pair_plans.clear();
 }

@@ -291,6 +291,7 @@ struct Matrix {
   void* mg = nullptr;                // mg.cu: multigrid hierarchy (MDB_PRECOND_MG)
   int dir_early_version = -1; bool dir_early_ok = false;   // assemble.cu: no constrained row is a streamed (simple) row for constraint version dir_early_version
   std::vector<std::pair<int, double>> asm_log;   // (grid operator, weight) of the mdb_jacobian calls since the values were last zeroed
+  void* qk_plans[MDB_MAX_CHILDREN] = {nullptr};   // generic.cu: classes / runs of the simple rows of a Qk (k > 1) child, built on first use
   std::map<std::vector<int>, void*> um_pair_plans;   // unstructured.cu: pair records of the owner-computes Jacobian kernel per subproblem list
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
@@ -497,6 +498,7 @@ bool halo_timed_out(Ctx* c);
 void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn);
 void um_free(Ctx* c);
 void um_pair_plan_free(void* plan);
+void qk_plan_free(void* plan);
 void um_build_dofmap(Ctx* c);
 void um_export_dofmap(Ctx* c, int64_t* cell_ptr, int64_t* cell_dofs);
 void um_assemble_constraints(Ctx* c, const int* sps, const mdb_bctype* bcs, int n);

@@ -11,6 +11,9 @@
 //                        (test/proportionalflowcoupling.hh:27-86,113-233; couplingutilities.hh:75-135), one thread per
 //                        face resp. per (face, evaluation)
 #include "exact_common.cuh"
+#include <cub/cub.cuh>
+#include <vector>
+#include <algorithm>
 
 namespace mdb {
 
@@ -129,6 +132,234 @@ static VolSpecG vol_spec_g(const Ctx* c, const GridOp& go, int child)
   return V;
 }
 
+// ---- simple rows of a Qk child: one representative per class, replicated ---------------------------------------------------------
+// On a structured mesh the rows of a Qk child fall into k^d classes by the position of their lattice point inside the cell (vertex,
+// edge along x, ..., cell interior).  A row is SIMPLE when every cell around its lattice point exists and carries the child's
+// subdomain byte, and the row holds nothing but its own block's volume links (length = prod_d (a_d == 0 ? 2k + 1 : k + 1)): all simple
+// rows of a class then hold the same values in the same column order (the numbering is lexicographic inside the entity groups), and
+// consecutive simple rows of a class form long runs of the value array (the DOFs of a group are numbered consecutively).  Per call
+// the owner-computes kernel evaluates the irregular rows in place and ONE representative row per class into a scratch image; a
+// streaming kernel replicates the images over the runs with aligned 256-byte warp stores — the HBM-write-bound path of the Q1 rows
+// (k_jacobian_fill_q1) for every Qk.  Built once per (matrix, child).
+#define QK_MAXCLS 8
+#define QK_MAXL 128
+struct QkRun { long long p0, p1; int cls, ns; };
+struct QkPlan {
+  int ncls = 0; int64_t nruns = 0, nirr = 0, nrep = 0;
+  int32_t* d_irr = nullptr;          // irregular rows (child-local index), ascending
+  int32_t* d_rep = nullptr;          // representative rows per class (child-local index; -1: the class has no simple row)
+  QkRun* d_runs = nullptr;
+  double* d_img = nullptr;           // QK_MAXCLS x QK_MAXL scratch images
+  bool usable = false;
+};
+void qk_plan_free(void* p)
+{
+  QkPlan* P = (QkPlan*)p;
+  if (!P) return;
+  if (P->d_irr) cudaFree(P->d_irr); if (P->d_rep) cudaFree(P->d_rep); if (P->d_runs) cudaFree(P->d_runs); if (P->d_img) cudaFree(P->d_img);
+  delete P;
+}
+
+// cls[gi] = class of a simple row, 255 otherwise; rep[class] = smallest simple row of the class
+template <int DIM>
+__global__ void k_qk_classify(MeshDesc m, const uint8_t* __restrict__ sd, ChildG ch, uint8_t sd0, const int64_t* __restrict__ rowptr, uint8_t* cls, int* rep)
+{
+  const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gi >= ch.size) return;
+  const int k = ch.k;
+  int64_t r = ch.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+  int klass = 0, mul = 1, len = 1;
+  bool ok = true;
+  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (d >= DIM) continue;
+    const int a = p[d] % k, c1 = p[d] / k;
+    klass += a * mul; mul *= k;
+    if (a == 0) { lo[d] = c1 - 1; hi[d] = c1; len *= 2 * k + 1; if (c1 - 1 < 0 || c1 >= m.n[d]) ok = false; }
+    else { lo[d] = hi[d] = c1; len *= k + 1; }
+  }
+  if (ok)
+    for (int cz = lo[2]; cz <= hi[2]; ++cz)
+      for (int cy = lo[1]; cy <= hi[1]; ++cy)
+        for (int cx = lo[0]; cx <= hi[0]; ++cx)
+          ok = ok && sd[cx + (int64_t)m.n[0] * (cy + (int64_t)m.n[1] * cz)] == sd0;
+  const int64_t g = ch.offset + gi;
+  ok = ok && (rowptr[g + 1] - rowptr[g] == len) && len <= QK_MAXL && klass < QK_MAXCLS;
+  cls[gi] = ok ? (uint8_t)klass : (uint8_t)255;
+  if (ok) atomicMin(rep + klass, (int)gi);
+}
+// first cell of the child's subdomain -> its subdomain byte
+__global__ void k_qk_first_sd(const uint8_t* __restrict__ sd, int64_t ncells, int subdomain, unsigned long long* out)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ncells; i += (int64_t)gridDim.x * blockDim.x)
+    if (subdomain < 0 || ((sd[i] >> subdomain) & 1)) { atomicMin(out, ((unsigned long long)i << 8) | sd[i]); return; }      // ascending per thread: the first hit is its smallest
+}
+__global__ void k_qk_flags(const uint8_t* __restrict__ cls, int64_t n, int32_t* irr, int32_t* head, int32_t* tail)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  irr[i] = cls[i] == 255 ? 1 : 0;
+  head[i] = (cls[i] != 255 && (i == 0 || cls[i - 1] != cls[i])) ? 1 : 0;          // a run of simple rows of one class starts here
+  tail[i] = (cls[i] != 255 && (i == n - 1 || cls[i + 1] != cls[i])) ? 1 : 0;      // ... and ends here
+}
+__global__ void k_qk_compact(const int32_t* __restrict__ flags, const int32_t* __restrict__ scan, int64_t n, int32_t* list)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) list[scan[i]] = (int32_t)i;
+}
+__global__ void k_qk_runs(const int32_t* __restrict__ start, const int32_t* __restrict__ last, int64_t nruns, const uint8_t* __restrict__ cls, int64_t child_offset,
+                          const int64_t* __restrict__ rowptr, QkRun* runs)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nruns) return;
+  const int64_t a = start[i], b = (int64_t)last[i] + 1;
+  QkRun R; R.p0 = rowptr[child_offset + a]; R.p1 = rowptr[child_offset + b]; R.cls = cls[a];
+  R.ns = (int)(rowptr[child_offset + a + 1] - rowptr[child_offset + a]);
+  runs[i] = R;
+}
+
+// images[cls] -> every run of the class.  Same store pattern as k_jacobian_fill_q1: chunks of 32 rows' worth of doubles on 256-byte
+// boundaries, the two edges of a run masked; the row length is a run-time value here.
+__global__ void __launch_bounds__(128, 12) k_qk_fill(const QkRun* __restrict__ runs, int64_t nruns, const double* __restrict__ images, double* __restrict__ val, int overwrite)
+{
+  __shared__ double img[QK_MAXCLS * QK_MAXL];
+  for (int i = threadIdx.x; i < QK_MAXCLS * QK_MAXL; i += blockDim.x) img[i] = images[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t run = blockIdx.x; run < nruns; run += gridDim.x) {
+    const QkRun R = runs[run];
+    const int ns = R.ns;
+    const double* S = img + R.cls * QK_MAXL;
+    const int chunk = 32 * ns;
+    const int64_t p0 = R.p0, p1 = R.p1, a0 = p0 & ~(int64_t)31;
+    const int inc = 32 % ns;
+    const int mm0 = (int)((a0 - p0 + lane + 32 * (int64_t)ns) % ns);
+    for (int64_t cb = a0 + (int64_t)warp * chunk; cb < p1; cb += (int64_t)(blockDim.x >> 5) * chunk) {
+      int mm = mm0;
+      if (cb >= p0 && cb + chunk <= p1) {
+        if (overwrite) for (int it = 0; it < ns; ++it) { val[cb + it * 32 + lane] = S[mm]; mm += inc; if (mm >= ns) mm -= ns; }
+        else for (int it = 0; it < ns; ++it) { val[cb + it * 32 + lane] += S[mm]; mm += inc; if (mm >= ns) mm -= ns; }
+      } else {
+        for (int it = 0; it < ns; ++it) {
+          const int64_t i = cb + it * 32 + lane;
+          if (i >= p0 && i < p1) { if (overwrite) val[i] = S[mm]; else val[i] += S[mm]; }
+          mm += inc; if (mm >= ns) mm -= ns;
+        }
+      }
+    }
+  }
+}
+
+// rows of a list (child-local indices); scratch != null: row i of the list goes to scratch + i * QK_MAXL with overwrite semantics
+template <int DIM>
+__global__ void __launch_bounds__(128) k_jacobian_rows_qk_list(MeshDesc m, const uint8_t* __restrict__ sd, ChildG ch, VolSpecG V, const double* __restrict__ Ae,
+                                                               const int32_t* __restrict__ list, int64_t nlist, const int64_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite, double* __restrict__ scratch)
+{
+  const int64_t li_ = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (li_ >= nlist) return;
+  const int64_t gi = list[li_];
+  if (gi < 0) return;
+  const int64_t g = ch.offset + gi;
+  const int64_t rs = rowptr[g], re = rowptr[g + 1];
+  double* out = scratch ? scratch + li_ * QK_MAXL - rs : val;
+  if (overwrite || scratch) for (int64_t q = rs; q < re; ++q) out[q] = 0.0;
+  int64_t r = ch.dof2lat[gi];
+  int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
+  for_incident_cells<DIM>(m, sd, ch, p, [&](const int* c, uint8_t s, int li) {
+    for (int v = 0; v < V.n; ++v) {
+      if (!cond_applies(V.cond_kind[v], V.mask[v], s)) continue;
+      const double* A = Ae + (size_t)V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + (size_t)li * ch.nloc;
+      for (int lj = 0; lj < ch.nloc; ++lj) {
+        const int32_t col = cell_dof<DIM>(ch, c, lj);
+        int64_t lo = rs, hi = re;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (colidx[mid] < col) lo = mid + 1; else hi = mid; }
+        out[lo] += A[lj];
+      }
+    }
+  });
+}
+
+static QkPlan* qk_plan(Ctx* c, Matrix& M, int child, const ChildG& ch)
+{
+  if (M.qk_plans[child]) return (QkPlan*)M.qk_plans[child];
+  const MeshDesc& m = c->mesh;
+  QkPlan* P = new QkPlan(); M.qk_plans[child] = P;
+  int ncls = 1; for (int d = 0; d < m.dim; ++d) ncls *= ch.k;
+  if (ncls > QK_MAXCLS || ch.size >= (int64_t)2147483647) return P;
+  P->ncls = ncls;
+  const int64_t n = ch.size;
+  unsigned long long* d_first = dalloc<unsigned long long>(1);
+  MDB_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(unsigned long long), c->stream));
+  MDB_LAUNCH(c, k_qk_first_sd, 148, 256, 0, c->d_cell_sd, m.ncells(), ch.subdomain, d_first);
+  unsigned long long first = 0;
+  MDB_CUDA(cudaMemcpyAsync(&first, d_first, sizeof(first), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  dfree(d_first);
+  if (first == ~0ull) return P;
+  const uint8_t sd0 = (uint8_t)(first & 255u);
+  uint8_t* d_cls = dalloc<uint8_t>(n);
+  P->d_rep = dalloc<int32_t>(QK_MAXCLS);
+  MDB_CUDA(cudaMemsetAsync(P->d_rep, 0x7F, QK_MAXCLS * sizeof(int32_t), c->stream));
+  if (m.dim == 2) MDB_LAUNCH(c, k_qk_classify<2>, cdiv(n, 256), 256, 0, m, c->d_cell_sd, ch, sd0, M.d_rowptr, d_cls, P->d_rep);
+  else MDB_LAUNCH(c, k_qk_classify<3>, cdiv(n, 256), 256, 0, m, c->d_cell_sd, ch, sd0, M.d_rowptr, d_cls, P->d_rep);
+  int32_t rep[QK_MAXCLS];
+  MDB_CUDA(cudaMemcpyAsync(rep, P->d_rep, sizeof(rep), cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < QK_MAXCLS; ++k) if (rep[k] == 0x7F7F7F7F) rep[k] = -1;
+  MDB_CUDA(cudaMemcpyAsync(P->d_rep, rep, sizeof(rep), cudaMemcpyHostToDevice, c->stream));
+  int32_t* d_irr = dalloc<int32_t>(n); int32_t* d_head = dalloc<int32_t>(n); int32_t* d_tail = dalloc<int32_t>(n); int32_t* d_scan = dalloc<int32_t>(n);
+  MDB_LAUNCH(c, k_qk_flags, cdiv(n, 256), 256, 0, d_cls, n, d_irr, d_head, d_tail);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, d_irr, d_scan, (int)n, c->stream);
+  void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+  auto count = [&](int32_t* flags) {
+    MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, flags, d_scan, (int)n, c->stream)); c->launches++;
+    int32_t ls = 0, lf = 0;
+    MDB_CUDA(cudaMemcpyAsync(&ls, d_scan + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaMemcpyAsync(&lf, flags + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    return (int64_t)ls + lf;
+  };
+  P->nirr = count(d_irr);
+  P->d_irr = dalloc<int32_t>(P->nirr > 0 ? P->nirr : 1);
+  MDB_LAUNCH(c, k_qk_compact, cdiv(n, 256), 256, 0, d_irr, d_scan, n, P->d_irr);
+  P->nruns = count(d_head);
+  int32_t* d_start = dalloc<int32_t>(P->nruns > 0 ? P->nruns : 1);
+  MDB_LAUNCH(c, k_qk_compact, cdiv(n, 256), 256, 0, d_head, d_scan, n, d_start);
+  const int64_t nlast = count(d_tail);
+  MDB_REQUIRE(nlast == P->nruns, MDB_EINVAL, "Qk plan: run heads and tails do not pair up");
+  int32_t* d_last = dalloc<int32_t>(P->nruns > 0 ? P->nruns : 1);
+  MDB_LAUNCH(c, k_qk_compact, cdiv(n, 256), 256, 0, d_tail, d_scan, n, d_last);
+  P->d_runs = dalloc<QkRun>(P->nruns > 0 ? P->nruns : 1);
+  if (P->nruns > 0) MDB_LAUNCH(c, k_qk_runs, cdiv(P->nruns, 128), 128, 0, d_start, d_last, P->nruns, d_cls, ch.offset, M.d_rowptr, P->d_runs);
+  // long runs (a whole entity group can be one run) are cut into pieces of whole rows so that the streaming kernel's blocks share them
+  if (P->nruns > 0) {
+    std::vector<QkRun> h(P->nruns), pieces;
+    MDB_CUDA(cudaMemcpyAsync(h.data(), P->d_runs, P->nruns * sizeof(QkRun), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    for (const QkRun& R : h) {
+      const long long piece = (long long)std::max(1, 32768 / R.ns) * R.ns;
+      for (long long q = R.p0; q < R.p1; q += piece) { QkRun r = R; r.p0 = q; r.p1 = std::min(q + piece, R.p1); pieces.push_back(r); }
+    }
+    cudaFree(P->d_runs);
+    P->nruns = (int64_t)pieces.size();
+    P->d_runs = dalloc<QkRun>(P->nruns);
+    MDB_CUDA(cudaMemcpyAsync(P->d_runs, pieces.data(), pieces.size() * sizeof(QkRun), cudaMemcpyHostToDevice, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  P->d_img = dalloc<double>(QK_MAXCLS * QK_MAXL);
+  MDB_CUDA(cudaMemsetAsync(P->d_img, 0, QK_MAXCLS * QK_MAXL * sizeof(double), c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_t); dfree(d_cls); dfree(d_irr); dfree(d_head); dfree(d_tail); dfree(d_scan); dfree(d_start); dfree(d_last);
+  P->usable = P->nruns > 0;
+  if (getenv("MDB_QK_DEBUG")) fprintf(stderr, "qk plan child %d: rows %lld irregular %lld runs %lld classes %d sd0 %d reps %d %d %d %d\n", child, (long long)n, (long long)P->nirr,
+                                      (long long)P->nruns, ncls, (int)sd0, rep[0], rep[1], rep[2], rep[3]);
+  return P;
+}
+
 // all rows of child `child` (launch_element_matrices must have run)
 void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& M, int child, bool overwrite)
 {
@@ -138,6 +369,19 @@ void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& M, int child, boo
   VolSpecG V = vol_spec_g(c, go, child);
   if (V.n == 0) {
     if (overwrite) MDB_CUDA(cudaMemsetAsync(M.d_val + M.child_begin[child], 0, (M.child_end[child] - M.child_begin[child]) * sizeof(double), c->stream));
+    return;
+  }
+  static const bool no_plan = getenv("MDB_QK_ALL_ROWS") != nullptr;               // A/B switch: every row through the owner-computes kernel
+  QkPlan* P = no_plan ? nullptr : qk_plan(c, M, child, ch);
+  if (P && P->usable) {
+    if (P->nirr > 0) {
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk_list<2>, cdiv(P->nirr, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_irr, P->nirr, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, (double*)nullptr);
+      else MDB_LAUNCH(c, k_jacobian_rows_qk_list<3>, cdiv(P->nirr, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_irr, P->nirr, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, (double*)nullptr);
+    }
+    if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk_list<2>, 1, 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_rep, (int64_t)QK_MAXCLS, M.d_rowptr, M.d_colidx, M.d_val, 1, P->d_img);
+    else MDB_LAUNCH(c, k_jacobian_rows_qk_list<3>, 1, 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_rep, (int64_t)QK_MAXCLS, M.d_rowptr, M.d_colidx, M.d_val, 1, P->d_img);
+    int grid = 148 * 12; if (grid > P->nruns) grid = (int)P->nruns;
+    MDB_LAUNCH(c, k_qk_fill, grid, 128, 0, P->d_runs, P->nruns, P->d_img, M.d_val, (int)overwrite);
     return;
   }
   if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk<2>, cdiv(ch.size, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite);

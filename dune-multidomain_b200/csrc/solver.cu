@@ -22,7 +22,7 @@ namespace mdb {
 
 // scalar slots
 // slots reduced together are adjacent (RHONEW,RR), (RR,PQ), (TR,TT): one ncclAllReduce serves a pair
-enum { S_RHO = 0, S_RHOLAST, S_RHONEW, S_RR, S_PQ, S_RR0, S_BETA, S_LAMBDA, S_DONE, S_ITER, S_RED2, S_ALPHA, S_OMEGA, S_H, S_TR, S_TT, S_HALF };
+enum { S_RHO = 0, S_RHOLAST, S_RHONEW, S_RR, S_PQ, S_RR0, S_BETA, S_LAMBDA, S_DONE, S_ITER, S_RED2, S_ALPHA, S_OMEGA, S_H, S_TR, S_TT, S_HALF, S_BREAK };
 
 __device__ __forceinline__ double block_sum(double v, double* sh)
 {
@@ -628,7 +628,7 @@ __global__ void k_cg_init_scalars(double* s, double reduction)
 {
   // S_RHONEW and S_RR were just reduced
   s[S_RHO] = s[S_RHONEW];
-  s[S_RR0] = s[S_RR]; s[S_RHOLAST] = 1.0; s[S_ITER] = 0.0; s[S_RED2] = reduction * reduction;
+  s[S_RR0] = s[S_RR]; s[S_RHOLAST] = 1.0; s[S_ITER] = 0.0; s[S_RED2] = reduction * reduction; s[S_BREAK] = 0.0;
   s[S_BETA] = s[S_RHO] / 1.0;
   s[S_DONE] = (s[S_RR] == 0.0) ? 1.0 : 0.0;
 }
@@ -691,7 +691,7 @@ __global__ void k_bi_init_scalars(double* s, double reduction)
 {
   // S_RR reduced; rho_new = rt.r = r.r
   s[S_RR0] = s[S_RR]; s[S_RHONEW] = s[S_RR]; s[S_RHO] = 1.0; s[S_ALPHA] = 1.0; s[S_OMEGA] = 1.0; s[S_ITER] = 0.0;
-  s[S_RED2] = reduction * reduction; s[S_HALF] = 0.0;
+  s[S_RED2] = reduction * reduction; s[S_HALF] = 0.0; s[S_BREAK] = 0.0;
   s[S_BETA] = 0.0;          // first iteration: p = r
   s[S_DONE] = (s[S_RR] == 0.0) ? 1.0 : 0.0;
 }
@@ -706,7 +706,15 @@ __global__ void k_bi_update_p(int64_t n, const double* __restrict__ s, const dou
     p[i] = pi; y[i] = dinv[i] * pi;
   }
 }
-__global__ void k_bi_derive_alpha(double* s) { if (s[S_DONE] != 0.0) return; s[S_ALPHA] = s[S_RHONEW] / s[S_H]; }
+// [UPSTREAM] BiCGSTABSolver::apply aborts with an ISTLError when |rho|, |h| or |omega| fall below EPSILON = 1e-80 (and a NaN fails its
+// comparisons likewise): here the loop stops (S_DONE) with S_BREAK set and the solve reports "not converged" instead of iterating on NaNs
+#define MDB_BICG_EPS 1e-80
+__global__ void k_bi_derive_alpha(double* s)
+{
+  if (s[S_DONE] != 0.0) return;
+  if (!(fabs(s[S_RHONEW]) > MDB_BICG_EPS) || !(fabs(s[S_H]) > MDB_BICG_EPS)) { s[S_DONE] = 1.0; s[S_BREAK] = 1.0; return; }
+  s[S_ALPHA] = s[S_RHONEW] / s[S_H];
+}
 // x += alpha y ; r -= alpha v ; y2 = dinv r ; partial0 = sum r^2
 __global__ void k_bi_update_s(int64_t n, const double* __restrict__ s, const double* __restrict__ dinv, const double* __restrict__ y,
                               const double* __restrict__ v, const uint8_t* __restrict__ owned, double* x, double* r, double* y2, double* partial)
@@ -729,7 +737,13 @@ __global__ void k_bi_derive_half(double* s)
   if (s[S_DONE] != 0.0) return;
   if (s[S_RR] <= s[S_RED2] * s[S_RR0]) { s[S_DONE] = 1.0; s[S_ITER] += 1.0; s[S_HALF] = 1.0; }
 }
-__global__ void k_bi_derive_omega(double* s) { if (s[S_DONE] != 0.0) return; s[S_OMEGA] = s[S_TR] / s[S_TT]; }
+__global__ void k_bi_derive_omega(double* s)
+{
+  if (s[S_DONE] != 0.0) return;
+  const double omega = s[S_TR] / s[S_TT];
+  if (!(fabs(omega) > MDB_BICG_EPS)) { s[S_DONE] = 1.0; s[S_BREAK] = 1.0; return; }
+  s[S_OMEGA] = omega;
+}
 // x += omega y2 ; r -= omega t ; partial0 = sum r^2 ; partial1 = sum rt r
 __global__ void k_bi_update_x(int64_t n, const double* __restrict__ s, const double* __restrict__ y2, const double* __restrict__ t,
                               const double* __restrict__ rt, const uint8_t* __restrict__ owned, double* x, double* r, double* partial)
@@ -888,7 +902,7 @@ int solve(Ctx* c, Matrix& M, int method, int precond, double reduction, int maxi
   float ms = 0.f;
   MDB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->phases["solve"].last_ms = ms;
-  const bool converged = hp[S_DONE] != 0.0;
+  const bool converged = hp[S_DONE] != 0.0 && hp[S_BREAK] == 0.0;
   if (multi && halo_timed_out(c)) throw Error(MDB_ENCCL, "halo exchange timed out waiting for a neighbour");
   if (stats) {
     stats->iterations = (int)hp[S_ITER];

