@@ -665,9 +665,9 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& M, double weight, bool ov
 // need only one lattice lookup per (dy,dz) line: lattice neighbours along axis 0 that are both present are numbered
 // consecutively.  Other rows gather over their incident cells.
 template <int DIM>
-__global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
-                                                            const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r,
-                                                            const int32_t* __restrict__ list, int64_t nlist)
+__device__ __forceinline__ void residual_volume_q1_body(const MeshDesc& m, const uint8_t* __restrict__ sd, const ChildQ1& ch, const VolSpec& V,
+                                                        const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r,
+                                                        const int32_t* __restrict__ list, int64_t nlist, int block)
 {
   constexpr int NL = 1 << DIM;
   constexpr int NS = (DIM == 3) ? 27 : 9;
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const ui
   }
   if (threadIdx.x < NS) sS[threadIdx.x] = Ae[V.slot[0] * MDB_MAXLOC * MDB_MAXLOC + NL * NL + threadIdx.x];
   __syncthreads();
-  const int64_t ti = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t ti = block * (int64_t)blockDim.x + threadIdx.x;
   if (ti >= (list ? nlist : ch.size)) return;
   const int64_t gi = list ? (int64_t)list[ti] : ti;
   const int32_t lp = ch.dof2lat[gi];
@@ -722,6 +722,23 @@ __global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const ui
   }
   if (list) atomicAdd(r + ch.offset + gi, s);        // row-list mode runs beside the boundary / coupling terms (mdb_residual): reduction, not load + store
   else r[ch.offset + gi] += s;
+}
+template <int DIM>
+__global__ void __launch_bounds__(256) k_residual_volume_q1(MeshDesc m, const uint8_t* __restrict__ sd, ChildQ1 ch, VolSpec V,
+                                                            const double* __restrict__ Ae, const double* __restrict__ x, double* __restrict__ r,
+                                                            const int32_t* __restrict__ list, int64_t nlist)
+{
+  residual_volume_q1_body<DIM>(m, sd, ch, V, Ae, x, r, list, nlist, (int)blockIdx.x);
+}
+// the row lists of ALL children in one launch (the kernel is latency bound: the children's rows overlap instead of queueing)
+struct RestJobs { int n; ChildQ1 ch[MDB_MAX_CHILDREN]; VolSpec V[MDB_MAX_CHILDREN]; const int32_t* list[MDB_MAX_CHILDREN]; int64_t nlist[MDB_MAX_CHILDREN]; int block0[MDB_MAX_CHILDREN + 1]; };
+template <int DIM>
+__global__ void __launch_bounds__(256) k_residual_volume_q1_jobs(MeshDesc m, const uint8_t* __restrict__ sd, RestJobs J, const double* __restrict__ Ae,
+                                                                 const double* __restrict__ x, double* __restrict__ r)
+{
+  int jb = 0;
+  while (jb + 1 < J.n && (int)blockIdx.x >= J.block0[jb + 1]) ++jb;
+  residual_volume_q1_body<DIM>(m, sd, J.ch[jb], J.V[jb], Ae, x, r, J.list[jb], J.nlist[jb], (int)blockIdx.x - J.block0[jb]);
 }
 
 // ---- residual, tiled variant (the default) ---------------------------------------------------------------------------------
@@ -1197,7 +1214,7 @@ static bool residual_stencil_applies(const Ctx* c, int child, const VolSpec& V)
 
 // part: -1 = both kernels, 0 = the streamed uniform rows, 1 = the other rows of the child (row-list gather)
 static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, const VolSpec& V, const double* d_x, double* d_r, int part = -1,
-                             MarchJobs* march = nullptr)
+                             MarchJobs* march = nullptr, RestJobs* rest = nullptr)
 {
   const MeshDesc& m = c->mesh;
   const Child& hc = c->children[child];
@@ -1245,7 +1262,10 @@ static bool residual_stencil(Ctx* c, GridOp& go, int child, const ChildQ1& ch, c
     else MDB_LAUNCH(c, k_residual_stencil<3>, grid, RS_ROWS, 0, n, rc, V.slot[0], go.d_res_fast[child], d_x, d_r);
   }
   const int64_t nrest = go.n_res_rest[child];
-  if (nrest > 0 && part != 0 && part != 2) {
+  if (nrest > 0 && part != 0 && part != 2 && rest) {
+    const int j = rest->n++;
+    rest->ch[j] = ch; rest->V[j] = V; rest->list[j] = go.d_res_rest[child]; rest->nlist[j] = nrest; rest->block0[j + 1] = rest->block0[j] + cdiv(nrest, 256);
+  } else if (nrest > 0 && part != 0 && part != 2) {
     if (m.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1<2>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
     else MDB_LAUNCH(c, k_residual_volume_q1<3>, cdiv(nrest, 256), 256, 0, m, c->d_cell_sd, ch, V, c->d_Ae, d_x, d_r, go.d_res_rest[child], nrest);
   }
@@ -1273,12 +1293,17 @@ void residual_volume_part(Ctx* c, const GridOp& go, double weight, const double*
 {
   (void)weight;
   MarchJobs J; J.n = 0; J.ntiles = 0;                                             // the marching tiles of all children go through ONE launch
+  RestJobs R; R.n = 0; R.block0[0] = 0;                                           // ... and so do their row lists
   for (int i = 0; i < (int)c->children.size(); ++i) {
     VolSpec V = vol_spec(c, go, i);
     if (V.n == 0 || c->children[i].size == 0) continue;
-    residual_stencil(c, const_cast<GridOp&>(go), i, child_q1(c, i), V, d_x, d_r, part, &J);
+    residual_stencil(c, const_cast<GridOp&>(go), i, child_q1(c, i), V, d_x, d_r, part, &J, &R);
   }
   if (J.n > 0) MDB_LAUNCH(c, k_residual_march, J.ntiles, RM_T, march_smem_pad(), c->ndof, J, d_x, d_r);
+  if (R.n > 0) {
+    if (c->mesh.dim == 2) MDB_LAUNCH(c, k_residual_volume_q1_jobs<2>, R.block0[R.n], 256, 0, c->mesh, c->d_cell_sd, R, c->d_Ae, d_x, d_r);
+    else MDB_LAUNCH(c, k_residual_volume_q1_jobs<3>, R.block0[R.n], 256, 0, c->mesh, c->d_cell_sd, R, c->d_Ae, d_x, d_r);
+  }
 }
 
 // plans (fast flags + row lists) of every child, built on the context stream before a split residual forks

@@ -785,14 +785,23 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
     // block slots to the short latency-bound kernels of the other two branches as its blocks retire (on the high-priority stream
     // it ran first and the branches serialised behind it: 0.265 ms per call against 0.2 ms).
     residual_prepare(c, G);
+    // MDB_RESIDUAL_TRACE=1: a timeline of the call's branches (events on the three streams, printed to stderr; synchronises)
+    static const bool trace = getenv("MDB_RESIDUAL_TRACE") != nullptr;
+    static cudaEvent_t tev[8] = {nullptr};
+    if (trace && !tev[0]) for (auto& e : tev) MDB_CUDA(cudaEventCreate(&e));
+    auto mark = [&](int i) { if (trace) MDB_CUDA(cudaEventRecord(tev[i], c->stream)); };
     c->phase_begin("residual_volume");
+    mark(0);
     launch_element_matrices(c, G.sps, weight);
+    mark(1);
     MDB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     {
       StreamScope third(c, c->copy_stream);                                     // every update of r on the three branches is a reduction
       MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
       residual_boundary(c, G, weight, vr.d);
+      mark(2);
       residual_coupling(c, G, weight, vx.d, vr.d);
+      mark(3);
       MDB_CUDA(cudaEventRecord(c->ev_copy_done, c->stream));
     }
     {
@@ -800,18 +809,29 @@ int mdb_residual(mdb_ctx* c, int go, double weight, const double* x, double* r)
       MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
       c->phase_end();
       c->phase_begin("residual_streamed");                                      // events on the auxiliary stream: the streaming kernel's own time inside the call
+      mark(4);
       residual_volume_part(c, G, weight, vx.d, vr.d, 0);
+      mark(5);
       c->phase_end();
       MDB_CUDA(cudaEventRecord(c->ev_join, c->stream));
     }
     c->phase_begin("residual_rows");
     residual_volume_part(c, G, weight, vx.d, vr.d, 1);
+    mark(6);
     c->phase_end();
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     MDB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
     c->phase_begin("residual_coupling");
     constrain_residual(c, vr.d);
     c->phase_end();
+    mark(7);
+    if (trace) {
+      MDB_CUDA(cudaEventSynchronize(tev[7]));
+      float t[8];
+      for (int i = 1; i < 8; ++i) MDB_CUDA(cudaEventElapsedTime(&t[i], tev[0], tev[i]));
+      fprintf(stderr, "residual trace (us from the start): elem %.1f | third: boundary %.1f coupling %.1f | aux: streamed %.1f .. %.1f | main: rows %.1f | end %.1f\n",
+              t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, t[6] * 1e3, t[7] * 1e3);
+    }
   } else {
     c->phase_begin("residual_volume");
     residual_volume(c, G, weight, vx.d, vr.d);

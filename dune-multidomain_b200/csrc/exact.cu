@@ -607,8 +607,12 @@ __global__ void k_lambda_volume(MeshDesc m, const uint8_t* __restrict__ sd, Lamb
 // (instationarypoissonoperator.hh:142-167).  One thread per boundary face.
 // All boundary planes of a subproblem go through ONE launch (the kernel is latency bound): job = (axis, side), blocks [block0, ...)
 struct PlaneJobs { int n; int axis[6], side[6], block0[7]; };
+// one launch for all Poisson subproblems of the grid operator: a boundary face is evaluated for the subproblems that apply to its cell
+// (participant order), instead of one launch per subproblem in which the faces of the other subdomains only exit
+#define MDB_LAMBDA_JOBS 4
+struct LambdaJobs { int n; LambdaSpec S[MDB_LAMBDA_JOBS]; SideMap map[MDB_LAMBDA_JOBS]; };
 template <int DIM, int K>
-__global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, LambdaSpec S, SideMap map, PlaneJobs J, double weight,
+__global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, LambdaJobs L, PlaneJobs J, double weight,
                                   double t, double* r)
 {
   constexpr int NL = cpow(K + 1, DIM);
@@ -624,7 +628,11 @@ __global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, La
   ijk[t0] = (int)(idx % m.n[t0]);
   if (DIM > 2) ijk[t1] = (int)(idx / m.n[t0]);
   int64_t c = ijk[0] + (int64_t)m.n[0] * (ijk[1] + (int64_t)m.n[1] * ijk[2]);
-  if (!cond_applies(S.cond_kind, S.mask, sd[c])) return;
+  const uint8_t sdc = sd[c];
+  for (int v = 0; v < L.n; ++v) {
+  const LambdaSpec& S = L.S[v]; const SideMap& map = L.map[v];
+  if (!cond_applies(S.cond_kind, S.mask, sdc)) continue;
+  if (S.bc.kind == MDB_BC_ALL_DIRICHLET) continue;
   double lo[3], up[3];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { lo[d] = m.coord(d, ijk[d]); up[d] = m.coord(d, ijk[d] + 1); }
@@ -656,11 +664,31 @@ __global__ void k_lambda_boundary(MeshDesc m, const uint8_t* __restrict__ sd, La
   cell_dofs_qk<DIM, K>(map, ijk, dofs);
 #pragma unroll
   for (int i = 0; i < NL; ++i) if (rl[i] != 0.0) atomicAdd(&r[dofs[i]], rl[i]);
+  }
 }
 
 void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r)
 {
   const MeshDesc& m = c->mesh;
+  LambdaJobs L1, L2; L1.n = 0; L2.n = 0;                  // subproblems on Q1 / on Qk (k = 2) children
+  auto launch = [&](const LambdaJobs& L, int K) {
+    PlaneJobs J; J.n = 0; J.block0[0] = 0;
+    for (int axis = 0; axis < m.dim; ++axis)
+      for (int side = 0; side < 2; ++side) {
+        // only physical boundary planes: a partition cut is a processor boundary (no boundary terms, globalassembler.hh:275-283)
+        if (side == 0 && !m.on_global_lower(axis, 0)) continue;
+        if (side == 1 && !m.on_global_upper(axis, m.n[axis])) continue;
+        int t0 = (axis == 0) ? 1 : 0, t1 = (axis == 2) ? 1 : 2;
+        int64_t nplane = (int64_t)m.n[t0] * ((m.dim > 2) ? m.n[t1] : 1);
+        J.axis[J.n] = axis; J.side[J.n] = side; J.block0[J.n + 1] = J.block0[J.n] + cdiv(nplane, 128); ++J.n;
+      }
+    if (J.n == 0) return;
+    const int nb = J.block0[J.n];
+    if (m.dim == 2 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<2, 1>), nb, 128, 0, m, c->d_cell_sd, L, J, weight, c->time, d_r);
+    else if (m.dim == 3 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<3, 1>), nb, 128, 0, m, c->d_cell_sd, L, J, weight, c->time, d_r);
+    else if (m.dim == 2) MDB_LAUNCH(c, (k_lambda_boundary<2, 2>), nb, 128, 0, m, c->d_cell_sd, L, J, weight, c->time, d_r);
+    else MDB_LAUNCH(c, (k_lambda_boundary<3, 2>), nb, 128, 0, m, c->d_cell_sd, L, J, weight, c->time, d_r);
+  };
   for (int s : go.sps) {
     const SubProblemDesc& sp = c->sps[s];
     if (sp.op_id != MDB_OP_POISSON) continue;
@@ -675,23 +703,12 @@ void residual_boundary(Ctx* c, const GridOp& go, double weight, double* d_r)
       else MDB_LAUNCH(c, (k_lambda_volume<3, 2>), cdiv(m.ncells(), 128), 128, 0, m, c->d_cell_sd, S, map, weight, c->time, d_r);
     }
     if (sp.poisson.bc.kind == MDB_BC_ALL_DIRICHLET) continue;   // no Neumann face anywhere
-    PlaneJobs J; J.n = 0; J.block0[0] = 0;
-    for (int axis = 0; axis < m.dim; ++axis)
-      for (int side = 0; side < 2; ++side) {
-        // only physical boundary planes: a partition cut is a processor boundary (no boundary terms, globalassembler.hh:275-283)
-        if (side == 0 && !m.on_global_lower(axis, 0)) continue;
-        if (side == 1 && !m.on_global_upper(axis, m.n[axis])) continue;
-        int t0 = (axis == 0) ? 1 : 0, t1 = (axis == 2) ? 1 : 2;
-        int64_t nplane = (int64_t)m.n[t0] * ((m.dim > 2) ? m.n[t1] : 1);
-        J.axis[J.n] = axis; J.side[J.n] = side; J.block0[J.n + 1] = J.block0[J.n] + cdiv(nplane, 128); ++J.n;
-      }
-    if (J.n == 0) continue;
-    const int nb = J.block0[J.n];
-    if (m.dim == 2 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<2, 1>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
-    else if (m.dim == 3 && K == 1) MDB_LAUNCH(c, (k_lambda_boundary<3, 1>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
-    else if (m.dim == 2) MDB_LAUNCH(c, (k_lambda_boundary<2, 2>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
-    else MDB_LAUNCH(c, (k_lambda_boundary<3, 2>), nb, 128, 0, m, c->d_cell_sd, S, map, J, weight, c->time, d_r);
+    LambdaJobs& L = (K == 1) ? L1 : L2;
+    if (L.n == MDB_LAMBDA_JOBS) { launch(L, K == 1 ? 1 : 2); L.n = 0; }
+    L.S[L.n] = S; L.map[L.n] = map; ++L.n;
   }
+  if (L1.n > 0) launch(L1, 1);
+  if (L2.n > 0) launch(L2, 2);
 }
 
 } // namespace mdb
