@@ -252,33 +252,38 @@ __global__ void __launch_bounds__(128, 12) k_qk_fill(const QkRun* __restrict__ r
   }
 }
 
-// rows of a list (child-local indices); scratch != null: row i of the list goes to scratch + i * QK_MAXL with overwrite semantics
+// rows of a list (child-local indices); scratch != null: row i of the list goes to scratch + i * QK_MAXL with overwrite semantics.
+// One WARP per row: lane lj handles local coefficient lj of every incident cell (the columns of one cell are distinct, so the lanes never
+// meet), the cells are visited one after the other in ascending order — every entry is summed in the reference's order, and the
+// dependent chain of a row is (cells) x (one binary search) instead of (cells) x (local coefficients) x (one binary search).
 template <int DIM>
 __global__ void __launch_bounds__(128) k_jacobian_rows_qk_list(MeshDesc m, const uint8_t* __restrict__ sd, ChildG ch, VolSpecG V, const double* __restrict__ Ae,
                                                                const int32_t* __restrict__ list, int64_t nlist, const int64_t* __restrict__ rowptr,
                                                                const int32_t* __restrict__ colidx, double* __restrict__ val, int overwrite, double* __restrict__ scratch)
 {
-  const int64_t li_ = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t li_ = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (li_ >= nlist) return;
   const int64_t gi = list[li_];
   if (gi < 0) return;
   const int64_t g = ch.offset + gi;
   const int64_t rs = rowptr[g], re = rowptr[g + 1];
   double* out = scratch ? scratch + li_ * QK_MAXL - rs : val;
-  if (overwrite || scratch) for (int64_t q = rs; q < re; ++q) out[q] = 0.0;
+  if (overwrite || scratch) for (int64_t q = rs + lane; q < re; q += 32) out[q] = 0.0;
+  __syncwarp();
   int64_t r = ch.dof2lat[gi];
   int p[3]; p[0] = (int)(r % ch.lat_n[0]); r /= ch.lat_n[0]; p[1] = (int)(r % ch.lat_n[1]); p[2] = (int)(r / ch.lat_n[1]);
   for_incident_cells<DIM>(m, sd, ch, p, [&](const int* c, uint8_t s, int li) {
-    for (int v = 0; v < V.n; ++v) {
-      if (!cond_applies(V.cond_kind[v], V.mask[v], s)) continue;
-      const double* A = Ae + (size_t)V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + (size_t)li * ch.nloc;
-      for (int lj = 0; lj < ch.nloc; ++lj) {
-        const int32_t col = cell_dof<DIM>(ch, c, lj);
-        int64_t lo = rs, hi = re;
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (colidx[mid] < col) lo = mid + 1; else hi = mid; }
-        out[lo] += A[lj];
+    for (int lj = lane; lj < ch.nloc; lj += 32) {
+      const int32_t col = cell_dof<DIM>(ch, c, lj);
+      int64_t lo = rs, hi = re;
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (colidx[mid] < col) lo = mid + 1; else hi = mid; }
+      for (int v = 0; v < V.n; ++v) {
+        if (!cond_applies(V.cond_kind[v], V.mask[v], s)) continue;
+        out[lo] += Ae[(size_t)V.slot[v] * MDB_MAXLOC * MDB_MAXLOC + (size_t)li * ch.nloc + lj];
       }
     }
+    __syncwarp();                                                             // the next cell's lanes may hit the columns this cell's lanes wrote
   });
 }
 
@@ -375,11 +380,11 @@ void jacobian_volume_generic(Ctx* c, const GridOp& go, Matrix& M, int child, boo
   QkPlan* P = no_plan ? nullptr : qk_plan(c, M, child, ch);
   if (P && P->usable) {
     if (P->nirr > 0) {
-      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk_list<2>, cdiv(P->nirr, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_irr, P->nirr, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, (double*)nullptr);
-      else MDB_LAUNCH(c, k_jacobian_rows_qk_list<3>, cdiv(P->nirr, 128), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_irr, P->nirr, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, (double*)nullptr);
+      if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk_list<2>, cdiv(P->nirr, 4), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_irr, P->nirr, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, (double*)nullptr);
+      else MDB_LAUNCH(c, k_jacobian_rows_qk_list<3>, cdiv(P->nirr, 4), 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_irr, P->nirr, M.d_rowptr, M.d_colidx, M.d_val, (int)overwrite, (double*)nullptr);
     }
-    if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk_list<2>, 1, 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_rep, (int64_t)QK_MAXCLS, M.d_rowptr, M.d_colidx, M.d_val, 1, P->d_img);
-    else MDB_LAUNCH(c, k_jacobian_rows_qk_list<3>, 1, 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_rep, (int64_t)QK_MAXCLS, M.d_rowptr, M.d_colidx, M.d_val, 1, P->d_img);
+    if (m.dim == 2) MDB_LAUNCH(c, k_jacobian_rows_qk_list<2>, QK_MAXCLS / 4, 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_rep, (int64_t)QK_MAXCLS, M.d_rowptr, M.d_colidx, M.d_val, 1, P->d_img);
+    else MDB_LAUNCH(c, k_jacobian_rows_qk_list<3>, QK_MAXCLS / 4, 128, 0, m, c->d_cell_sd, ch, V, c->d_Ae, P->d_rep, (int64_t)QK_MAXCLS, M.d_rowptr, M.d_colidx, M.d_val, 1, P->d_img);
     int grid = 148 * 12; if (grid > P->nruns) grid = (int)P->nruns;
     MDB_LAUNCH(c, k_qk_fill, grid, 128, 0, P->d_runs, P->nruns, P->d_img, M.d_val, (int)overwrite);
     return;
