@@ -488,10 +488,10 @@ class Mdb(Lib):
         return int(self._fn("scalars_exchanges", C.c_int64)(C.c_void_p(self.ctx)))
 
     def scalars_import(self, blobs):
-        buf = (C.c_char * (80 * len(blobs)))()
+        buf = (C.c_char * (80 * max(len(blobs), 1)))()
         for i, b in enumerate(blobs):
             buf[80 * i:80 * (i + 1)] = b
-        self._check(self._fn("scalars_import")(C.c_void_p(self.ctx), len(blobs), buf), "scalars_import")
+        self._check(self._fn("scalars_import")(C.c_void_p(self.ctx), len(blobs), buf), "scalars_import")       # an empty list disconnects
 
     def halo_import(self, lower_rank, lower_blob, upper_rank, upper_blob):
         self._check(self._fn("halo_import")(C.c_void_p(self.ctx), lower_rank, C.c_char_p(lower_blob) if lower_blob else None,

@@ -466,7 +466,7 @@ void jacobian_volume(Ctx* c, const GridOp& go, Matrix& m, double weight, bool ov
 void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& m, double weight, const double* d_x, bool late);
 // mortar.cu: EnrichedCoupling with MortarPoissonCoupling (test/testmortarpoisson.cc:117-250)
 void residual_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r);
-void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight, const double* d_x);
+void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight, const double* d_x, std::pair<int, int> key);
 // nd.cu: ConvectionDiffusionDGNeumannDirichletCoupling (test/neumanndirichletcoupling.hh)
 void residual_nd(Ctx* c, const CouplingDesc& cp, const FaceList& fl, double weight, const double* d_x, double* d_r);
 void jacobian_nd(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& m, double weight);

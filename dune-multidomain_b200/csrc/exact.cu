@@ -515,7 +515,7 @@ void jacobian_coupling(Ctx* c, const GridOp& go, Matrix& M, double weight, const
     const FaceList& fl = go.faces[k];
     if (fl.n == 0) continue;
     if ((cp.op_id == MDB_OP_ND_COUPLING) != late) continue;
-    if (cp.enriched()) { jacobian_enriched(c, cp, fl, M, weight, d_x); continue; }        // mortar.cu
+    if (cp.enriched()) { jacobian_enriched(c, cp, fl, M, weight, d_x, std::pair<int, int>((int)(&go - &c->gos[0]), (int)k)); continue; }        // mortar.cu
     if (cp.op_id == MDB_OP_ND_COUPLING) { jacobian_nd(c, cp, fl, M, weight); continue; }          // nd.cu
     CouplingParams P = coupling_params(cp);
     SideMap Ls = side_map(c, cp.local_sp), Rs = side_map(c, cp.remote_sp);

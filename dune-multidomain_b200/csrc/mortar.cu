@@ -14,6 +14,7 @@
 //                       mat_ss|mat_cs (j in the element) or mat_sc|mat_cc (j in the mortar space), couplingutilities.hh:338-386
 // This is a correctness configuration ("small"), interface-sized work: plain kernels, columns by binary search.
 #include "exact_common.cuh"
+#include <algorithm>
 
 namespace mdb {
 
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(64) k_mortar_residual(MeshDesc m, const uint8_
 template <int DIM, int K>
 __device__ void mortar_column(int sign, const MortarSpec& P, const Rule1D& R, const FaceGeo<DIM>& G, const int32_t* de, const int32_t* dc, int nc, int j,
                               double weight, double epsilon, const double* __restrict__ x, const int64_t* __restrict__ rowptr,
-                              const int32_t* __restrict__ colidx, double* val)
+                              const int32_t* __restrict__ colidx, double* val, uint16_t* slots, int64_t sbase, int64_t sstride, int have_slots)
 {
   constexpr int NL = cpow(K + 1, DIM), NC = MORTAR_MAXCOMP * (1 << (DIM - 1));
   const int nct = nc * P.ncomp;                                                                        // coefficients of the (power) coupling space on this face
@@ -151,13 +152,22 @@ __device__ void mortar_column(int sign, const MortarSpec& P, const Rule1D& R, co
   }
   mortar_alpha_power<DIM, K>(sign, P, R, G, u, uc, nc, up, up_c, 1.0);
   const int32_t col = (j < NL) ? de[j] : dc[j - NL];
+  // where entry (row, col) lives inside its row: searched once per (matrix, coupling) and kept as a 16-bit offset per (thread, entry),
+  // entry-major so that the threads of a warp read consecutive offsets (the binary searches were most of this kernel's time)
+  auto slot = [&](int i, int32_t row) -> int64_t {
+    const int64_t rs = rowptr[row];
+    if (have_slots) return rs + slots[sbase + (int64_t)i * sstride];
+    const int64_t pos = find_slot(rowptr, colidx, row, col);
+    if (slots) slots[sbase + (int64_t)i * sstride] = (uint16_t)(pos - rs);
+    return pos;
+  };
   for (int i = 0; i < NL; ++i) {                                                                      // mat_ss / mat_sc
     const double cval = (up[i] - down[i]) / delta;
-    atomicAdd(&val[find_slot(rowptr, colidx, de[i], col)], weight * cval);
+    atomicAdd(&val[slot(i, de[i])], weight * cval);
   }
   for (int i = 0; i < nct; ++i) {                                                                     // mat_cs / mat_cc
     const double cval = (up_c[i] - down_c[i]) / delta;
-    atomicAdd(&val[find_slot(rowptr, colidx, dc[i], col)], weight * cval);
+    atomicAdd(&val[slot(NL + i, dc[i])], weight * cval);
   }
 }
 
@@ -165,7 +175,7 @@ template <int DIM, int K1, int K2>
 __global__ void __launch_bounds__(64) k_mortar_jacobian(MeshDesc m, const uint8_t* __restrict__ sd, MortarSpec P, SideMap Ls, SideMap Rs, MortarMaps Cs,
                                                         const int32_t* __restrict__ fcell, const int8_t* __restrict__ fface, int64_t nfaces, double weight,
                                                         double epsilon, const double* __restrict__ x, const int64_t* __restrict__ rowptr,
-                                                        const int32_t* __restrict__ colidx, double* val)
+                                                        const int32_t* __restrict__ colidx, double* val, uint16_t* slots, int have_slots)
 {
   constexpr int NL1 = cpow(K1 + 1, DIM), NL2 = cpow(K2 + 1, DIM), NCB = 1 << (DIM - 1);
   const int NC = P.ncomp * NCB;                        // coefficients of the (power) coupling space per face
@@ -181,12 +191,12 @@ __global__ void __launch_bounds__(64) k_mortar_jacobian(MeshDesc m, const uint8_
   if (e < NL1 + NC) {
     if (e >= NL1 && nc == 0) return;
     int32_t ds[NL1]; cell_dofs_qk<DIM, K1>(Ls, G.ijk, ds);
-    mortar_column<DIM, K1>(+1, P, P.rule1, G, ds, dc, nc, e, weight, epsilon, x, rowptr, colidx, val);
+    mortar_column<DIM, K1>(+1, P, P.rule1, G, ds, dc, nc, e, weight, epsilon, x, rowptr, colidx, val, slots, t, nfaces * NP, have_slots);
   } else {
     const int j = e - (NL1 + NC);
     if (j >= NL2 && nc == 0) return;
     int32_t dn[NL2]; cell_dofs_qk<DIM, K2>(Rs, G.nijk, dn);
-    mortar_column<DIM, K2>(-1, P, P.rule2, G, dn, dc, nc, j, weight, epsilon, x, rowptr, colidx, val);
+    mortar_column<DIM, K2>(-1, P, P.rule2, G, dn, dc, nc, j, weight, epsilon, x, rowptr, colidx, val, slots, t, nfaces * NP, have_slots);
   }
 }
 
@@ -243,7 +253,7 @@ void residual_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, doubl
 #undef CALL
 }
 
-void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& M, double weight, const double* d_x)
+void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matrix& M, double weight, const double* d_x, std::pair<int, int> key)
 {
   const MeshDesc& m = c->mesh;
   MDB_REQUIRE(m.dim >= 2, MDB_EINVAL, "enriched couplings need dim >= 2");
@@ -257,7 +267,16 @@ void jacobian_enriched(Ctx* c, const CouplingDesc& cp, const FaceList& fl, Matri
   for (int d = 0; d < m.dim; ++d) { nl1 *= k1 + 1; nl2 *= k2 + 1; }
   const int64_t total = fl.n * (nl1 + nl2 + 2 * cp.ncomp * (1 << (m.dim - 1)));
   const double eps = 1e-8;                      // NumericalJacobianEnrichedCouplingTo*SubProblem() default, couplingutilities.hh:296-298
-#define CALL(D, A, B) MDB_LAUNCH(c, (k_mortar_jacobian<D, A, B>), cdiv(total, 64), 64, 0, m, c->d_cell_sd, P, Ls, Rs, Cs, fl.d_cell, fl.d_face, fl.n, weight, eps, d_x, M.d_rowptr, M.d_colidx, M.d_val)
+  // slot table of this (grid operator, coupling) in this matrix: filled by the first call (which searches), read by the later ones
+  static const bool no_slots = getenv("MDB_MORTAR_SEARCH") != nullptr;                 // A/B switch: binary search per entry on every call
+  const int smax = std::max(nl1, nl2) + cp.ncomp * (1 << (m.dim - 1));
+  uint16_t* slots = nullptr; int have = 0;
+  if (!no_slots && M.max_row < 65536) {
+    auto it = M.slot_tables.find(key);
+    if (it == M.slot_tables.end()) { slots = dalloc<uint16_t>((size_t)total * smax); M.slot_tables[key] = reinterpret_cast<uint8_t*>(slots); }
+    else { slots = reinterpret_cast<uint16_t*>(it->second); have = 1; }
+  }
+#define CALL(D, A, B) MDB_LAUNCH(c, (k_mortar_jacobian<D, A, B>), cdiv(total, 64), 64, 0, m, c->d_cell_sd, P, Ls, Rs, Cs, fl.d_cell, fl.d_face, fl.n, weight, eps, d_x, M.d_rowptr, M.d_colidx, M.d_val, slots, have)
   MDB_DISPATCH_MORTAR(m.dim, k1, k2, CALL);
 #undef CALL
 }

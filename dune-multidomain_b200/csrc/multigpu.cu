@@ -545,6 +545,7 @@ int mdb_scalars_import(mdb_ctx* c, int nranks, const void* blobs80)
 {
   MG_BEGIN(c)
   ScalarRing* R = (ScalarRing*)c->sring;
+  if (nranks == 0) { if (R && !c->sring_borrowed) R->connected = false; return MDB_OK; }      // disconnect: back to ncclAllReduce
   MDB_REQUIRE(R && R->mine && !c->sring_borrowed, MDB_ESTATE, "mdb_scalars_import: call mdb_scalars_export first");
   MDB_REQUIRE(nranks == c->nranks && blobs80, MDB_EINVAL, "mdb_scalars_import: one descriptor per rank of the communicator");
   for (int r = 0; r < nranks; ++r) R->win[r] = r == c->rank ? R->mine : open_peer(c, (const char*)blobs80 + 80 * (size_t)r);

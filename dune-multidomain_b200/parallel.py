@@ -74,9 +74,27 @@ def connect_scalars(dev, dist, rank, nranks):
     import os
     if nranks < 2 or nranks > 16 or os.environ.get("MDB_SCALARS_NCCL"):
         return False
+    # collective and all-or-nothing: a rank that cannot map a peer's window (no P2P path, IPC limits) takes every rank back to NCCL
+    try:
+        blob = dev.scalars_export()
+    except Exception:
+        blob = None
     blobs = [None] * nranks
-    dist.all_gather_object(blobs, dev.scalars_export())
-    dev.scalars_import(blobs)
+    dist.all_gather_object(blobs, blob)
+    ok = all(b is not None for b in blobs)
+    if ok:
+        try:
+            dev.scalars_import(blobs)
+        except Exception:
+            ok = False
+    oks = [None] * nranks
+    dist.all_gather_object(oks, ok)
+    if not all(oks):
+        try:
+            dev.scalars_import([])
+        except Exception:
+            pass
+        return False
     return True
 
 

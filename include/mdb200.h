@@ -469,7 +469,8 @@ int mdb_halo_import(mdb_ctx* ctx, int lower_rank, const void* lower_blob80, int 
  * 80-byte descriptor of a small window (after mdb_comm_init), the descriptors of ALL ranks are exchanged out of band and imported in
  * rank order (the own entry is ignored).  From then on the dot products of mdb_solve end in a single kernel that stores this rank's
  * partial sums into every peer's window over NVLink and adds the contributions in rank order: the same bits on every rank, no
- * library call per reduction.  Connect before mdb_mg_setup (the coarse levels share the windows).  At most 16 ranks.  The reference's
+ * library call per reduction.  Connect before mdb_mg_setup (the coarse levels share the windows).  At most 16 ranks.  nranks = 0 disconnects
+ * (every rank must do the same: the scalars then go through ncclAllReduce again).  The reference's
  * analogue is the MPI_Allreduce inside ISTL's OverlappingSchwarzScalarProduct (test/testoverlappinginstationarypoisson.cc:431-432). */
 int mdb_scalars_export(mdb_ctx* ctx, void* blob80);
 int mdb_scalars_import(mdb_ctx* ctx, int nranks, const void* blobs80);
