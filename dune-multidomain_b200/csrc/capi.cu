@@ -576,7 +576,7 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   if (c->mesh.partitioned) {
     // the add_* calls refuse these on a partitioned mesh; mdb_mesh_partition may also come AFTER them, so check again here
     for (const Child& ch : c->children)
-      MDB_REQUIRE(!ch.dg && !ch.iface && ch.k == 1, MDB_EINVAL, "mdb_finalize: a partitioned mesh carries Q1 spaces only (no Q2 / QkDG / coupling spaces)");
+      MDB_REQUIRE(!ch.dg && !ch.iface, MDB_EINVAL, "mdb_finalize: a partitioned mesh carries conforming Qk spaces only (no QkDG / coupling spaces)");
     for (const CouplingDesc& cp : c->cps)
       MDB_REQUIRE(cp.op_id != MDB_OP_ND_COUPLING && !cp.enriched(), MDB_EINVAL,
                   "mdb_finalize: Neumann-Dirichlet and enriched couplings are not supported on a partitioned mesh");

@@ -689,7 +689,11 @@ int mdb_get_ownership(mdb_ctx* c, const int64_t* child_global_base, uint8_t* own
   }
   if (owned_flags) std::memcpy(owned_flags, f.data(), c->ndof);
   if (global_index) {
-    // owned dofs of a child keep their relative order in the global (lexicographic, cut axis slowest) numbering
+    // owned dofs of a child keep their relative order in the global (lexicographic, cut axis slowest) numbering.  True for Q1 blocks
+    // only: a Qk (k > 1) block is numbered entity group by entity group, so its global numbers are not contiguous per rank
+    if (child_global_base)
+      for (const Child& ch : c->children)
+        MDB_REQUIRE(ch.k == 1, MDB_EINVAL, "mdb_get_ownership: global indices by rank offsets exist for Q1 blocks only (Qk: map through mdb_get_dofmap)");
     for (size_t i = 0; i < c->children.size(); ++i) {
       const Child& ch = c->children[i];
       int64_t next = child_global_base ? child_global_base[i] : ch.offset;

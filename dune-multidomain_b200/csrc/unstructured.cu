@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace mdb {
 
@@ -728,6 +729,38 @@ __global__ void k_um_pair_fill(UMDev m, UMSpace S, UMOps O, int64_t ndof, const 
   }
   for (; k < steps; ++k) rec[base + (int64_t)k * 32 + lane] = make_int4(-1, -1, -1, 0);
 }
+// Row i of a cell's element matrix for the pair kernel.  Same quantities as um_matrix_row, arranged for the instruction count (the
+// pair kernel is bound by instruction issue, not by HBM): the gradients are never normalised — grad_j . grad_i |det J| =
+// (G_j . G_i) / |det J| with G_1 = (b_y, -b_x), G_2 = (-a_y, a_x), G_0 = -(G_1 + G_2) — the reciprocal is rcp.approx refined by two
+// Newton steps (1 ulp; the IEEE division is ~25 instructions), products and sums are contracted explicitly (this file is compiled
+// with --fmad=false for the bit-matched finite-difference couplings; volume entries are held to 1e-12, not to the bit).
+__device__ __forceinline__ double um_rcp(double d)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  return fma(r, fma(-d, r, 1.0), r);
+}
+__device__ __forceinline__ void um_pair_row(const UMSp& s, const double2 p0, const double2 p1, const double2 p2, int i, double weight, double a[3])
+{
+  const double ax = p1.x - p0.x, ay = p1.y - p0.y, bx = p2.x - p0.x, by = p2.y - p0.y;
+  const double ie = fabs(fma(ax, by, -(ay * bx)));
+  if (s.op_id == MDB_OP_POISSON) {
+    const double scale = (weight * s.wsum) * um_rcp(ie);
+    const double g1x = by, g1y = -bx, g2x = -ay, g2y = ax, g0x = ay - by, g0y = bx - ax;
+    const double gix = scale * pick3(g0x, g1x, g2x, i), giy = scale * pick3(g0y, g1y, g2y, i);
+    a[0] = fma(g0x, gix, g0y * giy); a[1] = fma(g1x, gix, g1y * giy); a[2] = fma(g2x, gix, g2y * giy);
+    return;
+  }
+  int q0; const int nq = tri_rule(s.quad_order, &q0);
+  a[0] = a[1] = a[2] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double phi[3]; p1_basis(c_tri[q0 + q][0], c_tri[q0 + q][1], phi);
+    const double f = (weight * (c_tri[q0 + q][2] * ie)) * pick3(phi[0], phi[1], phi[2], i);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[j] = fma(phi[j], f, a[j]);
+  }
+}
 constexpr int UM_PROWS = 128;
 constexpr int UM_PIMG = UM_PROWS * 24;
 __global__ void __launch_bounds__(UM_PROWS) k_um_jacobian_pairs(UMDev m, UMOps O, int64_t ndof, const int4* __restrict__ rec, const int64_t* __restrict__ wptr,
@@ -770,18 +803,7 @@ __global__ void __launch_bounds__(UM_PROWS) k_um_jacobian_pairs(UMDev m, UMOps O
       if (cur.x >= 0) { q0 = __ldg(xy2 + cur.x); q1 = __ldg(xy2 + cur.y); q2 = __ldg(xy2 + cur.z); }
       if (c4.x < 0) continue;
       const uint32_t word = (uint32_t)c4.w;
-      Tri g;
-      g.p[0][0] = p0.x; g.p[0][1] = p0.y; g.p[1][0] = p1.x; g.p[1][1] = p1.y; g.p[2][0] = p2.x; g.p[2][1] = p2.y;
-      {
-        const double ax = p1.x - p0.x, ay = p1.y - p0.y, bx = p2.x - p0.x, by = p2.y - p0.y;
-        const double det = ax * by - ay * bx;
-        const double inv = 1.0 / det;
-        g.t[0][0] = by * inv; g.t[0][1] = -(ay * inv);
-        g.t[1][0] = -(bx * inv); g.t[1][1] = ax * inv;
-        g.ie = fabs(det);
-      }
-      double gp[3][2]; tri_gradients(g, gp);
-      double a[3]; um_matrix_row(O.sp[word >> 26], g, gp, (int)((word >> 24) & 3u), weight, a);
+      double a[3]; um_pair_row(O.sp[word >> 26], p0, p1, p2, (int)((word >> 24) & 3u), weight, a);
       const uint32_t s0 = word & 255u, s1 = (word >> 8) & 255u, s2 = (word >> 16) & 255u;
       if (s0 != 255u) dst[s0] += a[0];
       if (s1 != 255u) dst[s1] += a[1];
@@ -990,75 +1012,176 @@ void um_free(Ctx* c)
   delete u; c->um = nullptr;
 }
 
-// Mesh ingest: validation and the connectivity a grid manager provides (face neighbours, vertex -> cell), built once on the host.
+// Mesh ingest: validation and the connectivity a grid manager provides (face neighbours, edge numbers, vertex -> cell), built once
+// ON THE DEVICE from the caller's coordinate / connectivity arrays (round 1 and the first sessions of round 2 sorted 3 ne edge keys
+// with std::sort on the host: 1.5 - 3 s at 8.4 M triangles).  Everything is a sort or a scan:
+//   * face neighbours and edge numbers: 64-bit keys (min vertex << 32 | max vertex) of the 3 ne (cell, face) positions, stable radix
+//     sort with the position as payload -> the members of a group are adjacent and ascending in position; two members are each
+//     other's neighbour, three are a non-manifold mesh; the first member of a group is the edge's first appearance in (cell, local
+//     face) order, a scan over the first-appearance flags numbers the edges in that order (the P2 numbering of ufe.cu);
+//   * vertex -> cell: keys = vertex, payload = 4 cell + local vertex in position order, stable sort -> cells ascending per vertex;
+//     the offsets are a scan over integer counts;
+//   * boundary faces: positions without neighbour, compacted in ascending order.
+// The host keeps nothing: it only reads back the error word and three counts.
+enum { UM_ERR_RANGE = 1, UM_ERR_DEGENERATE = 2, UM_ERR_MANIFOLD = 4 };
+__global__ void k_um_ingest_cells(int64_t nv, int64_t ne, const int64_t* __restrict__ conn64, const double* __restrict__ xy, int32_t* conn, uint64_t* key,
+                                  int32_t* pos, uint32_t* vkey, int32_t* vpay, int32_t* vcount, int* err)
+{
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int64_t v[3]; bool ok = true;
+  for (int k = 0; k < 3; ++k) { v[k] = conn64[3 * e + k]; ok = ok && v[k] >= 0 && v[k] < nv; }
+  if (!ok) {                                       // keep the arrays well defined; the call fails on the error word
+    atomicOr(err, UM_ERR_RANGE);
+    for (int k = 0; k < 3; ++k) { conn[3 * e + k] = 0; key[3 * e + k] = ~0ull; pos[3 * e + k] = (int32_t)(3 * e + k); vkey[3 * e + k] = 0u; vpay[3 * e + k] = (int32_t)(4 * e + k); }
+    return;
+  }
+  const double ax = xy[2 * v[1]] - xy[2 * v[0]], ay = xy[2 * v[1] + 1] - xy[2 * v[0] + 1];
+  const double bx = xy[2 * v[2]] - xy[2 * v[0]], by = xy[2 * v[2] + 1] - xy[2 * v[0] + 1];
+  if (v[0] == v[1] || v[0] == v[2] || v[1] == v[2] || ax * by - ay * bx == 0.0) atomicOr(err, UM_ERR_DEGENERATE);
+  for (int k = 0; k < 3; ++k) {
+    conn[3 * e + k] = (int32_t)v[k];
+    vkey[3 * e + k] = (uint32_t)v[k]; vpay[3 * e + k] = (int32_t)(4 * e + k);
+    atomicAdd(vcount + v[k], 1);
+  }
+  for (int f = 0; f < 3; ++f) {
+    uint64_t a = (uint64_t)v[c_face_v[f][0]], b = (uint64_t)v[c_face_v[f][1]];
+    if (a > b) { const uint64_t t = a; a = b; b = t; }
+    key[3 * e + f] = (a << 32) | b; pos[3 * e + f] = (int32_t)(3 * e + f);
+  }
+}
+// sorted edge groups -> neighbours, first-appearance flags, the position of every member's first appearance
+__global__ void k_um_ingest_groups(int64_t n3, const uint64_t* __restrict__ key, const int32_t* __restrict__ pos, int32_t* nbr, int32_t* first_flag,
+                                   int32_t* first_pos, int* err)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n3) return;
+  const uint64_t k = key[i];
+  const bool head = i == 0 || key[i - 1] != k;
+  const bool more = i + 1 < n3 && key[i + 1] == k;
+  const int32_t p = pos[i];
+  if (head) {
+    if (more && i + 2 < n3 && key[i + 2] == k) atomicOr(err, UM_ERR_MANIFOLD);
+    nbr[p] = more ? pos[i + 1] / 3 : -1;
+    first_flag[p] = 1; first_pos[p] = p;
+  } else {
+    nbr[p] = pos[i - 1] / 3;
+    first_flag[p] = 0; first_pos[p] = pos[i - 1];      // valid for groups of two (anything longer is an error)
+  }
+}
+__global__ void k_um_ingest_edges(int64_t n3, const int32_t* __restrict__ first_pos, const int32_t* __restrict__ first_scan, const int32_t* __restrict__ nbr,
+                                  int32_t* cell_edge, int32_t* bflag)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n3) return;
+  cell_edge[i] = first_scan[first_pos[i]];
+  bflag[i] = nbr[i] < 0 ? 1 : 0;
+}
+__global__ void k_um_ingest_bfaces(int64_t n3, const int32_t* __restrict__ bflag, const int32_t* __restrict__ bscan, int32_t* bface)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n3 && bflag[i]) bface[bscan[i]] = (int32_t)i;
+}
+__global__ void k_um_bbox(int64_t nv, const double* __restrict__ xy, double* box)     // box = {min x, min y, -max x, -max y} kept as minima
+{
+  double lo0 = 1e300, lo1 = 1e300, hi0 = -1e300, hi1 = -1e300;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const double x = xy[2 * v], y = xy[2 * v + 1];
+    lo0 = fmin(lo0, x); lo1 = fmin(lo1, y); hi0 = fmax(hi0, x); hi1 = fmax(hi1, y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo0 = fmin(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); lo1 = fmin(lo1, __shfl_xor_sync(0xffffffffu, lo1, o));
+    hi0 = fmax(hi0, __shfl_xor_sync(0xffffffffu, hi0, o)); hi1 = fmax(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // order-preserving integer image of a double: min / max of the images = image of the min / max (exact, order independent)
+    auto enc = [](double d) { const long long b = __double_as_longlong(d); return b < 0 ? b ^ 0x7fffffffffffffffll : b; };
+    atomicMin((long long*)box + 0, enc(lo0)); atomicMin((long long*)box + 1, enc(lo1));
+    atomicMax((long long*)box + 2, enc(hi0)); atomicMax((long long*)box + 3, enc(hi1));
+  }
+}
+
 void um_ingest(Ctx* c, int64_t nv, const double* xy, int64_t ne, const int64_t* conn)
 {
   MDB_REQUIRE(nv >= 3 && ne >= 1 && nv < (int64_t)1 << 30 && ne < (int64_t)1 << 29, MDB_EINVAL, "mdb_mesh_unstructured: bad vertex / cell count");
-  std::vector<int32_t> hconn(3 * ne), nbr(3 * ne, -1), vptr(nv + 1, 0), v2c(3 * ne);
-  for (int64_t i = 0; i < 3 * ne; ++i) {
-    MDB_REQUIRE(conn[i] >= 0 && conn[i] < nv, MDB_EINVAL, "mdb_mesh_unstructured: vertex index out of range");
-    hconn[i] = (int32_t)conn[i];
-  }
-  for (int64_t e = 0; e < ne; ++e) {
-    const int32_t* v = &hconn[3 * e];
-    const double ax = xy[2 * v[1]] - xy[2 * v[0]], ay = xy[2 * v[1] + 1] - xy[2 * v[0] + 1];
-    const double bx = xy[2 * v[2]] - xy[2 * v[0]], by = xy[2 * v[2] + 1] - xy[2 * v[0] + 1];
-    MDB_REQUIRE(v[0] != v[1] && v[0] != v[2] && v[1] != v[2] && ax * by - ay * bx != 0.0, MDB_EINVAL, "mdb_mesh_unstructured: degenerate cell");
-  }
-  static const int fv[3][2] = {{0, 1}, {0, 2}, {1, 2}};
-  std::vector<std::pair<uint64_t, int32_t>> edges(3 * ne);
-  for (int64_t e = 0; e < ne; ++e)
-    for (int f = 0; f < 3; ++f) {
-      uint64_t a = hconn[3 * e + fv[f][0]], b = hconn[3 * e + fv[f][1]];
-      if (a > b) std::swap(a, b);
-      edges[3 * e + f] = {(a << 32) | b, (int32_t)(3 * e + f)};
-    }
-  std::sort(edges.begin(), edges.end());
-  // edge indices (P2 spaces, ufe.cu): the order of first appearance in (cell, local face) order.  Equal keys are sorted by their
-  // (cell, face) position, so the first member of a group is the first appearance.
-  std::vector<int32_t> first_of(3 * ne, -1), cell_edge(3 * ne, 0);
-  for (size_t i = 0; i < edges.size();) {
-    size_t j = i + 1;
-    while (j < edges.size() && edges[j].first == edges[i].first) ++j;
-    MDB_REQUIRE(j - i <= 2, MDB_EINVAL, "mdb_mesh_unstructured: more than two cells share a face (non-manifold mesh)");
-    if (j - i == 2) { nbr[edges[i].second] = edges[i + 1].second / 3; nbr[edges[i + 1].second] = edges[i].second / 3; }
-    first_of[edges[i].second] = 0;
-    for (size_t k = i; k < j; ++k) cell_edge[edges[k].second] = edges[i].second;      // for now: position of the first appearance
-    i = j;
-  }
-  int64_t nedges = 0;
-  for (int64_t i = 0; i < 3 * ne; ++i) if (first_of[i] == 0) first_of[i] = (int32_t)nedges++;
-  for (int64_t i = 0; i < 3 * ne; ++i) cell_edge[i] = first_of[cell_edge[i]];
-  for (int64_t i = 0; i < 3 * ne; ++i) vptr[hconn[i] + 1]++;
-  for (int64_t v = 0; v < nv; ++v) vptr[v + 1] += vptr[v];
-  {
-    std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
-    for (int64_t e = 0; e < ne; ++e) for (int k = 0; k < 3; ++k) v2c[fill[hconn[3 * e + k]]++] = (int32_t)(4 * e + k);    // cells ascending per vertex
-  }
+  const int64_t n3 = 3 * ne;
+  // inputs and the arrays that stay
+  double* d_xy = dalloc<double>(2 * nv); int32_t* d_conn = dalloc<int32_t>(n3); int32_t* d_nbr = dalloc<int32_t>(n3);
+  int32_t* d_v2c_ptr = dalloc<int32_t>(nv + 1); int32_t* d_v2c = dalloc<int32_t>(n3); int32_t* d_cell_edge = dalloc<int32_t>(n3);
+  // scratch
+  int64_t* d_conn64 = dalloc<int64_t>(n3);
+  uint64_t* d_key = dalloc<uint64_t>(n3); uint64_t* d_key2 = dalloc<uint64_t>(n3);
+  int32_t* d_pos = dalloc<int32_t>(n3); int32_t* d_pos2 = dalloc<int32_t>(n3);
+  uint32_t* d_vkey = dalloc<uint32_t>(n3); uint32_t* d_vkey2 = dalloc<uint32_t>(n3); int32_t* d_vpay = dalloc<int32_t>(n3);
+  int32_t* d_vcount = dalloc<int32_t>(nv + 1);
+  int32_t* d_flag = dalloc<int32_t>(n3); int32_t* d_scan = dalloc<int32_t>(n3); int32_t* d_fpos = dalloc<int32_t>(n3);
+  int* d_err = dalloc<int>(1);
+  int32_t* d_bface = nullptr;
+  auto release = [&](bool all) {
+    cudaFree(d_conn64); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_pos); cudaFree(d_pos2); cudaFree(d_vkey); cudaFree(d_vkey2); cudaFree(d_vpay);
+    cudaFree(d_vcount); cudaFree(d_flag); cudaFree(d_scan); cudaFree(d_fpos); cudaFree(d_err);
+    if (all) { cudaFree(d_xy); cudaFree(d_conn); cudaFree(d_nbr); cudaFree(d_v2c_ptr); cudaFree(d_v2c); cudaFree(d_cell_edge); if (d_bface) cudaFree(d_bface); }
+  };
+  int64_t nedges = 0, nbface = 0;
+  try {
+    MDB_CUDA(cudaMemcpyAsync(d_xy, xy, 2 * nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    MDB_CUDA(cudaMemcpyAsync(d_conn64, conn, n3 * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    MDB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+    MDB_CUDA(cudaMemsetAsync(d_vcount, 0, (nv + 1) * sizeof(int32_t), c->stream));
+    MDB_LAUNCH(c, k_um_ingest_cells, cdiv(ne, 256), 256, 0, nv, ne, d_conn64, d_xy, d_conn, d_key, d_pos, d_vkey, d_vpay, d_vcount, d_err);
+    int err = 0;
+    MDB_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    MDB_REQUIRE(!(err & UM_ERR_RANGE), MDB_EINVAL, "mdb_mesh_unstructured: vertex index out of range");
+    MDB_REQUIRE(!(err & UM_ERR_DEGENERATE), MDB_EINVAL, "mdb_mesh_unstructured: degenerate cell");
+    // the two sorts share one temporary buffer
+    size_t tb1 = 0, tb2 = 0, tb3 = 0;
+    const int vbits = 32 - __builtin_clz((unsigned)std::max<int64_t>(nv - 1, 1));
+    const int kbits = 32 + vbits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb1, d_key, d_key2, d_pos, d_pos2, (int)n3, 0, kbits, c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, d_vkey, d_vkey2, d_vpay, d_v2c, (int)n3, 0, vbits, c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_vcount, d_v2c_ptr, (int)(nv + 1), c->stream);
+    const size_t tb = std::max(std::max(tb1, tb2), std::max(tb3, (size_t)1));
+    void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb));
+    cudaError_t e1 = cub::DeviceRadixSort::SortPairs(d_t, tb1, d_key, d_key2, d_pos, d_pos2, (int)n3, 0, kbits, c->stream); c->launches++;
+    cudaError_t e2 = cub::DeviceRadixSort::SortPairs(d_t, tb2, d_vkey, d_vkey2, d_vpay, d_v2c, (int)n3, 0, vbits, c->stream); c->launches++;   // stable: cells ascending per vertex
+    cudaError_t e3 = cub::DeviceScan::ExclusiveSum(d_t, tb3, d_vcount, d_v2c_ptr, (int)(nv + 1), c->stream); c->launches++;
+    cudaError_t e4 = cudaStreamSynchronize(c->stream);
+    cudaFree(d_t);
+    MDB_CUDA(e1); MDB_CUDA(e2); MDB_CUDA(e3); MDB_CUDA(e4);
+    MDB_LAUNCH(c, k_um_ingest_groups, cdiv(n3, 256), 256, 0, n3, d_key2, d_pos2, d_nbr, d_flag, d_fpos, d_err);
+    nedges = um_scan(c, d_flag, d_scan, n3);
+    MDB_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    MDB_REQUIRE(!(err & UM_ERR_MANIFOLD), MDB_EINVAL, "mdb_mesh_unstructured: more than two cells share a face (non-manifold mesh)");
+    MDB_LAUNCH(c, k_um_ingest_edges, cdiv(n3, 256), 256, 0, n3, d_fpos, d_scan, d_nbr, d_cell_edge, d_flag);       // d_flag becomes the boundary flag
+    nbface = um_scan(c, d_flag, d_pos, n3);                                                                        // d_pos is free after the sort
+    d_bface = dalloc<int32_t>(nbface);
+    if (nbface > 0) MDB_LAUNCH(c, k_um_ingest_bfaces, cdiv(n3, 256), 256, 0, n3, d_flag, d_pos, d_bface);
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+  } catch (...) { release(true); throw; }
+  release(false);
   um_free(c);
   UMesh* u = new UMesh(); c->um = u;
   u->nv = nv; u->ne = ne;
-  u->d_xy = dalloc<double>(2 * nv); u->d_conn = dalloc<int32_t>(3 * ne); u->d_nbr = dalloc<int32_t>(3 * ne);
-  u->d_v2c_ptr = dalloc<int32_t>(nv + 1); u->d_v2c = dalloc<int32_t>(3 * ne);
-  u->nedges = nedges; u->d_cell_edge = dalloc<int32_t>(3 * ne); u->d_group = dalloc<int32_t>(ne);
-  MDB_CUDA(cudaMemcpyAsync(u->d_cell_edge, cell_edge.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
+  u->d_xy = d_xy; u->d_conn = d_conn; u->d_nbr = d_nbr; u->d_v2c_ptr = d_v2c_ptr; u->d_v2c = d_v2c;
+  u->nedges = nedges; u->d_cell_edge = d_cell_edge; u->d_group = dalloc<int32_t>(ne);
+  u->nbface = nbface; u->d_bface = d_bface;
   MDB_CUDA(cudaMemsetAsync(u->d_group, 0, ne * 4, c->stream));
-  MDB_CUDA(cudaMemcpyAsync(u->d_xy, xy, 2 * nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  MDB_CUDA(cudaMemcpyAsync(u->d_conn, hconn.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
-  MDB_CUDA(cudaMemcpyAsync(u->d_nbr, nbr.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
-  MDB_CUDA(cudaMemcpyAsync(u->d_v2c_ptr, vptr.data(), (nv + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-  MDB_CUDA(cudaMemcpyAsync(u->d_v2c, v2c.data(), 3 * ne * 4, cudaMemcpyHostToDevice, c->stream));
-  std::vector<int32_t> bface;
-  for (int64_t i = 0; i < 3 * ne; ++i) if (nbr[i] < 0) bface.push_back((int32_t)i);
-  u->nbface = (int64_t)bface.size();
-  u->d_bface = dalloc<int32_t>(bface.size());
-  if (!bface.empty()) MDB_CUDA(cudaMemcpyAsync(u->d_bface, bface.data(), bface.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  MDB_CUDA(cudaStreamSynchronize(c->stream));
-  c->h2d_bytes += 2 * nv * 8 + 3 * ne * 12 + (nv + 1) * 4;
+  c->h2d_bytes += 2 * nv * 8 + n3 * 8;
   // processing order of the cell-wise kernels: Morton order of the centroids (the numbering itself is the caller's and stays)
   {
-    double lo[2] = {xy[0], xy[1]}, hi[2] = {xy[0], xy[1]};
-    for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 2; ++d) { lo[d] = std::min(lo[d], xy[2 * v + d]); hi[d] = std::max(hi[d], xy[2 * v + d]); }
+    // bounding box on the device (exact and order independent: integer minima / maxima of an order-preserving image)
+    auto enc = [](double d) { long long b; std::memcpy(&b, &d, 8); return b < 0 ? b ^ 0x7fffffffffffffffll : b; };
+    auto dec = [](long long b) { if (b < 0) b ^= 0x7fffffffffffffffll; double d; std::memcpy(&d, &b, 8); return d; };
+    long long hbox[4] = {enc(1e300), enc(1e300), enc(-1e300), enc(-1e300)};
+    double* d_box = dalloc<double>(4);
+    MDB_CUDA(cudaMemcpyAsync(d_box, hbox, sizeof(hbox), cudaMemcpyHostToDevice, c->stream));
+    MDB_LAUNCH(c, k_um_bbox, std::min<int64_t>(cdiv(nv, 256), 148 * 8), 256, 0, nv, u->d_xy, d_box);
+    MDB_CUDA(cudaMemcpyAsync(hbox, d_box, sizeof(hbox), cudaMemcpyDeviceToHost, c->stream));
+    MDB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_box);
+    const double lo[2] = {dec(hbox[0]), dec(hbox[1])}, hi[2] = {dec(hbox[2]), dec(hbox[3])};
     uint32_t* d_code = dalloc<uint32_t>(ne); uint32_t* d_code2 = dalloc<uint32_t>(ne); int32_t* d_cell = dalloc<int32_t>(ne);
     u->d_cell_order = dalloc<int32_t>(ne);
     UMDev m = um_dev(c);

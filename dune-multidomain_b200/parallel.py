@@ -68,6 +68,24 @@ def global_child_bases(per_rank_child_counts, rank):
     return child_offset + below, int(child_total.sum())
 
 
+def slab_global_dofs(local_ptr, local_dofs, ndof_local, s, global_ptr, global_dofs):
+    """Container index in the ONE-RANK numbering of every local DOF of slab `s` (ghosts included), through the cell DOF maps
+    (mdb_get_dofmap of the local context and of a one-rank context / the oracle on the global mesh): local cell (i, j, k) is global
+    cell (i, j, k + offset) and both list their DOFs in the same local order.  This is the map for Qk (k > 1) blocks, whose global
+    numbers are not contiguous per rank (mdb_get_ownership's rank offsets hold for Q1 only)."""
+    dim, pa = s.dim, s.axis
+    nloc = int(np.prod(s.local_n))
+    stride_l = int(np.prod(s.local_n[:pa]))            # cells per layer (the cut axis is the slowest one)
+    c = np.arange(nloc, dtype=np.int64)
+    cg = c + int(s.cell_offset[pa]) * stride_l        # same in-layer index, shifted layer
+    g = -np.ones(ndof_local, dtype=np.int64)
+    ln = local_ptr[1:] - local_ptr[:-1]
+    assert np.array_equal(ln, (global_ptr[1:] - global_ptr[:-1])[cg]), "local and global cells carry different local spaces"
+    src = np.concatenate([np.arange(global_ptr[k], global_ptr[k + 1]) for k in cg]) if nloc else np.zeros(0, dtype=np.int64)
+    g[local_dofs] = global_dofs[src]
+    return g
+
+
 def connect_scalars(dev, dist, rank, nranks):
     """Map every rank's scalar window (mdb_scalars_export / mdb_scalars_import): the Krylov dot products are then all-reduced by peer
     stores over NVLink inside the reducing kernel instead of one ncclAllReduce each.  MDB_SCALARS_NCCL=1 skips it (A/B)."""

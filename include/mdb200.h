@@ -277,7 +277,10 @@ int mdb_mesh_unstructured(mdb_ctx* ctx, int dim, int64_t nv, const double* xyz, 
  * that every cell around an owned vertex is local and owned rows are assembled completely without communication.  Local
  * vertex plane 0 of such a rank and the top local plane of every rank but the last are ghost planes (owned by the
  * neighbours).  Faces on a cut are processor boundaries (no boundary terms, globalassembler.hh:275-283).  `lower/upper`
- * given to mdb_mesh_structured are those of the local slab.  Call after mdb_mesh_structured, before mdb_finalize. */
+ * given to mdb_mesh_structured are those of the local slab.  Call after mdb_mesh_structured, before mdb_finalize.
+ * Child spaces on a partitioned mesh: conforming Qk (Q1 and Q2; a Qk block owns the lattice planes [k, k n) of its slab — the k planes
+ * of the ghost cell layer belong to the rank below, the top plane to the rank above — and the halo exchange carries k planes up and
+ * one plane down per block).  QkDG and coupling (mortar) spaces and the Neumann-Dirichlet coupling are refused by mdb_finalize. */
 int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cell_offset,
                        const double* global_lower, const double* global_upper);
 /* One byte per cell: bit s set <=> cell belongs to subdomain s (<= 8 subdomains;
@@ -502,7 +505,10 @@ int mdb_owned_rows(mdb_ctx* ctx, int64_t* owned, int64_t* local_total);
 int mdb_owned_counts(mdb_ctx* ctx, int64_t* per_child);
 /* Export: one byte per local DOF, 1 = owned by this rank; and the global container index of every owned local DOF (-1
  * for ghosts) given the global index of this rank's first owned DOF of every child block (`child_global_base`,
- * nchildren entries: global child offset + owned rows of the lower ranks; NULL = local numbering). */
+ * nchildren entries: global child offset + owned rows of the lower ranks; NULL = local numbering).  The rank offsets describe the
+ * one-rank numbering for Q1 blocks only (lexicographic, cut axis slowest); a Qk (k > 1) block is numbered entity group by entity
+ * group, so with a non-NULL base the call is refused for such blocks: map local to global DOFs through the cell maps of
+ * mdb_get_dofmap (local cell (i, j, k) = global cell (i, j, k + cell_offset), same local order). */
 int mdb_get_ownership(mdb_ctx* ctx, const int64_t* child_global_base, uint8_t* owned_flags, int64_t* global_index);
 
 /* Row classes of the matrix: "simple" rows carry exactly the full 3^dim own-block stencil (their values are streamed by

@@ -111,6 +111,86 @@ def test_two_contexts_on_one_gpu(n):
         d.close()
 
 
+QK_CASES = [((capi.FE_Q1, capi.FE_Q2), (4, 5, 6)), ((capi.FE_Q2, capi.FE_Q2), (3, 4, 6)), ((capi.FE_Q2, capi.FE_Q1), (4, 3, 5))]
+
+
+def _global_oracle_fe(n, fe):
+    import orc
+    import problems
+    og = orc.Oracle()
+    Pg = problems.testpoisson(og, n, fe=fe)
+    ug = np.zeros(Pg.ndof)
+    og.interpolate(Pg.sps, Pg.gfn, ug)
+    og.jacobian(Pg.go, Pg.mat, ug, overwrite=True)
+    rg = np.zeros(Pg.ndof)
+    og.residual(Pg.go, ug, rg)
+    return og, Pg, ug, rg
+
+
+@pytest.mark.parametrize("fe,n", QK_CASES)
+def test_two_contexts_on_one_gpu_qk(fe, n):
+    """Slab partition with Qk (k = 2) child spaces (the shipped testpoisson is Q1 | Q2): two contexts of one process act as two ranks.
+    Ownership by lattice planes (k ghost planes below, one above), halo exchange of k planes up / one plane down, and the owned rows
+    of the partitioned assembly against the oracle's global matrix — the local -> global map goes through the cell DOF maps."""
+    import torch
+    import problems
+    R = 2
+    devs = [pkg.Mdb(0) for _ in range(R)]
+    slabs = [parallel.slab(n, r, R) for r in range(R)]
+    Ps = [problems.testpoisson(devs[r], n, fe=fe, slab=slabs[r]) for r in range(R)]
+    og, Pg, ug, rg = _global_oracle_fe(n, fe)
+    Ag = og.csr(Pg.mat)
+    pg, dg = og.get_dofmap()
+    blobs = [d.halo_export()[0] for d in devs]
+    devs[0].halo_import(-1, None, 1, blobs[1])
+    devs[1].halo_import(0, blobs[0], -1, None)
+    gfull, owned = [], []
+    seen = np.zeros(Pg.ndof, dtype=int)
+    for r in range(R):
+        pl, dl = devs[r].get_dofmap()
+        g = parallel.slab_global_dofs(pl, dl, Ps[r].ndof, slabs[r], pg, dg)
+        assert (g >= 0).all()
+        f, _ = devs[r].get_ownership(None)
+        assert int(f.sum()) == devs[r].owned_rows()[0] == sum(int(v) for v in devs[r].owned_counts())
+        gfull.append(g); owned.append(f.astype(bool))
+        seen[g[owned[r]]] += 1
+    assert (seen == 1).all()                   # every global DOF is owned by exactly one rank
+    for r in range(R):
+        d, P = devs[r], Ps[r]
+        u = np.zeros(P.ndof)
+        d.interpolate(P.sps, P.gfn, u)
+        assert np.allclose(u, ug[gfull[r]], rtol=1e-14, atol=0)
+        assert np.array_equal(d.get_constraints()[owned[r]], og.get_constraints()[gfull[r][owned[r]]])
+        u = np.ascontiguousarray(ug[gfull[r]])
+        d.jacobian(P.go, P.mat, u, overwrite=True)
+        rp, ci = d.matrix_get_pattern(P.mat)
+        va = d.matrix_get_values(P.mat)
+        scale = np.abs(Ag.data).max()
+        for row in np.where(owned[r])[0]:
+            a, b = rp[row], rp[row + 1]
+            ga, gb = Ag.indptr[gfull[r][row]], Ag.indptr[gfull[r][row] + 1]
+            cols = gfull[r][ci[a:b]]
+            order = np.argsort(cols)
+            assert np.array_equal(cols[order], Ag.indices[ga:gb])
+            assert np.abs(va[a:b][order] - Ag.data[ga:gb]).max() <= 1e-12 * scale
+        res = np.zeros(P.ndof)
+        d.residual(P.go, u, res)
+        assert np.abs(res[owned[r]] - rg[gfull[r][owned[r]]]).max() <= 1e-12 * np.abs(rg).max()
+    rng = np.random.default_rng(0)
+    xg = rng.uniform(-1, 1, Pg.ndof)
+    xd = [torch.from_numpy(np.where(owned[r], xg[gfull[r]], 1e300)).cuda() for r in range(R)]
+    torch.cuda.synchronize()
+    for r in range(R):
+        devs[r].halo_push(xd[r])
+        devs[r].synchronize()
+    for r in range(R):
+        devs[r].halo_wait(xd[r])
+        devs[r].synchronize()
+        assert np.array_equal(xd[r].cpu().numpy(), xg[gfull[r]])
+    for d in devs:
+        d.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -254,6 +334,85 @@ def test_multi_gpu_solve_matches_global_oracle(n):
         err = float(np.abs(dev_all / np.abs(dev_all).max() - ref_all / np.abs(ref_all).max()).max())
         ratios = [float(np.abs(a).max() / np.abs(b).max()) for a, b in zip(dev_dir, ref_dir)]
         assert err <= 1e-13, "%s: err %.3e, per-rank max ratios %s" % (name, err, ratios)
+
+
+def _rank_main_qk(rank, world, port, n, fe, ret):
+    import torch
+    import torch.distributed as dist
+    import problems
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        dev = pkg.Mdb(rank)
+        s = parallel.slab(n, rank, world)
+        P = problems.testpoisson(dev, n, fe=fe, slab=s)
+        link = parallel.connect(dev, dist, rank, world)
+        og, Pg, ug, rg = _global_oracle_fe(n, fe)
+        pg, dg = og.get_dofmap()
+        pl, dl = dev.get_dofmap()
+        gidx = parallel.slab_global_dofs(pl, dl, P.ndof, s, pg, dg)
+        owned = dev.get_ownership(None)[0].astype(bool)
+        assert link.global_ndof == Pg.ndof
+        u = torch.from_numpy(np.where(owned, ug[gidx], 1e300)).cuda()
+        r = torch.zeros_like(u)
+        z = torch.zeros_like(u)
+        torch.cuda.synchronize()
+        dev.halo_push(u)
+        dev.halo_wait(u)
+        dev.synchronize()
+        halo_ok = bool(np.array_equal(u.cpu().numpy(), ug[gidx]))
+        dev.jacobian(P.go, P.mat, u, overwrite=True)
+        dev.residual(P.go, u, r)
+        out = {}
+        for name, method, precond in (("cg", capi.SOLVER_CG, capi.PRECOND_JACOBI), ("bicgstab", capi.SOLVER_BICGSTAB, capi.PRECOND_JACOBI),
+                                      ("bcgs_ssor", capi.SOLVER_BICGSTAB, capi.PRECOND_SSOR)):
+            st = dev.solve(P.mat, r, z, method=method, precond=precond, reduction=1e-12, maxit=4000)
+            assert st.converged, name
+            out[name] = (st.iterations, z.cpu().numpy()[owned].copy())
+        xg = np.random.default_rng(0).uniform(-1, 1, Pg.ndof)
+        x = torch.from_numpy(np.where(owned, xg[gidx], 1e300)).cuda()
+        y = torch.zeros_like(x)
+        torch.cuda.synchronize()
+        dev.spmv(P.mat, x, y)
+        dev.synchronize()
+        ret[rank] = {"gidx": gidx[owned], "sol": out, "y": y.cpu().numpy()[owned], "res": r.cpu().numpy()[owned], "halo_ok": halo_ok}
+        dist.barrier()
+        dev.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fe,n", [((capi.FE_Q1, capi.FE_Q2), (4, 4, 8)), ((capi.FE_Q2, capi.FE_Q2), (3, 4, 8))])
+def test_multi_gpu_qk_solve_matches_global_oracle(fe, n):
+    """Qk (k = 2) child spaces on a slab partition, one process per GPU: residual, distributed SpMV and the Krylov solves (Jacobi,
+    block-Jacobi SSOR) against the oracle's global system."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_rank_main_qk, args=(world, _free_port(), n, fe, ret), nprocs=world, join=True)
+    og, Pg, ug, rg = _global_oracle_fe(n, fe)
+    Ag = og.csr(Pg.mat)
+    zg = spla.spsolve(sp.csc_matrix(Ag), rg)
+    yg = Ag @ np.random.default_rng(0).uniform(-1, 1, Pg.ndof)
+    seen = np.zeros(Pg.ndof, dtype=int)
+    for rank in range(world):
+        o = ret[rank]
+        assert o["halo_ok"]
+        seen[o["gidx"]] += 1
+        assert np.abs(o["res"] - rg[o["gidx"]]).max() <= 1e-12 * np.abs(rg).max()
+        for name in ("cg", "bicgstab", "bcgs_ssor"):
+            it, zz = o["sol"][name]
+            assert np.abs(zz - zg[o["gidx"]]).max() <= 1e-10 * np.abs(zg).max(), name
+        assert np.abs(o["y"] - yg[o["gidx"]]).max() <= 1e-12 * np.abs(yg).max()
+    assert (seen == 1).all()
+    for name in ("cg", "bicgstab", "bcgs_ssor"):
+        assert len({ret[rank]["sol"][name][0] for rank in range(world)}) == 1
 
 
 # ---- unstructured partition (recursive coordinate bisection, index-list halos: mdb_partition_lists) ------------------------------
