@@ -387,7 +387,6 @@ int mdb_add_space(mdb_ctx* c, int fe_kind, int subdomain)
     MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_space: too many child spaces");
     Child ch; ch.fe_kind = fe_kind; ch.k = (fe_kind == MDB_FE_Q1 || fe_kind == MDB_FE_DGQ1) ? 1 : 2; ch.subdomain = subdomain;
     ch.dg = fe_kind == MDB_FE_DGQ1 || fe_kind == MDB_FE_DGQ2;
-    MDB_REQUIRE(!(ch.dg && c->mesh.partitioned), MDB_EINVAL, "mdb_add_space: QkDG spaces are not supported on a partitioned mesh");
     c->children.push_back(ch);
     return (int)c->children.size() - 1;
   } catch (mdb::Error& e) { c->err = e.what(); return e.code; }
@@ -574,13 +573,20 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
   } else if (c->um) um_build_dofmap(c); else build_dofmap(c);
   c->phase_end();
   if (c->mesh.partitioned) {
-    // the add_* calls refuse these on a partitioned mesh; mdb_mesh_partition may also come AFTER them, so check again here
-    for (const Child& ch : c->children)
-      MDB_REQUIRE(!ch.dg && !ch.iface, MDB_EINVAL, "mdb_finalize: a partitioned mesh carries conforming Qk spaces only (no QkDG / coupling spaces)");
+    // the add_* calls refuse these on a partitioned mesh; mdb_mesh_partition may also come AFTER them, so check again here.
+    // Conforming Qk blocks: ownership by lattice planes and plane halos (setup_partition).  Cell-blocked QkDG blocks need the face
+    // neighbours of every owned cell, i.e. ghost cell layers on both sides of the slab: mdb_mesh_partition then only declares the cut
+    // (rank-independent coordinates, no cell sweeps over ghost cells) and ownership + halos come from mdb_partition_lists.
+    bool any_dg = false, any_conforming = false;
+    for (const Child& ch : c->children) {
+      MDB_REQUIRE(!ch.iface, MDB_EINVAL, "mdb_finalize: coupling (mortar) spaces are not supported on a partitioned mesh");
+      (ch.dg ? any_dg : any_conforming) = true;
+    }
+    MDB_REQUIRE(!(any_dg && any_conforming), MDB_EINVAL, "mdb_finalize: a partitioned mesh carries either conforming Qk or QkDG child spaces, not both");
     for (const CouplingDesc& cp : c->cps)
       MDB_REQUIRE(cp.op_id != MDB_OP_ND_COUPLING && !cp.enriched(), MDB_EINVAL,
                   "mdb_finalize: Neumann-Dirichlet and enriched couplings are not supported on a partitioned mesh");
-    setup_partition(c);
+    if (!any_dg) setup_partition(c);
   }
   c->finalized = true;
   if (ndof) *ndof = c->ndof;

@@ -591,7 +591,7 @@ int mdb_partition_lists(mdb_ctx* c, const uint8_t* owned_flags, int nneigh, cons
                         const int64_t* recv_ptr, const int32_t* recv_idx)
 {
   MG_BEGIN(c)
-  MDB_REQUIRE(c->finalized && !c->mesh.partitioned, MDB_ESTATE, "mdb_partition_lists: after mdb_finalize, on a mesh without a slab partition");
+  MDB_REQUIRE(c->finalized && (!c->mesh.partitioned || c->part_axis < 0), MDB_ESTATE, "mdb_partition_lists: after mdb_finalize, on a mesh without a plane (slab) partition");
   MDB_REQUIRE(owned_flags && nneigh >= 0 && nneigh <= MDB_MAX_NEIGH, MDB_EINVAL, "mdb_partition_lists: 0..16 neighbours");
   MDB_REQUIRE(nneigh == 0 || (neigh_ranks && send_ptr && recv_ptr), MDB_EINVAL, "mdb_partition_lists: null list");
   halo_lists_free(c);

@@ -86,6 +86,55 @@ def slab_global_dofs(local_ptr, local_dofs, ndof_local, s, global_ptr, global_do
     return g
 
 
+def slab2(global_n, rank, nranks, lower=None, upper=None):
+    """Slab of rank `rank` with ghost cell layers on BOTH sides: the local mesh of cell-blocked (QkDG) spaces, whose rows couple a cell
+    to its face neighbours — every face neighbour of an owned cell is local, so the owned rows are assembled completely without
+    communication.  The context is a plain structured mesh of the sub-box (no mdb_mesh_partition: the outer faces of the ghost layers
+    only touch ghost rows); ownership and halos go through index lists (cell_blocked_ids + connect_lists)."""
+    dim = len(global_n)
+    lower = [0.0] * dim if lower is None else list(lower)
+    upper = [1.0] * dim if upper is None else list(upper)
+    pa = dim - 1
+    n = int(global_n[pa])
+    if not (1 <= nranks <= n):
+        raise ValueError("cannot cut %d cell layers into %d slabs" % (n, nranks))
+    c0, c1 = (n * rank) // nranks, (n * (rank + 1)) // nranks
+    start, end = c0 - (1 if rank > 0 else 0), c1 + (1 if rank < nranks - 1 else 0)
+    local_n = [int(v) for v in global_n]
+    local_n[pa] = end - start
+    offset = [0] * dim
+    offset[pa] = start
+    h = (upper[pa] - lower[pa]) / n
+    llo, lup = list(lower), list(upper)
+    llo[pa], lup[pa] = lower[pa] + start * h, lower[pa] + end * h
+    bounds = np.array([(n * r) // nranks for r in range(nranks + 1)], dtype=np.int64)
+    return SimpleNamespace(dim=dim, axis=pa, global_n=tuple(int(v) for v in global_n), local_n=tuple(local_n), cell_offset=tuple(offset),
+                           owned_layers=(c0, c1), local_lower=tuple(llo), local_upper=tuple(lup), global_lower=tuple(lower),
+                           global_upper=tuple(upper), rank=rank, nranks=nranks, layer_bounds=bounds)
+
+
+def cell_blocked_ids(local_ptr, local_dofs, ndof_local, s):
+    """Per local DOF of a cell-blocked space on slab2 `s`: a rank-independent id (global cell, position in the cell's local space)
+    and the owner rank (the rank that owns the cell's layer).  Needs only the local cell DOF map (mdb_get_dofmap): every rank lists a
+    cell's DOFs in the same order."""
+    pa = s.axis
+    cpl = int(np.prod(s.local_n[:pa]))
+    ncell = int(np.prod(s.local_n))
+    ln = (local_ptr[1:] - local_ptr[:-1]).astype(np.int64)
+    width = int(ln.max()) if ncell else 1
+    cell = np.repeat(np.arange(ncell, dtype=np.int64), ln)
+    pos = np.arange(local_ptr[-1], dtype=np.int64) - np.repeat(local_ptr[:-1].astype(np.int64), ln)
+    gcell = cell + int(s.cell_offset[pa]) * cpl
+    layer = gcell // cpl
+    gid = -np.ones(ndof_local, dtype=np.int64)
+    owner = -np.ones(ndof_local, dtype=np.int64)
+    assert np.unique(local_dofs).size == local_dofs.size, "not a cell-blocked space: a DOF belongs to several cells"
+    gid[local_dofs] = gcell * width + pos
+    owner[local_dofs] = np.searchsorted(s.layer_bounds, layer, side="right") - 1
+    assert (gid >= 0).all()
+    return gid, owner
+
+
 def connect_scalars(dev, dist, rank, nranks):
     """Map every rank's scalar window (mdb_scalars_export / mdb_scalars_import): the Krylov dot products are then all-reduced by peer
     stores over NVLink inside the reducing kernel instead of one ncclAllReduce each.  MDB_SCALARS_NCCL=1 skips it (A/B)."""
@@ -233,8 +282,9 @@ def um_rank_problem(xy, conn, sd, nranks, rank, child_subdomains):
 
 
 def um_connect(dev, dist, rank, nranks, global_dof, owner):
-    """Ownership + halo lists + NCCL communicator + halo windows of an unstructured partition (mdb_partition_lists,
-    mdb_halo_import_lists).  `global_dof` / `owner` per local DOF (um_rank_problem).  Call after dev.finalize()."""
+    """Ownership + halo lists + NCCL communicator + halo windows of an index-list partition (mdb_partition_lists,
+    mdb_halo_import_lists): unstructured meshes (`global_dof` / `owner` per local DOF from um_rank_problem) and cell-blocked spaces on
+    two-sided slabs (cell_blocked_ids).  `global_dof` only has to be a rank-independent id.  Call after dev.finalize()."""
     owned = owner == rank
     ghosts = np.nonzero(~owned)[0]
     need = {}
@@ -271,3 +321,6 @@ def um_connect(dev, dist, rank, nranks, global_dof, owner):
     dev.halo_import_lists(blobs, caps, offs, slots)
     connect_scalars(dev, dist, rank, nranks)
     return SimpleNamespace(neighbours=neigh, send_count=int(send_ptr[-1]), recv_count=int(recv_ptr[-1]), owned_rows=int(owned.sum()))
+
+
+connect_lists = um_connect

@@ -280,7 +280,11 @@ int mdb_mesh_unstructured(mdb_ctx* ctx, int dim, int64_t nv, const double* xyz, 
  * given to mdb_mesh_structured are those of the local slab.  Call after mdb_mesh_structured, before mdb_finalize.
  * Child spaces on a partitioned mesh: conforming Qk (Q1 and Q2; a Qk block owns the lattice planes [k, k n) of its slab — the k planes
  * of the ghost cell layer belong to the rank below, the top plane to the rank above — and the halo exchange carries k planes up and
- * one plane down per block).  QkDG and coupling (mortar) spaces and the Neumann-Dirichlet coupling are refused by mdb_finalize. */
+ * one plane down per block).  Cell-blocked QkDG blocks (all children QkDG): a row couples a cell to its face neighbours, so the local
+ * slab carries ghost cell layers on BOTH sides; this call then only declares the cut (rank-independent coordinates, processor
+ * boundaries) and ownership + halos are declared per cell layer through mdb_partition_lists after mdb_finalize
+ * (dune-multidomain_b200/parallel.py: slab2, cell_blocked_ids, connect_lists).  Coupling (mortar) spaces, mixed conforming / QkDG
+ * children and the Neumann-Dirichlet coupling are refused by mdb_finalize. */
 int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cell_offset,
                        const double* global_lower, const double* global_upper);
 /* One byte per cell: bit s set <=> cell belongs to subdomain s (<= 8 subdomains;
@@ -487,7 +491,8 @@ int mdb_halo_wait(mdb_ctx* ctx, double* x);
 /* Bound of the device-side wait for a neighbour's planes (default: environment MDB_HALO_TIMEOUT_S, else 30 s).  A timeout is
  * reported once by the call that hit it (MDB_ENCCL) — a running Krylov loop stops at once — and then cleared. */
 int mdb_set_halo_timeout(mdb_ctx* ctx, double seconds);
-/* Partition of an UNSTRUCTURED mesh (recursive coordinate bisection of the cell centroids, a DOF belongs to the lowest rank
+/* Index-list partition: UNSTRUCTURED meshes, and QkDG spaces on a structured slab with two-sided ghost layers (mdb_mesh_partition).
+ * Unstructured meshes (recursive coordinate bisection of the cell centroids, a DOF belongs to the lowest rank
  * among the cells of its entity; the reference's analogue is the overlap-1 MPI grid of test/testoverlappinginstationarypoisson.cc:232-233).
  * The context holds the local mesh of one rank: every cell around an owned vertex plus their face neighbours, in global order, so the
  * owned rows are assembled completely without communication.  This call declares the ownership of the local DOFs and, per neighbour

@@ -137,7 +137,7 @@ def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE
 
 
 def dirichlet_neumann_dg(api, n, k=2, scaling=10.0, alpha=2.0, method=capi.DG_METHOD_SIPG, weights=capi.DG_WEIGHTS_ON, sd_bits=None, f=None,
-                         g=None, bc=None, coupled=True):
+                         g=None, bc=None, coupled=True, box=None):
     """BASELINE configs[0] AS SHIPPED: test/testpoisson-dirichlet-neumann.cc main() (:883-977) calls solve() with DGFEM2 =
     QkDGLocalFiniteElementMap<DF,double,2,dim> on both subdomains and dglop() = ConvectionDiffusionDG(params, SIPG, weightsOn, 2.0)
     (:864-881) over ConvectionDiffusionModelProblem (:169-285); the monolithic system (:449-456, :619-624) couples the two
@@ -145,7 +145,10 @@ def dirichlet_neumann_dg(api, n, k=2, scaling=10.0, alpha=2.0, method=capi.DG_ME
     ini mesh.refine = 9 -> 512^2 cells, 2 * 512 * 256 * 9 = 2 359 296 DOFs.  ConformingDirichletConstraints on a DG space
     constrains nothing: the Dirichlet data enter through alpha_boundary."""
     dim = len(n)
-    api.mesh_structured(n)
+    if box is None:
+        api.mesh_structured(n)
+    else:                       # multi-rank: this rank's sub-box (parallel.slab2: ghost cell layers on both sides) of the global mesh n
+        parallel.apply_slab(api, box)
     if sd_bits is None:
         api.subdomains_halfspace(0, 0.5, 0, 1)
     else:

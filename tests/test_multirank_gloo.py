@@ -412,3 +412,44 @@ def test_um_halo_lists_exchange_every_ghost_from_its_owner(world):
         ok, once, sym, ns, nr = ret[r]
         assert ok and once and sym and ns > 0 and nr > 0
     assert sum(ret[r][3] for r in range(world)) == sum(ret[r][4] for r in range(world))      # everything sent is received
+
+
+@pytest.mark.parametrize("n,k,world", [((6, 9), 2, 3), ((3, 4, 7), 1, 2)])
+def test_cell_blocked_slab_ids(n, k, world):
+    """parallel.slab2 + cell_blocked_ids (QkDG spaces on a partition, index-list halos): with the oracle as the context of every rank,
+    the ids agree with the one-rank numbering through the cell maps, every global DOF is owned exactly once, every ghost DOF is owned by
+    a neighbour, and the owned rows of the local matrices equal the global rows (no matrix communication)."""
+    import orc
+    import problems
+    og = orc.Oracle()
+    Pg = problems.dirichlet_neumann_dg(og, n, k=k)
+    x = np.random.default_rng(1).uniform(-1, 1, Pg.ndof)
+    og.jacobian(Pg.go, Pg.mat, x, overwrite=True)
+    Ag = og.csr(Pg.mat)
+    pg, dg = og.get_dofmap()
+    seen = np.zeros(Pg.ndof, dtype=int)
+    idmap = {}
+    for rank in range(world):
+        s = parallel.slab2(n, rank, world)
+        ol = orc.Oracle()
+        P = problems.dirichlet_neumann_dg(ol, n, k=k, box=s)
+        pl, dl = ol.get_dofmap()
+        ids, owner = parallel.cell_blocked_ids(pl, dl, P.ndof, s)
+        gidx = parallel.slab_global_dofs(pl, dl, P.ndof, s, pg, dg)
+        owned = owner == rank
+        seen[gidx[owned]] += 1
+        assert set(np.unique(owner[~owned])) <= {rank - 1, rank + 1}
+        for i, g in zip(ids, gidx):                     # a rank-independent id: the same global DOF carries the same id on every rank
+            assert idmap.setdefault(int(i), int(g)) == int(g)
+        ol.jacobian(P.go, P.mat, np.ascontiguousarray(x[gidx]), overwrite=True)
+        Al = ol.csr(P.mat)
+        for row in np.where(owned)[0]:
+            a, b = Al.indptr[row], Al.indptr[row + 1]
+            ga, gb = Ag.indptr[gidx[row]], Ag.indptr[gidx[row] + 1]
+            cols = gidx[Al.indices[a:b]]
+            order = np.argsort(cols)
+            assert np.array_equal(cols[order], Ag.indices[ga:gb])
+            assert np.abs(Al.data[a:b][order] - Ag.data[ga:gb]).max() <= 1e-12 * np.abs(Ag.data).max()
+        ol.close()
+    assert (seen == 1).all()
+    og.close()
