@@ -400,7 +400,6 @@ int mdb_add_coupling_space(mdb_ctx* c, int fe_kind, int left_cond_kind, uint32_t
     MDB_REQUIRE(c->have_mesh && !c->finalized, MDB_ESTATE, "mdb_add_coupling_space: need a mesh, before mdb_finalize");
     MDB_REQUIRE(fe_kind == MDB_FE_Q1, MDB_EINVAL, "mdb_add_coupling_space: only Q1 coupling spaces (vertex-attached mortar DOFs) have device kernels");
     MDB_REQUIRE(c->mesh.dim >= 2, MDB_EINVAL, "mdb_add_coupling_space: needs dim >= 2");
-    MDB_REQUIRE(!c->mesh.partitioned, MDB_EINVAL, "mdb_add_coupling_space: coupling spaces are not supported on a partitioned mesh");
     auto ok = [](int k) { return k == MDB_COND_EQUALITY || k == MDB_COND_SUBSET; };
     MDB_REQUIRE(ok(left_cond_kind) && ok(right_cond_kind), MDB_EINVAL, "mdb_add_coupling_space: bad condition");
     MDB_REQUIRE((int)c->children.size() < MDB_MAX_CHILDREN, MDB_EINVAL, "mdb_add_coupling_space: too many child spaces");
@@ -578,14 +577,10 @@ int mdb_finalize(mdb_ctx* c, int64_t* ndof)
     // neighbours of every owned cell, i.e. ghost cell layers on both sides of the slab: mdb_mesh_partition then only declares the cut
     // (rank-independent coordinates, no cell sweeps over ghost cells) and ownership + halos come from mdb_partition_lists.
     bool any_dg = false, any_conforming = false;
-    for (const Child& ch : c->children) {
-      MDB_REQUIRE(!ch.iface, MDB_EINVAL, "mdb_finalize: coupling (mortar) spaces are not supported on a partitioned mesh");
-      (ch.dg ? any_dg : any_conforming) = true;
-    }
+    for (const Child& ch : c->children) (ch.dg ? any_dg : any_conforming) = true;      // coupling (mortar) blocks are vertex-attached: conforming
     MDB_REQUIRE(!(any_dg && any_conforming), MDB_EINVAL, "mdb_finalize: a partitioned mesh carries either conforming Qk or QkDG child spaces, not both");
     for (const CouplingDesc& cp : c->cps)
-      MDB_REQUIRE(cp.op_id != MDB_OP_ND_COUPLING && !cp.enriched(), MDB_EINVAL,
-                  "mdb_finalize: Neumann-Dirichlet and enriched couplings are not supported on a partitioned mesh");
+      MDB_REQUIRE(cp.op_id != MDB_OP_ND_COUPLING, MDB_EINVAL, "mdb_finalize: the Neumann-Dirichlet coupling is not supported on a partitioned mesh");
     if (!any_dg) setup_partition(c);
   }
   c->finalized = true;

@@ -283,8 +283,9 @@ int mdb_mesh_unstructured(mdb_ctx* ctx, int dim, int64_t nv, const double* xyz, 
  * one plane down per block).  Cell-blocked QkDG blocks (all children QkDG): a row couples a cell to its face neighbours, so the local
  * slab carries ghost cell layers on BOTH sides; this call then only declares the cut (rank-independent coordinates, processor
  * boundaries) and ownership + halos are declared per cell layer through mdb_partition_lists after mdb_finalize
- * (dune-multidomain_b200/parallel.py: slab2, cell_blocked_ids, connect_lists).  Coupling (mortar) spaces, mixed conforming / QkDG
- * children and the Neumann-Dirichlet coupling are refused by mdb_finalize. */
+ * (dune-multidomain_b200/parallel.py: slab2, cell_blocked_ids, connect_lists).  Coupling (mortar) spaces are vertex-attached: their
+ * blocks are owned by lattice planes like Q1 blocks, enriched couplings work on a partition.  Mixed conforming / QkDG children and the
+ * Neumann-Dirichlet coupling (a one-directional operator driven by sub-block solves) are refused by mdb_finalize. */
 int mdb_mesh_partition(mdb_ctx* ctx, const int64_t* global_n, const int64_t* cell_offset,
                        const double* global_lower, const double* global_upper);
 /* One byte per cell: bit s set <=> cell belongs to subdomain s (<= 8 subdomains;

@@ -95,13 +95,17 @@ def dirichlet_neumann_q1(api, n):
     return testpoisson(api, n, intensity=10.0, split_axis=0, quad_order=6, f=capi.Function(capi.FN_DN_SOURCE))
 
 
-def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE_Q1), jac_mode=capi.JAC_FD_BITMATCH, sd_bits=None, ncomp=1):
+def testmortarpoisson(api, n, gamma_0=1.0, split_axis=0, fe=(capi.FE_Q1, capi.FE_Q1), jac_mode=capi.JAC_FD_BITMATCH, sd_bits=None, ncomp=1,
+                      slab=None):
     """test/testmortarpoisson.cc:281-432 (BASELINE configs[3]; 2-D refine 5 as shipped, dim = len(n) for the synthetic 3-D
     form): subdomains x0 < 0.5 -> 0, x0 > 0.5 -> 1 (:325-330), a Q1 space on each (:359-362), a Q1 mortar space
     on the interface faces inside in {0} / outside in {1} as the LAST child (:365-384), Poisson(f,b,j,4) on both sides
     (:400-401; f = 0, :38), EnrichedCoupling<SubProblem0,SubProblem1,MortarPoissonCoupling,2>(gamma_0) (:411-412)."""
     dim = len(n)
-    api.mesh_structured(n)
+    if slab is None:
+        api.mesh_structured(n)
+    else:                       # multi-rank: this rank's slab (+ ghost layer) of the global mesh n
+        parallel.apply_slab(api, slab)
     if sd_bits is None:
         api.subdomains_halfspace(split_axis, 0.5, 0, 1)
     else:

@@ -191,6 +191,100 @@ def test_two_contexts_on_one_gpu_qk(fe, n):
         d.close()
 
 
+MORTAR_CASES = [((4, 5, 6), 1, (capi.FE_Q1, capi.FE_Q1)), ((6, 8), 1, (capi.FE_Q1, capi.FE_Q1)), ((3, 4, 6), 2, (capi.FE_Q1, capi.FE_Q1)),
+                ((3, 3, 5), 1, (capi.FE_Q2, capi.FE_Q1))]
+
+
+def _global_oracle_mortar(n, ncomp, fe):
+    import orc
+    import problems
+    og = orc.Oracle()
+    Pg = problems.testmortarpoisson(og, n, ncomp=ncomp, fe=fe)
+    ug = np.random.default_rng(5).uniform(-1, 1, Pg.ndof)
+    og.jacobian(Pg.go, Pg.mat, ug, overwrite=True)
+    rg = np.zeros(Pg.ndof)
+    og.residual(Pg.go, ug, rg)
+    return og, Pg, ug, rg
+
+
+@pytest.mark.parametrize("n,ncomp,fe", MORTAR_CASES)
+def test_two_contexts_on_one_gpu_mortar(n, ncomp, fe):
+    """Enriched (mortar) couplings on a slab partition (BASELINE configs[3]): the coupling space is vertex-attached, so its block is
+    owned by lattice planes like a Q1 block.  Two contexts of one process act as two ranks; owned rows (element rows with their
+    mortar links, mortar rows) against the oracle's global matrix, residual, halo exchange of all blocks."""
+    import torch
+    import problems
+    R = 2
+    devs = [pkg.Mdb(0) for _ in range(R)]
+    slabs = [parallel.slab(n, r, R) for r in range(R)]
+    Ps = [problems.testmortarpoisson(devs[r], n, ncomp=ncomp, fe=fe, slab=slabs[r]) for r in range(R)]
+    og, Pg, ug, rg = _global_oracle_mortar(n, ncomp, fe)
+    Ag = og.csr(Pg.mat)
+    blobs = [d.halo_export()[0] for d in devs]
+    devs[0].halo_import(-1, None, 1, blobs[1])
+    devs[1].halo_import(0, blobs[0], -1, None)
+    # no cell carries the mortar DOFs, so the cell maps cannot give the local -> global map; every block of this system that is cut
+    # is a Q1 block (lexicographic, cut axis slowest), except a Q2 element block, which goes through the cell maps
+    counts = [[int(v) for v in d.owned_counts()] for d in devs]
+    assert sum(sum(c) for c in counts) == Pg.ndof
+    pg, dg = og.get_dofmap()
+    gfull, owned = [], []
+    for r in range(R):
+        f, _ = devs[r].get_ownership(None)
+        ow = f.astype(bool)
+        off = devs[r].get_child_offsets()
+        goff = og.get_child_offsets()
+        g = -np.ones(Ps[r].ndof, dtype=np.int64)
+        pl, dl = devs[r].get_dofmap()
+        gc = parallel.slab_global_dofs(pl, dl, Ps[r].ndof, slabs[r], pg, dg)        # element blocks (-1 on the mortar blocks)
+        for k in range(len(off) - 1):
+            a, b = off[k], off[k + 1]
+            if (gc[a:b] >= 0).all():
+                g[a:b] = gc[a:b]
+            else:                                                                   # mortar block: rank offsets
+                below = sum(counts[q][k] for q in range(r))
+                idx = np.nonzero(ow[a:b])[0]
+                g[a + idx] = goff[k] + below + np.arange(idx.size)
+        gfull.append(g); owned.append(ow)
+    xs = [torch.from_numpy(np.where(owned[r], gfull[r], -1).astype(np.float64)).cuda() for r in range(R)]
+    torch.cuda.synchronize()
+    for r in range(R):
+        devs[r].halo_push(xs[r])
+    for r in range(R):
+        devs[r].synchronize()
+    for r in range(R):
+        devs[r].halo_wait(xs[r])
+        devs[r].synchronize()
+        g = xs[r].cpu().numpy().astype(np.int64)
+        assert (g >= 0).all(), "a ghost DOF was not covered by the halo exchange"
+        assert np.array_equal(g[gfull[r] >= 0], gfull[r][gfull[r] >= 0])           # the two maps agree where both exist
+        gfull[r] = g
+    seen = np.zeros(Pg.ndof, dtype=int)
+    for r in range(R):
+        seen[gfull[r][owned[r]]] += 1
+    assert (seen == 1).all()
+    for r in range(R):
+        d, P = devs[r], Ps[r]
+        assert np.array_equal(d.get_constraints()[owned[r]], og.get_constraints()[gfull[r][owned[r]]])
+        u = np.ascontiguousarray(ug[gfull[r]])
+        d.jacobian(P.go, P.mat, u, overwrite=True)
+        rp, ci = d.matrix_get_pattern(P.mat)
+        va = d.matrix_get_values(P.mat)
+        scale = np.abs(Ag.data).max()
+        for row in np.where(owned[r])[0]:
+            a, b = rp[row], rp[row + 1]
+            ga, gb = Ag.indptr[gfull[r][row]], Ag.indptr[gfull[r][row] + 1]
+            cols = gfull[r][ci[a:b]]
+            order = np.argsort(cols)
+            assert np.array_equal(cols[order], Ag.indices[ga:gb])
+            assert np.abs(va[a:b][order] - Ag.data[ga:gb]).max() <= 1e-12 * scale
+        res = np.zeros(P.ndof)
+        d.residual(P.go, u, res)
+        assert np.abs(res[owned[r]] - rg[gfull[r][owned[r]]]).max() <= 1e-12 * np.abs(rg).max()
+    for d in devs:
+        d.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -518,6 +612,76 @@ def test_multi_gpu_dg_partition_matches_global_oracle(n, k):
     assert (seen == 1).all()
     for name in ("bicgstab", "bcgs_ssor"):
         assert len({ret[rank]["sol"][name][0] for rank in range(world)}) == 1
+
+
+def _rank_main_mortar(rank, world, port, n, ret):
+    import torch
+    import torch.distributed as dist
+    import problems
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        dev = pkg.Mdb(rank)
+        s = parallel.slab(n, rank, world)
+        P = problems.testmortarpoisson(dev, n, slab=s)
+        link = parallel.connect(dev, dist, rank, world)
+        flags, gidx = dev.get_ownership(link.child_global_base)          # all three blocks are Q1-like (vertex-attached, lexicographic)
+        owned = flags.astype(bool)
+        og, Pg, ug, rg = _global_oracle_mortar(n, 1, (capi.FE_Q1, capi.FE_Q1))
+        assert link.global_ndof == Pg.ndof
+        u = torch.from_numpy(np.where(owned, ug[np.maximum(gidx, 0)], 1e300)).cuda()
+        r = torch.zeros_like(u)
+        z = torch.zeros_like(u)
+        torch.cuda.synchronize()
+        dev.halo_push(u)
+        dev.halo_wait(u)
+        dev.jacobian(P.go, P.mat, u, overwrite=True)
+        dev.residual(P.go, u, r)
+        dev.set_ssor_sweeps(3)
+        st = dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_SSOR, reduction=1e-12, maxit=3000)
+        sol = (bool(st.converged), st.iterations, z.cpu().numpy()[owned].copy())
+        xg = np.random.default_rng(0).uniform(-1, 1, Pg.ndof)
+        x = torch.from_numpy(np.where(owned, xg[np.maximum(gidx, 0)], 1e300)).cuda()
+        y = torch.zeros_like(x)
+        torch.cuda.synchronize()
+        dev.spmv(P.mat, x, y)
+        dev.synchronize()
+        ret[rank] = {"gidx": gidx[owned], "sol": sol, "y": y.cpu().numpy()[owned], "res": r.cpu().numpy()[owned]}
+        dist.barrier()
+        dev.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [(4, 4, 8)])
+def test_multi_gpu_mortar_matches_global_oracle(n):
+    """testmortarpoisson (enriched coupling, Q1 mortar space) on a slab partition, one process per GPU: residual, distributed SpMV and
+    the reference's solver configuration (BiCGSTAB + SeqSSOR(3), block-Jacobi over the ranks) against the oracle's global system."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_rank_main_mortar, args=(world, _free_port(), n, ret), nprocs=world, join=True)
+    og, Pg, ug, rg = _global_oracle_mortar(n, 1, (capi.FE_Q1, capi.FE_Q1))
+    Ag = og.csr(Pg.mat)
+    zg = spla.spsolve(sp.csc_matrix(Ag), rg)
+    yg = Ag @ np.random.default_rng(0).uniform(-1, 1, Pg.ndof)
+    seen = np.zeros(Pg.ndof, dtype=int)
+    for rank in range(world):
+        o = ret[rank]
+        seen[o["gidx"]] += 1
+        assert np.abs(o["res"] - rg[o["gidx"]]).max() <= 1e-12 * np.abs(rg).max()
+        assert np.abs(o["y"] - yg[o["gidx"]]).max() <= 1e-12 * np.abs(yg).max()
+        conv, it, zz = o["sol"]
+        assert conv, "BiCGSTAB + block-Jacobi SSOR(3) did not converge on the mortar system"
+        assert np.abs(zz - zg[o["gidx"]]).max() <= 1e-9 * np.abs(zg).max()
+    assert (seen == 1).all()
+    assert len({ret[rank]["sol"][1] for rank in range(world)}) == 1
 
 
 # ---- unstructured partition (recursive coordinate bisection, index-list halos: mdb_partition_lists) ------------------------------
