@@ -138,7 +138,7 @@ void VecInOut::commit()
 
 static void free_matrix(Matrix& m)
 {
-  dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv); dfree(m.d_spmv_rest); dfree(m.d_ready); dfree(m.d_sweep_counter); dfree(m.d_sweep_perm); dfree(m.d_cell_perm); dfree(m.d_vrec); dfree(m.d_ilu);
+  dfree(m.d_rowptr); dfree(m.d_colidx); dfree(m.d_val); dfree(m.d_rowinfo); dfree(m.d_diag); dfree(m.d_dinv); dfree(m.d_spmv_rest); dfree(m.d_sr_chunks); dfree(m.d_ready); dfree(m.d_sweep_counter); dfree(m.d_sweep_perm); dfree(m.d_cell_perm); dfree(m.d_vrec); dfree(m.d_ilu);
   for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(m.d_irregular[i]); dfree(m.d_seg_start[i]); dfree(m.d_seg_span[i]); dfree(m.d_rr_rs[i]); dfree(m.d_rr_mask[i]); dfree(m.d_rr_meta[i]); dfree(m.d_rr_sd[i]); }
   for (auto& kv : m.slot_tables) cudaFree(kv.second);
   m.slot_tables.clear();

@@ -295,6 +295,9 @@ struct Matrix {
   std::map<std::vector<int>, void*> um_pair_plans;   // unstructured.cu: pair records of the owner-computes Jacobian kernel per subproblem list
   // SpMV: ascending list of the rows the stencil kernel leaves to the row-list kernel (solver.cu); -1 = not built yet
   int32_t* d_spmv_rest = nullptr; int64_t n_spmv_rest = -1;
+  // shift-run product (solver.cu, k_spmv_runs): chunks of <= 32 consecutive rows whose column lists are those of the row before
+  // shifted by one; -1 = not analysed yet, 0 = the matrix has too few such rows (vector-CSR kernel)
+  int4* d_sr_chunks = nullptr; int64_t n_sr_chunks = -1; int sr_maxm = 0;
 };
 
 struct Ctx {

@@ -10,6 +10,7 @@
 // gathered x (L1/L2 hits: neighbouring rows share columns) into shared memory, then one thread per row sums its segment.
 // Algorithmic bytes: 12*nnz + 20*nrows.
 #include "common.cuh"
+#include <cstring>
 #include <cmath>
 #include <cub/cub.cuh>
 
@@ -424,6 +425,263 @@ __global__ void __launch_bounds__(ST_ROWS, ST_BLOCKS) k_spmv_stencil(int64_t n, 
   }
 }
 
+// ---- shift-run product: structured numberings beyond Q1 (Qk entity groups) ----------------------------------------------------------
+// On a structured mesh consecutive rows of an entity group mostly hold the SAME column list shifted by one (row r + 1 couples to
+// column c + 1 wherever row r couples to c): along such a run the column indices need not be read at all.  The analysis is generic
+// (it looks at the CSR pattern only, once per matrix): same[r] = row r has the length of row r - 1 and col[r][k] = col[r-1][k] + 1 for
+// all k.  Maximal runs of at least SR_MINRUN rows are cut into chunks of <= 32 rows; a warp stages a chunk's values (one contiguous
+// span, coalesced loads) in shared memory, lane t then sums row t in column order — entry k of the span at t m + k (row lengths of Qk
+// rows are odd: conflict-free), x at col0[k] + t (coalesced) — so the product moves 8 bytes per stored entry instead of 12 and every
+// lane carries a row (the vector-CSR kernel leaves half its lanes idle on 9 / 15 / 25-entry rows).  Rows outside the runs go through
+// k_spmv_rows on a list.  Summation order = CSR order (the sequential order of the CPU product).
+#define SR_MAXLEN 32
+#define SR_MINRUN 8
+__global__ void k_sr_same(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t* head)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  bool same = r > 0;
+  if (same) {
+    const int64_t s = rowptr[r], e = rowptr[r + 1], s0 = rowptr[r - 1];
+    same = (e - s) == (s - s0) && (e - s) >= 1 && (e - s) <= SR_MAXLEN;
+    for (int64_t k = 0; same && k < e - s; ++k) same = colidx[s + k] == colidx[s0 + k] + 1;
+  }
+  head[r] = same ? 0 : 1;
+}
+// run id of every row = (inclusive scan of head) - 1 = exclusive scan + head - 1; start[run] by the heads
+__global__ void k_sr_starts(int64_t n, const int32_t* __restrict__ head, const int32_t* __restrict__ scan, int32_t* start)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r < n && head[r]) start[scan[r]] = (int32_t)r;
+}
+__global__ void k_sr_counts(int64_t nruns, int64_t n, const int32_t* __restrict__ start, const int64_t* __restrict__ rowptr, int32_t* nchunk, int* maxm)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nruns) return;
+  const int64_t a = start[i], b = (i + 1 < nruns) ? start[i + 1] : n;
+  const int64_t len = rowptr[a + 1] - rowptr[a];
+  nchunk[i] = (b - a >= SR_MINRUN && len >= 1 && len <= SR_MAXLEN) ? (int32_t)((b - a + 31) / 32) : 0;
+  if (nchunk[i] > 0) atomicMax(maxm, (int)len);
+}
+__global__ void k_sr_fill(int64_t n, const int32_t* __restrict__ head, const int32_t* __restrict__ scan, int64_t nruns, const int32_t* __restrict__ start,
+                          const int32_t* __restrict__ nchunk, const int32_t* __restrict__ choff, const int64_t* __restrict__ rowptr, int4* chunks, int32_t* rest)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t run = scan[r] + head[r] - 1;
+  const int64_t a = start[run], b = (run + 1 < nruns) ? start[run + 1] : n;
+  const bool kept = nchunk[run] > 0;
+  rest[r] = kept ? 0 : 1;
+  if (kept && ((r - a) & 31) == 0) {                       // a chunk record: first row, rows | row length << 8, first entry (64 bits)
+    const long long p0 = rowptr[r]; const int m = (int)(rowptr[r + 1] - p0);
+    chunks[choff[run] + ((r - a) >> 5)] = make_int4((int)r, (int)((b - r) < 32 ? (b - r) : 32) | (m << 8), (int)(p0 & 0xffffffffll), (int)(p0 >> 32));
+  }
+}
+#define SR_WARPS 4
+#define SR_STAGES 4
+// Values travel through a ring of SR_STAGES bulk-async copies per warp (ncu of the first, double-buffered version: 12 warps per SM with
+// one 6 KB copy in flight each = 77 KB per SM in flight, 7 300 cycles per chunk, DRAM 32 %: under load a copy takes microseconds, so the
+// bytes in flight bound the rate — the Q1 stencil kernel keeps ~150 KB per SM in flight).  Slots are sized by the longest row of the
+// matrix' runs (`slot` doubles, even), so 2 blocks x 4 warps x 4 stages fit an SM for 25-entry rows.
+template <int DOTS>
+__global__ void __launch_bounds__(32 * SR_WARPS) k_spmv_runs(int64_t nchunks, const int4* __restrict__ chunks, int slot, const int32_t* __restrict__ colidx,
+                                                            const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                                            const double* __restrict__ a, const uint8_t* __restrict__ owned, double* partial, int pofs,
+                                                            const double* __restrict__ done)
+{
+  extern __shared__ __align__(16) double sr_smem[];                  // [SR_WARPS][SR_STAGES][slot] values, then [SR_WARPS][SR_STAGES] mbarriers
+  __shared__ double sh[8];
+  if (done && done[S_DONE] != 0.0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* buf = sr_smem + (size_t)warp * SR_STAGES * slot;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sr_smem + (size_t)SR_WARPS * SR_STAGES * slot) + warp * SR_STAGES;
+  if (lane == 0) {
+    for (int i = 0; i < SR_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  struct Ck { int64_t r0, p0; int nr, m; };
+  const int4 none = make_int4(0, 0, 0, 0);
+  auto decode = [](const int4 q, Ck& C) {
+    C.r0 = q.x; C.nr = q.y & 255; C.m = q.y >> 8; C.p0 = (int64_t)(((unsigned long long)(unsigned)q.w << 32) | (unsigned)q.z);
+  };
+  auto issue = [&](const int4 q, int st) {                             // lane 0 only
+    Ck C; decode(q, C);
+    if (C.nr == 0) return;
+    const int64_t a0 = C.p0 & ~(int64_t)1;
+    const uint32_t bytes = (uint32_t)((((C.p0 + (int64_t)C.nr * C.m) - a0 + 1) & ~(int64_t)1) * 8);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + st)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf + (size_t)st * slot)),
+                 "l"(val + a0), "r"(bytes), "r"(smem_u32(bar + st))
+                 : "memory");
+  };
+  double d0 = 0.0, d1 = 0.0;
+  const int64_t step = (int64_t)gridDim.x * SR_WARPS;
+  const int64_t ck0 = blockIdx.x * (int64_t)SR_WARPS + warp;
+  // prologue: the first SR_STAGES - 1 chunks of this warp are in flight; chunk records are read SR_STAGES iterations ahead
+  for (int i = 0; i < SR_STAGES - 1; ++i) {
+    const int64_t cki = ck0 + i * step;
+    if (lane == 0 && cki < nchunks) issue(chunks[cki], i);
+  }
+  Ck C;
+  decode(ck0 < nchunks ? chunks[ck0] : none, C);
+  int4 qnext = ck0 + step < nchunks ? chunks[ck0 + step] : none;       // record of the chunk summed next
+  int4 qissue = ck0 + (SR_STAGES - 1) * step < nchunks ? chunks[ck0 + (SR_STAGES - 1) * step] : none;   // record of the chunk issued next
+  int cmine = (C.nr > 0 && lane < C.m) ? __ldg(colidx + C.p0 + lane) : 0;   // the run's column list: first row of the chunk, shifted by the lane
+  int st = 0;
+  uint32_t phases = 0u;                                                 // bit s = parity of stage s
+  for (int64_t ck = ck0; ck < nchunks; ck += step) {
+    // stage (st + SR_STAGES - 1) % SR_STAGES was consumed in the previous iteration (__syncwarp below): refill it
+    if (lane == 0) issue(qissue, (st + SR_STAGES - 1) % SR_STAGES);
+    qissue = ck + SR_STAGES * step < nchunks ? chunks[ck + SR_STAGES * step] : none;
+    Ck Cn; decode(qnext, Cn);
+    const int cnext = (Cn.nr > 0 && lane < Cn.m) ? __ldg(colidx + Cn.p0 + lane) : 0;
+    qnext = ck + 2 * step < nchunks ? chunks[ck + 2 * step] : none;
+    const bool live = lane < C.nr;
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(bar + st)), "r"((phases >> st) & 1u) : "memory");
+    phases ^= 1u << st;
+    const double* mine = buf + (size_t)st * slot + (C.p0 & 1) + lane * C.m;
+    double sum = 0.0;
+    int k = 0;
+    for (; k + 8 <= C.m; k += 8) {                                      // eight x loads in flight, summed in column order
+      double xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int cj = __shfl_sync(0xffffffffu, cmine, k + j); xv[j] = live ? x[(int64_t)cj + lane] : 0.0; }
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += mine[k + j] * xv[j];
+      }
+    }
+    for (; k < C.m; ++k) {
+      const int c0 = __shfl_sync(0xffffffffu, cmine, k);
+      if (live) sum += mine[k] * x[(int64_t)c0 + lane];
+    }
+    if (live) {
+      const int64_t r = C.r0 + lane;
+      y[r] = sum;
+      if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
+    }
+    __syncwarp();
+    C = Cn; cmine = cnext;
+    st = (st + 1) % SR_STAGES;
+  }
+  if (DOTS >= 1) {
+    double s0 = block_sum(d0, sh);
+    if (threadIdx.x == 0) partial[pofs + blockIdx.x] = s0;
+    if (DOTS >= 2) {
+      double s1 = block_sum(d1, sh);
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + pofs + blockIdx.x] = s1;
+    }
+  }
+}
+// The same chunks without shared memory: 8 lanes per row as in k_spmv_vec (full occupancy: the product is bound by load latency, not by
+// bytes), but the column list of the chunk's first row lives in the lanes (one coalesced load per 32 rows) — no column-index traffic and
+// no colidx -> x dependency: the value and x loads of 8 rows x 4 entries per lane are independent and issued together.
+template <int DOTS>
+__global__ void __launch_bounds__(256) k_spmv_runs_vec(int64_t nchunks, const int4* __restrict__ chunks, const int32_t* __restrict__ colidx,
+                                                       const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                                       const double* __restrict__ a, const uint8_t* __restrict__ owned, double* partial, int pofs,
+                                                       const double* __restrict__ done)
+{
+  __shared__ double sh[8];
+  if (done && done[S_DONE] != 0.0) return;
+  const int lane = threadIdx.x & 31, sub = lane & 7, g = lane >> 3;
+  double d0 = 0.0, d1 = 0.0;
+  const int64_t step = (int64_t)gridDim.x * 8;
+  for (int64_t ck = blockIdx.x * 8ll + (threadIdx.x >> 5); ck < nchunks; ck += step) {
+    const int4 q = chunks[ck];
+    const int64_t r0 = q.x; const int nr = q.y & 255, m = q.y >> 8;
+    const int64_t p0 = (int64_t)(((unsigned long long)(unsigned)q.w << 32) | (unsigned)q.z);
+    const int cmine = (lane < m) ? __ldg(colidx + p0 + lane) : 0;
+    int c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = __shfl_sync(0xffffffffu, cmine, (sub + 8 * j) & 31);
+#pragma unroll 2
+    for (int t = 0; t < 32; t += 4) {                                 // 4 rows per step, 8 lanes each
+      if (t >= nr) break;                                               // warp-uniform
+      const int row = t + g;
+      const bool live = row < nr;
+      const double* v = val + p0 + (int64_t)row * m;
+      double vv[4], xx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool on = live && sub + 8 * j < m;
+        vv[j] = on ? ld_stream_f64(v + sub + 8 * j) : 0.0;
+        xx[j] = on ? x[(int64_t)c[j] + row] : 0.0;
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sum += vv[j] * xx[j];
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, 8);
+      if (live && sub == 0) {
+        const int64_t r = r0 + row;
+        y[r] = sum;
+        if (DOTS >= 1 && (!owned || owned[r])) { d0 += sum * a[r]; if (DOTS >= 2) d1 += sum * sum; }
+      }
+    }
+  }
+  if (DOTS >= 1) {
+    double s0 = block_sum(d0, sh);
+    if (threadIdx.x == 0) partial[pofs + blockIdx.x] = s0;
+    if (DOTS >= 2) {
+      double s1 = block_sum(d1, sh);
+      if (threadIdx.x == 0) partial[MAX_PARTIAL_BLOCKS + pofs + blockIdx.x] = s1;
+    }
+  }
+}
+static int64_t sr_scan(Ctx* c, const int32_t* d_in, int32_t* d_out, int64_t n)
+{
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, d_in, d_out, (int)n, c->stream);
+  void* d_t = nullptr; MDB_CUDA(cudaMalloc(&d_t, tb ? tb : 1));
+  MDB_CUDA(cub::DeviceScan::ExclusiveSum(d_t, tb, d_in, d_out, (int)n, c->stream)); c->launches++;
+  int32_t ls = 0, lf = 0;
+  MDB_CUDA(cudaMemcpyAsync(&ls, d_out + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaMemcpyAsync(&lf, d_in + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_t);
+  return (int64_t)ls + lf;
+}
+// first product with this matrix: runs, chunks and the list of the remaining rows.  Leaves n_sr_chunks = 0 when fewer than 70 % of the
+// rows sit in runs (the vector-CSR kernel then takes the whole matrix).
+static void sr_analyse(Ctx* c, Matrix& M)
+{
+  const int64_t n = c->ndof;
+  M.n_sr_chunks = 0;
+  if (n < 2 || n >= (int64_t)2147483647 || M.max_row < 1) return;
+  int32_t* d_head = dalloc<int32_t>(n); int32_t* d_scan = dalloc<int32_t>(n);
+  MDB_LAUNCH(c, k_sr_same, cdiv(n, 256), 256, 0, n, M.d_rowptr, M.d_colidx, d_head);
+  const int64_t nruns = sr_scan(c, d_head, d_scan, n);
+  int32_t* d_start = dalloc<int32_t>(nruns); int32_t* d_nchunk = dalloc<int32_t>(nruns); int32_t* d_choff = dalloc<int32_t>(nruns);
+  MDB_LAUNCH(c, k_sr_starts, cdiv(n, 256), 256, 0, n, d_head, d_scan, d_start);
+  int* d_maxm = dalloc<int>(1);
+  MDB_CUDA(cudaMemsetAsync(d_maxm, 0, sizeof(int), c->stream));
+  MDB_LAUNCH(c, k_sr_counts, cdiv(nruns, 256), 256, 0, nruns, n, d_start, M.d_rowptr, d_nchunk, d_maxm);
+  int maxm = 0;
+  MDB_CUDA(cudaMemcpyAsync(&maxm, d_maxm, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  const int64_t nchunks = sr_scan(c, d_nchunk, d_choff, nruns);
+  int4* d_chunks = dalloc<int4>(nchunks > 0 ? nchunks : 1);
+  int32_t* d_rest = dalloc<int32_t>(n); int32_t* d_rscan = dalloc<int32_t>(n);
+  MDB_LAUNCH(c, k_sr_fill, cdiv(n, 256), 256, 0, n, d_head, d_scan, nruns, d_start, d_nchunk, d_choff, M.d_rowptr, d_chunks, d_rest);
+  const int64_t nrest = sr_scan(c, d_rest, d_rscan, n);
+  if (nchunks > 0 && (n - nrest) * 10 >= n * 7) {
+    dfree(M.d_spmv_rest);
+    M.d_spmv_rest = dalloc<int32_t>(nrest > 0 ? nrest : 1);
+    if (nrest > 0) MDB_LAUNCH(c, k_spmv_rest_compact, cdiv(n, 256), 256, 0, n, d_rest, d_rscan, M.d_spmv_rest);
+    M.n_spmv_rest = nrest;
+    M.d_sr_chunks = d_chunks; M.n_sr_chunks = nchunks; M.sr_maxm = maxm;
+    d_chunks = nullptr;
+  }
+  MDB_CUDA(cudaStreamSynchronize(c->stream));
+  if (getenv("MDB_SR_DEBUG")) fprintf(stderr, "shift-run analysis: %lld rows, %lld runs, %lld chunks, %lld rows outside -> %s\n", (long long)n, (long long)nruns,
+                                      (long long)nchunks, (long long)nrest, M.n_sr_chunks > 0 ? "run kernel" : "vector-CSR kernel");
+  dfree(d_head); dfree(d_scan); dfree(d_start); dfree(d_nchunk); dfree(d_choff); dfree(d_rest); dfree(d_rscan); dfree(d_maxm); if (d_chunks) dfree(d_chunks);
+}
+
 static int spmv_variant()
 {
   static int v = -1;
@@ -525,6 +783,49 @@ static void launch_spmv(Ctx* c, const Matrix& M, const double* x, double* y, con
         MDB_LAUNCH(c, k_spmv_rows<DOTS>, grid2, 256, 0, M.n_spmv_rest, M.d_spmv_rest, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial,
                    pofs + grid, done);
       return;
+    }
+    // structured numberings beyond Q1 (Qk entity groups): the shift-run kernel where the pattern has the runs for it
+    // MEASURED (B200, Q2 | Q2 on 2048^2 cells, 16.8 M rows, 2.7e8 entries, profiles/r02/qk_spmv_runs_r4.md): 99.9 % of the rows sit in
+    // runs; the product alone goes 0.99 -> 0.78 ms with k_spmv_runs_vec (x warm in L2 between repetitions), but inside CG, where four
+    // other vectors pass through L2 between two products, the iteration stays at 1.28 -> 1.31 ms: the product is bound by the latency
+    // of the x gathers, not by the column-index bytes.  The shared-memory ring kernel loses outright (1.12 - 2.58 ms: 8 - 12 warps per SM
+    // cannot hide the x loads; ncu: every stall a long scoreboard).  Both stay as switches; the default is the vector-CSR kernel.
+    static const char* runs_env = getenv("MDB_SPMV_RUNS");                  // unset: off; "staged": ring kernel; anything else: k_spmv_runs_vec
+    const bool no_runs = runs_env == nullptr;
+    bool qk = c->um == nullptr && !no_runs && M.max_row <= 4 * SR_MAXLEN;
+    for (const Child& ch : c->children) qk = qk && !ch.dg;
+    if (qk) {
+      Matrix& Mm = const_cast<Matrix&>(M);
+      if (M.n_sr_chunks < 0) sr_analyse(c, Mm);
+      if (M.n_sr_chunks > 0) {
+        const bool staged = std::strcmp(runs_env, "staged") == 0;            // A/B switch: the shared-memory ring kernel
+        int grid = 148 * 8;
+        size_t smem = 0; int slot = 0;
+        if (staged) {
+          slot = (32 * M.sr_maxm + 2 + 1) & ~1;                          // doubles per stage: a chunk's span from the 16-byte boundary below
+          smem = (size_t)SR_WARPS * SR_STAGES * slot * sizeof(double) + SR_WARPS * SR_STAGES * sizeof(unsigned long long);
+          static size_t configured[3] = {0, 0, 0};
+          if (smem > configured[DOTS]) {
+            MDB_CUDA(cudaFuncSetAttribute(k_spmv_runs<DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[DOTS] = smem;
+          }
+          int per_sm = (int)((226 * 1024) / (smem + 1024 + 128));
+          if (per_sm < 1) per_sm = 1;
+          grid = 148 * per_sm;                                           // resident blocks only: every warp keeps its ring full
+          if (grid > cdiv(M.n_sr_chunks, SR_WARPS)) grid = cdiv(M.n_sr_chunks, SR_WARPS);
+        } else if (grid > cdiv(M.n_sr_chunks, 8)) grid = cdiv(M.n_sr_chunks, 8);
+        int grid2 = 148 * 6;
+        if (grid2 > cdiv(M.n_spmv_rest, 32)) grid2 = cdiv(M.n_spmv_rest, 32);
+        if (grid2 > MAX_PARTIAL_BLOCKS - grid) grid2 = MAX_PARTIAL_BLOCKS - grid;      // one partial sum per block (grid-stride kernels)
+        if (nblocks) *nblocks = grid + grid2;
+        if (staged)
+          MDB_LAUNCH(c, k_spmv_runs<DOTS>, grid, 32 * SR_WARPS, smem, M.n_sr_chunks, M.d_sr_chunks, slot, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, 0, done);
+        else
+          MDB_LAUNCH(c, k_spmv_runs_vec<DOTS>, grid, 256, 0, M.n_sr_chunks, M.d_sr_chunks, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, 0, done);
+        if (grid2 > 0)
+          MDB_LAUNCH(c, k_spmv_rows<DOTS>, grid2, 256, 0, M.n_spmv_rest, M.d_spmv_rest, M.d_rowptr, M.d_colidx, M.d_val, x, y, a, c->d_owned, partial, grid, done);
+        return;
+      }
     }
     variant = 1;
   }
