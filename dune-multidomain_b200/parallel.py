@@ -24,6 +24,9 @@ def slab(global_n, rank, nranks, lower=None, upper=None):
     n = int(global_n[pa])
     if not (1 <= nranks <= n):
         raise ValueError("cannot cut %d cell layers into %d slabs" % (n, nranks))
+    if nranks > 1 and n // nranks < 2:
+        # mdb_mesh_partition tells the first rank by cell_offset == 0: the second rank's ghost layer must not be global layer 0
+        raise ValueError("the first slab must own at least two cell layers (%d layers over %d ranks)" % (n, nranks))
     c0 = (n * rank) // nranks
     c1 = (n * (rank + 1)) // nranks
     start = c0 - (1 if rank > 0 else 0)

@@ -111,7 +111,7 @@ def test_two_contexts_on_one_gpu(n):
         d.close()
 
 
-QK_CASES = [((capi.FE_Q1, capi.FE_Q2), (4, 5, 6)), ((capi.FE_Q2, capi.FE_Q2), (3, 4, 6)), ((capi.FE_Q2, capi.FE_Q1), (4, 3, 5))]
+QK_CASES = [((capi.FE_Q1, capi.FE_Q2), (4, 5, 6)), ((capi.FE_Q2, capi.FE_Q2), (3, 4, 6)), ((capi.FE_Q2, capi.FE_Q1), (4, 3, 7))]
 
 
 def _global_oracle_fe(n, fe):
@@ -127,23 +127,23 @@ def _global_oracle_fe(n, fe):
     return og, Pg, ug, rg
 
 
+@pytest.mark.parametrize("R", [2, 3])
 @pytest.mark.parametrize("fe,n", QK_CASES)
-def test_two_contexts_on_one_gpu_qk(fe, n):
+def test_two_contexts_on_one_gpu_qk(fe, n, R):
     """Slab partition with Qk (k = 2) child spaces (the shipped testpoisson is Q1 | Q2): two contexts of one process act as two ranks.
     Ownership by lattice planes (k ghost planes below, one above), halo exchange of k planes up / one plane down, and the owned rows
     of the partitioned assembly against the oracle's global matrix — the local -> global map goes through the cell DOF maps."""
     import torch
     import problems
-    R = 2
-    devs = [pkg.Mdb(0) for _ in range(R)]
+    devs = [pkg.Mdb(0) for _ in range(R)]                 # R = 3: the middle rank has ghosts on both sides and two neighbours
     slabs = [parallel.slab(n, r, R) for r in range(R)]
     Ps = [problems.testpoisson(devs[r], n, fe=fe, slab=slabs[r]) for r in range(R)]
     og, Pg, ug, rg = _global_oracle_fe(n, fe)
     Ag = og.csr(Pg.mat)
     pg, dg = og.get_dofmap()
     blobs = [d.halo_export()[0] for d in devs]
-    devs[0].halo_import(-1, None, 1, blobs[1])
-    devs[1].halo_import(0, blobs[0], -1, None)
+    for r in range(R):
+        devs[r].halo_import(r - 1 if r > 0 else -1, blobs[r - 1] if r > 0 else None, r + 1 if r < R - 1 else -1, blobs[r + 1] if r < R - 1 else None)
     gfull, owned = [], []
     seen = np.zeros(Pg.ndof, dtype=int)
     for r in range(R):
@@ -192,7 +192,7 @@ def test_two_contexts_on_one_gpu_qk(fe, n):
 
 
 MORTAR_CASES = [((4, 5, 6), 1, (capi.FE_Q1, capi.FE_Q1)), ((6, 8), 1, (capi.FE_Q1, capi.FE_Q1)), ((3, 4, 6), 2, (capi.FE_Q1, capi.FE_Q1)),
-                ((3, 3, 5), 1, (capi.FE_Q2, capi.FE_Q1))]
+                ((3, 3, 6), 1, (capi.FE_Q2, capi.FE_Q1))]
 
 
 def _global_oracle_mortar(n, ncomp, fe):
@@ -207,22 +207,22 @@ def _global_oracle_mortar(n, ncomp, fe):
     return og, Pg, ug, rg
 
 
+@pytest.mark.parametrize("R", [2, 3])
 @pytest.mark.parametrize("n,ncomp,fe", MORTAR_CASES)
-def test_two_contexts_on_one_gpu_mortar(n, ncomp, fe):
+def test_two_contexts_on_one_gpu_mortar(n, ncomp, fe, R):
     """Enriched (mortar) couplings on a slab partition (BASELINE configs[3]): the coupling space is vertex-attached, so its block is
     owned by lattice planes like a Q1 block.  Two contexts of one process act as two ranks; owned rows (element rows with their
     mortar links, mortar rows) against the oracle's global matrix, residual, halo exchange of all blocks."""
     import torch
     import problems
-    R = 2
     devs = [pkg.Mdb(0) for _ in range(R)]
     slabs = [parallel.slab(n, r, R) for r in range(R)]
     Ps = [problems.testmortarpoisson(devs[r], n, ncomp=ncomp, fe=fe, slab=slabs[r]) for r in range(R)]
     og, Pg, ug, rg = _global_oracle_mortar(n, ncomp, fe)
     Ag = og.csr(Pg.mat)
     blobs = [d.halo_export()[0] for d in devs]
-    devs[0].halo_import(-1, None, 1, blobs[1])
-    devs[1].halo_import(0, blobs[0], -1, None)
+    for r in range(R):
+        devs[r].halo_import(r - 1 if r > 0 else -1, blobs[r - 1] if r > 0 else None, r + 1 if r < R - 1 else -1, blobs[r + 1] if r < R - 1 else None)
     # no cell carries the mortar DOFs, so the cell maps cannot give the local -> global map; every block of this system that is cut
     # is a Q1 block (lexicographic, cut axis slowest), except a Q2 element block, which goes through the cell maps
     counts = [[int(v) for v in d.owned_counts()] for d in devs]

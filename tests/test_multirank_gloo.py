@@ -23,7 +23,7 @@ parallel = pkg.parallel
 
 
 def test_slab_arithmetic_covers_the_mesh_once():
-    for n, R in [(8, 2), (9, 2), (16, 3), (7, 7), (256, 8)]:
+    for n, R in [(8, 2), (9, 2), (16, 3), (14, 7), (256, 8)]:
         owned_cells, owned_planes = [], []
         for r in range(R):
             s = parallel.slab((4, 4, n), r, R)
@@ -37,6 +37,8 @@ def test_slab_arithmetic_covers_the_mesh_once():
         assert owned_planes == list(range(n + 1))
     with pytest.raises(ValueError):
         parallel.slab((4, 4, 2), 0, 3)
+    with pytest.raises(ValueError):             # the first slab must own two layers: mdb_mesh_partition tells the first rank by offset 0
+        parallel.slab((4, 4, 7), 1, 7)
 
 
 def test_global_child_bases():
