@@ -382,6 +382,102 @@ def stokes_darcy_extra(pkg, capi, levels=1):
         dev.close()
 
 
+def baseline_configs_extra(pkg, capi):
+    """Side lines (never part of `value`): the BASELINE.json configs that are not the benchmark's own workload, at their stated sizes, so that
+    one bench line carries all five.  configs[0] as shipped (DG-Q2 on 512^2, monolithic CVCF system), configs[2] (4096^2, 200 implicit Euler
+    steps), configs[3] (mortar coupling on 256^3); configs[1] is the line's workload, configs[4] is `extra.stokes_darcy`."""
+    import time
+    import torch
+    import problems
+    out = {}
+
+    def timed_ms(dev, fn, reps=10):
+        s = torch.cuda.ExternalStream(dev.stream())
+        for _ in range(3):
+            fn()
+        dev.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            fn()
+        e1.record(s)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # configs[0]: testpoisson-dirichlet-neumann as shipped — QkDG (k = 2) + ConvectionDiffusionDG, ini mesh.refine = 9
+    try:
+        dev = pkg.Mdb(torch.cuda.current_device())
+        t0 = time.perf_counter()
+        P = problems.dirichlet_neumann_dg(dev, (512, 512))
+        dev.synchronize()
+        setup = time.perf_counter() - t0
+        u = torch.zeros(P.ndof, dtype=torch.float64, device="cuda"); r = torch.zeros_like(u); z = torch.zeros_like(u)
+        ms_j = timed_ms(dev, lambda: dev.jacobian(P.go, P.mat, u, overwrite=True))
+        ms_r = timed_ms(dev, lambda: dev.residual(P.go, u, r))
+        r.zero_(); dev.residual(P.go, u, r)
+        st = dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_MG, reduction=1e-8, maxit=500)      # first call builds the hierarchy
+        st = dev.solve(P.mat, r, z, method=capi.SOLVER_BICGSTAB, precond=capi.PRECOND_MG, reduction=1e-8, maxit=500)
+        y = torch.zeros_like(u); dev.spmv(P.mat, z, y); dev.synchronize()
+        out["configs0_dirichlet_neumann_dgq2_512x512"] = {
+            "dofs": int(P.ndof), "nnz": int(dev.nnz[P.mat]), "setup_s": setup, "jacobian_ms": ms_j, "jacobian_dofs_per_s": P.ndof / ms_j * 1e3,
+            "jacobian_GBs_8nnz": 8.0 * dev.nnz[P.mat] / ms_j / 1e6, "residual_ms": ms_r,
+            "solve": {"method": "BiCGSTAB + multigrid V-cycle to 1e-8 (the reference: BiCGSTAB + SSOR(3), reduction 1e-8)", "iterations": int(st.iterations),
+                      "converged": bool(st.converged), "seconds": st.seconds, "rel_residual": float((y - r).norm() / r.norm())}}
+        dev.close()
+    except Exception as e:
+        out["configs0_dirichlet_neumann_dgq2_512x512"] = {"error": repr(e)}
+
+    # configs[2]: instationary two-subdomain problem with the proportional-flow coupling, 200 implicit Euler steps on 4096^2
+    try:
+        dev = pkg.Mdb(torch.cuda.current_device())
+        P = problems.instationary(dev, (4096, 4096))
+        u0 = torch.zeros(P.ndof, dtype=torch.float64, device="cuda"); u1 = torch.zeros_like(u0)
+        dev.interpolate(P.sps, P.gfn, u0, time=0.0)
+        steps, dt, its = 200, 0.04 / 200, 0
+        dev.synchronize(); t0 = time.perf_counter()
+        ok = True
+        for k in range(steps):
+            st = dev.onestep_apply(P.go0, P.go1, P.mat, P.sps, P.gfn, k * dt, dt, u0, u1, scheme=capi.ONESTEP_IMPLICIT_EULER, method=capi.SOLVER_BICGSTAB,
+                                   precond=capi.PRECOND_MG, reduction=1e-10, maxit=2000)
+            ok = ok and bool(st.converged)
+            its += int(st.iterations)
+            u0, u1 = u1, u0
+        dev.synchronize()
+        wall = time.perf_counter() - t0
+        out["configs2_instationary_4096x4096_200_steps"] = {
+            "dofs": int(P.ndof), "steps": steps, "dt": dt, "seconds": wall, "seconds_per_step": wall / steps, "linear_iterations": its, "all_converged": ok,
+            "dof_steps_per_s": P.ndof * steps / wall, "checksum_sum_u": float(u0.sum()),
+            "what": "per step: Jacobian of M + dt K (+ FD coupling), residual, BiCGSTAB + multigrid V-cycle to 1e-10, update — device vectors, "
+                    "mdb_onestep_apply (round 1 with BiCGSTAB + Jacobi: 207.8 s)"}
+        dev.close()
+    except Exception as e:
+        out["configs2_instationary_4096x4096_200_steps"] = {"error": repr(e)}
+
+    # configs[3]: testmortarpoisson (Q1 | Q1 + Q1 mortar space, EnrichedCoupling with the reference's FD Jacobians) on 256^3
+    try:
+        dev = pkg.Mdb(torch.cuda.current_device())
+        t0 = time.perf_counter()
+        P = problems.testmortarpoisson(dev, (256, 256, 256))
+        dev.synchronize()
+        setup = time.perf_counter() - t0
+        u = torch.zeros(P.ndof, dtype=torch.float64, device="cuda"); r = torch.zeros_like(u); y = torch.zeros_like(u)
+        dev.interpolate(P.sps, P.gfn, u)
+        ms_j = timed_ms(dev, lambda: dev.jacobian(P.go, P.mat, u, overwrite=True))
+        ms_r = timed_ms(dev, lambda: dev.residual(P.go, u, r))
+        ms_s = timed_ms(dev, lambda: dev.spmv(P.mat, u, y))
+        nnz = int(dev.nnz[P.mat])
+        off = dev.get_child_offsets()
+        out["configs3_testmortarpoisson_256x256x256"] = {
+            "dofs": int(P.ndof), "mortar_dofs": int(off[3] - off[2]), "nnz": nnz, "setup_s": setup, "jacobian_ms": ms_j, "jacobian_dofs_per_s": P.ndof / ms_j * 1e3,
+            "jacobian_GBs_8nnz": 8.0 * nnz / ms_j / 1e6, "residual_ms": ms_r, "spmv_ms": ms_s,
+            "what": "the volume rows stream as in the benchmark's workload; the mortar links (FD Jacobians per face, side and perturbed coefficient) "
+                    "are an interface-sized kernel beside the fill"}
+        dev.close()
+    except Exception as e:
+        out["configs3_testmortarpoisson_256x256x256"] = {"error": repr(e)}
+    return out
+
+
 def unstructured_partition_extra(pkg, capi, dist, rank, world, local_rank, peak, levels=None):
     """extra.unstructured_partition, at every N: the north star's "refined gmsh meshes at 1/2/4/8 GPUs".  The committed Gmsh file
     examples/filtration.msh (layout of the reference's test/stokesdarcy4.msh) is refined `levels` times, physical group > 0 -> subdomain 1
@@ -818,6 +914,11 @@ def _main(out):
                 extra["stokes_darcy"] = stokes_darcy_extra(pkg, capi)
             except Exception as e:
                 extra["stokes_darcy"] = {"error": repr(e)}
+            if not os.environ.get("MDB_BENCH_NO_CONFIGS"):
+                try:
+                    extra["baseline_configs"] = baseline_configs_extra(pkg, capi)
+                except Exception as e:
+                    extra["baseline_configs"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1 and not args.quick:
             line["cpu_baseline"] = cpu_baseline(S, args.cpu_sample_layers, 1)
         elif world == 1:

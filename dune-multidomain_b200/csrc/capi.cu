@@ -158,6 +158,8 @@ static void reset_spaces(Ctx* c)
   for (auto& go : c->gos) { for (auto& f : go.faces) { dfree(f.d_cell); dfree(f.d_face); } dfree(go.d_xneed); for (int i = 0; i < MDB_MAX_CHILDREN; ++i) { dfree(go.d_res_fast[i]); dfree(go.d_res_rest[i]); go.n_res_rest[i] = -1; } }
   for (auto& m : c->mats) free_matrix(m);
   c->gos.clear(); c->mats.clear();
+  for (auto& kv : c->mortar_tabs) cudaFree(kv.second);
+  c->mortar_tabs.clear();
   dfree(c->d_constrained); dfree(c->d_conlist);
   for (int i = 0; i < 4; ++i) dfree(c->d_stage[i]);
   dfree(c->d_work); c->work_n = 0; c->work_vecs = 0;

@@ -341,6 +341,7 @@ struct Ctx {
   // scratch
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   double* d_Ae = nullptr;            // element matrix table
+  std::map<int, double*> mortar_tabs; // mortar.cu: shape-function tables per enriched coupling (index into cps)
   double* d_ftab = nullptr;          // face shape-function tables of the coupling kernels
   double* d_ftab_g = nullptr;        // the same for Qk x Qk couplings (generic.cu)
   double* d_dgtab = nullptr;         // skeleton / boundary block tables of the QkDG kernels (dg.cu)

@@ -15,6 +15,7 @@
 // This is a correctness configuration ("small"), interface-sized work: plain kernels, columns by binary search.
 #include "exact_common.cuh"
 #include <algorithm>
+#include <cmath>
 
 namespace mdb {
 
@@ -24,6 +25,7 @@ struct MortarSpec {
   int ncomp;                           // component blocks of a power coupling space (test/testpowermortarpoisson.cc:186-189), <= MORTAR_MAXCOMP
   Rule1D rule1, rule2;                 // qorder = 2 max(order(lfsu), order(lfsu_c)) per side, testmortarpoisson.cc:193-195
   int lkind, rkind; uint32_t lmask, rmask;    // the coupling space's own predicate (gfs.contains(is))
+  const double* tab;                   // shape-function tables per (sign, face orientation), k_mortar_tables
 };
 
 // corner i of face (axis, side) of cell ijk: bit t of i = coordinate along the t-th axis other than `axis` ([UPSTREAM] Yasp)
@@ -39,56 +41,133 @@ template <int DIM> __device__ __forceinline__ void face_dofs(const SideMap& C, c
   }
 }
 
-// alpha_generic<sign> (testmortarpoisson.cc:156-244); same statements, same order as the CPU restatement.
-// __noinline__ on purpose: inlined into mortar_column (two calls around a dynamically indexed store into u / uc) nvcc 12.9
-// produced NaN coefficients for the second call whenever NL > 4 (observed on B200, both Jacobian modes; the host build of
-// the same source under ASan/UBSan is clean).  As a real call the function is correct for every instantiation.
-template <int DIM, int K>
-__device__ __noinline__ void mortar_alpha(int sign, double gamma_0, const Rule1D& R, const FaceGeo<DIM>& G, const double* x, const double* x_c, int nc, double* r,
-                             double* r_c, double weight)
+// alpha_generic<sign> (testmortarpoisson.cc:156-244): same statements, same order as the CPU restatement.  Until session 4 of round 2 every
+// thread evaluated the Qk shape functions and gradients at its quadrature points itself (qk_phi / qk_grad: Lagrange products with
+// divisions, local-memory arrays): BASELINE configs[3] at 256^3 spent 6.2 ms in the Jacobian of the 65 536 interface faces.
+// The functions below are __noinline__ on purpose: inlined into mortar_column (two calls around a dynamically indexed store into u / uc)
+// nvcc 12.9 produced NaN coefficients for the second call whenever NL > 4 (observed on B200, both Jacobian modes; the host build of the
+// same source under ASan/UBSan is clean).  As a real call the function is correct for every instantiation.
+// ---- the same operator from tables (session 4 of round 2) -------------------------------------------------------------------------------
+// What alpha_generic evaluates at a quadrature point — the element's shape functions and reference gradients at the face point seen from
+// the inside or the outside cell, the mortar shape functions, the weight — depends on the face only through its orientation (axis, side):
+// on a structured mesh these are at most 2 DIM x 2 small tables.  They are computed ONCE per coupling by the same device functions
+// (qk_phi, qk_grad, quad_point: the same bits), and the Jacobian / residual threads then run alpha_generic's statements in the same
+// order on table values.  Everything that depends on the cell (1 / extent per axis, gamma, the integration element) is still evaluated per
+// thread exactly as before, so every number that reaches the matrix keeps its rounding sequence (the parity tests hold at 1e-12 against the
+// oracle's finite differences, as with the function above).  BASELINE configs[3] at 256^3: Jacobian 6.2 ms with per-thread shape functions.
+#define MT_NQ 9
+#define MT_NL 27
+#define MT_V 0
+#define MT_JS (MT_NQ * MT_NL)
+#define MT_MU (MT_JS + MT_NQ * MT_NL * 3)
+#define MT_W (MT_MU + MT_NQ * 4)
+#define MT_STRIDE 1024
+template <int DIM>
+__global__ void k_mortar_tables(Rule1D rule1, Rule1D rule2, int k1, int k2, double* tab)
 {
-  constexpr int NL = cpow(K + 1, DIM);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * 6 * MT_NQ * MT_NL) return;
+  const int i = t % MT_NL, q = (t / MT_NL) % MT_NQ, o = (t / (MT_NL * MT_NQ)) % 6, sgn = t / (MT_NL * MT_NQ * 6);
+  const int K = sgn ? k2 : k1;
+  const Rule1D& R = sgn ? rule2 : rule1;
   const int nq = ipow(R.m, DIM - 1);
+  int NL = 1; for (int d = 0; d < DIM; ++d) NL *= K + 1;
+  if (o >= 2 * DIM || q >= nq) return;
+  const int axis = o / 2, side = o % 2;
+  double pos[3] = {0.0, 0.0, 0.0}, w; quad_point<DIM - 1>(R, q, pos, w);
+  double element_pos[3]; int tt = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) element_pos[d] = (d == axis) ? (double)(sgn ? 1 - side : side) : pos[tt++];     // FaceGeo::localInside / localOutside
+  double* T = tab + (size_t)(sgn * 6 + o) * MT_STRIDE;
+  if (i < NL) {
+    T[MT_V + q * MT_NL + i] = qk_phi<DIM>(K, i, element_pos);
+    double js[3] = {0.0, 0.0, 0.0}; qk_grad<DIM>(K, i, element_pos, js);
+    for (int d = 0; d < 3; ++d) T[MT_JS + (q * MT_NL + i) * 3 + d] = js[d];
+  }
+  if (i < (1 << (DIM - 1))) T[MT_MU + q * 4 + i] = qk_phi<DIM - 1>(1, i, pos);
+  if (i == 0) T[MT_W + q] = w;
+}
+template <int DIM, int K>
+__device__ __noinline__ void mortar_alpha_tab(int sign, double gamma_0, int nq, const double* __restrict__ tab, const FaceGeo<DIM>& G, const double* x,
+                                              const double* x_c, int nc, double* r, double* r_c, double weight)
+{
+  constexpr int NL = cpow(K + 1, DIM), NCB = 1 << (DIM - 1);
+  const double* __restrict__ T = tab + (size_t)((sign > 0 ? 0 : 6) + 2 * G.axis + G.side) * MT_STRIDE;
   const double gamma = gamma_0 / G.integrationElement();
   double jit[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) jit[d] = sign > 0 ? 1.0 / (G.up_i[d] - G.lo_i[d]) : 1.0 / (G.up_o[d] - G.lo_o[d]);
-  for (int q = 0; q < nq; ++q) {
-    double pos[3] = {0.0, 0.0, 0.0}, w; quad_point<DIM - 1>(R, q, pos, w);
-    double element_pos[3];
-    if (sign > 0) G.localInside(pos, element_pos); else G.localOutside(pos, element_pos);
-    double normal[DIM];
+  double normal[DIM];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) normal[d] = (d == G.axis) ? (G.side ? 1.0 : -1.0) : 0.0;
-    double v[NL], gradv[NL][DIM], mu[1 << (DIM - 1)];
-    for (int i = 0; i < NL; ++i) {
-      v[i] = qk_phi<DIM>(K, i, element_pos);
-      double js[3]; qk_grad<DIM>(K, i, element_pos, js);
+  for (int d = 0; d < DIM; ++d) normal[d] = (d == G.axis) ? (G.side ? 1.0 : -1.0) : 0.0;
+  if constexpr (NL <= 9) {
+    // small local spaces (Q1; Q2 in 2-D): coefficients and accumulators live in registers for the whole call — the caller's arrays are
+    // stack memory (this function is a real call), read once and written once instead of once per quadrature point.  Every r[i] still
+    // receives its terms one quadrature point after the other.
+    double xr[NL], xcr[NCB], ra[NL], rca[NCB];
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) gradv[i][d] = 0.0 + jit[d] * js[d];
+    for (int i = 0; i < NL; ++i) { xr[i] = x[i]; ra[i] = r[i]; }
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) { xcr[i] = i < nc ? x_c[i] : 0.0; rca[i] = i < nc ? r_c[i] : 0.0; }
+    for (int q = 0; q < nq; ++q) {
+      const double w = T[MT_W + q];
+      double u = 0.0, gradu[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gradu[d] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        u += xr[i] * T[MT_V + q * MT_NL + i];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gradu[d] += xr[i] * (0.0 + jit[d] * T[MT_JS + (q * MT_NL + i) * 3 + d]);
+      }
+      double lambda = 0.0;
+#pragma unroll
+      for (int i = 0; i < NCB; ++i) if (i < nc) lambda += xcr[i] * T[MT_MU + q * 4 + i];
+      const double factor = w * G.integrationElement();
+      double ngu = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) ngu += normal[d] * gradu[d];
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        const double vi = T[MT_V + q * MT_NL + i];
+        double ngv = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) ngv += normal[d] * (0.0 + jit[d] * T[MT_JS + (q * MT_NL + i) * 3 + d]);
+        ra[i] += weight * ((-ngu * vi - (u - lambda) * ngv + 2 * gamma * (u - lambda) * vi) * factor);
+      }
+#pragma unroll
+      for (int i = 0; i < NCB; ++i) if (i < nc) rca[i] += weight * ((ngu - 2 * gamma * (u - lambda)) * T[MT_MU + q * 4 + i] * factor);
     }
-    for (int i = 0; i < nc; ++i) mu[i] = qk_phi<DIM - 1>(1, i, pos);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) r[i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < NCB; ++i) if (i < nc) r_c[i] = rca[i];
+  } else {
+  for (int q = 0; q < nq; ++q) {
+    const double w = T[MT_W + q];
     double u = 0.0, gradu[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) gradu[d] = 0.0;
     for (int i = 0; i < NL; ++i) {
-      u += x[i] * v[i];
+      u += x[i] * T[MT_V + q * MT_NL + i];
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) gradu[d] += x[i] * gradv[i][d];
+      for (int d = 0; d < DIM; ++d) gradu[d] += x[i] * (0.0 + jit[d] * T[MT_JS + (q * MT_NL + i) * 3 + d]);
     }
     double lambda = 0.0;
-    for (int i = 0; i < nc; ++i) lambda += x_c[i] * mu[i];
+    for (int i = 0; i < nc; ++i) lambda += x_c[i] * T[MT_MU + q * 4 + i];
     const double factor = w * G.integrationElement();
     double ngu = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) ngu += normal[d] * gradu[d];
     for (int i = 0; i < NL; ++i) {
+      const double vi = T[MT_V + q * MT_NL + i];
       double ngv = 0.0;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) ngv += normal[d] * gradv[i][d];
-      r[i] += weight * ((-ngu * v[i] - (u - lambda) * ngv + 2 * gamma * (u - lambda) * v[i]) * factor);
+      for (int d = 0; d < DIM; ++d) ngv += normal[d] * (0.0 + jit[d] * T[MT_JS + (q * MT_NL + i) * 3 + d]);
+      r[i] += weight * ((-ngu * vi - (u - lambda) * ngv + 2 * gamma * (u - lambda) * vi) * factor);
     }
-    for (int i = 0; i < nc; ++i) r_c[i] += weight * ((ngu - 2 * gamma * (u - lambda)) * mu[i] * factor);
+    for (int i = 0; i < nc; ++i) r_c[i] += weight * ((ngu - 2 * gamma * (u - lambda)) * T[MT_MU + q * 4 + i] * factor);
+  }
   }
 }
 
@@ -99,7 +178,8 @@ __device__ __forceinline__ void mortar_alpha_power(int sign, const MortarSpec& P
                                                    int nc, double* r, double* r_c, double weight)
 {
   constexpr int NC = 1 << (DIM - 1);
-  for (int b = 0; b < P.ncomp; ++b) mortar_alpha<DIM, K>(sign, P.gamma_0, R, G, x, x_c + b * NC, nc, r, r_c + b * NC, weight);
+  const int nq = ipow(R.m, DIM - 1);
+  for (int b = 0; b < P.ncomp; ++b) mortar_alpha_tab<DIM, K>(sign, P.gamma_0, nq, P.tab, G, x, x_c + b * NC, nc, r, r_c + b * NC, weight);
 }
 
 struct MortarMaps { SideMap c[MORTAR_MAXCOMP]; };
@@ -208,13 +288,31 @@ static SideMap side_map_child(const Ctx* c, int child)
   return s;
 }
 
-static MortarSpec mortar_spec(const Ctx* c, const CouplingDesc& cp, int k1, int k2)
+static MortarSpec mortar_spec(Ctx* c, const CouplingDesc& cp, int k1, int k2)
 {
   MortarSpec P; P.gamma_0 = cp.mortar.gamma_0; P.jac_mode = cp.jac_mode;
   const Child& cc = c->children[cp.coupling_child];
   P.rule1 = gauss1d(2 * (k1 > cc.k ? k1 : cc.k)); P.rule2 = gauss1d(2 * (k2 > cc.k ? k2 : cc.k));
   P.lkind = cc.lkind; P.lmask = cc.lmask; P.rkind = cc.rkind; P.rmask = cc.rmask;
   P.ncomp = cp.ncomp;
+  // tables of this coupling: built by the first call, on the context stream, and complete before any kernel that reads them is queued
+  P.tab = nullptr;
+  const int nq1 = (int)std::lround(std::pow((double)P.rule1.m, c->mesh.dim - 1)), nq2 = (int)std::lround(std::pow((double)P.rule2.m, c->mesh.dim - 1));
+  MDB_REQUIRE(nq1 <= MT_NQ && nq2 <= MT_NQ, MDB_EINVAL, "enriched coupling: quadrature rule larger than the shape-function tables");
+  {
+    const int id = (int)(&cp - c->cps.data());
+    auto it = c->mortar_tabs.find(id);
+    if (it == c->mortar_tabs.end()) {
+      double* d = dalloc<double>((size_t)12 * MT_STRIDE);
+      MDB_CUDA(cudaMemsetAsync(d, 0, (size_t)12 * MT_STRIDE * sizeof(double), c->stream));
+      const int total = 2 * 6 * MT_NQ * MT_NL;
+      if (c->mesh.dim == 2) MDB_LAUNCH(c, k_mortar_tables<2>, cdiv(total, 128), 128, 0, P.rule1, P.rule2, k1, k2, d);
+      else MDB_LAUNCH(c, k_mortar_tables<3>, cdiv(total, 128), 128, 0, P.rule1, P.rule2, k1, k2, d);
+      MDB_CUDA(cudaStreamSynchronize(c->stream));
+      c->mortar_tabs[id] = d;
+      P.tab = d;
+    } else P.tab = it->second;
+  }
   return P;
 }
 
