@@ -333,7 +333,9 @@ def unstructured_extra(pkg, capi, peak, n=1024, reps=10):
             cpu = {"error": repr(e)}
         return {"cpu_port": cpu,
                 "workload": "2-D triangles (%d x %d squares, jittered), P1 | P1, Poisson + ProportionalFlowCoupling (FD Jacobian)" % (n, n),
-                "cells": int(ne), "dofs": int(ndof), "nnz": int(nnz), "ingest_host_s": t_ingest, "dofmap_constraints_pattern_s": t_setup,
+                "cells": int(ne), "dofs": int(ndof), "nnz": int(nnz), "ingest_s": t_ingest,
+                "ingest_what": "mdb_mesh_unstructured: upload + face neighbours / edge numbers / vertex->cell lists by device sorts and scans (host std::sort until session 4 of round 2: 0.4 - 1.0 s here)",
+                "dofmap_constraints_pattern_s": t_setup,
                 "jacobian_ms": ms_jac, "jacobian_dofs_per_s": ndof / (ms_jac * 1e-3), "jacobian_achieved_GBs": b_jac / (ms_jac * 1e-3) / 1e9,
                 "jacobian_frac": b_jac / (ms_jac * 1e-3) / 1e9 / peak, "residual_ms": ms_res, "residual_dofs_per_s": ndof / (ms_res * 1e-3)}
     finally:
