@@ -914,7 +914,13 @@ int mdb_jacobian(mdb_ctx* c, int go, int mat, double weight, const double* x, in
     jacobian_volume(c, G, M, weight, overwrite != 0, 1);
     c->phase_end();
   }
-  static const bool serial = getenv("MDB_JAC_SERIAL") != nullptr;           // A/B: the auxiliary branch on the main stream (stand-alone kernel times)
+  static const bool serial_env = getenv("MDB_JAC_SERIAL") != nullptr;       // A/B: the auxiliary branch on the main stream (stand-alone kernel times)
+  static const bool overlap_env = getenv("MDB_JAC_OVERLAP") != nullptr;     // A/B: two streams whatever the couplings
+  // Enriched (mortar) couplings: their FD kernel is bound by the latency of serial FP64 chains at 12 warps per SM; beside the fill both
+  // get slower than one after the other (256^3: fill 0.64 -> 0.90 ms, coupling 0.90 -> 1.57 ms, step 1.79 against 1.67 ms serial,
+  // profiles/r02/mortar_r4.md), so such a step runs on one stream.
+  bool serial = serial_env;
+  if (!overlap_env) for (int q : G.cps) serial = serial || c->cps[q].enriched();
   // Dirichlet rows beside the fill (auxiliary stream) when every writer of a constrained row is on that stream: no late coupling
   // (Neumann-Dirichlet) and no constrained row among the streamed ones
   static const bool dir_late = getenv("MDB_JAC_DIRICHLET_LATE") != nullptr;  // A/B: the pass after the join, as in round 1

@@ -276,7 +276,10 @@ mdb_ctx* coarsen(Ctx* f)
       // owned cell layers [c0, c1) of this slab; the coarse slab owns [c0/2, c1/2) and keeps one coarse ghost layer below
       const bool first = m.off[d] == 0;
       const int c0 = m.off[d] + (first ? 0 : 1), c1 = m.off[d] + m.n[d];
-      if (c0 % 2 != 0 || c1 % 2 != 0 || c1 - c0 < 2) ok = false;
+      // at least FOUR owned layers: the coarse slab then owns two.  A coarse first slab of one layer would put the second rank's ghost
+      // layer at global layer 0, and mdb_mesh_partition tells the first rank by cell offset 0 (found on 4 B200s with 16 layers:
+      // 4 -> 2 -> 1 layers per rank, "lower neighbour does not match the partition" at the third level)
+      if (c0 % 2 != 0 || c1 % 2 != 0 || c1 - c0 < 4) ok = false;
       offc[d] = c0 / 2 - (first ? 0 : 1); nc[d] = c1 / 2 - offc[d];
       shift = (int)(2 * offc[d] - m.off[d]);
     } else {
