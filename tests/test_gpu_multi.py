@@ -831,7 +831,8 @@ def test_multi_gpu_multigrid_matches_global_oracle(n):
     zg = spla.spsolve(sp.csc_matrix(og.csr(Pg.mat)), rg)
     for rank in range(world):
         o = ret[rank]
-        assert o["levels"] >= 3
+        # coarsening needs four owned layers per rank (a coarse slab keeps two): 16 / 32 layers give 3 / 4 levels on 2 ranks, 2 / 3 on 4
+        assert o["levels"] >= (3 if n[2] // world >= 8 else 2)
         for name in ("cg_jacobi", "cg_mg", "bcgs_mg"):
             assert np.abs(o["sol"][name][1] - zg[o["gidx"]]).max() <= 1e-10 * np.abs(zg).max(), name
         assert o["sol"]["cg_mg"][0] * 2 < o["sol"]["cg_jacobi"][0], (o["sol"]["cg_mg"][0], o["sol"]["cg_jacobi"][0])
