@@ -835,5 +835,7 @@ def test_multi_gpu_multigrid_matches_global_oracle(n):
         assert o["levels"] >= (3 if n[2] // world >= 8 else 2)
         for name in ("cg_jacobi", "cg_mg", "bcgs_mg"):
             assert np.abs(o["sol"][name][1] - zg[o["gidx"]]).max() <= 1e-10 * np.abs(zg).max(), name
-        assert o["sol"]["cg_mg"][0] * 2 < o["sol"]["cg_jacobi"][0], (o["sol"]["cg_mg"][0], o["sol"]["cg_jacobi"][0])
+        # a two-level hierarchy (4 layers per rank) ends on a Chebyshev-smoothed coarse level, not on a near-exact one: fewer iterations, no factor
+        gain = 2 if o["levels"] >= 3 else 1
+        assert o["sol"]["cg_mg"][0] * gain < o["sol"]["cg_jacobi"][0], (o["sol"]["cg_mg"][0], o["sol"]["cg_jacobi"][0])
     assert len({ret[r]["sol"]["cg_mg"][0] for r in range(world)}) == 1
