@@ -408,8 +408,10 @@ enum { MDB_SOLVER_CG = 0, MDB_SOLVER_BICGSTAB = 1, MDB_SOLVER_DIRECT = 2 };
 /* MDB_PRECOND_MG: one geometric multigrid V-cycle per application (csrc/mg.cu; not in the reference, whose preconditioners are
  * the sequential ISTL sweeps above): coarse operators by re-discretisation on meshes with half the cells per axis (the coarse
  * contexts replay the set-up and the (grid operator, weight) log of the mdb_jacobian calls that built the matrix), per-child trilinear
- * transfers, Chebyshev-Jacobi smoothing.  Structured meshes, Q1 spaces, Poisson / L2 + flow couplings, constraints from
- * mdb_constraints_assemble, single rank.  The V-cycle is symmetric positive definite: valid inside CG. */
+ * transfers, Chebyshev-Jacobi smoothing.  Structured meshes; Q1 children (Poisson / L2 + flow couplings; also on a slab partition
+ * after the collective mdb_mg_setup below) or QkDG children (ConvectionDiffusionDG, nested-space transfers; one rank); constraints
+ * from mdb_constraints_assemble.  Anything else is MDB_EINVAL.  The V-cycle is symmetric positive definite: valid inside CG,
+ * BiCGSTAB takes it as a right preconditioner. */
 enum { MDB_PRECOND_NONE = 0, MDB_PRECOND_JACOBI = 1, MDB_PRECOND_ILU0 = 2, MDB_PRECOND_SSOR = 3, MDB_PRECOND_MG = 4 };
 typedef struct mdb_solve_stats {
   int32_t iterations;

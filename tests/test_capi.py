@@ -34,6 +34,17 @@ def test_header_symbols_are_exported(lib):
         assert hasattr(lib, s), "libmdb200.so does not export %s" % s
 
 
+def test_every_entry_point_is_mapped_in_integration_md():
+    """INTEGRATION.md section 1 names, for every function the header declares, the reference interface it replaces (or says that
+    it has none).  Families are written with a wildcard (`mdb_halo_*`) or a slash (`mdb_create / mdb_destroy`)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    table = text[text.index("## 1."):text.index("## 2.")]
+    names = set(re.findall(r"\bmdb_[a-z0-9_]+\b", table))
+    stems = [w[:-1] for w in re.findall(r"\bmdb_[a-z0-9_]+_\*", table)]
+    missing = [s for s in _declared_symbols() if s not in names and not any(s.startswith(t) for t in stems)]
+    assert not missing, missing
+
+
 def test_struct_layouts_match_c():
     src = r"""
 #include <stdio.h>
