@@ -238,3 +238,30 @@ def test_implicit_euler_against_scipy():
     o.residual(P.go1, u0, R1, weight=-1.0)
     o.residual(P.go0, u1, R1, weight=dt)
     assert np.abs(R1).max() <= 1e-9 * np.abs(R).max()
+
+
+def test_one_step_schemes_have_their_orders():
+    """[UPSTREAM] ImplicitEulerParameter, OneStepThetaParameter(1/2) and Alexander2Parameter (alpha = 1 - sqrt(2)/2) as
+    tests/problems.one_step_method restates them (the stage equations the device's mdb_onestep_apply is checked against): on the
+    instationary two-subdomain problem with time-dependent Dirichlet data the error against a fine-step solution falls with order 1,
+    2 and 2.  Wrong stage coefficients, stage times or weights of the two grid operators lose the order."""
+    T = 0.4
+
+    def run(scheme, theta, nsteps):
+        o = orc.Oracle()
+        P = problems.instationary(o, (10, 8))
+        u = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u, time=0.0)
+        dt = T / nsteps
+        for s in range(nsteps):
+            u = problems.one_step_method(o, P, u, s * dt, dt, lambda mat, R, z: o.solve(mat, R, z, reduction=1e-14), scheme, theta)
+        return u
+
+    ref = run("alexander2", 0.0, 1024)
+    for scheme, theta, steps, order in (("implicit_euler", 1.0, (16, 32, 64), 1.0), ("theta", 0.5, (64, 128, 256), 2.0),
+                                        ("alexander2", 0.0, (8, 16, 32), 2.0)):
+        e = [np.abs(run(scheme, theta, n) - ref).max() for n in steps]
+        rates = [np.log2(e[i] / e[i + 1]) for i in range(2)]
+        assert all(abs(r - order) < 0.3 for r in rates), (scheme, e, rates)
+    # theta = 1 is implicit Euler, and both agree with the dedicated two-operator driver of implicit_euler_step
+    a, b = run("implicit_euler", 1.0, 4), run("theta", 1.0, 4)
+    assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
