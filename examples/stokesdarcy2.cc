@@ -4,7 +4,7 @@
 // weightsOn) subproblems, StokesDarcyCouplingOperator across the interface (finite-difference Jacobian with the ini's epsilon),
 // StationaryLinearProblemSolver with a direct solve (ISTLBackend_SEQ_SuperLU in the reference) from u = 0.
 //
-//   stokesdarcy2 <ini file> [refinements] [mesh file (overrides mesh.filename, relative to the ini's directory)]
+//   stokesdarcy2 <ini file> [refinements] [mesh file (overrides mesh.filename, relative to the ini's directory)] [VTK file prefix]
 //
 // Prints the grid sizes, "<n> DOF, <m> restricted" (:764), the solver statistics, the norm of the residual at the solution (:792-794)
 // and checksums of the four solution blocks.
@@ -127,6 +127,19 @@ int main(int argc, char** argv)
     ctx.check(mdb_get_child_offsets(ctx.get(), off), "mdb_get_child_offsets");
     const char* names[4] = {"v_0", "v_1", "p", "phi"};
     for (int k = 0; k < 4; ++k) std::printf("|%s| = %.12e  (%lld coefficients)\n", names[k], norm2(u, off[k], off[k + 1]), (long long)(off[k + 1] - off[k]));
+
+    // addSolutionToVTKWriter(vtkwriter, multigfs, u, subdomain_predicate(...)); vtkwriter.write("stokes" / "darcy")  :831-880.
+    // One conforming piece per subdomain: v_0, v_1 (P2: the vertex coefficients) and p on the Stokes view, the hydraulic head (orthonormal
+    // P3: every cell's polynomial at its corners, averaged per vertex) on the Darcy view.  The reference's derived fields (pressure and
+    // Darcy velocity from the potential, :871-880) are not written.  Off unless the deck says `output.vtk = true` (fifth argument: prefix).
+    if (parameters.has("output.vtk") && (parameters["output.vtk"] == "true" || parameters["output.vtk"] == "1")) {
+      const std::string prefix = argc > 4 ? std::string(argv[4]) : std::string();
+      VTKWriter stokes(grid, stokesGV), darcy(grid, darcyGV);
+      stokes.addSolution(multigfs, u, {&stokesgfs, &darcygfs});
+      darcy.addSolution(multigfs, u, {&stokesgfs, &darcygfs}, "phi");
+      stokes.write(prefix + "stokes"); darcy.write(prefix + "darcy");
+      std::printf("wrote %sstokes.vtu, %sdarcy.vtu\n", prefix.c_str(), prefix.c_str());
+    }
     return 0;
   } catch (Exception& e) { std::fprintf(stderr, "error %d: %s\n", e.code, e.what()); return 1; }
   catch (std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 1; }

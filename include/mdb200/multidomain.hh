@@ -10,6 +10,8 @@
 #ifndef MDB200_MULTIDOMAIN_HH
 #define MDB200_MULTIDOMAIN_HH
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -708,7 +710,8 @@ public:
 // VTKWriter<SDGV> vtkwriter(sdgv, VTK::conforming); addSolutionToVTKWriter(vtkwriter, multigfs, u, subdomain_predicate(sd));
 // vtkwriter.write(name, VTK::ascii)  — as every reference driver ends (e.g. test/testpoisson.cc:301-323).  One unstructured-grid
 // piece per subdomain: its cells (VTK_QUAD / VTK_HEXAHEDRON, VTK_TRIANGLE on simplex meshes), their vertices, and per child space living on that subdomain one
-// point-data array with the solution at the vertices (conforming output: for Q2 the corner values, like VTK::conforming).
+// point-data array with the solution at the vertices (conforming output: for Q2 / P2 the corner values, like VTK::conforming; an
+// orthonormal (modal DG) space is evaluated cell by cell at the corners and averaged per vertex).  Composite and vector spaces count with their leaves.
 class VTKWriter {
   MultiDomainGrid& grid_; int subdomain_;
   struct Field { std::string name; std::vector<double> point_values; };
@@ -740,9 +743,109 @@ class VTKWriter {
     for (int d = 0; d < dim; ++d) { const int64_t i = rem % n[d] + ((corner >> d) & 1); rem /= n[d]; idx += i * stride; stride *= n[d] + 1; }
     return idx;
   }
+  // ---- local spaces as the cell DOF maps list them ----------------------------------------------------------------------------
+  static void flatten(const GridFunctionSpace* g, std::vector<const GridFunctionSpace*>& out) {          // composite / vector spaces: their leaves in order
+    if (g->leaves.empty()) out.push_back(g); else for (size_t i = 0; i < g->leaves.size(); ++i) flatten(g->leaves[i], out);
+  }
 public:
+  // coefficients of a leaf space on one cell: (k+1)^dim for Qk / QkDG, binom(k + dim, dim) for Pk and the orthonormal basis of degree k
+  static int local_size(const GridFunctionSpace& h, int dim) {
+    int n = 1;
+    if (h.simplex) { for (int d = 1; d <= dim; ++d) n = n * (h.k + d) / d; return n; }
+    for (int d = 0; d < dim; ++d) n *= h.k + 1;
+    return n;
+  }
+  // local index of the shape function that sits at corner c.  Qk: lattice index with a_d = k * bit_d.  Pk on a triangle ([UPSTREAM]
+  // Pk2DLocalBasis: lattice order, i fastest): corner 0 -> 0, corner 1 -> k, corner 2 -> the last one; P1 on any simplex: c.
+  static int corner_index(const GridFunctionSpace& g, int dim, int c) {
+    if (g.simplex) return (g.k == 1 || c == 0) ? c : (c == 1 ? g.k : local_size(g, dim) - 1);
+    int li = 0, stride = 1;
+    for (int d = 0; d < dim; ++d) { li += g.k * ((c >> d) & 1) * stride; stride *= g.k + 1; }
+    return li;
+  }
+  // values of the orthonormal basis of degree k (OPBLocalFiniteElementMap, test/stokesdarcy2.cc:615) at the corners (0,0), (1,0), (0,1) of
+  // the reference triangle: out[c * n + i].  Gram-Schmidt of the monomials in Dune::MonomialBasis order (1 | x, y | x^2, xy, y^2 | ...) with
+  // respect to the L2 product of the reference triangle, i.e. L = C^-1 for the Cholesky factor C of G_ij = a! b! / (a + b + 2)!; here in
+  // long double (output only: the device and the oracle evaluate the 60-digit tables of csrc/opb_tables.h; a test compares the two)
+  static void opb_corner_values(int k, std::vector<double>& out) {
+    std::vector<int> ea, eb, pa(1, 0), pb(1, 0);
+    ea.push_back(0); eb.push_back(0);
+    for (int d = 1; d <= k; ++d) {
+      std::vector<int> ra(1, d), rb(1, 0);
+      for (size_t i = 0; i < pa.size(); ++i) { ra.push_back(pa[i]); rb.push_back(pb[i] + 1); }
+      ea.insert(ea.end(), ra.begin(), ra.end()); eb.insert(eb.end(), rb.begin(), rb.end());
+      pa = ra; pb = rb;
+    }
+    const int n = (int)ea.size();
+    std::vector<long double> fact(2 * k + 3, 1.0L);
+    for (size_t i = 1; i < fact.size(); ++i) fact[i] = fact[i - 1] * (long double)i;
+    std::vector<long double> C((size_t)n * n, 0.0L), L((size_t)n * n, 0.0L);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const int a = ea[i] + ea[j], b = eb[i] + eb[j];
+        long double t = fact[a] * fact[b] / fact[a + b + 2];
+        for (int m = 0; m < j; ++m) t -= C[(size_t)i * n + m] * C[(size_t)j * n + m];
+        C[(size_t)i * n + j] = i == j ? std::sqrt(t) : t / C[(size_t)j * n + j];
+      }
+    for (int col = 0; col < n; ++col)                                                    // C L = I by forward substitution
+      for (int i = col; i < n; ++i) {
+        long double t = i == col ? 1.0L : 0.0L;
+        for (int m = col; m < i; ++m) t -= C[(size_t)i * n + m] * L[(size_t)m * n + col];
+        L[(size_t)i * n + col] = t / C[(size_t)i * n + i];
+      }
+    out.assign((size_t)3 * n, 0.0);
+    for (int i = 0; i < n; ++i) {
+      long double v0 = 0.0L, v1 = 0.0L, v2 = 0.0L;                                         // a monomial x^a y^b is 1 at (1,0) iff b = 0, at (0,1) iff a = 0
+      for (int j = 0; j <= i; ++j) {
+        if (ea[j] == 0 && eb[j] == 0) v0 += L[(size_t)i * n + j];
+        if (eb[j] == 0) v1 += L[(size_t)i * n + j];
+        if (ea[j] == 0) v2 += L[(size_t)i * n + j];
+      }
+      out[(size_t)i] = (double)v0; out[(size_t)n + i] = (double)v1; out[(size_t)2 * n + i] = (double)v2;
+    }
+  }
+  // The evaluation behind addSolution on plain arrays (unit-tested on the CPU, tests/test_vtk_spaces.py): point values of leaf `gi` of
+  // `leaves` on the listed cells.  ptr / dofs: the cell DOF maps of mdb_get_dofmap (children in order, a child present iff its subdomain
+  // holds the cell); cell_points[ci * corners + c]: output point of corner c of listed cell ci.  Conforming spaces: the coefficient of the
+  // shape function at the corner.  Orthonormal (modal, discontinuous) spaces: the polynomial of each cell evaluated at its corners,
+  // averaged over the cells that meet in the point (the reference writes such spaces through a SubsamplingVTKWriter, one point per cell
+  // corner; a conforming piece holds one value per vertex).
+  static void point_values(const std::vector<const GridFunctionSpace*>& leaves, size_t gi, int dim, int corners, const std::vector<int64_t>& cells,
+                           const std::vector<uint8_t>& sd, const std::vector<int64_t>& ptr, const std::vector<int64_t>& dofs, const double* x,
+                           const std::vector<int64_t>& cell_points, std::vector<double>& values /* sized to the number of points */) {
+    const GridFunctionSpace* g = leaves[gi];
+    std::vector<double> corner_phi; std::vector<int> count;
+    const int nloc = local_size(*g, dim);
+    if (g->opb) {
+      if (dim != 2) throw Exception(MDB_EINVAL, "VTKWriter: orthonormal spaces are built on triangles only");
+      opb_corner_values(g->k, corner_phi); count.assign(values.size(), 0);
+      std::fill(values.begin(), values.end(), 0.0);
+    }
+    for (size_t ci = 0; ci < cells.size(); ++ci) {
+      const int64_t e = cells[ci];
+      int64_t off = ptr[(size_t)e];                    // position of this leaf's block inside the cell's local space
+      for (size_t hi = 0; hi < gi; ++hi) {
+        const GridFunctionSpace* h = leaves[hi];
+        if (h->coupling) continue;
+        if (h->gv.subdomain < 0 || ((sd[(size_t)e] >> h->gv.subdomain) & 1)) off += local_size(*h, dim);
+      }
+      if (off + nloc > ptr[(size_t)e + 1]) throw Exception(MDB_EINVAL, "VTKWriter: the cell DOF map is shorter than the listed spaces");
+      for (int c = 0; c < corners; ++c) {
+        const size_t pt = (size_t)cell_points[ci * (size_t)corners + (size_t)c];
+        if (g->opb) {
+          double v = 0.0;
+          for (int i = 0; i < nloc; ++i) v += x[(size_t)dofs[(size_t)(off + i)]] * corner_phi[(size_t)c * nloc + i];
+          values[pt] += v; count[pt] += 1;
+        } else {
+          values[pt] = x[(size_t)dofs[(size_t)(off + corner_index(*g, dim, c))]];
+        }
+      }
+    }
+    if (g->opb) for (size_t pt = 0; pt < values.size(); ++pt) if (count[pt]) values[pt] /= (double)count[pt];
+  }
   VTKWriter(MultiDomainGrid& grid, const SubDomainGridView& gv) : grid_(grid), subdomain_(gv.subdomain) {}
-  // addSolutionToVTKWriter(vtkwriter, multigfs, x, subdomain_predicate): every child space whose grid view is this writer's subdomain
+  // addSolutionToVTKWriter(vtkwriter, multigfs, x, subdomain_predicate): every leaf space whose grid view is this writer's subdomain
+  // (composite and vector spaces count with their leaves, test/stokesdarcy2.cc:836-846, :871-876)
   void addSolution(MultiDomainGridFunctionSpace& gfs, const Vector& x, std::initializer_list<const GridFunctionSpace*> children, const std::string& name = "u") {
     collect();
     gfs.update();
@@ -754,27 +857,18 @@ public:
     ctx.check(mdb_get_dofmap(ctx.get(), ptr.data(), dofs.data()), "mdb_get_dofmap");
     std::vector<uint8_t> sd((size_t)grid_.size0());
     ctx.check(mdb_get_subdomains(ctx.get(), sd.data()), "mdb_get_subdomains");
+    std::vector<const GridFunctionSpace*> leaves;
+    for (const GridFunctionSpace* g : children) flatten(g, leaves);
+    std::vector<int64_t> cell_points(cells_.size() * (size_t)corners());
+    for (size_t ci = 0; ci < cells_.size(); ++ci)
+      for (int c = 0; c < corners(); ++c) cell_points[ci * (size_t)corners() + (size_t)c] = point_of_vertex_[(size_t)vertex(cells_[ci], c)];
     int nout = 0;
-    for (const GridFunctionSpace* g : children) {
+    for (size_t gi = 0; gi < leaves.size(); ++gi) {
+      const GridFunctionSpace* g = leaves[gi];
       if (g->coupling || g->gv.subdomain != subdomain_) continue;              // the predicate
       Field f; f.name = (nout++ == 0) ? name : name + "_" + std::to_string(nout - 1);
       f.point_values.assign(vertex_of_point_.size(), 0.0);
-      for (size_t ci = 0; ci < cells_.size(); ++ci) {
-        const int64_t e = cells_[ci];
-        // position of this child's block inside the cell's local space: children in order, each present iff its subdomain holds the cell
-        int64_t off = ptr[(size_t)e];
-        for (const GridFunctionSpace* h : children) {
-          if (h == g) break;
-          if (h->coupling) continue;
-          if (h->gv.subdomain < 0 || ((sd[(size_t)e] >> h->gv.subdomain) & 1)) { int nl = 1; for (int d = 0; d < dim; ++d) nl *= h->k + 1; if (h->simplex) nl = dim + 1; off += nl; }
-        }
-        for (int c = 0; c < corners(); ++c) {
-          int li = 0, stride = 1;                                               // Qk local index of the corner: a_d = k * bit_d
-          for (int d = 0; d < dim; ++d) { li += g->k * ((c >> d) & 1) * stride; stride *= g->k + 1; }
-          if (g->simplex) li = c;                                               // P1: shape function c sits at corner c
-          f.point_values[(size_t)point_of_vertex_[(size_t)vertex(e, c)]] = x[(size_t)dofs[(size_t)(off + li)]];
-        }
-      }
+      point_values(leaves, gi, dim, corners(), cells_, sd, ptr, dofs, x.data(), cell_points, f.point_values);
       fields_.push_back(f);
     }
   }
