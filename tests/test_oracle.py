@@ -265,3 +265,81 @@ def test_one_step_schemes_have_their_orders():
     # theta = 1 is implicit Euler, and both agree with the dedicated two-operator driver of implicit_euler_step
     a, b = run("implicit_euler", 1.0, 4), run("theta", 1.0, 4)
     assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
+
+
+@pytest.mark.parametrize("n,axis", [((6, 8), 1), ((8, 6), 0), ((4, 3, 6), 2), ((3, 6, 4), 1)])
+def test_volume_blocks_are_kronecker_products(n, axis):
+    """Numbering and assembly pinned together by a construction that shares nothing with a cell loop: on a uniform mesh the Q1 Poisson
+    stiffness of a box is a sum of Kronecker products of the 1-D stiffness and mass matrices, K = sum_d (x)_e (e == d ? K1_e : M1_e),
+    indexed lexicographically with axis 0 fastest.  Each child block of the oracle's Jacobian (rows and columns of one subdomain's space:
+    SURVEY Appendix B — child blocks concatenated, each numbered lexicographically over its subdomain's vertices) must equal it on every
+    row that is neither Dirichlet-constrained (unit rows) nor within one cell layer of the interface (the coupling's ss / nn blocks)."""
+    o = orc.Oracle()
+    P = problems.testpoisson(o, n, split_axis=axis)
+    u = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u)
+    o.jacobian(P.go, P.mat, u, overwrite=True)
+    A = o.csr(P.mat)
+    con = o.get_constraints().astype(bool)
+    off = o.get_child_offsets()
+    dim = len(n)
+
+    def k1(m, h):
+        return sp.diags([-np.ones(m), np.r_[1.0, 2.0 * np.ones(m - 1), 1.0], -np.ones(m)], [-1, 0, 1]) / h
+
+    def m1(m, h):
+        return sp.diags([np.ones(m), np.r_[2.0, 4.0 * np.ones(m - 1), 2.0], np.ones(m)], [-1, 0, 1]) * (h / 6.0)
+
+    checked = 0
+    for child in (0, 1):
+        cells = list(n)
+        cells[axis] = n[axis] // 2                                  # each subdomain is half the box along the split axis
+        h = [1.0 / n[d] for d in range(dim)]
+        K = None
+        for d in range(dim):
+            term = None
+            for e in range(dim):                                    # axis 0 fastest: kron(last axis, ..., axis 0)
+                f = (k1 if e == d else m1)(cells[e], h[e])
+                term = f if term is None else sp.kron(f, term)
+            K = term if K is None else K + term
+        K = sp.csr_matrix(K)
+        size = int(np.prod([c + 1 for c in cells]))
+        assert off[child + 1] - off[child] == size
+        B = A[off[child]:off[child + 1], off[child]:off[child + 1]].toarray()
+        # lattice coordinate along the split axis of every DOF of the block
+        idx = np.arange(size)
+        stride = int(np.prod([c + 1 for c in cells[:axis]]))
+        j = (idx // stride) % (cells[axis] + 1)
+        near = (j >= cells[axis] - 1) if child == 0 else (j <= 1)   # the two vertex planes of the cell layer at the interface
+        rows = ~near & ~con[off[child]:off[child + 1]]
+        assert rows.sum() > 0
+        scale = np.abs(K.data).max()
+        assert np.abs(B[rows] - K.toarray()[rows]).max() <= 1e-13 * scale
+        # and those rows hold nothing outside their own block
+        full = A[off[child]:off[child + 1]].toarray()
+        full[:, off[child]:off[child + 1]] = 0.0
+        assert np.abs(full[rows]).max() == 0.0
+        checked += int(rows.sum())
+    assert checked > 0
+
+
+def test_mass_blocks_are_kronecker_products():
+    """The L2 operator of the instationary driver (dt1 grid operator, test/testinstationarypoisson.cc:225-226) the same way: every child
+    block of its matrix is the Kronecker product of the 1-D Q1 mass matrices — on ALL rows (no coupling, no Dirichlet handling enters
+    the mass operator's volume term; constrained rows are replaced by unit rows, so they are left out)."""
+    o = orc.Oracle()
+    n = (6, 4)
+    P = problems.instationary(o, n, split_axis=0)
+    u = np.zeros(P.ndof)
+    o.jacobian(P.go1, P.mat, u, overwrite=True)
+    A = o.csr(P.mat)
+    con = o.get_constraints().astype(bool)
+    off = o.get_child_offsets()
+
+    def m1(m, h):
+        return sp.diags([np.ones(m), np.r_[2.0, 4.0 * np.ones(m - 1), 2.0], np.ones(m)], [-1, 0, 1]) * (h / 6.0)
+    for child in (0, 1):
+        cells = [n[0] // 2, n[1]]
+        M = sp.kron(m1(cells[1], 1.0 / n[1]), m1(cells[0], 1.0 / n[0])).toarray()
+        B = A[off[child]:off[child + 1], off[child]:off[child + 1]].toarray()
+        rows = ~con[off[child]:off[child + 1]]
+        assert rows.sum() > 0 and np.abs(B[rows] - M[rows]).max() <= 1e-14 * np.abs(M).max()
