@@ -343,3 +343,100 @@ def test_mass_blocks_are_kronecker_products():
         B = A[off[child]:off[child + 1], off[child]:off[child + 1]].toarray()
         rows = ~con[off[child]:off[child + 1]]
         assert rows.sum() > 0 and np.abs(B[rows] - M[rows]).max() <= 1e-14 * np.abs(M).max()
+
+
+@pytest.mark.parametrize("n,axis,intensity", [((6, 4), 1, 2.0), ((4, 8), 0, 3.5), ((4, 2, 4), 2, 2.0), ((2, 4, 4), 0, 1.25)])
+def test_cvcf_penalty_and_flux_terms_in_closed_form(n, axis, intensity):
+    """ContinuousValueContinuousFlowCoupling (test/proportionalflowcoupling.hh:113-233) on the jump u = 0 | 1 across the interface, all
+    boundaries Neumann, no source: the volume terms vanish, the flux average vanishes (grad u = 0 on both sides), and what is left is
+    r1_i = int_Gamma [ -1/2 (grad phi1_i . n1) [u] + (alpha / h_F) [u] phi1_i ],  [u] = u1 - u2 = -1  (mirrored on side 2).
+    Because the shape functions of a side sum to one, the rows of a side add up to  -+ (alpha / h_F) |Gamma|  exactly — this pins the
+    penalty coefficient with h_F = |corner 0 - corner 1| of the face (:135), which the patch and symmetry tests cannot see (the penalty
+    vanishes on continuous functions).  In 2-D the single rows are closed forms too."""
+    o = orc.Oracle()
+    dim = len(n)
+    o.mesh_structured(n)
+    o.subdomains_halfspace(axis, 0.5, 0, 1)
+    c0, c1 = o.add_space(capi.FE_Q1, 0), o.add_space(capi.FE_Q1, 1)
+    pp = capi.PoissonParams()
+    pp.f = capi.Function(capi.FN_ZERO); pp.bc = capi.BCType(capi.BC_ALL_NEUMANN); pp.j = capi.Function(capi.FN_ZERO); pp.quad_order = 4
+    left = o.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1, [c0])
+    right = o.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 2, [c1])
+    cv = capi.CVCFParams(); cv.quad_order = 4; cv.intensity = intensity
+    cp = o.add_coupling(capi.OP_CVCF_COUPLING, cv, left, right, capi.JAC_FD_BITMATCH)
+    ndof = o.finalize()
+    assert o.constraints_assemble([left, right], [pp.bc, pp.bc]) == 0
+    go = o.gridoperator_create([left, right], [cp])
+    off = o.get_child_offsets()
+    u = np.zeros(ndof); u[off[1]:off[2]] = 1.0
+    r = np.zeros(ndof); o.residual(go, u, r)
+    h = [1.0 / m for m in n]
+    # the face's corner 0 -> corner 1 runs along the first axis of the face, i.e. the lowest axis that is not the normal
+    first_face_axis = 0 if axis != 0 else 1
+    h_F = h[first_face_axis]
+    gamma = 1.0                                             # area of the interface of the unit box
+    want = intensity / h_F * gamma
+    assert abs(r[off[0]:off[1]].sum() + want) <= 1e-12 * want
+    assert abs(r[off[1]:off[2]].sum() - want) <= 1e-12 * want
+    if dim == 2:
+        # single rows of side 1 (child 0): interface vertices carry -alpha / h_F * int phi + 1/2 int d_n phi, the layer behind them the
+        # gradient term alone with the opposite sign; int phi over the faces at an interior interface vertex = h_t, at an end vertex h_t / 2
+        t = 1 - axis
+        ht, hn = h[t], h[axis]
+        cells = list(n); cells[axis] = n[axis] // 2
+        ext = [c + 1 for c in cells]
+        blk = r[off[0]:off[1]].reshape(ext[1], ext[0])      # axis 0 fastest
+        top = blk[-1, :] if axis == 1 else blk[:, -1]
+        behind = blk[-2, :] if axis == 1 else blk[:, -2]
+        w = np.full(ext[t], ht); w[0] = w[-1] = ht / 2.0
+        assert np.abs(top - (-(intensity / h_F) * w + 0.5 * w / hn)).max() <= 1e-12 * want
+        assert np.abs(behind - (-0.5 * w / hn)).max() <= 1e-12 * want
+        rest = (blk[:-2, :] if axis == 1 else blk[:, :-2])
+        assert np.abs(rest).max() <= 1e-13 * want
+
+
+@pytest.mark.parametrize("n,axis", [((6, 4), 0), ((2, 4, 4), 2)])
+def test_proportional_flow_coupling_in_closed_form(n, axis):
+    """ProportionalFlowCoupling (test/proportionalflowcoupling.hh:27-86): r_s_i += k (u_s - u_n) phi_s_i, r_n_i -= k (u_s - u_n) phi_n_i on the
+    interface.  For the jump u = 0 | 1 the rows of the interface vertices are -+ k int phi_i (the trace mass of the vertex) and every other
+    row vanishes; its Jacobian blocks are -+ k times the trace mass matrix (checked through J u = r: the residual is linear)."""
+    o = orc.Oracle()
+    k = 2.5
+    o.mesh_structured(n)
+    o.subdomains_halfspace(axis, 0.5, 0, 1)
+    c0, c1 = o.add_space(capi.FE_Q1, 0), o.add_space(capi.FE_Q1, 1)
+    pp = capi.PoissonParams()
+    pp.f = capi.Function(capi.FN_ZERO); pp.bc = capi.BCType(capi.BC_ALL_NEUMANN); pp.j = capi.Function(capi.FN_ZERO); pp.quad_order = 4
+    left = o.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1, [c0])
+    right = o.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 2, [c1])
+    pf = capi.PropFlowParams(); pf.intensity = k
+    cp = o.add_coupling(capi.OP_PROPFLOW_COUPLING, pf, left, right, capi.JAC_FD_BITMATCH)
+    ndof = o.finalize()
+    o.constraints_assemble([left, right], [pp.bc, pp.bc])
+    go = o.gridoperator_create([left, right], [cp])
+    mat = o.matrix_create([go])
+    off = o.get_child_offsets()
+    u = np.zeros(ndof); u[off[1]:off[2]] = 1.0
+    r = np.zeros(ndof); o.residual(go, u, r)
+    dim = len(n)
+    h = [1.0 / m for m in n]
+    cells = list(n); cells[axis] = n[axis] // 2
+    ext = [c + 1 for c in cells]
+    # trace mass of a vertex: product over the tangential axes of h (interior) or h / 2 (end of the interface)
+    w = None
+    for d in reversed(range(dim)):                           # indexed [highest tangential axis, ..., lowest] like the reshape below
+        if d == axis:
+            continue
+        wd = np.full(ext[d], h[d]); wd[0] = wd[-1] = h[d] / 2.0
+        w = wd if w is None else np.multiply.outer(w, wd)
+    shape = tuple(reversed(ext))
+    b0 = r[off[0]:off[1]].reshape(shape)
+    b1 = r[off[1]:off[2]].reshape(shape)
+    ax = dim - 1 - axis                                      # position of the split axis in the reshaped array
+    top0 = np.take(b0, ext[axis] - 1, axis=ax)               # subdomain 0's interface plane is its last one, subdomain 1's its first
+    bot1 = np.take(b1, 0, axis=ax)
+    assert w.shape == top0.shape
+    assert np.abs(top0 + k * w).max() <= 1e-13 * k and np.abs(bot1 - k * w).max() <= 1e-13 * k
+    assert abs(np.abs(r).sum() - 2.0 * k) <= 1e-12 * k       # nothing else: the two planes carry k |Gamma| each
+    o.jacobian(go, mat, u, overwrite=True)
+    assert np.abs(o.csr(mat) @ u - r).max() <= 1e-8 * k      # FD Jacobian of a linear residual (epsilon = 1e-8)
