@@ -440,3 +440,61 @@ def test_proportional_flow_coupling_in_closed_form(n, axis):
     assert abs(np.abs(r).sum() - 2.0 * k) <= 1e-12 * k       # nothing else: the two planes carry k |Gamma| each
     o.jacobian(go, mat, u, overwrite=True)
     assert np.abs(o.csr(mat) @ u - r).max() <= 1e-8 * k      # FD Jacobian of a linear residual (epsilon = 1e-8)
+
+
+@pytest.mark.parametrize("n,axis", [((4, 6), 1), ((6, 4), 0), ((2, 3, 4), 2)])
+def test_source_and_neumann_terms_in_closed_form(n, axis):
+    """Poisson's lambda terms ([UPSTREAM] PDELab::Poisson; in-tree twin test/instationarypoissonoperator.hh:103-117, :142-167) with a
+    constant source c and a constant Neumann flux q on the whole outer boundary, at u = 0:  r_i = -c int phi_i + q int_{dOmega} phi_i.
+    On a uniform mesh both integrals are products of 1-D trapezoid weights over the SUBDOMAIN's lattice.  The interface is an interior
+    face on which the assembler calls the subproblem's boundary terms (residualassemblerfunctors.hh:80-86) and the boundary-type function
+    answers "none" (test/testpoisson.cc:54-57): a Neumann term there would add q |Gamma| to the interface rows — the closed form says no."""
+    c, q = 1.75, -0.6
+    o = orc.Oracle()
+    dim = len(n)
+    o.mesh_structured(n)
+    o.subdomains_halfspace(axis, 0.5, 0, 1)
+    c0, c1 = o.add_space(capi.FE_Q1, 0), o.add_space(capi.FE_Q1, 1)
+    pp = capi.PoissonParams()
+    pp.f = capi.Function(capi.FN_CONST, c); pp.bc = capi.BCType(capi.BC_ALL_NEUMANN); pp.j = capi.Function(capi.FN_CONST, q); pp.quad_order = 4
+    left = o.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 1, [c0])
+    right = o.add_subproblem(capi.OP_POISSON, pp, capi.COND_EQUALITY, 2, [c1])
+    cv = capi.CVCFParams(); cv.quad_order = 4; cv.intensity = 2.0
+    cp = o.add_coupling(capi.OP_CVCF_COUPLING, cv, left, right, capi.JAC_FD_BITMATCH)
+    ndof = o.finalize()
+    o.constraints_assemble([left, right], [pp.bc, pp.bc])
+    go = o.gridoperator_create([left, right], [cp])
+    off = o.get_child_offsets()
+    r = np.zeros(ndof); o.residual(go, np.zeros(ndof), r)
+    h = [1.0 / m for m in n]
+    total = 0.0
+    for child in (0, 1):
+        cells = list(n); cells[axis] = n[axis] // 2
+        ext = [m + 1 for m in cells]
+        w = []
+        for d in range(dim):
+            wd = np.full(ext[d], h[d]); wd[0] = wd[-1] = h[d] / 2.0
+            w.append(wd)
+        # is the lattice plane an OUTER boundary of the unit box?  (the interface plane of the split axis is not)
+        outer = []
+        for d in range(dim):
+            lo, hi = np.zeros(ext[d], dtype=bool), np.zeros(ext[d], dtype=bool)
+            lo[0] = not (d == axis and child == 1)
+            hi[-1] = not (d == axis and child == 0)
+            outer.append(lo | hi)
+
+        def tensor(factors):                             # array indexed [axis dim-1, ..., axis 0]
+            t = None
+            for d in reversed(range(dim)):
+                t = factors[d] if t is None else np.multiply.outer(t, factors[d])
+            return t
+        W = tensor(w)
+        B = np.zeros_like(W)
+        for d in range(dim):
+            B += tensor([outer[e].astype(float) if e == d else w[e] for e in range(dim)])
+        want = -c * W + q * B
+        got = r[off[child]:off[child + 1]].reshape(W.shape)
+        assert np.abs(got - want).max() <= 1e-13 * max(abs(c), abs(q)), child
+        total += got.sum()
+    area = 2.0 * dim                                     # surface of the unit box
+    assert abs(total - (-c * 1.0 + q * area)) <= 1e-12
