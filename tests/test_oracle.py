@@ -498,3 +498,48 @@ def test_source_and_neumann_terms_in_closed_form(n, axis):
         total += got.sum()
     area = 2.0 * dim                                     # surface of the unit box
     assert abs(total - (-c * 1.0 + q * area)) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [(8, 8), (4, 6), (4, 4, 6)])
+def test_dirichlet_set_unit_rows_and_interpolated_values(n):
+    """Constraints assembly (constraints.hh:312-558, constraintsfunctors.hh:41-131) for the testpoisson boundary types (test/testpoisson.cc:
+    49-71, evaluated at the FACE CENTRE; a Dirichlet face constrains all its vertices): the exact set from the lattice — x_0 = 0 everywhere,
+    x_0 = 1 where the face centre has x_1 < 0.5, nothing on x_1 = 0 / 1 and (3-D) nothing on the x_2 faces beyond what those faces' own
+    centres give — then [UPSTREAM] handle_dirichlet_constraints: constrained rows are unit rows while the COLUMNS of constrained DOFs stay
+    (the matrix is not symmetrised), and interpolation puts G(vertex) into the constrained coefficients."""
+    o = orc.Oracle()
+    dim = len(n)
+    P = problems.testpoisson(o, n, split_axis=1)
+    con = o.get_constraints().astype(bool)
+    off = o.get_child_offsets()
+    want = np.zeros(P.ndof, dtype=bool)
+    coords = np.zeros((P.ndof, dim))
+    for child in (0, 1):
+        cells = list(n); cells[1] = n[1] // 2
+        ext = [m + 1 for m in cells]
+        idx = np.arange(int(np.prod(ext)))
+        ijk = []
+        rem = idx.copy()
+        for d in range(dim):
+            ijk.append(rem % ext[d]); rem //= ext[d]
+        gj = ijk[1] + (n[1] // 2 if child == 1 else 0)                 # global vertex index along the split axis
+        x0_lo = ijk[0] == 0
+        # a coefficient on x_0 = 1 is constrained iff one of the faces there OF ITS OWN SUBDOMAIN'S CELLS has its centre below x_1 = 0.5:
+        # every such coefficient of the lower subdomain (its copy of the interface vertex included), none of the upper one
+        x0_hi = (ijk[0] == n[0]) & (child == 0)
+        flag = x0_lo | x0_hi
+        if dim == 3:
+            # faces x_2 = 0 / 1: centre x_1 in (0, 1) is never within 1e-6 of the ends, and the x_0 > 1 - 1e-6 test fails at a face centre
+            # (x_0 centre < 1): Dirichlet.  All their vertices are constrained.
+            flag |= (ijk[2] == 0) | (ijk[2] == n[2])
+        want[off[child]:off[child + 1]] = flag
+        g = [ijk[0] / n[0], gj / n[1]] + ([ijk[2] / n[2]] if dim == 3 else [])
+        coords[off[child]:off[child + 1]] = np.stack(g, axis=1)
+    assert np.array_equal(con, want)
+    u = np.zeros(P.ndof); o.interpolate(P.sps, P.gfn, u)
+    G = np.exp(-((coords - 0.5) ** 2).sum(axis=1))                      # G: exp(-|x - 0.5|^2), testpoisson.cc:92-99
+    assert np.abs(u - G).max() <= 1e-15
+    o.jacobian(P.go, P.mat, u, overwrite=True)
+    A = o.csr(P.mat).toarray()
+    assert np.array_equal(A[con], np.eye(P.ndof)[con])                  # unit rows
+    assert np.abs(A[~con][:, con]).max() > 0.01                         # the columns of constrained DOFs are kept (no symmetrisation)
