@@ -5,8 +5,11 @@
 // pdelab/multidomaingrid, none of which are present) and its own tests contain
 // no expected values.  This file is therefore a from-scratch CPU
 // restatement of the reference's algorithm for the hot path, pinned only by
-// self-derived known-answer tests (tests/test_oracle_*.py): closed-form Q1
-// element matrices, SciPy cross-checks, patch tests, FD-vs-analytic.
+// self-derived known-answer tests (tests/test_oracle*.py; the table in DESIGN.md
+// section 2 lists them per assumption): closed-form element matrices, child blocks
+// against Kronecker products of 1-D matrices, the couplings and the lambda terms in
+// closed form, the Dirichlet set from the lattice, the solver stack against SciPy /
+// textbook recurrences, patch tests, FD-vs-analytic, SciPy direct solves.
 //
 // Nothing under the product tree (dune-multidomain_b200/, include/) may include,
 // link or call this; only tests/, __graft_entry__.smoke() and bench.py's CPU
