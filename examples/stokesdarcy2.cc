@@ -130,13 +130,16 @@ int main(int argc, char** argv)
 
     // addSolutionToVTKWriter(vtkwriter, multigfs, u, subdomain_predicate(...)); vtkwriter.write("stokes" / "darcy")  :831-880.
     // One conforming piece per subdomain: v_0, v_1 (P2: the vertex coefficients) and p on the Stokes view, the hydraulic head (orthonormal
-    // P3: every cell's polynomial at its corners, averaged per vertex) on the Darcy view.  The reference's derived fields (pressure and
-    // Darcy velocity from the potential, :871-880) are not written.  Off unless the deck says `output.vtk = true` (fifth argument: prefix).
+    // P3: every cell's polynomial at its corners, averaged per vertex) with the reference's derived fields — pressure and Darcy velocity
+    // from the potential (:443-560) — on the Darcy view.  Off unless the deck says `output.vtk = true` (fifth argument: prefix).
     if (parameters.has("output.vtk") && (parameters["output.vtk"] == "true" || parameters["output.vtk"] == "1")) {
       const std::string prefix = argc > 4 ? std::string(argv[4]) : std::string();
       VTKWriter stokes(grid, stokesGV), darcy(grid, darcyGV);
       stokes.addSolution(multigfs, u, {&stokesgfs, &darcygfs});
       darcy.addSolution(multigfs, u, {&stokesgfs, &darcygfs}, "phi");
+      darcy.addDarcyFields(multigfs, u, {&stokesgfs, &darcygfs}, darcygfs, mesh.elementIndexToPhysicalGroup,       // "p", "v"  :876-884
+                           parameters.get("parameters.soil.permeability"), parameters.get("parameters.soil.permeability.low"), 1,
+                           parameters.get("parameters.soil.porosity"), parameters.get("parameters.gravity", 9.81), parameters.get("parameters.fluid.rho"));
       stokes.write(prefix + "stokes"); darcy.write(prefix + "darcy");
       std::printf("wrote %sstokes.vtu, %sdarcy.vtu\n", prefix.c_str(), prefix.c_str());
     }

@@ -767,9 +767,9 @@ public:
   // the reference triangle: out[c * n + i].  Gram-Schmidt of the monomials in Dune::MonomialBasis order (1 | x, y | x^2, xy, y^2 | ...) with
   // respect to the L2 product of the reference triangle, i.e. L = C^-1 for the Cholesky factor C of G_ij = a! b! / (a + b + 2)!; here in
   // long double (output only: the device and the oracle evaluate the 60-digit tables of csrc/opb_tables.h; a test compares the two)
-  static void opb_corner_values(int k, std::vector<double>& out) {
-    std::vector<int> ea, eb, pa(1, 0), pb(1, 0);
-    ea.push_back(0); eb.push_back(0);
+  static void opb_matrix(int k, std::vector<long double>& L, std::vector<int>& ea, std::vector<int>& eb) {
+    std::vector<int> pa(1, 0), pb(1, 0);
+    ea.assign(1, 0); eb.assign(1, 0);
     for (int d = 1; d <= k; ++d) {
       std::vector<int> ra(1, d), rb(1, 0);
       for (size_t i = 0; i < pa.size(); ++i) { ra.push_back(pa[i]); rb.push_back(pb[i] + 1); }
@@ -779,7 +779,8 @@ public:
     const int n = (int)ea.size();
     std::vector<long double> fact(2 * k + 3, 1.0L);
     for (size_t i = 1; i < fact.size(); ++i) fact[i] = fact[i - 1] * (long double)i;
-    std::vector<long double> C((size_t)n * n, 0.0L), L((size_t)n * n, 0.0L);
+    std::vector<long double> C((size_t)n * n, 0.0L);
+    L.assign((size_t)n * n, 0.0L);
     for (int i = 0; i < n; ++i)
       for (int j = 0; j <= i; ++j) {
         const int a = ea[i] + ea[j], b = eb[i] + eb[j];
@@ -793,16 +794,73 @@ public:
         for (int m = col; m < i; ++m) t -= C[(size_t)i * n + m] * L[(size_t)m * n + col];
         L[(size_t)i * n + col] = t / C[(size_t)i * n + i];
       }
+  }
+  // out[c * n + i] = phi_i(corner c); grad (optional) [(c * n + i) * 2 + d] = d phi_i / d xhat_d at corner c (REFERENCE gradients)
+  static void opb_corner_values(int k, std::vector<double>& out, std::vector<double>* grad = 0) {
+    std::vector<long double> L; std::vector<int> ea, eb;
+    opb_matrix(k, L, ea, eb);
+    const int n = (int)ea.size();
+    static const long double cx[3] = {0.0L, 1.0L, 0.0L}, cy[3] = {0.0L, 0.0L, 1.0L};
     out.assign((size_t)3 * n, 0.0);
-    for (int i = 0; i < n; ++i) {
-      long double v0 = 0.0L, v1 = 0.0L, v2 = 0.0L;                                         // a monomial x^a y^b is 1 at (1,0) iff b = 0, at (0,1) iff a = 0
-      for (int j = 0; j <= i; ++j) {
-        if (ea[j] == 0 && eb[j] == 0) v0 += L[(size_t)i * n + j];
-        if (eb[j] == 0) v1 += L[(size_t)i * n + j];
-        if (ea[j] == 0) v2 += L[(size_t)i * n + j];
+    if (grad) grad->assign((size_t)6 * n, 0.0);
+    for (int c = 0; c < 3; ++c) {
+      std::vector<long double> px(k + 1, 1.0L), py(k + 1, 1.0L);
+      for (int e = 1; e <= k; ++e) { px[e] = px[e - 1] * cx[c]; py[e] = py[e - 1] * cy[c]; }
+      for (int i = 0; i < n; ++i) {
+        long double v = 0.0L, gx = 0.0L, gy = 0.0L;
+        for (int j = 0; j <= i; ++j) {
+          const long double l = L[(size_t)i * n + j];
+          v += l * px[ea[j]] * py[eb[j]];
+          if (ea[j] > 0) gx += l * (long double)ea[j] * px[ea[j] - 1] * py[eb[j]];
+          if (eb[j] > 0) gy += l * (long double)eb[j] * px[ea[j]] * py[eb[j] - 1];
+        }
+        out[(size_t)c * n + i] = (double)v;
+        if (grad) { (*grad)[((size_t)c * n + i) * 2] = (double)gx; (*grad)[((size_t)c * n + i) * 2 + 1] = (double)gy; }
       }
-      out[(size_t)i] = (double)v0; out[(size_t)n + i] = (double)v1; out[(size_t)2 * n + i] = (double)v2;
     }
+  }
+  // The derived fields the reference adds to the Darcy piece (test/stokesdarcy2.cc:876-884), on plain arrays like point_values:
+  //   VTKPressureFromPotential (:443-494):   p = (phi - x_last) * gravity * density
+  //   VTKDarcyFlowFromPotential (:497-560):  v = -A grad(phi) / porosity,  A = the cell's (isotropic) tensor value (DarcyParameters::A :285-290)
+  // evaluated per cell at its corners from the orthonormal coefficients (grad = J^-T grad_ref on the affine triangle) and averaged per
+  // vertex.  corner_xy[(ci * 3 + c) * 2 + d]: coordinates of corner c of listed cell ci; cell_A[ci]: its tensor value.
+  static void darcy_point_fields(const std::vector<const GridFunctionSpace*>& leaves, size_t gi, const std::vector<int64_t>& cells, const std::vector<uint8_t>& sd,
+                                 const std::vector<int64_t>& ptr, const std::vector<int64_t>& dofs, const double* x, const std::vector<int64_t>& cell_points,
+                                 const std::vector<double>& corner_xy, const std::vector<double>& cell_A, double porosity, double gravity, double density,
+                                 std::vector<double>& p, std::vector<double>& v0, std::vector<double>& v1 /* all sized to the number of points */) {
+    const GridFunctionSpace* g = leaves[gi];
+    if (!g->opb) throw Exception(MDB_EINVAL, "VTKWriter: the Darcy fields are derived from an orthonormal (OPB) potential space");
+    const int nloc = local_size(*g, 2);
+    std::vector<double> phi, gphi; opb_corner_values(g->k, phi, &gphi);
+    std::vector<int> count(p.size(), 0);
+    std::fill(p.begin(), p.end(), 0.0); std::fill(v0.begin(), v0.end(), 0.0); std::fill(v1.begin(), v1.end(), 0.0);
+    for (size_t ci = 0; ci < cells.size(); ++ci) {
+      const int64_t e = cells[ci];
+      int64_t off = ptr[(size_t)e];
+      for (size_t hi = 0; hi < gi; ++hi) {
+        const GridFunctionSpace* h = leaves[hi];
+        if (h->coupling) continue;
+        if (h->gv.subdomain < 0 || ((sd[(size_t)e] >> h->gv.subdomain) & 1)) off += local_size(*h, 2);
+      }
+      if (off + nloc > ptr[(size_t)e + 1]) throw Exception(MDB_EINVAL, "VTKWriter: the cell DOF map is shorter than the listed spaces");
+      const double* P = &corner_xy[ci * 6];
+      const double ax = P[2] - P[0], ay = P[3] - P[1], bx = P[4] - P[0], by = P[5] - P[1];      // columns of J: x = P0 + a xhat + b yhat
+      const double det = ax * by - ay * bx;
+      for (int c = 0; c < 3; ++c) {
+        double val = 0.0, gx = 0.0, gy = 0.0;
+        for (int i = 0; i < nloc; ++i) {
+          const double u = x[(size_t)dofs[(size_t)(off + i)]];
+          val += u * phi[(size_t)c * nloc + i];
+          gx += u * gphi[((size_t)c * nloc + i) * 2]; gy += u * gphi[((size_t)c * nloc + i) * 2 + 1];
+        }
+        const double dx = (by * gx - ay * gy) / det, dy = (-bx * gx + ax * gy) / det;           // J^-T (gx, gy)
+        const size_t pt = (size_t)cell_points[ci * 3 + (size_t)c];
+        p[pt] += (val - P[2 * c + 1]) * gravity * density;
+        v0[pt] += -cell_A[ci] * dx / porosity; v1[pt] += -cell_A[ci] * dy / porosity;
+        count[pt] += 1;
+      }
+    }
+    for (size_t pt = 0; pt < p.size(); ++pt) if (count[pt]) { p[pt] /= count[pt]; v0[pt] /= count[pt]; v1[pt] /= count[pt]; }
   }
   // The evaluation behind addSolution on plain arrays (unit-tested on the CPU, tests/test_vtk_spaces.py): point values of leaf `gi` of
   // `leaves` on the listed cells.  ptr / dofs: the cell DOF maps of mdb_get_dofmap (children in order, a child present iff its subdomain
@@ -871,6 +929,41 @@ public:
       point_values(leaves, gi, dim, corners(), cells_, sd, ptr, dofs, x.data(), cell_points, f.point_values);
       fields_.push_back(f);
     }
+  }
+  // .addVertexFunction<VTKPressureFromPotential>(TreePath<1>(), "p", darcyParams).addVertexFunction(VTKDarcyFlowFromPotential(darcyParams),
+  // TreePath<1>(), "v")  (test/stokesdarcy2.cc:876-884): fields "p", "v_0", "v_1" derived from the potential space `potential` (a leaf of
+  // `children`).  groups: elementIndexToPhysicalGroup of the mesh; the tensor is kabs on cells of `high_group`, kabs_low elsewhere.
+  void addDarcyFields(MultiDomainGridFunctionSpace& gfs, const Vector& x, std::initializer_list<const GridFunctionSpace*> children, const GridFunctionSpace& potential,
+                      const std::vector<int>& groups, double kabs, double kabs_low, int high_group, double porosity, double gravity, double density) {
+    collect();
+    gfs.update();
+    if (!grid_.unstructured() || grid_.dimension() != 2) throw Exception(MDB_EINVAL, "addDarcyFields: triangle meshes");
+    Context& ctx = gfs.context();
+    std::vector<int64_t> ptr((size_t)grid_.size0() + 1);
+    ctx.check(mdb_get_dofmap(ctx.get(), ptr.data(), 0), "mdb_get_dofmap");
+    std::vector<int64_t> dofs((size_t)ptr.back());
+    ctx.check(mdb_get_dofmap(ctx.get(), ptr.data(), dofs.data()), "mdb_get_dofmap");
+    std::vector<uint8_t> sd((size_t)grid_.size0());
+    ctx.check(mdb_get_subdomains(ctx.get(), sd.data()), "mdb_get_subdomains");
+    std::vector<const GridFunctionSpace*> leaves;
+    for (const GridFunctionSpace* g : children) flatten(g, leaves);
+    size_t gi = leaves.size();
+    for (size_t i = 0; i < leaves.size(); ++i) if (leaves[i] == &potential) gi = i;
+    if (gi == leaves.size() || potential.gv.subdomain != subdomain_) throw Exception(MDB_EINVAL, "addDarcyFields: the potential space is not a leaf on this writer's subdomain");
+    std::vector<int64_t> cell_points(cells_.size() * 3);
+    std::vector<double> corner_xy(cells_.size() * 6), cell_A(cells_.size());
+    for (size_t ci = 0; ci < cells_.size(); ++ci) {
+      for (int c = 0; c < 3; ++c) {
+        const int64_t v = vertex(cells_[ci], c);
+        cell_points[ci * 3 + (size_t)c] = point_of_vertex_[(size_t)v];
+        corner_xy[(ci * 3 + (size_t)c) * 2] = grid_.vertices()[(size_t)(v * 2)]; corner_xy[(ci * 3 + (size_t)c) * 2 + 1] = grid_.vertices()[(size_t)(v * 2 + 1)];
+      }
+      cell_A[ci] = groups[(size_t)cells_[ci]] == high_group ? kabs : kabs_low;
+    }
+    Field p, v0, v1; p.name = "p"; v0.name = "v_0"; v1.name = "v_1";
+    p.point_values.assign(vertex_of_point_.size(), 0.0); v0.point_values = p.point_values; v1.point_values = p.point_values;
+    darcy_point_fields(leaves, gi, cells_, sd, ptr, dofs, x.data(), cell_points, corner_xy, cell_A, porosity, gravity, density, p.point_values, v0.point_values, v1.point_values);
+    fields_.push_back(p); fields_.push_back(v0); fields_.push_back(v1);
   }
   // write(name, VTK::ascii): name.vtu
   void write(const std::string& name) {

@@ -52,6 +52,9 @@ int main(int argc, char** argv) {
   std::FILE* fp = std::fopen(argv[1], "r");
   std::vector<long long> sdv = read_ints(fp), ptrv = read_ints(fp), dofv = read_ints(fp), cellv = read_ints(fp), cpv = read_ints(fp), npv = read_ints(fp);
   std::vector<double> x = read_doubles(fp);
+  const bool darcy = std::string(argv[2]).substr(0, 5) == "darcy";
+  std::vector<double> corner_xy, cell_A;
+  if (darcy) { corner_xy = read_doubles(fp); cell_A = read_doubles(fp); }
   std::fclose(fp);
   std::vector<uint8_t> sd(sdv.begin(), sdv.end());
   std::vector<int64_t> ptr(ptrv.begin(), ptrv.end()), dofs(dofv.begin(), dofv.end()), cells(cellv.begin(), cellv.end()), cp(cpv.begin(), cpv.end());
@@ -69,10 +72,16 @@ int main(int argc, char** argv) {
   VectorGridFunctionSpace v(SubDomainGridView(0), 2, 2);
   PkGridFunctionSpace p(SubDomainGridView(0), 1);
   CompositeGridFunctionSpace th({&v, &p});
-  OPBGridFunctionSpace phi(SubDomainGridView(1), std::atoi(argv[2]));
+  OPBGridFunctionSpace phi(SubDomainGridView(1), darcy ? std::atoi(argv[2] + 6) : std::atoi(argv[2]));
   std::vector<const GridFunctionSpace*> leaves;
   const GridFunctionSpace* tops[2] = {&th, &phi};
   for (int t = 0; t < 2; ++t) { std::vector<GridFunctionSpace*> l; const_cast<GridFunctionSpace*>(tops[t])->collect(l); leaves.insert(leaves.end(), l.begin(), l.end()); }
+  if (darcy) {                                          // the derived fields of the Darcy piece: argv[4..6] = porosity, gravity, density
+    std::vector<double> pp((size_t)npv[0], 0.0), v0(pp), v1(pp);
+    VTKWriter::darcy_point_fields(leaves, 3, cells, sd, ptr, dofs, x.data(), cp, corner_xy, cell_A, std::atof(argv[4]), std::atof(argv[5]), std::atof(argv[6]), pp, v0, v1);
+    for (size_t i = 0; i < pp.size(); ++i) std::printf("%zu %.17g %.17g %.17g\n", i, pp[i], v0[i], v1[i]);
+    return 0;
+  }
   for (size_t gi = 0; gi < leaves.size(); ++gi) {
     if (leaves[gi]->gv.subdomain != which) continue;
     std::vector<double> val((size_t)npv[0], 0.0);
@@ -218,3 +227,49 @@ def test_point_values_of_qk_spaces_are_the_corner_coefficients(harness, n, ks, w
     off = o.get_child_offsets()[which]
     want = x[off:off + int(used.sum())]
     assert ncells == len(sd) and np.array_equal(mine, want)
+
+
+@pytest.mark.parametrize("darcy_k", [3, 2])
+def test_derived_darcy_fields(harness, darcy_k):
+    """VTKPressureFromPotential and VTKDarcyFlowFromPotential (test/stokesdarcy2.cc:443-560) from the orthonormal coefficients: p = (phi - y)
+    g rho and v = -A grad(phi) / porosity per cell corner (A by physical group), averaged per vertex — against the oracle's basis, its
+    reference gradients and its cell geometry (J^-T)."""
+    xy, conn, groups = sdp.filtration_mesh(6, 4, seed=11)
+    ora = sdp.oracle()
+    H = sdp.setup(ora, xy, conn, groups, darcy_fe=sdo.FE_OPB1 + darcy_k - 1, params=sdp.ini_params(darcy_k=darcy_k))
+    ptr, dofs = ora.get_dofmap()
+    sd = np.where(groups > 0, 2, 1)
+    x = np.random.default_rng(9).uniform(-1.0, 1.0, H["ndof"])
+    cells = np.nonzero((sd >> 1) & 1)[0]
+    used = np.zeros(len(xy), dtype=bool); used[conn[cells].ravel()] = True
+    pov = np.full(len(xy), -1); pov[used] = np.arange(used.sum())
+    cp = pov[conn[cells]]
+    kabs, kabs_low, porosity, gravity, density = 1.16e-5, 1.16e-10, 0.01, 9.81, 1e3
+    cell_A = np.where(groups[cells] == 1, kabs, kabs_low)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "in.txt")
+        with open(path, "w") as fp:
+            for a in (sd, ptr, dofs, cells, cp, [used.sum()]):
+                _write(fp, a, "%d")
+            for a in (x, xy[conn[cells]], cell_A):
+                _write(fp, a, "%.17g")
+        out = subprocess.check_output([harness, path, "darcy:%d" % darcy_k, "1", repr(porosity), repr(gravity), repr(density)], text=True)
+    got = np.array([[float(t) for t in l.split()[1:]] for l in out.split("\n") if l])
+    off = ora.get_child_offsets()
+    n = sdo.fe_size(sdo.FE_OPB1 + darcy_k - 1)
+    npts = int(used.sum())
+    acc = np.zeros((npts, 3)); cnt = np.zeros(npts)
+    corners = ((0.0, 0.0), (1.0, 0.0), (0.0, 1.0))
+    for r, e in enumerate(cells):
+        coeff = x[off[3] + r * n: off[3] + (r + 1) * n]
+        _, jinvt, _ = ora._geo(int(e))                   # J^-T of the affine cell map
+        for c in range(3):
+            val, grad = sdo.opb_eval(darcy_k, *corners[c])
+            g = jinvt @ (coeff @ grad)
+            pt = pov[conn[e][c]]
+            acc[pt, 0] += (coeff @ val - xy[conn[e][c]][1]) * gravity * density
+            acc[pt, 1:] += -cell_A[r] * g / porosity
+            cnt[pt] += 1
+    want = acc / cnt[:, None]
+    for col in range(3):
+        assert np.abs(got[:, col] - want[:, col]).max() <= 1e-11 * np.abs(want[:, col]).max(), col
