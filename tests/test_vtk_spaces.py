@@ -95,6 +95,8 @@ int main(int argc, char** argv) {
 
 @pytest.fixture(scope="module")
 def harness():
+    if os.environ.get("MDB_VTK_HARNESS"):                # a prebuilt harness, e.g. one compiled with -fsanitize=address,undefined
+        return os.environ["MDB_VTK_HARNESS"]
     d = tempfile.mkdtemp()
     src = os.path.join(d, "h.cc")
     open(src, "w").write(HARNESS)
